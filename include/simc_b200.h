@@ -1,0 +1,253 @@
+/*
+ * simc_b200.h -- C ABI of libsimc_b200.so, the B200 implementation of SIMC's
+ * per-event Monte Carlo loop.
+ *
+ * The reference (JeffersonLab/simc_gfortran) has no plugin / FFI interface: the
+ * seam is the body of the event loop in `program simc` (simc.f:169-351), i.e.
+ *
+ *     call generate(main,vertex,orig,success)                       ! event.f:126
+ *     call montecarlo(orig,main,recon,success)                      ! simc.f:1310
+ *     call complete_recon_ev(recon,success)                         ! event.f:1056
+ *     call complete_main(.false.,main,vertex,vertex0,recon,success) ! event.f:1363
+ *     call inc(...) / counters / limits_update                      ! simc.f:229-336
+ *
+ * plus the "structure-free" single-arm entry points mc_hms / mc_shms / mc_sos /
+ * mc_hrsl / mc_hrsr (hms/mc_hms.f:1-4, shms/mc_shms.f:1-4, simulate.inc:177-179).
+ * A per-event call into a GPU is useless, so every entry point here is
+ * batch-level.  An unchanged Fortran driver keeps simc.f:1-165 (deck reading,
+ * init, calculate_central) and simc.f:354-620 (normalisation, reports) and
+ * replaces the loop by simc_b200_run(); see INTEGRATION.md for the
+ * ISO_C_BINDING shim.
+ *
+ * Conventions: plain C, caller-owned memory, HOST pointers unless a function
+ * says "device", int status return (0 = ok, <0 = error; text through
+ * simc_b200_last_error), no exceptions, no torch types.  All energies MeV,
+ * lengths cm, angles rad, deltas percent -- the reference's units
+ * (constants.inc:3-10).
+ */
+#ifndef SIMC_B200_H
+#define SIMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIMC_B200_ABI_VERSION 1
+
+/* ---- spectrometer ids: electron_arm / hadron_arm numbering of dbase.f:247-263 */
+enum {
+  SIMC_ARM_HMS  = 1,
+  SIMC_ARM_SOS  = 2,
+  SIMC_ARM_HRSR = 3,
+  SIMC_ARM_HRSL = 4,
+  SIMC_ARM_SHMS = 5
+};
+
+/* ---- status codes */
+enum {
+  SIMC_OK            =  0,
+  SIMC_ERR_ARG       = -1,   /* bad argument / unsupported flag combination */
+  SIMC_ERR_IO        = -2,   /* optics / table file unreadable or malformed (reference: `stop` in transp.f:319-389) */
+  SIMC_ERR_CUDA      = -3,   /* CUDA runtime error; there is NO CPU fallback */
+  SIMC_ERR_STATE     = -4    /* call order (e.g. run before load_optics) */
+};
+
+/* ---- basic records: field order follows modules.f so a Fortran `sequence`
+ *      type can be passed by reference where the layouts coincide. */
+typedef struct { double min, max; } simc_cut;                      /* modules.f:5  cutstype   */
+typedef struct { double lo, hi; } simc_range;                      /* modules.f:10 rangetype  */
+typedef struct { simc_cut delta, yptar, xptar, z; } simc_arm_cuts; /* modules.f:35 arm_cuts   */
+typedef struct { simc_cut delta, yptar, xptar, E; } simc_arm_limits; /* modules.f:202 arm_limits */
+typedef struct { simc_cut E, yptar, xptar; } simc_edge_arm;        /* modules.f:170 edge_arm  */
+typedef struct {                                                   /* modules.f:178 edge_true */
+  simc_edge_arm e, p;
+  simc_cut Em, Pm, Mrec, Trec, Trec_struck;
+} simc_edge;
+typedef struct {                                                   /* modules.f:210 gen_limits */
+  simc_arm_limits e, p;
+  simc_cut sumEgen, Trec;
+  double xwid, ywid;
+} simc_gen_limits;
+typedef struct {                                                   /* modules.f:150-165 spectrometer */
+  double P, theta, cos_th, sin_th, phi;
+  double off_x, off_y, off_z, off_xptar, off_yptar;
+} simc_spectrometer;
+typedef struct { double min, bin; } simc_axis;                     /* modules.f:195 axis (n is always 50: init.f:519-569) */
+
+/* target_info, target.inc:37-49 (only what the loop reads) */
+typedef struct {
+  double A, Z, N, mass_amu, M, mrec_amu, Mrec, rho, thick, angle, abundancy;
+  double length, zoffset, X0, X0_cm, L1, L2, fr1, fr2, xoffset, yoffset;
+  double Coulomb_ave, Coulomb_min, Coulomb_max, Coulomb_constant;
+  double Mtar_struck, Mrec_struck;
+  int32_t fr_pattern, can;
+} simc_target;
+
+#define SIMC_NHIST 50            /* bins per histogram, init.f:519-569 */
+
+/* Histogram slots of one set (simc.f:253-286).  The x' histograms of the gen
+ * and geni sets are filled with -xptar, as in the reference. */
+enum {
+  SIMC_H_E_DELTA = 0, SIMC_H_E_YPTAR, SIMC_H_E_XPTAR,
+  SIMC_H_P_DELTA,     SIMC_H_P_YPTAR, SIMC_H_P_XPTAR,
+  SIMC_H_EM,          SIMC_H_PM,
+  SIMC_H_PER_SET
+};
+
+/* Run constants: everything the loop body reads from /gnrl/ (simulate.inc:91-113),
+ * /radccom/ run-level part (radc.inc:13-19), /target_info/ (target.inc:52-53),
+ * /decd/ (simulate.inc:153-158), and the histogram axes H%*%min/bin.  Filled by
+ * the Fortran shim after calculate_central (simc.f:89), or by
+ * simc_b200_config_from_deck() for standalone runs. */
+typedef struct {
+  int32_t abi_version;                       /* = SIMC_B200_ABI_VERSION */
+
+  /* reaction flags, dbase.f:138-222 */
+  int32_t doing_phsp, doing_hyd_elast, doing_deuterium, doing_heavy, doing_eep;
+  int32_t doing_pion, doing_kaon, doing_delta, doing_rho, doing_semi;
+  int32_t doing_hydpi, doing_deutpi, doing_hepi;
+  int32_t doing_hydkaon, doing_deutkaon, doing_hekaon;
+  int32_t doing_hydsemi, doing_deutsemi;
+  int32_t doing_hplus, doing_decay;
+  int32_t which_pion, which_kaon;
+  /* switches */
+  int32_t using_rad, using_Eloss, using_Coulomb, correct_Eloss, correct_raster;
+  int32_t mc_smear, hard_cuts;
+  int32_t using_E_arm_montecarlo, using_P_arm_montecarlo;
+  int32_t electron_arm, hadron_arm;          /* SIMC_ARM_* */
+  int32_t using_HMScoll, using_SHMScoll, use_benhar_sf;
+  /* radiative flags, radc.inc:3-4 (after radc_init, init.f:621-629) */
+  int32_t rad_flag, extrad_flag, intcor_mode, use_expon, use_offshell_rad;
+  int32_t doing_tail[3];
+  int32_t hardwired_rad;
+  int32_t pad0;
+
+  /* /gnrl/ scalars */
+  double Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave;
+  double dE_edge_test, Egamma_gen_max, ctau, transparency;
+  /* /radccom/ run-level */
+  double etatzai, Egamma_tot_max, Egamma1_max, Egamma2_max, Egamma3_max, Egamma_res_limit;
+
+  simc_gen_limits   gen;
+  simc_spectrometer spec_e, spec_p;
+  simc_cut          cuts_Em, cuts_Pm;
+  simc_edge         edge, VERTEXedge;
+  simc_arm_cuts     SPedge_e, SPedge_p;
+  double            slop_MC_e_used[3], slop_MC_p_used[3];   /* delta, yptar, xptar (modules.f:297-327) */
+  simc_target       targ;
+
+  /* histogram axes, 3 sets x 8 (histograms_module.f:6-31): [set][slot], set 0 = RECON, 1 = gen, 2 = geni */
+  simc_axis         hist_axis[3][SIMC_H_PER_SET];
+
+  /* Reference weight (e.g. central%sigcc): fixes the fixed-point quantum of the
+   * deterministic weight accumulators, quantum = 2^(ilogb(w_ref)-64). <=0 -> 1. */
+  double w_ref;
+} simc_run_config;
+
+/* Number of STOP slots per arm in simc_accum.stop[][] (hms/struct_hms.inc,
+ * shms/struct_shms.inc, ...).  Slot 0 = trials, slot 1 = successes, slot 2 =
+ * events reaching the hut, slots 3.. = 2 + stop code (see simc_b200_stop_name). */
+#define SIMC_NSTOP 64
+
+/* 128-bit two's-complement fixed-point sum: value = (hi*2^64 + lo) * 2^qexp */
+typedef struct { uint64_t lo; int64_t hi; int32_t qexp; int32_t pad; } simc_fixed128;
+
+/* What the loop leaves behind (simc.f:229-350); everything is an exact
+ * integer or a min/max, hence independent of event order and GPU count. */
+typedef struct {
+  int64_t ntried, nsuccess, ncontribute, npasscuts, ncontribute_no_rad_proton; /* simulate.inc:60-61 */
+  simc_fixed128 wtcontribute;                  /* simc.f:304 */
+  simc_fixed128 sum_sigcc;                     /* simc.f:248 */
+  simc_fixed128 sumerr[8], sumerr2[8];         /* e: delta,xptar,yptar,ytar; p: same (simc.f:305-322) */
+  simc_fixed128 hist_w[6][SIMC_NHIST];         /* H%RECON e/p delta,yptar,xptar: sum of weights */
+  int64_t       hist_n[3][SIMC_H_PER_SET][SIMC_NHIST]; /* counts: [0]=RECON (only Em,Pm used) [1]=gen [2]=geni */
+  simc_range    contrib[32];                   /* limits_update order, event.f:19-72 */
+  simc_range    slop[8];                       /* MC e/p delta,yptar,xptar; total Em,Pm (event.f:75-87) */
+  int64_t       stop[2][SIMC_NSTOP];           /* [0] = electron arm, [1] = hadron arm */
+} simc_accum;
+
+typedef struct simc_handle simc_handle;
+
+/* lifecycle ------------------------------------------------------------- */
+int  simc_b200_abi_version(void);
+int  simc_b200_create(const simc_run_config* cfg, int device, simc_handle** out);
+void simc_b200_destroy(simc_handle* h);
+const char* simc_b200_last_error(const simc_handle* h);   /* h may be NULL: last create() error */
+int64_t simc_b200_sizeof(int which);                      /* 0: simc_run_config, 1: simc_accum (binding self-check) */
+/* Arithmetic variant.  1 (default) = "strict": separate multiply/add in the reference's
+ * order (an x86-64 gfortran -O build forms no FMA, Makefile:63), COSY sums bit-identical to
+ * such a build.  0 = "fast": fused multiply-add and re-associated monomials, ~1e-15 relative.
+ * The environment variable SIMC_B200_MODE=strict|fast sets the default at create(). */
+int simc_b200_set_mode(simc_handle* h, int strict_mode);
+int simc_b200_sync(simc_handle* h);                       /* waits for the handle's stream */
+
+/* optics --------------------------------------------------------------- *
+ * Replaces transp_init (shared/transp.f:294-474) and the first-call loaders of
+ * mc_*_recon (hms/mc_hms_recon.f:70-102): the reference's tables are SAVEd
+ * locals and cannot be handed over, so the library parses the COSY files. */
+int simc_b200_load_optics(simc_handle* h, int arm_id, const char* forward_path, const char* recon_path);
+
+/* Same tables passed as arrays (used by tests and by callers that have them in
+ * memory).  fwd_coeff[n_fwd_terms][5], fwd_expon[n_fwd_terms][5] (x,theta,y,phi,delta;
+ * TOF lines already dropped), fwd_class_start[n_classes+1], fwd_length_cm[n_classes]
+ * (the !LENGTH: comment x100, 0 if absent); rec_coeff[n_rec][4], rec_expon[n_rec][5]. */
+int simc_b200_set_optics(simc_handle* h, int arm_id,
+                         int n_classes, const int32_t* fwd_class_start,
+                         const double* fwd_coeff, const int8_t* fwd_expon, const double* fwd_length_cm,
+                         int n_rec, const double* rec_coeff, const int8_t* rec_expon);
+
+/* info[0..6] = n_classes, forward terms, non-zero forward coefficients, recon terms,
+ * compiled groups, packed coefficients, ops in the arm program */
+int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);
+
+/* the loop -------------------------------------------------------------- *
+ * Replaces simc.f:169-351 for tries first_try .. first_try+n_tries-1 of the
+ * counter-based stream `seed` (try t always sees the same random numbers, on
+ * any GPU).  Adds into *acc (zero it with simc_b200_accum_clear first). */
+int simc_b200_accum_clear(simc_handle* h, simc_accum* acc);
+int simc_b200_run(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, simc_accum* acc);
+
+/* Asynchronous pieces of simc_b200_run for callers that overlap or time the
+ * device work themselves (bench.py): launch on the handle's stream, then fetch. */
+int simc_b200_run_async(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed);
+int simc_b200_fetch(simc_handle* h, simc_accum* acc);          /* syncs, adds device accumulators into *acc, clears them */
+int simc_b200_device_accum(simc_handle* h, void** dev_ptr, int64_t* n_int64, void** dev_minmax, int64_t* n_minmax);
+void* simc_b200_stream(simc_handle* h);                        /* cudaStream_t */
+int64_t simc_b200_launch_count(const simc_handle* h);          /* kernels launched so far */
+
+/* single-arm parity entry point ---------------------------------------- *
+ * Batch form of mc_hms / mc_shms / ... (hms/mc_hms.f:1-4).  Row i of in[] is
+ * { dpp(%), x, y, z, dxdz, dydz, m2, p_spec, fry } (SoA: in[k*n+i]); the random
+ * stream is (seed, try=i).  out[k*n+i], k = 0..11:
+ * { dpp_recon, dxdz_recon(=dph), dydz_recon(=dth), y_recon, x_fp, dx_fp, y_fp, dy_fp,
+ *   pathlen, m2_final, resmult, n_draws } -- the in/out convention of
+ * mc_hms.f:428-431; rows that stop keep their pre-hut values where the
+ * reference would.  flags[i] = 0 if ok_spec else the stop code. */
+#define SIMC_TRANSPORT_NIN  9
+#define SIMC_TRANSPORT_NOUT 12
+int simc_b200_transport_batch(simc_handle* h, int arm_id, int64_t n,
+                              const double* in_soa, uint64_t seed,
+                              int ms_flag, int wcs_flag, int decay_flag, int using_coll,
+                              double* out_soa, int32_t* flags);
+/* Same with in/out already resident in device memory (HBM); used by bench.py
+ * for the HBM-resident timing leg.  Asynchronous on the handle's stream. */
+int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
+                              const double* d_in_soa, uint64_t seed,
+                              int ms_flag, int wcs_flag, int decay_flag, int using_coll,
+                              double* d_out_soa, int32_t* d_flags);
+
+/* whole-event parity entry point: per-try records instead of accumulators.
+ * rec[k*n+i], k = 0..SIMC_EVENT_NREC-1 (see simc_b200_event_field_name). */
+#define SIMC_EVENT_NREC 48
+int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
+                          double* rec_soa, int32_t* status);
+const char* simc_b200_event_field_name(int k);
+
+const char* simc_b200_stop_name(int arm_id, int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMC_B200_H */

@@ -1,0 +1,734 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see arms.hpp).  Literal, sequential restatement;
+// every block cites the reference lines it follows.
+#include "arms.hpp"
+
+namespace simc_oracle {
+
+// =====================================================================================
+// HMS
+// =====================================================================================
+namespace {
+namespace hms {
+// hms/apertures_hms.inc
+constexpr double r_Q1 = 20.50, r_Q2 = 30.22, r_Q3 = 30.22;
+constexpr double x_d1 = 34.29, y_d1 = 12.07, x_d2 = 27.94, y_d2 = 18.42, x_d3 = 13.97, y_d3 = 18.95;
+constexpr double x_d4 = 1.956, y_d4 = 20.32, x_d5 = 27.94, y_d5 = 12.065, r_d5 = 6.35, a_d6 = -0.114, b_d6 = 20.54;
+// hms/mc_hms.f:28-95
+constexpr double x_offset_pipes = 2.8, y_offset_pipes = 0.0;
+constexpr double h_entr = 4.575, v_entr = 11.646, h_exit = 4.759, v_exit = 12.114;
+constexpr double x_off = +0.000, y_off = +0.028, z_off = +40.17;
+constexpr double z_entr = 126.2e0 + z_off, z_exit = z_entr + 6.3e0;
+constexpr double z_dip1 = 64.77e0, z_dip2 = z_dip1 + 297.18e0, z_dip3 = z_dip2 + 115.57e0;
+
+// hms/mc_hms.f:445-492
+bool hit_dipole(double x, double y) {
+  const double x_local = std::fabs(x), y_local = std::fabs(y);
+  const bool check1 = (x_local <= x_d1) && (y_local <= y_d1);
+  const bool check2 = (x_local <= x_d2) && (y_local <= y_d2);
+  const bool check3 = (x_local <= x_d3) && (y_local <= y_d3);
+  const bool check4 = (x_local <= x_d4) && (y_local <= y_d4);
+  const bool check5 = ((x_local - x_d5) * (x_local - x_d5) + (y_local - y_d5) * (y_local - y_d5)) <= r_d5 * r_d5;
+  const bool check6 = (x_local >= x_d4) && (x_local <= x_d3) && ((y_local - a_d6 * x_local - b_d6) <= 0.0);
+  return !(check1 || check2 || check3 || check4 || check5 || check6);
+}
+
+// hms/mc_hms_hut.f:27-255 (geometry parameters)
+constexpr double hfoil_exit_radlen = 8.90, hfoil_exit_thick = 0.011 * 2.54;
+constexpr double hair_radlen = 30420.;
+constexpr double hdc_entr_radlen = 28.7, hdc_entr_thick = 0.001 * 2.54;
+constexpr double hdc_radlen = 16700.0, hdc_thick = 1.8;
+constexpr double hdc_wire_radlen = 0.35, hdc_wire_thick = 0.0000049;
+constexpr double hdc_cath_radlen = 7.2, hdc_cath_thick = 0.000177;
+constexpr double hdc_exit_radlen = 28.7, hdc_exit_thick = 0.001 * 2.54;
+constexpr double haer_entr_radlen = 8.90, haer_entr_thick = 0.15;
+constexpr double haer_radlen = 150.0, haer_thick = 9.0;
+constexpr double haer_air_radlen = 30420.0, haer_air_thick = 16.0;
+constexpr double haer_exit_radlen = 8.90, haer_exit_thick = 0.1;
+constexpr double hscin_radlen = 42.4;
+constexpr double hcer_entr_radlen = 8.90, hcer_entr_thick = 0.040 * 2.54;
+constexpr double hcer_radlen = 9620.0;
+constexpr double hcer_mir_radlen = 400.0, hcer_mir_thick = 2.0;
+constexpr double hcer_exit_radlen = 8.90, hcer_exit_thick = 0.040 * 2.54;
+constexpr double hdc_sigma = 0.030;
+constexpr int hdc_nr_cham = 2, hdc_nr_plan = 6;
+constexpr double hdc_1_zpos = -52.1084, hdc_2_zpos = 29.2608;
+constexpr double hdc_del_plane = hdc_thick + hdc_wire_thick + hdc_cath_thick;
+constexpr double hdc_1_left = 26.0, hdc_1_right = -26.0, hdc_1y_offset = 1.443, hdc_1_top = -56.5, hdc_1_bot = 56.5,
+                 hdc_1x_offset = 1.670;
+constexpr double hdc_2_left = 26.0, hdc_2_right = -26.0, hdc_2y_offset = 2.753, hdc_2_top = -56.5, hdc_2_bot = 56.5,
+                 hdc_2x_offset = 2.758;
+constexpr double haer_zentrance = 35.699, haer_zexit = 60.949;
+constexpr double hscin_1x_zpos = 77.830, hscin_1y_zpos = 97.520, hscin_2x_zpos = 298.820, hscin_2y_zpos = 318.510;
+constexpr double hscin_1x_thick = 1.067, hscin_1y_thick = 1.067, hscin_2x_thick = 1.067, hscin_2y_thick = 1.067;
+constexpr double hscin_1x_left = 37.75, hscin_1x_right = -37.75, hscin_1x_offset = -1.3;
+constexpr double hscin_1y_top = -60.25, hscin_1y_bot = 60.25, hscin_1y_offset = -1.3;
+constexpr double hcer_zentrance = 110.000, hcer_zmirror = 230.000, hcer_zexit = 265.000;
+constexpr double hcal_4ta_zpos = 371.69;
+constexpr int scintrig = 3;
+
+// mc_hms_hut, hms/mc_hms_hut.f:1-608
+bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag, double zinit) {
+  Rng& r = *t.rng;
+  const bool ms = a.ms_flag, wcs = a.wcs_flag, dec = a.decay_flag;
+  double radw, drift;
+  float xdc[12], ydc[12], zdc[12];
+  // :292-298  15% of events get doubled DC resolution
+  const double tmpran = r.grnd();
+  a.resmult = (tmpran < 0.15) ? 2.0 : 1.0;
+  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
+  int scincount = 0;
+
+  // :315-317 drift to a point 25 cm in front of DC1, exit foil
+  drift = (hdc_1_zpos - 25.000) - zinit;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  radw = hfoil_exit_thick / hfoil_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :321-326 air to DC1
+  drift = (hdc_1_zpos - 0.5 * hdc_nr_plan * hdc_del_plane) - (hdc_1_zpos - 25.000);
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+
+  for (int jchamber = 1; jchamber <= 2; ++jchamber) {
+    // :331-336 / :385-390 entrance window
+    radw = hdc_entr_thick / hdc_entr_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {   // :341-370 / :395-425
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_cath_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      radw = hdc_wire_thick / hdc_wire_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      double tmpran1 = 0., tmpran2 = 0.;
+      if (wcs) { tmpran1 = gauss1(r, 99.0); tmpran2 = gauss1(r, 99.0); }
+      xdc[npl_off + iplane - 1] = (float)(t.xs + hdc_sigma * tmpran1 * a.resmult);
+      ydc[npl_off + iplane - 1] = (float)(t.ys + hdc_sigma * tmpran2 * a.resmult);
+      if (iplane == 2 || iplane == 5) xdc[npl_off + iplane - 1] = 0.f;
+      else ydc[npl_off + iplane - 1] = 0.f;
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_wire_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+    }
+    radw = hdc_exit_thick / hdc_exit_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    if (jchamber == 1) {
+      if (t.xs > (hdc_1_bot - hdc_1x_offset) || t.xs < (hdc_1_top - hdc_1x_offset) ||
+          t.ys > (hdc_1_left - hdc_1y_offset) || t.ys < (hdc_1_right - hdc_1y_offset)) {
+        a.stop_code = hms_stop::DC1;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      // :379-384 air to DC2
+      drift = (hdc_2_zpos - 0.5 * hdc_nr_plan * hdc_del_plane) - (hdc_1_zpos + 0.5 * hdc_nr_plan * hdc_del_plane);
+      radw = drift / hair_radlen;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+    } else {
+      if (t.xs > (hdc_2_bot - hdc_2x_offset) || t.xs < (hdc_2_top - hdc_2x_offset) ||
+          t.ys > (hdc_2_left - hdc_2y_offset) || t.ys < (hdc_2_right - hdc_2y_offset)) {
+        a.stop_code = hms_stop::DC2;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    }
+  }
+  // :438-455 fit the track through REAL*4 arrays
+  for (int jchamber = 1; jchamber <= hdc_nr_cham; ++jchamber) {
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {
+      const double z0 = (jchamber == 1) ? hdc_1_zpos : hdc_2_zpos;
+      zdc[npl_off + iplane - 1] = (float)(z0 + (iplane - 0.5 - 0.5 * hdc_nr_plan) * hdc_del_plane);
+    }
+  }
+  float dxfp4, xfp4, dyfp4, yfp4;
+  lfit(zdc, xdc, 12, dxfp4, xfp4);
+  lfit(zdc, ydc, 12, dyfp4, yfp4);
+  a.x_fp = (double)xfp4;
+  a.y_fp = (double)yfp4;
+  a.dx_fp = (double)dxfp4;
+  a.dy_fp = (double)dyfp4;
+
+  // :460-483 aerogel
+  drift = haer_zentrance - hdc_2_zpos - 0.5 * hdc_nr_plan * hdc_del_plane;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = haer_entr_thick / haer_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = haer_thick;
+  radw = drift / haer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  drift = haer_air_thick;
+  radw = drift / haer_air_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = haer_exit_thick / haer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+
+  // All four scintillator planes are tested against the 1x/1y dimensions (A.7, :537-551).
+  auto in_scin = [&]() {
+    return t.ys < (hscin_1x_left + hscin_1y_offset) && t.ys > (hscin_1x_right + hscin_1y_offset) &&
+           t.xs < (hscin_1y_bot + hscin_1x_offset) && t.xs > (hscin_1y_top + hscin_1x_offset);
+  };
+  // :487-498 S1X
+  drift = hscin_1x_zpos - haer_zexit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_scin()) scincount++;
+  radw = hscin_1x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :500-510 S1Y
+  drift = hscin_1y_zpos - hscin_1x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_scin()) scincount++;
+  radw = hscin_1y_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :514-535 Cherenkov
+  drift = hcer_zentrance - hscin_1y_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_entr_thick / hcer_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_zmirror - hcer_zentrance;
+  radw = drift / hcer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_mir_thick / hcer_mir_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_zexit - hcer_zmirror;
+  radw = hcer_exit_thick / hcer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  radw = hcer_exit_thick / hcer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :537-551 S2X, S2Y
+  drift = hscin_2x_zpos - hcer_zexit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_scin()) scincount++;
+  radw = hscin_2x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hscin_2y_zpos - hscin_2x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_scin()) scincount++;
+  radw = hscin_2y_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  if (scincount < scintrig) {
+    a.stop_code = hms_stop::SCIN;
+    return false;
+  }
+  // :580-590 drift to the calorimeter (no cut applied)
+  drift = hcal_4ta_zpos - hscin_2y_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  return true;
+}
+}  // namespace hms
+}  // namespace
+
+// mc_hms, hms/mc_hms.f:1-441
+void mc_hms(Track& t, const ArmOptics& o, ArmCall& a) {
+  using namespace hms;
+  const int spectr_classes = o.fwd.n_classes();
+  if (spectr_classes != 12) throw std::runtime_error("MC_HMS, wrong number of transport classes");
+  const bool dec = a.decay_flag;
+  a.ok_spec = false;
+  a.stop_code = 0;
+  a.reached_hut = false;
+  bool dflag = false;
+  t.xs = a.x; t.ys = a.y; t.zs = a.z; t.dxdzs = a.dxdz; t.dydzs = a.dydz;
+  t.dpps = a.dpp;
+  double p = a.p_spec * (1. + t.dpps / 100.);
+  double& m2 = a.m2;
+  double xt, yt, zdrift;
+  auto stop = [&](int code) { a.stop_code = code; };
+
+  // :201-254 collimator
+  zdrift = z_entr;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (a.using_coll && (m2 > 100.0 * 100.0) && (m2 < 200.0 * 200.0)) {
+    throw std::runtime_error("oracle: mc_hms_coll (pion stepping through the collimator) not restated yet");
+  } else {
+    if (std::fabs(t.ys - y_off) > h_entr) return stop(hms_stop::SLIT_HOR);
+    if (std::fabs(t.xs - x_off) > v_entr) return stop(hms_stop::SLIT_VERT);
+    if (std::fabs(t.xs - x_off) > (-v_entr / h_entr * std::fabs(t.ys - y_off) + 3 * v_entr / 2))
+      return stop(hms_stop::SLIT_OCT);
+    zdrift = z_exit - z_entr;
+    project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+    if (std::fabs(t.ys - y_off) > h_exit) return stop(hms_stop::SLIT_HOR);
+    if (std::fabs(t.xs - x_off) > v_exit) return stop(hms_stop::SLIT_VERT);
+    if (std::fabs(t.xs - x_off) > (-v_exit / h_exit * std::fabs(t.ys - y_off) + 3 * v_exit / 2))
+      return stop(hms_stop::SLIT_OCT);
+  }
+  // :258-280 Q1
+  zdrift = o.fwd.cls[0].driftdist - z_exit;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q1 * r_Q1) return stop(hms_stop::Q1_IN);
+  transp(t, o.fwd, 2, dec, dflag, m2, p, 125.233e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q1 * r_Q1) return stop(hms_stop::Q1_MID);
+  transp(t, o.fwd, 3, dec, dflag, m2, p, 62.617e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q1 * r_Q1) return stop(hms_stop::Q1_OUT);
+  // :284-306 Q2
+  zdrift = o.fwd.cls[3].driftdist;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q2 * r_Q2) return stop(hms_stop::Q2_IN);
+  transp(t, o.fwd, 5, dec, dflag, m2, p, 143.90e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q2 * r_Q2) return stop(hms_stop::Q2_MID);
+  transp(t, o.fwd, 6, dec, dflag, m2, p, 71.95e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q2 * r_Q2) return stop(hms_stop::Q2_OUT);
+  // :310-332 Q3
+  zdrift = o.fwd.cls[6].driftdist;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q3 * r_Q3) return stop(hms_stop::Q3_IN);
+  transp(t, o.fwd, 8, dec, dflag, m2, p, 143.8e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q3 * r_Q3) return stop(hms_stop::Q3_MID);
+  transp(t, o.fwd, 9, dec, dflag, m2, p, 71.9e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r_Q3 * r_Q3) return stop(hms_stop::Q3_OUT);
+  // :337-396 dipole
+  zdrift = o.fwd.cls[9].driftdist;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, -6.0e0, xt, yt);
+  if (hit_dipole(xt, yt)) return stop(hms_stop::D1_IN);
+  transp(t, o.fwd, 11, dec, dflag, m2, p, 526.053e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 6.0e0, xt, yt);
+  if (hit_dipole(xt, yt)) return stop(hms_stop::D1_OUT);
+  if ((((xt - x_offset_pipes) * (xt - x_offset_pipes) + (yt - y_offset_pipes) * (yt - y_offset_pipes)) >
+       30.48 * 30.48) ||
+      (std::fabs((yt - y_offset_pipes)) > 20.5232))
+    return stop(hms_stop::D1_OUT);
+  zdrift = z_dip1;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (((t.xs - x_offset_pipes) * (t.xs - x_offset_pipes) + (t.ys - y_offset_pipes) * (t.ys - y_offset_pipes)) >
+      1145.518)
+    return stop(hms_stop::D1_OUT);
+  zdrift = z_dip2 - z_dip1;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (((t.xs - x_offset_pipes) * (t.xs - x_offset_pipes) + (t.ys - y_offset_pipes) * (t.ys - y_offset_pipes)) >
+      1512.2299)
+    return stop(hms_stop::D1_OUT);
+  zdrift = z_dip3 - z_dip2;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (((t.xs - x_offset_pipes) * (t.xs - x_offset_pipes) + (t.ys - y_offset_pipes) * (t.ys - y_offset_pipes)) >
+      2162.9383)
+    return stop(hms_stop::D1_OUT);
+
+  // :400-417 hut
+  a.reached_hut = true;
+  zdrift = o.fwd.cls[11].driftdist - z_dip3;
+  if (!hut(t, a, m2, p, dflag, -zdrift)) return;
+  // :419-437 reconstruct from the fitted focal-plane track
+  t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
+  double dpp_recon, dth_recon, dph_recon, y_recon;
+  o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon);
+  a.dpp = dpp_recon;
+  a.dxdz = dph_recon;
+  a.dydz = dth_recon;
+  a.y = y_recon;
+  a.ok_spec = true;
+}
+
+// =====================================================================================
+// SHMS
+// =====================================================================================
+namespace {
+namespace shms {
+// shms/apertures_shms.inc
+constexpr double r_HBx = 11.2, r_HBfym = -4.13, r_HBfyp = 11.75, r_HBmenym = -5.45, r_HBmenyp = 11.74;
+constexpr double r_HBmexym = -10.25, r_HBmexyp = 11.71, r_HBbym = -11.71, r_HBbyp = 11.70;
+constexpr double r_Q1 = 20.00, r_Q2 = 30.00, r_Q3 = 30.00, r_D1 = 30.00;
+// shms/mc_shms.f:233-318
+constexpr double h_entr = 8.5, v_entr = 12.5, h_exit = 8.65, v_exit = 12.85, x_off = +0.00, y_off = +0.00;
+constexpr double zd_hbin = 118.39, zd_hbmen = 17.61, zd_hbmex = 80.0, zd_hbout = 17.61;
+constexpr double z_entr = 25.189, z_thick = 6.35;
+constexpr double zd_q1in = 58.39, zd_q1men = 28.35, zd_q1mid = 93.65, zd_q1mex = 93.65, zd_q1out = 28.35;
+constexpr double zd_q2in = 25.55, zd_q2men = 39.1, zd_q2mid = 79.35, zd_q2mex = 79.35, zd_q2out = 39.1;
+constexpr double zd_q3in = 28.10, zd_q3men = 39.1, zd_q3mid = 79.35, zd_q3mex = 79.35, zd_q3out = 39.1;
+constexpr double zd_q3d1trans = 18.00, zd_d1flare = 30.10, zd_d1men = 39.47;
+constexpr double zd_d1mid = 36.406263, zd_d1mex = 36.406263, zd_d1out = 60.68, zd_fp = 307.95;
+// shms/hut.inc
+constexpr double hfoil_exit_radlen = 8.89, hfoil_exit_thick = 0.020 * 2.54;
+constexpr double hair_radlen = 30420.;
+constexpr double hdc_entr_radlen = 28.7, hdc_entr_thick = 0.001 * 2.54;
+constexpr double hdc_radlen = 16700.0, hdc_thick = 0.125 * 2.54;
+constexpr double hdc_wire_radlen = 0.35, hdc_wire_thick = 0.0000354;
+constexpr double hdc_cath_radlen = 28.6, hdc_cath_thick = 0.001 * 2.54;
+constexpr double hdc_exit_radlen = 28.7, hdc_exit_thick = 0.001 * 2.54;
+constexpr double hscin_radlen = 42.4;
+constexpr double hcer_entr_radlen = 19.63, hcer_entr_thick = 0.002 * 2.54;
+constexpr double hcer_1_radlen = 11700.0;
+constexpr double hcer_mirglass_radlen = 12.29, hcer_mirglass_thick = 0.3;
+constexpr double hcer_exit_radlen = 19.63, hcer_exit_thick = 0.002 * 2.54;
+constexpr double hcer_2_entr_radlen = 8.90, hcer_2_entr_thick = 0.040 * 2.54;
+constexpr double hcer_2_radlen = 1202.5;
+constexpr double hcer_mir_radlen = 400., hcer_mir_thick = 2.00;
+constexpr double hcer_2_exit_radlen = 8.90, hcer_2_exit_thick = 0.040 * 2.54;
+constexpr double hdc_sigma = 0.020;
+constexpr int hdc_nr_cham = 2, hdc_nr_plan = 6;
+constexpr double hdc_1_zpos = -40.656, hdc_2_zpos = 39.332;
+constexpr double hdc_1_left = 40.0, hdc_1_right = -40.0, hdc_1y_offset = 0.0, hdc_1_top = -40., hdc_1_bot = 40.,
+                 hdc_1x_offset = 0.0;
+constexpr double hdc_2_left = 40.0, hdc_2_right = -40.0, hdc_2y_offset = 0.0, hdc_2_top = -40., hdc_2_bot = 40.,
+                 hdc_2x_offset = 0.;
+constexpr double hscin_1x_zpos = 52.1, hscin_1y_zpos = 61.7, hscin_2x_zpos = 271.4, hscin_2y_zpos = 282.4;
+constexpr double hscin_1x_thick = 1.000 * 1.067, hscin_1y_thick = 1.000 * 1.067, hscin_2x_thick = 1.000 * 1.067,
+                 hscin_2y_thick = 1.000 * 1.067;
+constexpr double hscin_1x_left = 50., hscin_1x_right = -50., hscin_1x_offset = 0.0;
+constexpr double hscin_1y_top = -45., hscin_1y_bot = 45., hscin_1y_offset = 0.0;
+constexpr double hscin_2x_left = 55., hscin_2x_right = -55., hscin_2x_offset = 0.;
+constexpr double hscin_2y_top = -62.5, hscin_2y_bot = 62.5, hscin_2y_offset = 0;
+constexpr double hcer_1_zentrance = -291.700, hcer_1_zmirror = -84.900, hcer_1_zexit = -61.700;
+constexpr double hcer_2_zentrance = 72.600, hcer_2_zmirror = 179.400, hcer_2_zexit = 202.600;
+constexpr double hcal_4ta_zpos = 341.0;
+constexpr double hcal_left = 63.00, hcal_right = -63.00, hcal_top = -70.00, hcal_bottom = 70.00;
+
+// mc_shms_hut, shms/mc_shms_hut.f:1-458 with cer_flag=.true., vac_flag=.false.
+// (hard-wired in shms/mc_shms.f:352-353)
+bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag) {
+  Rng& r = *t.rng;
+  const bool ms = a.ms_flag, wcs = a.wcs_flag, dec = a.decay_flag;
+  double radw, drift;
+  float xdc[12], ydc[12], zdc[12];
+  const double hdc_del_plane = hdc_thick + hdc_wire_thick + hdc_cath_thick;   // run-time sum, :73
+  a.resmult = 1.0;
+  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
+
+  // :89-118 noble-gas Cherenkov
+  radw = hfoil_exit_thick / hfoil_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  radw = hcer_entr_thick / hcer_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_1_zmirror - hcer_1_zentrance - hcer_mirglass_thick / 2;
+  radw = drift / hcer_1_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_mirglass_thick / hcer_mirglass_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_1_zexit - hcer_1_zmirror - hcer_mirglass_thick / 2;
+  radw = drift / hcer_1_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_exit_thick / hcer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+
+  // :150-156 air to DC1
+  drift = (hdc_1_zpos - 0.5 * hdc_nr_plan * hdc_del_plane) - hcer_1_zexit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+
+  for (int jchamber = 1; jchamber <= 2; ++jchamber) {
+    radw = hdc_entr_thick / hdc_entr_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {   // :163-201 / :231-266
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_cath_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      radw = hdc_wire_thick / hdc_wire_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      double tmpran1 = 0., tmpran2 = 0.;
+      if (wcs) { tmpran1 = gauss1(r, 99.0); tmpran2 = gauss1(r, 99.0); }
+      xdc[npl_off + iplane - 1] = (float)(t.xs + hdc_sigma * tmpran1 * a.resmult);
+      ydc[npl_off + iplane - 1] = (float)(t.ys + hdc_sigma * tmpran2 * a.resmult);
+      if (iplane == 2 || iplane == 5) xdc[npl_off + iplane - 1] = 0.f;
+      else ydc[npl_off + iplane - 1] = 0.f;
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_wire_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+    }
+    radw = hdc_exit_thick / hdc_exit_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    if (jchamber == 1) {
+      if (t.xs > (hdc_1_bot - hdc_1x_offset) || t.xs < (hdc_1_top - hdc_1x_offset) ||
+          t.ys > (hdc_1_left - hdc_1y_offset) || t.ys < (hdc_1_right - hdc_1y_offset)) {
+        a.stop_code = shms_stop::DC1;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      // :222-226 air to DC2
+      drift = hdc_2_zpos - hdc_1_zpos - hdc_nr_plan * hdc_del_plane;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      radw = drift / hair_radlen;
+      if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+    } else {
+      if (t.xs > (hdc_2_bot - hdc_2x_offset) || t.xs < (hdc_2_top - hdc_2x_offset) ||
+          t.ys > (hdc_2_left - hdc_2y_offset) || t.ys < (hdc_2_right - hdc_2y_offset)) {
+        a.stop_code = shms_stop::DC2;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    }
+  }
+  // :290-318 S1X, S1Y
+  drift = hscin_1x_zpos - hdc_2_zpos - 0.5 * hdc_nr_plan * hdc_del_plane;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.ys > (hscin_1x_left + hscin_1y_offset) || t.ys < (hscin_1x_right + hscin_1y_offset)) {
+    a.stop_code = shms_stop::S1X;
+    return false;
+  }
+  radw = hscin_1x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hscin_1y_zpos - hscin_1x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.xs > (hscin_1y_bot + hscin_1x_offset) || t.xs < (hscin_1y_top + hscin_1x_offset)) {
+    a.stop_code = shms_stop::S1Y;
+    return false;
+  }
+  radw = hscin_1y_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :322-346 heavy-gas Cherenkov
+  drift = hcer_2_zentrance - hscin_1y_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_2_entr_thick / hcer_2_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_2_zmirror - hcer_2_zentrance;
+  radw = drift / hcer_2_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_mir_thick / hcer_mir_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_2_zexit - hcer_2_zmirror;
+  radw = drift / hcer_2_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_2_exit_thick / hcer_2_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :350-380 S2X, S2Y
+  drift = hscin_2x_zpos - hcer_2_zexit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.ys > (hscin_2x_left + hscin_2y_offset) || t.ys < (hscin_2x_right + hscin_2y_offset)) {
+    a.stop_code = shms_stop::S2X;
+    return false;
+  }
+  radw = hscin_2x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hscin_2y_zpos - hscin_2x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.xs > (hscin_2y_bot + hscin_2x_offset) || t.xs < (hscin_2y_top + hscin_2x_offset)) {
+    a.stop_code = shms_stop::S2Y;
+    return false;
+  }
+  radw = hscin_2y_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :384-398 calorimeter
+  drift = hcal_4ta_zpos - hscin_2y_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.ys > hcal_left || t.ys < hcal_right || t.xs > hcal_bottom || t.xs < hcal_top) {
+    a.stop_code = shms_stop::CAL;
+    return false;
+  }
+  // :402-424 track fit (REAL*4) and calorimeter fiducial cut on the fitted track
+  for (int jchamber = 1; jchamber <= hdc_nr_cham; ++jchamber) {
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {
+      const double z0 = (jchamber == 1) ? hdc_1_zpos : hdc_2_zpos;
+      zdc[npl_off + iplane - 1] = (float)(z0 + (iplane - 0.5 - 0.5 * hdc_nr_plan) * hdc_del_plane);
+    }
+  }
+  float dx, x0, dy, y0;
+  lfit(zdc, xdc, 12, dx, x0);
+  lfit(zdc, ydc, 12, dy, y0);
+  a.x_fp = x0; a.y_fp = y0; a.dx_fp = dx; a.dy_fp = dy;
+  const double xcal = a.x_fp + a.dx_fp * hcal_4ta_zpos;
+  const double ycal = a.y_fp + a.dy_fp * hcal_4ta_zpos;
+  if (ycal > (hcal_left - 5.0) || ycal < (hcal_right + 5.0) || xcal > (hcal_bottom - 5.0) ||
+      xcal < (hcal_top + 5.0)) {
+    a.stop_code = shms_stop::CAL_FID;
+    return false;
+  }
+  return true;
+}
+}  // namespace shms
+}  // namespace
+
+// mc_shms, shms/mc_shms.f:1-1110 (use_sieve=.false., use_coll=.true., skip_hb=.false.)
+void mc_shms(Track& t, const ArmOptics& o, ArmCall& a) {
+  using namespace shms;
+  if (o.fwd.n_classes() != 32) throw std::runtime_error("Bender-SHMS, wrong number of transport classes");
+  const bool dec = a.decay_flag;
+  a.ok_spec = false;
+  a.stop_code = 0;
+  a.reached_hut = false;
+  bool dflag = false;
+  t.dpps = a.dpp;
+  double p = a.p_spec * (1. + t.dpps / 100.);
+  t.xs = a.x; t.ys = a.y; t.zs = a.z; t.dxdzs = a.dxdz; t.dydzs = a.dydz;
+  double& m2 = a.m2;
+  double xt, yt, zdrift;
+  auto stop = [&](int code) { a.stop_code = code; };
+  auto r2 = [&]() { return t.xs * t.xs + t.ys * t.ys; };
+
+  // :414-492 horizontal bender
+  zdrift = zd_hbin;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_vaxis(t, 1.5, xt, yt);
+  yt = yt + 1.51;
+  if ((xt * xt > r_HBx * r_HBx) || (yt > r_HBfyp) || (yt < r_HBfym)) return stop(shms_stop::HB_IN);
+  zdrift = zd_hbmen;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_vaxis(t, 1.5, xt, yt);
+  yt = yt + 0.98;
+  if ((xt * xt > r_HBx * r_HBx) || (yt > r_HBmenyp) || (yt < r_HBmenym)) return stop(shms_stop::HB_MEN);
+  transp(t, o.fwd, 3, dec, dflag, m2, p, zd_hbmex, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_vaxis(t, -1.5, xt, yt);
+  yt = yt + 0.98;
+  if ((xt * xt > r_HBx * r_HBx) || (yt > r_HBmexyp) || (yt < r_HBmexym)) return stop(shms_stop::HB_MEX);
+  zdrift = zd_hbout;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_vaxis(t, -1.5, xt, yt);
+  yt = yt + 1.51;
+  if ((xt * xt > r_HBx * r_HBx) || (yt > r_HBbyp) || (yt < r_HBbym)) return stop(shms_stop::HB_OUT);
+
+  // :496-560 collimator
+  if (a.using_coll && (m2 > 100.0 * 100.0) && (m2 < 200.0 * 200.0)) {
+    throw std::runtime_error("oracle: mc_shms_coll (pion stepping through the collimator) not restated yet");
+  } else {
+    zdrift = z_entr;
+    project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+    xt = t.xs; yt = t.ys;
+    if (std::fabs(yt - y_off) > h_entr) return stop(shms_stop::SLIT_HOR);
+    if (std::fabs(xt - x_off) > v_entr) return stop(shms_stop::SLIT_VERT);
+    if (std::fabs(xt - x_off) > (-v_entr / h_entr * std::fabs(yt - y_off) + 3 * v_entr / 2))
+      return stop(shms_stop::SLIT_OCT);
+    zdrift = z_thick;
+    project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+    xt = t.xs; yt = t.ys;
+    if (std::fabs(yt - y_off) > (h_exit)) return stop(shms_stop::SLIT_HOR);
+    if (std::fabs(xt - x_off) > (v_exit)) return stop(shms_stop::SLIT_VERT);
+    if (std::fabs(xt - x_off) > ((-v_exit) / (h_exit)*std::fabs(yt - y_off) + 3 * (v_exit) / 2))
+      return stop(shms_stop::SLIT_OCT);
+  }
+  // :566-656 Q1
+  zdrift = zd_q1in - z_entr - z_thick;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(shms_stop::Q1_IN);
+  zdrift = zd_q1men;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(shms_stop::Q1_MEN);
+  transp(t, o.fwd, 7, dec, dflag, m2, p, zd_q1mid, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(shms_stop::Q1_MID);
+  transp(t, o.fwd, 8, dec, dflag, m2, p, zd_q1mex, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(shms_stop::Q1_MEX);
+  zdrift = zd_q1out;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(shms_stop::Q1_OUT);
+  // :660-745 Q2
+  zdrift = zd_q2in;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(shms_stop::Q2_IN);
+  zdrift = zd_q2men;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(shms_stop::Q2_MEN);
+  transp(t, o.fwd, 12, dec, dflag, m2, p, zd_q2mid, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(shms_stop::Q2_MID);
+  transp(t, o.fwd, 13, dec, dflag, m2, p, zd_q2mex, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(shms_stop::Q2_MEX);
+  zdrift = zd_q2out;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(shms_stop::Q2_OUT);
+  // :749-834 Q3
+  zdrift = zd_q3in;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(shms_stop::Q3_IN);
+  zdrift = zd_q3men;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(shms_stop::Q3_MEN);
+  transp(t, o.fwd, 17, dec, dflag, m2, p, zd_q3mid, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(shms_stop::Q3_MID);
+  transp(t, o.fwd, 18, dec, dflag, m2, p, zd_q3mex, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(shms_stop::Q3_MEX);
+  zdrift = zd_q3out;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(shms_stop::Q3_OUT);
+  // :838-1040 dipole: entrance, flare, magnetic entrance, 7 mid planes, magnetic exit, exit
+  zdrift = zd_q3d1trans;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_D1 * r_D1) return stop(shms_stop::D1_IN);
+  zdrift = zd_d1flare;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 9.200, xt, yt);
+  xt = xt - 3.5;
+  if ((xt * xt + yt * yt) > r_D1 * r_D1) return stop(shms_stop::D1_FLR);
+  zdrift = zd_d1men;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 9.200, xt, yt);
+  xt = xt + 2.82;
+  if ((xt * xt + yt * yt) > r_D1 * r_D1) return stop(shms_stop::D1_MEN);
+  static const double mid_ang[8] = {6.9, 4.6, 2.3, 0.0, -2.3, -4.6, -6.9, -9.2};
+  static const double mid_off[8] = {8.05, 11.75, 13.96, 14.70, 13.96, 11.75, 8.05, 2.82};
+  for (int k = 0; k < 8; ++k) {   // classes 23..30: mid1..mid7, mex
+    transp(t, o.fwd, 23 + k, dec, dflag, m2, p, (k < 7) ? zd_d1mid : zd_d1mex, a.pathlen);
+    xt = t.xs; yt = t.ys;
+    rotate_haxis(t, mid_ang[k], xt, yt);
+    xt = xt + mid_off[k];
+    if ((xt * xt + yt * yt) > r_D1 * r_D1) return stop(shms_stop::D1_MID1 + k);
+  }
+  zdrift = zd_d1out;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, -9.20, xt, yt);
+  xt = xt - 6.88;
+  if ((xt * xt + yt * yt) > r_D1 * r_D1) return stop(shms_stop::D1_OUT);
+  // :1044-1060 drift to the Cherenkov entrance (cer_flag=.true.)
+  zdrift = zd_fp + hcer_1_zentrance;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  a.reached_hut = true;
+  if (!hut(t, a, m2, p, dflag)) return;
+  // :1076-1094 recon
+  t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
+  double dpp_recon, dth_recon, dph_recon, y_recon;
+  o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon);
+  a.dpp = dpp_recon;
+  a.dxdz = dph_recon;
+  a.dydz = dth_recon;
+  a.y = y_recon;
+  a.ok_spec = true;
+}
+
+}  // namespace simc_oracle

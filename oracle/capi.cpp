@@ -1,0 +1,129 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  C entry points for tests/ (ctypes), smoke() and the
+// cpu_baseline leg of bench.py.  Never linked into, loaded by, or called from libsimc_b200.so.
+#include <cstring>
+#include <map>
+#include <string>
+#include "arms.hpp"
+
+using namespace simc_oracle;
+
+static std::map<int, ArmOptics> g_optics;
+static std::string g_err;
+
+extern "C" {
+
+const char* oracle_last_error() { return g_err.c_str(); }
+
+int oracle_load_optics(int arm, const char* fwd_path, const char* rec_path) {
+  try {
+    ArmOptics o;
+    o.fwd.load(fwd_path);
+    o.rec.load(rec_path);
+    g_optics[arm] = std::move(o);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// Table export: sizes first (pass null arrays), then data.  Layout = simc_b200_set_optics.
+int oracle_optics_sizes(int arm, int* n_classes, int* n_fwd_terms, int* n_rec) {
+  auto it = g_optics.find(arm);
+  if (it == g_optics.end()) { g_err = "optics not loaded"; return -1; }
+  *n_classes = it->second.fwd.n_classes();
+  int n = 0;
+  for (auto& c : it->second.fwd.cls) n += c.n_terms;
+  *n_fwd_terms = n;
+  *n_rec = it->second.rec.n_terms;
+  return 0;
+}
+int oracle_optics_export(int arm, int32_t* class_start, double* fwd_coeff, int8_t* fwd_expon, double* length_cm,
+                         int8_t* adrift, double* driftdist, double* rec_coeff, int8_t* rec_expon) {
+  auto it = g_optics.find(arm);
+  if (it == g_optics.end()) { g_err = "optics not loaded"; return -1; }
+  const ArmOptics& o = it->second;
+  int pos = 0, k = 0;
+  for (auto& c : o.fwd.cls) {
+    class_start[k] = pos;
+    length_cm[k] = c.length;
+    adrift[k] = c.adrift;
+    driftdist[k] = c.driftdist;
+    std::memcpy(fwd_coeff + 5 * pos, c.coeff.data(), sizeof(double) * 5 * c.n_terms);
+    std::memcpy(fwd_expon + 5 * pos, c.expon.data(), 5 * c.n_terms);
+    pos += c.n_terms;
+    ++k;
+  }
+  class_start[k] = pos;
+  std::memcpy(rec_coeff, o.rec.coeff.data(), sizeof(double) * 4 * o.rec.n_terms);
+  std::memcpy(rec_expon, o.rec.expon.data(), 5 * o.rec.n_terms);
+  return 0;
+}
+int oracle_set_optics(int arm, int n_classes, const int32_t* class_start, const double* fwd_coeff,
+                      const int8_t* fwd_expon, const double* length_cm, const int8_t* adrift, const double* driftdist,
+                      int n_rec, const double* rec_coeff, const int8_t* rec_expon) {
+  ArmOptics o;
+  for (int k = 0; k < n_classes; ++k) {
+    CosyClass c;
+    c.n_terms = class_start[k + 1] - class_start[k];
+    c.coeff.assign(fwd_coeff + 5 * class_start[k], fwd_coeff + 5 * class_start[k + 1]);
+    c.expon.assign(fwd_expon + 5 * class_start[k], fwd_expon + 5 * class_start[k + 1]);
+    c.length = length_cm[k];
+    c.adrift = adrift[k];
+    c.driftdist = driftdist[k];
+    o.fwd.cls.push_back(std::move(c));
+  }
+  o.rec.n_terms = n_rec;
+  o.rec.coeff.assign(rec_coeff, rec_coeff + 4 * n_rec);
+  o.rec.expon.assign(rec_expon, rec_expon + 5 * n_rec);
+  g_optics[arm] = std::move(o);
+  return 0;
+}
+
+// Batch form of mc_hms / mc_shms; same row layout as simc_b200_transport_batch.
+int oracle_transport_batch(int arm, int64_t n, const double* in, uint64_t seed, int ms_flag, int wcs_flag,
+                           int decay_flag, int using_coll, double ctau, double* out, int32_t* flags) {
+  auto it = g_optics.find(arm);
+  if (it == g_optics.end()) { g_err = "optics not loaded"; return -1; }
+  const ArmOptics& o = it->second;
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Rng rng;
+      rng.seed_philox(seed, (uint64_t)i);
+      Track t;
+      t.rng = &rng;
+      t.ctau = ctau;
+      ArmCall a;
+      a.dpp = in[0 * n + i]; a.x = in[1 * n + i]; a.y = in[2 * n + i]; a.z = in[3 * n + i];
+      a.dxdz = in[4 * n + i]; a.dydz = in[5 * n + i]; a.m2 = in[6 * n + i]; a.p_spec = in[7 * n + i];
+      a.fry = in[8 * n + i];
+      a.ms_flag = ms_flag; a.wcs_flag = wcs_flag; a.decay_flag = decay_flag; a.using_coll = using_coll;
+      t.Mh2_final = a.m2;
+      if (arm == 1) mc_hms(t, o, a);
+      else if (arm == 5) mc_shms(t, o, a);
+      else { g_err = "oracle: arm not restated yet"; return -1; }
+      out[0 * n + i] = a.dpp; out[1 * n + i] = a.dxdz; out[2 * n + i] = a.dydz; out[3 * n + i] = a.y;
+      out[4 * n + i] = a.x_fp; out[5 * n + i] = a.dx_fp; out[6 * n + i] = a.y_fp; out[7 * n + i] = a.dy_fp;
+      out[8 * n + i] = a.pathlen; out[9 * n + i] = a.m2; out[10 * n + i] = a.resmult;
+      out[11 * n + i] = (double)rng.draw;
+      flags[i] = a.ok_spec ? 0 : a.stop_code;
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// RANLUX known-answer access: n uniforms from grnd() after sgrnd(seed)
+int oracle_ranlux(int seed, int lux, int64_t n, double* out) {
+  RanluxState st;
+  st.rluxgo(lux, seed, 0, 0);
+  for (int64_t i = 0; i < n; ++i) st.ranlux(out + i, 1);
+  return 0;
+}
+int oracle_philox_block(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  Philox4x32::block(ctr, key, out);
+  return 0;
+}
+int oracle_philox_uniforms(uint64_t seed, uint64_t try_index, int64_t n, double* out) {
+  Rng r; r.seed_philox(seed, try_index);
+  for (int64_t i = 0; i < n; ++i) out[i] = r.grnd();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Arm programs: the single-arm Monte Carlos of the reference (hms/mc_hms.f + mc_hms_hut.f,
+// shms/mc_shms.f + mc_shms_hut.f, ...) expressed as a flat list of warp-uniform operations
+// that one CUDA thread per event interprets.  Every geometric constant is evaluated on the
+// host in IEEE double exactly as the Fortran parameter expression it comes from, so the
+// device compares against bit-identical limits.  POD only: shared by host and device code.
+#pragma once
+#include <stdint.h>
+
+namespace simc {
+
+enum ArmOpCode : int32_t {
+  OP_END = 0,
+  OP_PROJECT,        // a = z_drift                                   shared/project.f
+  OP_PROJECT_DD,     // z_drift = driftdist(class i0) + a             (mc_hms.f:258,284,310,337,411)
+  OP_TRANSP,         // i0 = class (1-based), a = zd                  shared/transp.f
+  OP_CUT_R2,         // stop if xs^2+ys^2 > a          (a = r*r)      e.g. mc_hms.f:261
+  OP_CUT_ABS_Y,      // stop if |ys-a| > b                            mc_hms.f:222
+  OP_CUT_ABS_X,      // stop if |xs-a| > b                            mc_hms.f:226
+  OP_CUT_OCT,        // stop if |xs-a| > c*|ys-b| + d                 mc_hms.f:230
+  OP_CUT_OFF_R2,     // stop if (xs-a)^2+(ys-b)^2 > c                 mc_hms.f:373
+  OP_ROT_H,          // (xt,yt) = rotate_haxis(xs,ys); a=tan,b=sin,c=cos; then xt += d
+  OP_ROT_V,          // (xt,yt) = rotate_vaxis(xs,ys); a=tan,b=sin,c=cos; then yt += d
+  OP_CUT_T_R2,       // stop if xt^2+yt^2 > a                         shms/mc_shms.f:866
+  OP_CUT_HB,         // stop if xt^2 > a or yt > b or yt < c          shms/mc_shms.f:425
+  OP_CUT_HMS_DIPOLE, // stop if hit_dipole(xt,yt)                     mc_hms.f:445-492
+  OP_CUT_HMS_PIPE,   // stop if (xt-a)^2+(yt-b)^2 > c or |yt-b| > d   mc_hms.f:361
+  OP_MARK_HUT,       // STOP_hut counter
+  OP_RESMULT_DRAW,   // one uniform; resmult = 2 if u < a else 1      mc_hms_hut.f:292-298
+  OP_RESMULT_ONE,    // resmult = 1                                   shms/mc_shms_hut.f:80
+  OP_MUSC,           // a = radw, b = sqrt(radw)                      shared/musc.f
+  OP_MUSC_EXT,       // a = radw, b = sqrt(radw), c = x_len           shared/musc_ext.f
+  OP_DC_PLANE,       // i0 = plane (0..11), i1 = 1 for a y plane, a = sigma   mc_hms_hut.f:351-364
+  OP_CUT_BOX,        // stop if xs > a or xs < b or ys > c or ys < d  mc_hms_hut.f:374
+  OP_SCIN_COUNT,     // count++ if ys < a and ys > b and xs < c and xs > d   mc_hms_hut.f:492
+  OP_SCIN_TRIG,      // stop if count < i0                            mc_hms_hut.f:570
+  OP_LFIT,           // fit focal-plane track through REAL*4 arrays   mc_hms_hut.f:438-455
+  OP_CUT_FP_CAL,     // xcal=x_fp+dx_fp*a ...; stop if ycal>b or ycal<c or xcal>d or xcal<e  mc_shms_hut.f:415
+  OP_RECON,          // mc_*_recon + overwrite dpp,y,dxdz,dydz        mc_hms.f:419-437
+  OP_UNSUPPORTED     // collimator stepping for pions etc.
+};
+
+struct ArmOp {
+  int32_t op;
+  int32_t code;      // stop code recorded when this op rejects the event
+  int32_t i0, i1;
+  double a, b, c, d, e;
+};
+
+constexpr int kMaxArmOps = 320;
+constexpr int kMaxClasses = 41;       // max_class, spectrometers.inc:6
+
+// One COSY map compiled into "groups": a run of consecutive file terms that share the
+// exponents of variables 3,4,5 and the degree m = e1+e2, with e2 strictly increasing.  The
+// group header packs e3,e4,e5,m (3 bits each) and, for k = e2 = 0..6, the 5-bit mask of
+// outputs whose coefficient is non-zero (0 = term absent).  Coefficients follow in (k, output)
+// order.  File order is preserved, so every output's sum sees its terms in the reference's
+// order; terms with a zero coefficient add exactly 0 in the reference and are skipped here.
+struct PolyClass {
+  int32_t group_begin, group_end;   // into hdr[]
+  int32_t coef_begin;               // into coef[]
+  int32_t n_terms;
+  double length_cm;                 // !LENGTH: comment (0 if none)
+  double driftdist_cm;              // extracted drift length if a pure drift
+  int32_t adrift;
+  int32_t pad;
+};
+
+struct ArmTablesDev {
+  const unsigned long long* hdr;    // group headers, forward classes then recon
+  const double* coef;               // packed non-zero coefficients
+  PolyClass fwd[kMaxClasses];       // 1-based class k -> fwd[k-1]
+  PolyClass rec;
+  int32_t n_classes;
+  int32_t n_ops;
+};
+
+}  // namespace simc

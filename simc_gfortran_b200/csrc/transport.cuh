@@ -1,0 +1,453 @@
+// Device side of single-arm transport + reconstruction: one thread per event interprets
+// the arm program (arm_program.h).  Replaces, per event, mc_hms/mc_shms/... with their hut
+// and recon routines and the shared primitives project/musc/musc_ext/rotate_*/transp/lfit.
+//
+// SIMC_STRICT=1 (compiled with -fmad=false): every product and sum is formed in the
+// reference's order with separate multiply and add, so the COSY sums are bit-identical to a
+// no-FMA x86-64 build; only libm calls (log, log10, acos, sin, cos) can differ in the last ulp.
+// SIMC_STRICT=0 (-fmad=true): the monomial products are re-associated (suffix product per
+// group) and fused multiply-adds are used; results agree to ~1e-15 relative.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "arm_program.h"
+#include "philox.cuh"
+
+#ifndef SIMC_STRICT
+#define SIMC_STRICT 1
+#endif
+#ifndef SIMC_VARIANT_NS
+#define SIMC_VARIANT_NS strict
+#endif
+
+namespace simc {
+namespace SIMC_VARIANT_NS {
+
+constexpr int kBlock = 128;               // threads per CTA for the event kernels
+// shared power table for the slow variables of a COSY map: [3 vars][7 exponents][kBlock]
+constexpr int kPowDoubles = 3 * 7 * kBlock;
+
+struct ArmDev {                           // lives in global memory, read through warp-uniform loads
+  ArmTablesDev tab;
+  ArmOp ops[kMaxArmOps];
+};
+
+struct TrackDev {
+  double xs, ys, dxdzs, dydzs, dpps;      // COMMON /track/ (spectrometers.inc:47-60)
+  double p, m2, pathlen;
+  double decdist, mh2_final, ctau;        // simulate.inc:183, :92, :153
+  double mc1, mbeta2;                     // cached Es/p/beta and beta^2 of musc (valid while p,m2 unchanged)
+  bool dflag;
+};
+
+struct ArmResult {
+  double x_fp, dx_fp, y_fp, dy_fp;
+  double dpp_rec, dth_rec, dph_rec, y_rec;
+  double resmult;
+  int stop_code;
+  bool reached_hut;
+  bool ok;
+};
+
+// constants.inc:17-42 (decay kinematics)
+#define SIMC_MPI 139.57018
+#define SIMC_MK 493.677
+#define SIMC_MMU 105.6583755
+#define SIMC_PI 3.141592653589793
+
+// gauss1.f:1-30
+__device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
+  for (;;) {
+    const double u1 = r.uniform();
+    const double u2 = r.uniform();
+    const double v1 = 2.0 * u1 - 1.0;
+    const double v2 = 2.0 * u2 - 1.0;
+    const double s = v1 * v1 + v2 * v2;
+    if (s > 1. || s == 0.) continue;
+    const double g = v1 * sqrt(-2. * log(s) / s);
+    if (fabs(g) > nsigmax) continue;
+    return g;
+  }
+}
+
+__device__ __forceinline__ void musc_refresh(TrackDev& t) {
+  const double beta = t.p / sqrt(t.m2 + t.p * t.p);
+  t.mc1 = 13.6 / t.p / beta;
+  t.mbeta2 = beta * beta;
+}
+
+// loren.f:1-26
+__device__ __forceinline__ void loren(double gam, double bx, double by, double bz, double e, double x, double y,
+                                      double z, double& pxf, double& pyf, double& pzf, double& pf1) {
+  const double gam1 = gam * gam / (1. + gam);
+  pxf = (1 + gam1 * bx * bx) * x + gam1 * bx * (by * y + bz * z) - gam * bx * e;
+  pyf = (1 + gam1 * by * by) * y + gam1 * by * (bx * x + bz * z) - gam * by * e;
+  pzf = (1 + gam1 * bz * bz) * z + gam1 * bz * (by * y + bx * x) - gam * bz * e;
+  pf1 = sqrt(pxf * pxf + pyf * pyf + pzf * pzf);
+}
+
+// decay kinematics common to project.f:67-110 and transp.f:147-186 / :236-275
+__device__ __noinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_spec, double beta, double gamma,
+                                             double kaon_pipi_mfinal) {
+  const double rph = r.uniform() * 2. * SIMC_PI;
+  const double rth1 = r.uniform() * 2. - 1.;
+  const double rth = acos(rth1);
+  double pr = 0.;
+  double m_final = SIMC_MMU;
+  const double m = sqrt(t.m2);
+  if (fabs(m - SIMC_MPI) < 2) pr = 29.783;
+  if (fabs(m - SIMC_MK) < 2) {
+    if (r.uniform() < 0.7) {
+      pr = 235.5;
+    } else {
+      pr = sqrt(SIMC_MK * SIMC_MK / 4. - SIMC_MPI * SIMC_MPI);
+      m_final = kaon_pipi_mfinal;
+    }
+  }
+  // pr == 0 is a fatal `stop` in the reference; the host refuses decay_flag for other masses.
+  const double er = sqrt(m_final * m_final + pr * pr);
+  const double pxr = pr * sin(rth) * cos(rph);
+  const double pyr = pr * sin(rth) * sin(rph);
+  const double pzr = pr * cos(rth);
+  const double nrm = sqrt(1. + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+  const double bx = -beta * t.dxdzs / nrm;
+  const double by = -beta * t.dydzs / nrm;
+  const double bz = -beta * 1. / nrm;
+  double pxf, pyf, pzf, pf;
+  loren(gamma, bx, by, bz, er, pxr, pyr, pzr, pxf, pyf, pzf, pf);
+  t.dxdzs = pxf / pzf;
+  t.dydzs = pyf / pzf;
+  t.dpps = 100. * (pf / p_spec - 1.);
+  t.p = pf;
+  t.m2 = m_final * m_final;
+  t.mh2_final = t.m2;
+  musc_refresh(t);
+}
+
+// shared/project.f:43-119, the branch that tests for a decay
+__device__ __noinline__ void project_decay(TrackDev& t, DevRng& r, double z_drift) {
+  const double p_spec = t.p / (1. + t.dpps / 100.);
+  const double beta = t.p / sqrt(t.p * t.p + t.m2);
+  const double gamma = 1. / sqrt(1. - beta * beta);
+  const double dlen = t.ctau * beta * gamma;
+  const double z_decay = -1. * dlen * log(1 - r.uniform());
+  if (z_decay > z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs)) {
+    t.decdist = t.decdist + z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.pathlen = t.pathlen + z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.xs = t.xs + t.dxdzs * z_drift;
+    t.ys = t.ys + t.dydzs * z_drift;
+  } else {
+    t.dflag = true;
+    t.decdist = t.decdist + z_decay;
+    t.pathlen = t.pathlen + z_decay;
+    t.xs = t.xs + t.dxdzs * z_decay / sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.ys = t.ys + t.dydzs * z_decay / sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    decay_in_flight(t, r, p_spec, beta, gamma, SIMC_MPI);
+    const double tmpdrift = z_drift - z_decay / sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.pathlen = t.pathlen + tmpdrift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.xs = t.xs + t.dxdzs * tmpdrift;
+    t.ys = t.ys + t.dydzs * tmpdrift;
+  }
+}
+
+// shared/project.f:1-122
+__device__ __forceinline__ void project(TrackDev& t, DevRng& r, double z_drift, bool decay_flag) {
+  if (!decay_flag || t.dflag) {
+    t.pathlen = t.pathlen + z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
+    t.xs = t.xs + t.dxdzs * z_drift;
+    t.ys = t.ys + t.dydzs * z_drift;
+  } else {
+    project_decay(t, r, z_drift);
+  }
+}
+
+// ---- grouped COSY polynomial ------------------------------------------------------------
+template <int M, int NOUT>
+__device__ __forceinline__ void poly_group(unsigned long long masks, const double (&xp)[7], const double (&tp)[7],
+                                           double s3, double s4, double s5, const double* __restrict__ coef, int& ci,
+                                           double (&sum)[NOUT]) {
+#if !SIMC_STRICT
+  double acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
+  unsigned any = 0;
+#endif
+#pragma unroll
+  for (int k = 0; k <= M; ++k) {
+    const unsigned om = (unsigned)(masks >> (5 * k)) & 31u;
+    if (om) {
+      double t = xp[M - k] * tp[k];
+#if SIMC_STRICT
+      t = t * s3;
+      t = t * s4;
+      t = t * s5;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+        if (om & (1u << o)) { sum[o] = sum[o] + t * __ldg(coef + ci); ++ci; }
+#else
+      any |= om;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+        if (om & (1u << o)) { acc[o] = fma(t, __ldg(coef + ci), acc[o]); ++ci; }
+#endif
+    }
+  }
+#if !SIMC_STRICT
+  const double b = s3 * s4 * s5;
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o)
+    if (any & (1u << o)) sum[o] = fma(b, acc[o], sum[o]);
+#endif
+}
+
+// Evaluates one compiled map at v = (v1..v5); pw = this thread's column of the shared power table.
+template <int NOUT>
+__device__ __forceinline__ void eval_poly(const PolyClass& pc, const unsigned long long* __restrict__ hdr,
+                                          const double* __restrict__ coef, const double (&v)[5], double* pw,
+                                          double (&sum)[NOUT]) {
+  double xp[7], tp[7];
+  // libgcc __powidf2 association: x^3 = x*(x*x), x^5 = x*(x^2)^2, x^6 = x^2*x^4
+  xp[0] = 1.0; xp[1] = v[0]; xp[2] = v[0] * v[0]; xp[3] = v[0] * xp[2]; xp[4] = xp[2] * xp[2];
+  xp[5] = v[0] * xp[4]; xp[6] = xp[2] * xp[4];
+  tp[0] = 1.0; tp[1] = v[1]; tp[2] = v[1] * v[1]; tp[3] = v[1] * tp[2]; tp[4] = tp[2] * tp[2];
+  tp[5] = v[1] * tp[4]; tp[6] = tp[2] * tp[4];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double a = v[2 + j], a2 = a * a, a4 = a2 * a2;
+    double* q = pw + j * 7 * kBlock;
+    q[0 * kBlock] = 1.0; q[1 * kBlock] = a; q[2 * kBlock] = a2; q[3 * kBlock] = a * a2; q[4 * kBlock] = a4;
+    q[5 * kBlock] = a * a4; q[6 * kBlock] = a2 * a4;
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) sum[o] = 0.0;
+  int ci = pc.coef_begin;
+  for (int g = pc.group_begin; g < pc.group_end; ++g) {
+    const unsigned long long h = __ldg(hdr + g);
+    const unsigned e3 = (unsigned)h & 7u, e4 = ((unsigned)h >> 3) & 7u, e5 = ((unsigned)h >> 6) & 7u;
+    const unsigned m = ((unsigned)h >> 9) & 7u;
+    const unsigned long long masks = h >> 12;
+    const double s3 = pw[(0 * 7 + e3) * kBlock], s4 = pw[(1 * 7 + e4) * kBlock], s5 = pw[(2 * 7 + e5) * kBlock];
+    switch (m) {
+      case 0: poly_group<0, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 1: poly_group<1, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 2: poly_group<2, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 3: poly_group<3, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 4: poly_group<4, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 5: poly_group<5, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      default: poly_group<6, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+    }
+  }
+}
+
+// shared/transp.f:134-279
+__device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& r, int klass, double zd,
+                                    bool decay_flag, double* pw) {
+  double p_spec = 0, beta = 0, gamma = 0, z_decay = 0;
+  const bool check = decay_flag && !t.dflag;
+  if (check) {
+    p_spec = t.p / (1. + t.dpps / 100.);
+    beta = t.p / sqrt(t.p * t.p + t.m2);
+    gamma = 1. / sqrt(1. - beta * beta);
+    const double dlen = t.ctau * beta * gamma;
+    z_decay = -1. * dlen * log(1 - r.uniform());
+    if (z_decay <= zd / 2) {
+      t.dflag = true;
+      t.decdist = t.decdist + z_decay;
+      decay_in_flight(t, r, p_spec, beta, gamma, SIMC_MK);      // m_final = Mk as written, transp.f:158
+    }
+  }
+  const double ray[5] = {t.xs, t.dxdzs * 1000., t.ys, t.dydzs * 1000., t.dpps};
+  double sum[5];
+  eval_poly<5>(arm->tab.fwd[klass - 1], arm->tab.hdr, arm->tab.coef, ray, pw, sum);
+  t.xs = sum[0];
+  t.dxdzs = sum[1] / 1000.;
+  t.ys = sum[2];
+  t.dydzs = sum[3] / 1000.;
+  const double delta_z = -sum[4];
+  if (decay_flag && !t.dflag) {
+    if (z_decay > zd + delta_z) {
+      t.decdist = t.decdist + (zd + delta_z);
+    } else {
+      t.dflag = true;
+      t.decdist = t.decdist + z_decay;
+      decay_in_flight(t, r, p_spec, beta, gamma, SIMC_MPI);
+    }
+  }
+  t.pathlen = t.pathlen + (zd + delta_z);
+}
+
+// hms/mc_hms.f:445-492 with hms/apertures_hms.inc
+__device__ __forceinline__ bool hms_hit_dipole(double x, double y) {
+  const double xl = fabs(x), yl = fabs(y);
+  const bool c1 = (xl <= 34.29) && (yl <= 12.07);
+  const bool c2 = (xl <= 27.94) && (yl <= 18.42);
+  const bool c3 = (xl <= 13.97) && (yl <= 18.95);
+  const bool c4 = (xl <= 1.956) && (yl <= 20.32);
+  const bool c5 = ((xl - 27.94) * (xl - 27.94) + (yl - 12.065) * (yl - 12.065)) <= 6.35 * 6.35;
+  const bool c6 = (xl >= 1.956) && (xl <= 13.97) && ((yl - (-0.114) * xl - 20.54) <= 0.0);
+  return !(c1 || c2 || c3 || c4 || c5 || c6);
+}
+
+// cern/lfit.f:11-61 with KEY=0: REAL*4 points, sums in 8-byte reals
+__device__ __forceinline__ void lfit12(const float* z, const float* y, float& a, float& b) {
+  a = 0.f; b = 0.f;
+  double count = 0., sumx = 0., sumy = 0., sumxy = 0., sumxx = 0.;
+  for (int j = 0; j < 12; ++j) {
+    if (y[j] == 0.f) continue;
+    sumx = sumx + (double)z[j];
+    sumy = sumy + (double)y[j];
+    count = count + 1.0;
+  }
+  if (count <= 1.) return;
+  const double ymed = sumy / count, xmed = sumx / count;
+  for (int j = 0; j < 12; ++j) {
+    if (y[j] == 0.f) continue;
+    const double sx = (double)z[j] - xmed, sy = (double)y[j] - ymed;
+    sumxy = sumxy + sx * sy;
+    sumxx = sumxx + sx * sx;
+  }
+  if (sumxx == 0.) return;
+  a = (float)(sumxy / sumxx);
+  b = (float)(ymed - (double)a * xmed);
+}
+
+struct ArmFlags {
+  bool ms_flag, wcs_flag, decay_flag, using_coll;
+};
+
+// Interprets the arm program for one event.  `pw` = this thread's column of the CTA's shared
+// power table.  On return `t` holds the track at the last plane reached; res.ok is ok_spec.
+__device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& rng, const ArmFlags f,
+                                        double fry, double* pw, ArmResult& res) {
+  res.ok = false; res.stop_code = 0; res.reached_hut = false; res.resmult = 0.0;
+  res.x_fp = res.dx_fp = res.y_fp = res.dy_fp = 0.0;
+  res.dpp_rec = res.dth_rec = res.dph_rec = res.y_rec = 0.0;
+  t.dflag = false;
+  musc_refresh(t);
+  double xt = 0., yt = 0.;
+  float xdc[12], ydc[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
+  int scincount = 0;
+  const int n_ops = arm->tab.n_ops;
+  for (int pc = 0; pc < n_ops; ++pc) {
+    const ArmOp* __restrict__ o = &arm->ops[pc];
+    const int op = __ldg(&o->op);
+    const double a = __ldg(&o->a), b = __ldg(&o->b), c = __ldg(&o->c), d = __ldg(&o->d);
+    bool stop = false;
+    switch (op) {
+      case OP_END: pc = n_ops; break;
+      case OP_PROJECT: project(t, rng, a, f.decay_flag); break;
+      case OP_TRANSP: transp(arm, t, rng, __ldg(&o->i0), a, f.decay_flag, pw); break;
+      case OP_CUT_R2: stop = (t.xs * t.xs + t.ys * t.ys) > a; break;
+      case OP_CUT_ABS_Y: stop = fabs(t.ys - a) > b; break;
+      case OP_CUT_ABS_X: stop = fabs(t.xs - a) > b; break;
+      case OP_CUT_OCT: stop = fabs(t.xs - a) > (c * fabs(t.ys - b) + d); break;
+      case OP_CUT_OFF_R2: stop = ((t.xs - a) * (t.xs - a) + (t.ys - b) * (t.ys - b)) > c; break;
+      case OP_ROT_H: {   // rotate_haxis.f:46-62
+        const double alpha = t.dxdzs, beta = t.dydzs;
+        const double alpha_p = (alpha + a) / (1. - alpha * a);
+        const double beta_p = beta / (c - alpha * b);
+        const double xi = t.xs;
+        xt = xi * (c + alpha_p * b);
+        yt = t.ys + xi * beta_p * b;
+        xt = xt + d;
+        break;
+      }
+      case OP_ROT_V: {   // rotate_vaxis.f:42-58
+        const double alpha = t.dydzs, beta = t.dxdzs;
+        const double alpha_p = (alpha + a) / (1. - alpha * a);
+        const double beta_p = beta / (c - alpha * b);
+        const double yi = t.ys;
+        yt = yi * (c + alpha_p * b);
+        xt = t.xs + yi * beta_p * b;
+        yt = yt + d;
+        break;
+      }
+      case OP_CUT_T_R2: stop = (xt * xt + yt * yt) > a; break;
+      case OP_CUT_HB: stop = (xt * xt > a) || (yt > b) || (yt < c); break;
+      case OP_CUT_HMS_DIPOLE: stop = hms_hit_dipole(xt, yt); break;
+      case OP_CUT_HMS_PIPE: stop = (((xt - a) * (xt - a) + (yt - b) * (yt - b)) > c) || (fabs(yt - b) > d); break;
+      case OP_MARK_HUT: res.reached_hut = true; break;
+      case OP_RESMULT_DRAW: res.resmult = (rng.uniform() < a) ? 2.0 : 1.0; break;
+      case OP_RESMULT_ONE: res.resmult = 1.0; break;
+      case OP_MUSC:        // musc.f:46-55, called as musc(m2,p,radw,dydzs,dxdzs)
+        if (f.ms_flag && a != 0.) {
+          const double ts = t.mc1 * b * (1 + 0.088 * log10(a / t.mbeta2));
+          t.dydzs = t.dydzs + ts * gauss1(rng, 99.0);
+          t.dxdzs = t.dxdzs + ts * gauss1(rng, 99.0);
+        }
+        break;
+      case OP_MUSC_EXT:    // musc_ext.f:37-51, called as musc_ext(m2,p,radw,drift,dydzs,dxdzs,ys,xs)
+        if (f.ms_flag && a != 0.) {
+          const double ts = t.mc1 * b * (1 + 0.088 * log10(a / t.mbeta2));
+          double g1 = gauss1(rng, 99.0);
+          double g2 = gauss1(rng, 99.0);
+          t.dxdzs = t.dxdzs + ts * g1;
+          t.xs = t.xs + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
+          g1 = gauss1(rng, 99.0);
+          g2 = gauss1(rng, 99.0);
+          t.dydzs = t.dydzs + ts * g1;
+          t.ys = t.ys + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
+        }
+        break;
+      case OP_DC_PLANE: {  // mc_hms_hut.f:351-364
+        double r1 = 0., r2 = 0.;
+        if (f.wcs_flag) { r1 = gauss1(rng, 99.0); r2 = gauss1(rng, 99.0); }
+        const int ip = __ldg(&o->i0);
+        if (__ldg(&o->i1)) { ydc[ip] = (float)(t.ys + a * r2 * res.resmult); xdc[ip] = 0.f; }
+        else { xdc[ip] = (float)(t.xs + a * r1 * res.resmult); ydc[ip] = 0.f; }
+        break;
+      }
+      case OP_CUT_BOX: stop = (t.xs > a) || (t.xs < b) || (t.ys > c) || (t.ys < d); break;
+      case OP_SCIN_COUNT: if (t.ys < a && t.ys > b && t.xs < c && t.xs > d) ++scincount; break;
+      case OP_SCIN_TRIG: stop = scincount < __ldg(&o->i0); break;
+      case OP_LFIT: {      // mc_hms_hut.f:438-455
+        float zdc[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const int iplane = (j % 6) + 1;
+          zdc[j] = (float)((j < 6 ? a : b) + (iplane - 0.5 - 0.5 * 6) * c);
+        }
+        float dx4, x4, dy4, y4;
+        lfit12(zdc, xdc, dx4, x4);
+        lfit12(zdc, ydc, dy4, y4);
+        res.x_fp = (double)x4; res.dx_fp = (double)dx4; res.y_fp = (double)y4; res.dy_fp = (double)dy4;
+        break;
+      }
+      case OP_CUT_FP_CAL: {   // mc_shms_hut.f:413-424
+        const double e = __ldg(&o->e);
+        const double xcal = res.x_fp + res.dx_fp * a;
+        const double ycal = res.y_fp + res.dy_fp * a;
+        stop = (ycal > b) || (ycal < c) || (xcal > d) || (xcal < e);
+        break;
+      }
+      case OP_RECON: {     // mc_hms.f:419-437 + mc_hms_recon.f:104-137
+        double hut[5];
+        hut[0] = res.x_fp / 100.;
+        hut[1] = res.dx_fp;
+        hut[2] = res.y_fp / 100.;
+        hut[3] = res.dy_fp;
+        hut[4] = fry / 100.;
+        if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
+        double sum[4];
+        eval_poly<4>(arm->tab.rec, arm->tab.hdr, arm->tab.coef, hut, pw, sum);
+        res.dph_rec = sum[0];
+        res.y_rec = sum[1] * 100.;
+        res.dth_rec = sum[2];
+        res.dpp_rec = sum[3] * 100.;
+        res.ok = true;
+        break;
+      }
+      case OP_UNSUPPORTED:
+        // collimator stepping for pions/muons (mc_hms_coll / mc_shms_coll): only when requested
+        stop = f.using_coll && (t.m2 > 100.0 * 100.0) && (t.m2 < 200.0 * 200.0);
+        break;
+      default: break;
+    }
+    if (stop) { res.stop_code = __ldg(&o->code); return; }
+  }
+}
+
+}  // namespace SIMC_VARIANT_NS
+}  // namespace simc

@@ -1,0 +1,311 @@
+"""ctypes binding of ``libsimc_b200.so`` (include/simc_b200.h).
+
+Mirrors the C ABI one to one; the structures below repeat the header's layouts and are
+checked against ``simc_b200_sizeof`` at load time.  Nothing here computes: a missing library
+or a missing GPU is a loud error, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
+TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
+EVENT_NREC = 48
+NHIST, H_PER_SET, NSTOP = 50, 8, 64
+ABI_VERSION = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class SimcError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsimc_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libsimc_b200.so")
+
+
+# ---- structures (same order as include/simc_b200.h) -------------------------------------
+class Cut(C.Structure):
+    _fields_ = [("min", C.c_double), ("max", C.c_double)]
+
+
+class Range(C.Structure):
+    _fields_ = [("lo", C.c_double), ("hi", C.c_double)]
+
+
+class ArmCuts(C.Structure):
+    _fields_ = [("delta", Cut), ("yptar", Cut), ("xptar", Cut), ("z", Cut)]
+
+
+class ArmLimits(C.Structure):
+    _fields_ = [("delta", Cut), ("yptar", Cut), ("xptar", Cut), ("E", Cut)]
+
+
+class EdgeArm(C.Structure):
+    _fields_ = [("E", Cut), ("yptar", Cut), ("xptar", Cut)]
+
+
+class Edge(C.Structure):
+    _fields_ = [("e", EdgeArm), ("p", EdgeArm), ("Em", Cut), ("Pm", Cut), ("Mrec", Cut), ("Trec", Cut),
+                ("Trec_struck", Cut)]
+
+
+class GenLimits(C.Structure):
+    _fields_ = [("e", ArmLimits), ("p", ArmLimits), ("sumEgen", Cut), ("Trec", Cut), ("xwid", C.c_double),
+                ("ywid", C.c_double)]
+
+
+class Spectrometer(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("P", "theta", "cos_th", "sin_th", "phi", "off_x", "off_y", "off_z",
+                                          "off_xptar", "off_yptar")]
+
+
+class Axis(C.Structure):
+    _fields_ = [("min", C.c_double), ("bin", C.c_double)]
+
+
+class Target(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "A", "Z", "N", "mass_amu", "M", "mrec_amu", "Mrec", "rho", "thick", "angle", "abundancy", "length",
+        "zoffset", "X0", "X0_cm", "L1", "L2", "fr1", "fr2", "xoffset", "yoffset", "Coulomb_ave", "Coulomb_min",
+        "Coulomb_max", "Coulomb_constant", "Mtar_struck", "Mrec_struck")] + [("fr_pattern", C.c_int32),
+                                                                              ("can", C.c_int32)]
+
+
+_INT_FLAGS = (
+    "abi_version",
+    "doing_phsp", "doing_hyd_elast", "doing_deuterium", "doing_heavy", "doing_eep",
+    "doing_pion", "doing_kaon", "doing_delta", "doing_rho", "doing_semi",
+    "doing_hydpi", "doing_deutpi", "doing_hepi",
+    "doing_hydkaon", "doing_deutkaon", "doing_hekaon",
+    "doing_hydsemi", "doing_deutsemi",
+    "doing_hplus", "doing_decay",
+    "which_pion", "which_kaon",
+    "using_rad", "using_Eloss", "using_Coulomb", "correct_Eloss", "correct_raster",
+    "mc_smear", "hard_cuts",
+    "using_E_arm_montecarlo", "using_P_arm_montecarlo",
+    "electron_arm", "hadron_arm",
+    "using_HMScoll", "using_SHMScoll", "use_benhar_sf",
+    "rad_flag", "extrad_flag", "intcor_mode", "use_expon", "use_offshell_rad",
+)
+_DBL_SCALARS = (
+    "Mh", "Mh2", "Ebeam", "dEbeam", "Ebeam_vertex_ave",
+    "dE_edge_test", "Egamma_gen_max", "ctau", "transparency",
+    "etatzai", "Egamma_tot_max", "Egamma1_max", "Egamma2_max", "Egamma3_max", "Egamma_res_limit",
+)
+
+
+class RunConfig(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in _INT_FLAGS] +
+                [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("pad0", C.c_int32)] +
+                [(n, C.c_double) for n in _DBL_SCALARS] +
+                [("gen", GenLimits), ("spec_e", Spectrometer), ("spec_p", Spectrometer),
+                 ("cuts_Em", Cut), ("cuts_Pm", Cut), ("edge", Edge), ("VERTEXedge", Edge),
+                 ("SPedge_e", ArmCuts), ("SPedge_p", ArmCuts),
+                 ("slop_MC_e_used", C.c_double * 3), ("slop_MC_p_used", C.c_double * 3),
+                 ("targ", Target), ("hist_axis", (Axis * H_PER_SET) * 3), ("w_ref", C.c_double)])
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.abi_version = ABI_VERSION
+
+
+class Fixed128(C.Structure):
+    _fields_ = [("lo", C.c_uint64), ("hi", C.c_int64), ("qexp", C.c_int32), ("pad", C.c_int32)]
+
+    def value(self) -> float:
+        v = (int(self.hi) << 64) + int(self.lo)
+        return float(v) * 2.0 ** int(self.qexp) if abs(v) < (1 << 1000) else float("inf")
+
+    def exact(self):
+        """(integer, exponent): value = integer * 2**exponent."""
+        return (int(self.hi) << 64) + int(self.lo), int(self.qexp)
+
+
+class Accum(C.Structure):
+    _fields_ = [("ntried", C.c_int64), ("nsuccess", C.c_int64), ("ncontribute", C.c_int64),
+                ("npasscuts", C.c_int64), ("ncontribute_no_rad_proton", C.c_int64),
+                ("wtcontribute", Fixed128), ("sum_sigcc", Fixed128),
+                ("sumerr", Fixed128 * 8), ("sumerr2", Fixed128 * 8),
+                ("hist_w", (Fixed128 * NHIST) * 6),
+                ("hist_n", ((C.c_int64 * NHIST) * H_PER_SET) * 3),
+                ("contrib", Range * 32), ("slop", Range * 8),
+                ("stop", (C.c_int64 * NSTOP) * 2)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsimc_b200.so from the package directory; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SimcError(-100, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              f"(or `make -C simc_gfortran_b200/csrc`); there is no CPU fallback")
+    L = C.CDLL(path)
+    L.simc_b200_last_error.restype = C.c_char_p
+    L.simc_b200_last_error.argtypes = [C.c_void_p]
+    L.simc_b200_stop_name.restype = C.c_char_p
+    L.simc_b200_stop_name.argtypes = [C.c_int, C.c_int]
+    L.simc_b200_stream.restype = C.c_void_p
+    L.simc_b200_stream.argtypes = [C.c_void_p]
+    L.simc_b200_launch_count.restype = C.c_int64
+    L.simc_b200_launch_count.argtypes = [C.c_void_p]
+    L.simc_b200_sizeof.restype = C.c_int64
+    L.simc_b200_sizeof.argtypes = [C.c_int]
+    L.simc_b200_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.simc_b200_destroy.argtypes = [C.c_void_p]
+    L.simc_b200_destroy.restype = None
+    L.simc_b200_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.simc_b200_load_optics.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
+    L.simc_b200_set_optics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_void_p]
+    L.simc_b200_optics_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    tb = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+          C.c_void_p]
+    L.simc_b200_transport_batch.argtypes = tb
+    L.simc_b200_transport_batch_device.argtypes = tb
+    L.simc_b200_sync.argtypes = [C.c_void_p]
+    for name, args in (("simc_b200_accum_clear", [C.c_void_p, C.c_void_p]),
+                       ("simc_b200_run", [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]),
+                       ("simc_b200_run_async", [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]),
+                       ("simc_b200_fetch", [C.c_void_p, C.c_void_p]),
+                       ("simc_b200_event_batch", [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p,
+                                                  C.c_void_p])):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = args
+    if hasattr(L, "simc_b200_event_field_name"):
+        L.simc_b200_event_field_name.restype = C.c_char_p
+        L.simc_b200_event_field_name.argtypes = [C.c_int]
+    # layout check: the ctypes mirrors must have the C sizes
+    for which, typ in ((0, RunConfig), (1, Accum)):
+        c_size = L.simc_b200_sizeof(which)
+        if c_size != C.sizeof(typ):
+            raise SimcError(-101, f"ABI mismatch: sizeof({typ.__name__}) is {C.sizeof(typ)} in Python, {c_size} in C")
+    _lib = L
+    return L
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Simc:
+    """One handle = one GPU + one run configuration (simc_b200_create)."""
+
+    def __init__(self, cfg: RunConfig | None = None, device: int = 0, mode: str | None = None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self.cfg = cfg
+        rc = self.L.simc_b200_create(C.byref(cfg) if cfg is not None else None, device, C.byref(self.h))
+        if rc != 0:
+            raise SimcError(rc, (self.L.simc_b200_last_error(None) or b"").decode())
+        if mode is not None:
+            self.set_mode(mode)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SimcError(rc, (self.L.simc_b200_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.simc_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mode(self, mode: str):
+        assert mode in ("strict", "fast")
+        self._check(self.L.simc_b200_set_mode(self.h, 1 if mode == "strict" else 0))
+
+    # ---- optics
+    def load_optics(self, arm: int, forward_path: str, recon_path: str):
+        self._check(self.L.simc_b200_load_optics(self.h, arm, forward_path.encode(), recon_path.encode()))
+
+    def set_optics(self, t):
+        cs = np.ascontiguousarray(t.class_start, dtype=np.int32)
+        fc = np.ascontiguousarray(t.fwd_coeff, dtype=np.float64)
+        fe = np.ascontiguousarray(t.fwd_expon, dtype=np.int8)
+        ln = np.ascontiguousarray(t.length_cm, dtype=np.float64)
+        rc_ = np.ascontiguousarray(t.rec_coeff, dtype=np.float64)
+        re_ = np.ascontiguousarray(t.rec_expon, dtype=np.int8)
+        self._check(self.L.simc_b200_set_optics(self.h, t.arm, len(cs) - 1, _ptr(cs), _ptr(fc), _ptr(fe), _ptr(ln),
+                                                len(rc_), _ptr(rc_), _ptr(re_)))
+
+    def optics_info(self, arm: int) -> dict:
+        info = np.zeros(8, dtype=np.int64)
+        self._check(self.L.simc_b200_optics_info(self.h, arm, _ptr(info)))
+        keys = ("n_classes", "fwd_terms", "fwd_nonzero", "rec_terms", "n_groups", "n_coef", "n_ops")
+        return dict(zip(keys, (int(x) for x in info[:7])))
+
+    # ---- single-arm batch (host buffers)
+    def transport_batch(self, arm: int, inp: np.ndarray, seed: int, ms_flag=True, wcs_flag=True, decay_flag=False,
+                        using_coll=False):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        assert inp.ndim == 2 and inp.shape[0] == TRANSPORT_NIN
+        n = inp.shape[1]
+        out = np.zeros((TRANSPORT_NOUT, n), dtype=np.float64)
+        flags = np.zeros(n, dtype=np.int32)
+        self._check(self.L.simc_b200_transport_batch(self.h, arm, n, _ptr(inp), seed, int(ms_flag), int(wcs_flag),
+                                                     int(decay_flag), int(using_coll), _ptr(out), _ptr(flags)))
+        return out, flags
+
+    def transport_batch_device(self, arm: int, n: int, d_in: int, seed: int, d_out: int, d_flags: int, ms_flag=True,
+                               wcs_flag=True, decay_flag=False, using_coll=False):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on the handle's stream."""
+        self._check(self.L.simc_b200_transport_batch_device(self.h, arm, n, C.c_void_p(d_in), seed, int(ms_flag),
+                                                            int(wcs_flag), int(decay_flag), int(using_coll),
+                                                            C.c_void_p(d_out), C.c_void_p(d_flags)))
+
+    def sync(self):
+        self._check(self.L.simc_b200_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.simc_b200_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.simc_b200_launch_count(self.h))
+
+    def stop_name(self, arm: int, code: int) -> str:
+        return self.L.simc_b200_stop_name(arm, code).decode()
+
+    # ---- the loop
+    def accum_clear(self, acc: Accum | None = None) -> Accum:
+        acc = acc if acc is not None else Accum()
+        self._check(self.L.simc_b200_accum_clear(self.h, C.byref(acc)))
+        return acc
+
+    def run(self, first_try: int, n_tries: int, seed: int, acc: Accum) -> Accum:
+        self._check(self.L.simc_b200_run(self.h, first_try, n_tries, seed, C.byref(acc)))
+        return acc
+
+    def run_async(self, first_try: int, n_tries: int, seed: int):
+        self._check(self.L.simc_b200_run_async(self.h, first_try, n_tries, seed))
+
+    def fetch(self, acc: Accum) -> Accum:
+        self._check(self.L.simc_b200_fetch(self.h, C.byref(acc)))
+        return acc
+
+    def event_batch(self, first_try: int, n: int, seed: int):
+        rec = np.zeros((EVENT_NREC, n), dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self.L.simc_b200_event_batch(self.h, first_try, n, seed, _ptr(rec), _ptr(status)))
+        return rec, status
+
+    def event_field_names(self):
+        return [self.L.simc_b200_event_field_name(k).decode() for k in range(EVENT_NREC)]

@@ -1,0 +1,110 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so) -- test infrastructure only.
+
+Only tests/, tools/make_fixtures.py, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-j8"], check=True, capture_output=True)
+    return ORACLE_SO
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# momentum (MeV/c) and mass^2 used for the synthetic single-arm rows of each spectrometer:
+# the C1 kinematics of SURVEY 8(d) (electron in the HMS, proton in the SHMS)
+ARM_KIN = {1: (4531.0, 0.51099906 ** 2), 5: (5122.0, 938.27231 ** 2), 2: (1300.0, 0.51099906 ** 2),
+           3: (1292.58, 493.677 ** 2), 4: (1571.272, 0.51099906 ** 2)}
+# half-widths of the generated box: delta %, x cm, y cm, dxdz, dydz (1.2 x the SPedge box of C1)
+ARM_BOX = {1: (12.0, 0.2, 2.5, 0.12, 0.06), 5: (18.0, 0.2, 2.5, 0.06, 0.11), 2: (24.0, 0.2, 2.0, 0.09, 0.09),
+           3: (6.0, 0.2, 2.0, 0.08, 0.04), 4: (6.0, 0.2, 2.0, 0.08, 0.04)}
+
+
+def transport_inputs(arm, n, seed, p_spec=None, m2=None):
+    """Seeded rows {dpp,x,y,z,dxdz,dydz,m2,p_spec,fry} (SoA [9,n]) for the single-arm entry points."""
+    rng = np.random.default_rng(seed + 1000 * arm)
+    box = ARM_BOX[arm]
+    inp = np.zeros((9, n))
+    inp[0] = rng.uniform(-box[0], box[0], n)
+    inp[1] = rng.uniform(-box[1], box[1], n)
+    inp[2] = rng.uniform(-box[2], box[2], n)
+    inp[4] = rng.uniform(-box[3], box[3], n)
+    inp[5] = rng.uniform(-box[4], box[4], n)
+    inp[6] = ARM_KIN[arm][1] if m2 is None else m2
+    inp[7] = ARM_KIN[arm][0] if p_spec is None else p_spec
+    inp[8] = inp[1]          # fry = xtar_init (simc.f:1441,1463) for HMS/SHMS
+    return inp
+
+
+class Oracle:
+    def __init__(self):
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        self.L = C.CDLL(ORACLE_SO)
+        self.L.oracle_last_error.restype = C.c_char_p
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.L.oracle_last_error().decode())
+
+    def has_arm(self, arm):
+        return arm in (1, 5)
+
+    def load_optics(self, arm, fwd, rec):
+        self._check(self.L.oracle_load_optics(arm, fwd.encode(), rec.encode()))
+
+    def export_optics(self, arm):
+        from simc_gfortran_b200.optics import OpticsTables
+        nc, nf, nr = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.oracle_optics_sizes(arm, C.byref(nc), C.byref(nf), C.byref(nr)))
+        t = OpticsTables(arm=arm, class_start=np.zeros(nc.value + 1, np.int32), fwd_coeff=np.zeros((nf.value, 5)),
+                         fwd_expon=np.zeros((nf.value, 5), np.int8), length_cm=np.zeros(nc.value),
+                         adrift=np.zeros(nc.value, np.int8), driftdist=np.zeros(nc.value),
+                         rec_coeff=np.zeros((nr.value, 4)), rec_expon=np.zeros((nr.value, 5), np.int8))
+        self._check(self.L.oracle_optics_export(arm, _p(t.class_start), _p(t.fwd_coeff), _p(t.fwd_expon),
+                                                _p(t.length_cm), _p(t.adrift), _p(t.driftdist), _p(t.rec_coeff),
+                                                _p(t.rec_expon)))
+        return t
+
+    def set_optics(self, t):
+        cs = np.ascontiguousarray(t.class_start, np.int32)
+        fc = np.ascontiguousarray(t.fwd_coeff, np.float64)
+        fe = np.ascontiguousarray(t.fwd_expon, np.int8)
+        ln = np.ascontiguousarray(t.length_cm, np.float64)
+        ad = np.ascontiguousarray(t.adrift, np.int8)
+        dd = np.ascontiguousarray(t.driftdist, np.float64)
+        rc_ = np.ascontiguousarray(t.rec_coeff, np.float64)
+        re_ = np.ascontiguousarray(t.rec_expon, np.int8)
+        self._check(self.L.oracle_set_optics(t.arm, len(cs) - 1, _p(cs), _p(fc), _p(fe), _p(ln), _p(ad), _p(dd),
+                                             len(rc_), _p(rc_), _p(re_)))
+
+    def transport_batch(self, arm, inp, seed, ms=True, wcs=True, decay=False, coll=False, ctau=0.0):
+        inp = np.ascontiguousarray(inp, np.float64)
+        n = inp.shape[1]
+        out = np.zeros((12, n))
+        flags = np.zeros(n, np.int32)
+        self._check(self.L.oracle_transport_batch(arm, C.c_int64(n), _p(inp), C.c_uint64(seed), int(ms), int(wcs),
+                                                  int(decay), int(coll), C.c_double(ctau), _p(out), _p(flags)))
+        return out, flags
+
+    def ranlux(self, seed, lux, n):
+        out = np.zeros(n)
+        self.L.oracle_ranlux(C.c_int(seed), C.c_int(lux), C.c_int64(n), _p(out))
+        return out
+
+    def philox_uniforms(self, seed, try_index, n):
+        out = np.zeros(n)
+        self.L.oracle_philox_uniforms(C.c_uint64(seed), C.c_uint64(try_index), C.c_int64(n), _p(out))
+        return out

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz.  Run HERE (needs /root/reference and the built oracle):
+
+    make -C oracle && python tools/make_fixtures.py
+
+* optics_<arm>.npz : the COSY tables of the shipped .dat files, parsed by the oracle's
+  restatement of transp_init / mc_*_recon's loader (shared/transp.f:294-474).
+* transport_<arm>.npz : seeded single-arm input rows and the ORACLE's outputs for them
+  (the reference cannot be executed here, so these are regression vectors of the oracle, not
+  reference outputs -- parity stays "unpinned").
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from simc_gfortran_b200.optics import OpticsTables  # noqa: E402
+from tests.oracle_lib import Oracle, transport_inputs  # noqa: E402
+
+REF = os.environ.get("SIMC_REFERENCE", "/root/reference")
+FILES = {
+    1: ("hms", "hms/forward_cosy.dat", "hms/recon_cosy.dat"),
+    5: ("shms", "shms/shms_forward.dat", "shms/shms_recon.dat"),
+    2: ("sos", "sos/forward_cosy.dat", "sos/recon_cosy.dat"),
+    3: ("hrsr", "hrsr/hrs_forward_cosy.dat", "hrsr/hrs_recon_cosy.dat"),
+    4: ("hrsl", "hrsl/hrs_forward_cosy.dat", "hrsl/hrs_recon_cosy.dat"),
+}
+
+
+def main():
+    orc = Oracle()
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for arm, (name, fwd, rec) in FILES.items():
+        orc.load_optics(arm, os.path.join(REF, fwd), os.path.join(REF, rec))
+        t = orc.export_optics(arm)
+        t.save(os.path.join(out_dir, f"optics_{name}.npz"))
+        print(name, "classes", t.n_classes, "fwd terms", len(t.fwd_coeff), "rec terms", len(t.rec_coeff))
+        if not orc.has_arm(arm):
+            continue
+        for tag, kw in (("", dict(ms=True, wcs=True, decay=False)),):
+            n = 4096
+            inp = transport_inputs(arm, n, seed=20240611)
+            out, flags = orc.transport_batch(arm, inp, seed=20240611, ctau=0.0, **kw)
+            np.savez_compressed(os.path.join(out_dir, f"transport_{name}{tag}.npz"), inp=inp, out=out, flags=flags,
+                                seed=20240611)
+            print("  golden rows", n, "accepted", int((flags == 0).sum()))
+
+
+if __name__ == "__main__":
+    main()
