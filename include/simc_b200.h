@@ -170,6 +170,14 @@ typedef struct {
 
 typedef struct simc_handle simc_handle;
 
+/* Host-only (no GPU needed): reads a CTP deck (`begin parm ... end parm`, infiles/*.inp) and
+ * performs the reference's one-time setup -- dbase_read post-processing (dbase.f:119-553),
+ * target_init (init.f:1-87), limits_init (init.f:91-572), radc_init (init.f:576-651) -- to fill
+ * *out.  extra_deck_dir: where `extra_dbase_file` is looked up (the reference uses infiles/).
+ * ngen / charge_mC return the deck's `ngen` and `EXPER%charge`.  err receives the message. */
+int simc_b200_config_from_deck(const char* deck_path, const char* extra_deck_dir, simc_run_config* out,
+                               int32_t* ngen, double* charge_mC, char* err, int errlen);
+
 /* lifecycle ------------------------------------------------------------- */
 int  simc_b200_abi_version(void);
 int  simc_b200_create(const simc_run_config* cfg, int device, simc_handle** out);
@@ -208,6 +216,7 @@ int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);
  * any GPU).  Adds into *acc (zero it with simc_b200_accum_clear first). */
 int simc_b200_accum_clear(simc_handle* h, simc_accum* acc);
 int simc_b200_run(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, simc_accum* acc);
+int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch);   /* tries per pass of the stage pipeline (default 2^20) */
 
 /* Asynchronous pieces of simc_b200_run for callers that overlap or time the
  * device work themselves (bench.py): launch on the handle's stream, then fetch. */
@@ -244,6 +253,16 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
 int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
                           double* rec_soa, int32_t* status);
 const char* simc_b200_event_field_name(int k);
+
+/* stage-level parity entry point for the radiative corrections and the cross-section weight ---- *
+ * radc_init_ev + basicrad_init_ev (init.f:655-813), peaked_rad_weight (radc.f:523-646) and sigep
+ * (physics_proton.f:1-22) on dumped per-event vertex vectors.  in[k*n+i], k = 0..15:
+ * { Ein, e.E, e.theta, ue.x, ue.y, ue.z, p.E, p.P, up.x, up.y, up.z, teff(1), teff(2), Egamma, Emin, Emax };
+ * out[k*n+i], k = 0..10: { bt(1), bt(2), lambda(1..3), g(4), hardcorfac, c(4), c_ext(0),
+ * peaked_rad_weight(basicrad_weight = 1), sigep }. */
+#define SIMC_RADC_NIN  16
+#define SIMC_RADC_NOUT 11
+int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa);
 
 const char* simc_b200_stop_name(int arm_id, int code);
 

@@ -3,7 +3,9 @@
 #include <cstring>
 #include <map>
 #include <string>
-#include "arms.hpp"
+#include <thread>
+#include <vector>
+#include "event.hpp"
 
 using namespace simc_oracle;
 
@@ -104,6 +106,70 @@ int oracle_transport_batch(int arm, int64_t n, const double* in, uint64_t seed, 
       out[8 * n + i] = a.pathlen; out[9 * n + i] = a.m2; out[10 * n + i] = a.resmult;
       out[11 * n + i] = (double)rng.draw;
       flags[i] = a.ok_spec ? 0 : a.stop_code;
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// The loop: tries [first, first+n) of stream `seed`, `threads` host threads (each owns a
+// contiguous range and its own accumulator; integer accumulators make the merge exact).
+int oracle_accum_clear(const simc_run_config* cfg, simc_accum* acc) {
+  simc_oracle::accum_clear(*cfg, *acc);
+  return 0;
+}
+int oracle_run(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, int threads, simc_accum* acc) {
+  auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
+  const ArmOptics* oe = ie == g_optics.end() ? nullptr : &ie->second;
+  const ArmOptics* op = ip == g_optics.end() ? nullptr : &ip->second;
+  if (threads < 1) threads = 1;
+  std::vector<simc_accum> part(threads);
+  std::vector<std::string> errs(threads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    accum_clear(*cfg, part[t]);
+    const int64_t b = first + n * t / threads, e = first + n * (t + 1) / threads;
+    th.emplace_back([&, t, b, e]() {
+      try { run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0); }
+      catch (const std::exception& ex) { errs[t] = ex.what(); }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int t = 0; t < threads; ++t) {
+    if (!errs[t].empty()) { g_err = errs[t]; return -1; }
+    merge_accum(*acc, part[t]);
+  }
+  return 0;
+}
+int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, double* rec,
+                       int32_t* status) {
+  auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
+  try {
+    run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
+              n, seed, nullptr, rec, status, n, 0);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// radc_init_ev + peaked_rad_weight + sigep on dumped vertex vectors (layout: simc_b200_radc_batch)
+int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Sim s; s.cfg = cfg;
+      EventMain main; Event v;
+      v.Ein = in[0 * n + i]; v.e.E = in[1 * n + i]; v.e.P = v.e.E; v.e.theta = in[2 * n + i];
+      v.ue.x = in[3 * n + i]; v.ue.y = in[4 * n + i]; v.ue.z = in[5 * n + i];
+      v.p.E = in[6 * n + i]; v.p.P = in[7 * n + i];
+      v.up.x = in[8 * n + i]; v.up.y = in[9 * n + i]; v.up.z = in[10 * n + i];
+      main.target.teff[0] = in[11 * n + i]; main.target.teff[1] = in[12 * n + i];
+      radc_init_ev(s, main, v);
+      const double w = peaked_rad_weight_public(s, v, in[13 * n + i], in[14 * n + i], in[15 * n + i]);
+      const RadEv& R = s.rad;
+      out[0 * n + i] = R.bt[0]; out[1 * n + i] = R.bt[1];
+      out[2 * n + i] = R.lambda[0]; out[3 * n + i] = R.lambda[1]; out[4 * n + i] = R.lambda[2];
+      out[5 * n + i] = R.g[4]; out[6 * n + i] = R.hardcorfac; out[7 * n + i] = R.c[4]; out[8 * n + i] = R.c_ext[0];
+      out[9 * n + i] = w;
+      v.Q2 = 2 * v.Ein * v.e.E * (1. - v.ue.z);
+      out[10 * n + i] = sigep(v);
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }

@@ -1,0 +1,606 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see event.hpp).
+// event.f (generate, complete_ev, complete_recon_ev, complete_main, physics_angles,
+// spectrometer_angles), physics_proton.f (sigep, fofa_best_fit, sigMott), simc.f (montecarlo,
+// loop body).  Reaction coverage: H(e,e'p) complete; the D/A(e,e'p) and hydrogen pi/K branches of
+// generate/complete_ev are restated where they share code, their cross sections are not (yet).
+#include <cmath>
+#include "event.hpp"
+
+namespace simc_oracle {
+
+using std::acos;
+using std::atan;
+using std::atan2;
+using std::cos;
+using std::fabs;
+using std::sin;
+using std::sqrt;
+using std::tan;
+
+// event.f:1572-1614
+void physics_angles(double theta0, double phi0, double dx, double dy, double& theta, double& phi) {
+  const double costh = cos(theta0), sinth = sin(theta0), sinph = sin(phi0);
+  const double r = sqrt(1. + dx * dx + dy * dy);
+  theta = acos((costh - dy * sinth * sinph) / r);
+  if (dx != 0.0) {
+    phi = atan((dy * costh + sinth * sinph) / dx);
+    if (phi <= 0) phi = phi + K::pi;
+    if (sinph < 0.) phi = phi + K::pi;
+  } else {
+    phi = phi0;
+  }
+}
+
+// event.f:1618-1648
+void spectrometer_angles(double theta0, double phi0, double& dx, double& dy, double theta, double phi) {
+  const double x = sin(theta) * cos(phi), y = sin(theta) * sin(phi), z = cos(theta);
+  const double x0 = sin(theta0) * cos(phi0), y0 = sin(theta0) * sin(phi0), z0 = cos(theta0);
+  const double cos_dtheta = x * x0 + y * y0 + z * z0;
+  dx = x / cos_dtheta;
+  dy = sqrt(1 / (cos_dtheta * cos_dtheta) - 1. - dx * dx);
+  const double y_event = y / cos_dtheta;
+  if (y_event < y0) dy = -dy;
+}
+
+// physics_proton.f:137-172
+static void fofa_best_fit(double qsquar, double& GE, double& GM) {
+  const double mu_p = 2.793;
+  const double Q2 = -qsquar * std::pow(K::hbarc, 2.) * 1.e-6;
+  const double Q = sqrt(std::max(Q2, 0.e0));
+  const double Q3 = std::pow(Q, 3.), Q4 = std::pow(Q, 4.), Q5 = std::pow(Q, 5.);
+  double denom = 1. + 0.62 * Q + 0.68 * Q2 + 2.8 * Q3 + 0.83 * Q4;
+  GE = 1. / denom;
+  denom = 1. + 0.35 * Q + 2.44 * Q2 + 0.5 * Q3 + 1.04 * Q4 + 0.34 * Q5;
+  GM = mu_p / denom;
+}
+// physics_proton.f:176-190
+static double sigMott(double e0, double theta, double Q2) {
+  const double sig = powi(2. * K::alpha * K::hbarc * e0 * cos(theta / 2.) / Q2, 2);
+  return sig * 1.e4;
+}
+// physics_proton.f:1-22
+double sigep(const Event& vertex) {
+  const double q4sq = vertex.Q2;
+  double GE, GM;
+  fofa_best_fit(-q4sq / (K::hbarc * K::hbarc), GE, GM);
+  const double qmu4mp = q4sq / 4. / K::Mp2;
+  const double W1p = GM * GM * qmu4mp;
+  const double W2p = (GE * GE + GM * GM * qmu4mp) / (1.0 + qmu4mp);
+  const double Wp = W2p + 2. * W1p * powi(tan(vertex.e.theta / 2.), 2);
+  return sigMott(vertex.e.E, vertex.e.theta, vertex.Q2) * vertex.e.E / vertex.Ein * Wp;
+}
+
+// event.f:432-1052
+bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
+  if (cfg.which_pion == 2 || cfg.which_pion == 3) throw std::runtime_error("oracle: Delta final states not restated");
+  main.jacobian = 1.0;
+  vertex.ue.x = sin(vertex.e.theta) * cos(vertex.e.phi);
+  vertex.ue.y = sin(vertex.e.theta) * sin(vertex.e.phi);
+  vertex.ue.z = cos(vertex.e.theta);
+  if (!cfg.doing_hyd_elast && !cfg.doing_rho) {
+    vertex.up.x = sin(vertex.p.theta) * cos(vertex.p.phi);
+    vertex.up.y = sin(vertex.p.theta) * sin(vertex.p.phi);
+    vertex.up.z = cos(vertex.p.theta);
+  }
+  if (cfg.doing_hyd_elast) {
+    vertex.e.E = vertex.Ein * Mh / (Mh + vertex.Ein * (1. - vertex.ue.z));
+    if (vertex.e.E > vertex.Ein) return false;
+    vertex.e.P = vertex.e.E;
+    vertex.e.delta = (vertex.e.P - cfg.spec_e.P) * 100. / cfg.spec_e.P;
+  }
+  vertex.nu = vertex.Ein - vertex.e.E;
+  vertex.Q2 = 2 * vertex.Ein * vertex.e.E * (1. - vertex.ue.z);
+  vertex.q = sqrt(vertex.Q2 + vertex.nu * vertex.nu);
+  vertex.xbj = vertex.Q2 / 2. / K::Mp / vertex.nu;
+  vertex.uq.x = -vertex.e.P * vertex.ue.x / vertex.q;
+  vertex.uq.y = -vertex.e.P * vertex.ue.y / vertex.q;
+  vertex.uq.z = (vertex.Ein - vertex.e.P * vertex.ue.z) / vertex.q;
+  if (fabs(vertex.uq.x * vertex.uq.x + vertex.uq.y * vertex.uq.y + vertex.uq.z * vertex.uq.z - 1) > 0.01)
+    throw std::runtime_error("Error in q vector normalization");
+
+  if (cfg.doing_hyd_elast) {   // :545-562
+    vertex.Em = 0.0;
+    vertex.Pm = 0.0;
+    vertex.Mrec = 0.0;
+    vertex.up.x = vertex.uq.x;
+    vertex.up.y = vertex.uq.y;
+    vertex.up.z = vertex.uq.z;
+    vertex.p.P = vertex.q;
+    vertex.p.theta = acos(vertex.up.z);
+    vertex.p.phi = atan2(vertex.up.y, vertex.up.x);
+    if (vertex.p.phi < 0.) vertex.p.phi = vertex.p.phi + 2. * K::pi;
+    spectrometer_angles(cfg.spec_p.theta, cfg.spec_p.phi, vertex.p.xptar, vertex.p.yptar, vertex.p.theta,
+                        vertex.p.phi);
+    vertex.p.E = sqrt(vertex.p.P * vertex.p.P + Mh2);
+    vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+  } else if (cfg.doing_deuterium) {   // :564-607
+    vertex.Em = targ.Mtar_struck + targ.Mrec - targ.M;
+    vertex.Mrec = targ.M - targ.Mtar_struck + vertex.Em;
+    const double a = -1. * vertex.q * (vertex.uq.x * vertex.up.x + vertex.uq.y * vertex.up.y + vertex.uq.z * vertex.up.z);
+    const double b = vertex.q * vertex.q;
+    const double c = vertex.nu + targ.M;
+    const double t = c * c - b + Mh2 - vertex.Mrec * vertex.Mrec;
+    const double QA = 4. * (a * a - c * c);
+    const double QB = 4. * c * t;
+    const double QC = -4. * a * a * Mh2 - t * t;
+    const double radical = QB * QB - 4. * QA * QC;
+    if (radical < 0) return false;
+    vertex.p.E = (-QB - sqrt(radical)) / 2. / QA;
+    if (vertex.p.E <= Mh) return false;
+    vertex.p.P = sqrt(vertex.p.E * vertex.p.E - Mh2);
+    vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+    main.jacobian = (t * (c - vertex.p.E) + 2 * c * vertex.p.E * (vertex.p.E - c)) /
+                    (2 * (a * a - c * c) * vertex.p.E + c * t);
+    main.jacobian = fabs(main.jacobian);
+  } else if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta) {   // :609-698, hydrogen targets only here
+    if (!(cfg.doing_hydpi || cfg.doing_hydkaon)) throw std::runtime_error("oracle: nuclear pi/K production not restated");
+    vertex.Pm = 0.0;   // pfer
+    vertex.Mrec = targ.M - targ.Mtar_struck + vertex.Em;
+    const double a = -1. * vertex.q * (vertex.uq.x * vertex.up.x + vertex.uq.y * vertex.up.y + vertex.uq.z * vertex.up.z);
+    const double b = vertex.q * vertex.q;
+    const double c = vertex.nu + targ.M;
+    const double t = c * c - b + Mh2 - targ.Mrec_struck * targ.Mrec_struck;
+    const double QA = 4. * (a * a - c * c);
+    const double QB = 4. * c * t;
+    const double QC = -4. * a * a * Mh2 - t * t;
+    const double radical = QB * QB - 4. * QA * QC;
+    if (radical < 0) return false;
+    vertex.p.E = (-QB - sqrt(radical)) / 2. / QA;
+    if (vertex.p.E < 0.0) return false;
+    const double E_rec = c - vertex.p.E;
+    if (E_rec <= targ.Mrec_struck) return false;
+    if (vertex.p.E <= Mh) return false;
+    vertex.p.P = sqrt(vertex.p.E * vertex.p.E - Mh2);
+    vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+  } else if (cfg.doing_phsp) {
+    vertex.p.P = cfg.spec_p.P;
+    vertex.p.E = sqrt(Mh2 + vertex.p.P * vertex.p.P);
+    vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+  } else if (cfg.doing_heavy) {
+    // nothing: E and P of both arms were generated
+  } else {
+    throw std::runtime_error("oracle: reaction not restated in complete_ev");
+  }
+
+  if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho || cfg.doing_semi) {   // :707-771
+    const double W2 = targ.Mtar_struck * targ.Mtar_struck + 2. * targ.Mtar_struck * vertex.nu - vertex.Q2;
+    main.W = sqrt(fabs(W2)) * W2 / fabs(W2);
+    main.epsilon = 1. / (1. + 2. * (1 + vertex.nu * vertex.nu / vertex.Q2) * powi(tan(vertex.e.theta / 2.), 2));
+    main.theta_pq = acos(vertex.up.x * vertex.uq.x + vertex.up.y * vertex.uq.y + vertex.up.z * vertex.uq.z);
+    main.t = vertex.Q2 - Mh2 + 2 * vertex.nu * vertex.p.E - 2 * vertex.p.P * vertex.q * cos(main.theta_pq);
+    main.tmin = vertex.Q2 - Mh2 + 2 * vertex.p.E * vertex.nu - 2 * vertex.p.P * vertex.q;
+    main.q2 = vertex.Q2;
+    const double qx = -vertex.uq.y, qy = vertex.uq.x, qz = vertex.uq.z;
+    const double px = -vertex.up.y, py = vertex.up.x, pz = vertex.up.z;
+    double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+    const double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+    dummy = sqrt(qx * qx + qy * qy);
+    const double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+    const double p_new_x = px * new_x_x + py * new_x_y + pz * new_x_z;
+    const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
+    main.phi_pq = atan2(p_new_y, p_new_x);
+    if (main.phi_pq < 0.e0) main.phi_pq = main.phi_pq + 2. * K::pi;
+  }
+
+  // :880-955 missing momentum
+  vertex.Pmx = vertex.p.P * vertex.up.x - vertex.q * vertex.uq.x;
+  vertex.Pmy = vertex.p.P * vertex.up.y - vertex.q * vertex.uq.y;
+  vertex.Pmz = vertex.p.P * vertex.up.z - vertex.q * vertex.uq.z;
+  vertex.Pmiss = sqrt(vertex.Pmx * vertex.Pmx + vertex.Pmy * vertex.Pmy + vertex.Pmz * vertex.Pmz);
+  vertex.Emiss = vertex.nu + targ.M - vertex.p.E;
+  const double oop_x = -vertex.uq.y, oop_y = vertex.uq.x;
+  vertex.PmPar = (vertex.Pmx * vertex.uq.x + vertex.Pmy * vertex.uq.y + vertex.Pmz * vertex.uq.z);
+  vertex.PmOop = (vertex.Pmx * oop_x + vertex.Pmy * oop_y) / sqrt(oop_x * oop_x + oop_y * oop_y);
+  vertex.PmPer = sqrt(std::max(0.e0, vertex.Pm * vertex.Pm - vertex.PmPar * vertex.PmPar - vertex.PmOop * vertex.PmOop));
+  if (cfg.doing_hyd_elast) {
+    vertex.Trec = 0.0;
+  } else if (cfg.doing_deuterium) {
+    vertex.Pm = vertex.Pmiss;
+    vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
+  } else if (cfg.doing_heavy) {
+    vertex.Pm = vertex.Pmiss;
+    vertex.Mrec = sqrt(vertex.Emiss * vertex.Emiss - vertex.Pmiss * vertex.Pmiss);
+    vertex.Em = targ.Mtar_struck + vertex.Mrec - targ.M;
+    vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
+  } else if (cfg.doing_hydpi || cfg.doing_hydkaon) {
+    vertex.Trec = 0.0;
+  }
+  s.ntup.krel = 0.0;
+
+  // :1013-1023 Jacobian of (xptar,yptar) -> solid angle
+  double r = sqrt(1. + vertex.e.yptar * vertex.e.yptar + vertex.e.xptar * vertex.e.xptar);
+  main.jacobian = main.jacobian / powi(r, 3);
+  if (cfg.doing_heavy || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_semi) {
+    r = sqrt(1. + vertex.p.yptar * vertex.p.yptar + vertex.p.xptar * vertex.p.xptar);
+    main.jacobian = main.jacobian / powi(r, 3);
+  }
+  // :1031-1040 energy loss of the outgoing particles
+  trip_thru_target(s, 2, main.target.z - targ.zoffset, vertex.e.E, vertex.e.theta, main.target.Eloss[1],
+                   main.target.teff[1], K::Me, 1);
+  trip_thru_target(s, 3, main.target.z - targ.zoffset, vertex.p.E, vertex.p.theta, main.target.Eloss[2],
+                   main.target.teff[2], Mh, 1);
+  if (!cfg.using_Eloss) {
+    main.target.Eloss[1] = 0.0;
+    main.target.Eloss[2] = 0.0;
+  }
+  radc_init_ev(s, main, vertex);
+  return true;
+}
+
+// event.f:126-428
+bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  Rng& rng = *s.rng;
+  const simc_gen_limits& gen = cfg.gen;
+  main.target.x = gauss1(rng, 3.0) * gen.xwid + targ.xoffset;
+  main.target.y = gauss1(rng, 3.0) * gen.ywid + targ.yoffset;
+  double t3, t4, t5, t6;
+  if (targ.fr_pattern == 1) {
+    t3 = rng.grnd() * K::pi;
+    t4 = rng.grnd() * K::pi;
+    t5 = cos(t3) * targ.fr1;
+    t6 = cos(t4) * targ.fr2;
+  } else if (targ.fr_pattern == 2) {
+    t3 = rng.grnd() * 2. * K::pi;
+    t4 = sqrt(rng.grnd()) * (targ.fr2 - targ.fr1) + targ.fr1;
+    t5 = cos(t3) * t4;
+    t6 = sin(t3) * t4;
+  } else if (targ.fr_pattern == 3) {
+    t3 = 2. * rng.grnd() - 1.0;
+    t4 = 2. * rng.grnd() - 1.0;
+    t5 = targ.fr1 * t3;
+    t6 = targ.fr2 * t4;
+  } else {
+    t5 = 0.0;
+    t6 = 0.0;
+  }
+  main.target.x = main.target.x + t5;
+  main.target.y = main.target.y + t6;
+  main.target.z = (0.5 - rng.grnd()) * targ.length + targ.zoffset;
+  main.target.rastery = t6;
+  main.target.rasterx = t5;
+  trip_thru_target(s, 1, main.target.z - targ.zoffset, cfg.Ebeam, 0.0e0, main.target.Eloss[0], main.target.teff[0],
+                   K::Me, 1);
+  if (!cfg.using_Eloss) main.target.Eloss[0] = 0.0;
+  if (cfg.using_Coulomb) main.target.Coulomb = targ.Coulomb_constant;
+  else main.target.Coulomb = 0.0;
+  vertex.Ein = cfg.Ebeam + (rng.grnd() - 0.5) * cfg.dEbeam + main.target.Coulomb - main.target.Eloss[0];
+  main.Ein_shift = vertex.Ein - cfg.Ebeam_vertex_ave;
+  main.Ee_shift = main.target.Coulomb - targ.Coulomb_ave;
+  main.gen_weight = 1.0;
+
+  vertex.e.yptar = gen.e.yptar.min + rng.grnd() * (gen.e.yptar.max - gen.e.yptar.min);
+  vertex.e.xptar = gen.e.xptar.min + rng.grnd() * (gen.e.xptar.max - gen.e.xptar.min);
+  if (cfg.doing_deuterium || cfg.doing_heavy || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_semi) {
+    vertex.p.yptar = gen.p.yptar.min + rng.grnd() * (gen.p.yptar.max - gen.p.yptar.min);
+    vertex.p.xptar = gen.p.xptar.min + rng.grnd() * (gen.p.xptar.max - gen.p.xptar.min);
+  }
+  if (cfg.doing_heavy || cfg.doing_semi) {
+    const double Emin = std::max(gen.p.E.min, gen.sumEgen.min - gen.e.E.max);
+    const double Emax = std::min(gen.p.E.max, gen.sumEgen.max - gen.e.E.min);
+    if (Emin > Emax) return false;
+    main.gen_weight = main.gen_weight * (Emax - Emin) / (gen.p.E.max - gen.p.E.min);
+    vertex.p.E = Emin + rng.grnd() * (Emax - Emin);
+    vertex.p.P = sqrt(vertex.p.E * vertex.p.E - cfg.Mh2);
+    vertex.p.delta = 100. * (vertex.p.P - cfg.spec_p.P) / cfg.spec_p.P;
+  }
+  if (cfg.doing_deuterium || cfg.doing_heavy || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho ||
+      cfg.doing_semi) {
+    double Emin = gen.e.E.min, Emax = gen.e.E.max;
+    if (cfg.doing_deuterium || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho) {
+      Emin = std::max(Emin, gen.sumEgen.min);
+      Emax = std::min(Emax, gen.sumEgen.max);
+    } else if (cfg.doing_heavy) {
+      Emin = std::max(Emin, gen.sumEgen.min - vertex.p.E);
+      Emax = std::min(Emax, gen.sumEgen.max - vertex.p.E);
+    }
+    if (Emin > Emax) return false;
+    main.gen_weight = main.gen_weight * (Emax - Emin) / (gen.e.E.max - gen.e.E.min);
+    vertex.e.E = Emin + rng.grnd() * (Emax - Emin);
+    vertex.e.P = vertex.e.E;
+    vertex.e.delta = 100. * (vertex.e.P - cfg.spec_e.P) / cfg.spec_e.P;
+  }
+  physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, vertex.e.xptar, vertex.e.yptar, vertex.e.theta, vertex.e.phi);
+  physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, vertex.p.xptar, vertex.p.yptar, vertex.p.theta, vertex.p.phi);
+  vertex.Em = 0.0;
+  if (cfg.doing_deutpi || cfg.doing_hepi || cfg.doing_deutkaon || cfg.doing_hekaon || cfg.doing_deutsemi)
+    throw std::runtime_error("oracle: Fermi-smeared production not restated");
+  if (!complete_ev(s, main, vertex)) return false;
+  main.sigcc = 1.0;
+  main.Trec = vertex.Trec;
+  bool success;
+  if (cfg.using_rad) {
+    success = generate_rad(s, main, vertex, orig);
+  } else {
+    success = true;
+    if (cfg.doing_heavy)
+      success = (vertex.Em >= cfg.VERTEXedge.Em.min && vertex.Em <= cfg.VERTEXedge.Em.max &&
+                 vertex.Pm >= cfg.VERTEXedge.Pm.min && vertex.Pm <= cfg.VERTEXedge.Pm.max);
+    if (success) orig = vertex;
+  }
+  return success;
+}
+
+// One arm of montecarlo: dispatch of simc.f:1463-1488 / :1716-1745
+static void run_arm(Sim& s, int arm_id, const ArmOptics* o, ArmCall& a) {
+  if (!o) throw std::runtime_error("oracle: optics not set for an arm in use");
+  if (arm_id == 1) mc_hms(s.trk, *o, a);
+  else if (arm_id == 5) mc_shms(s.trk, *o, a);
+  else throw std::runtime_error("oracle: spectrometer not restated yet");
+}
+
+// simc.f:1310-1852 (using_tgt_field = .false., no calorimeter arms)
+bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
+  const simc_run_config& cfg = *s.cfg;
+  const double Mh2 = cfg.Mh2, Mh = cfg.Mh;
+  s.ntup.resfac = 0.0;
+  double fry;
+  if (cfg.correct_raster) fry = -main.target.rastery;
+  else fry = 0.0;
+  double dang_in[2], dangles[2];
+  if (cfg.mc_smear) target_musc(s, orig.Ein, 1., main.target.teff[0], dang_in);
+  else { dang_in[0] = 0.0; dang_in[1] = 0.0; }
+
+  // ---- P arm
+  if (cfg.using_Eloss)
+    main.SP_p.delta = (sqrt(fabs(powi(orig.p.E - main.target.Eloss[2], 2) - Mh2)) - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+  else
+    main.SP_p.delta = orig.p.delta;
+  if (cfg.mc_smear) {
+    const double beta = orig.p.P / orig.p.E;
+    target_musc(s, orig.p.P, beta, main.target.teff[2], dangles);
+  } else { dangles[0] = 0.0; dangles[1] = 0.0; }
+  main.SP_p.yptar = orig.p.yptar + dangles[0] + dang_in[0];
+  main.SP_p.xptar = orig.p.xptar + dangles[1] + dang_in[1] * cfg.spec_p.cos_th;
+  if (cfg.using_P_arm_montecarlo) {
+    double x_P_arm = -main.target.y;
+    double y_P_arm = -main.target.x * cfg.spec_p.cos_th - main.target.z * cfg.spec_p.sin_th * sin(cfg.spec_p.phi);
+    double z_P_arm = main.target.z * cfg.spec_p.cos_th + main.target.x * cfg.spec_p.sin_th * sin(cfg.spec_p.phi);
+    x_P_arm = x_P_arm - cfg.spec_p.off_x;
+    y_P_arm = y_P_arm - cfg.spec_p.off_y;
+    z_P_arm = z_P_arm - cfg.spec_p.off_z;
+    const double dx_P_arm = main.SP_p.xptar - cfg.spec_p.off_xptar;
+    const double dy_P_arm = main.SP_p.yptar - cfg.spec_p.off_yptar;
+    x_P_arm = x_P_arm - z_P_arm * dx_P_arm;
+    y_P_arm = y_P_arm - z_P_arm * dy_P_arm;
+    z_P_arm = 0.0;
+    const double xtar_init_P = x_P_arm;
+    main.SP_p.z = y_P_arm;
+    ArmCall a;
+    a.p_spec = cfg.spec_p.P; a.th_spec = cfg.spec_p.theta; a.dpp = main.SP_p.delta;
+    a.x = x_P_arm; a.y = y_P_arm; a.z = z_P_arm; a.dxdz = dx_P_arm; a.dydz = dy_P_arm;
+    a.m2 = Mh2; a.ms_flag = cfg.mc_smear; a.wcs_flag = cfg.mc_smear; a.decay_flag = cfg.doing_decay;
+    a.pathlen = 0.0;
+    const int arm = cfg.hadron_arm;
+    a.fry = (arm == 1 || arm == 5 || arm == 6) ? xtar_init_P : fry;
+    a.using_coll = (arm == 1) ? cfg.using_HMScoll : (arm == 5 ? cfg.using_SHMScoll : 0);
+    run_arm(s, arm, s.optics_p, a);
+    s.ntup.resfac = a.resmult;
+    s.stop_p = a.ok_spec ? 0 : a.stop_code;
+    s.hut_p = a.reached_hut;
+    if (!a.ok_spec) return false;
+    main.RECON_p.delta = a.dpp;
+    main.RECON_p.yptar = a.dydz;
+    main.RECON_p.xptar = a.dxdz;
+    main.RECON_p.z = a.y;
+    main.FP_p.x = a.x_fp; main.FP_p.dx = a.dx_fp; main.FP_p.y = a.y_fp; main.FP_p.dy = a.dy_fp;
+    main.FP_p.path = a.pathlen;
+  } else {
+    main.RECON_p.delta = main.SP_p.delta;
+    main.RECON_p.yptar = main.SP_p.yptar;
+    main.RECON_p.xptar = main.SP_p.xptar;
+  }
+  recon.p.delta = main.RECON_p.delta;
+  recon.p.yptar = main.RECON_p.yptar;
+  recon.p.xptar = main.RECON_p.xptar;
+  recon.p.z = main.RECON_p.z;
+  recon.p.P = cfg.spec_p.P * (1. + recon.p.delta / 100.);
+  recon.p.E = sqrt(recon.p.P * recon.p.P + Mh2);
+  double dx_tmp = recon.p.xptar + cfg.spec_p.off_xptar;
+  double dy_tmp = recon.p.yptar + cfg.spec_p.off_yptar;
+  physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, dx_tmp, dy_tmp, recon.p.theta, recon.p.phi);
+  if (cfg.correct_Eloss) {
+    double eloss_P_arm, r;
+    trip_thru_target(s, 3, 0.0, recon.p.E, recon.p.theta, eloss_P_arm, r, Mh, 4);
+    recon.p.E = recon.p.E + eloss_P_arm;
+    recon.p.E = std::max(recon.p.E, sqrt(Mh2 + 0.000001));
+    recon.p.P = sqrt(recon.p.E * recon.p.E - Mh2);
+  }
+
+  // ---- E arm
+  main.SP_e.delta = 100 * (orig.e.E - main.target.Eloss[1] - main.target.Coulomb - cfg.spec_e.P) / cfg.spec_e.P;
+  if (cfg.mc_smear) target_musc(s, orig.e.P, 1., main.target.teff[1], dangles);
+  else { dangles[0] = 0.0; dangles[1] = 0.0; }
+  main.SP_e.yptar = orig.e.yptar + dangles[0] + dang_in[0];
+  main.SP_e.xptar = orig.e.xptar + dangles[1] + dang_in[1] * cfg.spec_e.cos_th;
+  if (cfg.using_E_arm_montecarlo) {
+    double x_E_arm = -main.target.y;
+    double y_E_arm = -main.target.x * cfg.spec_e.cos_th - main.target.z * cfg.spec_e.sin_th * sin(cfg.spec_e.phi);
+    double z_E_arm = main.target.z * cfg.spec_e.cos_th + main.target.x * cfg.spec_e.sin_th * sin(cfg.spec_e.phi);
+    x_E_arm = x_E_arm - cfg.spec_e.off_x;
+    y_E_arm = y_E_arm - cfg.spec_e.off_y;
+    z_E_arm = z_E_arm - cfg.spec_e.off_z;
+    const double dx_E_arm = main.SP_e.xptar - cfg.spec_e.off_xptar;
+    const double dy_E_arm = main.SP_e.yptar - cfg.spec_e.off_yptar;
+    x_E_arm = x_E_arm - z_E_arm * dx_E_arm;
+    y_E_arm = y_E_arm - z_E_arm * dy_E_arm;
+    z_E_arm = 0.0;
+    const double xtar_init_E = x_E_arm;
+    main.SP_e.z = y_E_arm;
+    ArmCall a;
+    a.p_spec = cfg.spec_e.P; a.th_spec = cfg.spec_e.theta; a.dpp = main.SP_e.delta;
+    a.x = x_E_arm; a.y = y_E_arm; a.z = z_E_arm; a.dxdz = dx_E_arm; a.dydz = dy_E_arm;
+    a.m2 = K::Me2; a.ms_flag = cfg.mc_smear; a.wcs_flag = cfg.mc_smear; a.decay_flag = false;
+    a.pathlen = 0.0;
+    const int arm = cfg.electron_arm;
+    a.fry = (arm == 1 || arm == 5 || arm == 6) ? xtar_init_E : fry;
+    a.using_coll = (arm == 1) ? cfg.using_HMScoll : (arm == 5 ? cfg.using_SHMScoll : 0);
+    run_arm(s, arm, s.optics_e, a);
+    s.ntup.resfac = s.ntup.resfac + a.resmult;
+    s.stop_e = a.ok_spec ? 0 : a.stop_code;
+    s.hut_e = a.reached_hut;
+    if (!a.ok_spec) return false;
+    main.RECON_e.delta = a.dpp;
+    main.RECON_e.yptar = a.dydz;
+    main.RECON_e.xptar = a.dxdz;
+    main.RECON_e.z = a.y;
+    main.FP_e.x = a.x_fp; main.FP_e.dx = a.dx_fp; main.FP_e.y = a.y_fp; main.FP_e.dy = a.dy_fp;
+    main.FP_e.path = a.pathlen;
+  } else {
+    main.RECON_e.delta = main.SP_e.delta;
+    main.RECON_e.yptar = main.SP_e.yptar;
+    main.RECON_e.xptar = main.SP_e.xptar;
+  }
+  recon.e.delta = main.RECON_e.delta;
+  recon.e.yptar = main.RECON_e.yptar;
+  recon.e.xptar = main.RECON_e.xptar;
+  recon.e.z = main.RECON_e.z;
+  recon.e.P = cfg.spec_e.P * (1. + recon.e.delta / 100.);
+  recon.e.E = recon.e.P;
+  dx_tmp = recon.e.xptar + cfg.spec_e.off_xptar;
+  dy_tmp = recon.e.yptar + cfg.spec_e.off_yptar;
+  physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, dx_tmp, dy_tmp, recon.e.theta, recon.e.phi);
+  if (cfg.correct_Eloss) {
+    double eloss_E_arm, r;
+    trip_thru_target(s, 2, 0.0, recon.e.E, recon.e.theta, eloss_E_arm, r, K::Me, 4);
+    recon.e.E = recon.e.E + eloss_E_arm;
+  }
+  recon.e.P = recon.e.E;
+  return true;
+}
+
+// event.f:1056-1359 (using_tgt_field = .false.)
+bool complete_recon_ev(Sim& s, Event& recon) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const double Mh2 = cfg.Mh2;
+  recon.Ein = cfg.Ebeam_vertex_ave - targ.Coulomb_ave;
+  recon.ue.x = sin(recon.e.theta) * cos(recon.e.phi);
+  recon.ue.y = sin(recon.e.theta) * sin(recon.e.phi);
+  recon.ue.z = cos(recon.e.theta);
+  recon.up.x = sin(recon.p.theta) * cos(recon.p.phi);
+  recon.up.y = sin(recon.p.theta) * sin(recon.p.phi);
+  recon.up.z = cos(recon.p.theta);
+  recon.nu = recon.Ein - recon.e.E;
+  recon.Q2 = 2 * recon.Ein * recon.e.E * (1 - recon.ue.z);
+  recon.q = sqrt(recon.Q2 + recon.nu * recon.nu);
+  recon.uq.x = -recon.e.P * recon.ue.x / recon.q;
+  recon.uq.y = -recon.e.P * recon.ue.y / recon.q;
+  recon.uq.z = (recon.Ein - recon.e.P * recon.ue.z) / recon.q;
+  const double W2 = K::Mp * K::Mp + 2. * K::Mp * recon.nu - recon.Q2;
+  recon.W = sqrt(fabs(W2)) * W2 / fabs(W2);
+  recon.xbj = recon.Q2 / 2. / K::Mp / recon.nu;
+  if (cfg.doing_phsp) {
+    recon.p.P = cfg.spec_p.P;
+    recon.p.E = sqrt(Mh2 + recon.p.P * recon.p.P);
+  }
+  recon.epsilon = 1. / (1. + 2. * (1 + recon.nu * recon.nu / recon.Q2) * powi(tan(recon.e.theta / 2.), 2));
+  recon.theta_pq = acos(std::min(1.0, recon.up.x * recon.uq.x + recon.up.y * recon.uq.y + recon.up.z * recon.uq.z));
+  const double qx = -recon.uq.y, qy = recon.uq.x, qz = recon.uq.z;
+  const double px = -recon.up.y, py = recon.up.x, pz = recon.up.z;
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  const double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  const double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+  const double p_new_x = px * new_x_x + py * new_x_y + pz * new_x_z;
+  const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
+  if ((p_new_x * p_new_x + p_new_y * p_new_y) == 0.) recon.phi_pq = 0.0;
+  else recon.phi_pq = acos(p_new_x / sqrt(p_new_x * p_new_x + p_new_y * p_new_y));
+  if (p_new_y < 0.) recon.phi_pq = 2 * K::pi - recon.phi_pq;
+  recon.Pmx = recon.p.P * recon.up.x - recon.q * recon.uq.x;
+  recon.Pmy = recon.p.P * recon.up.y - recon.q * recon.uq.y;
+  recon.Pmz = recon.p.P * recon.up.z - recon.q * recon.uq.z;
+  recon.Pm = sqrt(recon.Pmx * recon.Pmx + recon.Pmy * recon.Pmy + recon.Pmz * recon.Pmz);
+  const double oop_x = -recon.uq.y, oop_y = recon.uq.x;
+  recon.PmPar = (recon.Pmx * recon.uq.x + recon.Pmy * recon.uq.y + recon.Pmz * recon.uq.z);
+  recon.PmOop = (recon.Pmx * oop_x + recon.Pmy * oop_y) / sqrt(oop_x * oop_x + oop_y * oop_y);
+  recon.PmPer = sqrt(std::max(0.e0, recon.Pm * recon.Pm - recon.PmPar * recon.PmPar - recon.PmOop * recon.PmOop));
+  if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho || cfg.doing_semi) {
+    recon.Em = recon.nu + targ.Mtar_struck - recon.p.E;
+    const double mm2 = recon.Em * recon.Em - recon.Pm * recon.Pm;
+    s.ntup.mm = sqrt(fabs(mm2)) * fabs(mm2) / mm2;
+    const double mmA2 = powi(recon.nu + targ.M - recon.p.E, 2) - recon.Pm * recon.Pm;
+    s.ntup.mmA = sqrt(fabs(mmA2)) * fabs(mmA2) / mmA2;
+    s.ntup.t = recon.Q2 - Mh2 + 2 * (recon.nu * recon.p.E - recon.p.P * recon.q * cos(recon.theta_pq));
+  }
+  if (cfg.doing_hyd_elast) {
+    recon.Trec = 0.0;
+    recon.Em = recon.nu + targ.M - recon.p.E - recon.Trec;
+  } else if (cfg.doing_deuterium || cfg.doing_heavy) {
+    recon.Trec = sqrt(recon.Pm * recon.Pm + targ.Mrec * targ.Mrec) - targ.Mrec;
+    recon.Em = recon.nu + targ.Mtar_struck - recon.p.E - recon.Trec;
+  } else if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho) {
+    recon.Em = recon.nu + targ.Mtar_struck - recon.p.E;
+  }
+  return true;
+}
+
+// event.f:1363-1569
+bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Event& recon) {
+  const simc_run_config& cfg = *s.cfg;
+  if (cfg.doing_hyd_elast || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_phsp || cfg.doing_rho ||
+      cfg.doing_semi) {
+    main.SF_weight = 1.0;
+  } else {
+    throw std::runtime_error("oracle: spectral-function weights not restated yet");
+  }
+  if (main.SF_weight <= 0 && !force_sigcc) return false;
+  double tgtweight = 1.0;
+  if (cfg.doing_phsp) {
+    main.sigcc = 1.0;
+    main.sigcc_recon = 1.0;
+  } else if (cfg.doing_hyd_elast) {
+    main.sigcc = sigep(vertex);
+    main.sigcc_recon = sigep(recon);
+  } else {
+    throw std::runtime_error("oracle: cross section of this reaction not restated yet");
+  }
+  if (cfg.using_Coulomb) main.sigcc = main.sigcc * powi(1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam, 2);
+  main.weight = main.SF_weight * main.jacobian * main.gen_weight * main.sigcc;
+  main.weight = main.weight * tgtweight;
+  return true;
+}
+
+// loop body, simc.f:169-246
+TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon) {
+  const simc_run_config& cfg = *s.cfg;
+  TryResult r;
+  s.trk.rng = s.rng;
+  s.trk.ctau = cfg.ctau;
+  s.trk.Mh2_final = cfg.Mh2;
+  s.trk.decdist = 0.0;
+  s.ntup = NtupVars();
+  s.stop_e = -1; s.stop_p = -1; s.hut_e = s.hut_p = false;
+  bool success = generate(s, main, vertex, orig);
+  r.gen_success = success;
+  r.stage = 0;
+  if (success) { success = montecarlo(s, orig, main, recon); r.stage = success ? 3 : (s.stop_p > 0 ? 1 : 2); }
+  if (success) success = complete_recon_ev(s, recon);
+  if (success) success = complete_main(s, false, main, vertex, recon);
+  // NB the p-arm upper delta edge uses SPedge%e%delta%max (simc.f:237)
+  r.pass_cuts = !(recon.e.delta <= (cfg.SPedge_e.delta.min + cfg.slop_MC_e_used[0]) ||
+                  recon.e.delta >= (cfg.SPedge_e.delta.max - cfg.slop_MC_e_used[0]) ||
+                  recon.e.yptar <= (cfg.SPedge_e.yptar.min + cfg.slop_MC_e_used[1]) ||
+                  recon.e.yptar >= (cfg.SPedge_e.yptar.max - cfg.slop_MC_e_used[1]) ||
+                  recon.e.xptar <= (cfg.SPedge_e.xptar.min + cfg.slop_MC_e_used[2]) ||
+                  recon.e.xptar >= (cfg.SPedge_e.xptar.max - cfg.slop_MC_e_used[2]) ||
+                  recon.p.delta <= (cfg.SPedge_p.delta.min + cfg.slop_MC_p_used[0]) ||
+                  recon.p.delta >= (cfg.SPedge_e.delta.max - cfg.slop_MC_p_used[0]) ||
+                  recon.p.yptar <= (cfg.SPedge_p.yptar.min + cfg.slop_MC_p_used[1]) ||
+                  recon.p.yptar >= (cfg.SPedge_p.yptar.max - cfg.slop_MC_p_used[1]) ||
+                  recon.p.xptar <= (cfg.SPedge_p.xptar.min + cfg.slop_MC_p_used[2]) ||
+                  recon.p.xptar >= (cfg.SPedge_p.xptar.max - cfg.slop_MC_p_used[2]));
+  if (cfg.hard_cuts) {
+    if (!r.pass_cuts) success = false;
+    if (cfg.doing_eep && (recon.Em > cfg.cuts_Em.max)) success = false;
+  }
+  r.success = success;
+  if (success) r.stage = 4;
+  return r;
+}
+
+}  // namespace simc_oracle

@@ -1,0 +1,105 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked into libsimc_b200.so.
+// PARITY UNPINNED.  Event-level restatement: records of modules.f, COMMON /radccom/, and the
+// routines of event.f, radc.f, brem.f, init.f (per-event part), target.f, enerloss_new.f,
+// physics_proton.f, simc.f (montecarlo + loop body).
+#pragma once
+#include "../include/simc_b200.h"
+#include "arms.hpp"
+
+namespace simc_oracle {
+
+// modules.f:108-115 arm_full
+struct ArmFull { double delta = 0, xptar = 0, yptar = 0, z = 0, theta = 0, phi = 0, E = 0, P = 0; };
+struct Vec3 { double x = 0, y = 0, z = 0; };
+
+// modules.f:117-130 type event
+struct Event {
+  double Ein = 0, Em = 0, Pm = 0, Emiss = 0, Pmiss = 0, Pmx = 0, Pmy = 0, Pmz = 0, PmPar = 0, PmPer = 0, PmOop = 0;
+  double nu = 0, q = 0, Q2 = 0, Trec = 0, W = 0, Mrec = 0, epsilon = 0, theta_pq = 0, theta_tarq = 0, phi_pq = 0,
+         phi_targ = 0;
+  double beta = 0, phi_s = 0, phi_c = 0, zhad = 0, pt2 = 0, xbj = 0;
+  ArmFull e, p;
+  Vec3 ue, up, uq;
+};
+
+struct ArmSP { double delta = 0, yptar = 0, xptar = 0, z = 0; };
+struct ArmFP { double x = 0, dx = 0, y = 0, dy = 0, path = 0; };
+
+// modules.f:133-153 event_target + event_main
+struct EventMain {
+  double weight = 0, SF_weight = 0, gen_weight = 0, jacobian = 0, Ein_shift = 0, Ee_shift = 0;
+  double sigcc = 0, sigcc_recon = 0, sigcent = 0;
+  double epsilon = 0, theta_pq = 0, theta_tarq = 0, phi_pq = 0, phi_targ = 0, beta = 0, W = 0, t = 0, tmin = 0, q2 = 0;
+  double pcm = 0, thetacm = 0, phicm = 0, wcm = 0, davejac = 0, johnjac = 0;
+  struct { double x = 0, y = 0, z = 0, rasterx = 0, rastery = 0, teff[3] = {0, 0, 0}, Eloss[3] = {0, 0, 0}, Coulomb = 0; } target;
+  ArmSP SP_e, SP_p, RECON_e, RECON_p;
+  ArmFP FP_e, FP_p;
+  double Trec = 0;
+};
+
+// per-event part of COMMON /radccom/ (radc.inc:5-19)
+struct RadEv {
+  double etta = 0, frac[3] = {0, 0, 0}, lambda[3] = {0, 0, 0}, bt[2] = {0, 0}, hardcorfac = 0;
+  double c_int[4] = {0, 0, 0, 0}, c_ext[4] = {0, 0, 0, 0}, c[5] = {0, 0, 0, 0, 0}, g_int = 0, g_ext = 0,
+         g[5] = {0, 0, 0, 0, 0};
+  double Egamma_used[3] = {0, 0, 0}, Egamma_min[3] = {0, 0, 0}, Egamma_max[3] = {0, 0, 0};
+  int ntail = 0;
+  bool rad_proton_this_ev = false;
+};
+
+// simulate.inc:161-176 (the fields the loop touches)
+struct NtupVars { double radphot = 0, radarm = 0, resfac = 0, sigcm = 0, krel = 0, mm = 0, mmA = 0, t = 0; };
+
+// Everything one try needs: the run constants, both arms' optics, the RNG and the scratch
+// COMMON state.  One instance per try in counter-based mode (state starts from zero, see
+// DESIGN.md on the reference's stale-state quirks).
+struct Sim {
+  const simc_run_config* cfg = nullptr;
+  const ArmOptics* optics_e = nullptr;
+  const ArmOptics* optics_p = nullptr;
+  Rng* rng = nullptr;
+  RadEv rad;
+  NtupVars ntup;
+  Track trk;                     // COMMON /track/ + decdist, Mh2_final
+  int stop_e = 0, stop_p = 0;    // stop code of each arm (0 = ok), -1 = arm not entered
+  bool hut_e = false, hut_p = false;
+};
+
+// Result of one pass through the loop body, simc.f:169-351
+struct TryResult {
+  bool gen_success = false;      // after generate
+  bool success = false;          // after complete_main (+ hard cuts)
+  bool pass_cuts = false;
+  int stage = 0;                 // 0 failed in generate, 1 failed in P arm, 2 failed in E arm, 3 recon/main, 4 success
+};
+
+void physics_angles(double theta0, double phi0, double dx, double dy, double& theta, double& phi);      // event.f:1572
+void spectrometer_angles(double theta0, double phi0, double& dx, double& dy, double theta, double phi); // event.f:1618
+void trip_thru_target(Sim& s, int narm, double zpos, double energy, double theta, double& Eloss, double& radlen,
+                      double mass, int typeflag);                                                       // target.f:1
+void enerloss_new(Sim& s, double len, double dens, double zeff, double aeff, double epart, double mpart, int typeflag,
+                  double& Eloss);                                                                       // enerloss_new.f:1
+void target_musc(Sim& s, double p, double beta, double teff, double dangles[2]);                         // target.f:548
+double bremos(double egamma, double k_ix, double k_iy, double k_iz, double k_fx, double k_fy, double k_fz,
+              double p_ix, double p_iy, double p_iz, double p_fx, double p_fy, double p_fz, double p_fe,
+              bool radiate_proton, bool exponentiate, double& bsoft, double& bhard, double& dbsoft);     // brem.f:344
+double gamma_fn(double x);                                                                               // radc.f:92
+void radc_init_ev(Sim& s, EventMain& main, Event& vertex);                                               // init.f:655
+bool complete_ev(Sim& s, EventMain& main, Event& vertex);                                                // event.f:432
+bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig);                                  // radc.f:120
+bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig);                                      // event.f:126
+bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon);                                     // simc.f:1310
+bool complete_recon_ev(Sim& s, Event& recon);                                                            // event.f:1056
+bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Event& recon);              // event.f:1363
+double sigep(const Event& vertex);
+double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax);  // radc.f:523                                                                       // physics_proton.f:1
+
+// One try of the loop (simc.f:169-351) in counter-based mode.
+TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon);
+
+void accum_clear(const simc_run_config& cfg, simc_accum& a);
+void merge_accum(simc_accum& a, const simc_accum& b);
+void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
+               uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off);
+
+}  // namespace simc_oracle

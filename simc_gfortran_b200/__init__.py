@@ -4,10 +4,10 @@ The product is ``libsimc_b200.so`` (hand-written sm_100a CUDA kernels behind the
 ``include/simc_b200.h``); this package is the thin Python host side used by the tests and by
 ``bench.py``.  There is no CPU fallback: importing works anywhere, computing needs a GPU.
 """
-from .lib import (Simc, SimcError, lib_path, load_library, RunConfig, Accum, ARM_HMS, ARM_SOS, ARM_HRSR,
+from .lib import (config_from_deck, Simc, SimcError, lib_path, load_library, RunConfig, Accum, ARM_HMS, ARM_SOS, ARM_HRSR,
                   ARM_HRSL, ARM_SHMS, TRANSPORT_NIN, TRANSPORT_NOUT)
 from .optics import load_optics_fixture, OpticsTables
 
-__all__ = ["Simc", "SimcError", "lib_path", "load_library", "RunConfig", "Accum", "ARM_HMS", "ARM_SOS",
+__all__ = ["config_from_deck", "Simc", "SimcError", "lib_path", "load_library", "RunConfig", "Accum", "ARM_HMS", "ARM_SOS",
            "ARM_HRSR", "ARM_HRSL", "ARM_SHMS", "TRANSPORT_NIN", "TRANSPORT_NOUT", "load_optics_fixture",
            "OpticsTables"]

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <new>
@@ -15,6 +17,8 @@
 #include "optics_host.h"
 
 using namespace simc;
+
+size_t simc_dev_accum_minmax_offset();      // kernels.cu
 
 namespace {
 
@@ -40,6 +44,15 @@ struct simc_handle {
   long long launches = 0;
   // scratch for the host-pointer entry points
   double* d_in = nullptr; double* d_out = nullptr; int* d_flags = nullptr; long long scratch_n = 0;
+  // event loop
+  simc_run_config* d_cfg = nullptr;
+  double* d_state = nullptr; unsigned* d_lists = nullptr; unsigned* d_counts = nullptr; void* d_acc = nullptr;
+  long long loop_cap = 0;
+  long long batch = 1 << 20;           // tries per batch of the stage pipeline
+  int grid_blocks = 0;
+  int qexp_w = -64;
+  std::vector<unsigned char> acc_host;
+  double* d_rec = nullptr; int* d_status = nullptr; long long rec_n = 0;
 };
 
 namespace {
@@ -140,6 +153,13 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_in) cudaFree(h->d_in);
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_flags) cudaFree(h->d_flags);
+  if (h->d_cfg) cudaFree(h->d_cfg);
+  if (h->d_state) cudaFree(h->d_state);
+  if (h->d_lists) cudaFree(h->d_lists);
+  if (h->d_counts) cudaFree(h->d_counts);
+  if (h->d_acc) cudaFree(h->d_acc);
+  if (h->d_rec) cudaFree(h->d_rec);
+  if (h->d_status) cudaFree(h->d_status);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -264,29 +284,242 @@ int64_t simc_b200_sizeof(int which) {
 
 }  // extern "C"
 
-// ---- the event loop (implemented in loop.cu once generation/weights are in) ---------------
+
+// ---- the event loop ----------------------------------------------------------------------------
+namespace {
+
+int weight_qexp(const simc_run_config& cfg) {
+  const double w = cfg.w_ref > 0 ? cfg.w_ref : 1.0;
+  return std::ilogb(w) - 64;
+}
+
+// Which settings this build of the loop implements; everything else is refused loudly.
+int validate_loop_config(simc_handle* h) {
+  const simc_run_config& c = h->cfg;
+  if (!c.doing_hyd_elast || c.doing_deuterium || c.doing_heavy || c.doing_pion || c.doing_kaon || c.doing_delta ||
+      c.doing_rho || c.doing_semi || c.doing_phsp)
+    return fail(h, SIMC_ERR_ARG, "this build of the event loop implements H(e,e'p) (doing_hyd_elast) only");
+  if (c.using_rad && (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 ||
+                      !c.use_offshell_rad || c.use_expon != 0))
+    return fail(h, SIMC_ERR_ARG,
+                "radiative options outside rad_flag<=1, extrad_flag 1..2, intcor_mode=1, use_offshell_rad=1, "
+                "use_expon=0 are not implemented");
+  if (c.using_HMScoll || c.using_SHMScoll)
+    return fail(h, SIMC_ERR_ARG, "collimator stepping (using_HMScoll/using_SHMScoll) is not implemented");
+  for (int arm : {c.electron_arm, c.hadron_arm}) {
+    const bool used = (arm == c.electron_arm) ? c.using_E_arm_montecarlo : c.using_P_arm_montecarlo;
+    if (!used) continue;
+    auto it = h->arms.find(arm);
+    if (it == h->arms.end() || !it->second.loaded)
+      return fail(h, SIMC_ERR_STATE, "simc_b200_run: load the optics of both spectrometers first");
+  }
+  return SIMC_OK;
+}
+
+int ensure_loop_buffers(simc_handle* h, long long cap) {
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_cfg) {
+    CU(h, cudaMalloc(&h->d_cfg, sizeof(simc_run_config)));
+    CU(h, cudaMemcpy(h->d_cfg, &h->cfg, sizeof(simc_run_config), cudaMemcpyHostToDevice));
+    h->qexp_w = weight_qexp(h->cfg);
+    cudaDeviceProp prop;
+    CU(h, cudaGetDeviceProperties(&prop, h->device));
+    h->grid_blocks = prop.multiProcessorCount * 4;          // persistent stage kernels: 4 CTAs of 128 per SM
+    const size_t ab = strict::dev_accum_bytes();
+    CU(h, cudaMalloc(&h->d_acc, ab));
+    h->acc_host.assign(ab, 0);
+    CU(h, cudaMalloc(&h->d_counts, 4 * sizeof(unsigned)));
+  }
+  if (cap > h->loop_cap) {
+    if (h->d_state) cudaFree(h->d_state);
+    if (h->d_lists) cudaFree(h->d_lists);
+    h->d_state = nullptr; h->d_lists = nullptr; h->loop_cap = 0;
+    CU(h, cudaMalloc(&h->d_state, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)cap));
+    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 3 * (size_t)cap));
+    h->loop_cap = cap;
+  }
+  return SIMC_OK;
+}
+
+// device accumulators <- identity element (zeros; min/max keys of +-1e10)
+int clear_dev_accum(simc_handle* h) {
+  const size_t ab = strict::dev_accum_bytes();
+  std::vector<unsigned char> img(ab, 0);
+  // order-preserving keys of +1e10 / -1e10
+  auto key = [](double d) { long long i; std::memcpy(&i, &d, 8); return i >= 0 ? i : (i ^ 0x7fffffffffffffffLL); };
+  // layout knowledge lives in kernels.cu; ask it to translate an "empty" simc_accum instead
+  // (contrib/slop arrays sit at the tail of DevAccum: write them by offset helper)
+  const size_t off = simc_dev_accum_minmax_offset();
+  long long* mm = (long long*)(img.data() + off);
+  for (int i = 0; i < 32; ++i) mm[i] = key(1.0e10);          // contrib_lo
+  for (int i = 0; i < 32; ++i) mm[32 + i] = key(-1.0e10);    // contrib_hi
+  for (int i = 0; i < 8; ++i) mm[64 + i] = key(1.0e10);      // slop_lo
+  for (int i = 0; i < 8; ++i) mm[72 + i] = key(-1.0e10);     // slop_hi
+  CU(h, cudaMemcpyAsync(h->d_acc, img.data(), ab, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return SIMC_OK;
+}
+
+int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, bool record, double* d_rec,
+                int* d_status) {
+  int rc = validate_loop_config(h);
+  if (rc) return rc;
+  const bool fresh = (h->d_cfg == nullptr);
+  const long long cap = record ? n_tries : std::min<long long>(h->batch, n_tries);
+  rc = ensure_loop_buffers(h, std::max<long long>(cap, 1));
+  if (rc) return rc;
+  if (fresh) { rc = clear_dev_accum(h); if (rc) return rc; }
+  LoopLaunch a;
+  a.cfg = h->d_cfg;
+  a.arm_e = h->arms.count(h->cfg.electron_arm) ? h->arms[h->cfg.electron_arm].d_arm : nullptr;
+  a.arm_p = h->arms.count(h->cfg.hadron_arm) ? h->arms[h->cfg.hadron_arm].d_arm : nullptr;
+  a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
+  a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
+  a.grid_blocks = h->grid_blocks;
+  for (int64_t done = 0; done < n_tries;) {
+    const int64_t nb = std::min<int64_t>(n_tries - done, cap);
+    a.first_try = first_try + done;
+    a.n_tries = nb;
+    int nl = 0;
+    cudaError_t e = h->strict ? strict::launch_loop_batch(a, h->stream, &nl) : fast::launch_loop_batch(a, h->stream, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
+    done += nb;
+  }
+  return SIMC_OK;
+}
+
+}  // namespace
+
 extern "C" {
-#ifndef SIMC_HAVE_LOOP
+
 int simc_b200_accum_clear(simc_handle* h, simc_accum* acc) {
   if (!h || !acc) return SIMC_ERR_ARG;
   std::memset(acc, 0, sizeof(*acc));
+  const int qw = weight_qexp(h->cfg);
+  acc->wtcontribute.qexp = qw;
+  acc->sum_sigcc.qexp = qw;
+  for (int i = 0; i < 8; ++i) { acc->sumerr[i].qexp = -80; acc->sumerr2[i].qexp = -80; }
+  for (int k = 0; k < 6; ++k) for (int b = 0; b < SIMC_NHIST; ++b) acc->hist_w[k][b].qexp = qw;
+  for (int i = 0; i < 32; ++i) { acc->contrib[i].lo = 1.0e10; acc->contrib[i].hi = -1.0e10; }
+  for (int i = 0; i < 8; ++i) { acc->slop[i].lo = 1.0e10; acc->slop[i].hi = -1.0e10; }
   return SIMC_OK;
 }
-int simc_b200_run(simc_handle* h, int64_t, int64_t, uint64_t, simc_accum*) {
-  return fail(h, SIMC_ERR_STATE, "simc_b200_run: event loop not built into this library yet");
+
+int simc_b200_run_async(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n_tries < 0) return fail(h, SIMC_ERR_ARG, "simc_b200_run: n_tries < 0");
+  if (n_tries == 0) return validate_loop_config(h);
+  return run_batches(h, first_try, n_tries, seed, false, nullptr, nullptr);
 }
-int simc_b200_run_async(simc_handle* h, int64_t, int64_t, uint64_t) {
-  return fail(h, SIMC_ERR_STATE, "simc_b200_run_async: event loop not built into this library yet");
+
+int simc_b200_fetch(simc_handle* h, simc_accum* acc) {
+  if (!h || !acc) return SIMC_ERR_ARG;
+  if (!h->d_acc) return SIMC_OK;                       // nothing was run
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaMemcpyAsync(h->acc_host.data(), h->d_acc, h->acc_host.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (h->strict) strict::accum_to_host(h->acc_host.data(), acc, h->qexp_w);
+  else fast::accum_to_host(h->acc_host.data(), acc, h->qexp_w);
+  return clear_dev_accum(h);
 }
-int simc_b200_fetch(simc_handle* h, simc_accum*) {
-  return fail(h, SIMC_ERR_STATE, "simc_b200_fetch: event loop not built into this library yet");
+
+int simc_b200_run(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, simc_accum* acc) {
+  if (!h || !acc) return SIMC_ERR_ARG;
+  int rc = simc_b200_run_async(h, first_try, n_tries, seed);
+  if (rc) return rc;
+  return simc_b200_fetch(h, acc);
 }
-int simc_b200_device_accum(simc_handle* h, void**, int64_t*, void**, int64_t*) {
-  return fail(h, SIMC_ERR_STATE, "simc_b200_device_accum: event loop not built into this library yet");
+
+int simc_b200_device_accum(simc_handle* h, void** dev_ptr, int64_t* n_int64, void** dev_minmax, int64_t* n_minmax) {
+  if (!h) return SIMC_ERR_ARG;
+  if (!h->d_acc) {
+    int rc = validate_loop_config(h);
+    if (rc) return rc;
+    rc = ensure_loop_buffers(h, 1);
+    if (rc) return rc;
+    rc = clear_dev_accum(h);
+    if (rc) return rc;
+  }
+  const size_t off = simc_dev_accum_minmax_offset();
+  // [0, off): unsigned 64-bit sums (add across ranks as two's complement int64 pairs -- see DESIGN.md);
+  // [off, off+80*8): min/max keys: lo keys take MIN, hi keys take MAX; the STOP counters follow.
+  if (dev_ptr) *dev_ptr = h->d_acc;
+  if (n_int64) *n_int64 = (int64_t)(strict::dev_accum_bytes() / 8);
+  if (dev_minmax) *dev_minmax = (unsigned char*)h->d_acc + off;
+  if (n_minmax) *n_minmax = 80;
+  return SIMC_OK;
 }
-int simc_b200_event_batch(simc_handle* h, int64_t, int64_t, uint64_t, double*, int32_t*) {
-  return fail(h, SIMC_ERR_STATE, "simc_b200_event_batch: event loop not built into this library yet");
+
+int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch) {
+  if (!h || tries_per_batch < 128) return SIMC_ERR_ARG;
+  h->batch = tries_per_batch;
+  return SIMC_OK;
 }
-const char* simc_b200_event_field_name(int) { return ""; }
-#endif
+
+int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed, double* rec_soa,
+                          int32_t* status) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!rec_soa || !status))) return fail(h, SIMC_ERR_ARG, "simc_b200_event_batch: bad argument");
+  if (n == 0) return validate_loop_config(h);
+  CU(h, cudaSetDevice(h->device));
+  if (n > h->rec_n) {
+    if (h->d_rec) cudaFree(h->d_rec);
+    if (h->d_status) cudaFree(h->d_status);
+    h->d_rec = nullptr; h->d_status = nullptr; h->rec_n = 0;
+    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n));
+    CU(h, cudaMalloc(&h->d_status, sizeof(int) * (size_t)n));
+    h->rec_n = n;
+  }
+  int rc = validate_loop_config(h);
+  if (rc) return rc;
+  rc = ensure_loop_buffers(h, n);
+  if (rc) return rc;
+  // records of stages that were not reached read as zero
+  CU(h, cudaMemsetAsync(h->d_state, 0, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)h->loop_cap, h->stream));
+  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
+  rc = run_batches(h, first_try, n, seed, true, h->d_rec, h->d_status);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(rec_soa, h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(status, h->d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  // the accumulators also saw these tries: a parity dump is not part of a run, drop them
+  return clear_dev_accum(h);
 }
+
+int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!in_soa || !out_soa))) return fail(h, SIMC_ERR_ARG, "simc_b200_radc_batch: bad argument");
+  if (n == 0) return SIMC_OK;
+  const simc_run_config& c = h->cfg;
+  if (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 || !c.use_offshell_rad || c.use_expon != 0)
+    return fail(h, SIMC_ERR_ARG, "simc_b200_radc_batch: radiative options not implemented");
+  CU(h, cudaSetDevice(h->device));
+  int rc = ensure_loop_buffers(h, 1);
+  if (rc) return rc;
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(h, cudaMalloc(&d_in, sizeof(double) * SIMC_RADC_NIN * (size_t)n));
+  CU(h, cudaMalloc(&d_out, sizeof(double) * SIMC_RADC_NOUT * (size_t)n));
+  cudaError_t e = cudaMemcpyAsync(d_in, in_soa, sizeof(double) * SIMC_RADC_NIN * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = h->strict ? strict::launch_radc_batch(h->d_cfg, n, d_in, d_out, h->stream)
+                  : fast::launch_radc_batch(h->d_cfg, n, d_in, d_out, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_soa, d_out, sizeof(double) * SIMC_RADC_NOUT * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  h->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_radc_batch");
+  return SIMC_OK;
+}
+
+static const char* kEventFields[SIMC_EVENT_NREC] = {
+    "stage", "pass_cuts", "n_draws", "stop_p", "stop_e", "weight", "sigcc", "gen_weight", "jacobian", "sigcc_recon",
+    "vertex.Ein", "vertex.e.E", "vertex.e.delta", "vertex.e.yptar", "vertex.e.xptar", "vertex.p.E", "vertex.p.delta",
+    "vertex.p.yptar", "vertex.p.xptar", "vertex.Q2", "orig.e.E", "orig.p.E", "Egamma_used1", "Egamma_used2",
+    "Egamma_used3", "ntail", "target.x", "target.y", "target.z", "Eloss1", "Eloss2", "Eloss3", "SP.e.delta",
+    "SP.e.yptar", "SP.e.xptar", "SP.p.delta", "SP.p.yptar", "SP.p.xptar", "recon.e.delta", "recon.e.yptar",
+    "recon.e.xptar", "recon.p.delta", "recon.p.yptar", "recon.p.xptar", "recon.Em", "recon.Pm", "recon.W",
+    "hardcorfac"};
+const char* simc_b200_event_field_name(int k) { return (k >= 0 && k < SIMC_EVENT_NREC) ? kEventFields[k] : ""; }
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Event generation, vertex / reconstructed kinematics and weights on the device.
+// Replaces generate + complete_ev (event.f:126-1052), generate_rad (radc.f:120-519),
+// the target-to-spectrometer part of montecarlo (simc.f:1365-1443, 1623-1645, 1655-1846),
+// complete_recon_ev (event.f:1056-1359), complete_main (event.f:1363-1569) and sigep
+// (physics_proton.f:1-190).  Reaction coverage of this build: H(e,e'p); the host refuses the
+// other reaction flags at create().
+#pragma once
+#include "radc.cuh"
+
+namespace simc {
+
+#define SIMC_PI_D 3.141592653589793
+#define SIMC_ME 0.51099906
+#define SIMC_MP 938.27231
+#define SIMC_HBARC 197.327053
+#define SIMC_ALPHA (1. / 137.0359895)
+
+// event.f:1572-1614
+SIMC_HD void physics_angles(double theta0, double phi0, double dx, double dy, double& theta, double& phi) {
+  const double costh = cos(theta0), sinth = sin(theta0), sinph = sin(phi0);
+  const double r = sqrt(1. + dx * dx + dy * dy);
+  theta = acos((costh - dy * sinth * sinph) / r);
+  if (dx != 0.0) {
+    phi = atan((dy * costh + sinth * sinph) / dx);
+    if (phi <= 0) phi = phi + SIMC_PI_D;
+    if (sinph < 0.) phi = phi + SIMC_PI_D;
+  } else {
+    phi = phi0;
+  }
+}
+
+// event.f:1618-1648
+SIMC_HD void spectrometer_angles(double theta0, double phi0, double& dx, double& dy, double theta, double phi) {
+  const double x = sin(theta) * cos(phi), y = sin(theta) * sin(phi), z = cos(theta);
+  const double x0 = sin(theta0) * cos(phi0), y0 = sin(theta0) * sin(phi0), z0 = cos(theta0);
+  const double cos_dtheta = x * x0 + y * y0 + z * z0;
+  dx = x / cos_dtheta;
+  dy = sqrt(1 / (cos_dtheta * cos_dtheta) - 1. - dx * dx);
+  const double y_event = y / cos_dtheta;
+  if (y_event < y0) dy = -dy;
+}
+
+// sigep, fofa_best_fit, sigMott: physics_proton.f:1-22,137-190
+SIMC_HD double sigep(double Ein, double eE, double etheta, double Q2v) {
+  const double mu_p = 2.793;
+  const double qsquar = -Q2v / (SIMC_HBARC * SIMC_HBARC);
+  const double Q2 = -qsquar * (SIMC_HBARC * SIMC_HBARC) * 1.e-6;   // hbarc**2. : pow(x,2.) == x*x
+  const double Q = sqrt(fmax(Q2, 0.e0));
+  const double Q3 = pow(Q, 3.), Q4 = pow(Q, 4.), Q5 = pow(Q, 5.);
+  double denom = 1. + 0.62 * Q + 0.68 * Q2 + 2.8 * Q3 + 0.83 * Q4;
+  const double GE = 1. / denom;
+  denom = 1. + 0.35 * Q + 2.44 * Q2 + 0.5 * Q3 + 1.04 * Q4 + 0.34 * Q5;
+  const double GM = mu_p / denom;
+  const double qmu4mp = Q2v / 4. / (SIMC_MP * SIMC_MP);
+  const double W1p = GM * GM * qmu4mp;
+  const double W2p = (GE * GE + GM * GM * qmu4mp) / (1.0 + qmu4mp);
+  const double th2 = tan(etheta / 2.);
+  const double Wp = W2p + 2. * W1p * (th2 * th2);
+  const double m = 2. * SIMC_ALPHA * SIMC_HBARC * eE * cos(etheta / 2.) / Q2v;
+  const double sigMott = (m * m) * 1.e4;
+  return sigMott * eE / Ein * Wp;
+}
+
+// State of one try between the stages of the loop: the parts of `main`, `vertex`, `orig`
+// and /radccom/ that later stages read.
+struct EventState {
+  // main%target
+  double tx, ty, tz, rastery, Eloss[3], teff[3], Coulomb;
+  // main
+  double gen_weight, jacobian, Ein_shift, Ee_shift, Trec;
+  // vertex
+  double v_Ein, v_eE, v_edelta, v_eyptar, v_exptar, v_etheta, v_ephi;
+  double v_pE, v_pP, v_pdelta, v_pyptar, v_pxptar, v_ptheta, v_pphi;
+  double v_Q2, v_Em, v_Pm, v_Trec;
+  double uex, uey, uez, upx, upy, upz;
+  // orig (fields that differ from vertex)
+  double o_Ein, o_eE, o_edelta, o_pE, o_pP, o_pdelta;
+  RadEvDev rad;
+};
+
+// trip_thru_target with typeflag = 1 (sampled energy loss): one |gauss1(10)| per material with
+// thick > 0, in the reference's order target, Al, air, kevlar, mylar (target.f:46-52,170-180).
+template <class RNG, class GAUSS>
+SIMC_HD void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng, GAUSS gauss, int narm, double zpos,
+                                      double energy, double theta, double mass, double& Eloss, double& radlen) {
+  const simc_target& targ = cfg.targ;
+  const Material al = SIMC_MAT_AL;
+  const ParticleKin k = particle_kin(energy, mass);
+  double s_target, s_Al;
+  auto one = [&](double len, double dens, double z, double a) {
+    double x = 0.;
+    if (len * dens > 0.) x = fabs(gauss(rng, 10.0));
+    return enerloss_material(k, len, dens, z, a, x);
+  };
+  if (narm == 1) {
+    incoming_paths(targ, zpos, s_target, s_Al);
+    radlen = s_target / targ.X0_cm + s_Al / al.X0_cm;
+    const double e1 = one(s_target, targ.rho, targ.Z, targ.A);
+    const double e2 = one(s_Al, al.rho, al.Z, al.A);
+    Eloss = e1 + e2;
+    return;
+  }
+  const Material air = SIMC_MAT_AIR, kev = SIMC_MAT_KEVLAR, myl = SIMC_MAT_MYLAR;
+  const ArmWindows w = arm_windows(narm == 2 ? cfg.electron_arm : cfg.hadron_arm);
+  outgoing_paths(targ, w, zpos, theta, s_target, s_Al);
+  radlen = s_target / targ.X0_cm + s_Al / al.X0_cm + w.s_air / air.X0_cm + w.s_kevlar / kev.X0_cm +
+           w.s_mylar / myl.X0_cm;
+  const double e1 = one(s_target, targ.rho, targ.Z, targ.A);
+  const double e2 = one(s_Al, al.rho, al.Z, al.A);
+  const double e3 = one(w.s_air, air.rho, air.Z, air.A);
+  const double e4 = one(w.s_kevlar, kev.rho, kev.Z, kev.A);
+  const double e5 = one(w.s_mylar, myl.rho, myl.Z, myl.A);
+  Eloss = e1 + e2 + e3 + e4 + e5;
+}
+
+// complete_ev for H(e,e'p), event.f:432-1052.  Needs v_Ein, v_eyptar/xptar/theta/phi, tz; fills
+// the rest of the vertex, the jacobian, Eloss/teff(2:3) and the radiative constants.
+template <class RNG, class GAUSS>
+SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
+  const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
+  s.jacobian = 1.0;
+  s.uex = sin(s.v_etheta) * cos(s.v_ephi);
+  s.uey = sin(s.v_etheta) * sin(s.v_ephi);
+  s.uez = cos(s.v_etheta);
+  s.v_eE = s.v_Ein * Mh / (Mh + s.v_Ein * (1. - s.uez));
+  if (s.v_eE > s.v_Ein) return false;
+  const double eP = s.v_eE;
+  s.v_edelta = (eP - cfg.spec_e.P) * 100. / cfg.spec_e.P;
+  const double nu = s.v_Ein - s.v_eE;
+  s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
+  const double q = sqrt(s.v_Q2 + nu * nu);
+  const double uqx = -eP * s.uex / q;
+  const double uqy = -eP * s.uey / q;
+  const double uqz = (s.v_Ein - eP * s.uez) / q;
+  // |uq|^2-1 > 0.01 is a fatal `stop` in the reference (event.f:538); it cannot trigger here
+  s.v_Em = 0.0;
+  s.v_Pm = 0.0;
+  s.upx = uqx; s.upy = uqy; s.upz = uqz;
+  s.v_pP = q;
+  s.v_ptheta = acos(s.upz);
+  s.v_pphi = atan2(s.upy, s.upx);
+  if (s.v_pphi < 0.) s.v_pphi = s.v_pphi + 2. * SIMC_PI_D;
+  spectrometer_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
+  s.v_pE = sqrt(s.v_pP * s.v_pP + Mh2);
+  s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+  s.v_Trec = 0.0;
+  const double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
+  s.jacobian = s.jacobian / (r * (r * r));
+  const double zpos = s.tz - cfg.targ.zoffset;
+  trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
+  if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
+  VertexKin v;
+  v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = eP; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+  v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+  radc_init_ev(cfg, v, s.teff[0], s.teff[1], s.rad);
+  return true;
+}
+
+// generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
+  const simc_target& targ = cfg.targ;
+  s.tx = gauss(rng, 3.0) * cfg.gen.xwid + targ.xoffset;
+  s.ty = gauss(rng, 3.0) * cfg.gen.ywid + targ.yoffset;
+  double t3, t4, t5, t6;
+  if (targ.fr_pattern == 1) {
+    t3 = rng.uniform() * SIMC_PI_D;
+    t4 = rng.uniform() * SIMC_PI_D;
+    t5 = cos(t3) * targ.fr1;
+    t6 = cos(t4) * targ.fr2;
+  } else if (targ.fr_pattern == 2) {
+    t3 = rng.uniform() * 2. * SIMC_PI_D;
+    t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
+    t5 = cos(t3) * t4;
+    t6 = sin(t3) * t4;
+  } else if (targ.fr_pattern == 3) {
+    t3 = 2. * rng.uniform() - 1.0;
+    t4 = 2. * rng.uniform() - 1.0;
+    t5 = targ.fr1 * t3;
+    t6 = targ.fr2 * t4;
+  } else {
+    t5 = 0.0; t6 = 0.0;
+  }
+  s.tx = s.tx + t5;
+  s.ty = s.ty + t6;
+  s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
+  s.rastery = t6;
+  trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+  if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
+  s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
+  s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
+  s.Ein_shift = s.v_Ein - cfg.Ebeam_vertex_ave;
+  s.Ee_shift = s.Coulomb - targ.Coulomb_ave;
+  s.gen_weight = 1.0;
+  s.v_eyptar = cfg.gen.e.yptar.min + rng.uniform() * (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min);
+  s.v_exptar = cfg.gen.e.xptar.min + rng.uniform() * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min);
+  physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, s.v_exptar, s.v_eyptar, s.v_etheta, s.v_ephi);
+  // (the reference also converts the not-yet-known proton angles here, event.f:325; the result is
+  //  overwritten in complete_ev before anyone reads it)
+  s.v_Em = 0.0;
+  s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
+  s.rad.ntail = 0;
+  if (!complete_ev_hyd_elast(cfg, rng, gauss, s)) return false;
+  s.Trec = s.v_Trec;
+  if (!cfg.using_rad) {
+    s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
+    s.o_pdelta = s.v_pdelta;
+    return true;
+  }
+  // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208)
+  RadEvDev& R = s.rad;
+  {
+    const double x = rng.uniform();
+    if (x >= R.frac[0] + R.frac[1]) R.ntail = 3;
+    else if (x >= R.frac[0]) R.ntail = 2;
+    else R.ntail = 1;
+  }
+  const int ntail = R.ntail;
+  const double max_delta_Trec = fmax((s.v_Trec - cfg.VERTEXedge.Trec.min), (cfg.VERTEXedge.Trec.max - s.v_Trec));
+  double rad_weight = 1, bw, emin, emax;
+  auto vk = [&]() {
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    return v;
+  };
+  if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:234-337, hydrogen elastic limits :264-271
+    double ebeam_max = SIMC_MP * cfg.edge.e.E.max / (SIMC_MP - cfg.edge.e.E.max * (1. - s.uez));
+    if (ebeam_max < 0) ebeam_max = 1.e10;
+    const double ebeam_min = SIMC_MP * cfg.edge.e.E.min / (SIMC_MP - cfg.edge.e.E.min * (1. - s.uez));
+    emin = s.v_Ein - ebeam_max;
+    emax = s.v_Ein - ebeam_min;
+    emax = fmin(emax, cfg.edge.Em.max);
+    emax = fmin(emax, cfg.Egamma1_max);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    basicrad4(R, rng, emin, emax, R.Egamma_used[0], bw);
+    if (bw <= 0) return false;
+    s.v_Ein = s.v_Ein - R.Egamma_used[0];
+    const double eg1 = R.Egamma_used[0];
+    if (!complete_ev_hyd_elast(cfg, rng, gauss, s)) return false;     // re-entry, radc.f:324
+    R.Egamma_used[0] = eg1;
+    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[0], emin, emax, bw);
+  }
+  if (cfg.doing_tail[1] && ntail == 2) {          // radc.f:358-405
+    emin = s.v_eE - cfg.edge.e.E.max;
+    emax = s.v_eE - cfg.edge.e.E.min;
+    emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
+    emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);   // ntail != 0
+    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    basicrad4(R, rng, emin, emax, R.Egamma_used[1], bw);
+    if (bw <= 0) return false;
+    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[1], emin, emax, bw);
+  }
+  if (R.rad_proton_this_ev && ntail == 3) {       // radc.f:409-461
+    emin = s.v_pE - cfg.edge.p.E.max;
+    emax = s.v_pE - cfg.edge.p.E.min;
+    emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
+    emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
+    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    basicrad4(R, rng, emin, emax, R.Egamma_used[2], bw);
+    if (bw <= 0) return false;
+    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[2], emin, emax, bw);
+  }
+  // orig = vertex (+) radiation, radc.f:476-515
+  s.o_Ein = s.v_Ein + R.Egamma_used[0];
+  s.o_eE = s.v_eE - R.Egamma_used[1];
+  if (s.o_eE <= 0e0) return false;
+  s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
+  s.o_pE = s.v_pE - R.Egamma_used[2];
+  if (s.o_pE <= cfg.Mh) return false;
+  s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+  s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+  s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
+  return true;
+}
+
+// Target-to-spectrometer transformation of one arm, simc.f:1379-1443 (P) / :1655-1706 (E)
+struct ArmEntry {
+  double sp_delta, sp_yptar, sp_xptar, sp_z;      // main%SP
+  double x, y, dx, dy;                            // TRANSPORT coordinates at z = 0
+};
+SIMC_HD void arm_entry(const simc_spectrometer& sp, double tx, double ty, double tz, double sp_delta, double sp_yptar,
+                       double sp_xptar, ArmEntry& a) {
+  a.sp_delta = sp_delta; a.sp_yptar = sp_yptar; a.sp_xptar = sp_xptar;
+  double x_arm = -ty;
+  double y_arm = -tx * sp.cos_th - tz * sp.sin_th * sin(sp.phi);
+  double z_arm = tz * sp.cos_th + tx * sp.sin_th * sin(sp.phi);
+  x_arm = x_arm - sp.off_x;
+  y_arm = y_arm - sp.off_y;
+  z_arm = z_arm - sp.off_z;
+  a.dx = sp_xptar - sp.off_xptar;
+  a.dy = sp_yptar - sp.off_yptar;
+  a.x = x_arm - z_arm * a.dx;
+  a.y = y_arm - z_arm * a.dy;
+  a.sp_z = a.y;
+}
+
+}  // namespace simc

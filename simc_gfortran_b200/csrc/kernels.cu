@@ -7,6 +7,9 @@
 #endif
 #include "transport.cuh"
 #include "kernels.h"
+#include "loop.cuh"
+#include <string.h>
+#include <stddef.h>
 
 namespace simc {
 namespace SIMC_VARIANT_NS {
@@ -65,7 +68,105 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
   return cudaGetLastError();
 }
 
+// Stage-level parity entry point: radc_init_ev + peaked_rad_weight on dumped vertex inputs.
+__global__ void k_radc_batch(const simc_run_config* __restrict__ cfg, long long n, const double* __restrict__ in,
+                             double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  VertexKin v;
+  v.Ein = in[0 * n + i]; v.eE = in[1 * n + i]; v.eP = v.eE; v.etheta = in[2 * n + i];
+  v.uex = in[3 * n + i]; v.uey = in[4 * n + i]; v.uez = in[5 * n + i];
+  v.pE = in[6 * n + i]; v.pP = in[7 * n + i];
+  v.upx = in[8 * n + i]; v.upy = in[9 * n + i]; v.upz = in[10 * n + i];
+  RadEvDev R;
+  radc_init_ev(*cfg, v, in[11 * n + i], in[12 * n + i], R);
+  const double w = peaked_rad_weight(*cfg, R, v, in[13 * n + i], in[14 * n + i], in[15 * n + i], 1.0);
+  out[0 * n + i] = R.bt[0]; out[1 * n + i] = R.bt[1];
+  out[2 * n + i] = R.lambda[0]; out[3 * n + i] = R.lambda[1]; out[4 * n + i] = R.lambda[2];
+  out[5 * n + i] = R.g[4]; out[6 * n + i] = R.hardcorfac; out[7 * n + i] = R.c4; out[8 * n + i] = R.c_ext0;
+  out[9 * n + i] = w;
+  out[10 * n + i] = sigep(v.Ein, v.eE, v.etheta, 2 * v.Ein * v.eE * (1. - v.uez));
+}
+cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_radc_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const simc_run_config*)cfg, n, in, out);
+  return cudaGetLastError();
+}
+
 size_t arm_dev_bytes() { return sizeof(ArmDev); }
+size_t dev_accum_bytes() { return sizeof(DevAccum); }
+int n_state_fields() { return (int)F_NFIELDS; }
+
+// One batch of tries through the four stages (and the record dump in record mode).
+cudaError_t launch_loop_batch(const LoopLaunch& a, cudaStream_t s, int* n_launched) {
+  LoopArgs A;
+  A.cfg = (const simc_run_config*)a.cfg;
+  A.arm_e = (const ArmDev*)a.arm_e;
+  A.arm_p = (const ArmDev*)a.arm_p;
+  A.st.base = a.state; A.st.cap = a.cap;
+  A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
+  A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
+  A.record_mode = a.record_mode;
+  cudaError_t e = cudaMemsetAsync(a.counts, 0, 4 * sizeof(unsigned), s);
+  if (e != cudaSuccess) return e;
+  const long long need = (a.n_tries + kBlock - 1) / kBlock;
+  const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
+  k_generate<<<grid, kBlock, 0, s>>>(A);
+  k_arm<1><<<grid, kBlock, 0, s>>>(A);
+  k_arm<0><<<grid, kBlock, 0, s>>>(A);
+  k_finish<<<grid, kBlock, 0, s>>>(A);
+  *n_launched += 4;
+  if (a.record_mode && a.rec) {
+    k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
+    *n_launched += 1;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace SIMC_VARIANT_NS
+}  // namespace simc
+#if SIMC_STRICT
+// byte offset of the min/max key block inside DevAccum (same in both variants)
+size_t simc_dev_accum_minmax_offset() { return offsetof(simc::strict::DevAccum, contrib_lo); }
+#endif
+namespace simc {
+namespace SIMC_VARIANT_NS {
+static inline double key_to_double(long long k) {
+  const long long i = k >= 0 ? k : (k ^ 0x7fffffffffffffffLL);
+  double d;
+  memcpy(&d, &i, sizeof(d));
+  return d;
+}
+
+// Adds a host copy of the device accumulators into the public simc_accum.
+void accum_to_host(const void* dev_copy, void* out_v, int qexp_w) {
+  const DevAccum& d = *(const DevAccum*)dev_copy;
+  simc_accum& o = *(simc_accum*)out_v;
+  typedef __int128 i128;
+  auto addf = [](simc_fixed128& f, const unsigned long long* w, int qexp) {
+    i128 v = (((i128)f.hi << 64) | (i128)f.lo) + (((i128)(long long)w[1] << 64) | (i128)w[0]);
+    f.lo = (uint64_t)v; f.hi = (int64_t)(v >> 64); f.qexp = qexp;
+  };
+  o.ntried += (int64_t)d.counters[0]; o.nsuccess += (int64_t)d.counters[1]; o.ncontribute += (int64_t)d.counters[2];
+  o.npasscuts += (int64_t)d.counters[3]; o.ncontribute_no_rad_proton += (int64_t)d.counters[4];
+  addf(o.wtcontribute, d.wt, qexp_w);
+  addf(o.sum_sigcc, d.sigcc, qexp_w);
+  for (int i = 0; i < 8; ++i) { addf(o.sumerr[i], d.sumerr[i], -80); addf(o.sumerr2[i], d.sumerr2[i], -80); }
+  for (int h = 0; h < 6; ++h) for (int b = 0; b < SIMC_NHIST; ++b) addf(o.hist_w[h][b], d.hist_w[h][b], qexp_w);
+  for (int s = 0; s < 3; ++s) for (int h = 0; h < SIMC_H_PER_SET; ++h) for (int b = 0; b < SIMC_NHIST; ++b)
+    o.hist_n[s][h][b] += (int64_t)d.hist_n[s][h][b];
+  for (int i = 0; i < 32; ++i) {
+    const double lo = key_to_double(d.contrib_lo[i]), hi = key_to_double(d.contrib_hi[i]);
+    if (lo < o.contrib[i].lo) o.contrib[i].lo = lo;
+    if (hi > o.contrib[i].hi) o.contrib[i].hi = hi;
+  }
+  for (int i = 0; i < 8; ++i) {
+    const double lo = key_to_double(d.slop_lo[i]), hi = key_to_double(d.slop_hi[i]);
+    if (lo < o.slop[i].lo) o.slop[i].lo = lo;
+    if (hi > o.slop[i].hi) o.slop[i].hi = hi;
+  }
+  for (int w = 0; w < 2; ++w) for (int i = 0; i < SIMC_NSTOP; ++i) o.stop[w][i] += (int64_t)d.stop[w][i];
+}
 
 }  // namespace SIMC_VARIANT_NS
 }  // namespace simc

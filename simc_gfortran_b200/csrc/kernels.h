@@ -18,6 +18,40 @@ struct TransportBatchArgs {
   int* flags;               // [n] device
 };
 
+// Opaque to the host code: built and consumed inside kernels.cu (loop.cuh: LoopArgs).
+struct LoopLaunch {
+  const void* cfg;            // simc_run_config* (device)
+  const void* arm_e;          // ArmDev* (device)
+  const void* arm_p;
+  double* state;              // [n_state_fields][cap]
+  long long cap;
+  unsigned* lists;            // [3][cap]
+  unsigned* counts;           // [4]
+  void* acc;                  // DevAccum*
+  long long first_try, n_tries;
+  unsigned long long seed;
+  int qexp_w;
+  int record_mode;
+  double* rec;                // [SIMC_EVENT_NREC][n_tries] device, record mode only
+  int* status;
+  int grid_blocks;            // persistent grid for the stage kernels
+};
+
+namespace strict {
+cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s);
+cudaError_t launch_loop_batch(const LoopLaunch& a, cudaStream_t s, int* n_launched);
+size_t dev_accum_bytes();
+int n_state_fields();
+void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);
+}
+namespace fast {
+cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s);
+cudaError_t launch_loop_batch(const LoopLaunch& a, cudaStream_t s, int* n_launched);
+size_t dev_accum_bytes();
+int n_state_fields();
+void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);
+}
+
 namespace strict { cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s); size_t arm_dev_bytes(); }
 namespace fast   { cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s); size_t arm_dev_bytes(); }
 

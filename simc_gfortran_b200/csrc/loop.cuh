@@ -1,0 +1,457 @@
+// The event loop on the device (replaces simc.f:169-351): four stage kernels over a batch of
+// tries, with survivors compacted between stages so that warps stay full.
+//
+//   k_generate : one thread per try.  generate + complete_ev + generate_rad; geni histograms.
+//                Survivors get a slot in the SoA state buffer and an entry in list 0.
+//   k_arm<P>   : hadron arm.  target multiple scattering, SP quantities, TRANSPORT
+//                coordinates, single-arm Monte Carlo (transport.cuh), recon of the arm,
+//                most-probable energy-loss correction.  Survivors -> list 1.
+//   k_arm<E>   : electron arm, same.  Survivors -> list 2.
+//   k_finish   : complete_recon_ev + complete_main + pass_cuts + histogram / counter / sum /
+//                range accumulation into exact integer accumulators (DevAccum).
+//
+// Nothing here depends on the order in which slots are handed out: the random stream is keyed by
+// the try index, and every accumulator is an integer sum or a min/max.
+#pragma once
+#include "event.cuh"
+#include "transport.cuh"
+#include "kernels.h"
+
+namespace simc {
+namespace SIMC_VARIANT_NS {
+
+// ---- state buffer ------------------------------------------------------------------------
+enum StateField : int {
+  F_TRY = 0, F_DRAW, F_STAGE, F_STOP_P, F_STOP_E,
+  F_TX, F_TY, F_TZ, F_RASTERY, F_ELOSS0, F_ELOSS1, F_ELOSS2, F_TEFF0, F_TEFF1, F_TEFF2, F_COULOMB,
+  F_GENW, F_JAC, F_EINSHIFT, F_EESHIFT, F_MTREC,
+  F_VEIN, F_VEE, F_VEDELTA, F_VEYP, F_VEXP, F_VETHETA, F_VPE, F_VPP, F_VPDELTA, F_VPYP, F_VPXP, F_VQ2, F_VEM, F_VPM,
+  F_VTREC,
+  F_OEIN, F_OEE, F_OEDELTA, F_OPE, F_OPP, F_OPDELTA,
+  F_EG0, F_EG1, F_EG2, F_NTAIL, F_RADP, F_HARDCOR,
+  F_DANG0, F_DANG1,
+  F_SPP_D, F_SPP_Y, F_SPP_X, F_SPP_Z, F_RCP_D, F_RCP_Y, F_RCP_X, F_RCP_Z, F_FPP_PATH,
+  F_RP_P, F_RP_E, F_RP_TH, F_RP_PH, F_RESFAC,
+  F_SPE_D, F_SPE_Y, F_SPE_X, F_SPE_Z, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCE_Z, F_FPE_PATH,
+  F_RE_E, F_RE_TH, F_RE_PH,
+  F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_PASSCUTS, F_REM, F_RPM, F_RW,
+  F_NFIELDS
+};
+
+struct StateBuf {
+  double* base;
+  long long cap;
+  __device__ __forceinline__ double ld(int f, long long slot) const { return base[(long long)f * cap + slot]; }
+  __device__ __forceinline__ void st(int f, long long slot, double v) const { base[(long long)f * cap + slot] = v; }
+};
+
+// ---- exact accumulators --------------------------------------------------------------------
+struct DevAccum {
+  unsigned long long counters[8];                 // ntried, nsuccess, ncontribute, npasscuts, nco_no_rad_proton
+  unsigned long long wt[2], sigcc[2];             // 128-bit two's complement (lo, hi)
+  unsigned long long sumerr[8][2], sumerr2[8][2];
+  unsigned long long hist_w[6][SIMC_NHIST][2];
+  unsigned long long hist_n[3][SIMC_H_PER_SET][SIMC_NHIST];
+  long long contrib_lo[32], contrib_hi[32], slop_lo[8], slop_hi[8];   // order-preserving keys of doubles
+  unsigned long long stop[2][SIMC_NSTOP];
+};
+
+struct LoopArgs {
+  const simc_run_config* cfg;      // device copy
+  const ArmDev* arm_e;
+  const ArmDev* arm_p;
+  StateBuf st;
+  unsigned* lists;                 // [3][cap]
+  unsigned* counts;                // [0] slots handed out, [1..3] lengths of lists 0..2
+  DevAccum* acc;
+  long long first_try, n_tries;
+  unsigned long long seed;
+  int qexp_w;                      // quantum exponent of the weight sums
+  int record_mode;                 // every try gets a slot (parity entry point)
+};
+
+__device__ __forceinline__ long long dkey(double d) {          // monotonic double -> int64
+  const long long i = __double_as_longlong(d);
+  return i >= 0 ? i : (i ^ 0x7fffffffffffffffLL);
+}
+
+// double -> 128-bit fixed point with quantum 2^qexp, round to nearest even (same rule as the
+// oracle's to_fixed); values >= 2^62 quanta are already integers.
+__device__ __forceinline__ void to_fixed(double x, int qexp, unsigned long long& lo, unsigned long long& hi) {
+  const double sc = ldexp(x, -qexp);
+  if (!(fabs(sc) < 4.611686018427387904e18)) {
+    if (!(fabs(sc) < 1.0e38)) { lo = 0; hi = 0; return; }
+    const double h = floor(sc / 18446744073709551616.0);
+    const double l = sc - h * 18446744073709551616.0;
+    hi = (unsigned long long)(long long)h;
+    lo = (unsigned long long)l;
+    return;
+  }
+  const long long v = __double2ll_rn(sc);
+  lo = (unsigned long long)v;
+  hi = v < 0 ? ~0ULL : 0ULL;
+}
+__device__ __forceinline__ void add128(unsigned long long* dst, double x, int qexp) {
+  unsigned long long lo, hi;
+  to_fixed(x, qexp, lo, hi);
+  const unsigned long long old = atomicAdd(&dst[0], lo);
+  const unsigned long long carry = (old + lo < old) ? 1ULL : 0ULL;
+  if (hi + carry) atomicAdd(&dst[1], hi + carry);
+}
+__device__ __forceinline__ void upd_range(long long* lo, long long* hi, double v) {
+  const long long k = dkey(v);
+  atomicMin(lo, k);
+  atomicMax(hi, k);
+}
+// simc.f:624-640: ibin = nint(0.5+(val-min)/bin), kept if 1..50
+__device__ __forceinline__ int hist_bin(const simc_axis& ax, double val) {
+  const double r = round(0.5 + (val - ax.min) / ax.bin);
+  if (!(r >= 1.0 && r <= (double)SIMC_NHIST)) return -1;
+  return (int)r - 1;
+}
+
+// Warp-aggregated append: returns this lane's position in a list whose length is *counter.
+__device__ __forceinline__ unsigned warp_append(unsigned* counter, bool take) {
+  const unsigned mask = __ballot_sync(__activemask(), take);
+  if (!take) return 0u;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(mask) - 1;
+  unsigned base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+struct GaussFn {
+  __device__ __forceinline__ double operator()(DevRng& r, double nsig) const { return gauss1(r, nsig); }
+};
+
+// ---- stage 1: generation -------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
+  __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kBlock) (&h_geni[0][0])[i] = 0u;
+  __syncthreads();
+  const simc_run_config& cfg = *A.cfg;
+  const long long stride = (long long)gridDim.x * kBlock;
+  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < A.n_tries; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    const bool active = i < A.n_tries;
+    bool ok = false;
+    EventState s;
+    DevRng rng;
+    if (active) {
+      rng.init(A.seed, (unsigned long long)(A.first_try + i), 0u, 0u);
+      s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
+      ok = generate_hyd_elast(cfg, rng, GaussFn(), s);
+      // geni histograms: every try, from the vertex values (simc.f:253-262)
+      const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = hist_bin(cfg.hist_axis[2][k], gv[k]);
+        if (b >= 0) atomicAdd(&h_geni[k][b], 1u);
+      }
+    }
+    const bool want_slot = active && (ok || A.record_mode);
+    const unsigned slot = warp_append(&A.counts[0], want_slot);
+    if (want_slot) {
+      const StateBuf& S = A.st;
+      S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)rng.draw); S.st(F_STAGE, slot, ok ? 1.0 : 0.0);
+      S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
+      S.st(F_TX, slot, s.tx); S.st(F_TY, slot, s.ty); S.st(F_TZ, slot, s.tz); S.st(F_RASTERY, slot, s.rastery);
+      S.st(F_ELOSS0, slot, s.Eloss[0]); S.st(F_ELOSS1, slot, s.Eloss[1]); S.st(F_ELOSS2, slot, s.Eloss[2]);
+      S.st(F_TEFF0, slot, s.teff[0]); S.st(F_TEFF1, slot, s.teff[1]); S.st(F_TEFF2, slot, s.teff[2]);
+      S.st(F_COULOMB, slot, s.Coulomb);
+      S.st(F_GENW, slot, s.gen_weight); S.st(F_JAC, slot, s.jacobian); S.st(F_EINSHIFT, slot, s.Ein_shift);
+      S.st(F_EESHIFT, slot, s.Ee_shift); S.st(F_MTREC, slot, s.Trec);
+      S.st(F_VEIN, slot, s.v_Ein); S.st(F_VEE, slot, s.v_eE); S.st(F_VEDELTA, slot, s.v_edelta);
+      S.st(F_VEYP, slot, s.v_eyptar); S.st(F_VEXP, slot, s.v_exptar); S.st(F_VETHETA, slot, s.v_etheta);
+      S.st(F_VPE, slot, s.v_pE); S.st(F_VPP, slot, s.v_pP); S.st(F_VPDELTA, slot, s.v_pdelta);
+      S.st(F_VPYP, slot, s.v_pyptar); S.st(F_VPXP, slot, s.v_pxptar); S.st(F_VQ2, slot, s.v_Q2);
+      S.st(F_VEM, slot, s.v_Em); S.st(F_VPM, slot, s.v_Pm); S.st(F_VTREC, slot, s.v_Trec);
+      S.st(F_OEIN, slot, s.o_Ein); S.st(F_OEE, slot, s.o_eE); S.st(F_OEDELTA, slot, s.o_edelta);
+      S.st(F_OPE, slot, s.o_pE); S.st(F_OPP, slot, s.o_pP); S.st(F_OPDELTA, slot, s.o_pdelta);
+      S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
+      S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
+      S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
+    }
+    const unsigned pos = warp_append(&A.counts[1], active && ok);
+    if (active && ok) A.lists[0 * A.st.cap + pos] = slot;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kBlock) {
+    const unsigned v = (&h_geni[0][0])[i];
+    if (v) atomicAdd(&A.acc->hist_n[2][0][0] + i, (unsigned long long)v);
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&A.acc->counters[0], (unsigned long long)A.n_tries);
+}
+
+// ---- stages 2,3: the two arms ----------------------------------------------------------------
+// WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846)
+template <int WHICH>
+__global__ void __launch_bounds__(kBlock) k_arm(LoopArgs A) {
+  __shared__ double pw_s[kPowDoubles];
+  __shared__ unsigned s_stop[SIMC_NSTOP];
+  for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
+  __syncthreads();
+  const simc_run_config& cfg = *A.cfg;
+  const StateBuf& S = A.st;
+  const unsigned n_in = A.counts[1 + (WHICH == 1 ? 0 : 1)];
+  const unsigned* in_list = A.lists + (WHICH == 1 ? 0 : 1) * A.st.cap;
+  unsigned* out_list = A.lists + (WHICH == 1 ? 1 : 2) * A.st.cap;
+  unsigned* out_count = &A.counts[1 + (WHICH == 1 ? 1 : 2)];
+  const simc_spectrometer& sp = WHICH == 1 ? cfg.spec_p : cfg.spec_e;
+  const ArmDev* arm = WHICH == 1 ? A.arm_p : A.arm_e;
+  const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
+  const bool use_mc = WHICH == 1 ? cfg.using_P_arm_montecarlo != 0 : cfg.using_E_arm_montecarlo != 0;
+  const long long stride = (long long)gridDim.x * kBlock;
+  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    const bool active = i < n_in;
+    bool ok = false;
+    unsigned slot = 0;
+    if (active) {
+      slot = in_list[i];
+      DevRng rng;
+      rng.init(A.seed, (unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u,
+               (unsigned)S.ld(F_DRAW, slot));
+      const double tx = S.ld(F_TX, slot), ty = S.ld(F_TY, slot), tz = S.ld(F_TZ, slot);
+      double dang0, dang1, sp_delta, ang0 = 0.0, ang1 = 0.0;
+      const double Mh2 = cfg.Mh2;
+      if (WHICH == 1) {
+        // beam multiple scattering (simc.f:1365), then the hadron's (simc.f:1379-1399)
+        if (cfg.mc_smear) {
+          const double teff = S.ld(F_TEFF0, slot), p = S.ld(F_OEIN, slot);
+          const double ts = 13.6 / p / 1. * sqrt(teff) * (1 + 0.088 * log10(teff / (1. * 1.)));
+          dang0 = ts * gauss1(rng, 3.5);
+          dang1 = ts * gauss1(rng, 3.5);
+        } else { dang0 = 0.0; dang1 = 0.0; }
+        S.st(F_DANG0, slot, dang0); S.st(F_DANG1, slot, dang1);
+        const double opE = S.ld(F_OPE, slot), opP = S.ld(F_OPP, slot);
+        if (cfg.using_Eloss) {
+          const double d = opE - S.ld(F_ELOSS2, slot);
+          sp_delta = (sqrt(fabs(d * d - Mh2)) - sp.P) / sp.P * 100.;
+        } else sp_delta = S.ld(F_OPDELTA, slot);
+        if (cfg.mc_smear) {
+          const double beta = opP / opE, teff = S.ld(F_TEFF2, slot);
+          const double ts = 13.6 / opP / beta * sqrt(teff) * (1 + 0.088 * log10(teff / (beta * beta)));
+          ang0 = ts * gauss1(rng, 3.5);
+          ang1 = ts * gauss1(rng, 3.5);
+        }
+      } else {
+        dang0 = S.ld(F_DANG0, slot); dang1 = S.ld(F_DANG1, slot);
+        const double oeE = S.ld(F_OEE, slot);
+        sp_delta = 100 * (oeE - S.ld(F_ELOSS1, slot) - S.ld(F_COULOMB, slot) - sp.P) / sp.P;
+        if (cfg.mc_smear) {
+          const double teff = S.ld(F_TEFF1, slot);
+          const double ts = 13.6 / oeE / 1. * sqrt(teff) * (1 + 0.088 * log10(teff / (1. * 1.)));
+          ang0 = ts * gauss1(rng, 3.5);
+          ang1 = ts * gauss1(rng, 3.5);
+        }
+      }
+      const double o_yptar = S.ld(WHICH == 1 ? F_VPYP : F_VEYP, slot), o_xptar = S.ld(WHICH == 1 ? F_VPXP : F_VEXP, slot);
+      ArmEntry en;
+      arm_entry(sp, tx, ty, tz, sp_delta, o_yptar + ang0 + dang0, o_xptar + ang1 + dang1 * sp.cos_th, en);
+      double rc_delta, rc_yptar, rc_xptar, rc_z = 0.0, path = 0.0, resmult = 0.0;
+      int stop_code = 0;
+      bool hut = false;
+      if (use_mc) {
+        TrackDev t;
+        t.dpps = en.sp_delta; t.xs = en.x; t.ys = en.y; t.dxdzs = en.dx; t.dydzs = en.dy;
+        t.m2 = WHICH == 1 ? Mh2 : SIMC_ME * SIMC_ME;
+        t.p = sp.P * (1. + t.dpps / 100.);
+        t.pathlen = 0.0; t.decdist = 0.0; t.mh2_final = Mh2; t.ctau = cfg.ctau;
+        ArmFlags f;
+        f.ms_flag = cfg.mc_smear != 0; f.wcs_flag = cfg.mc_smear != 0;
+        f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
+        f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
+        const double fry_raster = cfg.correct_raster ? -S.ld(F_RASTERY, slot) : 0.0;
+        const double fry = (arm_id == 1 || arm_id == 5) ? en.x : fry_raster;    // xtar_init, simc.f:1441,1463
+        ArmResult res;
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res);
+        ok = res.ok;
+        stop_code = res.ok ? 0 : res.stop_code;
+        hut = res.reached_hut;
+        rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
+        path = t.pathlen; resmult = res.resmult;
+        atomicAdd(&s_stop[0], 1u);
+        if (ok) atomicAdd(&s_stop[1], 1u);
+        if (hut) atomicAdd(&s_stop[2], 1u);
+        if (stop_code > 0 && 2 + stop_code < SIMC_NSTOP) atomicAdd(&s_stop[2 + stop_code], 1u);
+      } else {
+        ok = true;
+        rc_delta = en.sp_delta; rc_yptar = en.sp_yptar; rc_xptar = en.sp_xptar;
+      }
+      S.st(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta); S.st(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot, en.sp_yptar);
+      S.st(WHICH == 1 ? F_SPP_X : F_SPE_X, slot, en.sp_xptar); S.st(WHICH == 1 ? F_SPP_Z : F_SPE_Z, slot, en.sp_z);
+      S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)stop_code);
+      S.st(F_DRAW, slot, (double)rng.draw);
+      if (WHICH == 1) S.st(F_RESFAC, slot, resmult);
+      if (ok) {
+        S.st(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta); S.st(WHICH == 1 ? F_RCP_Y : F_RCE_Y, slot, rc_yptar);
+        S.st(WHICH == 1 ? F_RCP_X : F_RCE_X, slot, rc_xptar); S.st(WHICH == 1 ? F_RCP_Z : F_RCE_Z, slot, rc_z);
+        S.st(WHICH == 1 ? F_FPP_PATH : F_FPE_PATH, slot, path);
+        // recon quantities of this arm, simc.f:1623-1645 / :1820-1846
+        double rP = sp.P * (1. + rc_delta / 100.);
+        double rE = WHICH == 1 ? sqrt(rP * rP + Mh2) : rP;
+        double rth, rph;
+        physics_angles(sp.theta, sp.phi, rc_xptar + sp.off_xptar, rc_yptar + sp.off_yptar, rth, rph);
+        if (cfg.correct_Eloss) {
+          double el, rl;
+          trip_thru_target_fixed(cfg.targ, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
+                                 el, rl);
+          rE = rE + el;
+          if (WHICH == 1) {
+            rE = fmax(rE, sqrt(Mh2 + 0.000001));
+            rP = sqrt(rE * rE - Mh2);
+          }
+        }
+        if (WHICH == 1) {
+          S.st(F_RP_P, slot, rP); S.st(F_RP_E, slot, rE); S.st(F_RP_TH, slot, rth); S.st(F_RP_PH, slot, rph);
+          S.st(F_STAGE, slot, 2.0);
+        } else {
+          S.st(F_RE_E, slot, rE); S.st(F_RE_TH, slot, rth); S.st(F_RE_PH, slot, rph);
+          S.st(F_RESFAC, slot, S.ld(F_RESFAC, slot) + resmult);
+          S.st(F_STAGE, slot, 3.0);
+        }
+      }
+    }
+    const unsigned pos = warp_append(out_count, active && ok);
+    if (active && ok) out_list[pos] = slot;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock)
+    if (s_stop[i]) atomicAdd(&A.acc->stop[WHICH][i], (unsigned long long)s_stop[i]);
+}
+
+// ---- stage 4: recon kinematics, weight, accumulation --------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
+  const simc_run_config& cfg = *A.cfg;
+  const StateBuf& S = A.st;
+  DevAccum* acc = A.acc;
+  const unsigned n_in = A.counts[3];
+  const unsigned* in_list = A.lists + 2 * A.st.cap;
+  const long long stride = (long long)gridDim.x * kBlock;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_in; i += stride) {
+    const unsigned slot = in_list[i];
+    // complete_recon_ev for H(e,e'p), event.f:1056-1359
+    const double r_Ein = cfg.Ebeam_vertex_ave - cfg.targ.Coulomb_ave;
+    const double reE = S.ld(F_RE_E, slot), reth = S.ld(F_RE_TH, slot), reph = S.ld(F_RE_PH, slot);
+    const double rpP = S.ld(F_RP_P, slot), rpE = S.ld(F_RP_E, slot), rpth = S.ld(F_RP_TH, slot), rpph = S.ld(F_RP_PH, slot);
+    const double reP = reE;
+    const double uex = sin(reth) * cos(reph), uey = sin(reth) * sin(reph), uez = cos(reth);
+    const double upx = sin(rpth) * cos(rpph), upy = sin(rpth) * sin(rpph), upz = cos(rpth);
+    const double nu = r_Ein - reE;
+    const double Q2 = 2 * r_Ein * reE * (1 - uez);
+    const double q = sqrt(Q2 + nu * nu);
+    const double uqx = -reP * uex / q, uqy = -reP * uey / q, uqz = (r_Ein - reP * uez) / q;
+    const double W2 = SIMC_MP * SIMC_MP + 2. * SIMC_MP * nu - Q2;
+    const double rW = sqrt(fabs(W2)) * W2 / fabs(W2);
+    const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
+    const double rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
+    const double rTrec = 0.0;
+    const double rEm = nu + cfg.targ.M - rpE - rTrec;
+    // complete_main, event.f:1363-1569
+    const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
+    double sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
+    const double sigcc_recon = sigep(r_Ein, reE, reth, Q2);
+    if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
+    const double SF_weight = 1.0;
+    double weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
+    weight = weight * 1.0;
+    // pass_cuts, simc.f:229-241 (p-arm upper delta edge uses SPedge%e%delta%max, as written)
+    const double red = S.ld(F_RCE_D, slot), rey = S.ld(F_RCE_Y, slot), rex = S.ld(F_RCE_X, slot), rez = S.ld(F_RCE_Z, slot);
+    const double rpd = S.ld(F_RCP_D, slot), rpy = S.ld(F_RCP_Y, slot), rpx = S.ld(F_RCP_X, slot), rpz = S.ld(F_RCP_Z, slot);
+    const bool pass_cuts = !(red <= (cfg.SPedge_e.delta.min + cfg.slop_MC_e_used[0]) ||
+                             red >= (cfg.SPedge_e.delta.max - cfg.slop_MC_e_used[0]) ||
+                             rey <= (cfg.SPedge_e.yptar.min + cfg.slop_MC_e_used[1]) ||
+                             rey >= (cfg.SPedge_e.yptar.max - cfg.slop_MC_e_used[1]) ||
+                             rex <= (cfg.SPedge_e.xptar.min + cfg.slop_MC_e_used[2]) ||
+                             rex >= (cfg.SPedge_e.xptar.max - cfg.slop_MC_e_used[2]) ||
+                             rpd <= (cfg.SPedge_p.delta.min + cfg.slop_MC_p_used[0]) ||
+                             rpd >= (cfg.SPedge_e.delta.max - cfg.slop_MC_p_used[0]) ||
+                             rpy <= (cfg.SPedge_p.yptar.min + cfg.slop_MC_p_used[1]) ||
+                             rpy >= (cfg.SPedge_p.yptar.max - cfg.slop_MC_p_used[1]) ||
+                             rpx <= (cfg.SPedge_p.xptar.min + cfg.slop_MC_p_used[2]) ||
+                             rpx >= (cfg.SPedge_p.xptar.max - cfg.slop_MC_p_used[2]));
+    bool success = true;
+    if (cfg.hard_cuts) {
+      if (!pass_cuts) success = false;
+      if (cfg.doing_eep && (rEm > cfg.cuts_Em.max)) success = false;
+    }
+    S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
+    S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
+    S.st(F_STAGE, slot, success ? 4.0 : 3.0);
+    if (!success) continue;
+    // ---- accumulation, simc.f:248-336
+    add128(acc->sigcc, sigcc, A.qexp_w);
+    atomicAdd(&acc->counters[1], 1ULL);
+    const double rec_vals[6] = {red, rey, rex, rpd, rpy, rpx};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int b = hist_bin(cfg.hist_axis[0][k], rec_vals[k]);
+      if (b >= 0) add128(acc->hist_w[k][b], weight, A.qexp_w);
+    }
+    { const int b = hist_bin(cfg.hist_axis[0][SIMC_H_EM], rEm); if (b >= 0) atomicAdd(&acc->hist_n[0][SIMC_H_EM][b], 1ULL); }
+    { const int b = hist_bin(cfg.hist_axis[0][SIMC_H_PM], rPm); if (b >= 0) atomicAdd(&acc->hist_n[0][SIMC_H_PM][b], 1ULL); }
+    const double v_ed = S.ld(F_VEDELTA, slot), v_ey = S.ld(F_VEYP, slot), v_ex = S.ld(F_VEXP, slot);
+    const double v_pd = S.ld(F_VPDELTA, slot), v_py = S.ld(F_VPYP, slot), v_px = S.ld(F_VPXP, slot);
+    const double v_Em = S.ld(F_VEM, slot), v_Pm = S.ld(F_VPM, slot), v_Trec = S.ld(F_VTREC, slot);
+    const double gen_vals[7] = {v_ed, v_ey, -v_ex, v_pd, v_py, -v_px, v_Em};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int b = hist_bin(cfg.hist_axis[1][k], gen_vals[k]);
+      if (b >= 0) atomicAdd(&acc->hist_n[1][k][b], 1ULL);
+    }
+    atomicAdd(&acc->counters[2], 1ULL);
+    if (S.ld(F_RADP, slot) == 0.0) atomicAdd(&acc->counters[4], 1ULL);
+    const double spe_d = S.ld(F_SPE_D, slot), spe_y = S.ld(F_SPE_Y, slot), spe_x = S.ld(F_SPE_X, slot), spe_z = S.ld(F_SPE_Z, slot);
+    const double spp_d = S.ld(F_SPP_D, slot), spp_y = S.ld(F_SPP_Y, slot), spp_x = S.ld(F_SPP_X, slot), spp_z = S.ld(F_SPP_Z, slot);
+    if (pass_cuts) {
+      atomicAdd(&acc->counters[3], 1ULL);
+      add128(acc->wt, weight, A.qexp_w);
+      const double err[8] = {red - spe_d, rex - v_ex, rey - v_ey, rez - spe_z, rpd - spp_d, rpx - v_px, rpy - v_py, rpz - spp_z};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { add128(acc->sumerr[k], err[k], -80); add128(acc->sumerr2[k], err[k] * err[k], -80); }
+    }
+    // limits_update, event.f:1-90
+    const double Ein_shift = S.ld(F_EINSHIFT, slot), Ee_shift = S.ld(F_EESHIFT, slot);
+    const double v_pE = S.ld(F_VPE, slot);
+    const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
+    const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
+    const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
+    const double cv[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), v_eE + v_pE - Ein_shift,
+                           o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
+                           spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};
+#pragma unroll
+    for (int k = 0; k < 30; ++k) upd_range(&acc->contrib_lo[k], &acc->contrib_hi[k], cv[k]);
+    const double sv[8] = {red - spe_d, rey - spe_y, rex - spe_x, rpd - spp_d, rpy - spp_y, rpx - spp_x,
+                          rEm - (o_Em - Ein_shift + Ee_shift), fabs(rPm) - fabs(o_Pm)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) upd_range(&acc->slop_lo[k], &acc->slop_hi[k], sv[k]);
+  }
+}
+
+// ---- parity entry point: per-try records (include/simc_b200.h: simc_b200_event_batch) ----------
+__global__ void k_records(LoopArgs A, double* __restrict__ rec, int* __restrict__ status, long long n) {
+  const StateBuf& S = A.st;
+  const unsigned n_slots = A.counts[0];
+  for (long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x; slot < n_slots;
+       slot += (long long)gridDim.x * blockDim.x) {
+    const long long i = (long long)S.ld(F_TRY, slot);
+    const int stage = (int)S.ld(F_STAGE, slot);
+    // stage codes of the oracle: 0 generate failed, 1 P arm failed, 2 E arm failed, 3 failed later, 4 success.
+    // F_STAGE holds how far the try got: 0 gen failed, 1 gen ok (P arm failed), 2 P ok (E arm failed), 3, 4.
+    const int fields[SIMC_EVENT_NREC] = {
+        F_STAGE, F_PASSCUTS, F_DRAW, F_STOP_P, F_STOP_E, F_WEIGHT, F_SIGCC, F_GENW, F_JAC, F_SIGCC_RECON,
+        F_VEIN, F_VEE, F_VEDELTA, F_VEYP, F_VEXP, F_VPE, F_VPDELTA, F_VPYP, F_VPXP, F_VQ2,
+        F_OEE, F_OPE, F_EG0, F_EG1, F_EG2, F_NTAIL, F_TX, F_TY, F_TZ, F_ELOSS0, F_ELOSS1, F_ELOSS2,
+        F_SPE_D, F_SPE_Y, F_SPE_X, F_SPP_D, F_SPP_Y, F_SPP_X, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCP_D, F_RCP_Y, F_RCP_X,
+        F_REM, F_RPM, F_RW, F_HARDCOR};
+    for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = S.ld(fields[k], slot);
+    rec[0 * n + i] = (double)stage;
+    status[i] = stage;
+  }
+}
+
+}  // namespace SIMC_VARIANT_NS
+}  // namespace simc

@@ -1,0 +1,557 @@
+// Host-side run initialisation: CTP deck reader and the one-time setup the reference does
+// before the loop -- dbase_read post-processing (dbase.f:119-553), target_init (init.f:1-87),
+// limits_init (init.f:91-572) with extreme_trip_thru_target (target.f:310-544), radc_init
+// (init.f:576-651) -- producing the simc_run_config the loop consumes.  In a drop-in
+// deployment the Fortran driver fills simc_run_config from its COMMON blocks instead
+// (INTEGRATION.md); this file exists so the library can run a deck without any Fortran.
+// Host code only (compiled by nvcc for the shared SIMC_HD helpers of target.cuh).
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include "../../include/simc_b200.h"
+#include "event.cuh"
+
+namespace simc {
+namespace {
+
+// ---- CTP "parm" deck: `begin parm <name>` ... `key = value ; comment` ... `end parm` -------------
+// Keys are matched case-insensitively; the pre-gfortran dotted form (targ.A) is accepted as an
+// alias of the % form (infiles/convert_inputfile.sh does that conversion for the reference).
+struct Deck {
+  std::map<std::string, std::string> kv;
+  static std::string norm(std::string k) {
+    std::string r;
+    for (char c : k) {
+      if (std::isspace((unsigned char)c)) continue;
+      r.push_back(c == '.' ? '%' : (char)std::tolower((unsigned char)c));
+    }
+    return r;
+  }
+  void load(const std::string& path) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Loading problem!  cannot open deck " + path);
+    std::string line;
+    bool in_parm = false;
+    while (std::getline(in, line)) {
+      const size_t sc = line.find(';');
+      if (sc != std::string::npos) line.erase(sc);
+      std::string t = line;
+      t.erase(0, t.find_first_not_of(" \t\r"));
+      if (t.empty()) continue;
+      std::string low = t;
+      std::transform(low.begin(), low.end(), low.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+      if (low.compare(0, 10, "begin parm") == 0) { in_parm = true; continue; }
+      if (low.compare(0, 8, "end parm") == 0) { in_parm = false; continue; }
+      if (!in_parm) continue;
+      const size_t eq = t.find('=');
+      if (eq == std::string::npos) continue;
+      std::string key = norm(t.substr(0, eq));
+      std::string val = t.substr(eq + 1);
+      val.erase(0, val.find_first_not_of(" \t"));
+      while (!val.empty() && std::isspace((unsigned char)val.back())) val.pop_back();
+      if (!val.empty() && val.front() == '\'') {
+        const size_t q = val.find('\'', 1);
+        val = val.substr(1, q == std::string::npos ? std::string::npos : q - 1);
+      }
+      kv[key] = val;
+    }
+  }
+  bool has(const char* k) const { return kv.count(norm(k)) != 0; }
+  double d(const char* k, double def = 0.0) const {
+    auto it = kv.find(norm(k));
+    if (it == kv.end() || it->second.empty()) return def;
+    std::string v = it->second;
+    for (char& c : v) if (c == 'd' || c == 'D') c = 'e';
+    return std::strtod(v.c_str(), nullptr);
+  }
+  int i(const char* k, int def = 0) const { return (int)std::lround(d(k, (double)def)); }
+  std::string s(const char* k) const { auto it = kv.find(norm(k)); return it == kv.end() ? std::string() : it->second; }
+};
+
+constexpr double Me = 0.51099906, Mp = 938.27231, Mn = 939.56563, Mpi = 139.57018, Mpi0 = 134.9766, Mk = 493.677,
+                 Md = 1875.613, amu = 931.49432, hbarc = 197.327053, pi = 3.141592653589793, alpha = 1. / 137.0359895,
+                 degrad = 180. / pi;
+
+struct TargetExt {          // target_info members only the init needs (target.inc:44-47)
+  double Eloss_ave[3], Eloss_min[3], Eloss_max[3], teff_ave[3], teff_min[3], teff_max[3], musc_max[3];
+};
+
+void trip(const simc_run_config& c, int narm, double zpos, double energy, double theta, double mass, int typeflag,
+          double& Eloss, double& radlen) {
+  trip_thru_target_fixed(c.targ, narm, narm == 2 ? c.electron_arm : c.hadron_arm, zpos, energy, theta, mass, typeflag,
+                         Eloss, radlen);
+}
+
+// target.f:310-544
+void extreme_trip_thru_target(const simc_run_config& c, TargetExt& x, double ebeam, simc_cut the, simc_cut thp,
+                              simc_cut pe, simc_cut pp, simc_cut z, double m) {
+  const simc_target& targ = c.targ;
+  const double inch_cm = 2.54, target_pi = 3.14159265358979;
+  const bool liquid = targ.Z < 2.4;
+  trip(c, 1, z.max, ebeam, 0.0, Me, 3, x.Eloss_max[0], x.teff_max[0]);
+  trip(c, 1, z.min, ebeam, 0.0, Me, 2, x.Eloss_min[0], x.teff_min[0]);
+  double energymin = pe.min, energymax = pe.max, E1, E2, E3, E4, t1, t2, t3, t4, zz, th1, th2;
+  auto corner = [&](const simc_cut& th, double& zz_, double& th1_, double& th2_) {
+    double th_corner_max;
+    if (z.max >= targ.length / 2.) th_corner_max = target_pi / 2.;
+    else th_corner_max = std::atan(1.25 * inch_cm / (targ.length / 2. - z.max));
+    const double th_corner_min = std::atan(1.25 * inch_cm / (targ.length / 2. - z.min));
+    if (th_corner_min <= th.max && th_corner_max >= th.min) {
+      const double th_corner = std::max(th_corner_min, th.min);
+      zz_ = targ.length / 2. - 1.25 * inch_cm / std::tan(th_corner);
+      th1_ = th_corner - .0001;
+      th2_ = th_corner + .0001;
+    } else {
+      zz_ = z.min; th1_ = th.min; th2_ = th.max;
+    }
+  };
+  if (!liquid) {
+    trip(c, 2, z.min, energymax, the.max, Me, 3, x.Eloss_max[1], x.teff_max[1]);
+    trip(c, 2, z.max, energymin, the.min, Me, 2, x.Eloss_min[1], x.teff_min[1]);
+  } else {
+    if (targ.can == 1) {
+      corner(the, zz, th1, th2);
+      trip(c, 2, zz, energymax, th1, Me, 3, E1, t1);
+      trip(c, 2, zz, energymax, th2, Me, 3, E2, t2);
+      x.Eloss_max[1] = std::max(E1, E2);
+      x.teff_max[1] = std::max(t1, t2);
+    } else {
+      zz = -(targ.length / 2.) / std::tan(the.min);
+      zz = std::max(zz, (-targ.length / 2.));
+      trip(c, 2, zz, energymax, the.min, Me, 3, x.Eloss_max[1], x.teff_max[1]);
+    }
+    x.Eloss_min[1] = 1.e10;
+    for (int i = 0; i <= 3; ++i) {
+      trip(c, 2, z.min + (i / 2) * (z.max - z.min), energymin, the.min + (i % 2) * (the.max - the.min), Me, 2, E1, t1);
+      if (E1 < x.Eloss_min[1]) { x.Eloss_min[1] = E1; x.teff_min[1] = t1; }
+    }
+  }
+  energymin = std::sqrt(pp.min * pp.min + m * m);
+  energymax = std::sqrt(pp.max * pp.max + m * m);
+  if (!liquid) {
+    trip(c, 3, z.min, energymin, thp.max, m, 3, E1, t1);
+    trip(c, 3, z.min, energymax, thp.max, m, 3, E2, t2);
+    x.Eloss_max[2] = std::max(E1, E2); x.teff_max[2] = std::max(t1, t2);
+    trip(c, 3, z.max, energymin, thp.min, m, 2, E1, t1);
+    trip(c, 3, z.max, energymax, thp.min, m, 2, E2, t2);
+    x.Eloss_min[2] = std::min(E1, E2); x.teff_min[2] = std::min(t1, t2);
+  } else {
+    if (targ.can == 1) {
+      corner(thp, zz, th1, th2);
+      trip(c, 3, zz, energymin, th1, m, 3, E1, t1);
+      trip(c, 3, zz, energymin, th2, m, 3, E2, t2);
+      trip(c, 3, zz, energymax, th1, m, 3, E3, t3);
+      trip(c, 3, zz, energymax, th2, m, 3, E4, t4);
+      x.Eloss_max[2] = std::max(std::max(E1, E2), std::max(E3, E4));
+      x.teff_max[2] = std::max(std::max(t1, t2), std::max(t3, t4));
+    } else {
+      zz = -(targ.length / 2.) / std::tan(the.min);       // the%min as written (target.f:513)
+      zz = std::max(zz, (-targ.length / 2.));
+      trip(c, 3, zz, energymin, thp.min, m, 3, E1, t1);
+      trip(c, 3, zz, energymax, thp.min, m, 3, E2, t2);
+      x.Eloss_max[2] = std::max(E1, E2); x.teff_max[2] = std::max(t1, t2);
+    }
+    x.Eloss_min[2] = 1.e10;
+    for (int i = 0; i <= 3; ++i) {
+      const double zi = z.min + (i / 2) * (z.max - z.min), thi = thp.min + (i % 2) * (thp.max - thp.min);
+      trip(c, 3, zi, energymin, thi, m, 2, E1, t1);
+      if (E1 < x.Eloss_min[2]) { x.Eloss_min[2] = E1; x.teff_min[2] = t1; zz = zi; th1 = thi; }
+    }
+    trip(c, 3, zz, energymax, th1, m, 2, E1, t1);
+    x.Eloss_min[2] = std::min(x.Eloss_min[2], E1);
+  }
+  // extreme multiple scattering, target.f:528-544 + target_musc entry (target.f:569-577)
+  auto ext_musc = [](double p, double beta, double teff) {
+    const double ts = 13.6 / p / beta * std::sqrt(teff) * (1 + 0.088 * std::log10(teff / (beta * beta)));
+    return ts * 3.5;
+  };
+  x.musc_max[0] = ext_musc(ebeam, 1., x.teff_max[0]);
+  x.musc_max[1] = ext_musc(pe.min, 1., x.teff_max[1]);
+  const double betap_min = pp.min / std::sqrt(pp.min * pp.min + m * m);
+  x.musc_max[2] = ext_musc(pp.min, betap_min, x.teff_max[2]);
+}
+
+void set_axis(simc_axis& a, double mn, double bin) { a.min = mn; a.bin = bin; }
+
+}  // namespace
+
+void config_from_deck(const std::string& path, const std::string& extra_dir, simc_run_config& c, int* ngen,
+                      double* charge_mC) {
+  Deck D;
+  D.load(path);
+  const std::string extra = D.s("extra_dbase_file");
+  if (!extra.empty()) {
+    std::string p = extra;
+    if (p.find('/') == std::string::npos) p = (extra_dir.empty() ? std::string("") : extra_dir + "/") + p;
+    if (p.find('.', p.find_last_of('/') == std::string::npos ? 0 : p.find_last_of('/')) == std::string::npos) p += ".inp";
+    D.load(p);
+  }
+  std::memset(&c, 0, sizeof(c));
+  c.abi_version = SIMC_B200_ABI_VERSION;
+  if (ngen) *ngen = D.i("ngen");
+  if (charge_mC) *charge_mC = D.d("EXPER%charge");
+  // ---- regallvars + convert_to_logical, dbase.f:967-1165
+  c.mc_smear = D.i("mc_smear") > 0;
+  c.electron_arm = D.i("electron_arm");
+  c.hadron_arm = D.i("hadron_arm");
+  c.transparency = D.d("transparency");
+  c.use_benhar_sf = D.i("use_benhar_sf") > 0;
+  c.Ebeam = D.d("Ebeam");
+  c.dEbeam = D.d("dEbeam");
+  c.doing_kaon = D.i("doing_kaon") > 0; c.which_kaon = D.i("which_kaon");
+  c.doing_pion = D.i("doing_pion") > 0; c.which_pion = D.i("which_pion");
+  c.doing_delta = D.i("doing_delta") > 0;
+  c.doing_semi = D.i("doing_semi") > 0;
+  c.doing_hplus = D.i("doing_hplus", 1) > 0;
+  c.doing_rho = D.i("doing_rho") > 0;
+  c.doing_decay = D.i("doing_decay") > 0;
+  c.doing_phsp = D.i("doing_phsp") > 0;
+  c.ctau = D.d("ctau");
+  simc_target& targ = c.targ;
+  targ.A = D.d("targ%A"); targ.Z = D.d("targ%Z"); targ.mass_amu = D.d("targ%mass_amu"); targ.mrec_amu = D.d("targ%mrec_amu");
+  targ.rho = D.d("targ%rho"); targ.thick = D.d("targ%thick"); targ.xoffset = D.d("targ%xoffset");
+  targ.yoffset = D.d("targ%yoffset"); targ.fr_pattern = D.i("targ%fr_pattern"); targ.fr1 = D.d("targ%fr1");
+  targ.fr2 = D.d("targ%fr2"); targ.zoffset = D.d("targ%zoffset"); targ.angle = D.d("targ%angle");
+  targ.abundancy = D.d("targ%abundancy"); targ.can = D.i("targ%can");
+  c.spec_e.P = D.d("spec%e%P"); c.spec_e.theta = D.d("spec%e%theta");
+  c.spec_p.P = D.d("spec%p%P"); c.spec_p.theta = D.d("spec%p%theta");
+  c.gen.ywid = D.d("gen%ywid"); c.gen.xwid = D.d("gen%xwid");
+  c.spec_e.off_x = D.d("spec%e%offset%x"); c.spec_e.off_y = D.d("spec%e%offset%y"); c.spec_e.off_z = D.d("spec%e%offset%z");
+  c.spec_e.off_xptar = D.d("spec%e%offset%xptar"); c.spec_e.off_yptar = D.d("spec%e%offset%yptar");
+  c.spec_p.off_x = D.d("spec%p%offset%x"); c.spec_p.off_y = D.d("spec%p%offset%y"); c.spec_p.off_z = D.d("spec%p%offset%z");
+  c.spec_p.off_xptar = D.d("spec%p%offset%xptar"); c.spec_p.off_yptar = D.d("spec%p%offset%yptar");
+  c.use_expon = D.i("use_expon");
+  const int one_tail = D.i("one_tail");
+  c.intcor_mode = D.i("intcor_mode");
+  c.hard_cuts = D.i("hard_cuts") > 0;
+  c.using_rad = D.i("using_rad") > 0;
+  const int spect_mode = D.i("spect_mode");
+  // min_max_init defaults (init.f:921-1190) for what the deck does not set
+  c.cuts_Em.min = D.has("cuts%Em%min") ? D.d("cuts%Em%min") : -1.0e10;
+  c.cuts_Em.max = D.has("cuts%Em%max") ? D.d("cuts%Em%max") : 1.0e10;
+  c.cuts_Pm.min = -1.0e10; c.cuts_Pm.max = 1.0e10;
+  c.using_Eloss = D.i("using_Eloss") > 0;
+  c.correct_Eloss = D.i("correct_Eloss") > 0;
+  c.correct_raster = D.i("correct_raster") > 0;
+  c.using_HMScoll = D.i("using_HMScoll") > 0;
+  c.using_SHMScoll = D.i("using_SHMScoll") > 0;
+  const int deForest_flag = D.i("deForest_flag");
+  c.rad_flag = D.i("rad_flag");
+  c.extrad_flag = D.i("extrad_flag");
+  c.using_Coulomb = D.i("using_Coulomb") > 0;
+  c.dE_edge_test = D.d("dE_edge_test");
+  c.use_offshell_rad = D.i("use_offshell_rad") > 0;
+  c.Egamma_gen_max = D.d("Egamma_gen_max");
+  if (D.i("using_tgt_field") > 0) throw std::runtime_error("using_tgt_field=1 (polarised-target field tracking) is out of scope");
+  if (D.i("doing_pizero") > 0) throw std::runtime_error("doing_pizero is out of scope");
+  auto spedge = [&](simc_arm_cuts& a, const char* arm) {
+    auto key = [&](const char* q, const char* mm) { return std::string("SPedge%") + arm + "%" + q + "%" + mm; };
+    a.delta.min = D.d(key("delta", "min").c_str()); a.delta.max = D.d(key("delta", "max").c_str());
+    a.yptar.min = D.d(key("yptar", "min").c_str()); a.yptar.max = D.d(key("yptar", "max").c_str());
+    a.xptar.min = D.d(key("xptar", "min").c_str()); a.xptar.max = D.d(key("xptar", "max").c_str());
+    a.z.min = -1.0e10; a.z.max = 1.0e10;
+  };
+  spedge(c.SPedge_e, "e");
+  spedge(c.SPedge_p, "p");
+
+  // ---- dbase_read, dbase.f:122-553
+  bool doing_semipi = false, doing_semika = false;
+  if (c.doing_pion && c.doing_semi) { doing_semipi = true; c.doing_pion = 0; }
+  if (c.doing_kaon && c.doing_semi) { doing_semika = true; c.doing_kaon = 0; }
+  const int nA = (int)std::lround(targ.A);
+  if (c.doing_pion) {
+    c.Mh = Mpi;
+    if (nA == 1 && c.which_pion == 1) throw std::runtime_error("Pi- production from Hydrogen not allowed!");
+    if (nA <= 2 && c.which_pion >= 10) throw std::runtime_error("Coherent production from Hydrogen/Deuterium not allowed!");
+    c.doing_hydpi = nA == 1; c.doing_deutpi = nA == 2; c.doing_hepi = nA >= 3;
+    if (c.which_pion >= 10) { c.doing_hydpi = 1; c.doing_deutpi = 0; c.doing_hepi = 0; }
+  } else if (c.doing_kaon) {
+    c.Mh = Mk;
+    if (nA == 1 && c.which_kaon == 2) throw std::runtime_error("Sigma- production from Hydrogen not allowed!");
+    c.doing_hydkaon = nA == 1; c.doing_deutkaon = nA == 2; c.doing_hekaon = nA >= 3;
+    if (c.which_kaon >= 10) { c.doing_hydkaon = 1; c.doing_deutkaon = 0; c.doing_hekaon = 0; }
+  } else if (c.doing_delta) {
+    c.Mh = Mp;
+  } else if (c.doing_semi) {
+    c.Mh = doing_semika ? Mk : Mpi;
+    c.doing_hydsemi = nA == 1; c.doing_deutsemi = nA == 2;
+  } else if (c.doing_rho) {
+    c.Mh = 769.3;
+  } else {
+    c.Mh = Mp;
+    c.doing_eep = 1;
+    c.doing_hyd_elast = nA == 1; c.doing_deuterium = nA == 2; c.doing_heavy = nA >= 3;
+  }
+  c.Mh2 = c.Mh * c.Mh;
+  if (c.doing_phsp) { c.rad_flag = 0; c.doing_eep = 0; c.doing_pion = 0; c.doing_kaon = 0; c.doing_delta = 0; c.doing_rho = 0; }
+  c.dEbeam = c.Ebeam * c.dEbeam / 100.;
+  for (simc_spectrometer* sp : {&c.spec_e, &c.spec_p}) {
+    sp->theta = std::fabs(sp->theta) / degrad;
+    sp->cos_th = std::cos(sp->theta);
+    sp->sin_th = std::sin(sp->theta);
+  }
+  auto arm_phi = [&](int arm, const char* what) {
+    if (arm == 1 || arm == 3 || arm == 7) return 3 * pi / 2.;
+    if (arm == 2 || arm == 4 || arm == 5 || arm == 6 || arm == 8) return pi / 2.;
+    throw std::runtime_error(std::string("I dont know what phi should be for the ") + what + " arm");
+  };
+  c.spec_e.phi = arm_phi(c.electron_arm, "electron");
+  c.spec_p.phi = arm_phi(c.hadron_arm, "hadron");
+  targ.N = targ.A - targ.Z;
+  targ.M = targ.mass_amu * amu;
+  targ.Mrec = targ.mrec_amu * amu;
+  if (nA == 1) { targ.M = Mp; targ.Mrec = 0.; }
+  else if (nA == 2) targ.M = Md;
+  else {
+    const double Mrec_guess = targ.M - Mp;
+    if (std::fabs(targ.Mrec - Mrec_guess) > 100.) targ.Mrec = Mrec_guess;
+  }
+  if (c.doing_eep) { targ.Mtar_struck = Mp; targ.Mrec_struck = 0.0; }
+  else if (c.doing_delta) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mpi; }
+  else if (c.doing_semi || c.doing_rho) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }
+  else if (c.doing_pion) {
+    if (c.which_pion == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mn; }
+    else if (c.which_pion == 1) { targ.Mtar_struck = Mn; targ.Mrec_struck = Mp; }
+    else if (c.which_pion == 2 || c.which_pion == 3) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1232.0; }
+    else throw std::runtime_error("coherent pion production is out of scope");
+  } else if (c.doing_kaon) {
+    if (c.which_kaon == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1115.68; }
+    else if (c.which_kaon == 1) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1192.64; }
+    else if (c.which_kaon == 2) { targ.Mtar_struck = Mn; targ.Mrec_struck = 1197.45; }
+    else throw std::runtime_error("coherent kaon production is out of scope");
+  }
+  if (nA == 2) targ.Mrec = Mp + Mn - targ.Mtar_struck;
+  targ.thick = targ.thick / 1000.;
+  targ.length = targ.thick / targ.rho;
+  targ.angle = targ.angle / degrad;
+  if (targ.Z < 2.4) {
+    if (std::fabs(targ.angle) > 0.0001) targ.angle = 0.0;
+    if (targ.can != 1 && targ.can != 2 && targ.can != 3) throw std::runtime_error("bad targ.can value");
+  }
+  if (std::sin(targ.angle) > 0.85) throw std::runtime_error("BAD targ.angle");
+  for (simc_spectrometer* sp : {&c.spec_e, &c.spec_p}) { sp->off_xptar /= 1000.; sp->off_yptar /= 1000.; }
+  for (simc_arm_cuts* a : {&c.SPedge_e, &c.SPedge_p}) {
+    if (a->delta.min <= -100.0) a->delta.min = -99.99;
+    a->yptar.min /= 1000.; a->yptar.max /= 1000.; a->xptar.min /= 1000.; a->xptar.max /= 1000.;
+  }
+  c.doing_tail[0] = one_tail == 0 || one_tail == 1 || one_tail == -2 || one_tail == -3;
+  c.doing_tail[1] = one_tail == 0 || one_tail == 2 || one_tail == -3 || one_tail == -1;
+  c.doing_tail[2] = one_tail == 0 || one_tail == 3 || one_tail == -1 || one_tail == -2;
+  if (std::abs(one_tail) > 3 && c.using_rad)
+    throw std::runtime_error("Moron! one_tail>3 turns radiation off, but using_rad wants it on.");
+  if (!c.using_rad) c.doing_tail[0] = c.doing_tail[1] = c.doing_tail[2] = 0;
+  c.hardwired_rad = c.Egamma_gen_max > 0.01;
+  c.using_E_arm_montecarlo = spect_mode != 1 && spect_mode != -1;
+  c.using_P_arm_montecarlo = spect_mode != 1 && spect_mode != -2;
+  if (c.doing_pion || c.doing_kaon || c.doing_delta || (c.cuts_Em.min == c.cuts_Em.max)) {
+    c.cuts_Em.min = -1.e6; c.cuts_Em.max = 1.e6;
+  }
+  if (std::abs(deForest_flag) > 1) throw std::runtime_error("Idiot! check setting of deForest_flag");
+  if (c.correct_Eloss && !c.using_Eloss) c.correct_Eloss = 0;
+  if ((int)std::lround(targ.Z) == 1) c.using_Coulomb = 0;
+
+  // ---- target_init, init.f:1-87
+  TargetExt X;
+  std::memset(&X, 0, sizeof(X));
+  targ.L1 = std::log(184.15) - std::log(targ.Z) / 3.0;
+  targ.L2 = std::log(1194.) - 2. * std::log(targ.Z) / 3.0;
+  if (targ.Z == 1) { targ.L1 = 5.31; targ.L2 = 6.144; }
+  {
+    const double za2 = (targ.Z * alpha) * (targ.Z * alpha);
+    const double fc = za2 * (1.202 + za2 * (-1.0369 + za2 * 1.008 / (za2 + 1)));
+    if (nA == 1) targ.X0 = 61.28;
+    else if (nA == 2) targ.X0 = 122.4;
+    else if (nA == 4) targ.X0 = 94.32;
+    else targ.X0 = 716.405 * targ.A / targ.Z / (targ.Z * (targ.L1 - fc) + targ.L2);
+  }
+  targ.X0_cm = targ.X0 / targ.rho;
+  trip(c, 1, 0.0, c.Ebeam, 0.0, Me, 4, X.Eloss_ave[0], X.teff_ave[0]);
+  trip(c, 2, 0.0, c.spec_e.P, c.spec_e.theta, Me, 4, X.Eloss_ave[1], X.teff_ave[1]);
+  trip(c, 3, 0.0, std::sqrt(c.spec_p.P * c.spec_p.P + c.Mh2), c.spec_p.theta, std::sqrt(c.Mh2), 4, X.Eloss_ave[2],
+       X.teff_ave[2]);
+  if (!c.using_Eloss) X.Eloss_ave[0] = X.Eloss_ave[1] = X.Eloss_ave[2] = 0.0;
+  if (c.using_Coulomb) {
+    targ.Coulomb_ave = 0.75 * 1.5 * (targ.Z - 1.) * alpha * hbarc /
+                       (1.1 * std::pow(targ.A, 1. / 3.) + 0.86 * std::pow(targ.A, -1. / 3.));
+    targ.Coulomb_constant = targ.Coulomb_ave;
+    targ.Coulomb_min = targ.Coulomb_constant;
+    targ.Coulomb_max = targ.Coulomb_constant;
+  }
+  if (c.doing_deuterium || (c.doing_heavy && !c.use_benhar_sf))
+    throw std::runtime_error("theory_init (momentum-distribution files) is not implemented in this build");
+
+  // ---- limits_init, init.f:91-572
+  auto slop_for = [](int arm, double* used) {
+    if (arm == 2) { used[0] = 1.0; used[1] = 0.008; used[2] = 0.008; }
+    else { used[0] = 0.5; used[1] = 0.005; used[2] = 0.005; }          // simulate.inc:20-44
+  };
+  if (c.using_E_arm_montecarlo) slop_for(c.electron_arm, c.slop_MC_e_used);
+  if (c.using_P_arm_montecarlo) slop_for(c.hadron_arm, c.slop_MC_p_used);
+  auto widen = [](simc_arm_cuts& a, const double* used) {
+    a.delta.min -= used[0]; a.delta.max += used[0];
+    a.yptar.min -= used[1]; a.yptar.max += used[1];
+    a.xptar.min -= used[2]; a.xptar.max += used[2];
+  };
+  widen(c.SPedge_e, c.slop_MC_e_used);
+  widen(c.SPedge_p, c.slop_MC_p_used);
+  simc_edge& edge = c.edge;
+  simc_edge& VE = c.VERTEXedge;
+  for (simc_edge* e : {&edge, &VE}) {          // min_max_init
+    for (simc_cut* q : {&e->e.E, &e->e.yptar, &e->e.xptar, &e->p.E, &e->p.yptar, &e->p.xptar, &e->Em, &e->Pm, &e->Mrec,
+                        &e->Trec, &e->Trec_struck}) { q->min = -1.0e10; q->max = 1.0e10; }
+  }
+  edge.e.E.min = (1. + c.SPedge_e.delta.min / 100.) * c.spec_e.P + targ.Coulomb_min - c.dE_edge_test;
+  edge.e.E.max = (1. + c.SPedge_e.delta.max / 100.) * c.spec_e.P + targ.Coulomb_max + c.dE_edge_test;
+  simc_cut pp;
+  pp.min = (1. + c.SPedge_p.delta.min / 100.) * c.spec_p.P - c.dE_edge_test;
+  pp.max = (1. + c.SPedge_p.delta.max / 100.) * c.spec_p.P + c.dE_edge_test;
+  pp.min = std::max(0.001e0, pp.min);
+  edge.p.E.min = std::sqrt(pp.min * pp.min + c.Mh2);
+  edge.p.E.max = std::sqrt(pp.max * pp.max + c.Mh2);
+  simc_cut the_phys, thp_phys, z;
+  the_phys.max = std::acos((c.spec_e.cos_th - c.spec_e.sin_th * c.SPedge_e.yptar.max) /
+                           std::sqrt(1. + c.SPedge_e.yptar.max * c.SPedge_e.yptar.max + c.SPedge_e.xptar.max * c.SPedge_e.xptar.max));
+  the_phys.min = std::acos((c.spec_e.cos_th - c.spec_e.sin_th * c.SPedge_e.yptar.min) /
+                           std::sqrt(1. + c.SPedge_e.yptar.min * c.SPedge_e.yptar.min));
+  thp_phys.max = std::acos((c.spec_p.cos_th - c.spec_p.sin_th * c.SPedge_p.yptar.max) /
+                           std::sqrt(1. + c.SPedge_p.yptar.max * c.SPedge_p.yptar.max + c.SPedge_p.xptar.max * c.SPedge_p.xptar.max));
+  thp_phys.min = std::acos((c.spec_p.cos_th - c.spec_p.sin_th * c.SPedge_p.yptar.min) /
+                           std::sqrt(1. + c.SPedge_p.yptar.min * c.SPedge_p.yptar.min));
+  z.min = -0.5 * targ.length;
+  z.max = 0.5 * targ.length;
+  extreme_trip_thru_target(c, X, c.Ebeam, the_phys, thp_phys, edge.e.E, pp, z, c.Mh);
+  if (!c.using_Eloss) for (int i = 0; i < 3; ++i) { X.Eloss_min[i] = 0.0; X.Eloss_max[i] = 0.0; }
+  if (!c.mc_smear) X.musc_max[0] = X.musc_max[1] = X.musc_max[2] = 0.;
+  edge.e.E.min += X.Eloss_min[1]; edge.e.E.max += X.Eloss_max[1];
+  edge.p.E.min += X.Eloss_min[2]; edge.p.E.max += X.Eloss_max[2];
+  edge.e.yptar.min = c.SPedge_e.yptar.min - X.musc_max[1]; edge.e.yptar.max = c.SPedge_e.yptar.max + X.musc_max[1];
+  edge.e.xptar.min = c.SPedge_e.xptar.min - X.musc_max[1]; edge.e.xptar.max = c.SPedge_e.xptar.max + X.musc_max[1];
+  edge.p.yptar.min = c.SPedge_p.yptar.min - X.musc_max[2]; edge.p.yptar.max = c.SPedge_p.yptar.max + X.musc_max[2];
+  edge.p.xptar.min = c.SPedge_p.xptar.min - X.musc_max[2]; edge.p.xptar.max = c.SPedge_p.xptar.max + X.musc_max[2];
+  c.Ebeam_vertex_ave = c.Ebeam + targ.Coulomb_ave - X.Eloss_ave[0];
+  const double Ebeam_max = c.Ebeam + c.dEbeam / 2. - X.Eloss_min[0] + targ.Coulomb_max;
+  const double Ebeam_min = c.Ebeam - c.dEbeam / 2. - X.Eloss_max[0] + targ.Coulomb_min;
+  if (c.doing_heavy) throw std::runtime_error("A(e,e'p) limits are not implemented in this build");
+  if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
+    VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
+    VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
+  } else {
+    throw std::runtime_error("nuclear-target limits are not implemented in this build");
+  }
+  if (c.doing_eep || c.doing_semi) {
+    VE.Trec_struck.min = 0.; VE.Trec_struck.max = 0.;
+  } else {
+    VE.Trec_struck.min = 0.;
+    VE.Trec_struck.max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck - edge.e.E.min - edge.p.E.min - VE.Em.min -
+                         VE.Trec.min;
+  }
+  c.Egamma_tot_max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck - edge.e.E.min - edge.p.E.min - VE.Em.min -
+                     VE.Trec.min - VE.Trec_struck.min;
+  if (c.hardwired_rad) c.Egamma_tot_max = c.Egamma_gen_max;
+  if (!c.using_rad) c.Egamma_tot_max = 0.0;
+  if (c.doing_tail[0]) c.Egamma1_max = c.Egamma_tot_max;
+  if (c.doing_tail[1]) c.Egamma2_max = c.Egamma_tot_max;
+  if (c.doing_tail[2]) c.Egamma3_max = c.Egamma_tot_max;
+  simc_gen_limits& gen = c.gen;
+  if (c.doing_hyd_elast) {
+    gen.sumEgen.min = 0.0; gen.sumEgen.max = 0.0;
+  } else if (c.doing_semi) {
+    gen.sumEgen.max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck;
+    gen.sumEgen.min = edge.e.E.min + edge.p.E.min;
+  } else {
+    gen.sumEgen.max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck - edge.p.E.min - VE.Em.min - VE.Trec.min -
+                      VE.Trec_struck.min;
+    gen.sumEgen.min = Ebeam_min + targ.Mtar_struck - targ.Mrec_struck - edge.p.E.max - VE.Em.max - VE.Trec.max -
+                      VE.Trec_struck.max - c.Egamma_tot_max;
+    gen.sumEgen.max = std::min(gen.sumEgen.max, edge.e.E.max + c.Egamma2_max);
+    gen.sumEgen.min = std::max(gen.sumEgen.min, edge.e.E.min);
+  }
+  gen.sumEgen.min -= c.dE_edge_test;
+  gen.sumEgen.max += c.dE_edge_test;
+  gen.sumEgen.min = std::max(0.e0, gen.sumEgen.min);
+  if (c.doing_hyd_elast) {
+    gen.e.E.min = edge.e.E.min;
+    gen.e.E.max = edge.e.E.max + c.Egamma2_max;
+  } else if (c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
+    gen.e.E.min = gen.sumEgen.min;
+    gen.e.E.max = gen.sumEgen.max;
+  } else {
+    gen.e.E.min = gen.sumEgen.min - edge.p.E.max - c.Egamma3_max;
+    gen.e.E.max = gen.sumEgen.max - edge.p.E.min;
+  }
+  gen.e.E.min = std::max(gen.e.E.min, edge.e.E.min);
+  gen.e.E.max = std::min(gen.e.E.max, edge.e.E.max + c.Egamma2_max);
+  gen.e.delta.min = (gen.e.E.min / c.spec_e.P - 1.) * 100.;
+  gen.e.delta.max = (gen.e.E.max / c.spec_e.P - 1.) * 100.;
+  gen.e.yptar = edge.e.yptar;
+  gen.e.xptar = edge.e.xptar;
+  if (c.doing_hyd_elast || c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
+    gen.p.E.min = edge.p.E.min;
+    gen.p.E.max = edge.p.E.max + c.Egamma3_max;
+  } else {
+    gen.p.E.min = gen.sumEgen.min - edge.e.E.max - c.Egamma2_max;
+    gen.p.E.max = gen.sumEgen.max - edge.e.E.min;
+  }
+  gen.p.E.min = std::max(gen.p.E.min, edge.p.E.min);
+  gen.p.E.max = std::min(gen.p.E.max, edge.p.E.max + c.Egamma3_max);
+  gen.p.delta.min = (std::sqrt(gen.p.E.min * gen.p.E.min - c.Mh2) / c.spec_p.P - 1.) * 100.;
+  gen.p.delta.max = (std::sqrt(gen.p.E.max * gen.p.E.max - c.Mh2) / c.spec_p.P - 1.) * 100.;
+  gen.p.yptar = edge.p.yptar;
+  gen.p.xptar = edge.p.xptar;
+  gen.Trec.min = -1.0e10; gen.Trec.max = 1.0e10;
+  // histogram axes, init.f:519-569 (the three sets share them)
+  const double nb = (double)SIMC_NHIST;
+  for (int s = 0; s < 3; ++s) {
+    simc_axis* ax = c.hist_axis[s];
+    set_axis(ax[SIMC_H_E_DELTA], gen.e.delta.min, (gen.e.delta.max - gen.e.delta.min) / nb);
+    set_axis(ax[SIMC_H_E_YPTAR], gen.e.yptar.min, (gen.e.yptar.max - gen.e.yptar.min) / nb);
+    set_axis(ax[SIMC_H_E_XPTAR], -gen.e.xptar.max, (gen.e.xptar.max - gen.e.xptar.min) / nb);
+    set_axis(ax[SIMC_H_P_DELTA], gen.p.delta.min, (gen.p.delta.max - gen.p.delta.min) / nb);
+    set_axis(ax[SIMC_H_P_YPTAR], gen.p.yptar.min, (gen.p.yptar.max - gen.p.yptar.min) / nb);
+    set_axis(ax[SIMC_H_P_XPTAR], -gen.p.xptar.max, (gen.p.xptar.max - gen.p.xptar.min) / nb);
+    set_axis(ax[SIMC_H_EM], VE.Em.min, (std::max(100.e0, VE.Em.max) - VE.Em.min) / nb);
+    set_axis(ax[SIMC_H_PM], VE.Pm.min, (std::max(100.e0, VE.Pm.max) - VE.Pm.min) / nb);
+  }
+  // ---- radc_init, init.f:576-651
+  if (c.extrad_flag == 0) {
+    if (c.rad_flag == 0) c.extrad_flag = 3;
+    else if (c.rad_flag >= 1 && c.rad_flag <= 3) c.extrad_flag = 1;
+  } else if (c.extrad_flag < 0) {
+    throw std::runtime_error("Imbecile! check your stupid setting of EXTRAD_FLAG");
+  }
+  c.etatzai = (12.0 + (targ.Z + 1.) / (targ.Z * targ.L1 + targ.L2)) / 9.0;
+  // ---- scale of the weights: the central-kinematics cross section (cf. calculate_central, simc.f:1143)
+  c.w_ref = 1.0;
+  if (c.doing_hyd_elast) {
+    const double Ein = c.Ebeam_vertex_ave, uez = std::cos(c.spec_e.theta);
+    const double eE = Ein * c.Mh / (c.Mh + Ein * (1. - uez));
+    const double w = sigep(Ein, eE, c.spec_e.theta, 2 * Ein * eE * (1. - uez));
+    if (w > 0 && std::isfinite(w)) c.w_ref = w;
+  }
+}
+
+}  // namespace simc
+
+extern "C" int simc_b200_config_from_deck(const char* deck_path, const char* extra_deck_dir, simc_run_config* out,
+                                          int32_t* ngen, double* charge_mC, char* err, int errlen) {
+  if (!deck_path || !out) return SIMC_ERR_ARG;
+  try {
+    int ng = 0;
+    double q = 0;
+    simc::config_from_deck(deck_path, extra_deck_dir ? extra_deck_dir : "", *out, &ng, &q);
+    if (ngen) *ngen = ng;
+    if (charge_mC) *charge_mC = q;
+    return SIMC_OK;
+  } catch (const std::exception& e) {
+    if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return SIMC_ERR_IO;
+  }
+}

@@ -183,6 +183,10 @@ def load_library():
                                                   C.c_void_p])):
         if hasattr(L, name):
             getattr(L, name).argtypes = args
+    L.simc_b200_config_from_deck.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,
+                                             C.c_int]
+    L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
+    L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     if hasattr(L, "simc_b200_event_field_name"):
         L.simc_b200_event_field_name.restype = C.c_char_p
         L.simc_b200_event_field_name.argtypes = [C.c_int]
@@ -193,6 +197,20 @@ def load_library():
             raise SimcError(-101, f"ABI mismatch: sizeof({typ.__name__}) is {C.sizeof(typ)} in Python, {c_size} in C")
     _lib = L
     return L
+
+
+def config_from_deck(deck_path: str, extra_deck_dir: str | None = None):
+    """(RunConfig, ngen, charge_mC) from a CTP deck; host only, no GPU needed."""
+    L = load_library()
+    cfg = RunConfig()
+    ngen = C.c_int32()
+    charge = C.c_double()
+    err = C.create_string_buffer(512)
+    rc = L.simc_b200_config_from_deck(deck_path.encode(), (extra_deck_dir or os.path.dirname(deck_path)).encode(),
+                                      C.byref(cfg), C.byref(ngen), C.byref(charge), err, 512)
+    if rc != 0:
+        raise SimcError(rc, err.value.decode())
+    return cfg, ngen.value, charge.value
 
 
 def _ptr(a: np.ndarray):
@@ -294,6 +312,9 @@ class Simc:
         self._check(self.L.simc_b200_run(self.h, first_try, n_tries, seed, C.byref(acc)))
         return acc
 
+    def set_batch(self, tries_per_batch: int):
+        self._check(self.L.simc_b200_set_batch(self.h, tries_per_batch))
+
     def run_async(self, first_try: int, n_tries: int, seed: int):
         self._check(self.L.simc_b200_run_async(self.h, first_try, n_tries, seed))
 
@@ -306,6 +327,13 @@ class Simc:
         status = np.zeros(n, dtype=np.int32)
         self._check(self.L.simc_b200_event_batch(self.h, first_try, n, seed, _ptr(rec), _ptr(status)))
         return rec, status
+
+    def radc_batch(self, inp: np.ndarray) -> np.ndarray:
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        assert inp.ndim == 2 and inp.shape[0] == 16
+        out = np.zeros((11, inp.shape[1]))
+        self._check(self.L.simc_b200_radc_batch(self.h, inp.shape[1], _ptr(inp), _ptr(out)))
+        return out
 
     def event_field_names(self):
         return [self.L.simc_b200_event_field_name(k).decode() for k in range(EVENT_NREC)]

@@ -108,3 +108,35 @@ class Oracle:
         out = np.zeros(n)
         self.L.oracle_philox_uniforms(C.c_uint64(seed), C.c_uint64(try_index), C.c_int64(n), _p(out))
         return out
+
+
+def _oracle_run(self, cfg, first, n, seed, threads=1):
+    """The loop of simc.f:169-351 on the CPU oracle; returns a simc_gfortran_b200.Accum."""
+    from simc_gfortran_b200.lib import Accum
+    acc = Accum()
+    self._check(self.L.oracle_accum_clear(C.byref(cfg), C.byref(acc)))
+    self._check(self.L.oracle_run(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), int(threads),
+                                  C.byref(acc)))
+    return acc
+
+
+def _oracle_event_batch(self, cfg, first, n, seed):
+    rec = np.zeros((48, n))
+    status = np.zeros(n, np.int32)
+    self._check(self.L.oracle_event_batch(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(rec),
+                                          _p(status)))
+    return rec, status
+
+
+Oracle.run = _oracle_run
+Oracle.event_batch = _oracle_event_batch
+
+
+def _oracle_radc_batch(self, cfg, inp):
+    inp = np.ascontiguousarray(inp, np.float64)
+    out = np.zeros((11, inp.shape[1]))
+    self._check(self.L.oracle_radc_batch(C.byref(cfg), C.c_int64(inp.shape[1]), _p(inp), _p(out)))
+    return out
+
+
+Oracle.radc_batch = _oracle_radc_batch
