@@ -186,7 +186,8 @@ const char* simc_b200_last_error(const simc_handle* h);   /* h may be NULL: last
 int64_t simc_b200_sizeof(int which);                      /* 0: simc_run_config, 1: simc_accum (binding self-check) */
 /* Arithmetic variant.  1 (default) = "strict": separate multiply/add in the reference's
  * order (an x86-64 gfortran -O build forms no FMA, Makefile:63), COSY sums bit-identical to
- * such a build.  0 = "fast": fused multiply-add and re-associated monomials, ~1e-15 relative.
+ * such a build.  0 = "fast": explicit fused multiply-add and re-associated monomials in the COSY
+ * polynomials only (~1e-15 relative); generation, radiation and weights are identical in both.
  * The environment variable SIMC_B200_MODE=strict|fast sets the default at create(). */
 int simc_b200_set_mode(simc_handle* h, int strict_mode);
 int simc_b200_sync(simc_handle* h);                       /* waits for the handle's stream */

@@ -1,5 +1,6 @@
 // CUDA kernels of libsimc_b200 (sm_100a).  Compiled twice: -DSIMC_STRICT=1 -fmad=false
-// (namespace simc::strict) and -DSIMC_STRICT=0 -fmad=true (namespace simc::fast).
+// (namespace simc::strict) and -DSIMC_STRICT=0 -fmad=false (namespace simc::fast: explicit fma()
+// and re-associated monomials in the COSY polynomials only).
 #if SIMC_STRICT
 #define SIMC_VARIANT_NS strict
 #else

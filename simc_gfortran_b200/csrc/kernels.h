@@ -1,5 +1,5 @@
-// Host-callable launchers of the two kernel variants (strict = -fmad=false, reference
-// association; fast = FMA + re-associated monomials).  Implemented in kernels.cu, which is
+// Host-callable launchers of the two kernel variants (strict = reference association,
+// no FMA; fast = explicit FMA + re-associated monomials in the COSY polynomials only).  Implemented in kernels.cu, which is
 // compiled twice.
 #pragma once
 #include <cuda_runtime.h>

@@ -5,8 +5,9 @@
 // SIMC_STRICT=1 (compiled with -fmad=false): every product and sum is formed in the
 // reference's order with separate multiply and add, so the COSY sums are bit-identical to a
 // no-FMA x86-64 build; only libm calls (log, log10, acos, sin, cos) can differ in the last ulp.
-// SIMC_STRICT=0 (-fmad=true): the monomial products are re-associated (suffix product per
-// group) and fused multiply-adds are used; results agree to ~1e-15 relative.
+// SIMC_STRICT=0: in the COSY polynomials only, the monomial products are re-associated (suffix
+// product per group) and explicit fused multiply-adds are used; results agree to ~1e-15 relative.
+// Everything else is the same no-FMA arithmetic (the whole library is built with -fmad=false).
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>

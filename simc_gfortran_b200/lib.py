@@ -227,6 +227,7 @@ class Simc:
         rc = self.L.simc_b200_create(C.byref(cfg) if cfg is not None else None, device, C.byref(self.h))
         if rc != 0:
             raise SimcError(rc, (self.L.simc_b200_last_error(None) or b"").decode())
+        self.mode = os.environ.get("SIMC_B200_MODE", "strict")
         if mode is not None:
             self.set_mode(mode)
 
@@ -247,6 +248,7 @@ class Simc:
 
     def set_mode(self, mode: str):
         assert mode in ("strict", "fast")
+        self.mode = mode
         self._check(self.L.simc_b200_set_mode(self.h, 1 if mode == "strict" else 0))
 
     # ---- optics
