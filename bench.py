@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- generated / accepted events per second of SIMC's event loop on B200.
+
+Workload (BASELINE.json configs[0], the configuration the metric and the 1e9 ev/s target are
+quoted on): C1 = H(e,e'p) elastic, HMS electron + SHMS proton, decks/c1_eep_hydrogen_hms_shms.inp.
+A step = one pass of the loop (simc.f:169-351) over --tries tries on every GPU; every rank
+works on its own range of the try index (weak scaling), and the integer accumulators are
+all-reduced over NCCL once at the end.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework
+    python bench.py --impl reference --steps K --warmup W    # CPU loop on the host cores (oracle port)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+DECK = os.path.join(ROOT, "decks", "c1_eep_hydrogen_hms_shms.inp")
+WORKLOAD = "C1 H(e,e'p) elastic, HMS e + SHMS p, radiative corrections on (decks/c1_eep_hydrogen_hms_shms.inp)"
+METRIC = "generated events/s (ntried per second), H(e,e'p) HMS+SHMS"
+
+
+# ---- algorithmic FLOPs: F_fwd(T) = 25 + 14 T per forward class call, F_rec = 25 + 12 T
+def algorithmic_flops(acc, optics):
+    total = 0.0
+    per_arm = []
+    for which, arm in ((0, optics["e"]), (1, optics["p"])):
+        calls = [int(x) for x in acc.transp_calls[which]]
+        n_terms = [int(arm.class_start[k + 1] - arm.class_start[k]) for k in range(arm.n_classes)]
+        f = sum(calls[k] * (25 + 14 * n_terms[k]) for k in range(arm.n_classes))
+        f += calls[47] * (25 + 12 * len(arm.rec_coeff))
+        per_arm.append(f)
+        total += f
+    return total, per_arm
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_loop(cfg, n, seed, threads, first=0, ranlux=True):
+    """The oracle's loop (CPU restatement of simc.f:169-351): test infrastructure used here only as
+    the CPU baseline / reference arm, never on the product path."""
+    from tests.oracle_lib import Oracle
+    from simc_gfortran_b200 import load_optics_fixture
+    orc = Oracle()
+    for arm in (cfg.electron_arm, cfg.hadron_arm):
+        orc.set_optics(load_optics_fixture(arm))
+    t0 = time.perf_counter()
+    acc = orc.run(cfg, first, n, seed, threads=threads, ranlux=ranlux)
+    dt = time.perf_counter() - t0
+    return acc, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from simc_gfortran_b200 import config_from_deck
+    cfg = config_from_deck(DECK)[0]
+    cores = os.cpu_count() or 1
+    n = args.cpu_tries if args.cpu_tries else 25000 * cores
+    for w in range(args.warmup):
+        cpu_loop(cfg, max(n // 8, 1000), 900 + w, cores)
+    tot_t, tot_n, tot_acc = 0.0, 0, 0
+    for k in range(args.steps):
+        acc, dt = cpu_loop(cfg, n, 1000 + k, cores, first=k * n)
+        tot_t += dt
+        tot_n += acc.ntried
+        tot_acc += acc.nsuccess
+    v = tot_n / tot_t
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "events/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "accepted_per_s": tot_acc / tot_t,
+            "config": {"workload": WORKLOAD, "tries_per_step": n,
+                       "note": "the Fortran reference cannot be built here (no gfortran, CTP needs SunRPC); this is its "
+                               "C++ restatement (oracle/), -O2 -ffp-contract=off, one thread per host core, each with its own "
+                               "RANLUX luxury-3 stream like independent simc processes"},
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} tries per step x {args.steps} steps, all host cores"},
+            "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tries", type=int, default=1 << 23, help="tries per step per GPU")
+    ap.add_argument("--batch", type=int, default=1 << 21, help="tries per pass of the stage pipeline")
+    ap.add_argument("--mode", default=os.environ.get("SIMC_B200_MODE", "strict"), choices=["strict", "fast"])
+    ap.add_argument("--cpu-tries", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from simc_gfortran_b200 import Accum, Simc, config_from_deck, load_optics_fixture
+    from simc_gfortran_b200.multi import allreduce_accum
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libsimc_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, _, charge = config_from_deck(DECK)
+    sim = Simc(cfg, device=local, mode=args.mode)
+    optics = {"e": load_optics_fixture(cfg.electron_arm), "p": load_optics_fixture(cfg.hadron_arm)}
+    sim.set_optics(optics["e"])
+    sim.set_optics(optics["p"])
+    sim.set_batch(args.batch)
+    ext = torch.cuda.ExternalStream(sim.stream)
+    n = args.tries
+    seed = 20240611
+    peak_fma, peak_muladd = sim.fp64_peak()
+
+    def first_try(step):
+        return (step * world + rank) * n          # disjoint ranges: results do not depend on the GPU count
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    acc = sim.accum_clear()
+    for w in range(args.warmup):
+        sim.run(first_try(10_000 + w), n, seed, acc)
+    # ---- device-timed region: K steps back to back, accumulators stay on the device
+    sim.stage_times(enable=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sim.launch_count
+    e0.record(ext)
+    for k in range(args.steps):
+        sim.run_async(first_try(k), n, seed)
+    e1.record(ext)
+    e1.synchronize()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = sim.launch_count - launches0
+    stage_ms, stage_launches = sim.stage_times(enable=False)
+    acc = sim.accum_clear()
+    sim.fetch(acc)
+    # ---- end-to-end: the public call with host accumulators (launch parameters in, accumulators out)
+    barrier()
+    t0 = time.perf_counter()
+    acc_e2e = sim.accum_clear()
+    for k in range(args.steps):
+        sim.run(first_try(100 + k), n, seed, acc_e2e)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    sampler.join()
+    # ---- one all-reduce of the integer accumulators (NCCL) ; max over ranks of the times
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        t_ar0 = time.perf_counter()
+        acc = allreduce_accum(acc, torch.device("cuda", local))
+        torch.cuda.synchronize()
+        allreduce_ms = (time.perf_counter() - t_ar0) * 1e3
+    else:
+        allreduce_ms = 0.0
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        tries_total = acc.ntried
+        assert tries_total == n * args.steps * world, (tries_total, n, args.steps, world)
+        gen_per_s = tries_total / (dev_ms * 1e-3)
+        acc_per_s = acc.nsuccess / (dev_ms * 1e-3)
+        flops, per_arm = algorithmic_flops(acc, optics)
+        flops_per_try = flops / tries_total
+        # dominant kernel = the stage with the largest device time (per-rank numbers of rank 0)
+        names = ["k_generate", "k_arm<hadron>", "k_arm<electron>", "k_finish"]
+        dom = int(np.argmax(stage_ms))
+        # FLOPs of the dominant kernel on THIS rank: per-arm share of rank 0 = total / world (weak scaling)
+        dom_flops = {1: per_arm[1], 2: per_arm[0]}.get(dom, 0.0) / world
+        achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12 if stage_ms[dom] > 0 else 0.0
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        line = {
+            "metric": METRIC, "value": gen_per_s, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "accepted_per_s": acc_per_s, "accepted_fraction": acc.nsuccess / tries_total,
+            "config": {"workload": WORKLOAD, "tries_per_step_per_gpu": n, "stage_batch": args.batch, "mode": args.mode,
+                       "rng": "Philox4x32-10 keyed (seed, try index)",
+                       "l2": "inputs are generated on chip; the per-stage state buffers (%.0f MB per batch) exceed the 126 MB L2"
+                             % (84 * 8 * args.batch / 1e6)},
+            "e2e": {"value": tries_total / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": 32,
+                    "d2h_bytes_per_step": C.sizeof(Accum),
+                    "note": "simc_b200_run() through the C ABI with host accumulators; a Monte Carlo step's only input "
+                            "is (first_try, n_tries, seed)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": names[dom], "achieved": achieved, "peak": peak_muladd, "unit": "TFLOP/s",
+                         "frac": achieved / peak_muladd if peak_muladd else None, "traffic": None,
+                         "peak_kind": "measured in this run: DMUL+DADD microbenchmark (no FMA, like the strict arithmetic); "
+                                      "DFMA peak %.1f TFLOP/s" % peak_fma,
+                         "flops_per_generated_event": flops_per_try,
+                         "whole_loop_tflops": flops / (dev_ms * 1e-3) / 1e12,
+                         "stage_ms": dict(zip(names, stage_ms)), "stage_launches": dict(zip(names, stage_launches)),
+                         "hbm_peak_gbs": hbm_peak},
+            "clocks": sampler.summary(),
+            "allreduce_ms": allreduce_ms,
+            "yield_per_mC": acc.wtcontribute.value() / tries_total *
+                            (1.0 / (cfg.targ.mass_amu / 3.75914e6 / (cfg.targ.abundancy / 100.) * abs(np.cos(cfg.targ.angle)) / (cfg.targ.thick * 1000.))) *
+                            (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min) * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min) * charge,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_tries if args.cpu_tries else 25000 * cores
+            acc_c, dt = cpu_loop(cfg, n_cpu, 7, cores)
+            line["cpu_baseline"] = {"value": acc_c.ntried / dt, "unit": "events/s", "cores": cores, "kind": "port",
+                                    "accepted_per_s": acc_c.nsuccess / dt,
+                                    "sample": f"{n_cpu} tries of the same deck on {cores} host threads (oracle restatement, not gfortran)"}
+        print(json.dumps(line))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

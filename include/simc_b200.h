@@ -166,11 +166,14 @@ typedef struct {
   simc_range    contrib[32];                   /* limits_update order, event.f:19-72 */
   simc_range    slop[8];                       /* MC e/p delta,yptar,xptar; total Em,Pm (event.f:75-87) */
   int64_t       stop[2][SIMC_NSTOP];           /* [0] = electron arm, [1] = hadron arm */
+  /* Work counters (not in the reference): calls of transp() per forward class, [arm][class-1], and
+   * calls of the reconstruction map in slot 47.  bench.py turns them into algorithmic FLOPs. */
+  int64_t       transp_calls[2][48];
 } simc_accum;
 
 typedef struct simc_handle simc_handle;
 
-/* Host-only (no GPU needed): reads a CTP deck (`begin parm ... end parm`, infiles/*.inp) and
+/* Host-only (no GPU needed): reads a CTP deck (`begin parm ... end parm`, the decks under infiles/) and
  * performs the reference's one-time setup -- dbase_read post-processing (dbase.f:119-553),
  * target_init (init.f:1-87), limits_init (init.f:91-572), radc_init (init.f:576-651) -- to fill
  * *out.  extra_deck_dir: where `extra_dbase_file` is looked up (the reference uses infiles/).
@@ -217,7 +220,14 @@ int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);
  * any GPU).  Adds into *acc (zero it with simc_b200_accum_clear first). */
 int simc_b200_accum_clear(simc_handle* h, simc_accum* acc);
 int simc_b200_run(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, simc_accum* acc);
-int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch);   /* tries per pass of the stage pipeline (default 2^20) */
+int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch);
+/* Per-stage device time of the loop, measured with CUDA events on the handle's stream while
+ * enabled: ms[0..3] = generate, hadron arm, electron arm, finish (sums since the last call);
+ * launches[0..3] = launches of each.  enable = 1/0 switches the event recording. */
+int simc_b200_stage_times(simc_handle* h, int enable, double* ms4, int64_t* launches4);
+/* FP64 pipe microbenchmark on this device: dependent-chain-free DFMA and DMUL+DADD loops.
+ * Returns TFLOP/s (FMA = 2 flops) for the roofline denominator. */
+int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_muladd);   /* tries per pass of the stage pipeline (default 2^20) */
 
 /* Asynchronous pieces of simc_b200_run for callers that overlap or time the
  * device work themselves (bench.py): launch on the handle's stream, then fetch. */

@@ -339,6 +339,7 @@ void mc_hms(Track& t, const ArmOptics& o, ArmCall& a) {
   // :419-437 reconstruct from the fitted focal-plane track
   t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
   double dpp_recon, dth_recon, dph_recon, y_recon;
+  if (t.calls) t.calls[47]++;
   o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon);
   a.dpp = dpp_recon;
   a.dxdz = dph_recon;
@@ -723,6 +724,7 @@ void mc_shms(Track& t, const ArmOptics& o, ArmCall& a) {
   // :1076-1094 recon
   t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
   double dpp_recon, dth_recon, dph_recon, y_recon;
+  if (t.calls) t.calls[47]++;
   o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon);
   a.dpp = dpp_recon;
   a.dxdz = dph_recon;

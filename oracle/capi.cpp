@@ -117,7 +117,16 @@ int oracle_accum_clear(const simc_run_config* cfg, simc_accum* acc) {
   simc_oracle::accum_clear(*cfg, *acc);
   return 0;
 }
+// rng_mode 0: the counter-based stream (same events as the B200 path); 1: RANLUX luxury 3 through
+// grnd()'s buffer, one sequential generator per thread seeded seed+t -- the reference's own
+// generator and its only parallel mode (several processes with different random_seed).
+int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, int threads, int rng_mode,
+                   simc_accum* acc);
 int oracle_run(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, int threads, simc_accum* acc) {
+  return oracle_run_rng(cfg, first, n, seed, threads, 0, acc);
+}
+int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, int threads, int rng_mode,
+                   simc_accum* acc) {
   auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
   const ArmOptics* oe = ie == g_optics.end() ? nullptr : &ie->second;
   const ArmOptics* op = ip == g_optics.end() ? nullptr : &ip->second;
@@ -129,7 +138,11 @@ int oracle_run(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t se
     accum_clear(*cfg, part[t]);
     const int64_t b = first + n * t / threads, e = first + n * (t + 1) / threads;
     th.emplace_back([&, t, b, e]() {
-      try { run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0); }
+      try {
+        RanluxState st;
+        if (rng_mode == 1) st.rluxgo(3, (int)(seed + 1 + t), 0, 0);
+        run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr);
+      }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
   }

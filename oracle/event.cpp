@@ -378,6 +378,7 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     const int arm = cfg.hadron_arm;
     a.fry = (arm == 1 || arm == 5 || arm == 6) ? xtar_init_P : fry;
     a.using_coll = (arm == 1) ? cfg.using_HMScoll : (arm == 5 ? cfg.using_SHMScoll : 0);
+    s.trk.calls = s.calls[1];
     run_arm(s, arm, s.optics_p, a);
     s.ntup.resfac = a.resmult;
     s.stop_p = a.ok_spec ? 0 : a.stop_code;
@@ -439,6 +440,7 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     const int arm = cfg.electron_arm;
     a.fry = (arm == 1 || arm == 5 || arm == 6) ? xtar_init_E : fry;
     a.using_coll = (arm == 1) ? cfg.using_HMScoll : (arm == 5 ? cfg.using_SHMScoll : 0);
+    s.trk.calls = s.calls[0];
     run_arm(s, arm, s.optics_e, a);
     s.ntup.resfac = s.ntup.resfac + a.resmult;
     s.stop_e = a.ok_spec ? 0 : a.stop_code;

@@ -63,6 +63,7 @@ struct Sim {
   Track trk;                     // COMMON /track/ + decdist, Mh2_final
   int stop_e = 0, stop_p = 0;    // stop code of each arm (0 = ok), -1 = arm not entered
   bool hut_e = false, hut_p = false;
+  long long calls[2][48] = {};   // [0] electron arm, [1] hadron arm
 };
 
 // Result of one pass through the loop body, simc.f:169-351
@@ -100,6 +101,7 @@ TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& re
 void accum_clear(const simc_run_config& cfg, simc_accum& a);
 void merge_accum(simc_accum& a, const simc_accum& b);
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
-               uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off);
+               uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
+               RanluxState* ranlux = nullptr);
 
 }  // namespace simc_oracle

@@ -65,6 +65,7 @@ void accumulate(const Sim& s, const TryResult& r, const EventMain& main, const E
     if (hut) a.stop[which][2]++;
     if (code > 0 && 2 + code < SIMC_NSTOP) a.stop[which][2 + code]++;
   };
+  for (int w = 0; w < 2; ++w) for (int k = 0; k < 48; ++k) a.transp_calls[w][k] += s.calls[w][k];
   stops(1, s.stop_p, s.hut_p);
   stops(0, s.stop_e, s.hut_e);
   if (r.success) add_fixed(a.sum_sigcc, main.sigcc);
@@ -142,6 +143,7 @@ void merge_accum(simc_accum& a, const simc_accum& b) {
   for (int i = 0; i < 32; ++i) { a.contrib[i].lo = std::min(a.contrib[i].lo, b.contrib[i].lo); a.contrib[i].hi = std::max(a.contrib[i].hi, b.contrib[i].hi); }
   for (int i = 0; i < 8; ++i) { a.slop[i].lo = std::min(a.slop[i].lo, b.slop[i].lo); a.slop[i].hi = std::max(a.slop[i].hi, b.slop[i].hi); }
   for (int w = 0; w < 2; ++w) for (int i = 0; i < SIMC_NSTOP; ++i) a.stop[w][i] += b.stop[w][i];
+  for (int w = 0; w < 2; ++w) for (int i = 0; i < 48; ++i) a.transp_calls[w][i] += b.transp_calls[w][i];
 }
 
 void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const Event& vertex, const Event& orig,
@@ -161,10 +163,12 @@ void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const 
 
 // tries [first, first+n) of stream `seed`; rec/status may be null
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
-               uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off) {
+               uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
+               RanluxState* ranlux) {
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
-    rng.seed_philox(seed, (uint64_t)(first + i));
+    if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
+    else rng.seed_philox(seed, (uint64_t)(first + i));
     Sim s;
     s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng;
     EventMain main;

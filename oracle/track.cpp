@@ -116,6 +116,7 @@ void CosyForward::load(const std::string& path) {
 void transp(Track& t, const CosyForward& f, int klass, bool decay_flag, bool& dflag, double& m2, double& ph,
             double zd, double& pathlen) {
   const CosyClass& c = f.cls.at(klass - 1);
+  if (t.calls) t.calls[klass - 1]++;
   double p_spec = 0, beta = 0, gamma = 0, z_decay = 0;
   if (decay_flag && !dflag) {
     p_spec = ph / (1. + t.dpps / 100.);

@@ -50,6 +50,7 @@ struct Track {
   double xs = 0, ys = 0, zs = 0, dxdzs = 0, dydzs = 0, dpps = 0;
   double ctau = 0, Mh2_final = 0, decdist = 0;
   Rng* rng = nullptr;
+  long long* calls = nullptr;   // work counters (transp calls per class, recon in slot 47), not in the reference
 };
 
 // gauss1.f:1-30

@@ -72,6 +72,8 @@ struct ArmTablesDev {
   PolyClass rec;
   int32_t n_classes;
   int32_t n_ops;
+  int32_t split_op;     // ops [0,split_op): entrance apertures (cheap, most rejections); [split_op,n_ops): the rest
+  int32_t pad;
 };
 
 }  // namespace simc

@@ -53,6 +53,12 @@ struct simc_handle {
   int qexp_w = -64;
   std::vector<unsigned char> acc_host;
   double* d_rec = nullptr; int* d_status = nullptr; long long rec_n = 0;
+  // optional per-stage timing
+  int timing = 0;
+  std::vector<cudaEvent_t> ev;                 // 5 events per batch, recycled
+  std::vector<int> ev_used;                    // number of batches whose events are pending
+  double stage_ms[4] = {0, 0, 0, 0};
+  long long stage_launches[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -328,14 +334,14 @@ int ensure_loop_buffers(simc_handle* h, long long cap) {
     const size_t ab = strict::dev_accum_bytes();
     CU(h, cudaMalloc(&h->d_acc, ab));
     h->acc_host.assign(ab, 0);
-    CU(h, cudaMalloc(&h->d_counts, 4 * sizeof(unsigned)));
+    CU(h, cudaMalloc(&h->d_counts, 8 * sizeof(unsigned)));
   }
   if (cap > h->loop_cap) {
     if (h->d_state) cudaFree(h->d_state);
     if (h->d_lists) cudaFree(h->d_lists);
     h->d_state = nullptr; h->d_lists = nullptr; h->loop_cap = 0;
     CU(h, cudaMalloc(&h->d_state, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)cap));
-    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 3 * (size_t)cap));
+    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 5 * (size_t)cap));
     h->loop_cap = cap;
   }
   return SIMC_OK;
@@ -376,14 +382,23 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
   a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;
+  size_t ev_pos = 5 * h->ev_used.size();
   for (int64_t done = 0; done < n_tries;) {
     const int64_t nb = std::min<int64_t>(n_tries - done, cap);
     a.first_try = first_try + done;
     a.n_tries = nb;
-    int nl = 0;
-    cudaError_t e = h->strict ? strict::launch_loop_batch(a, h->stream, &nl) : fast::launch_loop_batch(a, h->stream, &nl);
-    h->launches += nl;
-    if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
+    const int n_stage = record ? 5 : 4;
+    if (h->timing) {
+      while (h->ev.size() < ev_pos + 5) { cudaEvent_t e; CU(h, cudaEventCreate(&e)); h->ev.push_back(e); }
+      CU(h, cudaEventRecord(h->ev[ev_pos], h->stream));
+    }
+    for (int st = 0; st < n_stage; ++st) {
+      cudaError_t e = h->strict ? strict::launch_loop_stage(a, st, h->stream) : fast::launch_loop_stage(a, st, h->stream);
+      if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
+      h->launches += (st == 1 || st == 2) ? 2 : 1;
+      if (h->timing && st < 4) CU(h, cudaEventRecord(h->ev[ev_pos + 1 + st], h->stream));
+    }
+    if (h->timing) { ev_pos += 5; h->ev_used.push_back(1); }
     done += nb;
   }
   return SIMC_OK;
@@ -448,6 +463,63 @@ int simc_b200_device_accum(simc_handle* h, void** dev_ptr, int64_t* n_int64, voi
   if (n_int64) *n_int64 = (int64_t)(strict::dev_accum_bytes() / 8);
   if (dev_minmax) *dev_minmax = (unsigned char*)h->d_acc + off;
   if (n_minmax) *n_minmax = 80;
+  return SIMC_OK;
+}
+
+int simc_b200_stage_times(simc_handle* h, int enable, double* ms4, int64_t* launches4) {
+  if (!h) return SIMC_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (size_t b = 0; b < h->ev_used.size(); ++b) {
+    for (int st = 0; st < 4; ++st) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev[5 * b + st], h->ev[5 * b + st + 1]) == cudaSuccess) {
+        h->stage_ms[st] += ms;
+        h->stage_launches[st] += 1;
+      }
+    }
+  }
+  h->ev_used.clear();
+  for (int st = 0; st < 4; ++st) {
+    if (ms4) ms4[st] = h->stage_ms[st];
+    if (launches4) launches4[st] = h->stage_launches[st];
+    h->stage_ms[st] = 0; h->stage_launches[st] = 0;
+  }
+  h->timing = enable ? 1 : 0;
+  return SIMC_OK;
+}
+
+int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_muladd) {
+  if (!h) return SIMC_ERR_ARG;
+  CU(h, cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CU(h, cudaGetDeviceProperties(&prop, h->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* scratch = nullptr;
+  CU(h, cudaMalloc(&scratch, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double res[2] = {0, 0};
+  for (int fma = 1; fma >= 0; --fma) {
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(e0, h->stream);
+      cudaError_t e = strict::launch_fp64_peak(scratch, blocks, threads, iters, fma, h->stream);
+      cudaEventRecord(e1, h->stream);
+      cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { cudaFree(scratch); return cuda_fail(h, e, "fp64 peak kernel"); }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    res[fma ? 0 : 1] = best;
+    h->launches += 4;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(scratch);
+  if (tflops_fma) *tflops_fma = res[0];
+  if (tflops_muladd) *tflops_muladd = res[1];
   return SIMC_OK;
 }
 

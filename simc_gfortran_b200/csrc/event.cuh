@@ -16,12 +16,12 @@ namespace simc {
 #define SIMC_ALPHA (1. / 137.0359895)
 
 // event.f:1572-1614
-SIMC_HD void physics_angles(double theta0, double phi0, double dx, double dy, double& theta, double& phi) {
-  const double costh = cos(theta0), sinth = sin(theta0), sinph = sin(phi0);
+SIMC_HD_CALL void physics_angles(double theta0, double phi0, double dx, double dy, double& theta, double& phi) {
+  const double costh = m::cos(theta0), sinth = m::sin(theta0), sinph = m::sin(phi0);
   const double r = sqrt(1. + dx * dx + dy * dy);
-  theta = acos((costh - dy * sinth * sinph) / r);
+  theta = m::acos((costh - dy * sinth * sinph) / r);
   if (dx != 0.0) {
-    phi = atan((dy * costh + sinth * sinph) / dx);
+    phi = m::atan((dy * costh + sinth * sinph) / dx);
     if (phi <= 0) phi = phi + SIMC_PI_D;
     if (sinph < 0.) phi = phi + SIMC_PI_D;
   } else {
@@ -30,9 +30,9 @@ SIMC_HD void physics_angles(double theta0, double phi0, double dx, double dy, do
 }
 
 // event.f:1618-1648
-SIMC_HD void spectrometer_angles(double theta0, double phi0, double& dx, double& dy, double theta, double phi) {
-  const double x = sin(theta) * cos(phi), y = sin(theta) * sin(phi), z = cos(theta);
-  const double x0 = sin(theta0) * cos(phi0), y0 = sin(theta0) * sin(phi0), z0 = cos(theta0);
+SIMC_HD_CALL void spectrometer_angles(double theta0, double phi0, double& dx, double& dy, double theta, double phi) {
+  const double x = m::sin(theta) * m::cos(phi), y = m::sin(theta) * m::sin(phi), z = m::cos(theta);
+  const double x0 = m::sin(theta0) * m::cos(phi0), y0 = m::sin(theta0) * m::sin(phi0), z0 = m::cos(theta0);
   const double cos_dtheta = x * x0 + y * y0 + z * z0;
   dx = x / cos_dtheta;
   dy = sqrt(1 / (cos_dtheta * cos_dtheta) - 1. - dx * dx);
@@ -41,12 +41,12 @@ SIMC_HD void spectrometer_angles(double theta0, double phi0, double& dx, double&
 }
 
 // sigep, fofa_best_fit, sigMott: physics_proton.f:1-22,137-190
-SIMC_HD double sigep(double Ein, double eE, double etheta, double Q2v) {
+SIMC_HD_CALL double sigep(double Ein, double eE, double etheta, double Q2v) {
   const double mu_p = 2.793;
   const double qsquar = -Q2v / (SIMC_HBARC * SIMC_HBARC);
-  const double Q2 = -qsquar * (SIMC_HBARC * SIMC_HBARC) * 1.e-6;   // hbarc**2. : pow(x,2.) == x*x
+  const double Q2 = -qsquar * (SIMC_HBARC * SIMC_HBARC) * 1.e-6;   // hbarc**2. : m::pow(x,2.) == x*x
   const double Q = sqrt(fmax(Q2, 0.e0));
-  const double Q3 = pow(Q, 3.), Q4 = pow(Q, 4.), Q5 = pow(Q, 5.);
+  const double Q3 = m::pow(Q, 3.), Q4 = m::pow(Q, 4.), Q5 = m::pow(Q, 5.);
   double denom = 1. + 0.62 * Q + 0.68 * Q2 + 2.8 * Q3 + 0.83 * Q4;
   const double GE = 1. / denom;
   denom = 1. + 0.35 * Q + 2.44 * Q2 + 0.5 * Q3 + 1.04 * Q4 + 0.34 * Q5;
@@ -54,10 +54,10 @@ SIMC_HD double sigep(double Ein, double eE, double etheta, double Q2v) {
   const double qmu4mp = Q2v / 4. / (SIMC_MP * SIMC_MP);
   const double W1p = GM * GM * qmu4mp;
   const double W2p = (GE * GE + GM * GM * qmu4mp) / (1.0 + qmu4mp);
-  const double th2 = tan(etheta / 2.);
+  const double th2 = m::tan(etheta / 2.);
   const double Wp = W2p + 2. * W1p * (th2 * th2);
-  const double m = 2. * SIMC_ALPHA * SIMC_HBARC * eE * cos(etheta / 2.) / Q2v;
-  const double sigMott = (m * m) * 1.e4;
+  const double mott = 2. * SIMC_ALPHA * SIMC_HBARC * eE * m::cos(etheta / 2.) / Q2v;
+  const double sigMott = (mott * mott) * 1.e4;
   return sigMott * eE / Ein * Wp;
 }
 
@@ -81,7 +81,7 @@ struct EventState {
 // trip_thru_target with typeflag = 1 (sampled energy loss): one |gauss1(10)| per material with
 // thick > 0, in the reference's order target, Al, air, kevlar, mylar (target.f:46-52,170-180).
 template <class RNG, class GAUSS>
-SIMC_HD void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng, GAUSS gauss, int narm, double zpos,
+SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng, GAUSS gauss, int narm, double zpos,
                                       double energy, double theta, double mass, double& Eloss, double& radlen) {
   const simc_target& targ = cfg.targ;
   const Material al = SIMC_MAT_AL;
@@ -116,12 +116,12 @@ SIMC_HD void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng, GAUS
 // complete_ev for H(e,e'p), event.f:432-1052.  Needs v_Ein, v_eyptar/xptar/theta/phi, tz; fills
 // the rest of the vertex, the jacobian, Eloss/teff(2:3) and the radiative constants.
 template <class RNG, class GAUSS>
-SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
+SIMC_HD_CALL bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
   const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
   s.jacobian = 1.0;
-  s.uex = sin(s.v_etheta) * cos(s.v_ephi);
-  s.uey = sin(s.v_etheta) * sin(s.v_ephi);
-  s.uez = cos(s.v_etheta);
+  s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
+  s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
+  s.uez = m::cos(s.v_etheta);
   s.v_eE = s.v_Ein * Mh / (Mh + s.v_Ein * (1. - s.uez));
   if (s.v_eE > s.v_Ein) return false;
   const double eP = s.v_eE;
@@ -137,8 +137,8 @@ SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS g
   s.v_Pm = 0.0;
   s.upx = uqx; s.upy = uqy; s.upz = uqz;
   s.v_pP = q;
-  s.v_ptheta = acos(s.upz);
-  s.v_pphi = atan2(s.upy, s.upx);
+  s.v_ptheta = m::acos(s.upz);
+  s.v_pphi = m::atan2(s.upy, s.upx);
   if (s.v_pphi < 0.) s.v_pphi = s.v_pphi + 2. * SIMC_PI_D;
   spectrometer_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
   s.v_pE = sqrt(s.v_pP * s.v_pP + Mh2);
@@ -167,13 +167,13 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
   if (targ.fr_pattern == 1) {
     t3 = rng.uniform() * SIMC_PI_D;
     t4 = rng.uniform() * SIMC_PI_D;
-    t5 = cos(t3) * targ.fr1;
-    t6 = cos(t4) * targ.fr2;
+    t5 = m::cos(t3) * targ.fr1;
+    t6 = m::cos(t4) * targ.fr2;
   } else if (targ.fr_pattern == 2) {
     t3 = rng.uniform() * 2. * SIMC_PI_D;
     t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
-    t5 = cos(t3) * t4;
-    t6 = sin(t3) * t4;
+    t5 = m::cos(t3) * t4;
+    t6 = m::sin(t3) * t4;
   } else if (targ.fr_pattern == 3) {
     t3 = 2. * rng.uniform() - 1.0;
     t4 = 2. * rng.uniform() - 1.0;
@@ -292,8 +292,8 @@ SIMC_HD void arm_entry(const simc_spectrometer& sp, double tx, double ty, double
                        double sp_xptar, ArmEntry& a) {
   a.sp_delta = sp_delta; a.sp_yptar = sp_yptar; a.sp_xptar = sp_xptar;
   double x_arm = -ty;
-  double y_arm = -tx * sp.cos_th - tz * sp.sin_th * sin(sp.phi);
-  double z_arm = tz * sp.cos_th + tx * sp.sin_th * sin(sp.phi);
+  double y_arm = -tx * sp.cos_th - tz * sp.sin_th * m::sin(sp.phi);
+  double z_arm = tz * sp.cos_th + tx * sp.sin_th * m::sin(sp.phi);
   x_arm = x_arm - sp.off_x;
   y_arm = y_arm - sp.off_y;
   z_arm = z_arm - sp.off_z;

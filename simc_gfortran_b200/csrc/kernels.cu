@@ -22,17 +22,18 @@ k_transport_batch(const ArmDev* __restrict__ arm, long long n, const double* __r
                   int* __restrict__ flags) {
   __shared__ double pw_s[kPowDoubles];
   const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  bool alive = i < n;
+  const long long ii = alive ? i : 0;
   TrackDev t;
-  t.dpps = in[0 * n + i];
-  t.xs = in[1 * n + i];
-  t.ys = in[2 * n + i];
+  t.dpps = in[0 * n + ii];
+  t.xs = in[1 * n + ii];
+  t.ys = in[2 * n + ii];
   // in[3] = z is carried by the reference (zs) but never read by any single-arm routine
-  t.dxdzs = in[4 * n + i];
-  t.dydzs = in[5 * n + i];
-  t.m2 = in[6 * n + i];
-  const double p_spec = in[7 * n + i];
-  const double fry = in[8 * n + i];
+  t.dxdzs = in[4 * n + ii];
+  t.dydzs = in[5 * n + ii];
+  t.m2 = in[6 * n + ii];
+  const double p_spec = in[7 * n + ii];
+  const double fry = in[8 * n + ii];
   t.p = p_spec * (1. + t.dpps / 100.);     // mc_hms.f:181
   t.pathlen = 0.0;
   t.decdist = 0.0;
@@ -42,7 +43,15 @@ k_transport_batch(const ArmDev* __restrict__ arm, long long n, const double* __r
   DevRng rng;
   rng.init(seed, (unsigned long long)i, 0u, 0u);
   ArmResult res;
-  run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res);
+  arm_result_clear(res);
+  HutState hs;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { hs.xdc[k] = 0.f; hs.ydc[k] = 0.f; }
+  hs.scincount = 0;
+  t.dflag = false;
+  musc_refresh(t);
+  run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, 0, arm->tab.n_ops);
+  if (i >= n) return;
   out[0 * n + i] = res.ok ? res.dpp_rec : dpp_in;
   out[1 * n + i] = res.ok ? res.dph_rec : dxdz_in;
   out[2 * n + i] = res.ok ? res.dth_rec : dydz_in;
@@ -98,32 +107,6 @@ size_t arm_dev_bytes() { return sizeof(ArmDev); }
 size_t dev_accum_bytes() { return sizeof(DevAccum); }
 int n_state_fields() { return (int)F_NFIELDS; }
 
-// One batch of tries through the four stages (and the record dump in record mode).
-cudaError_t launch_loop_batch(const LoopLaunch& a, cudaStream_t s, int* n_launched) {
-  LoopArgs A;
-  A.cfg = (const simc_run_config*)a.cfg;
-  A.arm_e = (const ArmDev*)a.arm_e;
-  A.arm_p = (const ArmDev*)a.arm_p;
-  A.st.base = a.state; A.st.cap = a.cap;
-  A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
-  A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
-  A.record_mode = a.record_mode;
-  cudaError_t e = cudaMemsetAsync(a.counts, 0, 4 * sizeof(unsigned), s);
-  if (e != cudaSuccess) return e;
-  const long long need = (a.n_tries + kBlock - 1) / kBlock;
-  const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
-  k_generate<<<grid, kBlock, 0, s>>>(A);
-  k_arm<1><<<grid, kBlock, 0, s>>>(A);
-  k_arm<0><<<grid, kBlock, 0, s>>>(A);
-  k_finish<<<grid, kBlock, 0, s>>>(A);
-  *n_launched += 4;
-  if (a.record_mode && a.rec) {
-    k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
-    *n_launched += 1;
-  }
-  return cudaGetLastError();
-}
-
 }  // namespace SIMC_VARIANT_NS
 }  // namespace simc
 #if SIMC_STRICT
@@ -167,6 +150,56 @@ void accum_to_host(const void* dev_copy, void* out_v, int qexp_w) {
     if (hi > o.slop[i].hi) o.slop[i].hi = hi;
   }
   for (int w = 0; w < 2; ++w) for (int i = 0; i < SIMC_NSTOP; ++i) o.stop[w][i] += (int64_t)d.stop[w][i];
+  for (int w = 0; w < 2; ++w) for (int i = 0; i < 48; ++i) o.transp_calls[w][i] += (int64_t)d.transp_calls[w][i];
+}
+
+// ---- FP64 pipe microbenchmark (roofline denominator) ---------------------------------------------
+template <bool FMA>
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    if (FMA) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    } else {
+      a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c); a2 = __dadd_rn(__dmul_rn(a2, m), c);
+      a3 = __dadd_rn(__dmul_rn(a3, m), c); a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+      a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s) {
+  if (fma) k_fp64_peak<true><<<blocks, threads, 0, s>>>(scratch, iters);
+  else k_fp64_peak<false><<<blocks, threads, 0, s>>>(scratch, iters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
+  LoopArgs A;
+  A.cfg = (const simc_run_config*)a.cfg;
+  A.arm_e = (const ArmDev*)a.arm_e;
+  A.arm_p = (const ArmDev*)a.arm_p;
+  A.st.base = a.state; A.st.cap = a.cap;
+  A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
+  A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
+  A.record_mode = a.record_mode;
+  const long long need = (a.n_tries + kBlock - 1) / kBlock;
+  const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
+  if (stage == 0) {
+    cudaError_t e = cudaMemsetAsync(a.counts, 0, 8 * sizeof(unsigned), s);
+    if (e != cudaSuccess) return e;
+    k_generate<<<grid, kBlock, 0, s>>>(A);
+  } else if (stage == 1) {
+    k_arm<1, 0><<<grid, kBlock, 0, s>>>(A);
+    k_arm<1, 1><<<grid, kBlock, 0, s>>>(A);
+  } else if (stage == 2) {
+    k_arm<0, 0><<<grid, kBlock, 0, s>>>(A);
+    k_arm<0, 1><<<grid, kBlock, 0, s>>>(A);
+  } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
+  else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
+  return cudaGetLastError();
 }
 
 }  // namespace SIMC_VARIANT_NS

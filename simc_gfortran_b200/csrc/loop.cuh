@@ -35,6 +35,8 @@ enum StateField : int {
   F_SPE_D, F_SPE_Y, F_SPE_X, F_SPE_Z, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCE_Z, F_FPE_PATH,
   F_RE_E, F_RE_TH, F_RE_PH,
   F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_PASSCUTS, F_REM, F_RPM, F_RW,
+  // track of the arm in flight, between the two segments of its program
+  F_TK_XS, F_TK_YS, F_TK_DX, F_TK_DY, F_TK_DPP, F_TK_P, F_TK_M2, F_TK_PATH, F_TK_DECD, F_TK_DFLAG, F_TK_FRY,
   F_NFIELDS
 };
 
@@ -54,6 +56,7 @@ struct DevAccum {
   unsigned long long hist_n[3][SIMC_H_PER_SET][SIMC_NHIST];
   long long contrib_lo[32], contrib_hi[32], slop_lo[8], slop_hi[8];   // order-preserving keys of doubles
   unsigned long long stop[2][SIMC_NSTOP];
+  unsigned long long transp_calls[2][48];
 };
 
 struct LoopArgs {
@@ -61,8 +64,8 @@ struct LoopArgs {
   const ArmDev* arm_e;
   const ArmDev* arm_p;
   StateBuf st;
-  unsigned* lists;                 // [3][cap]
-  unsigned* counts;                // [0] slots handed out, [1..3] lengths of lists 0..2
+  unsigned* lists;                 // [5][cap]: gen ok | P entrance ok | P ok | E entrance ok | E ok
+  unsigned* counts;                // [0] slots handed out, [1..5] lengths of lists 0..4
   DevAccum* acc;
   long long first_try, n_tries;
   unsigned long long seed;
@@ -147,8 +150,7 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
       const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int b = hist_bin(cfg.hist_axis[2][k], gv[k]);
-        if (b >= 0) atomicAdd(&h_geni[k][b], 1u);
+        warp_hist_add(h_geni[k], hist_bin(cfg.hist_axis[2][k], gv[k]));
       }
     }
     const bool want_slot = active && (ok || A.record_mode);
@@ -186,106 +188,152 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
 }
 
 // ---- stages 2,3: the two arms ----------------------------------------------------------------
-// WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846)
-template <int WHICH>
+// WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846).
+// Each arm runs as two kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
+// coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
+// after almost no arithmetic); SEG 1 = magnets, hut, reconstruction for the compacted survivors.
+template <int WHICH, int SEG>
 __global__ void __launch_bounds__(kBlock) k_arm(LoopArgs A) {
   __shared__ double pw_s[kPowDoubles];
   __shared__ unsigned s_stop[SIMC_NSTOP];
+  __shared__ unsigned s_calls[48];
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
+  for (int i = threadIdx.x; i < 48; i += kBlock) s_calls[i] = 0u;
   __syncthreads();
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
-  const unsigned n_in = A.counts[1 + (WHICH == 1 ? 0 : 1)];
-  const unsigned* in_list = A.lists + (WHICH == 1 ? 0 : 1) * A.st.cap;
-  unsigned* out_list = A.lists + (WHICH == 1 ? 1 : 2) * A.st.cap;
-  unsigned* out_count = &A.counts[1 + (WHICH == 1 ? 1 : 2)];
+  const int in_idx = (WHICH == 1 ? 0 : 2) + SEG;          // list read by this kernel
+  const unsigned n_in = A.counts[1 + in_idx];
+  const unsigned* in_list = A.lists + (long long)in_idx * A.st.cap;
+  unsigned* out_list = A.lists + (long long)(in_idx + 1) * A.st.cap;
+  unsigned* out_count = &A.counts[1 + in_idx + 1];
   const simc_spectrometer& sp = WHICH == 1 ? cfg.spec_p : cfg.spec_e;
   const ArmDev* arm = WHICH == 1 ? A.arm_p : A.arm_e;
   const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
   const bool use_mc = WHICH == 1 ? cfg.using_P_arm_montecarlo != 0 : cfg.using_E_arm_montecarlo != 0;
+  const double Mh2 = cfg.Mh2;
+  ArmFlags f;
+  f.ms_flag = cfg.mc_smear != 0; f.wcs_flag = cfg.mc_smear != 0;
+  f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
+  f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
+  const int split = use_mc ? arm->tab.split_op : 0;
+  const int n_ops = use_mc ? arm->tab.n_ops : 0;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;
     const bool active = i < n_in;
+    const unsigned slot = active ? in_list[i] : 0u;
+    DevRng rng;
+    rng.init(A.seed, (unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u, (unsigned)S.ld(F_DRAW, slot));
+    TrackDev t;
+    ArmResult res;
+    arm_result_clear(res);
+    HutState hs;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { hs.xdc[k] = 0.f; hs.ydc[k] = 0.f; }
+    hs.scincount = 0;
+    double fry = 0.0;
+    bool alive = active;
     bool ok = false;
-    unsigned slot = 0;
-    if (active) {
-      slot = in_list[i];
-      DevRng rng;
-      rng.init(A.seed, (unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u,
-               (unsigned)S.ld(F_DRAW, slot));
-      const double tx = S.ld(F_TX, slot), ty = S.ld(F_TY, slot), tz = S.ld(F_TZ, slot);
-      double dang0, dang1, sp_delta, ang0 = 0.0, ang1 = 0.0;
-      const double Mh2 = cfg.Mh2;
-      if (WHICH == 1) {
-        // beam multiple scattering (simc.f:1365), then the hadron's (simc.f:1379-1399)
-        if (cfg.mc_smear) {
-          const double teff = S.ld(F_TEFF0, slot), p = S.ld(F_OEIN, slot);
-          const double ts = 13.6 / p / 1. * sqrt(teff) * (1 + 0.088 * log10(teff / (1. * 1.)));
-          dang0 = ts * gauss1(rng, 3.5);
-          dang1 = ts * gauss1(rng, 3.5);
-        } else { dang0 = 0.0; dang1 = 0.0; }
-        S.st(F_DANG0, slot, dang0); S.st(F_DANG1, slot, dang1);
-        const double opE = S.ld(F_OPE, slot), opP = S.ld(F_OPP, slot);
-        if (cfg.using_Eloss) {
-          const double d = opE - S.ld(F_ELOSS2, slot);
-          sp_delta = (sqrt(fabs(d * d - Mh2)) - sp.P) / sp.P * 100.;
-        } else sp_delta = S.ld(F_OPDELTA, slot);
-        if (cfg.mc_smear) {
-          const double beta = opP / opE, teff = S.ld(F_TEFF2, slot);
-          const double ts = 13.6 / opP / beta * sqrt(teff) * (1 + 0.088 * log10(teff / (beta * beta)));
-          ang0 = ts * gauss1(rng, 3.5);
-          ang1 = ts * gauss1(rng, 3.5);
+    if (SEG == 0) {
+      ArmEntry en;
+      en.sp_delta = en.sp_yptar = en.sp_xptar = en.sp_z = en.x = en.y = en.dx = en.dy = 0.0;
+      if (active) {
+        const double tx = S.ld(F_TX, slot), ty = S.ld(F_TY, slot), tz = S.ld(F_TZ, slot);
+        double dang0, dang1, sp_delta, ang0 = 0.0, ang1 = 0.0;
+        if (WHICH == 1) {
+          // beam multiple scattering (simc.f:1365), then the hadron's (simc.f:1379-1399)
+          if (cfg.mc_smear) {
+            const double teff = S.ld(F_TEFF0, slot), p = S.ld(F_OEIN, slot);
+            const double ts = 13.6 / p / 1. * sqrt(teff) * (1 + 0.088 * m::log10(teff / (1. * 1.)));
+            dang0 = ts * gauss1(rng, 3.5);
+            dang1 = ts * gauss1(rng, 3.5);
+          } else { dang0 = 0.0; dang1 = 0.0; }
+          S.st(F_DANG0, slot, dang0); S.st(F_DANG1, slot, dang1);
+          const double opE = S.ld(F_OPE, slot), opP = S.ld(F_OPP, slot);
+          if (cfg.using_Eloss) {
+            const double d = opE - S.ld(F_ELOSS2, slot);
+            sp_delta = (sqrt(fabs(d * d - Mh2)) - sp.P) / sp.P * 100.;
+          } else sp_delta = S.ld(F_OPDELTA, slot);
+          if (cfg.mc_smear) {
+            const double beta = opP / opE, teff = S.ld(F_TEFF2, slot);
+            const double ts = 13.6 / opP / beta * sqrt(teff) * (1 + 0.088 * m::log10(teff / (beta * beta)));
+            ang0 = ts * gauss1(rng, 3.5);
+            ang1 = ts * gauss1(rng, 3.5);
+          }
+        } else {
+          dang0 = S.ld(F_DANG0, slot); dang1 = S.ld(F_DANG1, slot);
+          const double oeE = S.ld(F_OEE, slot);
+          sp_delta = 100 * (oeE - S.ld(F_ELOSS1, slot) - S.ld(F_COULOMB, slot) - sp.P) / sp.P;
+          if (cfg.mc_smear) {
+            const double teff = S.ld(F_TEFF1, slot);
+            const double ts = 13.6 / oeE / 1. * sqrt(teff) * (1 + 0.088 * m::log10(teff / (1. * 1.)));
+            ang0 = ts * gauss1(rng, 3.5);
+            ang1 = ts * gauss1(rng, 3.5);
+          }
         }
+        const double o_yptar = S.ld(WHICH == 1 ? F_VPYP : F_VEYP, slot), o_xptar = S.ld(WHICH == 1 ? F_VPXP : F_VEXP, slot);
+        arm_entry(sp, tx, ty, tz, sp_delta, o_yptar + ang0 + dang0, o_xptar + ang1 + dang1 * sp.cos_th, en);
+        S.st(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta); S.st(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot, en.sp_yptar);
+        S.st(WHICH == 1 ? F_SPP_X : F_SPE_X, slot, en.sp_xptar); S.st(WHICH == 1 ? F_SPP_Z : F_SPE_Z, slot, en.sp_z);
+        const double fry_raster = cfg.correct_raster ? -S.ld(F_RASTERY, slot) : 0.0;
+        fry = (arm_id == 1 || arm_id == 5) ? en.x : fry_raster;    // xtar_init, simc.f:1441,1463
+      }
+      t.dpps = en.sp_delta; t.xs = en.x; t.ys = en.y; t.dxdzs = en.dx; t.dydzs = en.dy;
+      t.m2 = WHICH == 1 ? Mh2 : SIMC_ME * SIMC_ME;
+      t.p = sp.P * (1. + t.dpps / 100.);
+      t.pathlen = 0.0; t.decdist = 0.0; t.mh2_final = Mh2; t.ctau = cfg.ctau;
+      t.dflag = false;
+      musc_refresh(t);
+      if (use_mc) {
+        if (active) warp_count(&s_stop[0]);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, 0, split, s_calls);
+        ok = alive;
       } else {
-        dang0 = S.ld(F_DANG0, slot); dang1 = S.ld(F_DANG1, slot);
-        const double oeE = S.ld(F_OEE, slot);
-        sp_delta = 100 * (oeE - S.ld(F_ELOSS1, slot) - S.ld(F_COULOMB, slot) - sp.P) / sp.P;
-        if (cfg.mc_smear) {
-          const double teff = S.ld(F_TEFF1, slot);
-          const double ts = 13.6 / oeE / 1. * sqrt(teff) * (1 + 0.088 * log10(teff / (1. * 1.)));
-          ang0 = ts * gauss1(rng, 3.5);
-          ang1 = ts * gauss1(rng, 3.5);
+        ok = active;
+      }
+      if (active) {
+        S.st(F_DRAW, slot, (double)rng.draw);
+        if (ok) {
+          S.st(F_TK_XS, slot, t.xs); S.st(F_TK_YS, slot, t.ys); S.st(F_TK_DX, slot, t.dxdzs); S.st(F_TK_DY, slot, t.dydzs);
+          S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
+          S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0); S.st(F_TK_FRY, slot, fry);
+        } else {
+          S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
+          warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
+          if (WHICH == 1) S.st(F_RESFAC, slot, 0.0);
         }
       }
-      const double o_yptar = S.ld(WHICH == 1 ? F_VPYP : F_VEYP, slot), o_xptar = S.ld(WHICH == 1 ? F_VPXP : F_VEXP, slot);
-      ArmEntry en;
-      arm_entry(sp, tx, ty, tz, sp_delta, o_yptar + ang0 + dang0, o_xptar + ang1 + dang1 * sp.cos_th, en);
-      double rc_delta, rc_yptar, rc_xptar, rc_z = 0.0, path = 0.0, resmult = 0.0;
-      int stop_code = 0;
-      bool hut = false;
+    } else {
+      double rc_delta = 0, rc_yptar = 0, rc_xptar = 0, rc_z = 0.0, path = 0.0, resmult = 0.0;
+      if (active) {
+        t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
+        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
+        t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
+      } else {
+        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
+      }
+      t.mh2_final = Mh2; t.ctau = cfg.ctau;
+      musc_refresh(t);
       if (use_mc) {
-        TrackDev t;
-        t.dpps = en.sp_delta; t.xs = en.x; t.ys = en.y; t.dxdzs = en.dx; t.dydzs = en.dy;
-        t.m2 = WHICH == 1 ? Mh2 : SIMC_ME * SIMC_ME;
-        t.p = sp.P * (1. + t.dpps / 100.);
-        t.pathlen = 0.0; t.decdist = 0.0; t.mh2_final = Mh2; t.ctau = cfg.ctau;
-        ArmFlags f;
-        f.ms_flag = cfg.mc_smear != 0; f.wcs_flag = cfg.mc_smear != 0;
-        f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
-        f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
-        const double fry_raster = cfg.correct_raster ? -S.ld(F_RASTERY, slot) : 0.0;
-        const double fry = (arm_id == 1 || arm_id == 5) ? en.x : fry_raster;    // xtar_init, simc.f:1441,1463
-        ArmResult res;
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res);
-        ok = res.ok;
-        stop_code = res.ok ? 0 : res.stop_code;
-        hut = res.reached_hut;
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, split, n_ops, s_calls);
+        ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
         path = t.pathlen; resmult = res.resmult;
-        atomicAdd(&s_stop[0], 1u);
-        if (ok) atomicAdd(&s_stop[1], 1u);
-        if (hut) atomicAdd(&s_stop[2], 1u);
-        if (stop_code > 0 && 2 + stop_code < SIMC_NSTOP) atomicAdd(&s_stop[2 + stop_code], 1u);
+        if (active) {
+          if (res.reached_hut) warp_count(&s_stop[2]);
+          warp_hist_add(s_stop, ok ? 1 : (2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1));
+        }
       } else {
-        ok = true;
-        rc_delta = en.sp_delta; rc_yptar = en.sp_yptar; rc_xptar = en.sp_xptar;
+        ok = active;
+        rc_delta = S.ld(WHICH == 1 ? F_SPP_D : F_SPE_D, slot); rc_yptar = S.ld(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot);
+        rc_xptar = S.ld(WHICH == 1 ? F_SPP_X : F_SPE_X, slot);
       }
-      S.st(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta); S.st(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot, en.sp_yptar);
-      S.st(WHICH == 1 ? F_SPP_X : F_SPE_X, slot, en.sp_xptar); S.st(WHICH == 1 ? F_SPP_Z : F_SPE_Z, slot, en.sp_z);
-      S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)stop_code);
-      S.st(F_DRAW, slot, (double)rng.draw);
-      if (WHICH == 1) S.st(F_RESFAC, slot, resmult);
+      if (active) {
+        S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)(ok ? 0 : res.stop_code));
+        S.st(F_DRAW, slot, (double)rng.draw);
+        if (WHICH == 1) S.st(F_RESFAC, slot, resmult);
+      }
       if (ok) {
         S.st(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta); S.st(WHICH == 1 ? F_RCP_Y : F_RCE_Y, slot, rc_yptar);
         S.st(WHICH == 1 ? F_RCP_X : F_RCE_X, slot, rc_xptar); S.st(WHICH == 1 ? F_RCP_Z : F_RCE_Z, slot, rc_z);
@@ -315,119 +363,235 @@ __global__ void __launch_bounds__(kBlock) k_arm(LoopArgs A) {
         }
       }
     }
+    __syncwarp();
     const unsigned pos = warp_append(out_count, active && ok);
     if (active && ok) out_list[pos] = slot;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock)
     if (s_stop[i]) atomicAdd(&A.acc->stop[WHICH][i], (unsigned long long)s_stop[i]);
+  for (int i = threadIdx.x; i < 48; i += kBlock)
+    if (s_calls[i]) atomicAdd(&A.acc->transp_calls[WHICH][i], (unsigned long long)s_calls[i]);
 }
 
 // ---- stage 4: recon kinematics, weight, accumulation --------------------------------------------
+// Per-CTA accumulators in shared memory: every quantity is first reduced over the warp with
+// shuffles (integer adds / min / max: exact and order-free), then lane 0 adds it to the CTA's
+// copy; the CTA flushes once to the global DevAccum at the end of the kernel.
+struct BlockAcc {
+  unsigned long long sums[18][2];                    // wt, sigcc, sumerr[8], sumerr2[8]
+  unsigned long long hist_w[6][SIMC_NHIST][2];
+  unsigned hist_n[9][SIMC_NHIST];                    // gen (7), RECON Em, RECON Pm
+  unsigned counters[4];                              // nsuccess, ncontribute, npasscuts, nco_no_rad_proton
+  long long mins[40], maxs[40];                      // contrib (30 used of 32) + slop (8)
+};
+
+__device__ __forceinline__ void warp_add128(unsigned long long* dst, unsigned long long lo, unsigned long long hi) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long olo = __shfl_down_sync(0xffffffffu, lo, off);
+    const unsigned long long ohi = __shfl_down_sync(0xffffffffu, hi, off);
+    lo += olo;
+    hi += ohi + (lo < olo ? 1ULL : 0ULL);
+  }
+  if ((threadIdx.x & 31u) == 0 && (lo | hi)) {
+    const unsigned long long old = atomicAdd(&dst[0], lo);
+    const unsigned long long carry = (old + lo < old) ? 1ULL : 0ULL;
+    if (hi + carry) atomicAdd(&dst[1], hi + carry);
+  }
+}
+__device__ __forceinline__ void warp_sum128(unsigned long long* dst, bool valid, double x, int qexp) {
+  unsigned long long lo = 0, hi = 0;
+  if (valid) to_fixed(x, qexp, lo, hi);
+  warp_add128(dst, lo, hi);
+}
+__device__ __forceinline__ void warp_minmax(long long* mn, long long* mx, bool valid, double v) {
+  long long lo = valid ? dkey(v) : 0x7fffffffffffffffLL;
+  long long hi = valid ? dkey(v) : (long long)0x8000000000000000ULL;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = min(lo, __shfl_down_sync(0xffffffffu, lo, off));
+    hi = max(hi, __shfl_down_sync(0xffffffffu, hi, off));
+  }
+  if ((threadIdx.x & 31u) == 0) { atomicMin(mn, lo); atomicMax(mx, hi); }
+}
+__device__ __forceinline__ void warp_count_if(unsigned* dst, bool flag) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31u) == 0 && m) atomicAdd(dst, (unsigned)__popc(m));
+}
+
 __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
+  __shared__ BlockAcc B;
+  {
+    unsigned long long* w = (unsigned long long*)&B;
+    for (int i = threadIdx.x; i < (int)(sizeof(BlockAcc) / 8); i += kBlock) w[i] = 0ULL;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 40; i += kBlock) { B.mins[i] = 0x7fffffffffffffffLL; B.maxs[i] = (long long)0x8000000000000000ULL; }
+    __syncthreads();
+  }
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   DevAccum* acc = A.acc;
-  const unsigned n_in = A.counts[3];
-  const unsigned* in_list = A.lists + 2 * A.st.cap;
+  const unsigned n_in = A.counts[5];
+  const unsigned* in_list = A.lists + 4 * A.st.cap;
   const long long stride = (long long)gridDim.x * kBlock;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_in; i += stride) {
-    const unsigned slot = in_list[i];
-    // complete_recon_ev for H(e,e'p), event.f:1056-1359
-    const double r_Ein = cfg.Ebeam_vertex_ave - cfg.targ.Coulomb_ave;
-    const double reE = S.ld(F_RE_E, slot), reth = S.ld(F_RE_TH, slot), reph = S.ld(F_RE_PH, slot);
-    const double rpP = S.ld(F_RP_P, slot), rpE = S.ld(F_RP_E, slot), rpth = S.ld(F_RP_TH, slot), rpph = S.ld(F_RP_PH, slot);
-    const double reP = reE;
-    const double uex = sin(reth) * cos(reph), uey = sin(reth) * sin(reph), uez = cos(reth);
-    const double upx = sin(rpth) * cos(rpph), upy = sin(rpth) * sin(rpph), upz = cos(rpth);
-    const double nu = r_Ein - reE;
-    const double Q2 = 2 * r_Ein * reE * (1 - uez);
-    const double q = sqrt(Q2 + nu * nu);
-    const double uqx = -reP * uex / q, uqy = -reP * uey / q, uqz = (r_Ein - reP * uez) / q;
-    const double W2 = SIMC_MP * SIMC_MP + 2. * SIMC_MP * nu - Q2;
-    const double rW = sqrt(fabs(W2)) * W2 / fabs(W2);
-    const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
-    const double rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
-    const double rTrec = 0.0;
-    const double rEm = nu + cfg.targ.M - rpE - rTrec;
-    // complete_main, event.f:1363-1569
-    const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
-    double sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
-    const double sigcc_recon = sigep(r_Ein, reE, reth, Q2);
-    if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
-    const double SF_weight = 1.0;
-    double weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
-    weight = weight * 1.0;
-    // pass_cuts, simc.f:229-241 (p-arm upper delta edge uses SPedge%e%delta%max, as written)
-    const double red = S.ld(F_RCE_D, slot), rey = S.ld(F_RCE_Y, slot), rex = S.ld(F_RCE_X, slot), rez = S.ld(F_RCE_Z, slot);
-    const double rpd = S.ld(F_RCP_D, slot), rpy = S.ld(F_RCP_Y, slot), rpx = S.ld(F_RCP_X, slot), rpz = S.ld(F_RCP_Z, slot);
-    const bool pass_cuts = !(red <= (cfg.SPedge_e.delta.min + cfg.slop_MC_e_used[0]) ||
-                             red >= (cfg.SPedge_e.delta.max - cfg.slop_MC_e_used[0]) ||
-                             rey <= (cfg.SPedge_e.yptar.min + cfg.slop_MC_e_used[1]) ||
-                             rey >= (cfg.SPedge_e.yptar.max - cfg.slop_MC_e_used[1]) ||
-                             rex <= (cfg.SPedge_e.xptar.min + cfg.slop_MC_e_used[2]) ||
-                             rex >= (cfg.SPedge_e.xptar.max - cfg.slop_MC_e_used[2]) ||
-                             rpd <= (cfg.SPedge_p.delta.min + cfg.slop_MC_p_used[0]) ||
-                             rpd >= (cfg.SPedge_e.delta.max - cfg.slop_MC_p_used[0]) ||
-                             rpy <= (cfg.SPedge_p.yptar.min + cfg.slop_MC_p_used[1]) ||
-                             rpy >= (cfg.SPedge_p.yptar.max - cfg.slop_MC_p_used[1]) ||
-                             rpx <= (cfg.SPedge_p.xptar.min + cfg.slop_MC_p_used[2]) ||
-                             rpx >= (cfg.SPedge_p.xptar.max - cfg.slop_MC_p_used[2]));
-    bool success = true;
-    if (cfg.hard_cuts) {
-      if (!pass_cuts) success = false;
-      if (cfg.doing_eep && (rEm > cfg.cuts_Em.max)) success = false;
+  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    const bool active = i < n_in;
+    bool success = false, pass_cuts = false, no_rad_p = false;
+    double weight = 0, sigcc = 0, rEm = 0, rPm = 0;
+    double rec_vals[6] = {0, 0, 0, 0, 0, 0}, gen_vals[7] = {0, 0, 0, 0, 0, 0, 0}, err[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double cv[30], sv[8];
+#pragma unroll
+    for (int k = 0; k < 30; ++k) cv[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sv[k] = 0;
+    if (active) {
+      const unsigned slot = in_list[i];
+      // complete_recon_ev for H(e,e'p), event.f:1056-1359
+      const double r_Ein = cfg.Ebeam_vertex_ave - cfg.targ.Coulomb_ave;
+      const double reE = S.ld(F_RE_E, slot), reth = S.ld(F_RE_TH, slot), reph = S.ld(F_RE_PH, slot);
+      const double rpP = S.ld(F_RP_P, slot), rpE = S.ld(F_RP_E, slot), rpth = S.ld(F_RP_TH, slot), rpph = S.ld(F_RP_PH, slot);
+      const double reP = reE;
+      const double uex = sin(reth) * cos(reph), uey = sin(reth) * sin(reph), uez = cos(reth);
+      const double upx = sin(rpth) * cos(rpph), upy = sin(rpth) * sin(rpph), upz = cos(rpth);
+      const double nu = r_Ein - reE;
+      const double Q2 = 2 * r_Ein * reE * (1 - uez);
+      const double q = sqrt(Q2 + nu * nu);
+      const double uqx = -reP * uex / q, uqy = -reP * uey / q, uqz = (r_Ein - reP * uez) / q;
+      const double W2 = SIMC_MP * SIMC_MP + 2. * SIMC_MP * nu - Q2;
+      const double rW = sqrt(fabs(W2)) * W2 / fabs(W2);
+      const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
+      rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
+      const double rTrec = 0.0;
+      rEm = nu + cfg.targ.M - rpE - rTrec;
+      // complete_main, event.f:1363-1569
+      const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
+      sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
+      const double sigcc_recon = sigep(r_Ein, reE, reth, Q2);
+      if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
+      const double SF_weight = 1.0;
+      weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
+      weight = weight * 1.0;
+      // pass_cuts, simc.f:229-241 (p-arm upper delta edge uses SPedge%e%delta%max, as written)
+      const double red = S.ld(F_RCE_D, slot), rey = S.ld(F_RCE_Y, slot), rex = S.ld(F_RCE_X, slot), rez = S.ld(F_RCE_Z, slot);
+      const double rpd = S.ld(F_RCP_D, slot), rpy = S.ld(F_RCP_Y, slot), rpx = S.ld(F_RCP_X, slot), rpz = S.ld(F_RCP_Z, slot);
+      pass_cuts = !(red <= (cfg.SPedge_e.delta.min + cfg.slop_MC_e_used[0]) ||
+                    red >= (cfg.SPedge_e.delta.max - cfg.slop_MC_e_used[0]) ||
+                    rey <= (cfg.SPedge_e.yptar.min + cfg.slop_MC_e_used[1]) ||
+                    rey >= (cfg.SPedge_e.yptar.max - cfg.slop_MC_e_used[1]) ||
+                    rex <= (cfg.SPedge_e.xptar.min + cfg.slop_MC_e_used[2]) ||
+                    rex >= (cfg.SPedge_e.xptar.max - cfg.slop_MC_e_used[2]) ||
+                    rpd <= (cfg.SPedge_p.delta.min + cfg.slop_MC_p_used[0]) ||
+                    rpd >= (cfg.SPedge_e.delta.max - cfg.slop_MC_p_used[0]) ||
+                    rpy <= (cfg.SPedge_p.yptar.min + cfg.slop_MC_p_used[1]) ||
+                    rpy >= (cfg.SPedge_p.yptar.max - cfg.slop_MC_p_used[1]) ||
+                    rpx <= (cfg.SPedge_p.xptar.min + cfg.slop_MC_p_used[2]) ||
+                    rpx >= (cfg.SPedge_p.xptar.max - cfg.slop_MC_p_used[2]));
+      success = true;
+      if (cfg.hard_cuts) {
+        if (!pass_cuts) success = false;
+        if (cfg.doing_eep && (rEm > cfg.cuts_Em.max)) success = false;
+      }
+      S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
+      S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
+      S.st(F_STAGE, slot, success ? 4.0 : 3.0);
+      if (success) {
+        no_rad_p = S.ld(F_RADP, slot) == 0.0;
+        rec_vals[0] = red; rec_vals[1] = rey; rec_vals[2] = rex; rec_vals[3] = rpd; rec_vals[4] = rpy; rec_vals[5] = rpx;
+        const double v_ed = S.ld(F_VEDELTA, slot), v_ey = S.ld(F_VEYP, slot), v_ex = S.ld(F_VEXP, slot);
+        const double v_pd = S.ld(F_VPDELTA, slot), v_py = S.ld(F_VPYP, slot), v_px = S.ld(F_VPXP, slot);
+        const double v_Em = S.ld(F_VEM, slot), v_Pm = S.ld(F_VPM, slot), v_Trec = S.ld(F_VTREC, slot);
+        gen_vals[0] = v_ed; gen_vals[1] = v_ey; gen_vals[2] = -v_ex; gen_vals[3] = v_pd; gen_vals[4] = v_py;
+        gen_vals[5] = -v_px; gen_vals[6] = v_Em;
+        const double spe_d = S.ld(F_SPE_D, slot), spe_y = S.ld(F_SPE_Y, slot), spe_x = S.ld(F_SPE_X, slot), spe_z = S.ld(F_SPE_Z, slot);
+        const double spp_d = S.ld(F_SPP_D, slot), spp_y = S.ld(F_SPP_Y, slot), spp_x = S.ld(F_SPP_X, slot), spp_z = S.ld(F_SPP_Z, slot);
+        err[0] = red - spe_d; err[1] = rex - v_ex; err[2] = rey - v_ey; err[3] = rez - spe_z;
+        err[4] = rpd - spp_d; err[5] = rpx - v_px; err[6] = rpy - v_py; err[7] = rpz - spp_z;
+        // limits_update, event.f:1-90
+        const double Ein_shift = S.ld(F_EINSHIFT, slot), Ee_shift = S.ld(F_EESHIFT, slot);
+        const double v_pE = S.ld(F_VPE, slot);
+        const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
+        const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
+        const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
+        const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), v_eE + v_pE - Ein_shift,
+                               o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
+                               spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};
+#pragma unroll
+        for (int k = 0; k < 30; ++k) cv[k] = c_[k];
+        sv[0] = red - spe_d; sv[1] = rey - spe_y; sv[2] = rex - spe_x; sv[3] = rpd - spp_d; sv[4] = rpy - spp_y;
+        sv[5] = rpx - spp_x; sv[6] = rEm - (o_Em - Ein_shift + Ee_shift); sv[7] = fabs(rPm) - fabs(o_Pm);
+      }
     }
-    S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
-    S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
-    S.st(F_STAGE, slot, success ? 4.0 : 3.0);
-    if (!success) continue;
-    // ---- accumulation, simc.f:248-336
-    add128(acc->sigcc, sigcc, A.qexp_w);
-    atomicAdd(&acc->counters[1], 1ULL);
-    const double rec_vals[6] = {red, rey, rex, rpd, rpy, rpx};
+    // ---- accumulation, simc.f:248-336: whole warps take part, invalid lanes contribute the identity
+    if (!__any_sync(0xffffffffu, success)) continue;
+    warp_sum128(B.sums[1], success, sigcc, A.qexp_w);
+    warp_count_if(&B.counters[0], success);
+    warp_count_if(&B.counters[1], success);
+    warp_count_if(&B.counters[3], success && no_rad_p);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const int b = hist_bin(cfg.hist_axis[0][k], rec_vals[k]);
-      if (b >= 0) add128(acc->hist_w[k][b], weight, A.qexp_w);
+      const int b = success ? hist_bin(cfg.hist_axis[0][k], rec_vals[k]) : -1;
+      if (b >= 0) {          // bins differ between lanes: CTA-level 64-bit atomics with carry
+        unsigned long long lo, hi;
+        to_fixed(weight, A.qexp_w, lo, hi);
+        const unsigned long long old = atomicAdd(&B.hist_w[k][b][0], lo);
+        const unsigned long long carry = (old + lo < old) ? 1ULL : 0ULL;
+        if (hi + carry) atomicAdd(&B.hist_w[k][b][1], hi + carry);
+      }
     }
-    { const int b = hist_bin(cfg.hist_axis[0][SIMC_H_EM], rEm); if (b >= 0) atomicAdd(&acc->hist_n[0][SIMC_H_EM][b], 1ULL); }
-    { const int b = hist_bin(cfg.hist_axis[0][SIMC_H_PM], rPm); if (b >= 0) atomicAdd(&acc->hist_n[0][SIMC_H_PM][b], 1ULL); }
-    const double v_ed = S.ld(F_VEDELTA, slot), v_ey = S.ld(F_VEYP, slot), v_ex = S.ld(F_VEXP, slot);
-    const double v_pd = S.ld(F_VPDELTA, slot), v_py = S.ld(F_VPYP, slot), v_px = S.ld(F_VPXP, slot);
-    const double v_Em = S.ld(F_VEM, slot), v_Pm = S.ld(F_VPM, slot), v_Trec = S.ld(F_VTREC, slot);
-    const double gen_vals[7] = {v_ed, v_ey, -v_ex, v_pd, v_py, -v_px, v_Em};
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const int b = hist_bin(cfg.hist_axis[1][k], gen_vals[k]);
-      if (b >= 0) atomicAdd(&acc->hist_n[1][k][b], 1ULL);
+    for (int k = 0; k < 7; ++k) warp_hist_add(B.hist_n[k], success ? hist_bin(cfg.hist_axis[1][k], gen_vals[k]) : -1);
+    warp_hist_add(B.hist_n[7], success ? hist_bin(cfg.hist_axis[0][SIMC_H_EM], rEm) : -1);
+    warp_hist_add(B.hist_n[8], success ? hist_bin(cfg.hist_axis[0][SIMC_H_PM], rPm) : -1);
+    const bool pc = success && pass_cuts;
+    warp_count_if(&B.counters[2], pc);
+    if (__any_sync(0xffffffffu, pc)) {
+      warp_sum128(B.sums[0], pc, weight, A.qexp_w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        warp_sum128(B.sums[2 + k], pc, err[k], -80);
+        warp_sum128(B.sums[10 + k], pc, err[k] * err[k], -80);
+      }
     }
-    atomicAdd(&acc->counters[2], 1ULL);
-    if (S.ld(F_RADP, slot) == 0.0) atomicAdd(&acc->counters[4], 1ULL);
-    const double spe_d = S.ld(F_SPE_D, slot), spe_y = S.ld(F_SPE_Y, slot), spe_x = S.ld(F_SPE_X, slot), spe_z = S.ld(F_SPE_Z, slot);
-    const double spp_d = S.ld(F_SPP_D, slot), spp_y = S.ld(F_SPP_Y, slot), spp_x = S.ld(F_SPP_X, slot), spp_z = S.ld(F_SPP_Z, slot);
-    if (pass_cuts) {
-      atomicAdd(&acc->counters[3], 1ULL);
-      add128(acc->wt, weight, A.qexp_w);
-      const double err[8] = {red - spe_d, rex - v_ex, rey - v_ey, rez - spe_z, rpd - spp_d, rpx - v_px, rpy - v_py, rpz - spp_z};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { add128(acc->sumerr[k], err[k], -80); add128(acc->sumerr2[k], err[k] * err[k], -80); }
+    for (int k = 0; k < 30; ++k) warp_minmax(&B.mins[k], &B.maxs[k], success, cv[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) warp_minmax(&B.mins[32 + k], &B.maxs[32 + k], success, sv[k]);
+  }
+  __syncthreads();
+  // ---- flush the CTA's accumulators
+  for (int k = threadIdx.x; k < 18; k += kBlock) {
+    unsigned long long* dst = k == 0 ? acc->wt : k == 1 ? acc->sigcc : k < 10 ? acc->sumerr[k - 2] : acc->sumerr2[k - 10];
+    const unsigned long long lo = B.sums[k][0], hi = B.sums[k][1];
+    if (lo | hi) {
+      const unsigned long long old = atomicAdd(&dst[0], lo);
+      const unsigned long long carry = (old + lo < old) ? 1ULL : 0ULL;
+      if (hi + carry) atomicAdd(&dst[1], hi + carry);
     }
-    // limits_update, event.f:1-90
-    const double Ein_shift = S.ld(F_EINSHIFT, slot), Ee_shift = S.ld(F_EESHIFT, slot);
-    const double v_pE = S.ld(F_VPE, slot);
-    const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
-    const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
-    const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
-    const double cv[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), v_eE + v_pE - Ein_shift,
-                           o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
-                           spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};
-#pragma unroll
-    for (int k = 0; k < 30; ++k) upd_range(&acc->contrib_lo[k], &acc->contrib_hi[k], cv[k]);
-    const double sv[8] = {red - spe_d, rey - spe_y, rex - spe_x, rpd - spp_d, rpy - spp_y, rpx - spp_x,
-                          rEm - (o_Em - Ein_shift + Ee_shift), fabs(rPm) - fabs(o_Pm)};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) upd_range(&acc->slop_lo[k], &acc->slop_hi[k], sv[k]);
+  }
+  for (int k = threadIdx.x; k < 6 * SIMC_NHIST; k += kBlock) {
+    const unsigned long long lo = (&B.hist_w[0][0][0])[2 * k], hi = (&B.hist_w[0][0][0])[2 * k + 1];
+    if (lo | hi) {
+      unsigned long long* dst = &acc->hist_w[0][0][0] + 2 * k;
+      const unsigned long long old = atomicAdd(&dst[0], lo);
+      const unsigned long long carry = (old + lo < old) ? 1ULL : 0ULL;
+      if (hi + carry) atomicAdd(&dst[1], hi + carry);
+    }
+  }
+  for (int k = threadIdx.x; k < 9 * SIMC_NHIST; k += kBlock) {
+    const unsigned v = (&B.hist_n[0][0])[k];
+    if (!v) continue;
+    const int h = k / SIMC_NHIST, b = k % SIMC_NHIST;
+    unsigned long long* dst = h < 7 ? &acc->hist_n[1][h][b] : h == 7 ? &acc->hist_n[0][SIMC_H_EM][b] : &acc->hist_n[0][SIMC_H_PM][b];
+    atomicAdd(dst, (unsigned long long)v);
+  }
+  if (threadIdx.x < 4 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
+  for (int k = threadIdx.x; k < 40; k += kBlock) {
+    if (B.mins[k] == 0x7fffffffffffffffLL) continue;
+    if (k < 32) { atomicMin(&acc->contrib_lo[k], B.mins[k]); atomicMax(&acc->contrib_hi[k], B.maxs[k]); }
+    else { atomicMin(&acc->slop_lo[k - 32], B.mins[k]); atomicMax(&acc->slop_hi[k - 32], B.maxs[k]); }
   }
 }
 

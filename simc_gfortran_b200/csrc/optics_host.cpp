@@ -574,6 +574,10 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   }
   A.ops = P.ops;
   A.tab.n_ops = (int)P.ops.size();
+  // the loop compacts survivors after the entrance collimator: split behind its last cut
+  A.tab.split_op = 0;
+  for (int k = 0; k < (int)P.ops.size(); ++k)
+    if (P.ops[k].op == OP_CUT_OCT) A.tab.split_op = k + 1;
   return A;
 }
 

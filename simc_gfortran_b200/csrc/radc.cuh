@@ -26,20 +26,20 @@ SIMC_HD double sq(double x) { return x * x; }
 SIMC_HD double spence_approx(double ax) {
   const double bx = fabs(ax);
   if (bx <= 1) return 0.0;
-  const double l = log(bx);
+  const double l = m::log(bx);
   return -0.5 * (l * l);
 }
 
 // One interference term: inter (brem.f:216-240) and inter_prime (brem.f:581-596) share
 // amult and the two log-ratio factors.
-SIMC_HD void inter_pair(double alpha, double ar1, double ar2, double e1, double e2, double de, double& val,
+SIMC_HD_CALL void inter_pair(double alpha, double ar1, double ar2, double e1, double e2, double de, double& val,
                         double& prime) {
   const double pi = 3.141592653589793;
   const double de2 = e1 - e2;
   const double amult = -1. / (alpha * (ar1 - ar2));
-  const double l1 = log(fabs((ar1 - 1.) / ar1));
-  const double l2 = log(fabs((ar2 - 1.) / ar2));
-  double v = log(fabs((e2 / de) + ar1 * (de2 / de))) * l1 - log(fabs((e2 / de) + ar2 * (de2 / de))) * l2;
+  const double l1 = m::log(fabs((ar1 - 1.) / ar1));
+  const double l2 = m::log(fabs((ar2 - 1.) / ar2));
+  double v = m::log(fabs((e2 / de) + ar1 * (de2 / de))) * l1 - m::log(fabs((e2 / de) + ar2 * (de2 / de))) * l2;
   const double arg1 = (de2 / (e2 + ar1 * de2)) * (ar1 - 1.);
   const double arg2 = (de2 / (e2 + ar1 * de2)) * (ar1);
   const double arg3 = (de2 / (e2 + ar2 * de2)) * (ar2 - 1.);
@@ -70,7 +70,7 @@ SIMC_HD void interference(double aprod, const V4& a, const V4& b, double m_num, 
 // bremos, brem.f:344-577, with the electron along +z before scattering (k_i = (0,0,Ein)) and the
 // initial proton at rest, which is how both call sites use it (init.f:706, radc.f:600-623).
 // Energies in MeV on input.  Returns bsoft, bhard and d(bsoft)/dE (per MeV).
-SIMC_HD void bremos(double egamma, double ein, double kfx, double kfy, double kfz, double pfx, double pfy, double pfz,
+SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, double kfz, double pfx, double pfy, double pfz,
                     double pfe, bool radiate_proton, double& bsoft, double& bhard, double& dbsoft) {
   const double pi = 3.141592653589793, twopi = 2. * pi, ame = .00051099906, e2 = 1. / 137.0359895, mp = .93827231;
   const double de = egamma / 1000.;
@@ -79,16 +79,16 @@ SIMC_HD void bremos(double egamma, double ein, double kfx, double kfy, double kf
   k_f.x = kfx / 1000.; k_f.y = kfy / 1000.; k_f.z = kfz / 1000.;
   p_i.x = 0.; p_i.y = 0.; p_i.z = 0.;
   p_f.e = pfe / 1000.; p_f.x = pfx / 1000.; p_f.y = pfy / 1000.; p_f.z = pfz / 1000.;
-  // (...)**0.5 in the reference: pow(x,0.5) and sqrt(x) agree except for rare last-bit cases
+  // (...)**0.5 in the reference: m::pow(x,0.5) and sqrt(x) agree except for rare last-bit cases
   k_i.e = sqrt(k_i.x * k_i.x + k_i.y * k_i.y + k_i.z * k_i.z + ame * ame);
   k_f.e = sqrt(k_f.x * k_f.x + k_f.y * k_f.y + k_f.z * k_f.z + ame * ame);
   p_i.e = mp;
   const double q2 = -1. * (sq(k_f.e - k_i.e) - sq(k_f.x - k_i.x) - sq(k_f.y - k_i.y) - sq(k_f.z - k_i.z));
   const double ami = mp;
   const double amf = sqrt(sq(p_f.e) - sq(p_f.x) - sq(p_f.y) - sq(p_f.z));
-  const double bei = 1.e0 * (-1. / twopi) * log(k_i.e / de);
+  const double bei = 1.e0 * (-1. / twopi) * m::log(k_i.e / de);
   const double dbei = 1.e0 * (-1. / twopi) * (-1. / de);
-  const double bef = 1.e0 * (-1. / twopi) * log(k_f.e / de);
+  const double bef = 1.e0 * (-1. / twopi) * m::log(k_f.e / de);
   const double dbef = 1.e0 * (-1. / twopi) * (-1. / de);
   double bee, dbee;
   {   // e-e interference, brem.f:411-418 (its own form of ar1/ar2)
@@ -107,9 +107,9 @@ SIMC_HD void bremos(double egamma, double ein, double kfx, double kfy, double kf
   const double db = 2. * e2 * (dbei + dbef + dbee);
   double bz = 0.0, bzz = 0.0, dbz = 0.0, dbzz = 0.0;
   if (radiate_proton) {
-    const double bpi = 1.e0 * (-1. / twopi) * log(p_i.e / de);
+    const double bpi = 1.e0 * (-1. / twopi) * m::log(p_i.e / de);
     const double dbpi = 1.e0 * (-1. / twopi) * (-1. / de);
-    const double bpf = 1.e0 * (-1. / twopi) * log(p_f.e / de);
+    const double bpf = 1.e0 * (-1. / twopi) * m::log(p_f.e / de);
     const double dbpf = 1.e0 * (-1. / twopi) * (-1. / de);
     double bpp, dbpp, bepii, dbepii, bepff, dbepff, bepif, dbepif, bepfi, dbepfi;
     // alpha = ami^2+amf^2-2adot, ar uses 2 amf^2, root uses (ami*amf)^2           brem.f:430-437
@@ -134,13 +134,13 @@ SIMC_HD void bremos(double egamma, double ein, double kfx, double kfy, double kf
     dbz = 2. * e2 * (dbepii + dbepff + dbepif + dbepfi);
   }
   bsoft = b + bz + bzz;
-  bhard = -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * log(q2 / (ame * ame)));
+  bhard = -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * m::log(q2 / (ame * ame)));
   dbsoft = db + dbz + dbzz;
   dbsoft = dbsoft / 1000.;
 }
 
 // radc.f:92-116
-SIMC_HD double gamma_fn(double x) {
+SIMC_HD_CALL double gamma_fn(double x) {
   double g = 1.0;
   const int n = (int)round((x - 1) - 0.5);
   const double y = x - 1 - n;
@@ -155,17 +155,17 @@ SIMC_HD double gamma_fn(double x) {
 }
 
 // radc.f:768-821
-SIMC_HD double lambda_dave(int itail, bool doing_proton, double e1, double e2, double e3, double p3, double th) {
+SIMC_HD_CALL double lambda_dave(int itail, bool doing_proton, double e1, double e2, double e3, double p3, double th) {
   const double alpi = (1. / 137.0359895) / 3.141592653589793, Me = 0.51099906;
   double plus_term = 0.0;
   if (itail < 3) {
-    plus_term = log((1. - cos(th)) / 2.);
-    if (doing_proton) plus_term = plus_term + 2. * log(e1 / e2);
+    plus_term = m::log((1. - m::cos(th)) / 2.);
+    if (doing_proton) plus_term = plus_term + 2. * m::log(e1 / e2);
   }
-  if (itail == 1) return alpi * (2. * log(2. * e1 / Me) - 1. + plus_term);
-  if (itail == 2) return alpi * (2. * log(2. * e2 / Me) - 1. + plus_term);
+  if (itail == 1) return alpi * (2. * m::log(2. * e1 / Me) - 1. + plus_term);
+  if (itail == 2) return alpi * (2. * m::log(2. * e2 / Me) - 1. + plus_term);
   if (doing_proton) {
-    const double v = alpi * ((e3 / p3) * log((e3 + p3) / (e3 - p3)) - 2.);
+    const double v = alpi * ((e3 / p3) * m::log((e3 + p3) / (e3 - p3)) - 2.);
     return v < 0 ? 0.0 : v;
   }
   return 0.0;
@@ -178,7 +178,7 @@ struct VertexKin {     // what the radiative routines read from `vertex`
 
 // radc_init_ev + basicrad_init_ev, init.f:655-813.  Only the constants that the live branches
 // read afterwards are kept: g(0..4), c(4), c_ext(0), g_ext, hardcorfac, frac.
-SIMC_HD void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, double teff1, double teff2, RadEvDev& R) {
+SIMC_HD_CALL void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, double teff1, double teff2, RadEvDev& R) {
   const double Mp = 938.27231, euler = 0.577215665;
   R.bt[0] = cfg.etatzai * teff1;
   R.bt[1] = cfg.etatzai * teff2;
@@ -199,14 +199,14 @@ SIMC_HD void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, double
   R.g[2] = R.lambda[1] + R.bt[1];
   R.g[3] = R.lambda[2];
   R.g[0] = R.g[1] + R.g[2] + R.g[3];
-  double c_ext1 = R.bt[0] / pow(e1, R.bt[0]) / gamma_fn(1. + R.bt[0]);
-  double c_ext2 = R.bt[1] / pow(e2, R.bt[1]) / gamma_fn(1. + R.bt[1]);
+  double c_ext1 = R.bt[0] / m::pow(e1, R.bt[0]) / gamma_fn(1. + R.bt[0]);
+  double c_ext2 = R.bt[1] / m::pow(e2, R.bt[1]) / gamma_fn(1. + R.bt[1]);
   R.g_ext = R.bt[0] + R.bt[1];
   double c_ext0 = c_ext1 * c_ext2 * R.g_ext / R.bt[0] / R.bt[1];
   c_ext0 = c_ext0 * gamma_fn(1. + R.bt[0]) * gamma_fn(1. + R.bt[1]) / gamma_fn(1. + R.g_ext);
   R.c_ext0 = c_ext0;
-  double c4 = R.g[4] / pow(e1 * e2, R.g[4]) / gamma_fn(1. + R.g[4]);
-  if (R.g[3] > 0) c4 = c4 / pow(e3, R.g[4]);
+  double c4 = R.g[4] / m::pow(e1 * e2, R.g[4]) / gamma_fn(1. + R.g[4]);
+  if (R.g[3] > 0) c4 = c4 / m::pow(e3, R.g[4]);
   R.c4 = c4;
   (void)Mp; (void)euler;
   R.frac[0] = R.g[1] / R.g[0];
@@ -217,24 +217,24 @@ SIMC_HD void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, double
 // basicrad with itail=0 -> 4 (peaked basis), radc.f:3-88.  u is the uniform it draws; it is
 // only consumed when the function gets past its early returns (`drew`).
 template <class RNG>
-SIMC_HD void basicrad4(const RadEvDev& R, RNG& rng, double Egamma_lo, double Egamma_hi, double& Egamma,
+SIMC_HD_CALL void basicrad4(const RadEvDev& R, RNG& rng, double Egamma_lo, double Egamma_hi, double& Egamma,
                        double& weight) {
   Egamma = 0.0; weight = 0.0;
   const double g = R.g[4];
   if (g <= 0) { weight = 1.0; return; }
   if (Egamma_hi <= Egamma_lo || Egamma_hi <= 0) return;
-  const double power_hi = pow(Egamma_hi, g);
+  const double power_hi = m::pow(Egamma_hi, g);
   double power_lo = 0.0;
-  if (Egamma_lo > 0) power_lo = pow(Egamma_lo, g);
+  if (Egamma_lo > 0) power_lo = m::pow(Egamma_lo, g);
   const double ymin = power_lo / power_hi;
   const double y = ymin + rng.uniform() * (1. - ymin);
-  const double x = pow(y, 1. / g);
+  const double x = m::pow(y, 1. / g);
   Egamma = x * Egamma_hi;
   weight = R.c4 / g * (power_hi - power_lo);
 }
 
 // peaked_rad_weight, radc.f:523-646 (rad_flag = 0 branch; rad_flag = 1 returns basic*phi)
-SIMC_HD double peaked_rad_weight(const simc_run_config& cfg, const RadEvDev& R, const VertexKin& v, double Egamma,
+SIMC_HD_CALL double peaked_rad_weight(const simc_run_config& cfg, const RadEvDev& R, const VertexKin& v, double Egamma,
                                  double emin, double emax, double basicrad_weight) {
   const double eul = 0.577215665;
   if (cfg.rad_flag == 1) {
@@ -250,10 +250,10 @@ SIMC_HD double peaked_rad_weight(const simc_run_config& cfg, const RadEvDev& R, 
          R.rad_proton_this_ev, dsoft_intmax, dhard, dprime);
   double w;
   if (emin > 0)
-    w = R.c_ext0 / R.g_ext * (exp(-dsoft_intmax) * pow(emax, R.g_ext) - exp(-dsoft_intmin) * pow(emin, R.g_ext));
+    w = R.c_ext0 / R.g_ext * (m::exp(-dsoft_intmax) * m::pow(emax, R.g_ext) - m::exp(-dsoft_intmin) * m::pow(emin, R.g_ext));
   else
-    w = R.c_ext0 / R.g_ext * (exp(-dsoft_intmax) * pow(emax, R.g_ext));
-  w = w * exp(-eul * R.g[4]) / gamma_fn(1. + R.g[4]) * gamma_fn(1. + R.g[4] - R.bt[0] - R.bt[1]) *
+    w = R.c_ext0 / R.g_ext * (m::exp(-dsoft_intmax) * m::pow(emax, R.g_ext));
+  w = w * m::exp(-eul * R.g[4]) / gamma_fn(1. + R.g[4]) * gamma_fn(1. + R.g[4] - R.bt[0] - R.bt[1]) *
       gamma_fn(1. + R.bt[0]) * gamma_fn(1. + R.bt[1]) / gamma_fn(1. + R.g[4]);
   if (w < 0) w = 0;
   return w;

@@ -4,13 +4,39 @@
 // correction inputs) is the same for every material of one trip and is evaluated once.
 #pragma once
 #include <math.h>
+#include <cmath>
 #include "../../include/simc_b200.h"
 
 #if defined(__CUDACC__)
 #define SIMC_HD __host__ __device__ __forceinline__
+// Big routines are real functions on the device: the generation kernel inlined to 1.4 MB of SASS
+// and stalled on instruction fetch (profiles/r1_notes.md); called code keeps it inside the i-cache.
+#define SIMC_HD_CALL static __host__ __device__ __noinline__
 #else
 #define SIMC_HD inline
+#define SIMC_HD_CALL static inline
 #endif
+
+// libm entry points as out-of-line device functions (each inlined pow/sin/cos/acos is 1-3 KB of SASS)
+namespace simc {
+namespace m {
+#if defined(__CUDA_ARCH__)
+#define SIMC_MATH1(name) static __device__ __noinline__ double name(double x) { return ::name(x); }
+#else
+#define SIMC_MATH1(name) static inline double name(double x) { return std::name(x); }
+#endif
+SIMC_MATH1(log) SIMC_MATH1(log10) SIMC_MATH1(exp) SIMC_MATH1(sin) SIMC_MATH1(cos) SIMC_MATH1(tan)
+SIMC_MATH1(acos) SIMC_MATH1(atan)
+#undef SIMC_MATH1
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ double pow(double x, double y) { return ::pow(x, y); }
+static __device__ __noinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+#else
+static inline double pow(double x, double y) { return std::pow(x, y); }
+static inline double atan2(double y, double x) { return std::atan2(y, x); }
+#endif
+}  // namespace m
+}  // namespace simc
 
 namespace simc {
 
@@ -31,14 +57,14 @@ SIMC_HD ParticleKin particle_kin(double epart, double mpart) {
   k.gamma = epart / mpart;
   k.beta = sqrt(1. - 1. / (k.gamma * k.gamma));
   k.beta2 = k.beta * k.beta;
-  k.log10bg = log(k.beta * k.gamma) / log(10.);
-  k.two_log_gb = 2. * log(k.gamma * k.beta);
+  k.log10bg = m::log(k.beta * k.gamma) / m::log(10.);
+  k.two_log_gb = 2. * m::log(k.gamma * k.beta);
   return k;
 }
 
 // enerloss_new.f:30-85.  x = |gauss1(10)| for typeflag 1 (drawn by the caller, only when
 // thick > 0 -- the reference draws inside the thick>0 branch), 3 / 0.0067 / 1 for 2 / 3 / 4.
-SIMC_HD double enerloss_material(const ParticleKin& k, double len, double dens, double zeff, double aeff, double x) {
+SIMC_HD_CALL double enerloss_material(const ParticleKin& k, double len, double dens, double zeff, double aeff, double x) {
   const double me = 0.51099906;
   const double thick = len * dens;
   double eloss;
@@ -47,23 +73,23 @@ SIMC_HD double enerloss_material(const ParticleKin& k, double len, double dens, 
   } else {
     double I;
     if (zeff == 1) I = 21.8e-06;
-    else I = (16. * pow(zeff, 0.9)) * 1.0e-06;
+    else I = (16. * m::pow(zeff, 0.9)) * 1.0e-06;
     const double hnup = 28.816e-06 * sqrt(dens * zeff / aeff);
-    const double CO = log(hnup) - log(I) + 0.5;
+    const double CO = m::log(hnup) - m::log(I) + 0.5;
     double denscorr;
     if (k.log10bg < 0.) denscorr = 0.;
     else if (k.log10bg < 3.) {
       const double d = 3. - k.log10bg;
-      denscorr = CO + log(10.) * k.log10bg + fabs(CO / 27.) * (d * (d * d));
-    } else if (k.log10bg < 4.7) denscorr = CO + log(10.) * k.log10bg;
-    else denscorr = CO + log(10.) * 4.7;
+      denscorr = CO + m::log(10.) * k.log10bg + fabs(CO / 27.) * (d * (d * d));
+    } else if (k.log10bg < 4.7) denscorr = CO + m::log(10.) * k.log10bg;
+    else denscorr = CO + m::log(10.) * 4.7;
     const double eloss_mp_new = 0.1536e-03 * zeff / aeff * thick / k.beta2 *
-                                (log(me / (I * I)) + 1.063 + k.two_log_gb +
-                                 log(0.1536 * zeff / aeff * thick / k.beta2) - k.beta2 - denscorr);
+                                (m::log(me / (I * I)) + 1.063 + k.two_log_gb +
+                                 m::log(0.1536 * zeff / aeff * thick / k.beta2) - k.beta2 - denscorr);
     const double eloss_mp = eloss_mp_new * 1000.;
     const double chsi = 0.307075 / 2. * zeff / aeff * thick / k.beta2;
     double lambda;
-    if (x > 0.0) lambda = -2.0 * log(x);
+    if (x > 0.0) lambda = -2.0 * m::log(x);
     else lambda = 100000.;
     eloss = lambda * chsi + eloss_mp;
   }
@@ -87,35 +113,35 @@ SIMC_HD ArmWindows arm_windows(int arm) {
 }
 
 // Path lengths of trip_thru_target for an outgoing particle (narm = 2 or 3): target.f:102-168
-SIMC_HD void outgoing_paths(const simc_target& targ, const ArmWindows& w, double zpos, double theta, double& s_target,
+SIMC_HD_CALL void outgoing_paths(const simc_target& targ, const ArmWindows& w, double zpos, double theta, double& s_target,
                             double& s_Al) {
   const double inch_cm = 2.54, target_pi = 3.14159265358979;
   s_Al = w.s_Al;
   const double forward_path =
-      (targ.length / 2. - zpos) / fabs(cos(w.plus_angle ? theta + targ.angle : theta - targ.angle));
+      (targ.length / 2. - zpos) / fabs(m::cos(w.plus_angle ? theta + targ.angle : theta - targ.angle));
   s_target = forward_path;
   if (targ.Z < 2.4) {
     if (targ.can == 1) {
-      const double side_path = 1.325 * inch_cm / fabs(sin(theta));
+      const double side_path = 1.325 * inch_cm / fabs(m::sin(theta));
       if (forward_path < side_path) {
-        s_Al = s_Al + 0.005 * inch_cm / fabs(cos(theta));
+        s_Al = s_Al + 0.005 * inch_cm / fabs(m::cos(theta));
       } else {
         s_target = side_path;
-        s_Al = s_Al + 0.005 * inch_cm / fabs(sin(theta));
+        s_Al = s_Al + 0.005 * inch_cm / fabs(m::sin(theta));
       }
     } else if (targ.can == 2) {
-      const double tt = tan(theta);
+      const double tt = m::tan(theta);
       const double t = tt * tt;
       const double atmp = 1 + t;
       const double btmp = -2 * zpos * t;
       const double hl = targ.length / 2.;
       const double ctmp = zpos * zpos * t - hl * hl;
       const double z_can = (-btmp + sqrt(btmp * btmp - 4. * atmp * ctmp)) / 2. / atmp;
-      s_target = (z_can - zpos) / fabs(cos(theta));
+      s_target = (z_can - zpos) / fabs(m::cos(theta));
       const double costmp = z_can / (targ.length / 2.);
       double th_can = 0.;
-      if (fabs(costmp) <= 1) th_can = acos(z_can / (targ.length / 2.));
-      s_Al = s_Al + 0.0050 * inch_cm / fabs(sin(target_pi / 2 - (theta - th_can)));
+      if (fabs(costmp) <= 1) th_can = m::acos(z_can / (targ.length / 2.));
+      s_Al = s_Al + 0.0050 * inch_cm / fabs(m::sin(target_pi / 2 - (theta - th_can)));
     } else if (targ.can == 3) {
       const double ecir = 1.315 * 2.54;
       const double ecor = (1.315 + 0.0071) * 2.54;
@@ -123,12 +149,12 @@ SIMC_HD void outgoing_paths(const simc_target& targ, const ArmWindows& w, double
       const double twall = ecor - ecir;
       const double tcm = zpos + targ.length / 2.0;
       double tliquid, tal;
-      if ((tcm + ecir / tan(theta)) < entec) {
-        tliquid = ecir / sin(theta);
-        tal = twall / sin(theta);
+      if ((tcm + ecir / m::tan(theta)) < entec) {
+        tliquid = ecir / m::sin(theta);
+        tal = twall / m::sin(theta);
       } else {
-        const double u = (targ.length - ecir - tcm) * sin(theta);
-        tliquid = (sqrt(ecir * ecir - u * u) + (targ.length - ecir - tcm) * cos(theta));
+        const double u = (targ.length - ecir - tcm) * m::sin(theta);
+        tliquid = (sqrt(ecir * ecir - u * u) + (targ.length - ecir - tcm) * m::cos(theta));
         tal = +(sqrt(ecor * ecor - u * u) - sqrt(ecir * ecir - u * u)) * twall / (ecor - ecir);
       }
       s_Al = s_Al + tal;
@@ -141,7 +167,7 @@ SIMC_HD void outgoing_paths(const simc_target& targ, const ArmWindows& w, double
 SIMC_HD void incoming_paths(const simc_target& targ, double zpos, double& s_target, double& s_Al) {
   const double inch_cm = 2.54;
   s_Al = 0.0;
-  s_target = (targ.length / 2. + zpos) / fabs(cos(targ.angle));
+  s_target = (targ.length / 2. + zpos) / fabs(m::cos(targ.angle));
   if (targ.Z < 2.4) {
     if (targ.can == 1) s_Al = s_Al + 0.0028 * inch_cm;
     else if (targ.can == 2) s_Al = s_Al + 0.0050 * inch_cm;
@@ -152,7 +178,7 @@ SIMC_HD void incoming_paths(const simc_target& targ, double zpos, double& s_targ
 // trip_thru_target with a fixed typeflag 2/3/4 (no random numbers): used for the most-probable
 // energy-loss correction (simc.f:1637-1645) and by the host-side init (init.f:44-56,
 // target.f:310-544).  arm = spectrometer id for narm 2/3, ignored for narm 1.
-SIMC_HD void trip_thru_target_fixed(const simc_target& targ, int narm, int arm, double zpos, double energy,
+SIMC_HD_CALL void trip_thru_target_fixed(const simc_target& targ, int narm, int arm, double zpos, double energy,
                                     double theta, double mass, int typeflag, double& Eloss, double& radlen) {
   const Material al = SIMC_MAT_AL;
   const ParticleKin k = particle_kin(energy, mass);

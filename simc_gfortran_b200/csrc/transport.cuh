@@ -13,6 +13,7 @@
 #include <math.h>
 #include "arm_program.h"
 #include "philox.cuh"
+#include "target.cuh"
 
 #ifndef SIMC_STRICT
 #define SIMC_STRICT 1
@@ -56,19 +57,26 @@ struct ArmResult {
 #define SIMC_MMU 105.6583755
 #define SIMC_PI 3.141592653589793
 
-// gauss1.f:1-30
-__device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
-  for (;;) {
-    const double u1 = r.uniform();
-    const double u2 = r.uniform();
-    const double v1 = 2.0 * u1 - 1.0;
-    const double v2 = 2.0 * u2 - 1.0;
-    const double s = v1 * v1 + v2 * v2;
-    if (s > 1. || s == 0.) continue;
-    const double g = v1 * sqrt(-2. * log(s) / s);
-    if (fabs(g) > nsigmax) continue;
-    return g;
+// gauss1.f:1-30.  The rejection loop is run warp-synchronously: the lanes that called together
+// iterate together until each has its value, so they leave the function converged.
+__device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
+  const unsigned mask = __activemask();
+  double g = 0.0;
+  bool need = true;
+  while (__any_sync(mask, need)) {
+    if (need) {
+      const double u1 = r.uniform();
+      const double u2 = r.uniform();
+      const double v1 = 2.0 * u1 - 1.0;
+      const double v2 = 2.0 * u2 - 1.0;
+      const double s = v1 * v1 + v2 * v2;
+      if (!(s > 1. || s == 0.)) {
+        g = v1 * sqrt(-2. * m::log(s) / s);
+        if (!(fabs(g) > nsigmax)) need = false;
+      }
+    }
   }
+  return g;
 }
 
 __device__ __forceinline__ void musc_refresh(TrackDev& t) {
@@ -92,7 +100,7 @@ __device__ __noinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_sp
                                              double kaon_pipi_mfinal) {
   const double rph = r.uniform() * 2. * SIMC_PI;
   const double rth1 = r.uniform() * 2. - 1.;
-  const double rth = acos(rth1);
+  const double rth = m::acos(rth1);
   double pr = 0.;
   double m_final = SIMC_MMU;
   const double m = sqrt(t.m2);
@@ -107,9 +115,9 @@ __device__ __noinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_sp
   }
   // pr == 0 is a fatal `stop` in the reference; the host refuses decay_flag for other masses.
   const double er = sqrt(m_final * m_final + pr * pr);
-  const double pxr = pr * sin(rth) * cos(rph);
-  const double pyr = pr * sin(rth) * sin(rph);
-  const double pzr = pr * cos(rth);
+  const double pxr = pr * m::sin(rth) * m::cos(rph);
+  const double pyr = pr * m::sin(rth) * m::sin(rph);
+  const double pzr = pr * m::cos(rth);
   const double nrm = sqrt(1. + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
   const double bx = -beta * t.dxdzs / nrm;
   const double by = -beta * t.dydzs / nrm;
@@ -131,7 +139,7 @@ __device__ __noinline__ void project_decay(TrackDev& t, DevRng& r, double z_drif
   const double beta = t.p / sqrt(t.p * t.p + t.m2);
   const double gamma = 1. / sqrt(1. - beta * beta);
   const double dlen = t.ctau * beta * gamma;
-  const double z_decay = -1. * dlen * log(1 - r.uniform());
+  const double z_decay = -1. * dlen * m::log(1 - r.uniform());
   if (z_decay > z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs)) {
     t.decdist = t.decdist + z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
     t.pathlen = t.pathlen + z_drift * sqrt(1 + t.dxdzs * t.dxdzs + t.dydzs * t.dydzs);
@@ -203,7 +211,7 @@ __device__ __forceinline__ void poly_group(unsigned long long masks, const doubl
 
 // Evaluates one compiled map at v = (v1..v5); pw = this thread's column of the shared power table.
 template <int NOUT>
-__device__ __forceinline__ void eval_poly(const PolyClass& pc, const unsigned long long* __restrict__ hdr,
+__device__ __noinline__ void eval_poly(const PolyClass& pc, const unsigned long long* __restrict__ hdr,
                                           const double* __restrict__ coef, const double (&v)[5], double* pw,
                                           double (&sum)[NOUT]) {
   double xp[7], tp[7];
@@ -250,7 +258,7 @@ __device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t,
     beta = t.p / sqrt(t.p * t.p + t.m2);
     gamma = 1. / sqrt(1. - beta * beta);
     const double dlen = t.ctau * beta * gamma;
-    z_decay = -1. * dlen * log(1 - r.uniform());
+    z_decay = -1. * dlen * m::log(1 - r.uniform());
     if (z_decay <= zd / 2) {
       t.dflag = true;
       t.decdist = t.decdist + z_decay;
@@ -290,7 +298,7 @@ __device__ __forceinline__ bool hms_hit_dipole(double x, double y) {
 }
 
 // cern/lfit.f:11-61 with KEY=0: REAL*4 points, sums in 8-byte reals
-__device__ __forceinline__ void lfit12(const float* z, const float* y, float& a, float& b) {
+__device__ __noinline__ void lfit12(const float* z, const float* y, float& a, float& b) {
   a = 0.f; b = 0.f;
   double count = 0., sumx = 0., sumy = 0., sumxy = 0., sumxx = 0.;
   for (int j = 0; j < 12; ++j) {
@@ -312,34 +320,61 @@ __device__ __forceinline__ void lfit12(const float* z, const float* y, float& a,
   b = (float)(ymed - (double)a * xmed);
 }
 
+// Adds the number of currently converged lanes to *counter with one atomic (all of them are at
+// the same warp-uniform place of the arm program).
+__device__ __forceinline__ void warp_count(unsigned* counter) {
+  const unsigned m = __activemask();
+  if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(counter, (unsigned)__popc(m));
+}
+// Histogram increment aggregated over the lanes that hit the same bin (bin < 0: no increment).
+__device__ __forceinline__ void warp_hist_add(unsigned* hist, int bin) {
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, bin);
+  if (bin >= 0 && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+}
+
 struct ArmFlags {
   bool ms_flag, wcs_flag, decay_flag, using_coll;
 };
 
-// Interprets the arm program for one event.  `pw` = this thread's column of the CTA's shared
-// power table.  On return `t` holds the track at the last plane reached; res.ok is ok_spec.
-__device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& rng, const ArmFlags f,
-                                        double fry, double* pw, ArmResult& res) {
+// Hut state that has to survive from the drift-chamber planes to the fit (REAL*4 in the reference)
+struct HutState {
+  float xdc[12], ydc[12];
+  int scincount;
+};
+
+__device__ __forceinline__ void arm_result_clear(ArmResult& res) {
   res.ok = false; res.stop_code = 0; res.reached_hut = false; res.resmult = 0.0;
   res.x_fp = res.dx_fp = res.y_fp = res.dy_fp = 0.0;
   res.dpp_rec = res.dth_rec = res.dph_rec = res.y_rec = 0.0;
-  t.dflag = false;
-  musc_refresh(t);
+}
+
+// Interprets ops [op_begin, op_end) of the arm program.  EVERY lane of the warp must call this
+// (lanes without an event pass alive = false): the warp walks the program in lock step and
+// re-converges before each op, so a lane only idles while other lanes still have work in the same
+// op.  `alive` comes back false when the event stopped (res.stop_code) or finished (res.ok).
+// `pw` = this thread's column of the CTA's shared power table.
+__device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& rng, const ArmFlags f,
+                                        double fry, double* pw, ArmResult& res, HutState& hs, bool& alive,
+                                        int op_begin, int op_end, unsigned* call_counts = nullptr) {
   double xt = 0., yt = 0.;
-  float xdc[12], ydc[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
-  int scincount = 0;
-  const int n_ops = arm->tab.n_ops;
-  for (int pc = 0; pc < n_ops; ++pc) {
+  for (int pc = op_begin; pc < op_end; ++pc) {
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, alive)) break;
     const ArmOp* __restrict__ o = &arm->ops[pc];
     const int op = __ldg(&o->op);
+    if (op == OP_END) break;
+    if (!alive) continue;
     const double a = __ldg(&o->a), b = __ldg(&o->b), c = __ldg(&o->c), d = __ldg(&o->d);
     bool stop = false;
     switch (op) {
-      case OP_END: pc = n_ops; break;
       case OP_PROJECT: project(t, rng, a, f.decay_flag); break;
-      case OP_TRANSP: transp(arm, t, rng, __ldg(&o->i0), a, f.decay_flag, pw); break;
+      case OP_TRANSP: {
+        const int klass = __ldg(&o->i0);
+        if (call_counts) warp_count(&call_counts[klass - 1]);
+        transp(arm, t, rng, klass, a, f.decay_flag, pw);
+        break;
+      }
       case OP_CUT_R2: stop = (t.xs * t.xs + t.ys * t.ys) > a; break;
       case OP_CUT_ABS_Y: stop = fabs(t.ys - a) > b; break;
       case OP_CUT_ABS_X: stop = fabs(t.xs - a) > b; break;
@@ -374,14 +409,14 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
       case OP_RESMULT_ONE: res.resmult = 1.0; break;
       case OP_MUSC:        // musc.f:46-55, called as musc(m2,p,radw,dydzs,dxdzs)
         if (f.ms_flag && a != 0.) {
-          const double ts = t.mc1 * b * (1 + 0.088 * log10(a / t.mbeta2));
+          const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           t.dydzs = t.dydzs + ts * gauss1(rng, 99.0);
           t.dxdzs = t.dxdzs + ts * gauss1(rng, 99.0);
         }
         break;
       case OP_MUSC_EXT:    // musc_ext.f:37-51, called as musc_ext(m2,p,radw,drift,dydzs,dxdzs,ys,xs)
         if (f.ms_flag && a != 0.) {
-          const double ts = t.mc1 * b * (1 + 0.088 * log10(a / t.mbeta2));
+          const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           double g1 = gauss1(rng, 99.0);
           double g2 = gauss1(rng, 99.0);
           t.dxdzs = t.dxdzs + ts * g1;
@@ -396,13 +431,13 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         double r1 = 0., r2 = 0.;
         if (f.wcs_flag) { r1 = gauss1(rng, 99.0); r2 = gauss1(rng, 99.0); }
         const int ip = __ldg(&o->i0);
-        if (__ldg(&o->i1)) { ydc[ip] = (float)(t.ys + a * r2 * res.resmult); xdc[ip] = 0.f; }
-        else { xdc[ip] = (float)(t.xs + a * r1 * res.resmult); ydc[ip] = 0.f; }
+        if (__ldg(&o->i1)) { hs.ydc[ip] = (float)(t.ys + a * r2 * res.resmult); hs.xdc[ip] = 0.f; }
+        else { hs.xdc[ip] = (float)(t.xs + a * r1 * res.resmult); hs.ydc[ip] = 0.f; }
         break;
       }
       case OP_CUT_BOX: stop = (t.xs > a) || (t.xs < b) || (t.ys > c) || (t.ys < d); break;
-      case OP_SCIN_COUNT: if (t.ys < a && t.ys > b && t.xs < c && t.xs > d) ++scincount; break;
-      case OP_SCIN_TRIG: stop = scincount < __ldg(&o->i0); break;
+      case OP_SCIN_COUNT: if (t.ys < a && t.ys > b && t.xs < c && t.xs > d) ++hs.scincount; break;
+      case OP_SCIN_TRIG: stop = hs.scincount < __ldg(&o->i0); break;
       case OP_LFIT: {      // mc_hms_hut.f:438-455
         float zdc[12];
 #pragma unroll
@@ -411,8 +446,8 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
           zdc[j] = (float)((j < 6 ? a : b) + (iplane - 0.5 - 0.5 * 6) * c);
         }
         float dx4, x4, dy4, y4;
-        lfit12(zdc, xdc, dx4, x4);
-        lfit12(zdc, ydc, dy4, y4);
+        lfit12(zdc, hs.xdc, dx4, x4);
+        lfit12(zdc, hs.ydc, dy4, y4);
         res.x_fp = (double)x4; res.dx_fp = (double)dx4; res.y_fp = (double)y4; res.dy_fp = (double)dy4;
         break;
       }
@@ -432,12 +467,14 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         hut[4] = fry / 100.;
         if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
         double sum[4];
+        if (call_counts) warp_count(&call_counts[47]);
         eval_poly<4>(arm->tab.rec, arm->tab.hdr, arm->tab.coef, hut, pw, sum);
         res.dph_rec = sum[0];
         res.y_rec = sum[1] * 100.;
         res.dth_rec = sum[2];
         res.dpp_rec = sum[3] * 100.;
         res.ok = true;
+        alive = false;
         break;
       }
       case OP_UNSUPPORTED:
@@ -446,8 +483,9 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         break;
       default: break;
     }
-    if (stop) { res.stop_code = __ldg(&o->code); return; }
+    if (stop) { res.stop_code = __ldg(&o->code); alive = false; }
   }
+  __syncwarp();
 }
 
 }  // namespace SIMC_VARIANT_NS

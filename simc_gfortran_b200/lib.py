@@ -136,7 +136,8 @@ class Accum(C.Structure):
                 ("hist_w", (Fixed128 * NHIST) * 6),
                 ("hist_n", ((C.c_int64 * NHIST) * H_PER_SET) * 3),
                 ("contrib", Range * 32), ("slop", Range * 8),
-                ("stop", (C.c_int64 * NSTOP) * 2)]
+                ("stop", (C.c_int64 * NSTOP) * 2),
+                ("transp_calls", (C.c_int64 * 48) * 2)]
 
 
 _lib = None
@@ -187,6 +188,8 @@ def load_library():
                                              C.c_int]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.simc_b200_stage_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.simc_b200_fp64_peak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "simc_b200_event_field_name"):
         L.simc_b200_event_field_name.restype = C.c_char_p
         L.simc_b200_event_field_name.argtypes = [C.c_int]
@@ -316,6 +319,18 @@ class Simc:
 
     def set_batch(self, tries_per_batch: int):
         self._check(self.L.simc_b200_set_batch(self.h, tries_per_batch))
+
+    def stage_times(self, enable: bool = True):
+        """(ms[4], launches[4]) of generate / hadron arm / electron arm / finish since the last call."""
+        ms = (C.c_double * 4)()
+        nl = (C.c_int64 * 4)()
+        self._check(self.L.simc_b200_stage_times(self.h, int(enable), ms, nl))
+        return list(ms), list(nl)
+
+    def fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.L.simc_b200_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def run_async(self, first_try: int, n_tries: int, seed: int):
         self._check(self.L.simc_b200_run_async(self.h, first_try, n_tries, seed))

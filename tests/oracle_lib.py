@@ -110,13 +110,14 @@ class Oracle:
         return out
 
 
-def _oracle_run(self, cfg, first, n, seed, threads=1):
-    """The loop of simc.f:169-351 on the CPU oracle; returns a simc_gfortran_b200.Accum."""
+def _oracle_run(self, cfg, first, n, seed, threads=1, ranlux=False):
+    """The loop of simc.f:169-351 on the CPU oracle; returns a simc_gfortran_b200.Accum.
+    ranlux=True uses the reference's RANLUX stream (one generator per thread) instead of Philox."""
     from simc_gfortran_b200.lib import Accum
     acc = Accum()
     self._check(self.L.oracle_accum_clear(C.byref(cfg), C.byref(acc)))
-    self._check(self.L.oracle_run(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), int(threads),
-                                  C.byref(acc)))
+    self._check(self.L.oracle_run_rng(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), int(threads),
+                                      int(bool(ranlux)), C.byref(acc)))
     return acc
 
 

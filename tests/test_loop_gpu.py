@@ -139,6 +139,7 @@ def accum_equal_exact(a: Accum, b: Accum):
         assert getattr(a, f) == getattr(b, f), f
     assert np.array_equal(np.ctypeslib.as_array(a.hist_n), np.ctypeslib.as_array(b.hist_n))
     assert np.array_equal(np.ctypeslib.as_array(a.stop), np.ctypeslib.as_array(b.stop))
+    assert np.array_equal(np.ctypeslib.as_array(a.transp_calls), np.ctypeslib.as_array(b.transp_calls))
 
 
 def test_accumulators_against_oracle(sim, orc, cfg):
