@@ -51,10 +51,11 @@ constexpr int kMaxClasses = 41;       // max_class, spectrometers.inc:6
 
 // One COSY map compiled into "groups": a run of consecutive file terms that share the
 // exponents of variables 3,4,5 and the degree m = e1+e2, with e2 strictly increasing.  The
-// group header packs e3,e4,e5,m (3 bits each) and, for k = e2 = 0..6, the 5-bit mask of
-// outputs whose coefficient is non-zero (0 = term absent).  Coefficients follow in (k, output)
-// order.  File order is preserved, so every output's sum sees its terms in the reference's
-// order; terms with a zero coefficient add exactly 0 in the reference and are skipped here.
+// group header packs e3,e4,e5,m (3 bits each), a 7-bit mask of the k = e2 values present, and the
+// group's output pattern (union of the outputs with a non-zero coefficient, 5 bits).  One
+// coefficient per (present k, output of the pattern) follows in that order.  File order is
+// preserved, so every output's sum sees its terms in the reference's order; terms whose
+// coefficients are all zero add exactly 0 in the reference and are skipped here.
 struct PolyClass {
   int32_t group_begin, group_end;   // into hdr[]
   int32_t coef_begin;               // into coef[]

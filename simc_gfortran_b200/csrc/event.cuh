@@ -113,174 +113,205 @@ SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng,
   Eloss = e1 + e2 + e3 + e4 + e5;
 }
 
+// The generation code is one long straight line (no hot loop): if the warps of an SM drift apart
+// in it, each of them streams >100 KB of SASS through the instruction cache on its own and the
+// kernel stalls on instruction fetch (profiles/r1_notes.md).  SIMC_PHASE() re-aligns the warps of
+// the CTA between phases, so every thread of the CTA MUST walk through generate_hyd_elast /
+// complete_ev_hyd_elast, whether it has a live event or not (`run` guards the work).
+#if defined(__CUDA_ARCH__)
+#define SIMC_PHASE() __syncthreads()
+#else
+#define SIMC_PHASE() ((void)0)
+#endif
+
 // complete_ev for H(e,e'p), event.f:432-1052.  Needs v_Ein, v_eyptar/xptar/theta/phi, tz; fills
 // the rest of the vertex, the jacobian, Eloss/teff(2:3) and the radiative constants.
 template <class RNG, class GAUSS>
-SIMC_HD_CALL bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
+SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool run) {
   const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
-  s.jacobian = 1.0;
-  s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
-  s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
-  s.uez = m::cos(s.v_etheta);
-  s.v_eE = s.v_Ein * Mh / (Mh + s.v_Ein * (1. - s.uez));
-  if (s.v_eE > s.v_Ein) return false;
-  const double eP = s.v_eE;
-  s.v_edelta = (eP - cfg.spec_e.P) * 100. / cfg.spec_e.P;
-  const double nu = s.v_Ein - s.v_eE;
-  s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
-  const double q = sqrt(s.v_Q2 + nu * nu);
-  const double uqx = -eP * s.uex / q;
-  const double uqy = -eP * s.uey / q;
-  const double uqz = (s.v_Ein - eP * s.uez) / q;
-  // |uq|^2-1 > 0.01 is a fatal `stop` in the reference (event.f:538); it cannot trigger here
-  s.v_Em = 0.0;
-  s.v_Pm = 0.0;
-  s.upx = uqx; s.upy = uqy; s.upz = uqz;
-  s.v_pP = q;
-  s.v_ptheta = m::acos(s.upz);
-  s.v_pphi = m::atan2(s.upy, s.upx);
-  if (s.v_pphi < 0.) s.v_pphi = s.v_pphi + 2. * SIMC_PI_D;
-  spectrometer_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
-  s.v_pE = sqrt(s.v_pP * s.v_pP + Mh2);
-  s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
-  s.v_Trec = 0.0;
-  const double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
-  s.jacobian = s.jacobian / (r * (r * r));
+  if (run) {
+    s.jacobian = 1.0;
+    s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
+    s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
+    s.uez = m::cos(s.v_etheta);
+    s.v_eE = s.v_Ein * Mh / (Mh + s.v_Ein * (1. - s.uez));
+    if (s.v_eE > s.v_Ein) run = false;
+  }
+  if (run) {
+    const double eP = s.v_eE;
+    s.v_edelta = (eP - cfg.spec_e.P) * 100. / cfg.spec_e.P;
+    const double nu = s.v_Ein - s.v_eE;
+    s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
+    const double q = sqrt(s.v_Q2 + nu * nu);
+    const double uqx = -eP * s.uex / q;
+    const double uqy = -eP * s.uey / q;
+    const double uqz = (s.v_Ein - eP * s.uez) / q;
+    // |uq|^2-1 > 0.01 is a fatal `stop` in the reference (event.f:538); it cannot trigger here
+    s.v_Em = 0.0;
+    s.v_Pm = 0.0;
+    s.upx = uqx; s.upy = uqy; s.upz = uqz;
+    s.v_pP = q;
+    s.v_ptheta = m::acos(s.upz);
+    s.v_pphi = m::atan2(s.upy, s.upx);
+    if (s.v_pphi < 0.) s.v_pphi = s.v_pphi + 2. * SIMC_PI_D;
+    spectrometer_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
+    s.v_pE = sqrt(s.v_pP * s.v_pP + Mh2);
+    s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+    s.v_Trec = 0.0;
+    const double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+  }
   const double zpos = s.tz - cfg.targ.zoffset;
-  trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
-  trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
-  if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
-  VertexKin v;
-  v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = eP; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
-  v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
-  radc_init_ev(cfg, v, s.teff[0], s.teff[1], s.rad);
-  return true;
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
+  SIMC_PHASE();
+  if (run) {
+    if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    radc_init_ev(cfg, v, s.teff[0], s.teff[1], s.rad);
+  }
+  SIMC_PHASE();
+  return run;
 }
 
-// generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519
+// generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519.  `ok` in: the thread has
+// a try to generate; returns success.
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s) {
+SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
-  s.tx = gauss(rng, 3.0) * cfg.gen.xwid + targ.xoffset;
-  s.ty = gauss(rng, 3.0) * cfg.gen.ywid + targ.yoffset;
-  double t3, t4, t5, t6;
-  if (targ.fr_pattern == 1) {
-    t3 = rng.uniform() * SIMC_PI_D;
-    t4 = rng.uniform() * SIMC_PI_D;
-    t5 = m::cos(t3) * targ.fr1;
-    t6 = m::cos(t4) * targ.fr2;
-  } else if (targ.fr_pattern == 2) {
-    t3 = rng.uniform() * 2. * SIMC_PI_D;
-    t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
-    t5 = m::cos(t3) * t4;
-    t6 = m::sin(t3) * t4;
-  } else if (targ.fr_pattern == 3) {
-    t3 = 2. * rng.uniform() - 1.0;
-    t4 = 2. * rng.uniform() - 1.0;
-    t5 = targ.fr1 * t3;
-    t6 = targ.fr2 * t4;
-  } else {
-    t5 = 0.0; t6 = 0.0;
+  if (ok) {
+    s.tx = gauss(rng, 3.0) * cfg.gen.xwid + targ.xoffset;
+    s.ty = gauss(rng, 3.0) * cfg.gen.ywid + targ.yoffset;
+    double t3, t4, t5, t6;
+    if (targ.fr_pattern == 1) {
+      t3 = rng.uniform() * SIMC_PI_D;
+      t4 = rng.uniform() * SIMC_PI_D;
+      t5 = m::cos(t3) * targ.fr1;
+      t6 = m::cos(t4) * targ.fr2;
+    } else if (targ.fr_pattern == 2) {
+      t3 = rng.uniform() * 2. * SIMC_PI_D;
+      t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
+      t5 = m::cos(t3) * t4;
+      t6 = m::sin(t3) * t4;
+    } else if (targ.fr_pattern == 3) {
+      t3 = 2. * rng.uniform() - 1.0;
+      t4 = 2. * rng.uniform() - 1.0;
+      t5 = targ.fr1 * t3;
+      t6 = targ.fr2 * t4;
+    } else {
+      t5 = 0.0; t6 = 0.0;
+    }
+    s.tx = s.tx + t5;
+    s.ty = s.ty + t6;
+    s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
+    s.rastery = t6;
+    trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+    if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
+    s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
+    s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
+    s.Ein_shift = s.v_Ein - cfg.Ebeam_vertex_ave;
+    s.Ee_shift = s.Coulomb - targ.Coulomb_ave;
+    s.gen_weight = 1.0;
+    s.v_eyptar = cfg.gen.e.yptar.min + rng.uniform() * (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min);
+    s.v_exptar = cfg.gen.e.xptar.min + rng.uniform() * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min);
+    physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, s.v_exptar, s.v_eyptar, s.v_etheta, s.v_ephi);
+    // (the reference also converts the not-yet-known proton angles here, event.f:325; the result is
+    //  overwritten in complete_ev before anyone reads it)
+    s.v_Em = 0.0;
+    s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
+    s.rad.ntail = 0;
   }
-  s.tx = s.tx + t5;
-  s.ty = s.ty + t6;
-  s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
-  s.rastery = t6;
-  trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
-  if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
-  s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
-  s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
-  s.Ein_shift = s.v_Ein - cfg.Ebeam_vertex_ave;
-  s.Ee_shift = s.Coulomb - targ.Coulomb_ave;
-  s.gen_weight = 1.0;
-  s.v_eyptar = cfg.gen.e.yptar.min + rng.uniform() * (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min);
-  s.v_exptar = cfg.gen.e.xptar.min + rng.uniform() * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min);
-  physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, s.v_exptar, s.v_eyptar, s.v_etheta, s.v_ephi);
-  // (the reference also converts the not-yet-known proton angles here, event.f:325; the result is
-  //  overwritten in complete_ev before anyone reads it)
-  s.v_Em = 0.0;
-  s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
-  s.rad.ntail = 0;
-  if (!complete_ev_hyd_elast(cfg, rng, gauss, s)) return false;
-  s.Trec = s.v_Trec;
+  SIMC_PHASE();
+  ok = complete_ev_hyd_elast(cfg, rng, gauss, s, ok);
+  if (ok) s.Trec = s.v_Trec;
   if (!cfg.using_rad) {
-    s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
-    s.o_pdelta = s.v_pdelta;
-    return true;
+    if (ok) {
+      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
+      s.o_pdelta = s.v_pdelta;
+    }
+    return ok;
   }
-  // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208)
+  // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208).  The three tail
+  // blocks of the reference (radc.f:234-337, 358-405, 409-461) share one call site each of basicrad /
+  // complete_ev / peaked_rad_weight, so lanes that picked different tails stay converged.
   RadEvDev& R = s.rad;
-  {
+  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
+  int which = 0;
+  if (ok) {
     const double x = rng.uniform();
     if (x >= R.frac[0] + R.frac[1]) R.ntail = 3;
     else if (x >= R.frac[0]) R.ntail = 2;
     else R.ntail = 1;
+    const int ntail = R.ntail;
+    const double max_delta_Trec = fmax((s.v_Trec - cfg.VERTEXedge.Trec.min), (cfg.VERTEXedge.Trec.max - s.v_Trec));
+    if (cfg.doing_tail[0] && ntail == 1) {          // hydrogen elastic limits, radc.f:264-271
+      double ebeam_max = SIMC_MP * cfg.edge.e.E.max / (SIMC_MP - cfg.edge.e.E.max * (1. - s.uez));
+      if (ebeam_max < 0) ebeam_max = 1.e10;
+      const double ebeam_min = SIMC_MP * cfg.edge.e.E.min / (SIMC_MP - cfg.edge.e.E.min * (1. - s.uez));
+      emin = s.v_Ein - ebeam_max;
+      emax = s.v_Ein - ebeam_min;
+      emax = fmin(emax, cfg.edge.Em.max);
+      emax = fmin(emax, cfg.Egamma1_max);
+      which = 1;
+    } else if (cfg.doing_tail[1] && ntail == 2) {   // radc.f:358-374
+      emin = s.v_eE - cfg.edge.e.E.max;
+      emax = s.v_eE - cfg.edge.e.E.min;
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
+      emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);   // ntail != 0
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
+      which = 2;
+    } else if (R.rad_proton_this_ev && ntail == 3) {   // radc.f:409-425
+      emin = s.v_pE - cfg.edge.p.E.max;
+      emax = s.v_pE - cfg.edge.p.E.min;
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
+      emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
+      which = 3;
+    }
+    if (which) {
+      emin = emin - cfg.dE_edge_test;
+      emax = emax + cfg.dE_edge_test;
+      if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+      basicrad4(R, rng, emin, emax, eg, bw);
+      if (bw <= 0) ok = false;
+      else {
+        R.Egamma_used[which - 1] = eg;
+        if (which == 1) s.v_Ein = s.v_Ein - eg;
+      }
+    }
   }
-  const int ntail = R.ntail;
-  const double max_delta_Trec = fmax((s.v_Trec - cfg.VERTEXedge.Trec.min), (cfg.VERTEXedge.Trec.max - s.v_Trec));
-  double rad_weight = 1, bw, emin, emax;
-  auto vk = [&]() {
+  SIMC_PHASE();
+  const bool reenter = ok && which == 1;                       // radc.f:324
+  const bool re_ok = complete_ev_hyd_elast(cfg, rng, gauss, s, reenter);
+  if (reenter && !re_ok) ok = false;
+  if (ok && which) {
     VertexKin v;
     v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
     v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
-    return v;
-  };
-  if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:234-337, hydrogen elastic limits :264-271
-    double ebeam_max = SIMC_MP * cfg.edge.e.E.max / (SIMC_MP - cfg.edge.e.E.max * (1. - s.uez));
-    if (ebeam_max < 0) ebeam_max = 1.e10;
-    const double ebeam_min = SIMC_MP * cfg.edge.e.E.min / (SIMC_MP - cfg.edge.e.E.min * (1. - s.uez));
-    emin = s.v_Ein - ebeam_max;
-    emax = s.v_Ein - ebeam_min;
-    emax = fmin(emax, cfg.edge.Em.max);
-    emax = fmin(emax, cfg.Egamma1_max);
-    emin = emin - cfg.dE_edge_test;
-    emax = emax + cfg.dE_edge_test;
-    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
-    basicrad4(R, rng, emin, emax, R.Egamma_used[0], bw);
-    if (bw <= 0) return false;
-    s.v_Ein = s.v_Ein - R.Egamma_used[0];
-    const double eg1 = R.Egamma_used[0];
-    if (!complete_ev_hyd_elast(cfg, rng, gauss, s)) return false;     // re-entry, radc.f:324
-    R.Egamma_used[0] = eg1;
-    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[0], emin, emax, bw);
+    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
   }
-  if (cfg.doing_tail[1] && ntail == 2) {          // radc.f:358-405
-    emin = s.v_eE - cfg.edge.e.E.max;
-    emax = s.v_eE - cfg.edge.e.E.min;
-    emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
-    emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);   // ntail != 0
-    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
-    emin = emin - cfg.dE_edge_test;
-    emax = emax + cfg.dE_edge_test;
-    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
-    basicrad4(R, rng, emin, emax, R.Egamma_used[1], bw);
-    if (bw <= 0) return false;
-    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[1], emin, emax, bw);
+  SIMC_PHASE();
+  if (ok) {
+    // orig = vertex (+) radiation, radc.f:476-515
+    s.o_Ein = s.v_Ein + R.Egamma_used[0];
+    s.o_eE = s.v_eE - R.Egamma_used[1];
+    if (s.o_eE <= 0e0) ok = false;
   }
-  if (R.rad_proton_this_ev && ntail == 3) {       // radc.f:409-461
-    emin = s.v_pE - cfg.edge.p.E.max;
-    emax = s.v_pE - cfg.edge.p.E.min;
-    emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
-    emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
-    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
-    emin = emin - cfg.dE_edge_test;
-    emax = emax + cfg.dE_edge_test;
-    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
-    basicrad4(R, rng, emin, emax, R.Egamma_used[2], bw);
-    if (bw <= 0) return false;
-    rad_weight = peaked_rad_weight(cfg, R, vk(), R.Egamma_used[2], emin, emax, bw);
+  if (ok) {
+    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
+    s.o_pE = s.v_pE - R.Egamma_used[2];
+    if (s.o_pE <= cfg.Mh) ok = false;
   }
-  // orig = vertex (+) radiation, radc.f:476-515
-  s.o_Ein = s.v_Ein + R.Egamma_used[0];
-  s.o_eE = s.v_eE - R.Egamma_used[1];
-  if (s.o_eE <= 0e0) return false;
-  s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
-  s.o_pE = s.v_pE - R.Egamma_used[2];
-  if (s.o_pE <= cfg.Mh) return false;
-  s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
-  s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
-  s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
-  return true;
+  if (ok) {
+    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
+  }
+  return ok;
 }
 
 // Target-to-spectrometer transformation of one arm, simc.f:1379-1443 (P) / :1655-1706 (E)

@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
     bool ok = false;
     EventState s;
     DevRng rng;
+    rng.init(A.seed, (unsigned long long)(A.first_try + (active ? i : 0)), 0u, 0u);
+    s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
+    s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
+    ok = generate_hyd_elast(cfg, rng, GaussFn(), s, active);      // every thread of the CTA walks through it
     if (active) {
-      rng.init(A.seed, (unsigned long long)(A.first_try + i), 0u, 0u);
-      s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
-      ok = generate_hyd_elast(cfg, rng, GaussFn(), s);
       // geni histograms: every try, from the vertex values (simc.f:253-262)
       const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
 #pragma unroll
@@ -187,13 +188,16 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&A.acc->counters[0], (unsigned long long)A.n_tries);
 }
 
+#ifndef SIMC_ARM_MIN_BLOCKS
+#define SIMC_ARM_MIN_BLOCKS 4
+#endif
 // ---- stages 2,3: the two arms ----------------------------------------------------------------
 // WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846).
 // Each arm runs as two kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
 // coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
 // after almost no arithmetic); SEG 1 = magnets, hut, reconstruction for the compacted survivors.
 template <int WHICH, int SEG>
-__global__ void __launch_bounds__(kBlock) k_arm(LoopArgs A) {
+__global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A) {
   __shared__ double pw_s[kPowDoubles];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];

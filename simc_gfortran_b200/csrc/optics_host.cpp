@@ -161,14 +161,11 @@ PolyClass compile_terms(const CosyTerms& t, std::vector<unsigned long long>& hdr
   pc.group_begin = (int)hdr.size();
   pc.coef_begin = (int)coef.size();
   pc.n_terms = t.n();
-  int have = 0, ge3 = 0, ge4 = 0, ge5 = 0, gm = 0, lastk = -1;
-  unsigned long long masks = 0;
-  auto flush = [&]() {
-    if (!have) return;
-    hdr.push_back((unsigned long long)ge3 | ((unsigned long long)ge4 << 3) | ((unsigned long long)ge5 << 6) |
-                  ((unsigned long long)gm << 9) | (masks << 12));
-    have = 0; masks = 0; lastk = -1;
-  };
+  // pass 1: cut the term list into groups (same e3,e4,e5 and m = e1+e2, e2 strictly increasing)
+  struct Term { int k; unsigned om; const double* c; };
+  struct Group { int e3, e4, e5, m; std::vector<Term> terms; };
+  std::vector<Group> groups;
+  int lastk = -1;
   for (int i = 0; i < t.n(); ++i) {
     const int8_t* e = &t.expo[5 * i];
     for (int j = 0; j < 5; ++j)
@@ -179,17 +176,25 @@ PolyClass compile_terms(const CosyTerms& t, std::vector<unsigned long long>& hdr
     for (int o = 0; o < t.nout; ++o)
       if (t.coef[t.nout * i + o] != 0.0) om |= 1u << o;
     if (om == 0) continue;                         // adds exact zeros in the reference
-    const bool same = have && e[2] == ge3 && e[3] == ge4 && e[4] == ge5 && m == gm && e[1] > lastk;
-    if (!same) {
-      flush();
-      have = 1; ge3 = e[2]; ge4 = e[3]; ge5 = e[4]; gm = m;
-    }
-    masks |= (unsigned long long)om << (5 * e[1]);
+    if (nonzero) *nonzero += __builtin_popcount(om);
+    const bool same = !groups.empty() && groups.back().e3 == e[2] && groups.back().e4 == e[3] &&
+                      groups.back().e5 == e[4] && groups.back().m == m && e[1] > lastk;
+    if (!same) groups.push_back(Group{e[2], e[3], e[4], m, {}});
+    groups.back().terms.push_back(Term{e[1], om, &t.coef[t.nout * i]});
     lastk = e[1];
-    for (int o = 0; o < t.nout; ++o)
-      if (om & (1u << o)) { coef.push_back(t.coef[t.nout * i + o]); if (nonzero) ++*nonzero; }
   }
-  flush();
+  // pass 2: header = e3,e4,e5,m (3 bits each) | kmask (7 bits) << 12 | output pattern (5 bits) << 19;
+  // every present term stores one coefficient per output of the group's pattern (zeros included:
+  // adding term*0 is exact).
+  for (const Group& g : groups) {
+    unsigned kmask = 0, pat = 0;
+    for (const Term& tm : g.terms) { kmask |= 1u << tm.k; pat |= tm.om; }
+    hdr.push_back((unsigned long long)g.e3 | ((unsigned long long)g.e4 << 3) | ((unsigned long long)g.e5 << 6) |
+                  ((unsigned long long)g.m << 9) | ((unsigned long long)kmask << 12) | ((unsigned long long)pat << 19));
+    for (const Term& tm : g.terms)
+      for (int o = 0; o < t.nout; ++o)
+        if (pat & (1u << o)) coef.push_back(tm.c[o]);
+  }
   pc.group_end = (int)hdr.size();
   return pc;
 }

@@ -33,7 +33,7 @@ struct DevRng {
     r0 = c0; r1 = c1; r2 = c2; r3 = c3;
   }
 
-  __device__ __forceinline__ double uniform() {
+  __device__ __noinline__ double uniform() {
     const uint32_t b = draw >> 1;
     uint32_t lo, hi;
     if ((draw & 1u) && cached == b) {

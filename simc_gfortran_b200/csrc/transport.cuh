@@ -57,23 +57,30 @@ struct ArmResult {
 #define SIMC_MMU 105.6583755
 #define SIMC_PI 3.141592653589793
 
-// gauss1.f:1-30.  The rejection loop is run warp-synchronously: the lanes that called together
-// iterate together until each has its value, so they leave the function converged.
+// gauss1.f:1-30, warp-synchronous: the lanes that called together iterate together, so they leave
+// the function converged.  The polar rejection (s > 1) costs two uniforms per attempt and is
+// looped on its own; log/sqrt/div run once for all lanes, and only a lane whose |g| exceeds
+// nsigmax (never for 99, 0.3 % for 3) goes round again -- the same draws, in the same order.
 __device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
   const unsigned mask = __activemask();
   double g = 0.0;
   bool need = true;
   while (__any_sync(mask, need)) {
-    if (need) {
-      const double u1 = r.uniform();
-      const double u2 = r.uniform();
-      const double v1 = 2.0 * u1 - 1.0;
-      const double v2 = 2.0 * u2 - 1.0;
-      const double s = v1 * v1 + v2 * v2;
-      if (!(s > 1. || s == 0.)) {
-        g = v1 * sqrt(-2. * m::log(s) / s);
-        if (!(fabs(g) > nsigmax)) need = false;
+    double v1 = 0.0, s = 1.0;
+    bool open = need;
+    while (__any_sync(mask, open)) {
+      if (open) {
+        const double u1 = r.uniform();
+        const double u2 = r.uniform();
+        v1 = 2.0 * u1 - 1.0;
+        const double v2 = 2.0 * u2 - 1.0;
+        s = v1 * v1 + v2 * v2;
+        open = (s > 1. || s == 0.);
       }
+    }
+    if (need) {
+      g = v1 * sqrt(-2. * m::log(s) / s);
+      need = fabs(g) > nsigmax;
     }
   }
   return g;
@@ -171,33 +178,35 @@ __device__ __forceinline__ void project(TrackDev& t, DevRng& r, double z_drift, 
 }
 
 // ---- grouped COSY polynomial ------------------------------------------------------------
-template <int M, int NOUT>
-__device__ __forceinline__ void poly_group(unsigned long long masks, const double (&xp)[7], const double (&tp)[7],
+// One group: terms x^(M-k) theta^k * s3*s4*s5, k in kmask, all with the same output pattern.
+// M and the pattern are compile-time, so the power registers are indexed statically and no
+// per-output test is executed.  PAT = 0 means "pattern given at run time" (rare combinations).
+template <int M, int PAT, int NOUT>
+__device__ __forceinline__ void poly_group(unsigned kmask, unsigned rpat, const double (&xp)[7], const double (&tp)[7],
                                            double s3, double s4, double s5, const double* __restrict__ coef, int& ci,
                                            double (&sum)[NOUT]) {
+  const unsigned pat = PAT ? (unsigned)PAT : rpat;
 #if !SIMC_STRICT
   double acc[NOUT];
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
-  unsigned any = 0;
 #endif
 #pragma unroll
   for (int k = 0; k <= M; ++k) {
-    const unsigned om = (unsigned)(masks >> (5 * k)) & 31u;
-    if (om) {
-      double t = xp[M - k] * tp[k];
+    if (kmask & (1u << k)) {
+      // multiplying by an exact 1.0 (zero exponent) is exact: skip it where it is known statically
+      double t = (k == 0) ? xp[M] : (k == M) ? tp[M] : xp[M - k] * tp[k];
 #if SIMC_STRICT
       t = t * s3;
       t = t * s4;
       t = t * s5;
 #pragma unroll
       for (int o = 0; o < NOUT; ++o)
-        if (om & (1u << o)) { sum[o] = sum[o] + t * __ldg(coef + ci); ++ci; }
+        if (pat & (1u << o)) { sum[o] = sum[o] + t * __ldg(coef + ci); ++ci; }
 #else
-      any |= om;
 #pragma unroll
       for (int o = 0; o < NOUT; ++o)
-        if (om & (1u << o)) { acc[o] = fma(t, __ldg(coef + ci), acc[o]); ++ci; }
+        if (pat & (1u << o)) { acc[o] = fma(t, __ldg(coef + ci), acc[o]); ++ci; }
 #endif
     }
   }
@@ -205,15 +214,33 @@ __device__ __forceinline__ void poly_group(unsigned long long masks, const doubl
   const double b = s3 * s4 * s5;
 #pragma unroll
   for (int o = 0; o < NOUT; ++o)
-    if (any & (1u << o)) sum[o] = fma(b, acc[o], sum[o]);
+    if (pat & (1u << o)) sum[o] = fma(b, acc[o], sum[o]);
 #endif
+}
+
+template <int M, int NOUT>
+__device__ __forceinline__ void poly_group_m(unsigned kmask, unsigned pat, const double (&xp)[7], const double (&tp)[7],
+                                             double s3, double s4, double s5, const double* __restrict__ coef, int& ci,
+                                             double (&sum)[NOUT]) {
+  if (NOUT == 4) {          // reconstruction maps are dense: delta, y, theta, phi all present
+    if (pat == 15u) poly_group<M, 15, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum);
+    else poly_group<M, 0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum);
+  } else {                  // forward maps: mid-plane symmetry leaves (x,a), (y,b), dl and (x,a,dl)
+    switch (pat) {
+      case 3u: poly_group<M, 3, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 12u: poly_group<M, 12, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 16u: poly_group<M, 16, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 19u: poly_group<M, 19, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      default: poly_group<M, 0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+    }
+  }
 }
 
 // Evaluates one compiled map at v = (v1..v5); pw = this thread's column of the shared power table.
 template <int NOUT>
 __device__ __noinline__ void eval_poly(const PolyClass& pc, const unsigned long long* __restrict__ hdr,
-                                          const double* __restrict__ coef, const double (&v)[5], double* pw,
-                                          double (&sum)[NOUT]) {
+                                       const double* __restrict__ coef, const double (&v)[5], double* pw,
+                                       double (&sum)[NOUT]) {
   double xp[7], tp[7];
   // libgcc __powidf2 association: x^3 = x*(x*x), x^5 = x*(x^2)^2, x^6 = x^2*x^4
   xp[0] = 1.0; xp[1] = v[0]; xp[2] = v[0] * v[0]; xp[3] = v[0] * xp[2]; xp[4] = xp[2] * xp[2];
@@ -231,19 +258,19 @@ __device__ __noinline__ void eval_poly(const PolyClass& pc, const unsigned long 
   for (int o = 0; o < NOUT; ++o) sum[o] = 0.0;
   int ci = pc.coef_begin;
   for (int g = pc.group_begin; g < pc.group_end; ++g) {
-    const unsigned long long h = __ldg(hdr + g);
-    const unsigned e3 = (unsigned)h & 7u, e4 = ((unsigned)h >> 3) & 7u, e5 = ((unsigned)h >> 6) & 7u;
-    const unsigned m = ((unsigned)h >> 9) & 7u;
-    const unsigned long long masks = h >> 12;
+    const unsigned long long h64 = __ldg(hdr + g);
+    const unsigned h = (unsigned)h64;
+    const unsigned e3 = h & 7u, e4 = (h >> 3) & 7u, e5 = (h >> 6) & 7u, m = (h >> 9) & 7u;
+    const unsigned kmask = (h >> 12) & 127u, pat = (h >> 19) & 31u;
     const double s3 = pw[(0 * 7 + e3) * kBlock], s4 = pw[(1 * 7 + e4) * kBlock], s5 = pw[(2 * 7 + e5) * kBlock];
     switch (m) {
-      case 0: poly_group<0, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 1: poly_group<1, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 2: poly_group<2, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 3: poly_group<3, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 4: poly_group<4, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 5: poly_group<5, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      default: poly_group<6, NOUT>(masks, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 0: poly_group_m<0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 1: poly_group_m<1, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 2: poly_group_m<2, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 3: poly_group_m<3, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 4: poly_group_m<4, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      case 5: poly_group_m<5, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      default: poly_group_m<6, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
     }
   }
 }
