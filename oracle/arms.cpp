@@ -733,4 +733,581 @@ void mc_shms(Track& t, const ArmOptics& o, ArmCall& a) {
   a.ok_spec = true;
 }
 
+
+// =====================================================================================
+// SOS
+// =====================================================================================
+namespace {
+namespace sos {
+// sos/apertures_sos.inc
+constexpr double r2_quad = 163.84, w_bm01 = 8.0, w_bm02 = 8.0;
+constexpr double t_bm01_in = 41.32, b_bm01_in = -30.52, t_bm01_out = 53.05, b_bm01_out = -65.07;
+constexpr double t_bm02_in = 51.73, b_bm02_in = -66.38, t_bm02_out = 51.52, b_bm02_out = -55.85;
+constexpr double w_exit = 8.57, t_exit = 51.52, b_exit = -55.85;
+// sos/mc_sos.f:59-67
+constexpr double h_entr = 7.201, v_entr = 4.696, h_exit = 7.567, v_exit = 4.935;
+constexpr double z_entr = 126.3e0, z_exit = z_entr + 6.3e0;
+// sos/mc_sos_hut.f:45-191
+constexpr double sfoil_exit_radlen = 53.3, sfoil_exit_thick = 0.020 * 2.54, sfoil_exit_zpos = -3.22;
+constexpr double hut_pi = 3.141592654, hut_d_r = hut_pi / 180.;
+constexpr double sfoil_exit_ang = 0. * hut_d_r;
+constexpr double sair_radlen = 30420.;
+constexpr double sdc_radlen = 16700.0, sdc_thick = 0.61775;
+constexpr double sdc_wire_radlen = 0.35, sdc_wire_thick = 0.0000354;
+constexpr double sdc_cath_radlen = 28.7, sdc_cath_thick = 0.0005 * 2.54;
+constexpr double sscin_radlen = 42.4;
+constexpr double scer_entr_radlen = 8.90, scer_entr_thick = 0.050, scer_radlen = 4810.0;
+constexpr double scer_mir_radlen = 400.0, scer_mir_thick = 2.0, scer_exit_radlen = 8.90, scer_exit_thick = 0.050;
+constexpr double sdc_sigma = 0.030;
+constexpr int sdc_nr_cham = 2, sdc_nr_plan = 6;
+constexpr double sdc_1_zpos = 6.25, sdc_2_zpos = 55.77;
+constexpr double sdc_del_plane = sdc_thick + sdc_wire_thick + sdc_cath_thick;
+constexpr double sdc_1_left = 24.0, sdc_1_right = -24.0, sdc_1y_offset = -1.822, sdc_1_top = -32.0, sdc_1_bot = 32.0,
+                 sdc_1x_offset = 8.649;
+constexpr double sdc_2_left = 24.0, sdc_2_right = -24.0, sdc_2y_offset = -1.976, sdc_2_top = -32.0, sdc_2_bot = 32.0,
+                 sdc_2x_offset = -1.532;
+constexpr double sscin_1y_zpos = 73.61, sscin_1x_zpos = 97.11, sscin_2y_zpos = 249.51, sscin_2x_zpos = 290.81;
+constexpr double sscin_1x_thick = 1.040, sscin_1y_thick = 1.098, sscin_2x_thick = 1.040, sscin_2y_thick = 1.098;
+constexpr double sscin_1_left = 18.25, sscin_1_right = -18.25, sscin_1x_offset = 2.8, sscin_1_top = -31.75,
+                 sscin_1_bot = 31.75, sscin_1y_offset = 2.25;
+constexpr double sscin_2_left = 18.25, sscin_2_right = -18.25, sscin_2x_offset = 4.9, sscin_2_top = -56.25,
+                 sscin_2_bot = 56.25, sscin_2y_offset = 2.9;
+constexpr double scer_zentrance = 130.000, scer_zmirror = 155.000, scer_zexit = 160.000;
+constexpr double scal_4ta_zpos = 346.01;
+constexpr int scintrig = 3;
+
+// mc_sos_hut, sos/mc_sos_hut.f:1-548
+bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag, double zinit) {
+  Rng& r = *t.rng;
+  const bool ms = a.ms_flag, wcs = a.wcs_flag, dec = a.decay_flag;
+  double radw, drift;
+  float xdc[12], ydc[12], zdc[12];
+  // :251-257
+  const double tmpran = r.grnd();
+  a.resmult = (tmpran < 0.15) ? 2.0 : 1.0;
+  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
+  int scincount = 0;
+  // :282-287 exit foil (the tilt angle is zero in this version: tan = 0, cos = 1)
+  const double xt = t.xs + t.dxdzs * sfoil_exit_zpos;
+  drift = (sfoil_exit_zpos + xt * std::tan(sfoil_exit_ang)) - zinit;
+  if (drift <= 0.001) drift = 0.001;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  radw = sfoil_exit_thick / sfoil_exit_radlen / std::cos(sfoil_exit_ang);
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :297-301 air to the first chamber
+  drift = (sdc_1_zpos - 0.5 * sdc_nr_plan * sdc_del_plane) - (sfoil_exit_zpos + xt * std::tan(sfoil_exit_ang));
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  for (int jchamber = 1; jchamber <= 2; ++jchamber) {
+    const int npl_off = (jchamber - 1) * sdc_nr_plan;
+    for (int iplane = 1; iplane <= sdc_nr_plan; ++iplane) {   // :305-334 / :354-384
+      radw = sdc_cath_thick / sdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = 0.5 * sdc_thick;
+      radw = drift / sdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + sdc_cath_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      radw = sdc_wire_thick / sdc_wire_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      double tmpran1 = 0., tmpran2 = 0.;
+      if (wcs) { tmpran1 = gauss1(r, 99.0); tmpran2 = gauss1(r, 99.0); }
+      xdc[npl_off + iplane - 1] = (float)(t.xs + sdc_sigma * tmpran1 * a.resmult);
+      ydc[npl_off + iplane - 1] = (float)(t.ys + sdc_sigma * tmpran2 * a.resmult);
+      if (iplane == 1 || iplane == 3 || iplane == 5) xdc[npl_off + iplane - 1] = 0.f;
+      else ydc[npl_off + iplane - 1] = 0.f;
+      drift = 0.5 * sdc_thick;
+      radw = drift / sdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + sdc_wire_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+    }
+    if (jchamber == 1) {   // :335-350
+      if (t.xs > (sdc_1_bot - sdc_1x_offset) || t.xs < (sdc_1_top - sdc_1x_offset) ||
+          t.ys > (sdc_1_left - sdc_1y_offset) || t.ys < (sdc_1_right - sdc_1y_offset)) {
+        a.stop_code = sos_stop::DC1;
+        return false;
+      }
+      radw = sdc_cath_thick / sdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = sdc_2_zpos - sdc_1_zpos - sdc_nr_plan * sdc_del_plane;
+      radw = drift / sair_radlen;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+    } else {               // :385-393
+      if (t.xs > (sdc_2_bot - sdc_2x_offset) || t.xs < (sdc_2_top - sdc_2x_offset) ||
+          t.ys > (sdc_2_left - sdc_2y_offset) || t.ys < (sdc_2_right - sdc_2y_offset)) {
+        a.stop_code = sos_stop::DC2;
+        return false;
+      }
+      radw = sdc_cath_thick / sdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    }
+  }
+  // :399-414
+  for (int jchamber = 1; jchamber <= sdc_nr_cham; ++jchamber) {
+    const int npl_off = (jchamber - 1) * sdc_nr_plan;
+    for (int iplane = 1; iplane <= sdc_nr_plan; ++iplane) {
+      const double z0 = (jchamber == 1) ? sdc_1_zpos : sdc_2_zpos;
+      zdc[npl_off + iplane - 1] = (float)(z0 + (iplane - 0.5 - 0.5 * sdc_nr_plan) * sdc_del_plane);
+    }
+  }
+  float dxfp4, xfp4, dyfp4, yfp4;
+  lfit(zdc, xdc, 12, dxfp4, xfp4);
+  lfit(zdc, ydc, 12, dyfp4, yfp4);
+  a.x_fp = (double)xfp4;
+  a.y_fp = (double)yfp4;
+  a.dx_fp = (double)dxfp4;
+  a.dy_fp = (double)dyfp4;
+  auto in_s1 = [&]() {
+    return t.ys < (sscin_1_left + sscin_1y_offset) && t.ys > (sscin_1_right + sscin_1y_offset) &&
+           t.xs < (sscin_1_bot + sscin_1x_offset) && t.xs > (sscin_1_top + sscin_1x_offset);
+  };
+  auto in_s2 = [&]() {
+    return t.ys < (sscin_2_left + sscin_2y_offset) && t.ys > (sscin_2_right + sscin_2y_offset) &&
+           t.xs < (sscin_2_bot + sscin_2x_offset) && t.xs > (sscin_2_top + sscin_2x_offset);
+  };
+  // :418-438 S1Y, S1X
+  drift = sscin_1y_zpos - sdc_2_zpos - 0.5 * sdc_nr_plan * sdc_del_plane;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_s1()) scincount++;
+  radw = sscin_1y_thick / sscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = sscin_1x_zpos - sscin_1y_zpos;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_s1()) scincount++;
+  radw = sscin_1x_thick / sscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :442-464 Cherenkov
+  drift = scer_zentrance - sscin_1x_zpos;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = scer_entr_thick / scer_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = scer_zmirror - scer_zentrance;
+  radw = drift / scer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = scer_mir_thick / scer_mir_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = scer_zexit - scer_zmirror;
+  radw = drift / scer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = scer_exit_thick / scer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // :468-488 S2Y, S2X
+  drift = sscin_2y_zpos - scer_zexit;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_s2()) scincount++;
+  radw = sscin_2y_thick / sscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = sscin_2x_zpos - sscin_2y_zpos;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (in_s2()) scincount++;
+  radw = sscin_2x_thick / sscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  if (scincount < scintrig) {
+    a.stop_code = sos_stop::SCIN;
+    return false;
+  }
+  // :500-503 calorimeter (no cut)
+  drift = scal_4ta_zpos - sscin_2x_zpos;
+  radw = drift / sair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  return true;
+}
+}  // namespace sos
+}  // namespace
+
+// mc_sos, sos/mc_sos.f:1-394 (use_sieve = .false.)
+void mc_sos(Track& t, const ArmOptics& o, ArmCall& a) {
+  using namespace sos;
+  if (o.fwd.n_classes() != 10) throw std::runtime_error("MC_SOS, wrong number of transport classes");
+  const bool dec = a.decay_flag;
+  a.ok_spec = false;
+  a.stop_code = 0;
+  a.reached_hut = false;
+  bool dflag = false;
+  t.xs = a.x; t.ys = a.y; t.zs = a.z; t.dxdzs = a.dxdz; t.dydzs = a.dydz;
+  t.dpps = a.dpp;
+  double p = a.p_spec * (1. + t.dpps / 100.);
+  double& m2 = a.m2;
+  double xt, yt, zdrift;
+  auto stop = [&](int code) { a.stop_code = code; };
+  // :167-197 slit
+  zdrift = z_entr;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.ys) > h_entr) return stop(sos_stop::SLIT_HOR);
+  if (std::fabs(t.xs) > v_entr) return stop(sos_stop::SLIT_VERT);
+  if (std::fabs(t.xs) > (-v_entr / h_entr * std::fabs(t.ys) + 3 * v_entr / 2)) return stop(sos_stop::SLIT_OCT);
+  zdrift = z_exit - z_entr;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.ys) > h_exit) return stop(sos_stop::SLIT_HOR);
+  if (std::fabs(t.xs) > v_exit) return stop(sos_stop::SLIT_VERT);
+  if (std::fabs(t.xs) > (-v_exit / h_exit * std::fabs(t.ys) + 3 * v_exit / 2)) return stop(sos_stop::SLIT_OCT);
+  // :202-224 quad
+  zdrift = o.fwd.cls[0].driftdist - z_exit;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r2_quad) return stop(sos_stop::QUAD_IN);
+  transp(t, o.fwd, 2, dec, dflag, m2, p, 35.0e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r2_quad) return stop(sos_stop::QUAD_MID);
+  transp(t, o.fwd, 3, dec, dflag, m2, p, 35.0e0, a.pathlen);
+  if ((t.xs * t.xs + t.ys * t.ys) > r2_quad) return stop(sos_stop::QUAD_OUT);
+  // :228-277 the two bending magnets
+  transp(t, o.fwd, 4, dec, dflag, m2, p, 80.0e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, -45.0e0, xt, yt);
+  if ((yt > w_bm01) || (-yt > (w_bm01 - 0.05 * 2.54)) || (-xt > t_bm01_in) || (-xt < b_bm01_in))
+    return stop(sos_stop::BM01_IN);
+  transp(t, o.fwd, 5, dec, dflag, m2, p, 169.52e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 45.0e0, xt, yt);
+  if ((std::fabs(yt) > w_bm01) || (-xt > t_bm01_out) || (-xt < b_bm01_out)) return stop(sos_stop::BM01_OUT);
+  transp(t, o.fwd, 6, dec, dflag, m2, p, 80.80e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 49.0e0, xt, yt);
+  if ((std::fabs(yt) > w_bm02) || (-xt > t_bm02_in) || (-xt < b_bm02_in)) return stop(sos_stop::BM02_IN);
+  transp(t, o.fwd, 7, dec, dflag, m2, p, 77.06e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 57.0e0, xt, yt);
+  if ((std::fabs(yt) > w_bm02) || (-xt > t_bm02_out) || (-xt < b_bm02_out)) return stop(sos_stop::BM02_OUT);
+  // :307-347 exit flange, new exit aperture, extension box
+  transp(t, o.fwd, 8, dec, dflag, m2, p, 43.82e0, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 45.0e0, xt, yt);
+  if ((std::fabs(yt) > w_exit) || (-xt > t_exit) || (-xt < b_exit)) return stop(sos_stop::EXIT);
+  transp(t, o.fwd, 9, dec, dflag, m2, p, 44.34e0, a.pathlen);
+  const double tmpwidth = 10.998 + 0.10209 * (t.xs + 37.694);
+  if ((std::fabs(t.xs) > 37.694) || std::fabs(t.ys) > tmpwidth) return stop(sos_stop::EXIT);
+  t.xs = t.xs + 7.62 * t.dxdzs;
+  t.ys = t.ys + 7.62 * t.dydzs;
+  if ((std::fabs(t.xs) > 38.1) || std::fabs(t.ys) > 12.7) return stop(sos_stop::EXIT);
+  // :364-370 hut
+  a.reached_hut = true;
+  if (!hut(t, a, m2, p, dflag, -3.206267e0)) return;
+  // :373-388 recon
+  t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
+  double dpp_recon, dth_recon, dph_recon, y_recon;
+  if (t.calls) t.calls[47]++;
+  o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon, /*clamp_all=*/true);
+  a.dpp = dpp_recon;
+  a.dxdz = dph_recon;
+  a.dydz = dth_recon;
+  a.y = y_recon;
+  a.ok_spec = true;
+}
+
+// =====================================================================================
+// HRS (left = spectrometer 4, right = spectrometer 3)
+// =====================================================================================
+namespace {
+namespace hrs {
+// hrsl/apertures_hrsl.inc == hrsr/apertures_hrsr.inc
+constexpr double r_Q1 = 15.0, r_Q2 = 30.22, r_Q3 = 30.22;
+// hrsl/mc_hrsl_hut.f:28-140 == hrsr/mc_hrsr_hut.f
+constexpr double hfoil_exit_radlen = 3.56, hfoil_exit_thick = 0.01;
+constexpr double hair_radlen = 30420.;
+constexpr double hdc_entr_radlen = 34.4, hdc_entr_thick = 0.00018 * 2.54;
+constexpr double hdc_radlen = 16700.0, hdc_thick = 1.5;
+constexpr double hdc_wire_radlen = 0.35, hdc_wire_thick = 0.0000049;
+constexpr double hdc_cath_radlen = 7.2, hdc_cath_thick = 0.000177;
+constexpr double hdc_exit_radlen = 34.4, hdc_exit_thick = 0.00018 * 2.54;
+constexpr double hscin_radlen = 42.4;
+constexpr double hcer_entr_radlen = 8.90, hcer_entr_thick = 0.040 * 2.54, hcer_radlen = 36620.0;
+constexpr double hcer_mir_radlen = 400.0, hcer_mir_thick = 2.0, hcer_exit_radlen = 8.90, hcer_exit_thick = 0.040 * 2.54;
+constexpr double hdc_sigma = 0.0225;
+constexpr int hdc_nr_cham = 2, hdc_nr_plan = 6;
+constexpr double hdc_1_zpos = -25.0 + 25.0, hdc_2_zpos = 25.0 + 25.0;
+constexpr double hdc_del_plane = hdc_thick + hdc_wire_thick + hdc_cath_thick;
+constexpr double hdc_1_left = 14.4, hdc_1_right = -14.4, hdc_1y_offset = 0.000, hdc_1_top = -105.6, hdc_1_bot = 105.6,
+                 hdc_1x_offset = 0.000;
+constexpr double hdc_2_left = 14.4, hdc_2_right = -14.4, hdc_2y_offset = 0.000, hdc_2_top = -105.6, hdc_2_bot = 105.6,
+                 hdc_2x_offset = 0.000;
+constexpr double hscin_1x_zpos = 95.0 + 25.0, hscin_2x_zpos = 288.3 + 25.0;
+constexpr double hscin_1x_thick = 0.5 * 1.067, hscin_2x_thick = 0.5 * 1.067;
+constexpr double hscin_1x_left = 18.0, hscin_1x_right = -18.0, hscin_2x_left = 30.0, hscin_2x_right = -30.0;
+constexpr double hcer_zentrance = 137.0 + 25.0, hcer_zmirror = 197.0 + 25.0, hcer_zexit = 237.0 + 25.0;
+constexpr double hcal_4ta_zpos = 407.3 + 25.0;
+
+// mc_hrsl_hut / mc_hrsr_hut, hrsl/mc_hrsl_hut.f:1-470
+bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag, double zinit) {
+  Rng& r = *t.rng;
+  const bool ms = a.ms_flag, wcs = a.wcs_flag, dec = a.decay_flag;
+  double radw, drift, xt, yt;
+  float xdc[12], ydc[12], zdc[12];
+  for (int i = 0; i < 12; ++i) { xdc[i] = 0.f; ydc[i] = 0.f; }
+  a.resmult = 1.0;                                            // :184
+  // :190-200 exit foil, air to the first VDC
+  radw = hfoil_exit_thick / hfoil_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = (hdc_1_zpos - 0.5 * hdc_nr_plan * hdc_del_plane) - zinit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  for (int jchamber = 1; jchamber <= 2; ++jchamber) {
+    radw = hdc_entr_thick / hdc_entr_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_cath_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      radw = hdc_wire_thick / hdc_wire_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      double tmpran1 = 0., tmpran2 = 0.;
+      if (wcs) { tmpran1 = gauss1(r, 99.0); tmpran2 = gauss1(r, 99.0); }
+      xdc[npl_off + iplane - 1] = (float)(t.xs + hdc_sigma * tmpran1 * a.resmult);
+      ydc[npl_off + iplane - 1] = (float)(t.ys + hdc_sigma * tmpran2 * a.resmult);
+      if (iplane == 1 || iplane == 3 || iplane == 5) xdc[npl_off + iplane - 1] = 0.f;
+      else ydc[npl_off + iplane - 1] = 0.f;
+      drift = 0.5 * hdc_thick;
+      radw = drift / hdc_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = drift + hdc_wire_thick;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+    }
+    radw = hdc_exit_thick / hdc_exit_radlen;
+    if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    // the VDC frame is tested in the chamber plane, tilted 45 degrees
+    xt = t.xs; yt = t.ys;
+    rotate_haxis(t, 45.0, xt, yt);
+    if (jchamber == 1) {
+      if (xt > (hdc_1_bot - hdc_1x_offset) || xt < (hdc_1_top - hdc_1x_offset) ||
+          yt > (hdc_1_left - hdc_1y_offset) || yt < (hdc_1_right - hdc_1y_offset)) {
+        a.stop_code = hrs_stop::DC1;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+      drift = hdc_2_zpos - hdc_1_zpos - hdc_nr_plan * hdc_del_plane;
+      radw = drift / hair_radlen;
+      project(t, drift, dec, dflag, m2, p, a.pathlen);
+      if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+    } else {
+      if (xt > (hdc_2_bot - hdc_2x_offset) || xt < (hdc_2_top - hdc_2x_offset) ||
+          yt > (hdc_2_left - hdc_2y_offset) || yt < (hdc_2_right - hdc_2y_offset)) {
+        a.stop_code = hrs_stop::DC2;
+        return false;
+      }
+      radw = hdc_cath_thick / hdc_cath_radlen;
+      if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+    }
+  }
+  for (int jchamber = 1; jchamber <= hdc_nr_cham; ++jchamber) {
+    const int npl_off = (jchamber - 1) * hdc_nr_plan;
+    for (int iplane = 1; iplane <= hdc_nr_plan; ++iplane) {
+      const double z0 = (jchamber == 1) ? hdc_1_zpos : hdc_2_zpos;
+      zdc[npl_off + iplane - 1] = (float)(z0 + (iplane - 0.5 - 0.5 * hdc_nr_plan) * hdc_del_plane);
+    }
+  }
+  float dxfp4, xfp4, dyfp4, yfp4;
+  lfit(zdc, xdc, 12, dxfp4, xfp4);
+  lfit(zdc, ydc, 12, dyfp4, yfp4);
+  a.x_fp = (double)xfp4;
+  a.y_fp = (double)yfp4;
+  a.dx_fp = (double)dxfp4;
+  a.dy_fp = (double)dyfp4;
+  // S1
+  drift = hscin_1x_zpos - hdc_2_zpos - 0.5 * hdc_nr_plan * hdc_del_plane;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.ys > hscin_1x_left || t.ys < hscin_1x_right) {
+    a.stop_code = hrs_stop::S1;
+    return false;
+  }
+  radw = hscin_1x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // Cherenkov
+  drift = hcer_zentrance - hscin_1x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_entr_thick / hcer_entr_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_zmirror - hcer_zentrance;
+  radw = drift / hcer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_mir_thick / hcer_mir_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  drift = hcer_zexit - hcer_zmirror;
+  radw = drift / hcer_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  radw = hcer_exit_thick / hcer_exit_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // S2
+  drift = hscin_2x_zpos - hcer_zexit;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  if (t.ys > hscin_2x_left || t.ys < hscin_2x_right) {
+    a.stop_code = hrs_stop::S2;
+    return false;
+  }
+  radw = hscin_2x_thick / hscin_radlen;
+  if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
+  // calorimeter (no cut)
+  drift = hcal_4ta_zpos - hscin_2x_zpos;
+  radw = drift / hair_radlen;
+  project(t, drift, dec, dflag, m2, p, a.pathlen);
+  if (ms) musc_ext(r, m2, p, radw, drift, t.dydzs, t.dxdzs, t.ys, t.xs);
+  return true;
+}
+}  // namespace hrs
+}  // namespace
+
+// mc_hrsl (hrsl/mc_hrsl.f:1-551) and mc_hrsr (hrsr/mc_hrsr.f); they differ in the slit exit
+// half-gap (:58), the slit distance (:67) and the focal-plane y offset (:525 / :524).
+// The Makefile's -fdefault-real-8 makes the bare literals of rotate_haxis(-30.0,..) 8-byte reals.
+void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right) {
+  using namespace hrs;
+  if (o.fwd.n_classes() != 12)
+    throw std::runtime_error(right ? "MC_HRSR, wrong number of transport classes"
+                                   : "MC_HRSL, wrong number of transport classes");
+  const double h_entr = 3.145, v_entr = 6.090, h_exit = right ? 3.340 : 3.335, v_exit = 6.485;
+  const double y_off = 0.0, x_off = 0.0, z_off = 0.0;
+  const double z_entr = (right ? 110.0 : 110.9) + z_off, z_exit = z_entr + 8.0;
+  const bool dec = a.decay_flag;
+  a.ok_spec = false;
+  a.stop_code = 0;
+  a.reached_hut = false;
+  bool dflag = false;
+  t.xs = a.x; t.ys = a.y; t.zs = a.z; t.dxdzs = a.dxdz; t.dydzs = a.dydz;
+  t.dpps = a.dpp;
+  double p = a.p_spec * (1. + t.dpps / 100.);
+  double& m2 = a.m2;
+  double xt, yt, zdrift, ztmp;
+  auto stop = [&](int code) { a.stop_code = code; };
+  auto rad = [&]() { return std::sqrt(t.xs * t.xs + t.ys * t.ys); };
+  auto r2 = [&]() { return t.xs * t.xs + t.ys * t.ys; };
+  // :159-179 scattering-chamber exit pipes
+  zdrift = 65.686;
+  ztmp = zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 7.3787) return stop(hrs_stop::SLIT_HOR);
+  zdrift = 80.436 - ztmp;
+  ztmp = 80.436;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 7.4092) return stop(hrs_stop::SLIT_HOR);
+  // :184-218 rectangular collimator
+  zdrift = z_entr - ztmp;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.ys - y_off) > h_entr) return stop(hrs_stop::SLIT_HOR);
+  if (std::fabs(t.xs - x_off) > v_entr) return stop(hrs_stop::SLIT_VERT);
+  zdrift = z_exit - z_entr;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.ys - y_off) > h_exit) return stop(hrs_stop::SLIT_HOR);
+  if (std::fabs(t.xs - x_off) > v_exit) return stop(hrs_stop::SLIT_VERT);
+  // :222-279 Q1
+  ztmp = 135.064;
+  zdrift = ztmp - z_exit;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 12.5222) return stop(hrs_stop::Q1_IN);
+  zdrift = o.fwd.cls[0].driftdist - ztmp;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_IN);
+  transp(t, o.fwd, 2, dec, dflag, m2, p, 62.75333333, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_MID);
+  transp(t, o.fwd, 3, dec, dflag, m2, p, 31.37666667, a.pathlen);
+  if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_OUT);
+  zdrift = 300.464 - 253.16;
+  ztmp = zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 14.9225) return stop(hrs_stop::Q1_OUT);
+  // :281-349 Q2
+  zdrift = 314.464 - 300.464;
+  ztmp = ztmp + zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 20.9550) return stop(hrs_stop::Q2_IN);
+  zdrift = o.fwd.cls[3].driftdist - ztmp;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_IN);
+  transp(t, o.fwd, 5, dec, dflag, m2, p, 121.77333333, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_MID);
+  transp(t, o.fwd, 6, dec, dflag, m2, p, 60.88666667, a.pathlen);
+  if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_OUT);
+  zdrift = 609.664 - 553.020;
+  ztmp = zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 30.0073) return stop(hrs_stop::Q2_OUT);
+  zdrift = 641.800 - 609.664;
+  ztmp = ztmp + zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 30.0073) return stop(hrs_stop::Q2_OUT);
+  // :351-406 dipole
+  zdrift = 819.489 - 641.800;
+  ztmp = ztmp + zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.xs) > 50.0 || std::fabs(t.ys) > 15.0) return stop(hrs_stop::D1_IN);
+  zdrift = o.fwd.cls[6].driftdist - ztmp;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, -30.0, xt, yt);
+  if (std::fabs(xt - 2.500) > 52.5) return stop(hrs_stop::D1_IN);
+  if ((std::fabs(yt) + 0.01861 * xt) > 12.5) return stop(hrs_stop::D1_IN);
+  transp(t, o.fwd, 8, dec, dflag, m2, p, 659.73445725, a.pathlen);
+  xt = t.xs; yt = t.ys;
+  rotate_haxis(t, 30.0, xt, yt);
+  if (std::fabs(xt - 2.500) > 52.5) return stop(hrs_stop::D1_OUT);
+  if ((std::fabs(yt) + 0.01861 * xt) > 12.5) return stop(hrs_stop::D1_OUT);
+  zdrift = 1745.33546 - 1655.83446;
+  ztmp = zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 30.3276) return stop(hrs_stop::D1_OUT);
+  if (std::fabs(t.xs) > 50.0 || std::fabs(t.ys) > 15.0) return stop(hrs_stop::D1_OUT);
+  // :429-499 Q3
+  zdrift = 1759.00946 - 1745.33546;
+  ztmp = ztmp + zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (rad() > 30.3276) return stop(hrs_stop::Q3_IN);
+  zdrift = o.fwd.cls[8].driftdist - ztmp;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_IN);
+  transp(t, o.fwd, 10, dec, dflag, m2, p, 121.7866667, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_MID);
+  transp(t, o.fwd, 11, dec, dflag, m2, p, 60.89333333, a.pathlen);
+  if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_OUT);
+  zdrift = 2080.38746 - 1997.76446;
+  ztmp = zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.xs) > 35.56 || std::fabs(t.ys) > 17.145) return stop(hrs_stop::Q3_OUT);
+  zdrift = 2327.47246 - 2080.38746;
+  ztmp = ztmp + zdrift;
+  project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+  if (std::fabs(t.xs) > 99.76635 || std::fabs(t.ys) > 17.145) return stop(hrs_stop::Q3_OUT);
+  // :503-510 hut
+  a.reached_hut = true;
+  zdrift = o.fwd.cls[11].driftdist - ztmp;
+  if (!hut(t, a, m2, p, dflag, -zdrift)) return;
+  // :513-539 recon sees the fitted track; the returned y_fp is then shifted to the VDC centre
+  t.xs = a.x_fp; t.ys = a.y_fp; t.dxdzs = a.dx_fp; t.dydzs = a.dy_fp;
+  a.y_fp = a.y_fp - (right ? 0.48 : 0.78);
+  double dpp_recon, dth_recon, dph_recon, y_recon;
+  if (t.calls) t.calls[47]++;
+  o.rec.eval(t, a.fry, dpp_recon, dth_recon, dph_recon, y_recon);
+  a.dpp = dpp_recon;
+  a.dxdz = dph_recon;
+  a.dydz = dth_recon;
+  a.y = y_recon;
+  a.ok_spec = true;
+}
+
 }  // namespace simc_oracle

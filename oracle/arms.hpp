@@ -39,7 +39,19 @@ enum { OK = 0, HB_IN, HB_MEN, HB_MEX, HB_OUT, SLIT_HOR, SLIT_VERT, SLIT_OCT, Q1_
        CAL, CAL_FID, COLL };
 }
 
+namespace sos_stop {
+enum { OK = 0, SLIT_HOR, SLIT_VERT, SLIT_OCT, QUAD_IN, QUAD_MID, QUAD_OUT, BM01_IN, BM01_OUT, BM02_IN, BM02_OUT, EXIT,
+       DC1, DC2, SCIN };
+}
+namespace hrs_stop {
+enum { OK = 0, SLIT_HOR, SLIT_VERT, Q1_IN, Q1_MID, Q1_OUT, Q2_IN, Q2_MID, Q2_OUT, D1_IN, D1_OUT, Q3_IN, Q3_MID, Q3_OUT,
+       DC1, DC2, S1, S2 };
+}
+
 void mc_hms(Track& t, const ArmOptics& o, ArmCall& a);
+void mc_sos(Track& t, const ArmOptics& o, ArmCall& a);
+// right = true: mc_hrsr (spectrometer 3), false: mc_hrsl (spectrometer 4)
+void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right);
 void mc_shms(Track& t, const ArmOptics& o, ArmCall& a);
 
 }  // namespace simc_oracle

@@ -100,7 +100,9 @@ int oracle_transport_batch(int arm, int64_t n, const double* in, uint64_t seed, 
       t.Mh2_final = a.m2;
       if (arm == 1) mc_hms(t, o, a);
       else if (arm == 5) mc_shms(t, o, a);
-      else { g_err = "oracle: arm not restated yet"; return -1; }
+      else if (arm == 2) mc_sos(t, o, a);
+      else if (arm == 3 || arm == 4) mc_hrs(t, o, a, arm == 3);
+      else { g_err = "oracle: unknown spectrometer"; return -1; }
       out[0 * n + i] = a.dpp; out[1 * n + i] = a.dxdz; out[2 * n + i] = a.dydz; out[3 * n + i] = a.y;
       out[4 * n + i] = a.x_fp; out[5 * n + i] = a.dx_fp; out[6 * n + i] = a.y_fp; out[7 * n + i] = a.dy_fp;
       out[8 * n + i] = a.pathlen; out[9 * n + i] = a.m2; out[10 * n + i] = a.resmult;

@@ -330,7 +330,9 @@ static void run_arm(Sim& s, int arm_id, const ArmOptics* o, ArmCall& a) {
   if (!o) throw std::runtime_error("oracle: optics not set for an arm in use");
   if (arm_id == 1) mc_hms(s.trk, *o, a);
   else if (arm_id == 5) mc_shms(s.trk, *o, a);
-  else throw std::runtime_error("oracle: spectrometer not restated yet");
+  else if (arm_id == 2) mc_sos(s.trk, *o, a);
+  else if (arm_id == 3 || arm_id == 4) mc_hrs(s.trk, *o, a, arm_id == 3);
+  else throw std::runtime_error("oracle: spectrometer not restated (calorimeter arms are out of scope)");
 }
 
 // simc.f:1310-1852 (using_tgt_field = .false., no calorimeter arms)

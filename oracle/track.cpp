@@ -188,7 +188,7 @@ void CosyRecon::load(const std::string& path) {
 
 // hms/mc_hms_recon.f:104-137 (identical in shms/mc_shms_recon.f, sos, hrs)
 void CosyRecon::eval(const Track& t, double fry, double& delta_p, double& delta_t, double& delta_phi,
-                     double& y_tgt) const {
+                     double& y_tgt, bool clamp_all) const {
   double sum[4] = {0., 0., 0., 0.}, hut[5];
   hut[0] = t.xs / 100.;
   hut[1] = t.dxdzs;
@@ -196,6 +196,9 @@ void CosyRecon::eval(const Track& t, double fry, double& delta_p, double& delta_
   hut[3] = t.dydzs;
   hut[4] = fry / 100.;
   if (std::fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
+  if (clamp_all)
+    for (int i = 0; i < 4; ++i)
+      if (std::fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
   for (int i = 0; i < n_terms; ++i) {
     const int8_t* e = &expon[5 * i];
     const double term = powi(hut[0], e[0]) * powi(hut[1], e[1]) * powi(hut[2], e[2]) * powi(hut[3], e[3]) *

@@ -249,7 +249,9 @@ struct CosyRecon {
   // hms/mc_hms_recon.f:70-102
   void load(const std::string& path);
   // hms/mc_hms_recon.f:104-137
-  void eval(const Track& t, double fry, double& delta_p, double& delta_t, double& delta_phi, double& y_tgt) const;
+  // clamp_all: sos/mc_sos_recon.f:79-81 moves every |hut(i)| <= 1e-30 to 1e-30, the other arms only hut(5)
+  void eval(const Track& t, double fry, double& delta_p, double& delta_t, double& delta_phi, double& y_tgt,
+            bool clamp_all = false) const;
 };
 
 // shared/transp.f:134-279

@@ -36,6 +36,15 @@ enum ArmOpCode : int32_t {
   OP_LFIT,           // fit focal-plane track through REAL*4 arrays   mc_hms_hut.f:438-455
   OP_CUT_FP_CAL,     // xcal=x_fp+dx_fp*a ...; stop if ycal>b or ycal<c or xcal>d or xcal<e  mc_shms_hut.f:415
   OP_RECON,          // mc_*_recon + overwrite dpp,y,dxdz,dydz        mc_hms.f:419-437
+                     //   i0 = 1: clamp every |hut(i)| <= 1e-30 (sos/mc_sos_recon.f:79-81);
+                     //   a = shift taken off the returned y_fp afterwards (hrsl/mc_hrsl.f:525)
+  OP_CUT_R,          // stop if sqrt(xs^2+ys^2) > a                   hrsl/mc_hrsl.f:162
+  OP_CUT_T_ABSX,     // stop if |xt-a| > b                            hrsl/mc_hrsl.f:370
+  OP_CUT_T_TRAP,     // stop if |yt| + a*xt > b                       hrsl/mc_hrsl.f:377
+  OP_CUT_T_RECT,     // stop if xt > a or xt < b or yt > c or yt < d  hrsl/mc_hrsl_hut.f:286
+  OP_CUT_T_BOX,      // stop if yt > a or -yt > b or -xt > c or -xt < d   sos/mc_sos.f:234
+  OP_CUT_SOS_EXIT,   // w = a + b*(xs+c); stop if |xs| > c or |ys| > w    sos/mc_sos.f:328
+  OP_SHIFT,          // xs += a*dxdzs, ys += a*dydzs (no path length) sos/mc_sos.f:339
   OP_UNSUPPORTED     // collimator stepping for pions etc.
 };
 

@@ -227,9 +227,12 @@ struct Prog {
     ArmOp& a3 = add(OP_CUT_OCT, c_oct); a3.a = xoff; a3.b = yoff; a3.c = -v / h; a3.d = 3 * v / 2;
   }
   // the 2 x 6 drift-chamber planes, identical in mc_hms_hut.f:331-433 and mc_shms_hut.f:158-285
+  // yplanes: bit (ip-1) set when plane ip measures y (its x entry is zeroed); windows = false for
+  // the SOS chambers, which have no entrance/exit foils (sos/mc_sos_hut.f:303-343).
   void chamber(int jchamber, double entr_radw, double cath_radw, double gas_thick, double gas_radlen,
-               double cath_thick, double wire_thick, double wire_radw, double exit_radw, double sigma) {
-    musc(entr_radw);
+               double cath_thick, double wire_thick, double wire_radw, double exit_radw, double sigma,
+               unsigned yplanes = 0x12u, bool windows = true) {
+    if (windows) musc(entr_radw);
     for (int ip = 1; ip <= 6; ++ip) {
       musc(cath_radw);
       double drift = 0.5 * gas_thick;
@@ -238,14 +241,23 @@ struct Prog {
       project(drift);
       musc(wire_radw);
       ArmOp& o = add(OP_DC_PLANE);
-      o.i0 = (jchamber - 1) * 6 + ip - 1; o.i1 = (ip == 2 || ip == 5); o.a = sigma;
+      o.i0 = (jchamber - 1) * 6 + ip - 1; o.i1 = (yplanes >> (ip - 1)) & 1u; o.a = sigma;
       drift = 0.5 * gas_thick;
       musc(drift / gas_radlen);
       drift = drift + wire_thick;
       project(drift);
     }
-    musc(exit_radw);
+    if (windows) musc(exit_radw);
   }
+  int split = -1;                      // explicit survivor-compaction point (else: after the last octagon cut)
+  void cut_r(double r, int code) { add(OP_CUT_R, code).a = r; }
+  void cut_abs_xy(double xmax, double ymax, int code) { cut_box(xmax, -xmax, ymax, -ymax, code); }
+  // "drift the remaining distance of map class cls": length = b_target - (-(driftdist(cls) - ztmp))
+  void project_to_hut(int cls, double ztmp, double target_z) {
+    ArmOp& o = add(OP_PROJECT_DD); o.i0 = cls; o.a = -ztmp; o.b = target_z; o.i1 = 1;
+  }
+  // musc_ext over the drift just resolved from a map class (radw = drift / radlen)
+  void musc_ext_prev(double radlen) { ArmOp& o = add(OP_MUSC_EXT); o.i0 = 1; o.a = radlen; }
 };
 
 const double kInf = std::numeric_limits<double>::infinity();
@@ -532,6 +544,252 @@ void build_shms(Prog& P) {
   P.add(OP_END);
 }
 
+// ---- SOS: sos/mc_sos.f:115-391 + sos/mc_sos_hut.f:251-545 + sos/apertures_sos.inc -----------
+namespace sosc {
+enum { OK = 0, SLIT_HOR, SLIT_VERT, SLIT_OCT, QUAD_IN, QUAD_MID, QUAD_OUT, BM01_IN, BM01_OUT, BM02_IN, BM02_OUT, EXIT,
+       DC1, DC2, SCIN, N };
+const char* names[] = {"ok", "slit_hor", "slit_vert", "slit_oct", "quad_in", "quad_mid", "quad_out", "bm01_in",
+                       "bm01_out", "bm02_in", "bm02_out", "exit", "dc1", "dc2", "scin"};
+}
+void build_sos(Prog& P) {
+  using namespace sosc;
+  const double r2_quad = 163.84, w_bm01 = 8.0, w_bm02 = 8.0;
+  const double t_bm01_in = 41.32, b_bm01_in = -30.52, t_bm01_out = 53.05, b_bm01_out = -65.07;
+  const double t_bm02_in = 51.73, b_bm02_in = -66.38, t_bm02_out = 51.52, b_bm02_out = -55.85;
+  const double w_exit = 8.57, t_exit = 51.52, b_exit = -55.85;
+  const double h_entr = 7.201, v_entr = 4.696, h_exit = 7.567, v_exit = 4.935;
+  const double z_entr = 126.3e0, z_exit = z_entr + 6.3e0;
+  P.project(z_entr);
+  P.octagon(0.0, 0.0, h_entr, v_entr, SLIT_HOR, SLIT_VERT, SLIT_OCT);   // |xs - 0.0| == |xs| exactly
+  P.project(z_exit - z_entr);
+  P.octagon(0.0, 0.0, h_exit, v_exit, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+  P.project_dd(1, -z_exit);           P.add(OP_CUT_R2, QUAD_IN).a = r2_quad;
+  P.transp(2, 35.0e0);                P.add(OP_CUT_R2, QUAD_MID).a = r2_quad;
+  P.transp(3, 35.0e0);                P.add(OP_CUT_R2, QUAD_OUT).a = r2_quad;
+  auto tbox = [&](double deg, double yhi, double ylo, double top, double bot, int code) {
+    P.rot(OP_ROT_H, deg, 0.0);
+    ArmOp& o = P.add(OP_CUT_T_BOX, code); o.a = yhi; o.b = ylo; o.c = top; o.d = bot;
+  };
+  // |yt| > w  <=>  yt > w or -yt > w
+  P.transp(4, 80.0e0);                tbox(-45.0e0, w_bm01, w_bm01 - 0.05 * 2.54, t_bm01_in, b_bm01_in, BM01_IN);
+  P.transp(5, 169.52e0);              tbox(45.0e0, w_bm01, w_bm01, t_bm01_out, b_bm01_out, BM01_OUT);
+  P.transp(6, 80.80e0);               tbox(49.0e0, w_bm02, w_bm02, t_bm02_in, b_bm02_in, BM02_IN);
+  P.transp(7, 77.06e0);               tbox(57.0e0, w_bm02, w_bm02, t_bm02_out, b_bm02_out, BM02_OUT);
+  P.transp(8, 43.82e0);               tbox(45.0e0, w_exit, w_exit, t_exit, b_exit, EXIT);
+  P.transp(9, 44.34e0);
+  { ArmOp& o = P.add(OP_CUT_SOS_EXIT, EXIT); o.a = 10.998; o.b = 0.10209; o.c = 37.694; }
+  P.add(OP_SHIFT).a = 7.62;
+  P.cut_abs_xy(38.1, 12.7, EXIT);
+  P.add(OP_MARK_HUT);
+
+  // ---- hut ----
+  const double sfoil_exit_radlen = 53.3, sfoil_exit_thick = 0.020 * 2.54, sfoil_exit_zpos = -3.22;
+  const double sair_radlen = 30420., sdc_radlen = 16700.0, sdc_thick = 0.61775;
+  const double sdc_wire_radlen = 0.35, sdc_wire_thick = 0.0000354, sdc_cath_radlen = 28.7, sdc_cath_thick = 0.0005 * 2.54;
+  const double sscin_radlen = 42.4, scer_entr_radlen = 8.90, scer_entr_thick = 0.050, scer_radlen = 4810.0;
+  const double scer_mir_radlen = 400.0, scer_mir_thick = 2.0, scer_exit_radlen = 8.90, scer_exit_thick = 0.050;
+  const int sdc_nr_plan = 6;
+  const double sdc_1_zpos = 6.25, sdc_2_zpos = 55.77;
+  const double sdc_del_plane = sdc_thick + sdc_wire_thick + sdc_cath_thick;
+  const double sdc_1_left = 24.0, sdc_1_right = -24.0, sdc_1y_offset = -1.822, sdc_1_top = -32.0, sdc_1_bot = 32.0,
+               sdc_1x_offset = 8.649;
+  const double sdc_2_left = 24.0, sdc_2_right = -24.0, sdc_2y_offset = -1.976, sdc_2_top = -32.0, sdc_2_bot = 32.0,
+               sdc_2x_offset = -1.532;
+  const double sscin_1y_zpos = 73.61, sscin_1x_zpos = 97.11, sscin_2y_zpos = 249.51, sscin_2x_zpos = 290.81;
+  const double sscin_1x_thick = 1.040, sscin_1y_thick = 1.098, sscin_2x_thick = 1.040, sscin_2y_thick = 1.098;
+  const double sscin_1_left = 18.25, sscin_1_right = -18.25, sscin_1x_offset = 2.8, sscin_1_top = -31.75,
+               sscin_1_bot = 31.75, sscin_1y_offset = 2.25;
+  const double sscin_2_left = 18.25, sscin_2_right = -18.25, sscin_2x_offset = 4.9, sscin_2_top = -56.25,
+               sscin_2_bot = 56.25, sscin_2y_offset = 2.9;
+  const double scer_zentrance = 130.000, scer_zmirror = 155.000, scer_zexit = 160.000, scal_4ta_zpos = 346.01;
+  const double zinit = -3.206267e0;                     // mc_sos.f:369
+
+  P.add(OP_RESMULT_DRAW).a = 0.15;
+  // mc_sos_hut.f:282-287: the foil is untilted here (sfoil_exit_ang = 0), so xt*tan(ang) adds 0
+  const double foil_z = sfoil_exit_zpos + 0.0;
+  double drift = foil_z - zinit;
+  if (drift <= 0.001) drift = 0.001;
+  P.project(drift);
+  P.musc(sfoil_exit_thick / sfoil_exit_radlen / 1.0);
+  drift = (sdc_1_zpos - 0.5 * sdc_nr_plan * sdc_del_plane) - foil_z;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift);
+  P.chamber(1, 0., sdc_cath_thick / sdc_cath_radlen, sdc_thick, sdc_radlen, sdc_cath_thick, sdc_wire_thick,
+            sdc_wire_thick / sdc_wire_radlen, 0., 0.030, 0x15u, false);
+  P.cut_box(sdc_1_bot - sdc_1x_offset, sdc_1_top - sdc_1x_offset, sdc_1_left - sdc_1y_offset,
+            sdc_1_right - sdc_1y_offset, DC1);
+  P.musc(sdc_cath_thick / sdc_cath_radlen);
+  drift = sdc_2_zpos - sdc_1_zpos - sdc_nr_plan * sdc_del_plane;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift);
+  P.chamber(2, 0., sdc_cath_thick / sdc_cath_radlen, sdc_thick, sdc_radlen, sdc_cath_thick, sdc_wire_thick,
+            sdc_wire_thick / sdc_wire_radlen, 0., 0.030, 0x15u, false);
+  P.cut_box(sdc_2_bot - sdc_2x_offset, sdc_2_top - sdc_2x_offset, sdc_2_left - sdc_2y_offset,
+            sdc_2_right - sdc_2y_offset, DC2);
+  P.musc(sdc_cath_thick / sdc_cath_radlen);
+  { ArmOp& o = P.add(OP_LFIT); o.a = sdc_1_zpos; o.b = sdc_2_zpos; o.c = sdc_del_plane; }
+  auto scin = [&](int plane) {
+    ArmOp& o = P.add(OP_SCIN_COUNT);
+    if (plane == 1) {
+      o.a = sscin_1_left + sscin_1y_offset; o.b = sscin_1_right + sscin_1y_offset;
+      o.c = sscin_1_bot + sscin_1x_offset;  o.d = sscin_1_top + sscin_1x_offset;
+    } else {
+      o.a = sscin_2_left + sscin_2y_offset; o.b = sscin_2_right + sscin_2y_offset;
+      o.c = sscin_2_bot + sscin_2x_offset;  o.d = sscin_2_top + sscin_2x_offset;
+    }
+  };
+  drift = sscin_1y_zpos - sdc_2_zpos - 0.5 * sdc_nr_plan * sdc_del_plane;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift); scin(1); P.musc(sscin_1y_thick / sscin_radlen);
+  drift = sscin_1x_zpos - sscin_1y_zpos;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift); scin(1); P.musc(sscin_1x_thick / sscin_radlen);
+  drift = scer_zentrance - sscin_1x_zpos;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift);
+  P.musc(scer_entr_thick / scer_entr_radlen);
+  drift = scer_zmirror - scer_zentrance;
+  P.project(drift); P.musc_ext(drift / scer_radlen, drift);
+  P.musc(scer_mir_thick / scer_mir_radlen);
+  drift = scer_zexit - scer_zmirror;
+  P.project(drift); P.musc_ext(drift / scer_radlen, drift);
+  P.musc(scer_exit_thick / scer_exit_radlen);
+  drift = sscin_2y_zpos - scer_zexit;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift); scin(2); P.musc(sscin_2y_thick / sscin_radlen);
+  drift = sscin_2x_zpos - sscin_2y_zpos;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift); scin(2); P.musc(sscin_2x_thick / sscin_radlen);
+  P.add(OP_SCIN_TRIG, SCIN).i0 = 3;
+  drift = scal_4ta_zpos - sscin_2x_zpos;
+  P.project(drift); P.musc_ext(drift / sair_radlen, drift);
+  P.add(OP_RECON).i0 = 1;
+  P.add(OP_END);
+}
+
+// ---- HRS: hrsl/mc_hrsl.f:114-546 (hrsr/mc_hrsr.f) + hrs?/mc_hrs?_hut.f -----------------------
+namespace hrsc {
+enum { OK = 0, SLIT_HOR, SLIT_VERT, Q1_IN, Q1_MID, Q1_OUT, Q2_IN, Q2_MID, Q2_OUT, D1_IN, D1_OUT, Q3_IN, Q3_MID, Q3_OUT,
+       DC1, DC2, S1, S2, N };
+const char* names[] = {"ok", "slit_hor", "slit_vert", "Q1_in", "Q1_mid", "Q1_out", "Q2_in", "Q2_mid", "Q2_out",
+                       "D1_in", "D1_out", "Q3_in", "Q3_mid", "Q3_out", "dc1", "dc2", "s1", "s2"};
+}
+void build_hrs(Prog& P, bool right) {
+  using namespace hrsc;
+  const double r_Q1 = 15.0, r_Q2 = 30.22, r_Q3 = 30.22;
+  const double h_entr = 3.145, v_entr = 6.090, h_exit = right ? 3.340 : 3.335, v_exit = 6.485;
+  const double y_off = 0.0, x_off = 0.0, z_off = 0.0;
+  const double z_entr = (right ? 110.0 : 110.9) + z_off, z_exit = z_entr + 8.0;
+  double zdrift, ztmp;
+  auto slit = [&](double h, double v) {
+    ArmOp& a1 = P.add(OP_CUT_ABS_Y, SLIT_HOR); a1.a = y_off; a1.b = h;
+    ArmOp& a2 = P.add(OP_CUT_ABS_X, SLIT_VERT); a2.a = x_off; a2.b = v;
+  };
+  zdrift = 65.686; ztmp = zdrift;
+  P.project(zdrift);                  P.cut_r(7.3787, SLIT_HOR);
+  zdrift = 80.436 - ztmp; ztmp = 80.436;
+  P.project(zdrift);                  P.cut_r(7.4092, SLIT_HOR);
+  zdrift = z_entr - ztmp;
+  P.project(zdrift);                  slit(h_entr, v_entr);
+  zdrift = z_exit - z_entr;
+  P.project(zdrift);                  slit(h_exit, v_exit);
+  P.split = (int)P.ops.size();
+  ztmp = 135.064; zdrift = ztmp - z_exit;
+  P.project(zdrift);                  P.cut_r(12.5222, Q1_IN);
+  P.project_dd(1, -ztmp);             P.cut_r2(r_Q1, Q1_IN);
+  P.transp(2, 62.75333333);           P.cut_r2(r_Q1, Q1_MID);
+  P.transp(3, 31.37666667);           P.cut_r2(r_Q1, Q1_OUT);
+  zdrift = 300.464 - 253.16; ztmp = zdrift;
+  P.project(zdrift);                  P.cut_r(14.9225, Q1_OUT);
+  zdrift = 314.464 - 300.464; ztmp = ztmp + zdrift;
+  P.project(zdrift);                  P.cut_r(20.9550, Q2_IN);
+  P.project_dd(4, -ztmp);             P.cut_r2(r_Q2, Q2_IN);
+  P.transp(5, 121.77333333);          P.cut_r2(r_Q2, Q2_MID);
+  P.transp(6, 60.88666667);           P.cut_r2(r_Q2, Q2_OUT);
+  zdrift = 609.664 - 553.020; ztmp = zdrift;
+  P.project(zdrift);                  P.cut_r(30.0073, Q2_OUT);
+  zdrift = 641.800 - 609.664; ztmp = ztmp + zdrift;
+  P.project(zdrift);                  P.cut_r(30.0073, Q2_OUT);
+  zdrift = 819.489 - 641.800; ztmp = ztmp + zdrift;
+  P.project(zdrift);                  P.cut_abs_xy(50.0, 15.0, D1_IN);
+  P.project_dd(7, -ztmp);
+  auto dipole_face = [&](double deg, int code) {
+    P.rot(OP_ROT_H, deg, 0.0);
+    { ArmOp& o = P.add(OP_CUT_T_ABSX, code); o.a = 2.500; o.b = 52.5; }
+    { ArmOp& o = P.add(OP_CUT_T_TRAP, code); o.a = 0.01861; o.b = 12.5; }
+  };
+  dipole_face(-30.0, D1_IN);
+  P.transp(8, 659.73445725);          dipole_face(30.0, D1_OUT);
+  zdrift = 1745.33546 - 1655.83446; ztmp = zdrift;
+  P.project(zdrift);                  P.cut_r(30.3276, D1_OUT); P.cut_abs_xy(50.0, 15.0, D1_OUT);
+  zdrift = 1759.00946 - 1745.33546; ztmp = ztmp + zdrift;
+  P.project(zdrift);                  P.cut_r(30.3276, Q3_IN);
+  P.project_dd(9, -ztmp);             P.cut_r2(r_Q3, Q3_IN);
+  P.transp(10, 121.7866667);          P.cut_r2(r_Q3, Q3_MID);
+  P.transp(11, 60.89333333);          P.cut_r2(r_Q3, Q3_OUT);
+  zdrift = 2080.38746 - 1997.76446; ztmp = zdrift;
+  P.project(zdrift);                  P.cut_abs_xy(35.56, 17.145, Q3_OUT);
+  zdrift = 2327.47246 - 2080.38746; ztmp = ztmp + zdrift;
+  P.project(zdrift);                  P.cut_abs_xy(99.76635, 17.145, Q3_OUT);
+  P.add(OP_MARK_HUT);
+
+  // ---- hut ----
+  const double hfoil_exit_radlen = 3.56, hfoil_exit_thick = 0.01, hair_radlen = 30420.;
+  const double hdc_entr_radlen = 34.4, hdc_entr_thick = 0.00018 * 2.54, hdc_radlen = 16700.0, hdc_thick = 1.5;
+  const double hdc_wire_radlen = 0.35, hdc_wire_thick = 0.0000049, hdc_cath_radlen = 7.2, hdc_cath_thick = 0.000177;
+  const double hdc_exit_radlen = 34.4, hdc_exit_thick = 0.00018 * 2.54, hscin_radlen = 42.4;
+  const double hcer_entr_radlen = 8.90, hcer_entr_thick = 0.040 * 2.54, hcer_radlen = 36620.0;
+  const double hcer_mir_radlen = 400.0, hcer_mir_thick = 2.0, hcer_exit_radlen = 8.90, hcer_exit_thick = 0.040 * 2.54;
+  const int hdc_nr_plan = 6;
+  const double hdc_1_zpos = -25.0 + 25.0, hdc_2_zpos = 25.0 + 25.0;
+  const double hdc_del_plane = hdc_thick + hdc_wire_thick + hdc_cath_thick;
+  const double hdc_left = 14.4, hdc_right = -14.4, hdc_y_offset = 0.000, hdc_top = -105.6, hdc_bot = 105.6,
+               hdc_x_offset = 0.000;
+  const double hscin_1x_zpos = 95.0 + 25.0, hscin_2x_zpos = 288.3 + 25.0;
+  const double hscin_1x_thick = 0.5 * 1.067, hscin_2x_thick = 0.5 * 1.067;
+  const double hscin_1x_left = 18.0, hscin_1x_right = -18.0, hscin_2x_left = 30.0, hscin_2x_right = -30.0;
+  const double hcer_zentrance = 137.0 + 25.0, hcer_zmirror = 197.0 + 25.0, hcer_zexit = 237.0 + 25.0;
+  const double hcal_4ta_zpos = 407.3 + 25.0;
+
+  P.add(OP_RESMULT_ONE);
+  P.musc(hfoil_exit_thick / hfoil_exit_radlen);
+  // mc_hrsl.f:507-509: zinit = -(driftdist(12) - ztmp); drift = (first VDC plane) - zinit
+  P.project_to_hut(12, ztmp, hdc_1_zpos - 0.5 * hdc_nr_plan * hdc_del_plane);
+  P.musc_ext_prev(hair_radlen);
+  auto vdc_frame = [&](int code) {    // tested in the chamber plane, rotated by 45 degrees
+    P.rot(OP_ROT_H, 45.0, 0.0);
+    ArmOp& o = P.add(OP_CUT_T_RECT, code);
+    o.a = hdc_bot - hdc_x_offset; o.b = hdc_top - hdc_x_offset; o.c = hdc_left - hdc_y_offset; o.d = hdc_right - hdc_y_offset;
+  };
+  P.chamber(1, hdc_entr_thick / hdc_entr_radlen, hdc_cath_thick / hdc_cath_radlen, hdc_thick, hdc_radlen,
+            hdc_cath_thick, hdc_wire_thick, hdc_wire_thick / hdc_wire_radlen, hdc_exit_thick / hdc_exit_radlen, 0.0225,
+            0x15u);
+  vdc_frame(DC1);
+  P.musc(hdc_cath_thick / hdc_cath_radlen);
+  double drift = hdc_2_zpos - hdc_1_zpos - hdc_nr_plan * hdc_del_plane;
+  P.project(drift); P.musc_ext(drift / hair_radlen, drift);
+  P.chamber(2, hdc_entr_thick / hdc_entr_radlen, hdc_cath_thick / hdc_cath_radlen, hdc_thick, hdc_radlen,
+            hdc_cath_thick, hdc_wire_thick, hdc_wire_thick / hdc_wire_radlen, hdc_exit_thick / hdc_exit_radlen, 0.0225,
+            0x15u);
+  vdc_frame(DC2);
+  P.musc(hdc_cath_thick / hdc_cath_radlen);
+  { ArmOp& o = P.add(OP_LFIT); o.a = hdc_1_zpos; o.b = hdc_2_zpos; o.c = hdc_del_plane; }
+  drift = hscin_1x_zpos - hdc_2_zpos - 0.5 * hdc_nr_plan * hdc_del_plane;
+  P.project(drift); P.musc_ext(drift / hair_radlen, drift);
+  P.cut_box(kInf, -kInf, hscin_1x_left, hscin_1x_right, S1);
+  P.musc(hscin_1x_thick / hscin_radlen);
+  drift = hcer_zentrance - hscin_1x_zpos;
+  P.project(drift); P.musc_ext(drift / hair_radlen, drift);
+  P.musc(hcer_entr_thick / hcer_entr_radlen);
+  drift = hcer_zmirror - hcer_zentrance;
+  P.project(drift); P.musc_ext(drift / hcer_radlen, drift);
+  P.musc(hcer_mir_thick / hcer_mir_radlen);
+  drift = hcer_zexit - hcer_zmirror;
+  P.project(drift); P.musc_ext(drift / hcer_radlen, drift);
+  P.musc(hcer_exit_thick / hcer_exit_radlen);
+  drift = hscin_2x_zpos - hcer_zexit;
+  P.project(drift); P.musc_ext(drift / hair_radlen, drift);
+  P.cut_box(kInf, -kInf, hscin_2x_left, hscin_2x_right, S2);
+  P.musc(hscin_2x_thick / hscin_radlen);
+  drift = hcal_4ta_zpos - hscin_2x_zpos;
+  P.project(drift); P.musc_ext(drift / hair_radlen, drift);
+  P.add(OP_RECON).a = right ? 0.48 : 0.78;
+  P.add(OP_END);
+}
+
 }  // namespace
 
 CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec) {
@@ -540,8 +798,10 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   if (want < 0) throw std::runtime_error("unknown spectrometer id");
   if ((int)fwd.cls.size() != want) {
     throw std::runtime_error(arm_id == 1 ? "MC_HMS, wrong number of transport classes"
-                             : arm_id == 5 ? "Bender-SHMS, wrong number of transport classes"
-                                           : "wrong number of transport classes");
+                             : arm_id == 2 ? "MC_SOS, wrong number of transport classes"
+                             : arm_id == 3 ? "MC_HRSR, wrong number of transport classes"
+                             : arm_id == 4 ? "MC_HRSL, wrong number of transport classes"
+                                           : "Bender-SHMS, wrong number of transport classes");
   }
   std::memset(&A.tab, 0, sizeof(A.tab));
   A.tab.n_classes = (int)fwd.cls.size();
@@ -559,11 +819,13 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   Prog P;
   if (arm_id == 1) build_hms(P);
   else if (arm_id == 5) build_shms(P);
-  else throw std::runtime_error("arm program not built yet for this spectrometer");
+  else if (arm_id == 2) build_sos(P);
+  else build_hrs(P, arm_id == 3);
   if ((int)P.ops.size() > kMaxArmOps) throw std::runtime_error("arm program too long");
   // Drift lengths taken from the maps (driftdist(spectr,k), transp.f:419) are known now:
   // fold them into plain drifts with the reference's arithmetic.
-  for (ArmOp& o : P.ops) {
+  for (size_t k = 0; k < P.ops.size(); ++k) {
+    ArmOp& o = P.ops[k];
     if (o.op != OP_PROJECT_DD) continue;
     const double dd = fwd.driftdist_cm.at(o.i0 - 1);
     if (!fwd.adrift.at(o.i0 - 1))
@@ -576,6 +838,11 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
       o.a = dd + o.a;
     }
     o.op = OP_PROJECT; o.b = 0; o.i0 = 0; o.i1 = 0;
+    if (k + 1 < P.ops.size() && P.ops[k + 1].op == OP_MUSC_EXT && P.ops[k + 1].i0 == 1) {
+      ArmOp& m = P.ops[k + 1];           // radw = drift/radlen, mc_hrsl_hut.f:197-200
+      const double radw = o.a / m.a;
+      m.a = radw; m.b = std::sqrt(radw); m.c = o.a; m.i0 = 0;
+    }
   }
   A.ops = P.ops;
   A.tab.n_ops = (int)P.ops.size();
@@ -583,14 +850,19 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   A.tab.split_op = 0;
   for (int k = 0; k < (int)P.ops.size(); ++k)
     if (P.ops[k].op == OP_CUT_OCT) A.tab.split_op = k + 1;
+  if (P.split >= 0) A.tab.split_op = P.split;
   return A;
 }
 
 const char* stop_name(int arm_id, int code) {
   if (arm_id == 1 && code >= 0 && code < hmsc::N) return hmsc::names[code];
   if (arm_id == 5 && code >= 0 && code < shmsc::N) return shmsc::names[code];
+  if (arm_id == 2 && code >= 0 && code < sosc::N) return sosc::names[code];
+  if ((arm_id == 3 || arm_id == 4) && code >= 0 && code < hrsc::N) return hrsc::names[code];
   return "?";
 }
-int n_stop_codes(int arm_id) { return arm_id == 1 ? hmsc::N : arm_id == 5 ? shmsc::N : 0; }
+int n_stop_codes(int arm_id) {
+  return arm_id == 1 ? hmsc::N : arm_id == 5 ? shmsc::N : arm_id == 2 ? sosc::N : (arm_id == 3 || arm_id == 4) ? hrsc::N : 0;
+}
 
 }  // namespace simc

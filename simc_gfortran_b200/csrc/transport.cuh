@@ -463,6 +463,20 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         break;
       }
       case OP_CUT_BOX: stop = (t.xs > a) || (t.xs < b) || (t.ys > c) || (t.ys < d); break;
+      case OP_CUT_R: stop = sqrt(t.xs * t.xs + t.ys * t.ys) > a; break;
+      case OP_CUT_T_ABSX: stop = fabs(xt - a) > b; break;
+      case OP_CUT_T_TRAP: stop = (fabs(yt) + a * xt) > b; break;
+      case OP_CUT_T_RECT: stop = (xt > a) || (xt < b) || (yt > c) || (yt < d); break;
+      case OP_CUT_T_BOX: stop = (yt > a) || (-yt > b) || (-xt > c) || (-xt < d); break;
+      case OP_CUT_SOS_EXIT: {
+        const double tmpwidth = a + b * (t.xs + c);
+        stop = (fabs(t.xs) > c) || (fabs(t.ys) > tmpwidth);
+        break;
+      }
+      case OP_SHIFT:
+        t.xs = t.xs + a * t.dxdzs;
+        t.ys = t.ys + a * t.dydzs;
+        break;
       case OP_SCIN_COUNT: if (t.ys < a && t.ys > b && t.xs < c && t.xs > d) ++hs.scincount; break;
       case OP_SCIN_TRIG: stop = hs.scincount < __ldg(&o->i0); break;
       case OP_LFIT: {      // mc_hms_hut.f:438-455
@@ -493,6 +507,12 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         hut[3] = res.dy_fp;
         hut[4] = fry / 100.;
         if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
+        if (__ldg(&o->i0)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
+        }
+        if (a != 0.) res.y_fp = res.y_fp - a;
         double sum[4];
         if (call_counts) warp_count(&call_counts[47]);
         eval_poly<4>(arm->tab.rec, arm->tab.hdr, arm->tab.coef, hut, pw, sum);

@@ -21,7 +21,7 @@ def oracle():
 @pytest.fixture(scope="session")
 def oracle_with_optics(oracle):
     from simc_gfortran_b200 import load_optics_fixture
-    for arm in (1, 5):
+    for arm in (1, 2, 3, 4, 5):
         oracle.set_optics(load_optics_fixture(arm))
     return oracle
 

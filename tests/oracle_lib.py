@@ -44,7 +44,10 @@ def transport_inputs(arm, n, seed, p_spec=None, m2=None):
     inp[5] = rng.uniform(-box[4], box[4], n)
     inp[6] = ARM_KIN[arm][1] if m2 is None else m2
     inp[7] = ARM_KIN[arm][0] if p_spec is None else p_spec
-    inp[8] = inp[1]          # fry = xtar_init (simc.f:1441,1463) for HMS/SHMS
+    if arm in (1, 5):
+        inp[8] = inp[1]      # fry = xtar_init (simc.f:1441,1463) for HMS/SHMS
+    else:
+        inp[8] = rng.uniform(-0.1, 0.1, n)   # fry = -rastery for SOS/HRS (simc.f:1350,1472)
     return inp
 
 
@@ -60,7 +63,7 @@ class Oracle:
             raise RuntimeError("oracle: " + self.L.oracle_last_error().decode())
 
     def has_arm(self, arm):
-        return arm in (1, 5)
+        return arm in (1, 2, 3, 4, 5)
 
     def load_optics(self, arm, fwd, rec):
         self._check(self.L.oracle_load_optics(arm, fwd.encode(), rec.encode()))

@@ -73,14 +73,17 @@ def test_optics_file_invariants(arm, n_classes, drifts):
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_fixture_matches_reference_files(oracle):
     for arm, (fwd, rec) in {1: ("hms/forward_cosy.dat", "hms/recon_cosy.dat"),
-                            5: ("shms/shms_forward.dat", "shms/shms_recon.dat")}.items():
+                            5: ("shms/shms_forward.dat", "shms/shms_recon.dat"),
+                            2: ("sos/forward_cosy.dat", "sos/recon_cosy.dat"),
+                            3: ("hrsr/hrs_forward_cosy.dat", "hrsr/hrs_recon_cosy.dat"),
+                            4: ("hrsl/hrs_forward_cosy.dat", "hrsl/hrs_recon_cosy.dat")}.items():
         oracle.load_optics(arm, "/root/reference/" + fwd, "/root/reference/" + rec)
         a, b = oracle.export_optics(arm), load_optics_fixture(arm)
         for f in ("class_start", "fwd_coeff", "fwd_expon", "length_cm", "adrift", "driftdist", "rec_coeff", "rec_expon"):
             assert np.array_equal(getattr(a, f), getattr(b, f)), f
 
 
-@pytest.mark.parametrize("arm,name", [(1, "hms"), (5, "shms")])
+@pytest.mark.parametrize("arm,name", [(1, "hms"), (5, "shms"), (2, "sos"), (3, "hrsr"), (4, "hrsl")])
 def test_oracle_reproduces_golden_vectors(oracle_with_optics, arm, name):
     z = np.load(os.path.join(GOLDEN, f"transport_{name}.npz"))
     out, flags = oracle_with_optics.transport_batch(arm, z["inp"], int(z["seed"]))
@@ -89,7 +92,7 @@ def test_oracle_reproduces_golden_vectors(oracle_with_optics, arm, name):
     assert np.array_equal(z["inp"], transport_inputs(arm, z["inp"].shape[1], int(z["seed"])))
 
 
-@pytest.mark.parametrize("arm", [1, 5])
+@pytest.mark.parametrize("arm", [1, 5, 2, 3, 4])
 def test_forward_then_recon_recovers_the_ray(oracle_with_optics, arm):
     """Physics check that ties forward maps, hut and inverse maps together: with smearing off
     the reconstructed target quantities must equal the thrown ones to optics accuracy."""
@@ -104,7 +107,7 @@ def test_forward_then_recon_recovers_the_ray(oracle_with_optics, arm):
     assert np.abs(out[2][ok] - inp[5][ok]).max() < 2.5e-3         # yptar
     assert np.abs(out[3][ok] - inp[2][ok]).max() < 0.5            # ytar, cm
     # without multiple scattering / smearing only the resmult draw (HMS) consumes random numbers
-    assert set(np.unique(out[11][ok])) == ({1.0} if arm == 1 else {0.0})
+    assert set(np.unique(out[11][ok])) == ({1.0} if arm in (1, 2) else {0.0})
 
 
 def test_drift_class_equals_project(oracle_with_optics):

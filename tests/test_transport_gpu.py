@@ -38,20 +38,20 @@ def compare(out, flags, ref_out, ref_flags, rtol=RTOL):
 @pytest.fixture(scope="module", params=["strict", "fast"])
 def sim(request):
     s = Simc(mode=request.param)
-    for arm in (1, 5):
+    for arm in (1, 2, 3, 4, 5):
         s.set_optics(load_optics_fixture(arm))
     yield s
     s.close()
 
 
-@pytest.mark.parametrize("arm,name", [(1, "hms"), (5, "shms")])
+@pytest.mark.parametrize("arm,name", [(1, "hms"), (5, "shms"), (2, "sos"), (3, "hrsr"), (4, "hrsl")])
 def test_golden_vectors(sim, arm, name):
     z = np.load(os.path.join(GOLDEN, f"transport_{name}.npz"))
     out, flags = sim.transport_batch(arm, z["inp"], int(z["seed"]))
     compare(out, flags, z["out"], z["flags"])
 
 
-@pytest.mark.parametrize("arm", [1, 5])
+@pytest.mark.parametrize("arm", [1, 5, 2, 3, 4])
 @pytest.mark.parametrize("ms,wcs", [(True, True), (False, False), (True, False)])
 def test_against_oracle(sim, oracle_with_optics, arm, ms, wcs):
     n = 20000
@@ -62,7 +62,8 @@ def test_against_oracle(sim, oracle_with_optics, arm, ms, wcs):
     assert (flags == 0).sum() > 1000 and len(np.unique(flags)) > 5
 
 
-@pytest.mark.parametrize("arm,mass", [(1, 139.57018), (5, 139.57018), (5, 493.677)])
+@pytest.mark.parametrize("arm,mass", [(1, 139.57018), (5, 139.57018), (5, 493.677), (2, 139.57018), (3, 493.677),
+                                      (4, 139.57018)])
 def test_decay_in_flight(oracle_with_optics, arm, mass):
     """project/transp decay branches (shared/project.f:43-119, shared/transp.f:134-187,231-276)."""
     from simc_gfortran_b200 import RunConfig
@@ -88,7 +89,7 @@ def test_strict_polynomials_are_bit_exact(oracle_with_optics):
     focal plane, so the strict variant must reproduce the oracle's COSY sums bit for bit."""
     s = Simc(mode="strict")
     try:
-        for arm in (1, 5):
+        for arm in (1, 5, 2, 3, 4):
             s.set_optics(load_optics_fixture(arm))
             inp = transport_inputs(arm, 30000, seed=31 + arm)
             ref_out, ref_flags = oracle_with_optics.transport_batch(arm, inp, seed=1, ms=False, wcs=False)
@@ -121,7 +122,7 @@ def test_edge_cases(sim):
 def test_errors(sim):
     from simc_gfortran_b200 import SimcError
     with pytest.raises(SimcError) as e:
-        sim.transport_batch(3, np.zeros((9, 4)), 1)          # optics of that arm never loaded
+        sim.transport_batch(6, np.zeros((9, 4)), 1)          # optics of that arm never loaded
     assert e.value.code == -4
     with pytest.raises(SimcError):
         sim.load_optics(1, "/nonexistent/forward.dat", "/nonexistent/recon.dat")
@@ -134,7 +135,7 @@ def test_errors(sim):
     sim.set_optics(t)
 
 
-@pytest.mark.parametrize("arm", [1, 5])
+@pytest.mark.parametrize("arm", [1, 5, 2, 4])
 def test_file_reader_round_trip(sim, oracle_with_optics, tmp_path, arm):
     """The library's own reader of the reference's fixed-column format (transp_init semantics)."""
     t = load_optics_fixture(arm)
