@@ -169,6 +169,9 @@ typedef struct {
   /* Work counters (not in the reference): calls of transp() per forward class, [arm][class-1], and
    * calls of the reconstruction map in slot 47.  bench.py turns them into algorithmic FLOPs. */
   int64_t       transp_calls[2][48];
+  /* Contributing events whose weight needed a model this build lacks: peepi below W = 2 GeV blends in
+   * the MAID-2007 table (physics_pion.f:88-107); they are weighted with the parametrisation alone. */
+  int64_t       unsupported;
 } simc_accum;
 
 typedef struct simc_handle simc_handle;
@@ -260,7 +263,7 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
 
 /* whole-event parity entry point: per-try records instead of accumulators.
  * rec[k*n+i], k = 0..SIMC_EVENT_NREC-1 (see simc_b200_event_field_name). */
-#define SIMC_EVENT_NREC 48
+#define SIMC_EVENT_NREC 56
 int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
                           double* rec_soa, int32_t* status);
 const char* simc_b200_event_field_name(int k);

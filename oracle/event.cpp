@@ -553,19 +553,33 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     throw std::runtime_error("oracle: spectral-function weights not restated yet");
   }
   if (main.SF_weight <= 0 && !force_sigcc) return false;
-  double tgtweight = 1.0;
+  double tgtweight = 1.0, survivalprob = 1.0;
   if (cfg.doing_phsp) {
     main.sigcc = 1.0;
     main.sigcc_recon = 1.0;
   } else if (cfg.doing_hyd_elast) {
     main.sigcc = sigep(vertex);
     main.sigcc_recon = sigep(recon);
+  } else if (cfg.doing_pion) {
+    if (cfg.which_pion == 2 || cfg.which_pion == 3) throw std::runtime_error("oracle: Delta final states not restated");
+    main.sigcc = peepi(s, vertex, main);
+    main.sigcc_recon = 1.0;
+    if (cfg.which_pion == 1 || cfg.which_pion == 11) tgtweight = cfg.targ.N;
+    else tgtweight = cfg.targ.Z;
+  } else if (cfg.doing_kaon) {
+    main.sigcc = peeK(s, vertex, main, survivalprob);
+    main.sigcc_recon = 1.0;
+    if (cfg.which_kaon == 2 || cfg.which_kaon == 12) tgtweight = cfg.targ.N;
+    else tgtweight = cfg.targ.Z;
   } else {
     throw std::runtime_error("oracle: cross section of this reaction not restated yet");
   }
   if (cfg.using_Coulomb) main.sigcc = main.sigcc * powi(1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam, 2);
   main.weight = main.SF_weight * main.jacobian * main.gen_weight * main.sigcc;
   main.weight = main.weight * tgtweight;
+  // (doing_semika belongs to the semi-inclusive branch, not restated)
+  if (cfg.doing_kaon && !cfg.doing_decay) main.weight = main.weight * survivalprob;
+  s.ntup.survivalprob = survivalprob;
   return true;
 }
 

@@ -48,7 +48,10 @@ struct RadEv {
 };
 
 // simulate.inc:161-176 (the fields the loop touches)
-struct NtupVars { double radphot = 0, radarm = 0, resfac = 0, sigcm = 0, krel = 0, mm = 0, mmA = 0, t = 0; };
+struct NtupVars {
+  double radphot = 0, radarm = 0, resfac = 0, sigcm = 0, sigcm1 = 0, sigcm2 = 0, krel = 0, mm = 0, mmA = 0, t = 0;
+  double survivalprob = 1.0;       // local of complete_main (event.f:1373), kept for the parity records
+};
 
 // Everything one try needs: the run constants, both arms' optics, the RNG and the scratch
 // COMMON state.  One instance per try in counter-based mode (state starts from zero, see
@@ -63,6 +66,7 @@ struct Sim {
   Track trk;                     // COMMON /track/ + decdist, Mh2_final
   int stop_e = 0, stop_p = 0;    // stop code of each arm (0 = ok), -1 = arm not entered
   bool hut_e = false, hut_p = false;
+  bool low_w = false;            // peepi wanted the MAID table (W < 2 GeV), see physics_meson.cpp
   long long calls[2][48] = {};   // [0] electron arm, [1] hadron arm
 };
 
@@ -93,6 +97,8 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon);            
 bool complete_recon_ev(Sim& s, Event& recon);                                                            // event.f:1056
 bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Event& recon);              // event.f:1363
 double sigep(const Event& vertex);
+double peepi(Sim& s, const Event& vertex, EventMain& main);                                             // physics_pion.f:1
+double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob);                        // physics_kaon.f:1
 double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax);  // radc.f:523                                                                       // physics_proton.f:1
 
 // One try of the loop (simc.f:169-351) in counter-based mode.

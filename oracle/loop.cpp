@@ -92,6 +92,7 @@ void accumulate(const Sim& s, const TryResult& r, const EventMain& main, const E
     if (b >= 0) a.hist_n[1][k][b]++;
   }
   a.ncontribute++;
+  if (s.low_w) a.unsupported++;
   if (!s.rad.rad_proton_this_ev) a.ncontribute_no_rad_proton++;
   if (r.pass_cuts) {
     a.npasscuts++;
@@ -131,6 +132,7 @@ void accumulate(const Sim& s, const TryResult& r, const EventMain& main, const E
 void merge_accum(simc_accum& a, const simc_accum& b) {
   a.ntried += b.ntried; a.nsuccess += b.nsuccess; a.ncontribute += b.ncontribute; a.npasscuts += b.npasscuts;
   a.ncontribute_no_rad_proton += b.ncontribute_no_rad_proton;
+  a.unsupported += b.unsupported;
   auto addf = [](simc_fixed128& x, const simc_fixed128& y) {
     i128 v = (((i128)x.hi << 64) | (i128)x.lo) + (((i128)y.hi << 64) | (i128)y.lo);
     x.lo = (uint64_t)v; x.hi = (int64_t)(v >> 64);
@@ -157,7 +159,8 @@ void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const 
       main.target.x, main.target.y, main.target.z, main.target.Eloss[0], main.target.Eloss[1], main.target.Eloss[2],
       main.SP_e.delta, main.SP_e.yptar, main.SP_e.xptar, main.SP_p.delta, main.SP_p.yptar, main.SP_p.xptar,
       recon.e.delta, recon.e.yptar, recon.e.xptar, recon.p.delta, recon.p.yptar, recon.p.xptar,
-      recon.Em, recon.Pm, recon.W, s.rad.hardcorfac};
+      recon.Em, recon.Pm, recon.W, s.rad.hardcorfac,
+      main.thetacm, main.phicm, s.ntup.sigcm, main.davejac, s.ntup.survivalprob, s.ntup.mm, main.wcm, main.t};
   for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[k * n + i] = v[k];
 }
 

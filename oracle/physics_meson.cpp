@@ -1,0 +1,274 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see event.hpp).  PARITY UNPINNED.
+// Meson electroproduction weights: transform_to_cm (jacobians.f:1-282), peepi + sig_param_2021 +
+// exclfit (physics_pion.f:1-130, 738-854), peeK + sig_factorized (physics_kaon.f:1-236).
+// Hydrogen targets: pfer = 0, pferx/y/z = 0, efer = Mtar_struck (event.f:330-335); the Fermi
+// terms are kept in the formulas so that the arithmetic is the reference's.
+//
+// Not restated: the MAID-2007 table branch of peepi for W < 2 GeV (physics_pion.f:88-107, needs
+// the 15 MB maid07 table) -- such events are counted in simc_accum.unsupported; the Saghai model eekeek/eekeeks of peeK, which
+// only fills the ntuple column sigcm1 and never the weight (physics_kaon.f:100-115).
+#include <stdexcept>
+
+#include "event.hpp"
+
+namespace simc_oracle {
+
+namespace {
+struct Fermi { double pfer = 0.0, pferx = 0.0, pfery = 0.0, pferz = 0.0, efer = 0.0; };
+
+struct CmFrame {
+  double gstar, bstar, bstarx, bstary, bstarz;
+  double nustar, qstar, qstarx, qstary, qstarz;
+  double ehadcm, phadcm, phadcmx, phadcmy, phadcmz;
+  double ebeamcm, pbeamcm, pbeamcmx, pbeamcmy, pbeamcmz;
+  double etarcm, ptarcm, ptarcmx, ptarcmy, ptarcmz;
+  double thetacm, phicm, phiqn, jacobian, jac_old;
+};
+
+// jacobians.f:1-282
+void transform_to_cm(const Event& vertex, const EventMain& main, const Fermi& F, CmFrame& C) {
+  const double pi = K::pi;
+  const double pfer = F.pfer, pferx = F.pferx, pfery = F.pfery, pferz = F.pferz, efer = F.efer;
+  double tcos = vertex.up.x * vertex.uq.x + vertex.up.y * vertex.uq.y + vertex.up.z * vertex.uq.z;
+  if (tcos - 1. > 0. && tcos - 1. < 1.e-8) tcos = 1.0;
+  const double tsin = sqrt(1. - tcos * tcos);
+  double tfcos = pferx * vertex.uq.x + pfery * vertex.uq.y + pferz * vertex.uq.z;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double cospq = cos(main.phi_pq), sinpq = sin(main.phi_pq);
+  const double qx = -vertex.uq.y, qy = vertex.uq.x, qz = vertex.uq.z;
+  const double px = -pfery, py = pferx, pz = pferz;
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  const double tmp_x_x = -qx * qz / dummy, tmp_x_y = -qy * qz / dummy, tmp_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  const double tmp_y_x = qy / dummy, tmp_y_y = -qx / dummy, tmp_y_z = 0.0;
+  const double p_tmp_x = pfer * (px * tmp_x_x + py * tmp_x_y + pz * tmp_x_z);
+  const double p_tmp_y = pfer * (px * tmp_y_x + py * tmp_y_y + pz * tmp_y_z);
+  if (p_tmp_x == 0.) C.phiqn = 0.;
+  else C.phiqn = atan2(p_tmp_y, p_tmp_x);
+  if (C.phiqn < 0.) C.phiqn = C.phiqn + 2. * pi;
+  const double phiqn = C.phiqn;
+
+  const double pbeam = vertex.Ein;
+  const double beam_tmpx = pbeam * tmp_x_z, beam_tmpy = pbeam * tmp_y_z, beam_tmpz = pbeam * vertex.uq.z;
+  C.bstar = sqrt(powi(vertex.q + pfer * tfcos, 2) + powi(pfer * tfsin, 2)) / (efer + vertex.nu);
+  C.gstar = 1. / sqrt(1. - C.bstar * C.bstar);
+  C.bstarz = (vertex.q + pfer * tfcos) / (efer + vertex.nu);
+  C.bstarx = p_tmp_x / (efer + vertex.nu);
+  C.bstary = p_tmp_y / (efer + vertex.nu);
+  const double gstar = C.gstar, bstar = C.bstar, bstarx = C.bstarx, bstary = C.bstary, bstarz = C.bstarz;
+
+  loren(gstar, bstarx, bstary, bstarz, vertex.Ein, beam_tmpx, beam_tmpy, beam_tmpz, C.ebeamcm, C.pbeamcmx, C.pbeamcmy,
+        C.pbeamcmz, C.pbeamcm);
+  const double zero = 0.e0;
+  loren(gstar, bstarx, bstary, bstarz, vertex.nu, zero, zero, vertex.q, C.nustar, C.qstarx, C.qstary, C.qstarz, C.qstar);
+  const double phadz = vertex.p.P * tcos, phadx = vertex.p.P * tsin * cospq, phady = vertex.p.P * tsin * sinpq;
+  loren(gstar, bstarx, bstary, bstarz, vertex.p.E, phadx, phady, phadz, C.ehadcm, C.phadcmx, C.phadcmy, C.phadcmz,
+        C.phadcm);
+  C.thetacm = acos((C.phadcmx * C.qstarx + C.phadcmy * C.qstary + C.phadcmz * C.qstarz) / C.phadcm / C.qstar);
+  const double ptarz = pfer * tfcos, ptarx = p_tmp_x, ptary = p_tmp_y;
+  loren(gstar, bstarx, bstary, bstarz, efer, ptarx, ptary, ptarz, C.etarcm, C.ptarcmx, C.ptarcmy, C.ptarcmz, C.ptarcm);
+  const double qstarx = C.qstarx, qstary = C.qstary, qstarz = C.qstarz, qstar = C.qstar;
+  const double pbeamcmx = C.pbeamcmx, pbeamcmy = C.pbeamcmy, pbeamcmz = C.pbeamcmz;
+  const double phadcmx = C.phadcmx, phadcmy = C.phadcmy, phadcmz = C.phadcmz;
+
+  dummy = sqrt(powi(qstary * pbeamcmz - qstarz * pbeamcmy, 2) + powi(qstarz * pbeamcmx - qstarx * pbeamcmz, 2) +
+               powi(qstarx * pbeamcmy - qstary * pbeamcmx, 2));
+  const double tmp2_y_x = (qstary * pbeamcmz - qstarz * pbeamcmy) / dummy;
+  const double tmp2_y_y = (qstarz * pbeamcmx - qstarx * pbeamcmz) / dummy;
+  const double tmp2_y_z = (qstarx * pbeamcmy - qstary * pbeamcmx) / dummy;
+  dummy = sqrt(powi(tmp2_y_y * qstarz - tmp2_y_z * qstary, 2) + powi(tmp2_y_z * qstarx - tmp2_y_x * qstarz, 2) +
+               powi(tmp2_y_x * qstary - tmp2_y_y * qstarx, 2));
+  const double tmp2_x_x = (tmp2_y_y * qstarz - tmp2_y_z * qstary) / dummy;
+  const double tmp2_x_y = (tmp2_y_z * qstarx - tmp2_y_x * qstarz) / dummy;
+  const double tmp2_x_z = (tmp2_y_x * qstary - tmp2_y_y * qstarx) / dummy;
+  const double tmp2_z_x = qstarx / qstar, tmp2_z_y = qstary / qstar, tmp2_z_z = qstarz / qstar;
+  const double phadcm_tmp2x = phadcmx * tmp2_x_x + phadcmy * tmp2_x_y + phadcmz * tmp2_x_z;
+  const double phadcm_tmp2y = phadcmx * tmp2_y_x + phadcmy * tmp2_y_y + phadcmz * tmp2_y_z;
+  C.phicm = atan2(phadcm_tmp2y, phadcm_tmp2x);
+  if (C.phicm < 0.) C.phicm = 2. * pi + C.phicm;
+
+  // Jacobian dt dphi_cm -> dOmega_lab, jacobians.f:180-262
+  const double P = vertex.p.P, E = vertex.p.E;
+  const double psign = cos(phiqn) * cospq + sin(phiqn) * sinpq;
+  const double square_root = vertex.q + pfer * tfcos - P * tcos;
+  const double dp_dcos_num = P + (P * P * tcos - psign * pfer * P * tfsin * tcos / tsin) / square_root;
+  const double dp_dcos_den =
+      ((vertex.nu + efer - E) * P / E + P * tsin * tsin - psign * pfer * tfsin * tsin) / square_root - tcos;
+  const double dp_dcos = dp_dcos_num / dp_dcos_den;
+  const double dp_dphi_num = pfer * P * tsin * tfsin * (cos(phiqn) * sinpq - sin(phiqn) * cospq) / square_root;
+  const double dp_dphi_den =
+      tcos + (pfer * tsin * tfsin * psign - P * tsin * tsin - (vertex.nu + efer - E) * P / E) / square_root;
+  const double dp_dphi = dp_dphi_num / dp_dphi_den;
+  const double dt_dcos_lab = 2. * (vertex.q * P + (vertex.q * tcos - vertex.nu * P / E) * dp_dcos);
+  const double dt_dphi_lab = 2. * (vertex.q * tcos - vertex.nu * P / E) * dp_dphi;
+
+  const double dpxdphi = P * tsin * (-sinpq + (gstar - 1.) * bstarx / (bstar * bstar) * (bstary * cospq - bstarx * sinpq)) +
+                         ((phadcmx + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dphi;
+  const double dpydphi = P * tsin * (cospq + (gstar - 1.) * bstary / (bstar * bstar) * (bstary * cospq - bstarx * sinpq)) +
+                         ((phadcmy + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dphi;
+  const double dpzdphi = P * (gstar - 1.) / (bstar * bstar) * bstarz * tsin * (bstary * cospq - bstarx * sinpq) +
+                         ((phadcmz + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dphi;
+  const double dpxdcos =
+      -P * tcos / tsin *
+          (cospq + (gstar - 1.) * bstarx / (bstar * bstar) * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+      ((phadcmx + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dcos;
+  const double dpydcos =
+      -P * tcos / tsin *
+          (sinpq + (gstar - 1.) * bstary / (bstar * bstar) * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+      ((phadcmy + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dcos;
+  const double dpzdcos =
+      P * (1. - (gstar - 1.) / (bstar * bstar) * bstarz * tcos / tsin *
+                    (bstarx * cospq + bstary * sinpq - tsin / tcos * bstarz)) +
+      ((phadcmz + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dcos;
+
+  const double dpxnewdphi = dpxdphi * tmp2_x_x + dpydphi * tmp2_x_y + dpzdphi * tmp2_x_z;
+  const double dpynewdphi = dpxdphi * tmp2_y_x + dpydphi * tmp2_y_y + dpzdphi * tmp2_y_z;
+  const double dphicmdphi = (dpynewdphi * phadcm_tmp2x - phadcm_tmp2y * dpxnewdphi) /
+                            (phadcm_tmp2x * phadcm_tmp2x + phadcm_tmp2y * phadcm_tmp2y);
+  const double dpxnewdcos = dpxdcos * tmp2_x_x + dpydcos * tmp2_x_y + dpzdcos * tmp2_x_z;
+  const double dpynewdcos = dpxdcos * tmp2_y_x + dpydcos * tmp2_y_y + dpzdcos * tmp2_y_z;
+  const double dphicmdcos = (dpynewdcos * phadcm_tmp2x - phadcm_tmp2y * dpxnewdcos) /
+                            (phadcm_tmp2x * phadcm_tmp2x + phadcm_tmp2y * phadcm_tmp2y);
+  C.jacobian = fabs(dt_dcos_lab * dphicmdphi - dt_dphi_lab * dphicmdcos);
+  C.jac_old = 2 * (efer - 2 * pferz * pfer * E / P * tcos) * (vertex.q + pferz * pfer) * P /
+                  (efer + vertex.nu - (vertex.q + pferz * pfer) * E / P * tcos) -
+              2 * P * pfer;
+}
+
+// physics_pion.f:807-854
+double exclfit(double t, double thetacm, double phicm, double q2_gev, double s_gev, double eps, const double* pp,
+               double fpifact) {
+  const double* p = pp - 1;   // 1-based like the Fortran array
+  const double mtar_gev = 0.938;
+  const double fpi = fpifact / (1.0 + p[1] * q2_gev + p[2] * q2_gev * q2_gev);
+  const double q2fpi2 = q2_gev * (fpi * fpi);
+  double sigL = (p[3] + p[15] / q2_gev) * fabs(t) / powi(fabs(t) + 0.02, 2) * q2fpi2 * exp(p[4] * fabs(t));
+  sigL = sigL / (pow(s_gev, p[11]) + pow(sqrt(s_gev), p[17]));
+  double sigT = p[5] / q2_gev * exp(p[6] * (q2_gev * q2_gev));
+  sigT = sigT / (pow(s_gev, p[12]) + pow(sqrt(s_gev), p[16]));
+  sigT = sigT * exp(p[14] * fabs(t));
+  double sigLT = (p[7] / (1.0 + p[10] * q2_gev)) * exp(p[8] * fabs(t)) * sin(thetacm);
+  sigLT = sigLT / pow(s_gev, p[13]);
+  const double sigTT = (p[9] / (1. + 1.0 * q2_gev)) * exp(-7.0 * fabs(t)) * powi(sin(thetacm), 2);
+  const double sig219 =
+      (sigT + eps * sigL + eps * cos(2.0 * phicm) * sigTT + sqrt(2.0 * eps * (1.0 + eps)) * cos(phicm) * sigLT) / 1.0;
+  double sig = sig219 * 8.539 / powi(s_gev - mtar_gev * mtar_gev, 2);
+  sig = sig / 2.0 / 3.1415928 / 1.0e+06;
+  return sig;
+}
+
+// physics_pion.f:738-805 (charged pions)
+double sig_param_2021(double thcm, double phicm, double t, double q2, double wsq, double eps, int which_pion) {
+  static const double pp[17] = {1.60077, -0.01523, 37.08142, -4.11060, 23.26192, 0.00983, 0.87073, -5.77115, -271.08678,
+                                0.13766, -0.00855, 0.27885,  -1.13212, -1.50415, -6.34766, 0.55769, -0.01709};
+  static const double pm[17] = {1.75169, 0.11144, 47.35877, -4.69434, 1.60552, 0.00800, 0.44194, -2.29188, -41.67194,
+                                0.69475, 0.02527, -0.50178, -1.22825, -1.16878, 5.75825, -1.00355, 0.05055};
+  if (which_pion == 1 || which_pion == 11 || which_pion == 3) return exclfit(t, thcm, phicm, q2, wsq, eps, pm, 1.0);
+  return exclfit(t, thcm, phicm, q2, wsq, eps, pp, 1.0);
+}
+
+// physics_kaon.f:175-236
+double sig_factorized(double q2, double w, double t, double pk, double mrec) {
+  const double Mp = K::Mp, Mk2 = K::Mk2;
+  const double nu = (w * w + q2 - Mp * Mp) / 2. / Mp;
+  const double q = sqrt(q2 + nu * nu);
+  const double qcm = q * (Mp / w);
+  const double nucm = sqrt(qcm * qcm - q2);
+  const double tmin = -1. * (Mk2 - q2 - 2 * nucm * sqrt(pk * pk + Mk2) + 2 * qcm * pk);
+  const double q2val = q2 / 1.e6, w2val = w * w / 1.e6, pkval = pk / 1000., tval = t / 1.e6, tminval = tmin / 1.e6;
+  double fact_q, fact_t, fact_w = 0.0;
+  if (mrec < 1150.) {
+    fact_q = 1. / powi(q2val + 2.67, 2);
+    fact_t = exp(-2.1 * (tval - tminval));
+    if (w2val != 0) {
+      fact_w = 0.959 * 4.1959 * pkval / (sqrt(w2val) * (w2val - 0.93827 * 0.93827));
+      fact_w = fact_w + (0.18 * (1.72 * 1.72) * (0.10 * 0.10)) /
+                            (powi(w2val - 1.72 * 1.72, 2) + (1.72 * 1.72) * (0.10 * 0.10));
+    }
+  } else {
+    fact_q = 1. / powi(q2val + 0.79, 2);
+    fact_t = exp(-1.0 * (tval - tminval));
+    if (w2val != 0) fact_w = 0.959 * 4.1959 * pkval / (sqrt(w2val) * (w2val - 0.93827 * 0.93827));
+  }
+  return fact_q * fact_t * fact_w;
+}
+
+Fermi hydrogen_fermi(const simc_run_config& cfg) {
+  Fermi F;
+  F.efer = cfg.targ.Mtar_struck;          // event.f:335
+  return F;
+}
+}  // namespace
+
+// physics_pion.f:1-130
+double peepi(Sim& s, const Event& vertex, EventMain& main) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const Fermi F = hydrogen_fermi(cfg);
+  CmFrame C;
+  transform_to_cm(vertex, main, F, C);
+  main.thetacm = C.thetacm;
+  main.phicm = C.phicm;
+  main.pcm = C.phadcm;
+  main.davejac = C.jacobian;
+  main.johnjac = C.jac_old;
+  double tfcos = F.pferx * vertex.uq.x + F.pfery * vertex.uq.y + F.pferz * vertex.uq.z;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double sgev = powi(vertex.nu + F.efer, 2) - powi(vertex.q + F.pfer * tfcos, 2) - powi(F.pfer * tfsin, 2);
+  main.wcm = sqrt(sgev);
+  const double k_eq = (main.wcm * main.wcm - targ.Mtar_struck * targ.Mtar_struck) / 2. / targ.Mtar_struck;
+  s.ntup.sigcm1 =
+      sig_param_2021(C.thetacm, C.phicm, main.t / 1.e6, vertex.Q2 / 1.e6, sgev / 1.e6, main.epsilon, cfg.which_pion);
+  double sigma_eepi = s.ntup.sigcm1;
+  if (main.wcm < 2000) s.low_w = true;      // the MAID-2007 blend (physics_pion.f:88-107) is not restated: counted
+  s.ntup.sigcm = sigma_eepi;
+  const double fac = 1. / (1. - F.pferz * F.pfer / F.efer) * targ.Mtar_struck / F.efer;
+  const double gtpr = K::alpha / 2. / (K::pi * K::pi) * vertex.e.E / vertex.Ein * k_eq / vertex.Q2 / (1. - main.epsilon);
+  return sigma_eepi * C.jacobian * (gtpr * fac);
+}
+
+// physics_kaon.f:1-171
+double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const Fermi F = hydrogen_fermi(cfg);
+  CmFrame C;
+  transform_to_cm(vertex, main, F, C);
+  double jacobian = C.jacobian / (2. * C.phadcm * C.qstar);
+  double jac_old = C.jac_old / (2. * C.phadcm * C.qstar);
+  main.thetacm = C.thetacm;
+  main.phicm = C.phicm;
+  main.pcm = C.phadcm;
+  main.davejac = jacobian;
+  main.johnjac = jac_old;
+  double tfcos = F.pferx * vertex.uq.x + F.pfery * vertex.uq.y + F.pferz * vertex.uq.z;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double sgev = powi(vertex.nu + F.efer, 2) - powi(vertex.q + F.pfer * tfcos, 2) - powi(F.pfer * tfsin, 2);
+  main.wcm = sqrt(sgev);
+  s.ntup.sigcm2 = sig_factorized(vertex.Q2, main.wcm, main.t, C.phadcm, targ.Mrec_struck);
+  const double sigma_eek = s.ntup.sigcm2;
+  s.ntup.sigcm = sigma_eek;
+  const double k_eq = (main.wcm * main.wcm - targ.Mtar_struck * targ.Mtar_struck) / 2. / targ.Mtar_struck;
+  const double fac = 1. / (1. - F.pferz * F.pfer / F.efer) * targ.Mtar_struck / F.efer;
+  const double gtpr = K::alpha / 2. / (K::pi * K::pi) * vertex.e.E / vertex.Ein * k_eq / vertex.Q2 / (1. - main.epsilon);
+  const double result = sigma_eek * jacobian * (gtpr * fac);
+  survivalprob = 1.0;
+  if (!cfg.doing_decay) {
+    double zaero = 0.;
+    if (cfg.hadron_arm == 1) zaero = 0.;
+    else if (cfg.hadron_arm == 2) zaero = -82.8;
+    else if (cfg.hadron_arm == 3) zaero = -183.;
+    else if (cfg.hadron_arm == 4) zaero = -183.;
+    const double pathlen = main.FP_p.path + zaero * (1 + main.FP_p.dx * main.FP_p.dx + main.FP_p.dy * main.FP_p.dy);
+    const double betak = cfg.spec_p.P / sqrt(cfg.spec_p.P * cfg.spec_p.P + cfg.Mh2);
+    const double gammak = 1. / sqrt(1. - betak * betak);
+    survivalprob = 1. / exp(pathlen / (cfg.ctau * betak * gammak));
+    s.trk.decdist = survivalprob;
+  }
+  return result;
+}
+
+}  // namespace simc_oracle

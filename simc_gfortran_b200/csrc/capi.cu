@@ -302,9 +302,13 @@ int weight_qexp(const simc_run_config& cfg) {
 // Which settings this build of the loop implements; everything else is refused loudly.
 int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
-  if (!c.doing_hyd_elast || c.doing_deuterium || c.doing_heavy || c.doing_pion || c.doing_kaon || c.doing_delta ||
-      c.doing_rho || c.doing_semi || c.doing_phsp)
-    return fail(h, SIMC_ERR_ARG, "this build of the event loop implements H(e,e'p) (doing_hyd_elast) only");
+  const bool meson = (c.doing_hydpi && c.doing_pion) || (c.doing_hydkaon && c.doing_kaon);
+  if (!(c.doing_hyd_elast || meson) || c.doing_deuterium || c.doing_heavy || c.doing_delta || c.doing_rho || c.doing_semi ||
+      c.doing_phsp)
+    return fail(h, SIMC_ERR_ARG,
+                "this build of the event loop implements H(e,e'p), H(e,e'pi+-) and H(e,e'K+) (hydrogen targets)");
+  if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
+    return fail(h, SIMC_ERR_ARG, "Delta final states (which_pion = 2, 3) are not implemented");
   if (c.using_rad && (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 ||
                       !c.use_offshell_rad || c.use_expon != 0))
     return fail(h, SIMC_ERR_ARG,
@@ -591,7 +595,8 @@ static const char* kEventFields[SIMC_EVENT_NREC] = {
     "Egamma_used3", "ntail", "target.x", "target.y", "target.z", "Eloss1", "Eloss2", "Eloss3", "SP.e.delta",
     "SP.e.yptar", "SP.e.xptar", "SP.p.delta", "SP.p.yptar", "SP.p.xptar", "recon.e.delta", "recon.e.yptar",
     "recon.e.xptar", "recon.p.delta", "recon.p.yptar", "recon.p.xptar", "recon.Em", "recon.Pm", "recon.W",
-    "hardcorfac"};
+    "hardcorfac", "main.thetacm", "main.phicm", "ntup.sigcm", "main.davejac", "survivalprob", "ntup.mm", "main.wcm",
+    "main.t"};
 const char* simc_b200_event_field_name(int k) { return (k >= 0 && k < SIMC_EVENT_NREC) ? kEventFields[k] : ""; }
 
 }  // extern "C"

@@ -2,10 +2,11 @@
 // Replaces generate + complete_ev (event.f:126-1052), generate_rad (radc.f:120-519),
 // the target-to-spectrometer part of montecarlo (simc.f:1365-1443, 1623-1645, 1655-1846),
 // complete_recon_ev (event.f:1056-1359), complete_main (event.f:1363-1569) and sigep
-// (physics_proton.f:1-190).  Reaction coverage of this build: H(e,e'p); the host refuses the
-// other reaction flags at create().
+// (physics_proton.f:1-190).  Reaction coverage of this build: H(e,e'p), H(e,e'pi+-) and H(e,e'K+);
+// the host refuses the other reaction flags at create().
 #pragma once
 #include "radc.cuh"
+#include "physics_meson.cuh"
 
 namespace simc {
 
@@ -73,6 +74,8 @@ struct EventState {
   double v_pE, v_pP, v_pdelta, v_pyptar, v_pxptar, v_ptheta, v_pphi;
   double v_Q2, v_Em, v_Pm, v_Trec;
   double uex, uey, uez, upx, upy, upz;
+  // meson production only: vertex%nu, q, uq and main%epsilon, theta_pq, phi_pq, t, tmin, W
+  double v_nu, v_q, uqx, uqy, uqz, m_eps, m_thpq, m_phipq, m_t, m_tmin, m_W;
   // orig (fields that differ from vertex)
   double o_Ein, o_eE, o_edelta, o_pE, o_pP, o_pdelta;
   RadEvDev rad;
@@ -297,6 +300,225 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
   SIMC_PHASE();
   if (ok) {
     // orig = vertex (+) radiation, radc.f:476-515
+    s.o_Ein = s.v_Ein + R.Egamma_used[0];
+    s.o_eE = s.v_eE - R.Egamma_used[1];
+    if (s.o_eE <= 0e0) ok = false;
+  }
+  if (ok) {
+    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
+    s.o_pE = s.v_pE - R.Egamma_used[2];
+    if (s.o_pE <= cfg.Mh) ok = false;
+  }
+  if (ok) {
+    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
+  }
+  return ok;
+}
+
+// ---- H(e,e'pi) / H(e,e'K): complete_ev, event.f:432-1052 with doing_hydpi / doing_hydkaon ----------
+// Needs v_Ein, v_eE, the electron and hadron angles and tz; fills the hadron energy from the
+// two-body quadratic (event.f:634-698), W, epsilon, theta_pq, phi_pq, t (event.f:707-771), the
+// jacobian, Eloss/teff(2:3) and the radiative constants.
+template <class RNG, class GAUSS>
+SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+  const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
+  const simc_target& targ = cfg.targ;
+  if (run) {
+    s.jacobian = 1.0;
+    s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
+    s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
+    s.uez = m::cos(s.v_etheta);
+    s.upx = m::sin(s.v_ptheta) * m::cos(s.v_pphi);
+    s.upy = m::sin(s.v_ptheta) * m::sin(s.v_pphi);
+    s.upz = m::cos(s.v_ptheta);
+    const double eP = s.v_eE;
+    s.v_nu = s.v_Ein - s.v_eE;
+    s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
+    s.v_q = sqrt(s.v_Q2 + s.v_nu * s.v_nu);
+    s.uqx = -eP * s.uex / s.v_q;
+    s.uqy = -eP * s.uey / s.v_q;
+    s.uqz = (s.v_Ein - eP * s.uez) / s.v_q;
+    s.v_Pm = 0.0;                                   // pfer
+    const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
+    const double b = s.v_q * s.v_q;
+    const double c = s.v_nu + targ.M;
+    const double t = c * c - b + Mh2 - targ.Mrec_struck * targ.Mrec_struck;
+    const double QA = 4. * (a * a - c * c);
+    const double QB = 4. * c * t;
+    const double QC = -4. * (a * a) * Mh2 - t * t;
+    const double radical = QB * QB - 4. * QA * QC;
+    if (radical < 0) run = false;
+    if (run) {
+      s.v_pE = (-QB - sqrt(radical)) / 2. / QA;
+      if (s.v_pE < 0.0) run = false;
+      else if (c - s.v_pE <= targ.Mrec_struck) run = false;
+      else if (s.v_pE <= Mh) run = false;
+    }
+  }
+  if (run) {
+    s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
+    s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+    // event.f:707-771
+    const double W2 = targ.Mtar_struck * targ.Mtar_struck + 2. * targ.Mtar_struck * s.v_nu - s.v_Q2;
+    s.m_W = sqrt(fabs(W2)) * W2 / fabs(W2);
+    const double th2 = m::tan(s.v_etheta / 2.);
+    s.m_eps = 1. / (1. + 2. * (1 + s.v_nu * s.v_nu / s.v_Q2) * (th2 * th2));
+    s.m_thpq = m::acos(s.upx * s.uqx + s.upy * s.uqy + s.upz * s.uqz);
+    s.m_t = s.v_Q2 - Mh2 + 2 * s.v_nu * s.v_pE - 2 * s.v_pP * s.v_q * m::cos(s.m_thpq);
+    s.m_tmin = s.v_Q2 - Mh2 + 2 * s.v_pE * s.v_nu - 2 * s.v_pP * s.v_q;
+    const double qx = -s.uqy, qy = s.uqx, qz = s.uqz;
+    const double px = -s.upy, py = s.upx, pz = s.upz;
+    double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+    const double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+    dummy = sqrt(qx * qx + qy * qy);
+    const double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+    const double p_new_x = px * new_x_x + py * new_x_y + pz * new_x_z;
+    const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
+    s.m_phipq = m::atan2(p_new_y, p_new_x);
+    if (s.m_phipq < 0.e0) s.m_phipq = s.m_phipq + 2. * SIMC_PI_D;
+    s.v_Trec = 0.0;
+    // event.f:1013-1023: both arms' angles were generated
+    double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+    r = sqrt(1. + s.v_pyptar * s.v_pyptar + s.v_pxptar * s.v_pxptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+  }
+  const double zpos = s.tz - targ.zoffset;
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
+  SIMC_PHASE();
+  if (run) {
+    if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    radc_init_ev(cfg, v, s.teff[0], s.teff[1], s.rad);
+  }
+  SIMC_PHASE();
+  return run;
+}
+
+// generate + generate_rad for hydrogen meson production: event.f:126-428 (both arms' angles and the
+// electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
+// limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+  const simc_target& targ = cfg.targ;
+  const simc_gen_limits& gen = cfg.gen;
+  if (ok) {
+    s.tx = gauss(rng, 3.0) * gen.xwid + targ.xoffset;
+    s.ty = gauss(rng, 3.0) * gen.ywid + targ.yoffset;
+    double t3, t4, t5, t6;
+    if (targ.fr_pattern == 1) {
+      t3 = rng.uniform() * SIMC_PI_D;
+      t4 = rng.uniform() * SIMC_PI_D;
+      t5 = m::cos(t3) * targ.fr1;
+      t6 = m::cos(t4) * targ.fr2;
+    } else if (targ.fr_pattern == 2) {
+      t3 = rng.uniform() * 2. * SIMC_PI_D;
+      t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
+      t5 = m::cos(t3) * t4;
+      t6 = m::sin(t3) * t4;
+    } else if (targ.fr_pattern == 3) {
+      t3 = 2. * rng.uniform() - 1.0;
+      t4 = 2. * rng.uniform() - 1.0;
+      t5 = targ.fr1 * t3;
+      t6 = targ.fr2 * t4;
+    } else {
+      t5 = 0.0; t6 = 0.0;
+    }
+    s.tx = s.tx + t5;
+    s.ty = s.ty + t6;
+    s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
+    s.rastery = t6;
+    trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+    if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
+    s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
+    s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
+    s.Ein_shift = s.v_Ein - cfg.Ebeam_vertex_ave;
+    s.Ee_shift = s.Coulomb - targ.Coulomb_ave;
+    s.gen_weight = 1.0;
+    s.v_eyptar = gen.e.yptar.min + rng.uniform() * (gen.e.yptar.max - gen.e.yptar.min);
+    s.v_exptar = gen.e.xptar.min + rng.uniform() * (gen.e.xptar.max - gen.e.xptar.min);
+    s.v_pyptar = gen.p.yptar.min + rng.uniform() * (gen.p.yptar.max - gen.p.yptar.min);
+    s.v_pxptar = gen.p.xptar.min + rng.uniform() * (gen.p.xptar.max - gen.p.xptar.min);
+    // event.f:296-318
+    const double Emin = fmax(gen.e.E.min, gen.sumEgen.min), Emax = fmin(gen.e.E.max, gen.sumEgen.max);
+    if (Emin > Emax) ok = false;
+    if (ok) {
+      s.gen_weight = s.gen_weight * (Emax - Emin) / (gen.e.E.max - gen.e.E.min);
+      s.v_eE = Emin + rng.uniform() * (Emax - Emin);
+      s.v_edelta = 100. * (s.v_eE - cfg.spec_e.P) / cfg.spec_e.P;
+      physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, s.v_exptar, s.v_eyptar, s.v_etheta, s.v_ephi);
+      physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
+      s.v_Em = 0.0;
+      s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
+      s.rad.ntail = 0;
+    }
+  }
+  SIMC_PHASE();
+  ok = complete_ev_meson(cfg, rng, gauss, s, ok);
+  if (ok) s.Trec = s.v_Trec;
+  if (!cfg.using_rad) {
+    if (ok) {
+      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
+      s.o_pdelta = s.v_pdelta;
+    }
+    return ok;
+  }
+  RadEvDev& R = s.rad;
+  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
+  int which = 0;
+  if (ok) {
+    const double x = rng.uniform();
+    if (x >= R.frac[0] + R.frac[1]) R.ntail = 3;
+    else if (x >= R.frac[0]) R.ntail = 2;
+    else R.ntail = 1;
+    const int ntail = R.ntail;
+    if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:289-294
+      emin = 0.;
+      emax = gen.sumEgen.max - s.v_eE;
+      emax = fmin(emax, cfg.Egamma1_max);
+      which = 1;
+    } else if (cfg.doing_tail[1] && ntail == 2) {   // radc.f:358-374 without the (e,e'p) clauses
+      emin = s.v_eE - cfg.edge.e.E.max;
+      emax = s.v_eE - cfg.edge.e.E.min;
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
+      which = 2;
+    } else if (R.rad_proton_this_ev && ntail == 3) {   // radc.f:409-425
+      emin = s.v_pE - cfg.edge.p.E.max;
+      emax = s.v_pE - cfg.edge.p.E.min;
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
+      which = 3;
+    }
+    if (which) {
+      emin = emin - cfg.dE_edge_test;
+      emax = emax + cfg.dE_edge_test;
+      if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+      basicrad4(R, rng, emin, emax, eg, bw);
+      if (bw <= 0) ok = false;
+      else {
+        R.Egamma_used[which - 1] = eg;
+        if (which == 1) s.v_Ein = s.v_Ein - eg;
+      }
+    }
+  }
+  SIMC_PHASE();
+  const bool reenter = ok && which == 1;                       // radc.f:324
+  const bool re_ok = complete_ev_meson(cfg, rng, gauss, s, reenter);
+  if (reenter && !re_ok) ok = false;
+  if (ok && which) {
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
+  }
+  SIMC_PHASE();
+  if (ok) {
     s.o_Ein = s.v_Ein + R.Egamma_used[0];
     s.o_eE = s.v_eE - R.Egamma_used[1];
     if (s.o_eE <= 0e0) ok = false;

@@ -133,6 +133,7 @@ void accum_to_host(const void* dev_copy, void* out_v, int qexp_w) {
   };
   o.ntried += (int64_t)d.counters[0]; o.nsuccess += (int64_t)d.counters[1]; o.ncontribute += (int64_t)d.counters[2];
   o.npasscuts += (int64_t)d.counters[3]; o.ncontribute_no_rad_proton += (int64_t)d.counters[4];
+  o.unsupported += (int64_t)d.counters[5];
   addf(o.wtcontribute, d.wt, qexp_w);
   addf(o.sum_sigcc, d.sigcc, qexp_w);
   for (int i = 0; i < 8; ++i) { addf(o.sumerr[i], d.sumerr[i], -80); addf(o.sumerr2[i], d.sumerr2[i], -80); }

@@ -37,6 +37,10 @@ enum StateField : int {
   F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_PASSCUTS, F_REM, F_RPM, F_RW,
   // track of the arm in flight, between the two segments of its program
   F_TK_XS, F_TK_YS, F_TK_DX, F_TK_DY, F_TK_DPP, F_TK_P, F_TK_M2, F_TK_PATH, F_TK_DECD, F_TK_DFLAG, F_TK_FRY,
+  // meson production: vertex%nu, q, uq, up, main%epsilon, theta_pq, phi_pq, t, W; hadron focal-plane slopes;
+  // results of peepi / peeK
+  F_VNU, F_VQ, F_UQX, F_UQY, F_UQZ, F_UPX, F_UPY, F_UPZ, F_MEPS, F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
+  F_FPP_DX, F_FPP_DY, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM,
   F_NFIELDS
 };
 
@@ -49,7 +53,7 @@ struct StateBuf {
 
 // ---- exact accumulators --------------------------------------------------------------------
 struct DevAccum {
-  unsigned long long counters[8];                 // ntried, nsuccess, ncontribute, npasscuts, nco_no_rad_proton
+  unsigned long long counters[8];                 // ntried, nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported
   unsigned long long wt[2], sigcc[2];             // 128-bit two's complement (lo, hi)
   unsigned long long sumerr[8][2], sumerr2[8][2];
   unsigned long long hist_w[6][SIMC_NHIST][2];
@@ -145,7 +149,10 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
     rng.init(A.seed, (unsigned long long)(A.first_try + (active ? i : 0)), 0u, 0u);
     s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
-    ok = generate_hyd_elast(cfg, rng, GaussFn(), s, active);      // every thread of the CTA walks through it
+    // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
+    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
+    if (meson) ok = generate_meson(cfg, rng, GaussFn(), s, active);
+    else ok = generate_hyd_elast(cfg, rng, GaussFn(), s, active);
     if (active) {
       // geni histograms: every try, from the vertex values (simc.f:253-262)
       const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
@@ -176,6 +183,12 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
       S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
       S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
       S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
+      if (meson && ok) {
+        S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
+        S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
+        S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
+        S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
+      }
     }
     const unsigned pos = warp_append(&A.counts[1], active && ok);
     if (active && ok) A.lists[0 * A.st.cap + pos] = slot;
@@ -342,6 +355,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
         S.st(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta); S.st(WHICH == 1 ? F_RCP_Y : F_RCE_Y, slot, rc_yptar);
         S.st(WHICH == 1 ? F_RCP_X : F_RCE_X, slot, rc_xptar); S.st(WHICH == 1 ? F_RCP_Z : F_RCE_Z, slot, rc_z);
         S.st(WHICH == 1 ? F_FPP_PATH : F_FPE_PATH, slot, path);
+        if (WHICH == 1) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
         // recon quantities of this arm, simc.f:1623-1645 / :1820-1846
         double rP = sp.P * (1. + rc_delta / 100.);
         double rE = WHICH == 1 ? sqrt(rP * rP + Mh2) : rP;
@@ -386,7 +400,7 @@ struct BlockAcc {
   unsigned long long sums[18][2];                    // wt, sigcc, sumerr[8], sumerr2[8]
   unsigned long long hist_w[6][SIMC_NHIST][2];
   unsigned hist_n[9][SIMC_NHIST];                    // gen (7), RECON Em, RECON Pm
-  unsigned counters[4];                              // nsuccess, ncontribute, npasscuts, nco_no_rad_proton
+  unsigned counters[6];                              // nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported
   long long mins[40], maxs[40];                      // contrib (30 used of 32) + slop (8)
 };
 
@@ -442,7 +456,7 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;
     const bool active = i < n_in;
-    bool success = false, pass_cuts = false, no_rad_p = false;
+    bool success = false, pass_cuts = false, no_rad_p = false, low_w = false;
     double weight = 0, sigcc = 0, rEm = 0, rPm = 0;
     double rec_vals[6] = {0, 0, 0, 0, 0, 0}, gen_vals[7] = {0, 0, 0, 0, 0, 0, 0}, err[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double cv[30], sv[8];
@@ -468,15 +482,45 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
       const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const double rTrec = 0.0;
-      rEm = nu + cfg.targ.M - rpE - rTrec;
+      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
       // complete_main, event.f:1363-1569
       const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
-      sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
-      const double sigcc_recon = sigep(r_Ein, reE, reth, Q2);
+      double sigcc_recon, tgtweight = 1.0, survivalprob = 1.0;
+      if (!meson) {
+        rEm = nu + cfg.targ.M - rpE - rTrec;
+        sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
+        sigcc_recon = sigep(r_Ein, reE, reth, Q2);
+      } else {
+        // event.f:1306-1345: missing mass of the undetected system
+        rEm = nu + cfg.targ.Mtar_struck - rpE;
+        const double mm2 = rEm * rEm - rPm * rPm;
+        S.st(F_MM, slot, sqrt(fabs(mm2)) * fabs(mm2) / mm2);
+        MesonVertex mv;
+        mv.Ein = v_Ein; mv.eE = v_eE; mv.nu = S.ld(F_VNU, slot); mv.q = S.ld(F_VQ, slot); mv.Q2 = v_Q2;
+        mv.pP = S.ld(F_VPP, slot); mv.pE = S.ld(F_VPE, slot);
+        mv.uqx = S.ld(F_UQX, slot); mv.uqy = S.ld(F_UQY, slot); mv.uqz = S.ld(F_UQZ, slot);
+        mv.upx = S.ld(F_UPX, slot); mv.upy = S.ld(F_UPY, slot); mv.upz = S.ld(F_UPZ, slot);
+        mv.phi_pq = S.ld(F_MPHIPQ, slot); mv.t = S.ld(F_MT, slot); mv.epsilon = S.ld(F_MEPS, slot);
+        MesonWeight mw;
+        if (cfg.doing_pion) {
+          mw = peepi(cfg, mv);
+          tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
+        } else {
+          mw = peeK(cfg, mv);
+          tgtweight = (cfg.which_kaon == 2 || cfg.which_kaon == 12) ? cfg.targ.N : cfg.targ.Z;
+          if (!cfg.doing_decay) survivalprob = kaon_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
+        }
+        low_w = mw.low_w;
+        sigcc = mw.sigcc;
+        sigcc_recon = 1.0;
+        S.st(F_THCM, slot, mw.thetacm); S.st(F_PHICM, slot, mw.phicm); S.st(F_SIGCM, slot, mw.sigcm);
+        S.st(F_DAVEJAC, slot, mw.davejac); S.st(F_SURV, slot, survivalprob); S.st(F_WCM, slot, mw.wcm);
+      }
       if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
       const double SF_weight = 1.0;
       weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
-      weight = weight * 1.0;
+      weight = weight * tgtweight;
+      if (cfg.doing_kaon && !cfg.doing_decay) weight = weight * survivalprob;
       // pass_cuts, simc.f:229-241 (p-arm upper delta edge uses SPedge%e%delta%max, as written)
       const double red = S.ld(F_RCE_D, slot), rey = S.ld(F_RCE_Y, slot), rex = S.ld(F_RCE_X, slot), rez = S.ld(F_RCE_Z, slot);
       const double rpd = S.ld(F_RCP_D, slot), rpy = S.ld(F_RCP_Y, slot), rpx = S.ld(F_RCP_X, slot), rpz = S.ld(F_RCP_Z, slot);
@@ -518,7 +562,8 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
         const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
         const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
         const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
-        const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), v_eE + v_pE - Ein_shift,
+        const double sumEgen = meson ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
+        const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), sumEgen,
                                o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
                                spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};
 #pragma unroll
@@ -533,6 +578,7 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
     warp_count_if(&B.counters[0], success);
     warp_count_if(&B.counters[1], success);
     warp_count_if(&B.counters[3], success && no_rad_p);
+    warp_count_if(&B.counters[4], success && low_w);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int b = success ? hist_bin(cfg.hist_axis[0][k], rec_vals[k]) : -1;
@@ -591,7 +637,7 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
     unsigned long long* dst = h < 7 ? &acc->hist_n[1][h][b] : h == 7 ? &acc->hist_n[0][SIMC_H_EM][b] : &acc->hist_n[0][SIMC_H_PM][b];
     atomicAdd(dst, (unsigned long long)v);
   }
-  if (threadIdx.x < 4 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
+  if (threadIdx.x < 5 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
   for (int k = threadIdx.x; k < 40; k += kBlock) {
     if (B.mins[k] == 0x7fffffffffffffffLL) continue;
     if (k < 32) { atomicMin(&acc->contrib_lo[k], B.mins[k]); atomicMax(&acc->contrib_hi[k], B.maxs[k]); }
@@ -614,7 +660,7 @@ __global__ void k_records(LoopArgs A, double* __restrict__ rec, int* __restrict_
         F_VEIN, F_VEE, F_VEDELTA, F_VEYP, F_VEXP, F_VPE, F_VPDELTA, F_VPYP, F_VPXP, F_VQ2,
         F_OEE, F_OPE, F_EG0, F_EG1, F_EG2, F_NTAIL, F_TX, F_TY, F_TZ, F_ELOSS0, F_ELOSS1, F_ELOSS2,
         F_SPE_D, F_SPE_Y, F_SPE_X, F_SPP_D, F_SPP_Y, F_SPP_X, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCP_D, F_RCP_Y, F_RCP_X,
-        F_REM, F_RPM, F_RW, F_HARDCOR};
+        F_REM, F_RPM, F_RW, F_HARDCOR, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM, F_MT};
     for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = S.ld(fields[k], slot);
     rec[0 * n + i] = (double)stage;
     status[i] = stage;

@@ -1,0 +1,254 @@
+// Meson electroproduction weights on the device (and on the host for the central weight):
+// transform_to_cm (jacobians.f:1-282), peepi with sig_param_2021/exclfit (physics_pion.f:1-130,
+// 738-854), peeK with sig_factorized (physics_kaon.f:1-236).  Hydrogen targets: the struck
+// nucleon is at rest (pfer = 0, efer = Mtar_struck, event.f:330-335); the Fermi-momentum terms of
+// the reference formulas multiply that zero and are kept where they decide the rounding.
+//
+// Not built: the MAID-2007 table branch of peepi below W = 2 GeV (physics_pion.f:88-107) -- such
+// events are counted in simc_accum.unsupported and take the parametrisation alone; the Saghai
+// model of peeK (eekeek), which only feeds an ntuple column.
+#pragma once
+#include "target.cuh"
+
+namespace simc {
+
+struct MesonVertex {          // what the weights read from `vertex` / `main`
+  double Ein, eE, nu, q, Q2, pP, pE;
+  double uqx, uqy, uqz, upx, upy, upz;
+  double phi_pq, t, epsilon;
+};
+struct MesonCm {
+  double thetacm, phicm, pcm, qstar, jacobian, jac_old, wcm, sgev;
+};
+
+namespace mesondetail {
+struct MV4 { double e, x, y, z, p; };
+// loren.f:1-26
+SIMC_HD MV4 loren(double gam, double bx, double by, double bz, double e, double x, double y, double z) {
+  MV4 r;
+  const double gam1 = gam * gam / (1. + gam);
+  r.e = gam * (e - bx * x - by * y - bz * z);
+  r.x = (1 + gam1 * bx * bx) * x + gam1 * bx * (by * y + bz * z) - gam * bx * e;
+  r.y = (1 + gam1 * by * by) * y + gam1 * by * (bx * x + bz * z) - gam * by * e;
+  r.z = (1 + gam1 * bz * bz) * z + gam1 * bz * (by * y + bx * x) - gam * bz * e;
+  r.p = sqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+  return r;
+}
+SIMC_HD double msq(double x) { return x * x; }
+}  // namespace mesondetail
+
+// jacobians.f:1-282 for a nucleon at rest
+SIMC_HD_CALL void transform_to_cm(const MesonVertex& v, double efer, MesonCm& C) {
+  using namespace mesondetail;
+  const double pi = 3.141592653589793;
+  const double pfer = 0.0, pferx = 0.0, pfery = 0.0, pferz = 0.0;
+  double tcos = v.upx * v.uqx + v.upy * v.uqy + v.upz * v.uqz;
+  if (tcos - 1. > 0. && tcos - 1. < 1.e-8) tcos = 1.0;
+  const double tsin = sqrt(1. - tcos * tcos);
+  double tfcos = pferx * v.uqx + pfery * v.uqy + pferz * v.uqz;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double cospq = m::cos(v.phi_pq), sinpq = m::sin(v.phi_pq);
+  const double qx = -v.uqy, qy = v.uqx, qz = v.uqz;
+  const double px = -pfery, py = pferx, pz = pferz;
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  const double tmp_x_x = -qx * qz / dummy, tmp_x_y = -qy * qz / dummy, tmp_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  const double tmp_y_x = qy / dummy, tmp_y_y = -qx / dummy, tmp_y_z = 0.0;
+  const double p_tmp_x = pfer * (px * tmp_x_x + py * tmp_x_y + pz * tmp_x_z);
+  const double p_tmp_y = pfer * (px * tmp_y_x + py * tmp_y_y + pz * tmp_y_z);
+  double phiqn;
+  if (p_tmp_x == 0.) phiqn = 0.;
+  else phiqn = m::atan2(p_tmp_y, p_tmp_x);
+  if (phiqn < 0.) phiqn = phiqn + 2. * pi;
+  const double cosqn = m::cos(phiqn), sinqn = m::sin(phiqn);
+
+  const double pbeam = v.Ein;
+  const double beam_tmpx = pbeam * tmp_x_z, beam_tmpy = pbeam * tmp_y_z, beam_tmpz = pbeam * v.uqz;
+  const double bstar = sqrt(msq(v.q + pfer * tfcos) + msq(pfer * tfsin)) / (efer + v.nu);
+  const double gstar = 1. / sqrt(1. - bstar * bstar);
+  const double bstarz = (v.q + pfer * tfcos) / (efer + v.nu);
+  const double bstarx = p_tmp_x / (efer + v.nu);
+  const double bstary = p_tmp_y / (efer + v.nu);
+  const MV4 beam = loren(gstar, bstarx, bstary, bstarz, v.Ein, beam_tmpx, beam_tmpy, beam_tmpz);
+  const MV4 qs = loren(gstar, bstarx, bstary, bstarz, v.nu, 0.e0, 0.e0, v.q);
+  const double phadz = v.pP * tcos, phadx = v.pP * tsin * cospq, phady = v.pP * tsin * sinpq;
+  const MV4 had = loren(gstar, bstarx, bstary, bstarz, v.pE, phadx, phady, phadz);
+  C.thetacm = m::acos((had.x * qs.x + had.y * qs.y + had.z * qs.z) / had.p / qs.p);
+  C.pcm = had.p;
+  C.qstar = qs.p;
+
+  dummy = sqrt(msq(qs.y * beam.z - qs.z * beam.y) + msq(qs.z * beam.x - qs.x * beam.z) + msq(qs.x * beam.y - qs.y * beam.x));
+  const double tmp2_y_x = (qs.y * beam.z - qs.z * beam.y) / dummy;
+  const double tmp2_y_y = (qs.z * beam.x - qs.x * beam.z) / dummy;
+  const double tmp2_y_z = (qs.x * beam.y - qs.y * beam.x) / dummy;
+  dummy = sqrt(msq(tmp2_y_y * qs.z - tmp2_y_z * qs.y) + msq(tmp2_y_z * qs.x - tmp2_y_x * qs.z) +
+               msq(tmp2_y_x * qs.y - tmp2_y_y * qs.x));
+  const double tmp2_x_x = (tmp2_y_y * qs.z - tmp2_y_z * qs.y) / dummy;
+  const double tmp2_x_y = (tmp2_y_z * qs.x - tmp2_y_x * qs.z) / dummy;
+  const double tmp2_x_z = (tmp2_y_x * qs.y - tmp2_y_y * qs.x) / dummy;
+  const double had2x = had.x * tmp2_x_x + had.y * tmp2_x_y + had.z * tmp2_x_z;
+  const double had2y = had.x * tmp2_y_x + had.y * tmp2_y_y + had.z * tmp2_y_z;
+  C.phicm = m::atan2(had2y, had2x);
+  if (C.phicm < 0.) C.phicm = 2. * pi + C.phicm;
+
+  // dt dphi_cm -> dOmega_lab, jacobians.f:180-262
+  const double P = v.pP, E = v.pE;
+  const double psign = cosqn * cospq + sinqn * sinpq;
+  const double square_root = v.q + pfer * tfcos - P * tcos;
+  const double dp_dcos_num = P + (P * P * tcos - psign * pfer * P * tfsin * tcos / tsin) / square_root;
+  const double dp_dcos_den = ((v.nu + efer - E) * P / E + P * tsin * tsin - psign * pfer * tfsin * tsin) / square_root - tcos;
+  const double dp_dcos = dp_dcos_num / dp_dcos_den;
+  const double dp_dphi_num = pfer * P * tsin * tfsin * (cosqn * sinpq - sinqn * cospq) / square_root;
+  const double dp_dphi_den = tcos + (pfer * tsin * tfsin * psign - P * tsin * tsin - (v.nu + efer - E) * P / E) / square_root;
+  const double dp_dphi = dp_dphi_num / dp_dphi_den;
+  const double dt_dcos_lab = 2. * (v.q * P + (v.q * tcos - v.nu * P / E) * dp_dcos);
+  const double dt_dphi_lab = 2. * (v.q * tcos - v.nu * P / E) * dp_dphi;
+  const double b2 = bstar * bstar;
+  const double kx = (had.x + gstar * bstarx * E) / P - gstar * bstarx * P / E;
+  const double ky = (had.y + gstar * bstary * E) / P - gstar * bstary * P / E;
+  const double kz = (had.z + gstar * bstarz * E) / P - gstar * bstarz * P / E;
+  const double dpxdphi = P * tsin * (-sinpq + (gstar - 1.) * bstarx / b2 * (bstary * cospq - bstarx * sinpq)) + kx * dp_dphi;
+  const double dpydphi = P * tsin * (cospq + (gstar - 1.) * bstary / b2 * (bstary * cospq - bstarx * sinpq)) + ky * dp_dphi;
+  const double dpzdphi = P * (gstar - 1.) / b2 * bstarz * tsin * (bstary * cospq - bstarx * sinpq) + kz * dp_dphi;
+  const double dpxdcos =
+      -P * tcos / tsin * (cospq + (gstar - 1.) * bstarx / b2 * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+      kx * dp_dcos;
+  const double dpydcos =
+      -P * tcos / tsin * (sinpq + (gstar - 1.) * bstary / b2 * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+      ky * dp_dcos;
+  const double dpzdcos =
+      P * (1. - (gstar - 1.) / b2 * bstarz * tcos / tsin * (bstarx * cospq + bstary * sinpq - tsin / tcos * bstarz)) +
+      kz * dp_dcos;
+  const double dpxnewdphi = dpxdphi * tmp2_x_x + dpydphi * tmp2_x_y + dpzdphi * tmp2_x_z;
+  const double dpynewdphi = dpxdphi * tmp2_y_x + dpydphi * tmp2_y_y + dpzdphi * tmp2_y_z;
+  const double den = had2x * had2x + had2y * had2y;
+  const double dphicmdphi = (dpynewdphi * had2x - had2y * dpxnewdphi) / den;
+  const double dpxnewdcos = dpxdcos * tmp2_x_x + dpydcos * tmp2_x_y + dpzdcos * tmp2_x_z;
+  const double dpynewdcos = dpxdcos * tmp2_y_x + dpydcos * tmp2_y_y + dpzdcos * tmp2_y_z;
+  const double dphicmdcos = (dpynewdcos * had2x - had2y * dpxnewdcos) / den;
+  C.jacobian = fabs(dt_dcos_lab * dphicmdphi - dt_dphi_lab * dphicmdcos);
+  C.jac_old = 2 * (efer - 2 * pferz * pfer * E / P * tcos) * (v.q + pferz * pfer) * P /
+                  (efer + v.nu - (v.q + pferz * pfer) * E / P * tcos) -
+              2 * P * pfer;
+  // s of the photon-nucleon system, physics_pion.f:60-66 / physics_kaon.f:70-75
+  C.sgev = msq(v.nu + efer) - msq(v.q + pfer * tfcos) - msq(pfer * tfsin);
+  C.wcm = sqrt(C.sgev);
+}
+
+// physics_pion.f:807-854; p is the 1-based parameter array of the fit
+SIMC_HD_CALL double exclfit(double t, double thetacm, double phicm, double q2_gev, double s_gev, double eps,
+                            const double* pp, double fpifact) {
+  using mesondetail::msq;
+  const double* p = pp - 1;
+  const double mtar_gev = 0.938;
+  const double fpi = fpifact / (1.0 + p[1] * q2_gev + p[2] * (q2_gev * q2_gev));
+  const double q2fpi2 = q2_gev * (fpi * fpi);
+  const double at = fabs(t);
+  double sigL = (p[3] + p[15] / q2_gev) * at / msq(at + 0.02) * q2fpi2 * m::exp(p[4] * at);
+  sigL = sigL / (m::pow(s_gev, p[11]) + m::pow(sqrt(s_gev), p[17]));
+  double sigT = p[5] / q2_gev * m::exp(p[6] * (q2_gev * q2_gev));
+  sigT = sigT / (m::pow(s_gev, p[12]) + m::pow(sqrt(s_gev), p[16]));
+  sigT = sigT * m::exp(p[14] * at);
+  const double sth = m::sin(thetacm);
+  double sigLT = (p[7] / (1.0 + p[10] * q2_gev)) * m::exp(p[8] * at) * sth;
+  sigLT = sigLT / m::pow(s_gev, p[13]);
+  const double sigTT = (p[9] / (1. + 1.0 * q2_gev)) * m::exp(-7.0 * at) * (sth * sth);
+  const double sig219 = (sigT + eps * sigL + eps * m::cos(2.0 * phicm) * sigTT +
+                         sqrt(2.0 * eps * (1.0 + eps)) * m::cos(phicm) * sigLT) / 1.0;
+  double sig = sig219 * 8.539 / msq(s_gev - mtar_gev * mtar_gev);
+  sig = sig / 2.0 / 3.1415928 / 1.0e+06;
+  return sig;
+}
+
+// physics_pion.f:738-805, charged pions
+SIMC_HD_CALL double sig_param_2021(double thcm, double phicm, double t, double q2, double wsq, double eps, int which_pion) {
+  const double pp[17] = {1.60077, -0.01523, 37.08142, -4.11060, 23.26192, 0.00983, 0.87073, -5.77115, -271.08678,
+                         0.13766, -0.00855, 0.27885,  -1.13212, -1.50415, -6.34766, 0.55769, -0.01709};
+  const double pm[17] = {1.75169, 0.11144, 47.35877, -4.69434, 1.60552, 0.00800, 0.44194, -2.29188, -41.67194,
+                         0.69475, 0.02527, -0.50178, -1.22825, -1.16878, 5.75825, -1.00355, 0.05055};
+  if (which_pion == 1 || which_pion == 11 || which_pion == 3) return exclfit(t, thcm, phicm, q2, wsq, eps, pm, 1.0);
+  return exclfit(t, thcm, phicm, q2, wsq, eps, pp, 1.0);
+}
+
+// physics_kaon.f:175-236
+SIMC_HD_CALL double sig_factorized(double q2, double w, double t, double pk, double mrec) {
+  using mesondetail::msq;
+  const double Mp = 938.27231, Mk2 = 493.677 * 493.677;
+  const double nu = (w * w + q2 - Mp * Mp) / 2. / Mp;
+  const double q = sqrt(q2 + nu * nu);
+  const double qcm = q * (Mp / w);
+  const double nucm = sqrt(qcm * qcm - q2);
+  const double tmin = -1. * (Mk2 - q2 - 2 * nucm * sqrt(pk * pk + Mk2) + 2 * qcm * pk);
+  const double q2val = q2 / 1.e6, w2val = w * w / 1.e6, pkval = pk / 1000., tval = t / 1.e6, tminval = tmin / 1.e6;
+  double fact_q, fact_t, fact_w = 0.0;
+  if (mrec < 1150.) {
+    fact_q = 1. / msq(q2val + 2.67);
+    fact_t = m::exp(-2.1 * (tval - tminval));
+    if (w2val != 0) {
+      fact_w = 0.959 * 4.1959 * pkval / (sqrt(w2val) * (w2val - 0.93827 * 0.93827));
+      fact_w = fact_w + (0.18 * (1.72 * 1.72) * (0.10 * 0.10)) / (msq(w2val - 1.72 * 1.72) + (1.72 * 1.72) * (0.10 * 0.10));
+    }
+  } else {
+    fact_q = 1. / msq(q2val + 0.79);
+    fact_t = m::exp(-1.0 * (tval - tminval));
+    if (w2val != 0) fact_w = 0.959 * 4.1959 * pkval / (sqrt(w2val) * (w2val - 0.93827 * 0.93827));
+  }
+  return fact_q * fact_t * fact_w;
+}
+
+struct MesonWeight {
+  double sigcc, sigcm, thetacm, phicm, pcm, wcm, davejac, johnjac;
+  bool low_w;                 // W < 2 GeV: the reference would blend in the MAID table here
+};
+
+// physics_pion.f:1-130
+SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MesonVertex& v) {
+  const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
+  const double Mtar = cfg.targ.Mtar_struck, efer = Mtar, pfer = 0.0, pferz = 0.0;
+  MesonCm C;
+  transform_to_cm(v, efer, C);
+  MesonWeight w;
+  w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = C.jacobian; w.johnjac = C.jac_old; w.wcm = C.wcm;
+  const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;
+  const double sigcm1 = sig_param_2021(C.thetacm, C.phicm, v.t / 1.e6, v.Q2 / 1.e6, C.sgev / 1.e6, v.epsilon, cfg.which_pion);
+  w.low_w = C.wcm < 2000;
+  w.sigcm = sigcm1;
+  const double fac = 1. / (1. - pferz * pfer / efer) * Mtar / efer;
+  const double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * k_eq / v.Q2 / (1. - v.epsilon);
+  w.sigcc = sigcm1 * C.jacobian * (gtpr * fac);
+  return w;
+}
+
+// physics_kaon.f:1-171 (without the survival probability, which needs the focal-plane track)
+SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v) {
+  const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
+  const double Mtar = cfg.targ.Mtar_struck, efer = Mtar, pfer = 0.0, pferz = 0.0;
+  MesonCm C;
+  transform_to_cm(v, efer, C);
+  MesonWeight w;
+  const double jacobian = C.jacobian / (2. * C.pcm * C.qstar);
+  const double jac_old = C.jac_old / (2. * C.pcm * C.qstar);
+  w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = jacobian; w.johnjac = jac_old; w.wcm = C.wcm;
+  w.low_w = false;
+  const double sigcm2 = sig_factorized(v.Q2, C.wcm, v.t, C.pcm, cfg.targ.Mrec_struck);
+  w.sigcm = sigcm2;
+  const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;
+  const double fac = 1. / (1. - pferz * pfer / efer) * Mtar / efer;
+  const double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * k_eq / v.Q2 / (1. - v.epsilon);
+  w.sigcc = sigcm2 * jacobian * (gtpr * fac);
+  return w;
+}
+
+// physics_kaon.f:148-165: survival probability when decay is not simulated
+SIMC_HD_CALL double kaon_survival(const simc_run_config& cfg, double fp_path, double fp_dx, double fp_dy) {
+  double zaero = 0.;
+  if (cfg.hadron_arm == 2) zaero = -82.8;
+  else if (cfg.hadron_arm == 3 || cfg.hadron_arm == 4) zaero = -183.;
+  const double pathlen = fp_path + zaero * (1 + fp_dx * fp_dx + fp_dy * fp_dy);
+  const double betak = cfg.spec_p.P / sqrt(cfg.spec_p.P * cfg.spec_p.P + cfg.Mh2);
+  const double gammak = 1. / sqrt(1. - betak * betak);
+  return 1. / m::exp(pathlen / (cfg.ctau * betak * gammak));
+}
+
+}  // namespace simc

@@ -535,6 +535,24 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     const double eE = Ein * c.Mh / (c.Mh + Ein * (1. - uez));
     const double w = sigep(Ein, eE, c.spec_e.theta, 2 * Ein * eE * (1. - uez));
     if (w > 0 && std::isfinite(w)) c.w_ref = w;
+  } else if (c.doing_hydpi || c.doing_hydkaon) {
+    // central event: both particles along their spectrometer axes, electron at the central momentum
+    EventState s{};
+    s.v_Ein = c.Ebeam_vertex_ave; s.v_eE = c.spec_e.P;
+    s.v_etheta = c.spec_e.theta; s.v_ephi = c.spec_e.phi; s.v_ptheta = c.spec_p.theta; s.v_pphi = c.spec_p.phi;
+    s.tz = targ.zoffset;
+    simc_run_config quiet = c;                 // kinematics only: no energy loss draws, no radiative constants
+    quiet.using_Eloss = 0;
+    struct NoRng { double uniform() { return 0.5; } } rng;
+    auto nogauss = [](NoRng&, double) { return 0.0; };
+    if (complete_ev_meson(quiet, rng, nogauss, s, true)) {
+      MesonVertex mv;
+      mv.Ein = s.v_Ein; mv.eE = s.v_eE; mv.nu = s.v_nu; mv.q = s.v_q; mv.Q2 = s.v_Q2; mv.pP = s.v_pP; mv.pE = s.v_pE;
+      mv.uqx = s.uqx; mv.uqy = s.uqy; mv.uqz = s.uqz; mv.upx = s.upx; mv.upy = s.upy; mv.upz = s.upz;
+      mv.phi_pq = s.m_phipq; mv.t = s.m_t; mv.epsilon = s.m_eps;
+      const MesonWeight w = c.doing_pion ? peepi(c, mv) : peeK(c, mv);
+      if (w.sigcc > 0 && std::isfinite(w.sigcc)) c.w_ref = w.sigcc;
+    }
   }
 }
 

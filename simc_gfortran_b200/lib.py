@@ -13,7 +13,7 @@ import numpy as np
 
 ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
 TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
-EVENT_NREC = 48
+EVENT_NREC = 56
 NHIST, H_PER_SET, NSTOP = 50, 8, 64
 ABI_VERSION = 1
 
@@ -137,7 +137,7 @@ class Accum(C.Structure):
                 ("hist_n", ((C.c_int64 * NHIST) * H_PER_SET) * 3),
                 ("contrib", Range * 32), ("slop", Range * 8),
                 ("stop", (C.c_int64 * NSTOP) * 2),
-                ("transp_calls", (C.c_int64 * 48) * 2)]
+                ("transp_calls", (C.c_int64 * 48) * 2), ("unsupported", C.c_int64)]
 
 
 _lib = None

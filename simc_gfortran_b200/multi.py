@@ -42,6 +42,7 @@ def pack(acc: Accum):
     sums += list(np.ctypeslib.as_array(acc.hist_n).ravel())
     sums += list(np.ctypeslib.as_array(acc.stop).ravel())
     sums += list(np.ctypeslib.as_array(acc.transp_calls).ravel())
+    sums.append(acc.unsupported)
     mins = [_key(acc.contrib[i].lo) for i in range(32)] + [_key(acc.slop[i].lo) for i in range(8)]
     maxs = [_key(acc.contrib[i].hi) for i in range(32)] + [_key(acc.slop[i].hi) for i in range(8)]
     return (np.array(sums, dtype=np.int64), np.array(mins, dtype=np.int64), np.array(maxs, dtype=np.int64))
@@ -61,6 +62,7 @@ def unpack(acc: Accum, sums, mins, maxs) -> Accum:
         arr = np.ctypeslib.as_array(getattr(out, name))
         flat = np.array([next(it) for _ in range(arr.size)], dtype=np.int64).reshape(arr.shape)
         arr[...] = flat
+    out.unsupported = next(it)
     for i in range(32):
         out.contrib[i].lo, out.contrib[i].hi = _unkey(int(mins[i])), _unkey(int(maxs[i]))
     for i in range(8):

@@ -125,7 +125,7 @@ def _oracle_run(self, cfg, first, n, seed, threads=1, ranlux=False):
 
 
 def _oracle_event_batch(self, cfg, first, n, seed):
-    rec = np.zeros((48, n))
+    rec = np.zeros((56, n))
     status = np.zeros(n, np.int32)
     self._check(self.L.oracle_event_batch(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(rec),
                                           _p(status)))
