@@ -56,28 +56,38 @@ struct ArmOp {
 };
 
 constexpr int kMaxArmOps = 320;
+constexpr int kArmBlockThreads = 128;  // threads per CTA of every kernel that evaluates COSY maps (= kBlock)
 constexpr int kMaxClasses = 41;       // max_class, spectrometers.inc:6
 
-// One COSY map compiled into "groups": a run of consecutive file terms that share the
-// exponents of variables 3,4,5 and the degree m = e1+e2, with e2 strictly increasing.  The
-// group header packs e3,e4,e5,m (3 bits each), a 7-bit mask of the k = e2 values present, and the
-// group's output pattern (union of the outputs with a non-zero coefficient, 5 bits).  One
-// coefficient per (present k, output of the pattern) follows in that order.  File order is
-// preserved, so every output's sum sees its terms in the reference's order; terms whose
-// coefficients are all zero add exactly 0 in the reference and are skipped here.
+// One COSY map compiled into term records.  The reference evaluates every term as
+//   term = x^e1 * theta^e2 * y^e3 * phi^e4 * delta^e5   (left to right, unit factors included)
+//   sum(1:5) = sum(1:5) + term * coeff(1:5,i)           (all five outputs, zero coefficients included)
+// (shared/transp.f:205-214).  A record keeps exactly that shape so that the device loop has no
+// data-dependent branch: four byte offsets into the thread's shared power table
+// (x^a*theta^b | y^e | phi^e | delta^e) followed by the term's coefficients, zeros included.
+// Terms whose coefficients are all zero add exact zeros in the reference and are dropped.
+//   forward maps : 8 words of 8 bytes  = off[4] (uint32) + 5 coefficients + pad
+//   recon maps   : 6 words             = off[4] (uint32) + 4 coefficients
+constexpr int kPolyEntries = 28 + 3 * 7;      // (a,b) with a+b <= 6, then 7 powers of each slow variable
+constexpr int kRecWordsFwd = 8, kRecWordsRec = 6;
+// index of x^a*theta^b in the power table (a + b <= 6)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline constexpr int poly_xt_index(int a, int b) { return a * 7 - (a * (a - 1)) / 2 + b; }
+
 struct PolyClass {
-  int32_t group_begin, group_end;   // into hdr[]
-  int32_t coef_begin;               // into coef[]
-  int32_t n_terms;
+  int32_t rec_begin;                // into recs[], in 8-byte words (always even: records are 16-byte aligned)
+  int32_t n_rec;                    // records = terms with at least one non-zero coefficient
+  int32_t n_terms;                  // terms in the file
+  int32_t adrift;
   double length_cm;                 // !LENGTH: comment (0 if none)
   double driftdist_cm;              // extracted drift length if a pure drift
-  int32_t adrift;
-  int32_t pad;
 };
 
 struct ArmTablesDev {
-  const unsigned long long* hdr;    // group headers, forward classes then recon
-  const double* coef;               // packed non-zero coefficients
+  const double* recs;               // term records, forward classes then recon
+  const double* pad_ptr;
   PolyClass fwd[kMaxClasses];       // 1-based class k -> fwd[k-1]
   PolyClass rec;
   int32_t n_classes;

@@ -15,6 +15,7 @@
 #include "../../include/simc_b200.h"
 #include "kernels.h"
 #include "optics_host.h"
+#include "target.cuh"
 
 using namespace simc;
 
@@ -26,8 +27,7 @@ struct ArmSlot {
   bool loaded = false;
   CompiledArm host;
   void* d_arm = nullptr;                 // ArmDev
-  unsigned long long* d_hdr = nullptr;
-  double* d_coef = nullptr;
+  double* d_recs = nullptr;
 };
 
 std::string g_create_error;
@@ -78,8 +78,7 @@ int cuda_fail(simc_handle* h, cudaError_t e, const char* what) {
 
 void free_arm(ArmSlot& s) {
   if (s.d_arm) cudaFree(s.d_arm);
-  if (s.d_hdr) cudaFree(s.d_hdr);
-  if (s.d_coef) cudaFree(s.d_coef);
+  if (s.d_recs) cudaFree(s.d_recs);
   s = ArmSlot();
 }
 
@@ -88,16 +87,14 @@ int upload_arm(simc_handle* h, int arm_id, CompiledArm&& ca) {
   ArmSlot& s = h->arms[arm_id];
   free_arm(s);
   s.host = std::move(ca);
-  CU(h, cudaMalloc(&s.d_hdr, s.host.hdr.size() * sizeof(unsigned long long)));
-  CU(h, cudaMalloc(&s.d_coef, s.host.coef.size() * sizeof(double)));
-  CU(h, cudaMemcpy(s.d_hdr, s.host.hdr.data(), s.host.hdr.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  CU(h, cudaMemcpy(s.d_coef, s.host.coef.data(), s.host.coef.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CU(h, cudaMalloc(&s.d_recs, s.host.recs.size() * sizeof(double)));       // cudaMalloc: 256-byte aligned
+  CU(h, cudaMemcpy(s.d_recs, s.host.recs.data(), s.host.recs.size() * sizeof(double), cudaMemcpyHostToDevice));
   // ArmDev = { ArmTablesDev tab; ArmOp ops[kMaxArmOps]; } -- identical layout in both variants
   const size_t bytes = strict::arm_dev_bytes();
   std::vector<unsigned char> img(bytes, 0);
   ArmTablesDev tab = s.host.tab;
-  tab.hdr = s.d_hdr;
-  tab.coef = s.d_coef;
+  tab.recs = s.d_recs;
+  tab.pad_ptr = nullptr;
   std::memcpy(img.data(), &tab, sizeof(tab));
   std::memcpy(img.data() + sizeof(ArmTablesDev), s.host.ops.data(), s.host.ops.size() * sizeof(ArmOp));
   CU(h, cudaMalloc(&s.d_arm, bytes));
@@ -222,7 +219,7 @@ int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8) {
   if (it == h->arms.end() || !it->second.loaded) return fail(h, SIMC_ERR_STATE, "optics not loaded for this arm");
   const CompiledArm& c = it->second.host;
   info8[0] = c.tab.n_classes; info8[1] = c.fwd_terms; info8[2] = c.fwd_nonzero; info8[3] = c.rec_terms;
-  info8[4] = (int64_t)c.hdr.size(); info8[5] = (int64_t)c.coef.size(); info8[6] = (int64_t)c.ops.size(); info8[7] = 0;
+  info8[4] = (int64_t)c.recs.size(); info8[5] = (int64_t)c.fwd_nonzero; info8[6] = (int64_t)c.ops.size(); info8[7] = 0;
   return SIMC_OK;
 }
 
@@ -386,6 +383,11 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
   a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;
+  {
+    const MatTable mt = make_mat_table(h->cfg.targ);          // host libm, once per call
+    static_assert(sizeof(mt) == sizeof(a.mats), "MatTable layout");
+    std::memcpy(a.mats, &mt, sizeof(mt));
+  }
   size_t ev_pos = 5 * h->ev_used.size();
   for (int64_t done = 0; done < n_tries;) {
     const int64_t nb = std::min<int64_t>(n_tries - done, cap);

@@ -84,22 +84,23 @@ struct EventState {
 // trip_thru_target with typeflag = 1 (sampled energy loss): one |gauss1(10)| per material with
 // thick > 0, in the reference's order target, Al, air, kevlar, mylar (target.f:46-52,170-180).
 template <class RNG, class GAUSS>
-SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng, GAUSS gauss, int narm, double zpos,
-                                      double energy, double theta, double mass, double& Eloss, double& radlen) {
+SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, int narm,
+                                      double zpos, double energy, double theta, double mass, double& Eloss,
+                                      double& radlen) {
   const simc_target& targ = cfg.targ;
   const Material al = SIMC_MAT_AL;
-  const ParticleKin k = particle_kin(energy, mass);
+  const ParticleKin k = particle_kin(energy, mass, mt.targ.ln10);
   double s_target, s_Al;
-  auto one = [&](double len, double dens, double z, double a) {
+  auto one = [&](double len, const MatConst& mc) {
     double x = 0.;
-    if (len * dens > 0.) x = fabs(gauss(rng, 10.0));
-    return enerloss_material(k, len, dens, z, a, x);
+    if (len * mc.rho > 0.) x = fabs(gauss(rng, 10.0));
+    return enerloss_material(k, len, mc, x);
   };
   if (narm == 1) {
     incoming_paths(targ, zpos, s_target, s_Al);
     radlen = s_target / targ.X0_cm + s_Al / al.X0_cm;
-    const double e1 = one(s_target, targ.rho, targ.Z, targ.A);
-    const double e2 = one(s_Al, al.rho, al.Z, al.A);
+    const double e1 = one(s_target, mt.targ);
+    const double e2 = one(s_Al, mt.al);
     Eloss = e1 + e2;
     return;
   }
@@ -108,11 +109,11 @@ SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng,
   outgoing_paths(targ, w, zpos, theta, s_target, s_Al);
   radlen = s_target / targ.X0_cm + s_Al / al.X0_cm + w.s_air / air.X0_cm + w.s_kevlar / kev.X0_cm +
            w.s_mylar / myl.X0_cm;
-  const double e1 = one(s_target, targ.rho, targ.Z, targ.A);
-  const double e2 = one(s_Al, al.rho, al.Z, al.A);
-  const double e3 = one(w.s_air, air.rho, air.Z, air.A);
-  const double e4 = one(w.s_kevlar, kev.rho, kev.Z, kev.A);
-  const double e5 = one(w.s_mylar, myl.rho, myl.Z, myl.A);
+  const double e1 = one(s_target, mt.targ);
+  const double e2 = one(s_Al, mt.al);
+  const double e3 = one(w.s_air, mt.air);
+  const double e4 = one(w.s_kevlar, mt.kevlar);
+  const double e5 = one(w.s_mylar, mt.mylar);
   Eloss = e1 + e2 + e3 + e4 + e5;
 }
 
@@ -130,7 +131,7 @@ SIMC_HD_CALL void trip_thru_target_sampled(const simc_run_config& cfg, RNG& rng,
 // complete_ev for H(e,e'p), event.f:432-1052.  Needs v_Ein, v_eyptar/xptar/theta/phi, tz; fills
 // the rest of the vertex, the jacobian, Eloss/teff(2:3) and the radiative constants.
 template <class RNG, class GAUSS>
-SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
   const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
   if (run) {
     s.jacobian = 1.0;
@@ -166,9 +167,9 @@ SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS g
   }
   const double zpos = s.tz - cfg.targ.zoffset;
   SIMC_PHASE();
-  if (run) trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
   SIMC_PHASE();
-  if (run) trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
   SIMC_PHASE();
   if (run) {
     if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
@@ -184,7 +185,7 @@ SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS g
 // generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519.  `ok` in: the thread has
 // a try to generate; returns success.
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
   if (ok) {
     s.tx = gauss(rng, 3.0) * cfg.gen.xwid + targ.xoffset;
@@ -212,7 +213,7 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
     s.ty = s.ty + t6;
     s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
     s.rastery = t6;
-    trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+    trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
     if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
     s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
     s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
@@ -229,7 +230,7 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
     s.rad.ntail = 0;
   }
   SIMC_PHASE();
-  ok = complete_ev_hyd_elast(cfg, rng, gauss, s, ok);
+  ok = complete_ev_hyd_elast(cfg, mt, rng, gauss, s, ok);
   if (ok) s.Trec = s.v_Trec;
   if (!cfg.using_rad) {
     if (ok) {
@@ -289,7 +290,7 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
   }
   SIMC_PHASE();
   const bool reenter = ok && which == 1;                       // radc.f:324
-  const bool re_ok = complete_ev_hyd_elast(cfg, rng, gauss, s, reenter);
+  const bool re_ok = complete_ev_hyd_elast(cfg, mt, rng, gauss, s, reenter);
   if (reenter && !re_ok) ok = false;
   if (ok && which) {
     VertexKin v;
@@ -322,7 +323,7 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, RNG& rng, GAUSS gaus
 // two-body quadratic (event.f:634-698), W, epsilon, theta_pq, phi_pq, t (event.f:707-771), the
 // jacobian, Eloss/teff(2:3) and the radiative constants.
 template <class RNG, class GAUSS>
-SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
   const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
   const simc_target& targ = cfg.targ;
   if (run) {
@@ -387,9 +388,9 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss
   }
   const double zpos = s.tz - targ.zoffset;
   SIMC_PHASE();
-  if (run) trip_thru_target_sampled(cfg, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
   SIMC_PHASE();
-  if (run) trip_thru_target_sampled(cfg, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, Mh, s.Eloss[2], s.teff[2]);
   SIMC_PHASE();
   if (run) {
     if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
@@ -406,7 +407,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss
 // electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
 // limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;
   if (ok) {
@@ -435,7 +436,7 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, E
     s.ty = s.ty + t6;
     s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
     s.rastery = t6;
-    trip_thru_target_sampled(cfg, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+    trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
     if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
     s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
     s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
@@ -461,7 +462,7 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, E
     }
   }
   SIMC_PHASE();
-  ok = complete_ev_meson(cfg, rng, gauss, s, ok);
+  ok = complete_ev_meson(cfg, mt, rng, gauss, s, ok);
   if (ok) s.Trec = s.v_Trec;
   if (!cfg.using_rad) {
     if (ok) {
@@ -509,7 +510,7 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, RNG& rng, GAUSS gauss, E
   }
   SIMC_PHASE();
   const bool reenter = ok && which == 1;                       // radc.f:324
-  const bool re_ok = complete_ev_meson(cfg, rng, gauss, s, reenter);
+  const bool re_ok = complete_ev_meson(cfg, mt, rng, gauss, s, reenter);
   if (reenter && !re_ok) ok = false;
   if (ok && which) {
     VertexKin v;

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kBlock)
 k_transport_batch(const ArmDev* __restrict__ arm, long long n, const double* __restrict__ in,
                   unsigned long long seed, ArmFlags f, double ctau, double* __restrict__ out,
                   int* __restrict__ flags) {
-  __shared__ double pw_s[kPowDoubles];
+  extern __shared__ double pw_s[];
   const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   bool alive = i < n;
   const long long ii = alive ? i : 0;
@@ -73,7 +73,15 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
   ArmFlags f;
   f.ms_flag = a.ms_flag != 0; f.wcs_flag = a.wcs_flag != 0; f.decay_flag = a.decay_flag != 0;
   f.using_coll = a.using_coll != 0;
-  k_transport_batch<<<(unsigned)blocks, kBlock, 0, s>>>((const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+  {
+    static bool attr_set = false;       // > 48 KB of dynamic shared memory needs the opt-in, once per process
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_transport_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+  }
+  k_transport_batch<<<(unsigned)blocks, kBlock, kPowBytes, s>>>((const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
                                                         a.flags);
   return cudaGetLastError();
 }
@@ -186,18 +194,31 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
   A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
   A.record_mode = a.record_mode;
+  static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
+  memcpy(&A.mt, a.mats, sizeof(MatTable));
   const long long need = (a.n_tries + kBlock - 1) / kBlock;
   const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_arm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+  }
   if (stage == 0) {
     cudaError_t e = cudaMemsetAsync(a.counts, 0, 8 * sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
     k_generate<<<grid, kBlock, 0, s>>>(A);
   } else if (stage == 1) {
-    k_arm<1, 0><<<grid, kBlock, 0, s>>>(A);
-    k_arm<1, 1><<<grid, kBlock, 0, s>>>(A);
+    k_arm<1, 0><<<grid, kBlock, kPowBytes, s>>>(A);
+    k_arm<1, 1><<<grid, kBlock, kPowBytes, s>>>(A);
   } else if (stage == 2) {
-    k_arm<0, 0><<<grid, kBlock, 0, s>>>(A);
-    k_arm<0, 1><<<grid, kBlock, 0, s>>>(A);
+    k_arm<0, 0><<<grid, kBlock, kPowBytes, s>>>(A);
+    k_arm<0, 1><<<grid, kBlock, kPowBytes, s>>>(A);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   return cudaGetLastError();

@@ -35,6 +35,7 @@ struct LoopLaunch {
   double* rec;                // [SIMC_EVENT_NREC][n_tries] device, record mode only
   int* status;
   int grid_blocks;            // persistent grid for the stage kernels
+  double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
 };
 
 namespace strict {

@@ -65,6 +65,7 @@ struct DevAccum {
 
 struct LoopArgs {
   const simc_run_config* cfg;      // device copy
+  MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
   const ArmDev* arm_e;
   const ArmDev* arm_p;
   StateBuf st;
@@ -134,7 +135,10 @@ struct GaussFn {
 };
 
 // ---- stage 1: generation -------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
+#ifndef SIMC_GEN_MIN_BLOCKS
+#define SIMC_GEN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopArgs A) {
   __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
   for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kBlock) (&h_geni[0][0])[i] = 0u;
   __syncthreads();
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
-    if (meson) ok = generate_meson(cfg, rng, GaussFn(), s, active);
-    else ok = generate_hyd_elast(cfg, rng, GaussFn(), s, active);
+    if (meson) ok = generate_meson(cfg, A.mt, rng, GaussFn(), s, active);
+    else ok = generate_hyd_elast(cfg, A.mt, rng, GaussFn(), s, active);
     if (active) {
       // geni histograms: every try, from the vertex values (simc.f:253-262)
       const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kBlock) k_generate(LoopArgs A) {
 // after almost no arithmetic); SEG 1 = magnets, hut, reconstruction for the compacted survivors.
 template <int WHICH, int SEG>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A) {
-  __shared__ double pw_s[kPowDoubles];
+  extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
         physics_angles(sp.theta, sp.phi, rc_xptar + sp.off_xptar, rc_yptar + sp.off_yptar, rth, rph);
         if (cfg.correct_Eloss) {
           double el, rl;
-          trip_thru_target_fixed(cfg.targ, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
+          trip_thru_target_fixed(cfg.targ, A.mt, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
                                  el, rl);
           rE = rE + el;
           if (WHICH == 1) {

@@ -155,47 +155,32 @@ CosyTerms read_recon_map(const std::string& path) {
 // ------------------------------------------------------------------------------------------
 namespace {
 
-PolyClass compile_terms(const CosyTerms& t, std::vector<unsigned long long>& hdr, std::vector<double>& coef,
-                        long long* nonzero) {
+PolyClass compile_terms(const CosyTerms& t, std::vector<double>& recs, long long* nonzero, int block_threads) {
   PolyClass pc{};
-  pc.group_begin = (int)hdr.size();
-  pc.coef_begin = (int)coef.size();
+  pc.rec_begin = (int)recs.size();
   pc.n_terms = t.n();
-  // pass 1: cut the term list into groups (same e3,e4,e5 and m = e1+e2, e2 strictly increasing)
-  struct Term { int k; unsigned om; const double* c; };
-  struct Group { int e3, e4, e5, m; std::vector<Term> terms; };
-  std::vector<Group> groups;
-  int lastk = -1;
+  const int words = t.nout == 5 ? kRecWordsFwd : kRecWordsRec;
+  const uint32_t stride = (uint32_t)block_threads * 8u;          // bytes between two table entries of one thread
   for (int i = 0; i < t.n(); ++i) {
     const int8_t* e = &t.expo[5 * i];
     for (int j = 0; j < 5; ++j)
       if (e[j] < 0 || e[j] > 6) throw std::runtime_error("COSY exponent outside 0..6");
-    const int m = e[0] + e[1];
-    if (m > 6) throw std::runtime_error("COSY term of degree > 6 in (x,theta)");
-    unsigned om = 0;
+    if (e[0] + e[1] > 6) throw std::runtime_error("COSY term of degree > 6 in (x,theta)");
+    int nz = 0;
     for (int o = 0; o < t.nout; ++o)
-      if (t.coef[t.nout * i + o] != 0.0) om |= 1u << o;
-    if (om == 0) continue;                         // adds exact zeros in the reference
-    if (nonzero) *nonzero += __builtin_popcount(om);
-    const bool same = !groups.empty() && groups.back().e3 == e[2] && groups.back().e4 == e[3] &&
-                      groups.back().e5 == e[4] && groups.back().m == m && e[1] > lastk;
-    if (!same) groups.push_back(Group{e[2], e[3], e[4], m, {}});
-    groups.back().terms.push_back(Term{e[1], om, &t.coef[t.nout * i]});
-    lastk = e[1];
+      if (t.coef[t.nout * i + o] != 0.0) ++nz;
+    if (nz == 0) continue;                         // adds exact zeros in the reference
+    if (nonzero) *nonzero += nz;
+    const uint32_t off[4] = {(uint32_t)poly_xt_index(e[0], e[1]) * stride, (uint32_t)(28 + e[2]) * stride,
+                             (uint32_t)(35 + e[3]) * stride, (uint32_t)(42 + e[4]) * stride};
+    double w[2];
+    std::memcpy(w, off, sizeof(w));
+    recs.push_back(w[0]);
+    recs.push_back(w[1]);
+    for (int o = 0; o < t.nout; ++o) recs.push_back(t.coef[t.nout * i + o]);
+    for (int o = 2 + t.nout; o < words; ++o) recs.push_back(0.0);
+    pc.n_rec++;
   }
-  // pass 2: header = e3,e4,e5,m (3 bits each) | kmask (7 bits) << 12 | output pattern (5 bits) << 19;
-  // every present term stores one coefficient per output of the group's pattern (zeros included:
-  // adding term*0 is exact).
-  for (const Group& g : groups) {
-    unsigned kmask = 0, pat = 0;
-    for (const Term& tm : g.terms) { kmask |= 1u << tm.k; pat |= tm.om; }
-    hdr.push_back((unsigned long long)g.e3 | ((unsigned long long)g.e4 << 3) | ((unsigned long long)g.e5 << 6) |
-                  ((unsigned long long)g.m << 9) | ((unsigned long long)kmask << 12) | ((unsigned long long)pat << 19));
-    for (const Term& tm : g.terms)
-      for (int o = 0; o < t.nout; ++o)
-        if (pat & (1u << o)) coef.push_back(tm.c[o]);
-  }
-  pc.group_end = (int)hdr.size();
   return pc;
 }
 
@@ -806,7 +791,7 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   std::memset(&A.tab, 0, sizeof(A.tab));
   A.tab.n_classes = (int)fwd.cls.size();
   for (size_t k = 0; k < fwd.cls.size(); ++k) {
-    PolyClass pc = compile_terms(fwd.cls[k], A.hdr, A.coef, &A.fwd_nonzero);
+    PolyClass pc = compile_terms(fwd.cls[k], A.recs, &A.fwd_nonzero, kArmBlockThreads);
     pc.length_cm = k < fwd.length_cm.size() ? fwd.length_cm[k] : 0.0;
     pc.adrift = fwd.adrift[k];
     pc.driftdist_cm = fwd.driftdist_cm[k];
@@ -814,7 +799,7 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
     A.fwd_terms += fwd.cls[k].n();
   }
   if (rec.nout != 4) throw std::runtime_error("reconstruction map must have 4 outputs");
-  A.tab.rec = compile_terms(rec, A.hdr, A.coef, nullptr);
+  A.tab.rec = compile_terms(rec, A.recs, nullptr, kArmBlockThreads);
   A.rec_terms = rec.n();
   Prog P;
   if (arm_id == 1) build_hms(P);

@@ -30,9 +30,8 @@ CosyTerms read_recon_map(const std::string& path);
 void classify_drifts(ForwardMaps& f);
 
 struct CompiledArm {
-  std::vector<unsigned long long> hdr;
-  std::vector<double> coef;
-  ArmTablesDev tab;                      // hdr/coef pointers left null (device addresses are set by the caller)
+  std::vector<double> recs;              // term records (arm_program.h), 8-byte words
+  ArmTablesDev tab;                      // recs pointer left null (the device address is set by the caller)
   std::vector<ArmOp> ops;
   long long fwd_terms = 0, fwd_nonzero = 0, rec_terms = 0;
 };

@@ -86,7 +86,8 @@ struct TargetExt {          // target_info members only the init needs (target.i
 
 void trip(const simc_run_config& c, int narm, double zpos, double energy, double theta, double mass, int typeflag,
           double& Eloss, double& radlen) {
-  trip_thru_target_fixed(c.targ, narm, narm == 2 ? c.electron_arm : c.hadron_arm, zpos, energy, theta, mass, typeflag,
+  const MatTable mt = make_mat_table(c.targ);
+  trip_thru_target_fixed(c.targ, mt, narm, narm == 2 ? c.electron_arm : c.hadron_arm, zpos, energy, theta, mass, typeflag,
                          Eloss, radlen);
 }
 
@@ -545,7 +546,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     quiet.using_Eloss = 0;
     struct NoRng { double uniform() { return 0.5; } } rng;
     auto nogauss = [](NoRng&, double) { return 0.0; };
-    if (complete_ev_meson(quiet, rng, nogauss, s, true)) {
+    const MatTable mt = make_mat_table(c.targ);
+    if (complete_ev_meson(quiet, mt, rng, nogauss, s, true)) {
       MesonVertex mv;
       mv.Ein = s.v_Ein; mv.eE = s.v_eE; mv.nu = s.v_nu; mv.q = s.v_q; mv.Q2 = s.v_Q2; mv.pP = s.v_pP; mv.pE = s.v_pE;
       mv.uqx = s.uqx; mv.uqy = s.uqy; mv.uqz = s.uqz; mv.upx = s.upx; mv.upy = s.upy; mv.upz = s.upz;

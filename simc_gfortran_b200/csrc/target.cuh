@@ -51,43 +51,72 @@ struct Material { double rho, Z, A, X0_cm; };
 struct ParticleKin {
   double epart, mpart, gamma, beta, beta2, log10bg, two_log_gb;
 };
-SIMC_HD ParticleKin particle_kin(double epart, double mpart) {
+SIMC_HD ParticleKin particle_kin(double epart, double mpart, double ln10) {
   ParticleKin k;
   k.epart = epart; k.mpart = mpart;
   k.gamma = epart / mpart;
   k.beta = sqrt(1. - 1. / (k.gamma * k.gamma));
   k.beta2 = k.beta * k.beta;
-  k.log10bg = m::log(k.beta * k.gamma) / m::log(10.);
+  k.log10bg = m::log(k.beta * k.gamma) / ln10;
   k.two_log_gb = 2. * m::log(k.gamma * k.beta);
   return k;
 }
 
+// What enerloss_new computes from the material alone (enerloss_new.f:47-58,69-74): mean excitation
+// energy, plasma term, and the leading factors of the three Z/A products (each is the first operation
+// of its expression in the reference, so hoisting it does not change the rounding).  Evaluated once
+// per run on the host; the event loop reads the table from kernel parameters.
+struct MatConst { double rho, I, CO, co27, ln10, log_me_I2, p_mp, p_log, p_chsi; };
+struct MatTable { MatConst targ, al, air, kevlar, mylar; };
+
+SIMC_HD MatConst make_mat(double dens, double zeff, double aeff) {
+  const double me = 0.51099906;
+  MatConst c;
+  c.rho = dens;
+  if (zeff == 1) c.I = 21.8e-06;
+  else c.I = (16. * m::pow(zeff, 0.9)) * 1.0e-06;
+  const double hnup = 28.816e-06 * sqrt(dens * zeff / aeff);
+  c.CO = m::log(hnup) - m::log(c.I) + 0.5;
+  c.co27 = fabs(c.CO / 27.);
+  c.ln10 = m::log(10.);
+  c.log_me_I2 = m::log(me / (c.I * c.I));
+  c.p_mp = 0.1536e-03 * zeff / aeff;
+  c.p_log = 0.1536 * zeff / aeff;
+  c.p_chsi = 0.307075 / 2. * zeff / aeff;
+  return c;
+}
+SIMC_HD MatTable make_mat_table(const simc_target& targ) {
+  MatTable t;
+  t.targ = make_mat(targ.rho, targ.Z, targ.A);
+  const Material al = SIMC_MAT_AL, air = SIMC_MAT_AIR, kev = SIMC_MAT_KEVLAR, myl = SIMC_MAT_MYLAR;
+  t.al = make_mat(al.rho, al.Z, al.A);
+  t.air = make_mat(air.rho, air.Z, air.A);
+  t.kevlar = make_mat(kev.rho, kev.Z, kev.A);
+  t.mylar = make_mat(myl.rho, myl.Z, myl.A);
+  return t;
+}
+
 // enerloss_new.f:30-85.  x = |gauss1(10)| for typeflag 1 (drawn by the caller, only when
 // thick > 0 -- the reference draws inside the thick>0 branch), 3 / 0.0067 / 1 for 2 / 3 / 4.
-SIMC_HD_CALL double enerloss_material(const ParticleKin& k, double len, double dens, double zeff, double aeff, double x) {
-  const double me = 0.51099906;
-  const double thick = len * dens;
+SIMC_HD_CALL double enerloss_material(const ParticleKin& k, double len, const MatConst& mc, double x) {
+  const double thick = len * mc.rho;
   double eloss;
   if (thick <= 0.) {
     eloss = 0.;
   } else {
-    double I;
-    if (zeff == 1) I = 21.8e-06;
-    else I = (16. * m::pow(zeff, 0.9)) * 1.0e-06;
-    const double hnup = 28.816e-06 * sqrt(dens * zeff / aeff);
-    const double CO = m::log(hnup) - m::log(I) + 0.5;
+    const double CO = mc.CO;
     double denscorr;
     if (k.log10bg < 0.) denscorr = 0.;
     else if (k.log10bg < 3.) {
       const double d = 3. - k.log10bg;
-      denscorr = CO + m::log(10.) * k.log10bg + fabs(CO / 27.) * (d * (d * d));
-    } else if (k.log10bg < 4.7) denscorr = CO + m::log(10.) * k.log10bg;
-    else denscorr = CO + m::log(10.) * 4.7;
-    const double eloss_mp_new = 0.1536e-03 * zeff / aeff * thick / k.beta2 *
-                                (m::log(me / (I * I)) + 1.063 + k.two_log_gb +
-                                 m::log(0.1536 * zeff / aeff * thick / k.beta2) - k.beta2 - denscorr);
+      denscorr = CO + mc.ln10 * k.log10bg + mc.co27 * (d * (d * d));
+    } else if (k.log10bg < 4.7) denscorr = CO + mc.ln10 * k.log10bg;
+    else denscorr = CO + mc.ln10 * 4.7;
+    const double eloss_mp_new = mc.p_mp * thick / k.beta2 *
+                                (mc.log_me_I2 + 1.063 + k.two_log_gb + m::log(mc.p_log * thick / k.beta2) - k.beta2 -
+                                 denscorr);
     const double eloss_mp = eloss_mp_new * 1000.;
-    const double chsi = 0.307075 / 2. * zeff / aeff * thick / k.beta2;
+    const double chsi = mc.p_chsi * thick / k.beta2;
     double lambda;
     if (x > 0.0) lambda = -2.0 * m::log(x);
     else lambda = 100000.;
@@ -178,17 +207,17 @@ SIMC_HD void incoming_paths(const simc_target& targ, double zpos, double& s_targ
 // trip_thru_target with a fixed typeflag 2/3/4 (no random numbers): used for the most-probable
 // energy-loss correction (simc.f:1637-1645) and by the host-side init (init.f:44-56,
 // target.f:310-544).  arm = spectrometer id for narm 2/3, ignored for narm 1.
-SIMC_HD_CALL void trip_thru_target_fixed(const simc_target& targ, int narm, int arm, double zpos, double energy,
-                                    double theta, double mass, int typeflag, double& Eloss, double& radlen) {
+SIMC_HD_CALL void trip_thru_target_fixed(const simc_target& targ, const MatTable& mt, int narm, int arm, double zpos,
+                                    double energy, double theta, double mass, int typeflag, double& Eloss,
+                                    double& radlen) {
   const Material al = SIMC_MAT_AL;
-  const ParticleKin k = particle_kin(energy, mass);
+  const ParticleKin k = particle_kin(energy, mass, mt.targ.ln10);
   const double x = typeflag_x(typeflag);
   double s_target, s_Al;
   if (narm == 1) {
     incoming_paths(targ, zpos, s_target, s_Al);
     radlen = s_target / targ.X0_cm + s_Al / al.X0_cm;
-    Eloss = enerloss_material(k, s_target, targ.rho, targ.Z, targ.A, x) +
-            enerloss_material(k, s_Al, al.rho, al.Z, al.A, x);
+    Eloss = enerloss_material(k, s_target, mt.targ, x) + enerloss_material(k, s_Al, mt.al, x);
     return;
   }
   const Material air = SIMC_MAT_AIR, kev = SIMC_MAT_KEVLAR, myl = SIMC_MAT_MYLAR;
@@ -196,11 +225,11 @@ SIMC_HD_CALL void trip_thru_target_fixed(const simc_target& targ, int narm, int 
   outgoing_paths(targ, w, zpos, theta, s_target, s_Al);
   radlen = s_target / targ.X0_cm + s_Al / al.X0_cm + w.s_air / air.X0_cm + w.s_kevlar / kev.X0_cm +
            w.s_mylar / myl.X0_cm;
-  const double e1 = enerloss_material(k, s_target, targ.rho, targ.Z, targ.A, x);
-  const double e2 = enerloss_material(k, s_Al, al.rho, al.Z, al.A, x);
-  const double e3 = enerloss_material(k, w.s_air, air.rho, air.Z, air.A, x);
-  const double e4 = enerloss_material(k, w.s_kevlar, kev.rho, kev.Z, kev.A, x);
-  const double e5 = enerloss_material(k, w.s_mylar, myl.rho, myl.Z, myl.A, x);
+  const double e1 = enerloss_material(k, s_target, mt.targ, x);
+  const double e2 = enerloss_material(k, s_Al, mt.al, x);
+  const double e3 = enerloss_material(k, w.s_air, mt.air, x);
+  const double e4 = enerloss_material(k, w.s_kevlar, mt.kevlar, x);
+  const double e5 = enerloss_material(k, w.s_mylar, mt.mylar, x);
   Eloss = e1 + e2 + e3 + e4 + e5;
 }
 

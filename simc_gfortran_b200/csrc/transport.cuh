@@ -26,8 +26,10 @@ namespace simc {
 namespace SIMC_VARIANT_NS {
 
 constexpr int kBlock = 128;               // threads per CTA for the event kernels
-// shared power table for the slow variables of a COSY map: [3 vars][7 exponents][kBlock]
-constexpr int kPowDoubles = 3 * 7 * kBlock;
+static_assert(kBlock == kArmBlockThreads, "the record offsets are compiled for this CTA size");
+// shared power table of a COSY map: [kPolyEntries][kBlock] doubles, dynamic shared memory (49 KB)
+constexpr int kPowDoubles = kPolyEntries * kBlock;
+constexpr size_t kPowBytes = sizeof(double) * kPowDoubles;
 
 struct ArmDev {                           // lives in global memory, read through warp-uniform loads
   ArmTablesDev tab;
@@ -177,102 +179,83 @@ __device__ __forceinline__ void project(TrackDev& t, DevRng& r, double z_drift, 
   }
 }
 
-// ---- grouped COSY polynomial ------------------------------------------------------------
-// One group: terms x^(M-k) theta^k * s3*s4*s5, k in kmask, all with the same output pattern.
-// M and the pattern are compile-time, so the power registers are indexed statically and no
-// per-output test is executed.  PAT = 0 means "pattern given at run time" (rare combinations).
-template <int M, int PAT, int NOUT>
-__device__ __forceinline__ void poly_group(unsigned kmask, unsigned rpat, const double (&xp)[7], const double (&tp)[7],
-                                           double s3, double s4, double s5, const double* __restrict__ coef, int& ci,
-                                           double (&sum)[NOUT]) {
-  const unsigned pat = PAT ? (unsigned)PAT : rpat;
-#if !SIMC_STRICT
-  double acc[NOUT];
-#pragma unroll
-  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
-#endif
-#pragma unroll
-  for (int k = 0; k <= M; ++k) {
-    if (kmask & (1u << k)) {
-      // multiplying by an exact 1.0 (zero exponent) is exact: skip it where it is known statically
-      double t = (k == 0) ? xp[M] : (k == M) ? tp[M] : xp[M - k] * tp[k];
-#if SIMC_STRICT
-      t = t * s3;
-      t = t * s4;
-      t = t * s5;
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o)
-        if (pat & (1u << o)) { sum[o] = sum[o] + t * __ldg(coef + ci); ++ci; }
-#else
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o)
-        if (pat & (1u << o)) { acc[o] = fma(t, __ldg(coef + ci), acc[o]); ++ci; }
-#endif
-    }
-  }
-#if !SIMC_STRICT
-  const double b = s3 * s4 * s5;
-#pragma unroll
-  for (int o = 0; o < NOUT; ++o)
-    if (pat & (1u << o)) sum[o] = fma(b, acc[o], sum[o]);
-#endif
+// ---- COSY polynomial: branch-free term stream --------------------------------------------
+// The thread's column of the CTA's shared power table holds kPolyEntries doubles: x^a*theta^b for
+// a+b <= 6, then y^e, phi^e, delta^e for e = 0..6 (arm_program.h).  A term is four table reads,
+// three multiplies in the reference's left-to-right order (a unit factor multiplies exactly), and one
+// multiply + add per output with the coefficient read straight from the record, zeros included:
+// the same operations as shared/transp.f:205-214, with no data-dependent branch in the loop.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
 }
-
-template <int M, int NOUT>
-__device__ __forceinline__ void poly_group_m(unsigned kmask, unsigned pat, const double (&xp)[7], const double (&tp)[7],
-                                             double s3, double s4, double s5, const double* __restrict__ coef, int& ci,
-                                             double (&sum)[NOUT]) {
-  if (NOUT == 4) {          // reconstruction maps are dense: delta, y, theta, phi all present
-    if (pat == 15u) poly_group<M, 15, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum);
-    else poly_group<M, 0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum);
-  } else {                  // forward maps: mid-plane symmetry leaves (x,a), (y,b), dl and (x,a,dl)
-    switch (pat) {
-      case 3u: poly_group<M, 3, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 12u: poly_group<M, 12, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 16u: poly_group<M, 16, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 19u: poly_group<M, 19, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      default: poly_group<M, 0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-    }
-  }
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void ldg128(const double* p, double& a, double& b) {
+  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+__device__ __forceinline__ void ldg128u(const double* p, unsigned& a, unsigned& b, unsigned& c, unsigned& d) {
+  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
 }
 
 // Evaluates one compiled map at v = (v1..v5); pw = this thread's column of the shared power table.
 template <int NOUT>
-__device__ __noinline__ void eval_poly(const PolyClass& pc, const unsigned long long* __restrict__ hdr,
-                                       const double* __restrict__ coef, const double (&v)[5], double* pw,
-                                       double (&sum)[NOUT]) {
-  double xp[7], tp[7];
-  // libgcc __powidf2 association: x^3 = x*(x*x), x^5 = x*(x^2)^2, x^6 = x^2*x^4
-  xp[0] = 1.0; xp[1] = v[0]; xp[2] = v[0] * v[0]; xp[3] = v[0] * xp[2]; xp[4] = xp[2] * xp[2];
-  xp[5] = v[0] * xp[4]; xp[6] = xp[2] * xp[4];
-  tp[0] = 1.0; tp[1] = v[1]; tp[2] = v[1] * v[1]; tp[3] = v[1] * tp[2]; tp[4] = tp[2] * tp[2];
-  tp[5] = v[1] * tp[4]; tp[6] = tp[2] * tp[4];
+__device__ __noinline__ void eval_poly(const PolyClass& pc, const double* __restrict__ recs, const double (&v)[5],
+                                       double* pw, double (&sum)[NOUT]) {
+  const unsigned base = (unsigned)__cvta_generic_to_shared(pw);
+  constexpr unsigned S = kBlock * 8u;
+  {
+    double xp[7], tp[7];
+    // libgcc __powidf2 association: x^3 = x*(x*x), x^5 = x*(x^2)^2, x^6 = x^2*x^4
+    xp[0] = 1.0; xp[1] = v[0]; xp[2] = v[0] * v[0]; xp[3] = v[0] * xp[2]; xp[4] = xp[2] * xp[2];
+    xp[5] = v[0] * xp[4]; xp[6] = xp[2] * xp[4];
+    tp[0] = 1.0; tp[1] = v[1]; tp[2] = v[1] * v[1]; tp[3] = v[1] * tp[2]; tp[4] = tp[2] * tp[2];
+    tp[5] = v[1] * tp[4]; tp[6] = tp[2] * tp[4];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const double a = v[2 + j], a2 = a * a, a4 = a2 * a2;
-    double* q = pw + j * 7 * kBlock;
-    q[0 * kBlock] = 1.0; q[1 * kBlock] = a; q[2 * kBlock] = a2; q[3 * kBlock] = a * a2; q[4 * kBlock] = a4;
-    q[5 * kBlock] = a * a4; q[6 * kBlock] = a2 * a4;
-  }
+    for (int a = 0; a < 7; ++a)
 #pragma unroll
-  for (int o = 0; o < NOUT; ++o) sum[o] = 0.0;
-  int ci = pc.coef_begin;
-  for (int g = pc.group_begin; g < pc.group_end; ++g) {
-    const unsigned long long h64 = __ldg(hdr + g);
-    const unsigned h = (unsigned)h64;
-    const unsigned e3 = h & 7u, e4 = (h >> 3) & 7u, e5 = (h >> 6) & 7u, m = (h >> 9) & 7u;
-    const unsigned kmask = (h >> 12) & 127u, pat = (h >> 19) & 31u;
-    const double s3 = pw[(0 * 7 + e3) * kBlock], s4 = pw[(1 * 7 + e4) * kBlock], s5 = pw[(2 * 7 + e5) * kBlock];
-    switch (m) {
-      case 0: poly_group_m<0, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 1: poly_group_m<1, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 2: poly_group_m<2, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 3: poly_group_m<3, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 4: poly_group_m<4, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      case 5: poly_group_m<5, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
-      default: poly_group_m<6, NOUT>(kmask, pat, xp, tp, s3, s4, s5, coef, ci, sum); break;
+      for (int b = 0; b + a < 7; ++b)
+        sts_f64(base + (unsigned)poly_xt_index(a, b) * S, a == 0 ? tp[b] : b == 0 ? xp[a] : xp[a] * tp[b]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double a = v[2 + j], a2 = a * a, a4 = a2 * a2;
+      const unsigned q = base + (unsigned)(28 + 7 * j) * S;
+      sts_f64(q, 1.0); sts_f64(q + S, a); sts_f64(q + 2 * S, a2); sts_f64(q + 3 * S, a * a2); sts_f64(q + 4 * S, a4);
+      sts_f64(q + 5 * S, a * a4); sts_f64(q + 6 * S, a2 * a4);
     }
   }
+  double acc[NOUT];                    // registers: `sum` lives in the caller's frame
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
+  constexpr int W = NOUT == 5 ? kRecWordsFwd : kRecWordsRec;
+  const double* r = recs + pc.rec_begin;
+  const int n = pc.n_rec;
+#pragma unroll 2
+  for (int i = 0; i < n; ++i, r += W) {
+    unsigned o0, o1, o2, o3;
+    double c[6];
+    ldg128u(r, o0, o1, o2, o3);
+    ldg128(r + 2, c[0], c[1]);
+    ldg128(r + 4, c[2], c[3]);
+    if (NOUT == 5) c[4] = __ldg(r + 6);
+    double t = lds_f64(base + o0);
+    const double s3 = lds_f64(base + o1), s4 = lds_f64(base + o2), s5 = lds_f64(base + o3);
+    t = t * s3;
+    t = t * s4;
+    t = t * s5;
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) {
+#if SIMC_STRICT
+      acc[o] = acc[o] + t * c[o];
+#else
+      acc[o] = fma(t, c[o], acc[o]);
+#endif
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) sum[o] = acc[o];
 }
 
 // shared/transp.f:134-279
@@ -294,7 +277,7 @@ __device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t,
   }
   const double ray[5] = {t.xs, t.dxdzs * 1000., t.ys, t.dydzs * 1000., t.dpps};
   double sum[5];
-  eval_poly<5>(arm->tab.fwd[klass - 1], arm->tab.hdr, arm->tab.coef, ray, pw, sum);
+  eval_poly<5>(arm->tab.fwd[klass - 1], arm->tab.recs, ray, pw, sum);
   t.xs = sum[0];
   t.dxdzs = sum[1] / 1000.;
   t.ys = sum[2];
@@ -515,7 +498,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         if (a != 0.) res.y_fp = res.y_fp - a;
         double sum[4];
         if (call_counts) warp_count(&call_counts[47]);
-        eval_poly<4>(arm->tab.rec, arm->tab.hdr, arm->tab.coef, hut, pw, sum);
+        eval_poly<4>(arm->tab.rec, arm->tab.recs, hut, pw, sum);
         res.dph_rec = sum[0];
         res.y_rec = sum[1] * 100.;
         res.dth_rec = sum[2];

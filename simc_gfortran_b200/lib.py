@@ -27,7 +27,8 @@ class SimcError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libsimc_b200.so")
+    # SIMC_B200_LIB: an alternative build of the same library (tools/perf_sweep.sh tries compile-time knobs)
+    return os.environ.get("SIMC_B200_LIB") or os.path.join(_HERE, "libsimc_b200.so")
 
 
 # ---- structures (same order as include/simc_b200.h) -------------------------------------
