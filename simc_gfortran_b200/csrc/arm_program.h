@@ -63,13 +63,15 @@ constexpr int kMaxClasses = 41;       // max_class, spectrometers.inc:6
 //   term = x^e1 * theta^e2 * y^e3 * phi^e4 * delta^e5   (left to right, unit factors included)
 //   sum(1:5) = sum(1:5) + term * coeff(1:5,i)           (all five outputs, zero coefficients included)
 // (shared/transp.f:205-214).  A record keeps exactly that shape so that the device loop has no
-// data-dependent branch: four byte offsets into the thread's shared power table
-// (x^a*theta^b | y^e | phi^e | delta^e) followed by the term's coefficients, zeros included.
-// Terms whose coefficients are all zero add exact zeros in the reference and are dropped.
-//   forward maps : 8 words of 8 bytes  = off[4] (uint32) + 5 coefficients + pad
-//   recon maps   : 6 words             = off[4] (uint32) + 4 coefficients
+// data-dependent branch: one 8-byte word with four 16-bit byte offsets into the thread's shared power
+// table (x^a*theta^b | y^e | phi^e | delta^e), then the term's coefficients, zeros included
+// (forward maps 5, reconstruction maps 4 + one pad word): 6 words = 48 bytes.
+// Terms whose coefficients are all zero add exact zeros in the reference and are dropped.  Records
+// come in chunks of kRecChunk; the last chunk of a map is filled with records that multiply 1.0 by
+// zero coefficients (they add +0.0).  A warp stages one chunk at a time in shared memory.
 constexpr int kPolyEntries = 28 + 3 * 7;      // (a,b) with a+b <= 6, then 7 powers of each slow variable
-constexpr int kRecWordsFwd = 8, kRecWordsRec = 6;
+constexpr int kRecWords = 6;
+constexpr int kRecChunk = 8;                  // records per staged chunk: 8 * 48 bytes = 24 lanes * 16 bytes
 // index of x^a*theta^b in the power table (a + b <= 6)
 #if defined(__CUDACC__)
 __host__ __device__
@@ -77,8 +79,8 @@ __host__ __device__
 inline constexpr int poly_xt_index(int a, int b) { return a * 7 - (a * (a - 1)) / 2 + b; }
 
 struct PolyClass {
-  int32_t rec_begin;                // into recs[], in 8-byte words (always even: records are 16-byte aligned)
-  int32_t n_rec;                    // records = terms with at least one non-zero coefficient
+  int32_t rec_begin;                // into recs[], in 8-byte words (chunks are 16-byte aligned)
+  int32_t n_chunks;                 // chunks of kRecChunk records (terms with a non-zero coefficient + fill)
   int32_t n_terms;                  // terms in the file
   int32_t adrift;
   double length_cm;                 // !LENGTH: comment (0 if none)

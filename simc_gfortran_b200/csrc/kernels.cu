@@ -50,7 +50,8 @@ k_transport_batch(const ArmDev* __restrict__ arm, long long n, const double* __r
   hs.scincount = 0;
   t.dflag = false;
   musc_refresh(t);
-  run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, 0, arm->tab.n_ops);
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
+  run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, arm->tab.n_ops);
   if (i >= n) return;
   out[0 * n + i] = res.ok ? res.dpp_rec : dpp_in;
   out[1 * n + i] = res.ok ? res.dph_rec : dxdz_in;
@@ -76,12 +77,12 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
   {
     static bool attr_set = false;       // > 48 KB of dynamic shared memory needs the opt-in, once per process
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_transport_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      cudaError_t e = cudaFuncSetAttribute(k_transport_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
   }
-  k_transport_batch<<<(unsigned)blocks, kBlock, kPowBytes, s>>>((const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+  k_transport_batch<<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>((const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
                                                         a.flags);
   return cudaGetLastError();
 }
@@ -201,10 +202,10 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_arm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPowBytes);
+      cudaError_t e = cudaFuncSetAttribute(k_arm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
@@ -214,11 +215,11 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     k_generate<<<grid, kBlock, 0, s>>>(A);
   } else if (stage == 1) {
-    k_arm<1, 0><<<grid, kBlock, kPowBytes, s>>>(A);
-    k_arm<1, 1><<<grid, kBlock, kPowBytes, s>>>(A);
+    k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A);
+    k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A);
   } else if (stage == 2) {
-    k_arm<0, 0><<<grid, kBlock, kPowBytes, s>>>(A);
-    k_arm<0, 1><<<grid, kBlock, kPowBytes, s>>>(A);
+    k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A);
+    k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   return cudaGetLastError();

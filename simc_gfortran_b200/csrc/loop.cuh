@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
   for (int i = threadIdx.x; i < 48; i += kBlock) s_calls[i] = 0u;
   __syncthreads();
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   const int in_idx = (WHICH == 1 ? 0 : 2) + SEG;          // list read by this kernel
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
       musc_refresh(t);
       if (use_mc) {
         if (active) warp_count(&s_stop[0]);
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, 0, split, s_calls);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, split, s_calls);
         ok = alive;
       } else {
         ok = active;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
       t.mh2_final = Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
       if (use_mc) {
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, res, hs, alive, split, n_ops, s_calls);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split, n_ops, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
         path = t.pathlen; resmult = res.resmult;

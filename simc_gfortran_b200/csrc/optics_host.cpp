@@ -159,8 +159,17 @@ PolyClass compile_terms(const CosyTerms& t, std::vector<double>& recs, long long
   PolyClass pc{};
   pc.rec_begin = (int)recs.size();
   pc.n_terms = t.n();
-  const int words = t.nout == 5 ? kRecWordsFwd : kRecWordsRec;
   const uint32_t stride = (uint32_t)block_threads * 8u;          // bytes between two table entries of one thread
+  if ((uint64_t)(kPolyEntries - 1) * stride > 0xffffu) throw std::runtime_error("power-table offsets exceed 16 bits");
+  auto push = [&](int e1, int e2, int e3, int e4, int e5, const double* c) {
+    const uint64_t d = (uint64_t)(poly_xt_index(e1, e2) * stride) | ((uint64_t)((28 + e3) * stride) << 16) |
+                       ((uint64_t)((35 + e4) * stride) << 32) | ((uint64_t)((42 + e5) * stride) << 48);
+    double w;
+    std::memcpy(&w, &d, sizeof(w));
+    recs.push_back(w);
+    for (int o = 0; o < 5; ++o) recs.push_back(c && o < t.nout ? c[o] : 0.0);
+  };
+  int n_rec = 0;
   for (int i = 0; i < t.n(); ++i) {
     const int8_t* e = &t.expo[5 * i];
     for (int j = 0; j < 5; ++j)
@@ -171,16 +180,11 @@ PolyClass compile_terms(const CosyTerms& t, std::vector<double>& recs, long long
       if (t.coef[t.nout * i + o] != 0.0) ++nz;
     if (nz == 0) continue;                         // adds exact zeros in the reference
     if (nonzero) *nonzero += nz;
-    const uint32_t off[4] = {(uint32_t)poly_xt_index(e[0], e[1]) * stride, (uint32_t)(28 + e[2]) * stride,
-                             (uint32_t)(35 + e[3]) * stride, (uint32_t)(42 + e[4]) * stride};
-    double w[2];
-    std::memcpy(w, off, sizeof(w));
-    recs.push_back(w[0]);
-    recs.push_back(w[1]);
-    for (int o = 0; o < t.nout; ++o) recs.push_back(t.coef[t.nout * i + o]);
-    for (int o = 2 + t.nout; o < words; ++o) recs.push_back(0.0);
-    pc.n_rec++;
+    push(e[0], e[1], e[2], e[3], e[4], &t.coef[t.nout * i]);
+    ++n_rec;
   }
+  while (n_rec % kRecChunk) { push(0, 0, 0, 0, 0, nullptr); ++n_rec; }     // 1.0 * 0.0
+  pc.n_chunks = n_rec / kRecChunk;
   return pc;
 }
 

@@ -185,6 +185,9 @@ __device__ __forceinline__ void project(TrackDev& t, DevRng& r, double z_drift, 
 // three multiplies in the reference's left-to-right order (a unit factor multiplies exactly), and one
 // multiply + add per output with the coefficient read straight from the record, zeros included:
 // the same operations as shared/transp.f:205-214, with no data-dependent branch in the loop.
+// The records are warp-uniform: the warp copies them chunk by chunk (24 lanes x 16 bytes, one
+// coalesced load) into its own double-buffered ring in shared memory, one chunk ahead of the
+// arithmetic, and every lane reads them back as broadcasts.  ALL 32 LANES MUST CALL eval_poly.
 __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -193,19 +196,36 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-__device__ __forceinline__ void ldg128(const double* p, double& a, double& b) {
-  asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+__device__ __forceinline__ void lds128(unsigned addr, unsigned long long& a, double& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=d"(b) : "r"(addr));
 }
-__device__ __forceinline__ void ldg128u(const double* p, unsigned& a, unsigned& b, unsigned& c, unsigned& d) {
-  asm("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+__device__ __forceinline__ void lds128d(unsigned addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts128d(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void ldg128(const double* p, double& a, double& b) {
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
 }
 
-// Evaluates one compiled map at v = (v1..v5); pw = this thread's column of the shared power table.
+constexpr unsigned kChunkBytes = kRecChunk * kRecWords * 8u;        // 384
+constexpr unsigned kRingBytesPerWarp = 2u * kChunkBytes;            // double buffer
+constexpr size_t kArmSmemBytes = kPowBytes + (kBlock / 32) * kRingBytesPerWarp;
+
+// Evaluates one compiled map at v = (v1..v5).  pw = this thread's column of the shared power table,
+// ring = shared address of this warp's record ring.  Lanes without a live track pass anything finite.
 template <int NOUT>
 __device__ __noinline__ void eval_poly(const PolyClass& pc, const double* __restrict__ recs, const double (&v)[5],
-                                       double* pw, double (&sum)[NOUT]) {
+                                       double* pw, unsigned ring, double (&sum)[NOUT]) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(pw);
   constexpr unsigned S = kBlock * 8u;
+  const unsigned lane = threadIdx.x & 31u;
+  const bool loader = lane < kChunkBytes / 16u;
+  const double* g = recs + pc.rec_begin + 2 * lane;
+  const int nch = pc.n_chunks;
+  double n0 = 0.0, n1 = 0.0;
+  if (loader && nch > 0) ldg128(g, n0, n1);
   {
     double xp[7], tp[7];
     // libgcc __powidf2 association: x^3 = x*(x*x), x^5 = x*(x^2)^2, x^6 = x^2*x^4
@@ -226,43 +246,49 @@ __device__ __noinline__ void eval_poly(const PolyClass& pc, const double* __rest
       sts_f64(q + 5 * S, a * a4); sts_f64(q + 6 * S, a2 * a4);
     }
   }
-  double acc[NOUT];                    // registers: `sum` lives in the caller's frame
+  double acc[5];
 #pragma unroll
-  for (int o = 0; o < NOUT; ++o) acc[o] = 0.0;
-  constexpr int W = NOUT == 5 ? kRecWordsFwd : kRecWordsRec;
-  const double* r = recs + pc.rec_begin;
-  const int n = pc.n_rec;
-#pragma unroll 2
-  for (int i = 0; i < n; ++i, r += W) {
-    unsigned o0, o1, o2, o3;
-    double c[6];
-    ldg128u(r, o0, o1, o2, o3);
-    ldg128(r + 2, c[0], c[1]);
-    ldg128(r + 4, c[2], c[3]);
-    if (NOUT == 5) c[4] = __ldg(r + 6);
-    double t = lds_f64(base + o0);
-    const double s3 = lds_f64(base + o1), s4 = lds_f64(base + o2), s5 = lds_f64(base + o3);
-    t = t * s3;
-    t = t * s4;
-    t = t * s5;
+  for (int o = 0; o < 5; ++o) acc[o] = 0.0;
+  for (int c = 0; c < nch; ++c) {
+    const unsigned buf = ring + (unsigned)(c & 1) * kChunkBytes;
+    if (loader) sts128d(buf + lane * 16u, n0, n1);
+    if (loader && c + 1 < nch) ldg128(g + (size_t)(c + 1) * (kRecChunk * kRecWords), n0, n1);
+    __syncwarp();
 #pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
+    for (int k = 0; k < kRecChunk; ++k) {
+      const unsigned rb = buf + (unsigned)k * (kRecWords * 8u);
+      unsigned long long d;
+      double c0, c1, c2, c3, c4;
+      lds128(rb, d, c0);
+      lds128d(rb + 16u, c1, c2);
+      lds128d(rb + 32u, c3, c4);
+      double t = lds_f64(base + ((unsigned)d & 0xffffu));
+      const double s3 = lds_f64(base + ((unsigned)(d >> 16) & 0xffffu));
+      const double s4 = lds_f64(base + ((unsigned)(d >> 32) & 0xffffu));
+      const double s5 = lds_f64(base + (unsigned)(d >> 48));
+      t = t * s3;
+      t = t * s4;
+      t = t * s5;
 #if SIMC_STRICT
-      acc[o] = acc[o] + t * c[o];
+      acc[0] = acc[0] + t * c0; acc[1] = acc[1] + t * c1; acc[2] = acc[2] + t * c2; acc[3] = acc[3] + t * c3;
+      if (NOUT == 5) acc[4] = acc[4] + t * c4;
 #else
-      acc[o] = fma(t, c[o], acc[o]);
+      acc[0] = fma(t, c0, acc[0]); acc[1] = fma(t, c1, acc[1]); acc[2] = fma(t, c2, acc[2]); acc[3] = fma(t, c3, acc[3]);
+      if (NOUT == 5) acc[4] = fma(t, c4, acc[4]);
 #endif
     }
   }
+  __syncwarp();
 #pragma unroll
   for (int o = 0; o < NOUT; ++o) sum[o] = acc[o];
 }
 
 // shared/transp.f:134-279
+// Called by all 32 lanes (eval_poly is warp-cooperative); `live` = this lane has a track.
 __device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& r, int klass, double zd,
-                                    bool decay_flag, double* pw) {
+                                    bool decay_flag, double* pw, unsigned ring, bool live) {
   double p_spec = 0, beta = 0, gamma = 0, z_decay = 0;
-  const bool check = decay_flag && !t.dflag;
+  const bool check = live && decay_flag && !t.dflag;
   if (check) {
     p_spec = t.p / (1. + t.dpps / 100.);
     beta = t.p / sqrt(t.p * t.p + t.m2);
@@ -277,7 +303,8 @@ __device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t,
   }
   const double ray[5] = {t.xs, t.dxdzs * 1000., t.ys, t.dydzs * 1000., t.dpps};
   double sum[5];
-  eval_poly<5>(arm->tab.fwd[klass - 1], arm->tab.recs, ray, pw, sum);
+  eval_poly<5>(arm->tab.fwd[klass - 1], arm->tab.recs, ray, pw, ring, sum);
+  if (!live) return;
   t.xs = sum[0];
   t.dxdzs = sum[1] / 1000.;
   t.ys = sum[2];
@@ -336,6 +363,11 @@ __device__ __forceinline__ void warp_count(unsigned* counter) {
   const unsigned m = __activemask();
   if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(counter, (unsigned)__popc(m));
 }
+// Same with an explicit predicate, for places where dead lanes are converged with live ones.
+__device__ __forceinline__ void warp_count_if_alive(unsigned* counter, bool alive) {
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  if ((threadIdx.x & 31u) == 0 && m) atomicAdd(counter, (unsigned)__popc(m));
+}
 // Histogram increment aggregated over the lanes that hit the same bin (bin < 0: no increment).
 __device__ __forceinline__ void warp_hist_add(unsigned* hist, int bin) {
   const unsigned act = __activemask();
@@ -365,8 +397,8 @@ __device__ __forceinline__ void arm_result_clear(ArmResult& res) {
 // op.  `alive` comes back false when the event stopped (res.stop_code) or finished (res.ok).
 // `pw` = this thread's column of the CTA's shared power table.
 __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& rng, const ArmFlags f,
-                                        double fry, double* pw, ArmResult& res, HutState& hs, bool& alive,
-                                        int op_begin, int op_end, unsigned* call_counts = nullptr) {
+                                        double fry, double* pw, unsigned ring, ArmResult& res, HutState& hs,
+                                        bool& alive, int op_begin, int op_end, unsigned* call_counts = nullptr) {
   double xt = 0., yt = 0.;
   for (int pc = op_begin; pc < op_end; ++pc) {
     __syncwarp();
@@ -374,17 +406,45 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
     const ArmOp* __restrict__ o = &arm->ops[pc];
     const int op = __ldg(&o->op);
     if (op == OP_END) break;
-    if (!alive) continue;
     const double a = __ldg(&o->a), b = __ldg(&o->b), c = __ldg(&o->c), d = __ldg(&o->d);
+    // the two map evaluations are warp-cooperative: every lane goes in, dead ones compute on stale values
+    if (op == OP_TRANSP) {
+      const int klass = __ldg(&o->i0);
+      if (call_counts) warp_count_if_alive(&call_counts[klass - 1], alive);
+      transp(arm, t, rng, klass, a, f.decay_flag, pw, ring, alive);
+      continue;
+    }
+    if (op == OP_RECON) {     // mc_hms.f:419-437 + mc_hms_recon.f:104-137
+      double hut[5];
+      hut[0] = res.x_fp / 100.;
+      hut[1] = res.dx_fp;
+      hut[2] = res.y_fp / 100.;
+      hut[3] = res.dy_fp;
+      hut[4] = fry / 100.;
+      if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
+      if (__ldg(&o->i0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
+      }
+      double sum[4];
+      if (call_counts) warp_count_if_alive(&call_counts[47], alive);
+      eval_poly<4>(arm->tab.rec, arm->tab.recs, hut, pw, ring, sum);
+      if (alive) {
+        if (a != 0.) res.y_fp = res.y_fp - a;
+        res.dph_rec = sum[0];
+        res.y_rec = sum[1] * 100.;
+        res.dth_rec = sum[2];
+        res.dpp_rec = sum[3] * 100.;
+        res.ok = true;
+        alive = false;
+      }
+      continue;
+    }
+    if (!alive) continue;
     bool stop = false;
     switch (op) {
       case OP_PROJECT: project(t, rng, a, f.decay_flag); break;
-      case OP_TRANSP: {
-        const int klass = __ldg(&o->i0);
-        if (call_counts) warp_count(&call_counts[klass - 1]);
-        transp(arm, t, rng, klass, a, f.decay_flag, pw);
-        break;
-      }
       case OP_CUT_R2: stop = (t.xs * t.xs + t.ys * t.ys) > a; break;
       case OP_CUT_ABS_Y: stop = fabs(t.ys - a) > b; break;
       case OP_CUT_ABS_X: stop = fabs(t.xs - a) > b; break;
@@ -480,31 +540,6 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         const double xcal = res.x_fp + res.dx_fp * a;
         const double ycal = res.y_fp + res.dy_fp * a;
         stop = (ycal > b) || (ycal < c) || (xcal > d) || (xcal < e);
-        break;
-      }
-      case OP_RECON: {     // mc_hms.f:419-437 + mc_hms_recon.f:104-137
-        double hut[5];
-        hut[0] = res.x_fp / 100.;
-        hut[1] = res.dx_fp;
-        hut[2] = res.y_fp / 100.;
-        hut[3] = res.dy_fp;
-        hut[4] = fry / 100.;
-        if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
-        if (__ldg(&o->i0)) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
-        }
-        if (a != 0.) res.y_fp = res.y_fp - a;
-        double sum[4];
-        if (call_counts) warp_count(&call_counts[47]);
-        eval_poly<4>(arm->tab.rec, arm->tab.recs, hut, pw, sum);
-        res.dph_rec = sum[0];
-        res.y_rec = sum[1] * 100.;
-        res.dth_rec = sum[2];
-        res.dpp_rec = sum[3] * 100.;
-        res.ok = true;
-        alive = false;
         break;
       }
       case OP_UNSUPPORTED:

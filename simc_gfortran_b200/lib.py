@@ -272,7 +272,7 @@ class Simc:
     def optics_info(self, arm: int) -> dict:
         info = np.zeros(8, dtype=np.int64)
         self._check(self.L.simc_b200_optics_info(self.h, arm, _ptr(info)))
-        keys = ("n_classes", "fwd_terms", "fwd_nonzero", "rec_terms", "n_groups", "n_coef", "n_ops")
+        keys = ("n_classes", "fwd_terms", "fwd_nonzero", "rec_terms", "n_rec_words", "n_coef", "n_ops")
         return dict(zip(keys, (int(x) for x in info[:7])))
 
     # ---- single-arm batch (host buffers)
