@@ -122,7 +122,7 @@ typedef struct {
   int32_t rad_flag, extrad_flag, intcor_mode, use_expon, use_offshell_rad;
   int32_t doing_tail[3];
   int32_t hardwired_rad;
-  int32_t pad0;
+  int32_t deForest_flag;                     /* 0 = sigcc1, 1 = sigcc2, -1 = sigcc1 on shell (physics_proton.f:39-45) */
 
   /* /gnrl/ scalars */
   double Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave;
@@ -216,6 +216,13 @@ int simc_b200_set_optics(simc_handle* h, int arm_id,
 /* info[0..6] = n_classes, forward terms, non-zero forward coefficients, recon terms,
  * compiled groups, packed coefficients, ops in the arm program */
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);
+
+/* Benhar-type spectral function S(Em,Pm) for A(e,e'p) with use_benhar_sf (replaces sf_lookup_init,
+ * sf_lookup.f:1-80, called from dbase.f:594-621).  pm[n_pm], em[n_em] are the bin centres and
+ * sf[n_pm][n_em] (Em fastest, the file's order) the proton or neutron column the caller picked; the
+ * library normalises the sum to one like the reference.  load_sf_file reads benharsf_*.dat itself. */
+int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm, const double* em, const double* sf);
+int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag);
 
 /* the loop -------------------------------------------------------------- *
  * Replaces simc.f:169-351 for tries first_try .. first_try+n_tries-1 of the

@@ -10,6 +10,7 @@
 using namespace simc_oracle;
 
 static std::map<int, ArmOptics> g_optics;
+static SfTable g_sf;
 static std::string g_err;
 
 extern "C" {
@@ -79,6 +80,26 @@ int oracle_set_optics(int arm, int n_classes, const int32_t* class_start, const 
   return 0;
 }
 
+// sf_lookup_init (sf_lookup.f:1-80) from arrays: sf[iPm][iEm] in file order; normalised to sum 1 here.
+int oracle_set_sf_table(int n_pm, int n_em, const double* pm, const double* em, const double* sf) {
+  g_sf.numPm = n_pm; g_sf.numEm = n_em;
+  g_sf.Pmval.assign(pm, pm + n_pm);
+  g_sf.Emval.assign(em, em + n_em);
+  g_sf.sfval.assign(sf, sf + (size_t)n_pm * n_em);
+  double sftotnorm = 0.0;
+  for (int iPm = 0; iPm < n_pm; ++iPm)
+    for (int iEm = 0; iEm < n_em; ++iEm) sftotnorm = sftotnorm + g_sf.sfval[(size_t)iPm * n_em + iEm];
+  for (double& v : g_sf.sfval) v = v / sftotnorm;
+  return 0;
+}
+// sf_lookup_diff and deForest on dumped vectors: in [Em, Pm] x n -> out[n]
+int oracle_sf_batch(int64_t n, const double* em, const double* pm, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) out[i] = sf_lookup_diff(g_sf, em[i], pm[i]);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // Batch form of mc_hms / mc_shms; same row layout as simc_b200_transport_batch.
 int oracle_transport_batch(int arm, int64_t n, const double* in, uint64_t seed, int ms_flag, int wcs_flag,
                            int decay_flag, int using_coll, double ctau, double* out, int32_t* flags) {
@@ -143,7 +164,8 @@ int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_
       try {
         RanluxState st;
         if (rng_mode == 1) st.rluxgo(3, (int)(seed + 1 + t), 0, 0);
-        run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr);
+        run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr,
+                  g_sf.numPm ? &g_sf : nullptr);
       }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
@@ -160,7 +182,7 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
   auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
   try {
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
-              n, seed, nullptr, rec, status, n, 0);
+              n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }

@@ -549,8 +549,12 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
   if (cfg.doing_hyd_elast || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_phsp || cfg.doing_rho ||
       cfg.doing_semi) {
     main.SF_weight = 1.0;
+  } else if (cfg.use_benhar_sf && cfg.doing_heavy) {
+    if (!s.sf) throw std::runtime_error("oracle: spectral-function table not set");
+    const double weight = sf_lookup_diff(*s.sf, vertex.Em, vertex.Pm);
+    main.SF_weight = cfg.targ.Z * cfg.transparency * weight;
   } else {
-    throw std::runtime_error("oracle: spectral-function weights not restated yet");
+    throw std::runtime_error("oracle: momentum-distribution (theory file) weights not restated");
   }
   if (main.SF_weight <= 0 && !force_sigcc) return false;
   double tgtweight = 1.0, survivalprob = 1.0;
@@ -560,6 +564,9 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
   } else if (cfg.doing_hyd_elast) {
     main.sigcc = sigep(vertex);
     main.sigcc_recon = sigep(recon);
+  } else if (cfg.doing_deuterium || cfg.doing_heavy) {
+    main.sigcc = deForest(cfg, vertex);
+    main.sigcc_recon = deForest(cfg, recon);
   } else if (cfg.doing_pion) {
     if (cfg.which_pion == 2 || cfg.which_pion == 3) throw std::runtime_error("oracle: Delta final states not restated");
     main.sigcc = peepi(s, vertex, main);

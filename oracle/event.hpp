@@ -4,6 +4,7 @@
 // physics_proton.f, simc.f (montecarlo + loop body).
 #pragma once
 #include "../include/simc_b200.h"
+#include <vector>
 #include "arms.hpp"
 
 namespace simc_oracle {
@@ -53,6 +54,15 @@ struct NtupVars {
   double survivalprob = 1.0;       // local of complete_main (event.f:1373), kept for the parity records
 };
 
+// COMMON /sftable/ (sf_lookup.inc) after sf_lookup_init: normalised to sum 1
+struct SfTable {
+  int numPm = 0, numEm = 0;
+  std::vector<double> Pmval, Emval, sfval;   // sfval[iPm * numEm + iEm]
+};
+double sf_lookup(const SfTable& T, double Em, double Pm);            // sf_lookup.f:97-170
+double sf_lookup_diff(const SfTable& T, double Em, double Pm);       // sf_lookup.f:85-95
+double deForest(const simc_run_config& cfg, const struct Event& ev); // physics_proton.f:23-135
+
 // Everything one try needs: the run constants, both arms' optics, the RNG and the scratch
 // COMMON state.  One instance per try in counter-based mode (state starts from zero, see
 // DESIGN.md on the reference's stale-state quirks).
@@ -60,6 +70,7 @@ struct Sim {
   const simc_run_config* cfg = nullptr;
   const ArmOptics* optics_e = nullptr;
   const ArmOptics* optics_p = nullptr;
+  const SfTable* sf = nullptr;
   Rng* rng = nullptr;
   RadEv rad;
   NtupVars ntup;
@@ -108,6 +119,6 @@ void accum_clear(const simc_run_config& cfg, simc_accum& a);
 void merge_accum(simc_accum& a, const simc_accum& b);
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
-               RanluxState* ranlux = nullptr);
+               RanluxState* ranlux = nullptr, const SfTable* sf = nullptr);
 
 }  // namespace simc_oracle

@@ -167,13 +167,13 @@ void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const 
 // tries [first, first+n) of stream `seed`; rec/status may be null
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
-               RanluxState* ranlux) {
+               RanluxState* ranlux, const SfTable* sf) {
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
     if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
     else rng.seed_philox(seed, (uint64_t)(first + i));
     Sim s;
-    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng;
+    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf;
     EventMain main;
     Event vertex, orig, recon;
     const TryResult r = one_try(s, main, vertex, orig, recon);

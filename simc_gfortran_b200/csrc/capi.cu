@@ -53,6 +53,7 @@ struct simc_handle {
   int qexp_w = -64;
   std::vector<unsigned char> acc_host;
   double* d_rec = nullptr; int* d_status = nullptr; long long rec_n = 0;
+  double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
   // optional per-stage timing
   int timing = 0;
   std::vector<cudaEvent_t> ev;                 // 5 events per batch, recycled
@@ -163,8 +164,56 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_acc) cudaFree(h->d_acc);
   if (h->d_rec) cudaFree(h->d_rec);
   if (h->d_status) cudaFree(h->d_status);
+  if (h->d_sf) cudaFree(h->d_sf);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// sf_lookup_init (sf_lookup.f:1-80) from arrays
+int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm, const double* em, const double* sf) {
+  if (!h || !pm || !em || !sf) return SIMC_ERR_ARG;
+  if (n_pm < 2 || n_em < 2 || n_pm > 100 || n_em > 200)
+    return fail(h, SIMC_ERR_ARG, "spectral function: 2..100 Pm bins and 2..200 Em bins (sf_lookup.inc)");
+  CU(h, cudaSetDevice(h->device));
+  std::vector<double> img((size_t)n_pm + n_em + (size_t)n_pm * n_em);
+  std::copy(pm, pm + n_pm, img.begin());
+  std::copy(em, em + n_em, img.begin() + n_pm);
+  double sftotnorm = 0.0;
+  for (size_t i = 0; i < (size_t)n_pm * n_em; ++i) sftotnorm = sftotnorm + sf[i];
+  if (!(sftotnorm > 0)) return fail(h, SIMC_ERR_ARG, "spectral function sums to zero");
+  for (size_t i = 0; i < (size_t)n_pm * n_em; ++i) img[(size_t)n_pm + n_em + i] = sf[i] / sftotnorm;
+  if (h->d_sf) { cudaFree(h->d_sf); h->d_sf = nullptr; }
+  CU(h, cudaMalloc(&h->d_sf, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_sf, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->sf_npm = n_pm; h->sf_nem = n_em;
+  return SIMC_OK;
+}
+
+// The reference's file format (benharsf_*.dat): "numPm numEm", then numPm*numEm rows
+// "Pm Em S_proton S_neutron dPm dEm", Em running fastest (sf_lookup.f:17-49).
+int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open spectral function file ") + path);
+  int n_pm = 0, n_em = 0;
+  if (std::fscanf(f, "%d %d", &n_pm, &n_em) != 2 || n_pm < 2 || n_em < 2 || n_pm > 100 || n_em > 200) {
+    std::fclose(f);
+    return fail(h, SIMC_ERR_IO, "spectral function file: bad header");
+  }
+  std::vector<double> pm(n_pm), em(n_em), sf((size_t)n_pm * n_em);
+  for (int i = 0; i < n_pm; ++i)
+    for (int j = 0; j < n_em; ++j) {
+      double tPm, tEm, sp, sn, dPm, dEm;
+      if (std::fscanf(f, "%lf %lf %lf %lf %lf %lf", &tPm, &tEm, &sp, &sn, &dPm, &dEm) != 6) {
+        std::fclose(f);
+        return fail(h, SIMC_ERR_IO, "spectral function file: short read");
+      }
+      sf[(size_t)i * n_em + j] = proton_flag ? sp : sn;
+      if (j == 0) pm[i] = tPm;
+      if (i == 0) em[j] = tEm;
+    }
+  std::fclose(f);
+  return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
 }
 
 const char* simc_b200_last_error(const simc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -300,10 +349,14 @@ int weight_qexp(const simc_run_config& cfg) {
 int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
   const bool meson = (c.doing_hydpi && c.doing_pion) || (c.doing_hydkaon && c.doing_kaon);
-  if (!(c.doing_hyd_elast || meson) || c.doing_deuterium || c.doing_heavy || c.doing_delta || c.doing_rho || c.doing_semi ||
+  const bool heavy = c.doing_heavy && c.doing_eep && c.use_benhar_sf;
+  if (!(c.doing_hyd_elast || meson || heavy) || c.doing_deuterium || c.doing_delta || c.doing_rho || c.doing_semi ||
       c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
-                "this build of the event loop implements H(e,e'p), H(e,e'pi+-) and H(e,e'K+) (hydrogen targets)");
+                "this build of the event loop implements H(e,e'p), A(e,e'p) with a Benhar spectral function, "
+                "H(e,e'pi+-) and H(e,e'K+)");
+  if (heavy && !h->d_sf)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
   if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
     return fail(h, SIMC_ERR_ARG, "Delta final states (which_pion = 2, 3) are not implemented");
   if (c.using_rad && (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 ||
@@ -383,6 +436,9 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
   a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;
+  a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
+  a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
+  a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
   {
     const MatTable mt = make_mat_table(h->cfg.targ);          // host libm, once per call
     static_assert(sizeof(mt) == sizeof(a.mats), "MatTable layout");

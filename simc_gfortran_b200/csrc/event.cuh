@@ -7,6 +7,7 @@
 #pragma once
 #include "radc.cuh"
 #include "physics_meson.cuh"
+#include "physics_heavy.cuh"
 
 namespace simc {
 
@@ -512,6 +513,225 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, RNG&
   const bool reenter = ok && which == 1;                       // radc.f:324
   const bool re_ok = complete_ev_meson(cfg, mt, rng, gauss, s, reenter);
   if (reenter && !re_ok) ok = false;
+  if (ok && which) {
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
+  }
+  SIMC_PHASE();
+  if (ok) {
+    s.o_Ein = s.v_Ein + R.Egamma_used[0];
+    s.o_eE = s.v_eE - R.Egamma_used[1];
+    if (s.o_eE <= 0e0) ok = false;
+  }
+  if (ok) {
+    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
+    s.o_pE = s.v_pE - R.Egamma_used[2];
+    if (s.o_pE <= cfg.Mh) ok = false;
+  }
+  if (ok) {
+    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
+  }
+  return ok;
+}
+
+// ---- A(e,e'p) on a nucleus (doing_heavy): complete_ev, event.f:432-1052 --------------------------
+// Both energies and both directions are thrown; the kinematics only derive q, the missing
+// momentum/energy and the recoil system (event.f:914-955).
+template <class RNG, class GAUSS>
+SIMC_HD bool complete_ev_heavy(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s,
+                               bool run) {
+  const simc_target& targ = cfg.targ;
+  if (run) {
+    s.jacobian = 1.0;
+    s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
+    s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
+    s.uez = m::cos(s.v_etheta);
+    s.upx = m::sin(s.v_ptheta) * m::cos(s.v_pphi);
+    s.upy = m::sin(s.v_ptheta) * m::sin(s.v_pphi);
+    s.upz = m::cos(s.v_ptheta);
+    const double eP = s.v_eE;
+    s.v_nu = s.v_Ein - s.v_eE;
+    s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
+    s.v_q = sqrt(s.v_Q2 + s.v_nu * s.v_nu);
+    s.uqx = -eP * s.uex / s.v_q;
+    s.uqy = -eP * s.uey / s.v_q;
+    s.uqz = (s.v_Ein - eP * s.uez) / s.v_q;
+    // event.f:880-955
+    const double Pmx = s.v_pP * s.upx - s.v_q * s.uqx;
+    const double Pmy = s.v_pP * s.upy - s.v_q * s.uqy;
+    const double Pmz = s.v_pP * s.upz - s.v_q * s.uqz;
+    const double Pmiss = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
+    const double Emiss = s.v_nu + targ.M - s.v_pE;
+    s.v_Pm = Pmiss;
+    const double Mrec = sqrt(Emiss * Emiss - Pmiss * Pmiss);
+    s.v_Em = targ.Mtar_struck + Mrec - targ.M;
+    s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
+    double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+    r = sqrt(1. + s.v_pyptar * s.v_pyptar + s.v_pxptar * s.v_pxptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+  }
+  const double zpos = s.tz - targ.zoffset;
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 2, zpos, s.v_eE, s.v_etheta, SIMC_ME, s.Eloss[1], s.teff[1]);
+  SIMC_PHASE();
+  if (run) trip_thru_target_sampled(cfg, mt, rng, gauss, 3, zpos, s.v_pE, s.v_ptheta, cfg.Mh, s.Eloss[2], s.teff[2]);
+  SIMC_PHASE();
+  if (run) {
+    if (!cfg.using_Eloss) { s.Eloss[1] = 0.0; s.Eloss[2] = 0.0; }
+    VertexKin v;
+    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
+    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
+    radc_init_ev(cfg, v, s.teff[0], s.teff[1], s.rad);
+  }
+  SIMC_PHASE();
+  return run;
+}
+
+// generate + generate_rad for A(e,e'p): event.f:126-428 (hadron energy :283-294, electron energy
+// :296-318), radc.f:120-519 with the doing_heavy photon-energy limits (:249-263) and the Em/Pm window
+// test after the first tail (:340-350).
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_heavy(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+  const simc_target& targ = cfg.targ;
+  const simc_gen_limits& gen = cfg.gen;
+  if (ok) {
+    s.tx = gauss(rng, 3.0) * gen.xwid + targ.xoffset;
+    s.ty = gauss(rng, 3.0) * gen.ywid + targ.yoffset;
+    double t3, t4, t5, t6;
+    if (targ.fr_pattern == 1) {
+      t3 = rng.uniform() * SIMC_PI_D;
+      t4 = rng.uniform() * SIMC_PI_D;
+      t5 = m::cos(t3) * targ.fr1;
+      t6 = m::cos(t4) * targ.fr2;
+    } else if (targ.fr_pattern == 2) {
+      t3 = rng.uniform() * 2. * SIMC_PI_D;
+      t4 = sqrt(rng.uniform()) * (targ.fr2 - targ.fr1) + targ.fr1;
+      t5 = m::cos(t3) * t4;
+      t6 = m::sin(t3) * t4;
+    } else if (targ.fr_pattern == 3) {
+      t3 = 2. * rng.uniform() - 1.0;
+      t4 = 2. * rng.uniform() - 1.0;
+      t5 = targ.fr1 * t3;
+      t6 = targ.fr2 * t4;
+    } else {
+      t5 = 0.0; t6 = 0.0;
+    }
+    s.tx = s.tx + t5;
+    s.ty = s.ty + t6;
+    s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
+    s.rastery = t6;
+    trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
+    if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
+    s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
+    s.v_Ein = cfg.Ebeam + (rng.uniform() - 0.5) * cfg.dEbeam + s.Coulomb - s.Eloss[0];
+    s.Ein_shift = s.v_Ein - cfg.Ebeam_vertex_ave;
+    s.Ee_shift = s.Coulomb - targ.Coulomb_ave;
+    s.gen_weight = 1.0;
+    s.v_eyptar = gen.e.yptar.min + rng.uniform() * (gen.e.yptar.max - gen.e.yptar.min);
+    s.v_exptar = gen.e.xptar.min + rng.uniform() * (gen.e.xptar.max - gen.e.xptar.min);
+    s.v_pyptar = gen.p.yptar.min + rng.uniform() * (gen.p.yptar.max - gen.p.yptar.min);
+    s.v_pxptar = gen.p.xptar.min + rng.uniform() * (gen.p.xptar.max - gen.p.xptar.min);
+    {   // hadron energy, event.f:283-294
+      const double Emin = fmax(gen.p.E.min, gen.sumEgen.min - gen.e.E.max);
+      const double Emax = fmin(gen.p.E.max, gen.sumEgen.max - gen.e.E.min);
+      if (Emin > Emax) ok = false;
+      if (ok) {
+        s.gen_weight = s.gen_weight * (Emax - Emin) / (gen.p.E.max - gen.p.E.min);
+        s.v_pE = Emin + rng.uniform() * (Emax - Emin);
+        s.v_pP = sqrt(s.v_pE * s.v_pE - cfg.Mh2);
+        s.v_pdelta = 100. * (s.v_pP - cfg.spec_p.P) / cfg.spec_p.P;
+      }
+    }
+    if (ok) {   // electron energy, event.f:296-318
+      const double Emin = fmax(gen.e.E.min, gen.sumEgen.min - s.v_pE);
+      const double Emax = fmin(gen.e.E.max, gen.sumEgen.max - s.v_pE);
+      if (Emin > Emax) ok = false;
+      if (ok) {
+        s.gen_weight = s.gen_weight * (Emax - Emin) / (gen.e.E.max - gen.e.E.min);
+        s.v_eE = Emin + rng.uniform() * (Emax - Emin);
+        s.v_edelta = 100. * (s.v_eE - cfg.spec_e.P) / cfg.spec_e.P;
+        physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, s.v_exptar, s.v_eyptar, s.v_etheta, s.v_ephi);
+        physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, s.v_pxptar, s.v_pyptar, s.v_ptheta, s.v_pphi);
+        s.v_Em = 0.0;
+        s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
+        s.rad.ntail = 0;
+      }
+    }
+  }
+  SIMC_PHASE();
+  ok = complete_ev_heavy(cfg, mt, rng, gauss, s, ok);
+  if (ok) s.Trec = s.v_Trec;
+  const simc_edge& VE = cfg.VERTEXedge;
+  if (!cfg.using_rad) {
+    if (ok) ok = (s.v_Em >= VE.Em.min && s.v_Em <= VE.Em.max && s.v_Pm >= VE.Pm.min && s.v_Pm <= VE.Pm.max);
+    if (ok) {
+      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
+      s.o_pdelta = s.v_pdelta;
+    }
+    return ok;
+  }
+  RadEvDev& R = s.rad;
+  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0, max_delta_Trec = 0.0;
+  int which = 0, ntail = 0;
+  if (ok) {
+    const double x = rng.uniform();
+    if (x >= R.frac[0] + R.frac[1]) R.ntail = 3;
+    else if (x >= R.frac[0]) R.ntail = 2;
+    else R.ntail = 1;
+    ntail = R.ntail;
+    max_delta_Trec = fmax((s.v_Trec - VE.Trec.min), (VE.Trec.max - s.v_Trec));
+    if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:249-263
+      emin = s.v_Em - VE.Em.max - max_delta_Trec;
+      emax = s.v_Em - VE.Em.min + max_delta_Trec;
+      emax = fmin(emax, s.v_Em - cfg.edge.Em.min + max_delta_Trec);       // ntail != 0
+      emax = fmin(emax, cfg.Egamma1_max);
+      emin = emin - cfg.dE_edge_test;
+      emax = emax + cfg.dE_edge_test;
+      if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+      which = 1;
+      basicrad4(R, rng, emin, emax, eg, bw);
+      if (bw <= 0) ok = false;
+      else { R.Egamma_used[0] = eg; s.v_Ein = s.v_Ein - eg; }
+    }
+  }
+  SIMC_PHASE();
+  const bool reenter = ok && which == 1;                       // radc.f:324
+  const bool re_ok = complete_ev_heavy(cfg, mt, rng, gauss, s, reenter);
+  if (reenter && !re_ok) ok = false;
+  if (ok) {
+    // radc.f:340-350: the vertex must sit inside the spectral function's window
+    if (s.v_Em < VE.Em.min || s.v_Em > VE.Em.max || s.v_Pm < VE.Pm.min || s.v_Pm > VE.Pm.max) ok = false;
+  }
+  if (ok && !which) {
+    if (cfg.doing_tail[1] && ntail == 2) {          // radc.f:358-374
+      emin = s.v_eE - cfg.edge.e.E.max;
+      emax = s.v_eE - cfg.edge.e.E.min;
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
+      emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
+      which = 2;
+    } else if (R.rad_proton_this_ev && ntail == 3) {   // radc.f:409-425
+      emin = s.v_pE - cfg.edge.p.E.max;
+      emax = s.v_pE - cfg.edge.p.E.min;
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
+      emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
+      emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
+      which = 3;
+    }
+    if (which) {
+      emin = emin - cfg.dE_edge_test;
+      emax = emax + cfg.dE_edge_test;
+      if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+      basicrad4(R, rng, emin, emax, eg, bw);
+      if (bw <= 0) ok = false;
+      else R.Egamma_used[which - 1] = eg;
+    }
+  }
   if (ok && which) {
     VertexKin v;
     v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;

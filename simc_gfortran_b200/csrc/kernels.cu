@@ -197,6 +197,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.record_mode = a.record_mode;
   static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
   memcpy(&A.mt, a.mats, sizeof(MatTable));
+  A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
   const long long need = (a.n_tries + kBlock - 1) / kBlock;
   const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
   {

@@ -36,6 +36,10 @@ struct LoopLaunch {
   int* status;
   int grid_blocks;            // persistent grid for the stage kernels
   double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
+  const double* sf_pm;        // Benhar spectral function (device): Pm axis, Em axis, values [n_pm][n_em]
+  const double* sf_em;
+  const double* sf_val;
+  int sf_npm, sf_nem;
 };
 
 namespace strict {

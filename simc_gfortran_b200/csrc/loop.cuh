@@ -66,6 +66,7 @@ struct DevAccum {
 struct LoopArgs {
   const simc_run_config* cfg;      // device copy
   MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
+  SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   const ArmDev* arm_e;
   const ArmDev* arm_p;
   StateBuf st;
@@ -155,7 +156,9 @@ __global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopAr
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
+    const bool heavy = cfg.doing_heavy != 0;
     if (meson) ok = generate_meson(cfg, A.mt, rng, GaussFn(), s, active);
+    else if (heavy) ok = generate_heavy(cfg, A.mt, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast(cfg, A.mt, rng, GaussFn(), s, active);
     if (active) {
       // geni histograms: every try, from the vertex values (simc.f:253-262)
@@ -187,6 +190,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopAr
       S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
       S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
       S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
+      if (heavy && ok) {
+        S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
+        S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
+      }
       if (meson && ok) {
         S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
         S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
@@ -486,12 +493,30 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
       const double rW = sqrt(fabs(W2)) * W2 / fabs(W2);
       const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
-      const double rTrec = 0.0;
       const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
+      const bool heavy = cfg.doing_heavy != 0;
+      const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
       // complete_main, event.f:1363-1569
       const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
-      double sigcc_recon, tgtweight = 1.0, survivalprob = 1.0;
-      if (!meson) {
+      double sigcc_recon, tgtweight = 1.0, survivalprob = 1.0, SF_weight = 1.0;
+      if (heavy) {
+        rEm = nu + cfg.targ.Mtar_struck - rpE - rTrec;
+        bool bad = false;
+        SF_weight = cfg.targ.Z * cfg.transparency * sf_lookup_diff(A.sf, S.ld(F_VEM, slot), S.ld(F_VPM, slot), bad);
+        low_w = bad;                                   // counted in `unsupported`: the reference would `stop`
+        HeavyEv ev;
+        ev.Q2 = v_Q2; ev.q = S.ld(F_VQ, slot); ev.nu = S.ld(F_VNU, slot); ev.Pm = S.ld(F_VPM, slot);
+        ev.pE = S.ld(F_VPE, slot); ev.pP = S.ld(F_VPP, slot); ev.eE = v_eE; ev.etheta = v_eth;
+        ev.uqx = S.ld(F_UQX, slot); ev.uqy = S.ld(F_UQY, slot); ev.uqz = S.ld(F_UQZ, slot);
+        ev.upx = S.ld(F_UPX, slot); ev.upy = S.ld(F_UPY, slot); ev.upz = S.ld(F_UPZ, slot);
+        ev.Pmx = ev.pP * ev.upx - ev.q * ev.uqx; ev.Pmy = ev.pP * ev.upy - ev.q * ev.uqy; ev.Pmz = ev.pP * ev.upz - ev.q * ev.uqz;
+        sigcc = deForest(ev, cfg.Mh2, cfg.deForest_flag);
+        HeavyEv rv;
+        rv.Q2 = Q2; rv.q = q; rv.nu = nu; rv.Pm = rPm; rv.pE = rpE; rv.pP = rpP; rv.eE = reE; rv.etheta = reth;
+        rv.uqx = uqx; rv.uqy = uqy; rv.uqz = uqz; rv.upx = upx; rv.upy = upy; rv.upz = upz;
+        rv.Pmx = Pmx; rv.Pmy = Pmy; rv.Pmz = Pmz;
+        sigcc_recon = deForest(rv, cfg.Mh2, cfg.deForest_flag);
+      } else if (!meson) {
         rEm = nu + cfg.targ.M - rpE - rTrec;
         sigcc = sigep(v_Ein, v_eE, v_eth, v_Q2);
         sigcc_recon = sigep(r_Ein, reE, reth, Q2);
@@ -522,7 +547,6 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
         S.st(F_DAVEJAC, slot, mw.davejac); S.st(F_SURV, slot, survivalprob); S.st(F_WCM, slot, mw.wcm);
       }
       if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
-      const double SF_weight = 1.0;
       weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
       weight = weight * tgtweight;
       if (cfg.doing_kaon && !cfg.doing_decay) weight = weight * survivalprob;
@@ -541,7 +565,7 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
                     rpy >= (cfg.SPedge_p.yptar.max - cfg.slop_MC_p_used[1]) ||
                     rpx <= (cfg.SPedge_p.xptar.min + cfg.slop_MC_p_used[2]) ||
                     rpx >= (cfg.SPedge_p.xptar.max - cfg.slop_MC_p_used[2]));
-      success = true;
+      success = !(SF_weight <= 0.0);        // event.f:1435: no spectral strength here -> the try does not count
       if (cfg.hard_cuts) {
         if (!pass_cuts) success = false;
         if (cfg.doing_eep && (rEm > cfg.cuts_Em.max)) success = false;

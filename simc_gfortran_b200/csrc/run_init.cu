@@ -356,6 +356,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     c.cuts_Em.min = -1.e6; c.cuts_Em.max = 1.e6;
   }
   if (std::abs(deForest_flag) > 1) throw std::runtime_error("Idiot! check setting of deForest_flag");
+  c.deForest_flag = deForest_flag;
   if (c.correct_Eloss && !c.using_Eloss) c.correct_Eloss = 0;
   if ((int)std::lround(targ.Z) == 1) c.using_Coulomb = 0;
 
@@ -440,12 +441,34 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   c.Ebeam_vertex_ave = c.Ebeam + targ.Coulomb_ave - X.Eloss_ave[0];
   const double Ebeam_max = c.Ebeam + c.dEbeam / 2. - X.Eloss_min[0] + targ.Coulomb_max;
   const double Ebeam_min = c.Ebeam - c.dEbeam / 2. - X.Eloss_max[0] + targ.Coulomb_min;
-  if (c.doing_heavy) throw std::runtime_error("A(e,e'p) limits are not implemented in this build");
+  if (c.doing_heavy) {          // 'reconstructed' Em cuts, init.f:296-302
+    const double slop_Coulomb = targ.Coulomb_max - targ.Coulomb_ave;
+    double slop_Ebeam = c.dEbeam / 2. + slop_Coulomb;
+    double slop_Ee = c.slop_MC_e_used[0] / 100. * c.spec_e.P + slop_Coulomb;
+    const double r = std::sqrt(edge.p.E.max * edge.p.E.max - c.Mh2);
+    double slop_Ep = std::sqrt((r + c.slop_MC_p_used[0] / 100. * c.spec_p.P) * (r + c.slop_MC_p_used[0] / 100. * c.spec_p.P) +
+                               c.Mh2) - edge.p.E.max;
+    slop_Ebeam = slop_Ebeam + (X.Eloss_max[0] - X.Eloss_min[0]);
+    slop_Ee = slop_Ee + (X.Eloss_max[1] - X.Eloss_min[1]);
+    slop_Ep = slop_Ep + (X.Eloss_max[2] - X.Eloss_min[2]);
+    const double slop_total_Em = slop_Ebeam + slop_Ee + slop_Ep + c.dE_edge_test;
+    edge.Em.min = c.cuts_Em.min - slop_total_Em;
+    edge.Em.max = c.cuts_Em.max + slop_total_Em;
+    edge.Em.min = std::max(0.e0, edge.Em.min);
+  }
   if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
+  } else if (c.doing_heavy && c.use_benhar_sf) {      // init.f:331-343,379-386
+    VE.Pm.min = 0.0; VE.Pm.max = 790.0;
+    VE.Em.min = 0.0;                                  // E_Fermi: only theory_init sets it (init.f:856)
+    VE.Em.max = 1000.;
+    VE.Mrec.min = targ.M - targ.Mtar_struck + VE.Em.min;
+    VE.Mrec.max = targ.M - targ.Mtar_struck + VE.Em.max;
+    VE.Trec.min = std::sqrt(VE.Mrec.max * VE.Mrec.max + VE.Pm.min * VE.Pm.min) - VE.Mrec.max;
+    VE.Trec.max = std::sqrt(VE.Mrec.min * VE.Mrec.min + VE.Pm.max * VE.Pm.max) - VE.Mrec.min;
   } else {
-    throw std::runtime_error("nuclear-target limits are not implemented in this build");
+    throw std::runtime_error("limits for this target/reaction are not implemented in this build");
   }
   if (c.doing_eep || c.doing_semi) {
     VE.Trec_struck.min = 0.; VE.Trec_struck.max = 0.;
@@ -456,14 +479,27 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   }
   c.Egamma_tot_max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck - edge.e.E.min - edge.p.E.min - VE.Em.min -
                      VE.Trec.min - VE.Trec_struck.min;
+  if (c.doing_heavy) {
+    const double t2 = (edge.Em.max - VE.Em.min) + (VE.Trec.max - VE.Trec.min);
+    c.Egamma_tot_max = std::min(c.Egamma_tot_max, t2);
+  }
   if (c.hardwired_rad) c.Egamma_tot_max = c.Egamma_gen_max;
   if (!c.using_rad) c.Egamma_tot_max = 0.0;
   if (c.doing_tail[0]) c.Egamma1_max = c.Egamma_tot_max;
   if (c.doing_tail[1]) c.Egamma2_max = c.Egamma_tot_max;
   if (c.doing_tail[2]) c.Egamma3_max = c.Egamma_tot_max;
+  if (c.doing_heavy) {           // init.f:419-422
+    VE.Em.min = std::max(VE.Em.min, edge.Em.min - c.Egamma_tot_max);
+    VE.Em.max = std::min(VE.Em.max, edge.Em.max);
+  }
   simc_gen_limits& gen = c.gen;
   if (c.doing_hyd_elast) {
     gen.sumEgen.min = 0.0; gen.sumEgen.max = 0.0;
+  } else if (c.doing_heavy) {
+    gen.sumEgen.max = Ebeam_max + targ.Mtar_struck - VE.Trec.min - VE.Em.min;
+    gen.sumEgen.min = Ebeam_min + targ.Mtar_struck - VE.Trec.max - VE.Em.max - c.Egamma1_max;
+    gen.sumEgen.max = std::min(gen.sumEgen.max, edge.e.E.max + edge.p.E.max + c.Egamma_tot_max);
+    gen.sumEgen.min = std::max(gen.sumEgen.min, edge.e.E.min + edge.p.E.min);
   } else if (c.doing_semi) {
     gen.sumEgen.max = Ebeam_max + targ.Mtar_struck - targ.Mrec_struck;
     gen.sumEgen.min = edge.e.E.min + edge.p.E.min;
@@ -536,6 +572,25 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     const double eE = Ein * c.Mh / (c.Mh + Ein * (1. - uez));
     const double w = sigep(Ein, eE, c.spec_e.theta, 2 * Ein * eE * (1. - uez));
     if (w > 0 && std::isfinite(w)) c.w_ref = w;
+  } else if (c.doing_heavy) {
+    // central kinematics x a typical spectral-function density: S ~ 1/3200 per bin of 5 MeV x 20 MeV/c at Pm ~ 200 MeV/c
+    EventState s{};
+    s.v_Ein = c.Ebeam_vertex_ave; s.v_eE = c.spec_e.P; s.v_pP = c.spec_p.P; s.v_pE = std::sqrt(c.spec_p.P * c.spec_p.P + c.Mh2);
+    s.v_etheta = c.spec_e.theta; s.v_ephi = c.spec_e.phi; s.v_ptheta = c.spec_p.theta; s.v_pphi = c.spec_p.phi;
+    s.tz = targ.zoffset;
+    simc_run_config quiet = c;
+    quiet.using_Eloss = 0;
+    struct NoRng { double uniform() { return 0.5; } } rng;
+    auto nogauss = [](NoRng&, double) { return 0.0; };
+    const MatTable mt = make_mat_table(c.targ);
+    if (complete_ev_heavy(quiet, mt, rng, nogauss, s, true)) {
+      HeavyEv ev;
+      ev.Q2 = s.v_Q2; ev.q = s.v_q; ev.nu = s.v_nu; ev.Pm = s.v_Pm; ev.pE = s.v_pE; ev.pP = s.v_pP; ev.eE = s.v_eE;
+      ev.etheta = s.v_etheta; ev.uqx = s.uqx; ev.uqy = s.uqy; ev.uqz = s.uqz; ev.upx = s.upx; ev.upy = s.upy; ev.upz = s.upz;
+      ev.Pmx = ev.pP * ev.upx - ev.q * ev.uqx; ev.Pmy = ev.pP * ev.upy - ev.q * ev.uqy; ev.Pmz = ev.pP * ev.upz - ev.q * ev.uqz;
+      const double w = deForest(ev, c.Mh2, c.deForest_flag) * targ.Z * c.transparency / 3200. / (4. * 3.14159265 * 200. * 200. * 100.);
+      if (w > 0 && std::isfinite(w)) c.w_ref = w;
+    }
   } else if (c.doing_hydpi || c.doing_hydkaon) {
     // central event: both particles along their spectrometer axes, electron at the central momentum
     EventState s{};

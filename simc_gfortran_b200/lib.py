@@ -104,7 +104,7 @@ _DBL_SCALARS = (
 
 class RunConfig(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FLAGS] +
-                [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("pad0", C.c_int32)] +
+                [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("deForest_flag", C.c_int32)] +
                 [(n, C.c_double) for n in _DBL_SCALARS] +
                 [("gen", GenLimits), ("spec_e", Spectrometer), ("spec_p", Spectrometer),
                  ("cuts_Em", Cut), ("cuts_Pm", Cut), ("edge", Edge), ("VERTEXedge", Edge),
@@ -274,6 +274,18 @@ class Simc:
         self._check(self.L.simc_b200_optics_info(self.h, arm, _ptr(info)))
         keys = ("n_classes", "fwd_terms", "fwd_nonzero", "rec_terms", "n_rec_words", "n_coef", "n_ops")
         return dict(zip(keys, (int(x) for x in info[:7])))
+
+    # ---- Benhar spectral function, A(e,e'p)
+    def set_sf_table(self, pm, em, sf):
+        """pm[n_pm], em[n_em] bin centres; sf[n_pm, n_em] proton or neutron strength (un-normalised)."""
+        pm = np.ascontiguousarray(pm, dtype=np.float64)
+        em = np.ascontiguousarray(em, dtype=np.float64)
+        sf = np.ascontiguousarray(sf, dtype=np.float64)
+        assert sf.shape == (len(pm), len(em))
+        self._check(self.L.simc_b200_set_sf_table(self.h, len(pm), len(em), _ptr(pm), _ptr(em), _ptr(sf)))
+
+    def load_sf_file(self, path: str, proton: bool = True):
+        self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
 
     # ---- single-arm batch (host buffers)
     def transport_batch(self, arm: int, inp: np.ndarray, seed: int, ms_flag=True, wcs_flag=True, decay_flag=False,

@@ -65,6 +65,20 @@ class Oracle:
     def has_arm(self, arm):
         return arm in (1, 2, 3, 4, 5)
 
+    def set_sf_table(self, pm, em, sf):
+        pm = np.ascontiguousarray(pm, dtype=np.float64)
+        em = np.ascontiguousarray(em, dtype=np.float64)
+        sf = np.ascontiguousarray(sf, dtype=np.float64)
+        assert sf.shape == (len(pm), len(em))
+        self._check(self.L.oracle_set_sf_table(len(pm), len(em), _p(pm), _p(em), _p(sf)))
+
+    def sf_batch(self, em, pm):
+        em = np.ascontiguousarray(em, dtype=np.float64)
+        pm = np.ascontiguousarray(pm, dtype=np.float64)
+        out = np.zeros(len(em))
+        self._check(self.L.oracle_sf_batch(C.c_int64(len(em)), _p(em), _p(pm), _p(out)))
+        return out
+
     def load_optics(self, arm, fwd, rec):
         self._check(self.L.oracle_load_optics(arm, fwd.encode(), rec.encode()))
 

@@ -1,0 +1,67 @@
+"""CPU checks of the oracle's reaction-specific physics (no GPU): identities and sanity ranges for
+the meson-production weights (jacobians.f, physics_pion.f, physics_kaon.f) and the A(e,e'p)
+spectral-function weight (sf_lookup.f, physics_proton.f deForest)."""
+import os
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import config_from_deck
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def deck(name):
+    return config_from_deck(os.path.join(ROOT, "decks", name))[0]
+
+
+def test_spectral_function_is_normalised(oracle):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    oracle.set_sf_table(z["pm"], z["em"], z["sf_proton"])
+    pm, em = np.meshgrid(z["pm"], z["em"], indexing="ij")
+    d = oracle.sf_batch(em.ravel(), pm.ravel())
+    # sf_lookup_diff divides the bin content by 4 pi Pm^2 dPm dEm (sf_lookup.f:93): undo it on the grid
+    total = (d * 4 * 3.1415926535 * pm.ravel() ** 2 * 5.0 * 20.0).sum()
+    # sf_lookup_init normalises the table to one (sf_lookup.f:64-78).  Em exactly on the last grid point
+    # matches no branch of sf_lookup.f:135-157 (`Em > Emval(numEm)` and `Em < Emval(iEm+1)` both fail), so
+    # that column is missing from a sum over the grid itself.
+    last = z["sf_proton"][:, -1].sum() / z["sf_proton"].sum()
+    assert abs(total - (1.0 - last)) < 1e-9
+    # beyond the last Pm bin the lookup sticks to the last column (w1 = 0, w2 = 1)
+    a = oracle.sf_batch(np.array([22.5]), np.array([z["pm"][-1] + 100.0]))
+    b = oracle.sf_batch(np.array([22.5]), np.array([z["pm"][-1]]))
+    assert a[0] * (z["pm"][-1] + 100.0) ** 2 == pytest.approx(b[0] * z["pm"][-1] ** 2, rel=1e-12)
+
+
+def test_carbon_eep_events(oracle_with_optics):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    oracle_with_optics.set_sf_table(z["pm"], z["em"], z["sf_proton"])
+    cfg = deck("c2_eep_carbon_hms_sos.inp")
+    assert cfg.doing_heavy and not cfg.doing_hyd_elast and cfg.VERTEXedge.Pm.max == 790.0
+    rec, stage = oracle_with_optics.event_batch(cfg, 0, 20000, 11)
+    done = stage == 4
+    assert done.sum() > 500
+    assert np.all(rec[5][done] > 0) and np.all(rec[6][done] > 0) and np.all(rec[9][done] > 0)   # weight, sigcc, sigcc_recon
+    assert np.all(rec[45][done] < 900.0) and np.all(rec[44][done] > -50.0)                       # recon Pm, Em
+
+
+@pytest.mark.parametrize("name,mrec", [("c5_eek_hydrogen_hrsl_hrsr.inp", 1115.68), ("c3_eepi_hydrogen_hms_shms.inp", 939.56563)])
+def test_meson_production_events(oracle_with_optics, name, mrec):
+    cfg = deck(name)
+    rec, stage = oracle_with_optics.event_batch(cfg, 0, 30000, 5)
+    done = stage == 4
+    assert done.sum() > 100
+    thetacm, phicm, sigcm, wcm, t = rec[48][done], rec[49][done], rec[50][done], rec[54][done], rec[55][done]
+    assert np.all((thetacm >= 0) & (thetacm < 1.0)) and np.all((phicm >= 0) & (phicm <= 2 * np.pi + 1e-12))
+    assert np.all(sigcm > 0) and np.all(rec[5][done] > 0)
+    # W of the photon-nucleon system from the vertex: W^2 = Mp^2 + 2 Mp nu - Q2
+    Mp = 938.27231
+    nu = rec[10][done] - rec[11][done]
+    assert np.allclose(wcm, np.sqrt(Mp * Mp + 2 * Mp * nu - rec[19][done]), rtol=1e-12)
+    assert np.all(t > 0)                                              # -t in this convention (event.f:741)
+    assert abs(np.median(rec[53][done]) - mrec) < 15.0                # missing mass = undetected baryon (+ radiative tail)
+    surv = rec[52][done]
+    if cfg.doing_kaon:
+        assert np.all((surv > 0.03) & (surv < 0.5))                   # ~25 m of flight at beta*gamma*c*tau ~ 9.7 m
+    else:
+        assert np.all(surv == 1.0)

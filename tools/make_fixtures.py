@@ -50,5 +50,20 @@ def main():
             print("  golden rows", n, "accepted", int((flags == 0).sum()))
 
 
+def make_sf():
+    """benharsf_12.dat (the reference's data file for A = 12, dbase.f:600) -> tests/golden/benharsf_12.npz"""
+    rows = []
+    with open(os.path.join(REF, "benharsf_12.dat")) as f:
+        n_pm, n_em = (int(x) for x in f.readline().split())
+        for line in f:
+            if line.strip():
+                rows.append([float(x) for x in line.split()])
+    a = np.array(rows).reshape(n_pm, n_em, 6)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"), pm=a[:, 0, 0], em=a[0, :, 1],
+                        sf_proton=a[:, :, 2], sf_neutron=a[:, :, 3], dpm=a[:, 0, 4], dem=a[0, :, 5])
+    print("benharsf_12", n_pm, n_em, "sum", a[:, :, 2].sum())
+
+
 if __name__ == "__main__":
+    make_sf()
     main()
