@@ -7,46 +7,45 @@
 
 namespace simc {
 
+__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                              uint32_t c3, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  r0 = c0; r1 = c1; r2 = c2; r3 = c3;
+}
+__device__ __forceinline__ double philox_to_unit(uint32_t lo, uint32_t hi) {
+  const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 12;
+  return ((double)k + 0.5) * (1.0 / 4503599627370496.0);
+}
+// Draw `draw` of the stream: a pure function of its arguments (registers in, register out), so callers
+// keep their generator state in registers across the call.
+static __device__ __noinline__ double philox_uniform(uint32_t k0, uint32_t k1, uint32_t t0, uint32_t t1, uint32_t stream,
+                                              uint32_t draw) {
+  uint32_t r0, r1, r2, r3;
+  philox4x32_10(k0, k1, draw >> 1, stream, t0, t1, r0, r1, r2, r3);
+  return (draw & 1u) ? philox_to_unit(r2, r3) : philox_to_unit(r0, r1);
+}
+
 struct DevRng {
   uint32_t k0, k1, t0, t1, stream;
   uint32_t draw;
-  uint32_t w2, w3;        // second half of the cached block
-  uint32_t cached;        // block index whose second half is cached (0xffffffff = none)
 
   __device__ __forceinline__ void init(unsigned long long seed, unsigned long long try_index, uint32_t stream_id,
                                        uint32_t first_draw) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
     t0 = (uint32_t)try_index; t1 = (uint32_t)(try_index >> 32);
-    stream = stream_id; draw = first_draw; cached = 0xffffffffu; w2 = w3 = 0;
+    stream = stream_id; draw = first_draw;
   }
-
-  __device__ __forceinline__ void block(uint32_t b, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) const {
-    uint32_t c0 = b, c1 = stream, c2 = t0, c3 = t1, ka = k0, kb = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      const uint32_t n0 = hi1 ^ c1 ^ ka, n2 = hi0 ^ c3 ^ kb;
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
-    }
-    r0 = c0; r1 = c1; r2 = c2; r3 = c3;
-  }
-
-  __device__ __noinline__ double uniform() {
-    const uint32_t b = draw >> 1;
-    uint32_t lo, hi;
-    if ((draw & 1u) && cached == b) {
-      lo = w2; hi = w3;
-    } else {
-      uint32_t r0, r1, r2, r3;
-      block(b, r0, r1, r2, r3);
-      if (draw & 1u) { lo = r2; hi = r3; }
-      else { lo = r0; hi = r1; w2 = r2; w3 = r3; cached = b; }
-    }
+  __device__ __forceinline__ double uniform() {
+    const double u = philox_uniform(k0, k1, t0, t1, stream, draw);
     ++draw;
-    const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 12;
-    return ((double)k + 0.5) * (1.0 / 4503599627370496.0);
+    return u;
   }
 };
 

@@ -65,6 +65,12 @@ struct ArmResult {
 // nsigmax (never for 99, 0.3 % for 3) goes round again -- the same draws, in the same order.
 __device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
   const unsigned mask = __activemask();
+  // the generator runs on local copies: one read of the key at entry, one write of the draw count at exit
+  const uint32_t k0 = r.k0, k1 = r.k1, t0 = r.t0, t1 = r.t1, stream = r.stream;
+  uint32_t draw = r.draw;
+  // a pair (u1,u2) is one Philox block when `draw` is even; when it is odd the pair straddles two blocks
+  // and the unused half of the second one is kept for the next attempt
+  uint32_t h2 = 0, h3 = 0, hblock = 0xffffffffu;
   double g = 0.0;
   bool need = true;
   while (__any_sync(mask, need)) {
@@ -72,8 +78,21 @@ __device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
     bool open = need;
     while (__any_sync(mask, open)) {
       if (open) {
-        const double u1 = r.uniform();
-        const double u2 = r.uniform();
+        double u1, u2;
+        uint32_t r0, r1, r2, r3;
+        const uint32_t b = draw >> 1;
+        if (!(draw & 1u)) {
+          philox4x32_10(k0, k1, b, stream, t0, t1, r0, r1, r2, r3);
+          u1 = philox_to_unit(r0, r1);
+          u2 = philox_to_unit(r2, r3);
+        } else {
+          if (hblock != b) { philox4x32_10(k0, k1, b, stream, t0, t1, r0, r1, r2, r3); h2 = r2; h3 = r3; }
+          u1 = philox_to_unit(h2, h3);
+          philox4x32_10(k0, k1, b + 1u, stream, t0, t1, r0, r1, r2, r3);
+          u2 = philox_to_unit(r0, r1);
+          h2 = r2; h3 = r3; hblock = b + 1u;
+        }
+        draw += 2u;
         v1 = 2.0 * u1 - 1.0;
         const double v2 = 2.0 * u2 - 1.0;
         s = v1 * v1 + v2 * v2;
@@ -85,6 +104,7 @@ __device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
       need = fabs(g) > nsigmax;
     }
   }
+  r.draw = draw;
   return g;
 }
 
