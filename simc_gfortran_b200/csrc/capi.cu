@@ -26,7 +26,7 @@ namespace {
 struct ArmSlot {
   bool loaded = false;
   CompiledArm host;
-  void* d_arm = nullptr;                 // ArmDev
+  std::vector<unsigned char> img;        // ArmDev image (host): kernels take it by value
   double* d_recs = nullptr;
 };
 
@@ -78,7 +78,6 @@ int cuda_fail(simc_handle* h, cudaError_t e, const char* what) {
   } while (0)
 
 void free_arm(ArmSlot& s) {
-  if (s.d_arm) cudaFree(s.d_arm);
   if (s.d_recs) cudaFree(s.d_recs);
   s = ArmSlot();
 }
@@ -92,14 +91,13 @@ int upload_arm(simc_handle* h, int arm_id, CompiledArm&& ca) {
   CU(h, cudaMemcpy(s.d_recs, s.host.recs.data(), s.host.recs.size() * sizeof(double), cudaMemcpyHostToDevice));
   // ArmDev = { ArmTablesDev tab; ArmOp ops[kMaxArmOps]; } -- identical layout in both variants
   const size_t bytes = strict::arm_dev_bytes();
-  std::vector<unsigned char> img(bytes, 0);
+  std::vector<unsigned char>& img = s.img;
+  img.assign(bytes, 0);
   ArmTablesDev tab = s.host.tab;
   tab.recs = s.d_recs;
   tab.pad_ptr = nullptr;
   std::memcpy(img.data(), &tab, sizeof(tab));
   std::memcpy(img.data() + sizeof(ArmTablesDev), s.host.ops.data(), s.host.ops.size() * sizeof(ArmOp));
-  CU(h, cudaMalloc(&s.d_arm, bytes));
-  CU(h, cudaMemcpy(s.d_arm, img.data(), bytes, cudaMemcpyHostToDevice));
   s.loaded = true;
   return SIMC_OK;
 }
@@ -285,7 +283,7 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n, cons
   if (n == 0) return SIMC_OK;
   CU(h, cudaSetDevice(h->device));
   TransportBatchArgs a;
-  a.arm = it->second.d_arm; a.n = n; a.in = d_in_soa; a.seed = seed;
+  a.arm = it->second.img.data(); a.n = n; a.in = d_in_soa; a.seed = seed;
   a.ms_flag = ms_flag; a.wcs_flag = wcs_flag; a.decay_flag = decay_flag; a.using_coll = using_coll;
   a.ctau = h->cfg.ctau; a.out = d_out_soa; a.flags = d_flags;
   cudaError_t e = h->strict ? strict::launch_transport_batch(a, h->stream) : fast::launch_transport_batch(a, h->stream);
@@ -431,8 +429,8 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   if (fresh) { rc = clear_dev_accum(h); if (rc) return rc; }
   LoopLaunch a;
   a.cfg = h->d_cfg;
-  a.arm_e = h->arms.count(h->cfg.electron_arm) ? h->arms[h->cfg.electron_arm].d_arm : nullptr;
-  a.arm_p = h->arms.count(h->cfg.hadron_arm) ? h->arms[h->cfg.hadron_arm].d_arm : nullptr;
+  a.arm_e = h->arms.count(h->cfg.electron_arm) && h->arms[h->cfg.electron_arm].loaded ? h->arms[h->cfg.electron_arm].img.data() : nullptr;
+  a.arm_p = h->arms.count(h->cfg.hadron_arm) && h->arms[h->cfg.hadron_arm].loaded ? h->arms[h->cfg.hadron_arm].img.data() : nullptr;
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
   a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;

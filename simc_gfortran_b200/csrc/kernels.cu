@@ -17,10 +17,11 @@ namespace SIMC_VARIANT_NS {
 
 // Batch form of mc_hms / mc_shms / ... (hms/mc_hms.f:1-4): one thread per row.
 __global__ void __launch_bounds__(kBlock)
-k_transport_batch(const ArmDev* __restrict__ arm, long long n, const double* __restrict__ in,
+k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const double* __restrict__ in,
                   unsigned long long seed, ArmFlags f, double ctau, double* __restrict__ out,
                   int* __restrict__ flags) {
   extern __shared__ double pw_s[];
+  const ArmDev* arm = &arm_c;
   const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   bool alive = i < n;
   const long long ii = alive ? i : 0;
@@ -82,7 +83,7 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
       attr_set = true;
     }
   }
-  k_transport_batch<<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>((const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+  k_transport_batch<<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
                                                         a.flags);
   return cudaGetLastError();
 }
@@ -189,8 +190,9 @@ cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   LoopArgs A;
   A.cfg = (const simc_run_config*)a.cfg;
-  A.arm_e = (const ArmDev*)a.arm_e;
-  A.arm_p = (const ArmDev*)a.arm_p;
+  static const ArmDev no_arm = {};
+  const ArmDev& arm_e = a.arm_e ? *(const ArmDev*)a.arm_e : no_arm;
+  const ArmDev& arm_p = a.arm_p ? *(const ArmDev*)a.arm_p : no_arm;
   A.st.base = a.state; A.st.cap = a.cap;
   A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
   A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
@@ -216,11 +218,11 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     k_generate<<<grid, kBlock, 0, s>>>(A);
   } else if (stage == 1) {
-    k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A);
-    k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A);
+    k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
+    k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
   } else if (stage == 2) {
-    k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A);
-    k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A);
+    k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+    k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   return cudaGetLastError();

@@ -8,7 +8,7 @@
 namespace simc {
 
 struct TransportBatchArgs {
-  const void* arm;          // ArmDev* (device)
+  const void* arm;          // ArmDev image on the HOST: passed to the kernel by value (constant bank)
   long long n;
   const double* in;         // [9][n] device
   unsigned long long seed;
@@ -21,8 +21,8 @@ struct TransportBatchArgs {
 // Opaque to the host code: built and consumed inside kernels.cu (loop.cuh: LoopArgs).
 struct LoopLaunch {
   const void* cfg;            // simc_run_config* (device)
-  const void* arm_e;          // ArmDev* (device)
-  const void* arm_p;
+  const void* arm_e;          // ArmDev images on the HOST (null if the arm's Monte Carlo is off): each arm
+  const void* arm_p;          // kernel gets its program and map directory by value, in the constant bank
   double* state;              // [n_state_fields][cap]
   long long cap;
   unsigned* lists;            // [3][cap]

@@ -67,8 +67,6 @@ struct LoopArgs {
   const simc_run_config* cfg;      // device copy
   MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
-  const ArmDev* arm_e;
-  const ArmDev* arm_p;
   StateBuf st;
   unsigned* lists;                 // [5][cap]: gen ok | P entrance ok | P ok | E entrance ok | E ok
   unsigned* counts;                // [0] slots handed out, [1..5] lengths of lists 0..4
@@ -221,7 +219,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopAr
 // coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
 // after almost no arithmetic); SEG 1 = magnets, hut, reconstruction for the compacted survivors.
 template <int WHICH, int SEG>
-__global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A) {
+__global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
   extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
@@ -237,7 +235,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A)
   unsigned* out_list = A.lists + (long long)(in_idx + 1) * A.st.cap;
   unsigned* out_count = &A.counts[1 + in_idx + 1];
   const simc_spectrometer& sp = WHICH == 1 ? cfg.spec_p : cfg.spec_e;
-  const ArmDev* arm = WHICH == 1 ? A.arm_p : A.arm_e;
+  const ArmDev* arm = &arm_c;        // program + map directory live in the kernel's constant bank
   const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
   const bool use_mc = WHICH == 1 ? cfg.using_P_arm_montecarlo != 0 : cfg.using_E_arm_montecarlo != 0;
   const double Mh2 = cfg.Mh2;

@@ -236,7 +236,7 @@ constexpr size_t kArmSmemBytes = kPowBytes + (kBlock / 32) * kRingBytesPerWarp;
 // Evaluates one compiled map at v = (v1..v5).  pw = this thread's column of the shared power table,
 // ring = shared address of this warp's record ring.  Lanes without a live track pass anything finite.
 template <int NOUT>
-__device__ __noinline__ void eval_poly(const PolyClass& pc, const double* __restrict__ recs, const double (&v)[5],
+__device__ __forceinline__ void eval_poly(const PolyClass& pc, const double* __restrict__ recs, const double (&v)[5],
                                        double* pw, unsigned ring, double (&sum)[NOUT]) {
   const unsigned base = (unsigned)__cvta_generic_to_shared(pw);
   constexpr unsigned S = kBlock * 8u;
@@ -305,7 +305,7 @@ __device__ __noinline__ void eval_poly(const PolyClass& pc, const double* __rest
 
 // shared/transp.f:134-279
 // Called by all 32 lanes (eval_poly is warp-cooperative); `live` = this lane has a track.
-__device__ __noinline__ void transp(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& r, int klass, double zd,
+__device__ __forceinline__ void transp(const ArmDev* arm, TrackDev& t, DevRng& r, int klass, double zd,
                                     bool decay_flag, double* pw, unsigned ring, bool live) {
   double p_spec = 0, beta = 0, gamma = 0, z_decay = 0;
   const bool check = live && decay_flag && !t.dflag;
@@ -416,20 +416,20 @@ __device__ __forceinline__ void arm_result_clear(ArmResult& res) {
 // re-converges before each op, so a lane only idles while other lanes still have work in the same
 // op.  `alive` comes back false when the event stopped (res.stop_code) or finished (res.ok).
 // `pw` = this thread's column of the CTA's shared power table.
-__device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev& t, DevRng& rng, const ArmFlags f,
+__device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& rng, const ArmFlags f,
                                         double fry, double* pw, unsigned ring, ArmResult& res, HutState& hs,
                                         bool& alive, int op_begin, int op_end, unsigned* call_counts = nullptr) {
   double xt = 0., yt = 0.;
   for (int pc = op_begin; pc < op_end; ++pc) {
     __syncwarp();
     if (!__any_sync(0xffffffffu, alive)) break;
-    const ArmOp* __restrict__ o = &arm->ops[pc];
-    const int op = __ldg(&o->op);
+    const ArmOp* o = &arm->ops[pc];
+    const int op = o->op;
     if (op == OP_END) break;
-    const double a = __ldg(&o->a), b = __ldg(&o->b), c = __ldg(&o->c), d = __ldg(&o->d);
+    const double a = o->a, b = o->b, c = o->c, d = o->d;
     // the two map evaluations are warp-cooperative: every lane goes in, dead ones compute on stale values
     if (op == OP_TRANSP) {
-      const int klass = __ldg(&o->i0);
+      const int klass = o->i0;
       if (call_counts) warp_count_if_alive(&call_counts[klass - 1], alive);
       transp(arm, t, rng, klass, a, f.decay_flag, pw, ring, alive);
       continue;
@@ -442,7 +442,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
       hut[3] = res.dy_fp;
       hut[4] = fry / 100.;
       if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
-      if (__ldg(&o->i0)) {
+      if (o->i0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
@@ -520,8 +520,8 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
       case OP_DC_PLANE: {  // mc_hms_hut.f:351-364
         double r1 = 0., r2 = 0.;
         if (f.wcs_flag) { r1 = gauss1(rng, 99.0); r2 = gauss1(rng, 99.0); }
-        const int ip = __ldg(&o->i0);
-        if (__ldg(&o->i1)) { hs.ydc[ip] = (float)(t.ys + a * r2 * res.resmult); hs.xdc[ip] = 0.f; }
+        const int ip = o->i0;
+        if (o->i1) { hs.ydc[ip] = (float)(t.ys + a * r2 * res.resmult); hs.xdc[ip] = 0.f; }
         else { hs.xdc[ip] = (float)(t.xs + a * r1 * res.resmult); hs.ydc[ip] = 0.f; }
         break;
       }
@@ -541,7 +541,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         t.ys = t.ys + a * t.dydzs;
         break;
       case OP_SCIN_COUNT: if (t.ys < a && t.ys > b && t.xs < c && t.xs > d) ++hs.scincount; break;
-      case OP_SCIN_TRIG: stop = hs.scincount < __ldg(&o->i0); break;
+      case OP_SCIN_TRIG: stop = hs.scincount < o->i0; break;
       case OP_LFIT: {      // mc_hms_hut.f:438-455
         float zdc[12];
 #pragma unroll
@@ -556,7 +556,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         break;
       }
       case OP_CUT_FP_CAL: {   // mc_shms_hut.f:413-424
-        const double e = __ldg(&o->e);
+        const double e = o->e;
         const double xcal = res.x_fp + res.dx_fp * a;
         const double ycal = res.y_fp + res.dy_fp * a;
         stop = (ycal > b) || (ycal < c) || (xcal > d) || (xcal < e);
@@ -568,7 +568,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* __restrict__ arm, TrackDev
         break;
       default: break;
     }
-    if (stop) { res.stop_code = __ldg(&o->code); alive = false; }
+    if (stop) { res.stop_code = o->code; alive = false; }
   }
   __syncwarp();
 }
