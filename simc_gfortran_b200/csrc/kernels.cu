@@ -216,7 +216,11 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   if (stage == 0) {
     cudaError_t e = cudaMemsetAsync(a.counts, 0, 8 * sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
-    k_generate<<<grid, kBlock, 0, s>>>(A);
+    {
+      const long long gneed = (a.n_tries + kGenBlock - 1) / kGenBlock;
+      const long long gmax = (long long)a.grid_blocks * kBlock / kGenBlock;        // same number of resident threads
+      k_generate<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
+    }
   } else if (stage == 1) {
     k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
     k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);

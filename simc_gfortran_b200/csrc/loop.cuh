@@ -134,16 +134,23 @@ struct GaussFn {
 };
 
 // ---- stage 1: generation -------------------------------------------------------------------
-#ifndef SIMC_GEN_MIN_BLOCKS
-#define SIMC_GEN_MIN_BLOCKS 4
+// CTA size of the generation kernel: the code is one long straight line, and every CTA resident on an
+// SM streams it through the instruction cache at its own position; fewer, larger CTAs (whose warps the
+// phase barriers keep together) mean fewer streams.  Registers are capped at 65536 / (block * min blocks).
+#ifndef SIMC_GEN_BLOCK
+#define SIMC_GEN_BLOCK 256
 #endif
-__global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopArgs A) {
+#ifndef SIMC_GEN_MIN_BLOCKS
+#define SIMC_GEN_MIN_BLOCKS 2
+#endif
+constexpr int kGenBlock = SIMC_GEN_BLOCK;
+__global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopArgs A) {
   __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
-  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kBlock) (&h_geni[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) (&h_geni[0][0])[i] = 0u;
   __syncthreads();
   const simc_run_config& cfg = *A.cfg;
-  const long long stride = (long long)gridDim.x * kBlock;
-  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < A.n_tries; i0 += stride) {
+  const long long stride = (long long)gridDim.x * kGenBlock;
+  for (long long i0 = (long long)blockIdx.x * kGenBlock; i0 < A.n_tries; i0 += stride) {
     const long long i = i0 + threadIdx.x;
     const bool active = i < A.n_tries;
     bool ok = false;
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopAr
     if (active && ok) A.lists[0 * A.st.cap + pos] = slot;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kBlock) {
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) {
     const unsigned v = (&h_geni[0][0])[i];
     if (v) atomicAdd(&A.acc->hist_n[2][0][0] + i, (unsigned long long)v);
   }
