@@ -63,11 +63,11 @@ struct ArmResult {
 // the function converged.  The polar rejection (s > 1) costs two uniforms per attempt and is
 // looped on its own; log/sqrt/div run once for all lanes, and only a lane whose |g| exceeds
 // nsigmax (never for 99, 0.3 % for 3) goes round again -- the same draws, in the same order.
-__device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
+// Everything goes in and out by value (registers), so the caller's generator never touches memory.
+struct GaussOut { double g; uint32_t draw; };
+__device__ __noinline__ GaussOut gauss1v(uint32_t k0, uint32_t k1, uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw,
+                                         double nsigmax) {
   const unsigned mask = __activemask();
-  // the generator runs on local copies: one read of the key at entry, one write of the draw count at exit
-  const uint32_t k0 = r.k0, k1 = r.k1, t0 = r.t0, t1 = r.t1, stream = r.stream;
-  uint32_t draw = r.draw;
   // a pair (u1,u2) is one Philox block when `draw` is even; when it is odd the pair straddles two blocks
   // and the unused half of the second one is kept for the next attempt
   uint32_t h2 = 0, h3 = 0, hblock = 0xffffffffu;
@@ -104,8 +104,14 @@ __device__ __noinline__ double gauss1(DevRng& r, double nsigmax) {
       need = fabs(g) > nsigmax;
     }
   }
-  r.draw = draw;
-  return g;
+  GaussOut o;
+  o.g = g; o.draw = draw;
+  return o;
+}
+__device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
+  const GaussOut o = gauss1v(r.k0, r.k1, r.t0, r.t1, r.stream, r.draw, nsigmax);
+  r.draw = o.draw;
+  return o.g;
 }
 
 __device__ __forceinline__ void musc_refresh(TrackDev& t) {
@@ -125,7 +131,7 @@ __device__ __forceinline__ void loren(double gam, double bx, double by, double b
 }
 
 // decay kinematics common to project.f:67-110 and transp.f:147-186 / :236-275
-__device__ __noinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_spec, double beta, double gamma,
+__device__ __forceinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_spec, double beta, double gamma,
                                              double kaon_pipi_mfinal) {
   const double rph = r.uniform() * 2. * SIMC_PI;
   const double rth1 = r.uniform() * 2. - 1.;
@@ -163,7 +169,7 @@ __device__ __noinline__ void decay_in_flight(TrackDev& t, DevRng& r, double p_sp
 }
 
 // shared/project.f:43-119, the branch that tests for a decay
-__device__ __noinline__ void project_decay(TrackDev& t, DevRng& r, double z_drift) {
+__device__ __forceinline__ void project_decay(TrackDev& t, DevRng& r, double z_drift) {
   const double p_spec = t.p / (1. + t.dpps / 100.);
   const double beta = t.p / sqrt(t.p * t.p + t.m2);
   const double gamma = 1. / sqrt(1. - beta * beta);
