@@ -23,9 +23,26 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-DECK = os.path.join(ROOT, "decks", "c1_eep_hydrogen_hms_shms.inp")
-WORKLOAD = "C1 H(e,e'p) elastic, HMS e + SHMS p, radiative corrections on (decks/c1_eep_hydrogen_hms_shms.inp)"
+# BASELINE.json configs; C1 is the one the metric is quoted on and the default.  (C4, semi-inclusive, is not built.)
+CONFIGS = {
+    "c1": ("c1_eep_hydrogen_hms_shms.inp", "C1 H(e,e'p) elastic, HMS e + SHMS p, radiative corrections on"),
+    "c2": ("c2_eep_carbon_hms_sos.inp", "C2 C-12 A(e,e'p), Benhar spectral function, HMS e + SOS p, radiative corrections on"),
+    "c3": ("c3_eepi_hydrogen_hms_shms.inp", "C3 H(e,e'pi+)n with pion decay in flight, HMS e + SHMS pi"),
+    "c5": ("c5_eek_hydrogen_hrsl_hrsr.inp", "C5 H(e,e'K+)Lambda, HRS-L e + HRS-R K"),
+}
 METRIC = "generated events/s (ntried per second), H(e,e'p) HMS+SHMS"
+
+
+def deck_of(args):
+    name, what = CONFIGS[args.config]
+    return os.path.join(ROOT, "decks", name), f"{what} (decks/{name})"
+
+
+def sf_table():
+    """Spectral function of C2 (tests/golden/benharsf_12.npz = the reference's benharsf_12.dat)."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    return z["pm"], z["em"], z["sf_proton"]
 
 
 # ---- algorithmic FLOPs (SURVEY 8(d)): F_fwd(T) = 25 + 14 T per forward class call, F_rec = 25 + 12 T
@@ -82,6 +99,8 @@ def cpu_loop(cfg, n, seed, threads, first=0, ranlux=True):
     orc = Oracle()
     for arm in (cfg.electron_arm, cfg.hadron_arm):
         orc.set_optics(load_optics_fixture(arm))
+    if cfg.doing_heavy:
+        orc.set_sf_table(*sf_table())
     t0 = time.perf_counter()
     acc = orc.run(cfg, first, n, seed, threads=threads, ranlux=ranlux)
     dt = time.perf_counter() - t0
@@ -93,7 +112,8 @@ def run_reference(args):
     if rank != 0:
         return
     from simc_gfortran_b200 import config_from_deck
-    cfg = config_from_deck(DECK)[0]
+    deck, workload = deck_of(args)
+    cfg = config_from_deck(deck)[0]
     cores = os.cpu_count() or 1
     n = args.cpu_tries if args.cpu_tries else 25000 * cores
     for w in range(args.warmup):
@@ -109,7 +129,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "accepted_per_s": tot_acc / tot_t,
-            "config": {"workload": WORKLOAD, "tries_per_step": n,
+            "config": {"workload": workload, "tries_per_step": n,
                        "note": "the Fortran reference cannot be built here (no gfortran, CTP needs SunRPC); this is its "
                                "C++ restatement (oracle/), -O2 -ffp-contract=off, one thread per host core, each with its own "
                                "RANLUX luxury-3 stream like independent simc processes"},
@@ -131,6 +151,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("SIMC_B200_MODE", "strict"), choices=["strict", "fast"])
     ap.add_argument("--cpu-tries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the headline C1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -151,8 +172,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg, _, charge = config_from_deck(DECK)
+    deck, workload = deck_of(args)
+    cfg, _, charge = config_from_deck(deck)
     sim = Simc(cfg, device=local, mode=args.mode)
+    if cfg.doing_heavy:
+        sim.set_sf_table(*sf_table())
     optics = {"e": load_optics_fixture(cfg.electron_arm), "p": load_optics_fixture(cfg.hadron_arm)}
     sim.set_optics(optics["e"])
     sim.set_optics(optics["p"])
@@ -224,28 +248,39 @@ def main():
         flops_per_try = flops / tries_total
         # dominant kernel = the stage with the largest device time (per-rank numbers of rank 0)
         names = ["k_generate", "k_arm<hadron>", "k_arm<electron>", "k_finish"]
-        dom = int(np.argmax(stage_ms))
+        # dominant kernel: the arm stage with the largest device time.  Only the two arm stages have an algorithmic
+        # FLOP model (the COSY maps); should the generation kernel ever lead, the largest arm is still
+        # the one reported and `stage_ms` shows it.
+        dom = 1 if stage_ms[1] >= stage_ms[2] else 2
         # FLOPs of the dominant kernel on THIS rank: per-arm share of rank 0 = total / world (weak scaling)
-        dom_flops = {1: per_arm[1], 2: per_arm[0]}.get(dom, 0.0) / world
+        dom_flops = {1: per_arm[1], 2: per_arm[0]}[dom] / world
         achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12 if stage_ms[dom] > 0 else 0.0
+        # DRAM bytes of that stage per launch (= per batch of --batch tries), from one `ncu --set full` capture
+        traffic, traffic_src = None, None
+        tfile = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tfile) and args.config == "c1":
+            tj = json.load(open(tfile))
+            traffic = tj["bytes_per_2M_tries"][names[dom]] * args.batch / 2097152
+            traffic_src = tj["source"]
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
         line = {
-            "metric": METRIC, "value": gen_per_s, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.config == "c1" else "generated events/s (ntried per second), " + workload.split(",")[0],
+            "value": gen_per_s, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "accepted_per_s": acc_per_s, "accepted_fraction": acc.nsuccess / tries_total,
-            "config": {"workload": WORKLOAD, "tries_per_step_per_gpu": n, "stage_batch": args.batch, "mode": args.mode,
+            "config": {"workload": workload, "tries_per_step_per_gpu": n, "stage_batch": args.batch, "mode": args.mode,
                        "rng": "Philox4x32-10 keyed (seed, try index)",
                        "l2": "inputs are generated on chip; the per-stage state buffers (%.0f MB per batch) exceed the 126 MB L2"
-                             % (84 * 8 * args.batch / 1e6)},
+                             % (110 * 8 * args.batch / 1e6)},
             "e2e": {"value": tries_total / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": 32,
                     "d2h_bytes_per_step": C.sizeof(Accum),
                     "note": "simc_b200_run() through the C ABI with host accumulators; a Monte Carlo step's only input "
                             "is (first_try, n_tries, seed)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": names[dom], "achieved": achieved, "peak": peak_muladd, "unit": "TFLOP/s",
-                         "frac": achieved / peak_muladd if peak_muladd else None, "traffic": None,
+                         "frac": achieved / peak_muladd if peak_muladd else None, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_kind": "measured in this run: DMUL+DADD microbenchmark (no FMA, like the strict arithmetic); "
                                       "DFMA peak %.1f TFLOP/s" % peak_fma,
                          "flops_per_generated_event": flops_per_try,
