@@ -217,6 +217,14 @@ int simc_b200_set_optics(simc_handle* h, int arm_id,
  * compiled groups, packed coefficients, ops in the arm program */
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);
 
+/* Ntuple rows (replaces results_ntu_write, results_write.f:1-269): runs tries [first_try, first_try+n) like
+ * simc_b200_run -- without touching the accumulators -- and writes one row per contributing event, in try
+ * order, row-major rows[row][col] with *n_cols columns in the reference's order (NtupleInit.f:33-343;
+ * the left/right column swap of results_write.f:64-118 included).  rows must hold n * SIMC_NTUPLE_MAXCOL
+ * doubles.  try_of_row (may be NULL) receives the try index of each row. */
+int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed, double* rows, int32_t* n_cols,
+                           int64_t* n_rows, int64_t* try_of_row);
+
 /* Benhar-type spectral function S(Em,Pm) for A(e,e'p) with use_benhar_sf (replaces sf_lookup_init,
  * sf_lookup.f:1-80, called from dbase.f:594-621).  pm[n_pm], em[n_em] are the bin centres and
  * sf[n_pm][n_em] (Em fastest, the file's order) the proton or neutron column the caller picked; the
@@ -271,6 +279,9 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
 /* whole-event parity entry point: per-try records instead of accumulators.
  * rec[k*n+i], k = 0..SIMC_EVENT_NREC-1 (see simc_b200_event_field_name). */
 #define SIMC_EVENT_NREC 56
+/* Columns of one ntuple row, results_ntu_write (results_write.f:1-269): 46 for (e,e'p), 53 for pion and 55
+ * for kaon production (no target field). */
+#define SIMC_NTUPLE_MAXCOL 56
 int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
                           double* rec_soa, int32_t* status);
 const char* simc_b200_event_field_name(int k);

@@ -187,6 +187,20 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+int oracle_ntuple_batch(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, double* rows,
+                        int32_t* n_cols, int64_t* n_rows, int64_t* try_of_row) {
+  auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
+  try {
+    int nc = 0;
+    *n_rows = 0;
+    run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
+              n, seed, nullptr, nullptr, nullptr, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, rows, n_rows, &nc,
+              try_of_row);
+    *n_cols = nc;
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // radc_init_ev + peaked_rad_weight + sigep on dumped vertex vectors (layout: simc_b200_radc_batch)
 int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, double* out) {
   try {

@@ -115,10 +115,14 @@ double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, doub
 // One try of the loop (simc.f:169-351) in counter-based mode.
 TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon);
 
+// results_ntu_write, results_write.f:1-269 (no target field, no pi0): returns the number of columns
+int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const Event& orig, const Event& recon,
+                double* ntu);
 void accum_clear(const simc_run_config& cfg, simc_accum& a);
 void merge_accum(simc_accum& a, const simc_accum& b);
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
-               RanluxState* ranlux = nullptr, const SfTable* sf = nullptr);
+               RanluxState* ranlux = nullptr, const SfTable* sf = nullptr, double* ntu_rows = nullptr,
+               int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr);
 
 }  // namespace simc_oracle

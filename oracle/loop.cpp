@@ -164,10 +164,71 @@ void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const 
   for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[k * n + i] = v[k];
 }
 
+// results_ntu_write, results_write.f:1-269
+int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const Event& orig, const Event& recon,
+                double* out) {
+  const simc_run_config& cfg = *s.cfg;
+  double ntu[81] = {0};
+  double corrsing = 0, Pm_Heepx = 0, Pm_Heepy = 0, Pm_Heepz = 0;
+  const bool eep = cfg.doing_hyd_elast || cfg.doing_deuterium || cfg.doing_heavy;
+  if (eep) {
+    const double poftheta = K::Mp * cfg.Ebeam / (2 * cfg.Ebeam * powi(std::sin(recon.e.theta / 2.), 2) + K::Mp);
+    corrsing = recon.e.P - poftheta;
+    Pm_Heepz = -(recon.Pmy * recon.uq.y + recon.Pmz * recon.uq.z) / std::sqrt(recon.uq.y * recon.uq.y + recon.uq.z * recon.uq.z);
+    Pm_Heepy = (recon.Pmz * recon.uq.y - recon.Pmy * recon.uq.z) / std::sqrt(recon.uq.y * recon.uq.y + recon.uq.z * recon.uq.z);
+    Pm_Heepx = -recon.Pmx;
+  }
+  const int ea = cfg.electron_arm;
+  const bool e_right = (ea == 1 || ea == 3 || ea == 7);
+  const ArmFull& r1 = e_right ? recon.e : recon.p;
+  const ArmFull& r2 = e_right ? recon.p : recon.e;
+  const ArmFP& f1 = e_right ? main.FP_e : main.FP_p;
+  const ArmFP& f2 = e_right ? main.FP_p : main.FP_e;
+  const ArmFull& o1 = e_right ? orig.e : orig.p;
+  const ArmFull& o2 = e_right ? orig.p : orig.e;
+  const double s1 = e_right ? cfg.spec_e.sin_th : cfg.spec_p.sin_th;
+  const double s2 = e_right ? cfg.spec_p.sin_th : cfg.spec_e.sin_th;
+  ntu[1] = r1.delta; ntu[2] = r1.yptar; ntu[3] = r1.xptar; ntu[4] = r1.z;
+  ntu[5] = f1.x; ntu[6] = f1.dx; ntu[7] = f1.y; ntu[8] = f1.dy;
+  ntu[9] = o1.delta; ntu[10] = o1.yptar; ntu[11] = o1.xptar; ntu[12] = main.target.z * s1;
+  ntu[13] = r2.delta; ntu[14] = r2.yptar; ntu[15] = r2.xptar; ntu[16] = r2.z;
+  ntu[17] = f2.x; ntu[18] = f2.dx; ntu[19] = f2.y; ntu[20] = f2.dy;
+  ntu[21] = o2.delta; ntu[22] = o2.yptar; ntu[23] = o2.xptar; ntu[24] = -main.target.z * s2;
+  ntu[25] = recon.q / 1000.; ntu[26] = recon.nu / 1000.; ntu[27] = recon.Q2 / 1.e6; ntu[28] = recon.W / 1000.;
+  ntu[29] = recon.epsilon; ntu[30] = recon.Em / 1000.; ntu[31] = recon.Pm / 1000.; ntu[32] = recon.theta_pq;
+  ntu[33] = recon.phi_pq;
+  int ncol;
+  if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta) {
+    ntu[34] = s.ntup.mm / 1000.; ntu[35] = s.ntup.mmA / 1000.; ntu[36] = recon.p.P / 1000.; ntu[37] = s.ntup.t / 1.e6;
+    ntu[38] = recon.PmPar / 1000.; ntu[39] = recon.PmPer / 1000.; ntu[40] = recon.PmOop / 1000.;
+    ntu[41] = -main.target.rastery; ntu[42] = s.ntup.radphot / 1000.;
+    const double pfer = 0.0, pferx = 0.0, pfery = 0.0, pferz = 0.0;     // hydrogen, event.f:330-335
+    double dummy = pferx * vertex.uq.x + pfery * vertex.uq.y + pferz * vertex.uq.z;
+    if (dummy == 0) dummy = 1.e-20;
+    ntu[43] = pfer / 1000. * std::fabs(dummy) / dummy;
+    ntu[44] = main.sigcc; ntu[45] = s.ntup.sigcm; ntu[46] = main.weight; ntu[47] = s.trk.decdist;
+    ntu[48] = std::sqrt(s.trk.Mh2_final); ntu[49] = pfer / 1000. * dummy; ntu[50] = vertex.Q2 / 1.e6;
+    ntu[51] = main.W / 1.e3; ntu[52] = main.t / 1.e6; ntu[53] = main.phi_pq;
+    ncol = 53;
+    if (cfg.doing_kaon) { ntu[54] = s.ntup.sigcm1; ntu[55] = s.ntup.sigcm2; ncol = 55; }
+  } else if (eep) {
+    ntu[34] = corrsing / 1000.; ntu[35] = Pm_Heepx / 1000.; ntu[36] = Pm_Heepy / 1000.; ntu[37] = Pm_Heepz / 1000.;
+    ntu[38] = recon.PmPar / 1000.; ntu[39] = recon.PmPer / 1000.; ntu[40] = recon.PmOop / 1000.;
+    ntu[41] = -main.target.rastery; ntu[42] = s.ntup.radphot / 1000.; ntu[43] = main.sigcc; ntu[44] = main.weight;
+    ntu[45] = recon.e.theta; ntu[46] = recon.p.theta;
+    ncol = 46;
+  } else {
+    throw std::runtime_error("oracle: ntuple layout of this reaction not restated");
+  }
+  for (int i = 0; i < ncol; ++i) out[i] = ntu[i + 1];
+  return ncol;
+}
+
 // tries [first, first+n) of stream `seed`; rec/status may be null
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
-               RanluxState* ranlux, const SfTable* sf) {
+               RanluxState* ranlux, const SfTable* sf, double* ntu_rows, int64_t* n_rows, int* n_cols,
+               int64_t* try_of_row) {
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
     if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
@@ -180,6 +241,12 @@ void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics*
     if (acc) accumulate(s, r, main, vertex, orig, recon, *acc);
     if (rec) fill_record(s, r, main, vertex, orig, recon, rec, rec_stride, rec_off + i);
     if (status) status[rec_off + i] = r.stage;
+    if (ntu_rows && r.success) {
+      const int nc = fill_ntuple(s, main, vertex, orig, recon, ntu_rows + (*n_rows) * SIMC_NTUPLE_MAXCOL);
+      if (n_cols) *n_cols = nc;
+      if (try_of_row) try_of_row[*n_rows] = first + i;
+      ++*n_rows;
+    }
   }
 }
 

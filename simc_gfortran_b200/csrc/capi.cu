@@ -418,7 +418,7 @@ int clear_dev_accum(simc_handle* h) {
   return SIMC_OK;
 }
 
-int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, bool record, double* d_rec,
+int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, int record, double* d_rec,
                 int* d_status) {
   int rc = validate_loop_config(h);
   if (rc) return rc;
@@ -432,7 +432,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.arm_e = h->arms.count(h->cfg.electron_arm) && h->arms[h->cfg.electron_arm].loaded ? h->arms[h->cfg.electron_arm].img.data() : nullptr;
   a.arm_p = h->arms.count(h->cfg.hadron_arm) && h->arms[h->cfg.hadron_arm].loaded ? h->arms[h->cfg.hadron_arm].img.data() : nullptr;
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
-  a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record ? 1 : 0; a.rec = d_rec; a.status = d_status;
+  a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
@@ -485,7 +485,7 @@ int simc_b200_run_async(simc_handle* h, int64_t first_try, int64_t n_tries, uint
   if (!h) return SIMC_ERR_ARG;
   if (n_tries < 0) return fail(h, SIMC_ERR_ARG, "simc_b200_run: n_tries < 0");
   if (n_tries == 0) return validate_loop_config(h);
-  return run_batches(h, first_try, n_tries, seed, false, nullptr, nullptr);
+  return run_batches(h, first_try, n_tries, seed, 0, nullptr, nullptr);
 }
 
 int simc_b200_fetch(simc_handle* h, simc_accum* acc) {
@@ -610,13 +610,59 @@ int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t
   // records of stages that were not reached read as zero
   CU(h, cudaMemsetAsync(h->d_state, 0, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)h->loop_cap, h->stream));
   CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
-  rc = run_batches(h, first_try, n, seed, true, h->d_rec, h->d_status);
+  rc = run_batches(h, first_try, n, seed, 1, h->d_rec, h->d_status);
   if (rc) return rc;
   CU(h, cudaMemcpyAsync(rec_soa, h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaMemcpyAsync(status, h->d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   // the accumulators also saw these tries: a parity dump is not part of a run, drop them
   return clear_dev_accum(h);
+}
+
+// results_ntu_write for a range of tries: the loop in record mode 2, then the contributing rows in try order
+int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed, double* rows, int32_t* n_cols,
+                           int64_t* n_rows, int64_t* try_of_row) {
+  if (!h || !n_cols || !n_rows) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && !rows)) return fail(h, SIMC_ERR_ARG, "simc_b200_ntuple_batch: bad argument");
+  int rc = validate_loop_config(h);
+  if (rc) return rc;
+  const simc_run_config& c = h->cfg;
+  *n_cols = (c.doing_pion || c.doing_kaon) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
+  *n_rows = 0;
+  if (n == 0) return SIMC_OK;
+  static_assert(SIMC_NTUPLE_MAXCOL <= SIMC_EVENT_NREC, "the record buffer is shared with simc_b200_event_batch");
+  CU(h, cudaSetDevice(h->device));
+  if (n > h->rec_n) {
+    if (h->d_rec) cudaFree(h->d_rec);
+    if (h->d_status) cudaFree(h->d_status);
+    h->d_rec = nullptr; h->d_status = nullptr; h->rec_n = 0;
+    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n));
+    CU(h, cudaMalloc(&h->d_status, sizeof(int) * (size_t)n));
+    h->rec_n = n;
+  }
+  rc = ensure_loop_buffers(h, n);
+  if (rc) return rc;
+  // the accumulators of a run in progress must survive: park them
+  std::vector<unsigned char> saved(h->acc_host.size());
+  CU(h, cudaMemcpyAsync(saved.data(), h->d_acc, saved.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
+  rc = run_batches(h, first_try, n, seed, 2, h->d_rec, h->d_status);
+  if (rc) return rc;
+  std::vector<double> soa((size_t)SIMC_NTUPLE_MAXCOL * (size_t)n);
+  std::vector<int> status((size_t)n);
+  CU(h, cudaMemcpyAsync(soa.data(), h->d_rec, sizeof(double) * soa.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(status.data(), h->d_status, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_acc, saved.data(), saved.size(), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  int64_t r = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (status[i] != 4) continue;
+    for (int k = 0; k < *n_cols; ++k) rows[r * SIMC_NTUPLE_MAXCOL + k] = soa[(size_t)k * n + i];
+    if (try_of_row) try_of_row[r] = first_try + i;
+    ++r;
+  }
+  *n_rows = r;
+  return SIMC_OK;
 }
 
 int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa) {

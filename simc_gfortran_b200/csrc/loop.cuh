@@ -41,6 +41,9 @@ enum StateField : int {
   // results of peepi / peeK
   F_VNU, F_VQ, F_UQX, F_UQY, F_UQZ, F_UPX, F_UPY, F_UPZ, F_MEPS, F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
   F_FPP_DX, F_FPP_DY, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM,
+  // ntuple rows (record mode only): focal-plane positions, decay bookkeeping, then the row itself
+  F_FPP_X, F_FPP_Y, F_FPE_X, F_FPE_DX, F_FPE_Y, F_FPE_DY, F_DECDIST, F_MH2FINAL,
+  F_NTU0, F_NTU_LAST = F_NTU0 + SIMC_NTUPLE_MAXCOL - 1,
   F_NFIELDS
 };
 
@@ -347,7 +350,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       } else {
         t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
       }
-      t.mh2_final = Mh2; t.ctau = cfg.ctau;
+      // a hadron that decayed before the collimator carries its daughter's mass (Mh2_final, simulate.inc:92)
+      t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
       if (use_mc) {
         run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split, n_ops, s_calls);
@@ -373,6 +377,15 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         S.st(WHICH == 1 ? F_RCP_X : F_RCE_X, slot, rc_xptar); S.st(WHICH == 1 ? F_RCP_Z : F_RCE_Z, slot, rc_z);
         S.st(WHICH == 1 ? F_FPP_PATH : F_FPE_PATH, slot, path);
         if (WHICH == 1) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
+        if (A.record_mode) {
+          if (WHICH == 1) {
+            S.st(F_FPP_X, slot, res.x_fp); S.st(F_FPP_Y, slot, res.y_fp);
+            S.st(F_DECDIST, slot, t.decdist); S.st(F_MH2FINAL, slot, t.mh2_final);
+          } else {
+            S.st(F_FPE_X, slot, res.x_fp); S.st(F_FPE_DX, slot, res.dx_fp); S.st(F_FPE_Y, slot, res.y_fp);
+            S.st(F_FPE_DY, slot, res.dy_fp);
+          }
+        }
         // recon quantities of this arm, simc.f:1623-1645 / :1820-1846
         double rP = sp.P * (1. + rc_delta / 100.);
         double rE = WHICH == 1 ? sqrt(rP * rP + Mh2) : rP;
@@ -578,6 +591,80 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
       S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
       S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
       S.st(F_STAGE, slot, success ? 4.0 : 3.0);
+      if (success && A.record_mode) {
+        // ---- ntuple row, results_ntu_write (results_write.f:1-269); complete_recon_ev's remaining
+        // quantities (event.f:1150-1300) are only needed here
+        const double th2 = m::tan(reth / 2.);
+        const double r_eps = 1. / (1. + 2. * (1 + nu * nu / Q2) * (th2 * th2));
+        const double r_thpq = m::acos(fmin(1.0, upx * uqx + upy * uqy + upz * uqz));
+        const double qx = -uqy, qy = uqx, qz = uqz, px = -upy, py = upx, pz = upz;
+        double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+        const double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+        dummy = sqrt(qx * qx + qy * qy);
+        const double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+        const double p_new_x = px * new_x_x + py * new_x_y + pz * new_x_z;
+        const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
+        double r_phipq;
+        if ((p_new_x * p_new_x + p_new_y * p_new_y) == 0.) r_phipq = 0.0;
+        else r_phipq = m::acos(p_new_x / sqrt(p_new_x * p_new_x + p_new_y * p_new_y));
+        if (p_new_y < 0.) r_phipq = 2 * SIMC_PI_D - r_phipq;
+        const double oop_x = -uqy, oop_y = uqx;
+        const double PmPar = (Pmx * uqx + Pmy * uqy + Pmz * uqz);
+        const double PmOop = (Pmx * oop_x + Pmy * oop_y) / sqrt(oop_x * oop_x + oop_y * oop_y);
+        const double PmPer = sqrt(fmax(0.e0, rPm * rPm - PmPar * PmPar - PmOop * PmOop));
+        double ntu[SIMC_NTUPLE_MAXCOL + 1];
+#pragma unroll
+        for (int k = 0; k <= SIMC_NTUPLE_MAXCOL; ++k) ntu[k] = 0.0;
+        const int ea = cfg.electron_arm;
+        const bool e_right = (ea == 1 || ea == 3 || ea == 7);
+        const double tz = S.ld(F_TZ, slot);
+        const double eb[12] = {red, rey, rex, rez, S.ld(F_FPE_X, slot), S.ld(F_FPE_DX, slot), S.ld(F_FPE_Y, slot),
+                               S.ld(F_FPE_DY, slot), S.ld(F_OEDELTA, slot), S.ld(F_VEYP, slot), S.ld(F_VEXP, slot), cfg.spec_e.sin_th};
+        const double pb[12] = {rpd, rpy, rpx, rpz, S.ld(F_FPP_X, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_Y, slot),
+                               S.ld(F_FPP_DY, slot), S.ld(F_OPDELTA, slot), S.ld(F_VPYP, slot), S.ld(F_VPXP, slot), cfg.spec_p.sin_th};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          ntu[1 + k] = e_right ? eb[k] : pb[k];
+          ntu[13 + k] = e_right ? pb[k] : eb[k];
+        }
+        ntu[12] = tz * (e_right ? eb[11] : pb[11]);
+        ntu[24] = -tz * (e_right ? pb[11] : eb[11]);
+        ntu[25] = q / 1000.; ntu[26] = nu / 1000.; ntu[27] = Q2 / 1.e6; ntu[28] = rW / 1000.; ntu[29] = r_eps;
+        ntu[30] = rEm / 1000.; ntu[31] = rPm / 1000.; ntu[32] = r_thpq; ntu[33] = r_phipq;
+        const double radphot = S.ld(F_EG0, slot) + S.ld(F_EG1, slot) + S.ld(F_EG2, slot);
+        const double wfinal = weight;                  // survival probability already applied above
+        if (meson) {
+          const double mm2 = rEm * rEm - rPm * rPm;
+          const double e_A = nu + cfg.targ.M - rpE;
+          const double mmA2 = e_A * e_A - rPm * rPm;
+          ntu[34] = (sqrt(fabs(mm2)) * fabs(mm2) / mm2) / 1000.;
+          ntu[35] = (sqrt(fabs(mmA2)) * fabs(mmA2) / mmA2) / 1000.;
+          ntu[36] = rpP / 1000.;
+          ntu[37] = (Q2 - cfg.Mh2 + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
+          ntu[38] = PmPar / 1000.; ntu[39] = PmPer / 1000.; ntu[40] = PmOop / 1000.;
+          ntu[41] = -S.ld(F_RASTERY, slot); ntu[42] = radphot / 1000.;
+          ntu[43] = 0.0 / 1000. * fabs(1.e-20) / 1.e-20;
+          ntu[44] = sigcc; ntu[45] = S.ld(F_SIGCM, slot); ntu[46] = wfinal;
+          ntu[47] = (cfg.doing_kaon && !cfg.doing_decay) ? survivalprob : S.ld(F_DECDIST, slot);
+          ntu[48] = sqrt(S.ld(F_MH2FINAL, slot));
+          ntu[49] = 0.0 / 1000. * 1.e-20;
+          ntu[50] = v_Q2 / 1.e6; ntu[51] = S.ld(F_MW, slot) / 1.e3; ntu[52] = S.ld(F_MT, slot) / 1.e6; ntu[53] = S.ld(F_MPHIPQ, slot);
+          if (cfg.doing_kaon) { ntu[54] = 0.0; ntu[55] = S.ld(F_SIGCM, slot); }
+        } else {
+          const double sh = m::sin(reth / 2.);
+          const double poftheta = SIMC_MP * cfg.Ebeam / (2 * cfg.Ebeam * (sh * sh) + SIMC_MP);
+          const double nrm = sqrt(uqy * uqy + uqz * uqz);
+          ntu[34] = (reP - poftheta) / 1000.;
+          ntu[35] = (-Pmx) / 1000.;
+          ntu[36] = ((Pmz * uqy - Pmy * uqz) / nrm) / 1000.;
+          ntu[37] = (-(Pmy * uqy + Pmz * uqz) / nrm) / 1000.;
+          ntu[38] = PmPar / 1000.; ntu[39] = PmPer / 1000.; ntu[40] = PmOop / 1000.;
+          ntu[41] = -S.ld(F_RASTERY, slot); ntu[42] = radphot / 1000.; ntu[43] = sigcc; ntu[44] = wfinal;
+          ntu[45] = reth; ntu[46] = rpth;
+        }
+#pragma unroll
+        for (int k = 0; k < SIMC_NTUPLE_MAXCOL; ++k) S.st(F_NTU0 + k, slot, ntu[k + 1]);
+      }
       if (success) {
         no_rad_p = S.ld(F_RADP, slot) == 0.0;
         rec_vals[0] = red; rec_vals[1] = rey; rec_vals[2] = rex; rec_vals[3] = rpd; rec_vals[4] = rpy; rec_vals[5] = rpx;
@@ -695,8 +782,12 @@ __global__ void k_records(LoopArgs A, double* __restrict__ rec, int* __restrict_
         F_OEE, F_OPE, F_EG0, F_EG1, F_EG2, F_NTAIL, F_TX, F_TY, F_TZ, F_ELOSS0, F_ELOSS1, F_ELOSS2,
         F_SPE_D, F_SPE_Y, F_SPE_X, F_SPP_D, F_SPP_Y, F_SPP_X, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCP_D, F_RCP_Y, F_RCP_X,
         F_REM, F_RPM, F_RW, F_HARDCOR, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM, F_MT};
-    for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = S.ld(fields[k], slot);
-    rec[0 * n + i] = (double)stage;
+    if (A.record_mode == 2) {        // ntuple columns instead of the parity record
+      for (int k = 0; k < SIMC_NTUPLE_MAXCOL; ++k) rec[(long long)k * n + i] = S.ld(F_NTU0 + k, slot);
+    } else {
+      for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = S.ld(fields[k], slot);
+      rec[0 * n + i] = (double)stage;
+    }
     status[i] = stage;
   }
 }

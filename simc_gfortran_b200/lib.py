@@ -14,6 +14,7 @@ import numpy as np
 ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
 TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
 EVENT_NREC = 56
+NTUPLE_MAXCOL = 56
 NHIST, H_PER_SET, NSTOP = 50, 8, 64
 ABI_VERSION = 1
 
@@ -286,6 +287,16 @@ class Simc:
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
+
+    # ---- ntuple rows (results_ntu_write)
+    def ntuple_batch(self, first_try: int, n: int, seed: int):
+        """-> (rows[n_rows, n_cols], try_of_row[n_rows]) for the contributing tries of the range."""
+        rows = np.zeros((max(n, 1), NTUPLE_MAXCOL), dtype=np.float64)
+        tries = np.zeros(max(n, 1), dtype=np.int64)
+        nc, nr = C.c_int32(0), C.c_int64(0)
+        self._check(self.L.simc_b200_ntuple_batch(self.h, C.c_int64(first_try), C.c_int64(n), C.c_uint64(seed), _ptr(rows),
+                                                  C.byref(nc), C.byref(nr), _ptr(tries)))
+        return rows[:nr.value, :nc.value].copy(), tries[:nr.value].copy()
 
     # ---- single-arm batch (host buffers)
     def transport_batch(self, arm: int, inp: np.ndarray, seed: int, ms_flag=True, wcs_flag=True, decay_flag=False,

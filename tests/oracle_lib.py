@@ -146,6 +146,16 @@ def _oracle_event_batch(self, cfg, first, n, seed):
     return rec, status
 
 
+def _oracle_ntuple_batch(self, cfg, first, n, seed):
+    rows = np.zeros((max(n, 1), 56))
+    tries = np.zeros(max(n, 1), np.int64)
+    nc, nr = C.c_int32(0), C.c_int64(0)
+    self._check(self.L.oracle_ntuple_batch(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(rows),
+                                           C.byref(nc), C.byref(nr), _p(tries)))
+    return rows[:nr.value, :nc.value].copy(), tries[:nr.value].copy()
+
+
+Oracle.ntuple_batch = _oracle_ntuple_batch
 Oracle.run = _oracle_run
 Oracle.event_batch = _oracle_event_batch
 

@@ -1,0 +1,60 @@
+"""GPU parity of the ntuple rows (results_ntu_write, results_write.f:1-269) for C1, C2, C3 and C5:
+same contributing tries, same column count and order, values within the whole-event tolerances of
+tests/test_loop_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import Simc, config_from_deck, load_optics_fixture
+from tests.test_loop_gpu import LOOSE, RECON_LOOSE
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = {
+    "c1": ("c1_eep_hydrogen_hms_shms.inp", (1, 5), 46),
+    "c2": ("c2_eep_carbon_hms_sos.inp", (1, 2), 46),
+    "c3": ("c3_eepi_hydrogen_hms_shms.inp", (1, 5), 53),
+    "c5": ("c5_eek_hydrogen_hrsl_hrsr.inp", (4, 3), 55),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_ntuple_rows(oracle_with_optics, name):
+    deck, arms, ncol = CASES[name]
+    cfg = config_from_deck(os.path.join(ROOT, "decks", deck))[0]
+    sim = Simc(cfg, mode="strict")
+    try:
+        for arm in arms:
+            sim.set_optics(load_optics_fixture(arm))
+        if cfg.doing_heavy:
+            z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+            sim.set_sf_table(z["pm"], z["em"], z["sf_proton"])
+            oracle_with_optics.set_sf_table(z["pm"], z["em"], z["sf_proton"])
+        n = 30000
+        # a run in progress must not notice the dump
+        acc0 = sim.accum_clear()
+        sim.run(0, 5000, 1, acc0)
+        rows, tries = sim.ntuple_batch(100, n, 17)
+        acc1 = sim.accum_clear()
+        sim.fetch(acc1)
+        assert acc1.ntried == 0 or acc1.ntried == acc0.ntried
+        ref, ref_tries = oracle_with_optics.ntuple_batch(cfg, 100, n, 17)
+        assert rows.shape[1] == ref.shape[1] == ncol
+        assert np.array_equal(tries, ref_tries)
+        assert len(rows) > 100
+        # columns: scale = typical magnitude of the column (angles and small quantities pass through zero)
+        scale = np.maximum(np.abs(ref).max(axis=0), 1e-30)
+        err = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-3 * scale[None, :])
+        assert err.max() <= RECON_LOOSE, (int(np.argmax(err.max(axis=0))), float(err.max()))
+        assert (err > LOOSE).mean() < 0.05
+        # the electron is on the right (HMS, HRS-R) or on the left: columns 1-12 hold that side
+        e_right = cfg.electron_arm in (1, 3)
+        spec_e = cfg.spec_e.P
+        # hsdeltai / ssdeltai are the generated deltas: |delta| within the generation window
+        assert np.all(np.abs(rows[:, 8]) < 60) and np.all(np.abs(rows[:, 20]) < 60)
+        assert np.all(rows[:, 26] > 0)                      # Q2
+        assert e_right or name == "c5"
+        assert spec_e > 0
+    finally:
+        sim.close()
