@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tries", type=int, default=1 << 23, help="tries per step per GPU")
-    ap.add_argument("--batch", type=int, default=1 << 21, help="tries per pass of the stage pipeline")
+    ap.add_argument("--batch", type=int, default=1 << 22, help="tries per pass of the stage pipeline")
     ap.add_argument("--mode", default=os.environ.get("SIMC_B200_MODE", "strict"), choices=["strict", "fast"])
     ap.add_argument("--cpu-tries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -95,7 +95,8 @@ struct ArmTablesDev {
   int32_t n_classes;
   int32_t n_ops;
   int32_t split_op;     // ops [0,split_op): entrance apertures (cheap, most rejections); [split_op,n_ops): the rest
-  int32_t pad;
+  int32_t split2_op;    // optional second compaction point inside the magnets (0 = none): survivors of
+                        // [split_op,split2_op) are compacted again before [split2_op,n_ops)
 };
 
 }  // namespace simc

@@ -393,7 +393,7 @@ int ensure_loop_buffers(simc_handle* h, long long cap) {
     if (h->d_lists) cudaFree(h->d_lists);
     h->d_state = nullptr; h->d_lists = nullptr; h->loop_cap = 0;
     CU(h, cudaMalloc(&h->d_state, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)cap));
-    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 5 * (size_t)cap));
+    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 7 * (size_t)cap));
     h->loop_cap = cap;
   }
   return SIMC_OK;
@@ -455,7 +455,12 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
     for (int st = 0; st < n_stage; ++st) {
       cudaError_t e = h->strict ? strict::launch_loop_stage(a, st, h->stream) : fast::launch_loop_stage(a, st, h->stream);
       if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
-      h->launches += (st == 1 || st == 2) ? 2 : 1;
+      if (st == 1 || st == 2) {
+        const ArmTablesDev* tab = (const ArmTablesDev*)(st == 1 ? a.arm_p : a.arm_e);
+        h->launches += (tab && tab->split2_op > tab->split_op) ? 3 : 2;
+      } else {
+        h->launches += 1;
+      }
       if (h->timing && st < 4) CU(h, cudaEventRecord(h->ev[ev_pos + 1 + st], h->stream));
     }
     if (h->timing) { ev_pos += 5; h->ev_used.push_back(1); }

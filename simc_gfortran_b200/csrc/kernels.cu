@@ -209,6 +209,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
@@ -223,9 +225,11 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     }
   } else if (stage == 1) {
     k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
+    if (arm_p.tab.split2_op > arm_p.tab.split_op) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
     k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
   } else if (stage == 2) {
     k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+    if (arm_e.tab.split2_op > arm_e.tab.split_op) k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
     k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);

@@ -71,8 +71,8 @@ struct LoopArgs {
   MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   StateBuf st;
-  unsigned* lists;                 // [5][cap]: gen ok | P entrance ok | P ok | E entrance ok | E ok
-  unsigned* counts;                // [0] slots handed out, [1..5] lengths of lists 0..4
+  unsigned* lists;                 // [7][cap]: gen ok | P entrance ok | P middle ok | P ok | E entrance ok | E middle ok | E ok
+  unsigned* counts;                // [0] slots handed out, [1..7] lengths of lists 0..6
   DevAccum* acc;
   long long first_try, n_tries;
   unsigned long long seed;
@@ -225,9 +225,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
 #endif
 // ---- stages 2,3: the two arms ----------------------------------------------------------------
 // WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846).
-// Each arm runs as two kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
+// Each arm runs as two or three kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
 // coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
-// after almost no arithmetic); SEG 1 = magnets, hut, reconstruction for the compacted survivors.
+// after almost no arithmetic); SEG 2 (only for arms with a second compaction point) = the first magnet
+// apertures; SEG 1 = the rest of the magnets, hut, reconstruction for the compacted survivors.
 template <int WHICH, int SEG>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
   extern __shared__ double pw_s[];
@@ -239,11 +240,14 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
-  const int in_idx = (WHICH == 1 ? 0 : 2) + SEG;          // list read by this kernel
+  const bool has_mid = arm_c.tab.split2_op > arm_c.tab.split_op;
+  const int base_idx = WHICH == 1 ? 0 : 3;                // list read by SEG 0 of this arm
+  const int in_idx = SEG == 0 ? base_idx : SEG == 2 ? base_idx + 1 : (has_mid ? base_idx + 2 : base_idx + 1);
+  const int out_idx = SEG == 0 ? base_idx + 1 : SEG == 2 ? base_idx + 2 : base_idx + 3;
   const unsigned n_in = A.counts[1 + in_idx];
   const unsigned* in_list = A.lists + (long long)in_idx * A.st.cap;
-  unsigned* out_list = A.lists + (long long)(in_idx + 1) * A.st.cap;
-  unsigned* out_count = &A.counts[1 + in_idx + 1];
+  unsigned* out_list = A.lists + (long long)out_idx * A.st.cap;
+  unsigned* out_count = &A.counts[1 + out_idx];
   const simc_spectrometer& sp = WHICH == 1 ? cfg.spec_p : cfg.spec_e;
   const ArmDev* arm = &arm_c;        // program + map directory live in the kernel's constant bank
   const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
@@ -254,6 +258,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
   f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
   const int split = use_mc ? arm->tab.split_op : 0;
+  const int split2 = use_mc && has_mid ? arm->tab.split2_op : split;
   const int n_ops = use_mc ? arm->tab.n_ops : 0;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
@@ -341,6 +346,30 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
           if (WHICH == 1) S.st(F_RESFAC, slot, 0.0);
         }
       }
+    } else if (SEG == 2) {
+      if (active) {
+        t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
+        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
+        t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
+      } else {
+        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
+      }
+      t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
+      musc_refresh(t);
+      run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split, split2, s_calls);
+      ok = alive;
+      if (active) {
+        S.st(F_DRAW, slot, (double)rng.draw);
+        if (ok) {
+          S.st(F_TK_XS, slot, t.xs); S.st(F_TK_YS, slot, t.ys); S.st(F_TK_DX, slot, t.dxdzs); S.st(F_TK_DY, slot, t.dydzs);
+          S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
+          S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0);
+        } else {
+          S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
+          warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
+          if (WHICH == 1) S.st(F_RESFAC, slot, 0.0);
+        }
+      }
     } else {
       double rc_delta = 0, rc_yptar = 0, rc_xptar = 0, rc_z = 0.0, path = 0.0, resmult = 0.0;
       if (active) {
@@ -354,7 +383,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
       if (use_mc) {
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split, n_ops, s_calls);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split2, n_ops, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
         path = t.pathlen; resmult = res.resmult;
@@ -480,8 +509,8 @@ __global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   DevAccum* acc = A.acc;
-  const unsigned n_in = A.counts[5];
-  const unsigned* in_list = A.lists + 4 * A.st.cap;
+  const unsigned n_in = A.counts[7];
+  const unsigned* in_list = A.lists + 6 * A.st.cap;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;

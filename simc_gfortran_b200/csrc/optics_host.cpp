@@ -239,6 +239,7 @@ struct Prog {
     if (windows) musc(exit_radw);
   }
   int split = -1;                      // explicit survivor-compaction point (else: after the last octagon cut)
+  int split2 = 0;                      // second compaction point (0 = none)
   void cut_r(double r, int code) { add(OP_CUT_R, code).a = r; }
   void cut_abs_xy(double xmax, double ymax, int code) { cut_box(xmax, -xmax, ymax, -ymax, code); }
   // "drift the remaining distance of map class cls": length = b_target - (-(driftdist(cls) - ztmp))
@@ -424,6 +425,7 @@ void build_shms(Prog& P) {
   P.transp(7, zd_q1mid);           P.cut_r2(r_Q1, Q1_MID);
   P.transp(8, zd_q1mex);           P.cut_r2(r_Q1, Q1_MEX);
   P.project(zd_q1out);             P.cut_r2(r_Q1, Q1_OUT);
+  P.split2 = (int)P.ops.size();    // a quarter of the tracks that pass the slit still die inside Q1 (C1: 14 k of 60 k)
   P.project(zd_q2in);              P.cut_r2(r_Q2, Q2_IN);
   P.project(zd_q2men);             P.cut_r2(r_Q2, Q2_MEN);
   P.transp(12, zd_q2mid);          P.cut_r2(r_Q2, Q2_MID);
@@ -840,6 +842,7 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   for (int k = 0; k < (int)P.ops.size(); ++k)
     if (P.ops[k].op == OP_CUT_OCT) A.tab.split_op = k + 1;
   if (P.split >= 0) A.tab.split_op = P.split;
+  A.tab.split2_op = P.split2 > A.tab.split_op ? P.split2 : 0;
   return A;
 }
 
