@@ -91,3 +91,26 @@ def test_c1_run_level_sanity(oracle_with_optics, cfg):
     lumi = 1.0 / targetfac
     y = acc.wtcontribute.value() * lumi * genvol / acc.ntried
     assert 5.0 < y < 80.0        # ~4e-6 ub/sr x 0.024 sr x 20% x 1.1e9 ub^-1/mC ~ 20 counts per mC
+
+
+def test_counter_based_stream_is_statistically_equivalent_to_ranlux(oracle_with_optics, cfg):
+    """The product replaces the reference's sequential RANLUX by a counter-based Philox stream.  The
+    two cannot give the same events; they must give the same distributions: acceptance (binomial),
+    normalised yield (weighted sum) and the generated / reconstructed count histograms (chi^2)."""
+    n = 240000
+    a = oracle_with_optics.run(cfg, 0, n, 11, threads=8, ranlux=True)
+    b = oracle_with_optics.run(cfg, 0, n, 11, threads=8, ranlux=False)
+    pa, pb = a.nsuccess / n, b.nsuccess / n
+    sig = np.sqrt(pa * (1 - pa) / n + pb * (1 - pb) / n)
+    assert abs(pa - pb) < 4.5 * sig, (pa, pb, sig)
+    ya, yb = a.wtcontribute.value() / n, b.wtcontribute.value() / n
+    # relative statistical error of a weighted yield ~ 1/sqrt(npasscuts) x (weight spread ~ 1.5)
+    rel = 1.5 * np.sqrt(1.0 / a.npasscuts + 1.0 / b.npasscuts)
+    assert abs(ya - yb) / yb < 4.5 * rel, (ya, yb, rel)
+    ha, hb = np.ctypeslib.as_array(a.hist_n).astype(float), np.ctypeslib.as_array(b.hist_n).astype(float)
+    for s_, k in ((2, 0), (2, 1), (2, 3), (1, 0), (1, 3), (1, 4)):          # geni / gen: e delta, e yptar, p delta, p yptar
+        x, y = ha[s_, k], hb[s_, k]
+        m = (x + y) > 20
+        chi2 = ((x[m] - y[m]) ** 2 / (x[m] + y[m])).sum()
+        ndf = m.sum()
+        assert chi2 < ndf + 5 * np.sqrt(2 * ndf), (s_, k, chi2, ndf)
