@@ -149,7 +149,12 @@ struct GaussFn {
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
 __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopArgs A) {
   __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
+  // the out-of-line energy-loss routines take the material table by reference: give them shared memory,
+  // not a generic pointer into the kernel-parameter bank
+  __shared__ MatTable mt_s;
   for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) (&h_geni[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kGenBlock)
+    ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
   __syncthreads();
   const simc_run_config& cfg = *A.cfg;
   const long long stride = (long long)gridDim.x * kGenBlock;
@@ -165,9 +170,9 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
     const bool heavy = cfg.doing_heavy != 0;
-    if (meson) ok = generate_meson(cfg, A.mt, rng, GaussFn(), s, active);
-    else if (heavy) ok = generate_heavy(cfg, A.mt, rng, GaussFn(), s, active);
-    else ok = generate_hyd_elast(cfg, A.mt, rng, GaussFn(), s, active);
+    if (meson) ok = generate_meson(cfg, mt_s, rng, GaussFn(), s, active);
+    else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
+    else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);
     if (active) {
       // geni histograms: every try, from the vertex values (simc.f:253-262)
       const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
@@ -234,6 +239,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
+  __shared__ MatTable mt_s;
+  for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kBlock) ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
   for (int i = threadIdx.x; i < 48; i += kBlock) s_calls[i] = 0u;
   __syncthreads();
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         physics_angles(sp.theta, sp.phi, rc_xptar + sp.off_xptar, rc_yptar + sp.off_yptar, rth, rph);
         if (cfg.correct_Eloss) {
           double el, rl;
-          trip_thru_target_fixed(cfg.targ, A.mt, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
+          trip_thru_target_fixed(cfg.targ, mt_s, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
                                  el, rl);
           rE = rE + el;
           if (WHICH == 1) {
