@@ -504,7 +504,10 @@ __device__ __forceinline__ void warp_count_if(unsigned* dst, bool flag) {
   if ((threadIdx.x & 31u) == 0 && m) atomicAdd(dst, (unsigned)__popc(m));
 }
 
-__global__ void __launch_bounds__(kBlock) k_finish(LoopArgs A) {
+#ifndef SIMC_FIN_MIN_BLOCKS
+#define SIMC_FIN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs A) {
   __shared__ BlockAcc B;
   {
     unsigned long long* w = (unsigned long long*)&B;
