@@ -95,8 +95,9 @@ struct ArmTablesDev {
   int32_t n_classes;
   int32_t n_ops;
   int32_t split_op;     // ops [0,split_op): entrance apertures (cheap, most rejections); [split_op,n_ops): the rest
-  int32_t split2_op;    // optional second compaction point inside the magnets (0 = none): survivors of
-                        // [split_op,split2_op) are compacted again before [split2_op,n_ops)
+  int32_t n_mid;        // further compaction points behind split_op (0..3), increasing op indices:
+  int32_t mid_op[3];    // survivors are compacted again before ops [mid_op[k], ...)
+  int32_t pad;
 };
 
 }  // namespace simc

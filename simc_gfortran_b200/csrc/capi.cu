@@ -386,14 +386,14 @@ int ensure_loop_buffers(simc_handle* h, long long cap) {
     const size_t ab = strict::dev_accum_bytes();
     CU(h, cudaMalloc(&h->d_acc, ab));
     h->acc_host.assign(ab, 0);
-    CU(h, cudaMalloc(&h->d_counts, 8 * sizeof(unsigned)));
+    CU(h, cudaMalloc(&h->d_counts, 16 * sizeof(unsigned)));
   }
   if (cap > h->loop_cap) {
     if (h->d_state) cudaFree(h->d_state);
     if (h->d_lists) cudaFree(h->d_lists);
     h->d_state = nullptr; h->d_lists = nullptr; h->loop_cap = 0;
     CU(h, cudaMalloc(&h->d_state, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)cap));
-    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 7 * (size_t)cap));
+    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 11 * (size_t)cap));
     h->loop_cap = cap;
   }
   return SIMC_OK;
@@ -457,7 +457,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
       if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
       if (st == 1 || st == 2) {
         const ArmTablesDev* tab = (const ArmTablesDev*)(st == 1 ? a.arm_p : a.arm_e);
-        h->launches += (tab && tab->split2_op > tab->split_op) ? 3 : 2;
+        h->launches += 2 + (tab ? tab->n_mid : 0);
       } else {
         h->launches += 1;
       }

@@ -197,6 +197,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
   A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
   A.record_mode = a.record_mode;
+  A.mid_k = 0;
   static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
   memcpy(&A.mt, a.mats, sizeof(MatTable));
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
@@ -216,7 +217,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     }
   }
   if (stage == 0) {
-    cudaError_t e = cudaMemsetAsync(a.counts, 0, 8 * sizeof(unsigned), s);
+    cudaError_t e = cudaMemsetAsync(a.counts, 0, 16 * sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
     {
       const long long gneed = (a.n_tries + kGenBlock - 1) / kGenBlock;
@@ -225,11 +226,11 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     }
   } else if (stage == 1) {
     k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
-    if (arm_p.tab.split2_op > arm_p.tab.split_op) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
+    for (int k = 0; k < arm_p.tab.n_mid; ++k) { A.mid_k = k; k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p); }
     k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
   } else if (stage == 2) {
     k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
-    if (arm_e.tab.split2_op > arm_e.tab.split_op) k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+    for (int k = 0; k < arm_e.tab.n_mid; ++k) { A.mid_k = k; k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e); }
     k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);

@@ -71,8 +71,9 @@ struct LoopArgs {
   MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   StateBuf st;
-  unsigned* lists;                 // [7][cap]: gen ok | P entrance ok | P middle ok | P ok | E entrance ok | E middle ok | E ok
-  unsigned* counts;                // [0] slots handed out, [1..7] lengths of lists 0..6
+  unsigned* lists;                 // [11][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same
+  unsigned* counts;                // [0] slots handed out, [1..11] lengths of lists 0..10
+  int mid_k;                       // which middle segment a k_arm<*,2> launch runs
   DevAccum* acc;
   long long first_try, n_tries;
   unsigned long long seed;
@@ -230,10 +231,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
 #endif
 // ---- stages 2,3: the two arms ----------------------------------------------------------------
 // WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846).
-// Each arm runs as two or three kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
+// Each arm runs as two to five kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
 // coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
-// after almost no arithmetic); SEG 2 (only for arms with a second compaction point) = the first magnet
-// apertures; SEG 1 = the rest of the magnets, hut, reconstruction for the compacted survivors.
+// after almost no arithmetic); SEG 2 (once per further compaction point of the arm program, A.mid_k) = a
+// stretch of magnets; SEG 1 = the rest (always the whole hut) and reconstruction for the compacted survivors.
 template <int WHICH, int SEG>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
   extern __shared__ double pw_s[];
@@ -247,10 +248,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
-  const bool has_mid = arm_c.tab.split2_op > arm_c.tab.split_op;
-  const int base_idx = WHICH == 1 ? 0 : 3;                // list read by SEG 0 of this arm
-  const int in_idx = SEG == 0 ? base_idx : SEG == 2 ? base_idx + 1 : (has_mid ? base_idx + 2 : base_idx + 1);
-  const int out_idx = SEG == 0 ? base_idx + 1 : SEG == 2 ? base_idx + 2 : base_idx + 3;
+  const int n_mid = arm_c.tab.n_mid;
+  const int base_idx = WHICH == 1 ? 0 : 5;                // list read by SEG 0 of this arm
+  const int in_idx = SEG == 0 ? base_idx : SEG == 2 ? base_idx + 1 + A.mid_k : base_idx + 1 + n_mid;
+  const int out_idx = SEG == 0 ? base_idx + 1 : SEG == 2 ? base_idx + 2 + A.mid_k : base_idx + 5;
   const unsigned n_in = A.counts[1 + in_idx];
   const unsigned* in_list = A.lists + (long long)in_idx * A.st.cap;
   unsigned* out_list = A.lists + (long long)out_idx * A.st.cap;
@@ -265,7 +266,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
   f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
   const int split = use_mc ? arm->tab.split_op : 0;
-  const int split2 = use_mc && has_mid ? arm->tab.split2_op : split;
+  // op range of this launch: [0,split) | [split or mid_op[k-1], mid_op[k]) | [last compaction point, n_ops)
+  const int mid_begin = (SEG == 2 && A.mid_k > 0) ? arm->tab.mid_op[A.mid_k - 1] : split;
+  const int mid_end = SEG == 2 ? arm->tab.mid_op[A.mid_k] : split;
+  const int last_begin = use_mc && n_mid > 0 ? arm->tab.mid_op[n_mid - 1] : split;
   const int n_ops = use_mc ? arm->tab.n_ops : 0;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       }
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
-      run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split, split2, s_calls);
+      run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, mid_begin, mid_end, s_calls);
       ok = alive;
       if (active) {
         S.st(F_DRAW, slot, (double)rng.draw);
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
       if (use_mc) {
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, split2, n_ops, s_calls);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, last_begin, n_ops, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
         path = t.pathlen; resmult = res.resmult;
@@ -519,8 +523,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   DevAccum* acc = A.acc;
-  const unsigned n_in = A.counts[7];
-  const unsigned* in_list = A.lists + 6 * A.st.cap;
+  const unsigned n_in = A.counts[11];
+  const unsigned* in_list = A.lists + 10 * A.st.cap;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;

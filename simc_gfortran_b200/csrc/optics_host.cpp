@@ -239,7 +239,8 @@ struct Prog {
     if (windows) musc(exit_radw);
   }
   int split = -1;                      // explicit survivor-compaction point (else: after the last octagon cut)
-  int split2 = 0;                      // second compaction point (0 = none)
+  std::vector<int> mids;               // further compaction points (where a sizeable fraction of tracks has died)
+  void mid_here() { mids.push_back((int)ops.size()); }
   void cut_r(double r, int code) { add(OP_CUT_R, code).a = r; }
   void cut_abs_xy(double xmax, double ymax, int code) { cut_box(xmax, -xmax, ymax, -ymax, code); }
   // "drift the remaining distance of map class cls": length = b_target - (-(driftdist(cls) - ztmp))
@@ -425,7 +426,7 @@ void build_shms(Prog& P) {
   P.transp(7, zd_q1mid);           P.cut_r2(r_Q1, Q1_MID);
   P.transp(8, zd_q1mex);           P.cut_r2(r_Q1, Q1_MEX);
   P.project(zd_q1out);             P.cut_r2(r_Q1, Q1_OUT);
-  P.split2 = (int)P.ops.size();    // a quarter of the tracks that pass the slit still die inside Q1 (C1: 14 k of 60 k)
+  P.mid_here();                    // a quarter of the tracks that pass the slit still die inside Q1 (C1: 14 k of 60 k)
   P.project(zd_q2in);              P.cut_r2(r_Q2, Q2_IN);
   P.project(zd_q2men);             P.cut_r2(r_Q2, Q2_MEN);
   P.transp(12, zd_q2mid);          P.cut_r2(r_Q2, Q2_MID);
@@ -475,6 +476,7 @@ void build_shms(Prog& P) {
   const double hcal_4ta_zpos = 341.0, hcal_left = 63.00, hcal_right = -63.00, hcal_top = -70.00, hcal_bottom = 70.00;
   const double hdc_del_plane = hdc_thick + hdc_wire_thick + hdc_cath_thick;
 
+  P.mid_here();                    // 10-25 % more are lost in the dipole: the hut (2/3 of the remaining work) runs on full warps
   P.project(zd_fp + hcer_1_zentrance);                     // cer_flag = .true. (mc_shms.f:352,1045)
   P.add(OP_MARK_HUT);
   P.add(OP_RESMULT_ONE);
@@ -706,6 +708,7 @@ void build_hrs(Prog& P, bool right) {
   P.transp(8, 659.73445725);          dipole_face(30.0, D1_OUT);
   zdrift = 1745.33546 - 1655.83446; ztmp = zdrift;
   P.project(zdrift);                  P.cut_r(30.3276, D1_OUT); P.cut_abs_xy(50.0, 15.0, D1_OUT);
+  P.mid_here();                       // C5: 2/3 of the tracks that pass the slit are gone behind the dipole
   zdrift = 1759.00946 - 1745.33546; ztmp = ztmp + zdrift;
   P.project(zdrift);                  P.cut_r(30.3276, Q3_IN);
   P.project_dd(9, -ztmp);             P.cut_r2(r_Q3, Q3_IN);
@@ -715,6 +718,7 @@ void build_hrs(Prog& P, bool right) {
   P.project(zdrift);                  P.cut_abs_xy(35.56, 17.145, Q3_OUT);
   zdrift = 2327.47246 - 2080.38746; ztmp = ztmp + zdrift;
   P.project(zdrift);                  P.cut_abs_xy(99.76635, 17.145, Q3_OUT);
+  P.mid_here();                       // and half of the rest in Q3
   P.add(OP_MARK_HUT);
 
   // ---- hut ----
@@ -842,7 +846,10 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   for (int k = 0; k < (int)P.ops.size(); ++k)
     if (P.ops[k].op == OP_CUT_OCT) A.tab.split_op = k + 1;
   if (P.split >= 0) A.tab.split_op = P.split;
-  A.tab.split2_op = P.split2 > A.tab.split_op ? P.split2 : 0;
+  A.tab.n_mid = 0;
+  for (int m : P.mids)
+    if (A.tab.n_mid < 3 && m > (A.tab.n_mid ? A.tab.mid_op[A.tab.n_mid - 1] : A.tab.split_op) && m < (int)P.ops.size())
+      A.tab.mid_op[A.tab.n_mid++] = m;
   return A;
 }
 
