@@ -110,6 +110,8 @@ typedef struct {
   int32_t doing_hydpi, doing_deutpi, doing_hepi;
   int32_t doing_hydkaon, doing_deutkaon, doing_hekaon;
   int32_t doing_hydsemi, doing_deutsemi;
+  int32_t doing_semipi, doing_semika;        /* dbase.f:125-134: doing_semi splits off doing_pion / doing_kaon */
+  int32_t do_fermi;                          /* dbase.f:1148: Fermi motion in semi-inclusive D(e,e'h)X */
   int32_t doing_hplus, doing_decay;
   int32_t which_pion, which_kaon;
   /* switches */
@@ -232,6 +234,29 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
 int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm, const double* em, const double* sf);
 int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag);
 
+/* Nucleon momentum distribution of the deuteron (or 3He/4He/C) for Fermi-smeared meson production:
+ * replaces the read of deut.dat / he3.dat / he4.dat / c12.dat in dbase.f:563-587.  pval[n] (MeV/c) and the
+ * cumulative probability mprob[n]; the library divides by mprob[n-1] like the reference.  n <= 2000. */
+int simc_b200_set_pfermi_table(simc_handle* h, int n, const double* pval, const double* mprob);
+int simc_b200_load_pfermi_file(simc_handle* h, const char* path);
+
+/* CTEQ5 parton distributions for the semi-inclusive weight peepiX (semi_physics.f:226-264): replaces
+ * SetCtq5 / ReadTbl (cteq5/Ctq5Pdf.f:193-281).  xv[nx+1], qv[nt+1] (GeV, as in the file: the library
+ * takes Log(Q/Lambda) like ReadTbl), upd[(nx+1)*(nt+1)*(nfmx+3)] in the file's order.
+ * load_cteq5_file reads a cteq5*.tbl itself. */
+int simc_b200_set_cteq5_table(simc_handle* h, int nx, int nt, int nfmx, double lambda, double qini, double qmax,
+                              double xmin, const double* xv, const double* qv, const double* upd);
+int simc_b200_load_cteq5_file(simc_handle* h, const char* path);
+
+/* stage-level parity entry point for the semi-inclusive weight: peepiX (semi_physics.f:1-617) with
+ * Ctq5Pdf, the Bosted fragmentation fit and F1F2IN21 on dumped vertex vectors.  in[k*n+i], k = 0..15:
+ * { Ein, e.E, nu, Q2, q, uq.x, uq.y, uq.z, pt2, zhad, theta_pq, pfer, pferx, pfery, pferz, efer };
+ * out[k*n+i], k = 0..15: { sigma_eepiX, sighad (ntup%sigcm), davejac, xbj used, u, ubar, d, dbar, s, sbar,
+ * F1p, F2p, F1n, F2n, sige, 0 }. */
+#define SIMC_SEMI_NIN  16
+#define SIMC_SEMI_NOUT 16
+int simc_b200_semi_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa);
+
 /* the loop -------------------------------------------------------------- *
  * Replaces simc.f:169-351 for tries first_try .. first_try+n_tries-1 of the
  * counter-based stream `seed` (try t always sees the same random numbers, on
@@ -279,8 +304,8 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
 /* whole-event parity entry point: per-try records instead of accumulators.
  * rec[k*n+i], k = 0..SIMC_EVENT_NREC-1 (see simc_b200_event_field_name). */
 #define SIMC_EVENT_NREC 56
-/* Columns of one ntuple row, results_ntu_write (results_write.f:1-269): 46 for (e,e'p), 53 for pion and 55
- * for kaon production (no target field). */
+/* Columns of one ntuple row, results_ntu_write (results_write.f:1-269): 46 for (e,e'p), 53 for pion, 55
+ * for kaon and 56 for semi-inclusive production (no target field). */
 #define SIMC_NTUPLE_MAXCOL 56
 int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
                           double* rec_soa, int32_t* status);

@@ -11,6 +11,8 @@ using namespace simc_oracle;
 
 static std::map<int, ArmOptics> g_optics;
 static SfTable g_sf;
+static PfermiTable g_pfermi;
+static Cteq5Table g_pdf;
 static std::string g_err;
 
 extern "C" {
@@ -165,7 +167,8 @@ int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_
         RanluxState st;
         if (rng_mode == 1) st.rluxgo(3, (int)(seed + 1 + t), 0, 0);
         run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr,
-                  g_sf.numPm ? &g_sf : nullptr);
+                  g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr, nullptr,
+                  g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
       }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
@@ -182,7 +185,8 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
   auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
   try {
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
-              n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr);
+              n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr,
+              nullptr, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
@@ -195,7 +199,7 @@ int oracle_ntuple_batch(const simc_run_config* cfg, int64_t first, int64_t n, ui
     *n_rows = 0;
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, nullptr, nullptr, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, rows, n_rows, &nc,
-              try_of_row);
+              try_of_row, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
     *n_cols = nc;
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -221,6 +225,57 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
       out[9 * n + i] = w;
       v.Q2 = 2 * v.Ein * v.e.E * (1. - v.ue.z);
       out[10 * n + i] = sigep(v);
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// dbase.f:563-587: momentum distribution, cumulative probability normalised to its last entry
+int oracle_set_pfermi_table(int n, const double* pval, const double* mprob) {
+  g_pfermi.pval.assign(pval, pval + n);
+  g_pfermi.mprob.assign(mprob, mprob + n);
+  for (int ii = 0; ii < n; ++ii) g_pfermi.mprob[ii] = g_pfermi.mprob[ii] / mprob[n - 1];
+  return 0;
+}
+// ReadTbl, cteq5/Ctq5Pdf.f:239-281, from arrays
+int oracle_set_cteq5_table(int nx, int nt, int nfmx, double al, double qini, double qmax, double xmin,
+                           const double* xv, const double* qv, const double* upd) {
+  g_pdf.set(nx, nt, nfmx, al, qini, qmax, xmin, xv, qv, upd);
+  return 0;
+}
+// Ctq5Pdf on dumped (x, Q) pairs
+int oracle_ctq5pdf_batch(int iparton, int64_t n, const double* x, const double* q, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) { double Q = q[i]; out[i] = Ctq5Pdf(g_pdf, iparton, x[i], Q); }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// SF of F1F2IN21 on dumped (W2, Q2) pairs: out[6][n] = f1p, fLp, f2p, f1n, fLn, f2n
+int oracle_christy_batch(int64_t n, const double* w2, const double* q2, double* out) {
+  for (int64_t i = 0; i < n; ++i)
+    christy_sf(w2[i], q2[i], out[0 * n + i], out[1 * n + i], out[2 * n + i], out[3 * n + i], out[4 * n + i], out[5 * n + i]);
+  return 0;
+}
+// peepiX on dumped vertex vectors (layout: simc_b200_semi_batch)
+int oracle_semi_batch(const simc_run_config* cfg, int64_t n, const double* in, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Sim s; s.cfg = cfg; s.pdf = g_pdf.Nx ? &g_pdf : nullptr;
+      EventMain main; Event v;
+      v.Ein = in[0 * n + i]; v.e.E = in[1 * n + i]; v.nu = in[2 * n + i]; v.Q2 = in[3 * n + i]; v.q = in[4 * n + i];
+      v.uq.x = in[5 * n + i]; v.uq.y = in[6 * n + i]; v.uq.z = in[7 * n + i];
+      v.pt2 = in[8 * n + i]; v.zhad = in[9 * n + i]; v.theta_pq = in[10 * n + i];
+      s.pfer = in[11 * n + i]; s.pferx = in[12 * n + i]; s.pfery = in[13 * n + i]; s.pferz = in[14 * n + i];
+      s.efer = in[15 * n + i];
+      double surv = 1.0;
+      simc_run_config c2 = *cfg;
+      c2.doing_decay = 1;                 // no survival probability here (needs the focal-plane track)
+      s.cfg = &c2;
+      SemiDebug d;
+      const double sig = peepiX(s, v, main, surv, &d);
+      const double o[SIMC_SEMI_NOUT] = {sig, s.ntup.sigcm, main.davejac, d.xbj, d.u, d.ubar, d.d, d.dbar, d.s, d.sbar,
+                                        d.F1p, d.F2p, d.F1n, d.F2n, d.sige, 0.0};
+      for (int k = 0; k < SIMC_SEMI_NOUT; ++k) out[k * n + i] = o[k];
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }

@@ -159,7 +159,7 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     vertex.p.P = cfg.spec_p.P;
     vertex.p.E = sqrt(Mh2 + vertex.p.P * vertex.p.P);
     vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
-  } else if (cfg.doing_heavy) {
+  } else if (cfg.doing_heavy || cfg.doing_semi) {
     // nothing: E and P of both arms were generated
   } else {
     throw std::runtime_error("oracle: reaction not restated in complete_ev");
@@ -207,8 +207,18 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
   } else if (cfg.doing_hydpi || cfg.doing_hydkaon) {
     vertex.Trec = 0.0;
+  } else if (cfg.doing_semi) {
+    vertex.Pm = vertex.Pmiss;
+    vertex.Em = vertex.Emiss;
   }
   s.ntup.krel = 0.0;
+  if (cfg.doing_semi) {   // :979-996
+    if ((powi(targ.Mtar_struck + vertex.nu - vertex.p.E, 2) - vertex.Pmiss * vertex.Pmiss) < powi(K::Mp + K::Mpi0, 2))
+      return false;
+    vertex.zhad = vertex.p.E / vertex.nu;
+    vertex.pt2 = vertex.p.P * vertex.p.P * (1.0 - powi(cos(main.theta_pq), 2));
+    if (vertex.zhad > 1.0) return false;
+  }
 
   // :1013-1023 Jacobian of (xptar,yptar) -> solid angle
   double r = sqrt(1. + vertex.e.yptar * vertex.e.yptar + vertex.e.xptar * vertex.e.xptar);
@@ -306,9 +316,36 @@ bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
   }
   physics_angles(cfg.spec_e.theta, cfg.spec_e.phi, vertex.e.xptar, vertex.e.yptar, vertex.e.theta, vertex.e.phi);
   physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, vertex.p.xptar, vertex.p.yptar, vertex.p.theta, vertex.p.phi);
+  // :327-373 Fermi momentum (drawn for deuterium semi-inclusive production whether or not do_fermi is set)
+  s.pfer = 0.0; s.pferx = 0.0; s.pfery = 0.0; s.pferz = 0.0;
   vertex.Em = 0.0;
-  if (cfg.doing_deutpi || cfg.doing_hepi || cfg.doing_deutkaon || cfg.doing_hekaon || cfg.doing_deutsemi)
-    throw std::runtime_error("oracle: Fermi-smeared production not restated");
+  s.efer = targ.Mtar_struck;
+  if (cfg.doing_deutpi || cfg.doing_hepi || cfg.doing_deutkaon || cfg.doing_hekaon)
+    throw std::runtime_error("oracle: Fermi-smeared exclusive production not restated");
+  if (cfg.doing_deutsemi) {
+    if (!s.pfermi || s.pfermi->pval.empty()) throw std::runtime_error("oracle: momentum distribution not set");
+    const std::vector<double>& pval = s.pfermi->pval;
+    const std::vector<double>& mprob = s.pfermi->mprob;
+    const int nump = (int)pval.size();
+    const double ranprob = rng.grnd();
+    int ii = 1;
+    while (ranprob > mprob[ii - 1] && ii < nump) ii = ii + 1;
+    double pferlo, pferhi;
+    if (ii == 1) pferlo = 0;
+    else pferlo = (pval[ii - 2] + pval[ii - 1]) / 2;
+    if (ii == nump) pferhi = pval[nump - 1];
+    else pferhi = (pval[ii - 1] + pval[ii]) / 2;
+    s.pfer = pferlo + (pferhi - pferlo) * rng.grnd();
+    const double ranth1 = rng.grnd() * 2. - 1.0;
+    const double ranth = acos(ranth1);
+    const double ranph = rng.grnd() * 2. * K::pi;
+    s.pferx = sin(ranth) * cos(ranph);
+    s.pfery = sin(ranth) * sin(ranph);
+    s.pferz = cos(ranth);
+    vertex.Em = K::Mp + K::Mn - targ.M;
+    const double m_spec = targ.M - targ.Mtar_struck + vertex.Em;
+    s.efer = targ.M - sqrt(m_spec * m_spec + s.pfer * s.pfer);
+  }
   if (!complete_ev(s, main, vertex)) return false;
   main.sigcc = 1.0;
   main.Trec = vertex.Trec;
@@ -531,6 +568,10 @@ bool complete_recon_ev(Sim& s, Event& recon) {
     s.ntup.mmA = sqrt(fabs(mmA2)) * fabs(mmA2) / mmA2;
     s.ntup.t = recon.Q2 - Mh2 + 2 * (recon.nu * recon.p.E - recon.p.P * recon.q * cos(recon.theta_pq));
   }
+  if (cfg.doing_semi || cfg.doing_rho) {   // :1336-1339
+    recon.zhad = recon.p.E / recon.nu;
+    recon.pt2 = recon.p.P * recon.p.P * (1.0 - powi(cos(recon.theta_pq), 2));
+  }
   if (cfg.doing_hyd_elast) {
     recon.Trec = 0.0;
     recon.Em = recon.nu + targ.M - recon.p.E - recon.Trec;
@@ -578,14 +619,18 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     main.sigcc_recon = 1.0;
     if (cfg.which_kaon == 2 || cfg.which_kaon == 12) tgtweight = cfg.targ.N;
     else tgtweight = cfg.targ.Z;
+  } else if (cfg.doing_semi) {
+    // NB peepiX reads vertex%theta_pq (semi_physics.f:243), which nothing ever assigns (complete_ev fills
+    // main%theta_pq, event.f:727): it is zero, so the reference's jacobian has cos(theta_pq) = 1.  Reproduced.
+    main.sigcc = peepiX(s, vertex, main, survivalprob);
+    main.sigcc_recon = 1.0;
   } else {
     throw std::runtime_error("oracle: cross section of this reaction not restated yet");
   }
   if (cfg.using_Coulomb) main.sigcc = main.sigcc * powi(1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam, 2);
   main.weight = main.SF_weight * main.jacobian * main.gen_weight * main.sigcc;
   main.weight = main.weight * tgtweight;
-  // (doing_semika belongs to the semi-inclusive branch, not restated)
-  if (cfg.doing_kaon && !cfg.doing_decay) main.weight = main.weight * survivalprob;
+  if ((cfg.doing_kaon || cfg.doing_semika) && !cfg.doing_decay) main.weight = main.weight * survivalprob;
   s.ntup.survivalprob = survivalprob;
   return true;
 }

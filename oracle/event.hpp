@@ -51,6 +51,7 @@ struct RadEv {
 // simulate.inc:161-176 (the fields the loop touches)
 struct NtupVars {
   double radphot = 0, radarm = 0, resfac = 0, sigcm = 0, sigcm1 = 0, sigcm2 = 0, krel = 0, mm = 0, mmA = 0, t = 0;
+  double xfermi = 0;
   double survivalprob = 1.0;       // local of complete_main (event.f:1373), kept for the parity records
 };
 
@@ -58,6 +59,25 @@ struct NtupVars {
 struct SfTable {
   int numPm = 0, numEm = 0;
   std::vector<double> Pmval, Emval, sfval;   // sfval[iPm * numEm + iEm]
+};
+// momentum distribution of dbase.f:563-587 (deut.dat ...): mprob normalised to mprob(nump) = 1
+struct PfermiTable {
+  std::vector<double> pval, mprob;
+};
+// COMMON /CtqPar1/ /CtqPar2/ /XQrange/ /QCDtable/ after ReadTbl (cteq5/Ctq5Pdf.f:239-281)
+struct Cteq5Table {
+  int Nx = 0, Nt = 0, NfMx = 0;
+  double Al = 0, Alambda = 0, Qini = 0, Qmax = 0, Xmin = 0;
+  std::vector<double> XV, QL, UPD;
+  void set(int nx, int nt, int nfmx, double al, double qini, double qmax, double xmin, const double* xv,
+           const double* qv, const double* upd);
+};
+double Ctq5Pdf(const Cteq5Table& T, int Iparton, double X, double& Q);          // Ctq5Pdf.f:69
+void christy_sf(double w2, double q2, double& f1p, double& fLp, double& f2p, double& f1n, double& fLn,
+                double& f2n);                                                    // F1F2IN21_v1.0.f:2345
+struct SemiDebug {
+  double xbj = 0, u = 0, ubar = 0, d = 0, dbar = 0, s = 0, sbar = 0, F1p = 0, F2p = 0, F1n = 0, F2n = 0, sighad = 0,
+         sige = 0;
 };
 double sf_lookup(const SfTable& T, double Em, double Pm);            // sf_lookup.f:97-170
 double sf_lookup_diff(const SfTable& T, double Em, double Pm);       // sf_lookup.f:85-95
@@ -71,7 +91,10 @@ struct Sim {
   const ArmOptics* optics_e = nullptr;
   const ArmOptics* optics_p = nullptr;
   const SfTable* sf = nullptr;
+  const PfermiTable* pfermi = nullptr;
+  const Cteq5Table* pdf = nullptr;
   Rng* rng = nullptr;
+  double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
   RadEv rad;
   NtupVars ntup;
   Track trk;                     // COMMON /track/ + decdist, Mh2_final
@@ -110,6 +133,7 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
 double sigep(const Event& vertex);
 double peepi(Sim& s, const Event& vertex, EventMain& main);                                             // physics_pion.f:1
 double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob);                        // physics_kaon.f:1
+double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob, SemiDebug* dbg = nullptr); // semi_physics.f:1
 double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax);  // radc.f:523                                                                       // physics_proton.f:1
 
 // One try of the loop (simc.f:169-351) in counter-based mode.
@@ -123,6 +147,7 @@ void merge_accum(simc_accum& a, const simc_accum& b);
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
                RanluxState* ranlux = nullptr, const SfTable* sf = nullptr, double* ntu_rows = nullptr,
-               int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr);
+               int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr,
+               const PfermiTable* pfermi = nullptr, const Cteq5Table* pdf = nullptr);
 
 }  // namespace simc_oracle

@@ -211,6 +211,17 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[51] = main.W / 1.e3; ntu[52] = main.t / 1.e6; ntu[53] = main.phi_pq;
     ncol = 53;
     if (cfg.doing_kaon) { ntu[54] = s.ntup.sigcm1; ntu[55] = s.ntup.sigcm2; ncol = 55; }
+  } else if (cfg.doing_semi || cfg.doing_rho) {      // results_write.f:187-213
+    ntu[34] = s.ntup.mm / 1000.; ntu[35] = recon.p.P / 1000.; ntu[36] = s.ntup.t / 1.e6;
+    ntu[37] = -main.target.rastery; ntu[38] = s.ntup.radphot / 1000.; ntu[39] = main.sigcc; ntu[40] = main.sigcent;
+    ntu[41] = main.weight; ntu[42] = s.trk.decdist; ntu[43] = std::sqrt(s.trk.Mh2_final);
+    ntu[44] = recon.zhad; ntu[45] = vertex.zhad; ntu[46] = recon.pt2 / 1.e06; ntu[47] = vertex.pt2 / 1.e06;
+    ntu[48] = recon.xbj; ntu[49] = vertex.xbj; ntu[50] = std::acos(vertex.uq.z); ntu[51] = s.ntup.sigcm;
+    ntu[52] = main.davejac; ntu[53] = main.johnjac;
+    const double dummy = s.pferx * vertex.uq.x + s.pfery * vertex.uq.y + s.pferz * vertex.uq.z;
+    ntu[54] = s.pfer / 1000. * std::fabs(dummy) / dummy;      // NaN for hydrogen (0/0), as in the reference
+    ntu[55] = s.ntup.xfermi; ntu[56] = main.phi_pq;
+    ncol = 56;
   } else if (eep) {
     ntu[34] = corrsing / 1000.; ntu[35] = Pm_Heepx / 1000.; ntu[36] = Pm_Heepy / 1000.; ntu[37] = Pm_Heepz / 1000.;
     ntu[38] = recon.PmPar / 1000.; ntu[39] = recon.PmPer / 1000.; ntu[40] = recon.PmOop / 1000.;
@@ -228,13 +239,13 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
                RanluxState* ranlux, const SfTable* sf, double* ntu_rows, int64_t* n_rows, int* n_cols,
-               int64_t* try_of_row) {
+               int64_t* try_of_row, const PfermiTable* pfermi, const Cteq5Table* pdf) {
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
     if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
     else rng.seed_philox(seed, (uint64_t)(first + i));
     Sim s;
-    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf;
+    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf; s.pfermi = pfermi; s.pdf = pdf;
     EventMain main;
     Event vertex, orig, recon;
     const TryResult r = one_try(s, main, vertex, orig, recon);

@@ -54,6 +54,8 @@ struct simc_handle {
   std::vector<unsigned char> acc_host;
   double* d_rec = nullptr; int* d_status = nullptr; long long rec_n = 0;
   double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
+  double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
+  double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
   // optional per-stage timing
   int timing = 0;
   std::vector<cudaEvent_t> ev;                 // 5 events per batch, recycled
@@ -163,6 +165,8 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_rec) cudaFree(h->d_rec);
   if (h->d_status) cudaFree(h->d_status);
   if (h->d_sf) cudaFree(h->d_sf);
+  if (h->d_pdf) cudaFree(h->d_pdf);
+  if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -212,6 +216,91 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
     }
   std::fclose(f);
   return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+}
+
+// dbase.f:563-587 from arrays: cumulative probability divided by its last entry
+int simc_b200_set_pfermi_table(simc_handle* h, int n, const double* pval, const double* mprob) {
+  if (!h || !pval || !mprob) return SIMC_ERR_ARG;
+  if (n < 2 || n > 2000) return fail(h, SIMC_ERR_ARG, "momentum distribution: 2..2000 rows (dbase.f:581)");
+  std::vector<double> img(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) { img[i] = pval[i]; img[n + i] = mprob[i] / mprob[n - 1]; }
+  for (int i = 1; i < n; ++i)
+    if (!(img[n + i] >= img[n + i - 1]) || !(pval[i] > pval[i - 1]))
+      return fail(h, SIMC_ERR_ARG, "momentum distribution: pval must increase and mprob must be a cumulative probability");
+  CU(h, cudaSetDevice(h->device));
+  if (h->d_pfm) { cudaFree(h->d_pfm); h->d_pfm = nullptr; }
+  CU(h, cudaMalloc(&h->d_pfm, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_pfm, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->pfm_n = n;
+  return SIMC_OK;
+}
+
+// The reference's file format (deut.dat, he3.dat, ...): rows "p  cumulative probability", list-directed
+// (Fortran `d` exponents), at most 2000 rows (dbase.f:581-584)
+int simc_b200_load_pfermi_file(simc_handle* h, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open momentum distribution file ") + path);
+  std::vector<double> pval, mprob;
+  char line[512];
+  while (pval.size() < 2000 && std::fgets(line, sizeof line, f)) {
+    for (char* c = line; *c; ++c) if (*c == 'd' || *c == 'D') *c = 'e';
+    double p, q;
+    if (std::sscanf(line, "%lf %lf", &p, &q) == 2) { pval.push_back(p); mprob.push_back(q); }
+  }
+  std::fclose(f);
+  if (pval.size() < 2) return fail(h, SIMC_ERR_IO, "momentum distribution file: fewer than two rows");
+  return simc_b200_set_pfermi_table(h, (int)pval.size(), pval.data(), mprob.data());
+}
+
+// ReadTbl (cteq5/Ctq5Pdf.f:239-281) from arrays
+int simc_b200_set_cteq5_table(simc_handle* h, int nx, int nt, int nfmx, double lambda, double qini, double qmax,
+                              double xmin, const double* xv, const double* qv, const double* upd) {
+  if (!h || !xv || !qv || !upd) return SIMC_ERR_ARG;
+  (void)qini; (void)qmax; (void)xmin;        // only used for warnings in the reference
+  if (nx < 2 || nx > 105 || nt < 2 || nt > 25 || nfmx < 3 || nfmx > 6 || !(lambda > 0))
+    return fail(h, SIMC_ERR_ARG, "CTEQ5 table: 2 <= Nx <= 105, 2 <= Nt <= 25, 3 <= NfMx <= 6 (Ctq5Pdf.f:117)");
+  const size_t npts = (size_t)(nx + 1) * (nt + 1) * (nfmx + 3);
+  std::vector<double> img((size_t)(nx + 1) + (nt + 1) + npts);
+  for (int i = 0; i <= nx; ++i) img[i] = xv[i];
+  for (int i = 0; i <= nt; ++i) img[(size_t)nx + 1 + i] = std::log(qv[i] / lambda);
+  std::copy(upd, upd + npts, img.begin() + (nx + 1) + (nt + 1));
+  for (int i = 1; i <= nx; ++i) if (!(xv[i] > xv[i - 1])) return fail(h, SIMC_ERR_ARG, "CTEQ5 table: x grid must increase");
+  for (int i = 1; i <= nt; ++i) if (!(qv[i] > qv[i - 1])) return fail(h, SIMC_ERR_ARG, "CTEQ5 table: Q grid must increase");
+  CU(h, cudaSetDevice(h->device));
+  if (h->d_pdf) { cudaFree(h->d_pdf); h->d_pdf = nullptr; }
+  CU(h, cudaMalloc(&h->d_pdf, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_pdf, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->pdf_nx = nx; h->pdf_nt = nt; h->pdf_nfmx = nfmx; h->pdf_al = lambda;
+  return SIMC_OK;
+}
+
+// cteq5*.tbl: comment lines alternate with list-directed numeric blocks (Ctq5Pdf.f:250-279)
+int simc_b200_load_cteq5_file(simc_handle* h, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open CTEQ5 table ") + path);
+  char line[1024];
+  auto skip = [&]() { return std::fgets(line, sizeof line, f) != nullptr; };
+  auto read_n = [&](std::vector<double>& v, size_t n) {
+    v.resize(n);
+    for (size_t i = 0; i < n; ++i) if (std::fscanf(f, "%lf", &v[i]) != 1) return false;
+    int c;
+    while ((c = std::fgetc(f)) != EOF && c != '\n') {}       // rest of the last numeric line
+    return true;
+  };
+  std::vector<double> head, dims, q, x, upd;
+  bool ok = skip() && skip() && read_n(head, 9) && skip() && read_n(dims, 3);
+  int nx = 0, nt = 0, nfmx = 0;
+  if (ok) {
+    nx = (int)dims[0]; nt = (int)dims[1]; nfmx = (int)dims[2];
+    ok = nx >= 2 && nx <= 105 && nt >= 2 && nt <= 25 && nfmx >= 3 && nfmx <= 6;
+  }
+  ok = ok && skip() && read_n(q, 2 + (size_t)nt + 1) && skip() && read_n(x, 1 + (size_t)nx + 1) && skip() &&
+       read_n(upd, (size_t)(nx + 1) * (nt + 1) * (nfmx + 3));
+  std::fclose(f);
+  if (!ok) return fail(h, SIMC_ERR_IO, "CTEQ5 table: malformed file");
+  return simc_b200_set_cteq5_table(h, nx, nt, nfmx, head[2], q[0], q[1], x[0], x.data() + 1, q.data() + 2, upd.data());
 }
 
 const char* simc_b200_last_error(const simc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -348,11 +437,16 @@ int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
   const bool meson = (c.doing_hydpi && c.doing_pion) || (c.doing_hydkaon && c.doing_kaon);
   const bool heavy = c.doing_heavy && c.doing_eep && c.use_benhar_sf;
-  if (!(c.doing_hyd_elast || meson || heavy) || c.doing_deuterium || c.doing_delta || c.doing_rho || c.doing_semi ||
-      c.doing_phsp)
+  const bool semi = c.doing_semi && c.doing_semipi && (c.doing_hydsemi || c.doing_deutsemi) && !c.doing_pion && !c.doing_kaon;
+  if (!(c.doing_hyd_elast || meson || heavy || semi) || c.doing_deuterium || c.doing_delta || c.doing_rho ||
+      (c.doing_semi && !semi) || c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
                 "this build of the event loop implements H(e,e'p), A(e,e'p) with a Benhar spectral function, "
-                "H(e,e'pi+-) and H(e,e'K+)");
+                "H(e,e'pi+-), H(e,e'K+) and semi-inclusive H/D(e,e'pi+-)X");
+  if (semi && !h->d_pdf)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive production needs the CTEQ5 table (simc_b200_set_cteq5_table) first");
+  if (semi && c.doing_deutsemi && !h->d_pfm)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: D(e,e'pi)X needs the momentum distribution (simc_b200_set_pfermi_table) first");
   if (heavy && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
   if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
@@ -437,6 +531,8 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
+  a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
+  a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
   {
     const MatTable mt = make_mat_table(h->cfg.targ);          // host libm, once per call
     static_assert(sizeof(mt) == sizeof(a.mats), "MatTable layout");
@@ -632,7 +728,7 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   int rc = validate_loop_config(h);
   if (rc) return rc;
   const simc_run_config& c = h->cfg;
-  *n_cols = (c.doing_pion || c.doing_kaon) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
+  *n_cols = c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
   *n_rows = 0;
   if (n == 0) return SIMC_OK;
   static_assert(SIMC_NTUPLE_MAXCOL <= SIMC_EVENT_NREC, "the record buffer is shared with simc_b200_event_batch");
@@ -692,6 +788,32 @@ int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double
   cudaFree(d_in); cudaFree(d_out);
   h->launches += 1;
   if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_radc_batch");
+  return SIMC_OK;
+}
+
+int simc_b200_semi_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!in_soa || !out_soa))) return fail(h, SIMC_ERR_ARG, "simc_b200_semi_batch: bad argument");
+  if (!h->d_pdf) return fail(h, SIMC_ERR_STATE, "simc_b200_semi_batch: set the CTEQ5 table first");
+  if (!h->cfg.doing_semipi) return fail(h, SIMC_ERR_ARG, "simc_b200_semi_batch: only semi-inclusive pions are implemented (no fDSS)");
+  if (n == 0) return SIMC_OK;
+  CU(h, cudaSetDevice(h->device));
+  int rc = ensure_loop_buffers(h, 1);
+  if (rc) return rc;
+  LoopLaunch a{};
+  a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(h, cudaMalloc(&d_in, sizeof(double) * SIMC_SEMI_NIN * (size_t)n));
+  CU(h, cudaMalloc(&d_out, sizeof(double) * SIMC_SEMI_NOUT * (size_t)n));
+  cudaError_t e = cudaMemcpyAsync(d_in, in_soa, sizeof(double) * SIMC_SEMI_NIN * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = h->strict ? strict::launch_semi_batch(h->d_cfg, a, n, d_in, d_out, h->stream)
+                  : fast::launch_semi_batch(h->d_cfg, a, n, d_in, d_out, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_soa, d_out, sizeof(double) * SIMC_SEMI_NOUT * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  h->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_semi_batch");
   return SIMC_OK;
 }
 

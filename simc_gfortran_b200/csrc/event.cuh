@@ -8,6 +8,7 @@
 #include "radc.cuh"
 #include "physics_meson.cuh"
 #include "physics_heavy.cuh"
+#include "physics_semi.cuh"
 
 namespace simc {
 
@@ -77,6 +78,8 @@ struct EventState {
   double uex, uey, uez, upx, upy, upz;
   // meson production only: vertex%nu, q, uq and main%epsilon, theta_pq, phi_pq, t, tmin, W
   double v_nu, v_q, uqx, uqy, uqz, m_eps, m_thpq, m_phipq, m_t, m_tmin, m_W;
+  // semi-inclusive production: vertex%zhad, pt2 and COMMON /pfermi_stuff/ (simulate.inc:212-217)
+  double v_zhad, v_pt2, pfer, pferx, pfery, pferz, efer;
   // orig (fields that differ from vertex)
   double o_Ein, o_eE, o_edelta, o_pE, o_pP, o_pdelta;
   RadEvDev rad;
@@ -342,26 +345,30 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.uqx = -eP * s.uex / s.v_q;
     s.uqy = -eP * s.uey / s.v_q;
     s.uqz = (s.v_Ein - eP * s.uez) / s.v_q;
-    s.v_Pm = 0.0;                                   // pfer
-    const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
-    const double b = s.v_q * s.v_q;
-    const double c = s.v_nu + targ.M;
-    const double t = c * c - b + Mh2 - targ.Mrec_struck * targ.Mrec_struck;
-    const double QA = 4. * (a * a - c * c);
-    const double QB = 4. * c * t;
-    const double QC = -4. * (a * a) * Mh2 - t * t;
-    const double radical = QB * QB - 4. * QA * QC;
-    if (radical < 0) run = false;
-    if (run) {
-      s.v_pE = (-QB - sqrt(radical)) / 2. / QA;
-      if (s.v_pE < 0.0) run = false;
-      else if (c - s.v_pE <= targ.Mrec_struck) run = false;
-      else if (s.v_pE <= Mh) run = false;
+    if (!cfg.doing_semi) {                          // semi-inclusive: the hadron energy was thrown (event.f:289-297)
+      s.v_Pm = 0.0;                                 // pfer
+      const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
+      const double b = s.v_q * s.v_q;
+      const double c = s.v_nu + targ.M;
+      const double t = c * c - b + Mh2 - targ.Mrec_struck * targ.Mrec_struck;
+      const double QA = 4. * (a * a - c * c);
+      const double QB = 4. * c * t;
+      const double QC = -4. * (a * a) * Mh2 - t * t;
+      const double radical = QB * QB - 4. * QA * QC;
+      if (radical < 0) run = false;
+      if (run) {
+        s.v_pE = (-QB - sqrt(radical)) / 2. / QA;
+        if (s.v_pE < 0.0) run = false;
+        else if (c - s.v_pE <= targ.Mrec_struck) run = false;
+        else if (s.v_pE <= Mh) run = false;
+      }
     }
   }
   if (run) {
-    s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
-    s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+    if (!cfg.doing_semi) {
+      s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
+      s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+    }
     // event.f:707-771
     const double W2 = targ.Mtar_struck * targ.Mtar_struck + 2. * targ.Mtar_struck * s.v_nu - s.v_Q2;
     s.m_W = sqrt(fabs(W2)) * W2 / fabs(W2);
@@ -381,6 +388,25 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.m_phipq = m::atan2(p_new_y, p_new_x);
     if (s.m_phipq < 0.e0) s.m_phipq = s.m_phipq + 2. * SIMC_PI_D;
     s.v_Trec = 0.0;
+    if (cfg.doing_semi) {     // event.f:880-886, 952-955, 979-996: Pm, Em of the undetected system; z and pt^2
+      const double Pmx = s.v_pP * s.upx - s.v_q * s.uqx;
+      const double Pmy = s.v_pP * s.upy - s.v_q * s.uqy;
+      const double Pmz = s.v_pP * s.upz - s.v_q * s.uqz;
+      const double Pmiss = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
+      s.v_Pm = Pmiss;
+      s.v_Em = s.v_nu + targ.M - s.v_pE;
+      const double e_x = targ.Mtar_struck + s.v_nu - s.v_pE;
+      const double thr = SIMC_MP + 134.9766;
+      if ((e_x * e_x - Pmiss * Pmiss) < thr * thr) run = false;
+      if (run) {
+        s.v_zhad = s.v_pE / s.v_nu;
+        const double cth = m::cos(s.m_thpq);
+        s.v_pt2 = s.v_pP * s.v_pP * (1.0 - cth * cth);
+        if (s.v_zhad > 1.0) run = false;
+      }
+    }
+  }
+  if (run) {
     // event.f:1013-1023: both arms' angles were generated
     double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
     s.jacobian = s.jacobian / (r * (r * r));
@@ -408,7 +434,8 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
 // electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
 // limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev& pfm, RNG& rng, GAUSS gauss,
+                            EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;
   if (ok) {
@@ -448,8 +475,20 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, RNG&
     s.v_exptar = gen.e.xptar.min + rng.uniform() * (gen.e.xptar.max - gen.e.xptar.min);
     s.v_pyptar = gen.p.yptar.min + rng.uniform() * (gen.p.yptar.max - gen.p.yptar.min);
     s.v_pxptar = gen.p.xptar.min + rng.uniform() * (gen.p.xptar.max - gen.p.xptar.min);
-    // event.f:296-318
-    const double Emin = fmax(gen.e.E.min, gen.sumEgen.min), Emax = fmin(gen.e.E.max, gen.sumEgen.max);
+    if (cfg.doing_semi) {   // hadron energy, event.f:289-297
+      const double Emin = fmax(gen.p.E.min, gen.sumEgen.min - gen.e.E.max);
+      const double Emax = fmin(gen.p.E.max, gen.sumEgen.max - gen.e.E.min);
+      if (Emin > Emax) ok = false;
+      if (ok) {
+        s.gen_weight = s.gen_weight * (Emax - Emin) / (gen.p.E.max - gen.p.E.min);
+        s.v_pE = Emin + rng.uniform() * (Emax - Emin);
+        s.v_pP = sqrt(s.v_pE * s.v_pE - cfg.Mh2);
+        s.v_pdelta = 100. * (s.v_pP - cfg.spec_p.P) / cfg.spec_p.P;
+      }
+    }
+    // event.f:296-318 (semi-inclusive: the plain electron-arm limits)
+    const double Emin = cfg.doing_semi ? gen.e.E.min : fmax(gen.e.E.min, gen.sumEgen.min);
+    const double Emax = cfg.doing_semi ? gen.e.E.max : fmin(gen.e.E.max, gen.sumEgen.max);
     if (Emin > Emax) ok = false;
     if (ok) {
       s.gen_weight = s.gen_weight * (Emax - Emin) / (gen.e.E.max - gen.e.E.min);
@@ -460,6 +499,33 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, RNG&
       s.v_Em = 0.0;
       s.rad.Egamma_used[0] = s.rad.Egamma_used[1] = s.rad.Egamma_used[2] = 0.0;
       s.rad.ntail = 0;
+      // event.f:327-373: nucleon momentum in the deuteron (thrown whether or not do_fermi uses it)
+      s.pfer = 0.0; s.pferx = 0.0; s.pfery = 0.0; s.pferz = 0.0;
+      s.efer = targ.Mtar_struck;
+      if (cfg.doing_deutsemi) {
+        const double ranprob = rng.uniform();
+        const int nump = pfm.nump;
+        // first ii (1-based) with ranprob <= mprob(ii), capped at nump: the reference's linear scan
+        // (event.f:341-343) on a non-decreasing table
+        int lo = 0, hi = nump - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (ranprob > pfm.mprob[mid]) lo = mid + 1; else hi = mid;
+        }
+        const int ii = lo + 1;
+        const double pferlo = ii == 1 ? 0.0 : (pfm.pval[ii - 2] + pfm.pval[ii - 1]) / 2;
+        const double pferhi = ii == nump ? pfm.pval[nump - 1] : (pfm.pval[ii - 1] + pfm.pval[ii]) / 2;
+        s.pfer = pferlo + (pferhi - pferlo) * rng.uniform();
+        const double ranth1 = rng.uniform() * 2. - 1.0;
+        const double ranth = m::acos(ranth1);
+        const double ranph = rng.uniform() * 2. * SIMC_PI_D;
+        s.pferx = m::sin(ranth) * m::cos(ranph);
+        s.pfery = m::sin(ranth) * m::sin(ranph);
+        s.pferz = m::cos(ranth);
+        s.v_Em = SIMC_MP + 939.56563 - targ.M;
+        const double m_spec = targ.M - targ.Mtar_struck + s.v_Em;
+        s.efer = targ.M - sqrt(m_spec * m_spec + s.pfer * s.pfer);
+      }
     }
   }
   SIMC_PHASE();

@@ -113,6 +113,39 @@ cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, do
   return cudaGetLastError();
 }
 
+// Stage-level parity entry point: peepiX on dumped vertex vectors (include/simc_b200.h: simc_b200_semi_batch)
+static Cteq5Dev make_pdf(const LoopLaunch& a) {
+  Cteq5Dev T;
+  T.xv = a.pdf_buf; T.ql = a.pdf_buf ? a.pdf_buf + (a.pdf_nx + 1) : nullptr;
+  T.upd = a.pdf_buf ? a.pdf_buf + (a.pdf_nx + 1) + (a.pdf_nt + 1) : nullptr;
+  T.nx = a.pdf_nx; T.nt = a.pdf_nt; T.nfmx = a.pdf_nfmx; T.al = a.pdf_al;
+  return T;
+}
+__global__ void k_semi_batch(const simc_run_config* __restrict__ cfg, Cteq5Dev T, long long n, const double* __restrict__ in,
+                             double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SemiVertex v;
+  v.Ein = in[0 * n + i]; v.eE = in[1 * n + i]; v.nu = in[2 * n + i]; v.Q2 = in[3 * n + i]; v.q = in[4 * n + i];
+  v.uqx = in[5 * n + i]; v.uqy = in[6 * n + i]; v.uqz = in[7 * n + i]; v.pt2 = in[8 * n + i]; v.zhad = in[9 * n + i];
+  v.theta_pq = in[10 * n + i]; v.pfer = in[11 * n + i]; v.pferx = in[12 * n + i]; v.pfery = in[13 * n + i];
+  v.pferz = in[14 * n + i]; v.efer = in[15 * n + i];
+  double dbg[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) dbg[k] = 0.0;
+  const SemiWeight w = peepiX(*cfg, T, v, dbg);
+  out[0 * n + i] = w.sigcc; out[1 * n + i] = w.sighad; out[2 * n + i] = w.davejac; out[3 * n + i] = w.xbj;
+#pragma unroll
+  for (int k = 0; k < 11; ++k) out[(4 + k) * n + i] = dbg[k];
+  out[15 * n + i] = w.bad ? 1.0 : 0.0;
+}
+cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long long n, const double* in, double* out,
+                              cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_semi_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const simc_run_config*)cfg, make_pdf(tables), n, in, out);
+  return cudaGetLastError();
+}
+
 size_t arm_dev_bytes() { return sizeof(ArmDev); }
 size_t dev_accum_bytes() { return sizeof(DevAccum); }
 int n_state_fields() { return (int)F_NFIELDS; }
@@ -201,6 +234,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
   memcpy(&A.mt, a.mats, sizeof(MatTable));
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
+  A.pdf = make_pdf(a);
+  A.pfm.pval = a.pfm_buf; A.pfm.mprob = a.pfm_buf ? a.pfm_buf + a.pfm_n : nullptr; A.pfm.nump = a.pfm_n;
   const long long need = (a.n_tries + kBlock - 1) / kBlock;
   const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
   {

@@ -40,10 +40,16 @@ struct LoopLaunch {
   const double* sf_em;
   const double* sf_val;
   int sf_npm, sf_nem;
+  const double* pdf_buf;      // CTEQ5 table (device): [xv(nx+1) | ql(nt+1) | upd]; null unless set
+  int pdf_nx, pdf_nt, pdf_nfmx;
+  double pdf_al;
+  const double* pfm_buf;      // momentum distribution (device): [pval(n) | mprob(n)]; null unless set
+  int pfm_n;
 };
 
 namespace strict {
 cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s);
+cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long long n, const double* in, double* out, cudaStream_t s);
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s);   // 0 gen, 1 P arm, 2 E arm, 3 finish, 4 records
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s);
 size_t dev_accum_bytes();
@@ -52,6 +58,7 @@ void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qe
 }
 namespace fast {
 cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s);
+cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long long n, const double* in, double* out, cudaStream_t s);
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s);   // 0 gen, 1 P arm, 2 E arm, 3 finish, 4 records
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s);
 size_t dev_accum_bytes();

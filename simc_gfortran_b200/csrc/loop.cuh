@@ -41,6 +41,8 @@ enum StateField : int {
   // results of peepi / peeK
   F_VNU, F_VQ, F_UQX, F_UQY, F_UQZ, F_UPX, F_UPY, F_UPZ, F_MEPS, F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
   F_FPP_DX, F_FPP_DY, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM,
+  // semi-inclusive production: vertex%zhad, pt2 and the thrown nucleon momentum (COMMON /pfermi_stuff/)
+  F_ZHAD, F_PT2, F_PFER, F_PFERX, F_PFERY, F_PFERZ, F_EFER, F_XFERMI,
   // ntuple rows (record mode only): focal-plane positions, decay bookkeeping, then the row itself
   F_FPP_X, F_FPP_Y, F_FPE_X, F_FPE_DX, F_FPE_Y, F_FPE_DY, F_DECDIST, F_MH2FINAL,
   F_NTU0, F_NTU_LAST = F_NTU0 + SIMC_NTUPLE_MAXCOL - 1,
@@ -70,6 +72,8 @@ struct LoopArgs {
   const simc_run_config* cfg;      // device copy
   MatTable mt;                     // per-material energy-loss constants (target.cuh), made on the host
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
+  Cteq5Dev pdf;                    // CTEQ5 parton distributions (semi-inclusive production only)
+  PfermiDev pfm;                   // nucleon momentum distribution (deuterium semi-inclusive production only)
   StateBuf st;
   unsigned* lists;                 // [11][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same
   unsigned* counts;                // [0] slots handed out, [1..11] lengths of lists 0..10
@@ -169,9 +173,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
-    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
+    const bool semi = cfg.doing_semi != 0;
+    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi;
     const bool heavy = cfg.doing_heavy != 0;
-    if (meson) ok = generate_meson(cfg, mt_s, rng, GaussFn(), s, active);
+    if (meson) ok = generate_meson(cfg, mt_s, A.pfm, rng, GaussFn(), s, active);
     else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);
     if (active) {
@@ -213,6 +218,11 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
         S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
         S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
         S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
+        if (semi) {
+          S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); S.st(F_PFER, slot, s.pfer);
+          S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery); S.st(F_PFERZ, slot, s.pferz);
+          S.st(F_EFER, slot, s.efer);
+        }
       }
     }
     const unsigned pos = warp_append(&A.counts[1], active && ok);
@@ -554,7 +564,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       const double rW = sqrt(fabs(W2)) * W2 / fabs(W2);
       const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
-      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon;
+      const bool semi = cfg.doing_semi != 0;
+      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi;
       const bool heavy = cfg.doing_heavy != 0;
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
       // complete_main, event.f:1363-1569
@@ -593,7 +604,21 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         mv.upx = S.ld(F_UPX, slot); mv.upy = S.ld(F_UPY, slot); mv.upz = S.ld(F_UPZ, slot);
         mv.phi_pq = S.ld(F_MPHIPQ, slot); mv.t = S.ld(F_MT, slot); mv.epsilon = S.ld(F_MEPS, slot);
         MesonWeight mw;
-        if (cfg.doing_pion) {
+        if (semi) {
+          // peepiX reads vertex%theta_pq, which nothing assigns (complete_ev fills main%theta_pq): zero,
+          // i.e. cos(theta_pq) = 1 in the reference's jacobian (semi_physics.f:243).  Reproduced.
+          SemiVertex sv_;
+          sv_.Ein = v_Ein; sv_.eE = v_eE; sv_.nu = mv.nu; sv_.Q2 = v_Q2; sv_.q = mv.q;
+          sv_.uqx = mv.uqx; sv_.uqy = mv.uqy; sv_.uqz = mv.uqz;
+          sv_.pt2 = S.ld(F_PT2, slot); sv_.zhad = S.ld(F_ZHAD, slot); sv_.theta_pq = 0.0;
+          sv_.pfer = S.ld(F_PFER, slot); sv_.pferx = S.ld(F_PFERX, slot); sv_.pfery = S.ld(F_PFERY, slot);
+          sv_.pferz = S.ld(F_PFERZ, slot); sv_.efer = S.ld(F_EFER, slot);
+          const SemiWeight w_ = peepiX(cfg, A.pdf, sv_, nullptr);
+          mw.sigcc = w_.sigcc; mw.sigcm = w_.sighad; mw.davejac = w_.davejac; mw.low_w = w_.bad;
+          mw.thetacm = 0.0; mw.phicm = 0.0; mw.wcm = 0.0;
+          S.st(F_XFERMI, slot, w_.xfermi);      // ntup%xfermi, semi_physics.f:250
+          if (!cfg.doing_decay) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
+        } else if (cfg.doing_pion) {
           mw = peepi(cfg, mv);
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
         } else {
@@ -610,7 +635,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
       weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
       weight = weight * tgtweight;
-      if (cfg.doing_kaon && !cfg.doing_decay) weight = weight * survivalprob;
+      if ((cfg.doing_kaon || cfg.doing_semika) && !cfg.doing_decay) weight = weight * survivalprob;
       // pass_cuts, simc.f:229-241 (p-arm upper delta edge uses SPedge%e%delta%max, as written)
       const double red = S.ld(F_RCE_D, slot), rey = S.ld(F_RCE_Y, slot), rex = S.ld(F_RCE_X, slot), rez = S.ld(F_RCE_Z, slot);
       const double rpd = S.ld(F_RCP_D, slot), rpy = S.ld(F_RCP_Y, slot), rpx = S.ld(F_RCP_X, slot), rpz = S.ld(F_RCP_Z, slot);
@@ -676,7 +701,24 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         ntu[30] = rEm / 1000.; ntu[31] = rPm / 1000.; ntu[32] = r_thpq; ntu[33] = r_phipq;
         const double radphot = S.ld(F_EG0, slot) + S.ld(F_EG1, slot) + S.ld(F_EG2, slot);
         const double wfinal = weight;                  // survival probability already applied above
-        if (meson) {
+        if (semi) {          // results_write.f:187-213
+          const double mm2 = rEm * rEm - rPm * rPm;
+          ntu[34] = (sqrt(fabs(mm2)) * fabs(mm2) / mm2) / 1000.;
+          ntu[35] = rpP / 1000.;
+          ntu[36] = (Q2 - cfg.Mh2 + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
+          ntu[37] = -S.ld(F_RASTERY, slot); ntu[38] = radphot / 1000.; ntu[39] = sigcc; ntu[40] = 0.0; ntu[41] = wfinal;
+          ntu[42] = !cfg.doing_decay ? survivalprob : S.ld(F_DECDIST, slot);
+          ntu[43] = sqrt(S.ld(F_MH2FINAL, slot));
+          const double cth = m::cos(r_thpq);
+          ntu[44] = rpE / nu; ntu[45] = S.ld(F_ZHAD, slot);
+          ntu[46] = (rpP * rpP * (1.0 - cth * cth)) / 1.e06; ntu[47] = S.ld(F_PT2, slot) / 1.e06;
+          ntu[48] = Q2 / 2. / SIMC_MP / nu; ntu[49] = v_Q2 / 2. / SIMC_MP / S.ld(F_VNU, slot);
+          ntu[50] = m::acos(S.ld(F_UQZ, slot)); ntu[51] = S.ld(F_SIGCM, slot); ntu[52] = S.ld(F_DAVEJAC, slot); ntu[53] = 0.0;
+          const double dummy = S.ld(F_PFERX, slot) * S.ld(F_UQX, slot) + S.ld(F_PFERY, slot) * S.ld(F_UQY, slot) +
+                               S.ld(F_PFERZ, slot) * S.ld(F_UQZ, slot);
+          ntu[54] = S.ld(F_PFER, slot) / 1000. * fabs(dummy) / dummy;     // NaN for hydrogen (0/0), as in the reference
+          ntu[55] = S.ld(F_XFERMI, slot); ntu[56] = S.ld(F_MPHIPQ, slot);
+        } else if (meson) {
           const double mm2 = rEm * rEm - rPm * rPm;
           const double e_A = nu + cfg.targ.M - rpE;
           const double mmA2 = e_A * e_A - rPm * rPm;
@@ -726,7 +768,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
         const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
         const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
-        const double sumEgen = meson ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
+        const double sumEgen = (meson && !semi) ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
         const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), sumEgen,
                                o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
                                spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};

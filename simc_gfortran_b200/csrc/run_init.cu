@@ -284,6 +284,10 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   } else if (c.doing_semi) {
     c.Mh = doing_semika ? Mk : Mpi;
     c.doing_hydsemi = nA == 1; c.doing_deutsemi = nA == 2;
+    c.doing_semipi = doing_semipi; c.doing_semika = doing_semika;
+    c.do_fermi = D.i("do_fermi") > 0;
+    if (c.doing_hydsemi && c.do_fermi) c.do_fermi = 0;      // 'Cannot do Fermi motion for Hydrogen!' (dbase.f:202-206)
+    if (nA >= 3) throw std::runtime_error("semi-inclusive production from A >= 3 (doing_hesemi) is not implemented in this build");
   } else if (c.doing_rho) {
     c.Mh = 769.3;
   } else {
@@ -567,7 +571,11 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   c.etatzai = (12.0 + (targ.Z + 1.) / (targ.Z * targ.L1 + targ.L2)) / 9.0;
   // ---- scale of the weights: the central-kinematics cross section (cf. calculate_central, simc.f:1143)
   c.w_ref = 1.0;
-  if (c.doing_hyd_elast) {
+  if (c.doing_semi) {
+    // semi-inclusive cross sections are a few nb/GeV/sr^2 = 1e-9 ub/MeV/sr^2; the weight needs the parton
+    // tables, which a deck does not carry, so the scale is nominal
+    c.w_ref = 1.0e-9;
+  } else if (c.doing_hyd_elast) {
     const double Ein = c.Ebeam_vertex_ave, uez = std::cos(c.spec_e.theta);
     const double eE = Ein * c.Mh / (c.Mh + Ein * (1. - uez));
     const double w = sigep(Ein, eE, c.spec_e.theta, 2 * Ein * eE * (1. - uez));

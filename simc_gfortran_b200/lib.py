@@ -87,6 +87,7 @@ _INT_FLAGS = (
     "doing_hydpi", "doing_deutpi", "doing_hepi",
     "doing_hydkaon", "doing_deutkaon", "doing_hekaon",
     "doing_hydsemi", "doing_deutsemi",
+    "doing_semipi", "doing_semika", "do_fermi",
     "doing_hplus", "doing_decay",
     "which_pion", "which_kaon",
     "using_rad", "using_Eloss", "using_Coulomb", "correct_Eloss", "correct_raster",
@@ -190,6 +191,12 @@ def load_library():
                                              C.c_int]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.simc_b200_load_pfermi_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_set_cteq5_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_load_cteq5_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_semi_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_stage_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.simc_b200_fp64_peak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "simc_b200_event_field_name"):
@@ -287,6 +294,36 @@ class Simc:
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
+
+    # ---- semi-inclusive production: momentum distribution (deut.dat) and CTEQ5 parton distributions
+    def set_pfermi_table(self, pval, mprob):
+        pval = np.ascontiguousarray(pval, dtype=np.float64)
+        mprob = np.ascontiguousarray(mprob, dtype=np.float64)
+        assert pval.shape == mprob.shape and pval.ndim == 1
+        self._check(self.L.simc_b200_set_pfermi_table(self.h, len(pval), _ptr(pval), _ptr(mprob)))
+
+    def load_pfermi_file(self, path: str):
+        self._check(self.L.simc_b200_load_pfermi_file(self.h, path.encode()))
+
+    def set_cteq5_table(self, t):
+        """t: dict with nx, nt, nfmx, lam, qini, qmax, xmin, xv[nx+1], qv[nt+1], upd (the fields of a cteq5*.tbl)."""
+        xv = np.ascontiguousarray(t["xv"], dtype=np.float64)
+        qv = np.ascontiguousarray(t["qv"], dtype=np.float64)
+        upd = np.ascontiguousarray(t["upd"], dtype=np.float64)
+        nx, nt, nfmx = int(t["nx"]), int(t["nt"]), int(t["nfmx"])
+        assert len(xv) == nx + 1 and len(qv) == nt + 1 and len(upd) == (nx + 1) * (nt + 1) * (nfmx + 3)
+        self._check(self.L.simc_b200_set_cteq5_table(self.h, nx, nt, nfmx, float(t["lam"]), float(t["qini"]),
+                                                     float(t["qmax"]), float(t["xmin"]), _ptr(xv), _ptr(qv), _ptr(upd)))
+
+    def load_cteq5_file(self, path: str):
+        self._check(self.L.simc_b200_load_cteq5_file(self.h, path.encode()))
+
+    def semi_batch(self, inp: np.ndarray) -> np.ndarray:
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        assert inp.ndim == 2 and inp.shape[0] == 16
+        out = np.zeros((16, inp.shape[1]))
+        self._check(self.L.simc_b200_semi_batch(self.h, inp.shape[1], _ptr(inp), _ptr(out)))
+        return out
 
     # ---- ntuple rows (results_ntu_write)
     def ntuple_batch(self, first_try: int, n: int, seed: int):

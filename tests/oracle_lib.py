@@ -168,3 +168,64 @@ def _oracle_radc_batch(self, cfg, inp):
 
 
 Oracle.radc_batch = _oracle_radc_batch
+
+
+# ---- semi-inclusive production (C4): tables and stage-level entry points ---------------------------
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_cteq5_fixture():
+    """tests/golden/cteq5m.npz (tools/make_fixtures.py: the reference's cteq5/cteq5m.tbl)."""
+    z = np.load(os.path.join(GOLDEN, "cteq5m.npz"))
+    return {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
+
+
+def load_pfermi_fixture():
+    """tests/golden/pfermi_deut.npz (the reference's deut.dat)."""
+    z = np.load(os.path.join(GOLDEN, "pfermi_deut.npz"))
+    return z["pval"], z["mprob"]
+
+
+def _oracle_set_pfermi_table(self, pval, mprob):
+    pval = np.ascontiguousarray(pval, np.float64)
+    mprob = np.ascontiguousarray(mprob, np.float64)
+    self._check(self.L.oracle_set_pfermi_table(len(pval), _p(pval), _p(mprob)))
+
+
+def _oracle_set_cteq5_table(self, t):
+    xv = np.ascontiguousarray(t["xv"], np.float64)
+    qv = np.ascontiguousarray(t["qv"], np.float64)
+    upd = np.ascontiguousarray(t["upd"], np.float64)
+    self._check(self.L.oracle_set_cteq5_table(int(t["nx"]), int(t["nt"]), int(t["nfmx"]), C.c_double(t["lam"]),
+                                              C.c_double(t["qini"]), C.c_double(t["qmax"]), C.c_double(t["xmin"]),
+                                              _p(xv), _p(qv), _p(upd)))
+
+
+def _oracle_ctq5pdf_batch(self, iparton, x, q):
+    x = np.ascontiguousarray(x, np.float64)
+    q = np.ascontiguousarray(q, np.float64)
+    out = np.zeros(len(x))
+    self._check(self.L.oracle_ctq5pdf_batch(int(iparton), C.c_int64(len(x)), _p(x), _p(q), _p(out)))
+    return out
+
+
+def _oracle_christy_batch(self, w2, q2):
+    w2 = np.ascontiguousarray(w2, np.float64)
+    q2 = np.ascontiguousarray(q2, np.float64)
+    out = np.zeros((6, len(w2)))
+    self._check(self.L.oracle_christy_batch(C.c_int64(len(w2)), _p(w2), _p(q2), _p(out)))
+    return out
+
+
+def _oracle_semi_batch(self, cfg, inp):
+    inp = np.ascontiguousarray(inp, np.float64)
+    out = np.zeros((16, inp.shape[1]))
+    self._check(self.L.oracle_semi_batch(C.byref(cfg), C.c_int64(inp.shape[1]), _p(inp), _p(out)))
+    return out
+
+
+Oracle.set_pfermi_table = _oracle_set_pfermi_table
+Oracle.set_cteq5_table = _oracle_set_cteq5_table
+Oracle.ctq5pdf_batch = _oracle_ctq5pdf_batch
+Oracle.christy_batch = _oracle_christy_batch
+Oracle.semi_batch = _oracle_semi_batch

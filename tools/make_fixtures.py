@@ -64,6 +64,53 @@ def make_sf():
     print("benharsf_12", n_pm, n_em, "sum", a[:, :, 2].sum())
 
 
+def read_cteq5_tbl(path):
+    """ReadTbl (cteq5/Ctq5Pdf.f:239-281): list-directed reads between comment lines."""
+    with open(path) as f:
+        lines = f.read().split("\n")
+    toks = " ".join(lines[2:]).replace("D", "E")
+    # line 3: Dr, Fl, Al, masses; then 'NX NT NfMx' header + values; then QINI.. ; XMIN.. ; table
+    it = iter(lines)
+    next(it); next(it)
+    dr, fl, al, *masses = (float(x) for x in next(it).split())
+    next(it)
+    nx, nt, nfmx = (int(x) for x in next(it).split())
+    next(it)
+    rest = []
+    for line in it:
+        rest.append(line)
+    def take(block_lines, n):
+        vals = []
+        while len(vals) < n:
+            vals += [float(x) for x in block_lines.pop(0).split()]
+        assert len(vals) == n, (len(vals), n)
+        return vals
+    q = take(rest, 2 + nt + 1)
+    rest.pop(0)
+    x = take(rest, 1 + nx + 1)
+    rest.pop(0)
+    upd = take(rest, (nx + 1) * (nt + 1) * (nfmx + 3))
+    return dict(nx=nx, nt=nt, nfmx=nfmx, lam=al, qini=q[0], qmax=q[1], qv=np.array(q[2:]), xmin=x[0],
+                xv=np.array(x[1:]), upd=np.array(upd))
+
+
+def make_semi():
+    """cteq5/cteq5m.tbl (SetCtq5 with Iset = 1, semi_physics.f:226-229) and deut.dat (dbase.f:564) ->
+    tests/golden/cteq5m.npz, tests/golden/pfermi_deut.npz"""
+    t = read_cteq5_tbl(os.path.join(REF, "cteq5", "cteq5m.tbl"))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cteq5m.npz"), **t)
+    print("cteq5m", t["nx"], t["nt"], t["nfmx"], t["lam"], len(t["upd"]))
+    rows = []
+    with open(os.path.join(REF, "deut.dat")) as f:
+        for line in f:
+            if line.strip():
+                rows.append([float(x.replace("d", "e").replace("D", "e")) for x in line.split()])
+    a = np.array(rows)[:2000]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pfermi_deut.npz"), pval=a[:, 0], mprob=a[:, 1])
+    print("deut.dat", a.shape, a[-1])
+
+
 if __name__ == "__main__":
     make_sf()
+    make_semi()
     main()
