@@ -186,6 +186,12 @@ typedef struct simc_handle simc_handle;
 int simc_b200_config_from_deck(const char* deck_path, const char* extra_deck_dir, simc_run_config* out,
                                int32_t* ngen, double* charge_mC, char* err, int errlen);
 
+/* Same, for decks whose setup reads a data file of the reference's working directory: D(e,e'p) and
+ * A(e,e'p) without use_benhar_sf take VERTEXedge%Pm and E_Fermi from h2.theory / c12.theory / fe56.theory /
+ * au197.theory (init.f:326-343, 838-856), looked up in data_dir.  data_dir may be NULL for all other decks. */
+int simc_b200_config_from_deck_data(const char* deck_path, const char* extra_deck_dir, const char* data_dir,
+                                    simc_run_config* out, int32_t* ngen, double* charge_mC, char* err, int errlen);
+
 /* lifecycle ------------------------------------------------------------- */
 int  simc_b200_abi_version(void);
 int  simc_b200_create(const simc_run_config* cfg, int device, simc_handle** out);
@@ -233,6 +239,19 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
  * library normalises the sum to one like the reference.  load_sf_file reads benharsf_*.dat itself. */
 int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm, const double* em, const double* sf);
 int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag);
+
+/* Independent-particle spectral function for D(e,e'p) and A(e,e'p) without use_benhar_sf: replaces
+ * theory_init (init.f:828-905) and its COMMON /theory/ (simulate.inc:116-131).  One momentum distribution
+ * rho_i(Pm) per shell i < n_shells (<= 21): nprot[i] protons, mean removal energy em[i], Lorentzian width
+ * emsig[i], normalisation bs_norm[i] (the four columns of the file's shell lines); n_pm[i] equidistant
+ * points (<= 500) starting at pm_first[i] with spacing pm_bin[i], values rho[] concatenated shell after
+ * shell.  absorption and e_fermi are the file's first line.  The library scales nprot by the absorption,
+ * divides rho by bs_norm and integrates the Lorentzians above e_fermi like the reference.
+ * load_theory_file reads h2.theory / c12.theory / fe56.theory / au197.theory itself. */
+int simc_b200_set_theory_table(simc_handle* h, int n_shells, double absorption, double e_fermi, const double* nprot,
+                               const double* em, const double* emsig, const double* bs_norm, const int32_t* n_pm,
+                               const double* pm_first, const double* pm_bin, const double* rho);
+int simc_b200_load_theory_file(simc_handle* h, const char* path);
 
 /* Nucleon momentum distribution of the deuteron (or 3He/4He/C) for Fermi-smeared meson production:
  * replaces the read of deut.dat / he3.dat / he4.dat / c12.dat in dbase.f:563-587.  pval[n] (MeV/c) and the

@@ -1,5 +1,6 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY.  C entry points for tests/ (ctypes), smoke() and the
 // cpu_baseline leg of bench.py.  Never linked into, loaded by, or called from libsimc_b200.so.
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -13,6 +14,7 @@ static std::map<int, ArmOptics> g_optics;
 static SfTable g_sf;
 static PfermiTable g_pfermi;
 static Cteq5Table g_pdf;
+static TheoryTable g_theory;
 static std::string g_err;
 
 extern "C" {
@@ -168,7 +170,8 @@ int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_
         if (rng_mode == 1) st.rluxgo(3, (int)(seed + 1 + t), 0, 0);
         run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr,
                   g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr, nullptr,
-                  g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
+                  g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
+              g_theory.nrhoPm ? &g_theory : nullptr);
       }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
@@ -186,7 +189,8 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
   try {
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr,
-              nullptr, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
+              nullptr, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
+              g_theory.nrhoPm ? &g_theory : nullptr);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
@@ -199,7 +203,8 @@ int oracle_ntuple_batch(const simc_run_config* cfg, int64_t first, int64_t n, ui
     *n_rows = 0;
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, nullptr, nullptr, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, rows, n_rows, &nc,
-              try_of_row, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr);
+              try_of_row, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
+              g_theory.nrhoPm ? &g_theory : nullptr);
     *n_cols = nc;
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -228,6 +233,35 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// theory_init (init.f:828-905) from arrays: layout of simc_b200_set_theory_table
+int oracle_set_theory_table(int doing_heavy, int n_shells, double absorption, double e_fermi, const double* nprot,
+                            const double* em, const double* emsig, const double* bs_norm, const int32_t* n_pm,
+                            const double* pm_first, const double* pm_bin, const double* rho) {
+  TheoryTable T;
+  T.nrhoPm = n_shells; T.E_Fermi = e_fermi;
+  size_t pos = 0;
+  for (int m = 0; m < n_shells; ++m) {
+    T.nprot.push_back(nprot[m] * absorption);
+    T.Em.push_back(em[m]); T.Emsig.push_back(emsig[m]); T.bs_norm.push_back(bs_norm[m]);
+    T.n.push_back(n_pm[m]);
+    T.pm_bin.push_back(pm_bin[m]);
+    T.pm_min.push_back(pm_first[m] - pm_bin[m] / 2.);
+    std::vector<double> r(rho + pos, rho + pos + n_pm[m]);
+    for (double& v : r) v = v / bs_norm[m];
+    T.rho.push_back(std::move(r));
+    pos += n_pm[m];
+    double em_int = 1.;
+    if (doing_heavy) em_int = (K::pi / 2. + std::atan((em[m] - e_fermi) / (0.5 * emsig[m]))) / K::pi;
+    T.Em_int.push_back(em_int);
+  }
+  g_theory = std::move(T);
+  return 0;
+}
+int oracle_theory_batch(const simc_run_config* cfg, int64_t n, const double* em, const double* pm, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = theory_sf_weight(*cfg, g_theory, em[i], pm[i]);
+  return 0;
 }
 
 // dbase.f:563-587: momentum distribution, cumulative probability normalised to its last entry

@@ -584,6 +584,31 @@ bool complete_recon_ev(Sim& s, Event& recon) {
   return true;
 }
 
+// event.f:1402-1428: linear interpolation of rho_i(Pm), Lorentzian in Em for A > 2
+double theory_sf_weight(const simc_run_config& cfg, const TheoryTable& T, double Em, double Pm) {
+  double SF_weight = 0.0;
+  for (int i = 0; i < T.nrhoPm; ++i) {
+    double weight = 0.0;
+    const double r = (Pm - T.pm_min[i]) / T.pm_bin[i];
+    if (r >= 0 && r <= T.n[i]) {
+      int iPm1 = (int)std::lround(r);          // nint
+      if (iPm1 == 0) iPm1 = 1;
+      if (iPm1 == T.n[i]) iPm1 = T.n[i] - 1;
+      const double frac = r + 0.5 - (double)iPm1;
+      const double b = T.rho[i][iPm1 - 1];
+      const double a = T.rho[i][iPm1] - b;
+      weight = a * frac + b;
+    }
+    if (cfg.doing_heavy) {
+      const double width = T.Emsig[i] / 2.0;
+      if (Em < T.E_Fermi) weight = 0.0;
+      weight = weight / K::pi / T.Em_int[i] * width / (powi(Em - T.Em[i], 2) + width * width);
+    }
+    SF_weight = SF_weight + weight * T.nprot[i];
+  }
+  return SF_weight;
+}
+
 // event.f:1363-1569
 bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Event& recon) {
   const simc_run_config& cfg = *s.cfg;
@@ -594,8 +619,11 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     if (!s.sf) throw std::runtime_error("oracle: spectral-function table not set");
     const double weight = sf_lookup_diff(*s.sf, vertex.Em, vertex.Pm);
     main.SF_weight = cfg.targ.Z * cfg.transparency * weight;
+  } else if (cfg.doing_deuterium || (cfg.doing_heavy && !cfg.use_benhar_sf)) {
+    if (!s.theory) throw std::runtime_error("oracle: theory table not set");
+    main.SF_weight = theory_sf_weight(cfg, *s.theory, vertex.Em, vertex.Pm);
   } else {
-    throw std::runtime_error("oracle: momentum-distribution (theory file) weights not restated");
+    throw std::runtime_error("oracle: no spectral-function weight for this reaction");
   }
   if (main.SF_weight <= 0 && !force_sigcc) return false;
   double tgtweight = 1.0, survivalprob = 1.0;

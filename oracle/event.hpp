@@ -60,6 +60,15 @@ struct SfTable {
   int numPm = 0, numEm = 0;
   std::vector<double> Pmval, Emval, sfval;   // sfval[iPm * numEm + iEm]
 };
+// COMMON /theory/ after theory_init (init.f:828-905): independent-particle spectral function
+struct TheoryTable {
+  int nrhoPm = 0;
+  double E_Fermi = 0;
+  std::vector<double> nprot, Em, Emsig, bs_norm, Em_int;      // per shell
+  std::vector<int> n;                                          // Pm_theory(i)%n
+  std::vector<double> pm_min, pm_bin;                          // Pm_theory(i)%min, %bin
+  std::vector<std::vector<double>> rho;                        // theory(i, 1:n), already divided by bs_norm
+};
 // momentum distribution of dbase.f:563-587 (deut.dat ...): mprob normalised to mprob(nump) = 1
 struct PfermiTable {
   std::vector<double> pval, mprob;
@@ -93,6 +102,7 @@ struct Sim {
   const SfTable* sf = nullptr;
   const PfermiTable* pfermi = nullptr;
   const Cteq5Table* pdf = nullptr;
+  const TheoryTable* theory = nullptr;
   Rng* rng = nullptr;
   double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
   RadEv rad;
@@ -148,6 +158,8 @@ void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics*
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
                RanluxState* ranlux = nullptr, const SfTable* sf = nullptr, double* ntu_rows = nullptr,
                int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr,
-               const PfermiTable* pfermi = nullptr, const Cteq5Table* pdf = nullptr);
+               const PfermiTable* pfermi = nullptr, const Cteq5Table* pdf = nullptr,
+               const TheoryTable* theory = nullptr);
+double theory_sf_weight(const simc_run_config& cfg, const TheoryTable& T, double Em, double Pm);     // event.f:1402-1428
 
 }  // namespace simc_oracle

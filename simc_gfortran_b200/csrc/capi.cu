@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "optics_host.h"
 #include "target.cuh"
+#include "tables_host.h"
 
 using namespace simc;
 
@@ -56,6 +57,7 @@ struct simc_handle {
   double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
   double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
+  double* d_theory = nullptr; int theory_nrho = 0; double theory_efermi = 0;   // physics_heavy.cuh: TheoryDev
   // optional per-stage timing
   int timing = 0;
   std::vector<cudaEvent_t> ev;                 // 5 events per batch, recycled
@@ -167,6 +169,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_sf) cudaFree(h->d_sf);
   if (h->d_pdf) cudaFree(h->d_pdf);
   if (h->d_pfm) cudaFree(h->d_pfm);
+  if (h->d_theory) cudaFree(h->d_theory);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -216,6 +219,54 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
     }
   std::fclose(f);
   return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+}
+
+// theory_init (init.f:828-905) from arrays
+int simc_b200_set_theory_table(simc_handle* h, int n_shells, double absorption, double e_fermi, const double* nprot,
+                               const double* em, const double* emsig, const double* bs_norm, const int32_t* n_pm,
+                               const double* pm_first, const double* pm_bin, const double* rho) {
+  if (!h || !nprot || !em || !emsig || !bs_norm || !n_pm || !pm_first || !pm_bin || !rho) return SIMC_ERR_ARG;
+  if (n_shells < 1 || n_shells > 21) return fail(h, SIMC_ERR_ARG, "theory table: 1..21 momentum distributions (simulate.inc:118)");
+  size_t total = 0;
+  for (int m = 0; m < n_shells; ++m) {
+    if (n_pm[m] < 2 || n_pm[m] > 500) return fail(h, SIMC_ERR_ARG, "theory table: 2..500 points per distribution (simulate.inc:117)");
+    if (!(pm_bin[m] > 0) || !(bs_norm[m] != 0)) return fail(h, SIMC_ERR_ARG, "theory table: bad bin width or normalisation");
+    total += (size_t)n_pm[m];
+  }
+  const bool heavy = h->cfg.doing_heavy != 0;
+  const double pi = 3.141592653589793;
+  std::vector<double> img(8 * (size_t)n_shells + total);
+  size_t pos = 8 * (size_t)n_shells, src = 0;
+  for (int m = 0; m < n_shells; ++m) {
+    double* sh = img.data() + 8 * m;
+    sh[0] = nprot[m] * absorption;
+    sh[1] = em[m]; sh[2] = emsig[m];
+    sh[3] = heavy ? (pi / 2. + std::atan((em[m] - e_fermi) / (0.5 * emsig[m]))) / pi : 1.;      // init.f:896-901
+    sh[4] = pm_first[m] - pm_bin[m] / 2.;
+    sh[5] = pm_bin[m];
+    sh[6] = (double)n_pm[m];
+    sh[7] = (double)pos;
+    for (int k = 0; k < n_pm[m]; ++k) img[pos + k] = rho[src + k] / bs_norm[m];
+    pos += n_pm[m]; src += n_pm[m];
+  }
+  CU(h, cudaSetDevice(h->device));
+  if (h->d_theory) { cudaFree(h->d_theory); h->d_theory = nullptr; }
+  CU(h, cudaMalloc(&h->d_theory, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_theory, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  h->theory_nrho = n_shells; h->theory_efermi = e_fermi;
+  return SIMC_OK;
+}
+
+int simc_b200_load_theory_file(simc_handle* h, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  try {
+    const TheoryFile T = read_theory_file(path);
+    std::vector<int32_t> n(T.n_pm.begin(), T.n_pm.end());
+    return simc_b200_set_theory_table(h, T.n_shells, T.absorption, T.e_fermi, T.nprot.data(), T.em.data(), T.emsig.data(),
+                                      T.bs_norm.data(), n.data(), T.pm_first.data(), T.pm_bin.data(), T.rho.data());
+  } catch (const std::exception& e) {
+    return fail(h, SIMC_ERR_IO, e.what());
+  }
 }
 
 // dbase.f:563-587 from arrays: cumulative probability divided by its last entry
@@ -436,18 +487,21 @@ int weight_qexp(const simc_run_config& cfg) {
 int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
   const bool meson = (c.doing_hydpi && c.doing_pion) || (c.doing_hydkaon && c.doing_kaon);
-  const bool heavy = c.doing_heavy && c.doing_eep && c.use_benhar_sf;
+  const bool heavy = c.doing_heavy && c.doing_eep && !c.doing_deuterium;
+  const bool deut = c.doing_deuterium && c.doing_eep && !c.doing_heavy;
   const bool semi = c.doing_semi && c.doing_semipi && (c.doing_hydsemi || c.doing_deutsemi) && !c.doing_pion && !c.doing_kaon;
-  if (!(c.doing_hyd_elast || meson || heavy || semi) || c.doing_deuterium || c.doing_delta || c.doing_rho ||
-      (c.doing_semi && !semi) || c.doing_phsp)
+  if (!(c.doing_hyd_elast || meson || heavy || deut || semi) || c.doing_delta || c.doing_rho || (c.doing_semi && !semi) ||
+      c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
-                "this build of the event loop implements H(e,e'p), A(e,e'p) with a Benhar spectral function, "
-                "H(e,e'pi+-), H(e,e'K+) and semi-inclusive H/D(e,e'pi+-)X");
+                "this build of the event loop implements H(e,e'p), D(e,e'p), A(e,e'p) with a Benhar or an "
+                "independent-particle spectral function, H(e,e'pi+-), H(e,e'K+) and semi-inclusive H/D(e,e'pi+-)X");
+  if ((deut || (heavy && !c.use_benhar_sf)) && !h->d_theory)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: this reaction needs the theory table (simc_b200_set_theory_table / load_theory_file) first");
   if (semi && !h->d_pdf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive production needs the CTEQ5 table (simc_b200_set_cteq5_table) first");
   if (semi && c.doing_deutsemi && !h->d_pfm)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: D(e,e'pi)X needs the momentum distribution (simc_b200_set_pfermi_table) first");
-  if (heavy && !h->d_sf)
+  if (heavy && c.use_benhar_sf && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
   if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
     return fail(h, SIMC_ERR_ARG, "Delta final states (which_pion = 2, 3) are not implemented");
@@ -533,6 +587,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
   a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
+  a.theory_buf = h->d_theory; a.theory_nrho = h->theory_nrho; a.theory_efermi = h->theory_efermi;
   {
     const MatTable mt = make_mat_table(h->cfg.targ);          // host libm, once per call
     static_assert(sizeof(mt) == sizeof(a.mats), "MatTable layout");

@@ -345,7 +345,34 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.uqx = -eP * s.uex / s.v_q;
     s.uqy = -eP * s.uey / s.v_q;
     s.uqz = (s.v_Ein - eP * s.uez) / s.v_q;
-    if (!cfg.doing_semi) {                          // semi-inclusive: the hadron energy was thrown (event.f:289-297)
+    if (cfg.doing_deuterium) {                      // event.f:565-607: E_p from the two-body quadratic, |dEp'/dEm|
+      s.v_Em = targ.Mtar_struck + targ.Mrec - targ.M;
+      const double Mrec = targ.M - targ.Mtar_struck + s.v_Em;
+      const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
+      const double b = s.v_q * s.v_q;
+      const double c = s.v_nu + targ.M;
+      const double t = c * c - b + Mh2 - Mrec * Mrec;
+      const double QA = 4. * (a * a - c * c);
+      const double QB = 4. * c * t;
+      const double QC = -4. * (a * a) * Mh2 - t * t;
+      const double radical = QB * QB - 4. * QA * QC;
+      if (radical < 0) run = false;
+      if (run) {
+        s.v_pE = (-QB - sqrt(radical)) / 2. / QA;
+        if (s.v_pE <= Mh) run = false;
+      }
+      if (run) {
+        s.jacobian = fabs((t * (c - s.v_pE) + 2 * c * s.v_pE * (s.v_pE - c)) / (2 * (a * a - c * c) * s.v_pE + c * t));
+        s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
+        s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+        // event.f:880-886, 939-941
+        const double Pmx = s.v_pP * s.upx - s.v_q * s.uqx;
+        const double Pmy = s.v_pP * s.upy - s.v_q * s.uqy;
+        const double Pmz = s.v_pP * s.upz - s.v_q * s.uqz;
+        s.v_Pm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
+        s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
+      }
+    } else if (!cfg.doing_semi) {                   // semi-inclusive: the hadron energy was thrown (event.f:289-297)
       s.v_Pm = 0.0;                                 // pfer
       const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
       const double b = s.v_q * s.v_q;
@@ -364,7 +391,13 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
       }
     }
   }
-  if (run) {
+  if (run && cfg.doing_deuterium) {
+    // event.f:1013-1016: only the electron's (xptar, yptar) -> solid angle factor (doing_deuterium is not in
+    // the list of event.f:1019-1020)
+    const double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
+    s.jacobian = s.jacobian / (r * (r * r));
+  }
+  if (run && !cfg.doing_deuterium) {
     if (!cfg.doing_semi) {
       s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
       s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
@@ -406,7 +439,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
       }
     }
   }
-  if (run) {
+  if (run && !cfg.doing_deuterium) {
     // event.f:1013-1023: both arms' angles were generated
     double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
     s.jacobian = s.jacobian / (r * (r * r));
@@ -547,19 +580,34 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
     else if (x >= R.frac[0]) R.ntail = 2;
     else R.ntail = 1;
     const int ntail = R.ntail;
-    if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:289-294
-      emin = 0.;
-      emax = gen.sumEgen.max - s.v_eE;
+    const bool eep = cfg.doing_eep != 0;            // D(e,e'p): the measured-Em clauses of radc.f:369-374, 420-425
+    const double max_delta_Trec = fmax((s.v_Trec - cfg.VERTEXedge.Trec.min), (cfg.VERTEXedge.Trec.max - s.v_Trec));
+    if (cfg.doing_tail[0] && ntail == 1) {          // radc.f:280-294
+      if (cfg.doing_deuterium) {
+        emax = fmin(cfg.Egamma1_max, gen.sumEgen.max - s.v_eE);
+        emin = gen.sumEgen.min - s.v_eE;            // ntail != 0
+      } else {
+        emin = 0.;
+        emax = gen.sumEgen.max - s.v_eE;
+      }
       emax = fmin(emax, cfg.Egamma1_max);
       which = 1;
-    } else if (cfg.doing_tail[1] && ntail == 2) {   // radc.f:358-374 without the (e,e'p) clauses
+    } else if (cfg.doing_tail[1] && ntail == 2) {   // radc.f:358-374
       emin = s.v_eE - cfg.edge.e.E.max;
       emax = s.v_eE - cfg.edge.e.E.min;
+      if (eep) {
+        emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
+        emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);
+      }
       emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
       which = 2;
     } else if (R.rad_proton_this_ev && ntail == 3) {   // radc.f:409-425
       emin = s.v_pE - cfg.edge.p.E.max;
       emax = s.v_pE - cfg.edge.p.E.min;
+      if (eep) {
+        emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
+        emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
+      }
       emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
       which = 3;
     }

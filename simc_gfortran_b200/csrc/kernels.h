@@ -43,6 +43,9 @@ struct LoopLaunch {
   const double* pdf_buf;      // CTEQ5 table (device): [xv(nx+1) | ql(nt+1) | upd]; null unless set
   int pdf_nx, pdf_nt, pdf_nfmx;
   double pdf_al;
+  const double* theory_buf;   // independent-particle spectral function (device), physics_heavy.cuh: TheoryDev
+  int theory_nrho;
+  double theory_efermi;
   const double* pfm_buf;      // momentum distribution (device): [pval(n) | mprob(n)]; null unless set
   int pfm_n;
 };

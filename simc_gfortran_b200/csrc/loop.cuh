@@ -74,6 +74,7 @@ struct LoopArgs {
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   Cteq5Dev pdf;                    // CTEQ5 parton distributions (semi-inclusive production only)
   PfermiDev pfm;                   // nucleon momentum distribution (deuterium semi-inclusive production only)
+  TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
   unsigned* lists;                 // [11][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same
   unsigned* counts;                // [0] slots handed out, [1..11] lengths of lists 0..10
@@ -174,8 +175,9 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool semi = cfg.doing_semi != 0;
-    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi;
+    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
     const bool heavy = cfg.doing_heavy != 0;
+    s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
     if (meson) ok = generate_meson(cfg, mt_s, A.pfm, rng, GaussFn(), s, active);
     else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);
@@ -566,7 +568,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const bool semi = cfg.doing_semi != 0;
       const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi;
-      const bool heavy = cfg.doing_heavy != 0;
+      const bool deut = cfg.doing_deuterium != 0;
+      const bool heavy = cfg.doing_heavy != 0 || deut;          // (e,e'p) from a nucleus: deForest, A-1 recoil
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
       // complete_main, event.f:1363-1569
       const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
@@ -574,7 +577,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       if (heavy) {
         rEm = nu + cfg.targ.Mtar_struck - rpE - rTrec;
         bool bad = false;
-        SF_weight = cfg.targ.Z * cfg.transparency * sf_lookup_diff(A.sf, S.ld(F_VEM, slot), S.ld(F_VPM, slot), bad);
+        if (cfg.use_benhar_sf && !deut)
+          SF_weight = cfg.targ.Z * cfg.transparency * sf_lookup_diff(A.sf, S.ld(F_VEM, slot), S.ld(F_VPM, slot), bad);
+        else                                           // event.f:1402-1428
+          SF_weight = theory_sf_weight(A.theory, !deut, S.ld(F_VEM, slot), S.ld(F_VPM, slot));
         low_w = bad;                                   // counted in `unsupported`: the reference would `stop`
         HeavyEv ev;
         ev.Q2 = v_Q2; ev.q = S.ld(F_VQ, slot); ev.nu = S.ld(F_VNU, slot); ev.Pm = S.ld(F_VPM, slot);
@@ -768,7 +774,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
         const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
         const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
-        const double sumEgen = (meson && !semi) ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
+        const double sumEgen = ((meson && !semi) || deut) ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
         const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), sumEgen,
                                o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
                                spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};

@@ -14,6 +14,44 @@ struct SfDev {                // device pointers; val[iPm * n_em + iEm]
   int n_pm, n_em;
 };
 
+// Independent-particle spectral function of COMMON /theory/ (simulate.inc:116-131) after theory_init
+// (init.f:828-905).  buf: 8 doubles per shell { nprot*absorption, Em, Emsig, Em_int, Pm min, Pm bin, n, offset of
+// rho in buf }, then the distributions rho_i(Pm) / bs_norm_i.
+struct TheoryDev {
+  const double* buf;
+  int nrho;
+  double e_fermi;
+};
+// event.f:1402-1428: linear interpolation of rho_i(Pm); Lorentzian in Em above E_Fermi for A > 2
+SIMC_HD_CALL double theory_sf_weight(const TheoryDev& T, bool heavy, double Em, double Pm) {
+  const double pi = 3.141592653589793;
+  double SF_weight = 0.0;
+  for (int i = 0; i < T.nrho; ++i) {
+    const double* sh = T.buf + 8 * i;
+    const int n = (int)sh[6];
+    double weight = 0.0;
+    const double r = (Pm - sh[4]) / sh[5];
+    if (r >= 0 && r <= n) {
+      int iPm1 = (int)round(r);                 // nint: half away from zero
+      if (iPm1 == 0) iPm1 = 1;
+      if (iPm1 == n) iPm1 = n - 1;
+      const double frac = r + 0.5 - (double)iPm1;
+      const double* rho = T.buf + (long long)sh[7];
+      const double b = rho[iPm1 - 1];
+      const double a = rho[iPm1] - b;
+      weight = a * frac + b;
+    }
+    if (heavy) {
+      const double width = sh[2] / 2.0;
+      if (Em < T.e_fermi) weight = 0.0;
+      const double dE = Em - sh[1];
+      weight = weight / pi / sh[3] * width / (dE * dE + width * width);
+    }
+    SF_weight = SF_weight + weight * sh[0];
+  }
+  return SF_weight;
+}
+
 // sf_lookup.f:97-170 (1-based indices of the Fortran kept in the helpers)
 SIMC_HD_CALL double sf_lookup(const SfDev& T, double Em, double Pm, bool& bad) {
   const int numPm = T.n_pm, numEm = T.n_em;

@@ -18,6 +18,7 @@
 #include <string>
 #include "../../include/simc_b200.h"
 #include "event.cuh"
+#include "tables_host.h"
 
 namespace simc {
 namespace {
@@ -184,8 +185,8 @@ void set_axis(simc_axis& a, double mn, double bin) { a.min = mn; a.bin = bin; }
 
 }  // namespace
 
-void config_from_deck(const std::string& path, const std::string& extra_dir, simc_run_config& c, int* ngen,
-                      double* charge_mC) {
+void config_from_deck(const std::string& path, const std::string& extra_dir, const std::string& data_dir,
+                      simc_run_config& c, int* ngen, double* charge_mC) {
   Deck D;
   D.load(path);
   const std::string extra = D.s("extra_dbase_file");
@@ -391,8 +392,22 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     targ.Coulomb_min = targ.Coulomb_constant;
     targ.Coulomb_max = targ.Coulomb_constant;
   }
-  if (c.doing_deuterium || (c.doing_heavy && !c.use_benhar_sf))
-    throw std::runtime_error("theory_init (momentum-distribution files) is not implemented in this build");
+  // theory_init (init.f:828-905): the deck setup needs the Pm range of the distributions and E_Fermi
+  double theory_pm_max = 0.0, E_Fermi = 0.0;
+  if (c.doing_deuterium || (c.doing_heavy && !c.use_benhar_sf)) {
+    if (data_dir.empty())
+      throw std::runtime_error(std::string("this deck needs ") + theory_file_for(nA) +
+                               ": use simc_b200_config_from_deck_data with the directory that holds it");
+    const TheoryFile T = read_theory_file(data_dir + "/" + theory_file_for(nA));
+    E_Fermi = T.e_fermi;
+    const bool deut = T.n_shells == 1 && T.e_fermi < 1.0;              // init.f:889
+    if (deut != (c.doing_deuterium != 0))
+      throw std::runtime_error("theory file and target disagree on doing_deuterium (init.f:889)");
+    for (int i = 0; i < (c.doing_deuterium ? 1 : T.n_shells); ++i) {
+      const double mn = T.pm_first[i] - T.pm_bin[i] / 2., mx = T.pm_last[i] + T.pm_bin[i] / 2.;
+      theory_pm_max = std::max(theory_pm_max, std::max(std::fabs(mn), std::fabs(mx)));
+    }
+  }
 
   // ---- limits_init, init.f:91-572
   auto slop_for = [](int arm, double* used) {
@@ -463,9 +478,16 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
-  } else if (c.doing_heavy && c.use_benhar_sf) {      // init.f:331-343,379-386
-    VE.Pm.min = 0.0; VE.Pm.max = 790.0;
-    VE.Em.min = 0.0;                                  // E_Fermi: only theory_init sets it (init.f:856)
+  } else if (c.doing_deuterium) {                     // init.f:326-330,379-386
+    VE.Em.min = Mp + Mn - targ.M; VE.Em.max = Mp + Mn - targ.M;
+    VE.Pm.min = 0.0; VE.Pm.max = theory_pm_max;
+    VE.Mrec.min = targ.M - targ.Mtar_struck + VE.Em.min;
+    VE.Mrec.max = targ.M - targ.Mtar_struck + VE.Em.max;
+    VE.Trec.min = std::sqrt(VE.Mrec.max * VE.Mrec.max + VE.Pm.min * VE.Pm.min) - VE.Mrec.max;
+    VE.Trec.max = std::sqrt(VE.Mrec.min * VE.Mrec.min + VE.Pm.max * VE.Pm.max) - VE.Mrec.min;
+  } else if (c.doing_heavy) {                         // init.f:331-343,379-386
+    VE.Pm.min = 0.0; VE.Pm.max = c.use_benhar_sf ? 790.0 : theory_pm_max;
+    VE.Em.min = E_Fermi;                              // only theory_init sets it (init.f:856): 0 with use_benhar_sf
     VE.Em.max = 1000.;
     VE.Mrec.min = targ.M - targ.Mtar_struck + VE.Em.min;
     VE.Mrec.max = targ.M - targ.Mtar_struck + VE.Em.max;
@@ -521,7 +543,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   if (c.doing_hyd_elast) {
     gen.e.E.min = edge.e.E.min;
     gen.e.E.max = edge.e.E.max + c.Egamma2_max;
-  } else if (c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
+  } else if (c.doing_deuterium || c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
     gen.e.E.min = gen.sumEgen.min;
     gen.e.E.max = gen.sumEgen.max;
   } else {
@@ -534,7 +556,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
   gen.e.delta.max = (gen.e.E.max / c.spec_e.P - 1.) * 100.;
   gen.e.yptar = edge.e.yptar;
   gen.e.xptar = edge.e.xptar;
-  if (c.doing_hyd_elast || c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
+  if (c.doing_hyd_elast || c.doing_deuterium || c.doing_pion || c.doing_kaon || c.doing_rho || c.doing_delta) {
     gen.p.E.min = edge.p.E.min;
     gen.p.E.max = edge.p.E.max + c.Egamma3_max;
   } else {
@@ -575,6 +597,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
     // semi-inclusive cross sections are a few nb/GeV/sr^2 = 1e-9 ub/MeV/sr^2; the weight needs the parton
     // tables, which a deck does not carry, so the scale is nominal
     c.w_ref = 1.0e-9;
+  } else if (c.doing_deuterium) {
+    c.w_ref = 1.0e-5;          // sigma_cc1 (~1e2 ub/sr) x rho(Pm ~ 100 MeV/c) (~1e-7 MeV^-3): nominal
   } else if (c.doing_hyd_elast) {
     const double Ein = c.Ebeam_vertex_ave, uez = std::cos(c.spec_e.theta);
     const double eE = Ein * c.Mh / (c.Mh + Ein * (1. - uez));
@@ -625,11 +649,17 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, sim
 
 extern "C" int simc_b200_config_from_deck(const char* deck_path, const char* extra_deck_dir, simc_run_config* out,
                                           int32_t* ngen, double* charge_mC, char* err, int errlen) {
+  return simc_b200_config_from_deck_data(deck_path, extra_deck_dir, nullptr, out, ngen, charge_mC, err, errlen);
+}
+
+extern "C" int simc_b200_config_from_deck_data(const char* deck_path, const char* extra_deck_dir, const char* data_dir,
+                                               simc_run_config* out, int32_t* ngen, double* charge_mC, char* err,
+                                               int errlen) {
   if (!deck_path || !out) return SIMC_ERR_ARG;
   try {
     int ng = 0;
     double q = 0;
-    simc::config_from_deck(deck_path, extra_deck_dir ? extra_deck_dir : "", *out, &ng, &q);
+    simc::config_from_deck(deck_path, extra_deck_dir ? extra_deck_dir : "", data_dir ? data_dir : "", *out, &ng, &q);
     if (ngen) *ngen = ng;
     if (charge_mC) *charge_mC = q;
     return SIMC_OK;

@@ -189,6 +189,10 @@ def load_library():
             getattr(L, name).argtypes = args
     L.simc_b200_config_from_deck.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p,
                                              C.c_int]
+    L.simc_b200_config_from_deck_data.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_char_p, C.c_int]
+    L.simc_b200_set_theory_table.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 8
+    L.simc_b200_load_theory_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -211,15 +215,17 @@ def load_library():
     return L
 
 
-def config_from_deck(deck_path: str, extra_deck_dir: str | None = None):
-    """(RunConfig, ngen, charge_mC) from a CTP deck; host only, no GPU needed."""
+def config_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir: str | None = None):
+    """(RunConfig, ngen, charge_mC) from a CTP deck; host only, no GPU needed.  data_dir: where the reference's
+    working-directory data files live (h2.theory, c12.theory, ... for D(e,e'p) / A(e,e'p) without use_benhar_sf)."""
     L = load_library()
     cfg = RunConfig()
     ngen = C.c_int32()
     charge = C.c_double()
     err = C.create_string_buffer(512)
-    rc = L.simc_b200_config_from_deck(deck_path.encode(), (extra_deck_dir or os.path.dirname(deck_path)).encode(),
-                                      C.byref(cfg), C.byref(ngen), C.byref(charge), err, 512)
+    rc = L.simc_b200_config_from_deck_data(deck_path.encode(), (extra_deck_dir or os.path.dirname(deck_path)).encode(),
+                                           data_dir.encode() if data_dir else None,
+                                           C.byref(cfg), C.byref(ngen), C.byref(charge), err, 512)
     if rc != 0:
         raise SimcError(rc, err.value.decode())
     return cfg, ngen.value, charge.value
@@ -294,6 +300,20 @@ class Simc:
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
+
+    # ---- independent-particle spectral function (h2.theory, c12.theory, ...): D(e,e'p), A(e,e'p) without Benhar
+    def set_theory_table(self, t):
+        """t: dict with n_shells, absorption, e_fermi, nprot, em, emsig, bs_norm, n_pm, pm_first, pm_bin, rho."""
+        a = {k: np.ascontiguousarray(t[k], dtype=np.float64) for k in ("nprot", "em", "emsig", "bs_norm", "pm_first",
+                                                                       "pm_bin", "rho")}
+        n_pm = np.ascontiguousarray(t["n_pm"], dtype=np.int32)
+        self._check(self.L.simc_b200_set_theory_table(self.h, int(t["n_shells"]), float(t["absorption"]),
+                                                      float(t["e_fermi"]), _ptr(a["nprot"]), _ptr(a["em"]),
+                                                      _ptr(a["emsig"]), _ptr(a["bs_norm"]), _ptr(n_pm),
+                                                      _ptr(a["pm_first"]), _ptr(a["pm_bin"]), _ptr(a["rho"])))
+
+    def load_theory_file(self, path: str):
+        self._check(self.L.simc_b200_load_theory_file(self.h, path.encode()))
 
     # ---- semi-inclusive production: momentum distribution (deut.dat) and CTEQ5 parton distributions
     def set_pfermi_table(self, pval, mprob):

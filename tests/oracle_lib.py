@@ -229,3 +229,43 @@ Oracle.set_cteq5_table = _oracle_set_cteq5_table
 Oracle.ctq5pdf_batch = _oracle_ctq5pdf_batch
 Oracle.christy_batch = _oracle_christy_batch
 Oracle.semi_batch = _oracle_semi_batch
+
+
+# ---- independent-particle spectral function (theory files) -------------------------------------------
+def load_theory_fixture(name):
+    """tests/golden/theory_h2.npz / theory_c12.npz (tools/make_fixtures.py: the reference's *.theory files)."""
+    z = np.load(os.path.join(GOLDEN, f"theory_{name}.npz"))
+    return {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
+
+
+def write_theory_file(t, path):
+    """Writes a theory table in the reference's text format (read back by theory_init-style readers)."""
+    with open(path, "w") as f:
+        f.write(f"{int(t['n_shells'])}\t{float(t['absorption'])!r}\t{float(t['e_fermi'])!r}\n")
+        for m in range(int(t["n_shells"])):
+            f.write(f"{float(t['nprot'][m])!r}\t{float(t['em'][m])!r}\t{float(t['emsig'][m])!r}\t{float(t['bs_norm'][m])!r}\n")
+        pos = 0
+        for m in range(int(t["n_shells"])):
+            for k in range(int(t["n_pm"][m])):
+                f.write(f"  {float(t['pm_first'][m] + k * t['pm_bin'][m])!r}  {float(t['rho'][pos + k])!r}\n")
+            pos += int(t["n_pm"][m])
+
+
+def _oracle_set_theory_table(self, t, doing_heavy):
+    a = {k: np.ascontiguousarray(t[k], np.float64) for k in ("nprot", "em", "emsig", "bs_norm", "pm_first", "pm_bin", "rho")}
+    n_pm = np.ascontiguousarray(t["n_pm"], np.int32)
+    self._check(self.L.oracle_set_theory_table(int(bool(doing_heavy)), int(t["n_shells"]), C.c_double(t["absorption"]),
+                                               C.c_double(t["e_fermi"]), _p(a["nprot"]), _p(a["em"]), _p(a["emsig"]),
+                                               _p(a["bs_norm"]), _p(n_pm), _p(a["pm_first"]), _p(a["pm_bin"]), _p(a["rho"])))
+
+
+def _oracle_theory_batch(self, cfg, em, pm):
+    em = np.ascontiguousarray(em, np.float64)
+    pm = np.ascontiguousarray(pm, np.float64)
+    out = np.zeros(len(em))
+    self._check(self.L.oracle_theory_batch(C.byref(cfg), C.c_int64(len(em)), _p(em), _p(pm), _p(out)))
+    return out
+
+
+Oracle.set_theory_table = _oracle_set_theory_table
+Oracle.theory_batch = _oracle_theory_batch

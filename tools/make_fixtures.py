@@ -110,7 +110,30 @@ def make_semi():
     print("deut.dat", a.shape, a[-1])
 
 
+def read_theory(path):
+    """theory_init's file format (init.f:853-868): header, shell lines, then (Pm, rho) rows; a shell ends where
+    Pm stops increasing."""
+    toks = open(path).read().split()
+    n_shells, absorption, e_fermi = int(toks[0]), float(toks[1]), float(toks[2])
+    sh = np.array([float(x) for x in toks[3:3 + 4 * n_shells]]).reshape(n_shells, 4)
+    rows = np.array([float(x) for x in toks[3 + 4 * n_shells:]]).reshape(-1, 2)
+    cuts = [0] + [i for i in range(1, len(rows)) if rows[i, 0] <= rows[i - 1, 0]] + [len(rows)]
+    assert len(cuts) == n_shells + 1, (len(cuts), n_shells)
+    return dict(n_shells=n_shells, absorption=absorption, e_fermi=e_fermi, nprot=sh[:, 0], em=sh[:, 1], emsig=sh[:, 2],
+                bs_norm=sh[:, 3], n_pm=np.diff(cuts).astype(np.int32), pm_first=rows[cuts[:-1], 0],
+                pm_bin=rows[np.array(cuts[:-1]) + 1, 0] - rows[cuts[:-1], 0], rho=rows[:, 1])
+
+
+def make_theory():
+    """h2.theory and c12.theory (theory_init, init.f:838-851) -> tests/golden/theory_h2.npz, theory_c12.npz"""
+    for name in ("h2", "c12"):
+        t = read_theory(os.path.join(REF, name + ".theory"))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"theory_{name}.npz"), **t)
+        print(name, t["n_shells"], t["n_pm"], t["pm_first"], t["pm_bin"], t["e_fermi"])
+
+
 if __name__ == "__main__":
     make_sf()
     make_semi()
+    make_theory()
     main()
