@@ -202,7 +202,7 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[34] = s.ntup.mm / 1000.; ntu[35] = s.ntup.mmA / 1000.; ntu[36] = recon.p.P / 1000.; ntu[37] = s.ntup.t / 1.e6;
     ntu[38] = recon.PmPar / 1000.; ntu[39] = recon.PmPer / 1000.; ntu[40] = recon.PmOop / 1000.;
     ntu[41] = -main.target.rastery; ntu[42] = s.ntup.radphot / 1000.;
-    const double pfer = 0.0, pferx = 0.0, pfery = 0.0, pferz = 0.0;     // hydrogen, event.f:330-335
+    const double pfer = s.pfer, pferx = s.pferx, pfery = s.pfery, pferz = s.pferz;     // zero for hydrogen, event.f:330-335
     double dummy = pferx * vertex.uq.x + pfery * vertex.uq.y + pferz * vertex.uq.z;
     if (dummy == 0) dummy = 1.e-20;
     ntu[43] = pfer / 1000. * std::fabs(dummy) / dummy;

@@ -194,9 +194,10 @@ double sig_factorized(double q2, double w, double t, double pk, double mrec) {
   return fact_q * fact_t * fact_w;
 }
 
-Fermi hydrogen_fermi(const simc_run_config& cfg) {
+// COMMON /pfermi_stuff/ as generate left it (event.f:327-373): at rest for hydrogen (efer = Mtar_struck)
+Fermi fermi_of(const Sim& s) {
   Fermi F;
-  F.efer = cfg.targ.Mtar_struck;          // event.f:335
+  F.pfer = s.pfer; F.pferx = s.pferx; F.pfery = s.pfery; F.pferz = s.pferz; F.efer = s.efer;
   return F;
 }
 }  // namespace
@@ -205,7 +206,7 @@ Fermi hydrogen_fermi(const simc_run_config& cfg) {
 double peepi(Sim& s, const Event& vertex, EventMain& main) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
-  const Fermi F = hydrogen_fermi(cfg);
+  const Fermi F = fermi_of(s);
   CmFrame C;
   transform_to_cm(vertex, main, F, C);
   main.thetacm = C.thetacm;
@@ -233,7 +234,7 @@ double peepi(Sim& s, const Event& vertex, EventMain& main) {
 double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
-  const Fermi F = hydrogen_fermi(cfg);
+  const Fermi F = fermi_of(s);
   CmFrame C;
   transform_to_cm(vertex, main, F, C);
   double jacobian = C.jacobian / (2. * C.phadcm * C.qstar);

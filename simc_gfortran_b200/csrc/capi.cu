@@ -290,18 +290,13 @@ int simc_b200_set_pfermi_table(simc_handle* h, int n, const double* pval, const 
 // (Fortran `d` exponents), at most 2000 rows (dbase.f:581-584)
 int simc_b200_load_pfermi_file(simc_handle* h, const char* path) {
   if (!h || !path) return SIMC_ERR_ARG;
-  FILE* f = std::fopen(path, "r");
-  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open momentum distribution file ") + path);
-  std::vector<double> pval, mprob;
-  char line[512];
-  while (pval.size() < 2000 && std::fgets(line, sizeof line, f)) {
-    for (char* c = line; *c; ++c) if (*c == 'd' || *c == 'D') *c = 'e';
-    double p, q;
-    if (std::sscanf(line, "%lf %lf", &p, &q) == 2) { pval.push_back(p); mprob.push_back(q); }
+  try {
+    std::vector<double> pval, mprob;
+    read_pfermi_file(path, pval, mprob);
+    return simc_b200_set_pfermi_table(h, (int)pval.size(), pval.data(), mprob.data());
+  } catch (const std::exception& e) {
+    return fail(h, SIMC_ERR_IO, e.what());
   }
-  std::fclose(f);
-  if (pval.size() < 2) return fail(h, SIMC_ERR_IO, "momentum distribution file: fewer than two rows");
-  return simc_b200_set_pfermi_table(h, (int)pval.size(), pval.data(), mprob.data());
 }
 
 // ReadTbl (cteq5/Ctq5Pdf.f:239-281) from arrays
@@ -486,7 +481,7 @@ int weight_qexp(const simc_run_config& cfg) {
 // Which settings this build of the loop implements; everything else is refused loudly.
 int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
-  const bool meson = (c.doing_hydpi && c.doing_pion) || (c.doing_hydkaon && c.doing_kaon);
+  const bool meson = ((c.doing_hydpi || c.doing_deutpi) && c.doing_pion) || ((c.doing_hydkaon || c.doing_deutkaon) && c.doing_kaon);
   const bool heavy = c.doing_heavy && c.doing_eep && !c.doing_deuterium;
   const bool deut = c.doing_deuterium && c.doing_eep && !c.doing_heavy;
   const bool semi = c.doing_semi && c.doing_semipi && (c.doing_hydsemi || c.doing_deutsemi) && !c.doing_pion && !c.doing_kaon;
@@ -499,8 +494,8 @@ int validate_loop_config(simc_handle* h) {
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: this reaction needs the theory table (simc_b200_set_theory_table / load_theory_file) first");
   if (semi && !h->d_pdf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive production needs the CTEQ5 table (simc_b200_set_cteq5_table) first");
-  if (semi && c.doing_deutsemi && !h->d_pfm)
-    return fail(h, SIMC_ERR_STATE, "simc_b200_run: D(e,e'pi)X needs the momentum distribution (simc_b200_set_pfermi_table) first");
+  if (((semi && c.doing_deutsemi) || c.doing_deutpi || c.doing_deutkaon) && !h->d_pfm)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: production from deuterium needs the momentum distribution (simc_b200_set_pfermi_table) first");
   if (heavy && c.use_benhar_sf && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
   if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))

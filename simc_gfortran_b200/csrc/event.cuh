@@ -373,10 +373,15 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
         s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
       }
     } else if (!cfg.doing_semi) {                   // semi-inclusive: the hadron energy was thrown (event.f:289-297)
-      s.v_Pm = 0.0;                                 // pfer
-      const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
-      const double b = s.v_q * s.v_q;
-      const double c = s.v_nu + targ.M;
+      s.v_Pm = s.pfer;                              // event.f:633 (zero for hydrogen)
+      double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
+      double b = s.v_q * s.v_q;
+      double c = s.v_nu + targ.M;
+      if (cfg.doing_deutpi || cfg.doing_deutkaon) {   // event.f:646-654: Fermi motion and binding
+        a = a - fabs(s.pfer) * (s.pferx * s.upx + s.pfery * s.upy + s.pferz * s.upz);
+        b = b + s.pfer * s.pfer + 2 * s.v_q * fabs(s.pfer) * (s.pferx * s.uqx + s.pfery * s.uqy + s.pferz * s.uqz);
+        c = s.v_nu + s.efer;
+      }
       const double t = c * c - b + Mh2 - targ.Mrec_struck * targ.Mrec_struck;
       const double QA = 4. * (a * a - c * c);
       const double QB = 4. * c * t;
@@ -421,6 +426,10 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.m_phipq = m::atan2(p_new_y, p_new_x);
     if (s.m_phipq < 0.e0) s.m_phipq = s.m_phipq + 2. * SIMC_PI_D;
     s.v_Trec = 0.0;
+    if (cfg.doing_deutpi || cfg.doing_deutkaon) {   // event.f:945-947: recoil of the spectator nucleon
+      const double Mrec = targ.M - targ.Mtar_struck + s.v_Em;
+      s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
+    }
     if (cfg.doing_semi) {     // event.f:880-886, 952-955, 979-996: Pm, Em of the undetected system; z and pt^2
       const double Pmx = s.v_pP * s.upx - s.v_q * s.uqx;
       const double Pmy = s.v_pP * s.upy - s.v_q * s.uqy;
@@ -535,7 +544,7 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
       // event.f:327-373: nucleon momentum in the deuteron (thrown whether or not do_fermi uses it)
       s.pfer = 0.0; s.pferx = 0.0; s.pfery = 0.0; s.pferz = 0.0;
       s.efer = targ.Mtar_struck;
-      if (cfg.doing_deutsemi) {
+      if (cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon) {
         const double ranprob = rng.uniform();
         const int nump = pfm.nump;
         // first ii (1-based) with ranprob <= mprob(ii), capped at nump: the reference's linear scan

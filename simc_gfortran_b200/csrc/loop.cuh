@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool semi = cfg.doing_semi != 0;
-    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+    const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon;        // nucleon momentum thrown
+    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_deutpi || cfg.doing_deutkaon || semi ||
+                       cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+    s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     const bool heavy = cfg.doing_heavy != 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
     if (meson) ok = generate_meson(cfg, mt_s, A.pfm, rng, GaussFn(), s, active);
@@ -220,10 +223,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
         S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
         S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
         S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
-        if (semi) {
-          S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); S.st(F_PFER, slot, s.pfer);
-          S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery); S.st(F_PFERZ, slot, s.pferz);
-          S.st(F_EFER, slot, s.efer);
+        if (semi) { S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); }
+        if (semi || fermi) {
+          S.st(F_PFER, slot, s.pfer); S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery);
+          S.st(F_PFERZ, slot, s.pferz); S.st(F_EFER, slot, s.efer);
         }
       }
     }
@@ -567,13 +570,19 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const bool semi = cfg.doing_semi != 0;
-      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || semi;
+      const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon;
+      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_deutpi || cfg.doing_deutkaon || semi;
       const bool deut = cfg.doing_deuterium != 0;
       const bool heavy = cfg.doing_heavy != 0 || deut;          // (e,e'p) from a nucleus: deForest, A-1 recoil
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
       // complete_main, event.f:1363-1569
       const double v_Ein = S.ld(F_VEIN, slot), v_eE = S.ld(F_VEE, slot), v_eth = S.ld(F_VETHETA, slot), v_Q2 = S.ld(F_VQ2, slot);
       double sigcc_recon, tgtweight = 1.0, survivalprob = 1.0, SF_weight = 1.0;
+      double mv_pfer[4] = {0.0, 0.0, 0.0, 0.0};           // pfer, pferx, pfery, pferz of this event
+      if (fermi) {
+        mv_pfer[0] = S.ld(F_PFER, slot); mv_pfer[1] = S.ld(F_PFERX, slot); mv_pfer[2] = S.ld(F_PFERY, slot);
+        mv_pfer[3] = S.ld(F_PFERZ, slot);
+      }
       if (heavy) {
         rEm = nu + cfg.targ.Mtar_struck - rpE - rTrec;
         bool bad = false;
@@ -609,6 +618,11 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         mv.uqx = S.ld(F_UQX, slot); mv.uqy = S.ld(F_UQY, slot); mv.uqz = S.ld(F_UQZ, slot);
         mv.upx = S.ld(F_UPX, slot); mv.upy = S.ld(F_UPY, slot); mv.upz = S.ld(F_UPZ, slot);
         mv.phi_pq = S.ld(F_MPHIPQ, slot); mv.t = S.ld(F_MT, slot); mv.epsilon = S.ld(F_MEPS, slot);
+        mv.pfer = 0.0; mv.pferx = 0.0; mv.pfery = 0.0; mv.pferz = 0.0; mv.efer = cfg.targ.Mtar_struck;
+        if (fermi) {
+          mv.pfer = S.ld(F_PFER, slot); mv.pferx = S.ld(F_PFERX, slot); mv.pfery = S.ld(F_PFERY, slot);
+          mv.pferz = S.ld(F_PFERZ, slot); mv.efer = S.ld(F_EFER, slot);
+        }
         MesonWeight mw;
         if (semi) {
           // peepiX reads vertex%theta_pq, which nothing assigns (complete_ev fills main%theta_pq): zero,
@@ -617,8 +631,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           sv_.Ein = v_Ein; sv_.eE = v_eE; sv_.nu = mv.nu; sv_.Q2 = v_Q2; sv_.q = mv.q;
           sv_.uqx = mv.uqx; sv_.uqy = mv.uqy; sv_.uqz = mv.uqz;
           sv_.pt2 = S.ld(F_PT2, slot); sv_.zhad = S.ld(F_ZHAD, slot); sv_.theta_pq = 0.0;
-          sv_.pfer = S.ld(F_PFER, slot); sv_.pferx = S.ld(F_PFERX, slot); sv_.pfery = S.ld(F_PFERY, slot);
-          sv_.pferz = S.ld(F_PFERZ, slot); sv_.efer = S.ld(F_EFER, slot);
+          sv_.pfer = mv.pfer; sv_.pferx = mv.pferx; sv_.pfery = mv.pfery; sv_.pferz = mv.pferz; sv_.efer = mv.efer;
           const SemiWeight w_ = peepiX(cfg, A.pdf, sv_, nullptr);
           mw.sigcc = w_.sigcc; mw.sigcm = w_.sighad; mw.davejac = w_.davejac; mw.low_w = w_.bad;
           mw.thetacm = 0.0; mw.phicm = 0.0; mw.wcm = 0.0;
@@ -734,11 +747,13 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           ntu[37] = (Q2 - cfg.Mh2 + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
           ntu[38] = PmPar / 1000.; ntu[39] = PmPer / 1000.; ntu[40] = PmOop / 1000.;
           ntu[41] = -S.ld(F_RASTERY, slot); ntu[42] = radphot / 1000.;
-          ntu[43] = 0.0 / 1000. * fabs(1.e-20) / 1.e-20;
+          double pdot = mv_pfer[1] * S.ld(F_UQX, slot) + mv_pfer[2] * S.ld(F_UQY, slot) + mv_pfer[3] * S.ld(F_UQZ, slot);
+          if (pdot == 0) pdot = 1.e-20;
+          ntu[43] = mv_pfer[0] / 1000. * fabs(pdot) / pdot;
           ntu[44] = sigcc; ntu[45] = S.ld(F_SIGCM, slot); ntu[46] = wfinal;
           ntu[47] = (cfg.doing_kaon && !cfg.doing_decay) ? survivalprob : S.ld(F_DECDIST, slot);
           ntu[48] = sqrt(S.ld(F_MH2FINAL, slot));
-          ntu[49] = 0.0 / 1000. * 1.e-20;
+          ntu[49] = mv_pfer[0] / 1000. * pdot;
           ntu[50] = v_Q2 / 1.e6; ntu[51] = S.ld(F_MW, slot) / 1.e3; ntu[52] = S.ld(F_MT, slot) / 1.e6; ntu[53] = S.ld(F_MPHIPQ, slot);
           if (cfg.doing_kaon) { ntu[54] = 0.0; ntu[55] = S.ld(F_SIGCM, slot); }
         } else {

@@ -1,8 +1,8 @@
 // Meson electroproduction weights on the device (and on the host for the central weight):
 // transform_to_cm (jacobians.f:1-282), peepi with sig_param_2021/exclfit (physics_pion.f:1-130,
-// 738-854), peeK with sig_factorized (physics_kaon.f:1-236).  Hydrogen targets: the struck
-// nucleon is at rest (pfer = 0, efer = Mtar_struck, event.f:330-335); the Fermi-momentum terms of
-// the reference formulas multiply that zero and are kept where they decide the rounding.
+// 738-854), peeK with sig_factorized (physics_kaon.f:1-236).  The struck nucleon's momentum and energy
+// (pfer, efer) come with the vertex: at rest for hydrogen (pfer = 0, efer = Mtar_struck, event.f:330-335),
+// thrown from the deuteron's momentum distribution for D(e,e'pi/K) (event.f:337-367).
 //
 // Not built: the MAID-2007 table branch of peepi below W = 2 GeV (physics_pion.f:88-107) -- such
 // events are counted in simc_accum.unsupported and take the parametrisation alone; the Saghai
@@ -16,6 +16,8 @@ struct MesonVertex {          // what the weights read from `vertex` / `main`
   double Ein, eE, nu, q, Q2, pP, pE;
   double uqx, uqy, uqz, upx, upy, upz;
   double phi_pq, t, epsilon;
+  // COMMON /pfermi_stuff/ (simulate.inc:212-217) as generate left it: zero and Mtar_struck for hydrogen
+  double pfer, pferx, pfery, pferz, efer;
 };
 struct MesonCm {
   double thetacm, phicm, pcm, qstar, jacobian, jac_old, wcm, sgev;
@@ -37,11 +39,11 @@ SIMC_HD MV4 loren(double gam, double bx, double by, double bz, double e, double 
 SIMC_HD double msq(double x) { return x * x; }
 }  // namespace mesondetail
 
-// jacobians.f:1-282 for a nucleon at rest
-SIMC_HD_CALL void transform_to_cm(const MesonVertex& v, double efer, MesonCm& C) {
+// jacobians.f:1-282
+SIMC_HD_CALL void transform_to_cm(const MesonVertex& v, MesonCm& C) {
   using namespace mesondetail;
   const double pi = 3.141592653589793;
-  const double pfer = 0.0, pferx = 0.0, pfery = 0.0, pferz = 0.0;
+  const double pfer = v.pfer, pferx = v.pferx, pfery = v.pfery, pferz = v.pferz, efer = v.efer;
   double tcos = v.upx * v.uqx + v.upy * v.uqy + v.upz * v.uqz;
   if (tcos - 1. > 0. && tcos - 1. < 1.e-8) tcos = 1.0;
   const double tsin = sqrt(1. - tcos * tcos);
@@ -205,9 +207,9 @@ struct MesonWeight {
 // physics_pion.f:1-130
 SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MesonVertex& v) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
-  const double Mtar = cfg.targ.Mtar_struck, efer = Mtar, pfer = 0.0, pferz = 0.0;
+  const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
   MesonCm C;
-  transform_to_cm(v, efer, C);
+  transform_to_cm(v, C);
   MesonWeight w;
   w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = C.jacobian; w.johnjac = C.jac_old; w.wcm = C.wcm;
   const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;
@@ -223,9 +225,9 @@ SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MesonVertex& v)
 // physics_kaon.f:1-171 (without the survival probability, which needs the focal-plane track)
 SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
-  const double Mtar = cfg.targ.Mtar_struck, efer = Mtar, pfer = 0.0, pferz = 0.0;
+  const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
   MesonCm C;
-  transform_to_cm(v, efer, C);
+  transform_to_cm(v, C);
   MesonWeight w;
   const double jacobian = C.jacobian / (2. * C.pcm * C.qstar);
   const double jac_old = C.jac_old / (2. * C.pcm * C.qstar);

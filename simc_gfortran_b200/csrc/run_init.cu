@@ -409,6 +409,18 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     }
   }
 
+  // momentum distribution of dbase.f:563-587: the deck setup needs pval(nump) (init.f:348-352)
+  double pfermi_max = 0.0;
+  if (c.doing_deutpi || c.doing_deutkaon) {
+    if (data_dir.empty())
+      throw std::runtime_error("this deck needs deut.dat: use simc_b200_config_from_deck_data with the directory that holds it");
+    std::vector<double> pval, mprob;
+    read_pfermi_file(data_dir + "/deut.dat", pval, mprob);
+    pfermi_max = pval.back();
+  }
+  if (c.doing_hepi || c.doing_hekaon)
+    throw std::runtime_error("pion/kaon production from A > 2 (generate_em) is not implemented in this build");
+
   // ---- limits_init, init.f:91-572
   auto slop_for = [](int arm, double* used) {
     if (arm == 2) { used[0] = 1.0; used[1] = 0.008; used[2] = 0.008; }
@@ -478,6 +490,13 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
+  } else if (c.doing_deutpi || c.doing_deutkaon) {    // init.f:348-352,379-386
+    VE.Em.min = Mp + Mn - targ.M; VE.Em.max = Mp + Mn - targ.M;
+    VE.Pm.min = 0.0; VE.Pm.max = pfermi_max;
+    VE.Mrec.min = targ.M - targ.Mtar_struck + VE.Em.min;
+    VE.Mrec.max = targ.M - targ.Mtar_struck + VE.Em.max;
+    VE.Trec.min = std::sqrt(VE.Mrec.max * VE.Mrec.max + VE.Pm.min * VE.Pm.min) - VE.Mrec.max;
+    VE.Trec.max = std::sqrt(VE.Mrec.min * VE.Mrec.min + VE.Pm.max * VE.Pm.max) - VE.Mrec.min;
   } else if (c.doing_deuterium) {                     // init.f:326-330,379-386
     VE.Em.min = Mp + Mn - targ.M; VE.Em.max = Mp + Mn - targ.M;
     VE.Pm.min = 0.0; VE.Pm.max = theory_pm_max;
@@ -623,9 +642,14 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       const double w = deForest(ev, c.Mh2, c.deForest_flag) * targ.Z * c.transparency / 3200. / (4. * 3.14159265 * 200. * 200. * 100.);
       if (w > 0 && std::isfinite(w)) c.w_ref = w;
     }
-  } else if (c.doing_hydpi || c.doing_hydkaon) {
-    // central event: both particles along their spectrometer axes, electron at the central momentum
+  } else if (c.doing_hydpi || c.doing_hydkaon || c.doing_deutpi || c.doing_deutkaon) {
+    // central event: both particles along their spectrometer axes, electron at the central momentum, nucleon at rest
     EventState s{};
+    s.efer = targ.Mtar_struck;
+    if (c.doing_deutpi || c.doing_deutkaon) {
+      s.v_Em = Mp + Mn - targ.M;
+      s.efer = targ.M - (targ.M - targ.Mtar_struck + s.v_Em);
+    }
     s.v_Ein = c.Ebeam_vertex_ave; s.v_eE = c.spec_e.P;
     s.v_etheta = c.spec_e.theta; s.v_ephi = c.spec_e.phi; s.v_ptheta = c.spec_p.theta; s.v_pphi = c.spec_p.phi;
     s.tz = targ.zoffset;
@@ -639,6 +663,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       mv.Ein = s.v_Ein; mv.eE = s.v_eE; mv.nu = s.v_nu; mv.q = s.v_q; mv.Q2 = s.v_Q2; mv.pP = s.v_pP; mv.pE = s.v_pE;
       mv.uqx = s.uqx; mv.uqy = s.uqy; mv.uqz = s.uqz; mv.upx = s.upx; mv.upy = s.upy; mv.upz = s.upz;
       mv.phi_pq = s.m_phipq; mv.t = s.m_t; mv.epsilon = s.m_eps;
+      mv.pfer = 0.0; mv.pferx = 0.0; mv.pfery = 0.0; mv.pferz = 0.0; mv.efer = targ.Mtar_struck;
       const MesonWeight w = c.doing_pion ? peepi(c, mv) : peeK(c, mv);
       if (w.sigcc > 0 && std::isfinite(w.sigcc)) c.w_ref = w.sigcc;
     }

@@ -52,6 +52,21 @@ inline TheoryFile read_theory_file(const std::string& path) {
   return T;
 }
 
+// deut.dat / he3.dat / ...: rows "p  cumulative probability" with Fortran `d` exponents, at most 2000
+// (dbase.f:581-584)
+inline void read_pfermi_file(const std::string& path, std::vector<double>& pval, std::vector<double>& mprob) {
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) throw std::runtime_error("cannot open momentum distribution file " + path);
+  char line[512];
+  while (pval.size() < 2000 && std::fgets(line, sizeof line, f)) {
+    for (char* c = line; *c; ++c) if (*c == 'd' || *c == 'D') *c = 'e';
+    double p, q;
+    if (std::sscanf(line, "%lf %lf", &p, &q) == 2) { pval.push_back(p); mprob.push_back(q); }
+  }
+  std::fclose(f);
+  if (pval.size() < 2) throw std::runtime_error("momentum distribution file " + path + ": fewer than two rows");
+}
+
 // theory_file of init.f:838-851
 inline const char* theory_file_for(int nA) {
   return nA == 2 ? "h2.theory" : nA == 12 ? "c12.theory" : nA == 56 ? "fe56.theory" : nA == 197 ? "au197.theory" : "c12.theory";

@@ -269,3 +269,10 @@ def _oracle_theory_batch(self, cfg, em, pm):
 
 Oracle.set_theory_table = _oracle_set_theory_table
 Oracle.theory_batch = _oracle_theory_batch
+
+
+def write_pfermi_file(pval, mprob, path):
+    """deut.dat-style momentum distribution in the reference's text format (Fortran d exponents included)."""
+    with open(path, "w") as f:
+        for a, b in zip(pval, mprob):
+            f.write(f"  {float(a)!r}       {float(b):.15e}".replace("e-", "d-").replace("e+", "d+") + "\n")

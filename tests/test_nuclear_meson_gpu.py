@@ -1,0 +1,127 @@
+"""GPU parity tests for Fermi-smeared exclusive meson production from deuterium: D(e,e'pi+)nn, D(e,e'pi-)pp
+(HMS + SHMS, decay in flight) and D(e,e'K+)Lambda n (HRS-L + HRS-R).  The struck nucleon's momentum is thrown
+from deut.dat (event.f:337-367); the hadron energy solves the two-body quadratic with Fermi motion and
+binding (event.f:636-698); peepi / peeK see the moving nucleon through transform_to_cm (jacobians.f)."""
+import os
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import Simc, config_from_deck, load_optics_fixture
+from tests.oracle_lib import load_pfermi_fixture, write_pfermi_file
+from tests.test_loop_gpu import LOOSE, RECON_LOOSE, RTOL, SCALE, accum_equal_exact, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = {
+    "d_piplus": ("d2_eepi_deuterium_hms_shms.inp", (1, 5), None),
+    "d_piminus": ("d2_eepi_deuterium_hms_shms.inp", (1, 5), ("which_pion = 0", "which_pion = 1")),
+    "d_kaon": ("d3_eek_deuterium_hrsl_hrsr.inp", (4, 3), None),
+}
+SC = SCALE.copy()
+SC[50] = 1e-12
+SC[51] = 1e-3
+SC[53] = 1.0
+SC[55] = 1e3
+
+
+@pytest.fixture(scope="module")
+def data_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("deut")
+    write_pfermi_file(*load_pfermi_fixture(), str(d / "deut.dat"))
+    return d
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def case(request, oracle_with_optics, data_dir):
+    deck, arms, edit = CASES[request.param]
+    path = os.path.join(ROOT, "decks", deck)
+    if edit:
+        txt = open(path).read()
+        assert edit[0] in txt
+        path = str(data_dir / (request.param + ".inp"))
+        open(path, "w").write(txt.replace(edit[0], edit[1]))
+    cfg = config_from_deck(path, data_dir=str(data_dir))[0]
+    pval, mprob = load_pfermi_fixture()
+    oracle_with_optics.set_pfermi_table(pval, mprob)
+    s = Simc(cfg, mode="strict")
+    for arm in arms:
+        s.set_optics(load_optics_fixture(arm))
+    s.load_pfermi_file(str(data_dir / "deut.dat"))
+    yield request.param, cfg, s, oracle_with_optics
+    s.close()
+
+
+def test_setup(case):
+    name, cfg, sim, orc = case
+    assert cfg.VERTEXedge.Pm.max == 1190.0 and abs(cfg.VERTEXedge.Em.min - 2.22494) < 1e-3     # init.f:348-352
+    if name == "d_piminus":
+        assert cfg.targ.Mtar_struck == 939.56563 and cfg.targ.Mrec_struck == 938.27231          # n -> pi- p
+
+
+def test_event_records(case):
+    name, cfg, sim, orc = case
+    n = 40000
+    ref, ref_stage = orc.event_batch(cfg, 500, n, 31)
+    rec, stage = sim.event_batch(500, n, 31)
+    assert np.array_equal(stage, ref_stage), f"{(stage != ref_stage).sum()} tries end at a different stage"
+    for k in (0, 2, 3, 4):
+        assert np.array_equal(rec[k], ref[k]), sim.event_field_names()[k]
+    names = sim.event_field_names()
+    gen_ok = stage >= 1
+    for k in (8, 13, 14, 17, 18, 26, 27, 28, 29):
+        e = rel_err(rec[k][gen_ok], ref[k][gen_ok], SC[k])
+        assert e.max() <= RTOL, (names[k], float(e.max()))
+    groups = (
+        ([7] + list(range(10, 32)) + [35, 36, 37, 47], stage >= 1, LOOSE),
+        ([32, 33, 34], stage >= 2, LOOSE),
+        ([41, 42, 43], stage >= 2, RECON_LOOSE),
+        ([38, 39, 40], stage >= 3, RECON_LOOSE),
+        ([1, 5, 6, 9, 44, 45, 46, 52, 53], stage == 4, RECON_LOOSE),
+        ([48, 49, 50, 51, 54, 55], stage == 4, LOOSE),
+    )
+    for fields, mask, tol in groups:
+        for k in fields:
+            e = rel_err(rec[k][mask], ref[k][mask], SC[k])
+            assert e.max() <= tol, (names[k], float(e.max()))
+    done = stage == 4
+    assert done.sum() > (30 if name == "d_kaon" else 300) and (stage == 0).sum() > 10
+    # Fermi motion smears the missing mass of the undetected system around the free-nucleon value
+    mm = rec[53][done]
+    centre = 1115.68 if name == "d_kaon" else (938.27231 if name == "d_piminus" else 939.56563)
+    # (the radiative tail reaches far up at 11 GeV: compare the low edge and the median loosely)
+    assert centre - 40.0 < np.percentile(mm, 5) < centre + 25.0 and np.median(mm) < centre + 80.0 and mm.std() > 3.0
+
+
+def test_accumulators_against_oracle(case):
+    name, cfg, sim, orc = case
+    n = 60000
+    ref = orc.run(cfg, 0, n, 4, threads=8)
+    acc = sim.accum_clear()
+    sim.run(0, n, 4, acc)
+    accum_equal_exact(acc, ref)
+    assert acc.unsupported == ref.unsupported == 0
+    for f in ("wtcontribute", "sum_sigcc"):
+        a, b = getattr(acc, f).value(), getattr(ref, f).value()
+        assert abs(a - b) <= RECON_LOOSE * abs(b), f
+        assert getattr(acc, f).qexp == getattr(ref, f).qexp
+    for k in range(30):
+        assert abs(acc.contrib[k].lo - ref.contrib[k].lo) <= 1e-7 * max(1.0, abs(ref.contrib[k].lo)), k
+        assert abs(acc.contrib[k].hi - ref.contrib[k].hi) <= 1e-7 * max(1.0, abs(ref.contrib[k].hi)), k
+
+
+def test_ntuple_rows(case):
+    name, cfg, sim, orc = case
+    ref, ref_try = orc.ntuple_batch(cfg, 100, 30000, 12)
+    rows, tries = sim.ntuple_batch(100, 30000, 12)
+    ncol = 55 if name == "d_kaon" else 53
+    assert rows.shape == ref.shape and rows.shape[1] == ncol and rows.shape[0] > (20 if name == "d_kaon" else 200)
+    assert np.array_equal(tries, ref_try)
+    scale = np.ones(ncol)
+    scale[43] = scale[44] = scale[45] = 1e-12
+    for k in range(ncol):
+        e = rel_err(rows[:, k], ref[:, k], scale[k])
+        assert e.max() <= RECON_LOOSE, (k, float(e.max()))
+    # columns 43 / 49 (1-based): signed |p_fermi| and p_fermi along q, GeV/c
+    assert np.abs(rows[:, 42]).max() < 1.19 and np.median(np.abs(rows[:, 42])) > 0.02
+    assert np.all(np.sign(rows[:, 42]) == np.sign(rows[:, 48]))
