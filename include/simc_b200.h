@@ -267,6 +267,16 @@ int simc_b200_set_cteq5_table(simc_handle* h, int nx, int nt, int nfmx, double l
                               double xmin, const double* xv, const double* qv, const double* upd);
 int simc_b200_load_cteq5_file(simc_handle* h, const char* path);
 
+/* MAID-2007 table of peepi's low-W branch (sigmaid, physics_pion.f:577-640): below W = 2 GeV the pion
+ * weight blends the parametrisation with MAID (physics_pion.f:131-154).  ipi = 3: pi+ n (maidpipn.dat),
+ * ipi = 4: pi- p (maidpimp.dat).  tbl[25][46][6][4]: Q2 bin, W bin, the six cos(theta*) bins sigmaid uses
+ * (cthmin/cthmax, physics_pion.f:601-602) and the columns sigma_T, L/T, LT/T, TT/T that enter sig0.
+ * load_maid_file reads the reference's file ('(f11.6,18f8.4)', 23 angle rows per (Q2, W) bin) itself.
+ * Without the table, contributing events below W = 2 GeV take the parametrisation alone and are counted in
+ * simc_accum.unsupported. */
+int simc_b200_set_maid_table(simc_handle* h, int ipi, const double* tbl);
+int simc_b200_load_maid_file(simc_handle* h, int ipi, const char* path);
+
 /* stage-level parity entry point for the semi-inclusive weight: peepiX (semi_physics.f:1-617) with
  * Ctq5Pdf, the Bosted fragmentation fit and F1F2IN21 on dumped vertex vectors.  in[k*n+i], k = 0..15:
  * { Ein, e.E, nu, Q2, q, uq.x, uq.y, uq.z, pt2, zhad, theta_pq, pfer, pferx, pfery, pferz, efer };

@@ -15,6 +15,7 @@ static SfTable g_sf;
 static PfermiTable g_pfermi;
 static Cteq5Table g_pdf;
 static TheoryTable g_theory;
+static MaidTable g_maid;
 static std::string g_err;
 
 extern "C" {
@@ -171,7 +172,7 @@ int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_
         run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr,
                   g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr, nullptr,
                   g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
       }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
@@ -190,7 +191,7 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr,
               nullptr, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
@@ -204,7 +205,7 @@ int oracle_ntuple_batch(const simc_run_config* cfg, int64_t first, int64_t n, ui
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, nullptr, nullptr, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, rows, n_rows, &nc,
               try_of_row, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
     *n_cols = nc;
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -233,6 +234,18 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// maidtbl slice of simc_b200_set_maid_table; n = 0 clears it
+int oracle_set_maid_table(int ipi, int64_t n, const double* tbl) {
+  if (ipi != 3 && ipi != 4) { g_err = "ipi must be 3 or 4"; return -1; }
+  g_maid.tbl[ipi - 3].assign(tbl, tbl + n);
+  return 0;
+}
+int oracle_sigmaid_batch(int ipi, int64_t n, const double* q2, const double* w, const double* e0, const double* costh,
+                         const double* phi, double* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = sigmaid_sig0(g_maid, ipi, q2[i], w[i], e0[i], costh[i], phi[i]);
+  return 0;
 }
 
 // theory_init (init.f:828-905) from arrays: layout of simc_b200_set_theory_table

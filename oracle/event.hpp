@@ -69,6 +69,11 @@ struct TheoryTable {
   std::vector<double> pm_min, pm_bin;                          // Pm_theory(i)%min, %bin
   std::vector<std::vector<double>> rho;                        // theory(i, 1:n), already divided by bs_norm
 };
+// maidtbl of sigmaid (physics_pion.f:596): [ipi 3,4][25][46][ith 1..6][columns 1..4], the part sig0 reads
+struct MaidTable {
+  std::vector<double> tbl[2];           // [0]: pi+ n (ipi = 3), [1]: pi- p (ipi = 4); empty = not set
+};
+double sigmaid_sig0(const MaidTable& M, int ipi, double q2, double w, double e0, double costh, double phi);
 // momentum distribution of dbase.f:563-587 (deut.dat ...): mprob normalised to mprob(nump) = 1
 struct PfermiTable {
   std::vector<double> pval, mprob;
@@ -103,6 +108,7 @@ struct Sim {
   const PfermiTable* pfermi = nullptr;
   const Cteq5Table* pdf = nullptr;
   const TheoryTable* theory = nullptr;
+  const MaidTable* maid = nullptr;
   Rng* rng = nullptr;
   double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
   RadEv rad;
@@ -159,7 +165,7 @@ void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics*
                RanluxState* ranlux = nullptr, const SfTable* sf = nullptr, double* ntu_rows = nullptr,
                int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr,
                const PfermiTable* pfermi = nullptr, const Cteq5Table* pdf = nullptr,
-               const TheoryTable* theory = nullptr);
+               const TheoryTable* theory = nullptr, const MaidTable* maid = nullptr);
 double theory_sf_weight(const simc_run_config& cfg, const TheoryTable& T, double Em, double Pm);     // event.f:1402-1428
 
 }  // namespace simc_oracle

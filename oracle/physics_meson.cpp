@@ -4,8 +4,8 @@
 // Hydrogen targets: pfer = 0, pferx/y/z = 0, efer = Mtar_struck (event.f:330-335); the Fermi
 // terms are kept in the formulas so that the arithmetic is the reference's.
 //
-// Not restated: the MAID-2007 table branch of peepi for W < 2 GeV (physics_pion.f:88-107, needs
-// the 15 MB maid07 table) -- such events are counted in simc_accum.unsupported; the Saghai model eekeek/eekeeks of peeK, which
+// The MAID-2007 branch of peepi for W < 2 GeV (sigmaid, physics_pion.f:131-154, 577-728) needs the caller's
+// table; without it such events are counted in simc_accum.unsupported.  Not restated: the Saghai model eekeek/eekeeks of peeK, which
 // only fills the ntuple column sigcm1 and never the weight (physics_kaon.f:100-115).
 #include <stdexcept>
 
@@ -202,6 +202,41 @@ Fermi fermi_of(const Sim& s) {
 }
 }  // namespace
 
+// sigmaid, physics_pion.f:577-728: nearest-bin lookup in the MAID-2007 table; only sig0 is used by peepi
+double sigmaid_sig0(const MaidTable& M, int ipi, double q2, double w, double e0, double costh, double phi) {
+  static const double cthmin[6] = {-0.20, 0.20, 0.44, 0.63, 0.78, 0.90};
+  static const double cthmax[6] = {0.20, 0.44, 0.63, 0.78, 0.90, 1.0};
+  const double am = 0.9383;
+  const std::vector<double>& T = M.tbl[ipi - 3];
+  double sig0 = 0.;
+  if (w < 1.08) return sig0;
+  const double nu = (w * w - am * am + q2) / 2. / am;
+  if (nu > e0) return sig0;
+  const double ep = e0 - nu;
+  const double sin2 = q2 / 4. / e0 / ep;
+  if (sin2 <= 0.0 || sin2 > 1.) return sig0;
+  const double eps = 1. / (1. + 2. * (1. + nu * nu / q2) * sin2 / (1. - sin2));
+  int iq = (int)((q2 + 0.1) / 0.2);
+  iq = std::min(25, std::max(1, iq));
+  int iw = (int)((w - 1.090) / 0.020);
+  iw = std::min(46, std::max(1, iw));
+  int ith = 0;
+  for (int i = 1; i <= 6; ++i)
+    if (costh >= cthmin[i - 1] && costh <= cthmax[i - 1]) ith = i;
+  ith = std::min(6, std::max(1, ith));
+  double wfact = 1.;
+  if (w > 1.232) wfact = (w - 1.132) / 0.100;
+  const double* row = &T[(((size_t)(iq - 1) * 46 + (iw - 1)) * 6 + (ith - 1)) * 4];
+  const double ST = row[0] / std::max(0.2, q2) / wfact;
+  const double SL = row[1] * ST;
+  const double STL = row[2] * ST;
+  const double STT = row[3] * ST;
+  const double CSF = cos(phi);
+  const double CS2F = cos(2. * phi);
+  sig0 = ST + eps * SL + sqrt(2. * eps * (1. + eps)) * CSF * STL + eps * CS2F * STT;
+  return sig0;
+}
+
 // physics_pion.f:1-130
 double peepi(Sim& s, const Event& vertex, EventMain& main) {
   const simc_run_config& cfg = *s.cfg;
@@ -223,7 +258,18 @@ double peepi(Sim& s, const Event& vertex, EventMain& main) {
   s.ntup.sigcm1 =
       sig_param_2021(C.thetacm, C.phicm, main.t / 1.e6, vertex.Q2 / 1.e6, sgev / 1.e6, main.epsilon, cfg.which_pion);
   double sigma_eepi = s.ntup.sigcm1;
-  if (main.wcm < 2000) s.low_w = true;      // the MAID-2007 blend (physics_pion.f:88-107) is not restated: counted
+  if (main.wcm < 2000) {                    // physics_pion.f:131-154: blend with MAID-2007 below W = 2 GeV
+    const int ipi = (cfg.which_pion == 1 || cfg.which_pion == 11 || cfg.which_pion == 3) ? 4 : 3;
+    if (s.maid && !s.maid->tbl[ipi - 3].empty()) {
+      const double Q2gev = vertex.Q2 / 1.e6, Wgev = main.wcm / 1000.0, cthcm = cos(C.thetacm), E0 = vertex.Ein / 1000.0;
+      const double sig0 = sigmaid_sig0(*s.maid, ipi, Q2gev, Wgev, E0, cthcm, C.phicm);
+      s.ntup.sigcm2 = sig0 / C.phadcm / C.qstar / 2.;
+      const double fac1 = std::min(1., std::max(0., (Wgev - 1.5) / 0.4));
+      sigma_eepi = s.ntup.sigcm1 * fac1 + s.ntup.sigcm2 * (1 - fac1);
+    } else {
+      s.low_w = true;                       // table not provided: parametrisation alone, counted in `unsupported`
+    }
+  }
   s.ntup.sigcm = sigma_eepi;
   const double fac = 1. / (1. - F.pferz * F.pfer / F.efer) * targ.Mtar_struck / F.efer;
   const double gtpr = K::alpha / 2. / (K::pi * K::pi) * vertex.e.E / vertex.Ein * k_eq / vertex.Q2 / (1. - main.epsilon);

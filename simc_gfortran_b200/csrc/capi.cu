@@ -57,6 +57,7 @@ struct simc_handle {
   double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
   double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
+  double* d_maid[2] = {nullptr, nullptr};                  // MAID-2007 slices: [0] pi+ n (ipi 3), [1] pi- p (ipi 4)
   double* d_theory = nullptr; int theory_nrho = 0; double theory_efermi = 0;   // physics_heavy.cuh: TheoryDev
   // optional per-stage timing
   int timing = 0;
@@ -170,6 +171,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_pdf) cudaFree(h->d_pdf);
   if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->d_theory) cudaFree(h->d_theory);
+  for (double* p : h->d_maid) if (p) cudaFree(p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -219,6 +221,47 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
     }
   std::fclose(f);
   return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+}
+
+// maidtbl of sigmaid (physics_pion.f:596-625): the slice sig0 reads
+int simc_b200_set_maid_table(simc_handle* h, int ipi, const double* tbl) {
+  if (!h || !tbl) return SIMC_ERR_ARG;
+  if (ipi != 3 && ipi != 4) return fail(h, SIMC_ERR_ARG, "MAID table: ipi = 3 (pi+ n) or 4 (pi- p); neutral pions are out of scope");
+  CU(h, cudaSetDevice(h->device));
+  double*& d = h->d_maid[ipi - 3];
+  const size_t bytes = sizeof(double) * 25 * 46 * 6 * 4;
+  if (!d) CU(h, cudaMalloc(&d, bytes));
+  CU(h, cudaMemcpy(d, tbl, bytes, cudaMemcpyHostToDevice));
+  return SIMC_OK;
+}
+
+// maidpipn.dat / maidpimp.dat: 25 x 46 x 23 rows of '(f11.6,18f8.4)' (physics_pion.f:611-625); sigmaid only
+// ever indexes the first six angle rows (ith = 1..6) and sig0 the first four columns
+int simc_b200_load_maid_file(simc_handle* h, int ipi, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open MAID table ") + path);
+  std::vector<double> tbl((size_t)25 * 46 * 6 * 4);
+  char line[512];
+  bool ok = true;
+  for (int iq = 0; iq < 25 && ok; ++iq)
+    for (int iw = 0; iw < 46 && ok; ++iw)
+      for (int ith = 0; ith < 23 && ok; ++ith) {
+        if (!std::fgets(line, sizeof line, f)) { ok = false; break; }
+        if (ith >= 6) continue;
+        const size_t len = std::strlen(line);
+        const int start[4] = {0, 11, 19, 27}, width[4] = {11, 8, 8, 8};
+        for (int j = 0; j < 4; ++j) {
+          if (len < (size_t)(start[j] + width[j])) { ok = false; break; }
+          char field[16];
+          std::memcpy(field, line + start[j], width[j]);
+          field[width[j]] = 0;
+          tbl[(((size_t)iq * 46 + iw) * 6 + ith) * 4 + j] = std::atof(field);
+        }
+      }
+  std::fclose(f);
+  if (!ok) return fail(h, SIMC_ERR_IO, "MAID table: short or malformed file");
+  return simc_b200_set_maid_table(h, ipi, tbl.data());
 }
 
 // theory_init (init.f:828-905) from arrays
@@ -582,6 +625,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
   a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
+  a.maid_buf = h->d_maid[(h->cfg.which_pion == 1 || h->cfg.which_pion == 11 || h->cfg.which_pion == 3) ? 1 : 0];
   a.theory_buf = h->d_theory; a.theory_nrho = h->theory_nrho; a.theory_efermi = h->theory_efermi;
   {
     const MatTable mt = make_mat_table(h->cfg.targ);          // host libm, once per call

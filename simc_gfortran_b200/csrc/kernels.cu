@@ -235,6 +235,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   memcpy(&A.mt, a.mats, sizeof(MatTable));
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
   A.pdf = make_pdf(a);
+  A.maid.tbl = a.maid_buf;
   A.theory.buf = a.theory_buf; A.theory.nrho = a.theory_nrho; A.theory.e_fermi = a.theory_efermi;
   A.pfm.pval = a.pfm_buf; A.pfm.mprob = a.pfm_buf ? a.pfm_buf + a.pfm_n : nullptr; A.pfm.nump = a.pfm_n;
   const long long need = (a.n_tries + kBlock - 1) / kBlock;

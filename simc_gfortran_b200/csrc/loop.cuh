@@ -74,6 +74,7 @@ struct LoopArgs {
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   Cteq5Dev pdf;                    // CTEQ5 parton distributions (semi-inclusive production only)
   PfermiDev pfm;                   // nucleon momentum distribution (deuterium semi-inclusive production only)
+  MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
   unsigned* lists;                 // [11][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           S.st(F_XFERMI, slot, w_.xfermi);      // ntup%xfermi, semi_physics.f:250
           if (!cfg.doing_decay) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
         } else if (cfg.doing_pion) {
-          mw = peepi(cfg, mv);
+          mw = peepi(cfg, A.maid, mv);
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
         } else {
           mw = peeK(cfg, mv);

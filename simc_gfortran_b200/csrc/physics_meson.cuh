@@ -4,9 +4,9 @@
 // (pfer, efer) come with the vertex: at rest for hydrogen (pfer = 0, efer = Mtar_struck, event.f:330-335),
 // thrown from the deuteron's momentum distribution for D(e,e'pi/K) (event.f:337-367).
 //
-// Not built: the MAID-2007 table branch of peepi below W = 2 GeV (physics_pion.f:88-107) -- such
-// events are counted in simc_accum.unsupported and take the parametrisation alone; the Saghai
-// model of peeK (eekeek), which only feeds an ntuple column.
+// The MAID-2007 branch of peepi below W = 2 GeV (sigmaid, physics_pion.f:131-154, 577-728) reads the caller's
+// table (simc_b200_set_maid_table); without it such events take the parametrisation alone and are counted in
+// simc_accum.unsupported.  Not built: the Saghai model of peeK (eekeek), which only feeds an ntuple column.
 #pragma once
 #include "target.cuh"
 
@@ -199,13 +199,49 @@ SIMC_HD_CALL double sig_factorized(double q2, double w, double t, double pk, dou
   return fact_q * fact_t * fact_w;
 }
 
+// maidtbl of sigmaid (physics_pion.f:596), the slice sig0 reads: [25 Q2][46 W][6 cos(theta*)][4 columns] for the
+// charge state of this run (ipi = 3: pi+ n, 4: pi- p); null = table not provided
+struct MaidDev { const double* tbl; };
+
+// sigmaid, physics_pion.f:577-728: nearest-bin lookup in the MAID-2007 table; peepi only uses sig0
+SIMC_HD_CALL double sigmaid_sig0(const MaidDev& M, double q2, double w, double e0, double costh, double phi) {
+  const double am = 0.9383;
+  if (w < 1.08) return 0.;
+  const double nu = (w * w - am * am + q2) / 2. / am;
+  if (nu > e0) return 0.;
+  const double ep = e0 - nu;
+  const double sin2 = q2 / 4. / e0 / ep;
+  if (sin2 <= 0.0 || sin2 > 1.) return 0.;
+  const double eps = 1. / (1. + 2. * (1. + nu * nu / q2) * sin2 / (1. - sin2));
+  int iq = (int)((q2 + 0.1) / 0.2);
+  iq = min(25, max(1, iq));
+  int iw = (int)((w - 1.090) / 0.020);
+  iw = min(46, max(1, iw));
+  // cthmin / cthmax of physics_pion.f:601-602: the last bin whose closed interval holds costh, else the first
+  int ith = 1;
+  if (costh >= -0.20 && costh <= 0.20) ith = 1;
+  if (costh >= 0.20 && costh <= 0.44) ith = 2;
+  if (costh >= 0.44 && costh <= 0.63) ith = 3;
+  if (costh >= 0.63 && costh <= 0.78) ith = 4;
+  if (costh >= 0.78 && costh <= 0.90) ith = 5;
+  if (costh >= 0.90 && costh <= 1.0) ith = 6;
+  double wfact = 1.;
+  if (w > 1.232) wfact = (w - 1.132) / 0.100;
+  const double* row = M.tbl + (((long long)(iq - 1) * 46 + (iw - 1)) * 6 + (ith - 1)) * 4;
+  const double ST = row[0] / fmax(0.2, q2) / wfact;
+  const double SL = row[1] * ST;
+  const double STL = row[2] * ST;
+  const double STT = row[3] * ST;
+  return ST + eps * SL + sqrt(2. * eps * (1. + eps)) * m::cos(phi) * STL + eps * m::cos(2. * phi) * STT;
+}
+
 struct MesonWeight {
   double sigcc, sigcm, thetacm, phicm, pcm, wcm, davejac, johnjac;
   bool low_w;                 // W < 2 GeV: the reference would blend in the MAID table here
 };
 
 // physics_pion.f:1-130
-SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MesonVertex& v) {
+SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MaidDev& maid, const MesonVertex& v) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
   const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
   MesonCm C;
@@ -214,11 +250,23 @@ SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MesonVertex& v)
   w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = C.jacobian; w.johnjac = C.jac_old; w.wcm = C.wcm;
   const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;
   const double sigcm1 = sig_param_2021(C.thetacm, C.phicm, v.t / 1.e6, v.Q2 / 1.e6, C.sgev / 1.e6, v.epsilon, cfg.which_pion);
-  w.low_w = C.wcm < 2000;
-  w.sigcm = sigcm1;
+  double sigma_eepi = sigcm1;
+  w.low_w = false;
+  if (C.wcm < 2000) {                       // physics_pion.f:131-154: blend with MAID-2007 below W = 2 GeV
+    if (maid.tbl) {
+      const double Wgev = C.wcm / 1000.0;
+      const double sig0 = sigmaid_sig0(maid, v.Q2 / 1.e6, Wgev, v.Ein / 1000.0, m::cos(C.thetacm), C.phicm);
+      const double sigcm2 = sig0 / C.pcm / C.qstar / 2.;
+      const double fac1 = fmin(1., fmax(0., (Wgev - 1.5) / 0.4));
+      sigma_eepi = sigcm1 * fac1 + sigcm2 * (1 - fac1);
+    } else {
+      w.low_w = true;                       // table not provided: parametrisation alone, counted in `unsupported`
+    }
+  }
+  w.sigcm = sigma_eepi;
   const double fac = 1. / (1. - pferz * pfer / efer) * Mtar / efer;
   const double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * k_eq / v.Q2 / (1. - v.epsilon);
-  w.sigcc = sigcm1 * C.jacobian * (gtpr * fac);
+  w.sigcc = sigma_eepi * C.jacobian * (gtpr * fac);
   return w;
 }
 

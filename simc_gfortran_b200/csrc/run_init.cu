@@ -664,7 +664,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       mv.uqx = s.uqx; mv.uqy = s.uqy; mv.uqz = s.uqz; mv.upx = s.upx; mv.upy = s.upy; mv.upz = s.upz;
       mv.phi_pq = s.m_phipq; mv.t = s.m_t; mv.epsilon = s.m_eps;
       mv.pfer = 0.0; mv.pferx = 0.0; mv.pfery = 0.0; mv.pferz = 0.0; mv.efer = targ.Mtar_struck;
-      const MesonWeight w = c.doing_pion ? peepi(c, mv) : peeK(c, mv);
+      const MesonWeight w = c.doing_pion ? peepi(c, MaidDev{nullptr}, mv) : peeK(c, mv);
       if (w.sigcc > 0 && std::isfinite(w.sigcc)) c.w_ref = w.sigcc;
     }
   }

@@ -193,6 +193,8 @@ def load_library():
                                                   C.c_char_p, C.c_int]
     L.simc_b200_set_theory_table.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 8
     L.simc_b200_load_theory_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_set_maid_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.simc_b200_load_maid_file.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -300,6 +302,16 @@ class Simc:
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
+
+    # ---- MAID-2007 table of peepi's low-W branch
+    def set_maid_table(self, ipi: int, tbl):
+        """ipi = 3 (pi+ n) or 4 (pi- p); tbl[25, 46, 6, 4] (see include/simc_b200.h)."""
+        tbl = np.ascontiguousarray(tbl, dtype=np.float64)
+        assert tbl.shape == (25, 46, 6, 4)
+        self._check(self.L.simc_b200_set_maid_table(self.h, int(ipi), _ptr(tbl)))
+
+    def load_maid_file(self, ipi: int, path: str):
+        self._check(self.L.simc_b200_load_maid_file(self.h, int(ipi), path.encode()))
 
     # ---- independent-particle spectral function (h2.theory, c12.theory, ...): D(e,e'p), A(e,e'p) without Benhar
     def set_theory_table(self, t):

@@ -276,3 +276,38 @@ def write_pfermi_file(pval, mprob, path):
     with open(path, "w") as f:
         for a, b in zip(pval, mprob):
             f.write(f"  {float(a)!r}       {float(b):.15e}".replace("e-", "d-").replace("e+", "d+") + "\n")
+
+
+# ---- MAID-2007 table (peepi below W = 2 GeV) ------------------------------------------------------------
+def load_maid_fixture(ipi):
+    """tests/golden/maid_pipn.npz (ipi 3) / maid_pimp.npz (ipi 4): the slice [25, 46, 6, 4] sigmaid's sig0 reads."""
+    z = np.load(os.path.join(GOLDEN, "maid_pipn.npz" if ipi == 3 else "maid_pimp.npz"))
+    return z["tbl"]
+
+
+def write_maid_file(tbl, path):
+    """The reference's layout: 25 x 46 x 23 rows of (f11.6,18f8.4); rows / columns the fixture lacks are zero."""
+    with open(path, "w") as f:
+        for iq in range(25):
+            for iw in range(46):
+                for ith in range(23):
+                    v = np.zeros(18)
+                    if ith < 6:
+                        v[:4] = tbl[iq, iw, ith]
+                    f.write(f"{v[0]:11.5f}" + "".join(f"{x:8.4f}" for x in v[1:]) + "\n")
+
+
+def _oracle_set_maid_table(self, ipi, tbl):
+    tbl = np.ascontiguousarray(tbl, np.float64).ravel() if tbl is not None else np.zeros(0)
+    self._check(self.L.oracle_set_maid_table(int(ipi), C.c_int64(len(tbl)), _p(tbl)))
+
+
+def _oracle_sigmaid_batch(self, ipi, q2, w, e0, costh, phi):
+    arrs = [np.ascontiguousarray(a, np.float64) for a in (q2, w, e0, costh, phi)]
+    out = np.zeros(len(arrs[0]))
+    self._check(self.L.oracle_sigmaid_batch(int(ipi), C.c_int64(len(out)), *[_p(a) for a in arrs], _p(out)))
+    return out
+
+
+Oracle.set_maid_table = _oracle_set_maid_table
+Oracle.sigmaid_batch = _oracle_sigmaid_batch

@@ -65,3 +65,27 @@ def test_meson_production_events(oracle_with_optics, name, mrec):
         assert np.all((surv > 0.03) & (surv < 0.5))                   # ~25 m of flight at beta*gamma*c*tau ~ 9.7 m
     else:
         assert np.all(surv == 1.0)
+
+
+def test_sigmaid_nearest_bin_lookup(oracle):
+    """sigmaid (physics_pion.f:577-728): sig0 = ST (1 + eps L/T + ...) from the nearest (Q2, W, cos theta*) bin;
+    zero below W = 1.08 GeV and for unphysical kinematics; on the Delta peak sigma_T is several ub/sr."""
+    from tests.oracle_lib import load_maid_fixture
+    tbl = load_maid_fixture(3)
+    oracle.set_maid_table(3, tbl)
+    try:
+        one = np.ones(1)
+        assert oracle.sigmaid_batch(3, 0.4 * one, 1.07 * one, 1.645 * one, 0.5 * one, 0.3 * one)[0] == 0.0
+        assert oracle.sigmaid_batch(3, 0.4 * one, 1.9 * one, 1.0 * one, 0.5 * one, 0.3 * one)[0] == 0.0     # nu > E0
+        q2, w, e0, cth, phi = 0.4, 1.232, 1.645, 0.5, np.pi / 2
+        am = 0.9383
+        nu = (w * w - am * am + q2) / 2 / am
+        sin2 = q2 / 4 / e0 / (e0 - nu)
+        eps = 1 / (1 + 2 * (1 + nu * nu / q2) * sin2 / (1 - sin2))
+        row = tbl[int((q2 + 0.1) / 0.2) - 1, int((w - 1.090) / 0.020) - 1, 2]          # cos theta* in [0.44, 0.63]
+        st = row[0] / max(0.2, q2)
+        want = st * (1 + eps * row[1] + np.sqrt(2 * eps * (1 + eps)) * np.cos(phi) * row[2] + eps * np.cos(2 * phi) * row[3])
+        got = oracle.sigmaid_batch(3, q2 * one, w * one, e0 * one, cth * one, phi * one)[0]
+        assert abs(got - want) < 1e-12 * abs(want) and 2.0 < got < 40.0
+    finally:
+        oracle.set_maid_table(3, None)

@@ -132,7 +132,24 @@ def make_theory():
         print(name, t["n_shells"], t["n_pm"], t["pm_first"], t["pm_bin"], t["e_fermi"])
 
 
+def make_maid():
+    """maidpipn.dat / maidpimp.dat (sigmaid, physics_pion.f:611-625) -> tests/golden/maid_pipn.npz, maid_pimp.npz:
+    the six angle rows and four columns sig0 reads, [25, 46, 6, 4]."""
+    for name in ("pipn", "pimp"):
+        tbl = np.zeros((25, 46, 6, 4))
+        with open(os.path.join(REF, f"maid{name}.dat")) as f:
+            for iq in range(25):
+                for iw in range(46):
+                    for ith in range(23):
+                        line = f.readline()
+                        if ith < 6:
+                            tbl[iq, iw, ith] = [float(line[0:11]), float(line[11:19]), float(line[19:27]), float(line[27:35])]
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"maid_{name}.npz"), tbl=tbl)
+        print("maid", name, tbl.shape, tbl[..., 0].max())
+
+
 if __name__ == "__main__":
+    make_maid()
     make_sf()
     make_semi()
     make_theory()
