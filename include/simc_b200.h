@@ -277,6 +277,14 @@ int simc_b200_load_cteq5_file(simc_handle* h, const char* path);
 int simc_b200_set_maid_table(simc_handle* h, int ipi, const double* tbl);
 int simc_b200_load_maid_file(simc_handle* h, int ipi, const char* path);
 
+/* DSS fragmentation functions for semi-inclusive kaon production (doing_semi with doing_kaon): replaces the
+ * first-call table read of fDSS (fdss/fdss.f:60-125; peepiX asks for kaons at NLO, fdss/KANLO.GRID).
+ * parton[34][24][9]: the file's rows in reading order (x index slowest, then Q2 index), nine columns
+ * (u+ubar, d+dbar, s+sbar, c, b, gluon, u-ubar, d-dbar, s-sbar, each times z).  The library divides out the
+ * (1-z)^4 z^0.5 shape like the reference.  load_fdss_file reads a *.GRID file ('9(1PE10.3)') itself. */
+int simc_b200_set_fdss_table(simc_handle* h, const double* parton);
+int simc_b200_load_fdss_file(simc_handle* h, const char* path);
+
 /* stage-level parity entry point for the semi-inclusive weight: peepiX (semi_physics.f:1-617) with
  * Ctq5Pdf, the Bosted fragmentation fit and F1F2IN21 on dumped vertex vectors.  in[k*n+i], k = 0..15:
  * { Ein, e.E, nu, Q2, q, uq.x, uq.y, uq.z, pt2, zhad, theta_pq, pfer, pferx, pfery, pferz, efer };

@@ -16,6 +16,7 @@ static PfermiTable g_pfermi;
 static Cteq5Table g_pdf;
 static TheoryTable g_theory;
 static MaidTable g_maid;
+static FdssTable g_fdss;
 static std::string g_err;
 
 extern "C" {
@@ -172,7 +173,7 @@ int oracle_run_rng(const simc_run_config* cfg, int64_t first, int64_t n, uint64_
         run_range(*cfg, oe, op, b, e - b, seed, &part[t], nullptr, nullptr, 0, 0, rng_mode == 1 ? &st : nullptr,
                   g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr, nullptr,
                   g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid, g_fdss.set ? &g_fdss : nullptr);
       }
       catch (const std::exception& ex) { errs[t] = ex.what(); }
     });
@@ -191,7 +192,7 @@ int oracle_event_batch(const simc_run_config* cfg, int64_t first, int64_t n, uin
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, rec, status, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, nullptr, nullptr, nullptr,
               nullptr, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid, g_fdss.set ? &g_fdss : nullptr);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
@@ -205,7 +206,7 @@ int oracle_ntuple_batch(const simc_run_config* cfg, int64_t first, int64_t n, ui
     run_range(*cfg, ie == g_optics.end() ? nullptr : &ie->second, ip == g_optics.end() ? nullptr : &ip->second, first,
               n, seed, nullptr, nullptr, nullptr, n, 0, nullptr, g_sf.numPm ? &g_sf : nullptr, rows, n_rows, &nc,
               try_of_row, g_pfermi.pval.empty() ? nullptr : &g_pfermi, g_pdf.Nx ? &g_pdf : nullptr,
-              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid);
+              g_theory.nrhoPm ? &g_theory : nullptr, &g_maid, g_fdss.set ? &g_fdss : nullptr);
     *n_cols = nc;
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
@@ -234,6 +235,17 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// fDSS tables from the rows of a *.GRID file (layout of simc_b200_set_fdss_table)
+int oracle_set_fdss_table(const double* parton) {
+  g_fdss.init(parton);
+  return 0;
+}
+int oracle_fdss_batch(int ic, int64_t n, const double* x, const double* q2, double* out) {
+  for (int64_t i = 0; i < n; ++i)
+    fDSS(g_fdss, ic, x[i], q2[i], out[0 * n + i], out[1 * n + i], out[2 * n + i], out[3 * n + i], out[4 * n + i], out[5 * n + i]);
+  return 0;
 }
 
 // maidtbl slice of simc_b200_set_maid_table; n = 0 clears it
@@ -307,7 +319,7 @@ int oracle_christy_batch(int64_t n, const double* w2, const double* q2, double* 
 int oracle_semi_batch(const simc_run_config* cfg, int64_t n, const double* in, double* out) {
   try {
     for (int64_t i = 0; i < n; ++i) {
-      Sim s; s.cfg = cfg; s.pdf = g_pdf.Nx ? &g_pdf : nullptr;
+      Sim s; s.cfg = cfg; s.pdf = g_pdf.Nx ? &g_pdf : nullptr; s.fdss = g_fdss.set ? &g_fdss : nullptr;
       EventMain main; Event v;
       v.Ein = in[0 * n + i]; v.e.E = in[1 * n + i]; v.nu = in[2 * n + i]; v.Q2 = in[3 * n + i]; v.q = in[4 * n + i];
       v.uq.x = in[5 * n + i]; v.uq.y = in[6 * n + i]; v.uq.z = in[7 * n + i];

@@ -89,6 +89,16 @@ struct Cteq5Table {
 double Ctq5Pdf(const Cteq5Table& T, int Iparton, double X, double& Q);          // Ctq5Pdf.f:69
 void christy_sf(double w2, double q2, double& f1p, double& fLp, double& f2p, double& f1n, double& fLn,
                 double& f2n);                                                    // F1F2IN21_v1.0.f:2345
+// SAVEd tables of fDSS after its first call (fdss/fdss.f:106-125): XUTOTF, XDTOTF, XSTOTF, XUVALF, XDVALF,
+// XSVALF as (NX=35, NQ=24) column-major arrays, and ARRF = log of the grids
+struct FdssTable {
+  bool set = false;
+  double tab[6][35 * 24];
+  double arrf[35 + 24];
+  void init(const double* parton);           // parton[34][24][9], the file's reading order
+};
+void fDSS(const FdssTable& T, int IC, double X, double Q2, double& U, double& UB, double& D, double& DB, double& S,
+          double& SB);                       // fdss/fdss.f:1-215 for IH = 2, IO = 1
 struct SemiDebug {
   double xbj = 0, u = 0, ubar = 0, d = 0, dbar = 0, s = 0, sbar = 0, F1p = 0, F2p = 0, F1n = 0, F2n = 0, sighad = 0,
          sige = 0;
@@ -109,6 +119,7 @@ struct Sim {
   const Cteq5Table* pdf = nullptr;
   const TheoryTable* theory = nullptr;
   const MaidTable* maid = nullptr;
+  const FdssTable* fdss = nullptr;
   Rng* rng = nullptr;
   double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
   RadEv rad;
@@ -165,7 +176,8 @@ void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics*
                RanluxState* ranlux = nullptr, const SfTable* sf = nullptr, double* ntu_rows = nullptr,
                int64_t* n_rows = nullptr, int* n_cols = nullptr, int64_t* try_of_row = nullptr,
                const PfermiTable* pfermi = nullptr, const Cteq5Table* pdf = nullptr,
-               const TheoryTable* theory = nullptr, const MaidTable* maid = nullptr);
+               const TheoryTable* theory = nullptr, const MaidTable* maid = nullptr,
+               const FdssTable* fdss = nullptr);
 double theory_sf_weight(const simc_run_config& cfg, const TheoryTable& T, double Em, double Pm);     // event.f:1402-1428
 
 }  // namespace simc_oracle

@@ -239,13 +239,13 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
 void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics* op, int64_t first, int64_t n,
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
                RanluxState* ranlux, const SfTable* sf, double* ntu_rows, int64_t* n_rows, int* n_cols,
-               int64_t* try_of_row, const PfermiTable* pfermi, const Cteq5Table* pdf, const TheoryTable* theory, const MaidTable* maid) {
+               int64_t* try_of_row, const PfermiTable* pfermi, const Cteq5Table* pdf, const TheoryTable* theory, const MaidTable* maid, const FdssTable* fdss) {
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
     if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
     else rng.seed_philox(seed, (uint64_t)(first + i));
     Sim s;
-    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf; s.pfermi = pfermi; s.pdf = pdf; s.theory = theory; s.maid = maid;
+    s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf; s.pfermi = pfermi; s.pdf = pdf; s.theory = theory; s.maid = maid; s.fdss = fdss;
     EventMain main;
     Event vertex, orig, recon;
     const TryResult r = one_try(s, main, vertex, orig, recon);

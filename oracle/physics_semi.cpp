@@ -113,6 +113,77 @@ double Ctq5Pdf(const Cteq5Table& T, int Iparton, double X, double& Q) {
   return v;
 }
 
+// ---- DSS fragmentation functions ----------------------------------------------------------------------
+static const double kFdssQS[24] = {1., 1.25, 1.5, 2.5, 4.0, 6.4, 1.0e1, 1.5e1, 2.5e1, 4.0e1, 6.4e1, 1.0e2, 1.8e2, 3.2e2,
+                                   5.8e2, 1.0e3, 1.8e3, 3.2e3, 5.8e3, 1.0e4, 1.8e4, 3.2e4, 5.8e4, 1.0e5};
+static const double kFdssXB[35] = {0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.095, 0.1, 0.125, 0.15, 0.175,
+                                   0.2, 0.225, 0.25, 0.275, 0.3, 0.325, 0.35, 0.375, 0.4, 0.45, 0.5, 0.55, 0.6, 0.65,
+                                   0.7, 0.75, 0.8, 0.85, 0.9, 0.93, 1.0};
+// fdss/fdss.f:96-125: PARTON(k,N,M) / ((1-x)^4 x^0.5), zero at x = 1; ARRF = log of the two grids
+void FdssTable::init(const double* parton) {
+  const int NX = 35, NQ = 24;
+  const int col[6] = {0, 1, 2, 6, 7, 8};       // UTOT, DTOT, STOT, UVAL, DVAL, SVAL
+  for (int iq = 0; iq < NQ; ++iq) {
+    for (int ix = 0; ix < NX - 1; ++ix) {
+      const double XB0 = kFdssXB[ix], XB1 = 1. - kFdssXB[ix];
+      for (int k = 0; k < 6; ++k)
+        tab[k][iq * NX + ix] = parton[((size_t)ix * NQ + iq) * 9 + col[k]] / (powi(XB1, 4) * pow(XB0, 0.5));
+    }
+    for (int k = 0; k < 6; ++k) tab[k][iq * NX + NX - 1] = 0.;
+  }
+  for (int ix = 0; ix < NX; ++ix) arrf[ix] = log(kFdssXB[ix]);
+  for (int iq = 0; iq < NQ; ++iq) arrf[NX + iq] = log(kFdssQS[iq]);
+  set = true;
+}
+// fFINT (fdss/fdss.f:218-259) for NARG = 2: bilinear interpolation, linear extrapolation outside the grid
+static double fFINT2(const double* ARG, const double* ENT, const double* TABLE) {
+  const int NENT[2] = {35, 24};
+  double D[2];
+  int IENT[2];
+  int KD = 1, M = 1, JA = 1;
+  for (int I = 1; I <= 2; ++I) {
+    const int JB = JA - 1 + NENT[I - 1];
+    int J;
+    for (J = JA; J <= JB; ++J)
+      if (ARG[I - 1] <= ENT[J - 1]) break;
+    if (J > JB) J = JB;
+    if (J == JA) J = J + 1;
+    const int JR = J - 1;
+    D[I - 1] = (ENT[J - 1] - ARG[I - 1]) / (ENT[J - 1] - ENT[JR - 1]);
+    IENT[I - 1] = J - JA;
+    KD = KD + IENT[I - 1] * M;
+    M = M * NENT[I - 1];
+    JA = JB + 1;
+  }
+  double r = 0.;
+  // NCOMB runs (1,1), (1,0), (0,1), (0,0); FAC multiplies the first argument's factor first
+  r = r + ((1. * (1. - D[0])) * (1. - D[1])) * TABLE[KD - 1];
+  r = r + ((1. * (1. - D[0])) * D[1]) * TABLE[KD - 35 - 1];
+  r = r + ((1. * D[0]) * (1. - D[1])) * TABLE[KD - 1 - 1];
+  r = r + ((1. * D[0]) * D[1]) * TABLE[KD - 1 - 35 - 1];
+  return r;
+}
+// fDSS, fdss/fdss.f:1-215 (kaons at NLO; the charm, bottom and gluon functions are not used by peepiX).
+// The reference forms (1.D0-X)**4 in REAL(16) (no -fdefault-double-8); the double product below
+// differs from that in the last bit at most.
+void fDSS(const FdssTable& T, int IC, double X, double Q2, double& U, double& UB, double& D, double& DB, double& S,
+          double& SB) {
+  const double XT[2] = {log(X), log(Q2)};
+  const double shape = powi(1. - X, 4) * pow(X, 0.5);
+  const double UTOT = fFINT2(XT, T.arrf, T.tab[0]) * shape;
+  const double DTOT = fFINT2(XT, T.arrf, T.tab[1]) * shape;
+  const double STOT = fFINT2(XT, T.arrf, T.tab[2]) * shape;
+  const double UVAL = fFINT2(XT, T.arrf, T.tab[3]) * shape;
+  const double DVAL = fFINT2(XT, T.arrf, T.tab[4]) * shape;
+  const double SVAL = fFINT2(XT, T.arrf, T.tab[5]) * shape;
+  const double Up = (UTOT + UVAL) / 2., UBp = (UTOT - UVAL) / 2.;
+  const double Dp = (DTOT + DVAL) / 2., DBp = (DTOT - DVAL) / 2.;
+  const double Sp = (STOT + SVAL) / 2., SBp = (STOT - SVAL) / 2.;
+  if (IC == 1) { U = Up; UB = UBp; D = Dp; DB = DBp; S = Sp; SB = SBp; }
+  else if (IC == -1) { U = UBp; UB = Up; D = DBp; DB = Dp; S = SBp; SB = Sp; }
+  else throw std::runtime_error("fDSS: WRONG CHARGE");
+}
+
 // ---- Christy 2021 free-nucleon fit ----------------------------------------------------------------
 // data xval of rescsp (F1F2IN21_v1.0.f:201-222) and xvaln of rescsn (:332-353)
 static const double kXvalP[100] = {
@@ -350,7 +421,7 @@ static double Rhad_global(double A, double z) {
 double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob, SemiDebug* dbg) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
-  if (!cfg.doing_semipi) throw std::runtime_error("oracle: semi-inclusive kaons (fDSS) not restated");
+  if (cfg.doing_semika && !s.fdss) throw std::runtime_error("oracle: fDSS table not set");
   if (!s.pdf) throw std::runtime_error("oracle: CTEQ5 table not set");
   static const double pf[12] = {1.0424, -0.1714, 1.8960, -0.0307, 0.1636, -0.1272, -4.2093, 5.0103, 2.7406, -0.5778, 3.5292, 7.3910};
   static const double pu[12] = {0.7840, 0.2369, 1.4238, 0.1484, 0.1518, -1.2923, -1.5710, 3.0305, 1.1995, 1.3553, 2.5868, 8.0666};
@@ -365,7 +436,7 @@ double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob
   const double Eprime = vertex.e.E;
   const double pt2 = vertex.pt2;
   const double zhad = vertex.zhad;
-  const double mhad = K::Mpi;
+  const double mhad = cfg.doing_semika ? K::Mk : K::Mpi;
   const double mtar = targ.Mtar_struck;
   const double Ehad = zhad * nu;
   const double phad = sqrt(Ehad * Ehad - mhad * mhad);
@@ -405,20 +476,25 @@ double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob
   const double sA = targZ * sq + targN * sq;
   const double sbarA = targZ * sbar + targN * sbar;
   const double sum_sq = qu * qu * (uA + ubarA) + qd * qd * (dA + dbarA) + qs * qs * (sA + sbarA);
-  // Peter Bosted's fit of 9/20/2021, semi_physics.f:464-495
-  const double xp = 2. * xbj / (1. + sqrt(1. + 4. * (xbj * xbj) * (Mp_gev * Mp_gev) / Q2gev));
-  const double zp = (zhad / 2.) * (xp / xbj) *
-                    (1. + sqrt(1 - 4 * (xbj * xbj) * (Mp_gev * Mp_gev) * (Mpi_gev * Mpi_gev + pt2gev) / (zhad * zhad) /
-                                       (Q2gev * Q2gev)));
-  const double sv = log(Q2gev / 2.);
-  double yf = pf[0] * pow(zp, pf[1] + pf[3] * sv + pf[8] / w) * pow(1. - zp, pf[2] + pf[4] * sv + pf[9] / w);
-  yf = yf * (1. + pf[5] * zp + pf[6] * (zp * zp) + pf[7] * powi(zp, 3)) * (1. + pf[10] / w + pf[11] / (w * w));
-  double yu = pu[0] * pow(zp, pu[1] + pu[3] * sv + pu[8] / w) * pow(1. - zp, pu[2] + pu[4] * sv + pu[9] / w);
-  yu = yu * (1. + pu[5] * zp + pu[6] * (zp * zp) + pu[7] * powi(zp, 3)) * (1. + pu[10] / w + pu[11] / (w * w));
-  double u1, d1;
-  if (cfg.doing_hplus) { u1 = yf; d1 = yu; }
-  else { u1 = yu; d1 = yf; }
-  const double ub = d1, db = u1, s1 = yu, sb = s1;
+  double u1, d1, ub, db, s1, sb;
+  if (cfg.doing_semipi) {
+    // Peter Bosted's fit of 9/20/2021, semi_physics.f:464-495
+    const double xp = 2. * xbj / (1. + sqrt(1. + 4. * (xbj * xbj) * (Mp_gev * Mp_gev) / Q2gev));
+    const double zp = (zhad / 2.) * (xp / xbj) *
+                      (1. + sqrt(1 - 4 * (xbj * xbj) * (Mp_gev * Mp_gev) * (Mpi_gev * Mpi_gev + pt2gev) / (zhad * zhad) /
+                                         (Q2gev * Q2gev)));
+    const double sv = log(Q2gev / 2.);
+    double yf = pf[0] * pow(zp, pf[1] + pf[3] * sv + pf[8] / w) * pow(1. - zp, pf[2] + pf[4] * sv + pf[9] / w);
+    yf = yf * (1. + pf[5] * zp + pf[6] * (zp * zp) + pf[7] * powi(zp, 3)) * (1. + pf[10] / w + pf[11] / (w * w));
+    double yu = pu[0] * pow(zp, pu[1] + pu[3] * sv + pu[8] / w) * pow(1. - zp, pu[2] + pu[4] * sv + pu[9] / w);
+    yu = yu * (1. + pu[5] * zp + pu[6] * (zp * zp) + pu[7] * powi(zp, 3)) * (1. + pu[10] / w + pu[11] / (w * w));
+    if (cfg.doing_hplus) { u1 = yf; d1 = yu; }
+    else { u1 = yu; d1 = yf; }
+    ub = d1; db = u1; s1 = yu; sb = s1;
+  } else {
+    // kaons: DSS fragmentation functions at NLO, semi_physics.f:496-506
+    fDSS(*s.fdss, cfg.doing_hplus ? 1 : -1, zhad, Q2gev, u1, ub, d1, db, s1, sb);
+  }
   const double dsigdz = (qu * qu * uA * u1 + qu * qu * ubarA * ub + qd * qd * dA * d1 + qd * qd * dbarA * db +
                          qs * qs * sA * s1 + qs * qs * sbarA * sb) / sum_sq / zhad;
   const double b = 1. / (0.120 * (zhad * zhad) + 0.200);

@@ -17,6 +17,7 @@
 #include "optics_host.h"
 #include "target.cuh"
 #include "tables_host.h"
+#include "physics_semi.cuh"
 
 using namespace simc;
 
@@ -57,6 +58,7 @@ struct simc_handle {
   double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
   double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
+  double* d_fdss = nullptr;                                // fDSS tables (physics_semi.cuh: FdssDev)
   double* d_maid[2] = {nullptr, nullptr};                  // MAID-2007 slices: [0] pi+ n (ipi 3), [1] pi- p (ipi 4)
   double* d_theory = nullptr; int theory_nrho = 0; double theory_efermi = 0;   // physics_heavy.cuh: TheoryDev
   // optional per-stage timing
@@ -172,6 +174,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->d_theory) cudaFree(h->d_theory);
   for (double* p : h->d_maid) if (p) cudaFree(p);
+  if (h->d_fdss) cudaFree(h->d_fdss);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -221,6 +224,54 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
     }
   std::fclose(f);
   return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+}
+
+// First-call initialisation of fDSS (fdss/fdss.f:96-125) from the rows of a *.GRID file
+int simc_b200_set_fdss_table(simc_handle* h, const double* parton) {
+  if (!h || !parton) return SIMC_ERR_ARG;
+  static const double QS[24] = {1., 1.25, 1.5, 2.5, 4.0, 6.4, 1.0e1, 1.5e1, 2.5e1, 4.0e1, 6.4e1, 1.0e2, 1.8e2, 3.2e2,
+                                5.8e2, 1.0e3, 1.8e3, 3.2e3, 5.8e3, 1.0e4, 1.8e4, 3.2e4, 5.8e4, 1.0e5};
+  static const double XB[35] = {0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.095, 0.1, 0.125, 0.15, 0.175,
+                                0.2, 0.225, 0.25, 0.275, 0.3, 0.325, 0.35, 0.375, 0.4, 0.45, 0.5, 0.55, 0.6, 0.65,
+                                0.7, 0.75, 0.8, 0.85, 0.9, 0.93, 1.0};
+  const int NX = 35, NQ = 24;
+  const int col[6] = {0, 1, 2, 6, 7, 8};       // UTOT, DTOT, STOT, UVAL, DVAL, SVAL
+  std::vector<double> img(kFdssTab0 + 6 * 840, 0.0);
+  for (int ix = 0; ix < NX; ++ix) img[ix] = std::log(XB[ix]);
+  for (int iq = 0; iq < NQ; ++iq) img[NX + iq] = std::log(QS[iq]);
+  for (int iq = 0; iq < NQ; ++iq)
+    for (int ix = 0; ix < NX - 1; ++ix) {
+      const double XB0 = XB[ix], XB1 = 1. - XB[ix];
+      const double x2 = XB1 * XB1;
+      for (int k = 0; k < 6; ++k)
+        img[kFdssTab0 + k * 840 + iq * NX + ix] = parton[((size_t)ix * NQ + iq) * 9 + col[k]] / ((x2 * x2) * std::pow(XB0, 0.5));
+    }
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_fdss) CU(h, cudaMalloc(&h->d_fdss, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_fdss, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return SIMC_OK;
+}
+
+// fdss/*.GRID: 34 x 24 rows of '9(1PE10.3)' (fdss/fdss.f:96-104)
+int simc_b200_load_fdss_file(simc_handle* h, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(h, SIMC_ERR_IO, std::string("cannot open fragmentation-function grid ") + path);
+  std::vector<double> parton((size_t)34 * 24 * 9);
+  char line[256];
+  bool ok = true;
+  for (int r = 0; r < 34 * 24 && ok; ++r) {
+    if (!std::fgets(line, sizeof line, f) || std::strlen(line) < 90) { ok = false; break; }
+    for (int k = 0; k < 9; ++k) {
+      char field[16];
+      std::memcpy(field, line + 10 * k, 10);
+      field[10] = 0;
+      parton[(size_t)r * 9 + k] = std::atof(field);
+    }
+  }
+  std::fclose(f);
+  if (!ok) return fail(h, SIMC_ERR_IO, "fragmentation-function grid: short or malformed file");
+  return simc_b200_set_fdss_table(h, parton.data());
 }
 
 // maidtbl of sigmaid (physics_pion.f:596-625): the slice sig0 reads
@@ -527,7 +578,8 @@ int validate_loop_config(simc_handle* h) {
   const bool meson = ((c.doing_hydpi || c.doing_deutpi) && c.doing_pion) || ((c.doing_hydkaon || c.doing_deutkaon) && c.doing_kaon);
   const bool heavy = c.doing_heavy && c.doing_eep && !c.doing_deuterium;
   const bool deut = c.doing_deuterium && c.doing_eep && !c.doing_heavy;
-  const bool semi = c.doing_semi && c.doing_semipi && (c.doing_hydsemi || c.doing_deutsemi) && !c.doing_pion && !c.doing_kaon;
+  const bool semi = c.doing_semi && (c.doing_semipi || c.doing_semika) && (c.doing_hydsemi || c.doing_deutsemi) &&
+                    !c.doing_pion && !c.doing_kaon;
   if (!(c.doing_hyd_elast || meson || heavy || deut || semi) || c.doing_delta || c.doing_rho || (c.doing_semi && !semi) ||
       c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
@@ -535,6 +587,8 @@ int validate_loop_config(simc_handle* h) {
                 "independent-particle spectral function, H(e,e'pi+-), H(e,e'K+) and semi-inclusive H/D(e,e'pi+-)X");
   if ((deut || (heavy && !c.use_benhar_sf)) && !h->d_theory)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: this reaction needs the theory table (simc_b200_set_theory_table / load_theory_file) first");
+  if (semi && c.doing_semika && !h->d_fdss)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive kaon production needs the DSS grid (simc_b200_set_fdss_table) first");
   if (semi && !h->d_pdf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive production needs the CTEQ5 table (simc_b200_set_cteq5_table) first");
   if (((semi && c.doing_deutsemi) || c.doing_deutpi || c.doing_deutkaon) && !h->d_pfm)
@@ -625,6 +679,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
   a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
+  a.fdss_buf = h->d_fdss;
   a.maid_buf = h->d_maid[(h->cfg.which_pion == 1 || h->cfg.which_pion == 11 || h->cfg.which_pion == 3) ? 1 : 0];
   a.theory_buf = h->d_theory; a.theory_nrho = h->theory_nrho; a.theory_efermi = h->theory_efermi;
   {
@@ -889,13 +944,14 @@ int simc_b200_semi_batch(simc_handle* h, int64_t n, const double* in_soa, double
   if (!h) return SIMC_ERR_ARG;
   if (n < 0 || (n > 0 && (!in_soa || !out_soa))) return fail(h, SIMC_ERR_ARG, "simc_b200_semi_batch: bad argument");
   if (!h->d_pdf) return fail(h, SIMC_ERR_STATE, "simc_b200_semi_batch: set the CTEQ5 table first");
-  if (!h->cfg.doing_semipi) return fail(h, SIMC_ERR_ARG, "simc_b200_semi_batch: only semi-inclusive pions are implemented (no fDSS)");
+  if (h->cfg.doing_semika && !h->d_fdss) return fail(h, SIMC_ERR_STATE, "simc_b200_semi_batch: set the DSS grid first");
   if (n == 0) return SIMC_OK;
   CU(h, cudaSetDevice(h->device));
   int rc = ensure_loop_buffers(h, 1);
   if (rc) return rc;
   LoopLaunch a{};
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
+  a.fdss_buf = h->d_fdss;
   double *d_in = nullptr, *d_out = nullptr;
   CU(h, cudaMalloc(&d_in, sizeof(double) * SIMC_SEMI_NIN * (size_t)n));
   CU(h, cudaMalloc(&d_out, sizeof(double) * SIMC_SEMI_NOUT * (size_t)n));

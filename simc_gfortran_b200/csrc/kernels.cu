@@ -121,7 +121,7 @@ static Cteq5Dev make_pdf(const LoopLaunch& a) {
   T.nx = a.pdf_nx; T.nt = a.pdf_nt; T.nfmx = a.pdf_nfmx; T.al = a.pdf_al;
   return T;
 }
-__global__ void k_semi_batch(const simc_run_config* __restrict__ cfg, Cteq5Dev T, long long n, const double* __restrict__ in,
+__global__ void k_semi_batch(const simc_run_config* __restrict__ cfg, Cteq5Dev T, FdssDev F, long long n, const double* __restrict__ in,
                              double* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -133,7 +133,7 @@ __global__ void k_semi_batch(const simc_run_config* __restrict__ cfg, Cteq5Dev T
   double dbg[11];
 #pragma unroll
   for (int k = 0; k < 11; ++k) dbg[k] = 0.0;
-  const SemiWeight w = peepiX(*cfg, T, v, dbg);
+  const SemiWeight w = peepiX(*cfg, T, F, v, dbg);
   out[0 * n + i] = w.sigcc; out[1 * n + i] = w.sighad; out[2 * n + i] = w.davejac; out[3 * n + i] = w.xbj;
 #pragma unroll
   for (int k = 0; k < 11; ++k) out[(4 + k) * n + i] = dbg[k];
@@ -142,7 +142,8 @@ __global__ void k_semi_batch(const simc_run_config* __restrict__ cfg, Cteq5Dev T
 cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long long n, const double* in, double* out,
                               cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  k_semi_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const simc_run_config*)cfg, make_pdf(tables), n, in, out);
+  k_semi_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const simc_run_config*)cfg, make_pdf(tables), FdssDev{tables.fdss_buf}, n, in,
+                                                            out);
   return cudaGetLastError();
 }
 
@@ -236,6 +237,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
   A.pdf = make_pdf(a);
   A.maid.tbl = a.maid_buf;
+  A.fdss.buf = a.fdss_buf;
   A.theory.buf = a.theory_buf; A.theory.nrho = a.theory_nrho; A.theory.e_fermi = a.theory_efermi;
   A.pfm.pval = a.pfm_buf; A.pfm.mprob = a.pfm_buf ? a.pfm_buf + a.pfm_n : nullptr; A.pfm.nump = a.pfm_n;
   const long long need = (a.n_tries + kBlock - 1) / kBlock;

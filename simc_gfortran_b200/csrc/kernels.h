@@ -43,6 +43,7 @@ struct LoopLaunch {
   const double* pdf_buf;      // CTEQ5 table (device): [xv(nx+1) | ql(nt+1) | upd]; null unless set
   int pdf_nx, pdf_nt, pdf_nfmx;
   double pdf_al;
+  const double* fdss_buf;     // fDSS tables (device), physics_semi.cuh: FdssDev; null unless set
   const double* maid_buf;     // MAID-2007 slice [25][46][6][4] of this run's charge state (device); null unless set
   const double* theory_buf;   // independent-particle spectral function (device), physics_heavy.cuh: TheoryDev
   int theory_nrho;

@@ -74,6 +74,7 @@ struct LoopArgs {
   SfDev sf;                        // Benhar spectral function (A(e,e'p) only)
   Cteq5Dev pdf;                    // CTEQ5 parton distributions (semi-inclusive production only)
   PfermiDev pfm;                   // nucleon momentum distribution (deuterium semi-inclusive production only)
+  FdssDev fdss;                    // DSS fragmentation functions (semi-inclusive kaons only)
   MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
@@ -633,11 +634,11 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           sv_.uqx = mv.uqx; sv_.uqy = mv.uqy; sv_.uqz = mv.uqz;
           sv_.pt2 = S.ld(F_PT2, slot); sv_.zhad = S.ld(F_ZHAD, slot); sv_.theta_pq = 0.0;
           sv_.pfer = mv.pfer; sv_.pferx = mv.pferx; sv_.pfery = mv.pfery; sv_.pferz = mv.pferz; sv_.efer = mv.efer;
-          const SemiWeight w_ = peepiX(cfg, A.pdf, sv_, nullptr);
+          const SemiWeight w_ = peepiX(cfg, A.pdf, A.fdss, sv_, nullptr);
           mw.sigcc = w_.sigcc; mw.sigcm = w_.sighad; mw.davejac = w_.davejac; mw.low_w = w_.bad;
           mw.thetacm = 0.0; mw.phicm = 0.0; mw.wcm = 0.0;
           S.st(F_XFERMI, slot, w_.xfermi);      // ntup%xfermi, semi_physics.f:250
-          if (!cfg.doing_decay) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
+          if (!cfg.doing_decay && !w_.early) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
         } else if (cfg.doing_pion) {
           mw = peepi(cfg, A.maid, mv);
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;

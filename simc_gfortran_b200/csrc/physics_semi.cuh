@@ -8,8 +8,8 @@
 // touches 6 flavours x 9 values of it).  The six flavours of one event share the (x, Q) cell, so the two
 // binary searches run once per event instead of once per call.  The reference evaluates the nucleon fit
 // twice per event (F1F2IN21 for the proton, then for the neutron, each computing both); here once.
-// Not built: kaon fragmentation (fDSS), doing_pizero, the "central" cross section (never requested:
-// event.f:1521-1523).
+// Kaons (doing_semika) take the DSS fragmentation functions fDSS / fFINT (fdss/fdss.f) from a second table.
+// Not built: doing_pizero, the "central" cross section (never requested: event.f:1521-1523).
 #pragma once
 #include "target.cuh"
 
@@ -28,6 +28,51 @@ struct PfermiDev {              // dbase.f:563-587: pval(1:nump), mprob(1:nump) 
   const double* mprob;
   int nump;
 };
+
+// SAVEd tables of fDSS after its first call (fdss/fdss.f:96-125), one device buffer:
+// [ARRF: log x (35), log Q2 (24) | pad | XUTOTF, XDTOTF, XSTOTF, XUVALF, XDVALF, XSVALF as (35, 24) column-major]
+struct FdssDev { const double* buf; };
+constexpr int kFdssTab0 = 60;                 // offset of the first table in the buffer
+
+// fFINT (fdss/fdss.f:218-259) for two arguments: the interval search of both axes, shared by the six tables
+struct FdssCell { double d0, d1; int kd; };
+SIMC_HD FdssCell fdss_cell(const FdssDev& T, double lx, double lq) {
+  FdssCell c;
+  int j = 1;                                  // first J in 1..35 with ARG <= ENT(J), else 35; never the first point
+  while (j < 35 && !(lx <= T.buf[j - 1])) ++j;
+  if (j == 1) j = 2;
+  c.d0 = (T.buf[j - 1] - lx) / (T.buf[j - 1] - T.buf[j - 2]);
+  int k = 1;
+  while (k < 24 && !(lq <= T.buf[35 + k - 1])) ++k;
+  if (k == 1) k = 2;
+  c.d1 = (T.buf[35 + k - 1] - lq) / (T.buf[35 + k - 1] - T.buf[35 + k - 2]);
+  c.kd = (j - 1) + (k - 1) * 35;              // 0-based index of TABLE(KD)
+  return c;
+}
+SIMC_HD double fdss_interp(const double* tab, const FdssCell& c) {
+  double r = 0.;
+  r = r + ((1. * (1. - c.d0)) * (1. - c.d1)) * tab[c.kd];
+  r = r + ((1. * (1. - c.d0)) * c.d1) * tab[c.kd - 35];
+  r = r + ((1. * c.d0) * (1. - c.d1)) * tab[c.kd - 1];
+  r = r + ((1. * c.d0) * c.d1) * tab[c.kd - 1 - 35];
+  return r;
+}
+// fDSS (fdss/fdss.f:1-215) for kaons at NLO: z D(z, Q2) of u, ubar, d, dbar, s, sbar into a hadron of charge ic
+SIMC_HD_CALL void fDSS(const FdssDev& T, int ic, double X, double Q2, double* out6) {
+  const FdssCell c = fdss_cell(T, m::log(X), m::log(Q2));
+  const double x1 = 1. - X;
+  const double x1s = x1 * x1;
+  const double shape = (x1s * x1s) * m::pow(X, 0.5);
+  const double* t0 = T.buf + kFdssTab0;
+  const double UTOT = fdss_interp(t0, c) * shape, DTOT = fdss_interp(t0 + 840, c) * shape;
+  const double STOT = fdss_interp(t0 + 2 * 840, c) * shape, UVAL = fdss_interp(t0 + 3 * 840, c) * shape;
+  const double DVAL = fdss_interp(t0 + 4 * 840, c) * shape, SVAL = fdss_interp(t0 + 5 * 840, c) * shape;
+  const double Up = (UTOT + UVAL) / 2., UBp = (UTOT - UVAL) / 2.;
+  const double Dp = (DTOT + DVAL) / 2., DBp = (DTOT - DVAL) / 2.;
+  const double Sp = (STOT + SVAL) / 2., SBp = (STOT - SVAL) / 2.;
+  if (ic == 1) { out6[0] = Up; out6[1] = UBp; out6[2] = Dp; out6[3] = DBp; out6[4] = Sp; out6[5] = SBp; }
+  else { out6[0] = UBp; out6[1] = Up; out6[2] = DBp; out6[3] = Dp; out6[4] = SBp; out6[5] = Sp; }
+}
 
 // POLINT with N = 3 (cteq5/Ctq5Pdf.f:308-352): Neville's scheme exactly as the reference walks it
 SIMC_HD double polint3(const double xa0, const double xa1, const double xa2, const double ya0, const double ya1,
@@ -307,23 +352,25 @@ struct SemiVertex {            // what peepiX reads from `vertex`, `main` and CO
 struct SemiWeight {
   double sigcc, sighad, davejac, xbj, xfermi;
   bool bad;                    // x < 0 (possible with do_fermi): a `Stop` in Ctq5Pdf, Ctq5Pdf.f:80-83
+  bool early;                  // returned zero before the parton densities (threshold, semi_physics.f:283-287)
 };
 
 // peepiX with doing_cent = .false. (semi_physics.f:1-617), pions.  dbg (may be null) receives
 // { u, ubar, d, dbar, s, sbar, F1p, F2p, F1n, F2n, sige } for the stage-level parity entry point.
-SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev& T, const SemiVertex& v, double* dbg) {
+SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev& T, const FdssDev& F, const SemiVertex& v,
+                               double* dbg) {
   const double pf[12] = {1.0424, -0.1714, 1.8960, -0.0307, 0.1636, -0.1272, -4.2093, 5.0103, 2.7406, -0.5778, 3.5292, 7.3910};
   const double pu[12] = {0.7840, 0.2369, 1.4238, 0.1484, 0.1518, -1.2923, -1.5710, 3.0305, 1.1995, 1.3553, 2.5868, 8.0666};
   const double Mpi = 139.57018, Mp = 938.27231, hbarc = 197.327053, alpha = 1. / 137.0359895, pi = 3.141592653589793;
   const double qu = 2. / 3., qd = -1. / 3., qs = -1. / 3.;
   SemiWeight R;
-  R.sigcc = 0.0; R.sighad = 0.0; R.davejac = 0.0; R.xbj = 0.0; R.xfermi = 0.0; R.bad = false;
+  R.sigcc = 0.0; R.sighad = 0.0; R.davejac = 0.0; R.xbj = 0.0; R.xfermi = 0.0; R.bad = false; R.early = true;
   const simc_target& targ = cfg.targ;
   const double targA = targ.A, targZ = targ.Z, targN = targA - targZ;
   const double Mpi_gev = Mpi / 1000.0, Mp_gev = Mp / 1000.0;
   const double nu = v.nu, Q2 = v.Q2, Eb = v.Ein, Eprime = v.eE, pt2 = v.pt2, zhad = v.zhad;
   const double qx = v.uqx * v.q, qy = v.uqy * v.q, qz = v.uqz * v.q;
-  const double mhad = Mpi;
+  const double mhad = cfg.doing_semika ? 493.677 : Mpi;
   const double mtar = targ.Mtar_struck;
   const double Ehad = zhad * nu;
   const double phad = sqrt(Ehad * Ehad - mhad * mhad);
@@ -362,21 +409,28 @@ SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev& T, co
   const double sA = targZ * sq + targN * sq;
   const double sbarA = targZ * sbar + targN * sbar;
   const double sum_sq = qu * qu * (uA + ubarA) + qd * qd * (dA + dbarA) + qs * qs * (sA + sbarA);
-  // Bosted's fragmentation fit of 9/20/2021 in the modified scaling variable zp, semi_physics.f:464-495
-  const double xp = 2. * xbj / (1. + sqrt(1. + 4. * (xbj * xbj) * (Mp_gev * Mp_gev) / Q2gev));
-  const double zp = (zhad / 2.) * (xp / xbj) *
-                    (1. + sqrt(1 - 4 * (xbj * xbj) * (Mp_gev * Mp_gev) * (Mpi_gev * Mpi_gev + pt2gev) / (zhad * zhad) /
-                                       (Q2gev * Q2gev)));
-  const double sv = m::log(Q2gev / 2.);
-  const double zp3 = zp * (zp * zp);
-  double yf = pf[0] * m::pow(zp, pf[1] + pf[3] * sv + pf[8] / w) * m::pow(1. - zp, pf[2] + pf[4] * sv + pf[9] / w);
-  yf = yf * (1. + pf[5] * zp + pf[6] * (zp * zp) + pf[7] * zp3) * (1. + pf[10] / w + pf[11] / (w * w));
-  double yu = pu[0] * m::pow(zp, pu[1] + pu[3] * sv + pu[8] / w) * m::pow(1. - zp, pu[2] + pu[4] * sv + pu[9] / w);
-  yu = yu * (1. + pu[5] * zp + pu[6] * (zp * zp) + pu[7] * zp3) * (1. + pu[10] / w + pu[11] / (w * w));
-  double u1, d1;
-  if (cfg.doing_hplus) { u1 = yf; d1 = yu; }
-  else { u1 = yu; d1 = yf; }
-  const double ub = d1, db = u1, s1 = yu, sb = s1;
+  double u1, d1, ub, db, s1, sb;
+  if (cfg.doing_semipi) {
+    // Bosted's fragmentation fit of 9/20/2021 in the modified scaling variable zp, semi_physics.f:464-495
+    const double xp = 2. * xbj / (1. + sqrt(1. + 4. * (xbj * xbj) * (Mp_gev * Mp_gev) / Q2gev));
+    const double zp = (zhad / 2.) * (xp / xbj) *
+                      (1. + sqrt(1 - 4 * (xbj * xbj) * (Mp_gev * Mp_gev) * (Mpi_gev * Mpi_gev + pt2gev) / (zhad * zhad) /
+                                         (Q2gev * Q2gev)));
+    const double sv = m::log(Q2gev / 2.);
+    const double zp3 = zp * (zp * zp);
+    double yf = pf[0] * m::pow(zp, pf[1] + pf[3] * sv + pf[8] / w) * m::pow(1. - zp, pf[2] + pf[4] * sv + pf[9] / w);
+    yf = yf * (1. + pf[5] * zp + pf[6] * (zp * zp) + pf[7] * zp3) * (1. + pf[10] / w + pf[11] / (w * w));
+    double yu = pu[0] * m::pow(zp, pu[1] + pu[3] * sv + pu[8] / w) * m::pow(1. - zp, pu[2] + pu[4] * sv + pu[9] / w);
+    yu = yu * (1. + pu[5] * zp + pu[6] * (zp * zp) + pu[7] * zp3) * (1. + pu[10] / w + pu[11] / (w * w));
+    if (cfg.doing_hplus) { u1 = yf; d1 = yu; }
+    else { u1 = yu; d1 = yf; }
+    ub = d1; db = u1; s1 = yu; sb = s1;
+  } else {
+    // kaons: DSS fragmentation functions at NLO, semi_physics.f:496-506
+    double ff[6];
+    fDSS(F, cfg.doing_hplus ? 1 : -1, zhad, Q2gev, ff);
+    u1 = ff[0]; ub = ff[1]; d1 = ff[2]; db = ff[3]; s1 = ff[4]; sb = ff[5];
+  }
   const double dsigdz = (qu * qu * uA * u1 + qu * qu * ubarA * ub + qd * qd * dA * d1 + qd * qd * dbarA * db +
                          qs * qs * sA * s1 + qs * qs * sbarA * sb) / sum_sq / zhad;
   const double b = 1. / (0.120 * (zhad * zhad) + 0.200);
@@ -399,6 +453,7 @@ SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev& T, co
   double fac = 1.0;
   if (cfg.do_fermi) fac = 1. / (1. - v.pferz * v.pfer / v.efer) * mtar / v.efer;
   sigma = sigma * fac;
+  R.early = false;
   R.sigcc = sigma;
   R.sighad = sighad;
   R.davejac = jacobian * 1000.0;

@@ -195,6 +195,8 @@ def load_library():
     L.simc_b200_load_theory_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_maid_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.simc_b200_load_maid_file.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.simc_b200_set_fdss_table.argtypes = [C.c_void_p, C.c_void_p]
+    L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -302,6 +304,16 @@ class Simc:
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))
+
+    # ---- DSS fragmentation functions (semi-inclusive kaons)
+    def set_fdss_table(self, parton):
+        """parton[34, 24, 9]: the rows of a fdss/*.GRID file in reading order."""
+        parton = np.ascontiguousarray(parton, dtype=np.float64)
+        assert parton.shape == (34, 24, 9)
+        self._check(self.L.simc_b200_set_fdss_table(self.h, _ptr(parton)))
+
+    def load_fdss_file(self, path: str):
+        self._check(self.L.simc_b200_load_fdss_file(self.h, path.encode()))
 
     # ---- MAID-2007 table of peepi's low-W branch
     def set_maid_table(self, ipi: int, tbl):

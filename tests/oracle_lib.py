@@ -311,3 +311,32 @@ def _oracle_sigmaid_batch(self, ipi, q2, w, e0, costh, phi):
 
 Oracle.set_maid_table = _oracle_set_maid_table
 Oracle.sigmaid_batch = _oracle_sigmaid_batch
+
+
+# ---- DSS fragmentation functions (semi-inclusive kaons) ------------------------------------------------
+def load_fdss_fixture():
+    """tests/golden/fdss_kanlo.npz: the rows of the reference's fdss/KANLO.GRID, [34, 24, 9]."""
+    return np.load(os.path.join(GOLDEN, "fdss_kanlo.npz"))["parton"]
+
+
+def write_fdss_file(parton, path):
+    with open(path, "w") as f:
+        for row in np.asarray(parton).reshape(-1, 9):
+            f.write("".join(f"{x:10.3E}" for x in row) + "\n")
+
+
+def _oracle_set_fdss_table(self, parton):
+    parton = np.ascontiguousarray(parton, np.float64)
+    self._check(self.L.oracle_set_fdss_table(_p(parton)))
+
+
+def _oracle_fdss_batch(self, ic, x, q2):
+    x = np.ascontiguousarray(x, np.float64)
+    q2 = np.ascontiguousarray(q2, np.float64)
+    out = np.zeros((6, len(x)))
+    self._check(self.L.oracle_fdss_batch(int(ic), C.c_int64(len(x)), _p(x), _p(q2), _p(out)))
+    return out
+
+
+Oracle.set_fdss_table = _oracle_set_fdss_table
+Oracle.fdss_batch = _oracle_fdss_batch

@@ -142,3 +142,23 @@ def test_fermi_momentum_sampling_follows_table(orc):
         # the acceptance and the fermi flux factor reweight only mildly
         assert abs(np.quantile(pf, frac) - p_tab) < 0.35 * p_tab + 5, (frac, np.quantile(pf, frac), p_tab)
     assert np.all(rows[:, 54] > 0) and np.abs(rows[:, 54] / rows[:, 48] - 1).max() > 0.02     # xfermi vs vertex xbj
+
+
+def test_fdss_kaon_fragmentation_functions(orc):
+    """fDSS (fdss/fdss.f): bilinear interpolation in (log z, log Q2) of z D(z) / ((1-z)^4 sqrt z); exact at grid
+    nodes; favoured fragmentation (u -> K+, sbar -> K+) dominates; K- is the charge conjugate."""
+    from tests.oracle_lib import load_fdss_fixture
+    grid = load_fdss_fixture()
+    orc.set_fdss_table(grid)
+    xb = np.array([0.2, 0.4, 0.6, 0.8])
+    ix = np.array([14, 22, 26, 30])
+    q2 = np.full(4, 4.0)          # QS(5)
+    kp = orc.fdss_batch(1, xb, q2)
+    km = orc.fdss_batch(-1, xb, q2)
+    utot, uval = grid[ix, 4, 0], grid[ix, 4, 6]
+    assert np.allclose(kp[0], (utot + uval) / 2, rtol=1e-12) and np.allclose(kp[1], (utot - uval) / 2, rtol=1e-12)
+    assert np.array_equal(kp[0], km[1]) and np.array_equal(kp[5], km[4])
+    assert np.all(kp[0] > kp[1]) and np.all(kp[5] > kp[4])              # u -> K+ and sbar -> K+ are favoured
+    mid = orc.fdss_batch(1, np.array([0.5]), np.array([np.sqrt(4.0 * 6.4)]))[0]
+    lo, hi = orc.fdss_batch(1, np.array([0.5, 0.5]), np.array([4.0, 6.4]))[0]
+    assert abs(mid - 0.5 * (lo + hi)) < 1e-12 * lo                       # linear in log Q2

@@ -214,3 +214,90 @@ def test_tables_are_required():
         assert "momentum distribution" in str(ei.value)
     finally:
         s.close()
+
+
+# ---- semi-inclusive kaons: DSS fragmentation functions (fdss/fdss.f) ------------------------------------
+@pytest.fixture(scope="module", params=["d_kplus_nodecay", "d_kminus"])
+def kaon_case(request, oracle_with_optics, tmp_path_factory):
+    from tests.oracle_lib import load_fdss_fixture, write_fdss_file
+    txt = open(DECK).read()
+    txt = txt.replace("doing_kaon = 0", "doing_kaon = 1").replace("doing_pion = 1", "doing_pion = 0").replace("ctau = 780.4", "ctau = 371.3")
+    if request.param == "d_kplus_nodecay":
+        txt = txt.replace("doing_hplus = 0", "doing_hplus = 1").replace("doing_decay = 1", "doing_decay = 0")
+    d = tmp_path_factory.mktemp("semika")
+    path = str(d / "deck.inp")
+    open(path, "w").write(txt)
+    cfg = config_from_deck(path)[0]
+    assert cfg.doing_semika and not cfg.doing_semipi and not cfg.doing_kaon and abs(cfg.Mh - 493.677) < 1e-9
+    orc = oracle_with_optics
+    t, (pval, mprob), grid = load_cteq5_fixture(), load_pfermi_fixture(), load_fdss_fixture()
+    orc.set_cteq5_table(t)
+    orc.set_pfermi_table(pval, mprob)
+    orc.set_fdss_table(grid)
+    s = Simc(cfg, mode="strict")
+    for arm in (1, 5):
+        s.set_optics(load_optics_fixture(arm))
+    s.set_cteq5_table(t)
+    s.set_pfermi_table(pval, mprob)
+    gpath = str(d / "KANLO.GRID")
+    write_fdss_file(grid, gpath)
+    s.load_fdss_file(gpath)
+    yield request.param, cfg, s, orc
+    s.close()
+
+
+def test_kaon_peepix_on_dumped_vectors(kaon_case):
+    name, cfg, sim, orc = kaon_case
+    inp = semi_inputs(20000, 6, fermi=False)
+    ref = orc.semi_batch(cfg, inp)
+    out = sim.semi_batch(inp)
+    assert (ref[0] > 0).sum() > 10000
+    assert np.array_equal(out[0] == 0, ref[0] == 0)
+    scale = [1e-15, 1e-7, 1e-3, 1e-3] + [1e-6] * 10 + [1e-14]
+    for k in range(15):
+        assert np.array_equal(np.isnan(out[k]), np.isnan(ref[k])), k
+        e = rel_err(out[k], ref[k], scale[k])
+        assert np.nanmax(e) <= RTOL, (k, float(np.nanmax(e)))
+
+
+def test_kaon_loop(kaon_case):
+    name, cfg, sim, orc = kaon_case
+    n = 60000
+    ref = orc.run(cfg, 0, n, 4, threads=8)
+    acc = sim.accum_clear()
+    sim.run(0, n, 4, acc)
+    accum_equal_exact(acc, ref)
+    assert acc.unsupported == ref.unsupported == 0 and acc.nsuccess > 200
+    a, b = acc.wtcontribute.value(), ref.wtcontribute.value()
+    assert abs(a - b) <= RECON_LOOSE * abs(b)
+    rec, stage = sim.event_batch(0, 20000, 8)
+    rref, sref = orc.event_batch(cfg, 0, 20000, 8)
+    assert np.array_equal(stage, sref)
+    done = stage == 4
+    for k in (5, 6, 50, 51, 52):
+        e = rel_err(rec[k][done], rref[k][done], SC[k])
+        assert e.max() <= RECON_LOOSE, (k, float(e.max()))
+    if name == "d_kplus_nodecay":
+        # kaons over ~20 m of SHMS at 3.2 GeV/c (c tau = 3.7 m): survival applied to the weight (event.f:1560)
+        # (events below the two-hadron threshold leave peepiX before the survival probability: weight 0, prob 1)
+        live = done & (rec[6] > 0)
+        assert live.sum() > 50 and np.all((rec[52][live] > 0.2) & (rec[52][live] < 0.7))
+        assert np.all(rec[52][done & (rec[6] == 0)] == 1.0)
+    else:
+        assert np.all(rec[52][done] == 1.0)
+
+
+def test_kaon_needs_the_grid(kaon_case):
+    name, cfg, sim, orc = kaon_case
+    s2 = Simc(cfg, mode="strict")
+    try:
+        for arm in (1, 5):
+            s2.set_optics(load_optics_fixture(arm))
+        s2.set_cteq5_table(load_cteq5_fixture())
+        s2.set_pfermi_table(*load_pfermi_fixture())
+        acc = s2.accum_clear()
+        with pytest.raises(Exception) as ei:
+            s2.run(0, 100, 1, acc)
+        assert "DSS" in str(ei.value)
+    finally:
+        s2.close()

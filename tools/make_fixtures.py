@@ -148,7 +148,20 @@ def make_maid():
         print("maid", name, tbl.shape, tbl[..., 0].max())
 
 
+def make_fdss():
+    """fdss/KANLO.GRID (fDSS with IH = 2, IO = 1: kaons at NLO, semi_physics.f:497-505) -> tests/golden/fdss_kanlo.npz"""
+    rows = []
+    with open(os.path.join(REF, "fdss", "KANLO.GRID")) as f:
+        for line in f:
+            if len(line) >= 90:
+                rows.append([float(line[10 * k:10 * k + 10]) for k in range(9)])
+    a = np.array(rows).reshape(34, 24, 9)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fdss_kanlo.npz"), parton=a)
+    print("fdss KANLO", a.shape)
+
+
 if __name__ == "__main__":
+    make_fdss()
     make_maid()
     make_sf()
     make_semi()
