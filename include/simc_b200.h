@@ -239,6 +239,10 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
  * library normalises the sum to one like the reference.  load_sf_file reads benharsf_*.dat itself. */
 int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm, const double* em, const double* sf);
 int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag);
+/* Widths dEm(1:numEm) of the table's Em bins (the file's last column): only generate_em (sf_lookup.f:181-245)
+ * reads them, i.e. pion/kaon production from A > 2, where the spectral function also supplies the missing
+ * energy of the struck nucleon.  load_sf_file sets them itself; after set_sf_table call this one. */
+int simc_b200_set_sf_em_widths(simc_handle* h, int n_em, const double* dem);
 
 /* Independent-particle spectral function for D(e,e'p) and A(e,e'p) without use_benhar_sf: replaces
  * theory_init (init.f:828-905) and its COMMON /theory/ (simulate.inc:116-131).  One momentum distribution

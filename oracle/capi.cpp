@@ -96,7 +96,21 @@ int oracle_set_sf_table(int n_pm, int n_em, const double* pm, const double* em, 
   for (int iPm = 0; iPm < n_pm; ++iPm)
     for (int iEm = 0; iEm < n_em; ++iEm) sftotnorm = sftotnorm + g_sf.sfval[(size_t)iPm * n_em + iEm];
   for (double& v : g_sf.sfval) v = v / sftotnorm;
+  g_sf.dEm.clear();
   return 0;
+}
+int oracle_set_sf_em_widths(int n_em, const double* dem) {
+  g_sf.dEm.assign(dem, dem + n_em);
+  return 0;
+}
+int oracle_generate_em_batch(uint64_t seed, int64_t n, const double* pm, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Rng rng; rng.seed_philox(seed, (uint64_t)i);
+      out[i] = generate_em(g_sf, rng, pm[i]);
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 // sf_lookup_diff and deForest on dumped vectors: in [Em, Pm] x n -> out[n]
 int oracle_sf_batch(int64_t n, const double* em, const double* pm, double* out) {

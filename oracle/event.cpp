@@ -136,13 +136,12 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
                     (2 * (a * a - c * c) * vertex.p.E + c * t);
     main.jacobian = fabs(main.jacobian);
   } else if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta) {   // :609-698, hydrogen targets only here
-    if (cfg.doing_hepi || cfg.doing_hekaon) throw std::runtime_error("oracle: pi/K production from A > 2 (generate_em) not restated");
     vertex.Pm = s.pfer;
     vertex.Mrec = targ.M - targ.Mtar_struck + vertex.Em;
     double a = -1. * vertex.q * (vertex.uq.x * vertex.up.x + vertex.uq.y * vertex.up.y + vertex.uq.z * vertex.up.z);
     double b = vertex.q * vertex.q;
     double c = vertex.nu + targ.M;
-    if (cfg.doing_deutpi || cfg.doing_deutkaon) {      // :646-654 Fermi motion and binding
+    if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {      // :646-654 Fermi motion and binding
       a = a - fabs(s.pfer) * (s.pferx * vertex.up.x + s.pfery * vertex.up.y + s.pferz * vertex.up.z);
       b = b + s.pfer * s.pfer +
           2 * vertex.q * fabs(s.pfer) * (s.pferx * vertex.uq.x + s.pfery * vertex.uq.y + s.pferz * vertex.uq.z);
@@ -213,7 +212,7 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
   } else if (cfg.doing_hydpi || cfg.doing_hydkaon) {
     vertex.Trec = 0.0;
-  } else if (cfg.doing_deutpi || cfg.doing_deutkaon) {
+  } else if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
   } else if (cfg.doing_semi) {
     vertex.Pm = vertex.Pmiss;
@@ -328,9 +327,7 @@ bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
   s.pfer = 0.0; s.pferx = 0.0; s.pfery = 0.0; s.pferz = 0.0;
   vertex.Em = 0.0;
   s.efer = targ.Mtar_struck;
-  if (cfg.doing_hepi || cfg.doing_hekaon)
-    throw std::runtime_error("oracle: pi/K production from A > 2 (generate_em) not restated");
-  if (cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon) {
+  if (cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {
     if (!s.pfermi || s.pfermi->pval.empty()) throw std::runtime_error("oracle: momentum distribution not set");
     const std::vector<double>& pval = s.pfermi->pval;
     const std::vector<double>& mprob = s.pfermi->mprob;
@@ -350,7 +347,12 @@ bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
     s.pferx = sin(ranth) * cos(ranph);
     s.pfery = sin(ranth) * sin(ranph);
     s.pferz = cos(ranth);
-    vertex.Em = K::Mp + K::Mn - targ.M;
+    if (cfg.doing_hepi || cfg.doing_hekaon) {      // :368-372
+      if (!s.sf) throw std::runtime_error("oracle: spectral-function table not set");
+      vertex.Em = generate_em(*s.sf, rng, s.pfer);
+    } else {
+      vertex.Em = K::Mp + K::Mn - targ.M;
+    }
     const double m_spec = targ.M - targ.Mtar_struck + vertex.Em;
     s.efer = targ.M - sqrt(m_spec * m_spec + s.pfer * s.pfer);
   }

@@ -59,7 +59,13 @@ struct NtupVars {
 struct SfTable {
   int numPm = 0, numEm = 0;
   std::vector<double> Pmval, Emval, sfval;   // sfval[iPm * numEm + iEm]
+  std::vector<double> dEm;                   // width of each Em bin (generate_em only)
 };
+// SAVEd locals of sf_lookup (-fno-automatic): a call whose Em matches no branch (Em == Emval(numEm)) reuses
+// the interval of the previous call, which generate_em relies on (sf_lookup.f:139-160, 196-203)
+struct SfLookupState { double Em1 = 0, Em2 = 1, sf1 = 0, sf2 = 0; };
+double sf_lookup_state(const SfTable& T, double Em, double Pm, SfLookupState& st);
+double generate_em(const SfTable& T, class Rng& rng, double Pm);     // sf_lookup.f:181-245
 // COMMON /theory/ after theory_init (init.f:828-905): independent-particle spectral function
 struct TheoryTable {
   int nrhoPm = 0;

@@ -10,6 +10,10 @@ namespace simc_oracle {
 
 // sf_lookup.f:97-170.  1-based indices like the Fortran.
 double sf_lookup(const SfTable& T, double Em, double Pm) {
+  SfLookupState st;
+  return sf_lookup_state(T, Em, Pm, st);
+}
+double sf_lookup_state(const SfTable& T, double Em, double Pm, SfLookupState& st) {
   const int numPm = T.numPm, numEm = T.numEm;
   auto Pmval = [&](int i) { return T.Pmval[i - 1]; };
   auto Emval = [&](int i) { return T.Emval[i - 1]; };
@@ -29,7 +33,7 @@ double sf_lookup(const SfTable& T, double Em, double Pm) {
     if (std::fabs(w1 * Pmval(iPm) + w2 * Pmval(iPm + 1) - Pm) > 0.0001) throw std::runtime_error("sf_lookup: bad Pm weights");
   }
   if (std::fabs(w1 + w2 - 1) > 0.0001) throw std::runtime_error("sf_lookup: w1+w2 != 1");
-  double Em1 = 0, Em2 = 1, sf1 = 0, sf2 = 0;
+  double &Em1 = st.Em1, &Em2 = st.Em2, &sf1 = st.sf1, &sf2 = st.sf2;
   if (Em <= Emval(1)) {
     Em1 = Emval(1); Em2 = Emval(2);
     sf1 = w1 * sfval(1, iPm) + w2 * sfval(1, iPm + 1);
@@ -51,6 +55,24 @@ double sf_lookup(const SfTable& T, double Em, double Pm) {
   double SF = logsf;
   if (SF < 1.e-20) SF = 0;
   return SF;
+}
+
+// generate_em, sf_lookup.f:181-245: missing energy from the spectral function's Em distribution at fixed Pm
+double generate_em(const SfTable& T, Rng& rng, double Pm) {
+  const int numEm = T.numEm;
+  if ((int)T.dEm.size() != numEm) throw std::runtime_error("oracle: generate_em needs the Em bin widths");
+  std::vector<double> y(numEm + 1);
+  SfLookupState st;
+  y[1] = sf_lookup_state(T, T.Emval[0], Pm, st);
+  for (int iEm = 2; iEm <= numEm; ++iEm) {
+    y[iEm] = sf_lookup_state(T, T.Emval[iEm - 1], Pm, st);
+    y[iEm] = y[iEm] + y[iEm - 1];
+  }
+  for (int iEm = 1; iEm <= numEm; ++iEm) y[iEm] = y[iEm] / y[numEm];
+  const double ranprob = rng.grnd();
+  int ind = 1;
+  while (ranprob > y[ind]) ind = ind + 1;
+  return T.Emval[ind - 1] + T.dEm[ind - 1] * (rng.grnd() - 0.5);
 }
 
 // sf_lookup.f:85-95

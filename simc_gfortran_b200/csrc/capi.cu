@@ -56,6 +56,7 @@ struct simc_handle {
   std::vector<unsigned char> acc_host;
   double* d_rec = nullptr; int* d_status = nullptr; long long rec_n = 0;
   double* d_sf = nullptr; int sf_npm = 0, sf_nem = 0;      // Benhar spectral function: [pm | em | val]
+  double* d_sf_dem = nullptr;                              // widths of its Em bins (generate_em)
   double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
   double* d_fdss = nullptr;                                // fDSS tables (physics_semi.cuh: FdssDev)
@@ -170,6 +171,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_rec) cudaFree(h->d_rec);
   if (h->d_status) cudaFree(h->d_status);
   if (h->d_sf) cudaFree(h->d_sf);
+  if (h->d_sf_dem) cudaFree(h->d_sf_dem);
   if (h->d_pdf) cudaFree(h->d_pdf);
   if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->d_theory) cudaFree(h->d_theory);
@@ -196,6 +198,16 @@ int simc_b200_set_sf_table(simc_handle* h, int n_pm, int n_em, const double* pm,
   CU(h, cudaMalloc(&h->d_sf, img.size() * sizeof(double)));
   CU(h, cudaMemcpy(h->d_sf, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
   h->sf_npm = n_pm; h->sf_nem = n_em;
+  if (h->d_sf_dem) { cudaFree(h->d_sf_dem); h->d_sf_dem = nullptr; }       // belongs to the previous table
+  return SIMC_OK;
+}
+
+int simc_b200_set_sf_em_widths(simc_handle* h, int n_em, const double* dem) {
+  if (!h || !dem) return SIMC_ERR_ARG;
+  if (!h->d_sf || n_em != h->sf_nem) return fail(h, SIMC_ERR_STATE, "set_sf_em_widths: set the spectral function first (same number of Em bins)");
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_sf_dem) CU(h, cudaMalloc(&h->d_sf_dem, sizeof(double) * n_em));
+  CU(h, cudaMemcpy(h->d_sf_dem, dem, sizeof(double) * n_em, cudaMemcpyHostToDevice));
   return SIMC_OK;
 }
 
@@ -210,7 +222,7 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
     std::fclose(f);
     return fail(h, SIMC_ERR_IO, "spectral function file: bad header");
   }
-  std::vector<double> pm(n_pm), em(n_em), sf((size_t)n_pm * n_em);
+  std::vector<double> pm(n_pm), em(n_em), sf((size_t)n_pm * n_em), dem(n_em);
   for (int i = 0; i < n_pm; ++i)
     for (int j = 0; j < n_em; ++j) {
       double tPm, tEm, sp, sn, dPm, dEm;
@@ -220,10 +232,12 @@ int simc_b200_load_sf_file(simc_handle* h, const char* path, int proton_flag) {
       }
       sf[(size_t)i * n_em + j] = proton_flag ? sp : sn;
       if (j == 0) pm[i] = tPm;
-      if (i == 0) em[j] = tEm;
+      if (i == 0) { em[j] = tEm; dem[j] = dEm; }
     }
   std::fclose(f);
-  return simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+  const int rc = simc_b200_set_sf_table(h, n_pm, n_em, pm.data(), em.data(), sf.data());
+  if (rc) return rc;
+  return simc_b200_set_sf_em_widths(h, n_em, dem.data());
 }
 
 // First-call initialisation of fDSS (fdss/fdss.f:96-125) from the rows of a *.GRID file
@@ -575,7 +589,9 @@ int weight_qexp(const simc_run_config& cfg) {
 // Which settings this build of the loop implements; everything else is refused loudly.
 int validate_loop_config(simc_handle* h) {
   const simc_run_config& c = h->cfg;
-  const bool meson = ((c.doing_hydpi || c.doing_deutpi) && c.doing_pion) || ((c.doing_hydkaon || c.doing_deutkaon) && c.doing_kaon);
+  const bool meson = ((c.doing_hydpi || c.doing_deutpi || c.doing_hepi) && c.doing_pion) ||
+                     ((c.doing_hydkaon || c.doing_deutkaon || c.doing_hekaon) && c.doing_kaon);
+  const bool he_meson = meson && (c.doing_hepi || c.doing_hekaon);
   const bool heavy = c.doing_heavy && c.doing_eep && !c.doing_deuterium;
   const bool deut = c.doing_deuterium && c.doing_eep && !c.doing_heavy;
   const bool semi = c.doing_semi && (c.doing_semipi || c.doing_semika) && (c.doing_hydsemi || c.doing_deutsemi) &&
@@ -591,8 +607,11 @@ int validate_loop_config(simc_handle* h) {
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive kaon production needs the DSS grid (simc_b200_set_fdss_table) first");
   if (semi && !h->d_pdf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: semi-inclusive production needs the CTEQ5 table (simc_b200_set_cteq5_table) first");
-  if (((semi && c.doing_deutsemi) || c.doing_deutpi || c.doing_deutkaon) && !h->d_pfm)
-    return fail(h, SIMC_ERR_STATE, "simc_b200_run: production from deuterium needs the momentum distribution (simc_b200_set_pfermi_table) first");
+  if (((semi && c.doing_deutsemi) || c.doing_deutpi || c.doing_deutkaon || he_meson) && !h->d_pfm)
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: production from a nucleus needs the momentum distribution (simc_b200_set_pfermi_table) first");
+  if (he_meson && (!h->d_sf || !h->d_sf_dem))
+    return fail(h, SIMC_ERR_STATE, "simc_b200_run: pion/kaon production from A > 2 needs the spectral function with its Em bin widths "
+                                   "(simc_b200_load_sf_file, or set_sf_table + set_sf_em_widths) first");
   if (heavy && c.use_benhar_sf && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
   if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
@@ -676,7 +695,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.grid_blocks = h->grid_blocks;
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
-  a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem;
+  a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem; a.sf_dem = h->d_sf_dem;
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
   a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
   a.fdss_buf = h->d_fdss;

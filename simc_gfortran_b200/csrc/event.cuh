@@ -377,7 +377,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
       double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
       double b = s.v_q * s.v_q;
       double c = s.v_nu + targ.M;
-      if (cfg.doing_deutpi || cfg.doing_deutkaon) {   // event.f:646-654: Fermi motion and binding
+      if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {   // event.f:646-654: Fermi motion and binding
         a = a - fabs(s.pfer) * (s.pferx * s.upx + s.pfery * s.upy + s.pferz * s.upz);
         b = b + s.pfer * s.pfer + 2 * s.v_q * fabs(s.pfer) * (s.pferx * s.uqx + s.pfery * s.uqy + s.pferz * s.uqz);
         c = s.v_nu + s.efer;
@@ -426,7 +426,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.m_phipq = m::atan2(p_new_y, p_new_x);
     if (s.m_phipq < 0.e0) s.m_phipq = s.m_phipq + 2. * SIMC_PI_D;
     s.v_Trec = 0.0;
-    if (cfg.doing_deutpi || cfg.doing_deutkaon) {   // event.f:945-947: recoil of the spectator nucleon
+    if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {   // event.f:945-947: recoil of the spectator system
       const double Mrec = targ.M - targ.Mtar_struck + s.v_Em;
       s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
     }
@@ -476,8 +476,8 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
 // electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
 // limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev& pfm, RNG& rng, GAUSS gauss,
-                            EventState& s, bool ok) {
+SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev& pfm, const SfDev& sf, RNG& rng,
+                            GAUSS gauss, EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;
   if (ok) {
@@ -544,7 +544,7 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
       // event.f:327-373: nucleon momentum in the deuteron (thrown whether or not do_fermi uses it)
       s.pfer = 0.0; s.pferx = 0.0; s.pfery = 0.0; s.pferz = 0.0;
       s.efer = targ.Mtar_struck;
-      if (cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon) {
+      if (cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {
         const double ranprob = rng.uniform();
         const int nump = pfm.nump;
         // first ii (1-based) with ranprob <= mprob(ii), capped at nump: the reference's linear scan
@@ -564,7 +564,13 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
         s.pferx = m::sin(ranth) * m::cos(ranph);
         s.pfery = m::sin(ranth) * m::sin(ranph);
         s.pferz = m::cos(ranth);
-        s.v_Em = SIMC_MP + 939.56563 - targ.M;
+        if (cfg.doing_hepi || cfg.doing_hekaon) {      // event.f:368-372
+          const double u1 = rng.uniform();
+          const double u2 = rng.uniform();
+          s.v_Em = generate_em(sf, s.pfer, u1, u2);
+        } else {
+          s.v_Em = SIMC_MP + 939.56563 - targ.M;
+        }
         const double m_spec = targ.M - targ.Mtar_struck + s.v_Em;
         s.efer = targ.M - sqrt(m_spec * m_spec + s.pfer * s.pfer);
       }

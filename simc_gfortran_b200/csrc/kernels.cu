@@ -234,7 +234,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.mid_k = 0;
   static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
   memcpy(&A.mt, a.mats, sizeof(MatTable));
-  A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem;
+  A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem; A.sf.dem = a.sf_dem;
   A.pdf = make_pdf(a);
   A.maid.tbl = a.maid_buf;
   A.fdss.buf = a.fdss_buf;

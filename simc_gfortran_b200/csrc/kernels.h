@@ -40,6 +40,7 @@ struct LoopLaunch {
   const double* sf_em;
   const double* sf_val;
   int sf_npm, sf_nem;
+  const double* sf_dem;       // widths of the Em bins (generate_em); null unless set
   const double* pdf_buf;      // CTEQ5 table (device): [xv(nx+1) | ql(nt+1) | upd]; null unless set
   int pdf_nx, pdf_nt, pdf_nfmx;
   double pdf_al;

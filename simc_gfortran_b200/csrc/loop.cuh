@@ -177,13 +177,12 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool semi = cfg.doing_semi != 0;
-    const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon;        // nucleon momentum thrown
-    const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_deutpi || cfg.doing_deutkaon || semi ||
-                       cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+    const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;   // nucleon momentum thrown
+    const bool meson = cfg.doing_pion || cfg.doing_kaon || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     const bool heavy = cfg.doing_heavy != 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
-    if (meson) ok = generate_meson(cfg, mt_s, A.pfm, rng, GaussFn(), s, active);
+    if (meson) ok = generate_meson(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active);
     else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);
     if (active) {
@@ -572,8 +571,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       const double Pmx = rpP * upx - q * uqx, Pmy = rpP * upy - q * uqy, Pmz = rpP * upz - q * uqz;
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const bool semi = cfg.doing_semi != 0;
-      const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon;
-      const bool meson = cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_deutpi || cfg.doing_deutkaon || semi;
+      const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;
+      const bool meson = cfg.doing_pion || cfg.doing_kaon || semi;
       const bool deut = cfg.doing_deuterium != 0;
       const bool heavy = cfg.doing_heavy != 0 || deut;          // (e,e'p) from a nucleus: deForest, A-1 recoil
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349

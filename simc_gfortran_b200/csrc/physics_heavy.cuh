@@ -12,7 +12,49 @@ struct SfDev {                // device pointers; val[iPm * n_em + iEm]
   const double* em;
   const double* val;
   int n_pm, n_em;
+  const double* dem;          // widths of the Em bins (generate_em only; null unless set)
 };
+
+// generate_em (sf_lookup.f:181-245): missing energy drawn from the spectral function's Em distribution at fixed
+// Pm.  The reference calls sf_lookup at every grid energy; at a grid point the interpolation returns the grid
+// value (the slope term is 0 * finite), except at the last one, where no branch of sf_lookup matches and its
+// SAVEd interval of the previous call is reused: sf(n-1) + (E_n - E_n-1) * (sf(n) - sf(n-1)) / (E_n - E_n-1).
+// u1, u2: the two uniforms generate_em draws.  Two passes over the column pair instead of a 200-entry array.
+SIMC_HD_CALL double generate_em(const SfDev& T, double Pm, double u1, double u2) {
+  const int numPm = T.n_pm, numEm = T.n_em;
+  int iPm;
+  double w1, w2;
+  if (Pm >= T.pm[numPm - 1]) { iPm = numPm - 1; w1 = 0; w2 = 1; }
+  else if (Pm <= T.pm[0]) { iPm = 1; w1 = 1; w2 = 0; }
+  else {
+    int ind = 1;
+    while (Pm > T.pm[ind - 1]) ind = ind + 1;
+    iPm = ind - 1;
+    w2 = (Pm - T.pm[iPm - 1]) / (T.pm[iPm] - T.pm[iPm - 1]);
+    w1 = (T.pm[iPm] - Pm) / (T.pm[iPm] - T.pm[iPm - 1]);
+  }
+  const double* c1 = T.val + (size_t)(iPm - 1) * numEm;      // sfval(:, iPm), sfval(:, iPm+1)
+  const double* c2 = c1 + numEm;
+  auto yval = [&](int iEm) {                                 // what sf_lookup returns for Em = Emval(iEm)
+    double v = w1 * c1[iEm - 1] + w2 * c2[iEm - 1];
+    if (iEm == numEm) {
+      const double sf1 = w1 * c1[numEm - 2] + w2 * c2[numEm - 2];
+      const double Em1 = T.em[numEm - 2], Em2 = T.em[numEm - 1];
+      v = (sf1 + (Em2 - Em1) * (v - sf1) / (Em2 - Em1));
+    }
+    if (v < 1.e-20) v = 0;
+    return v;
+  };
+  double total = yval(1);
+  for (int iEm = 2; iEm <= numEm; ++iEm) total = yval(iEm) + total;
+  double cum = yval(1);
+  int ind = 1;
+  while (u1 > cum / total) {           // NaN (no strength at this Pm) compares false: ind = 1, as in the reference
+    ind = ind + 1;
+    cum = yval(ind) + cum;
+  }
+  return T.em[ind - 1] + T.dem[ind - 1] * (u2 - 0.5);
+}
 
 // Independent-particle spectral function of COMMON /theory/ (simulate.inc:116-131) after theory_init
 // (init.f:828-905).  buf: 8 doubles per shell { nprot*absorption, Em, Emsig, Em_int, Pm min, Pm bin, n, offset of

@@ -409,17 +409,34 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     }
   }
 
-  // momentum distribution of dbase.f:563-587: the deck setup needs pval(nump) (init.f:348-352)
-  double pfermi_max = 0.0;
-  if (c.doing_deutpi || c.doing_deutkaon) {
+  // momentum distribution of dbase.f:563-587 and, for A > 2, the spectral function of dbase.f:594-621: the deck
+  // setup needs pval(nump) and Emval(numEm) (init.f:348-357)
+  double pfermi_max = 0.0, sf_em_max = 0.0;
+  if (c.doing_deutpi || c.doing_deutkaon || c.doing_hepi || c.doing_hekaon) {
+    const bool he = c.doing_hepi || c.doing_hekaon;
+    const char* pfile = !he ? "deut.dat" : nA == 3 ? "he3.dat" : nA == 4 ? "he4.dat" : "c12.dat";
     if (data_dir.empty())
-      throw std::runtime_error("this deck needs deut.dat: use simc_b200_config_from_deck_data with the directory that holds it");
+      throw std::runtime_error(std::string("this deck needs ") + pfile + ": use simc_b200_config_from_deck_data with the directory that holds it");
     std::vector<double> pval, mprob;
-    read_pfermi_file(data_dir + "/deut.dat", pval, mprob);
+    read_pfermi_file(data_dir + "/" + pfile, pval, mprob);
     pfermi_max = pval.back();
+    if (he) {
+      const char* sfile = nA == 3 ? "benharsf_3mod.dat" : nA == 4 ? "benharsf_4.dat" : nA == 56 ? "benharsf_56.dat"
+                          : nA == 197 ? "benharsf_197.dat" : "benharsf_12.dat";
+      const std::string path = data_dir + "/" + sfile;
+      FILE* f = std::fopen(path.c_str(), "r");
+      if (!f) throw std::runtime_error("cannot open spectral function file " + path);
+      int n_pm = 0, n_em = 0;
+      bool ok = std::fscanf(f, "%d %d", &n_pm, &n_em) == 2 && n_em >= 2 && n_em <= 200;
+      for (int j = 0; ok && j < n_em; ++j) {            // first Pm row: Em of every bin
+        double v[6];
+        ok = std::fscanf(f, "%lf %lf %lf %lf %lf %lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6;
+        sf_em_max = v[1];
+      }
+      std::fclose(f);
+      if (!ok) throw std::runtime_error("spectral function file " + path + ": bad header or short read");
+    }
   }
-  if (c.doing_hepi || c.doing_hekaon)
-    throw std::runtime_error("pion/kaon production from A > 2 (generate_em) is not implemented in this build");
 
   // ---- limits_init, init.f:91-572
   auto slop_for = [](int arm, double* used) {
@@ -490,6 +507,13 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
+  } else if (c.doing_hepi || c.doing_hekaon) {        // init.f:353-357,379-386
+    VE.Em.min = targ.Mtar_struck + targ.Mrec - targ.M; VE.Em.max = sf_em_max;
+    VE.Pm.min = 0.0; VE.Pm.max = pfermi_max;
+    VE.Mrec.min = targ.M - targ.Mtar_struck + VE.Em.min;
+    VE.Mrec.max = targ.M - targ.Mtar_struck + VE.Em.max;
+    VE.Trec.min = std::sqrt(VE.Mrec.max * VE.Mrec.max + VE.Pm.min * VE.Pm.min) - VE.Mrec.max;
+    VE.Trec.max = std::sqrt(VE.Mrec.min * VE.Mrec.min + VE.Pm.max * VE.Pm.max) - VE.Mrec.min;
   } else if (c.doing_deutpi || c.doing_deutkaon) {    // init.f:348-352,379-386
     VE.Em.min = Mp + Mn - targ.M; VE.Em.max = Mp + Mn - targ.M;
     VE.Pm.min = 0.0; VE.Pm.max = pfermi_max;
@@ -642,12 +666,12 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       const double w = deForest(ev, c.Mh2, c.deForest_flag) * targ.Z * c.transparency / 3200. / (4. * 3.14159265 * 200. * 200. * 100.);
       if (w > 0 && std::isfinite(w)) c.w_ref = w;
     }
-  } else if (c.doing_hydpi || c.doing_hydkaon || c.doing_deutpi || c.doing_deutkaon) {
+  } else if (c.doing_pion || c.doing_kaon) {
     // central event: both particles along their spectrometer axes, electron at the central momentum, nucleon at rest
     EventState s{};
     s.efer = targ.Mtar_struck;
-    if (c.doing_deutpi || c.doing_deutkaon) {
-      s.v_Em = Mp + Mn - targ.M;
+    if (!(c.doing_hydpi || c.doing_hydkaon)) {
+      s.v_Em = (c.doing_hepi || c.doing_hekaon) ? targ.Mtar_struck + targ.Mrec - targ.M : Mp + Mn - targ.M;
       s.efer = targ.M - (targ.M - targ.Mtar_struck + s.v_Em);
     }
     s.v_Ein = c.Ebeam_vertex_ave; s.v_eE = c.spec_e.P;

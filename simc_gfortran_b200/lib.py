@@ -197,6 +197,7 @@ def load_library():
     L.simc_b200_load_maid_file.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
     L.simc_b200_set_fdss_table.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_set_sf_em_widths.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -301,6 +302,11 @@ class Simc:
         sf = np.ascontiguousarray(sf, dtype=np.float64)
         assert sf.shape == (len(pm), len(em))
         self._check(self.L.simc_b200_set_sf_table(self.h, len(pm), len(em), _ptr(pm), _ptr(em), _ptr(sf)))
+
+    def set_sf_em_widths(self, dem):
+        """Widths of the table's Em bins (generate_em: pion/kaon production from A > 2)."""
+        dem = np.ascontiguousarray(dem, dtype=np.float64)
+        self._check(self.L.simc_b200_set_sf_em_widths(self.h, len(dem), _ptr(dem)))
 
     def load_sf_file(self, path: str, proton: bool = True):
         self._check(self.L.simc_b200_load_sf_file(self.h, path.encode(), 1 if proton else 0))

@@ -340,3 +340,36 @@ def _oracle_fdss_batch(self, ic, x, q2):
 
 Oracle.set_fdss_table = _oracle_set_fdss_table
 Oracle.fdss_batch = _oracle_fdss_batch
+
+
+# ---- A > 2 meson production: generate_em --------------------------------------------------------------
+def load_he3_fixtures():
+    """(pval, mprob) of he3.dat and the Benhar-type table of benharsf_3mod.dat (tests/golden/*.npz)."""
+    z = np.load(os.path.join(GOLDEN, "pfermi_he3.npz"))
+    return (z["pval"], z["mprob"]), np.load(os.path.join(GOLDEN, "benharsf_3mod.npz"))
+
+
+def write_sf_file(z, path):
+    """benharsf_*.dat layout: 'numPm numEm', then rows 'Pm Em S_p S_n dPm dEm' with Em running fastest."""
+    with open(path, "w") as f:
+        f.write(f"{len(z['pm'])} {len(z['em'])}\n")
+        for i, pm in enumerate(z["pm"]):
+            for j, em in enumerate(z["em"]):
+                f.write(f"{float(pm)!r} {float(em)!r} {float(z['sf_proton'][i, j])!r} {float(z['sf_neutron'][i, j])!r} "
+                        f"{float(z['dpm'][i])!r} {float(z['dem'][j])!r}\n")
+
+
+def _oracle_set_sf_em_widths(self, dem):
+    dem = np.ascontiguousarray(dem, np.float64)
+    self._check(self.L.oracle_set_sf_em_widths(len(dem), _p(dem)))
+
+
+def _oracle_generate_em_batch(self, seed, pm):
+    pm = np.ascontiguousarray(pm, np.float64)
+    out = np.zeros(len(pm))
+    self._check(self.L.oracle_generate_em_batch(C.c_uint64(seed), C.c_int64(len(pm)), _p(pm), _p(out)))
+    return out
+
+
+Oracle.set_sf_em_widths = _oracle_set_sf_em_widths
+Oracle.generate_em_batch = _oracle_generate_em_batch

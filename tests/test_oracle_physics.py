@@ -89,3 +89,21 @@ def test_sigmaid_nearest_bin_lookup(oracle):
         assert abs(got - want) < 1e-12 * abs(want) and 2.0 < got < 40.0
     finally:
         oracle.set_maid_table(3, None)
+
+
+def test_generate_em_follows_the_spectral_function(oracle):
+    """generate_em (sf_lookup.f:181-245): Em is drawn from the table's Em distribution at the given Pm -- the
+    fraction of draws in the first bin equals the normalised strength of that bin."""
+    from tests.oracle_lib import load_he3_fixtures
+    _, sf = load_he3_fixtures()
+    oracle.set_sf_table(sf["pm"], sf["em"], sf["sf_proton"])
+    oracle.set_sf_em_widths(sf["dem"])
+    ipm = 4
+    pm = float(sf["pm"][ipm])
+    em = oracle.generate_em_batch(11, np.full(40000, pm))
+    col = sf["sf_proton"][ipm].copy()
+    col[-1] = col[-2] + (col[-1] - col[-2])          # last grid point: the reused interval gives the grid value
+    frac = col / col.sum()
+    first = (np.abs(em - sf["em"][0]) <= sf["dem"][0] / 2).mean()
+    assert abs(first - frac[0]) < 4 * np.sqrt(frac[0] * (1 - frac[0]) / len(em)) + 1e-3
+    assert em.min() >= sf["em"][0] - sf["dem"][0] / 2 and em.max() <= sf["em"][-1] + sf["dem"][-1] / 2

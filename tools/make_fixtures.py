@@ -160,7 +160,29 @@ def make_fdss():
     print("fdss KANLO", a.shape)
 
 
+def make_he3():
+    """he3.dat (dbase.f:566-567) and benharsf_3mod.dat (dbase.f:596-598) -> tests/golden/pfermi_he3.npz, benharsf_3mod.npz"""
+    rows = []
+    with open(os.path.join(REF, "he3.dat")) as f:
+        for line in f:
+            if line.strip():
+                rows.append([float(x.replace("d", "e").replace("D", "e")) for x in line.split()[:2]])
+    a = np.array(rows)[:2000]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pfermi_he3.npz"), pval=a[:, 0], mprob=a[:, 1])
+    rows = []
+    with open(os.path.join(REF, "benharsf_3mod.dat")) as f:
+        n_pm, n_em = (int(x) for x in f.readline().split())
+        for line in f:
+            if line.strip():
+                rows.append([float(x) for x in line.split()])
+    b = np.array(rows).reshape(n_pm, n_em, 6)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "benharsf_3mod.npz"), pm=b[:, 0, 0], em=b[0, :, 1],
+                        sf_proton=b[:, :, 2], sf_neutron=b[:, :, 3], dpm=b[:, 0, 4], dem=b[0, :, 5])
+    print("he3", a.shape, n_pm, n_em)
+
+
 if __name__ == "__main__":
+    make_he3()
     make_fdss()
     make_maid()
     make_sf()
