@@ -364,6 +364,31 @@ int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double
 
 const char* simc_b200_stop_name(int arm_id, int code);
 
+/* end of run ------------------------------------------------------------- *
+ * Host-only.  Replaces the normalisation and resolution block of program simc (simc.f:94-101, 366-432):
+ * luminosity from the charge and the target, the generation volume of the reaction, normfac, the normalised
+ * yield wtcontribute*normfac, and mean / rms of the reconstruction errors. */
+typedef struct {
+  double luminosity;          /* ub^-1, simc.f:94-101 */
+  double genvol;              /* product of the generated ranges, simc.f:376-396 */
+  double normfac;             /* luminosity / ntried * nevent * genvol (1 for doing_phsp), simc.f:368-398 */
+  double yield;               /* wtcontribute * normfac: counts for EXPER%charge, simc.f:399 */
+  double central_sigcc_ave;   /* sum_sigcc / nevent */
+  double aveerr[8], resol[8]; /* e: delta, xptar, yptar, ytar; p: same (simc.f:406-431); 0 if npasscuts <= 1 */
+} simc_results;
+int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, double charge_mC, simc_results* out);
+
+/* Ntuple file in the reference's layout (NtupleInit.f:32,352-355; results_write.f:264-266): a Fortran
+ * unformatted sequential file -- record "NtupleSize" (int32), one 16-character record per tag, then one
+ * 8-byte record per column of every row; each record sits between two 4-byte length markers.  This is what
+ * util/root_tree/make_root_tree.f and util/ntuple read.  ntuple_tags fills tags[n][17] (NUL-terminated) for
+ * the reaction of cfg and returns n (46 / 53 / 55 / 56), or < 0. */
+int simc_b200_ntuple_tags(const simc_run_config* cfg, char (*tags)[17], int max_tags);
+typedef struct simc_ntuple_file simc_ntuple_file;
+int simc_b200_ntuple_open(const simc_run_config* cfg, const char* path, simc_ntuple_file** out);
+int simc_b200_ntuple_append(simc_ntuple_file* f, const double* rows, int64_t n_rows);   /* rows[n_rows][SIMC_NTUPLE_MAXCOL] */
+int simc_b200_ntuple_close(simc_ntuple_file* f);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,131 @@
+// End-of-run host code of the C ABI: normalisation (simc.f:94-101, 366-432) and the ntuple file writer
+// (NtupleInit.f, results_write.f:264-266).  No device code.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "../../include/simc_b200.h"
+
+namespace {
+
+double fixed_value(const simc_fixed128& f) {
+  const long double v = (long double)f.hi * 18446744073709551616.0L + (long double)f.lo;
+  return (double)std::ldexp(v, f.qexp);
+}
+
+// NtupleInit.f:33-343 (no target field, no pi0, no rho)
+const char* const kCommon[33] = {"hsdelta", "hsyptar", "hsxptar", "hsytar", "hsxfp", "hsxpfp", "hsyfp", "hsypfp", "hsdeltai",
+                                 "hsyptari", "hsxptari", "hsytari", "ssdelta", "ssyptar", "ssxptar", "ssytar", "ssxfp",
+                                 "ssxpfp", "ssyfp", "ssypfp", "ssdeltai", "ssyptari", "ssxptari", "ssytari", "q", "nu",
+                                 "Q2", "W", "epsilon", "Em", "Pm", "thetapq", "phipq"};
+const char* const kMeson[22] = {"missmass", "mmnuc", "phad", "t", "pmpar", "pmper", "pmoop", "fry", "radphot", "pfermi",
+                                "siglab", "sigcm", "Weight", "decdist", "Mhadron", "pdotqhat", "Q2i", "Wi", "ti", "phipqi",
+                                "saghai", "factor"};
+const char* const kSemi[23] = {"missmass", "ppi", "t", "fry", "radphot", "siglab", "sigcent", "Weight", "decdist", "Mhadron",
+                               "z", "zi", "pt2", "pt2i", "xbj", "xbji", "thqi", "sighad", "jacobian", "centjac", "pfermi",
+                               "xfermi", "phipqi"};
+const char* const kEep[13] = {"corrsing", "Pmx", "Pmy", "Pmz", "PmPar", "PmPer", "PmOop", "fry", "radphot", "sigcc", "Weight",
+                              "theta_e", "theta_p"};
+
+}  // namespace
+
+struct simc_ntuple_file {
+  FILE* f;
+  int n_cols;
+};
+
+extern "C" {
+
+int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, double charge_mC, simc_results* out) {
+  if (!cfg || !acc || !out) return SIMC_ERR_ARG;
+  std::memset(out, 0, sizeof(*out));
+  const simc_target& targ = cfg->targ;
+  // simc.f:94-101 (targ%thick is in g/cm^2 at this point, dbase.f:496)
+  const double targetfac = targ.mass_amu / 3.75914e+6 / (targ.abundancy / 100.) * std::fabs(std::cos(targ.angle)) / (targ.thick * 1000.);
+  out->luminosity = charge_mC / targetfac;
+  const simc_gen_limits& gen = cfg->gen;
+  double normfac = out->luminosity / (double)acc->ntried * (double)acc->nsuccess;
+  const double domega_e = (gen.e.yptar.max - gen.e.yptar.min) * (gen.e.xptar.max - gen.e.xptar.min);
+  const double domega_p = cfg->doing_rho ? 4. * 3.141592653589793 : (gen.p.yptar.max - gen.p.yptar.min) * (gen.p.xptar.max - gen.p.xptar.min);
+  double genvol = domega_e;
+  if (cfg->doing_deuterium || cfg->doing_heavy || cfg->doing_pion || cfg->doing_kaon || cfg->doing_delta || cfg->doing_rho ||
+      cfg->doing_semi)
+    genvol = genvol * domega_p * (gen.e.E.max - gen.e.E.min);
+  if (cfg->doing_heavy || cfg->doing_semi) genvol = genvol * (gen.p.E.max - gen.p.E.min);
+  normfac = normfac * genvol;
+  if (cfg->doing_phsp) normfac = 1.0;
+  out->genvol = genvol;
+  out->normfac = normfac;
+  out->yield = fixed_value(acc->wtcontribute) * normfac;
+  out->central_sigcc_ave = acc->nsuccess > 0 ? fixed_value(acc->sum_sigcc) / (double)acc->nsuccess : 0.0;
+  if (acc->npasscuts > 1) {
+    const double tmpnum = (double)acc->npasscuts;
+    for (int k = 0; k < 8; ++k) {
+      const double s1 = fixed_value(acc->sumerr[k]), s2 = fixed_value(acc->sumerr2[k]);
+      out->aveerr[k] = s1 / tmpnum;
+      out->resol[k] = std::sqrt(std::fmax(0., (s2 / tmpnum) - (s1 / tmpnum) * (s1 / tmpnum)));
+    }
+  }
+  return SIMC_OK;
+}
+
+int simc_b200_ntuple_tags(const simc_run_config* cfg, char (*tags)[17], int max_tags) {
+  if (!cfg || !tags) return SIMC_ERR_ARG;
+  const char* const* tail;
+  int n_tail;
+  if (cfg->doing_pion || cfg->doing_kaon || cfg->doing_delta) { tail = kMeson; n_tail = cfg->doing_kaon ? 22 : 20; }
+  else if (cfg->doing_semi || cfg->doing_rho) { tail = kSemi; n_tail = 23; }
+  else if (cfg->doing_hyd_elast || cfg->doing_deuterium || cfg->doing_heavy) { tail = kEep; n_tail = 13; }
+  else return SIMC_ERR_ARG;
+  const int n = 33 + n_tail;
+  if (n > max_tags) return SIMC_ERR_ARG;
+  for (int i = 0; i < n; ++i) {
+    std::memset(tags[i], 0, 17);
+    std::strncpy(tags[i], i < 33 ? kCommon[i] : tail[i - 33], 16);
+  }
+  return n;
+}
+
+static bool put_record(FILE* f, const void* p, int32_t len) {
+  return std::fwrite(&len, 4, 1, f) == 1 && std::fwrite(p, 1, (size_t)len, f) == (size_t)len && std::fwrite(&len, 4, 1, f) == 1;
+}
+
+int simc_b200_ntuple_open(const simc_run_config* cfg, const char* path, simc_ntuple_file** out) {
+  if (!cfg || !path || !out) return SIMC_ERR_ARG;
+  *out = nullptr;
+  char tags[80][17];
+  const int n = simc_b200_ntuple_tags(cfg, tags, 80);
+  if (n < 0) return n;
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return SIMC_ERR_IO;
+  const int32_t size = n;
+  bool ok = put_record(f, &size, 4);                     // write(NtupleIO) NtupleSize
+  for (int i = 0; i < n && ok; ++i) {
+    char rec[16];
+    std::memset(rec, ' ', 16);                           // character*16, blank padded
+    std::memcpy(rec, tags[i], std::strlen(tags[i]));
+    ok = put_record(f, rec, 16);
+  }
+  if (!ok) { std::fclose(f); return SIMC_ERR_IO; }
+  simc_ntuple_file* h = new (std::nothrow) simc_ntuple_file{f, n};
+  if (!h) { std::fclose(f); return SIMC_ERR_IO; }
+  *out = h;
+  return SIMC_OK;
+}
+
+int simc_b200_ntuple_append(simc_ntuple_file* h, const double* rows, int64_t n_rows) {
+  if (!h || (n_rows > 0 && !rows)) return SIMC_ERR_ARG;
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int k = 0; k < h->n_cols; ++k)                  // do i=1,NtupleSize: write(NtupleIO) ntu(i)
+      if (!put_record(h->f, &rows[r * SIMC_NTUPLE_MAXCOL + k], 8)) return SIMC_ERR_IO;
+  return SIMC_OK;
+}
+
+int simc_b200_ntuple_close(simc_ntuple_file* h) {
+  if (!h) return SIMC_ERR_ARG;
+  const int rc = std::fclose(h->f) == 0 ? SIMC_OK : SIMC_ERR_IO;
+  delete h;
+  return rc;
+}
+
+}  // extern "C"

@@ -146,6 +146,12 @@ class Accum(C.Structure):
 _lib = None
 
 
+class Results(C.Structure):
+    """simc_results (include/simc_b200.h): normalisation and resolutions of a finished run."""
+    _fields_ = [("luminosity", C.c_double), ("genvol", C.c_double), ("normfac", C.c_double), ("yield_", C.c_double),
+                ("central_sigcc_ave", C.c_double), ("aveerr", C.c_double * 8), ("resol", C.c_double * 8)]
+
+
 def load_library():
     """Loads libsimc_b200.so from the package directory; raises if it has not been built."""
     global _lib
@@ -198,6 +204,11 @@ def load_library():
     L.simc_b200_set_fdss_table.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_sf_em_widths.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.simc_b200_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.simc_b200_ntuple_tags.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.simc_b200_ntuple_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.simc_b200_ntuple_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.simc_b200_ntuple_close.argtypes = [C.c_void_p]
     L.simc_b200_set_batch.argtypes = [C.c_void_p, C.c_int64]
     L.simc_b200_radc_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_set_pfermi_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -234,6 +245,63 @@ def config_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir
     if rc != 0:
         raise SimcError(rc, err.value.decode())
     return cfg, ngen.value, charge.value
+
+
+def normalise(cfg: RunConfig, acc, charge_mC: float) -> Results:
+    """simc.f:94-101, 366-432: luminosity, generation volume, normfac, normalised yield, resolutions.  Host only."""
+    L = load_library()
+    r = Results()
+    rc = L.simc_b200_normalise(C.byref(cfg), C.byref(acc), float(charge_mC), C.byref(r))
+    if rc:
+        raise SimcError(rc, "simc_b200_normalise")
+    return r
+
+
+def ntuple_tags(cfg: RunConfig):
+    L = load_library()
+    buf = (C.c_char * 17 * 80)()
+    n = L.simc_b200_ntuple_tags(C.byref(cfg), buf, 80)
+    if n < 0:
+        raise SimcError(n, "simc_b200_ntuple_tags")
+    return [bytes(buf[i]).split(b"\0")[0].decode() for i in range(n)]
+
+
+def write_ntuple_file(cfg: RunConfig, path: str, rows: np.ndarray):
+    """rows[n, n_cols] -> the reference's unformatted .bin ntuple (NtupleInit.f, results_write.f:264-266).  Host only."""
+    L = load_library()
+    h = C.c_void_p()
+    rc = L.simc_b200_ntuple_open(C.byref(cfg), path.encode(), C.byref(h))
+    if rc:
+        raise SimcError(rc, "simc_b200_ntuple_open")
+    full = np.zeros((len(rows), NTUPLE_MAXCOL))
+    full[:, :rows.shape[1]] = rows
+    rc = L.simc_b200_ntuple_append(h, _ptr(full), len(full))
+    rc2 = L.simc_b200_ntuple_close(h)
+    if rc or rc2:
+        raise SimcError(rc or rc2, "simc_b200_ntuple_append/close")
+
+
+def read_ntuple_file(path: str):
+    """Reads a Fortran unformatted sequential ntuple the way util/root_tree/make_root_tree.f does:
+    -> (tags, rows[n, n_cols])."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    pos = 0
+
+    def record():
+        nonlocal pos
+        n = int(raw[pos:pos + 4].view(np.int32)[0])
+        body = raw[pos + 4:pos + 4 + n]
+        assert int(raw[pos + 4 + n:pos + 8 + n].view(np.int32)[0]) == n, "record markers disagree"
+        pos += 8 + n
+        return body
+    size = int(record().view(np.int32)[0])
+    tags = [bytes(record()).decode().rstrip() for _ in range(size)]
+    rest = raw[pos:]
+    assert len(rest) % (16 * size) == 0
+    recs = rest.reshape(-1, 16)
+    assert np.all(recs[:, :4].copy().view(np.int32) == 8) and np.all(recs[:, 12:].copy().view(np.int32) == 8)
+    vals = recs[:, 4:12].copy().view(np.float64).reshape(-1, size)
+    return tags, vals
 
 
 def _ptr(a: np.ndarray):

@@ -1,0 +1,85 @@
+"""End-to-end test of the stand-alone driver `simc_b200` (what program simc does around its loop): deck ->
+optics and tables from a working directory laid out like the reference's -> run -> normalised .hist summary and
+.bin ntuple.  Compared with the same run made through the Python host API on the same files."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import Simc, config_from_deck, load_optics_fixture
+from simc_gfortran_b200.lib import normalise, ntuple_tags, read_ntuple_file
+from simc_gfortran_b200.optics import write_cosy_files
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "simc_gfortran_b200", "simc_b200")
+FILES = {1: ("hms/forward_cosy.dat", "hms/recon_cosy.dat"), 5: ("shms/shms_forward.dat", "shms/shms_recon.dat")}
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("simc_work")
+    for arm, (fwd, rec) in FILES.items():
+        os.makedirs(d / os.path.dirname(fwd), exist_ok=True)
+        write_cosy_files(load_optics_fixture(arm), str(d / fwd), str(d / rec))
+    return d
+
+
+def run_driver(workdir, ngen, out, extra=()):
+    txt = open(os.path.join(ROOT, "decks", "c1_eep_hydrogen_hms_shms.inp")).read()
+    txt, n = re.subn(r"ngen = -?\d+", f"ngen = {ngen}", txt, count=1)
+    assert n == 1
+    deck = str(workdir / f"deck_{out}.inp")
+    open(deck, "w").write(txt)
+    if not os.path.exists(DRIVER):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([DRIVER, deck, "--data", str(workdir), "--out", str(workdir / out), "--seed", "5", *extra],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    hist = {}
+    for line in open(str(workdir / out) + ".hist"):
+        m = re.match(r"^([A-Za-z_.() ]+?) = ([-+0-9.eE]+)$", line.strip())
+        if m:
+            hist[m.group(1)] = float(m.group(2))
+    return deck, hist
+
+
+def test_fixed_number_of_tries(workdir):
+    deck, hist = run_driver(workdir, -60000, "tries", ("--ntuple", "1", "--chunk", "25000"))
+    cfg, ngen, charge = config_from_deck(deck)
+    sim = Simc(cfg, mode="strict")
+    try:
+        for arm, (fwd, rec) in FILES.items():
+            sim.load_optics(arm, str(workdir / fwd), str(workdir / rec))
+        acc = sim.accum_clear()
+        sim.run(0, 60000, 5, acc)
+        rows, _ = sim.ntuple_batch(0, 60000, 5)
+    finally:
+        sim.close()
+    res = normalise(cfg, acc, charge)
+    assert hist["Ntried"] == 60000 and hist["Ncontribute"] == acc.ncontribute and hist["Npasscuts"] == acc.npasscuts
+    assert abs(hist["normalised_yield"] / res.yield_ - 1) < 1e-8 and abs(hist["normfac"] / res.normfac - 1) < 1e-8
+    assert abs(hist["resol.e.delta"] - res.resol[0]) < 1e-6 * abs(res.resol[0])
+    tags, vals = read_ntuple_file(str(workdir / "tries.bin"))
+    assert tags == ntuple_tags(cfg) and vals.shape == rows.shape == (acc.ncontribute, 46)
+    assert np.array_equal(vals, rows)                   # same kernels, same tries: identical rows
+    # the weights in the file, normalised, give the yield of the summary (events inside the cuts)
+    assert hist["normalised_yield"] <= vals[:, 43].sum() * res.normfac * (1 + 1e-9)
+
+
+def test_until_n_successes(workdir):
+    """ngen > 0 (simc.f:346-350): stop at exactly N successes; the try range is bisected, every try reproducible."""
+    _, hist = run_driver(workdir, 2500, "succ", ("--chunk", "20000"))
+    assert hist["Ncontribute"] == 2500
+    assert 2500 / 0.35 < hist["Ntried"] < 2500 / 0.1
+
+
+def test_missing_file_is_an_error(workdir, tmp_path):
+    txt = open(os.path.join(ROOT, "decks", "c1_eep_hydrogen_hms_shms.inp")).read()
+    deck = str(tmp_path / "d.inp")
+    open(deck, "w").write(txt)
+    r = subprocess.run([DRIVER, deck, "--data", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "load_optics" in r.stderr
