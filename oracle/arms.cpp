@@ -244,6 +244,110 @@ bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag, double zinit)
 }  // namespace hms
 }  // namespace
 
+// mc_hms_coll (hms/mc_hms_coll.f:1-147) / mc_shms_coll (shms/mc_shms_coll.f): a pion or muon is stepped through
+// the 6.3 cm tungsten collimator in 20 slices; inside the material it may be absorbed (pions, pion_coll_absorb),
+// scatters (musc) and loses energy (enerloss_new with a sampled fluctuation), and decays in flight (project).
+namespace {
+struct CollGeom { double h_entr, v_entr, h_exit, v_exit, x_off, y_off, thick, radl; };
+
+// hms/pion_coll_absorb.f:1-95
+double pion_coll_absorb(double ppi, double thick) {
+  static const double T[14] = {85.0, 125.0, 165.0, 205.0, 245.0, 315.0, 584.02, 711.95, 870.12, 1227.57, 1446.58, 1865.29,
+                               2858.0, 4159.0};
+  static const double sigreac[14] = {26.03, 84.47, 117.3, 117.4, 101.9, 69.58, 42.5, 44.7, 47.9, 46.5, 45.2, 39.6, 35.34, 33.15};
+  static const double qreac[14] = {0.948, 0.659, 0.56, 0.5342, 0.5452, 0.60796, 0.699, 0.689, 0.679, 0.683, 0.688, 0.704,
+                                   0.7483, 0.7705};
+  const double Navagadro = 6.0221367e+23, mpi = 139.56995, mate_dens = 17.0, mate_A = 171.57;
+  const double Epi = std::sqrt(ppi * ppi + mpi * mpi);
+  const double Tpi = Epi - mpi;
+  double sigA = 0.0;
+  for (int i = 1; i <= 13; ++i) {
+    if ((Tpi > T[i - 1]) && (Tpi <= T[i])) {
+      const double Thi = T[i], Tlo = T[i - 1];
+      const double sigAhi = sigreac[i] * std::pow(mate_A, qreac[i]);
+      const double sigAlo = sigreac[i - 1] * std::pow(mate_A, qreac[i - 1]);
+      sigA = (sigAlo * (Thi - Tpi) + sigAhi * (Tpi - Tlo)) / (Thi - Tlo);
+      sigA = sigA * 1.e-27;
+    }
+  }
+  if (Tpi > T[13]) {
+    sigA = sigreac[13] * std::pow(mate_A, qreac[13]);
+    sigA = sigA * 1.e-27;
+  }
+  const double lambdai = mate_dens * Navagadro * sigA / mate_A;
+  return std::exp(-(0.0 + thick * lambdai));
+}
+
+// enerloss_new.f:1-85 with typeflag = 1 (same arithmetic as oracle/target.cpp, on the arm's generator)
+double coll_enerloss(Track& t, double len, double dens, double zeff, double aeff, double epart, double mpart) {
+  const double me = 0.51099906;
+  const double thick = len * dens;
+  const double gamma = epart / mpart;
+  const double beta = std::sqrt(1. - 1. / (gamma * gamma));
+  const double I = zeff == 1 ? 21.8e-06 : (16. * std::pow(zeff, 0.9)) * 1.0e-06;
+  const double hnup = 28.816e-06 * std::sqrt(dens * zeff / aeff);
+  const double log10bg = std::log(beta * gamma) / std::log(10.);
+  const double CO = std::log(hnup) - std::log(I) + 0.5;
+  double denscorr;
+  if (log10bg < 0.) denscorr = 0.;
+  else if (log10bg < 3.) denscorr = CO + std::log(10.) * log10bg + std::fabs(CO / 27.) * powi(3. - log10bg, 3);
+  else if (log10bg < 4.7) denscorr = CO + std::log(10.) * log10bg;
+  else denscorr = CO + std::log(10.) * 4.7;
+  double Eloss;
+  if (thick <= 0.) {
+    Eloss = 0.;
+  } else {
+    const double Eloss_mp_new = 0.1536e-03 * zeff / aeff * thick / (beta * beta) *
+                                (std::log(me / (I * I)) + 1.063 + 2. * std::log(gamma * beta) +
+                                 std::log(0.1536 * zeff / aeff * thick / (beta * beta)) - beta * beta - denscorr);
+    const double Eloss_mp = Eloss_mp_new * 1000.;
+    const double chsi = 0.307075 / 2. * zeff / aeff * thick / (beta * beta);
+    const double x = std::fabs(gauss1(*t.rng, 10.0));
+    const double lambda = x > 0.0 ? -2.0 * std::log(x) : 100000.;
+    Eloss = lambda * chsi + Eloss_mp;
+  }
+  if (Eloss > (epart - mpart)) Eloss = (epart - mpart) - 0.0000001;
+  return Eloss;
+}
+
+bool mc_coll(Track& t, const CollGeom& G, ArmCall& a, double& m2, double& p, bool decay_flag, bool& dflag) {
+  const int nstep = 20;
+  const double coll_dens = 17.0, zcoll = 69.45, acoll = 171.56797;
+  const double step_size = G.thick / nstep;
+  double h_step = G.h_entr, v_step = G.v_entr;
+  double epart = std::sqrt(p * p + m2);
+  double thick_temp = 0.0;
+  for (int n = 1; n <= nstep; ++n) {
+    bool step_flag = false;
+    if (std::fabs(t.ys - G.y_off) > h_step) { step_flag = true; a.coll_steps[0]++; thick_temp = step_size; }
+    if (std::fabs(t.xs - G.x_off) > v_step) { step_flag = true; a.coll_steps[1]++; thick_temp = step_size; }
+    if (std::fabs(t.xs - G.x_off) > (-v_step / h_step * std::fabs(t.ys - G.y_off) + 3 * v_step / 2)) {
+      step_flag = true; a.coll_steps[2]++; thick_temp = step_size;
+    }
+    const double thick = thick_temp;
+    if (step_flag) {
+      if (m2 > 12000. && m2 < 20000.) {            // pions only: hadronic interaction
+        const double trans = pion_coll_absorb(p, thick);
+        const double rantemp = t.rng->grnd();
+        if (rantemp > trans) return false;
+      }
+      const double coll_radw = thick / G.radl;
+      musc(*t.rng, m2, p, coll_radw, t.dydzs, t.dxdzs);
+      epart = std::sqrt(p * p + m2);
+      const double eloss = coll_enerloss(t, thick, coll_dens, zcoll, acoll, epart, std::sqrt(m2));
+      epart = epart - eloss;
+      if (epart < std::sqrt(m2)) return false;
+      p = std::sqrt(epart * epart - m2);
+      t.dpps = 100. * (p / a.p_spec - 1.);
+    }
+    project(t, step_size, decay_flag, dflag, m2, p, a.pathlen);
+    h_step = h_step + (G.h_exit - G.h_entr) / nstep;
+    v_step = v_step + (G.v_exit - G.v_entr) / nstep;
+  }
+  return true;
+}
+}  // namespace
+
 // mc_hms, hms/mc_hms.f:1-441
 void mc_hms(Track& t, const ArmOptics& o, ArmCall& a) {
   using namespace hms;
@@ -265,7 +369,8 @@ void mc_hms(Track& t, const ArmOptics& o, ArmCall& a) {
   zdrift = z_entr;
   project(t, zdrift, dec, dflag, m2, p, a.pathlen);
   if (a.using_coll && (m2 > 100.0 * 100.0) && (m2 < 200.0 * 200.0)) {
-    throw std::runtime_error("oracle: mc_hms_coll (pion stepping through the collimator) not restated yet");
+    const CollGeom G{4.575, 11.646, 4.759, 12.114, 0.000, +0.028, 6.30, 0.41753};      // hms/mc_hms_coll.f:17-34
+    if (!mc_coll(t, G, a, m2, p, dec, dflag)) return stop(hms_stop::COLL);
   } else {
     if (std::fabs(t.ys - y_off) > h_entr) return stop(hms_stop::SLIT_HOR);
     if (std::fabs(t.xs - x_off) > v_entr) return stop(hms_stop::SLIT_VERT);
@@ -626,7 +731,10 @@ void mc_shms(Track& t, const ArmOptics& o, ArmCall& a) {
 
   // :496-560 collimator
   if (a.using_coll && (m2 > 100.0 * 100.0) && (m2 < 200.0 * 200.0)) {
-    throw std::runtime_error("oracle: mc_shms_coll (pion stepping through the collimator) not restated yet");
+    zdrift = z_entr;
+    project(t, zdrift, dec, dflag, m2, p, a.pathlen);
+    const CollGeom G{8.50, 12.50, 8.65, 12.85, 0.000, +0.000, 6.35, 0.42084};          // shms/mc_shms_coll.f:17-34
+    if (!mc_coll(t, G, a, m2, p, dec, dflag)) return stop(shms_stop::COLL);
   } else {
     zdrift = z_entr;
     project(t, zdrift, dec, dflag, m2, p, a.pathlen);

@@ -25,6 +25,9 @@ struct ArmCall {
   bool using_coll = false;                                   // using_HMScoll / using_SHMScoll
   int stop_code = 0;                                         // 0 = ok, else where it stopped (our enumeration)
   bool reached_hut = false;
+  // mc_hms_coll / mc_shms_coll bump the slit STOP counters once per 0.3 cm step spent in the material, whether
+  // or not the pion survives (hms/mc_hms_coll.f:95-115): hor, vert, oct
+  int coll_steps[3] = {0, 0, 0};
 };
 
 // stop codes, shared with include/simc_b200.h (simc_b200_stop_name)

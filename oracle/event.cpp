@@ -430,6 +430,7 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     s.trk.calls = s.calls[1];
     run_arm(s, arm, s.optics_p, a);
     s.ntup.resfac = a.resmult;
+    for (int k = 0; k < 3; ++k) s.coll_steps[1][k] = a.coll_steps[k];
     s.stop_p = a.ok_spec ? 0 : a.stop_code;
     s.hut_p = a.reached_hut;
     if (!a.ok_spec) return false;
@@ -492,6 +493,7 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     s.trk.calls = s.calls[0];
     run_arm(s, arm, s.optics_e, a);
     s.ntup.resfac = s.ntup.resfac + a.resmult;
+    for (int k = 0; k < 3; ++k) s.coll_steps[0][k] = a.coll_steps[k];
     s.stop_e = a.ok_spec ? 0 : a.stop_code;
     s.hut_e = a.reached_hut;
     if (!a.ok_spec) return false;

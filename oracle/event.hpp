@@ -135,6 +135,7 @@ struct Sim {
   bool hut_e = false, hut_p = false;
   bool low_w = false;            // peepi wanted the MAID table (W < 2 GeV), see physics_meson.cpp
   long long calls[2][48] = {};   // [0] electron arm, [1] hadron arm
+  int coll_steps[2][3] = {};     // slit STOP counter increments made inside mc_*_coll (hor, vert, oct), per arm
 };
 
 // Result of one pass through the loop body, simc.f:169-351

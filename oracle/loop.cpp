@@ -68,6 +68,13 @@ void accumulate(const Sim& s, const TryResult& r, const EventMain& main, const E
   for (int w = 0; w < 2; ++w) for (int k = 0; k < 48; ++k) a.transp_calls[w][k] += s.calls[w][k];
   stops(1, s.stop_p, s.hut_p);
   stops(0, s.stop_e, s.hut_e);
+  // steps spent in the collimator material bump the slit counters (mc_hms_coll.f:95-115), survivors included
+  for (int w = 0; w < 2; ++w) {
+    const int arm = w == 0 ? cfg.electron_arm : cfg.hadron_arm;
+    const int first = arm == 1 ? hms_stop::SLIT_HOR : arm == 5 ? shms_stop::SLIT_HOR : -1;
+    if (first < 0) continue;
+    for (int k = 0; k < 3; ++k) a.stop[w][2 + first + k] += s.coll_steps[w][k];
+  }
   if (r.success) add_fixed(a.sum_sigcc, main.sigcc);
   // geni: every try (simc.f:253-262)
   const double geni_vals[8] = {vertex.e.delta, vertex.e.yptar, -vertex.e.xptar, vertex.p.delta,

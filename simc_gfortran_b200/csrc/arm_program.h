@@ -45,7 +45,11 @@ enum ArmOpCode : int32_t {
   OP_CUT_T_BOX,      // stop if yt > a or -yt > b or -xt > c or -xt < d   sos/mc_sos.f:234
   OP_CUT_SOS_EXIT,   // w = a + b*(xs+c); stop if |xs| > c or |ys| > w    sos/mc_sos.f:328
   OP_SHIFT,          // xs += a*dxdzs, ys += a*dydzs (no path length) sos/mc_sos.f:339
-  OP_UNSUPPORTED     // collimator stepping for pions etc.
+  OP_COLL,           // mc_hms_coll / mc_shms_coll: pions and muons step through the collimator when using_coll.
+                     //   a..d = h_entr, v_entr, h_exit, v_exit, e = y_off, i0 = ops to skip when taken (the plain
+                     //   aperture checks), i1 = stop code of SLIT_HOR (VERT, OCT follow); the next two ops are data
+  OP_COLL_DATA       // [1]: a = step size, b = radiation length, c..e = rho, CO, |CO/27| of the collimator material;
+                     // [2]: a..e = ln10, log(me/I^2), and the three Z/A products (target.cuh: MatConst)
 };
 
 struct ArmOp {

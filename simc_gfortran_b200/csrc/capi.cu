@@ -522,7 +522,8 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n, cons
   auto it = h->arms.find(arm_id);
   if (it == h->arms.end() || !it->second.loaded)
     return fail(h, SIMC_ERR_STATE, "simc_b200_transport_batch: optics not loaded for this arm");
-  if (using_coll) return fail(h, SIMC_ERR_ARG, "collimator stepping (mc_hms_coll/mc_shms_coll) is not implemented");
+  if (using_coll && arm_id != SIMC_ARM_HMS && arm_id != SIMC_ARM_SHMS)
+    return fail(h, SIMC_ERR_ARG, "collimator stepping exists for the HMS and the SHMS only (mc_hms_coll / mc_shms_coll)");
   if (n == 0) return SIMC_OK;
   CU(h, cudaSetDevice(h->device));
   TransportBatchArgs a;
@@ -621,8 +622,6 @@ int validate_loop_config(simc_handle* h) {
     return fail(h, SIMC_ERR_ARG,
                 "radiative options outside rad_flag<=1, extrad_flag 1..2, intcor_mode=1, use_offshell_rad=1, "
                 "use_expon=0 are not implemented");
-  if (c.using_HMScoll || c.using_SHMScoll)
-    return fail(h, SIMC_ERR_ARG, "collimator stepping (using_HMScoll/using_SHMScoll) is not implemented");
   for (int arm : {c.electron_arm, c.hadron_arm}) {
     const bool used = (arm == c.electron_arm) ? c.using_E_arm_montecarlo : c.using_P_arm_montecarlo;
     if (!used) continue;
@@ -693,6 +692,8 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
   a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record; a.rec = d_rec; a.status = d_status;
   a.grid_blocks = h->grid_blocks;
+  auto coll = [&](int arm) { return arm == SIMC_ARM_HMS ? h->cfg.using_HMScoll : arm == SIMC_ARM_SHMS ? h->cfg.using_SHMScoll : 0; };
+  a.coll_e = coll(h->cfg.electron_arm); a.coll_p = coll(h->cfg.hadron_arm);
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem; a.sf_dem = h->d_sf_dem;

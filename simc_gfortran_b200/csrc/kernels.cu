@@ -16,6 +16,7 @@ namespace simc {
 namespace SIMC_VARIANT_NS {
 
 // Batch form of mc_hms / mc_shms / ... (hms/mc_hms.f:1-4): one thread per row.
+template <bool WITH_COLL>
 __global__ void __launch_bounds__(kBlock)
 k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const double* __restrict__ in,
                   unsigned long long seed, ArmFlags f, double ctau, double* __restrict__ out,
@@ -36,6 +37,7 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   const double p_spec = in[7 * n + ii];
   const double fry = in[8 * n + ii];
   t.p = p_spec * (1. + t.dpps / 100.);     // mc_hms.f:181
+  t.p_spec = p_spec;
   t.pathlen = 0.0;
   t.decdist = 0.0;
   t.mh2_final = t.m2;
@@ -52,7 +54,7 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   t.dflag = false;
   musc_refresh(t);
   const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
-  run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, arm->tab.n_ops);
+  run_arm<WITH_COLL>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, arm->tab.n_ops);
   if (i >= n) return;
   out[0 * n + i] = res.ok ? res.dpp_rec : dpp_in;
   out[1 * n + i] = res.ok ? res.dph_rec : dxdz_in;
@@ -78,13 +80,18 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
   {
     static bool attr_set = false;       // > 48 KB of dynamic shared memory needs the opt-in, once per process
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_transport_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      cudaError_t e = cudaFuncSetAttribute(k_transport_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_transport_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
   }
-  k_transport_batch<<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
-                                                        a.flags);
+  if (f.using_coll)
+    k_transport_batch<true><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+                                                                a.flags);
+  else
+    k_transport_batch<false><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+                                                                 a.flags);
   return cudaGetLastError();
 }
 
@@ -251,6 +258,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
@@ -264,11 +273,13 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       k_generate<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
     }
   } else if (stage == 1) {
-    k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
+    if (a.coll_p) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
+    else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
     for (int k = 0; k < arm_p.tab.n_mid; ++k) { A.mid_k = k; k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p); }
     k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
   } else if (stage == 2) {
-    k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+    if (a.coll_e) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+    else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
     for (int k = 0; k < arm_e.tab.n_mid; ++k) { A.mid_k = k; k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e); }
     k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
   } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);

@@ -35,6 +35,7 @@ struct LoopLaunch {
   double* rec;                // [SIMC_EVENT_NREC][n_tries] device, record mode only
   int* status;
   int grid_blocks;            // persistent grid for the stage kernels
+  int coll_e, coll_p;         // the arm steps pions through its collimator (using_HMScoll / using_SHMScoll)
   double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
   const double* sf_pm;        // Benhar spectral function (device): Pm axis, Em axis, values [n_pm][n_em]
   const double* sf_em;

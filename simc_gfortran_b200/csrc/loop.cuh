@@ -251,8 +251,11 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
 // coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
 // after almost no arithmetic); SEG 2 (once per further compaction point of the arm program, A.mid_k) = a
 // stretch of magnets; SEG 1 = the rest (always the whole hut) and reconstruction for the compacted survivors.
-template <int WHICH, int SEG>
+// SEG_ = 3: SEG 0 built with the collimator stepping (using_HMScoll / using_SHMScoll).
+template <int WHICH, int SEG_>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
+  constexpr int SEG = SEG_ == 3 ? 0 : SEG_;
+  constexpr bool kColl = SEG_ == 3;
   extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
@@ -351,12 +354,13 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       t.dpps = en.sp_delta; t.xs = en.x; t.ys = en.y; t.dxdzs = en.dx; t.dydzs = en.dy;
       t.m2 = WHICH == 1 ? Mh2 : SIMC_ME * SIMC_ME;
       t.p = sp.P * (1. + t.dpps / 100.);
+      t.p_spec = sp.P;
       t.pathlen = 0.0; t.decdist = 0.0; t.mh2_final = Mh2; t.ctau = cfg.ctau;
       t.dflag = false;
       musc_refresh(t);
       if (use_mc) {
         if (active) warp_count(&s_stop[0]);
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, split, s_calls);
+        run_arm<kColl>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, split, s_calls, s_stop);
         ok = alive;
       } else {
         ok = active;
@@ -376,10 +380,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
     } else if (SEG == 2) {
       if (active) {
         t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
-        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
+        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.p_spec = sp.P; t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
         t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
       } else {
-        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
+        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.p_spec = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
       }
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
@@ -401,10 +405,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       double rc_delta = 0, rc_yptar = 0, rc_xptar = 0, rc_z = 0.0, path = 0.0, resmult = 0.0;
       if (active) {
         t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
-        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
+        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.p_spec = sp.P; t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
         t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
       } else {
-        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
+        t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.p_spec = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
       }
       // a hadron that decayed before the collimator carries its daughter's mass (Mh2_final, simulate.inc:92)
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;

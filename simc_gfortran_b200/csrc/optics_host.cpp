@@ -189,6 +189,11 @@ PolyClass compile_terms(const CosyTerms& t, std::vector<double>& recs, long long
 }
 
 // ---- op list helpers -------------------------------------------------------------------
+}  // namespace
+}  // namespace simc
+#include "target.cuh"
+namespace simc {
+namespace {
 struct Prog {
   std::vector<ArmOp> ops;
   ArmOp& add(int op, int code = 0) {
@@ -198,6 +203,17 @@ struct Prog {
     return ops.back();
   }
   void project(double z) { add(OP_PROJECT).a = z; }
+  // mc_hms_coll.f:17-47 / mc_shms_coll.f:17-47: geometry, 20 steps, tungsten-alloy constants
+  void collimator(double h_entr, double v_entr, double h_exit, double v_exit, double y_off, double thick, double radl,
+                  int n_skip, int slit_hor_code, int coll_code) {
+    ArmOp& o = add(OP_COLL, coll_code);
+    o.a = h_entr; o.b = v_entr; o.c = h_exit; o.d = v_exit; o.e = y_off; o.i0 = n_skip; o.i1 = slit_hor_code;
+    const MatConst mc = make_mat(17.0, 69.45, 171.56797);
+    ArmOp& d1 = add(OP_COLL_DATA);
+    d1.a = thick / 20; d1.b = radl; d1.c = mc.rho; d1.d = mc.CO; d1.e = mc.co27;
+    ArmOp& d2 = add(OP_COLL_DATA);
+    d2.a = mc.ln10; d2.b = mc.log_me_I2; d2.c = mc.p_mp; d2.d = mc.p_log; d2.e = mc.p_chsi;
+  }
   void project_dd(int cls, double plus) { ArmOp& o = add(OP_PROJECT_DD); o.i0 = cls; o.a = plus; }
   void transp(int cls, double zd) { ArmOp& o = add(OP_TRANSP); o.i0 = cls; o.a = zd; }
   void cut_r2(double r, int code) { add(OP_CUT_R2, code).a = r * r; }
@@ -270,10 +286,15 @@ void build_hms(Prog& P) {
   const double xop = 2.8, yop = 0.0;
   const double r_Q1 = 20.50, r_Q2 = 30.22, r_Q3 = 30.22;       // apertures_hms.inc
   P.project(z_entr);
-  P.add(OP_UNSUPPORTED, COLL).i0 = 1;                          // only taken when using_coll && pion mass
-  P.octagon(x_off, y_off, h_entr, v_entr, SLIT_HOR, SLIT_VERT, SLIT_OCT);
-  P.project(z_exit - z_entr);
-  P.octagon(x_off, y_off, h_exit, v_exit, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+  {   // mc_hms.f:204-254: pions / muons step through the collimator when using_HMScoll, else two aperture checks
+    const size_t at = P.ops.size();
+    P.collimator(h_entr, v_entr, h_exit, v_exit, y_off, 6.30, 0.41753, 0, SLIT_HOR, COLL);
+    const size_t first = P.ops.size();
+    P.octagon(x_off, y_off, h_entr, v_entr, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+    P.project(z_exit - z_entr);
+    P.octagon(x_off, y_off, h_exit, v_exit, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+    P.ops[at].i0 = (int)(P.ops.size() - first);
+  }
   P.project_dd(1, -z_exit);           P.cut_r2(r_Q1, Q1_IN);
   P.transp(2, 125.233e0);             P.cut_r2(r_Q1, Q1_MID);
   P.transp(3, 62.617e0);              P.cut_r2(r_Q1, Q1_OUT);
@@ -414,12 +435,16 @@ void build_shms(Prog& P) {
   P.project(zd_hbmen);             hb(0.98, r_HBmenyp, r_HBmenym, 1.5, HB_MEN);
   P.transp(3, zd_hbmex);           hb(0.98, r_HBmexyp, r_HBmexym, -1.5, HB_MEX);
   P.project(zd_hbout);             hb(1.51, r_HBbyp, r_HBbym, -1.5, HB_OUT);
-  P.add(OP_UNSUPPORTED, COLL).i0 = 1;
-  P.project(z_entr);
-  P.octagon(x_off, y_off, h_entr, v_entr, SLIT_HOR, SLIT_VERT, SLIT_OCT);
-  P.project(z_thick);
-  {  // exit side is written ((-v_exit)/(h_exit)*|y| + 3*(v_exit)/2): same arithmetic as the entrance form
+  P.project(z_entr);               // first statement of both branches of shms/mc_shms.f:503-560
+  {   // pions / muons step through the collimator when using_SHMScoll (mc_shms_coll), else two aperture checks
+    const size_t at = P.ops.size();
+    P.collimator(8.50, 12.50, 8.65, 12.85, 0.000, 6.35, 0.42084, 0, SLIT_HOR, COLL);
+    const size_t first = P.ops.size();
+    P.octagon(x_off, y_off, h_entr, v_entr, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+    P.project(z_thick);
+    // exit side is written ((-v_exit)/(h_exit)*|y| + 3*(v_exit)/2): same arithmetic as the entrance form
     P.octagon(x_off, y_off, h_exit, v_exit, SLIT_HOR, SLIT_VERT, SLIT_OCT);
+    P.ops[at].i0 = (int)(P.ops.size() - first);
   }
   P.project(zd_q1in - z_entr - z_thick); P.cut_r2(r_Q1, Q1_IN);
   P.project(zd_q1men);             P.cut_r2(r_Q1, Q1_MEN);

@@ -41,6 +41,7 @@ struct TrackDev {
   double p, m2, pathlen;
   double decdist, mh2_final, ctau;        // simulate.inc:183, :92, :153
   double mc1, mbeta2;                     // cached Es/p/beta and beta^2 of musc (valid while p,m2 unchanged)
+  double p_spec;                          // the arm's central momentum (argument of mc_hms / mc_hms_coll)
   bool dflag;
 };
 
@@ -417,15 +418,109 @@ __device__ __forceinline__ void arm_result_clear(ArmResult& res) {
   res.dpp_rec = res.dth_rec = res.dph_rec = res.y_rec = 0.0;
 }
 
+// hms/pion_coll_absorb.f:1-95: transmission of a pion through `thick` cm of the collimator alloy
+__device__ const double kCollT[14] = {85.0, 125.0, 165.0, 205.0, 245.0, 315.0, 584.02, 711.95, 870.12, 1227.57, 1446.58,
+                                      1865.29, 2858.0, 4159.0};
+__device__ const double kCollSig[14] = {26.03, 84.47, 117.3, 117.4, 101.9, 69.58, 42.5, 44.7, 47.9, 46.5, 45.2, 39.6, 35.34,
+                                        33.15};
+__device__ const double kCollQ[14] = {0.948, 0.659, 0.56, 0.5342, 0.5452, 0.60796, 0.699, 0.689, 0.679, 0.683, 0.688, 0.704,
+                                      0.7483, 0.7705};
+__device__ __noinline__ double pion_coll_absorb(double ppi, double thick) {
+  const double* T = kCollT;
+  const double* sigreac = kCollSig;
+  const double* qreac = kCollQ;
+  const double Navagadro = 6.0221367e+23, mpi = 139.56995, mate_dens = 17.0, mate_A = 171.57;
+  const double Tpi = sqrt(ppi * ppi + mpi * mpi) - mpi;
+  double sigA = 0.0;
+  for (int i = 1; i <= 13; ++i) {
+    if ((Tpi > T[i - 1]) && (Tpi <= T[i])) {
+      const double Thi = T[i], Tlo = T[i - 1];
+      const double sigAhi = sigreac[i] * m::pow(mate_A, qreac[i]);
+      const double sigAlo = sigreac[i - 1] * m::pow(mate_A, qreac[i - 1]);
+      sigA = (sigAlo * (Thi - Tpi) + sigAhi * (Tpi - Tlo)) / (Thi - Tlo);
+      sigA = sigA * 1.e-27;
+    }
+  }
+  if (Tpi > T[13]) sigA = (sigreac[13] * m::pow(mate_A, qreac[13])) * 1.e-27;
+  const double lambdai = mate_dens * Navagadro * sigA / mate_A;
+  return m::exp(-(0.0 + thick * lambdai));
+}
+
+__device__ __forceinline__ bool collimator_steps_body(const ArmOp* o, TrackDev& t, DevRng& rng, bool decay_flag, unsigned* stop_counts);
+// mc_hms_coll (hms/mc_hms_coll.f:1-147) / mc_shms_coll: 20 slices through the collimator; in the material the
+// particle may be absorbed (pions), scatters, loses energy (sampled), and decays in flight.  `o` is the OP_COLL
+// op, followed by its two data ops.  Returns false when the particle is lost.  The slit STOP counters are bumped
+// once per slice spent in the material, survivors included (mc_hms_coll.f:95-115).
+// Track and generator go in and out by value, so the caller's copies stay in registers (this code only runs for
+// decks with using_HMScoll / using_SHMScoll).
+struct CollOut { TrackDev t; uint32_t draw; bool ok; };
+__device__ __noinline__ CollOut collimator_steps(const ArmOp* o, TrackDev t, DevRng rng, bool decay_flag, unsigned* stop_counts) {
+  CollOut R;
+  R.ok = collimator_steps_body(o, t, rng, decay_flag, stop_counts);
+  R.t = t; R.draw = rng.draw;
+  return R;
+}
+__device__ __forceinline__ bool collimator_steps_body(const ArmOp* o, TrackDev& t, DevRng& rng, bool decay_flag, unsigned* stop_counts) {
+  const ArmOp* d1 = o + 1;
+  const ArmOp* d2 = o + 2;
+  MatConst mc;
+  mc.rho = d1->c; mc.I = 0.; mc.CO = d1->d; mc.co27 = d1->e; mc.ln10 = d2->a; mc.log_me_I2 = d2->b; mc.p_mp = d2->c;
+  mc.p_log = d2->d; mc.p_chsi = d2->e;
+  const int nstep = 20;
+  const double step_size = d1->a, radl = d1->b, y_off = o->e;
+  const double p_spec = t.p_spec;
+  double h_step = o->a, v_step = o->b;
+  for (int n = 1; n <= nstep; ++n) {
+    const bool hor = fabs(t.ys - y_off) > h_step;
+    const bool ver = fabs(t.xs - 0.000) > v_step;
+    const bool oct = fabs(t.xs - 0.000) > (-v_step / h_step * fabs(t.ys - y_off) + 3 * v_step / 2);
+    if (stop_counts) {
+      if (hor) atomicAdd(&stop_counts[2 + o->i1], 1u);
+      if (ver) atomicAdd(&stop_counts[2 + o->i1 + 1], 1u);
+      if (oct) atomicAdd(&stop_counts[2 + o->i1 + 2], 1u);
+    }
+    if (hor || ver || oct) {
+      const double thick = step_size;
+      if (t.m2 > 12000. && t.m2 < 20000.) {          // pions only: hadronic interaction
+        const double trans = pion_coll_absorb(t.p, thick);
+        if (rng.uniform() > trans) return false;
+      }
+      const double radw = thick / radl;
+      const double ts = t.mc1 * sqrt(radw) * (1 + 0.088 * m::log10(radw / t.mbeta2));      // musc(m2,p,radw,dydzs,dxdzs)
+      t.dydzs = t.dydzs + ts * gauss1(rng, 99.0);
+      t.dxdzs = t.dxdzs + ts * gauss1(rng, 99.0);
+      double epart = sqrt(t.p * t.p + t.m2);
+      const double mpart = sqrt(t.m2);
+      const ParticleKin k = particle_kin(epart, mpart, mc.ln10);
+      const double x = fabs(gauss1(rng, 10.0));
+      const double eloss = enerloss_material(k, thick, mc, x);
+      epart = epart - eloss;
+      if (epart < mpart) return false;
+      t.p = sqrt(epart * epart - t.m2);
+      t.dpps = 100. * (t.p / p_spec - 1.);
+      musc_refresh(t);
+    }
+    project(t, rng, step_size, decay_flag);
+    h_step = h_step + (o->c - o->a) / nstep;
+    v_step = v_step + (o->d - o->b) / nstep;
+  }
+  return true;
+}
+
 // Interprets ops [op_begin, op_end) of the arm program.  EVERY lane of the warp must call this
 // (lanes without an event pass alive = false): the warp walks the program in lock step and
 // re-converges before each op, so a lane only idles while other lanes still have work in the same
 // op.  `alive` comes back false when the event stopped (res.stop_code) or finished (res.ok).
 // `pw` = this thread's column of the CTA's shared power table.
+// WITH_COLL: the kernel was built with the collimator stepping of OP_COLL (only launched for decks that ask for
+// it, so that the other kernels do not carry its call).
+template <bool WITH_COLL = false>
 __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& rng, const ArmFlags f,
                                         double fry, double* pw, unsigned ring, ArmResult& res, HutState& hs,
-                                        bool& alive, int op_begin, int op_end, unsigned* call_counts = nullptr) {
+                                        bool& alive, int op_begin, int op_end, unsigned* call_counts = nullptr,
+                                        unsigned* stop_counts = nullptr) {
   double xt = 0., yt = 0.;
+  int skip_until = 0;          // this lane ignores ops before this index (set by OP_COLL)
   for (int pc = op_begin; pc < op_end; ++pc) {
     __syncwarp();
     if (!__any_sync(0xffffffffu, alive)) break;
@@ -467,7 +562,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       }
       continue;
     }
-    if (!alive) continue;
+    if (!alive || pc < skip_until) continue;
     bool stop = false;
     switch (op) {
       case OP_PROJECT: project(t, rng, a, f.decay_flag); break;
@@ -568,10 +663,16 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
         stop = (ycal > b) || (ycal < c) || (xcal > d) || (xcal < e);
         break;
       }
-      case OP_UNSUPPORTED:
-        // collimator stepping for pions/muons (mc_hms_coll / mc_shms_coll): only when requested
-        stop = f.using_coll && (t.m2 > 100.0 * 100.0) && (t.m2 < 200.0 * 200.0);
+      case OP_COLL:
+        // mc_hms.f:206 / mc_shms.f:503: pions and muons are stepped through the collimator material
+        if (WITH_COLL && f.using_coll && (t.m2 > 100.0 * 100.0) && (t.m2 < 200.0 * 200.0)) {
+          const CollOut co = collimator_steps(o, t, rng, f.decay_flag, stop_counts);
+          t = co.t; rng.draw = co.draw;
+          stop = !co.ok;
+          skip_until = pc + 3 + o->i0;          // the plain aperture checks belong to the other branch
+        }
         break;
+      case OP_COLL_DATA: break;
       default: break;
     }
     if (stop) { res.stop_code = o->code; alive = false; }
