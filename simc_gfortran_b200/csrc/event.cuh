@@ -476,7 +476,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
 // electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
 // limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev& pfm, const SfDev& sf, RNG& rng,
+SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev pfm, const SfDev sf, RNG& rng,
                             GAUSS gauss, EventState& s, bool ok) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;

@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     const bool heavy = cfg.doing_heavy != 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
+    // (tables by value: a reference into the kernel parameters handed to an out-of-line function would make the
+    //  compiler copy all of LoopArgs to every thread's stack -- +600 bytes of frame, +10 % kernel time)
     if (meson) ok = generate_meson(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active);
     else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);

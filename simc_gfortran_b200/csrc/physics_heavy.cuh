@@ -20,7 +20,7 @@ struct SfDev {                // device pointers; val[iPm * n_em + iEm]
 // value (the slope term is 0 * finite), except at the last one, where no branch of sf_lookup matches and its
 // SAVEd interval of the previous call is reused: sf(n-1) + (E_n - E_n-1) * (sf(n) - sf(n-1)) / (E_n - E_n-1).
 // u1, u2: the two uniforms generate_em draws.  Two passes over the column pair instead of a 200-entry array.
-SIMC_HD_CALL double generate_em(const SfDev& T, double Pm, double u1, double u2) {
+SIMC_HD_CALL double generate_em(const SfDev T, double Pm, double u1, double u2) {   // by value: see loop.cuh
   const int numPm = T.n_pm, numEm = T.n_em;
   int iPm;
   double w1, w2;
@@ -65,7 +65,7 @@ struct TheoryDev {
   double e_fermi;
 };
 // event.f:1402-1428: linear interpolation of rho_i(Pm); Lorentzian in Em above E_Fermi for A > 2
-SIMC_HD_CALL double theory_sf_weight(const TheoryDev& T, bool heavy, double Em, double Pm) {
+SIMC_HD_CALL double theory_sf_weight(const TheoryDev T, bool heavy, double Em, double Pm) {
   const double pi = 3.141592653589793;
   double SF_weight = 0.0;
   for (int i = 0; i < T.nrho; ++i) {
@@ -95,7 +95,7 @@ SIMC_HD_CALL double theory_sf_weight(const TheoryDev& T, bool heavy, double Em, 
 }
 
 // sf_lookup.f:97-170 (1-based indices of the Fortran kept in the helpers)
-SIMC_HD_CALL double sf_lookup(const SfDev& T, double Em, double Pm, bool& bad) {
+SIMC_HD_CALL double sf_lookup(const SfDev T, double Em, double Pm, bool& bad) {
   const int numPm = T.n_pm, numEm = T.n_em;
 #define SF_PM(i) T.pm[(i) - 1]
 #define SF_EM(i) T.em[(i) - 1]
@@ -145,7 +145,7 @@ SIMC_HD_CALL double sf_lookup(const SfDev& T, double Em, double Pm, bool& bad) {
 }
 
 // sf_lookup.f:85-95
-SIMC_HD_CALL double sf_lookup_diff(const SfDev& T, double Em, double Pm, bool& bad) {
+SIMC_HD_CALL double sf_lookup_diff(const SfDev T, double Em, double Pm, bool& bad) {
   const double SF = sf_lookup(T, Em, Pm, bad);
   return SF / 4 / 3.1415926535 / (Pm * Pm) / 5.0 / 20.0;
 }

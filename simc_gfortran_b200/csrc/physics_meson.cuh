@@ -204,7 +204,7 @@ SIMC_HD_CALL double sig_factorized(double q2, double w, double t, double pk, dou
 struct MaidDev { const double* tbl; };
 
 // sigmaid, physics_pion.f:577-728: nearest-bin lookup in the MAID-2007 table; peepi only uses sig0
-SIMC_HD_CALL double sigmaid_sig0(const MaidDev& M, double q2, double w, double e0, double costh, double phi) {
+SIMC_HD_CALL double sigmaid_sig0(const MaidDev M, double q2, double w, double e0, double costh, double phi) {
   const double am = 0.9383;
   if (w < 1.08) return 0.;
   const double nu = (w * w - am * am + q2) / 2. / am;
@@ -241,7 +241,7 @@ struct MesonWeight {
 };
 
 // physics_pion.f:1-130
-SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MaidDev& maid, const MesonVertex& v) {
+SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MaidDev maid, const MesonVertex& v) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
   const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
   MesonCm C;

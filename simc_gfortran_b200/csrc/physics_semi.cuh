@@ -58,7 +58,7 @@ SIMC_HD double fdss_interp(const double* tab, const FdssCell& c) {
   return r;
 }
 // fDSS (fdss/fdss.f:1-215) for kaons at NLO: z D(z, Q2) of u, ubar, d, dbar, s, sbar into a hadron of charge ic
-SIMC_HD_CALL void fDSS(const FdssDev& T, int ic, double X, double Q2, double* out6) {
+SIMC_HD_CALL void fDSS(const FdssDev T, int ic, double X, double Q2, double* out6) {
   const FdssCell c = fdss_cell(T, m::log(X), m::log(Q2));
   const double x1 = 1. - X;
   const double x1s = x1 * x1;
@@ -357,7 +357,7 @@ struct SemiWeight {
 
 // peepiX with doing_cent = .false. (semi_physics.f:1-617), pions.  dbg (may be null) receives
 // { u, ubar, d, dbar, s, sbar, F1p, F2p, F1n, F2n, sige } for the stage-level parity entry point.
-SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev& T, const FdssDev& F, const SemiVertex& v,
+SIMC_HD_CALL SemiWeight peepiX(const simc_run_config& cfg, const Cteq5Dev T, const FdssDev F, const SemiVertex& v,
                                double* dbg) {
   const double pf[12] = {1.0424, -0.1714, 1.8960, -0.0307, 0.1636, -0.1272, -4.2093, 5.0103, 2.7406, -0.5778, 3.5292, 7.3910};
   const double pu[12] = {0.7840, 0.2369, 1.4238, 0.1484, 0.1518, -1.2923, -1.5710, 3.0305, 1.1995, 1.3553, 2.5868, 8.0666};
