@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     const unsigned slot = warp_append(&A.counts[0], want_slot);
     if (want_slot) {
       const StateBuf& S = A.st;
-      S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)rng.draw); S.st(F_STAGE, slot, ok ? 1.0 : 0.0);
-      S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
+      S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)rng.draw);
+      if (A.record_mode) {      // only the per-try records read these
+        S.st(F_STAGE, slot, ok ? 1.0 : 0.0); S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
+      }
       S.st(F_TX, slot, s.tx); S.st(F_TY, slot, s.ty); S.st(F_TZ, slot, s.tz); S.st(F_RASTERY, slot, s.rastery);
       S.st(F_ELOSS0, slot, s.Eloss[0]); S.st(F_ELOSS1, slot, s.Eloss[1]); S.st(F_ELOSS2, slot, s.Eloss[2]);
       S.st(F_TEFF0, slot, s.teff[0]); S.st(F_TEFF1, slot, s.teff[1]); S.st(F_TEFF2, slot, s.teff[2]);
@@ -374,9 +376,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
           S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
           S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0); S.st(F_TK_FRY, slot, fry);
         } else {
-          S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
+          if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
           warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
-          if (WHICH == 1) S.st(F_RESFAC, slot, 0.0);
         }
       }
     } else if (SEG == 2) {
@@ -398,9 +399,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
           S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
           S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0);
         } else {
-          S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
+          if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
           warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
-          if (WHICH == 1) S.st(F_RESFAC, slot, 0.0);
         }
       }
     } else {
@@ -430,9 +430,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         rc_xptar = S.ld(WHICH == 1 ? F_SPP_X : F_SPE_X, slot);
       }
       if (active) {
-        S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)(ok ? 0 : res.stop_code));
+        if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)(ok ? 0 : res.stop_code));
         S.st(F_DRAW, slot, (double)rng.draw);
-        if (WHICH == 1) S.st(F_RESFAC, slot, resmult);
       }
       if (ok) {
         S.st(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta); S.st(WHICH == 1 ? F_RCP_Y : F_RCE_Y, slot, rc_yptar);
@@ -465,11 +464,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         }
         if (WHICH == 1) {
           S.st(F_RP_P, slot, rP); S.st(F_RP_E, slot, rE); S.st(F_RP_TH, slot, rth); S.st(F_RP_PH, slot, rph);
-          S.st(F_STAGE, slot, 2.0);
+          if (A.record_mode) S.st(F_STAGE, slot, 2.0);
         } else {
           S.st(F_RE_E, slot, rE); S.st(F_RE_TH, slot, rth); S.st(F_RE_PH, slot, rph);
-          S.st(F_RESFAC, slot, S.ld(F_RESFAC, slot) + resmult);
-          S.st(F_STAGE, slot, 3.0);
+          if (A.record_mode) S.st(F_STAGE, slot, 3.0);
         }
       }
     }
@@ -618,7 +616,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         // event.f:1306-1345: missing mass of the undetected system
         rEm = nu + cfg.targ.Mtar_struck - rpE;
         const double mm2 = rEm * rEm - rPm * rPm;
-        S.st(F_MM, slot, sqrt(fabs(mm2)) * fabs(mm2) / mm2);
+        if (A.record_mode) S.st(F_MM, slot, sqrt(fabs(mm2)) * fabs(mm2) / mm2);
         MesonVertex mv;
         mv.Ein = v_Ein; mv.eE = v_eE; mv.nu = S.ld(F_VNU, slot); mv.q = S.ld(F_VQ, slot); mv.Q2 = v_Q2;
         mv.pP = S.ld(F_VPP, slot); mv.pE = S.ld(F_VPE, slot);
@@ -642,7 +640,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           const SemiWeight w_ = peepiX(cfg, A.pdf, A.fdss, sv_, nullptr);
           mw.sigcc = w_.sigcc; mw.sigcm = w_.sighad; mw.davejac = w_.davejac; mw.low_w = w_.bad;
           mw.thetacm = 0.0; mw.phicm = 0.0; mw.wcm = 0.0;
-          S.st(F_XFERMI, slot, w_.xfermi);      // ntup%xfermi, semi_physics.f:250
+          if (A.record_mode) S.st(F_XFERMI, slot, w_.xfermi);      // ntup%xfermi, semi_physics.f:250
           if (!cfg.doing_decay && !w_.early) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
         } else if (cfg.doing_pion) {
           mw = peepi(cfg, A.maid, mv);
@@ -655,8 +653,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         low_w = mw.low_w;
         sigcc = mw.sigcc;
         sigcc_recon = 1.0;
-        S.st(F_THCM, slot, mw.thetacm); S.st(F_PHICM, slot, mw.phicm); S.st(F_SIGCM, slot, mw.sigcm);
-        S.st(F_DAVEJAC, slot, mw.davejac); S.st(F_SURV, slot, survivalprob); S.st(F_WCM, slot, mw.wcm);
+        if (A.record_mode) {
+          S.st(F_THCM, slot, mw.thetacm); S.st(F_PHICM, slot, mw.phicm); S.st(F_SIGCM, slot, mw.sigcm);
+          S.st(F_DAVEJAC, slot, mw.davejac); S.st(F_SURV, slot, survivalprob); S.st(F_WCM, slot, mw.wcm);
+        }
       }
       if (cfg.using_Coulomb) { const double c = 1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam; sigcc = sigcc * (c * c); }
       weight = SF_weight * S.ld(F_JAC, slot) * S.ld(F_GENW, slot) * sigcc;
@@ -682,9 +682,11 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         if (!pass_cuts) success = false;
         if (cfg.doing_eep && (rEm > cfg.cuts_Em.max)) success = false;
       }
-      S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
-      S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
-      S.st(F_STAGE, slot, success ? 4.0 : 3.0);
+      if (A.record_mode) {      // only the per-try records and the ntuple rows read these
+        S.st(F_WEIGHT, slot, weight); S.st(F_SIGCC, slot, sigcc); S.st(F_SIGCC_RECON, slot, sigcc_recon);
+        S.st(F_PASSCUTS, slot, pass_cuts ? 1.0 : 0.0); S.st(F_REM, slot, rEm); S.st(F_RPM, slot, rPm); S.st(F_RW, slot, rW);
+        S.st(F_STAGE, slot, success ? 4.0 : 3.0);
+      }
       if (success && A.record_mode) {
         // ---- ntuple row, results_ntu_write (results_write.f:1-269); complete_recon_ev's remaining
         // quantities (event.f:1150-1300) are only needed here
