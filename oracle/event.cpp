@@ -155,6 +155,10 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     if (radical < 0) return false;
     vertex.p.E = (-QB - sqrt(radical)) / 2. / QA;
     if (vertex.p.E < 0.0) return false;
+    const double Ehad2 = (-QB + sqrt(radical)) / 2. / QA;
+    if (cfg.doing_delta) {                       // :682-684 choose one of the two solutions
+      if (s.rng->grnd() > 0.5) vertex.p.E = Ehad2;
+    }
     const double E_rec = c - vertex.p.E;
     if (E_rec <= targ.Mrec_struck) return false;
     if (vertex.p.E <= Mh) return false;
@@ -210,7 +214,7 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     vertex.Mrec = sqrt(vertex.Emiss * vertex.Emiss - vertex.Pmiss * vertex.Pmiss);
     vertex.Em = targ.Mtar_struck + vertex.Mrec - targ.M;
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
-  } else if (cfg.doing_hydpi || cfg.doing_hydkaon) {
+  } else if (cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_delta) {   // doing_hyddelta: hydrogen only here
     vertex.Trec = 0.0;
   } else if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
@@ -654,6 +658,9 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     main.sigcc_recon = 1.0;
     if (cfg.which_pion == 1 || cfg.which_pion == 11) tgtweight = cfg.targ.N;
     else tgtweight = cfg.targ.Z;
+  } else if (cfg.doing_delta) {                 // :1511-1513
+    main.sigcc = peedelta(s, vertex, main);
+    main.sigcc_recon = 1.0;
   } else if (cfg.doing_kaon) {
     main.sigcc = peeK(s, vertex, main, survivalprob);
     main.sigcc_recon = 1.0;

@@ -166,6 +166,7 @@ bool complete_recon_ev(Sim& s, Event& recon);                                   
 bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Event& recon);              // event.f:1363
 double sigep(const Event& vertex);
 double peepi(Sim& s, const Event& vertex, EventMain& main);                                             // physics_pion.f:1
+double peedelta(Sim& s, const Event& vertex, EventMain& main);                                          // physics_delta.f:1
 double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob);                        // physics_kaon.f:1
 double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob, SemiDebug* dbg = nullptr); // semi_physics.f:1
 double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax);  // radc.f:523                                                                       // physics_proton.f:1

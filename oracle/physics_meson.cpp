@@ -318,4 +318,51 @@ double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob) 
   return result;
 }
 
+// physics_pion.f:404-465
+double sig_blok(double thetacm, double phicm, double t, double q2_gev, double s_gev, double eps, double mtar_gev, int which_pion) {
+  double sigl = 27.8 * exp(-11.5 * fabs(t));
+  double sigt = 10.0 * (5. * fabs(t)) * exp(-5. * fabs(t));
+  const double siglt = 0.0 * sin(thetacm);
+  double sigtt = -(4.0 * sigl + 0.5 * sigt) * powi(sin(thetacm), 2);
+  if (which_pion == 1 || which_pion == 11 || which_pion == 3) {
+    sigt = sigt * 0.25 * (1. + 3. * exp(-10. * fabs(t)));
+    sigtt = sigtt * 0.25 * (1. + 3. * exp(-10. * fabs(t)));
+  }
+  const double fpi = 1. / (1. + 1.65 * q2_gev + 0.5 * powi(q2_gev, 2));
+  const double fpi2 = powi(fpi, 2);
+  sigl = sigl * (fpi2 * q2_gev) / 0.1215;
+  sigt = sigt / (0.3 + q2_gev);
+  sigtt = sigtt / (0.3 + q2_gev);
+  const double sig219 = (sigt + eps * sigl + eps * cos(2. * phicm) * sigtt + sqrt(2.0 * eps * (1. + eps)) * cos(phicm) * siglt) / 1.e0;
+  double sig = sig219 * 15.333 / powi(s_gev - powi(mtar_gev, 2), 2);
+  sig = sig / 2. / K::pi / 1.e+06;
+  return sig;
+}
+
+// physics_delta.f:1-135
+double peedelta(Sim& s, const Event& vertex, EventMain& main) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const Fermi F = fermi_of(s);
+  CmFrame C;
+  transform_to_cm(vertex, main, F, C);
+  main.thetacm = C.thetacm;
+  main.phicm = C.phicm;
+  main.pcm = C.phadcm;
+  main.davejac = C.jacobian;
+  main.johnjac = C.jac_old;
+  double tfcos = F.pferx * vertex.uq.x + F.pfery * vertex.uq.y + F.pferz * vertex.uq.z;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double sgev = powi(vertex.nu + F.efer, 2) - powi(vertex.q + F.pfer * tfcos, 2) - powi(F.pfer * tfsin, 2);
+  main.wcm = sqrt(sgev);
+  const double k_eq = (main.wcm * main.wcm - targ.Mtar_struck * targ.Mtar_struck) / 2. / targ.Mtar_struck;
+  s.ntup.sigcm1 = sig_blok(C.thetacm, C.phicm, main.t / 1.e6, vertex.Q2 / 1.e6, sgev / 1.e6, main.epsilon,
+                           targ.Mtar_struck / 1000., cfg.which_pion);
+  s.ntup.sigcm = s.ntup.sigcm1;
+  const double fac = 1. / (1. - F.pferz * F.pfer / F.efer) * targ.Mtar_struck / F.efer;
+  const double gtpr = K::alpha / 2. / (K::pi * K::pi) * vertex.e.E / vertex.Ein * k_eq / vertex.Q2 / (1. - main.epsilon);
+  return 1.0 * C.jacobian * (gtpr * fac);
+}
+
 }  // namespace simc_oracle

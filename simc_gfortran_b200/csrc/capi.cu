@@ -597,11 +597,18 @@ int validate_loop_config(simc_handle* h) {
   const bool deut = c.doing_deuterium && c.doing_eep && !c.doing_heavy;
   const bool semi = c.doing_semi && (c.doing_semipi || c.doing_semika) && (c.doing_hydsemi || c.doing_deutsemi) &&
                     !c.doing_pion && !c.doing_kaon;
-  if (!(c.doing_hyd_elast || meson || heavy || deut || semi) || c.doing_delta || c.doing_rho || (c.doing_semi && !semi) ||
-      c.doing_phsp)
+  const bool delta = c.doing_delta && !c.doing_pion && !c.doing_kaon && !c.doing_semi && !c.doing_eep &&
+                     std::lround(c.targ.A) == 1;
+  if (!(c.doing_hyd_elast || meson || heavy || deut || semi || delta) || (c.doing_delta && !delta) || c.doing_rho ||
+      (c.doing_semi && !semi) || c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
                 "this build of the event loop implements H(e,e'p), D(e,e'p), A(e,e'p) with a Benhar or an "
-                "independent-particle spectral function, H(e,e'pi+-), H(e,e'K+) and semi-inclusive H/D(e,e'pi+-)X");
+                "independent-particle spectral function, H/D/A(e,e'pi+-), H/D/A(e,e'K+), H(e,e'p)pi0 and semi-inclusive "
+                "H/D(e,e'pi+-/K+-)X");
+  if (delta && c.using_rad)
+    return fail(h, SIMC_ERR_ARG,
+                "doing_delta with using_rad: the reference sets no photon-energy limits for this reaction "
+                "(radc.f:249-294 has no doing_delta case), so the radiated run is undefined; set using_rad = 0");
   if ((deut || (heavy && !c.use_benhar_sf)) && !h->d_theory)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: this reaction needs the theory table (simc_b200_set_theory_table / load_theory_file) first");
   if (semi && c.doing_semika && !h->d_fdss)
@@ -897,7 +904,7 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   int rc = validate_loop_config(h);
   if (rc) return rc;
   const simc_run_config& c = h->cfg;
-  *n_cols = c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
+  *n_cols = c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon || c.doing_delta) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
   *n_rows = 0;
   if (n == 0) return SIMC_OK;
   static_assert(SIMC_NTUPLE_MAXCOL <= SIMC_EVENT_NREC, "the record buffer is shared with simc_b200_event_batch");

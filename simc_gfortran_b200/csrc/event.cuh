@@ -391,6 +391,11 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
       if (run) {
         s.v_pE = (-QB - sqrt(radical)) / 2. / QA;
         if (s.v_pE < 0.0) run = false;
+        if (run && cfg.doing_delta) {               // event.f:680-684: one of the two solutions, by a coin toss
+          const double Ehad2 = (-QB + sqrt(radical)) / 2. / QA;
+          if (rng.uniform() > 0.5) s.v_pE = Ehad2;
+        }
+        if (!run) {}
         else if (c - s.v_pE <= targ.Mrec_struck) run = false;
         else if (s.v_pE <= Mh) run = false;
       }

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     const bool semi = cfg.doing_semi != 0;
     const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;   // nucleon momentum thrown
-    const bool meson = cfg.doing_pion || cfg.doing_kaon || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+    const bool meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     const bool heavy = cfg.doing_heavy != 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const bool semi = cfg.doing_semi != 0;
       const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;
-      const bool meson = cfg.doing_pion || cfg.doing_kaon || semi;
+      const bool meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || semi;
       const bool deut = cfg.doing_deuterium != 0;
       const bool heavy = cfg.doing_heavy != 0 || deut;          // (e,e'p) from a nucleus: deForest, A-1 recoil
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
@@ -645,6 +645,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         } else if (cfg.doing_pion) {
           mw = peepi(cfg, A.maid, mv);
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
+        } else if (cfg.doing_delta) {
+          mw = peedelta(cfg, mv);                      // event.f:1511-1513; tgtweight stays 1
         } else {
           mw = peeK(cfg, mv);
           tgtweight = (cfg.which_kaon == 2 || cfg.which_kaon == 12) ? cfg.targ.N : cfg.targ.Z;

@@ -270,6 +270,49 @@ SIMC_HD_CALL MesonWeight peepi(const simc_run_config& cfg, const MaidDev maid, c
   return w;
 }
 
+// physics_pion.f:404-465: fit to Brauel et al.; dsigma/dt/dphi_cm in ub/MeV^2/rad
+SIMC_HD double sig_blok(double thetacm, double phicm, double t, double q2_gev, double s_gev, double eps, double mtar_gev,
+                        int which_pion) {
+  const double pi = 3.141592653589793;
+  double sigl = 27.8 * m::exp(-11.5 * fabs(t));
+  double sigt = 10.0 * (5. * fabs(t)) * m::exp(-5. * fabs(t));
+  const double siglt = 0.0 * m::sin(thetacm);
+  const double sth = m::sin(thetacm);
+  double sigtt = -(4.0 * sigl + 0.5 * sigt) * (sth * sth);
+  if (which_pion == 1 || which_pion == 11 || which_pion == 3) {
+    sigt = sigt * 0.25 * (1. + 3. * m::exp(-10. * fabs(t)));
+    sigtt = sigtt * 0.25 * (1. + 3. * m::exp(-10. * fabs(t)));
+  }
+  const double fpi = 1. / (1. + 1.65 * q2_gev + 0.5 * (q2_gev * q2_gev));
+  const double fpi2 = fpi * fpi;
+  sigl = sigl * (fpi2 * q2_gev) / 0.1215;
+  sigt = sigt / (0.3 + q2_gev);
+  sigtt = sigtt / (0.3 + q2_gev);
+  const double sig219 = (sigt + eps * sigl + eps * m::cos(2. * phicm) * sigtt + sqrt(2.0 * eps * (1. + eps)) * m::cos(phicm) * siglt) / 1.e0;
+  const double d = s_gev - mtar_gev * mtar_gev;
+  double sig = sig219 * 15.333 / (d * d);
+  sig = sig / 2. / pi / 1.e+06;
+  return sig;
+}
+
+// physics_delta.f:1-135: H(e,e'p)pi0.  The weight is phase space times the virtual-photon flux (the model value
+// multiplies by 1.0, physics_delta.f:131); sig_blok only feeds the ntuple's sigcm column.
+SIMC_HD_CALL MesonWeight peedelta(const simc_run_config& cfg, const MesonVertex& v) {
+  const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
+  const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
+  MesonCm C;
+  transform_to_cm(v, C);
+  MesonWeight w;
+  w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = C.jacobian; w.johnjac = C.jac_old; w.wcm = C.wcm;
+  w.low_w = false;
+  const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;
+  w.sigcm = sig_blok(C.thetacm, C.phicm, v.t / 1.e6, v.Q2 / 1.e6, C.sgev / 1.e6, v.epsilon, Mtar / 1000., cfg.which_pion);
+  const double fac = 1. / (1. - pferz * pfer / efer) * Mtar / efer;
+  const double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * k_eq / v.Q2 / (1. - v.epsilon);
+  w.sigcc = 1.0 * C.jacobian * (gtpr * fac);
+  return w;
+}
+
 // physics_kaon.f:1-171 (without the survival probability, which needs the focal-plane track)
 SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;

@@ -280,8 +280,9 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     if (nA == 1 && c.which_kaon == 2) throw std::runtime_error("Sigma- production from Hydrogen not allowed!");
     c.doing_hydkaon = nA == 1; c.doing_deutkaon = nA == 2; c.doing_hekaon = nA >= 3;
     if (c.which_kaon >= 10) { c.doing_hydkaon = 1; c.doing_deutkaon = 0; c.doing_hekaon = 0; }
-  } else if (c.doing_delta) {
+  } else if (c.doing_delta) {                    // dbase.f:182-190: the reference warns for A >= 2 ("only set up for proton target")
     c.Mh = Mp;
+    if (nA != 1) throw std::runtime_error("Delta production (doing_delta) is only set up for a proton target");
   } else if (c.doing_semi) {
     c.Mh = doing_semika ? Mk : Mpi;
     c.doing_hydsemi = nA == 1; c.doing_deutsemi = nA == 2;
@@ -504,7 +505,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     edge.Em.max = c.cuts_Em.max + slop_total_Em;
     edge.Em.min = std::max(0.e0, edge.Em.min);
   }
-  if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_semi) {
+  if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_delta || c.doing_semi) {   // doing_delta: hydrogen only here
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
   } else if (c.doing_hepi || c.doing_hekaon) {        // init.f:353-357,379-386
@@ -666,11 +667,11 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       const double w = deForest(ev, c.Mh2, c.deForest_flag) * targ.Z * c.transparency / 3200. / (4. * 3.14159265 * 200. * 200. * 100.);
       if (w > 0 && std::isfinite(w)) c.w_ref = w;
     }
-  } else if (c.doing_pion || c.doing_kaon) {
+  } else if (c.doing_pion || c.doing_kaon || c.doing_delta) {
     // central event: both particles along their spectrometer axes, electron at the central momentum, nucleon at rest
     EventState s{};
     s.efer = targ.Mtar_struck;
-    if (!(c.doing_hydpi || c.doing_hydkaon)) {
+    if (!(c.doing_hydpi || c.doing_hydkaon || c.doing_delta)) {
       s.v_Em = (c.doing_hepi || c.doing_hekaon) ? targ.Mtar_struck + targ.Mrec - targ.M : Mp + Mn - targ.M;
       s.efer = targ.M - (targ.M - targ.Mtar_struck + s.v_Em);
     }
@@ -688,7 +689,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       mv.uqx = s.uqx; mv.uqy = s.uqy; mv.uqz = s.uqz; mv.upx = s.upx; mv.upy = s.upy; mv.upz = s.upz;
       mv.phi_pq = s.m_phipq; mv.t = s.m_t; mv.epsilon = s.m_eps;
       mv.pfer = 0.0; mv.pferx = 0.0; mv.pfery = 0.0; mv.pferz = 0.0; mv.efer = targ.Mtar_struck;
-      const MesonWeight w = c.doing_pion ? peepi(c, MaidDev{nullptr}, mv) : peeK(c, mv);
+      const MesonWeight w = c.doing_pion ? peepi(c, MaidDev{nullptr}, mv) : c.doing_delta ? peedelta(c, mv) : peeK(c, mv);
       if (w.sigcc > 0 && std::isfinite(w.sigcc)) c.w_ref = w.sigcc;
     }
   }

@@ -67,6 +67,30 @@ def test_meson_production_events(oracle_with_optics, name, mrec):
         assert np.all(surv == 1.0)
 
 
+def test_delta_production_events(oracle_with_optics):
+    """H(e,e'p)pi0 (physics_delta.f): the missing mass of the detected e + p is the pion's, the weight is flux times
+    the CM jacobian (no model factor), and sig_blok's value rides along in the sigcm column."""
+    cfg = deck("e1_eep_pi0_hydrogen_sos_hms.inp")
+    assert cfg.doing_delta and not cfg.doing_pion and cfg.using_rad == 0
+    rec, stage = oracle_with_optics.event_batch(cfg, 0, 40000, 5)
+    done = stage == 4
+    assert done.sum() > 300 and (stage == 0).sum() > 1000             # the low root of the quadratic mostly fails the limits
+    assert abs(np.median(rec[53][done]) - 139.57018) < 25.0           # missing mass ~ m_pi (resolution of a 5 GeV/c proton)
+    wcm, sigcm, davejac, sigcc = rec[54][done], rec[50][done], rec[51][done], rec[6][done]
+    assert np.all((wcm > 938.27231 + 139.57018) & (wcm < 2200.0))     # above the pion threshold; the SOS window is wide
+    assert np.all(np.isfinite(sigcm)) and np.all(sigcc > 0)           # the Brauel fit may go negative out here; it is not in the weight
+    # sigcc = jacobian * gtpr (pfer = 0 -> fac = 1): recompute the flux from the vertex columns
+    Mp, alpha = 938.27231, 1.0 / 137.0359895
+    Ein, eE, Q2 = rec[10][done], rec[11][done], rec[19][done]
+    k_eq = (wcm * wcm - Mp * Mp) / 2.0 / Mp
+    nu = Ein - eE
+    th2 = Q2 / (4.0 * Ein * eE - Q2)                                   # tan^2(theta/2) from Q2 = 4 E E' sin^2(theta/2)
+    eps = 1.0 / (1.0 + 2.0 * (1.0 + nu * nu / Q2) * th2)
+    gtpr = alpha / 2.0 / np.pi ** 2 * eE / Ein * k_eq / Q2 / (1.0 - eps)
+    coul = (1.0 + cfg.targ.Coulomb_ave / cfg.Ebeam) ** 2 if cfg.using_Coulomb else 1.0
+    assert np.allclose(sigcc, davejac * gtpr * coul, rtol=1e-9)
+
+
 def test_sigmaid_nearest_bin_lookup(oracle):
     """sigmaid (physics_pion.f:577-728): sig0 = ST (1 + eps L/T + ...) from the nearest (Q2, W, cos theta*) bin;
     zero below W = 1.08 GeV and for unphysical kinematics; on the Delta peak sigma_T is several ub/sr."""
