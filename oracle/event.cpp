@@ -75,7 +75,6 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
   const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
-  if (cfg.which_pion == 2 || cfg.which_pion == 3) throw std::runtime_error("oracle: Delta final states not restated");
   main.jacobian = 1.0;
   vertex.ue.x = sin(vertex.e.theta) * cos(vertex.e.phi);
   vertex.ue.y = sin(vertex.e.theta) * sin(vertex.e.phi);
@@ -653,8 +652,14 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     main.sigcc = deForest(cfg, vertex);
     main.sigcc_recon = deForest(cfg, recon);
   } else if (cfg.doing_pion) {
-    if (cfg.which_pion == 2 || cfg.which_pion == 3) throw std::runtime_error("oracle: Delta final states not restated");
     main.sigcc = peepi(s, vertex, main);
+    if (cfg.which_pion == 2) {                    // :1464-1476 (doing_pizero is out of scope)
+      if (cfg.doing_hydpi) main.sigcc = 0.4 * main.sigcc;
+      else if (cfg.doing_deutpi) main.sigcc = 0.4 * main.sigcc + 0.8 * main.sigcc;
+    } else if (cfg.which_pion == 3) {             // :1477-1491
+      if (cfg.doing_hydpi) main.sigcc = 0.55 * main.sigcc;
+      else if (cfg.doing_deutpi) main.sigcc = 0.55 * main.sigcc + 0.99 * main.sigcc;
+    }
     main.sigcc_recon = 1.0;
     if (cfg.which_pion == 1 || cfg.which_pion == 11) tgtweight = cfg.targ.N;
     else tgtweight = cfg.targ.Z;

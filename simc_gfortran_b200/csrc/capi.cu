@@ -622,8 +622,6 @@ int validate_loop_config(simc_handle* h) {
                                    "(simc_b200_load_sf_file, or set_sf_table + set_sf_em_widths) first");
   if (heavy && c.use_benhar_sf && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
-  if (c.doing_pion && (c.which_pion == 2 || c.which_pion == 3))
-    return fail(h, SIMC_ERR_ARG, "Delta final states (which_pion = 2, 3) are not implemented");
   if (c.using_rad && (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 ||
                       !c.use_offshell_rad || c.use_expon != 0))
     return fail(h, SIMC_ERR_ARG,

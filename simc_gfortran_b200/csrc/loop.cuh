@@ -644,6 +644,14 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           if (!cfg.doing_decay && !w_.early) survivalprob = semi_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
         } else if (cfg.doing_pion) {
           mw = peepi(cfg, A.maid, mv);
+          // event.f:1464-1490: Delta final states scale the pi-N cross section (empirical coefficients of 2021/2023)
+          if (cfg.which_pion == 2) {
+            if (cfg.doing_hydpi) mw.sigcc = 0.4 * mw.sigcc;
+            else if (cfg.doing_deutpi) mw.sigcc = 0.4 * mw.sigcc + 0.8 * mw.sigcc;
+          } else if (cfg.which_pion == 3) {
+            if (cfg.doing_hydpi) mw.sigcc = 0.55 * mw.sigcc;
+            else if (cfg.doing_deutpi) mw.sigcc = 0.55 * mw.sigcc + 0.99 * mw.sigcc;
+          }
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
         } else if (cfg.doing_delta) {
           mw = peedelta(cfg, mv);                      // event.f:1511-1513; tgtweight stays 1
