@@ -273,11 +273,14 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     c.Mh = Mpi;
     if (nA == 1 && c.which_pion == 1) throw std::runtime_error("Pi- production from Hydrogen not allowed!");
     if (nA <= 2 && c.which_pion >= 10) throw std::runtime_error("Coherent production from Hydrogen/Deuterium not allowed!");
+    if (nA == 3 && c.which_pion == 11) throw std::runtime_error("Coherent Pi- production from 3He not allowed!");
+    if (nA == 4 && c.which_pion >= 10) throw std::runtime_error("Coherent production from 4He not allowed!");
     c.doing_hydpi = nA == 1; c.doing_deutpi = nA == 2; c.doing_hepi = nA >= 3;
     if (c.which_pion >= 10) { c.doing_hydpi = 1; c.doing_deutpi = 0; c.doing_hepi = 0; }
   } else if (c.doing_kaon) {
     c.Mh = Mk;
     if (nA == 1 && c.which_kaon == 2) throw std::runtime_error("Sigma- production from Hydrogen not allowed!");
+    if (nA <= 2 && c.which_kaon >= 10) throw std::runtime_error("Coherent production from Hydrogen/Deuterium not allowed!");
     c.doing_hydkaon = nA == 1; c.doing_deutkaon = nA == 2; c.doing_hekaon = nA >= 3;
     if (c.which_kaon >= 10) { c.doing_hydkaon = 1; c.doing_deutkaon = 0; c.doing_hekaon = 0; }
   } else if (c.doing_delta) {                    // dbase.f:182-190: the reference warns for A >= 2 ("only set up for proton target")
@@ -328,12 +331,23 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     if (c.which_pion == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mn; }
     else if (c.which_pion == 1) { targ.Mtar_struck = Mn; targ.Mrec_struck = Mp; }
     else if (c.which_pion == 2 || c.which_pion == 3) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1232.0; }
-    else throw std::runtime_error("coherent pion production is out of scope");
+    else if (c.which_pion == 10 || c.which_pion == 11) {        // dbase.f:365-390: A(e,e'pi)A', production from a heavy "proton"
+      targ.Mtar_struck = targ.M; targ.Mrec_struck = targ.Mrec;
+      const double Mrec_guess = c.which_pion == 10 ? targ.M - Mp + Mn : targ.M - Mn + Mp;
+      if (std::fabs(targ.Mrec_struck - Mrec_guess) > 100.) targ.Mrec_struck = Mrec_guess;
+      targ.Mrec = 0.;
+    } else throw std::runtime_error("Bad value for which_pion");
   } else if (c.doing_kaon) {
     if (c.which_kaon == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1115.68; }
     else if (c.which_kaon == 1) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1192.64; }
     else if (c.which_kaon == 2) { targ.Mtar_struck = Mn; targ.Mrec_struck = 1197.45; }
-    else throw std::runtime_error("coherent kaon production is out of scope");
+    else if (c.which_kaon >= 10 && c.which_kaon <= 12) {        // dbase.f:409-438: bound hypernucleus in the final state
+      targ.Mtar_struck = targ.M; targ.Mrec_struck = targ.Mrec;
+      const double Mrec_guess = c.which_kaon == 10 ? targ.M - Mp + 1115.68 : c.which_kaon == 11 ? targ.M - Mp + 1192.64
+                                                                                                 : targ.M - Mn + 1197.45;
+      if (std::fabs(targ.Mrec_struck - Mrec_guess) > 100.) targ.Mrec_struck = Mrec_guess;
+      targ.Mrec = 0.;
+    } else throw std::runtime_error("Bad value for which_kaon");
   }
   if (nA == 2) targ.Mrec = Mp + Mn - targ.Mtar_struck;
   targ.thick = targ.thick / 1000.;
