@@ -12,8 +12,37 @@
 #include <string.h>
 #include <stddef.h>
 
+#include <mutex>
+
 namespace simc {
 namespace SIMC_VARIANT_NS {
+
+// Writes the Philox round keys of `seed` into this variant's constant memory on the current device, if they are not
+// there already.  The constant is device-wide, so a change of seed waits for whatever is in flight on the device
+// first (another handle may still be running with the old one); launches with the seed already loaded cost a compare.
+// The caller holds rng_key_mutex() until its kernels are enqueued, so that wait sees them.
+static std::mutex& rng_key_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+static cudaError_t ensure_rng_key_locked(unsigned long long seed) {
+  static unsigned long long cur[64];
+  static bool valid[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (valid[dev] && cur[dev] == seed) return cudaSuccess;
+  uint32_t rk[20];
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(c_philox_rk, rk, sizeof(rk));
+  if (e != cudaSuccess) return e;
+  cur[dev] = seed; valid[dev] = true;
+  return cudaSuccess;
+}
 
 // Batch form of mc_hms / mc_shms / ... (hms/mc_hms.f:1-4): one thread per row.
 template <bool WITH_COLL>
@@ -44,7 +73,7 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   t.ctau = ctau;
   const double dpp_in = t.dpps, y_in = t.ys, dxdz_in = t.dxdzs, dydz_in = t.dydzs;
   DevRng rng;
-  rng.init(seed, (unsigned long long)i, 0u, 0u);
+  rng.init((unsigned long long)i, 0u, 0u);
   ArmResult res;
   arm_result_clear(res);
   HutState hs;
@@ -85,6 +114,11 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
+  }
+  std::lock_guard<std::mutex> key_lock(rng_key_mutex());
+  {
+    const cudaError_t e = ensure_rng_key_locked(a.seed);
+    if (e != cudaSuccess) return e;
   }
   if (f.using_coll)
     k_transport_batch<true><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
@@ -229,6 +263,11 @@ cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters
 }
 
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
+  std::lock_guard<std::mutex> key_lock(rng_key_mutex());
+  {
+    const cudaError_t e = ensure_rng_key_locked(a.seed);
+    if (e != cudaSuccess) return e;
+  }
   LoopArgs A;
   A.cfg = (const simc_run_config*)a.cfg;
   static const ArmDev no_arm = {};

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     bool ok = false;
     EventState s;
     DevRng rng;
-    rng.init(A.seed, (unsigned long long)(A.first_try + (active ? i : 0)), 0u, 0u);
+    rng.init((unsigned long long)(A.first_try + (active ? i : 0)), 0u, 0u);
     s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
     const bool active = i < n_in;
     const unsigned slot = active ? in_list[i] : 0u;
     DevRng rng;
-    rng.init(A.seed, (unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u, (unsigned)S.ld(F_DRAW, slot));
+    rng.init((unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u, (unsigned)S.ld(F_DRAW, slot));
     TrackDev t;
     ArmResult res;
     arm_result_clear(res);

@@ -7,15 +7,20 @@
 
 namespace simc {
 
-__device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
-                                              uint32_t c3, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+// The ten round keys of the run's seed (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85) sit in constant memory: a round is
+// then two wide multiplies and two three-input XORs with a constant-bank operand, without the two per-thread key
+// additions (a third of the generator's instructions).  The host writes them before the first launch with a new
+// seed (ensure_rng_key in kernels.cu).  One copy per translation unit (strict / fast).
+static __constant__ uint32_t c_philox_rk[20];
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t& r0, uint32_t& r1,
+                                              uint32_t& r2, uint32_t& r3) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    const uint32_t n0 = hi1 ^ c1 ^ c_philox_rk[2 * r], n2 = hi0 ^ c3 ^ c_philox_rk[2 * r + 1];
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   r0 = c0; r1 = c1; r2 = c2; r3 = c3;
 }
@@ -23,27 +28,34 @@ __device__ __forceinline__ double philox_to_unit(uint32_t lo, uint32_t hi) {
   const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 12;
   return ((double)k + 0.5) * (1.0 / 4503599627370496.0);
 }
+// 2u - 1 for the same draw, as gauss1 forms it (gauss1.f: v = 2.*grnd() - 1.): with k the 52-bit integer,
+// 2u - 1 = k*2^-51 + 2^-52 - 1.  The double with mantissa k in [2,4) is 2 + k*2^-51; minus 3 is exact (a multiple of
+// 2^-51 below 1 in size), and adding 2^-52 rounds the same real number the reference rounds: bit-identical to
+// 2.0 * philox_to_unit() - 1.0 with two additions instead of a conversion, an addition, two multiplies and a subtraction.
+__device__ __forceinline__ double philox_to_pm1(uint32_t lo, uint32_t hi) {
+  const unsigned long long k = (((unsigned long long)hi << 32) | lo) >> 12;
+  const double d = __longlong_as_double((long long)(k | 0x4000000000000000ULL));
+  return (d - 3.0) + 2.220446049250313e-16;
+}
 // Draw `draw` of the stream: a pure function of its arguments (registers in, register out), so callers
 // keep their generator state in registers across the call.
-static __device__ __noinline__ double philox_uniform(uint32_t k0, uint32_t k1, uint32_t t0, uint32_t t1, uint32_t stream,
-                                              uint32_t draw) {
+static __device__ __noinline__ double philox_uniform(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw) {
   uint32_t r0, r1, r2, r3;
-  philox4x32_10(k0, k1, draw >> 1, stream, t0, t1, r0, r1, r2, r3);
+  philox4x32_10(draw >> 1, stream, t0, t1, r0, r1, r2, r3);
   return (draw & 1u) ? philox_to_unit(r2, r3) : philox_to_unit(r0, r1);
 }
 
 struct DevRng {
-  uint32_t k0, k1, t0, t1, stream;
+  uint32_t t0, t1, stream;
   uint32_t draw;
 
-  __device__ __forceinline__ void init(unsigned long long seed, unsigned long long try_index, uint32_t stream_id,
-                                       uint32_t first_draw) {
-    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
+  // (the seed itself is in c_philox_rk)
+  __device__ __forceinline__ void init(unsigned long long try_index, uint32_t stream_id, uint32_t first_draw) {
     t0 = (uint32_t)try_index; t1 = (uint32_t)(try_index >> 32);
     stream = stream_id; draw = first_draw;
   }
   __device__ __forceinline__ double uniform() {
-    const double u = philox_uniform(k0, k1, t0, t1, stream, draw);
+    const double u = philox_uniform(t0, t1, stream, draw);
     ++draw;
     return u;
   }

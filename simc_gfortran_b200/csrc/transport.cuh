@@ -66,7 +66,7 @@ struct ArmResult {
 // nsigmax (never for 99, 0.3 % for 3) goes round again -- the same draws, in the same order.
 // Everything goes in and out by value (registers), so the caller's generator never touches memory.
 struct GaussOut { double g; uint32_t draw; };
-__device__ __noinline__ GaussOut gauss1v(uint32_t k0, uint32_t k1, uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw,
+__device__ __noinline__ GaussOut gauss1v(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw,
                                          double nsigmax) {
   const unsigned mask = __activemask();
   // a pair (u1,u2) is one Philox block when `draw` is even; when it is odd the pair straddles two blocks
@@ -79,23 +79,21 @@ __device__ __noinline__ GaussOut gauss1v(uint32_t k0, uint32_t k1, uint32_t t0, 
     bool open = need;
     while (__any_sync(mask, open)) {
       if (open) {
-        double u1, u2;
-        uint32_t r0, r1, r2, r3;
+        uint32_t r0, r1, r2, r3, w0, w1, w2, w3;          // (w0,w1) = words of u1, (w2,w3) = words of u2
         const uint32_t b = draw >> 1;
         if (!(draw & 1u)) {
-          philox4x32_10(k0, k1, b, stream, t0, t1, r0, r1, r2, r3);
-          u1 = philox_to_unit(r0, r1);
-          u2 = philox_to_unit(r2, r3);
+          philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3);
+          w0 = r0; w1 = r1; w2 = r2; w3 = r3;
         } else {
-          if (hblock != b) { philox4x32_10(k0, k1, b, stream, t0, t1, r0, r1, r2, r3); h2 = r2; h3 = r3; }
-          u1 = philox_to_unit(h2, h3);
-          philox4x32_10(k0, k1, b + 1u, stream, t0, t1, r0, r1, r2, r3);
-          u2 = philox_to_unit(r0, r1);
+          if (hblock != b) { philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3); h2 = r2; h3 = r3; }
+          w0 = h2; w1 = h3;
+          philox4x32_10(b + 1u, stream, t0, t1, r0, r1, r2, r3);
+          w2 = r0; w3 = r1;
           h2 = r2; h3 = r3; hblock = b + 1u;
         }
         draw += 2u;
-        v1 = 2.0 * u1 - 1.0;
-        const double v2 = 2.0 * u2 - 1.0;
+        v1 = philox_to_pm1(w0, w1);                        // 2.*grnd() - 1., bit for bit (philox.cuh)
+        const double v2 = philox_to_pm1(w2, w3);
         s = v1 * v1 + v2 * v2;
         open = (s > 1. || s == 0.);
       }
@@ -110,7 +108,7 @@ __device__ __noinline__ GaussOut gauss1v(uint32_t k0, uint32_t k1, uint32_t t0, 
   return o;
 }
 __device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
-  const GaussOut o = gauss1v(r.k0, r.k1, r.t0, r.t1, r.stream, r.draw, nsigmax);
+  const GaussOut o = gauss1v(r.t0, r.t1, r.stream, r.draw, nsigmax);
   r.draw = o.draw;
   return o.g;
 }
