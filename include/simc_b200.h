@@ -24,6 +24,14 @@
  * simc_b200_last_error), no exceptions, no torch types.  All energies MeV,
  * lengths cm, angles rad, deltas percent -- the reference's units
  * (constants.inc:3-10).
+ *
+ * Threads: a handle is used by one thread at a time (the reference is not
+ * re-entrant at all: COMMON /track/, SAVEd tables).  Several handles may run
+ * from several threads; the random generator's round keys of the seed sit in
+ * device-wide constant memory, so two handles on the SAME device running with
+ * DIFFERENT seeds at the same time take turns (a change of seed waits for the
+ * work in flight on that device).  One process per GPU, the layout of
+ * bench.py and multi.py, never meets this.
  */
 #ifndef SIMC_B200_H
 #define SIMC_B200_H
