@@ -184,6 +184,52 @@ def test_run_is_independent_of_batching_and_order(sim):
     assert bytes(a) == bytes(b)
 
 
+def test_two_handles_with_different_seeds_interleaved(cfg):
+    """The generator's round keys are device-wide constant memory (philox.cuh): two handles on one device that run with
+    different seeds, their launches interleaved (asynchronous runs in small batches, also from two threads), must each
+    see their own stream -- a change of seed waits for the work in flight."""
+    import threading
+    n = 40000
+    sims = []
+    try:
+        for _ in range(2):
+            s = Simc(cfg, mode="strict")
+            for arm in (1, 5):
+                s.set_optics(load_optics_fixture(arm))
+            s.set_batch(4096)
+            sims.append(s)
+        want = []
+        for s, seed in zip(sims, (11, 12)):
+            a = s.accum_clear()
+            s.run(0, n, seed, a)
+            want.append(bytes(a))
+        assert want[0] != want[1]
+        # one thread, launches alternating between the handles
+        accs = [s.accum_clear() for s in sims]            # (also sets the host copy's ranges to empty)
+        for k in range(0, n, 8000):
+            sims[0].run_async(k, 8000, 11)
+            sims[1].run_async(k, 8000, 12)
+        got = [bytes(s.fetch(a)) for s, a in zip(sims, accs)]
+        assert got == want
+        # two threads, one handle each
+        out = [None, None]
+
+        def work(i, seed):
+            a = sims[i].accum_clear()
+            sims[i].run(0, n, seed, a)
+            out[i] = bytes(a)
+
+        th = [threading.Thread(target=work, args=(i, seed)) for i, seed in enumerate((11, 12))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        assert out == want
+    finally:
+        for s in sims:
+            s.close()
+
+
 def test_empty_and_errors(cfg):
     from simc_gfortran_b200 import SimcError
     s = Simc(cfg)
