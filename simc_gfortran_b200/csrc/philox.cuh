@@ -37,25 +37,41 @@ __device__ __forceinline__ double philox_to_pm1(uint32_t lo, uint32_t hi) {
   const double d = __longlong_as_double((long long)(k | 0x4000000000000000ULL));
   return (d - 3.0) + 2.220446049250313e-16;
 }
-// Draw `draw` of the stream: a pure function of its arguments (registers in, register out), so callers
-// keep their generator state in registers across the call.
-static __device__ __noinline__ double philox_uniform(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw) {
-  uint32_t r0, r1, r2, r3;
-  philox4x32_10(draw >> 1, stream, t0, t1, r0, r1, r2, r3);
-  return (draw & 1u) ? philox_to_unit(r2, r3) : philox_to_unit(r0, r1);
+// A block gives two draws: the even draw d of a try is words (0,1) of block d/2, the odd draw d+1 words (2,3).
+// The generator keeps the upper half of the block of its last even draw (h2, h3), so INVARIANT: whenever `draw` is
+// odd, (h2, h3) are words (2,3) of block draw/2 -- an odd draw costs no Philox evaluation, and gauss1 (which takes its
+// uniforms in pairs) starts an odd-aligned pair without recomputing the block the pair begins in.
+struct PhiloxHalf { uint32_t lo0, lo1, hi0, hi1; };
+static __device__ __noinline__ PhiloxHalf philox_block(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t block) {
+  PhiloxHalf r;
+  philox4x32_10(block, stream, t0, t1, r.lo0, r.lo1, r.hi0, r.hi1);
+  return r;
 }
 
 struct DevRng {
   uint32_t t0, t1, stream;
   uint32_t draw;
+  uint32_t h2, h3;
 
   // (the seed itself is in c_philox_rk)
   __device__ __forceinline__ void init(unsigned long long try_index, uint32_t stream_id, uint32_t first_draw) {
     t0 = (uint32_t)try_index; t1 = (uint32_t)(try_index >> 32);
     stream = stream_id; draw = first_draw;
+    h2 = 0u; h3 = 0u;
+    if (first_draw & 1u) {                       // resuming in the middle of a block
+      const PhiloxHalf r = philox_block(t0, t1, stream, first_draw >> 1);
+      h2 = r.hi0; h3 = r.hi1;
+    }
   }
   __device__ __forceinline__ double uniform() {
-    const double u = philox_uniform(t0, t1, stream, draw);
+    double u;
+    if (draw & 1u) {
+      u = philox_to_unit(h2, h3);
+    } else {
+      const PhiloxHalf r = philox_block(t0, t1, stream, draw >> 1);
+      u = philox_to_unit(r.lo0, r.lo1);
+      h2 = r.hi0; h3 = r.hi1;
+    }
     ++draw;
     return u;
   }

@@ -65,13 +65,12 @@ struct ArmResult {
 // looped on its own; log/sqrt/div run once for all lanes, and only a lane whose |g| exceeds
 // nsigmax (never for 99, 0.3 % for 3) goes round again -- the same draws, in the same order.
 // Everything goes in and out by value (registers), so the caller's generator never touches memory.
-struct GaussOut { double g; uint32_t draw; };
-__device__ __noinline__ GaussOut gauss1v(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw,
+struct GaussOut { double g; uint32_t draw, h2, h3; };
+__device__ __noinline__ GaussOut gauss1v(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw, uint32_t h2, uint32_t h3,
                                          double nsigmax) {
   const unsigned mask = __activemask();
-  // a pair (u1,u2) is one Philox block when `draw` is even; when it is odd the pair straddles two blocks
-  // and the unused half of the second one is kept for the next attempt
-  uint32_t h2 = 0, h3 = 0, hblock = 0xffffffffu;
+  // a pair (u1,u2) is one Philox block when `draw` is even; when it is odd the pair starts with the half block the
+  // generator holds (DevRng's invariant) and ends in the lower half of the next block, whose upper half is kept
   double g = 0.0;
   bool need = true;
   while (__any_sync(mask, need)) {
@@ -85,11 +84,10 @@ __device__ __noinline__ GaussOut gauss1v(uint32_t t0, uint32_t t1, uint32_t stre
           philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3);
           w0 = r0; w1 = r1; w2 = r2; w3 = r3;
         } else {
-          if (hblock != b) { philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3); h2 = r2; h3 = r3; }
           w0 = h2; w1 = h3;
           philox4x32_10(b + 1u, stream, t0, t1, r0, r1, r2, r3);
           w2 = r0; w3 = r1;
-          h2 = r2; h3 = r3; hblock = b + 1u;
+          h2 = r2; h3 = r3;
         }
         draw += 2u;
         v1 = philox_to_pm1(w0, w1);                        // 2.*grnd() - 1., bit for bit (philox.cuh)
@@ -104,12 +102,12 @@ __device__ __noinline__ GaussOut gauss1v(uint32_t t0, uint32_t t1, uint32_t stre
     }
   }
   GaussOut o;
-  o.g = g; o.draw = draw;
+  o.g = g; o.draw = draw; o.h2 = h2; o.h3 = h3;
   return o;
 }
 __device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
-  const GaussOut o = gauss1v(r.t0, r.t1, r.stream, r.draw, nsigmax);
-  r.draw = o.draw;
+  const GaussOut o = gauss1v(r.t0, r.t1, r.stream, r.draw, r.h2, r.h3, nsigmax);
+  r.draw = o.draw; r.h2 = o.h2; r.h3 = o.h3;
   return o.g;
 }
 
@@ -451,11 +449,11 @@ __device__ __forceinline__ bool collimator_steps_body(const ArmOp* o, TrackDev& 
 // once per slice spent in the material, survivors included (mc_hms_coll.f:95-115).
 // Track and generator go in and out by value, so the caller's copies stay in registers (this code only runs for
 // decks with using_HMScoll / using_SHMScoll).
-struct CollOut { TrackDev t; uint32_t draw; bool ok; };
+struct CollOut { TrackDev t; uint32_t draw, h2, h3; bool ok; };
 __device__ __noinline__ CollOut collimator_steps(const ArmOp* o, TrackDev t, DevRng rng, bool decay_flag, unsigned* stop_counts) {
   CollOut R;
   R.ok = collimator_steps_body(o, t, rng, decay_flag, stop_counts);
-  R.t = t; R.draw = rng.draw;
+  R.t = t; R.draw = rng.draw; R.h2 = rng.h2; R.h3 = rng.h3;
   return R;
 }
 __device__ __forceinline__ bool collimator_steps_body(const ArmOp* o, TrackDev& t, DevRng& rng, bool decay_flag, unsigned* stop_counts) {
@@ -665,7 +663,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
         // mc_hms.f:206 / mc_shms.f:503: pions and muons are stepped through the collimator material
         if (WITH_COLL && f.using_coll && (t.m2 > 100.0 * 100.0) && (t.m2 < 200.0 * 200.0)) {
           const CollOut co = collimator_steps(o, t, rng, f.decay_flag, stop_counts);
-          t = co.t; rng.draw = co.draw;
+          t = co.t; rng.draw = co.draw; rng.h2 = co.h2; rng.h3 = co.h3;
           stop = !co.ok;
           skip_until = pc + 3 + o->i0;          // the plain aperture checks belong to the other branch
         }
