@@ -111,6 +111,51 @@ __device__ __forceinline__ double gauss1(DevRng& r, double nsigmax) {
   return o.g;
 }
 
+// Two consecutive gauss1(99.) calls -- every Gaussian of the hut comes in such pairs (musc, musc_ext, the two
+// smearings of a chamber plane).  A lane that has accepted its first pair of uniforms goes straight on to draw for
+// the second while slower lanes still work on their first, so the warp makes max(n1 + n2) trips through the
+// rejection loop instead of max(n1) + max(n2); each lane consumes exactly the draws of the two sequential calls.
+// |g| <= 12 for the smallest s the 52-bit uniforms can produce, so the nsigmax = 99 test can never fire.
+struct Gauss2Out { double g1, g2; uint32_t draw, h2, h3; };
+__device__ __noinline__ Gauss2Out gauss2v(uint32_t t0, uint32_t t1, uint32_t stream, uint32_t draw, uint32_t h2, uint32_t h3) {
+  const unsigned mask = __activemask();
+  double va = 0.0, sa = 1.0, vb = 0.0, sb = 1.0;
+  int k = 0;
+  while (__any_sync(mask, k < 2)) {
+    if (k < 2) {
+      uint32_t r0, r1, r2, r3, w0, w1, w2, w3;
+      const uint32_t b = draw >> 1;
+      if (!(draw & 1u)) {
+        philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3);
+        w0 = r0; w1 = r1; w2 = r2; w3 = r3;
+      } else {
+        w0 = h2; w1 = h3;
+        philox4x32_10(b + 1u, stream, t0, t1, r0, r1, r2, r3);
+        w2 = r0; w3 = r1;
+        h2 = r2; h3 = r3;
+      }
+      draw += 2u;
+      const double v1 = philox_to_pm1(w0, w1);
+      const double v2 = philox_to_pm1(w2, w3);
+      const double s = v1 * v1 + v2 * v2;
+      if (!(s > 1. || s == 0.)) {
+        if (k == 0) { va = v1; sa = s; } else { vb = v1; sb = s; }
+        ++k;
+      }
+    }
+  }
+  Gauss2Out o;
+  o.g1 = va * sqrt(-2. * m::log(sa) / sa);
+  o.g2 = vb * sqrt(-2. * m::log(sb) / sb);
+  o.draw = draw; o.h2 = h2; o.h3 = h3;
+  return o;
+}
+__device__ __forceinline__ void gauss2(DevRng& r, double& g1, double& g2) {
+  const Gauss2Out o = gauss2v(r.t0, r.t1, r.stream, r.draw, r.h2, r.h3);
+  r.draw = o.draw; r.h2 = o.h2; r.h3 = o.h3;
+  g1 = o.g1; g2 = o.g2;
+}
+
 __device__ __forceinline__ void musc_refresh(TrackDev& t) {
   const double beta = t.p / sqrt(t.m2 + t.p * t.p);
   t.mc1 = 13.6 / t.p / beta;
@@ -597,26 +642,27 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       case OP_MUSC:        // musc.f:46-55, called as musc(m2,p,radw,dydzs,dxdzs)
         if (f.ms_flag && a != 0.) {
           const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
-          t.dydzs = t.dydzs + ts * gauss1(rng, 99.0);
-          t.dxdzs = t.dxdzs + ts * gauss1(rng, 99.0);
+          double g1, g2;
+          gauss2(rng, g1, g2);
+          t.dydzs = t.dydzs + ts * g1;
+          t.dxdzs = t.dxdzs + ts * g2;
         }
         break;
       case OP_MUSC_EXT:    // musc_ext.f:37-51, called as musc_ext(m2,p,radw,drift,dydzs,dxdzs,ys,xs)
         if (f.ms_flag && a != 0.) {
           const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
-          double g1 = gauss1(rng, 99.0);
-          double g2 = gauss1(rng, 99.0);
+          double g1, g2;
+          gauss2(rng, g1, g2);
           t.dxdzs = t.dxdzs + ts * g1;
           t.xs = t.xs + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
-          g1 = gauss1(rng, 99.0);
-          g2 = gauss1(rng, 99.0);
+          gauss2(rng, g1, g2);
           t.dydzs = t.dydzs + ts * g1;
           t.ys = t.ys + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
         }
         break;
       case OP_DC_PLANE: {  // mc_hms_hut.f:351-364
         double r1 = 0., r2 = 0.;
-        if (f.wcs_flag) { r1 = gauss1(rng, 99.0); r2 = gauss1(rng, 99.0); }
+        if (f.wcs_flag) gauss2(rng, r1, r2);
         const int ip = o->i0;
         if (o->i1) { hs.ydc[ip] = (float)(t.ys + a * r2 * res.resmult); hs.xdc[ip] = 0.f; }
         else { hs.xdc[ip] = (float)(t.xs + a * r1 * res.resmult); hs.ydc[ip] = 0.f; }
