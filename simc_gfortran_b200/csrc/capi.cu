@@ -656,7 +656,7 @@ int ensure_loop_buffers(simc_handle* h, long long cap) {
     if (h->d_lists) cudaFree(h->d_lists);
     h->d_state = nullptr; h->d_lists = nullptr; h->loop_cap = 0;
     CU(h, cudaMalloc(&h->d_state, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)cap));
-    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * 11 * (size_t)cap));
+    CU(h, cudaMalloc(&h->d_lists, sizeof(unsigned) * kLoopLists * (size_t)cap));
     h->loop_cap = cap;
   }
   return SIMC_OK;
@@ -699,6 +699,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   a.grid_blocks = h->grid_blocks;
   auto coll = [&](int arm) { return arm == SIMC_ARM_HMS ? h->cfg.using_HMScoll : arm == SIMC_ARM_SHMS ? h->cfg.using_SHMScoll : 0; };
   a.coll_e = coll(h->cfg.electron_arm); a.coll_p = coll(h->cfg.hadron_arm);
+  a.using_rad = h->cfg.using_rad;
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem; a.sf_dem = h->d_sf_dem;
@@ -729,7 +730,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
         const ArmTablesDev* tab = (const ArmTablesDev*)(st == 1 ? a.arm_p : a.arm_e);
         h->launches += 2 + (tab ? tab->n_mid : 0);
       } else {
-        h->launches += 1;
+        h->launches += (st == 0 || st == 3) && a.using_rad ? 2 : 1;
       }
       if (h->timing && st < 4) CU(h, cudaEventRecord(h->ev[ev_pos + 1 + st], h->stream));
     }

@@ -186,10 +186,47 @@ SIMC_HD bool complete_ev_hyd_elast(const simc_run_config& cfg, const MatTable& m
   return run;
 }
 
+// What generate_rad leaves for later: which tail radiates (0: none), the photon-energy limits and the
+// basicrad weight.  peaked_rad_weight (radc.f:523-646) draws no random number and only scales
+// main%gen_weight, so it is evaluated for the tries that survive both spectrometers (k_radw, loop.cuh).
+struct GenRad { double emin, emax, eg, bw; int which; };
+
+// orig = vertex (+) radiation, radc.f:476-515.  main%gen_weight keeps its pre-radiation value here:
+// gen_weight * rad_weight / hardcorfac (radc.f:518) is applied by k_radw.
+SIMC_HD bool generate_finalize(const simc_run_config& cfg, EventState& s, bool ok) {
+  if (!cfg.using_rad) {
+    if (ok) {
+      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
+      s.o_pdelta = s.v_pdelta;
+    }
+    return ok;
+  }
+  const RadEvDev& R = s.rad;
+  if (ok) {
+    s.o_Ein = s.v_Ein + R.Egamma_used[0];
+    s.o_eE = s.v_eE - R.Egamma_used[1];
+    if (s.o_eE <= 0e0) ok = false;
+  }
+  if (ok) {
+    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
+    s.o_pE = s.v_pE - R.Egamma_used[2];
+    if (s.o_pE <= cfg.Mh) ok = false;
+  }
+  if (ok) {
+    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
+  }
+  return ok;
+}
+
 // generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519.  `ok` in: the thread has
-// a try to generate; returns success.
+// a try to generate; returns success.  The work is cut where generate_rad re-enters complete_ev
+// (radc.f:324, the tries whose incoming electron radiates): *_first runs up to the photon energy of the
+// chosen tail; tries with gr.which == 1 then go through *_second on compacted warps (k_regen), the others
+// are complete.  Every try consumes its random numbers in the reference's order.
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_hyd_elast_first(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok,
+                                      GenRad& gr) {
   const simc_target& targ = cfg.targ;
   if (ok) {
     s.tx = gauss(rng, 3.0) * cfg.gen.xwid + targ.xoffset;
@@ -236,18 +273,11 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, const MatTable& mt, 
   SIMC_PHASE();
   ok = complete_ev_hyd_elast(cfg, mt, rng, gauss, s, ok);
   if (ok) s.Trec = s.v_Trec;
-  if (!cfg.using_rad) {
-    if (ok) {
-      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
-      s.o_pdelta = s.v_pdelta;
-    }
-    return ok;
-  }
-  // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208).  The three tail
-  // blocks of the reference (radc.f:234-337, 358-405, 409-461) share one call site each of basicrad /
-  // complete_ev / peaked_rad_weight, so lanes that picked different tails stay converged.
+  gr.emin = 0.0; gr.emax = 0.0; gr.eg = 0.0; gr.bw = 0.0; gr.which = 0;
+  if (!cfg.using_rad) return ok;
+  // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208).
   RadEvDev& R = s.rad;
-  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
+  double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
   int which = 0;
   if (ok) {
     const double x = rng.uniform();
@@ -292,34 +322,13 @@ SIMC_HD bool generate_hyd_elast(const simc_run_config& cfg, const MatTable& mt, 
       }
     }
   }
-  SIMC_PHASE();
-  const bool reenter = ok && which == 1;                       // radc.f:324
-  const bool re_ok = complete_ev_hyd_elast(cfg, mt, rng, gauss, s, reenter);
-  if (reenter && !re_ok) ok = false;
-  if (ok && which) {
-    VertexKin v;
-    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
-    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
-    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
-  }
-  SIMC_PHASE();
-  if (ok) {
-    // orig = vertex (+) radiation, radc.f:476-515
-    s.o_Ein = s.v_Ein + R.Egamma_used[0];
-    s.o_eE = s.v_eE - R.Egamma_used[1];
-    if (s.o_eE <= 0e0) ok = false;
-  }
-  if (ok) {
-    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
-    s.o_pE = s.v_pE - R.Egamma_used[2];
-    if (s.o_pE <= cfg.Mh) ok = false;
-  }
-  if (ok) {
-    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
-    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
-    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
-  }
+  gr.emin = emin; gr.emax = emax; gr.eg = eg; gr.bw = bw; gr.which = which;
   return ok;
+}
+// second pass through complete_ev for the tries whose incoming electron radiated (radc.f:324)
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_hyd_elast_second(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+  return complete_ev_hyd_elast(cfg, mt, rng, gauss, s, run);
 }
 
 // ---- H(e,e'pi) / H(e,e'K): complete_ev, event.f:432-1052 with doing_hydpi / doing_hydkaon ----------
@@ -481,8 +490,8 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
 // electron energy are thrown, :283-318), radc.f:120-519 with the doing_pion/doing_kaon photon-energy
 // limits (:289-294) and no Em constraints on tails 2 and 3 (doing_eep = .false.).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, const PfermiDev pfm, const SfDev sf, RNG& rng,
-                            GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_meson_first(const simc_run_config& cfg, const MatTable& mt, const PfermiDev pfm, const SfDev sf, RNG& rng,
+                                  GAUSS gauss, EventState& s, bool ok, GenRad& gr) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;
   if (ok) {
@@ -584,15 +593,10 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
   SIMC_PHASE();
   ok = complete_ev_meson(cfg, mt, rng, gauss, s, ok);
   if (ok) s.Trec = s.v_Trec;
-  if (!cfg.using_rad) {
-    if (ok) {
-      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
-      s.o_pdelta = s.v_pdelta;
-    }
-    return ok;
-  }
+  gr.emin = 0.0; gr.emax = 0.0; gr.eg = 0.0; gr.bw = 0.0; gr.which = 0;
+  if (!cfg.using_rad) return ok;
   RadEvDev& R = s.rad;
-  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
+  double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
   int which = 0;
   if (ok) {
     const double x = rng.uniform();
@@ -643,33 +647,12 @@ SIMC_HD bool generate_meson(const simc_run_config& cfg, const MatTable& mt, cons
       }
     }
   }
-  SIMC_PHASE();
-  const bool reenter = ok && which == 1;                       // radc.f:324
-  const bool re_ok = complete_ev_meson(cfg, mt, rng, gauss, s, reenter);
-  if (reenter && !re_ok) ok = false;
-  if (ok && which) {
-    VertexKin v;
-    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
-    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
-    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
-  }
-  SIMC_PHASE();
-  if (ok) {
-    s.o_Ein = s.v_Ein + R.Egamma_used[0];
-    s.o_eE = s.v_eE - R.Egamma_used[1];
-    if (s.o_eE <= 0e0) ok = false;
-  }
-  if (ok) {
-    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
-    s.o_pE = s.v_pE - R.Egamma_used[2];
-    if (s.o_pE <= cfg.Mh) ok = false;
-  }
-  if (ok) {
-    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
-    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
-    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
-  }
+  gr.emin = emin; gr.emax = emax; gr.eg = eg; gr.bw = bw; gr.which = which;
   return ok;
+}
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_meson_second(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+  return complete_ev_meson(cfg, mt, rng, gauss, s, run);
 }
 
 // ---- A(e,e'p) on a nucleus (doing_heavy): complete_ev, event.f:432-1052 --------------------------
@@ -730,7 +713,8 @@ SIMC_HD bool complete_ev_heavy(const simc_run_config& cfg, const MatTable& mt, R
 // :296-318), radc.f:120-519 with the doing_heavy photon-energy limits (:249-263) and the Em/Pm window
 // test after the first tail (:340-350).
 template <class RNG, class GAUSS>
-SIMC_HD bool generate_heavy(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok) {
+SIMC_HD bool generate_heavy_first(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool ok,
+                                  GenRad& gr) {
   const simc_target& targ = cfg.targ;
   const simc_gen_limits& gen = cfg.gen;
   if (ok) {
@@ -801,16 +785,13 @@ SIMC_HD bool generate_heavy(const simc_run_config& cfg, const MatTable& mt, RNG&
   ok = complete_ev_heavy(cfg, mt, rng, gauss, s, ok);
   if (ok) s.Trec = s.v_Trec;
   const simc_edge& VE = cfg.VERTEXedge;
+  gr.emin = 0.0; gr.emax = 0.0; gr.eg = 0.0; gr.bw = 0.0; gr.which = 0;
   if (!cfg.using_rad) {
     if (ok) ok = (s.v_Em >= VE.Em.min && s.v_Em <= VE.Em.max && s.v_Pm >= VE.Pm.min && s.v_Pm <= VE.Pm.max);
-    if (ok) {
-      s.o_Ein = s.v_Ein; s.o_eE = s.v_eE; s.o_edelta = s.v_edelta; s.o_pE = s.v_pE; s.o_pP = s.v_pP;
-      s.o_pdelta = s.v_pdelta;
-    }
     return ok;
   }
   RadEvDev& R = s.rad;
-  double rad_weight = 1, bw = 0, emin = 0.0, emax = 0.0, eg = 0.0, max_delta_Trec = 0.0;
+  double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0, max_delta_Trec = 0.0;
   int which = 0, ntail = 0;
   if (ok) {
     const double x = rng.uniform();
@@ -833,11 +814,8 @@ SIMC_HD bool generate_heavy(const simc_run_config& cfg, const MatTable& mt, RNG&
       else { R.Egamma_used[0] = eg; s.v_Ein = s.v_Ein - eg; }
     }
   }
-  SIMC_PHASE();
-  const bool reenter = ok && which == 1;                       // radc.f:324
-  const bool re_ok = complete_ev_heavy(cfg, mt, rng, gauss, s, reenter);
-  if (reenter && !re_ok) ok = false;
-  if (ok) {
+  // tries with which == 1 re-enter complete_ev (radc.f:324) in generate_heavy_second; the others go on here
+  if (ok && !which) {
     // radc.f:340-350: the vertex must sit inside the spectral function's window
     if (s.v_Em < VE.Em.min || s.v_Em > VE.Em.max || s.v_Pm < VE.Pm.min || s.v_Pm > VE.Pm.max) ok = false;
   }
@@ -866,27 +844,17 @@ SIMC_HD bool generate_heavy(const simc_run_config& cfg, const MatTable& mt, RNG&
       else R.Egamma_used[which - 1] = eg;
     }
   }
-  if (ok && which) {
-    VertexKin v;
-    v.Ein = s.v_Ein; v.eE = s.v_eE; v.eP = s.v_eE; v.etheta = s.v_etheta; v.pE = s.v_pE; v.pP = s.v_pP;
-    v.uex = s.uex; v.uey = s.uey; v.uez = s.uez; v.upx = s.upx; v.upy = s.upy; v.upz = s.upz;
-    rad_weight = peaked_rad_weight(cfg, R, v, eg, emin, emax, bw);
-  }
-  SIMC_PHASE();
+  gr.emin = emin; gr.emax = emax; gr.eg = eg; gr.bw = bw; gr.which = which;
+  return ok;
+}
+// second pass through complete_ev for the tries whose incoming electron radiated (radc.f:324), then the
+// spectral-function window of radc.f:340-350
+template <class RNG, class GAUSS>
+SIMC_HD bool generate_heavy_second(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
+  bool ok = complete_ev_heavy(cfg, mt, rng, gauss, s, run);
+  const simc_edge& VE = cfg.VERTEXedge;
   if (ok) {
-    s.o_Ein = s.v_Ein + R.Egamma_used[0];
-    s.o_eE = s.v_eE - R.Egamma_used[1];
-    if (s.o_eE <= 0e0) ok = false;
-  }
-  if (ok) {
-    s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
-    s.o_pE = s.v_pE - R.Egamma_used[2];
-    if (s.o_pE <= cfg.Mh) ok = false;
-  }
-  if (ok) {
-    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
-    s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
-    s.gen_weight = s.gen_weight * rad_weight / R.hardcorfac;
+    if (s.v_Em < VE.Em.min || s.v_Em > VE.Em.max || s.v_Pm < VE.Pm.min || s.v_Pm > VE.Pm.max) ok = false;
   }
   return ok;
 }

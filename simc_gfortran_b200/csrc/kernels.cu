@@ -310,6 +310,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       const long long gneed = (a.n_tries + kGenBlock - 1) / kGenBlock;
       const long long gmax = (long long)a.grid_blocks * kBlock / kGenBlock;        // same number of resident threads
       k_generate<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
+      if (a.using_rad) k_regen<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
     }
   } else if (stage == 1) {
     if (a.coll_p) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
@@ -321,7 +322,10 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
     for (int k = 0; k < arm_e.tab.n_mid; ++k) { A.mid_k = k; k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e); }
     k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
-  } else if (stage == 3) k_finish<<<grid, kBlock, 0, s>>>(A);
+  } else if (stage == 3) {
+    if (a.using_rad) k_radw<<<grid, kBlock, 0, s>>>(A, a.record_mode ? 0 : 10);
+    k_finish<<<grid, kBlock, 0, s>>>(A);
+  }
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   return cudaGetLastError();
 }

@@ -7,6 +7,8 @@
 
 namespace simc {
 
+constexpr int kLoopLists = 12;   // survivor lists of the event loop (loop.cuh: LoopArgs::lists)
+
 struct TransportBatchArgs {
   const void* arm;          // ArmDev image on the HOST: passed to the kernel by value (constant bank)
   long long n;
@@ -25,8 +27,8 @@ struct LoopLaunch {
   const void* arm_p;          // kernel gets its program and map directory by value, in the constant bank
   double* state;              // [n_state_fields][cap]
   long long cap;
-  unsigned* lists;            // [3][cap]
-  unsigned* counts;           // [4]
+  unsigned* lists;            // [kLoopLists][cap] (loop.cuh: LoopArgs)
+  unsigned* counts;           // [16]
   void* acc;                  // DevAccum*
   long long first_try, n_tries;
   unsigned long long seed;
@@ -36,6 +38,7 @@ struct LoopLaunch {
   int* status;
   int grid_blocks;            // persistent grid for the stage kernels
   int coll_e, coll_p;         // the arm steps pions through its collimator (using_HMScoll / using_SHMScoll)
+  int using_rad;              // radiative corrections on: second generation pass (k_regen) and k_radw are launched
   double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
   const double* sf_pm;        // Benhar spectral function (device): Pm axis, Em axis, values [n_pm][n_em]
   const double* sf_em;

@@ -45,6 +45,11 @@ enum StateField : int {
   F_ZHAD, F_PT2, F_PFER, F_PFERX, F_PFERY, F_PFERZ, F_EFER, F_XFERMI,
   // ntuple rows (record mode only): focal-plane positions, decay bookkeeping, then the row itself
   F_FPP_X, F_FPP_Y, F_FPE_X, F_FPE_DX, F_FPE_Y, F_FPE_DY, F_DECDIST, F_MH2FINAL,
+  // what the deferred peaked_rad_weight reads (k_radw): the electron's direction, the per-event radiative
+  // constants and generate_rad's photon-energy limits; and the angles a try carries into its second pass
+  // through complete_ev (k_regen)
+  F_UEX, F_UEY, F_UEZ, F_RC_CEXT0, F_RC_GEXT, F_RC_G1, F_RC_G2, F_RC_G4, F_RC_BT0, F_RC_BT1,
+  F_RD_EMIN, F_RD_EMAX, F_RD_EG, F_RD_BW, F_RD_WHICH, F_VEPHI, F_VPTHETA, F_VPPHI,
   F_NTU0, F_NTU_LAST = F_NTU0 + SIMC_NTUPLE_MAXCOL - 1,
   F_NFIELDS
 };
@@ -78,8 +83,9 @@ struct LoopArgs {
   MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
-  unsigned* lists;                 // [11][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same
-  unsigned* counts;                // [0] slots handed out, [1..11] lengths of lists 0..10
+  unsigned* lists;                 // [12][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same |
+                                   //            11: tries that go through complete_ev a second time (k_regen)
+  unsigned* counts;                // [0] slots handed out, [1..12] lengths of lists 0..11
   int mid_k;                       // which middle segment a k_arm<*,2> launch runs
   DevAccum* acc;
   long long first_try, n_tries;
@@ -145,7 +151,7 @@ struct GaussFn {
 };
 
 // ---- stage 1: generation -------------------------------------------------------------------
-// CTA size of the generation kernel: the code is one long straight line, and every CTA resident on an
+// CTA size of the generation kernels: the code is one long straight line, and every CTA resident on an
 // SM streams it through the instruction cache at its own position; fewer, larger CTAs (whose warps the
 // phase barriers keep together) mean fewer streams.  Registers are capped at 65536 / (block * min blocks).
 #ifndef SIMC_GEN_BLOCK
@@ -155,95 +161,242 @@ struct GaussFn {
 #define SIMC_GEN_MIN_BLOCKS 2
 #endif
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
+constexpr int kRegenList = 11;
+
+struct GenFlags { bool semi, fermi, meson, heavy; };
+__device__ __forceinline__ GenFlags gen_flags(const simc_run_config& cfg) {
+  GenFlags g;
+  g.semi = cfg.doing_semi != 0;
+  g.fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;   // nucleon momentum thrown
+  g.meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || g.semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+  g.heavy = cfg.doing_heavy != 0;
+  return g;
+}
+
+// geni histograms: every try, from the vertex values it ended with (simc.f:253-262)
+__device__ __forceinline__ void geni_hist(const simc_run_config& cfg, unsigned (*h_geni)[SIMC_NHIST], const EventState& s) {
+  const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) warp_hist_add(h_geni[k], hist_bin(cfg.hist_axis[2][k], gv[k]));
+}
+
+// The try's record in the state buffer.  `carry`: the try is on its way to k_regen, which also needs the angles
+// and main%Trec of the first pass.
+__device__ __forceinline__ void store_event(const LoopArgs& A, const GenFlags& g, unsigned slot, long long i, unsigned draw,
+                                            const EventState& s, const GenRad& gr, bool ok, bool carry) {
+  const StateBuf& S = A.st;
+  S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)draw);
+  if (A.record_mode) {      // only the per-try records read these
+    S.st(F_STAGE, slot, ok ? 1.0 : 0.0); S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
+  }
+  S.st(F_TX, slot, s.tx); S.st(F_TY, slot, s.ty); S.st(F_TZ, slot, s.tz); S.st(F_RASTERY, slot, s.rastery);
+  S.st(F_ELOSS0, slot, s.Eloss[0]); S.st(F_ELOSS1, slot, s.Eloss[1]); S.st(F_ELOSS2, slot, s.Eloss[2]);
+  S.st(F_TEFF0, slot, s.teff[0]); S.st(F_TEFF1, slot, s.teff[1]); S.st(F_TEFF2, slot, s.teff[2]);
+  S.st(F_COULOMB, slot, s.Coulomb);
+  S.st(F_GENW, slot, s.gen_weight); S.st(F_JAC, slot, s.jacobian); S.st(F_EINSHIFT, slot, s.Ein_shift);
+  S.st(F_EESHIFT, slot, s.Ee_shift); S.st(F_MTREC, slot, s.Trec);
+  S.st(F_VEIN, slot, s.v_Ein); S.st(F_VEE, slot, s.v_eE); S.st(F_VEDELTA, slot, s.v_edelta);
+  S.st(F_VEYP, slot, s.v_eyptar); S.st(F_VEXP, slot, s.v_exptar); S.st(F_VETHETA, slot, s.v_etheta);
+  S.st(F_VPE, slot, s.v_pE); S.st(F_VPP, slot, s.v_pP); S.st(F_VPDELTA, slot, s.v_pdelta);
+  S.st(F_VPYP, slot, s.v_pyptar); S.st(F_VPXP, slot, s.v_pxptar); S.st(F_VQ2, slot, s.v_Q2);
+  S.st(F_VEM, slot, s.v_Em); S.st(F_VPM, slot, s.v_Pm); S.st(F_VTREC, slot, s.v_Trec);
+  S.st(F_OEIN, slot, s.o_Ein); S.st(F_OEE, slot, s.o_eE); S.st(F_OEDELTA, slot, s.o_edelta);
+  S.st(F_OPE, slot, s.o_pE); S.st(F_OPP, slot, s.o_pP); S.st(F_OPDELTA, slot, s.o_pdelta);
+  S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
+  S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
+  S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
+  S.st(F_UEX, slot, s.uex); S.st(F_UEY, slot, s.uey); S.st(F_UEZ, slot, s.uez);
+  S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
+  S.st(F_RC_CEXT0, slot, s.rad.c_ext0); S.st(F_RC_GEXT, slot, s.rad.g_ext); S.st(F_RC_G1, slot, s.rad.g[1]);
+  S.st(F_RC_G2, slot, s.rad.g[2]); S.st(F_RC_G4, slot, s.rad.g[4]); S.st(F_RC_BT0, slot, s.rad.bt[0]);
+  S.st(F_RC_BT1, slot, s.rad.bt[1]);
+  S.st(F_RD_EMIN, slot, gr.emin); S.st(F_RD_EMAX, slot, gr.emax); S.st(F_RD_EG, slot, gr.eg); S.st(F_RD_BW, slot, gr.bw);
+  S.st(F_RD_WHICH, slot, (double)gr.which);
+  if (carry) {
+    S.st(F_VEPHI, slot, s.v_ephi); S.st(F_VPTHETA, slot, s.v_ptheta); S.st(F_VPPHI, slot, s.v_pphi);
+  }
+  if ((g.heavy || g.meson) && (ok || carry)) {
+    S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
+    S.st(F_UQZ, slot, s.uqz);
+  }
+  if (g.meson && (ok || carry)) {
+    S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
+    S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
+    if (g.semi) { S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); }
+    if (g.semi || g.fermi) {
+      S.st(F_PFER, slot, s.pfer); S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery);
+      S.st(F_PFERZ, slot, s.pferz); S.st(F_EFER, slot, s.efer);
+    }
+  }
+}
+
+// What a try brings into its second pass through complete_ev: everything the first pass left in `vertex`,
+// `main` and /radccom/ (complete_ev overwrites what it derives; a try that fails half-way keeps the rest for
+// the geni histograms, as in the one-pass reference).
+__device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g, unsigned slot, EventState& s, GenRad& gr) {
+  const StateBuf& S = A.st;
+  s.tx = S.ld(F_TX, slot); s.ty = S.ld(F_TY, slot); s.tz = S.ld(F_TZ, slot); s.rastery = S.ld(F_RASTERY, slot);
+  s.Eloss[0] = S.ld(F_ELOSS0, slot); s.Eloss[1] = S.ld(F_ELOSS1, slot); s.Eloss[2] = S.ld(F_ELOSS2, slot);
+  s.teff[0] = S.ld(F_TEFF0, slot); s.teff[1] = S.ld(F_TEFF1, slot); s.teff[2] = S.ld(F_TEFF2, slot);
+  s.Coulomb = S.ld(F_COULOMB, slot);
+  s.gen_weight = S.ld(F_GENW, slot); s.jacobian = S.ld(F_JAC, slot); s.Ein_shift = S.ld(F_EINSHIFT, slot);
+  s.Ee_shift = S.ld(F_EESHIFT, slot); s.Trec = S.ld(F_MTREC, slot);
+  s.v_Ein = S.ld(F_VEIN, slot); s.v_eE = S.ld(F_VEE, slot); s.v_edelta = S.ld(F_VEDELTA, slot);
+  s.v_eyptar = S.ld(F_VEYP, slot); s.v_exptar = S.ld(F_VEXP, slot); s.v_etheta = S.ld(F_VETHETA, slot);
+  s.v_ephi = S.ld(F_VEPHI, slot);
+  s.v_pE = S.ld(F_VPE, slot); s.v_pP = S.ld(F_VPP, slot); s.v_pdelta = S.ld(F_VPDELTA, slot);
+  s.v_pyptar = S.ld(F_VPYP, slot); s.v_pxptar = S.ld(F_VPXP, slot); s.v_ptheta = S.ld(F_VPTHETA, slot);
+  s.v_pphi = S.ld(F_VPPHI, slot); s.v_Q2 = S.ld(F_VQ2, slot);
+  s.v_Em = S.ld(F_VEM, slot); s.v_Pm = S.ld(F_VPM, slot); s.v_Trec = S.ld(F_VTREC, slot);
+  s.uex = S.ld(F_UEX, slot); s.uey = S.ld(F_UEY, slot); s.uez = S.ld(F_UEZ, slot);
+  s.upx = S.ld(F_UPX, slot); s.upy = S.ld(F_UPY, slot); s.upz = S.ld(F_UPZ, slot);
+  s.rad.Egamma_used[0] = S.ld(F_EG0, slot); s.rad.Egamma_used[1] = S.ld(F_EG1, slot); s.rad.Egamma_used[2] = S.ld(F_EG2, slot);
+  s.rad.ntail = (int)S.ld(F_NTAIL, slot);
+  s.rad.rad_proton_this_ev = S.ld(F_RADP, slot) != 0.0; s.rad.hardcorfac = S.ld(F_HARDCOR, slot);
+  s.rad.c_ext0 = S.ld(F_RC_CEXT0, slot); s.rad.g_ext = S.ld(F_RC_GEXT, slot); s.rad.g[1] = S.ld(F_RC_G1, slot);
+  s.rad.g[2] = S.ld(F_RC_G2, slot); s.rad.g[4] = S.ld(F_RC_G4, slot); s.rad.bt[0] = S.ld(F_RC_BT0, slot);
+  s.rad.bt[1] = S.ld(F_RC_BT1, slot);
+  gr.emin = S.ld(F_RD_EMIN, slot); gr.emax = S.ld(F_RD_EMAX, slot); gr.eg = S.ld(F_RD_EG, slot); gr.bw = S.ld(F_RD_BW, slot);
+  gr.which = (int)S.ld(F_RD_WHICH, slot);
+  s.v_nu = 0; s.v_q = 0; s.uqx = 0; s.uqy = 0; s.uqz = 0;
+  s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
+  s.v_zhad = 0; s.v_pt2 = 0; s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = A.cfg->targ.Mtar_struck;
+  if (g.heavy || g.meson) {
+    s.v_nu = S.ld(F_VNU, slot); s.v_q = S.ld(F_VQ, slot); s.uqx = S.ld(F_UQX, slot); s.uqy = S.ld(F_UQY, slot);
+    s.uqz = S.ld(F_UQZ, slot);
+  }
+  if (g.meson) {
+    s.m_eps = S.ld(F_MEPS, slot); s.m_thpq = S.ld(F_MTHPQ, slot); s.m_phipq = S.ld(F_MPHIPQ, slot);
+    s.m_t = S.ld(F_MT, slot); s.m_W = S.ld(F_MW, slot);
+    if (g.semi) { s.v_zhad = S.ld(F_ZHAD, slot); s.v_pt2 = S.ld(F_PT2, slot); }
+    if (g.semi || g.fermi) {
+      s.pfer = S.ld(F_PFER, slot); s.pferx = S.ld(F_PFERX, slot); s.pfery = S.ld(F_PFERY, slot);
+      s.pferz = S.ld(F_PFERZ, slot); s.efer = S.ld(F_EFER, slot);
+    }
+  }
+}
+
+__device__ __forceinline__ void gen_shared_init(const LoopArgs& A, unsigned (*h_geni)[SIMC_NHIST], MatTable& mt_s) {
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) (&h_geni[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kGenBlock)
+    ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void gen_shared_flush(const LoopArgs& A, unsigned (*h_geni)[SIMC_NHIST]) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) {
+    const unsigned v = (&h_geni[0][0])[i];
+    if (v) atomicAdd(&A.acc->hist_n[2][0][0] + i, (unsigned long long)v);
+  }
+}
+
+// First pass: one thread per try.  generate, complete_ev, and generate_rad up to the photon energy of the tail
+// that radiates.  A try whose incoming electron radiated (a third of them) goes to list kRegenList for its
+// second pass through complete_ev on compacted warps; all others are complete here.
 __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(LoopArgs A) {
   __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
   // the out-of-line energy-loss routines take the material table by reference: give them shared memory,
   // not a generic pointer into the kernel-parameter bank
   __shared__ MatTable mt_s;
-  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) (&h_geni[0][0])[i] = 0u;
-  for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kGenBlock)
-    ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
-  __syncthreads();
+  gen_shared_init(A, h_geni, mt_s);
   const simc_run_config& cfg = *A.cfg;
+  const GenFlags g = gen_flags(cfg);
   const long long stride = (long long)gridDim.x * kGenBlock;
   for (long long i0 = (long long)blockIdx.x * kGenBlock; i0 < A.n_tries; i0 += stride) {
     const long long i = i0 + threadIdx.x;
     const bool active = i < A.n_tries;
     bool ok = false;
     EventState s;
+    GenRad gr;
     DevRng rng;
     rng.init((unsigned long long)(A.first_try + (active ? i : 0)), 0u, 0u);
     s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
-    const bool semi = cfg.doing_semi != 0;
-    const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;   // nucleon momentum thrown
-    const bool meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
-    const bool heavy = cfg.doing_heavy != 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
     // (tables by value: a reference into the kernel parameters handed to an out-of-line function would make the
     //  compiler copy all of LoopArgs to every thread's stack -- +600 bytes of frame, +10 % kernel time)
-    if (meson) ok = generate_meson(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active);
-    else if (heavy) ok = generate_heavy(cfg, mt_s, rng, GaussFn(), s, active);
-    else ok = generate_hyd_elast(cfg, mt_s, rng, GaussFn(), s, active);
-    if (active) {
-      // geni histograms: every try, from the vertex values (simc.f:253-262)
-      const double gv[8] = {s.v_edelta, s.v_eyptar, -s.v_exptar, s.v_pdelta, s.v_pyptar, -s.v_pxptar, s.v_Em, s.v_Pm};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        warp_hist_add(h_geni[k], hist_bin(cfg.hist_axis[2][k], gv[k]));
-      }
-    }
-    const bool want_slot = active && (ok || A.record_mode);
+    if (g.meson) ok = generate_meson_first(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active, gr);
+    else if (g.heavy) ok = generate_heavy_first(cfg, mt_s, rng, GaussFn(), s, active, gr);
+    else ok = generate_hyd_elast_first(cfg, mt_s, rng, GaussFn(), s, active, gr);
+    const bool carry = active && ok && gr.which == 1;       // radc.f:324: complete_ev once more
+    if (!carry) ok = generate_finalize(cfg, s, ok);
+    if (active && !carry) geni_hist(cfg, h_geni, s);
+    const bool want_slot = active && (ok || carry || A.record_mode);
     const unsigned slot = warp_append(&A.counts[0], want_slot);
-    if (want_slot) {
-      const StateBuf& S = A.st;
-      S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)rng.draw);
-      if (A.record_mode) {      // only the per-try records read these
-        S.st(F_STAGE, slot, ok ? 1.0 : 0.0); S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
-      }
-      S.st(F_TX, slot, s.tx); S.st(F_TY, slot, s.ty); S.st(F_TZ, slot, s.tz); S.st(F_RASTERY, slot, s.rastery);
-      S.st(F_ELOSS0, slot, s.Eloss[0]); S.st(F_ELOSS1, slot, s.Eloss[1]); S.st(F_ELOSS2, slot, s.Eloss[2]);
-      S.st(F_TEFF0, slot, s.teff[0]); S.st(F_TEFF1, slot, s.teff[1]); S.st(F_TEFF2, slot, s.teff[2]);
-      S.st(F_COULOMB, slot, s.Coulomb);
-      S.st(F_GENW, slot, s.gen_weight); S.st(F_JAC, slot, s.jacobian); S.st(F_EINSHIFT, slot, s.Ein_shift);
-      S.st(F_EESHIFT, slot, s.Ee_shift); S.st(F_MTREC, slot, s.Trec);
-      S.st(F_VEIN, slot, s.v_Ein); S.st(F_VEE, slot, s.v_eE); S.st(F_VEDELTA, slot, s.v_edelta);
-      S.st(F_VEYP, slot, s.v_eyptar); S.st(F_VEXP, slot, s.v_exptar); S.st(F_VETHETA, slot, s.v_etheta);
-      S.st(F_VPE, slot, s.v_pE); S.st(F_VPP, slot, s.v_pP); S.st(F_VPDELTA, slot, s.v_pdelta);
-      S.st(F_VPYP, slot, s.v_pyptar); S.st(F_VPXP, slot, s.v_pxptar); S.st(F_VQ2, slot, s.v_Q2);
-      S.st(F_VEM, slot, s.v_Em); S.st(F_VPM, slot, s.v_Pm); S.st(F_VTREC, slot, s.v_Trec);
-      S.st(F_OEIN, slot, s.o_Ein); S.st(F_OEE, slot, s.o_eE); S.st(F_OEDELTA, slot, s.o_edelta);
-      S.st(F_OPE, slot, s.o_pE); S.st(F_OPP, slot, s.o_pP); S.st(F_OPDELTA, slot, s.o_pdelta);
-      S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
-      S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
-      S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
-      if (heavy && ok) {
-        S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
-        S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
-      }
-      if (meson && ok) {
-        S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
-        S.st(F_UQZ, slot, s.uqz); S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
-        S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
-        S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
-        if (semi) { S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); }
-        if (semi || fermi) {
-          S.st(F_PFER, slot, s.pfer); S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery);
-          S.st(F_PFERZ, slot, s.pferz); S.st(F_EFER, slot, s.efer);
-        }
-      }
+    if (want_slot) store_event(A, g, slot, i, rng.draw, s, gr, ok && !carry, carry);
+    const unsigned pos = warp_append(&A.counts[1], active && ok && !carry);
+    if (active && ok && !carry) A.lists[0 * A.st.cap + pos] = slot;
+    const unsigned pos2 = warp_append(&A.counts[1 + kRegenList], carry);
+    if (carry) A.lists[(long long)kRegenList * A.st.cap + pos2] = slot;
+  }
+  gen_shared_flush(A, h_geni);
+  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&A.acc->counters[0], (unsigned long long)A.n_tries);
+}
+
+// Second pass (generate_rad, radc.f:324): the tries of list kRegenList go through complete_ev again with the
+// radiated beam energy, on full warps.
+__global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopArgs A) {
+  __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
+  __shared__ MatTable mt_s;
+  gen_shared_init(A, h_geni, mt_s);
+  const simc_run_config& cfg = *A.cfg;
+  const GenFlags g = gen_flags(cfg);
+  const StateBuf& S = A.st;
+  const unsigned n_in = A.counts[1 + kRegenList];
+  const unsigned* in_list = A.lists + (long long)kRegenList * A.st.cap;
+  const long long stride = (long long)gridDim.x * kGenBlock;
+  for (long long i0 = (long long)blockIdx.x * kGenBlock; i0 < n_in; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    const bool active = i < n_in;
+    const unsigned slot = active ? in_list[i] : 0u;
+    const long long itry = (long long)S.ld(F_TRY, slot);
+    EventState s;
+    GenRad gr;
+    load_event(A, g, slot, s, gr);
+    DevRng rng;
+    rng.init((unsigned long long)(A.first_try + itry), 0u, (unsigned)S.ld(F_DRAW, slot));
+    bool ok;
+    if (g.meson) ok = generate_meson_second(cfg, mt_s, rng, GaussFn(), s, active);
+    else if (g.heavy) ok = generate_heavy_second(cfg, mt_s, rng, GaussFn(), s, active);
+    else ok = generate_hyd_elast_second(cfg, mt_s, rng, GaussFn(), s, active);
+    ok = generate_finalize(cfg, s, ok);
+    if (active) {
+      geni_hist(cfg, h_geni, s);
+      store_event(A, g, slot, itry, rng.draw, s, gr, ok, false);
     }
     const unsigned pos = warp_append(&A.counts[1], active && ok);
     if (active && ok) A.lists[0 * A.st.cap + pos] = slot;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < SIMC_H_PER_SET * SIMC_NHIST; i += kGenBlock) {
-    const unsigned v = (&h_geni[0][0])[i];
-    if (v) atomicAdd(&A.acc->hist_n[2][0][0] + i, (unsigned long long)v);
+  gen_shared_flush(A, h_geni);
+}
+
+// peaked_rad_weight (radc.f:523-646) and main%gen_weight = gen_weight * rad_weight / hardcorfac (radc.f:518) for
+// the tries of list `list_idx`: the survivors of both arms in a run, every generated try in record mode.
+__global__ void __launch_bounds__(kBlock, 4) k_radw(LoopArgs A, int list_idx) {
+  const simc_run_config& cfg = *A.cfg;
+  const StateBuf& S = A.st;
+  const unsigned n_in = A.counts[1 + list_idx];
+  const unsigned* in_list = A.lists + (long long)list_idx * A.st.cap;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_in; i += (long long)gridDim.x * kBlock) {
+    const unsigned slot = in_list[i];
+    const int which = (int)S.ld(F_RD_WHICH, slot);
+    double rad_weight = 1;
+    if (which) {
+      RadEvDev R;
+      R.c_ext0 = S.ld(F_RC_CEXT0, slot); R.g_ext = S.ld(F_RC_GEXT, slot); R.g[1] = S.ld(F_RC_G1, slot);
+      R.g[2] = S.ld(F_RC_G2, slot); R.g[4] = S.ld(F_RC_G4, slot); R.bt[0] = S.ld(F_RC_BT0, slot); R.bt[1] = S.ld(F_RC_BT1, slot);
+      R.rad_proton_this_ev = S.ld(F_RADP, slot) != 0.0;
+      VertexKin v;
+      v.Ein = S.ld(F_VEIN, slot); v.eE = S.ld(F_VEE, slot); v.eP = v.eE; v.etheta = S.ld(F_VETHETA, slot);
+      v.pE = S.ld(F_VPE, slot); v.pP = S.ld(F_VPP, slot);
+      v.uex = S.ld(F_UEX, slot); v.uey = S.ld(F_UEY, slot); v.uez = S.ld(F_UEZ, slot);
+      v.upx = S.ld(F_UPX, slot); v.upy = S.ld(F_UPY, slot); v.upz = S.ld(F_UPZ, slot);
+      rad_weight = peaked_rad_weight(cfg, R, v, S.ld(F_RD_EG, slot), S.ld(F_RD_EMIN, slot), S.ld(F_RD_EMAX, slot), S.ld(F_RD_BW, slot));
+    }
+    S.st(F_GENW, slot, S.ld(F_GENW, slot) * rad_weight / S.ld(F_HARDCOR, slot));
   }
-  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&A.acc->counters[0], (unsigned long long)A.n_tries);
 }
 
 #ifndef SIMC_ARM_MIN_BLOCKS

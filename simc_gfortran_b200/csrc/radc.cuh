@@ -31,7 +31,11 @@ SIMC_HD double spence_approx(double ax) {
 }
 
 // One interference term: inter (brem.f:216-240) and inter_prime (brem.f:581-596) share
-// amult and the two log-ratio factors.
+// amult and the two log-ratio factors.  WHAT selects the outputs a caller reads (the arithmetic of each
+// is the reference's, untouched): kBremPrime = d(b)/dE only (radc_init_ev reads nothing else of bremos
+// besides bhard), kBremSoft = b only (peaked_rad_weight), kBremAll = both.
+constexpr int kBremAll = 0, kBremPrime = 1, kBremSoft = 2;
+template <int WHAT>
 SIMC_HD_CALL void inter_pair(double alpha, double ar1, double ar2, double e1, double e2, double de, double& val,
                         double& prime) {
   const double pi = 3.141592653589793;
@@ -39,20 +43,24 @@ SIMC_HD_CALL void inter_pair(double alpha, double ar1, double ar2, double e1, do
   const double amult = -1. / (alpha * (ar1 - ar2));
   const double l1 = m::log(fabs((ar1 - 1.) / ar1));
   const double l2 = m::log(fabs((ar2 - 1.) / ar2));
-  double v = m::log(fabs((e2 / de) + ar1 * (de2 / de))) * l1 - m::log(fabs((e2 / de) + ar2 * (de2 / de))) * l2;
-  const double arg1 = (de2 / (e2 + ar1 * de2)) * (ar1 - 1.);
-  const double arg2 = (de2 / (e2 + ar1 * de2)) * (ar1);
-  const double arg3 = (de2 / (e2 + ar2 * de2)) * (ar2 - 1.);
-  const double arg4 = (de2 / (e2 + ar2 * de2)) * (ar2);
-  v = v - spence_approx(arg1) + spence_approx(arg2) + spence_approx(arg3) - spence_approx(arg4);
-  val = v * amult / (pi);
-  prime = (-1. / de) * amult / pi * (l1 - l2);
+  val = 0.0; prime = 0.0;
+  if (WHAT != kBremPrime) {
+    double v = m::log(fabs((e2 / de) + ar1 * (de2 / de))) * l1 - m::log(fabs((e2 / de) + ar2 * (de2 / de))) * l2;
+    const double arg1 = (de2 / (e2 + ar1 * de2)) * (ar1 - 1.);
+    const double arg2 = (de2 / (e2 + ar1 * de2)) * (ar1);
+    const double arg3 = (de2 / (e2 + ar2 * de2)) * (ar2 - 1.);
+    const double arg4 = (de2 / (e2 + ar2 * de2)) * (ar2);
+    v = v - spence_approx(arg1) + spence_approx(arg2) + spence_approx(arg3) - spence_approx(arg4);
+    val = v * amult / (pi);
+  }
+  if (WHAT != kBremSoft) prime = (-1. / de) * amult / pi * (l1 - l2);
 }
 
 SIMC_HD double dot4(const V4& a, const V4& b) { return a.e * b.e - a.x * b.x - a.y * b.y - a.z * b.z; }
 
 // One of the six interference contributions of bremos (brem.f:420-491): masses m1 (the one whose
 // square enters the numerator of ar1/ar2) and m2.
+template <int WHAT>
 SIMC_HD void interference(double aprod, const V4& a, const V4& b, double m_num, double m_oth, double de, double& bsum,
                           double& dbsum) {
   const double adot = dot4(a, b);
@@ -62,7 +70,7 @@ SIMC_HD void interference(double aprod, const V4& a, const V4& b, double m_num, 
   const double ar1 = (2. * m_num * m_num - 2. * adot + root) / (2. * alpha);
   const double ar2 = (2. * m_num * m_num - 2. * adot - root) / (2. * alpha);
   double v, p;
-  inter_pair(alpha, ar1, ar2, a.e, b.e, de, v, p);
+  inter_pair<WHAT>(alpha, ar1, ar2, a.e, b.e, de, v, p);
   bsum = aprod * adot * v;
   dbsum = aprod * adot * p;
 }
@@ -70,6 +78,7 @@ SIMC_HD void interference(double aprod, const V4& a, const V4& b, double m_num, 
 // bremos, brem.f:344-577, with the electron along +z before scattering (k_i = (0,0,Ein)) and the
 // initial proton at rest, which is how both call sites use it (init.f:706, radc.f:600-623).
 // Energies in MeV on input.  Returns bsoft, bhard and d(bsoft)/dE (per MeV).
+template <int WHAT = kBremAll>
 SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, double kfz, double pfx, double pfy, double pfz,
                     double pfe, bool radiate_proton, double& bsoft, double& bhard, double& dbsoft) {
   const double pi = 3.141592653589793, twopi = 2. * pi, ame = .00051099906, e2 = 1. / 137.0359895, mp = .93827231;
@@ -86,9 +95,9 @@ SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, doub
   const double q2 = -1. * (sq(k_f.e - k_i.e) - sq(k_f.x - k_i.x) - sq(k_f.y - k_i.y) - sq(k_f.z - k_i.z));
   const double ami = mp;
   const double amf = sqrt(sq(p_f.e) - sq(p_f.x) - sq(p_f.y) - sq(p_f.z));
-  const double bei = 1.e0 * (-1. / twopi) * m::log(k_i.e / de);
+  const double bei = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / twopi) * m::log(k_i.e / de);
   const double dbei = 1.e0 * (-1. / twopi) * (-1. / de);
-  const double bef = 1.e0 * (-1. / twopi) * m::log(k_f.e / de);
+  const double bef = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / twopi) * m::log(k_f.e / de);
   const double dbef = 1.e0 * (-1. / twopi) * (-1. / de);
   double bee, dbee;
   {   // e-e interference, brem.f:411-418 (its own form of ar1/ar2)
@@ -99,7 +108,7 @@ SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, doub
     const double ar1 = 0.5 + root / (2. * alpha);
     const double ar2 = 0.5 - root / (2. * alpha);
     double v, p;
-    inter_pair(alpha, ar1, ar2, k_i.e, k_f.e, de, v, p);
+    inter_pair<WHAT>(alpha, ar1, ar2, k_i.e, k_f.e, de, v, p);
     bee = -1.e0 * adot * v;
     dbee = -1.e0 * adot * p;
   }
@@ -107,9 +116,9 @@ SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, doub
   const double db = 2. * e2 * (dbei + dbef + dbee);
   double bz = 0.0, bzz = 0.0, dbz = 0.0, dbzz = 0.0;
   if (radiate_proton) {
-    const double bpi = 1.e0 * (-1. / twopi) * m::log(p_i.e / de);
+    const double bpi = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / twopi) * m::log(p_i.e / de);
     const double dbpi = 1.e0 * (-1. / twopi) * (-1. / de);
-    const double bpf = 1.e0 * (-1. / twopi) * m::log(p_f.e / de);
+    const double bpf = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / twopi) * m::log(p_f.e / de);
     const double dbpf = 1.e0 * (-1. / twopi) * (-1. / de);
     double bpp, dbpp, bepii, dbepii, bepff, dbepff, bepif, dbepif, bepfi, dbepfi;
     // alpha = ami^2+amf^2-2adot, ar uses 2 amf^2, root uses (ami*amf)^2           brem.f:430-437
@@ -121,20 +130,20 @@ SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, doub
       const double ar1 = (2. * amf * amf - 2. * adot + root) / (2. * alpha);
       const double ar2 = (2. * amf * amf - 2. * adot - root) / (2. * alpha);
       double v, p;
-      inter_pair(alpha, ar1, ar2, p_i.e, p_f.e, de, v, p);
+      inter_pair<WHAT>(alpha, ar1, ar2, p_i.e, p_f.e, de, v, p);
       bpp = -1.e0 * adot * v; dbpp = -1.e0 * adot * p;
     }
-    interference(-1.e0, k_i, p_i, ami, ame, de, bepii, dbepii);   // ei-pi  brem.f:439-446
-    interference(-1.e0, k_f, p_f, amf, ame, de, bepff, dbepff);   // ef-pf  brem.f:448-455
-    interference(1.e0, k_i, p_f, amf, ame, de, bepif, dbepif);    // ei-pf  brem.f:457-464
-    interference(1.e0, k_f, p_i, ami, ame, de, bepfi, dbepfi);    // ef-pi  brem.f:466-473
+    interference<WHAT>(-1.e0, k_i, p_i, ami, ame, de, bepii, dbepii);   // ei-pi  brem.f:439-446
+    interference<WHAT>(-1.e0, k_f, p_f, amf, ame, de, bepff, dbepff);   // ef-pf  brem.f:448-455
+    interference<WHAT>(1.e0, k_i, p_f, amf, ame, de, bepif, dbepif);    // ei-pf  brem.f:457-464
+    interference<WHAT>(1.e0, k_f, p_i, ami, ame, de, bepfi, dbepfi);    // ef-pi  brem.f:466-473
     bzz = 2. * e2 * (bpi + bpf + bpp);
     bz = 2. * e2 * (bepii + bepff + bepif + bepfi);
     dbzz = 2. * e2 * (dbpi + dbpf + dbpp);
     dbz = 2. * e2 * (dbepii + dbepff + dbepif + dbepfi);
   }
   bsoft = b + bz + bzz;
-  bhard = -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * m::log(q2 / (ame * ame)));
+  bhard = WHAT == kBremSoft ? 0.0 : -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * m::log(q2 / (ame * ame)));
   dbsoft = db + dbz + dbzz;
   dbsoft = dbsoft / 1000.;
 }
@@ -189,7 +198,7 @@ SIMC_HD_CALL void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, d
   R.rad_proton_this_ev = R.lambda[2] > 0;
   const double Ecutoff = 450.;
   double dsoft, dhard, dsoft_prime;
-  bremos(Ecutoff, v.Ein, v.eP * v.uex, v.eP * v.uey, v.eP * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+  bremos<kBremPrime>(Ecutoff, v.Ein, v.eP * v.uex, v.eP * v.uey, v.eP * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
          R.rad_proton_this_ev, dsoft, dhard, dsoft_prime);
   R.hardcorfac = 1. / (1. - dhard);
   R.g[4] = -dsoft_prime * Ecutoff + R.bt[0] + R.bt[1];
@@ -244,9 +253,9 @@ SIMC_HD_CALL double peaked_rad_weight(const simc_run_config& cfg, const RadEvDev
   }
   double dsoft_intmin = 1.0, dsoft_intmax, dhard, dprime;
   if (emin > 0)
-    bremos(emin, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+    bremos<kBremSoft>(emin, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
            R.rad_proton_this_ev, dsoft_intmin, dhard, dprime);
-  bremos(emax, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+  bremos<kBremSoft>(emax, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
          R.rad_proton_this_ev, dsoft_intmax, dhard, dprime);
   double w;
   if (emin > 0)
