@@ -229,6 +229,20 @@ int simc_b200_set_optics(simc_handle* h, int arm_id,
                          const double* fwd_coeff, const int8_t* fwd_expon, const double* fwd_length_cm,
                          int n_rec, const double* rec_coeff, const int8_t* rec_expon);
 
+/* Compiled maps.  The RNG-free stretches of an arm program -- magnet apertures, drifts and the COSY forward maps
+ * between them (shared/transp.f:134-279 without decay) -- run as straight-line kernels generated from the loaded
+ * tables (csrc/mapgen.h) and compiled for sm_100a with NVRTC; cubins are cached in <library dir>/jit_cache (or
+ * $SIMC_B200_JIT_CACHE).  Arms with decay in flight or collimator stepping use the record interpreter, which is also
+ * what on = 0 selects for everything (parity twin; default on, $SIMC_B200_COMPILED_MAPS=0 turns it off). */
+int simc_b200_set_compiled_maps(simc_handle* h, int on);
+/* Device-free: generate + compile the stretches of one set of optics tables (same arrays as simc_b200_set_optics) and
+ * leave the cubin in cache_dir (NULL: the default cache).  info4 = stretches, source bytes, cubin bytes, 1 if it was
+ * cached already; msg receives the compiler log on failure. */
+int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_class_start, const double* fwd_coeff,
+                                const int8_t* fwd_expon, const double* fwd_length_cm, int n_rec, const double* rec_coeff,
+                                const int8_t* rec_expon, int strict_mode, const char* cache_dir, const char* dump_source_path,
+                                int64_t* info4, char* msg, int msg_len);
+
 /* info[0..6] = n_classes, forward terms, non-zero forward coefficients, recon terms,
  * compiled groups, packed coefficients, ops in the arm program */
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);

@@ -14,6 +14,8 @@
 #include <vector>
 #include "../../include/simc_b200.h"
 #include "kernels.h"
+#include "mapgen.h"
+#include "jit.h"
 #include "optics_host.h"
 #include "target.cuh"
 #include "tables_host.h"
@@ -30,6 +32,12 @@ struct ArmSlot {
   CompiledArm host;
   std::vector<unsigned char> img;        // ArmDev image (host): kernels take it by value
   double* d_recs = nullptr;
+  // compiled stretches of the program (mapgen.h): one generated kernel per RNG-free stretch
+  std::vector<StretchSpec> stretches;
+  int hut_begin = 0;                     // first op that is not static
+  JitModule jit;
+  bool jit_ready = false;
+  int jit_strict = -1;                   // arithmetic variant the module was generated for
 };
 
 std::string g_create_error;
@@ -40,12 +48,16 @@ struct simc_handle {
   simc_run_config cfg;
   int device = 0;
   int strict = 1;
+  int compiled_maps = 1;               // run RNG-free stretches of the arm programs as generated kernels (mapgen.h)
   cudaStream_t stream = nullptr;
   std::map<int, ArmSlot> arms;
   std::string err;
   long long launches = 0;
   // scratch for the host-pointer entry points
   double* d_in = nullptr; double* d_out = nullptr; int* d_flags = nullptr; long long scratch_n = 0;
+  // scratch of the compiled path of transport_batch: track rows, survivor lists, counters (kernels.h)
+  double* tb_tk = nullptr; unsigned* tb_lists = nullptr; unsigned* tb_counts = nullptr; unsigned long long* tb_sink = nullptr;
+  long long tb_n = 0;
   // event loop
   simc_run_config* d_cfg = nullptr;
   double* d_state = nullptr; unsigned* d_lists = nullptr; unsigned* d_counts = nullptr; void* d_acc = nullptr;
@@ -87,7 +99,32 @@ int cuda_fail(simc_handle* h, cudaError_t e, const char* what) {
 
 void free_arm(ArmSlot& s) {
   if (s.d_recs) cudaFree(s.d_recs);
+  jit_unload(s.jit);
   s = ArmSlot();
+}
+
+// Cuts of the arm program for the compiled path: RNG-free stretches from op 0 up to the first op that needs the
+// interpreter (the hut), split at the loop's compaction points.
+void plan_stretches(ArmSlot& s) {
+  const std::vector<ArmOp>& ops = s.host.ops;
+  int hut = 0;
+  while (hut < (int)ops.size() && op_is_static(ops[hut].op)) ++hut;
+  s.hut_begin = hut;
+  s.stretches.clear();
+  std::vector<int> cuts;
+  cuts.push_back(0);
+  const ArmTablesDev& tab = s.host.tab;
+  if (tab.split_op > 0 && tab.split_op < hut) cuts.push_back(tab.split_op);
+  for (int k = 0; k < tab.n_mid; ++k)
+    if (tab.mid_op[k] > cuts.back() && tab.mid_op[k] < hut) cuts.push_back(tab.mid_op[k]);
+  cuts.push_back(hut);
+  for (size_t k = 0; k + 1 < cuts.size(); ++k)
+    if (cuts[k + 1] > cuts[k]) s.stretches.push_back(StretchSpec{cuts[k], cuts[k + 1]});
+}
+
+int map_min_blocks() {
+  if (const char* e = std::getenv("SIMC_B200_MAP_MINBLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) return v; }
+  return 3;
 }
 
 int upload_arm(simc_handle* h, int arm_id, CompiledArm&& ca) {
@@ -107,6 +144,21 @@ int upload_arm(simc_handle* h, int arm_id, CompiledArm&& ca) {
   std::memcpy(img.data(), &tab, sizeof(tab));
   std::memcpy(img.data() + sizeof(ArmTablesDev), s.host.ops.data(), s.host.ops.size() * sizeof(ArmOp));
   s.loaded = true;
+  return SIMC_OK;
+}
+
+int ensure_compiled(simc_handle* h, ArmSlot& s);
+
+int ensure_tb_scratch(simc_handle* h, long long n) {
+  if (n <= h->tb_n) return SIMC_OK;
+  if (h->tb_tk) cudaFree(h->tb_tk);
+  if (h->tb_lists) cudaFree(h->tb_lists);
+  h->tb_tk = nullptr; h->tb_lists = nullptr; h->tb_n = 0;
+  CU(h, cudaMalloc(&h->tb_tk, sizeof(double) * 12 * (size_t)n));
+  CU(h, cudaMalloc(&h->tb_lists, sizeof(unsigned) * (kArmLists + 1) * (size_t)n));
+  if (!h->tb_counts) CU(h, cudaMalloc(&h->tb_counts, sizeof(unsigned) * (kArmLists + 1)));
+  if (!h->tb_sink) CU(h, cudaMalloc(&h->tb_sink, sizeof(unsigned long long) * (SIMC_NSTOP + 48)));
+  h->tb_n = n;
   return SIMC_OK;
 }
 
@@ -147,6 +199,8 @@ int simc_b200_create(const simc_run_config* cfg, int device, simc_handle** out) 
   h->device = device;
   const char* mode = std::getenv("SIMC_B200_MODE");
   h->strict = !(mode && std::strcmp(mode, "fast") == 0);
+  const char* cm = std::getenv("SIMC_B200_COMPILED_MAPS");
+  h->compiled_maps = !(cm && std::strcmp(cm, "0") == 0);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     std::string m = std::string("simc_b200_create: ") + cudaGetErrorString(e);
     delete h;
@@ -166,6 +220,10 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_cfg) cudaFree(h->d_cfg);
   if (h->d_state) cudaFree(h->d_state);
   if (h->d_lists) cudaFree(h->d_lists);
+  if (h->tb_tk) cudaFree(h->tb_tk);
+  if (h->tb_lists) cudaFree(h->tb_lists);
+  if (h->tb_counts) cudaFree(h->tb_counts);
+  if (h->tb_sink) cudaFree(h->tb_sink);
   if (h->d_counts) cudaFree(h->d_counts);
   if (h->d_acc) cudaFree(h->d_acc);
   if (h->d_rec) cudaFree(h->d_rec);
@@ -503,6 +561,62 @@ int simc_b200_set_optics(simc_handle* h, int arm_id, int n_classes, const int32_
   }
 }
 
+int simc_b200_set_compiled_maps(simc_handle* h, int on) {
+  if (!h) return SIMC_ERR_ARG;
+  h->compiled_maps = on ? 1 : 0;
+  return SIMC_OK;
+}
+
+// Device-free: runs the map compiler on a set of optics tables and leaves the cubin in the cache directory, so that
+// a later run with the same tables loads it without calling NVRTC.  __graft_entry__.build() does this for the
+// shipped optics.  info4: stretches, source bytes, cubin bytes, 1 if the cubin was already cached.
+int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_class_start, const double* fwd_coeff,
+                                const int8_t* fwd_expon, const double* fwd_length_cm, int n_rec, const double* rec_coeff,
+                                const int8_t* rec_expon, int strict_mode, const char* cache_dir, const char* dump_source_path,
+                                int64_t* info4, char* msg, int msg_len) {
+  auto say = [&](const std::string& m) { if (msg && msg_len > 0) { std::snprintf(msg, (size_t)msg_len, "%s", m.c_str()); } };
+  if (!fwd_class_start || !fwd_coeff || !fwd_expon || !rec_coeff || !rec_expon || n_classes <= 0 || n_rec <= 0) {
+    say("bad argument");
+    return SIMC_ERR_ARG;
+  }
+  try {
+    ForwardMaps f;
+    for (int k = 0; k < n_classes; ++k) {
+      CosyTerms t;
+      const int b = fwd_class_start[k], e = fwd_class_start[k + 1];
+      if (e < b) throw std::runtime_error("fwd_class_start must be non-decreasing");
+      t.coef.assign(fwd_coeff + 5 * (size_t)b, fwd_coeff + 5 * (size_t)e);
+      t.expo.assign(fwd_expon + 5 * (size_t)b, fwd_expon + 5 * (size_t)e);
+      f.cls.push_back(std::move(t));
+      f.length_cm.push_back(fwd_length_cm ? fwd_length_cm[k] : 0.0);
+    }
+    classify_drifts(f);
+    CosyTerms r;
+    r.nout = 4;
+    r.coef.assign(rec_coeff, rec_coeff + 4 * (size_t)n_rec);
+    r.expo.assign(rec_expon, rec_expon + 5 * (size_t)n_rec);
+    ArmSlot s;
+    s.host = compile_arm(arm_id, f, r);
+    plan_stretches(s);
+    const std::string src = generate_stretch_source(s.host, s.stretches, strict_mode != 0, map_min_blocks());
+    if (dump_source_path && *dump_source_path) {
+      FILE* fp = std::fopen(dump_source_path, "w");
+      if (fp) { std::fwrite(src.data(), 1, src.size(), fp); std::fclose(fp); }
+    }
+    std::string cubin, err;
+    bool cached = false;
+    if (!jit_compile_cubin(src, cache_dir ? std::string(cache_dir) : jit_default_cache_dir(), cubin, &cached, err)) {
+      say(err);
+      return SIMC_ERR_STATE;
+    }
+    if (info4) { info4[0] = (int64_t)s.stretches.size(); info4[1] = (int64_t)src.size(); info4[2] = (int64_t)cubin.size(); info4[3] = cached ? 1 : 0; }
+    return SIMC_OK;
+  } catch (const std::exception& e) {
+    say(e.what());
+    return SIMC_ERR_IO;
+  }
+}
+
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8) {
   if (!h || !info8) return SIMC_ERR_ARG;
   auto it = h->arms.find(arm_id);
@@ -530,9 +644,24 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n, cons
   a.arm = it->second.img.data(); a.n = n; a.in = d_in_soa; a.seed = seed;
   a.ms_flag = ms_flag; a.wcs_flag = wcs_flag; a.decay_flag = decay_flag; a.using_coll = using_coll;
   a.ctau = h->cfg.ctau; a.out = d_out_soa; a.flags = d_flags;
+  a.n_stretch = 0; a.hut_begin = 0; a.tk = nullptr; a.lists = nullptr; a.counts = nullptr; a.sink = nullptr;
+  if (h->compiled_maps && !decay_flag && !using_coll) {
+    // the RNG-free stretches of the program run as generated kernels (mapgen.h), as in the event loop
+    ArmSlot& slot = it->second;
+    int rc = ensure_compiled(h, slot);
+    if (rc) return rc;
+    if (!slot.stretches.empty()) {
+      rc = ensure_tb_scratch(h, n);
+      if (rc) return rc;
+      a.n_stretch = (int)slot.stretches.size();
+      for (int k = 0; k < a.n_stretch; ++k) a.stretch_fn[k] = slot.jit.fns[k];
+      a.hut_begin = slot.hut_begin;
+      a.tk = h->tb_tk; a.lists = h->tb_lists; a.counts = h->tb_counts; a.sink = h->tb_sink;
+    }
+  }
   cudaError_t e = h->strict ? strict::launch_transport_batch(a, h->stream) : fast::launch_transport_batch(a, h->stream);
   if (e != cudaSuccess) return cuda_fail(h, e, "k_transport_batch launch");
-  h->launches += 1;
+  h->launches += a.n_stretch > 0 ? 3 + a.n_stretch : 1;
   return SIMC_OK;
 }
 
@@ -637,6 +766,8 @@ int validate_loop_config(simc_handle* h) {
   return SIMC_OK;
 }
 
+int clear_dev_accum(simc_handle* h);
+
 int ensure_loop_buffers(simc_handle* h, long long cap) {
   CU(h, cudaSetDevice(h->device));
   if (!h->d_cfg) {
@@ -649,7 +780,10 @@ int ensure_loop_buffers(simc_handle* h, long long cap) {
     const size_t ab = strict::dev_accum_bytes();
     CU(h, cudaMalloc(&h->d_acc, ab));
     h->acc_host.assign(ab, 0);
-    CU(h, cudaMalloc(&h->d_counts, 16 * sizeof(unsigned)));
+    CU(h, cudaMalloc(&h->d_counts, kLoopCounts * sizeof(unsigned)));
+    // freshly allocated accumulators hold the identity element, whichever entry point made them
+    const int rc = clear_dev_accum(h);
+    if (rc) return rc;
   }
   if (cap > h->loop_cap) {
     if (h->d_state) cudaFree(h->d_state);
@@ -681,15 +815,76 @@ int clear_dev_accum(simc_handle* h) {
   return SIMC_OK;
 }
 
+// Generated kernels of one arm: source from the map compiler, cubin from the cache or NVRTC, loaded once.
+int ensure_compiled(simc_handle* h, ArmSlot& s) {
+  if (s.jit_ready && s.jit_strict == h->strict) return SIMC_OK;
+  jit_unload(s.jit);
+  s.jit_ready = false;
+  s.jit_strict = h->strict;
+  plan_stretches(s);
+  if (s.stretches.empty()) { s.jit_ready = true; return SIMC_OK; }
+  std::string src, cubin, err;
+  try {
+    src = generate_stretch_source(s.host, s.stretches, h->strict != 0, map_min_blocks());
+  } catch (const std::exception& e) {
+    return fail(h, SIMC_ERR_STATE, std::string("map compiler: ") + e.what());
+  }
+  bool cached = false;
+  if (!jit_compile_cubin(src, jit_default_cache_dir(), cubin, &cached, err)) return fail(h, SIMC_ERR_STATE, err);
+  std::vector<std::string> names;
+  for (size_t k = 0; k < s.stretches.size(); ++k) names.push_back("seg_" + std::to_string(k));
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaFree(0));                                    // the primary context is current for the driver API
+  if (!jit_load(cubin, names, s.jit, err)) return fail(h, SIMC_ERR_CUDA, err);
+  s.jit.from_cache = cached;
+  s.jit_ready = true;
+  return SIMC_OK;
+}
+
+// The chain of kernels of one spectrometer (kernels.h: ArmSchedule).
+int build_schedule(simc_handle* h, int arm_id, bool use_mc, bool decay, bool coll, ArmSchedule& sc) {
+  sc.n = 0;
+  auto push = [&](int kind, int b, int e, void* fn) { sc.st[sc.n++] = ArmStage{kind, b, e, fn}; };
+  auto it = h->arms.find(arm_id);
+  if (!use_mc || it == h->arms.end() || !it->second.loaded) {
+    push(ARM_STAGE_ENTRY, 0, 0, nullptr);
+    push(ARM_STAGE_LAST, 0, 0, nullptr);
+    return SIMC_OK;
+  }
+  ArmSlot& s = it->second;
+  const ArmTablesDev& tab = s.host.tab;
+  const int n_ops = tab.n_ops;
+  const bool compiled = h->compiled_maps && !decay && !coll;
+  int pos = 0;
+  if (compiled) {
+    const int rc = ensure_compiled(h, s);
+    if (rc) return rc;
+  }
+  if (compiled && !s.stretches.empty()) {
+    push(ARM_STAGE_ENTRY, 0, 0, nullptr);
+    for (size_t k = 0; k < s.stretches.size(); ++k) push(ARM_STAGE_COMPILED, s.stretches[k].begin, s.stretches[k].end, s.jit.fns[k]);
+    pos = s.hut_begin;
+  } else {
+    push(ARM_STAGE_ENTRY, 0, tab.split_op, nullptr);
+    pos = tab.split_op;
+  }
+  for (int k = 0; k < tab.n_mid; ++k) {
+    if (tab.mid_op[k] <= pos || tab.mid_op[k] >= n_ops) continue;
+    if (sc.n >= kArmLists - 1) break;
+    push(ARM_STAGE_MIDDLE, pos, tab.mid_op[k], nullptr);
+    pos = tab.mid_op[k];
+  }
+  push(ARM_STAGE_LAST, pos, n_ops, nullptr);
+  return SIMC_OK;
+}
+
 int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, int record, double* d_rec,
                 int* d_status) {
   int rc = validate_loop_config(h);
   if (rc) return rc;
-  const bool fresh = (h->d_cfg == nullptr);
   const long long cap = record ? n_tries : std::min<long long>(h->batch, n_tries);
   rc = ensure_loop_buffers(h, std::max<long long>(cap, 1));
   if (rc) return rc;
-  if (fresh) { rc = clear_dev_accum(h); if (rc) return rc; }
   LoopLaunch a;
   a.cfg = h->d_cfg;
   a.arm_e = h->arms.count(h->cfg.electron_arm) && h->arms[h->cfg.electron_arm].loaded ? h->arms[h->cfg.electron_arm].img.data() : nullptr;
@@ -700,6 +895,10 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
   auto coll = [&](int arm) { return arm == SIMC_ARM_HMS ? h->cfg.using_HMScoll : arm == SIMC_ARM_SHMS ? h->cfg.using_SHMScoll : 0; };
   a.coll_e = coll(h->cfg.electron_arm); a.coll_p = coll(h->cfg.hadron_arm);
   a.using_rad = h->cfg.using_rad;
+  rc = build_schedule(h, h->cfg.hadron_arm, h->cfg.using_P_arm_montecarlo != 0, h->cfg.doing_decay != 0, a.coll_p != 0, a.sched_p);
+  if (rc) return rc;
+  rc = build_schedule(h, h->cfg.electron_arm, h->cfg.using_E_arm_montecarlo != 0, false, a.coll_e != 0, a.sched_e);
+  if (rc) return rc;
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem; a.sf_dem = h->d_sf_dem;
@@ -726,12 +925,7 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
     for (int st = 0; st < n_stage; ++st) {
       cudaError_t e = h->strict ? strict::launch_loop_stage(a, st, h->stream) : fast::launch_loop_stage(a, st, h->stream);
       if (e != cudaSuccess) return cuda_fail(h, e, "event-loop kernel launch");
-      if (st == 1 || st == 2) {
-        const ArmTablesDev* tab = (const ArmTablesDev*)(st == 1 ? a.arm_p : a.arm_e);
-        h->launches += 2 + (tab ? tab->n_mid : 0);
-      } else {
-        h->launches += (st == 0 || st == 3) && a.using_rad ? 2 : 1;
-      }
+      h->launches += h->strict ? strict::launches_of_stage(a, st) : fast::launches_of_stage(a, st);
       if (h->timing && st < 4) CU(h, cudaEventRecord(h->ev[ev_pos + 1 + st], h->stream));
     }
     if (h->timing) { ev_pos += 5; h->ev_used.push_back(1); }
@@ -923,7 +1117,11 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   CU(h, cudaMemcpyAsync(saved.data(), h->d_acc, saved.size(), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
   rc = run_batches(h, first_try, n, seed, 2, h->d_rec, h->d_status);
-  if (rc) return rc;
+  if (rc) {      // put the parked accumulators back before reporting the failure
+    cudaMemcpyAsync(h->d_acc, saved.data(), saved.size(), cudaMemcpyHostToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    return rc;
+  }
   std::vector<double> soa((size_t)SIMC_NTUPLE_MAXCOL * (size_t)n);
   std::vector<int> status((size_t)n);
   CU(h, cudaMemcpyAsync(soa.data(), h->d_rec, sizeof(double) * soa.size(), cudaMemcpyDeviceToHost, h->stream));

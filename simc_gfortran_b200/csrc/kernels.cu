@@ -9,10 +9,12 @@
 #include "transport.cuh"
 #include "kernels.h"
 #include "loop.cuh"
+#include "jit.h"
 #include <string.h>
 #include <stddef.h>
 
 #include <mutex>
+#include <algorithm>
 
 namespace simc {
 namespace SIMC_VARIANT_NS {
@@ -45,15 +47,20 @@ static cudaError_t ensure_rng_key_locked(unsigned long long seed) {
 }
 
 // Batch form of mc_hms / mc_shms / ... (hms/mc_hms.f:1-4): one thread per row.
+// tk == nullptr: the whole program from the input rows.  tk != nullptr (compiled path): the rows of `list` resume
+// at op_begin from the track the generated stretches left in tk.
 template <bool WITH_COLL>
 __global__ void __launch_bounds__(kBlock)
 k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const double* __restrict__ in,
                   unsigned long long seed, ArmFlags f, double ctau, double* __restrict__ out,
-                  int* __restrict__ flags) {
+                  int* __restrict__ flags, int op_begin, const double* __restrict__ tk, const unsigned* __restrict__ list,
+                  const unsigned* __restrict__ count) {
   extern __shared__ double pw_s[];
   const ArmDev* arm = &arm_c;
-  const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  bool alive = i < n;
+  const long long j = (long long)blockIdx.x * kBlock + threadIdx.x;
+  const long long n_rows = tk ? (long long)*count : n;
+  bool alive = j < n_rows;
+  const long long i = tk ? (alive ? (long long)list[j] : 0) : j;
   const long long ii = alive ? i : 0;
   TrackDev t;
   t.dpps = in[0 * n + ii];
@@ -72,6 +79,10 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   t.mh2_final = t.m2;
   t.ctau = ctau;
   const double dpp_in = t.dpps, y_in = t.ys, dxdz_in = t.dxdzs, dydz_in = t.dydzs;
+  if (tk) {        // rows of tk: xs, ys, dxdzs, dydzs, dpps, p, m2, pathlen (loop.cuh F_TK_*)
+    t.xs = tk[0 * n + ii]; t.ys = tk[1 * n + ii]; t.dxdzs = tk[2 * n + ii]; t.dydzs = tk[3 * n + ii];
+    t.dpps = tk[4 * n + ii]; t.pathlen = tk[7 * n + ii];
+  }
   DevRng rng;
   rng.init((unsigned long long)i, 0u, 0u);
   ArmResult res;
@@ -83,8 +94,8 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   t.dflag = false;
   musc_refresh(t);
   const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
-  run_arm<WITH_COLL>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, arm->tab.n_ops);
-  if (i >= n) return;
+  run_arm<WITH_COLL>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, arm->tab.n_ops);
+  if (j >= n_rows) return;
   out[0 * n + i] = res.ok ? res.dpp_rec : dpp_in;
   out[1 * n + i] = res.ok ? res.dph_rec : dxdz_in;
   out[2 * n + i] = res.ok ? res.dth_rec : dydz_in;
@@ -98,6 +109,32 @@ k_transport_batch(const __grid_constant__ ArmDev arm_c, long long n, const doubl
   out[10 * n + i] = res.resmult;
   out[11 * n + i] = (double)rng.draw;
   flags[i] = res.ok ? 0 : res.stop_code;
+}
+
+// compiled path, first kernel: the rows become tracks (mc_hms.f:181), every row is on list 0
+__global__ void k_tb_load(long long n, const double* __restrict__ in, double* __restrict__ tk, unsigned* __restrict__ list0,
+                          unsigned* __restrict__ counts, int n_counts, unsigned long long* __restrict__ sink, int n_sink) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_counts) counts[i] = i == 0 ? (unsigned)n : 0u;
+  if (i < n_sink) sink[i] = 0ULL;
+  if (i >= n) return;
+  const double dpp = in[0 * n + i], p_spec = in[7 * n + i];
+  tk[0 * n + i] = in[1 * n + i]; tk[1 * n + i] = in[2 * n + i]; tk[2 * n + i] = in[4 * n + i]; tk[3 * n + i] = in[5 * n + i];
+  tk[4 * n + i] = dpp; tk[5 * n + i] = p_spec * (1. + dpp / 100.); tk[6 * n + i] = in[6 * n + i]; tk[7 * n + i] = 0.0;
+  tk[11 * n + i] = -1.0;            // stop code of the compiled stretches (none yet)
+  list0[i] = (unsigned)i;
+}
+// compiled path, last kernel: the rows a compiled stretch stopped (mc_hms returns its inputs untouched for them)
+__global__ void k_tb_stopped(long long n, const double* __restrict__ in, const double* __restrict__ tk, double* __restrict__ out,
+                             int* __restrict__ flags) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double code = tk[11 * n + i];
+  if (code < 0.0) return;
+  out[0 * n + i] = in[0 * n + i]; out[1 * n + i] = in[4 * n + i]; out[2 * n + i] = in[5 * n + i]; out[3 * n + i] = in[2 * n + i];
+  out[4 * n + i] = 0.0; out[5 * n + i] = 0.0; out[6 * n + i] = 0.0; out[7 * n + i] = 0.0;
+  out[8 * n + i] = tk[7 * n + i]; out[9 * n + i] = in[6 * n + i]; out[10 * n + i] = 0.0; out[11 * n + i] = 0.0;
+  flags[i] = (int)code;
 }
 
 cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) {
@@ -120,12 +157,38 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
     const cudaError_t e = ensure_rng_key_locked(a.seed);
     if (e != cudaSuccess) return e;
   }
+  if (a.n_stretch > 0 && !f.using_coll && !f.decay_flag) {
+    // compiled path: rows -> tracks, the generated stretches with compaction in between, the interpreter from the
+    // hut on for the survivors, then the rows that stopped on the way
+    const int n_sink = SIMC_NSTOP + 48;
+    const long long nb = (std::max<long long>(a.n, n_sink) + 255) / 256;
+    k_tb_load<<<(unsigned)nb, 256, 0, s>>>(a.n, a.in, a.tk, a.lists, a.counts, a.n_stretch + 1, a.sink, n_sink);
+    for (int k = 0; k < a.n_stretch; ++k) {
+      double* tk = a.tk;
+      long long cap = a.n;
+      const unsigned* in_list = a.lists + (long long)k * a.n;
+      const unsigned* in_count = a.counts + k;
+      unsigned* out_list = a.lists + (long long)(k + 1) * a.n;
+      unsigned* out_count = a.counts + k + 1;
+      unsigned long long* stop_acc = a.sink;
+      unsigned long long* calls_acc = a.sink + SIMC_NSTOP;
+      double* stop_field = a.tk + 11 * a.n;
+      void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
+      const long long g = std::min<long long>(blocks, 148 * 8);
+      if (jit_launch(a.stretch_fn[k], (unsigned)g, kBlock, (void*)s, args) != 0) return cudaErrorLaunchFailure;
+    }
+    k_transport_batch<false><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
+                                                                 a.flags, a.hut_begin, a.tk, a.lists + (long long)a.n_stretch * a.n,
+                                                                 a.counts + a.n_stretch);
+    k_tb_stopped<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a.n, a.in, a.tk, a.out, a.flags);
+    return cudaGetLastError();
+  }
   if (f.using_coll)
     k_transport_batch<true><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
-                                                                a.flags);
+                                                                a.flags, 0, nullptr, nullptr, nullptr);
   else
     k_transport_batch<false><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
-                                                                 a.flags);
+                                                                 a.flags, 0, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
@@ -277,7 +340,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.lists = a.lists; A.counts = a.counts; A.acc = (DevAccum*)a.acc;
   A.first_try = a.first_try; A.n_tries = a.n_tries; A.seed = a.seed; A.qexp_w = a.qexp_w;
   A.record_mode = a.record_mode;
-  A.mid_k = 0;
+  A.op_begin = 0; A.op_end = 0; A.in_idx = 0; A.out_idx = 0;
   static_assert(sizeof(MatTable) == sizeof(a.mats), "MatTable layout");
   memcpy(&A.mt, a.mats, sizeof(MatTable));
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem; A.sf.dem = a.sf_dem;
@@ -304,7 +367,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     }
   }
   if (stage == 0) {
-    cudaError_t e = cudaMemsetAsync(a.counts, 0, 16 * sizeof(unsigned), s);
+    cudaError_t e = cudaMemsetAsync(a.counts, 0, kLoopCounts * sizeof(unsigned), s);
     if (e != cudaSuccess) return e;
     {
       const long long gneed = (a.n_tries + kGenBlock - 1) / kGenBlock;
@@ -312,22 +375,58 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       k_generate<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
       if (a.using_rad) k_regen<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
     }
-  } else if (stage == 1) {
-    if (a.coll_p) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
-    else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
-    for (int k = 0; k < arm_p.tab.n_mid; ++k) { A.mid_k = k; k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p); }
-    k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_p);
-  } else if (stage == 2) {
-    if (a.coll_e) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
-    else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
-    for (int k = 0; k < arm_e.tab.n_mid; ++k) { A.mid_k = k; k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e); }
-    k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm_e);
+  } else if (stage == 1 || stage == 2) {
+    // one spectrometer: the chain of stages of its schedule, survivors handed on from list to list
+    const bool hadron = stage == 1;
+    const ArmSchedule& sc = hadron ? a.sched_p : a.sched_e;
+    const ArmDev& arm = hadron ? arm_p : arm_e;
+    const int coll = hadron ? a.coll_p : a.coll_e;
+    const int base = hadron ? 0 : kArmLists;
+    int in = base, out = base + 1;
+    for (int k = 0; k < sc.n; ++k) {
+      const ArmStage& st = sc.st[k];
+      if (k == sc.n - 1) out = base + kArmLists;
+      A.op_begin = st.begin; A.op_end = st.end; A.in_idx = in; A.out_idx = out;
+      if (st.kind == ARM_STAGE_ENTRY) {
+        if (hadron) { if (coll) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
+        else { if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
+      } else if (st.kind == ARM_STAGE_COMPILED) {
+        // generated straight-line kernel (mapgen.h); ABI in mapgen.h
+        double* tk = a.state + (long long)F_TK_XS * a.cap;
+        long long cap = a.cap;
+        const unsigned* in_list = a.lists + (long long)in * a.cap;
+        const unsigned* in_count = a.counts + 1 + in;
+        unsigned* out_list = a.lists + (long long)out * a.cap;
+        unsigned* out_count = a.counts + 1 + out;
+        DevAccum* acc = (DevAccum*)a.acc;
+        unsigned long long* stop_acc = &acc->stop[hadron ? 1 : 0][0];
+        unsigned long long* calls_acc = &acc->transp_calls[hadron ? 1 : 0][0];
+        double* stop_field = a.record_mode ? a.state + (long long)(hadron ? F_STOP_P : F_STOP_E) * a.cap : nullptr;
+        void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
+        const int rc = jit_launch(st.fn, grid, kBlock, (void*)s, args);
+        if (rc != 0) return cudaErrorLaunchFailure;
+      } else if (st.kind == ARM_STAGE_MIDDLE) {
+        if (hadron) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        else k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+      } else {
+        if (hadron) k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        else k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+      }
+      in = out; out = out + 1;
+    }
   } else if (stage == 3) {
-    if (a.using_rad) k_radw<<<grid, kBlock, 0, s>>>(A, a.record_mode ? 0 : 10);
+    if (a.using_rad) k_radw<<<grid, kBlock, 0, s>>>(A, a.record_mode ? 0 : 2 * kArmLists);
     k_finish<<<grid, kBlock, 0, s>>>(A);
   }
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   return cudaGetLastError();
+}
+
+int launches_of_stage(const LoopLaunch& a, int stage) {
+  if (stage == 0 || stage == 3) return a.using_rad ? 2 : 1;
+  if (stage == 1) return a.sched_p.n;
+  if (stage == 2) return a.sched_e.n;
+  return 1;
 }
 
 }  // namespace SIMC_VARIANT_NS

@@ -7,7 +7,20 @@
 
 namespace simc {
 
-constexpr int kLoopLists = 12;   // survivor lists of the event loop (loop.cuh: LoopArgs::lists)
+// Survivor lists of the event loop (loop.cuh: LoopArgs::lists): 0 = generated; 1..8 = hadron-arm stages (8 = the arm's
+// survivors); 9..16 = electron-arm stages (16 = survivors of both arms); 17 = tries on their way to k_regen.
+constexpr int kArmLists = 8;
+constexpr int kLoopLists = 2 * kArmLists + 2;
+constexpr int kRegenListIdx = 2 * kArmLists + 1;
+constexpr int kLoopCounts = 32;                 // [0] slots handed out, [1 + l] length of list l
+
+// How one spectrometer's program is cut into kernels.  ENTRY: k_arm<W,0> (target multiple scattering, SP quantities,
+// TRANSPORT coordinates, then ops [begin,end)); COMPILED: a generated straight-line kernel (mapgen.h) for an RNG-free
+// stretch; MIDDLE: k_arm<W,2>, the interpreter on a stretch; LAST: k_arm<W,1>, the interpreter up to the end of the
+// program, reconstruction and the arm's recon quantities.  Survivors are compacted between stages.
+enum ArmStageKind : int { ARM_STAGE_ENTRY = 0, ARM_STAGE_COMPILED = 1, ARM_STAGE_MIDDLE = 2, ARM_STAGE_LAST = 3 };
+struct ArmStage { int kind; int begin, end; void* fn; };
+struct ArmSchedule { int n; ArmStage st[kArmLists]; };
 
 struct TransportBatchArgs {
   const void* arm;          // ArmDev image on the HOST: passed to the kernel by value (constant bank)
@@ -18,6 +31,15 @@ struct TransportBatchArgs {
   double ctau;
   double* out;              // [12][n] device
   int* flags;               // [n] device
+  // compiled path (mapgen.h): the RNG-free stretches [0, hut_begin) run as generated kernels on a scratch track
+  // buffer, the interpreter takes over at hut_begin for the survivors.  n_stretch = 0: interpreter only.
+  int n_stretch;
+  void* stretch_fn[kArmLists];
+  int hut_begin;
+  double* tk;               // [12][n] device scratch: 11 track rows (loop.cuh F_TK_*) + the stop code
+  unsigned* lists;          // [n_stretch + 1][n] device scratch
+  unsigned* counts;         // [n_stretch + 1] device scratch
+  unsigned long long* sink; // [SIMC_NSTOP + 48] device scratch for the stop / call counters the kernels keep
 };
 
 // Opaque to the host code: built and consumed inside kernels.cu (loop.cuh: LoopArgs).
@@ -39,6 +61,7 @@ struct LoopLaunch {
   int grid_blocks;            // persistent grid for the stage kernels
   int coll_e, coll_p;         // the arm steps pions through its collimator (using_HMScoll / using_SHMScoll)
   int using_rad;              // radiative corrections on: second generation pass (k_regen) and k_radw are launched
+  ArmSchedule sched_e, sched_p;
   double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
   const double* sf_pm;        // Benhar spectral function (device): Pm axis, Em axis, values [n_pm][n_em]
   const double* sf_em;
@@ -65,6 +88,7 @@ cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters
 size_t dev_accum_bytes();
 int n_state_fields();
 void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);
+int launches_of_stage(const LoopLaunch& a, int stage);
 }
 namespace fast {
 cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s);
@@ -74,6 +98,7 @@ cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters
 size_t dev_accum_bytes();
 int n_state_fields();
 void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);
+int launches_of_stage(const LoopLaunch& a, int stage);
 }
 
 namespace strict { cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s); size_t arm_dev_bytes(); }

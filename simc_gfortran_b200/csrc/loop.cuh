@@ -54,6 +54,10 @@ enum StateField : int {
   F_NFIELDS
 };
 
+// the compiled stretches (mapgen.h) address the track by row offsets from F_TK_XS
+static_assert(F_TK_YS == F_TK_XS + 1 && F_TK_DX == F_TK_XS + 2 && F_TK_DY == F_TK_XS + 3 && F_TK_DPP == F_TK_XS + 4 &&
+              F_TK_P == F_TK_XS + 5 && F_TK_M2 == F_TK_XS + 6 && F_TK_PATH == F_TK_XS + 7, "track rows: mapgen.h");
+
 struct StateBuf {
   double* base;
   long long cap;
@@ -83,10 +87,10 @@ struct LoopArgs {
   MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
-  unsigned* lists;                 // [12][cap]: gen ok | P: entrance ok, up to 3 middle segments ok, arm ok | E: same |
-                                   //            11: tries that go through complete_ev a second time (k_regen)
-  unsigned* counts;                // [0] slots handed out, [1..12] lengths of lists 0..11
-  int mid_k;                       // which middle segment a k_arm<*,2> launch runs
+  unsigned* lists;                 // [kLoopLists][cap] (kernels.h)
+  unsigned* counts;                // [0] slots handed out, [1 + l] length of list l
+  int op_begin, op_end;            // ops of the arm program a k_arm launch runs (kernels.h: ArmStage)
+  int in_idx, out_idx;             // the list it reads, the list its survivors go to
   DevAccum* acc;
   long long first_try, n_tries;
   unsigned long long seed;
@@ -161,7 +165,7 @@ struct GaussFn {
 #define SIMC_GEN_MIN_BLOCKS 2
 #endif
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
-constexpr int kRegenList = 11;
+constexpr int kRegenList = kRegenListIdx;
 
 struct GenFlags { bool semi, fermi, meson, heavy; };
 __device__ __forceinline__ GenFlags gen_flags(const simc_run_config& cfg) {
@@ -404,10 +408,12 @@ __global__ void __launch_bounds__(kBlock, 4) k_radw(LoopArgs A, int list_idx) {
 #endif
 // ---- stages 2,3: the two arms ----------------------------------------------------------------
 // WHICH = 1: hadron arm (simc.f:1374-1645), WHICH = 0: electron arm (simc.f:1647-1846).
-// Each arm runs as two to five kernels: SEG 0 = target multiple scattering, SP quantities, TRANSPORT
-// coordinates and the entrance apertures up to the collimator (where most rejected tracks die,
-// after almost no arithmetic); SEG 2 (once per further compaction point of the arm program, A.mid_k) = a
-// stretch of magnets; SEG 1 = the rest (always the whole hut) and reconstruction for the compacted survivors.
+// Each arm runs as a chain of kernels with the survivors compacted in between (kernels.h: ArmSchedule; the host
+// cuts the program): SEG 0 = target multiple scattering, SP quantities, TRANSPORT coordinates, then ops
+// [A.op_begin, A.op_end) (the entrance apertures, where most rejected tracks die after almost no arithmetic; empty
+// when a compiled stretch takes over from op 0); SEG 2 = the interpreter on a stretch of ops; SEG 1 = the rest of the
+// program (always the whole hut), reconstruction, and the arm's recon quantities.  Compiled stretches (mapgen.h)
+// run between them on the same track fields (F_TK_*).
 // SEG_ = 3: SEG 0 built with the collimator stepping (using_HMScoll / using_SHMScoll).
 template <int WHICH, int SEG_>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
@@ -424,14 +430,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
-  const int n_mid = arm_c.tab.n_mid;
-  const int base_idx = WHICH == 1 ? 0 : 5;                // list read by SEG 0 of this arm
-  const int in_idx = SEG == 0 ? base_idx : SEG == 2 ? base_idx + 1 + A.mid_k : base_idx + 1 + n_mid;
-  const int out_idx = SEG == 0 ? base_idx + 1 : SEG == 2 ? base_idx + 2 + A.mid_k : base_idx + 5;
-  const unsigned n_in = A.counts[1 + in_idx];
-  const unsigned* in_list = A.lists + (long long)in_idx * A.st.cap;
-  unsigned* out_list = A.lists + (long long)out_idx * A.st.cap;
-  unsigned* out_count = &A.counts[1 + out_idx];
+  const unsigned n_in = A.counts[1 + A.in_idx];
+  const unsigned* in_list = A.lists + (long long)A.in_idx * A.st.cap;
+  unsigned* out_list = A.lists + (long long)A.out_idx * A.st.cap;
+  unsigned* out_count = &A.counts[1 + A.out_idx];
   const simc_spectrometer& sp = WHICH == 1 ? cfg.spec_p : cfg.spec_e;
   const ArmDev* arm = &arm_c;        // program + map directory live in the kernel's constant bank
   const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
@@ -441,12 +443,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   f.ms_flag = cfg.mc_smear != 0; f.wcs_flag = cfg.mc_smear != 0;
   f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
   f.using_coll = arm_id == 1 ? cfg.using_HMScoll != 0 : (arm_id == 5 ? cfg.using_SHMScoll != 0 : false);
-  const int split = use_mc ? arm->tab.split_op : 0;
-  // op range of this launch: [0,split) | [split or mid_op[k-1], mid_op[k]) | [last compaction point, n_ops)
-  const int mid_begin = (SEG == 2 && A.mid_k > 0) ? arm->tab.mid_op[A.mid_k - 1] : split;
-  const int mid_end = SEG == 2 ? arm->tab.mid_op[A.mid_k] : split;
-  const int last_begin = use_mc && n_mid > 0 ? arm->tab.mid_op[n_mid - 1] : split;
-  const int n_ops = use_mc ? arm->tab.n_ops : 0;
+  // op range of this launch (the host cuts the program into stages, kernels.h: ArmSchedule)
+  const int op_begin = use_mc ? A.op_begin : 0, op_end = use_mc ? A.op_end : 0;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;
@@ -517,7 +515,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       musc_refresh(t);
       if (use_mc) {
         if (active) warp_count(&s_stop[0]);
-        run_arm<kColl>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, 0, split, s_calls, s_stop);
+        run_arm<kColl>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls, s_stop);
         ok = alive;
       } else {
         ok = active;
@@ -543,7 +541,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       }
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
-      run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, mid_begin, mid_end, s_calls);
+      run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
       ok = alive;
       if (active) {
         S.st(F_DRAW, slot, (double)rng.draw);
@@ -569,7 +567,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
       if (use_mc) {
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, last_begin, n_ops, s_calls);
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
         path = t.pathlen; resmult = res.resmult;
@@ -696,8 +694,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   DevAccum* acc = A.acc;
-  const unsigned n_in = A.counts[11];
-  const unsigned* in_list = A.lists + 10 * A.st.cap;
+  const unsigned n_in = A.counts[1 + 2 * kArmLists];
+  const unsigned* in_list = A.lists + (long long)(2 * kArmLists) * A.st.cap;
   const long long stride = (long long)gridDim.x * kBlock;
   for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;

@@ -823,6 +823,7 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
                              : arm_id == 4 ? "MC_HRSL, wrong number of transport classes"
                                            : "Bender-SHMS, wrong number of transport classes");
   }
+  A.fwd = fwd; A.rec = rec; A.arm_id = arm_id;
   std::memset(&A.tab, 0, sizeof(A.tab));
   A.tab.n_classes = (int)fwd.cls.size();
   for (size_t k = 0; k < fwd.cls.size(); ++k) {
@@ -875,6 +876,32 @@ CompiledArm compile_arm(int arm_id, const ForwardMaps& fwd, const CosyTerms& rec
   for (int m : P.mids)
     if (A.tab.n_mid < 3 && m > (A.tab.n_mid ? A.tab.mid_op[A.tab.n_mid - 1] : A.tab.split_op) && m < (int)P.ops.size())
       A.tab.mid_op[A.tab.n_mid++] = m;
+  // Gaussian look-ahead (transport.cuh: GaussQueue): every op that draws gauss1(99.) pairs carries, in its unused
+  // `code` word, how many Gaussians the program draws from this op up to the next point where the stream of
+  // Gaussians is interrupted -- another kind of draw (the resmult uniform, the collimator stepping) or a
+  // compaction point of the loop, where the kernel ends.  Low half: multiple-scattering draws (ms_flag), high half:
+  // chamber-resolution draws (wcs_flag).
+  {
+    unsigned rem_ms = 0, rem_wcs = 0;
+    for (int k = (int)A.ops.size() - 1; k >= 0; --k) {
+      ArmOp& o = A.ops[k];
+      if (o.op == OP_MUSC && o.a != 0.) rem_ms += 2;
+      else if (o.op == OP_MUSC_EXT && o.a != 0.) rem_ms += 4;
+      else if (o.op == OP_DC_PLANE) rem_wcs += 2;
+      if (o.op == OP_MUSC || o.op == OP_MUSC_EXT || o.op == OP_DC_PLANE) {
+        if (rem_ms > 0xffffu || rem_wcs > 0xffffu) throw std::runtime_error("arm program: too many Gaussian draws");
+        o.code = (int32_t)(rem_ms | (rem_wcs << 16));
+      }
+      bool barrier = (o.op == OP_RESMULT_DRAW || o.op == OP_COLL || o.op == OP_COLL_DATA || k == A.tab.split_op ||
+                      o.op == OP_TRANSP || o.op == OP_RECON);        // the maps use the queue's shared memory
+      for (int m = 0; m < A.tab.n_mid; ++m) barrier = barrier || (k == A.tab.mid_op[m]);
+      if (barrier) {
+        // ops before k count up to here only; op k itself starts a new stretch (its own draws were added above)
+        if (o.op == OP_MUSC || o.op == OP_MUSC_EXT || o.op == OP_DC_PLANE) { /* keeps its count */ }
+        rem_ms = 0; rem_wcs = 0;
+      }
+    }
+  }
   return A;
 }
 

@@ -34,6 +34,9 @@ struct CompiledArm {
   ArmTablesDev tab;                      // recs pointer left null (the device address is set by the caller)
   std::vector<ArmOp> ops;
   long long fwd_terms = 0, fwd_nonzero = 0, rec_terms = 0;
+  ForwardMaps fwd;                       // the maps as read (file order), for the map compiler (mapgen.h)
+  CosyTerms rec;
+  int arm_id = 0;
 };
 
 // Compiles the maps into groups and appends the arm's op list.  using_coll selects the

@@ -27,8 +27,13 @@ namespace SIMC_VARIANT_NS {
 
 constexpr int kBlock = 128;               // threads per CTA for the event kernels
 static_assert(kBlock == kArmBlockThreads, "the record offsets are compiled for this CTA size");
-// shared power table of a COSY map: [kPolyEntries][kBlock] doubles, dynamic shared memory (49 KB)
-constexpr int kPowDoubles = kPolyEntries * kBlock;
+// shared power table of a COSY map: [kPolyEntries][kBlock] doubles, dynamic shared memory (49 KB).  The hut has
+// no map before its reconstruction, so the same columns hold each thread's queue of Gaussians there
+// (GaussQueue below), which needs one row more: kPowRows rows of kBlock doubles.
+constexpr int kGaussQ = 20;                      // Gaussians a thread draws ahead
+constexpr int kPowRows = kPolyEntries + 1;
+static_assert(2 * kGaussQ + (kGaussQ + 1) / 2 <= kPowRows, "the Gaussian queue must fit the thread's column");
+constexpr int kPowDoubles = kPowRows * kBlock;
 constexpr size_t kPowBytes = sizeof(double) * kPowDoubles;
 
 struct ArmDev {                           // lives in global memory, read through warp-uniform loads
@@ -275,6 +280,114 @@ __device__ __forceinline__ void sts128d(unsigned addr, double a, double b) {
 }
 __device__ __forceinline__ void ldg128(const double* p, double& a, double& b) {
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+
+// ---- Gaussians drawn ahead -------------------------------------------------------------------
+// Inside the hut every random number is a gauss1(99.) (musc, musc_ext, the chamber resolutions; hundreds per
+// track), and the sequence is fixed by the arm program.  Drawn one call at a time, the warp waits for its slowest
+// lane in every call: ~2.5 trips through the polar rejection loop per Gaussian where a lane alone needs 4/pi.
+// Here every lane draws its next `n` Gaussians in one go, at its own pace, into its column of the shared power
+// table (free until the reconstruction map): the warp waits for max over lanes of the SUM of the trips
+// (~1.5 per Gaussian for n = 20), and log/sqrt/div then run for all lanes with no divergence.  Each lane consumes
+// exactly the uniforms of the sequential calls, in the same order.  Rows of the column: [0,Q) v1 then g,
+// [Q,2Q) s, then the draw counter after each Gaussian as 32-bit words (a track that stops with Gaussians still
+// queued must report the number of draws it really consumed).
+struct GaussQueue {
+  unsigned base;          // shared address of row 0 of this thread's column
+  int pos, avail;         // warp-uniform: next entry, entries left
+  uint32_t draw_before;   // draw counter before entry 0
+};
+constexpr unsigned kRowBytes = kBlock * 8u;
+__device__ __forceinline__ void gq_init(GaussQueue& q, const double* pw) {
+  q.base = (unsigned)__cvta_generic_to_shared(pw); q.pos = 0; q.avail = 0; q.draw_before = 0u;
+}
+__device__ __forceinline__ unsigned gq_draw_addr(const GaussQueue& q, int k) {
+  // 32-bit words behind the 2*Q double rows, two per 8-byte slot of the thread's OWN column (other threads'
+  // columns may hold a power table at the same time: warps do not walk the program in step)
+  return q.base + (unsigned)(2 * kGaussQ + (k >> 1)) * kRowBytes + (unsigned)(k & 1) * 4u;
+}
+// All 32 lanes call; `live` lanes draw n_new Gaussians behind the `q.avail` entries still queued (moved to the front).
+// Queue and generator go in and out by value, so that the caller's copies stay in registers.
+struct GqOut { uint32_t draw, h2, h3, draw_before; };
+__device__ __noinline__ GqOut gq_fill_v(GaussQueue q, DevRng rng, int n_new, bool live) {
+  const unsigned mask = 0xffffffffu;
+  // entries left over from the last fill go to the front
+  if (q.pos > 0) {
+    if (q.avail > 0) {
+      uint32_t db;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(db) : "r"(gq_draw_addr(q, q.pos - 1)));
+      q.draw_before = db;
+      for (int j = 0; j < q.avail; ++j) {
+        const double g = lds_f64(q.base + (unsigned)(q.pos + j) * kRowBytes);
+        uint32_t d;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(gq_draw_addr(q, q.pos + j)));
+        sts_f64(q.base + (unsigned)j * kRowBytes, g);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(gq_draw_addr(q, j)), "r"(d) : "memory");
+      }
+    } else {
+      q.draw_before = rng.draw;
+    }
+    q.pos = 0;
+  } else if (q.avail == 0) {
+    q.draw_before = rng.draw;
+  }
+  const int first = q.avail;
+  const int target = live ? first + n_new : 0;
+  int k = live ? first : 0;
+  uint32_t draw = rng.draw, h2 = rng.h2, h3 = rng.h3;
+  const uint32_t t0 = rng.t0, t1 = rng.t1, stream = rng.stream;
+  while (__any_sync(mask, k < target)) {
+    if (k < target) {
+      uint32_t r0, r1, r2, r3, w0, w1, w2, w3;
+      const uint32_t b = draw >> 1;
+      if (!(draw & 1u)) {
+        philox4x32_10(b, stream, t0, t1, r0, r1, r2, r3);
+        w0 = r0; w1 = r1; w2 = r2; w3 = r3;
+      } else {
+        w0 = h2; w1 = h3;
+        philox4x32_10(b + 1u, stream, t0, t1, r0, r1, r2, r3);
+        w2 = r0; w3 = r1;
+        h2 = r2; h3 = r3;
+      }
+      draw += 2u;
+      const double v1 = philox_to_pm1(w0, w1);
+      const double v2 = philox_to_pm1(w2, w3);
+      const double sq = v1 * v1 + v2 * v2;
+      if (!(sq > 1. || sq == 0.)) {
+        sts_f64(q.base + (unsigned)k * kRowBytes, v1);
+        sts_f64(q.base + (unsigned)(kGaussQ + k) * kRowBytes, sq);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(gq_draw_addr(q, k)), "r"(draw) : "memory");
+        ++k;
+      }
+    }
+  }
+  // gauss1.f: g = v1*sqrt(-2.*log(s)/s); |g| <= 12 for the smallest s the 52-bit uniforms can give, so the
+  // nsigmax = 99 test of these calls can never fire
+  if (live) {
+#pragma unroll 2
+    for (int j = first; j < first + n_new; ++j) {
+      const double v1 = lds_f64(q.base + (unsigned)j * kRowBytes);
+      const double sq = lds_f64(q.base + (unsigned)(kGaussQ + j) * kRowBytes);
+      sts_f64(q.base + (unsigned)j * kRowBytes, v1 * sqrt(-2. * m::log(sq) / sq));
+    }
+  }
+  __syncwarp();
+  GqOut o;
+  o.draw = draw; o.h2 = h2; o.h3 = h3; o.draw_before = q.draw_before;
+  return o;
+}
+__device__ __forceinline__ void gq_fill(GaussQueue& q, DevRng& rng, int n_new, bool live) {
+  const GqOut o = gq_fill_v(q, rng, n_new, live);
+  rng.draw = o.draw; rng.h2 = o.h2; rng.h3 = o.h3;
+  q.draw_before = o.draw_before; q.avail += n_new; q.pos = 0;
+}
+__device__ __forceinline__ double gq_at(const GaussQueue& q, int k) { return lds_f64(q.base + (unsigned)k * kRowBytes); }
+// The draw counter of a track that stops now, with q.avail Gaussians drawn ahead but not consumed
+__device__ __forceinline__ uint32_t gq_draw_consumed(const GaussQueue& q) {
+  if (q.pos == 0) return q.draw_before;
+  uint32_t d;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(gq_draw_addr(q, q.pos - 1)));
+  return d;
 }
 
 constexpr unsigned kChunkBytes = kRecChunk * kRecWords * 8u;        // 384
@@ -562,6 +675,10 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
                                         unsigned* stop_counts = nullptr) {
   double xt = 0., yt = 0.;
   int skip_until = 0;          // this lane ignores ops before this index (set by OP_COLL)
+  // Gaussians are drawn ahead (GaussQueue) unless decays in flight put other draws between them
+  const bool use_q = !f.decay_flag;
+  GaussQueue gq;
+  gq_init(gq, pw);
   for (int pc = op_begin; pc < op_end; ++pc) {
     __syncwarp();
     if (!__any_sync(0xffffffffu, alive)) break;
@@ -603,6 +720,20 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       }
       continue;
     }
+    // this op's Gaussians: entries [qoff, qoff + need) of the queue; pos/avail stay warp-uniform
+    int qoff = 0;
+    if (use_q && (op == OP_MUSC || op == OP_MUSC_EXT || op == OP_DC_PLANE)) {
+      const int need = op == OP_DC_PLANE ? (f.wcs_flag ? 2 : 0) : ((f.ms_flag && a != 0.) ? (op == OP_MUSC ? 2 : 4) : 0);
+      if (need > gq.avail) {
+        const unsigned code = (unsigned)o->code;      // Gaussians from this op to the end of the stretch (optics_host.cpp)
+        const int rem = (f.ms_flag ? (int)(code & 0xffffu) : 0) + (f.wcs_flag ? (int)(code >> 16) : 0);
+        int n_new = rem - gq.avail;
+        if (n_new > kGaussQ - gq.avail) n_new = kGaussQ - gq.avail;
+        gq_fill(gq, rng, n_new, alive);
+      }
+      qoff = gq.pos;
+      gq.pos += need; gq.avail -= need;
+    }
     if (!alive || pc < skip_until) continue;
     bool stop = false;
     switch (op) {
@@ -643,7 +774,8 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
         if (f.ms_flag && a != 0.) {
           const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           double g1, g2;
-          gauss2(rng, g1, g2);
+          if (use_q) { g1 = gq_at(gq, qoff); g2 = gq_at(gq, qoff + 1); }
+          else gauss2(rng, g1, g2);
           t.dydzs = t.dydzs + ts * g1;
           t.dxdzs = t.dxdzs + ts * g2;
         }
@@ -652,17 +784,22 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
         if (f.ms_flag && a != 0.) {
           const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           double g1, g2;
-          gauss2(rng, g1, g2);
+          if (use_q) { g1 = gq_at(gq, qoff); g2 = gq_at(gq, qoff + 1); }
+          else gauss2(rng, g1, g2);
           t.dxdzs = t.dxdzs + ts * g1;
           t.xs = t.xs + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
-          gauss2(rng, g1, g2);
+          if (use_q) { g1 = gq_at(gq, qoff + 2); g2 = gq_at(gq, qoff + 3); }
+          else gauss2(rng, g1, g2);
           t.dydzs = t.dydzs + ts * g1;
           t.ys = t.ys + ts * c * g2 / 3.4641016151377544 + ts * c * g1 / 2.;
         }
         break;
       case OP_DC_PLANE: {  // mc_hms_hut.f:351-364
         double r1 = 0., r2 = 0.;
-        if (f.wcs_flag) gauss2(rng, r1, r2);
+        if (f.wcs_flag) {
+          if (use_q) { r1 = gq_at(gq, qoff); r2 = gq_at(gq, qoff + 1); }
+          else gauss2(rng, r1, r2);
+        }
         const int ip = o->i0;
         if (o->i1) { hs.ydc[ip] = (float)(t.ys + a * r2 * res.resmult); hs.xdc[ip] = 0.f; }
         else { hs.xdc[ip] = (float)(t.xs + a * r1 * res.resmult); hs.ydc[ip] = 0.f; }
@@ -717,7 +854,10 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       case OP_COLL_DATA: break;
       default: break;
     }
-    if (stop) { res.stop_code = o->code; alive = false; }
+    if (stop) {
+      res.stop_code = o->code; alive = false;
+      if (use_q && gq.avail > 0) rng.draw = gq_draw_consumed(gq);      // give back the Gaussians drawn ahead
+    }
   }
   __syncwarp();
 }

@@ -176,6 +176,9 @@ def load_library():
     L.simc_b200_destroy.argtypes = [C.c_void_p]
     L.simc_b200_destroy.restype = None
     L.simc_b200_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.simc_b200_set_compiled_maps.argtypes = [C.c_void_p, C.c_int]
+    L.simc_b200_precompile_optics.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p,
+                                               C.c_char_p, C.c_void_p, C.c_char_p, C.c_int])
     L.simc_b200_load_optics.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
     L.simc_b200_set_optics.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_void_p]
@@ -308,10 +311,30 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def precompile_optics(t, strict: bool = True, cache_dir: str | None = None, dump_source: str | None = None):
+    """Runs the map compiler on optics tables `t` (no GPU needed) and leaves the cubin in the cache.
+    Returns (stretches, source bytes, cubin bytes, was_cached)."""
+    L = load_library()
+    cs = np.ascontiguousarray(t.class_start, dtype=np.int32)
+    fc = np.ascontiguousarray(t.fwd_coeff, dtype=np.float64)
+    fe = np.ascontiguousarray(t.fwd_expon, dtype=np.int8)
+    ln = np.ascontiguousarray(t.length_cm, dtype=np.float64)
+    rc = np.ascontiguousarray(t.rec_coeff, dtype=np.float64)
+    re_ = np.ascontiguousarray(t.rec_expon, dtype=np.int8)
+    info = (C.c_int64 * 4)()
+    msg = C.create_string_buffer(8192)
+    r = L.simc_b200_precompile_optics(int(t.arm), len(cs) - 1, _ptr(cs), _ptr(fc), _ptr(fe), _ptr(ln), len(rc), _ptr(rc), _ptr(re_),
+                                      1 if strict else 0, cache_dir.encode() if cache_dir else None,
+                                      dump_source.encode() if dump_source else None, info, msg, 8192)
+    if r != 0:
+        raise SimcError(r, msg.value.decode())
+    return tuple(int(x) for x in info)
+
+
 class Simc:
     """One handle = one GPU + one run configuration (simc_b200_create)."""
 
-    def __init__(self, cfg: RunConfig | None = None, device: int = 0, mode: str | None = None):
+    def __init__(self, cfg: RunConfig | None = None, device: int = 0, mode: str | None = None, compiled_maps: bool | None = None):
         self.L = load_library()
         self.h = C.c_void_p()
         self.cfg = cfg
@@ -321,6 +344,8 @@ class Simc:
         self.mode = os.environ.get("SIMC_B200_MODE", "strict")
         if mode is not None:
             self.set_mode(mode)
+        if compiled_maps is not None:
+            self.set_compiled_maps(compiled_maps)
 
     def _check(self, rc: int):
         if rc != 0:
@@ -341,6 +366,11 @@ class Simc:
         assert mode in ("strict", "fast")
         self.mode = mode
         self._check(self.L.simc_b200_set_mode(self.h, 1 if mode == "strict" else 0))
+
+    def set_compiled_maps(self, on: bool):
+        """Generated straight-line kernels for the RNG-free stretches of the arm programs (default on); off = the
+        record interpreter everywhere."""
+        self._check(self.L.simc_b200_set_compiled_maps(self.h, 1 if on else 0))
 
     # ---- optics
     def load_optics(self, arm: int, forward_path: str, recon_path: str):

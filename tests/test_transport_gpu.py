@@ -168,3 +168,20 @@ def test_large_batch_properties(sim):
     sub = slice(1000000, 1000000 + 4096)
     again, flags2 = sim.transport_batch(1, inp[:, :1000000 + 4096].copy(), 77)
     assert np.array_equal(again[:, sub], out[:, sub]) and np.array_equal(flags2[sub], flags[sub])
+
+
+@pytest.mark.parametrize("arm", [1, 5, 2, 3, 4])
+def test_compiled_stretches_equal_the_interpreter(sim, arm):
+    """The generated straight-line kernels (csrc/mapgen.h: magnet apertures, drifts, COSY forward maps with unit
+    factors and zero coefficients dropped) against the record interpreter on the same rows: every output bit for
+    bit, in both arithmetic variants (dropping x**0 factors and +-0.0 addends cannot change a bit)."""
+    inp = transport_inputs(arm, 60000, seed=7 + arm)
+    a, fa = sim.transport_batch(arm, inp, 11)
+    sim.set_compiled_maps(False)
+    try:
+        b, fb = sim.transport_batch(arm, inp, 11)
+    finally:
+        sim.set_compiled_maps(True)
+    assert np.array_equal(fa, fb)
+    assert (fa == 0).sum() > 1000 and len(np.unique(fa)) > 8          # accepted tracks and many different stops
+    assert np.array_equal(a, b), f"{(a != b).any(axis=0).sum()} rows differ"
