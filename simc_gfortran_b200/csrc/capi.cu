@@ -122,9 +122,17 @@ void plan_stretches(ArmSlot& s) {
     if (cuts[k + 1] > cuts[k]) s.stretches.push_back(StretchSpec{cuts[k], cuts[k + 1]});
 }
 
+// Launch shape of the generated kernels: two CTAs of 256 threads per SM (128 registers per thread).  The warps of a
+// CTA enter every map together (a __syncthreads in front of each), so an SM streams the straight-line code through
+// its instruction cache twice, not once per warp.  Measured on C1 (profiles/README.md, step 14): 128x3, 192x2,
+// 384x1, 512x1 within 1 %; 256x1 and 128x2 (fewer warps) 3 % slower.
+int map_block_threads() {
+  if (const char* e = std::getenv("SIMC_B200_MAP_BLOCK")) { const int v = std::atoi(e); if (v >= 64 && v <= 1024 && v % 32 == 0) return v; }
+  return 256;
+}
 int map_min_blocks() {
   if (const char* e = std::getenv("SIMC_B200_MAP_MINBLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) return v; }
-  return 3;
+  return 2;
 }
 
 int upload_arm(simc_handle* h, int arm_id, CompiledArm&& ca) {
@@ -598,7 +606,7 @@ int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_cl
     ArmSlot s;
     s.host = compile_arm(arm_id, f, r);
     plan_stretches(s);
-    const std::string src = generate_stretch_source(s.host, s.stretches, strict_mode != 0, map_min_blocks());
+    const std::string src = generate_stretch_source(s.host, s.stretches, strict_mode != 0, map_block_threads(), map_min_blocks());
     if (dump_source_path && *dump_source_path) {
       FILE* fp = std::fopen(dump_source_path, "w");
       if (fp) { std::fwrite(src.data(), 1, src.size(), fp); std::fclose(fp); }
@@ -656,6 +664,9 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n, cons
       a.n_stretch = (int)slot.stretches.size();
       for (int k = 0; k < a.n_stretch; ++k) a.stretch_fn[k] = slot.jit.fns[k];
       a.hut_begin = slot.hut_begin;
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      a.stretch_block = map_block_threads(); a.stretch_grid = sms * map_min_blocks();
       a.tk = h->tb_tk; a.lists = h->tb_lists; a.counts = h->tb_counts; a.sink = h->tb_sink;
     }
   }
@@ -825,7 +836,7 @@ int ensure_compiled(simc_handle* h, ArmSlot& s) {
   if (s.stretches.empty()) { s.jit_ready = true; return SIMC_OK; }
   std::string src, cubin, err;
   try {
-    src = generate_stretch_source(s.host, s.stretches, h->strict != 0, map_min_blocks());
+    src = generate_stretch_source(s.host, s.stretches, h->strict != 0, map_block_threads(), map_min_blocks());
   } catch (const std::exception& e) {
     return fail(h, SIMC_ERR_STATE, std::string("map compiler: ") + e.what());
   }
@@ -844,7 +855,10 @@ int ensure_compiled(simc_handle* h, ArmSlot& s) {
 // The chain of kernels of one spectrometer (kernels.h: ArmSchedule).
 int build_schedule(simc_handle* h, int arm_id, bool use_mc, bool decay, bool coll, ArmSchedule& sc) {
   sc.n = 0;
-  auto push = [&](int kind, int b, int e, void* fn) { sc.st[sc.n++] = ArmStage{kind, b, e, fn}; };
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int mblock = map_block_threads(), mgrid = sms * map_min_blocks();
+  auto push = [&](int kind, int b, int e, void* fn) { sc.st[sc.n++] = ArmStage{kind, b, e, fn, mblock, mgrid}; };
   auto it = h->arms.find(arm_id);
   if (!use_mc || it == h->arms.end() || !it->second.loaded) {
     push(ARM_STAGE_ENTRY, 0, 0, nullptr);

@@ -174,8 +174,8 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
       unsigned long long* calls_acc = a.sink + SIMC_NSTOP;
       double* stop_field = a.tk + 11 * a.n;
       void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
-      const long long g = std::min<long long>(blocks, 148 * 8);
-      if (jit_launch(a.stretch_fn[k], (unsigned)g, kBlock, (void*)s, args) != 0) return cudaErrorLaunchFailure;
+      const long long g = std::min<long long>((a.n + a.stretch_block - 1) / a.stretch_block, a.stretch_grid);
+      if (jit_launch(a.stretch_fn[k], (unsigned)g, (unsigned)a.stretch_block, (void*)s, args) != 0) return cudaErrorLaunchFailure;
     }
     k_transport_batch<false><<<(unsigned)blocks, kBlock, kArmSmemBytes, s>>>(*(const ArmDev*)a.arm, a.n, a.in, a.seed, f, a.ctau, a.out,
                                                                  a.flags, a.hut_begin, a.tk, a.lists + (long long)a.n_stretch * a.n,
@@ -403,7 +403,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         unsigned long long* calls_acc = &acc->transp_calls[hadron ? 1 : 0][0];
         double* stop_field = a.record_mode ? a.state + (long long)(hadron ? F_STOP_P : F_STOP_E) * a.cap : nullptr;
         void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
-        const int rc = jit_launch(st.fn, grid, kBlock, (void*)s, args);
+        const int rc = jit_launch(st.fn, (unsigned)st.grid, (unsigned)st.block, (void*)s, args);
         if (rc != 0) return cudaErrorLaunchFailure;
       } else if (st.kind == ARM_STAGE_MIDDLE) {
         if (hadron) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);

@@ -19,7 +19,7 @@ constexpr int kLoopCounts = 32;                 // [0] slots handed out, [1 + l]
 // stretch; MIDDLE: k_arm<W,2>, the interpreter on a stretch; LAST: k_arm<W,1>, the interpreter up to the end of the
 // program, reconstruction and the arm's recon quantities.  Survivors are compacted between stages.
 enum ArmStageKind : int { ARM_STAGE_ENTRY = 0, ARM_STAGE_COMPILED = 1, ARM_STAGE_MIDDLE = 2, ARM_STAGE_LAST = 3 };
-struct ArmStage { int kind; int begin, end; void* fn; };
+struct ArmStage { int kind; int begin, end; void* fn; int block, grid; };   // block / grid: launch shape of a compiled stage
 struct ArmSchedule { int n; ArmStage st[kArmLists]; };
 
 struct TransportBatchArgs {
@@ -35,6 +35,7 @@ struct TransportBatchArgs {
   // buffer, the interpreter takes over at hut_begin for the survivors.  n_stretch = 0: interpreter only.
   int n_stretch;
   void* stretch_fn[kArmLists];
+  int stretch_block, stretch_grid;   // launch shape the stretches were generated for
   int hut_begin;
   double* tk;               // [12][n] device scratch: 11 track rows (loop.cuh F_TK_*) + the stop code
   unsigned* lists;          // [n_stretch + 1][n] device scratch

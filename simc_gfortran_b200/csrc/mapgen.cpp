@@ -89,7 +89,7 @@ void emit_map(Out& o, const CosyTerms& m, bool strict) {
 
 void emit_op(Out& o, const CompiledArm& arm, const ArmOp& op, bool strict) {
   const std::string a = lit(op.a), b = lit(op.b), c = lit(op.c), d = lit(op.d);
-  const std::string stop = " { stop_code = " + std::to_string(op.code) + "; break; }";
+  const std::string stop = " { stop_code = " + std::to_string(op.code) + "; alive = false; }";
   switch (op.op) {
     case OP_PROJECT:       // shared/project.f, no decay
       o.line("      path = path + " + a + " * sqrt(1 + dx * dx + dy * dy);");
@@ -196,46 +196,55 @@ __device__ __forceinline__ unsigned warp_append(unsigned* counter, bool take) {
 
 }  // namespace
 
-std::string generate_stretch_source(const CompiledArm& arm, const std::vector<StretchSpec>& segs, bool strict, int min_blocks) {
+std::string generate_stretch_source(const CompiledArm& arm, const std::vector<StretchSpec>& segs, bool strict, int block_threads,
+                                    int min_blocks) {
   Out o;
   std::string pre = kPreamble;
   const std::string key = "@NSTOP@";
   pre.replace(pre.find(key), key.size(), std::to_string(SIMC_NSTOP));
+  pre += "#define BLOCK " + std::to_string(block_threads) + "\n";
   o.s += pre;
   for (size_t k = 0; k < segs.size(); ++k) {
-    o.line("extern \"C\" __global__ void __launch_bounds__(128, " + std::to_string(min_blocks) + ") seg_" + std::to_string(k) +
+    o.line("extern \"C\" __global__ void __launch_bounds__(BLOCK, " + std::to_string(min_blocks) + ") seg_" + std::to_string(k) +
            "(double* __restrict__ tk, long long cap, const unsigned* __restrict__ in_list, const unsigned* __restrict__ in_count,");
     o.line("    unsigned* __restrict__ out_list, unsigned* __restrict__ out_count, unsigned long long* __restrict__ stop_acc,");
     o.line("    unsigned long long* __restrict__ calls_acc, double* __restrict__ stop_field) {");
     o.line("  __shared__ unsigned s_stop[NSTOP];");
     o.line("  __shared__ unsigned s_calls[48];");
-    o.line("  for (int i = threadIdx.x; i < NSTOP; i += 128) s_stop[i] = 0u;");
-    o.line("  for (int i = threadIdx.x; i < 48; i += 128) s_calls[i] = 0u;");
+    o.line("  for (int i = threadIdx.x; i < NSTOP; i += BLOCK) s_stop[i] = 0u;");
+    o.line("  for (int i = threadIdx.x; i < 48; i += BLOCK) s_calls[i] = 0u;");
     o.line("  __syncthreads();");
     o.line("  const unsigned n_in = *in_count;");
-    o.line("  for (long long i0 = (long long)blockIdx.x * 128; i0 < n_in; i0 += (long long)gridDim.x * 128) {");
+    o.line("  for (long long i0 = (long long)blockIdx.x * BLOCK; i0 < n_in; i0 += (long long)gridDim.x * BLOCK) {");
     o.line("    const long long i = i0 + threadIdx.x;");
     o.line("    const bool active = i < n_in;");
-    o.line("    bool ok = false;");
+    o.line("    bool alive = active;");
     o.line("    unsigned slot = 0u;");
+    o.line("    double xs = 0., ys = 0., dx = 0., dy = 0., dpp = 0., path = 0., xt = 0., yt = 0.;");
+    o.line("    int stop_code = -1;");
     o.line("    if (active) {");
     o.line("      slot = in_list[i];");
-    o.line("      double xs = tk[0 * cap + slot], ys = tk[1 * cap + slot], dx = tk[2 * cap + slot], dy = tk[3 * cap + slot];");
-    o.line("      double dpp = tk[4 * cap + slot], path = tk[7 * cap + slot];");
-    o.line("      double xt = 0., yt = 0.;");
-    o.line("      int stop_code = -1;");
-    o.line("      do {");
+    o.line("      xs = tk[0 * cap + slot]; ys = tk[1 * cap + slot]; dx = tk[2 * cap + slot]; dy = tk[3 * cap + slot];");
+    o.line("      dpp = tk[4 * cap + slot]; path = tk[7 * cap + slot];");
+    o.line("    }");
     for (int pc = segs[k].begin; pc < segs[k].end; ++pc) {
-      emit_op(o, arm, arm.ops.at(pc), strict);
+      const ArmOp& op = arm.ops.at(pc);
+      if (op.op == OP_COLL || op.op == OP_COLL_DATA) continue;
+      // the warps of the CTA enter every map together: its code is tens of KB of straight line, and warps that
+      // drift apart in it stall on instruction fetch (each streams the code through the cache on its own)
+      if (op.op == OP_TRANSP) o.line("    __syncthreads();");
+      o.line("    if (alive) {");
+      emit_op(o, arm, op, strict);
+      o.line("    }");
     }
-    o.line("      } while (0);");
-    o.line("      (void)xt; (void)yt;");
+    o.line("    (void)xt; (void)yt;");
+    o.line("    const bool ok = alive;");
+    o.line("    if (active) {");
     o.line("      tk[7 * cap + slot] = path;");
     o.line("      if (stop_code >= 0) {");
     o.line("        if (stop_field) stop_field[slot] = (double)stop_code;");
     o.line("        if (2 + stop_code < NSTOP) atomicAdd(&s_stop[2 + stop_code], 1u);");
     o.line("      } else {");
-    o.line("        ok = true;");
     o.line("        tk[0 * cap + slot] = xs; tk[1 * cap + slot] = ys; tk[2 * cap + slot] = dx; tk[3 * cap + slot] = dy;");
     o.line("        tk[4 * cap + slot] = dpp;");
     o.line("      }");
@@ -245,8 +254,8 @@ std::string generate_stretch_source(const CompiledArm& arm, const std::vector<St
     o.line("    if (ok) out_list[pos] = slot;");
     o.line("  }");
     o.line("  __syncthreads();");
-    o.line("  for (int i = threadIdx.x; i < NSTOP; i += 128) if (s_stop[i]) atomicAdd(&stop_acc[i], (unsigned long long)s_stop[i]);");
-    o.line("  for (int i = threadIdx.x; i < 48; i += 128) if (s_calls[i]) atomicAdd(&calls_acc[i], (unsigned long long)s_calls[i]);");
+    o.line("  for (int i = threadIdx.x; i < NSTOP; i += BLOCK) if (s_stop[i]) atomicAdd(&stop_acc[i], (unsigned long long)s_stop[i]);");
+    o.line("  for (int i = threadIdx.x; i < 48; i += BLOCK) if (s_calls[i]) atomicAdd(&calls_acc[i], (unsigned long long)s_calls[i]);");
     o.line("}");
   }
   return o.s;

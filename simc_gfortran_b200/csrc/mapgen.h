@@ -25,6 +25,8 @@ struct StretchSpec { int begin, end; };      // ops [begin, end)
 // tk = row F_TK_XS of the state buffer (rows: xs, ys, dxdzs, dydzs, dpps, p, m2, pathlen, ...; loop.cuh), cap = row
 // length; survivors are appended to out_list; a stopped track leaves its path length in tk, its stop code in
 // stop_field[slot] (if not null) and in stop_acc[2 + code]; calls_acc[class - 1] counts the map evaluations.
-std::string generate_stretch_source(const CompiledArm& arm, const std::vector<StretchSpec>& segs, bool strict, int min_blocks);
+// block_threads / min_blocks: CTA size and minimum resident CTAs per SM the kernels are built for (launch bounds).
+std::string generate_stretch_source(const CompiledArm& arm, const std::vector<StretchSpec>& segs, bool strict, int block_threads,
+                                    int min_blocks);
 
 }  // namespace simc
