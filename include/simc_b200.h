@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SIMC_B200_ABI_VERSION 1
+#define SIMC_B200_ABI_VERSION 2
 
 /* ---- spectrometer ids: electron_arm / hadron_arm numbering of dbase.f:247-263 */
 enum {
@@ -182,6 +182,11 @@ typedef struct {
   /* Contributing events whose weight needed a model this build lacks: peepi below W = 2 GeV blends in
    * the MAID-2007 table (physics_pion.f:88-107); they are weighted with the parametrisation alone. */
   int64_t       unsupported;
+  /* Contributing events whose weight or cross section is NaN, infinite or beyond the range of the fixed-point sums
+   * (|w| >= 1e38 quanta, i.e. ~2^62 * w_ref): they are counted in ncontribute / npasscuts like in the reference but
+   * add nothing to wtcontribute, sum_sigcc and the weighted histograms -- the reference's sums would turn NaN.
+   * Non-zero means: look at the run (e.g. semi-inclusive events with x clipped to 1). */
+  int64_t       nonfinite;
 } simc_accum;
 
 typedef struct simc_handle simc_handle;
@@ -384,6 +389,24 @@ const char* simc_b200_event_field_name(int k);
 #define SIMC_RADC_NOUT 11
 int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa);
 
+/* Stage-level parity entry point for the end of the loop body: complete_recon_ev (event.f:1056-1359), complete_main
+ * (event.f:1363-1569: spectral-function weight, sigep / deForest / peepi / peedelta / peeK / peepiX, Coulomb factor,
+ * final weight), pass_cuts and the hard cuts (simc.f:219-246) on dumped per-event vectors -- what those routines read
+ * from `recon`, `vertex`, `main` and COMMON /pfermi_stuff/ after montecarlo returned.  in[k*n+i], k =
+ *  0 recon.e.E   1 recon.e.theta  2 recon.e.phi    3 recon.p.P     4 recon.p.E    5 recon.p.theta  6 recon.p.phi
+ *  7 vertex.Ein  8 vertex.e.E     9 vertex.e.theta 10 vertex.Q2   11 vertex.nu   12 vertex.q
+ * 13 vertex.p.E 14 vertex.p.P    15-17 vertex.uq   18-20 vertex.up 21 vertex.Em  22 vertex.Pm
+ * 23 main.phi_pq 24 main.t       25 main.epsilon   26 main.jacobian 27 main.gen_weight
+ * 28 vertex.zhad 29 vertex.pt2   30 pfer  31-33 pferx,y,z  34 efer
+ * 35 main.FP.p.path  36 main.FP.p.dx  37 main.FP.p.dy
+ * 38-40 recon.e.delta,yptar,xptar   41-43 recon.p.delta,yptar,xptar
+ * out[k*n+i], k = 0 success  1 pass_cuts  2 main.weight  3 main.sigcc  4 main.sigcc_recon  5 recon.Em  6 recon.Pm
+ *  7 recon.W  8 main.thetacm  9 main.phicm  10 ntup.sigcm  11 main.davejac  12 survivalprob  13 ntup.mm  14 main.wcm
+ * The run's tables (spectral function, theory, CTEQ5, DSS, MAID) must be set as for simc_b200_run. */
+#define SIMC_WEIGHT_NIN  44
+#define SIMC_WEIGHT_NOUT 15
+int simc_b200_weight_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa);
+
 const char* simc_b200_stop_name(int arm_id, int code);
 
 /* end of run ------------------------------------------------------------- *
@@ -395,10 +418,12 @@ typedef struct {
   double genvol;              /* product of the generated ranges, simc.f:376-396 */
   double normfac;             /* luminosity / ntried * nevent * genvol (1 for doing_phsp), simc.f:368-398 */
   double yield;               /* wtcontribute * normfac: counts for EXPER%charge, simc.f:399 */
-  double central_sigcc_ave;   /* sum_sigcc / nevent */
+  double central_sigcc_ave;   /* sum_sigcc / nevent, simc.f:959 */
+  int64_t nevent;             /* simc.f:346-350: ntried when ngen < 0 (every try counts), the successes when ngen > 0 */
   double aveerr[8], resol[8]; /* e: delta, xptar, yptar, ytar; p: same (simc.f:406-431); 0 if npasscuts <= 1 */
 } simc_results;
-int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, double charge_mC, simc_results* out);
+/* ngen: the deck's ngen (its sign selects what nevent counts). */
+int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, int32_t ngen, double charge_mC, simc_results* out);
 
 /* Ntuple file in the reference's layout (NtupleInit.f:32,352-355; results_write.f:264-266): a Fortran
  * unformatted sequential file -- record "NtupleSize" (int32), one 16-character record per tag, then one

@@ -354,6 +354,76 @@ int oracle_semi_batch(const simc_run_config* cfg, int64_t n, const double* in, d
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
+// ---- end of the loop body on dumped vectors (twin of simc_b200_weight_batch, include/simc_b200.h) ----------
+static void weight_tables(Sim& s) {
+  s.sf = g_sf.numPm ? &g_sf : nullptr; s.pfermi = g_pfermi.pval.empty() ? nullptr : &g_pfermi; s.pdf = g_pdf.Nx ? &g_pdf : nullptr;
+  s.theory = g_theory.nrhoPm ? &g_theory : nullptr; s.maid = &g_maid; s.fdss = g_fdss.set ? &g_fdss : nullptr;
+}
+// Dumps, for tries [first, first+n), what complete_recon_ev and complete_main read once montecarlo has returned
+// (valid[i] = 0: the try did not get that far).
+int oracle_weight_inputs(const simc_run_config* cfg, int64_t first, int64_t n, uint64_t seed, double* in, int32_t* valid) {
+  auto ie = g_optics.find(cfg->electron_arm), ip = g_optics.find(cfg->hadron_arm);
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Rng rng;
+      rng.seed_philox(seed, (uint64_t)(first + i));
+      Sim s;
+      s.cfg = cfg; s.optics_e = ie == g_optics.end() ? nullptr : &ie->second; s.optics_p = ip == g_optics.end() ? nullptr : &ip->second;
+      s.rng = &rng;
+      weight_tables(s);
+      EventMain main;
+      Event vertex, orig, recon;
+      TryResult r;
+      const bool ok = try_until_recon(s, main, vertex, orig, recon, r);
+      valid[i] = ok ? 1 : 0;
+      const double v[SIMC_WEIGHT_NIN] = {
+          recon.e.E, recon.e.theta, recon.e.phi, recon.p.P, recon.p.E, recon.p.theta, recon.p.phi,
+          vertex.Ein, vertex.e.E, vertex.e.theta, vertex.Q2, vertex.nu, vertex.q, vertex.p.E, vertex.p.P,
+          vertex.uq.x, vertex.uq.y, vertex.uq.z, vertex.up.x, vertex.up.y, vertex.up.z, vertex.Em, vertex.Pm,
+          main.phi_pq, main.t, main.epsilon, main.jacobian, main.gen_weight, vertex.zhad, vertex.pt2,
+          s.pfer, s.pferx, s.pfery, s.pferz, s.efer, main.FP_p.path, main.FP_p.dx, main.FP_p.dy,
+          recon.e.delta, recon.e.yptar, recon.e.xptar, recon.p.delta, recon.p.yptar, recon.p.xptar};
+      for (int k = 0; k < SIMC_WEIGHT_NIN; ++k) in[k * n + i] = ok ? v[k] : 0.0;
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+int oracle_weight_batch(const simc_run_config* cfg, int64_t n, const double* in, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i) {
+      Sim s;
+      s.cfg = cfg;
+      weight_tables(s);
+      EventMain main;
+      Event vertex, recon;
+      auto I = [&](int k) { return in[k * n + i]; };
+      recon.e.E = I(0); recon.e.P = recon.e.E; recon.e.theta = I(1); recon.e.phi = I(2);
+      recon.p.P = I(3); recon.p.E = I(4); recon.p.theta = I(5); recon.p.phi = I(6);
+      vertex.Ein = I(7); vertex.e.E = I(8); vertex.e.P = vertex.e.E; vertex.e.theta = I(9); vertex.Q2 = I(10); vertex.nu = I(11);
+      vertex.q = I(12); vertex.p.E = I(13); vertex.p.P = I(14);
+      vertex.uq.x = I(15); vertex.uq.y = I(16); vertex.uq.z = I(17); vertex.up.x = I(18); vertex.up.y = I(19); vertex.up.z = I(20);
+      vertex.Em = I(21); vertex.Pm = I(22);
+      // event.f:880-886: the vector the cross sections of (e,e'p) read
+      vertex.Pmx = vertex.p.P * vertex.up.x - vertex.q * vertex.uq.x;
+      vertex.Pmy = vertex.p.P * vertex.up.y - vertex.q * vertex.uq.y;
+      vertex.Pmz = vertex.p.P * vertex.up.z - vertex.q * vertex.uq.z;
+      main.phi_pq = I(23); main.t = I(24); main.epsilon = I(25); main.jacobian = I(26); main.gen_weight = I(27);
+      vertex.zhad = I(28); vertex.pt2 = I(29);
+      s.pfer = I(30); s.pferx = I(31); s.pfery = I(32); s.pferz = I(33); s.efer = I(34);
+      main.FP_p.path = I(35); main.FP_p.dx = I(36); main.FP_p.dy = I(37);
+      recon.e.delta = I(38); recon.e.yptar = I(39); recon.e.xptar = I(40);
+      recon.p.delta = I(41); recon.p.yptar = I(42); recon.p.xptar = I(43);
+      TryResult r;
+      finish_try(s, main, vertex, recon, true, r);
+      const double o[SIMC_WEIGHT_NOUT] = {r.success ? 1.0 : 0.0, r.pass_cuts ? 1.0 : 0.0, main.weight, main.sigcc, main.sigcc_recon,
+                                          recon.Em, recon.Pm, recon.W, main.thetacm, main.phicm, s.ntup.sigcm, main.davejac,
+                                          s.ntup.survivalprob, s.ntup.mm, main.wcm};
+      for (int k = 0; k < SIMC_WEIGHT_NOUT; ++k) out[k * n + i] = o[k];
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 // RANLUX known-answer access: n uniforms from grnd() after sgrnd(seed)
 int oracle_ranlux(int seed, int lux, int64_t n, double* out) {
   RanluxState st;

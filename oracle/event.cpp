@@ -687,10 +687,9 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
   return true;
 }
 
-// loop body, simc.f:169-246
-TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon) {
+// loop body, simc.f:169-246, first half: generate + montecarlo
+bool try_until_recon(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon, TryResult& r) {
   const simc_run_config& cfg = *s.cfg;
-  TryResult r;
   s.trk.rng = s.rng;
   s.trk.ctau = cfg.ctau;
   s.trk.Mh2_final = cfg.Mh2;
@@ -701,6 +700,12 @@ TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& re
   r.gen_success = success;
   r.stage = 0;
   if (success) { success = montecarlo(s, orig, main, recon); r.stage = success ? 3 : (s.stop_p > 0 ? 1 : 2); }
+  return success;
+}
+
+// second half: complete_recon_ev, complete_main, pass_cuts, hard cuts (simc.f:219-246)
+void finish_try(Sim& s, EventMain& main, Event& vertex, Event& recon, bool success, TryResult& r) {
+  const simc_run_config& cfg = *s.cfg;
   if (success) success = complete_recon_ev(s, recon);
   if (success) success = complete_main(s, false, main, vertex, recon);
   // NB the p-arm upper delta edge uses SPedge%e%delta%max (simc.f:237)
@@ -722,6 +727,12 @@ TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& re
   }
   r.success = success;
   if (success) r.stage = 4;
+}
+
+TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon) {
+  TryResult r;
+  const bool success = try_until_recon(s, main, vertex, orig, recon, r);
+  finish_try(s, main, vertex, recon, success, r);
   return r;
 }
 

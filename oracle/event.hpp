@@ -173,6 +173,8 @@ double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, doub
 
 // One try of the loop (simc.f:169-351) in counter-based mode.
 TryResult one_try(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon);
+bool try_until_recon(Sim& s, EventMain& main, Event& vertex, Event& orig, Event& recon, TryResult& r);   // generate + montecarlo
+void finish_try(Sim& s, EventMain& main, Event& vertex, Event& recon, bool success, TryResult& r);       // the rest of the loop body
 
 // results_ntu_write, results_write.f:1-269 (no target field, no pi0): returns the number of columns
 int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const Event& orig, const Event& recon,

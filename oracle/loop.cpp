@@ -100,6 +100,10 @@ void accumulate(const Sim& s, const TryResult& r, const EventMain& main, const E
   }
   a.ncontribute++;
   if (s.low_w) a.unsupported++;
+  {   // weights the fixed-point sums drop (NaN, inf, out of range): counted, like the product does
+    const int qw = a.wtcontribute.qexp;
+    if (!(std::fabs(std::ldexp(main.weight, -qw)) < 1.0e38) || !(std::fabs(std::ldexp(main.sigcc, -qw)) < 1.0e38)) a.nonfinite++;
+  }
   if (!s.rad.rad_proton_this_ev) a.ncontribute_no_rad_proton++;
   if (r.pass_cuts) {
     a.npasscuts++;
@@ -140,6 +144,7 @@ void merge_accum(simc_accum& a, const simc_accum& b) {
   a.ntried += b.ntried; a.nsuccess += b.nsuccess; a.ncontribute += b.ncontribute; a.npasscuts += b.npasscuts;
   a.ncontribute_no_rad_proton += b.ncontribute_no_rad_proton;
   a.unsupported += b.unsupported;
+  a.nonfinite += b.nonfinite;
   auto addf = [](simc_fixed128& x, const simc_fixed128& y) {
     i128 v = (((i128)x.hi << 64) | (i128)x.lo) + (((i128)y.hi << 64) | (i128)y.lo);
     x.lo = (uint64_t)v; x.hi = (int64_t)(v >> 64);

@@ -728,7 +728,7 @@ int weight_qexp(const simc_run_config& cfg) {
 }
 
 // Which settings this build of the loop implements; everything else is refused loudly.
-int validate_loop_config(simc_handle* h) {
+int validate_loop_config(simc_handle* h, bool need_optics = true) {
   const simc_run_config& c = h->cfg;
   const bool meson = ((c.doing_hydpi || c.doing_deutpi || c.doing_hepi) && c.doing_pion) ||
                      ((c.doing_hydkaon || c.doing_deutkaon || c.doing_hekaon) && c.doing_kaon);
@@ -767,7 +767,7 @@ int validate_loop_config(simc_handle* h) {
     return fail(h, SIMC_ERR_ARG,
                 "radiative options outside rad_flag<=1, extrad_flag 1..2, intcor_mode=1, use_offshell_rad=1, "
                 "use_expon=0 are not implemented");
-  for (int arm : {c.electron_arm, c.hadron_arm}) {
+  if (need_optics) for (int arm : {c.electron_arm, c.hadron_arm}) {
     const bool used = (arm == c.electron_arm) ? c.using_E_arm_montecarlo : c.using_P_arm_montecarlo;
     if (!used) continue;
     auto it = h->arms.find(arm);
@@ -892,27 +892,25 @@ int build_schedule(simc_handle* h, int arm_id, bool use_mc, bool decay, bool col
   return SIMC_OK;
 }
 
-int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, int record, double* d_rec,
-                int* d_status) {
-  int rc = validate_loop_config(h);
-  if (rc) return rc;
-  const long long cap = record ? n_tries : std::min<long long>(h->batch, n_tries);
-  rc = ensure_loop_buffers(h, std::max<long long>(cap, 1));
-  if (rc) return rc;
-  LoopLaunch a;
+// Everything a loop kernel needs besides the range of tries: buffers, tables, the stage schedules of both arms.
+int prepare_launch(simc_handle* h, LoopLaunch& a, uint64_t seed, int record, bool with_arms) {
+  int rc = SIMC_OK;
+  a = LoopLaunch{};
   a.cfg = h->d_cfg;
   a.arm_e = h->arms.count(h->cfg.electron_arm) && h->arms[h->cfg.electron_arm].loaded ? h->arms[h->cfg.electron_arm].img.data() : nullptr;
   a.arm_p = h->arms.count(h->cfg.hadron_arm) && h->arms[h->cfg.hadron_arm].loaded ? h->arms[h->cfg.hadron_arm].img.data() : nullptr;
   a.state = h->d_state; a.cap = h->loop_cap; a.lists = h->d_lists; a.counts = h->d_counts; a.acc = h->d_acc;
-  a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record; a.rec = d_rec; a.status = d_status;
+  a.seed = seed; a.qexp_w = h->qexp_w; a.record_mode = record;
   a.grid_blocks = h->grid_blocks;
   auto coll = [&](int arm) { return arm == SIMC_ARM_HMS ? h->cfg.using_HMScoll : arm == SIMC_ARM_SHMS ? h->cfg.using_SHMScoll : 0; };
   a.coll_e = coll(h->cfg.electron_arm); a.coll_p = coll(h->cfg.hadron_arm);
   a.using_rad = h->cfg.using_rad;
-  rc = build_schedule(h, h->cfg.hadron_arm, h->cfg.using_P_arm_montecarlo != 0, h->cfg.doing_decay != 0, a.coll_p != 0, a.sched_p);
-  if (rc) return rc;
-  rc = build_schedule(h, h->cfg.electron_arm, h->cfg.using_E_arm_montecarlo != 0, false, a.coll_e != 0, a.sched_e);
-  if (rc) return rc;
+  if (with_arms) {
+    rc = build_schedule(h, h->cfg.hadron_arm, h->cfg.using_P_arm_montecarlo != 0, h->cfg.doing_decay != 0, a.coll_p != 0, a.sched_p);
+    if (rc) return rc;
+    rc = build_schedule(h, h->cfg.electron_arm, h->cfg.using_E_arm_montecarlo != 0, false, a.coll_e != 0, a.sched_e);
+    if (rc) return rc;
+  }
   a.sf_pm = h->d_sf; a.sf_em = h->d_sf ? h->d_sf + h->sf_npm : nullptr;
   a.sf_val = h->d_sf ? h->d_sf + h->sf_npm + h->sf_nem : nullptr;
   a.sf_npm = h->sf_npm; a.sf_nem = h->sf_nem; a.sf_dem = h->d_sf_dem;
@@ -926,6 +924,20 @@ int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t see
     static_assert(sizeof(mt) == sizeof(a.mats), "MatTable layout");
     std::memcpy(a.mats, &mt, sizeof(mt));
   }
+  return SIMC_OK;
+}
+
+int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, int record, double* d_rec,
+                int* d_status) {
+  int rc = validate_loop_config(h);
+  if (rc) return rc;
+  const long long cap = record ? n_tries : std::min<long long>(h->batch, n_tries);
+  rc = ensure_loop_buffers(h, std::max<long long>(cap, 1));
+  if (rc) return rc;
+  LoopLaunch a;
+  rc = prepare_launch(h, a, seed, record, true);
+  if (rc) return rc;
+  a.rec = d_rec; a.status = d_status;
   size_t ev_pos = 5 * h->ev_used.size();
   for (int64_t done = 0; done < n_tries;) {
     const int64_t nb = std::min<int64_t>(n_tries - done, cap);
@@ -1202,6 +1214,41 @@ int simc_b200_semi_batch(simc_handle* h, int64_t n, const double* in_soa, double
   cudaFree(d_in); cudaFree(d_out);
   h->launches += 1;
   if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_semi_batch");
+  return SIMC_OK;
+}
+
+int simc_b200_weight_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!in_soa || !out_soa))) return fail(h, SIMC_ERR_ARG, "simc_b200_weight_batch: bad argument");
+  int rc = validate_loop_config(h, false);
+  if (rc) return rc;
+  if (n == 0) return SIMC_OK;
+  CU(h, cudaSetDevice(h->device));
+  rc = ensure_loop_buffers(h, n);
+  if (rc) return rc;
+  // the accumulators of a run in progress must survive: park them
+  std::vector<unsigned char> saved(h->acc_host.size());
+  CU(h, cudaMemcpyAsync(saved.data(), h->d_acc, saved.size(), cudaMemcpyDeviceToHost, h->stream));
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(h, cudaMalloc(&d_in, sizeof(double) * SIMC_WEIGHT_NIN * (size_t)n));
+  CU(h, cudaMalloc(&d_out, sizeof(double) * SIMC_WEIGHT_NOUT * (size_t)n));
+  LoopLaunch a;
+  rc = prepare_launch(h, a, 0, 1, false);
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    a.rec = d_in; a.wb_out = d_out; a.n_tries = n; a.first_try = 0;
+    // what the end of the loop body does not write for this reaction reads as zero
+    e = cudaMemsetAsync(h->d_state, 0, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)h->loop_cap, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in_soa, sizeof(double) * SIMC_WEIGHT_NIN * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = h->strict ? strict::launch_loop_stage(a, 5, h->stream) : fast::launch_loop_stage(a, 5, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_soa, d_out, sizeof(double) * SIMC_WEIGHT_NOUT * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_acc, saved.data(), saved.size(), cudaMemcpyHostToDevice, h->stream);
+  const cudaError_t e2 = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  h->launches += 3;
+  if (rc) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess) return cuda_fail(h, e != cudaSuccess ? e : e2, "simc_b200_weight_batch");
   return SIMC_OK;
 }
 

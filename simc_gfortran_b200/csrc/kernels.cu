@@ -137,24 +137,41 @@ __global__ void k_tb_stopped(long long n, const double* __restrict__ in, const d
   flags[i] = (int)code;
 }
 
+// > 48 KB of dynamic shared memory needs an opt-in per function AND per device (the attribute lives in the context):
+// done once for every device a handle runs on.  The caller holds rng_key_mutex().
+static cudaError_t ensure_smem_opt_in_locked() {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (done[dev]) return cudaSuccess;
+  const int bytes = (int)kArmSmemBytes;
+  e = cudaFuncSetAttribute(k_transport_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_transport_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  done[dev] = true;
+  return cudaSuccess;
+}
+
 cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
   const long long blocks = (a.n + kBlock - 1) / kBlock;
   ArmFlags f;
   f.ms_flag = a.ms_flag != 0; f.wcs_flag = a.wcs_flag != 0; f.decay_flag = a.decay_flag != 0;
   f.using_coll = a.using_coll != 0;
-  {
-    static bool attr_set = false;       // > 48 KB of dynamic shared memory needs the opt-in, once per process
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_transport_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_transport_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-  }
   std::lock_guard<std::mutex> key_lock(rng_key_mutex());
   {
-    const cudaError_t e = ensure_rng_key_locked(a.seed);
+    cudaError_t e = ensure_smem_opt_in_locked();
+    if (e == cudaSuccess) e = ensure_rng_key_locked(a.seed);
     if (e != cudaSuccess) return e;
   }
   if (a.n_stretch > 0 && !f.using_coll && !f.decay_flag) {
@@ -282,6 +299,7 @@ void accum_to_host(const void* dev_copy, void* out_v, int qexp_w) {
   o.ntried += (int64_t)d.counters[0]; o.nsuccess += (int64_t)d.counters[1]; o.ncontribute += (int64_t)d.counters[2];
   o.npasscuts += (int64_t)d.counters[3]; o.ncontribute_no_rad_proton += (int64_t)d.counters[4];
   o.unsupported += (int64_t)d.counters[5];
+  o.nonfinite += (int64_t)d.counters[6];
   addf(o.wtcontribute, d.wt, qexp_w);
   addf(o.sum_sigcc, d.sigcc, qexp_w);
   for (int i = 0; i < 8; ++i) { addf(o.sumerr[i], d.sumerr[i], -80); addf(o.sumerr2[i], d.sumerr2[i], -80); }
@@ -352,19 +370,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   const long long need = (a.n_tries + kBlock - 1) / kBlock;
   const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
   {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_arm<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kArmSmemBytes);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    const cudaError_t e = ensure_smem_opt_in_locked();
+    if (e != cudaSuccess) return e;
   }
   if (stage == 0) {
     cudaError_t e = cudaMemsetAsync(a.counts, 0, kLoopCounts * sizeof(unsigned), s);
@@ -419,6 +426,12 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     k_finish<<<grid, kBlock, 0, s>>>(A);
   }
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
+  else if (stage == 5) {      // simc_b200_weight_batch: a.rec = input rows, a.wb_out = output rows, a.n_tries rows
+    const unsigned nb = (unsigned)((a.n_tries + 255) / 256);
+    k_wb_load<<<nb, 256, 0, s>>>(A, a.n_tries, a.rec);
+    k_finish<<<grid, kBlock, 0, s>>>(A);
+    k_wb_store<<<nb, 256, 0, s>>>(A, a.n_tries, a.wb_out);
+  }
   return cudaGetLastError();
 }
 

@@ -57,6 +57,7 @@ struct LoopLaunch {
   unsigned long long seed;
   int qexp_w;
   int record_mode;
+  double* wb_out;             // simc_b200_weight_batch (stage 5): [SIMC_WEIGHT_NOUT][n_tries] device; its input rows are `rec`
   double* rec;                // [SIMC_EVENT_NREC][n_tries] device, record mode only
   int* status;
   int grid_blocks;            // persistent grid for the stage kernels

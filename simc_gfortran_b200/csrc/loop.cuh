@@ -67,7 +67,7 @@ struct StateBuf {
 
 // ---- exact accumulators --------------------------------------------------------------------
 struct DevAccum {
-  unsigned long long counters[8];                 // ntried, nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported
+  unsigned long long counters[8];                 // ntried, nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported, nonfinite
   unsigned long long wt[2], sigcc[2];             // 128-bit two's complement (lo, hi)
   unsigned long long sumerr[8][2], sumerr2[8][2];
   unsigned long long hist_w[6][SIMC_NHIST][2];
@@ -641,7 +641,7 @@ struct BlockAcc {
   unsigned long long sums[18][2];                    // wt, sigcc, sumerr[8], sumerr2[8]
   unsigned long long hist_w[6][SIMC_NHIST][2];
   unsigned hist_n[9][SIMC_NHIST];                    // gen (7), RECON Em, RECON Pm
-  unsigned counters[6];                              // nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported
+  unsigned counters[6];                              // nsuccess, ncontribute, npasscuts, nco_no_rad_proton, unsupported, nonfinite
   long long mins[40], maxs[40];                      // contrib (30 used of 32) + slop (8)
 };
 
@@ -976,6 +976,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
     warp_count_if(&B.counters[1], success);
     warp_count_if(&B.counters[3], success && no_rad_p);
     warp_count_if(&B.counters[4], success && low_w);
+    // weights the fixed-point sums cannot hold (NaN, inf, |w| >= 1e38 quanta): to_fixed drops them, count them
+    warp_count_if(&B.counters[5], success && (!(fabs(ldexp(weight, -A.qexp_w)) < 1.0e38) || !(fabs(ldexp(sigcc, -A.qexp_w)) < 1.0e38)));
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const int b = success ? hist_bin(cfg.hist_axis[0][k], rec_vals[k]) : -1;
@@ -1034,12 +1036,38 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
     unsigned long long* dst = h < 7 ? &acc->hist_n[1][h][b] : h == 7 ? &acc->hist_n[0][SIMC_H_EM][b] : &acc->hist_n[0][SIMC_H_PM][b];
     atomicAdd(dst, (unsigned long long)v);
   }
-  if (threadIdx.x < 5 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
+  if (threadIdx.x < 6 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
   for (int k = threadIdx.x; k < 40; k += kBlock) {
     if (B.mins[k] == 0x7fffffffffffffffLL) continue;
     if (k < 32) { atomicMin(&acc->contrib_lo[k], B.mins[k]); atomicMax(&acc->contrib_hi[k], B.maxs[k]); }
     else { atomicMin(&acc->slop_lo[k - 32], B.mins[k]); atomicMax(&acc->slop_hi[k - 32], B.maxs[k]); }
   }
+}
+
+// ---- parity entry point: the end of the loop body on dumped vectors (simc_b200_weight_batch) ----------
+// Row i of the input becomes slot i of the state buffer, the list of survivors is 0..n-1, k_finish runs in record
+// mode, and k_wb_store collects what it left.  Column order: include/simc_b200.h.
+__global__ void k_wb_load(LoopArgs A, long long n, const double* __restrict__ in) {
+  const StateBuf& S = A.st;
+  const int fields[SIMC_WEIGHT_NIN] = {
+      F_RE_E, F_RE_TH, F_RE_PH, F_RP_P, F_RP_E, F_RP_TH, F_RP_PH, F_VEIN, F_VEE, F_VETHETA, F_VQ2, F_VNU, F_VQ, F_VPE, F_VPP,
+      F_UQX, F_UQY, F_UQZ, F_UPX, F_UPY, F_UPZ, F_VEM, F_VPM, F_MPHIPQ, F_MT, F_MEPS, F_JAC, F_GENW, F_ZHAD, F_PT2,
+      F_PFER, F_PFERX, F_PFERY, F_PFERZ, F_EFER, F_FPP_PATH, F_FPP_DX, F_FPP_DY, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCP_D, F_RCP_Y, F_RCP_X};
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) A.counts[1 + 2 * kArmLists] = (unsigned)n;
+  if (i >= n) return;
+  for (int k = 0; k < SIMC_WEIGHT_NIN; ++k) S.st(fields[k], i, in[(long long)k * n + i]);
+  S.st(F_TRY, i, (double)i);
+  A.lists[(long long)(2 * kArmLists) * A.st.cap + i] = (unsigned)i;
+}
+__global__ void k_wb_store(LoopArgs A, long long n, double* __restrict__ out) {
+  const StateBuf& S = A.st;
+  const int fields[SIMC_WEIGHT_NOUT] = {F_STAGE, F_PASSCUTS, F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_REM, F_RPM, F_RW, F_THCM, F_PHICM,
+                                        F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM};
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < SIMC_WEIGHT_NOUT; ++k) out[(long long)k * n + i] = S.ld(fields[k], i);
+  out[0 * n + i] = S.ld(F_STAGE, i) == 4.0 ? 1.0 : 0.0;
 }
 
 // ---- parity entry point: per-try records (include/simc_b200.h: simc_b200_event_batch) ----------

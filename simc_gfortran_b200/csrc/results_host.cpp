@@ -36,7 +36,7 @@ struct simc_ntuple_file {
 
 extern "C" {
 
-int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, double charge_mC, simc_results* out) {
+int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, int32_t ngen, double charge_mC, simc_results* out) {
   if (!cfg || !acc || !out) return SIMC_ERR_ARG;
   std::memset(out, 0, sizeof(*out));
   const simc_target& targ = cfg->targ;
@@ -44,7 +44,11 @@ int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, doubl
   const double targetfac = targ.mass_amu / 3.75914e+6 / (targ.abundancy / 100.) * std::fabs(std::cos(targ.angle)) / (targ.thick * 1000.);
   out->luminosity = charge_mC / targetfac;
   const simc_gen_limits& gen = cfg->gen;
-  double normfac = out->luminosity / (double)acc->ntried * (double)acc->nsuccess;
+  // simc.f:346-350: with ngen < 0 every try counts as an event (nevent = ntried when the loop ends), with
+  // ngen > 0 only the successes do; simc.f:368: normfac = luminosity/ntried*nevent
+  const double nevent = ngen < 0 ? (double)acc->ntried : (double)acc->nsuccess;
+  out->nevent = (int64_t)nevent;
+  double normfac = acc->ntried > 0 ? out->luminosity / (double)acc->ntried * nevent : 0.0;
   const double domega_e = (gen.e.yptar.max - gen.e.yptar.min) * (gen.e.xptar.max - gen.e.xptar.min);
   const double domega_p = cfg->doing_rho ? 4. * 3.141592653589793 : (gen.p.yptar.max - gen.p.yptar.min) * (gen.p.xptar.max - gen.p.xptar.min);
   double genvol = domega_e;
@@ -57,7 +61,7 @@ int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, doubl
   out->genvol = genvol;
   out->normfac = normfac;
   out->yield = fixed_value(acc->wtcontribute) * normfac;
-  out->central_sigcc_ave = acc->nsuccess > 0 ? fixed_value(acc->sum_sigcc) / (double)acc->nsuccess : 0.0;
+  out->central_sigcc_ave = nevent > 0 ? fixed_value(acc->sum_sigcc) / nevent : 0.0;      // simc.f:959
   if (acc->npasscuts > 1) {
     const double tmpnum = (double)acc->npasscuts;
     for (int k = 0; k < 8; ++k) {

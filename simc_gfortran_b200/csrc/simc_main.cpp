@@ -3,7 +3,7 @@
 // the reference's working directory (hms/forward_cosy.dat, benharsf_12.dat, deut.dat, ...), runs the loop on one
 // GPU, normalises (simc.f:366-432) and writes
 //   <out>.hist  run summary: counters, normalisation, resolutions, STOP counters, the 24 acceptance histograms
-//   <out>.bin   ntuple in the reference's unformatted layout (if --ntuple 1 or the deck's Nntu > 0 is passed)
+//   <out>.bin   ntuple in the reference's unformatted layout (with --ntuple 1; the deck's Nntu is not read)
 // The .hist text is this program's own format (key = value), not the reference's 600-line report.
 #include <cmath>
 #include <cstdio>
@@ -114,8 +114,10 @@ int main(int argc, char** argv) {
     }
     simc_accum before = acc;
     if ((rc = simc_b200_run(h, first, n, (uint64_t)seed, &acc))) return die(h, "simc_b200_run", rc);
-    if (want_success >= 0 && acc.nsuccess > want_success) {
-      // overshoot: bisect the try range so that exactly `want_success` successes are kept (try t is reproducible)
+    if (want_success >= 0 && acc.nsuccess >= want_success) {
+      // the reference stops at the try that yields the ngen-th success (simc.f:346-350): bisect the range for the
+      // smallest number of tries with that many successes (try t is reproducible), so that no failed try behind
+      // the last success is counted in ntried, the geni histograms or the STOP counters
       long long lo = 0, hi = n;
       while (hi - lo > 1) {
         const long long mid = (lo + hi) / 2;
@@ -138,7 +140,7 @@ int main(int argc, char** argv) {
   }
   if (nt) simc_b200_ntuple_close(nt);
   simc_results res;
-  simc_b200_normalise(&cfg, &acc, charge, &res);
+  simc_b200_normalise(&cfg, &acc, ngen, charge, &res);
 
   FILE* f = std::fopen((out + ".hist").c_str(), "w");
   if (!f) { std::fprintf(stderr, "simc_b200: cannot write %s.hist\n", out.c_str()); return 1; }

@@ -12,11 +12,12 @@ import os
 import numpy as np
 
 ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
+WEIGHT_NIN, WEIGHT_NOUT = 44, 15
 TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
 EVENT_NREC = 56
 NTUPLE_MAXCOL = 56
 NHIST, H_PER_SET, NSTOP = 50, 8, 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -140,7 +141,7 @@ class Accum(C.Structure):
                 ("hist_n", ((C.c_int64 * NHIST) * H_PER_SET) * 3),
                 ("contrib", Range * 32), ("slop", Range * 8),
                 ("stop", (C.c_int64 * NSTOP) * 2),
-                ("transp_calls", (C.c_int64 * 48) * 2), ("unsupported", C.c_int64)]
+                ("transp_calls", (C.c_int64 * 48) * 2), ("unsupported", C.c_int64), ("nonfinite", C.c_int64)]
 
 
 _lib = None
@@ -149,7 +150,7 @@ _lib = None
 class Results(C.Structure):
     """simc_results (include/simc_b200.h): normalisation and resolutions of a finished run."""
     _fields_ = [("luminosity", C.c_double), ("genvol", C.c_double), ("normfac", C.c_double), ("yield_", C.c_double),
-                ("central_sigcc_ave", C.c_double), ("aveerr", C.c_double * 8), ("resol", C.c_double * 8)]
+                ("central_sigcc_ave", C.c_double), ("nevent", C.c_int64), ("aveerr", C.c_double * 8), ("resol", C.c_double * 8)]
 
 
 def load_library():
@@ -177,6 +178,7 @@ def load_library():
     L.simc_b200_destroy.restype = None
     L.simc_b200_set_mode.argtypes = [C.c_void_p, C.c_int]
     L.simc_b200_set_compiled_maps.argtypes = [C.c_void_p, C.c_int]
+    L.simc_b200_weight_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_precompile_optics.argtypes = ([C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p,
                                                C.c_char_p, C.c_void_p, C.c_char_p, C.c_int])
     L.simc_b200_load_optics.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
@@ -207,7 +209,7 @@ def load_library():
     L.simc_b200_set_fdss_table.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_sf_em_widths.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-    L.simc_b200_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.simc_b200_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     L.simc_b200_ntuple_tags.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.simc_b200_ntuple_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.simc_b200_ntuple_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -250,11 +252,13 @@ def config_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir
     return cfg, ngen.value, charge.value
 
 
-def normalise(cfg: RunConfig, acc, charge_mC: float) -> Results:
-    """simc.f:94-101, 366-432: luminosity, generation volume, normfac, normalised yield, resolutions.  Host only."""
+def normalise(cfg: RunConfig, acc, ngen: int, charge_mC: float) -> Results:
+    """simc.f:94-101, 366-432: luminosity, generation volume, normfac, normalised yield, resolutions.  Host only.
+    ngen: the deck's ngen -- negative: that many tries, every try counts as an event (nevent = ntried); positive:
+    until that many successes (nevent = successes), simc.f:346-350."""
     L = load_library()
     r = Results()
-    rc = L.simc_b200_normalise(C.byref(cfg), C.byref(acc), float(charge_mC), C.byref(r))
+    rc = L.simc_b200_normalise(C.byref(cfg), C.byref(acc), int(ngen), float(charge_mC), C.byref(r))
     if rc:
         raise SimcError(rc, "simc_b200_normalise")
     return r
@@ -366,6 +370,16 @@ class Simc:
         assert mode in ("strict", "fast")
         self.mode = mode
         self._check(self.L.simc_b200_set_mode(self.h, 1 if mode == "strict" else 0))
+
+    def weight_batch(self, inp: np.ndarray) -> np.ndarray:
+        """complete_recon_ev + complete_main + pass_cuts on dumped vectors: inp [WEIGHT_NIN, n] -> [WEIGHT_NOUT, n]
+        (column order: include/simc_b200.h)."""
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        assert inp.ndim == 2 and inp.shape[0] == WEIGHT_NIN
+        n = inp.shape[1]
+        out = np.zeros((WEIGHT_NOUT, n))
+        self._check(self.L.simc_b200_weight_batch(self.h, n, _ptr(inp), _ptr(out)))
+        return out
 
     def set_compiled_maps(self, on: bool):
         """Generated straight-line kernels for the RNG-free stretches of the arm programs (default on); off = the

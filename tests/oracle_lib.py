@@ -373,3 +373,24 @@ def _oracle_generate_em_batch(self, seed, pm):
 
 Oracle.set_sf_em_widths = _oracle_set_sf_em_widths
 Oracle.generate_em_batch = _oracle_generate_em_batch
+
+
+# ---- end of the loop body on dumped vectors (twin of simc_b200_weight_batch) --------------------------
+def _oracle_weight_inputs(self, cfg, first, n, seed):
+    """What complete_recon_ev / complete_main read for tries [first, first+n) once montecarlo returned:
+    (inp [44, n], valid [n])."""
+    inp = np.zeros((44, n))
+    valid = np.zeros(n, dtype=np.int32)
+    self._check(self.L.oracle_weight_inputs(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(inp), _p(valid)))
+    return inp, valid.astype(bool)
+
+
+def _oracle_weight_batch(self, cfg, inp):
+    inp = np.ascontiguousarray(inp, np.float64)
+    out = np.zeros((15, inp.shape[1]))
+    self._check(self.L.oracle_weight_batch(C.byref(cfg), C.c_int64(inp.shape[1]), _p(inp), _p(out)))
+    return out
+
+
+Oracle.weight_inputs = _oracle_weight_inputs
+Oracle.weight_batch = _oracle_weight_batch

@@ -59,7 +59,7 @@ def test_fixed_number_of_tries(workdir):
         rows, _ = sim.ntuple_batch(0, 60000, 5)
     finally:
         sim.close()
-    res = normalise(cfg, acc, charge)
+    res = normalise(cfg, acc, ngen, charge)
     assert hist["Ntried"] == 60000 and hist["Ncontribute"] == acc.ncontribute and hist["Npasscuts"] == acc.npasscuts
     assert abs(hist["normalised_yield"] / res.yield_ - 1) < 1e-8 and abs(hist["normfac"] / res.normfac - 1) < 1e-8
     assert abs(hist["resol.e.delta"] - res.resol[0]) < 1e-6 * abs(res.resol[0])

@@ -33,15 +33,23 @@ def test_normalisation_hydrogen_elastic():
     for k in range(8):
         acc.sumerr[k] = fixed(150000 * 0.01 * (k + 1))
         acc.sumerr2[k] = fixed(150000 * ((0.01 * (k + 1)) ** 2 + 0.04))
-    r = normalise(cfg, acc, charge)
+    assert ngen < 0                      # every shipped deck asks for |ngen| tries
+    r = normalise(cfg, acc, ngen, charge)
     # simc.f:94-101: EXPER%charge / (mass_amu / 3.75914e6 / abundancy * cos(angle) / (thick [mg/cm2]))
     lumi = charge / (cfg.targ.mass_amu / 3.75914e6 / (cfg.targ.abundancy / 100.) / (cfg.targ.thick * 1000.))
     assert abs(r.luminosity / lumi - 1) < 1e-14
     genvol = (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min) * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min)     # 2-fold
     assert abs(r.genvol / genvol - 1) < 1e-14
-    assert abs(r.normfac / (lumi / 1000000 * 200000 * genvol) - 1) < 1e-14
+    # simc.f:346-350,368: ngen < 0 -> nevent counts every try, normfac = luminosity/ntried*nevent*genvol = luminosity*genvol
+    assert r.nevent == 1000000
+    assert abs(r.normfac / (lumi * genvol) - 1) < 1e-14
     assert abs(r.yield_ / (3.5 * r.normfac) - 1) < 1e-11
-    assert abs(r.central_sigcc_ave - 0.25) < 1e-11
+    assert abs(r.central_sigcc_ave - 200000 * 0.25 / 1000000) < 1e-11              # simc.f:959: sum_sigcc/nevent
+    # ngen > 0: the loop runs until ngen successes, nevent = successes
+    r2 = normalise(cfg, acc, 200000, charge)
+    assert r2.nevent == 200000
+    assert abs(r2.normfac / (lumi / 1000000 * 200000 * genvol) - 1) < 1e-14
+    assert abs(r2.central_sigcc_ave - 0.25) < 1e-11
     for k in range(8):
         assert abs(r.aveerr[k] - 0.01 * (k + 1)) < 1e-10 and abs(r.resol[k] - 0.2) < 1e-9
 
@@ -57,7 +65,7 @@ def test_generation_volume_by_reaction(name, fold):
         (g.p.xptar.max - g.p.xptar.min) * (g.e.E.max - g.e.E.min)
     if fold == 6:
         v *= g.p.E.max - g.p.E.min            # simc.f:392-394: doing_heavy .or. doing_semi
-    assert abs(normalise(cfg, acc, charge).genvol / v - 1) < 1e-14
+    assert abs(normalise(cfg, acc, -10, charge).genvol / v - 1) < 1e-14
 
 
 def test_ntuple_tags_follow_ntupleinit():
