@@ -248,6 +248,14 @@ int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_cl
                                 const int8_t* rec_expon, int strict_mode, const char* cache_dir, const char* dump_source_path,
                                 int64_t* info4, char* msg, int msg_len);
 
+/* Device-free: the library's COSY file readers (the semantics of transp_init, shared/transp.f:294-474, and of the
+ * first call of mc_*_recon, hms/mc_hms_recon.f:70-102) on one forward / reconstruction pair, as the arrays
+ * simc_b200_set_optics takes; fwd_class_start needs 42 entries.  n_out[3] = classes, forward terms, recon terms. */
+int simc_b200_read_optics_files(const char* forward_path, const char* recon_path, int32_t max_fwd_terms, int32_t max_rec_terms,
+                                int32_t* fwd_class_start, double* fwd_coeff, int8_t* fwd_expon, double* fwd_length_cm,
+                                int32_t* fwd_adrift, double* fwd_driftdist_cm, double* rec_coeff, int8_t* rec_expon,
+                                int32_t* n_out, char* msg, int msg_len);
+
 /* info[0..6] = n_classes, forward terms, non-zero forward coefficients, recon terms,
  * compiled groups, packed coefficients, ops in the arm program */
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8);

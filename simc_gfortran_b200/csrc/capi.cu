@@ -625,6 +625,45 @@ int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_cl
   }
 }
 
+// Device-free: the product's COSY readers (transp_init / mc_*_recon first-call semantics, optics_host.cpp) on a pair
+// of files, returned as the arrays simc_b200_set_optics takes.  Capacities in terms; counts come back in n_out[3] =
+// {classes, forward terms, recon terms}.
+int simc_b200_read_optics_files(const char* forward_path, const char* recon_path, int32_t max_fwd_terms, int32_t max_rec_terms,
+                                int32_t* fwd_class_start, double* fwd_coeff, int8_t* fwd_expon, double* fwd_length_cm,
+                                int32_t* fwd_adrift, double* fwd_driftdist_cm, double* rec_coeff, int8_t* rec_expon,
+                                int32_t* n_out, char* msg, int msg_len) {
+  auto say = [&](const std::string& m) { if (msg && msg_len > 0) std::snprintf(msg, (size_t)msg_len, "%s", m.c_str()); };
+  if (!forward_path || !recon_path || !fwd_class_start || !fwd_coeff || !fwd_expon || !rec_coeff || !rec_expon || !n_out) {
+    say("NULL argument");
+    return SIMC_ERR_ARG;
+  }
+  try {
+    const ForwardMaps f = read_forward_maps(forward_path);
+    const CosyTerms r = read_recon_map(recon_path);
+    int32_t pos = 0;
+    for (size_t k = 0; k < f.cls.size(); ++k) {
+      fwd_class_start[k] = pos;
+      const int n = f.cls[k].n();
+      if (pos + n > max_fwd_terms) { say("forward capacity too small"); return SIMC_ERR_ARG; }
+      std::memcpy(fwd_coeff + 5 * (size_t)pos, f.cls[k].coef.data(), sizeof(double) * 5 * (size_t)n);
+      std::memcpy(fwd_expon + 5 * (size_t)pos, f.cls[k].expo.data(), 5 * (size_t)n);
+      if (fwd_length_cm) fwd_length_cm[k] = f.length_cm[k];
+      if (fwd_adrift) fwd_adrift[k] = f.adrift[k];
+      if (fwd_driftdist_cm) fwd_driftdist_cm[k] = f.driftdist_cm[k];
+      pos += n;
+    }
+    fwd_class_start[f.cls.size()] = pos;
+    if (r.n() > max_rec_terms) { say("recon capacity too small"); return SIMC_ERR_ARG; }
+    std::memcpy(rec_coeff, r.coef.data(), sizeof(double) * 4 * (size_t)r.n());
+    std::memcpy(rec_expon, r.expo.data(), 5 * (size_t)r.n());
+    n_out[0] = (int32_t)f.cls.size(); n_out[1] = pos; n_out[2] = r.n();
+    return SIMC_OK;
+  } catch (const std::exception& e) {
+    say(e.what());
+    return SIMC_ERR_IO;
+  }
+}
+
 int simc_b200_optics_info(simc_handle* h, int arm_id, int64_t* info8) {
   if (!h || !info8) return SIMC_ERR_ARG;
   auto it = h->arms.find(arm_id);
