@@ -22,6 +22,7 @@ static std::string g_err;
 extern "C" {
 
 const char* oracle_last_error() { return g_err.c_str(); }
+void oracle_set_error(const char* m) { g_err = m ? m : ""; }
 
 int oracle_load_optics(int arm, const char* fwd_path, const char* rec_path) {
   try {
