@@ -2,6 +2,40 @@
 // every block cites the reference lines it follows.
 #include "arms.hpp"
 
+
+// the reference's build flags (Makefile:63, -fdefault-real-8 without -fdefault-double-8) turn every
+// `...d0` literal into a REAL(16) constant; hrsl/mc_hrsl.f:248-466 and hrsl/mc_hrsl_hut.f:293,356 (same in hrsr)
+// pass such literals by reference to REAL*8 dummies, which then read the low 8 bytes of the 16-byte value:
+// 62.75333333d0 -> -1.3e-41, 121.77333333d0 -> -3.1e+232, 45.0d0 -> 0.0, ...  `as_written` (default, what the
+// product implements: the intended lengths and the 45 degree chamber tilt) or `as_built` (that reinterpretation,
+// reproduced from a libquadmath probe) is chosen with oracle_set_hrs_literals(); tests/test_oracle_hrs_literals.py shows
+// what changes (path length, hence the kaon survival probability; the un-rotated VDC frame).
+#include <cstdint>
+#include <cstring>
+static bool g_hrs_as_built = false;
+extern "C" void oracle_set_hrs_literals(int as_built) { g_hrs_as_built = as_built != 0; }
+static double hrs_lit(double as_written, const char* decimal) {
+  if (!g_hrs_as_built) return as_written;
+  // low 8 bytes of the binary128 value of each literal, printed by tools/hrs_literal_probe.cpp (libquadmath)
+  static const struct { const char* lit; uint64_t lo; } kTable[] = {
+      {"62.75333333", 0xb7729d815ab37fcaULL},    // -1.3355790489890208e-41
+      {"31.37666667", 0xa595a644f8ad7b4eULL},    // -1.2493079844832989e-127
+      {"121.77333333", 0xf03430085b6e3ac6ULL},   // -3.1341656965427691e+232
+      {"60.88666667", 0x6745b46a2a6b3888ULL},    //  3.0220523071482735e+189
+      {"659.73445725", 0xb139c94f69ca9ef5ULL},   // -1.4594567076032913e-71
+      {"121.7866667", 0xb27100f41bc62f24ULL},    // -1.0091251298040999e-65
+      {"60.89333333", 0xd62aef6cdfd2381cULL},    // -1.235519403111592e+107
+      {"45.0", 0x0000000000000000ULL},           //  0
+  };
+  for (const auto& e : kTable)
+    if (std::strcmp(e.lit, decimal) == 0) {
+      double d;
+      std::memcpy(&d, &e.lo, sizeof(d));
+      return d;
+    }
+  return as_written;
+}
+
 namespace simc_oracle {
 
 // =====================================================================================
@@ -1194,7 +1228,7 @@ bool hut(Track& t, ArmCall& a, double& m2, double& p, bool& dflag, double zinit)
     if (ms) musc(r, m2, p, radw, t.dydzs, t.dxdzs);
     // the VDC frame is tested in the chamber plane, tilted 45 degrees
     xt = t.xs; yt = t.ys;
-    rotate_haxis(t, 45.0, xt, yt);
+    rotate_haxis(t, hrs_lit(45.0, "45.0"), xt, yt);          // 45.0d0 in the reference (mc_hrsl_hut.f:293,356)
     if (jchamber == 1) {
       if (xt > (hdc_1_bot - hdc_1x_offset) || xt < (hdc_1_top - hdc_1x_offset) ||
           yt > (hdc_1_left - hdc_1y_offset) || yt < (hdc_1_right - hdc_1y_offset)) {
@@ -1332,9 +1366,9 @@ void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right) {
   zdrift = o.fwd.cls[0].driftdist - ztmp;
   project(t, zdrift, dec, dflag, m2, p, a.pathlen);
   if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_IN);
-  transp(t, o.fwd, 2, dec, dflag, m2, p, 62.75333333, a.pathlen);
+  transp(t, o.fwd, 2, dec, dflag, m2, p, hrs_lit(62.75333333, "62.75333333"), a.pathlen);
   if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_MID);
-  transp(t, o.fwd, 3, dec, dflag, m2, p, 31.37666667, a.pathlen);
+  transp(t, o.fwd, 3, dec, dflag, m2, p, hrs_lit(31.37666667, "31.37666667"), a.pathlen);
   if (r2() > r_Q1 * r_Q1) return stop(hrs_stop::Q1_OUT);
   zdrift = 300.464 - 253.16;
   ztmp = zdrift;
@@ -1348,9 +1382,9 @@ void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right) {
   zdrift = o.fwd.cls[3].driftdist - ztmp;
   project(t, zdrift, dec, dflag, m2, p, a.pathlen);
   if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_IN);
-  transp(t, o.fwd, 5, dec, dflag, m2, p, 121.77333333, a.pathlen);
+  transp(t, o.fwd, 5, dec, dflag, m2, p, hrs_lit(121.77333333, "121.77333333"), a.pathlen);
   if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_MID);
-  transp(t, o.fwd, 6, dec, dflag, m2, p, 60.88666667, a.pathlen);
+  transp(t, o.fwd, 6, dec, dflag, m2, p, hrs_lit(60.88666667, "60.88666667"), a.pathlen);
   if (r2() > r_Q2 * r_Q2) return stop(hrs_stop::Q2_OUT);
   zdrift = 609.664 - 553.020;
   ztmp = zdrift;
@@ -1371,7 +1405,7 @@ void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right) {
   rotate_haxis(t, -30.0, xt, yt);
   if (std::fabs(xt - 2.500) > 52.5) return stop(hrs_stop::D1_IN);
   if ((std::fabs(yt) + 0.01861 * xt) > 12.5) return stop(hrs_stop::D1_IN);
-  transp(t, o.fwd, 8, dec, dflag, m2, p, 659.73445725, a.pathlen);
+  transp(t, o.fwd, 8, dec, dflag, m2, p, hrs_lit(659.73445725, "659.73445725"), a.pathlen);
   xt = t.xs; yt = t.ys;
   rotate_haxis(t, 30.0, xt, yt);
   if (std::fabs(xt - 2.500) > 52.5) return stop(hrs_stop::D1_OUT);
@@ -1389,9 +1423,9 @@ void mc_hrs(Track& t, const ArmOptics& o, ArmCall& a, bool right) {
   zdrift = o.fwd.cls[8].driftdist - ztmp;
   project(t, zdrift, dec, dflag, m2, p, a.pathlen);
   if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_IN);
-  transp(t, o.fwd, 10, dec, dflag, m2, p, 121.7866667, a.pathlen);
+  transp(t, o.fwd, 10, dec, dflag, m2, p, hrs_lit(121.7866667, "121.7866667"), a.pathlen);
   if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_MID);
-  transp(t, o.fwd, 11, dec, dflag, m2, p, 60.89333333, a.pathlen);
+  transp(t, o.fwd, 11, dec, dflag, m2, p, hrs_lit(60.89333333, "60.89333333"), a.pathlen);
   if (r2() > r_Q3 * r_Q3) return stop(hrs_stop::Q3_OUT);
   zdrift = 2080.38746 - 1997.76446;
   ztmp = zdrift;
