@@ -167,7 +167,7 @@ def main():
     import torch
     import torch.distributed as dist
     from simc_gfortran_b200 import Accum, Simc, config_from_deck, load_optics_fixture
-    from simc_gfortran_b200.multi import allreduce_accum
+    from simc_gfortran_b200.multi import allreduce_device
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,23 +231,33 @@ def main():
     # ---- end-to-end: the public call with host accumulators (launch parameters in, accumulators out)
     barrier()
     t0 = time.perf_counter()
+    # every step ends like a run ends: ONE collective over NVLink (all-gather of the device accumulator blocks on the
+    # handle's stream + the library's fold kernel, multi.py), then the total comes back to the host of every rank
     acc_e2e = sim.accum_clear()
+    ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    allreduce_ms = 0.0
     for k in range(args.steps):
-        sim.run(first_try(100 + k), n, seed, acc_e2e)
+        if world == 1:
+            sim.run(first_try(100 + k), n, seed, acc_e2e)
+        else:
+            sim.run_async(first_try(100 + k), n, seed)
+            ar0.record(ext)
+            allreduce_device(sim)
+            ar1.record(ext)
+            sim.fetch(acc_e2e)            # every rank adds the all-rank total of this step
+            allreduce_ms += ar0.elapsed_time(ar1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join()
-    # ---- one all-reduce of the integer accumulators (NCCL) ; max over ranks of the times
+    # ---- the device-timed steps end the same way (outside their timed region: `value` is the loop alone)
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        t_ar0 = time.perf_counter()
-        acc = allreduce_accum(acc, torch.device("cuda", local))
-        torch.cuda.synchronize()
-        allreduce_ms = (time.perf_counter() - t_ar0) * 1e3
-    else:
-        allreduce_ms = 0.0
+        # the accumulators of the device-timed steps were fetched per rank above: fold them on the host
+        from simc_gfortran_b200.multi import allreduce_accum
+        acc = allreduce_accum(acc)
+        assert acc_e2e.ntried == n * args.steps * world, (acc_e2e.ntried, n, args.steps, world)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
@@ -299,7 +309,9 @@ def main():
                          "stage_ms": dict(zip(names, stage_ms)), "stage_launches": dict(zip(names, stage_launches)),
                          "hbm_peak_gbs": hbm_peak},
             "clocks": sampler.summary(),
-            "allreduce_ms": allreduce_ms,
+            "allreduce_ms_per_step": allreduce_ms / args.steps,
+            "collective": "inside the e2e region, once per step: all_gather_into_tensor (NCCL) of the device accumulator "
+                          "blocks + k_reduce_gathered, on the handle's stream" if world > 1 else "none (one GPU)",
             "yield_per_mC": acc.wtcontribute.value() / tries_total *
                             (1.0 / (cfg.targ.mass_amu / 3.75914e6 / (cfg.targ.abundancy / 100.) * abs(np.cos(cfg.targ.angle)) / (cfg.targ.thick * 1000.))) *
                             (cfg.gen.e.yptar.max - cfg.gen.e.yptar.min) * (cfg.gen.e.xptar.max - cfg.gen.e.xptar.min) * charge,

@@ -353,6 +353,16 @@ int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_mulad
 int simc_b200_run_async(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed);
 int simc_b200_fetch(simc_handle* h, simc_accum* acc);          /* syncs, adds device accumulators into *acc, clears them */
 int simc_b200_device_accum(simc_handle* h, void** dev_ptr, int64_t* n_int64, void** dev_minmax, int64_t* n_minmax);
+/* Multi-GPU end of run: one process per GPU, each on its own range of the try index; the only exchange of
+ * the whole path is ONE all-gather of the device accumulator blocks (simc_b200_device_accum: n_int64 words per rank,
+ * e.g. ncclAllGather / torch.distributed.all_gather_into_tensor on the handle's stream), after which every rank folds
+ * the n_ranks blocks into its own with simc_b200_reduce_gathered (device pointer, rank after rank; a kernel on the
+ * handle's stream: counters add, 128-bit sums add with carry, range keys take min / max -- integers, so all ranks hold
+ * identical bits) and reads the total with simc_b200_fetch.  simc_b200_accum_merge is the host form of the same fold for
+ * accumulators already fetched (CPU ranks, separate runs of one deck): exact, SIMC_ERR_ARG if two non-empty
+ * fixed-point sums sit on different quanta (different w_ref). */
+int simc_b200_reduce_gathered(simc_handle* h, const void* d_gathered, int n_ranks);
+int simc_b200_accum_merge(simc_accum* into, const simc_accum* from);
 void* simc_b200_stream(simc_handle* h);                        /* cudaStream_t */
 int64_t simc_b200_launch_count(const simc_handle* h);          /* kernels launched so far */
 

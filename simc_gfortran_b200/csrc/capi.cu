@@ -1061,6 +1061,16 @@ int simc_b200_device_accum(simc_handle* h, void** dev_ptr, int64_t* n_int64, voi
   return SIMC_OK;
 }
 
+int simc_b200_reduce_gathered(simc_handle* h, const void* d_gathered, int n_ranks) {
+  if (!h || !d_gathered || n_ranks < 1) return SIMC_ERR_ARG;
+  if (!h->d_acc) return fail(h, SIMC_ERR_STATE, "simc_b200_reduce_gathered: no device accumulators (call simc_b200_device_accum first)");
+  CU(h, cudaSetDevice(h->device));
+  const cudaError_t e = simc_launch_reduce_gathered(d_gathered, n_ranks, h->d_acc, h->stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "k_reduce_gathered launch");
+  h->launches += 1;
+  return SIMC_OK;
+}
+
 int simc_b200_stage_times(simc_handle* h, int enable, double* ms4, int64_t* launches4) {
   if (!h) return SIMC_ERR_ARG;
   CU(h, cudaSetDevice(h->device));

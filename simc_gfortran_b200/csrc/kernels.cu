@@ -277,6 +277,52 @@ int n_state_fields() { return (int)F_NFIELDS; }
 #if SIMC_STRICT
 // byte offset of the min/max key block inside DevAccum (same in both variants)
 size_t simc_dev_accum_minmax_offset() { return offsetof(simc::strict::DevAccum, contrib_lo); }
+
+// Multi-GPU end of run: `gathered` holds one DevAccum per rank (what a single all-gather of the
+// accumulator blocks delivers); every rank folds them into its own block.  One thread per 64-bit word: counters and
+// count histograms add, 128-bit fixed-point sums add with the carry of their low word, range keys take min / max.
+// Integer arithmetic only, so every rank ends with the same bits whatever the order of the ranks.
+namespace {
+__global__ void k_reduce_gathered(const unsigned long long* __restrict__ gathered, int n_ranks, unsigned long long* __restrict__ out) {
+  typedef simc::strict::DevAccum A;
+  constexpr unsigned kWords = sizeof(A) / 8;
+  constexpr unsigned kPairLo = offsetof(A, wt) / 8, kPairHi = offsetof(A, hist_n) / 8;      // (lo, hi) pairs
+  constexpr unsigned kMinMax = offsetof(A, contrib_lo) / 8, kAfterMinMax = offsetof(A, stop) / 8;
+  const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= kWords) return;
+  if (w >= kPairLo && w < kPairHi) {
+    if ((w - kPairLo) & 1u) return;                        // the thread of the low word does the pair
+    unsigned long long lo = 0, hi = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+      const unsigned long long a = gathered[(size_t)r * kWords + w], b = gathered[(size_t)r * kWords + w + 1];
+      const unsigned long long s = lo + a;
+      hi += b + (s < lo ? 1ull : 0ull);
+      lo = s;
+    }
+    out[w] = lo; out[w + 1] = hi;
+    return;
+  }
+  if (w >= kMinMax && w < kAfterMinMax) {
+    const unsigned k = w - kMinMax;                        // contrib_lo[32] contrib_hi[32] slop_lo[8] slop_hi[8]
+    const bool is_min = k < 32 || (k >= 64 && k < 72);
+    long long v = (long long)gathered[w];
+    for (int r = 1; r < n_ranks; ++r) {
+      const long long x = (long long)gathered[(size_t)r * kWords + w];
+      v = is_min ? (x < v ? x : v) : (x > v ? x : v);
+    }
+    out[w] = (unsigned long long)v;
+    return;
+  }
+  unsigned long long s = 0;
+  for (int r = 0; r < n_ranks; ++r) s += gathered[(size_t)r * kWords + w];
+  out[w] = s;
+}
+}  // namespace
+cudaError_t simc_launch_reduce_gathered(const void* gathered, int n_ranks, void* dev_accum, cudaStream_t s) {
+  const unsigned words = sizeof(simc::strict::DevAccum) / 8;
+  k_reduce_gathered<<<(words + 255) / 256, 256, 0, s>>>((const unsigned long long*)gathered, n_ranks, (unsigned long long*)dev_accum);
+  return cudaGetLastError();
+}
 #endif
 namespace simc {
 namespace SIMC_VARIANT_NS {

@@ -103,6 +103,11 @@ void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qe
 int launches_of_stage(const LoopLaunch& a, int stage);
 }
 
+}  // namespace simc
+// variant-independent (compiled once, in the strict translation unit)
+cudaError_t simc_launch_reduce_gathered(const void* gathered, int n_ranks, void* dev_accum, cudaStream_t s);
+namespace simc {
+
 namespace strict { cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s); size_t arm_dev_bytes(); }
 namespace fast   { cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s); size_t arm_dev_bytes(); }
 

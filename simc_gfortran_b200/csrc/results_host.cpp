@@ -73,6 +73,43 @@ int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, int32
   return SIMC_OK;
 }
 
+int simc_b200_accum_merge(simc_accum* into, const simc_accum* from) {
+  if (!into || !from) return SIMC_ERR_ARG;
+  typedef __int128 i128;
+  auto addf = [](simc_fixed128& a, const simc_fixed128& b) -> bool {
+    if (a.qexp != b.qexp) {
+      const bool a0 = a.lo == 0 && a.hi == 0, b0 = b.lo == 0 && b.hi == 0;
+      if (b0) return true;                               // nothing to add
+      if (!a0) return false;                             // two non-empty sums on different quanta cannot be added exactly
+      a.qexp = b.qexp;
+    }
+    const i128 v = (((i128)a.hi << 64) | (i128)a.lo) + (((i128)b.hi << 64) | (i128)b.lo);
+    a.lo = (uint64_t)v; a.hi = (int64_t)(v >> 64);
+    return true;
+  };
+  bool ok = true;
+  into->ntried += from->ntried; into->nsuccess += from->nsuccess; into->ncontribute += from->ncontribute;
+  into->npasscuts += from->npasscuts; into->ncontribute_no_rad_proton += from->ncontribute_no_rad_proton;
+  into->unsupported += from->unsupported; into->nonfinite += from->nonfinite;
+  ok &= addf(into->wtcontribute, from->wtcontribute);
+  ok &= addf(into->sum_sigcc, from->sum_sigcc);
+  for (int i = 0; i < 8; ++i) { ok &= addf(into->sumerr[i], from->sumerr[i]); ok &= addf(into->sumerr2[i], from->sumerr2[i]); }
+  for (int k = 0; k < 6; ++k) for (int b = 0; b < SIMC_NHIST; ++b) ok &= addf(into->hist_w[k][b], from->hist_w[k][b]);
+  for (int s = 0; s < 3; ++s) for (int k = 0; k < SIMC_H_PER_SET; ++k) for (int b = 0; b < SIMC_NHIST; ++b)
+    into->hist_n[s][k][b] += from->hist_n[s][k][b];
+  for (int i = 0; i < 32; ++i) {
+    if (from->contrib[i].lo < into->contrib[i].lo) into->contrib[i].lo = from->contrib[i].lo;
+    if (from->contrib[i].hi > into->contrib[i].hi) into->contrib[i].hi = from->contrib[i].hi;
+  }
+  for (int i = 0; i < 8; ++i) {
+    if (from->slop[i].lo < into->slop[i].lo) into->slop[i].lo = from->slop[i].lo;
+    if (from->slop[i].hi > into->slop[i].hi) into->slop[i].hi = from->slop[i].hi;
+  }
+  for (int w = 0; w < 2; ++w) for (int i = 0; i < SIMC_NSTOP; ++i) into->stop[w][i] += from->stop[w][i];
+  for (int w = 0; w < 2; ++w) for (int i = 0; i < 48; ++i) into->transp_calls[w][i] += from->transp_calls[w][i];
+  return ok ? SIMC_OK : SIMC_ERR_ARG;
+}
+
 int simc_b200_ntuple_tags(const simc_run_config* cfg, char (*tags)[17], int max_tags) {
   if (!cfg || !tags) return SIMC_ERR_ARG;
   const char* const* tail;

@@ -223,6 +223,9 @@ def load_library():
     L.simc_b200_load_cteq5_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_semi_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.simc_b200_stage_times.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.simc_b200_device_accum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_reduce_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.simc_b200_accum_merge.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_fp64_peak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "simc_b200_event_field_name"):
         L.simc_b200_event_field_name.restype = C.c_char_p
@@ -250,6 +253,15 @@ def config_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir
     if rc != 0:
         raise SimcError(rc, err.value.decode())
     return cfg, ngen.value, charge.value
+
+
+def accum_merge(into: Accum, other: Accum) -> Accum:
+    """into += other, exactly (simc_b200_accum_merge): counters and 128-bit sums add, ranges widen.  Host only."""
+    L = load_library()
+    rc = L.simc_b200_accum_merge(C.byref(into), C.byref(other))
+    if rc != 0:
+        raise SimcError(rc, "simc_b200_accum_merge: fixed-point sums on different quanta (different w_ref)")
+    return into
 
 
 def normalise(cfg: RunConfig, acc, ngen: int, charge_mC: float) -> Results:
@@ -561,6 +573,17 @@ class Simc:
     def fetch(self, acc: Accum) -> Accum:
         self._check(self.L.simc_b200_fetch(self.h, C.byref(acc)))
         return acc
+
+    def device_accum(self):
+        """(device pointer, number of 64-bit words) of the handle's accumulator block (simc_b200_device_accum)."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._check(self.L.simc_b200_device_accum(self.h, C.byref(ptr), C.byref(n), None, None))
+        return int(ptr.value), int(n.value)
+
+    def reduce_gathered(self, d_gathered: int, n_ranks: int):
+        """Folds n_ranks accumulator blocks (device pointer, rank after rank) into the handle's own; asynchronous on
+        the handle's stream (simc_b200_reduce_gathered)."""
+        self._check(self.L.simc_b200_reduce_gathered(self.h, C.c_void_p(d_gathered), n_ranks))
 
     def event_batch(self, first_try: int, n: int, seed: int):
         rec = np.zeros((EVENT_NREC, n), dtype=np.float64)
