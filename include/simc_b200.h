@@ -316,6 +316,16 @@ int simc_b200_load_cteq5_file(simc_handle* h, const char* path);
 int simc_b200_set_maid_table(simc_handle* h, int ipi, const double* tbl);
 int simc_b200_load_maid_file(simc_handle* h, int ipi, const char* path);
 
+/* Saghai amplitude tables of peeK's ntuple column sigcm1 (eekeek / eekeeks, physics_kaon.f:241-489; COMMON arrays of
+ * simulate.inc:188-195 filled by dbase.f:644-679).  which = 0: K+ Lambda, tbl[12][10*11*19] = zrff1..6 then ziff1..6;
+ * which = 1: K+ Sigma0, tbl[12][20*10*19] = zsrff1..6 then zsiff1..6; each table in Fortran storage order (s index
+ * fastest, then Q2, then angle), REAL*4 like the reference's.  The model never enters the weight (physics_kaon.f:112);
+ * without the tables the column is zero.  load_saghai_files reads saghai_proton.dat and saghai_sigma0.dat from dir;
+ * read_saghai_file (device-free) parses one of them into tbl. */
+int simc_b200_set_saghai_table(simc_handle* h, int which, const float* tbl);
+int simc_b200_load_saghai_files(simc_handle* h, const char* dir);
+int simc_b200_read_saghai_file(const char* path, int which, float* tbl, char* msg, int msg_len);
+
 /* DSS fragmentation functions for semi-inclusive kaon production (doing_semi with doing_kaon): replaces the
  * first-call table read of fDSS (fdss/fdss.f:60-125; peepiX asks for kaons at NLO, fdss/KANLO.GRID).
  * parton[34][24][9]: the file's rows in reading order (x index slowest, then Q2 index), nine columns

@@ -17,6 +17,8 @@ static Cteq5Table g_pdf;
 static TheoryTable g_theory;
 static MaidTable g_maid;
 static FdssTable g_fdss;
+static SaghaiTable g_saghai;
+namespace simc_oracle { const SaghaiTable* saghai_tables() { return &g_saghai; } }
 static std::string g_err;
 
 extern "C" {
@@ -263,6 +265,26 @@ int oracle_fdss_batch(int ic, int64_t n, const double* x, const double* q2, doub
   return 0;
 }
 
+// Saghai amplitude tables (simc_b200_set_saghai_table): which = 0 K+ Lambda (12 x 10*11*19), 1 K+ Sigma0
+// (12 x 20*10*19); n = 0 clears
+int oracle_set_saghai_table(int which, int64_t n, const float* tbl) {
+  if (which < 0 || which > 1) return -1;
+  (which == 0 ? g_saghai.proton : g_saghai.sigma0).assign(tbl, tbl + n);
+  return 0;
+}
+// eekeek / eekeeks on arrays (ss in GeV^2, q22 in MeV^2, angles in rad)
+int oracle_saghai_batch(int lambda, double mrec_struck, int64_t n, const double* ss, const double* q22, const double* angl,
+                        const double* theta, const double* phi, const double* epsi, double* out) {
+  try {
+    for (int64_t i = 0; i < n; ++i)
+      out[i] = simc_oracle::eekeek(g_saghai, lambda != 0, mrec_struck, ss[i], q22[i], angl[i], theta[i], phi[i], epsi[i]);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// cern/fint.f on one point
+double oracle_fint(int narg, const float* arg, const int* nent, const float* ent, const float* table) {
+  return simc_oracle::fint(narg, arg, nent, ent, table);
+}
 // maidtbl slice of simc_b200_set_maid_table; n = 0 clears it
 int oracle_set_maid_table(int ipi, int64_t n, const double* tbl) {
   if (ipi != 3 && ipi != 4) { g_err = "ipi must be 3 or 4"; return -1; }

@@ -80,6 +80,17 @@ struct MaidTable {
   std::vector<double> tbl[2];           // [0]: pi+ n (ipi = 3), [1]: pi- p (ipi = 4); empty = not set
 };
 double sigmaid_sig0(const MaidTable& M, int ipi, double q2, double w, double e0, double costh, double phi);
+// Saghai amplitude tables of eekeek / eekeeks (simulate.inc:188-195, read by dbase.f:644-679), REAL*4: twelve tables
+// per channel in the order zrff1..6, ziff1..6 (real then imaginary parts), each in Fortran storage order
+// (iread fastest, then iq2, then iang).  proton: (10,11,19), sigma0: (20,10,19).  Empty = not set.
+struct SaghaiTable {
+  std::vector<float> proton, sigma0;
+};
+const SaghaiTable* saghai_tables();           // what oracle_set_saghai_table stored (capi.cpp); never null
+double fint(int narg, const float* arg, const int* nent, const float* ent, const float* table);       // cern/fint.f:10-76
+// physics_kaon.f:241-355 (lambda = true) / 357-489: sigma_eep of the Saghai model
+double eekeek(const SaghaiTable& T, bool lambda, double mrec_struck, double ss, double q22, double angl, double theta,
+              double phi, double epsi);
 // momentum distribution of dbase.f:563-587 (deut.dat ...): mprob normalised to mprob(nump) = 1
 struct PfermiTable {
   std::vector<double> pval, mprob;

@@ -5,8 +5,17 @@
 // terms are kept in the formulas so that the arithmetic is the reference's.
 //
 // The MAID-2007 branch of peepi for W < 2 GeV (sigmaid, physics_pion.f:131-154, 577-728) needs the caller's
-// table; without it such events are counted in simc_accum.unsupported.  Not restated: the Saghai model eekeek/eekeeks of peeK, which
-// only fills the ntuple column sigcm1 and never the weight (physics_kaon.f:100-115).
+// table; without it such events are counted in simc_accum.unsupported.  The Saghai model eekeek / eekeeks of peeK
+// (physics_kaon.f:241-489 with CERNLIB's fint, cern/fint.f) only fills the ntuple column sigcm1, never the weight
+// (physics_kaon.f:100-115); it is evaluated when its tables are set (oracle_set_saghai_table).
+//
+// Types of fint under the reference's flags (Makefile:63, -fdefault-real-8): ARG, ENT and TABLE are REAL*4 as
+// declared; WEIGHT, X, H, ETA and the function result are default REAL, i.e. 8 bytes.  The restatement follows the
+// source as written.  (As BUILT, eekeek declares `real*4 fint` while the function returns a default REAL: on x86-64
+// the caller then reads the low half of a double as a float.  Like the HRS REAL(16) literals of SURVEY A.5 this is
+// recorded, not reproduced: the column is a diagnostic and the as-written value is the meaningful one.)
+#include <algorithm>
+#include <complex>
 #include <stdexcept>
 
 #include "event.hpp"
@@ -277,6 +286,133 @@ double peepi(Sim& s, const Event& vertex, EventMain& main) {
 }
 
 // physics_kaon.f:1-171
+// cern/fint.f:10-76: multilinear interpolation (with linear extrapolation outside the grid) in up to 5 arguments.
+// Indices are kept 1-based like the source.
+double fint(int narg, const float* arg, const int* nent, const float* ent, const float* table) {
+  double result = 0.;
+  if (narg < 1 || narg > 5) throw std::runtime_error("fint: narg not within range");
+  int index[33];
+  double weight[33];
+  int lmax = 0, istep = 1, knots = 1;
+  index[1] = 1;
+  weight[1] = 1.;
+  for (int n = 1; n <= narg; ++n) {
+    const double x = arg[n - 1];
+    const int ndim = nent[n - 1];
+    int loca = lmax;
+    const int lmin = lmax + 1;
+    lmax = lmax + ndim;
+    int ishift = 0;
+    double eta = 0.;
+    bool on_node = false;                       // labels 20 / 21: the argument sits on a grid point
+    if (ndim > 2) {
+      int locb = lmax + 1, locc = 0;
+      bool hit = false;
+      do {                                      // label 11
+        locc = (loca + locb) / 2;
+        const double d = x - (double)ent[locc - 1];
+        if (d < 0.) locb = locc;
+        else if (d == 0.) { hit = true; break; }
+        else loca = locc;
+      } while (locb - loca > 1);
+      if (hit) {
+        ishift = (locc - lmin) * istep;
+        on_node = true;
+      } else {
+        loca = std::min(std::max(loca, lmin), lmax - 1);
+        ishift = (loca - lmin) * istep;
+        eta = (x - (double)ent[loca - 1]) / (double)(float)(ent[loca] - ent[loca - 1]);    // REAL*4 difference
+      }
+    } else {
+      if (ndim == 1) continue;                  // label 100 directly: istep is not advanced (as written)
+      const double h = x - (double)ent[lmin - 1];
+      if (h == 0.) { istep = istep * ndim; continue; }
+      ishift = istep;
+      if (x - (double)ent[lmin] == 0.) on_node = true;
+      else {
+        ishift = 0;
+        eta = h / (double)(float)(ent[lmin] - ent[lmin - 1]);
+      }
+    }
+    if (on_node) {
+      for (int k = 1; k <= knots; ++k) index[k] = index[k] + ishift;
+    } else {
+      for (int k = 1; k <= knots; ++k) {
+        index[k] = index[k] + ishift;
+        index[k + knots] = index[k] + istep;
+        weight[k + knots] = weight[k] * eta;
+        weight[k] = weight[k] - weight[k + knots];
+      }
+      knots = 2 * knots;
+    }
+    istep = istep * ndim;
+  }
+  for (int k = 1; k <= knots; ++k) result = result + weight[k] * (double)table[index[k] - 1];
+  return result;
+}
+
+// physics_kaon.f:241-355 (eekeek: K+ Lambda) and 357-489 (eekeeks: K+ Sigma0); the two differ in their grids only
+double eekeek(const SaghaiTable& T, bool lambda, double mrec_struck, double ss, double q22, double angl, double theta,
+              double phi, double epsi) {
+  using std::complex;
+  const std::vector<float>& tab = lambda ? T.proton : T.sigma0;
+  const double w = sqrt(ss) * 1000.;
+  double skc2 = powi(w * w - K::Mk2 - mrec_struck * mrec_struck, 2) - 4. * K::Mk2 * (mrec_struck * mrec_struck);
+  skc2 = std::max(skc2, 0.);
+  const double skc = sqrt(skc2) / 2. / w;
+  const double q0 = -(-q22 - w * w + K::Mp2) / 2. / K::Mp;
+  const double q0c = (-q22 + q0 * K::Mp) / w;
+  const double qr = sqrt(q22) / q0c;
+  const double aflx = skc / 2. / w / (w * w - K::Mp2) * (K::hbarc * K::hbarc) * 10000.;
+  const double aflxl = aflx * (qr * qr);
+  const double an = angl * 180. / K::pi;
+  const double x = cos(angl), sx = sin(angl);
+  float px[3], pa[50];
+  int pna[3];
+  px[0] = (float)ss;
+  px[1] = (float)(q22 / 1.e+06);
+  px[2] = (float)an;
+  size_t n_tab;
+  if (lambda) {
+    pna[0] = 10; pna[1] = 11; pna[2] = 19;
+    double ps = 2.6, qs = 0.0, as = 0.0;
+    for (int i = 1; i <= 10; ++i) { pa[i - 1] = (float)ps; ps = ps + 0.3; }
+    for (int i = 11; i <= 21; ++i) { pa[i - 1] = (float)qs; qs = qs + 0.2; }
+    for (int i = 22; i <= 40; ++i) { pa[i - 1] = (float)as; as = as + 10.; }
+    n_tab = 10 * 11 * 19;
+  } else {
+    pna[0] = 20; pna[1] = 10; pna[2] = 19;
+    static const double grid[30] = {2.851, 2.898, 2.945, 2.991, 3.038, 3.085, 3.132, 3.320, 3.507, 3.695,
+                                    3.883, 4.070, 4.258, 4.446, 4.633, 4.821, 5.009, 5.196, 5.384, 5.572,
+                                    0.0,   0.250, 0.376, 0.520, 0.750, 1.000, 1.250, 1.500, 1.750, 2.000};
+    for (int i = 0; i < 30; ++i) pa[i] = (float)grid[i];
+    double as = 0.0;
+    for (int i = 31; i <= 49; ++i) { pa[i - 1] = (float)as; as = as + 10.; }
+    n_tab = 20 * 10 * 19;
+  }
+  if (tab.size() != 12 * n_tab) throw std::runtime_error("eekeek: Saghai table not set");
+  double zf[2][6];
+  for (int k = 0; k < 6; ++k) {
+    zf[0][k] = fint(3, px, pna, pa, tab.data() + (size_t)k * n_tab);
+    zf[1][k] = fint(3, px, pna, pa, tab.data() + (size_t)(6 + k) * n_tab);
+  }
+  const complex<double> z1a(zf[0][0], zf[1][0]), z2a(zf[0][1], zf[1][1]), z3a(zf[0][2], zf[1][2]),
+      z4a(zf[0][3], zf[1][3]), z7a(zf[0][4], zf[1][4]), z8a(zf[0][5], zf[1][5]);
+  auto abs2 = [](const complex<double>& z) { const double a = std::abs(z); return a * a; };   // abs(z)**2
+  const double dsigt00 =
+      aflx * (abs2(z1a) + abs2(z2a) + 2. * std::real(std::conj(z1a) * z2a) * x +
+              0.5 * (sx * sx) * (abs2(z3a) + abs2(z4a) +
+                                 2. * std::real(std::conj(z1a) * z4a - std::conj(z2a) * z3a + std::conj(z3a) * z4a * x)));
+  const double dsigl00 = aflxl * epsi * (abs2(z7a) + abs2(z8a) + 2. * std::real(std::conj(z7a) * z8a) * x);
+  const double dsigp00 = aflx * epsi * powi(sin(theta), 2) * cos(2. * phi) *
+                         (0.5 * abs2(z3a) + 0.5 * abs2(z4a) +
+                          std::real(std::conj(z1a) * z4a - std::conj(z2a) * z3a + std::conj(z3a) * z4a * x));
+  const double dsigi00 = aflx * sqrt(2. * (qr * qr) * epsi * (1. + epsi)) * sin(theta) * cos(phi) *
+                         std::real(z7a * (std::conj(z3a) - std::conj(z2a) + std::conj(z4a) * x) +
+                                   z8a * (std::conj(z1a) + std::conj(z3a) * x + std::conj(z4a)));
+  return dsigt00 + dsigl00 + dsigp00 + dsigi00;
+}
+
 double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
@@ -295,6 +431,15 @@ double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob) 
   const double tfsin = sqrt(1. - tfcos * tfcos);
   const double sgev = powi(vertex.nu + F.efer, 2) - powi(vertex.q + F.pfer * tfcos, 2) - powi(F.pfer * tfsin, 2);
   main.wcm = sqrt(sgev);
+  // physics_kaon.f:100-108.  `phi` is a local of peeK that nothing assigns; with -fno-automatic it is static
+  // storage, i.e. zero ("WE ARE ALWAYS CALCULATING FOR PHI=0", physics_kaon.f:97-98).
+  {
+    const SaghaiTable* T = saghai_tables();
+    const bool lambda = targ.Mrec_struck < 1150.;
+    const double phi = 0.0;
+    if (!(lambda ? T->proton : T->sigma0).empty())
+      s.ntup.sigcm1 = eekeek(*T, lambda, targ.Mrec_struck, sgev / 1.e6, vertex.Q2, main.thetacm, main.theta_pq, phi, main.epsilon);
+  }
   s.ntup.sigcm2 = sig_factorized(vertex.Q2, main.wcm, main.t, C.phadcm, targ.Mrec_struck);
   const double sigma_eek = s.ntup.sigcm2;
   s.ntup.sigcm = sigma_eek;

@@ -72,6 +72,7 @@ struct simc_handle {
   double* d_pdf = nullptr; int pdf_nx = 0, pdf_nt = 0, pdf_nfmx = 0; double pdf_al = 0;   // CTEQ5: [xv | ql | upd]
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
   double* d_fdss = nullptr;                                // fDSS tables (physics_semi.cuh: FdssDev)
+  float* d_saghai[2] = {nullptr, nullptr};                 // Saghai amplitude tables: [0] K+ Lambda, [1] K+ Sigma0
   double* d_maid[2] = {nullptr, nullptr};                  // MAID-2007 slices: [0] pi+ n (ipi 3), [1] pi- p (ipi 4)
   double* d_theory = nullptr; int theory_nrho = 0; double theory_efermi = 0;   // physics_heavy.cuh: TheoryDev
   // optional per-stage timing
@@ -242,6 +243,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->d_theory) cudaFree(h->d_theory);
   for (double* p : h->d_maid) if (p) cudaFree(p);
+  for (float* p : h->d_saghai) if (p) cudaFree(p);
   if (h->d_fdss) cudaFree(h->d_fdss);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -352,6 +354,129 @@ int simc_b200_load_fdss_file(simc_handle* h, const char* path) {
   std::fclose(f);
   if (!ok) return fail(h, SIMC_ERR_IO, "fragmentation-function grid: short or malformed file");
   return simc_b200_set_fdss_table(h, parton.data());
+}
+
+// Saghai amplitude tables (simulate.inc:188-195): which = 0: zrff1..6, ziff1..6 of K+ Lambda, each (10,11,19);
+// which = 1: zsrff1..6, zsiff1..6 of K+ Sigma0, each (20,10,19); Fortran storage order.  The grids eekeek / eekeeks
+// build in their `pa` arrays (physics_kaon.f:285-304, 398-431: REAL*8 sums stored as REAL*4) go in front.
+int simc_b200_set_saghai_table(simc_handle* h, int which, const float* tbl) {
+  if (!h || !tbl || which < 0 || which > 1) return SIMC_ERR_ARG;
+  const int n1 = which ? 20 : 10, n2 = which ? 10 : 11, n3 = 19;
+  const size_t n_tab = (size_t)n1 * n2 * n3;
+  std::vector<float> buf(64 + 12 * n_tab, 0.f);
+  if (which == 0) {
+    double ps = 2.6, qs = 0.0, as = 0.0;
+    for (int i = 0; i < 10; ++i) { buf[i] = (float)ps; ps = ps + 0.3; }
+    for (int i = 10; i < 21; ++i) { buf[i] = (float)qs; qs = qs + 0.2; }
+    for (int i = 21; i < 40; ++i) { buf[i] = (float)as; as = as + 10.; }
+  } else {
+    static const double grid[30] = {2.851, 2.898, 2.945, 2.991, 3.038, 3.085, 3.132, 3.320, 3.507, 3.695,
+                                    3.883, 4.070, 4.258, 4.446, 4.633, 4.821, 5.009, 5.196, 5.384, 5.572,
+                                    0.0,   0.250, 0.376, 0.520, 0.750, 1.000, 1.250, 1.500, 1.750, 2.000};
+    for (int i = 0; i < 30; ++i) buf[i] = (float)grid[i];
+    double as = 0.0;
+    for (int i = 30; i < 49; ++i) { buf[i] = (float)as; as = as + 10.; }
+  }
+  std::memcpy(buf.data() + 64, tbl, sizeof(float) * 12 * n_tab);
+  CU(h, cudaSetDevice(h->device));
+  float*& d = h->d_saghai[which];
+  if (!d) CU(h, cudaMalloc(&d, sizeof(float) * buf.size()));
+  CU(h, cudaMemcpy(d, buf.data(), sizeof(float) * buf.size(), cudaMemcpyHostToDevice));
+  return SIMC_OK;
+}
+
+// saghai_proton.dat / saghai_sigma0.dat as dbase.f:644-679 reads them: per (iread, iq2) of the Lambda file one
+// header line, then per angle a line of five kinematic numbers and two lines '(6e12.4)' of (re, im) pairs; the
+// Sigma0 file repeats the header line for every angle.
+namespace {
+bool read_saghai_file(const std::string& path, int which, std::vector<float>& tbl, std::string& err) {
+  const int n1 = which ? 20 : 10, n2 = which ? 10 : 11, n3 = 19;
+  const size_t n_tab = (size_t)n1 * n2 * n3;
+  tbl.assign(12 * n_tab, 0.f);
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) { err = "cannot open " + path; return false; }
+  char line[256];
+  // read(3,*) dum1,dum2: list-directed, two numbers from the next line
+  auto next_list2 = [&]() -> bool {
+    if (!std::fgets(line, sizeof(line), f)) return false;
+    char* p = line;
+    for (int got = 0; got < 2; ++got) {
+      char* e = nullptr;
+      std::strtod(p, &e);
+      if (e == p) return false;
+      p = e;
+    }
+    return true;
+  };
+  // read(3,'(6e12.4)'): n fields of twelve columns from the next line; a short line is padded with blanks and a
+  // blank field is zero.  (saghai_sigma0.dat starts with a fragment of a line, so each of the reference's reads of
+  // that file sits one line early -- its amplitude reads pick up the kinematic line and the first amplitude line.
+  // The tables are what the reference's own read statements make of the file.)
+  auto next = [&](double* v, int n) -> bool {
+    if (!std::fgets(line, sizeof(line), f)) return false;
+    size_t len = std::strlen(line);
+    while (len > 0 && (line[len - 1] == '\n' || line[len - 1] == '\r')) line[--len] = 0;
+    for (int k = 0; k < n; ++k) {
+      char field[13];
+      for (int c = 0; c < 12; ++c) { const size_t at = (size_t)12 * k + c; field[c] = at < len ? line[at] : ' '; }
+      field[12] = 0;
+      char* e = nullptr;
+      const double x = std::strtod(field, &e);
+      if (e == field) {
+        for (const char* q = field; *q; ++q) if (*q != ' ') return false;
+        v[k] = 0.;
+      } else {
+        for (const char* q = e; *q; ++q) if (*q != ' ') return false;
+        v[k] = x;
+      }
+    }
+    return true;
+  };
+  bool ok = true;
+  double v[6];
+  for (int ir = 0; ir < n1 && ok; ++ir)
+    for (int iq = 0; iq < n2 && ok; ++iq) {
+      if (which == 0) ok = next_list2();
+      for (int ia = 0; ia < n3 && ok; ++ia) {
+        if (which == 1) ok = next_list2();
+        ok = ok && next(v, 5);
+        const size_t at = (size_t)ir + (size_t)n1 * ((size_t)iq + (size_t)n2 * ia);
+        // zrff1, ziff1, zrff2, ziff2, zrff3, ziff3 / zrff4 ... ziff6; REAL*4 variables
+        ok = ok && next(v, 6);
+        if (ok) for (int k = 0; k < 3; ++k) { tbl[(size_t)k * n_tab + at] = (float)v[2 * k]; tbl[(size_t)(6 + k) * n_tab + at] = (float)v[2 * k + 1]; }
+        ok = ok && next(v, 6);
+        if (ok) for (int k = 0; k < 3; ++k) { tbl[(size_t)(3 + k) * n_tab + at] = (float)v[2 * k]; tbl[(size_t)(9 + k) * n_tab + at] = (float)v[2 * k + 1]; }
+      }
+    }
+  std::fclose(f);
+  if (!ok) err = path + ": malformed Saghai table";
+  return ok;
+}
+}  // namespace
+
+int simc_b200_read_saghai_file(const char* path, int which, float* tbl, char* msg, int msg_len) {
+  if (!path || !tbl || which < 0 || which > 1) return SIMC_ERR_ARG;
+  std::vector<float> t;
+  std::string err;
+  if (!read_saghai_file(path, which, t, err)) {
+    if (msg && msg_len > 0) std::snprintf(msg, msg_len, "%s", err.c_str());
+    return SIMC_ERR_IO;
+  }
+  std::memcpy(tbl, t.data(), sizeof(float) * t.size());
+  return SIMC_OK;
+}
+
+int simc_b200_load_saghai_files(simc_handle* h, const char* dir) {
+  if (!h || !dir) return SIMC_ERR_ARG;
+  const char* names[2] = {"saghai_proton.dat", "saghai_sigma0.dat"};
+  for (int which = 0; which < 2; ++which) {
+    std::vector<float> t;
+    std::string err;
+    if (!read_saghai_file(std::string(dir) + "/" + names[which], which, t, err)) return fail(h, SIMC_ERR_IO, err);
+    const int rc = simc_b200_set_saghai_table(h, which, t.data());
+    if (rc) return rc;
+  }
+  return SIMC_OK;
 }
 
 // maidtbl of sigmaid (physics_pion.f:596-625): the slice sig0 reads
@@ -956,6 +1081,11 @@ int prepare_launch(simc_handle* h, LoopLaunch& a, uint64_t seed, int record, boo
   a.pdf_buf = h->d_pdf; a.pdf_nx = h->pdf_nx; a.pdf_nt = h->pdf_nt; a.pdf_nfmx = h->pdf_nfmx; a.pdf_al = h->pdf_al;
   a.pfm_buf = h->d_pfm; a.pfm_n = h->pfm_n;
   a.fdss_buf = h->d_fdss;
+  {
+    const int which = h->cfg.targ.Mrec_struck < 1150. ? 0 : 1;       // physics_kaon.f:100: Lambda below, Sigma0 above
+    a.saghai_buf = h->cfg.doing_kaon ? h->d_saghai[which] : nullptr;
+    a.saghai_n[0] = which ? 20 : 10; a.saghai_n[1] = which ? 10 : 11; a.saghai_n[2] = 19;
+  }
   a.maid_buf = h->d_maid[(h->cfg.which_pion == 1 || h->cfg.which_pion == 11 || h->cfg.which_pion == 3) ? 1 : 0];
   a.theory_buf = h->d_theory; a.theory_nrho = h->theory_nrho; a.theory_efermi = h->theory_efermi;
   {

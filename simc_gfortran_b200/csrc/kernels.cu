@@ -410,6 +410,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.sf.pm = a.sf_pm; A.sf.em = a.sf_em; A.sf.val = a.sf_val; A.sf.n_pm = a.sf_npm; A.sf.n_em = a.sf_nem; A.sf.dem = a.sf_dem;
   A.pdf = make_pdf(a);
   A.maid.tbl = a.maid_buf;
+  A.saghai = SaghaiDev{a.saghai_buf, a.saghai_n[0], a.saghai_n[1], a.saghai_n[2]};
   A.fdss.buf = a.fdss_buf;
   A.theory.buf = a.theory_buf; A.theory.nrho = a.theory_nrho; A.theory.e_fermi = a.theory_efermi;
   A.pfm.pval = a.pfm_buf; A.pfm.mprob = a.pfm_buf ? a.pfm_buf + a.pfm_n : nullptr; A.pfm.nump = a.pfm_n;

@@ -75,6 +75,8 @@ struct LoopLaunch {
   double pdf_al;
   const double* fdss_buf;     // fDSS tables (device), physics_semi.cuh: FdssDev; null unless set
   const double* maid_buf;     // MAID-2007 slice [25][46][6][4] of this run's charge state (device); null unless set
+  const float* saghai_buf;    // Saghai tables of this run's hyperon (device), physics_meson.cuh: SaghaiDev; null unless set
+  int saghai_n[3];
   const double* theory_buf;   // independent-particle spectral function (device), physics_heavy.cuh: TheoryDev
   int theory_nrho;
   double theory_efermi;

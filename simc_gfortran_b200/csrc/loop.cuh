@@ -85,6 +85,7 @@ struct LoopArgs {
   PfermiDev pfm;                   // nucleon momentum distribution (deuterium semi-inclusive production only)
   FdssDev fdss;                    // DSS fragmentation functions (semi-inclusive kaons only)
   MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
+  SaghaiDev saghai;                // Saghai amplitude tables of peeK's ntuple column sigcm1 (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
   StateBuf st;
   unsigned* lists;                 // [kLoopLists][cap] (kernels.h)
@@ -701,7 +702,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
     const long long i = i0 + threadIdx.x;
     const bool active = i < n_in;
     bool success = false, pass_cuts = false, no_rad_p = false, low_w = false;
-    double weight = 0, sigcc = 0, rEm = 0, rPm = 0;
+    double weight = 0, sigcc = 0, rEm = 0, rPm = 0, sigcm1 = 0;
     double rec_vals[6] = {0, 0, 0, 0, 0, 0}, gen_vals[7] = {0, 0, 0, 0, 0, 0, 0}, err[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double cv[30], sv[8];
 #pragma unroll
@@ -807,7 +808,9 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         } else if (cfg.doing_delta) {
           mw = peedelta(cfg, mv);                      // event.f:1511-1513; tgtweight stays 1
         } else {
-          mw = peeK(cfg, mv);
+          // the Saghai model only feeds ntuple column 54: evaluated where rows / records are produced
+          mw = peeK(cfg, mv, A.record_mode ? A.saghai : SaghaiDev{nullptr, 0, 0, 0}, S.ld(F_MTHPQ, slot));
+          sigcm1 = mw.sigcm1;
           tgtweight = (cfg.which_kaon == 2 || cfg.which_kaon == 12) ? cfg.targ.N : cfg.targ.Z;
           if (!cfg.doing_decay) survivalprob = kaon_survival(cfg, S.ld(F_FPP_PATH, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_DY, slot));
         }
@@ -925,7 +928,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           ntu[48] = sqrt(S.ld(F_MH2FINAL, slot));
           ntu[49] = mv_pfer[0] / 1000. * pdot;
           ntu[50] = v_Q2 / 1.e6; ntu[51] = S.ld(F_MW, slot) / 1.e3; ntu[52] = S.ld(F_MT, slot) / 1.e6; ntu[53] = S.ld(F_MPHIPQ, slot);
-          if (cfg.doing_kaon) { ntu[54] = 0.0; ntu[55] = S.ld(F_SIGCM, slot); }
+          if (cfg.doing_kaon) { ntu[54] = sigcm1; ntu[55] = S.ld(F_SIGCM, slot); }
         } else {
           const double sh = m::sin(reth / 2.);
           const double poftheta = SIMC_MP * cfg.Ebeam / (2 * cfg.Ebeam * (sh * sh) + SIMC_MP);

@@ -6,7 +6,9 @@
 //
 // The MAID-2007 branch of peepi below W = 2 GeV (sigmaid, physics_pion.f:131-154, 577-728) reads the caller's
 // table (simc_b200_set_maid_table); without it such events take the parametrisation alone and are counted in
-// simc_accum.unsupported.  Not built: the Saghai model of peeK (eekeek), which only feeds an ntuple column.
+// simc_accum.unsupported.  The Saghai model of peeK (eekeek / eekeeks, physics_kaon.f:241-489, with CERNLIB's fint)
+// feeds the ntuple column sigcm1 only; it is evaluated where rows are produced, when the caller has set its tables
+// (simc_b200_set_saghai_table).
 #pragma once
 #include "target.cuh"
 
@@ -237,6 +239,7 @@ SIMC_HD_CALL double sigmaid_sig0(const MaidDev M, double q2, double w, double e0
 
 struct MesonWeight {
   double sigcc, sigcm, thetacm, phicm, pcm, wcm, davejac, johnjac;
+  double sigcm1;              // peeK only: the Saghai model (ntup%sigcm1), 0 unless asked for
   bool low_w;                 // W < 2 GeV: the reference would blend in the MAID table here
 };
 
@@ -313,8 +316,111 @@ SIMC_HD_CALL MesonWeight peedelta(const simc_run_config& cfg, const MesonVertex&
   return w;
 }
 
+// Saghai amplitude tables on the device: buf = [50 grid values (the `pa` array of eekeek / eekeeks) | 14 pad |
+// 12 tables of n1*n2*n3 REAL*4 in Fortran storage order: zrff1..6 then ziff1..6].  Null unless set.
+struct SaghaiDev { const float* buf; int n1, n2, n3; };
+
+// One argument of CERNLIB's fint (cern/fint.f:24-53) on a grid of more than two points: the cell and the
+// interpolation fraction, or the node itself when the argument sits on one (no split of the knots then).
+// X, ETA are default REAL (8 bytes under the reference's -fdefault-real-8), ENT is REAL*4 and the grid spacing is a
+// REAL*4 difference.
+struct FintAxis { int cell; double eta; bool split; };
+SIMC_HD FintAxis fint_axis(const float* ent, int n, float arg) {
+  const double x = arg;
+  FintAxis a;
+  int lo = -1, hi = n;                    // bisection like the source: ent[lo] < x < ent[hi] (virtual ends)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) / 2;
+    const double d = x - (double)ent[mid];
+    if (d == 0.) { a.cell = mid; a.eta = 0.; a.split = false; return a; }
+    if (d < 0.) hi = mid; else lo = mid;
+  }
+  lo = lo < 0 ? 0 : (lo > n - 2 ? n - 2 : lo);
+  a.cell = lo;
+  a.eta = (x - (double)ent[lo]) / (double)(ent[lo + 1] - ent[lo]);
+  a.split = true;
+  return a;
+}
+
+// physics_kaon.f:241-355 (K+ Lambda) / 357-489 (K+ Sigma0): the two routines differ in their grids only, which the
+// host wrote in front of the tables.  All twelve fint calls share their arguments, so cell and weights are made once;
+// the knots are visited in fint's order (first argument fastest) with fint's weights w - w*eta and w*eta.
+SIMC_HD_CALL double saghai_sigma(const SaghaiDev S, double mrec_struck, double ss, double q22, double angl, double theta,
+                                 double phi, double epsi) {
+  const double pi = 3.141592653589793, Mk2 = 493.677 * 493.677, Mp = 938.27231, Mp2 = Mp * Mp, hbarc = 197.327053;
+  const double w = sqrt(ss) * 1000.;
+  double skc2 = mesondetail::msq(w * w - Mk2 - mrec_struck * mrec_struck) - 4. * Mk2 * (mrec_struck * mrec_struck);
+  skc2 = skc2 > 0. ? skc2 : 0.;
+  const double skc = sqrt(skc2) / 2. / w;
+  const double q0 = -(-q22 - w * w + Mp2) / 2. / Mp;
+  const double q0c = (-q22 + q0 * Mp) / w;
+  const double qr = sqrt(q22) / q0c;
+  const double aflx = skc / 2. / w / (w * w - Mp2) * (hbarc * hbarc) * 10000.;
+  const double aflxl = aflx * (qr * qr);
+  const double an = angl * 180. / pi;
+  const double x = m::cos(angl), sx = m::sin(angl);
+  const float* ent = S.buf;
+  const FintAxis a1 = fint_axis(ent, S.n1, (float)ss);
+  const FintAxis a2 = fint_axis(ent + S.n1, S.n2, (float)(q22 / 1.e+06));
+  const FintAxis a3 = fint_axis(ent + S.n1 + S.n2, S.n3, (float)an);
+  int idx[8];
+  double wt[8];
+  int knots = 1, istep = 1;
+  idx[0] = 0; wt[0] = 1.;
+  const FintAxis ax[3] = {a1, a2, a3};
+  const int nd[3] = {S.n1, S.n2, S.n3};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int shift = ax[d].cell * istep;
+    if (!ax[d].split) {
+      for (int k = 0; k < knots; ++k) idx[k] += shift;
+    } else {
+      for (int k = 0; k < knots; ++k) {
+        idx[k] += shift;
+        idx[k + knots] = idx[k] + istep;
+        wt[k + knots] = wt[k] * ax[d].eta;
+        wt[k] = wt[k] - wt[k + knots];
+      }
+      knots *= 2;
+    }
+    istep *= nd[d];
+  }
+  const size_t n_tab = (size_t)S.n1 * S.n2 * S.n3;
+  const float* tab = S.buf + 64;
+  double zr[6], zi[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double r = 0., i = 0.;
+    for (int j = 0; j < knots; ++j) {
+      r = r + wt[j] * (double)tab[(size_t)k * n_tab + idx[j]];
+      i = i + wt[j] * (double)tab[(size_t)(6 + k) * n_tab + idx[j]];
+    }
+    zr[k] = r; zi[k] = i;
+  }
+  // amplitudes z1, z2, z3, z4, z7, z8 = slots 0..5; abs(z)**2, real(conjg(a)*b) written out
+  auto abs2 = [](double re, double im) { const double a = hypot(re, im); return a * a; };
+  auto rcab = [](double ar, double ai, double br, double bi) { return ar * br + ai * bi; };          // real(conjg(a)*b)
+  const double a1_ = abs2(zr[0], zi[0]), a2_ = abs2(zr[1], zi[1]), a3_ = abs2(zr[2], zi[2]), a4_ = abs2(zr[3], zi[3]);
+  const double a7_ = abs2(zr[4], zi[4]), a8_ = abs2(zr[5], zi[5]);
+  // real(conjg(z1)*z4 - conjg(z2)*z3 + conjg(z3)*z4*x), left to right like the complex expression
+  const double mix = (rcab(zr[0], zi[0], zr[3], zi[3]) - rcab(zr[1], zi[1], zr[2], zi[2])) + rcab(zr[2], zi[2], zr[3], zi[3]) * x;
+  const double dsigt00 = aflx * (a1_ + a2_ + 2. * rcab(zr[0], zi[0], zr[1], zi[1]) * x + 0.5 * (sx * sx) * (a3_ + a4_ + 2. * mix));
+  const double dsigl00 = aflxl * epsi * (a7_ + a8_ + 2. * rcab(zr[4], zi[4], zr[5], zi[5]) * x);
+  const double sth = m::sin(theta);
+  const double dsigp00 = aflx * epsi * (sth * sth) * m::cos(2. * phi) * (0.5 * a3_ + 0.5 * a4_ + mix);
+  // real(z7*(conjg(z3) - conjg(z2) + conjg(z4)*x) + z8*(conjg(z1) + conjg(z3)*x + conjg(z4)))
+  const double br = (zr[2] - zr[1]) + zr[3] * x, bi = (-zi[2] + zi[1]) + (-zi[3]) * x;
+  const double cr = (zr[0] + zr[2] * x) + zr[3], ci = (-zi[0] + (-zi[2]) * x) + (-zi[3]);
+  const double inter = (zr[4] * br - zi[4] * bi) + (zr[5] * cr - zi[5] * ci);
+  const double dsigi00 = aflx * sqrt(2. * (qr * qr) * epsi * (1. + epsi)) * sth * m::cos(phi) * inter;
+  return dsigt00 + dsigl00 + dsigp00 + dsigi00;
+}
+
 // physics_kaon.f:1-171 (without the survival probability, which needs the focal-plane track)
-SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v) {
+// saghai.buf != null: also evaluate the Saghai model at main%theta_pq (physics_kaon.f:100-108; `phi` is an
+// unassigned static local there, i.e. zero: "WE ARE ALWAYS CALCULATING FOR PHI=0")
+SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v, const SaghaiDev saghai = SaghaiDev{nullptr, 0, 0, 0},
+                              double theta_pq = 0.) {
   const double pi = 3.141592653589793, alpha = 1. / 137.0359895;
   const double Mtar = cfg.targ.Mtar_struck, efer = v.efer, pfer = v.pfer, pferz = v.pferz;
   MesonCm C;
@@ -324,6 +430,8 @@ SIMC_HD_CALL MesonWeight peeK(const simc_run_config& cfg, const MesonVertex& v) 
   const double jac_old = C.jac_old / (2. * C.pcm * C.qstar);
   w.thetacm = C.thetacm; w.phicm = C.phicm; w.pcm = C.pcm; w.davejac = jacobian; w.johnjac = jac_old; w.wcm = C.wcm;
   w.low_w = false;
+  w.sigcm1 = 0.;
+  if (saghai.buf) w.sigcm1 = saghai_sigma(saghai, cfg.targ.Mrec_struck, C.sgev / 1.e6, v.Q2, C.thetacm, theta_pq, 0.0, v.epsilon);
   const double sigcm2 = sig_factorized(v.Q2, C.wcm, v.t, C.pcm, cfg.targ.Mrec_struck);
   w.sigcm = sigcm2;
   const double k_eq = (C.wcm * C.wcm - Mtar * Mtar) / 2. / Mtar;

@@ -94,6 +94,13 @@ int main(int argc, char** argv) {
     if (FILE* t = std::fopen(f.c_str(), "r")) { std::fclose(t); if ((rc = simc_b200_load_maid_file(h, piminus ? 4 : 3, f.c_str()))) return die(h, "simc_b200_load_maid_file", rc); }
   }
 
+  if (cfg.doing_kaon) {       // optional: the Saghai model only fills ntuple column 54 (zero without its tables)
+    if (FILE* t = std::fopen((data + "/saghai_proton.dat").c_str(), "r")) {
+      std::fclose(t);
+      if ((rc = simc_b200_load_saghai_files(h, data.c_str()))) return die(h, "simc_b200_load_saghai_files", rc);
+    }
+  }
+
   simc_accum acc;
   if ((rc = simc_b200_accum_clear(h, &acc))) return die(h, "simc_b200_accum_clear", rc);
   simc_ntuple_file* nt = nullptr;

@@ -206,6 +206,9 @@ def load_library():
     L.simc_b200_load_theory_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_maid_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.simc_b200_load_maid_file.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+    L.simc_b200_set_saghai_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.simc_b200_load_saghai_files.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_read_saghai_file.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_char_p, C.c_int]
     L.simc_b200_set_fdss_table.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_sf_em_widths.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -253,6 +256,19 @@ def config_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir
     if rc != 0:
         raise SimcError(rc, err.value.decode())
     return cfg, ngen.value, charge.value
+
+
+def read_saghai_file(path: str, which: int) -> np.ndarray:
+    """The library's reader of saghai_proton.dat (which = 0) / saghai_sigma0.dat (1), host only: float32
+    [12, 19, n_q2, n_s] (the Fortran arrays' memory order)."""
+    L = load_library()
+    n1, n2 = (10, 11) if which == 0 else (20, 10)
+    tbl = np.zeros((12, 19, n2, n1), dtype=np.float32)
+    msg = C.create_string_buffer(512)
+    rc = L.simc_b200_read_saghai_file(path.encode(), int(which), _ptr(tbl), msg, 512)
+    if rc != 0:
+        raise SimcError(rc, msg.value.decode())
+    return tbl
 
 
 def accum_merge(into: Accum, other: Accum) -> Accum:
@@ -451,6 +467,16 @@ class Simc:
         tbl = np.ascontiguousarray(tbl, dtype=np.float64)
         assert tbl.shape == (25, 46, 6, 4)
         self._check(self.L.simc_b200_set_maid_table(self.h, int(ipi), _ptr(tbl)))
+
+    def set_saghai_table(self, which: int, tbl):
+        """Saghai amplitude tables of peeK's ntuple column sigcm1: which = 0 K+ Lambda [12][19*11*10], 1 K+ Sigma0
+        [12][19*10*20], float32 in the Fortran arrays' memory order (simc_b200_set_saghai_table)."""
+        tbl = np.ascontiguousarray(tbl, dtype=np.float32)
+        assert tbl.size == 12 * 19 * (110 if which == 0 else 200)
+        self._check(self.L.simc_b200_set_saghai_table(self.h, int(which), _ptr(tbl)))
+
+    def load_saghai_files(self, directory: str):
+        self._check(self.L.simc_b200_load_saghai_files(self.h, directory.encode()))
 
     def load_maid_file(self, ipi: int, path: str):
         self._check(self.L.simc_b200_load_maid_file(self.h, int(ipi), path.encode()))

@@ -313,6 +313,42 @@ Oracle.set_maid_table = _oracle_set_maid_table
 Oracle.sigmaid_batch = _oracle_sigmaid_batch
 
 
+# ---- Saghai amplitude tables (ntuple column sigcm1 of kaon production) ---------------------------------
+def load_saghai_fixture(which):
+    """tests/golden/saghai.npz: which = 0 K+ Lambda [12, 19, 11, 10], 1 K+ Sigma0 [12, 19, 10, 20], float32, as
+    dbase.f:644-679 reads saghai_proton.dat / saghai_sigma0.dat (zrff1..6 then ziff1..6; memory order = the Fortran
+    arrays')."""
+    z = np.load(os.path.join(GOLDEN, "saghai.npz"))
+    return np.ascontiguousarray(z["proton" if which == 0 else "sigma0"], np.float32)
+
+
+def _oracle_set_saghai_table(self, which, tbl):
+    tbl = np.ascontiguousarray(tbl, np.float32).ravel() if tbl is not None else np.zeros(0, np.float32)
+    self._check(self.L.oracle_set_saghai_table(int(which), C.c_int64(len(tbl)), _p(tbl)))
+
+
+def _oracle_saghai_batch(self, lam, mrec_struck, ss, q22, angl, theta, phi, epsi):
+    arrs = [np.ascontiguousarray(a, np.float64) for a in (ss, q22, angl, theta, phi, epsi)]
+    out = np.zeros(len(arrs[0]))
+    self._check(self.L.oracle_saghai_batch(int(bool(lam)), C.c_double(mrec_struck), C.c_int64(len(out)),
+                                           *[_p(a) for a in arrs], _p(out)))
+    return out
+
+
+def _oracle_fint(self, arg, nent, ent, table):
+    arg = np.ascontiguousarray(arg, np.float32)
+    nent = np.ascontiguousarray(nent, np.int32)
+    ent = np.ascontiguousarray(ent, np.float32)
+    table = np.ascontiguousarray(table, np.float32)
+    self.L.oracle_fint.restype = C.c_double
+    return float(self.L.oracle_fint(len(arg), _p(arg), _p(nent), _p(ent), _p(table)))
+
+
+Oracle.set_saghai_table = _oracle_set_saghai_table
+Oracle.saghai_batch = _oracle_saghai_batch
+Oracle.fint = _oracle_fint
+
+
 # ---- DSS fragmentation functions (semi-inclusive kaons) ------------------------------------------------
 def load_fdss_fixture():
     """tests/golden/fdss_kanlo.npz: the rows of the reference's fdss/KANLO.GRID, [34, 24, 9]."""

@@ -148,6 +148,37 @@ def make_maid():
         print("maid", name, tbl.shape, tbl[..., 0].max())
 
 
+def make_saghai():
+    """saghai_proton.dat / saghai_sigma0.dat as dbase.f:644-679 reads them -> tests/golden/saghai.npz: proton
+    [12, 19, 11, 10] and sigma0 [12, 19, 10, 20] float32 (zrff1..6 then ziff1..6; C order of the Fortran arrays
+    (iread, iq2, iang), i.e. iread fastest).  '(6e12.4)' fields are cut by column like a Fortran formatted read."""
+    out = {}
+    for which, (name, n1, n2) in enumerate((("proton", 10, 11), ("sigma0", 20, 10))):
+        tbl = np.zeros((12, 19, n2, n1), dtype=np.float32)
+        with open(os.path.join(REF, f"saghai_{name}.dat")) as f:
+            for ir in range(n1):
+                for iq in range(n2):
+                    if which == 0:
+                        f.readline()
+                    for ia in range(19):
+                        if which == 1:
+                            f.readline()
+                        f.readline()
+                        for half in range(2):
+                            line = f.readline().rstrip("\n").ljust(72)
+                            # a blank field reads as zero (the Sigma0 file starts with a fragment of a line, so
+                            # every read of dbase.f:662-676 sits one line early: its "amplitude" lines are the
+                            # five-number kinematic line and the first amplitude line -- reproduced as read)
+                            v = [np.float32(float(line[12 * k:12 * k + 12].strip() or 0.0)) for k in range(6)]
+                            for k in range(3):
+                                tbl[3 * half + k, ia, iq, ir] = v[2 * k]
+                                tbl[6 + 3 * half + k, ia, iq, ir] = v[2 * k + 1]
+            # saghai_proton.dat goes on (14 values of s in the file, dbase.f reads the first 10)
+        out[name] = tbl
+        print("saghai", name, tbl.shape, float(np.abs(tbl).max()))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "saghai.npz"), **out)
+
+
 def make_fdss():
     """fdss/KANLO.GRID (fDSS with IH = 2, IO = 1: kaons at NLO, semi_physics.f:497-505) -> tests/golden/fdss_kanlo.npz"""
     rows = []
@@ -185,6 +216,7 @@ if __name__ == "__main__":
     make_he3()
     make_fdss()
     make_maid()
+    make_saghai()
     make_sf()
     make_semi()
     make_theory()
