@@ -411,10 +411,17 @@ const char* simc_b200_event_field_name(int k);
  * radc_init_ev + basicrad_init_ev (init.f:655-813), peaked_rad_weight (radc.f:523-646) and sigep
  * (physics_proton.f:1-22) on dumped per-event vertex vectors.  in[k*n+i], k = 0..15:
  * { Ein, e.E, e.theta, ue.x, ue.y, ue.z, p.E, p.P, up.x, up.y, up.z, teff(1), teff(2), Egamma, Emin, Emax };
- * out[k*n+i], k = 0..10: { bt(1), bt(2), lambda(1..3), g(4), hardcorfac, c(4), c_ext(0),
- * peaked_rad_weight(basicrad_weight = 1), sigep }. */
+ * out[k*n+i], k = 0..25: { bt(1), bt(2), lambda(1..3), g(4), hardcorfac, c(4), c_ext(0),
+ * peaked_rad_weight(basicrad_weight = 1), sigep,
+ * c(1), c(2), c(3), c(0), c_int(0), g_int                       (basicrad_init_ev, init.f:732-813),
+ * extrad_phi(1,Ein,e.E,Egamma), extrad_phi(2,...)               (radc.f:668-707, the handle's extrad_flag),
+ * schwinger's dsoft, dhard at Ecutoff = 450                     (radc.f:711-742),
+ * extrad_friedrich(Ein, Egamma, bt(1)/etatzai): dbrem, dbrem'   (radc.f:650-664),
+ * brem(Ein, e.E, 450, rad_proton_this_ev): bsoft, bhard, dbsoft (brem.f:6-214) }.
+ * Every radiative option of the handle's run constants is honoured (rad_flag, extrad_flag, intcor_mode,
+ * use_offshell_rad). */
 #define SIMC_RADC_NIN  16
-#define SIMC_RADC_NOUT 11
+#define SIMC_RADC_NOUT 26
 int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double* out_soa);
 
 /* Stage-level parity entry point for the end of the loop body: complete_recon_ev (event.f:1056-1359), complete_main

@@ -240,6 +240,8 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
       v.p.E = in[6 * n + i]; v.p.P = in[7 * n + i];
       v.up.x = in[8 * n + i]; v.up.y = in[9 * n + i]; v.up.z = in[10 * n + i];
       main.target.teff[0] = in[11 * n + i]; main.target.teff[1] = in[12 * n + i];
+      v.Q2 = 2 * v.Ein * v.e.E * (1. - v.ue.z);
+      v.nu = v.Ein - v.e.E;
       radc_init_ev(s, main, v);
       const double w = peaked_rad_weight_public(s, v, in[13 * n + i], in[14 * n + i], in[15 * n + i]);
       const RadEv& R = s.rad;
@@ -247,8 +249,23 @@ int oracle_radc_batch(const simc_run_config* cfg, int64_t n, const double* in, d
       out[2 * n + i] = R.lambda[0]; out[3 * n + i] = R.lambda[1]; out[4 * n + i] = R.lambda[2];
       out[5 * n + i] = R.g[4]; out[6 * n + i] = R.hardcorfac; out[7 * n + i] = R.c[4]; out[8 * n + i] = R.c_ext[0];
       out[9 * n + i] = w;
-      v.Q2 = 2 * v.Ein * v.e.E * (1. - v.ue.z);
       out[10 * n + i] = sigep(v);
+      // the constants of the (Egamma1, Egamma2, Egamma3) basis and the pieces of the other option branches
+      out[11 * n + i] = R.c[1]; out[12 * n + i] = R.c[2]; out[13 * n + i] = R.c[3]; out[14 * n + i] = R.c[0];
+      out[15 * n + i] = R.c_int[0]; out[16 * n + i] = R.g_int;
+      const int eflag = cfg->extrad_flag;
+      out[17 * n + i] = extrad_phi_public(s, 1, v.Ein, v.e.E, in[13 * n + i]);
+      out[18 * n + i] = extrad_phi_public(s, 2, v.Ein, v.e.E, in[13 * n + i]);
+      (void)eflag;
+      double ds, dh;
+      schwinger(*cfg, 1.0, 450., v, true, ds, dh);
+      out[19 * n + i] = ds; out[20 * n + i] = dh;
+      double db, dbp;
+      extrad_friedrich(cfg->etatzai, v.Ein, in[13 * n + i], R.bt[0] / cfg->etatzai, db, dbp);
+      out[21 * n + i] = db; out[22 * n + i] = dbp;
+      double bs, bh, dbs;
+      brem(v.Ein, v.e.E, 450., R.rad_proton_this_ev, false, bs, bh, dbs);
+      out[23 * n + i] = bs; out[24 * n + i] = bh; out[25 * n + i] = dbs;
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }

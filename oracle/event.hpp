@@ -167,6 +167,13 @@ void target_musc(Sim& s, double p, double beta, double teff, double dangles[2]);
 double bremos(double egamma, double k_ix, double k_iy, double k_iz, double k_fx, double k_fy, double k_fz,
               double p_ix, double p_iy, double p_iz, double p_fx, double p_fy, double p_fz, double p_fe,
               bool radiate_proton, bool exponentiate, double& bsoft, double& bhard, double& dbsoft);     // brem.f:344
+double brem(double ein, double eout, double egamma, bool radiate_proton, bool exponentiate, double& bsoft,
+            double& bhard, double& dbsoft);                                                                       // brem.f:6
+double spen(double x);                                                                                     // radc.f:746
+double schwinger(const simc_run_config& cfg, double etta, double Ecutoff, const Event& vertex, bool include_hard,
+                 double& dsoft, double& dhard);                                                              // radc.f:711
+void extrad_friedrich(double etatzai, double Ei, double Ecutoff, double trad, double& dbrem, double& dbrem_prime);   // radc.f:650
+double extrad_phi_public(Sim& s, int itail, double E1, double E2, double Egamma);                           // radc.f:668
 double gamma_fn(double x);                                                                               // radc.f:92
 void radc_init_ev(Sim& s, EventMain& main, Event& vertex);                                               // init.f:655
 bool complete_ev(Sim& s, EventMain& main, Event& vertex);                                                // event.f:432

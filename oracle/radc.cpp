@@ -1,8 +1,10 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see event.hpp).
 // brem.f (bremos, inter, inter_prime, spence), radc.f (basicrad, gamma, generate_rad,
 // peaked_rad_weight, extrad_phi, lambda_dave), init.f:655-813 (radc_init_ev, basicrad_init_ev).
-// Live option set of every shipped deck: rad_flag=0, extrad_flag<=2,
-// intcor_mode=1, use_offshell_rad=1, use_expon=0; other settings are refused by the caller.
+// Every option branch is restated: rad_flag 0..3, extrad_flag 1..3, intcor_mode 0/1 (schwinger),
+// use_offshell_rad 0/1 (brem / bremos).  The reference is built with -fno-automatic (Makefile:63): locals are
+// static and start at zero, so a local that an option setting never assigns (dsoft_prime under intcor_mode=0,
+// dsoft_intmin/max under rad_flag=1 with extrad_flag=3) reads as 0.0 -- restated as zero-initialised locals.
 #include <cmath>
 #include "event.hpp"
 
@@ -41,6 +43,145 @@ static double inter_prime(double alpha, double ar1, double ar2, double de) {
   const double pi = 3.141592653589793;
   const double amult = -1. / (alpha * (ar1 - ar2));
   return (-1. / de) * amult / pi * (log(fabs((ar1 - 1.) / ar1)) - log(fabs((ar2 - 1.) / ar2)));
+}
+
+// brem.f:6-214: the on-shell calculation (elastic e-p kinematics from ein, eout alone).
+// include_hard = calculate_spence = .true. (init.f:646-647); produce_output off.
+double brem(double ein, double eout, double egamma, bool radiate_proton, bool exponentiate, double& bsoft,
+            double& bhard, double& dbsoft) {
+  const double pi = 3.141592653589793, am = .93827231, ame = .00051099906, e2 = 1. / 137.0359895;
+  const bool calculate_spence = true, include_hard = true;
+  const double ak = ein / 1000., akp = eout / 1000., de = egamma / 1000.;
+  const double eang = 2. * std::asin(std::pow(am / (2. * ak) * (ak / akp - 1.), 0.5));
+  const double q2 = 4. * ak * akp * powi(std::sin(eang / 2.), 2);
+  const double ape = am + ak - akp;
+  const double ap = sqrt(powi(ape, 2) - powi(am, 2));
+  const double pang = std::acos((ak - akp * std::cos(eang)) / ap);
+  double aprod, adot, alpha, ar1, ar2;
+  aprod = 1.e0;
+  const double bei = aprod * (-1. / (2. * pi)) * log(ak / de);
+  const double dbei = aprod * (1. / (2. * pi * de));
+  aprod = 1.e0;
+  const double bef = aprod * (-1. / (2. * pi)) * log(akp / de);
+  const double dbef = aprod * (1. / (2. * pi * de));
+  // e-e interference
+  aprod = -1.e0;
+  adot = ak * akp * (1. - std::cos(eang));
+  alpha = 2. * powi(ame, 2) - 2. * adot;
+  ar1 = 0.5 + sqrt(powi(adot, 2) - powi(ame, 4)) / alpha;
+  ar2 = 0.5 - sqrt(powi(adot, 2) - powi(ame, 4)) / alpha;
+  const double bee = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, ak, akp, de);
+  const double dbee = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+  double bpi = 0, bpf = 0, bpp = 0, bepii = 0, bepff = 0, bepif = 0, bepfi = 0;
+  double dbpi = 0, dbpf = 0, dbpp = 0, dbepii = 0, dbepff = 0, dbepif = 0, dbepfi = 0;
+  if (radiate_proton) {
+    aprod = 1.e0;
+    bpi = aprod * (-1. / (2. * pi)) * log(am / de);
+    dbpi = aprod * (1. / (2. * pi * de));
+    aprod = 1.e0;
+    bpf = aprod * (-1. / (2. * pi)) * log(ape / de);
+    dbpf = aprod * (1 / (2. * pi * de));
+    // p-p
+    aprod = -1.e0;
+    adot = am * ape;
+    alpha = 2. * powi(am, 2) - 2. * adot;
+    ar1 = 0.5 + sqrt(powi(adot, 2) - powi(am, 4)) / alpha;
+    ar2 = 0.5 - sqrt(powi(adot, 2) - powi(am, 4)) / alpha;
+    bpp = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, am, ape, de);
+    dbpp = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+    // ei-pi
+    aprod = -1.e0;
+    adot = ak * am;
+    alpha = powi(am, 2) + powi(ame, 2) - 2. * adot;
+    ar1 = (powi(am, 2) - adot + sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    ar2 = (powi(am, 2) - adot - sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    bepii = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, ak, am, de);
+    dbepii = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+    // ef-pf
+    aprod = -1.e0;
+    adot = akp * ape - akp * ap * std::cos(eang + pang);
+    alpha = powi(am, 2) + powi(ame, 2) - 2. * adot;
+    ar1 = (powi(am, 2) - adot + sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    ar2 = (powi(am, 2) - adot - sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    bepff = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, akp, ape, de);
+    dbepff = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+    // ei-pf
+    aprod = 1.e0;
+    adot = ak * ape - ak * ap * std::cos(pang);
+    alpha = powi(am, 2) + powi(ame, 2) - 2. * adot;
+    ar1 = (powi(am, 2) - adot + sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    ar2 = (powi(am, 2) - adot - sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    bepif = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, ak, ape, de);
+    dbepif = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+    // ef-pi
+    aprod = 1.e0;
+    adot = akp * am;
+    alpha = powi(am, 2) + powi(ame, 2) - 2. * adot;
+    ar1 = (powi(am, 2) - adot + sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    ar2 = (powi(am, 2) - adot - sqrt(powi(adot, 2) - powi(ame * am, 2))) / alpha;
+    bepfi = aprod * adot * inter(calculate_spence, alpha, ar1, ar2, akp, am, de);
+    dbepfi = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (log((ar1 - 1) / ar1) - log((ar2 - 1) / ar2));
+  }
+  const double b = 2. * e2 * (bei + bef + bee);
+  double bz, bzz;
+  if (radiate_proton) {
+    bzz = 2. * e2 * (bpi + bpf + bpp);
+    bz = 2. * e2 * (bepii + bepff + bepif + bepfi);
+  } else {
+    bzz = 0.0; bz = 0.0;
+  }
+  bsoft = b + bz + bzz;
+  bhard = -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * log(q2 / powi(ame, 2)));
+  const double db = 2. * e2 * (dbei + dbef + dbee);
+  double dbz, dbzz;
+  if (radiate_proton) {
+    dbzz = 2. * e2 * (dbpi + dbpf + dbpp);
+    dbz = 2. * e2 * (dbepii + dbepff + dbepif + dbepfi);
+  } else {
+    dbzz = 0.0; dbz = 0.0;
+  }
+  dbsoft = db + dbz + dbzz;
+  dbsoft = dbsoft / 1000.;
+  double r;
+  if (exponentiate) r = -dbsoft / std::exp(bsoft);
+  else r = 1. - dbsoft;
+  if (include_hard) r = r * (1. - bhard);
+  return r;
+}
+
+// radc.f:746-764 (Abramowitz & Stegun 27.7.2 series)
+double spen(double x) {
+  double y = 1.0, s = 0.0;
+  int i = 0;
+  while (i <= 100 && fabs(y) > fabs(s) * 1.e-4) {
+    i = i + 1;
+    y = x * y;
+    s = s + y / (double)(i * i);
+  }
+  return s;
+}
+
+// radc.f:711-742
+double schwinger(const simc_run_config& cfg, double etta, double Ecutoff, const Event& vertex, bool include_hard,
+                 double& dsoft, double& dhard) {
+  const double lq = log(vertex.Q2 / powi(K::Me, 2)) - 1.0;
+  const double s2 = powi(std::sin(vertex.e.theta / 2.), 2);
+  const double b = 1. + 2. * vertex.nu * s2 / (cfg.targ.A * K::amu);
+  const double spence_ = spen(1. - s2) - 2.5893784;
+  dsoft = K::alpi * lq * log(vertex.Ein / powi(etta, 2) * vertex.e.E * b / powi(Ecutoff, 2));
+  dhard = -K::alpi * (2.166666 * lq + spence_ - powi(log(vertex.Ein / vertex.e.E), 2) / 2.0);
+  double r;
+  if (cfg.use_expon == 0) r = std::exp(dsoft);
+  else r = 1. + dsoft;
+  if (include_hard) r = r / (1. - dhard);
+  return r;
+}
+
+// radc.f:650-664
+void extrad_friedrich(double etatzai, double Ei, double Ecutoff, double trad, double& dbrem, double& dbrem_prime) {
+  const double x = Ecutoff / Ei;
+  dbrem = trad * (-(etatzai - 0.5) - etatzai * log(x) + etatzai * x - 0.5 * powi(x, 2));
+  dbrem_prime = -trad / Ei * (etatzai / x - etatzai + x);
 }
 
 // brem.f:344-577.  include_hard = calculate_spence = .true. (init.f:646-647)
@@ -237,12 +378,16 @@ void radc_init_ev(Sim& s, EventMain& main, Event& vertex) {
                                   vertex.e.theta);
   R.rad_proton_this_ev = R.lambda[2] > 0;
   const double Ecutoff = 450.;
+  // dsoft_prime is a static local (-fno-automatic) that schwinger never assigns: it reads 0.0 under intcor_mode=0
   double dsoft = 0, dhard = 0, dsoft_prime = 0;
-  if (cfg.intcor_mode == 0 || !cfg.use_offshell_rad)
-    throw std::runtime_error("oracle: only intcor_mode=1 with use_offshell_rad=1 is restated (SURVEY A.10)");
-  bremos(Ecutoff, 0., 0., vertex.Ein, vertex.e.P * vertex.ue.x, vertex.e.P * vertex.ue.y, vertex.e.P * vertex.ue.z,
-         0., 0., 0., vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
-         R.rad_proton_this_ev, cfg.use_expon == 1, dsoft, dhard, dsoft_prime);
+  if (cfg.intcor_mode == 0)
+    schwinger(cfg, R.etta, Ecutoff, vertex, true, dsoft, dhard);
+  else if (!cfg.use_offshell_rad)
+    brem(vertex.Ein, vertex.e.E, Ecutoff, R.rad_proton_this_ev, cfg.use_expon == 1, dsoft, dhard, dsoft_prime);
+  else
+    bremos(Ecutoff, 0., 0., vertex.Ein, vertex.e.P * vertex.ue.x, vertex.e.P * vertex.ue.y, vertex.e.P * vertex.ue.z,
+           0., 0., 0., vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
+           R.rad_proton_this_ev, cfg.use_expon == 1, dsoft, dhard, dsoft_prime);
   R.hardcorfac = 1. / (1. - dhard);
   R.g[4] = -dsoft_prime * Ecutoff + R.bt[0] + R.bt[1];
   basicrad_init_ev(s, vertex.Ein, vertex.e.E, vertex.p.E);
@@ -277,30 +422,57 @@ static double extrad_phi(Sim& s, int itail, double E1, double E2, double Egamma)
     if (itail == 0) phi = 1. - (R.bt[0] / E[1] + R.bt[1] / E[2]) / (R.g[1] + R.g[2]) * Egamma;
     else if (itail == 1 || itail == 2) phi = 1. - R.bt[itail - 1] / E[itail] / R.g[itail] * Egamma;
   } else if (s.cfg->extrad_flag == 3) {
-    throw std::runtime_error("oracle: extrad_flag=3 (Friedrich) not restated");
+    if (itail == 0) throw std::runtime_error("Idiot! a multiplicative factor EXTRAD_PHI is not defined for peaking approx and EXTRAD_FLAG>2!");
+    if (itail == 1 || itail == 2) {
+      const double etatzai = s.cfg->etatzai;
+      const double x = Egamma / E[itail];
+      const double t = R.bt[itail - 1] / etatzai;
+      phi = phi * (1. - x + powi(x, 2) / etatzai) * std::exp(t * ((etatzai - 0.5) - etatzai * x + powi(x, 2) / 2.)) *
+            gamma_fn(1. + R.bt[itail - 1]);
+    }
   }
   return phi;
 }
 
-// radc.f:523-646, the rad_flag=0, extrad_flag<=2, use_offshell_rad branch
+// radc.f:523-646
 static double peaked_rad_weight(Sim& s, const Event& vertex, double Egamma, double emin, double emax,
                                 double basicrad_val_reciprocal, double basicrad_weight) {
   const RadEv& R = s.rad;
   const simc_run_config& cfg = *s.cfg;
   const double ein = vertex.Ein, eout = vertex.e.E, eul = 0.577215665;
-  (void)eout; (void)basicrad_val_reciprocal;
-  double phi_ext = extrad_phi(s, 0, ein, eout, Egamma);
-  if (cfg.rad_flag == 1) return basicrad_weight * phi_ext;
-  double dsoft_intmin = 1.0, dsoft_intmax, dhard, dprime;
-  if (emin > 0)
-    bremos(emin, 0., 0., ein, vertex.e.E * vertex.ue.x, vertex.e.E * vertex.ue.y, vertex.e.E * vertex.ue.z, 0., 0.,
-           0., vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
-           R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmin, dhard, dprime);
-  else
-    dsoft_intmin = 1.0;
-  bremos(emax, 0., 0., ein, vertex.e.E * vertex.ue.x, vertex.e.E * vertex.ue.y, vertex.e.E * vertex.ue.z, 0., 0., 0.,
-         vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
-         R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmax, dhard, dprime);
+  (void)basicrad_val_reciprocal;
+  // static locals of the reference (zero until an executed branch assigns them)
+  double dsoft_intmin = 0.0, dsoft_intmax = 0.0, dhard = 0.0, dprime = 0.0;
+  double phi_ext = 1.0;
+  if (cfg.extrad_flag <= 2) {
+    phi_ext = extrad_phi(s, 0, ein, eout, Egamma);
+    if (cfg.rad_flag == 1) return basicrad_weight * phi_ext;
+    // dsoft_extmin/max and dsoft_ext_prime (radc.f:574-578) are computed and never read
+  } else {
+    // Friedrich prescription: computed and never read (radc.f:580-585)
+    const double t1 = R.bt[0] / cfg.etatzai, t2 = R.bt[1] / cfg.etatzai;
+    double d1, d1p, d2, d2p;
+    extrad_friedrich(cfg.etatzai, ein, Egamma, t1, d1, d1p);
+    extrad_friedrich(cfg.etatzai, eout, Egamma, t2, d2, d2p);
+  }
+  if (cfg.rad_flag == 0) {
+    if (!cfg.use_offshell_rad) {
+      if (emin > 0) brem(ein, eout, emin, R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmin, dhard, dprime);
+      else dsoft_intmin = 1.0;
+      brem(ein, eout, emax, R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmax, dhard, dprime);
+    } else {
+      if (emin > 0)
+        bremos(emin, 0., 0., ein, vertex.e.E * vertex.ue.x, vertex.e.E * vertex.ue.y, vertex.e.E * vertex.ue.z, 0., 0.,
+               0., vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
+               R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmin, dhard, dprime);
+      else
+        dsoft_intmin = 1.0;
+      bremos(emax, 0., 0., ein, vertex.e.E * vertex.ue.x, vertex.e.E * vertex.ue.y, vertex.e.E * vertex.ue.z, 0., 0., 0.,
+             vertex.p.P * vertex.up.x, vertex.p.P * vertex.up.y, vertex.p.P * vertex.up.z, vertex.p.E,
+             R.rad_proton_this_ev, cfg.use_expon == 1, dsoft_intmax, dhard, dprime);
+    }
+  }
+  // (rad_flag = 1 with extrad_flag = 3 gets here with dsoft_int* never assigned: radc.f:627-631 sets other locals)
   double w;
   if (emin > 0)
     w = R.c_ext[0] / R.g_ext *
@@ -316,21 +488,29 @@ static double peaked_rad_weight(Sim& s, const Event& vertex, double Egamma, doub
 double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax) {
   return peaked_rad_weight(s, vertex, Egamma, emin, emax, 0.0, 1.0);
 }
+double extrad_phi_public(Sim& s, int itail, double E1, double E2, double Egamma) { return extrad_phi(s, itail, E1, E2, Egamma); }
 
-// radc.f:120-519 for rad_flag <= 1 (peaked basis: exactly one tail radiates)
+// radc.f:120-519
 bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
   const simc_run_config& cfg = *s.cfg;
   RadEv& R = s.rad;
   double rad_weight = 1;
   for (int i = 0; i < 3; ++i) R.Egamma_used[i] = 0.0;
   s.ntup.radphot = 0.; s.ntup.radarm = 0.;
-  if (cfg.rad_flag > 1) throw std::runtime_error("oracle: rad_flag>1 not restated (SURVEY A.10)");
-  const int peaked_basis_flag = 0;
-  {
+  int peaked_basis_flag = 1;
+  if (cfg.rad_flag <= 1) {
+    peaked_basis_flag = 0;
     const double x = s.rng->grnd();
     if (x >= R.frac[0] + R.frac[1]) R.ntail = 3;
     else if (x >= R.frac[0]) R.ntail = 2;
     else R.ntail = 1;
+  } else if (cfg.rad_flag == 2) {
+    R.ntail = (int)(s.rng->grnd() * 3.) + 1;
+    if (R.ntail == 4) R.ntail = 3;
+  } else if (cfg.rad_flag == 3) {
+    R.ntail = 0;
+  } else {
+    throw std::runtime_error("Idiot! rad_flag is set stupidly");
   }
   const int ntail = R.ntail;
   const double max_delta_Trec =
@@ -354,6 +534,10 @@ bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
     } else if (cfg.doing_deuterium) {
       Egamma_max[1] = std::min(cfg.Egamma1_max, cfg.gen.sumEgen.max - vertex.e.E);
       if (ntail != 0) Egamma_min[1] = cfg.gen.sumEgen.min - vertex.e.E;
+      // ntail = 0: Egamma_min(1) keeps the value the previous event left in COMMON /radccom/, which only ever
+      // decreases from its initial zero (dE_edge_test is subtracted below): any value <= 0 gives the same
+      // basicrad, so zero stands for it here
+      else Egamma_min[1] = 0.0;
     } else if (cfg.doing_pion || cfg.doing_kaon || cfg.doing_rho || cfg.doing_semi) {
       Egamma_min[1] = 0.;
       Egamma_max[1] = cfg.gen.sumEgen.max - vertex.e.E;
@@ -368,8 +552,11 @@ bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
     vertex.Ein = vertex.Ein - Egamma_used[1];
     if (!complete_ev(s, main, vertex)) return false;
     rad_weight = rad_weight * basicrad_weight;
-    rad_weight = peaked_rad_weight(s, vertex, Egamma_used[1], Egamma_min[1], Egamma_max[1], basicrad_val_reciprocal,
-                                   basicrad_weight);
+    if (cfg.rad_flag <= 1)
+      rad_weight = peaked_rad_weight(s, vertex, Egamma_used[1], Egamma_min[1], Egamma_max[1], basicrad_val_reciprocal,
+                                     basicrad_weight);
+    else
+      rad_weight = rad_weight * extrad_phi(s, 1, vertex.Ein, vertex.e.E, Egamma_used[1]);
   }
   if (cfg.doing_heavy) {
     if (vertex.Em < cfg.VERTEXedge.Em.min || vertex.Em > cfg.VERTEXedge.Em.max || vertex.Pm < cfg.VERTEXedge.Pm.min ||
@@ -393,8 +580,11 @@ bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
              basicrad_val_reciprocal);
     if (basicrad_weight <= 0) return false;
     rad_weight = rad_weight * basicrad_weight;
-    rad_weight = peaked_rad_weight(s, vertex, Egamma_used[2], Egamma_min[2], Egamma_max[2], basicrad_val_reciprocal,
-                                   basicrad_weight);
+    if (cfg.rad_flag <= 1)
+      rad_weight = peaked_rad_weight(s, vertex, Egamma_used[2], Egamma_min[2], Egamma_max[2], basicrad_val_reciprocal,
+                                     basicrad_weight);
+    else
+      rad_weight = rad_weight * extrad_phi(s, 2, vertex.Ein, vertex.e.E, Egamma_used[2]);
   }
   // tail 3: hadron
   if (R.rad_proton_this_ev && (ntail == 0 || ntail == 3)) {
@@ -414,8 +604,11 @@ bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
              basicrad_val_reciprocal);
     if (basicrad_weight <= 0) return false;
     rad_weight = rad_weight * basicrad_weight;
-    rad_weight = peaked_rad_weight(s, vertex, Egamma_used[3], Egamma_min[3], Egamma_max[3], basicrad_val_reciprocal,
-                                   basicrad_weight);
+    if (cfg.rad_flag <= 1)
+      rad_weight = peaked_rad_weight(s, vertex, Egamma_used[3], Egamma_min[3], Egamma_max[3], basicrad_val_reciprocal,
+                                     basicrad_weight);
+    else
+      rad_weight = rad_weight * extrad_phi(s, 3, vertex.Ein, vertex.e.E, Egamma_used[3]);
   }
   // orig = vertex + radiation, radc.f:476-515
   orig = vertex;

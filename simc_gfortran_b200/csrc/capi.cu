@@ -926,11 +926,10 @@ int validate_loop_config(simc_handle* h, bool need_optics = true) {
                                    "(simc_b200_load_sf_file, or set_sf_table + set_sf_em_widths) first");
   if (heavy && c.use_benhar_sf && !h->d_sf)
     return fail(h, SIMC_ERR_STATE, "simc_b200_run: A(e,e'p) needs the spectral function (simc_b200_set_sf_table) first");
-  if (c.using_rad && (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 ||
-                      !c.use_offshell_rad || c.use_expon != 0))
-    return fail(h, SIMC_ERR_ARG,
-                "radiative options outside rad_flag<=1, extrad_flag 1..2, intcor_mode=1, use_offshell_rad=1, "
-                "use_expon=0 are not implemented");
+  // every radiative option branch is built (radc.cuh); what is left is what the reference itself stops on
+  // (radc.f:211 'rad_flag is set stupidly', init.f:627 extrad_flag < 0; extrad_flag = 0 is resolved by radc_init)
+  if (c.using_rad && (c.rad_flag < 0 || c.rad_flag > 3 || c.extrad_flag < 1 || c.extrad_flag > 3))
+    return fail(h, SIMC_ERR_ARG, "radiative options: rad_flag must be 0..3 and extrad_flag 1..3 (after radc_init)");
   if (need_optics) for (int arm : {c.electron_arm, c.hadron_arm}) {
     const bool used = (arm == c.electron_arm) ? c.using_E_arm_montecarlo : c.using_P_arm_montecarlo;
     if (!used) continue;
@@ -1349,8 +1348,8 @@ int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double
   if (n < 0 || (n > 0 && (!in_soa || !out_soa))) return fail(h, SIMC_ERR_ARG, "simc_b200_radc_batch: bad argument");
   if (n == 0) return SIMC_OK;
   const simc_run_config& c = h->cfg;
-  if (c.rad_flag > 1 || c.extrad_flag > 2 || c.extrad_flag < 1 || c.intcor_mode != 1 || !c.use_offshell_rad || c.use_expon != 0)
-    return fail(h, SIMC_ERR_ARG, "simc_b200_radc_batch: radiative options not implemented");
+  if (c.rad_flag < 0 || c.rad_flag > 3 || c.extrad_flag < 1 || c.extrad_flag > 3)
+    return fail(h, SIMC_ERR_ARG, "simc_b200_radc_batch: rad_flag must be 0..3 and extrad_flag 1..3 (after radc_init)");
   CU(h, cudaSetDevice(h->device));
   int rc = ensure_loop_buffers(h, 1);
   if (rc) return rc;

@@ -219,6 +219,119 @@ SIMC_HD bool generate_finalize(const simc_run_config& cfg, EventState& s, bool o
   return ok;
 }
 
+// ---- generate_rad in the (Egamma1, Egamma2, Egamma3) basis, radc.f:120-519 with rad_flag = 2 (one tail, chosen with
+// equal probability) or 3 (all tails radiate).  Each tail draws its photon energy from BASICRAD with that tail's own
+// (g, c) and the weight is the product of the BASICRAD weights and extrad_phi(itail).  Cut where the reference
+// re-enters complete_ev (radc.f:324): *_first ends with tail 1, *_rest does the tails behind it (in k_regen for the
+// tries whose tail 1 was active, at once for the others).  gr.which = 4 marks the finished weight in gr.bw.
+template <class RNG>
+SIMC_HD_CALL bool generate_rad_basis_rest(const simc_run_config& cfg, RNG& rng, EventState& s, GenRad& gr, bool after_tail1) {
+  RadEvDev& R = s.rad;
+  const int ntail = R.ntail;
+  const simc_edge& VE = cfg.VERTEXedge;
+  double rad_weight = 1;
+  if (after_tail1) {
+    rad_weight = rad_weight * gr.bw;
+    rad_weight = rad_weight * extrad_phi(cfg, R, 1, s.v_Ein, s.v_eE, R.Egamma_used[0]);
+  } else if (cfg.doing_heavy) {     // radc.f:340-350 (the second pass makes this test itself)
+    if (s.v_Em < VE.Em.min || s.v_Em > VE.Em.max || s.v_Pm < VE.Pm.min || s.v_Pm > VE.Pm.max) return false;
+  }
+  // max_delta_Trec is formed before tail 1 from the vertex%Trec of the first pass, which main%Trec still holds
+  const double max_delta_Trec = fmax((s.Trec - VE.Trec.min), (VE.Trec.max - s.Trec));
+  const bool eep = cfg.doing_eep != 0;
+  const bool tail2 = cfg.doing_tail[1] && (ntail == 0 || ntail == 2);
+  const bool tail3 = R.rad_proton_this_ev && (ntail == 0 || ntail == 3);
+  BasisConst B;
+  if (tail2 || tail3) B = basis_constants(R, s.v_Ein, s.v_eE, s.v_pE);
+  if (tail2) {                      // radc.f:354-404
+    double emin = s.v_eE - cfg.edge.e.E.max;
+    double emax = s.v_eE - cfg.edge.e.E.min;
+    if (eep) {
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] + max_delta_Trec);
+      if (ntail != 0 || !R.rad_proton_this_ev) emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - max_delta_Trec);
+    }
+    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0]);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    double eg, bw;
+    basicrad_tail(R.g[2], B.c[2], rng, emin, emax, eg, bw);
+    if (bw <= 0) return false;
+    R.Egamma_used[1] = eg;
+    rad_weight = rad_weight * bw;
+    rad_weight = rad_weight * extrad_phi(cfg, R, 2, s.v_Ein, s.v_eE, eg);
+  }
+  if (tail3) {                      // radc.f:408-455
+    double emin = s.v_pE - cfg.edge.p.E.max;
+    double emax = s.v_pE - cfg.edge.p.E.min;
+    if (eep) {
+      emax = fmin(emax, (cfg.edge.Em.max - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] + max_delta_Trec);
+      emin = fmax(emin, (cfg.edge.Em.min - s.v_Em) - R.Egamma_used[0] - R.Egamma_used[1] - max_delta_Trec);
+    }
+    emax = fmin(emax, cfg.Egamma_tot_max - R.Egamma_used[0] - R.Egamma_used[1]);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    double eg, bw;
+    basicrad_tail(R.g[3], B.c[3], rng, emin, emax, eg, bw);
+    if (bw <= 0) return false;
+    R.Egamma_used[2] = eg;
+    rad_weight = rad_weight * bw;
+    rad_weight = rad_weight * extrad_phi(cfg, R, 3, s.v_Ein, s.v_eE, eg);
+  }
+  gr.which = 4; gr.bw = rad_weight;
+  return true;
+}
+template <class RNG>
+SIMC_HD_CALL bool generate_rad_basis_first(const simc_run_config& cfg, RNG& rng, EventState& s, GenRad& gr) {
+  RadEvDev& R = s.rad;
+  const simc_edge& VE = cfg.VERTEXedge;
+  if (cfg.rad_flag == 2) {          // radc.f:206-208
+    R.ntail = (int)(rng.uniform() * 3.) + 1;
+    if (R.ntail == 4) R.ntail = 3;
+  } else {
+    R.ntail = 0;
+  }
+  const int ntail = R.ntail;
+  if (cfg.doing_tail[0] && (ntail == 0 || ntail == 1)) {
+    const double max_delta_Trec = fmax((s.v_Trec - VE.Trec.min), (VE.Trec.max - s.v_Trec));
+    double emin = 0.0, emax = 0.0;
+    if (cfg.doing_heavy) {          // radc.f:249-255
+      emin = s.v_Em - VE.Em.max - max_delta_Trec;
+      emax = s.v_Em - VE.Em.min + max_delta_Trec;
+      if (ntail != 0) emax = fmin(emax, s.v_Em - cfg.edge.Em.min + max_delta_Trec);
+    } else if (cfg.doing_hyd_elast) {   // radc.f:264-271
+      double ebeam_max = SIMC_MP * cfg.edge.e.E.max / (SIMC_MP - cfg.edge.e.E.max * (1. - s.uez));
+      if (ebeam_max < 0) ebeam_max = 1.e10;
+      const double ebeam_min = SIMC_MP * cfg.edge.e.E.min / (SIMC_MP - cfg.edge.e.E.min * (1. - s.uez));
+      emin = s.v_Ein - ebeam_max;
+      emax = s.v_Ein - ebeam_min;
+      emax = fmin(emax, cfg.edge.Em.max);
+    } else if (cfg.doing_deuterium) {   // radc.f:275-277
+      emax = fmin(cfg.Egamma1_max, cfg.gen.sumEgen.max - s.v_eE);
+      // ntail = 0: Egamma_min(1) keeps what the previous event left in COMMON /radccom/, which starts at zero and only
+      // decreases (dE_edge_test is subtracted every event); any value <= 0 gives the same BASICRAD: zero stands for it
+      emin = ntail != 0 ? cfg.gen.sumEgen.min - s.v_eE : 0.0;
+    } else {                        // pion / kaon / semi-inclusive, radc.f:283-291
+      emin = 0.;
+      emax = cfg.gen.sumEgen.max - s.v_eE;
+    }
+    emax = fmin(emax, cfg.Egamma1_max);
+    emin = emin - cfg.dE_edge_test;
+    emax = emax + cfg.dE_edge_test;
+    if (cfg.hardwired_rad) emax = cfg.Egamma_gen_max;
+    const BasisConst B = basis_constants(R, s.v_Ein, s.v_eE, s.v_pE);
+    double eg, bw;
+    basicrad_tail(R.g[1], B.c[1], rng, emin, emax, eg, bw);
+    if (bw <= 0) return false;
+    R.Egamma_used[0] = eg;
+    s.v_Ein = s.v_Ein - eg;
+    gr.emin = emin; gr.emax = emax; gr.eg = eg; gr.bw = bw; gr.which = 1;      // on to complete_ev (k_regen)
+    return true;
+  }
+  return generate_rad_basis_rest(cfg, rng, s, gr, false);
+}
+
 // generate + generate_rad for H(e,e'p): event.f:126-428, radc.f:120-519.  `ok` in: the thread has
 // a try to generate; returns success.  The work is cut where generate_rad re-enters complete_ev
 // (radc.f:324, the tries whose incoming electron radiates): *_first runs up to the photon energy of the
@@ -275,6 +388,7 @@ SIMC_HD bool generate_hyd_elast_first(const simc_run_config& cfg, const MatTable
   if (ok) s.Trec = s.v_Trec;
   gr.emin = 0.0; gr.emax = 0.0; gr.eg = 0.0; gr.bw = 0.0; gr.which = 0;
   if (!cfg.using_rad) return ok;
+  if (cfg.rad_flag >= 2) return ok ? generate_rad_basis_first(cfg, rng, s, gr) : false;
   // ---- generate_rad, peaked basis: exactly one tail radiates (radc.f:198-208).
   RadEvDev& R = s.rad;
   double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
@@ -595,6 +709,7 @@ SIMC_HD bool generate_meson_first(const simc_run_config& cfg, const MatTable& mt
   if (ok) s.Trec = s.v_Trec;
   gr.emin = 0.0; gr.emax = 0.0; gr.eg = 0.0; gr.bw = 0.0; gr.which = 0;
   if (!cfg.using_rad) return ok;
+  if (cfg.rad_flag >= 2) return ok ? generate_rad_basis_first(cfg, rng, s, gr) : false;
   RadEvDev& R = s.rad;
   double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0;
   int which = 0;
@@ -790,6 +905,7 @@ SIMC_HD bool generate_heavy_first(const simc_run_config& cfg, const MatTable& mt
     if (ok) ok = (s.v_Em >= VE.Em.min && s.v_Em <= VE.Em.max && s.v_Pm >= VE.Pm.min && s.v_Pm <= VE.Pm.max);
     return ok;
   }
+  if (cfg.rad_flag >= 2) return ok ? generate_rad_basis_first(cfg, rng, s, gr) : false;
   RadEvDev& R = s.rad;
   double bw = 0, emin = 0.0, emax = 0.0, eg = 0.0, max_delta_Trec = 0.0;
   int which = 0, ntail = 0;

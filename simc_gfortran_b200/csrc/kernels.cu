@@ -182,7 +182,7 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
     k_tb_load<<<(unsigned)nb, 256, 0, s>>>(a.n, a.in, a.tk, a.lists, a.counts, a.n_stretch + 1, a.sink, n_sink);
     for (int k = 0; k < a.n_stretch; ++k) {
       double* tk = a.tk;
-      long long cap = a.n;
+      long long fs = a.n, ss = 1;          // this entry point's own scratch rows: [field][row]
       const unsigned* in_list = a.lists + (long long)k * a.n;
       const unsigned* in_count = a.counts + k;
       unsigned* out_list = a.lists + (long long)(k + 1) * a.n;
@@ -190,7 +190,7 @@ cudaError_t launch_transport_batch(const TransportBatchArgs& a, cudaStream_t s) 
       unsigned long long* stop_acc = a.sink;
       unsigned long long* calls_acc = a.sink + SIMC_NSTOP;
       double* stop_field = a.tk + 11 * a.n;
-      void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
+      void* args[] = {&tk, &fs, &ss, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
       const long long g = std::min<long long>((a.n + a.stretch_block - 1) / a.stretch_block, a.stretch_grid);
       if (jit_launch(a.stretch_fn[k], (unsigned)g, (unsigned)a.stretch_block, (void*)s, args) != 0) return cudaErrorLaunchFailure;
     }
@@ -227,6 +227,21 @@ __global__ void k_radc_batch(const simc_run_config* __restrict__ cfg, long long 
   out[5 * n + i] = R.g[4]; out[6 * n + i] = R.hardcorfac; out[7 * n + i] = R.c4; out[8 * n + i] = R.c_ext0;
   out[9 * n + i] = w;
   out[10 * n + i] = sigep(v.Ein, v.eE, v.etheta, 2 * v.Ein * v.eE * (1. - v.uez));
+  // the (Egamma1, Egamma2, Egamma3) basis and the pieces of the other option branches (include/simc_b200.h)
+  const BasisConst B = basis_constants(R, v.Ein, v.eE, v.pE);
+  out[11 * n + i] = B.c[1]; out[12 * n + i] = B.c[2]; out[13 * n + i] = B.c[3]; out[14 * n + i] = B.c[0];
+  out[15 * n + i] = B.c_int0; out[16 * n + i] = B.g_int;
+  out[17 * n + i] = extrad_phi(*cfg, R, 1, v.Ein, v.eE, in[13 * n + i]);
+  out[18 * n + i] = extrad_phi(*cfg, R, 2, v.Ein, v.eE, in[13 * n + i]);
+  double ds, dh;
+  schwinger(*cfg, 450., v.Ein, v.eE, v.etheta, 2 * v.Ein * v.eE * (1. - v.uez), v.Ein - v.eE, ds, dh);
+  out[19 * n + i] = ds; out[20 * n + i] = dh;
+  double db, dbp;
+  extrad_friedrich(cfg->etatzai, v.Ein, in[13 * n + i], R.bt[0] / cfg->etatzai, db, dbp);
+  out[21 * n + i] = db; out[22 * n + i] = dbp;
+  double bs, bh, dbs;
+  brem_onshell<kBremAll>(v.Ein, v.eE, 450., R.rad_proton_this_ev, bs, bh, dbs);
+  out[23 * n + i] = bs; out[24 * n + i] = bh; out[25 * n + i] = dbs;
 }
 cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
@@ -270,7 +285,7 @@ cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long lo
 
 size_t arm_dev_bytes() { return sizeof(ArmDev); }
 size_t dev_accum_bytes() { return sizeof(DevAccum); }
-int n_state_fields() { return (int)F_NFIELDS; }
+int n_state_fields() { return SIMC_STATE_AOS ? kStateStride : (int)F_NFIELDS; }
 
 }  // namespace SIMC_VARIANT_NS
 }  // namespace simc
@@ -446,8 +461,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         else { if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
       } else if (st.kind == ARM_STAGE_COMPILED) {
         // generated straight-line kernel (mapgen.h); ABI in mapgen.h
-        double* tk = a.state + (long long)F_TK_XS * a.cap;
-        long long cap = a.cap;
+        long long fs = state_field_stride(a.cap), ss = state_slot_stride();
+        double* tk = a.state + (long long)F_TK_XS * fs;
         const unsigned* in_list = a.lists + (long long)in * a.cap;
         const unsigned* in_count = a.counts + 1 + in;
         unsigned* out_list = a.lists + (long long)out * a.cap;
@@ -455,8 +470,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         DevAccum* acc = (DevAccum*)a.acc;
         unsigned long long* stop_acc = &acc->stop[hadron ? 1 : 0][0];
         unsigned long long* calls_acc = &acc->transp_calls[hadron ? 1 : 0][0];
-        double* stop_field = a.record_mode ? a.state + (long long)(hadron ? F_STOP_P : F_STOP_E) * a.cap : nullptr;
-        void* args[] = {&tk, &cap, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
+        double* stop_field = a.record_mode ? a.state + (long long)(hadron ? F_STOP_P : F_STOP_E) * fs : nullptr;
+        void* args[] = {&tk, &fs, &ss, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
         const int rc = jit_launch(st.fn, (unsigned)st.grid, (unsigned)st.block, (void*)s, args);
         if (rc != 0) return cudaErrorLaunchFailure;
       } else if (st.kind == ARM_STAGE_MIDDLE) {

@@ -22,48 +22,97 @@ namespace SIMC_VARIANT_NS {
 
 // ---- state buffer ------------------------------------------------------------------------
 enum StateField : int {
-  F_TRY = 0, F_DRAW, F_STAGE, F_STOP_P, F_STOP_E,
-  F_TX, F_TY, F_TZ, F_RASTERY, F_ELOSS0, F_ELOSS1, F_ELOSS2, F_TEFF0, F_TEFF1, F_TEFF2, F_COULOMB,
-  F_GENW, F_JAC, F_EINSHIFT, F_EESHIFT, F_MTREC,
-  F_VEIN, F_VEE, F_VEDELTA, F_VEYP, F_VEXP, F_VETHETA, F_VPE, F_VPP, F_VPDELTA, F_VPYP, F_VPXP, F_VQ2, F_VEM, F_VPM,
-  F_VTREC,
-  F_OEIN, F_OEE, F_OEDELTA, F_OPE, F_OPP, F_OPDELTA,
-  F_EG0, F_EG1, F_EG2, F_NTAIL, F_RADP, F_HARDCOR,
-  F_DANG0, F_DANG1,
-  F_SPP_D, F_SPP_Y, F_SPP_X, F_SPP_Z, F_RCP_D, F_RCP_Y, F_RCP_X, F_RCP_Z, F_FPP_PATH,
-  F_RP_P, F_RP_E, F_RP_TH, F_RP_PH, F_RESFAC,
-  F_SPE_D, F_SPE_Y, F_SPE_X, F_SPE_Z, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCE_Z, F_FPE_PATH,
-  F_RE_E, F_RE_TH, F_RE_PH,
-  F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_PASSCUTS, F_REM, F_RPM, F_RW,
-  // track of the arm in flight, between the two segments of its program
-  F_TK_XS, F_TK_YS, F_TK_DX, F_TK_DY, F_TK_DPP, F_TK_P, F_TK_M2, F_TK_PATH, F_TK_DECD, F_TK_DFLAG, F_TK_FRY,
-  // meson production: vertex%nu, q, uq, up, main%epsilon, theta_pq, phi_pq, t, W; hadron focal-plane slopes;
-  // results of peepi / peeK
-  F_VNU, F_VQ, F_UQX, F_UQY, F_UQZ, F_UPX, F_UPY, F_UPZ, F_MEPS, F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
-  F_FPP_DX, F_FPP_DY, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM,
-  // semi-inclusive production: vertex%zhad, pt2 and the thrown nucleon momentum (COMMON /pfermi_stuff/)
-  F_ZHAD, F_PT2, F_PFER, F_PFERX, F_PFERY, F_PFERZ, F_EFER, F_XFERMI,
+  // ---- the block k_generate / k_regen write in one go (store_event / load_event): F_GEN_END doubles in groups of
+  // four (one 32-byte sector each), grouped by the kernels that read them later
+  F_TRY = 0, F_DRAW, F_NTAIL, F_RADP,
+  F_TX, F_TY, F_TZ, F_RASTERY,
+  F_ELOSS0, F_ELOSS1, F_ELOSS2, F_COULOMB,
+  F_TEFF0, F_TEFF1, F_TEFF2, F_GENW,
+  F_OEIN, F_OEE, F_OEDELTA, F_OPE,
+  F_OPP, F_OPDELTA, F_VPYP, F_VPXP,
+  F_VEYP, F_VEXP, F_VEDELTA, F_VPDELTA,
+  F_VEIN, F_VEE, F_VETHETA, F_VQ2,
+  F_VPE, F_VPP, F_VEM, F_VPM,
+  F_UEX, F_UEY, F_UEZ, F_HARDCOR,
+  F_UPX, F_UPY, F_UPZ, F_VTREC,
+  F_RC_CEXT0, F_RC_GEXT, F_RC_G1, F_RC_G2,
+  F_RC_G4, F_RC_BT0, F_RC_BT1, F_RD_WHICH,
+  F_RD_EMIN, F_RD_EMAX, F_RD_EG, F_RD_BW,
+  F_JAC, F_EINSHIFT, F_EESHIFT, F_MTREC,
+  F_EG0, F_EG1, F_EG2, F_VEPHI,
+  F_VPTHETA, F_VPPHI, F_VNU, F_VQ,
+  F_UQX, F_UQY, F_UQZ, F_MEPS,
+  F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
+  F_ZHAD, F_PT2, F_PFER, F_EFER,
+  F_PFERX, F_PFERY, F_PFERZ, F_GEN_PAD,
+  F_GEN_END,
+  // ---- written by the later stages
+  F_STAGE = F_GEN_END, F_STOP_P, F_STOP_E, F_RESFAC,
+  F_DANG0, F_DANG1, F_FPP_PATH, F_FPE_PATH,
+  F_SPP_D, F_SPP_Y, F_SPP_X, F_SPP_Z, F_RCP_D, F_RCP_Y, F_RCP_X, F_RCP_Z,
+  F_SPE_D, F_SPE_Y, F_SPE_X, F_SPE_Z, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCE_Z,
+  F_RP_P, F_RP_E, F_RP_TH, F_RP_PH, F_RE_E, F_RE_TH, F_RE_PH, F_FPP_DX,
+  F_FPP_DY, F_WEIGHT, F_SIGCC, F_SIGCC_RECON, F_PASSCUTS, F_REM, F_RPM, F_RW,
+  // track of the arm in flight, between the segments of its program (two sectors per slot)
+  F_TK_XS, F_TK_YS, F_TK_DX, F_TK_DY, F_TK_DPP, F_TK_P, F_TK_M2, F_TK_PATH, F_TK_DECD, F_TK_DFLAG, F_TK_FRY, F_TK_PAD,
+  // results of peepi / peeK / peepiX (record mode)
+  F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM, F_XFERMI,
   // ntuple rows (record mode only): focal-plane positions, decay bookkeeping, then the row itself
   F_FPP_X, F_FPP_Y, F_FPE_X, F_FPE_DX, F_FPE_Y, F_FPE_DY, F_DECDIST, F_MH2FINAL,
-  // what the deferred peaked_rad_weight reads (k_radw): the electron's direction, the per-event radiative
-  // constants and generate_rad's photon-energy limits; and the angles a try carries into its second pass
-  // through complete_ev (k_regen)
-  F_UEX, F_UEY, F_UEZ, F_RC_CEXT0, F_RC_GEXT, F_RC_G1, F_RC_G2, F_RC_G4, F_RC_BT0, F_RC_BT1,
-  F_RD_EMIN, F_RD_EMAX, F_RD_EG, F_RD_BW, F_RD_WHICH, F_VEPHI, F_VPTHETA, F_VPPHI,
   F_NTU0, F_NTU_LAST = F_NTU0 + SIMC_NTUPLE_MAXCOL - 1,
   F_NFIELDS
 };
+static_assert(F_GEN_END % 4 == 0 && F_TK_XS % 4 == 0 && F_SPP_D % 4 == 0 && F_SPE_D % 4 == 0 && F_RCP_D % 4 == 0 &&
+              F_RCE_D % 4 == 0 && F_RP_P % 4 == 0 && F_TX % 4 == 0 && F_ELOSS0 % 4 == 0 && F_TEFF0 % 4 == 0 && F_OEIN % 4 == 0 &&
+              F_OPP % 4 == 0 && F_VEYP % 4 == 0, "32-byte groups");
 
 // the compiled stretches (mapgen.h) address the track by row offsets from F_TK_XS
 static_assert(F_TK_YS == F_TK_XS + 1 && F_TK_DX == F_TK_XS + 2 && F_TK_DY == F_TK_XS + 3 && F_TK_DPP == F_TK_XS + 4 &&
               F_TK_P == F_TK_XS + 5 && F_TK_M2 == F_TK_XS + 6 && F_TK_PATH == F_TK_XS + 7, "track rows: mapgen.h");
 
+// Layout of the state buffer.  SIMC_STATE_AOS = 1 (default): one record of kStateStride doubles per slot
+// (base[slot * kStateStride + field]).  From the first aperture on, the survivors are a shrinking, scattered subset of
+// the slots (a fifth of them reach k_finish), so a warp's 32 loads of one field touch 32 different 32-byte sectors
+// whatever the layout; with records, the other three doubles of each sector are the neighbouring fields of the same
+// event, which the kernel reads next, instead of three events that died.  SIMC_STATE_AOS = 0: struct of arrays
+// (base[field * cap + slot]), the round-1 layout, coalesced only while every slot is alive.
+#ifndef SIMC_STATE_AOS
+#define SIMC_STATE_AOS 1
+#endif
+constexpr int kStateStride = (F_NFIELDS + 15) / 16 * 16;      // records start on 128-byte lines
+// 32-byte accesses (sm_100: ld/st.global.v4.f64), for groups of four fields that start at a multiple of four
+__device__ __forceinline__ void st_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_v4(const double* p, double& a, double& b, double& c, double& d) {
+  asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
 struct StateBuf {
   double* base;
   long long cap;
+#if SIMC_STATE_AOS
+  __device__ __forceinline__ double ld(int f, long long slot) const { return base[slot * kStateStride + f]; }
+  __device__ __forceinline__ void st(int f, long long slot, double v) const { base[slot * kStateStride + f] = v; }
+  __device__ __forceinline__ void ld4(int f, long long slot, double& a, double& b, double& c, double& d) const {
+    ld_v4(base + slot * kStateStride + f, a, b, c, d);
+  }
+  __device__ __forceinline__ void st4(int f, long long slot, double a, double b, double c, double d) const {
+    st_v4(base + slot * kStateStride + f, a, b, c, d);
+  }
+#else
   __device__ __forceinline__ double ld(int f, long long slot) const { return base[(long long)f * cap + slot]; }
   __device__ __forceinline__ void st(int f, long long slot, double v) const { base[(long long)f * cap + slot] = v; }
+  __device__ __forceinline__ void ld4(int f, long long slot, double& a, double& b, double& c, double& d) const {
+    a = ld(f, slot); b = ld(f + 1, slot); c = ld(f + 2, slot); d = ld(f + 3, slot);
+  }
+  __device__ __forceinline__ void st4(int f, long long slot, double a, double b, double c, double d) const {
+    st(f, slot, a); st(f + 1, slot, b); st(f + 2, slot, c); st(f + 3, slot, d);
+  }
+#endif
 };
+// strides (in doubles) from field to field and from slot to slot, for code that addresses the buffer itself (mapgen.h)
+__host__ __device__ inline long long state_field_stride(long long cap) { return SIMC_STATE_AOS ? 1 : cap; }
+__host__ __device__ inline long long state_slot_stride() { return SIMC_STATE_AOS ? kStateStride : 1; }
 
 // ---- exact accumulators --------------------------------------------------------------------
 struct DevAccum {
@@ -185,53 +234,53 @@ __device__ __forceinline__ void geni_hist(const simc_run_config& cfg, unsigned (
   for (int k = 0; k < 8; ++k) warp_hist_add(h_geni[k], hist_bin(cfg.hist_axis[2][k], gv[k]));
 }
 
-// The try's record in the state buffer.  `carry`: the try is on its way to k_regen, which also needs the angles
-// and main%Trec of the first pass.
+// The try's record in the state buffer: the first F_GEN_END fields, written (and, for the second pass of a try whose
+// incoming electron radiated, read back) as 32-byte groups.  Fields a reaction does not use hold zeros.
 __device__ __forceinline__ void store_event(const LoopArgs& A, const GenFlags& g, unsigned slot, long long i, unsigned draw,
                                             const EventState& s, const GenRad& gr, bool ok, bool carry) {
   const StateBuf& S = A.st;
-  S.st(F_TRY, slot, (double)i); S.st(F_DRAW, slot, (double)draw);
+  (void)carry;
+  double r[F_GEN_END];
+  r[F_TRY] = (double)i; r[F_DRAW] = (double)draw; r[F_NTAIL] = (double)s.rad.ntail; r[F_RADP] = s.rad.rad_proton_this_ev ? 1.0 : 0.0;
+  r[F_TX] = s.tx; r[F_TY] = s.ty; r[F_TZ] = s.tz; r[F_RASTERY] = s.rastery;
+  r[F_ELOSS0] = s.Eloss[0]; r[F_ELOSS1] = s.Eloss[1]; r[F_ELOSS2] = s.Eloss[2]; r[F_COULOMB] = s.Coulomb;
+  r[F_TEFF0] = s.teff[0]; r[F_TEFF1] = s.teff[1]; r[F_TEFF2] = s.teff[2]; r[F_GENW] = s.gen_weight;
+  r[F_OEIN] = s.o_Ein; r[F_OEE] = s.o_eE; r[F_OEDELTA] = s.o_edelta; r[F_OPE] = s.o_pE;
+  r[F_OPP] = s.o_pP; r[F_OPDELTA] = s.o_pdelta; r[F_VPYP] = s.v_pyptar; r[F_VPXP] = s.v_pxptar;
+  r[F_VEYP] = s.v_eyptar; r[F_VEXP] = s.v_exptar; r[F_VEDELTA] = s.v_edelta; r[F_VPDELTA] = s.v_pdelta;
+  r[F_VEIN] = s.v_Ein; r[F_VEE] = s.v_eE; r[F_VETHETA] = s.v_etheta; r[F_VQ2] = s.v_Q2;
+  r[F_VPE] = s.v_pE; r[F_VPP] = s.v_pP; r[F_VEM] = s.v_Em; r[F_VPM] = s.v_Pm;
+  r[F_UEX] = s.uex; r[F_UEY] = s.uey; r[F_UEZ] = s.uez; r[F_HARDCOR] = s.rad.hardcorfac;
+  r[F_UPX] = s.upx; r[F_UPY] = s.upy; r[F_UPZ] = s.upz; r[F_VTREC] = s.v_Trec;
+  r[F_RC_CEXT0] = s.rad.c_ext0; r[F_RC_GEXT] = s.rad.g_ext; r[F_RC_G1] = s.rad.g[1]; r[F_RC_G2] = s.rad.g[2];
+  r[F_RC_G4] = s.rad.g[4]; r[F_RC_BT0] = s.rad.bt[0]; r[F_RC_BT1] = s.rad.bt[1]; r[F_RD_WHICH] = (double)gr.which;
+  r[F_RD_EMIN] = gr.emin; r[F_RD_EMAX] = gr.emax; r[F_RD_EG] = gr.eg; r[F_RD_BW] = gr.bw;
+  r[F_JAC] = s.jacobian; r[F_EINSHIFT] = s.Ein_shift; r[F_EESHIFT] = s.Ee_shift; r[F_MTREC] = s.Trec;
+  r[F_EG0] = s.rad.Egamma_used[0]; r[F_EG1] = s.rad.Egamma_used[1]; r[F_EG2] = s.rad.Egamma_used[2]; r[F_VEPHI] = s.v_ephi;
+  r[F_VPTHETA] = s.v_ptheta; r[F_VPPHI] = s.v_pphi;
+  const bool hm = g.heavy || g.meson;
+  r[F_VNU] = hm ? s.v_nu : 0.0; r[F_VQ] = hm ? s.v_q : 0.0;
+  r[F_UQX] = hm ? s.uqx : 0.0; r[F_UQY] = hm ? s.uqy : 0.0; r[F_UQZ] = hm ? s.uqz : 0.0; r[F_MEPS] = g.meson ? s.m_eps : 0.0;
+  r[F_MTHPQ] = g.meson ? s.m_thpq : 0.0; r[F_MPHIPQ] = g.meson ? s.m_phipq : 0.0; r[F_MT] = g.meson ? s.m_t : 0.0;
+  r[F_MW] = g.meson ? s.m_W : 0.0;
+  const bool fm = g.meson && (g.semi || g.fermi);
+  r[F_ZHAD] = (g.meson && g.semi) ? s.v_zhad : 0.0; r[F_PT2] = (g.meson && g.semi) ? s.v_pt2 : 0.0;
+  r[F_PFER] = fm ? s.pfer : 0.0; r[F_EFER] = fm ? s.efer : 0.0;
+  r[F_PFERX] = fm ? s.pferx : 0.0; r[F_PFERY] = fm ? s.pfery : 0.0; r[F_PFERZ] = fm ? s.pferz : 0.0; r[F_GEN_PAD] = 0.0;
+  // the groups past F_VPPHI only matter to the reactions that fill them
+  const int n_groups = hm ? F_GEN_END / 4 : (F_VQ + 1) / 4;
+#if SIMC_STATE_AOS
+  double* rec = S.base + (long long)slot * kStateStride;
+#pragma unroll
+  for (int k = 0; k < F_GEN_END / 4; ++k)
+    if (k < n_groups) st_v4(rec + 4 * k, r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+#else
+#pragma unroll
+  for (int k = 0; k < F_GEN_END; ++k)
+    if (k < 4 * n_groups) S.st(k, slot, r[k]);
+#endif
   if (A.record_mode) {      // only the per-try records read these
     S.st(F_STAGE, slot, ok ? 1.0 : 0.0); S.st(F_STOP_P, slot, -1.0); S.st(F_STOP_E, slot, -1.0);
-  }
-  S.st(F_TX, slot, s.tx); S.st(F_TY, slot, s.ty); S.st(F_TZ, slot, s.tz); S.st(F_RASTERY, slot, s.rastery);
-  S.st(F_ELOSS0, slot, s.Eloss[0]); S.st(F_ELOSS1, slot, s.Eloss[1]); S.st(F_ELOSS2, slot, s.Eloss[2]);
-  S.st(F_TEFF0, slot, s.teff[0]); S.st(F_TEFF1, slot, s.teff[1]); S.st(F_TEFF2, slot, s.teff[2]);
-  S.st(F_COULOMB, slot, s.Coulomb);
-  S.st(F_GENW, slot, s.gen_weight); S.st(F_JAC, slot, s.jacobian); S.st(F_EINSHIFT, slot, s.Ein_shift);
-  S.st(F_EESHIFT, slot, s.Ee_shift); S.st(F_MTREC, slot, s.Trec);
-  S.st(F_VEIN, slot, s.v_Ein); S.st(F_VEE, slot, s.v_eE); S.st(F_VEDELTA, slot, s.v_edelta);
-  S.st(F_VEYP, slot, s.v_eyptar); S.st(F_VEXP, slot, s.v_exptar); S.st(F_VETHETA, slot, s.v_etheta);
-  S.st(F_VPE, slot, s.v_pE); S.st(F_VPP, slot, s.v_pP); S.st(F_VPDELTA, slot, s.v_pdelta);
-  S.st(F_VPYP, slot, s.v_pyptar); S.st(F_VPXP, slot, s.v_pxptar); S.st(F_VQ2, slot, s.v_Q2);
-  S.st(F_VEM, slot, s.v_Em); S.st(F_VPM, slot, s.v_Pm); S.st(F_VTREC, slot, s.v_Trec);
-  S.st(F_OEIN, slot, s.o_Ein); S.st(F_OEE, slot, s.o_eE); S.st(F_OEDELTA, slot, s.o_edelta);
-  S.st(F_OPE, slot, s.o_pE); S.st(F_OPP, slot, s.o_pP); S.st(F_OPDELTA, slot, s.o_pdelta);
-  S.st(F_EG0, slot, s.rad.Egamma_used[0]); S.st(F_EG1, slot, s.rad.Egamma_used[1]);
-  S.st(F_EG2, slot, s.rad.Egamma_used[2]); S.st(F_NTAIL, slot, (double)s.rad.ntail);
-  S.st(F_RADP, slot, s.rad.rad_proton_this_ev ? 1.0 : 0.0); S.st(F_HARDCOR, slot, s.rad.hardcorfac);
-  S.st(F_UEX, slot, s.uex); S.st(F_UEY, slot, s.uey); S.st(F_UEZ, slot, s.uez);
-  S.st(F_UPX, slot, s.upx); S.st(F_UPY, slot, s.upy); S.st(F_UPZ, slot, s.upz);
-  S.st(F_RC_CEXT0, slot, s.rad.c_ext0); S.st(F_RC_GEXT, slot, s.rad.g_ext); S.st(F_RC_G1, slot, s.rad.g[1]);
-  S.st(F_RC_G2, slot, s.rad.g[2]); S.st(F_RC_G4, slot, s.rad.g[4]); S.st(F_RC_BT0, slot, s.rad.bt[0]);
-  S.st(F_RC_BT1, slot, s.rad.bt[1]);
-  S.st(F_RD_EMIN, slot, gr.emin); S.st(F_RD_EMAX, slot, gr.emax); S.st(F_RD_EG, slot, gr.eg); S.st(F_RD_BW, slot, gr.bw);
-  S.st(F_RD_WHICH, slot, (double)gr.which);
-  if (carry) {
-    S.st(F_VEPHI, slot, s.v_ephi); S.st(F_VPTHETA, slot, s.v_ptheta); S.st(F_VPPHI, slot, s.v_pphi);
-  }
-  if ((g.heavy || g.meson) && (ok || carry)) {
-    S.st(F_VNU, slot, s.v_nu); S.st(F_VQ, slot, s.v_q); S.st(F_UQX, slot, s.uqx); S.st(F_UQY, slot, s.uqy);
-    S.st(F_UQZ, slot, s.uqz);
-  }
-  if (g.meson && (ok || carry)) {
-    S.st(F_MEPS, slot, s.m_eps); S.st(F_MTHPQ, slot, s.m_thpq); S.st(F_MPHIPQ, slot, s.m_phipq);
-    S.st(F_MT, slot, s.m_t); S.st(F_MW, slot, s.m_W);
-    if (g.semi) { S.st(F_ZHAD, slot, s.v_zhad); S.st(F_PT2, slot, s.v_pt2); }
-    if (g.semi || g.fermi) {
-      S.st(F_PFER, slot, s.pfer); S.st(F_PFERX, slot, s.pferx); S.st(F_PFERY, slot, s.pfery);
-      S.st(F_PFERZ, slot, s.pferz); S.st(F_EFER, slot, s.efer);
-    }
   }
 }
 
@@ -240,45 +289,48 @@ __device__ __forceinline__ void store_event(const LoopArgs& A, const GenFlags& g
 // the geni histograms, as in the one-pass reference).
 __device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g, unsigned slot, EventState& s, GenRad& gr) {
   const StateBuf& S = A.st;
-  s.tx = S.ld(F_TX, slot); s.ty = S.ld(F_TY, slot); s.tz = S.ld(F_TZ, slot); s.rastery = S.ld(F_RASTERY, slot);
-  s.Eloss[0] = S.ld(F_ELOSS0, slot); s.Eloss[1] = S.ld(F_ELOSS1, slot); s.Eloss[2] = S.ld(F_ELOSS2, slot);
-  s.teff[0] = S.ld(F_TEFF0, slot); s.teff[1] = S.ld(F_TEFF1, slot); s.teff[2] = S.ld(F_TEFF2, slot);
-  s.Coulomb = S.ld(F_COULOMB, slot);
-  s.gen_weight = S.ld(F_GENW, slot); s.jacobian = S.ld(F_JAC, slot); s.Ein_shift = S.ld(F_EINSHIFT, slot);
-  s.Ee_shift = S.ld(F_EESHIFT, slot); s.Trec = S.ld(F_MTREC, slot);
-  s.v_Ein = S.ld(F_VEIN, slot); s.v_eE = S.ld(F_VEE, slot); s.v_edelta = S.ld(F_VEDELTA, slot);
-  s.v_eyptar = S.ld(F_VEYP, slot); s.v_exptar = S.ld(F_VEXP, slot); s.v_etheta = S.ld(F_VETHETA, slot);
-  s.v_ephi = S.ld(F_VEPHI, slot);
-  s.v_pE = S.ld(F_VPE, slot); s.v_pP = S.ld(F_VPP, slot); s.v_pdelta = S.ld(F_VPDELTA, slot);
-  s.v_pyptar = S.ld(F_VPYP, slot); s.v_pxptar = S.ld(F_VPXP, slot); s.v_ptheta = S.ld(F_VPTHETA, slot);
-  s.v_pphi = S.ld(F_VPPHI, slot); s.v_Q2 = S.ld(F_VQ2, slot);
-  s.v_Em = S.ld(F_VEM, slot); s.v_Pm = S.ld(F_VPM, slot); s.v_Trec = S.ld(F_VTREC, slot);
-  s.uex = S.ld(F_UEX, slot); s.uey = S.ld(F_UEY, slot); s.uez = S.ld(F_UEZ, slot);
-  s.upx = S.ld(F_UPX, slot); s.upy = S.ld(F_UPY, slot); s.upz = S.ld(F_UPZ, slot);
-  s.rad.Egamma_used[0] = S.ld(F_EG0, slot); s.rad.Egamma_used[1] = S.ld(F_EG1, slot); s.rad.Egamma_used[2] = S.ld(F_EG2, slot);
-  s.rad.ntail = (int)S.ld(F_NTAIL, slot);
-  s.rad.rad_proton_this_ev = S.ld(F_RADP, slot) != 0.0; s.rad.hardcorfac = S.ld(F_HARDCOR, slot);
-  s.rad.c_ext0 = S.ld(F_RC_CEXT0, slot); s.rad.g_ext = S.ld(F_RC_GEXT, slot); s.rad.g[1] = S.ld(F_RC_G1, slot);
-  s.rad.g[2] = S.ld(F_RC_G2, slot); s.rad.g[4] = S.ld(F_RC_G4, slot); s.rad.bt[0] = S.ld(F_RC_BT0, slot);
-  s.rad.bt[1] = S.ld(F_RC_BT1, slot);
-  gr.emin = S.ld(F_RD_EMIN, slot); gr.emax = S.ld(F_RD_EMAX, slot); gr.eg = S.ld(F_RD_EG, slot); gr.bw = S.ld(F_RD_BW, slot);
-  gr.which = (int)S.ld(F_RD_WHICH, slot);
-  s.v_nu = 0; s.v_q = 0; s.uqx = 0; s.uqy = 0; s.uqz = 0;
-  s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
-  s.v_zhad = 0; s.v_pt2 = 0; s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = A.cfg->targ.Mtar_struck;
-  if (g.heavy || g.meson) {
-    s.v_nu = S.ld(F_VNU, slot); s.v_q = S.ld(F_VQ, slot); s.uqx = S.ld(F_UQX, slot); s.uqy = S.ld(F_UQY, slot);
-    s.uqz = S.ld(F_UQZ, slot);
+  double r[F_GEN_END];
+  const bool hm = g.heavy || g.meson;
+  const int n_groups = hm ? F_GEN_END / 4 : (F_VQ + 1) / 4;
+#if SIMC_STATE_AOS
+  const double* rec = S.base + (long long)slot * kStateStride;
+#pragma unroll
+  for (int k = 0; k < F_GEN_END / 4; ++k) {
+    if (k < n_groups) ld_v4(rec + 4 * k, r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+    else { r[4 * k] = 0.0; r[4 * k + 1] = 0.0; r[4 * k + 2] = 0.0; r[4 * k + 3] = 0.0; }
   }
-  if (g.meson) {
-    s.m_eps = S.ld(F_MEPS, slot); s.m_thpq = S.ld(F_MTHPQ, slot); s.m_phipq = S.ld(F_MPHIPQ, slot);
-    s.m_t = S.ld(F_MT, slot); s.m_W = S.ld(F_MW, slot);
-    if (g.semi) { s.v_zhad = S.ld(F_ZHAD, slot); s.v_pt2 = S.ld(F_PT2, slot); }
-    if (g.semi || g.fermi) {
-      s.pfer = S.ld(F_PFER, slot); s.pferx = S.ld(F_PFERX, slot); s.pfery = S.ld(F_PFERY, slot);
-      s.pferz = S.ld(F_PFERZ, slot); s.efer = S.ld(F_EFER, slot);
-    }
-  }
+#else
+#pragma unroll
+  for (int k = 0; k < F_GEN_END; ++k) r[k] = k < 4 * n_groups ? S.ld(k, slot) : 0.0;
+#endif
+  s.tx = r[F_TX]; s.ty = r[F_TY]; s.tz = r[F_TZ]; s.rastery = r[F_RASTERY];
+  s.Eloss[0] = r[F_ELOSS0]; s.Eloss[1] = r[F_ELOSS1]; s.Eloss[2] = r[F_ELOSS2];
+  s.teff[0] = r[F_TEFF0]; s.teff[1] = r[F_TEFF1]; s.teff[2] = r[F_TEFF2];
+  s.Coulomb = r[F_COULOMB];
+  s.gen_weight = r[F_GENW]; s.jacobian = r[F_JAC]; s.Ein_shift = r[F_EINSHIFT];
+  s.Ee_shift = r[F_EESHIFT]; s.Trec = r[F_MTREC];
+  s.v_Ein = r[F_VEIN]; s.v_eE = r[F_VEE]; s.v_edelta = r[F_VEDELTA];
+  s.v_eyptar = r[F_VEYP]; s.v_exptar = r[F_VEXP]; s.v_etheta = r[F_VETHETA];
+  s.v_ephi = r[F_VEPHI];
+  s.v_pE = r[F_VPE]; s.v_pP = r[F_VPP]; s.v_pdelta = r[F_VPDELTA];
+  s.v_pyptar = r[F_VPYP]; s.v_pxptar = r[F_VPXP]; s.v_ptheta = r[F_VPTHETA];
+  s.v_pphi = r[F_VPPHI]; s.v_Q2 = r[F_VQ2];
+  s.v_Em = r[F_VEM]; s.v_Pm = r[F_VPM]; s.v_Trec = r[F_VTREC];
+  s.uex = r[F_UEX]; s.uey = r[F_UEY]; s.uez = r[F_UEZ];
+  s.upx = r[F_UPX]; s.upy = r[F_UPY]; s.upz = r[F_UPZ];
+  s.rad.Egamma_used[0] = r[F_EG0]; s.rad.Egamma_used[1] = r[F_EG1]; s.rad.Egamma_used[2] = r[F_EG2];
+  s.rad.ntail = (int)r[F_NTAIL];
+  s.rad.rad_proton_this_ev = r[F_RADP] != 0.0; s.rad.hardcorfac = r[F_HARDCOR];
+  s.rad.c_ext0 = r[F_RC_CEXT0]; s.rad.g_ext = r[F_RC_GEXT]; s.rad.g[1] = r[F_RC_G1];
+  s.rad.g[2] = r[F_RC_G2]; s.rad.g[4] = r[F_RC_G4]; s.rad.bt[0] = r[F_RC_BT0];
+  s.rad.bt[1] = r[F_RC_BT1];
+  gr.emin = r[F_RD_EMIN]; gr.emax = r[F_RD_EMAX]; gr.eg = r[F_RD_EG]; gr.bw = r[F_RD_BW];
+  gr.which = (int)r[F_RD_WHICH];
+  s.v_nu = r[F_VNU]; s.v_q = r[F_VQ]; s.uqx = r[F_UQX]; s.uqy = r[F_UQY]; s.uqz = r[F_UQZ];
+  s.m_eps = r[F_MEPS]; s.m_thpq = r[F_MTHPQ]; s.m_phipq = r[F_MPHIPQ]; s.m_t = r[F_MT]; s.m_W = r[F_MW]; s.m_tmin = 0;
+  s.v_zhad = r[F_ZHAD]; s.v_pt2 = r[F_PT2];
+  s.pfer = r[F_PFER]; s.pferx = r[F_PFERX]; s.pfery = r[F_PFERY]; s.pferz = r[F_PFERZ];
+  s.efer = (g.meson && (g.semi || g.fermi)) ? r[F_EFER] : A.cfg->targ.Mtar_struck;
 }
 
 __device__ __forceinline__ void gen_shared_init(const LoopArgs& A, unsigned (*h_geni)[SIMC_NHIST], MatTable& mt_s) {
@@ -366,6 +418,8 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopAr
     if (g.meson) ok = generate_meson_second(cfg, mt_s, rng, GaussFn(), s, active);
     else if (g.heavy) ok = generate_heavy_second(cfg, mt_s, rng, GaussFn(), s, active);
     else ok = generate_hyd_elast_second(cfg, mt_s, rng, GaussFn(), s, active);
+    // rad_flag = 2, 3: the tails behind tail 1 (radc.f:354-455)
+    if (cfg.rad_flag >= 2) ok = (active && ok) ? generate_rad_basis_rest(cfg, rng, s, gr, true) : false;
     ok = generate_finalize(cfg, s, ok);
     if (active) {
       geni_hist(cfg, h_geni, s);
@@ -388,7 +442,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_radw(LoopArgs A, int list_idx) {
     const unsigned slot = in_list[i];
     const int which = (int)S.ld(F_RD_WHICH, slot);
     double rad_weight = 1;
-    if (which) {
+    if (which == 4) {               // rad_flag = 2, 3: the weight was finished at generation (generate_rad_basis_*)
+      rad_weight = S.ld(F_RD_BW, slot);
+    } else if (which) {
       RadEvDev R;
       R.c_ext0 = S.ld(F_RC_CEXT0, slot); R.g_ext = S.ld(F_RC_GEXT, slot); R.g[1] = S.ld(F_RC_G1, slot);
       R.g[2] = S.ld(F_RC_G2, slot); R.g[4] = S.ld(F_RC_G4, slot); R.bt[0] = S.ld(F_RC_BT0, slot); R.bt[1] = S.ld(F_RC_BT1, slot);
@@ -467,44 +523,50 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       ArmEntry en;
       en.sp_delta = en.sp_yptar = en.sp_xptar = en.sp_z = en.x = en.y = en.dx = en.dy = 0.0;
       if (active) {
-        const double tx = S.ld(F_TX, slot), ty = S.ld(F_TY, slot), tz = S.ld(F_TZ, slot);
-        double dang0, dang1, sp_delta, ang0 = 0.0, ang1 = 0.0;
+        // the generation record comes in 32-byte groups (StateField): target position, energy losses, thicknesses,
+        // the `orig` energies and the generated angles
+        double tx, ty, tz, rastery, el0, el1, el2, coul, tf0, tf1, tf2, genw, oEin, oeE, oed, opE, opP, opd, vpy, vpx;
+        S.ld4(F_TX, slot, tx, ty, tz, rastery);
+        S.ld4(F_ELOSS0, slot, el0, el1, el2, coul);
+        S.ld4(F_TEFF0, slot, tf0, tf1, tf2, genw);
+        S.ld4(F_OEIN, slot, oEin, oeE, oed, opE);
+        double dang0, dang1, sp_delta, ang0 = 0.0, ang1 = 0.0, o_yptar, o_xptar;
         if (WHICH == 1) {
+          S.ld4(F_OPP, slot, opP, opd, vpy, vpx);
+          o_yptar = vpy; o_xptar = vpx;
           // beam multiple scattering (simc.f:1365), then the hadron's (simc.f:1379-1399)
           if (cfg.mc_smear) {
-            const double teff = S.ld(F_TEFF0, slot), p = S.ld(F_OEIN, slot);
+            const double teff = tf0, p = oEin;
             const double ts = 13.6 / p / 1. * sqrt(teff) * (1 + 0.088 * m::log10(teff / (1. * 1.)));
             dang0 = ts * gauss1(rng, 3.5);
             dang1 = ts * gauss1(rng, 3.5);
           } else { dang0 = 0.0; dang1 = 0.0; }
           S.st(F_DANG0, slot, dang0); S.st(F_DANG1, slot, dang1);
-          const double opE = S.ld(F_OPE, slot), opP = S.ld(F_OPP, slot);
           if (cfg.using_Eloss) {
-            const double d = opE - S.ld(F_ELOSS2, slot);
+            const double d = opE - el2;
             sp_delta = (sqrt(fabs(d * d - Mh2)) - sp.P) / sp.P * 100.;
-          } else sp_delta = S.ld(F_OPDELTA, slot);
+          } else sp_delta = opd;
           if (cfg.mc_smear) {
-            const double beta = opP / opE, teff = S.ld(F_TEFF2, slot);
+            const double beta = opP / opE, teff = tf2;
             const double ts = 13.6 / opP / beta * sqrt(teff) * (1 + 0.088 * m::log10(teff / (beta * beta)));
             ang0 = ts * gauss1(rng, 3.5);
             ang1 = ts * gauss1(rng, 3.5);
           }
         } else {
+          double ved, vpd;
+          S.ld4(F_VEYP, slot, o_yptar, o_xptar, ved, vpd);
           dang0 = S.ld(F_DANG0, slot); dang1 = S.ld(F_DANG1, slot);
-          const double oeE = S.ld(F_OEE, slot);
-          sp_delta = 100 * (oeE - S.ld(F_ELOSS1, slot) - S.ld(F_COULOMB, slot) - sp.P) / sp.P;
+          sp_delta = 100 * (oeE - el1 - coul - sp.P) / sp.P;
           if (cfg.mc_smear) {
-            const double teff = S.ld(F_TEFF1, slot);
+            const double teff = tf1;
             const double ts = 13.6 / oeE / 1. * sqrt(teff) * (1 + 0.088 * m::log10(teff / (1. * 1.)));
             ang0 = ts * gauss1(rng, 3.5);
             ang1 = ts * gauss1(rng, 3.5);
           }
         }
-        const double o_yptar = S.ld(WHICH == 1 ? F_VPYP : F_VEYP, slot), o_xptar = S.ld(WHICH == 1 ? F_VPXP : F_VEXP, slot);
         arm_entry(sp, tx, ty, tz, sp_delta, o_yptar + ang0 + dang0, o_xptar + ang1 + dang1 * sp.cos_th, en);
-        S.st(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta); S.st(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot, en.sp_yptar);
-        S.st(WHICH == 1 ? F_SPP_X : F_SPE_X, slot, en.sp_xptar); S.st(WHICH == 1 ? F_SPP_Z : F_SPE_Z, slot, en.sp_z);
-        const double fry_raster = cfg.correct_raster ? -S.ld(F_RASTERY, slot) : 0.0;
+        S.st4(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta, en.sp_yptar, en.sp_xptar, en.sp_z);
+        const double fry_raster = cfg.correct_raster ? -rastery : 0.0;
         fry = (arm_id == 1 || arm_id == 5) ? en.x : fry_raster;    // xtar_init, simc.f:1441,1463
       }
       t.dpps = en.sp_delta; t.xs = en.x; t.ys = en.y; t.dxdzs = en.dx; t.dydzs = en.dy;
@@ -524,9 +586,9 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       if (active) {
         S.st(F_DRAW, slot, (double)rng.draw);
         if (ok) {
-          S.st(F_TK_XS, slot, t.xs); S.st(F_TK_YS, slot, t.ys); S.st(F_TK_DX, slot, t.dxdzs); S.st(F_TK_DY, slot, t.dydzs);
-          S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
-          S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0); S.st(F_TK_FRY, slot, fry);
+          S.st4(F_TK_XS, slot, t.xs, t.ys, t.dxdzs, t.dydzs);
+          S.st4(F_TK_DPP, slot, t.dpps, t.p, t.m2, t.pathlen);
+          S.st4(F_TK_DECD, slot, t.decdist, t.dflag ? 1.0 : 0.0, fry, 0.0);
         } else {
           if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
           warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
@@ -534,9 +596,11 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       }
     } else if (SEG == 2) {
       if (active) {
-        t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
-        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.p_spec = sp.P; t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
-        t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
+        double dfl, pad;
+        S.ld4(F_TK_XS, slot, t.xs, t.ys, t.dxdzs, t.dydzs);
+        S.ld4(F_TK_DPP, slot, t.dpps, t.p, t.m2, t.pathlen);
+        S.ld4(F_TK_DECD, slot, t.decdist, dfl, fry, pad);
+        t.p_spec = sp.P; t.dflag = dfl != 0.0;
       } else {
         t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.p_spec = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
       }
@@ -547,9 +611,9 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       if (active) {
         S.st(F_DRAW, slot, (double)rng.draw);
         if (ok) {
-          S.st(F_TK_XS, slot, t.xs); S.st(F_TK_YS, slot, t.ys); S.st(F_TK_DX, slot, t.dxdzs); S.st(F_TK_DY, slot, t.dydzs);
-          S.st(F_TK_DPP, slot, t.dpps); S.st(F_TK_P, slot, t.p); S.st(F_TK_M2, slot, t.m2); S.st(F_TK_PATH, slot, t.pathlen);
-          S.st(F_TK_DECD, slot, t.decdist); S.st(F_TK_DFLAG, slot, t.dflag ? 1.0 : 0.0);
+          S.st4(F_TK_XS, slot, t.xs, t.ys, t.dxdzs, t.dydzs);
+          S.st4(F_TK_DPP, slot, t.dpps, t.p, t.m2, t.pathlen);
+          S.st4(F_TK_DECD, slot, t.decdist, t.dflag ? 1.0 : 0.0, fry, 0.0);
         } else {
           if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)res.stop_code);
           warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
@@ -558,9 +622,11 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
     } else {
       double rc_delta = 0, rc_yptar = 0, rc_xptar = 0, rc_z = 0.0, path = 0.0, resmult = 0.0;
       if (active) {
-        t.xs = S.ld(F_TK_XS, slot); t.ys = S.ld(F_TK_YS, slot); t.dxdzs = S.ld(F_TK_DX, slot); t.dydzs = S.ld(F_TK_DY, slot);
-        t.dpps = S.ld(F_TK_DPP, slot); t.p = S.ld(F_TK_P, slot); t.p_spec = sp.P; t.m2 = S.ld(F_TK_M2, slot); t.pathlen = S.ld(F_TK_PATH, slot);
-        t.decdist = S.ld(F_TK_DECD, slot); t.dflag = S.ld(F_TK_DFLAG, slot) != 0.0; fry = S.ld(F_TK_FRY, slot);
+        double dfl, pad;
+        S.ld4(F_TK_XS, slot, t.xs, t.ys, t.dxdzs, t.dydzs);
+        S.ld4(F_TK_DPP, slot, t.dpps, t.p, t.m2, t.pathlen);
+        S.ld4(F_TK_DECD, slot, t.decdist, dfl, fry, pad);
+        t.p_spec = sp.P; t.dflag = dfl != 0.0;
       } else {
         t.xs = t.ys = t.dxdzs = t.dydzs = t.dpps = 0.0; t.p = sp.P; t.p_spec = sp.P; t.m2 = Mh2; t.pathlen = 0.0; t.decdist = 0.0; t.dflag = false;
       }
@@ -586,8 +652,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         S.st(F_DRAW, slot, (double)rng.draw);
       }
       if (ok) {
-        S.st(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta); S.st(WHICH == 1 ? F_RCP_Y : F_RCE_Y, slot, rc_yptar);
-        S.st(WHICH == 1 ? F_RCP_X : F_RCE_X, slot, rc_xptar); S.st(WHICH == 1 ? F_RCP_Z : F_RCE_Z, slot, rc_z);
+        S.st4(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta, rc_yptar, rc_xptar, rc_z);
         S.st(WHICH == 1 ? F_FPP_PATH : F_FPE_PATH, slot, path);
         if (WHICH == 1) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
         if (A.record_mode) {
@@ -615,7 +680,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
           }
         }
         if (WHICH == 1) {
-          S.st(F_RP_P, slot, rP); S.st(F_RP_E, slot, rE); S.st(F_RP_TH, slot, rth); S.st(F_RP_PH, slot, rph);
+          S.st4(F_RP_P, slot, rP, rE, rth, rph);
           if (A.record_mode) S.st(F_STAGE, slot, 2.0);
         } else {
           S.st(F_RE_E, slot, rE); S.st(F_RE_TH, slot, rth); S.st(F_RE_PH, slot, rph);

@@ -206,7 +206,7 @@ std::string generate_stretch_source(const CompiledArm& arm, const std::vector<St
   o.s += pre;
   for (size_t k = 0; k < segs.size(); ++k) {
     o.line("extern \"C\" __global__ void __launch_bounds__(BLOCK, " + std::to_string(min_blocks) + ") seg_" + std::to_string(k) +
-           "(double* __restrict__ tk, long long cap, const unsigned* __restrict__ in_list, const unsigned* __restrict__ in_count,");
+           "(double* __restrict__ tk, long long fs, long long ss, const unsigned* __restrict__ in_list, const unsigned* __restrict__ in_count,");
     o.line("    unsigned* __restrict__ out_list, unsigned* __restrict__ out_count, unsigned long long* __restrict__ stop_acc,");
     o.line("    unsigned long long* __restrict__ calls_acc, double* __restrict__ stop_field) {");
     o.line("  __shared__ unsigned s_stop[NSTOP];");
@@ -224,8 +224,9 @@ std::string generate_stretch_source(const CompiledArm& arm, const std::vector<St
     o.line("    int stop_code = -1;");
     o.line("    if (active) {");
     o.line("      slot = in_list[i];");
-    o.line("      xs = tk[0 * cap + slot]; ys = tk[1 * cap + slot]; dx = tk[2 * cap + slot]; dy = tk[3 * cap + slot];");
-    o.line("      dpp = tk[4 * cap + slot]; path = tk[7 * cap + slot];");
+    o.line("      double* const t = tk + (long long)slot * ss;");
+    o.line("      xs = t[0 * fs]; ys = t[1 * fs]; dx = t[2 * fs]; dy = t[3 * fs];");
+    o.line("      dpp = t[4 * fs]; path = t[7 * fs];");
     o.line("    }");
     for (int pc = segs[k].begin; pc < segs[k].end; ++pc) {
       const ArmOp& op = arm.ops.at(pc);
@@ -240,13 +241,14 @@ std::string generate_stretch_source(const CompiledArm& arm, const std::vector<St
     o.line("    (void)xt; (void)yt;");
     o.line("    const bool ok = alive;");
     o.line("    if (active) {");
-    o.line("      tk[7 * cap + slot] = path;");
+    o.line("      double* const t = tk + (long long)slot * ss;");
+    o.line("      t[7 * fs] = path;");
     o.line("      if (stop_code >= 0) {");
-    o.line("        if (stop_field) stop_field[slot] = (double)stop_code;");
+    o.line("        if (stop_field) stop_field[(long long)slot * ss] = (double)stop_code;");
     o.line("        if (2 + stop_code < NSTOP) atomicAdd(&s_stop[2 + stop_code], 1u);");
     o.line("      } else {");
-    o.line("        tk[0 * cap + slot] = xs; tk[1 * cap + slot] = ys; tk[2 * cap + slot] = dx; tk[3 * cap + slot] = dy;");
-    o.line("        tk[4 * cap + slot] = dpp;");
+    o.line("        t[0 * fs] = xs; t[1 * fs] = ys; t[2 * fs] = dx; t[3 * fs] = dy;");
+    o.line("        t[4 * fs] = dpp;");
     o.line("      }");
     o.line("    }");
     o.line("    __syncwarp();");

@@ -20,11 +20,12 @@ bool op_is_static(int op);
 struct StretchSpec { int begin, end; };      // ops [begin, end)
 
 // One translation unit with kernels "seg_0" ... "seg_{n-1}".  Kernel ABI (all device pointers):
-//   seg_k(double* tk, long long cap, const unsigned* in_list, const unsigned* in_count, unsigned* out_list,
+//   seg_k(double* tk, long long fs, long long ss, const unsigned* in_list, const unsigned* in_count, unsigned* out_list,
 //         unsigned* out_count, unsigned long long* stop_acc, unsigned long long* calls_acc, double* stop_field)
-// tk = row F_TK_XS of the state buffer (rows: xs, ys, dxdzs, dydzs, dpps, p, m2, pathlen, ...; loop.cuh), cap = row
-// length; survivors are appended to out_list; a stopped track leaves its path length in tk, its stop code in
-// stop_field[slot] (if not null) and in stop_acc[2 + code]; calls_acc[class - 1] counts the map evaluations.
+// tk = field F_TK_XS of slot 0 in the state buffer (fields: xs, ys, dxdzs, dydzs, dpps, p, m2, pathlen, ...; loop.cuh);
+// field k of slot s is tk[k * fs + s * ss] (records: fs = 1, ss = record length; rows: fs = row length, ss = 1);
+// survivors are appended to out_list; a stopped track leaves its path length in tk, its stop code in
+// stop_field[slot * ss] (if not null) and in stop_acc[2 + code]; calls_acc[class - 1] counts the map evaluations.
 // block_threads / min_blocks: CTA size and minimum resident CTAs per SM the kernels are built for (launch bounds).
 std::string generate_stretch_source(const CompiledArm& arm, const std::vector<StretchSpec>& segs, bool strict, int block_threads,
                                     int min_blocks);

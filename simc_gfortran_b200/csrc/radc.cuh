@@ -1,9 +1,14 @@
 // Radiative corrections on the device: per-event constants (radc_init_ev, basicrad_init_ev,
 // init.f:655-813), soft-photon factors (bremos / inter / inter_prime / spence, brem.f:216-596),
 // photon-energy sampling and weights (basicrad, peaked_rad_weight, extrad_phi, gamma,
-// lambda_dave; radc.f).  Implements the option set every shipped deck uses:
-// rad_flag <= 1, extrad_flag <= 2, intcor_mode = 1, use_offshell_rad = 1; the host refuses
-// anything else at create().
+// lambda_dave; radc.f), plus the option branches no shipped deck selects: the on-shell brem (brem.f:6-214,
+// use_offshell_rad = 0), schwinger (radc.f:711, intcor_mode = 0), the Friedrich form of extrad_phi
+// (extrad_flag = 3) and the (Egamma1, Egamma2, Egamma3) basis of rad_flag = 2, 3.  Those live in out-of-line
+// functions behind run-constant branches, so the default path (rad_flag 0, extrad_flag 2, intcor_mode 1,
+// use_offshell_rad 1) executes what it executed before.
+// The reference is built with -fno-automatic (Makefile:63): a local that an option setting never assigns
+// (dsoft_prime under intcor_mode = 0; dsoft_intmin/max under rad_flag = 1 with extrad_flag = 3) is static and
+// reads 0.0.
 #pragma once
 #include <math.h>
 #include "target.cuh"
@@ -148,6 +153,112 @@ SIMC_HD_CALL void bremos(double egamma, double ein, double kfx, double kfy, doub
   dbsoft = dbsoft / 1000.;
 }
 
+// brem, brem.f:6-214: the on-shell soft-photon calculation (elastic e-p kinematics rebuilt from ein, eout).
+// Same WHAT convention as bremos.  include_hard = calculate_spence = .true. (init.f:646-647).
+template <int WHAT>
+SIMC_HD_CALL void brem_onshell(double ein, double eout, double egamma, bool radiate_proton, double& bsoft, double& bhard,
+                               double& dbsoft) {
+  const double pi = 3.141592653589793, am = .93827231, ame = .00051099906, e2 = 1. / 137.0359895;
+  const double ak = ein / 1000., akp = eout / 1000., de = egamma / 1000.;
+  // (...)**0.5 in the reference: sqrt, as in bremos above (glibc pow(x, 0.5) is correctly rounded but for rare arguments)
+  const double eang = 2. * m::asin(sqrt(am / (2. * ak) * (ak / akp - 1.)));
+  const double sh = m::sin(eang / 2.);
+  const double q2 = 4. * ak * akp * (sh * sh);
+  const double ape = am + ak - akp;
+  const double ap = sqrt(ape * ape - am * am);
+  const double pang = m::acos((ak - akp * m::cos(eang)) / ap);
+  const double ame2 = ame * ame, ame4 = ame2 * ame2, am2 = am * am, am4 = am2 * am2;
+  // one interference term: value through inter_pair (= inter, brem.f:216-240); the derivative as brem writes it,
+  // aprod*adot/(pi*alpha*(ar1-ar2)*de)*(log((ar1-1)/ar1)-log((ar2-1)/ar2)), without inter_prime's abs()
+  auto term = [&](double aprod, double adot, double alpha, double ar1, double ar2, double e1, double e2_, double& b,
+                  double& db) {
+    double v = 0.0, p = 0.0;
+    if (WHAT != kBremPrime) inter_pair<kBremSoft>(alpha, ar1, ar2, e1, e2_, de, v, p);
+    b = aprod * adot * v;
+    db = 0.0;
+    if (WHAT != kBremSoft)
+      db = aprod * adot / (pi * alpha * (ar1 - ar2) * de) * (m::log((ar1 - 1) / ar1) - m::log((ar2 - 1) / ar2));
+  };
+  const double bei = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / (2. * pi)) * m::log(ak / de);
+  const double dbei = 1.e0 * (1. / (2. * pi * de));
+  const double bef = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / (2. * pi)) * m::log(akp / de);
+  const double dbef = 1.e0 * (1. / (2. * pi * de));
+  double bee, dbee;
+  {
+    const double adot = ak * akp * (1. - m::cos(eang));
+    const double alpha = 2. * ame2 - 2. * adot;
+    const double root = sqrt(adot * adot - ame4);
+    term(-1.e0, adot, alpha, 0.5 + root / alpha, 0.5 - root / alpha, ak, akp, bee, dbee);
+  }
+  double bz = 0.0, bzz = 0.0, dbz = 0.0, dbzz = 0.0;
+  if (radiate_proton) {
+    const double bpi = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / (2. * pi)) * m::log(am / de);
+    const double dbpi = 1.e0 * (1. / (2. * pi * de));
+    const double bpf = WHAT == kBremPrime ? 0.0 : 1.e0 * (-1. / (2. * pi)) * m::log(ape / de);
+    const double dbpf = 1.e0 * (1 / (2. * pi * de));
+    double bpp, dbpp, bepii, dbepii, bepff, dbepff, bepif, dbepif, bepfi, dbepfi;
+    {
+      const double adot = am * ape;
+      const double alpha = 2. * am2 - 2. * adot;
+      const double root = sqrt(adot * adot - am4);
+      term(-1.e0, adot, alpha, 0.5 + root / alpha, 0.5 - root / alpha, am, ape, bpp, dbpp);
+    }
+    const double mm = ame * am, mm2 = mm * mm;
+    auto ep = [&](double aprod, double adot, double e1, double e2_, double& b, double& db) {
+      const double alpha = am2 + ame2 - 2. * adot;
+      const double root = sqrt(adot * adot - mm2);
+      term(aprod, adot, alpha, (am2 - adot + root) / alpha, (am2 - adot - root) / alpha, e1, e2_, b, db);
+    };
+    ep(-1.e0, ak * am, ak, am, bepii, dbepii);
+    ep(-1.e0, akp * ape - akp * ap * m::cos(eang + pang), akp, ape, bepff, dbepff);
+    ep(1.e0, ak * ape - ak * ap * m::cos(pang), ak, ape, bepif, dbepif);
+    ep(1.e0, akp * am, akp, am, bepfi, dbepfi);
+    bzz = 2. * e2 * (bpi + bpf + bpp);
+    bz = 2. * e2 * (bepii + bepff + bepif + bepfi);
+    dbzz = 2. * e2 * (dbpi + dbpf + dbpp);
+    dbz = 2. * e2 * (dbepii + dbepff + dbepif + dbepfi);
+  }
+  const double b = 2. * e2 * (bei + bef + bee);
+  const double db = 2. * e2 * (dbei + dbef + dbee);
+  bsoft = b + bz + bzz;
+  bhard = -1. * (e2 / pi) * (-28 / 9. + 13. / 6. * m::log(q2 / ame2));
+  dbsoft = db + dbz + dbzz;
+  dbsoft = dbsoft / 1000.;
+}
+
+// spen, radc.f:746-764 (Abramowitz & Stegun 27.7.2)
+SIMC_HD_CALL double spen(double x) {
+  double y = 1.0, s = 0.0;
+  int i = 0;
+  while (i <= 100 && fabs(y) > fabs(s) * 1.e-4) {
+    i = i + 1;
+    y = x * y;
+    s = s + y / (double)(i * i);
+  }
+  return s;
+}
+
+// schwinger, radc.f:711-742 (etta = 1, init.f:688).  The function value itself is read by no caller.
+SIMC_HD_CALL void schwinger(const simc_run_config& cfg, double Ecutoff, double Ein, double eE, double etheta, double Q2,
+                            double nu, double& dsoft, double& dhard) {
+  const double alpi = (1. / 137.0359895) / 3.141592653589793, Me = 0.51099906, amu = 931.49432, etta = 1.0;
+  const double lq = m::log(Q2 / (Me * Me)) - 1.0;
+  const double sh = m::sin(etheta / 2.);
+  const double s2 = sh * sh;
+  const double b = 1. + 2. * nu * s2 / (cfg.targ.A * amu);
+  const double spence = spen(1. - s2) - 2.5893784;
+  dsoft = alpi * lq * m::log(Ein / (etta * etta) * eE * b / (Ecutoff * Ecutoff));
+  const double lr = m::log(Ein / eE);
+  dhard = -alpi * (2.166666 * lq + spence - (lr * lr) / 2.0);
+}
+
+// extrad_friedrich, radc.f:650-664
+SIMC_HD_CALL void extrad_friedrich(double etatzai, double Ei, double Ecutoff, double trad, double& dbrem, double& dbrem_prime) {
+  const double x = Ecutoff / Ei;
+  dbrem = trad * (-(etatzai - 0.5) - etatzai * m::log(x) + etatzai * x - 0.5 * (x * x));
+  dbrem_prime = -trad / Ei * (etatzai / x - etatzai + x);
+}
+
 // radc.f:92-116
 SIMC_HD_CALL double gamma_fn(double x) {
   double g = 1.0;
@@ -197,9 +308,14 @@ SIMC_HD_CALL void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, d
   R.lambda[2] = lambda_dave(3, dp, v.Ein, v.eE, v.pE, v.pP, v.etheta);
   R.rad_proton_this_ev = R.lambda[2] > 0;
   const double Ecutoff = 450.;
-  double dsoft, dhard, dsoft_prime;
-  bremos<kBremPrime>(Ecutoff, v.Ein, v.eP * v.uex, v.eP * v.uey, v.eP * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
-         R.rad_proton_this_ev, dsoft, dhard, dsoft_prime);
+  double dsoft, dhard, dsoft_prime = 0.0;       // (static local of the reference: schwinger leaves it at zero)
+  if (cfg.intcor_mode == 0)
+    schwinger(cfg, Ecutoff, v.Ein, v.eE, v.etheta, 2 * v.Ein * v.eE * (1. - v.uez), v.Ein - v.eE, dsoft, dhard);
+  else if (!cfg.use_offshell_rad)
+    brem_onshell<kBremPrime>(v.Ein, v.eE, Ecutoff, R.rad_proton_this_ev, dsoft, dhard, dsoft_prime);
+  else
+    bremos<kBremPrime>(Ecutoff, v.Ein, v.eP * v.uex, v.eP * v.uey, v.eP * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+           R.rad_proton_this_ev, dsoft, dhard, dsoft_prime);
   R.hardcorfac = 1. / (1. - dhard);
   R.g[4] = -dsoft_prime * Ecutoff + R.bt[0] + R.bt[1];
   // basicrad_init_ev(e1=Ein, e2=e.E, e3=p.E)
@@ -223,6 +339,72 @@ SIMC_HD_CALL void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, d
   R.frac[2] = R.g[3] / R.g[0];
 }
 
+// basicrad_init_ev's constants of the (Egamma1, Egamma2, Egamma3) basis, init.f:755-806: c_int(i), c(i), and the
+// combined c_int(0), c(0), g_int.  Only rad_flag >= 2 reads c(1..3); they are rebuilt on demand from lambda, bt, g
+// and the energies radc_init_ev was called with (the event record does not carry them).
+struct BasisConst { double c[4], c_int0, g_int; };
+SIMC_HD_CALL BasisConst basis_constants(const RadEvDev& R, double e1, double e2, double e3) {
+  const double Mp = 938.27231, euler = 0.577215665, one = 1.;
+  const double e[4] = {0, e1, e2, e3};
+  const double* lambda = R.lambda - 1;
+  const double* bt = R.bt - 1;
+  const double* g = R.g;
+  double c_int[4], c_ext[4];
+  c_int[1] = lambda[1] / m::pow(e[1] * e[2], lambda[1] / 2.);
+  c_int[2] = lambda[2] / m::pow(e[1] * e[2], lambda[2] / 2.);
+  c_int[3] = lambda[3] / m::pow(Mp * e[3], lambda[3] / 2.);
+  for (int i = 1; i <= 3; ++i) c_int[i] = c_int[i] * m::exp(-euler * lambda[i]) / gamma_fn(one + lambda[i]);
+  BasisConst B;
+  B.g_int = lambda[1] + lambda[2] + lambda[3];
+  c_int[0] = c_int[1] * c_int[2] * B.g_int / lambda[1] / lambda[2];
+  if (lambda[3] > 0) c_int[0] = c_int[0] * c_int[3] / lambda[3];
+  c_int[0] = c_int[0] * gamma_fn(one + lambda[1]) * gamma_fn(one + lambda[2]) * gamma_fn(one + lambda[3]) / gamma_fn(one + B.g_int);
+  B.c_int0 = c_int[0];
+  for (int i = 1; i <= 2; ++i) c_ext[i] = bt[i] / m::pow(e[i], bt[i]) / gamma_fn(one + bt[i]);
+  for (int i = 1; i <= 2; ++i)
+    B.c[i] = c_int[i] * c_ext[i] * g[i] / lambda[i] / bt[i] * gamma_fn(one + lambda[i]) * gamma_fn(one + bt[i]) / gamma_fn(one + g[i]);
+  B.c[3] = c_int[3];
+  B.c[0] = B.c[1] * B.c[2] * g[0] / g[1] / g[2];
+  if (g[3] > 0) B.c[0] = B.c[0] * B.c[3] / g[3];
+  B.c[0] = B.c[0] * gamma_fn(one + g[1]) * gamma_fn(one + g[2]) * gamma_fn(one + g[3]) / gamma_fn(one + g[0]);
+  return B;
+}
+
+// basicrad for one tail of that basis (itail = 1..3), radc.f:3-88
+template <class RNG>
+SIMC_HD_CALL void basicrad_tail(double g, double c, RNG& rng, double Egamma_lo, double Egamma_hi, double& Egamma, double& weight) {
+  Egamma = 0.0; weight = 0.0;
+  if (g <= 0) { weight = 1.0; return; }
+  if (Egamma_hi <= Egamma_lo || Egamma_hi <= 0) return;
+  const double power_hi = m::pow(Egamma_hi, g);
+  double power_lo = 0.0;
+  if (Egamma_lo > 0) power_lo = m::pow(Egamma_lo, g);
+  const double ymin = power_lo / power_hi;
+  const double y = ymin + rng.uniform() * (1. - ymin);
+  const double x = m::pow(y, 1. / g);
+  Egamma = x * Egamma_hi;
+  weight = c / g * (power_hi - power_lo);
+}
+
+// extrad_phi, radc.f:668-707.  itail = 0 with extrad_flag = 3 is a `stop` in the reference: create() refuses the
+// only setting that reaches it (rad_flag <= 1 never calls it with extrad_flag = 3, rad_flag >= 2 never with itail 0).
+SIMC_HD_CALL double extrad_phi(const simc_run_config& cfg, const RadEvDev& R, int itail, double E1, double E2, double Egamma) {
+  const double E[3] = {0, E1, E2};
+  double phi = 1.0;
+  if (cfg.extrad_flag == 2) {
+    if (itail == 0) phi = 1. - (R.bt[0] / E[1] + R.bt[1] / E[2]) / (R.g[1] + R.g[2]) * Egamma;
+    else if (itail == 1 || itail == 2) phi = 1. - R.bt[itail - 1] / E[itail] / R.g[itail] * Egamma;
+  } else if (cfg.extrad_flag == 3) {
+    if (itail == 1 || itail == 2) {
+      const double x = Egamma / E[itail];
+      const double t = R.bt[itail - 1] / cfg.etatzai;
+      phi = phi * (1. - x + (x * x) / cfg.etatzai) * m::exp(t * ((cfg.etatzai - 0.5) - cfg.etatzai * x + (x * x) / 2.)) *
+            gamma_fn(1. + R.bt[itail - 1]);
+    }
+  }
+  return phi;
+}
+
 // basicrad with itail=0 -> 4 (peaked basis), radc.f:3-88.  u is the uniform it draws; it is
 // only consumed when the function gets past its early returns (`drew`).
 template <class RNG>
@@ -242,21 +424,26 @@ SIMC_HD_CALL void basicrad4(const RadEvDev& R, RNG& rng, double Egamma_lo, doubl
   weight = R.c4 / g * (power_hi - power_lo);
 }
 
-// peaked_rad_weight, radc.f:523-646 (rad_flag = 0 branch; rad_flag = 1 returns basic*phi)
+// peaked_rad_weight, radc.f:523-646.  What the external branches compute besides phi_ext (dsoft_ext*, the Friedrich
+// terms of extrad_flag = 3) is never read by the reference and is left out.
 SIMC_HD_CALL double peaked_rad_weight(const simc_run_config& cfg, const RadEvDev& R, const VertexKin& v, double Egamma,
                                  double emin, double emax, double basicrad_weight) {
   const double eul = 0.577215665;
-  if (cfg.rad_flag == 1) {
-    double phi_ext = 1.0;
-    if (cfg.extrad_flag == 2) phi_ext = 1. - (R.bt[0] / v.Ein + R.bt[1] / v.eE) / (R.g[1] + R.g[2]) * Egamma;
-    return basicrad_weight * phi_ext;
+  if (cfg.extrad_flag <= 2 && cfg.rad_flag == 1) return basicrad_weight * extrad_phi(cfg, R, 0, v.Ein, v.eE, Egamma);
+  double dsoft_intmin = 0.0, dsoft_intmax = 0.0, dhard, dprime;      // static locals of the reference: zero until assigned
+  if (cfg.rad_flag == 0) {
+    dsoft_intmin = 1.0;
+    if (!cfg.use_offshell_rad) {
+      if (emin > 0) brem_onshell<kBremSoft>(v.Ein, v.eE, emin, R.rad_proton_this_ev, dsoft_intmin, dhard, dprime);
+      brem_onshell<kBremSoft>(v.Ein, v.eE, emax, R.rad_proton_this_ev, dsoft_intmax, dhard, dprime);
+    } else {
+      if (emin > 0)
+        bremos<kBremSoft>(emin, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+               R.rad_proton_this_ev, dsoft_intmin, dhard, dprime);
+      bremos<kBremSoft>(emax, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
+             R.rad_proton_this_ev, dsoft_intmax, dhard, dprime);
+    }
   }
-  double dsoft_intmin = 1.0, dsoft_intmax, dhard, dprime;
-  if (emin > 0)
-    bremos<kBremSoft>(emin, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
-           R.rad_proton_this_ev, dsoft_intmin, dhard, dprime);
-  bremos<kBremSoft>(emax, v.Ein, v.eE * v.uex, v.eE * v.uey, v.eE * v.uez, v.pP * v.upx, v.pP * v.upy, v.pP * v.upz, v.pE,
-         R.rad_proton_this_ev, dsoft_intmax, dhard, dprime);
   double w;
   if (emin > 0)
     w = R.c_ext0 / R.g_ext * (m::exp(-dsoft_intmax) * m::pow(emax, R.g_ext) - m::exp(-dsoft_intmin) * m::pow(emin, R.g_ext));

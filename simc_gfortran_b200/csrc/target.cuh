@@ -26,7 +26,7 @@ namespace m {
 #define SIMC_MATH1(name) static inline double name(double x) { return std::name(x); }
 #endif
 SIMC_MATH1(log) SIMC_MATH1(log10) SIMC_MATH1(exp) SIMC_MATH1(sin) SIMC_MATH1(cos) SIMC_MATH1(tan)
-SIMC_MATH1(acos) SIMC_MATH1(atan)
+SIMC_MATH1(acos) SIMC_MATH1(atan) SIMC_MATH1(asin)
 #undef SIMC_MATH1
 #if defined(__CUDA_ARCH__)
 static __device__ __noinline__ double pow(double x, double y) { return ::pow(x, y); }

@@ -15,6 +15,7 @@ ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
 WEIGHT_NIN, WEIGHT_NOUT = 44, 15
 TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
 EVENT_NREC = 56
+RADC_NOUT = 26
 NTUPLE_MAXCOL = 56
 NHIST, H_PER_SET, NSTOP = 50, 8, 64
 ABI_VERSION = 2
@@ -620,7 +621,7 @@ class Simc:
     def radc_batch(self, inp: np.ndarray) -> np.ndarray:
         inp = np.ascontiguousarray(inp, dtype=np.float64)
         assert inp.ndim == 2 and inp.shape[0] == 16
-        out = np.zeros((11, inp.shape[1]))
+        out = np.zeros((RADC_NOUT, inp.shape[1]))
         self._check(self.L.simc_b200_radc_batch(self.h, inp.shape[1], _ptr(inp), _ptr(out)))
         return out
 

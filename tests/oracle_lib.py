@@ -19,6 +19,9 @@ def build_oracle():
     return ORACLE_SO
 
 
+RADC_NOUT = 26          # include/simc_b200.h: SIMC_RADC_NOUT
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -162,7 +165,7 @@ Oracle.event_batch = _oracle_event_batch
 
 def _oracle_radc_batch(self, cfg, inp):
     inp = np.ascontiguousarray(inp, np.float64)
-    out = np.zeros((11, inp.shape[1]))
+    out = np.zeros((RADC_NOUT, inp.shape[1]))
     self._check(self.L.oracle_radc_batch(C.byref(cfg), C.c_int64(inp.shape[1]), _p(inp), _p(out)))
     return out
 

@@ -124,6 +124,11 @@ def test_radc_stage(sim, orc, cfg):
     ref = orc.radc_batch(cfg, inp)
     out = sim.radc_batch(inp)
     err = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-300)
+    # columns 23-25 are the on-shell `brem` (brem.f:6-214), which this deck does not use: it rebuilds the scattering
+    # angle as 2*asin(sqrt(..)) and feeds it to the same ill-conditioned interference terms, so a last-ulp difference
+    # between the CUDA and glibc asin/cos (a few % of the arguments) shows at 1e-9; tests/test_rad_options_gpu.py
+    assert err[23:].max() < 1e-7
+    err = err[:23]
     # The reference writes the energies as (...)**0.5 (brem.f:383-384,398): that is glibc pow(x,0.5),
     # which differs from the correctly rounded sqrt in the last bit for ~2e-4 of the arguments, and
     # bremos amplifies one ulp of k_f%e by ~1e7.  Those rows are allowed, and counted.
