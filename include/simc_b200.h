@@ -349,6 +349,7 @@ int simc_b200_semi_batch(simc_handle* h, int64_t n, const double* in_soa, double
  * any GPU).  Adds into *acc (zero it with simc_b200_accum_clear first). */
 int simc_b200_accum_clear(simc_handle* h, simc_accum* acc);
 int simc_b200_run(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, simc_accum* acc);
+/* tries per pass of the stage pipeline (default 2^20) */
 int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch);
 /* Per-stage device time of the loop, measured with CUDA events on the handle's stream while
  * enabled: ms[0..3] = generate, hadron arm, electron arm, finish (sums since the last call);
@@ -356,7 +357,10 @@ int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch);
 int simc_b200_stage_times(simc_handle* h, int enable, double* ms4, int64_t* launches4);
 /* FP64 pipe microbenchmark on this device: dependent-chain-free DFMA and DMUL+DADD loops.
  * Returns TFLOP/s (FMA = 2 flops) for the roofline denominator. */
-int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_muladd);   /* tries per pass of the stage pipeline (default 2^20) */
+int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_muladd);
+/* The device's double-precision log and log10 (csrc/fastlog.cuh; the loop's most frequent library calls, where the
+ * reference calls libm: gauss1.f:24, musc.f:52, enerloss_new.f, brem.f) on n host values: a check entry point. */
+int simc_b200_log_batch(simc_handle* h, int64_t n, const double* x, double* out_log, double* out_log10);
 
 /* Asynchronous pieces of simc_b200_run for callers that overlap or time the
  * device work themselves (bench.py): launch on the handle's stream, then fetch. */

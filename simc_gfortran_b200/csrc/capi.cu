@@ -1257,6 +1257,25 @@ int simc_b200_fp64_peak(simc_handle* h, double* tflops_fma, double* tflops_mulad
   return SIMC_OK;
 }
 
+int simc_b200_log_batch(simc_handle* h, int64_t n, const double* x, double* out_log, double* out_log10) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!x || !out_log || !out_log10))) return fail(h, SIMC_ERR_ARG, "simc_b200_log_batch: bad argument");
+  if (n == 0) return SIMC_OK;
+  CU(h, cudaSetDevice(h->device));
+  double *d_x = nullptr, *d_o = nullptr;
+  CU(h, cudaMalloc(&d_x, sizeof(double) * (size_t)n));
+  cudaError_t e = cudaMalloc(&d_o, sizeof(double) * 2 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = h->strict ? strict::launch_log_batch(n, d_x, d_o, h->stream) : fast::launch_log_batch(n, d_x, d_o, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_log, d_o, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_log10, d_o + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_x); cudaFree(d_o);
+  h->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_log_batch");
+  return SIMC_OK;
+}
+
 int simc_b200_set_batch(simc_handle* h, int64_t tries_per_batch) {
   if (!h || tries_per_batch < 128) return SIMC_ERR_ARG;
   h->batch = tries_per_batch;

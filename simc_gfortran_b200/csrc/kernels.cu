@@ -398,6 +398,19 @@ __global__ void k_fp64_peak(double* out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// check entry point of the device logarithms (fastlog.cuh): out[0..n) = log(x), out[n..2n) = log10(x)
+__global__ void k_log_batch(long long n, const double* __restrict__ x, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = m::log(x[i]);
+  out[n + i] = m::log10(x[i]);
+}
+cudaError_t launch_log_batch(long long n, const double* x, double* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_log_batch<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, x, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s) {
   if (fma) k_fp64_peak<true><<<blocks, threads, 0, s>>>(scratch, iters);
   else k_fp64_peak<false><<<blocks, threads, 0, s>>>(scratch, iters);

@@ -18,14 +18,19 @@
 #endif
 
 // libm entry points as out-of-line device functions (each inlined pow/sin/cos/acos is 1-3 KB of SASS)
+#include "fastlog.cuh"
 namespace simc {
 namespace m {
 #if defined(__CUDA_ARCH__)
 #define SIMC_MATH1(name) static __device__ __noinline__ double name(double x) { return ::name(x); }
+// the logarithms are the loop's most frequent library calls: table-driven versions, 0.51 ulp (fastlog.cuh)
+static __device__ __noinline__ double log(double x) { return fastlog::log(x); }
+static __device__ __noinline__ double log10(double x) { return fastlog::log10(x); }
 #else
 #define SIMC_MATH1(name) static inline double name(double x) { return std::name(x); }
+SIMC_MATH1(log) SIMC_MATH1(log10)
 #endif
-SIMC_MATH1(log) SIMC_MATH1(log10) SIMC_MATH1(exp) SIMC_MATH1(sin) SIMC_MATH1(cos) SIMC_MATH1(tan)
+SIMC_MATH1(exp) SIMC_MATH1(sin) SIMC_MATH1(cos) SIMC_MATH1(tan)
 SIMC_MATH1(acos) SIMC_MATH1(atan) SIMC_MATH1(asin)
 #undef SIMC_MATH1
 #if defined(__CUDA_ARCH__)

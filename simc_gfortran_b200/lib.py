@@ -231,6 +231,7 @@ def load_library():
     L.simc_b200_reduce_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.simc_b200_accum_merge.argtypes = [C.c_void_p, C.c_void_p]
     L.simc_b200_fp64_peak.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_log_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     if hasattr(L, "simc_b200_event_field_name"):
         L.simc_b200_event_field_name.restype = C.c_char_p
         L.simc_b200_event_field_name.argtypes = [C.c_int]
@@ -593,6 +594,13 @@ class Simc:
         a, b = C.c_double(), C.c_double()
         self._check(self.L.simc_b200_fp64_peak(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def log_batch(self, x: np.ndarray):
+        """The device's log and log10 (fastlog.cuh) of x."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        a, b = np.zeros_like(x), np.zeros_like(x)
+        self._check(self.L.simc_b200_log_batch(self.h, x.size, _ptr(x), _ptr(a), _ptr(b)))
+        return a, b
 
     def run_async(self, first_try: int, n_tries: int, seed: int):
         self._check(self.L.simc_b200_run_async(self.h, first_try, n_tries, seed))
