@@ -46,18 +46,44 @@ def sf_table():
     return z["pm"], z["em"], z["sf_proton"]
 
 
-# ---- algorithmic FLOPs: F_fwd(T) = 25 + 14 T per forward class call, F_rec = 25 + 12 T
-def algorithmic_flops(acc, optics):
-    total = 0.0
+# ---- algorithmic work per stage ---------------------------------------------------------------
+# One FP64 add, mul, div or sqrt = 1 flop; library calls (log, log10, pow, exp, sin, cos, acos, atan) are counted
+# separately as "transcendentals" and enter `achieved` at FLOPS_PER_TRANS flops each (the table-driven log of
+# csrc/fastlog.cuh is 22 FP64 operations; the CUDA library's pow / sincos are more).
+#   COSY maps   : forward class with T terms 25 + 14 T, reconstruction 25 + 12 T, times the measured call counts
+#   hut         : ~4 kflop + ~330 sqrt and ~280 transcendentals per track that reaches the hut (202 gauss1 + 77 musc)
+#   generation  : ~2.5 kflop + ~250 transcendentals per try (bremos, enerloss_new, trip_thru_target; C1 figures)
+#   finish      : per event that passed both arms: recon kinematics + 2 x sigep ~0.4 kflop + 12, and the deferred
+#                 peaked_rad_weight (2 x bremos) ~0.6 kflop + 130 when radiation is on
+FLOPS_PER_TRANS = 25.0
+HUT_FLOPS, HUT_TRANS = 4330.0, 280.0
+GEN_FLOPS, GEN_TRANS = 2500.0, 250.0
+FIN_FLOPS, FIN_TRANS = 400.0, 12.0
+RADW_FLOPS, RADW_TRANS = 600.0, 130.0
+
+
+def map_flops(acc, optics):
     per_arm = []
     for which, arm in ((0, optics["e"]), (1, optics["p"])):
         calls = [int(x) for x in acc.transp_calls[which]]
         n_terms = [int(arm.class_start[k + 1] - arm.class_start[k]) for k in range(arm.n_classes)]
         f = sum(calls[k] * (25 + 14 * n_terms[k]) for k in range(arm.n_classes))
         f += calls[47] * (25 + 12 * len(arm.rec_coeff))
-        per_arm.append(f)
-        total += f
-    return total, per_arm
+        per_arm.append(float(f))
+    return per_arm
+
+
+def stage_model(acc, optics, using_rad):
+    """Algorithmic (flops, transcendentals) of the four stages for the tries in `acc`."""
+    maps_e, maps_p = map_flops(acc, optics)
+    hut_e, hut_p = float(acc.stop[0][2]), float(acc.stop[1][2])          # tracks that reached the hut
+    n_fin = float(acc.stop[0][1])                                         # passed both arms (E arm runs last)
+    fin_f = FIN_FLOPS + (RADW_FLOPS if using_rad else 0.0)
+    fin_t = FIN_TRANS + (RADW_TRANS if using_rad else 0.0)
+    return {"k_generate": (acc.ntried * GEN_FLOPS, acc.ntried * GEN_TRANS),
+            "k_arm<hadron>": (maps_p + hut_p * HUT_FLOPS, hut_p * HUT_TRANS),
+            "k_arm<electron>": (maps_e + hut_e * HUT_FLOPS, hut_e * HUT_TRANS),
+            "k_finish": (n_fin * fin_f, n_fin * fin_t)}
 
 
 class ClockSampler(threading.Thread):
@@ -265,23 +291,29 @@ def main():
         assert tries_total == n * args.steps * world, (tries_total, n, args.steps, world)
         gen_per_s = tries_total / (dev_ms * 1e-3)
         acc_per_s = acc.nsuccess / (dev_ms * 1e-3)
-        flops, per_arm = algorithmic_flops(acc, optics)
-        flops_per_try = flops / tries_total
-        # dominant kernel = the stage with the largest device time (per-rank numbers of rank 0)
         names = ["k_generate", "k_arm<hadron>", "k_arm<electron>", "k_finish"]
-        # dominant kernel: the arm stage with the largest device time.  Only the two arm stages have an algorithmic
-        # FLOP model (the COSY maps); should the generation kernel ever lead, the largest arm is still
-        # the one reported and `stage_ms` shows it.
-        dom = 1 if stage_ms[1] >= stage_ms[2] else 2
-        # FLOPs of the dominant kernel on THIS rank: per-arm share of rank 0 = total / world (weak scaling)
-        dom_flops = {1: per_arm[1], 2: per_arm[0]}[dom] / world
-        achieved = dom_flops / (stage_ms[dom] * 1e-3) / 1e12 if stage_ms[dom] > 0 else 0.0
+        model = stage_model(acc, optics, bool(cfg.using_rad))
+        total_f = sum(v[0] for v in model.values())
+        total_t = sum(v[1] for v in model.values())
+        flops = total_f + FLOPS_PER_TRANS * total_t
+        flops_per_try = flops / tries_total
+        # dominant kernel = the stage with the largest device time (per-rank numbers of rank 0; its share of the
+        # all-rank counts is 1 / world: weak scaling)
+        dom = max(range(4), key=lambda k: stage_ms[k])
+        stages = {}
+        for k, nm in enumerate(names):
+            f, t = model[nm]
+            w = (f + FLOPS_PER_TRANS * t) / world
+            stages[nm] = {"ms": stage_ms[k], "launches": stage_launches[k], "flops": f / world, "transcendentals": t / world,
+                          "tflops": w / (stage_ms[k] * 1e-3) / 1e12 if stage_ms[k] > 0 else 0.0}
+            stages[nm]["frac"] = stages[nm]["tflops"] / peak_muladd if peak_muladd else None
+        achieved = stages[names[dom]]["tflops"]
         # DRAM bytes of that stage per launch (= per batch of --batch tries), from one `ncu --set full` capture
         traffic, traffic_src = None, None
-        tfile = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tfile = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tfile) and args.config == "c1":
             tj = json.load(open(tfile))
-            traffic = tj["bytes_per_2M_tries"][names[dom]] * args.batch / 2097152
+            traffic = tj["bytes_per_4M_tries"][names[dom]] * args.batch / 4194304
             traffic_src = tj["source"]
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
@@ -306,6 +338,13 @@ def main():
                                       "DFMA peak %.1f TFLOP/s" % peak_fma,
                          "flops_per_generated_event": flops_per_try,
                          "whole_loop_tflops": flops / (dev_ms * 1e-3) / 1e12,
+                         "whole_loop_frac": flops / (dev_ms * 1e-3) / 1e12 / peak_muladd if peak_muladd else None,
+                         "model": "SURVEY 8(d): maps 25+14T / 25+12T per call (measured calls), hut %.0f flop + %.0f transc. "
+                                  "per track in a hut, generation %.0f + %.0f per try, finish %.0f + %.0f (+ %.0f + %.0f "
+                                  "peaked_rad_weight) per event through both arms; 1 transcendental = %.0f flops"
+                                  % (HUT_FLOPS, HUT_TRANS, GEN_FLOPS, GEN_TRANS, FIN_FLOPS, FIN_TRANS, RADW_FLOPS, RADW_TRANS,
+                                     FLOPS_PER_TRANS),
+                         "stages": stages,
                          "stage_ms": dict(zip(names, stage_ms)), "stage_launches": dict(zip(names, stage_launches)),
                          "hbm_peak_gbs": hbm_peak},
             "clocks": sampler.summary(),

@@ -464,6 +464,41 @@ typedef struct {
 /* ngen: the deck's ngen (its sign selects what nevent counts). */
 int simc_b200_normalise(const simc_run_config* cfg, const simc_accum* acc, int32_t ngen, double charge_mC, simc_results* out);
 
+/* ---- the reference's end-of-run text files (simc.f:446-1139), byte layout of the Fortran formats ---------------- */
+/* Init-only values subroutine report prints beyond simc_run_config (targ%Eloss / teff / musc_max extremes of
+ * limits_init, slop%total%Em%used, deck switches the loop does not read). */
+typedef struct {
+  int32_t ngen, random_seed, one_tail;
+  int32_t doing_pizero, pizero_ngamma, use_first_cer, using_tgt_field;
+  int32_t doing_hyddelta, doing_deutdelta, doing_hedelta, doing_hydrho, doing_deutrho, doing_herho;
+  int32_t pad;
+  double charge_mC;
+  double Eloss_ave[3], Eloss_min[3], Eloss_max[3];      /* targ%Eloss(1:3): beam, e, hadron */
+  double teff_ave[3], teff_min[3], teff_max[3];
+  double musc_max[3], musc_nsig_max;
+  double slop_total_Em_used;
+  char theory_file[128];
+} simc_report_info;
+int simc_b200_report_info_from_deck(const char* deck_path, const char* extra_deck_dir, const char* data_dir,
+                                    simc_report_info* out, char* err, int errlen);
+/* event_central (modules.f:156-168) as calculate_central fills it (simc.f:1143-1306): the event with both particles on
+ * the spectrometer axes through complete_recon_ev, radc_init_ev and complete_main(force_sigcc).  Kinematics and
+ * radiative constants are host arithmetic; sigcc goes through simc_b200_weight_batch on h (pass h = NULL to skip it). */
+typedef struct {
+  double e_delta, e_xptar, e_yptar, p_delta, p_xptar, p_yptar;
+  double Q2, q, nu, Em, Pm, W, MM, sigcc;
+  double hardcorfac, etatzai, frac[3], lambda[3], bt[2], c_int[4], c_ext[4], c[4], g_int, g_ext, g[4];
+} simc_central;
+int simc_b200_central_event(simc_handle* h, const simc_run_config* cfg, const simc_report_info* info, simc_central* out);
+/* <base>.geni (STOP counters, simc.f:446-537), <base>.gen (histograms, simc.f:539-612), <base>.hist (subroutine
+ * report, simc.f:644-1139; timestring = ctime() text of the loop's start and end). */
+/* The Fortran edit descriptors Fw.d (kind 'F') and Ew.d (kind 'E', 0.dddE+ee form) as the writers produce them. */
+int simc_b200_format_real(int kind, int w, int d, double v, char* out, int outlen);
+int simc_b200_write_geni(const char* path, const simc_run_config* cfg, const simc_accum* acc);
+int simc_b200_write_gen(const char* path, const simc_run_config* cfg, const simc_accum* acc);
+int simc_b200_write_hist(const char* path, const simc_run_config* cfg, const simc_report_info* info, const simc_central* central,
+                         const simc_accum* acc, const simc_results* res, const char* timestring1, const char* timestring2);
+
 /* Ntuple file in the reference's layout (NtupleInit.f:32,352-355; results_write.f:264-266): a Fortran
  * unformatted sequential file -- record "NtupleSize" (int32), one 16-character record per tag, then one
  * 8-byte record per column of every row; each record sits between two 4-byte length markers.  This is what

@@ -5,9 +5,11 @@ The product is ``libsimc_b200.so`` (hand-written sm_100a CUDA kernels behind the
 ``bench.py``.  There is no CPU fallback: importing works anywhere, computing needs a GPU.
 """
 from .lib import (config_from_deck, Simc, SimcError, lib_path, load_library, RunConfig, Accum, ARM_HMS, ARM_SOS, ARM_HRSR,
-                  ARM_HRSL, ARM_SHMS, TRANSPORT_NIN, TRANSPORT_NOUT, precompile_optics)
+                  ARM_HRSL, ARM_SHMS, TRANSPORT_NIN, TRANSPORT_NOUT, precompile_optics, report_info_from_deck, central_event,
+                  write_reports, ReportInfo, Central)
 from .optics import load_optics_fixture, OpticsTables
 
 __all__ = ["config_from_deck", "Simc", "SimcError", "lib_path", "load_library", "RunConfig", "Accum", "ARM_HMS", "ARM_SOS",
            "ARM_HRSR", "ARM_HRSL", "ARM_SHMS", "TRANSPORT_NIN", "TRANSPORT_NOUT", "load_optics_fixture",
-           "OpticsTables", "precompile_optics"]
+           "OpticsTables", "precompile_optics", "report_info_from_deck", "central_event", "write_reports", "ReportInfo",
+           "Central"]

@@ -342,7 +342,7 @@ SIMC_HD_CALL void radc_init_ev(const simc_run_config& cfg, const VertexKin& v, d
 // basicrad_init_ev's constants of the (Egamma1, Egamma2, Egamma3) basis, init.f:755-806: c_int(i), c(i), and the
 // combined c_int(0), c(0), g_int.  Only rad_flag >= 2 reads c(1..3); they are rebuilt on demand from lambda, bt, g
 // and the energies radc_init_ev was called with (the event record does not carry them).
-struct BasisConst { double c[4], c_int0, g_int; };
+struct BasisConst { double c[4], c_int[4], c_ext[4], c_int0, g_int; };
 SIMC_HD_CALL BasisConst basis_constants(const RadEvDev& R, double e1, double e2, double e3) {
   const double Mp = 938.27231, euler = 0.577215665, one = 1.;
   const double e[4] = {0, e1, e2, e3};
@@ -361,6 +361,10 @@ SIMC_HD_CALL BasisConst basis_constants(const RadEvDev& R, double e1, double e2,
   c_int[0] = c_int[0] * gamma_fn(one + lambda[1]) * gamma_fn(one + lambda[2]) * gamma_fn(one + lambda[3]) / gamma_fn(one + B.g_int);
   B.c_int0 = c_int[0];
   for (int i = 1; i <= 2; ++i) c_ext[i] = bt[i] / m::pow(e[i], bt[i]) / gamma_fn(one + bt[i]);
+  c_ext[3] = 0.0;
+  c_ext[0] = c_ext[1] * c_ext[2] * (bt[1] + bt[2]) / bt[1] / bt[2];
+  c_ext[0] = c_ext[0] * gamma_fn(one + bt[1]) * gamma_fn(one + bt[2]) / gamma_fn(one + (bt[1] + bt[2]));
+  for (int i = 0; i < 4; ++i) { B.c_int[i] = c_int[i]; B.c_ext[i] = c_ext[i]; }
   for (int i = 1; i <= 2; ++i)
     B.c[i] = c_int[i] * c_ext[i] * g[i] / lambda[i] / bt[i] * gamma_fn(one + lambda[i]) * gamma_fn(one + bt[i]) / gamma_fn(one + g[i]);
   B.c[3] = c_int[3];

@@ -186,7 +186,8 @@ void set_axis(simc_axis& a, double mn, double bin) { a.min = mn; a.bin = bin; }
 }  // namespace
 
 void config_from_deck(const std::string& path, const std::string& extra_dir, const std::string& data_dir,
-                      simc_run_config& c, int* ngen, double* charge_mC) {
+                      simc_run_config& c, int* ngen, double* charge_mC, simc_report_info* info = nullptr) {
+  double slop_total_Em_used = 0.0;
   Deck D;
   D.load(path);
   const std::string extra = D.s("extra_dbase_file");
@@ -515,6 +516,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     slop_Ee = slop_Ee + (X.Eloss_max[1] - X.Eloss_min[1]);
     slop_Ep = slop_Ep + (X.Eloss_max[2] - X.Eloss_min[2]);
     const double slop_total_Em = slop_Ebeam + slop_Ee + slop_Ep + c.dE_edge_test;
+    slop_total_Em_used = slop_total_Em;
     edge.Em.min = c.cuts_Em.min - slop_total_Em;
     edge.Em.max = c.cuts_Em.max + slop_total_Em;
     edge.Em.min = std::max(0.e0, edge.Em.min);
@@ -706,6 +708,22 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
       const MesonWeight w = c.doing_pion ? peepi(c, MaidDev{nullptr}, mv) : c.doing_delta ? peedelta(c, mv) : peeK(c, mv);
       if (w.sigcc > 0 && std::isfinite(w.sigcc)) c.w_ref = w.sigcc;
     }
+  }
+  if (info) {         // what subroutine report (simc.f:644-1139) prints beyond the run constants
+    std::memset(info, 0, sizeof(*info));
+    info->ngen = D.i("ngen"); info->random_seed = D.i("random_seed"); info->one_tail = one_tail;
+    info->doing_pizero = D.i("doing_pizero") > 0; info->pizero_ngamma = D.i("pizero_ngamma");
+    info->use_first_cer = D.i("use_first_cer", 1) > 0; info->using_tgt_field = D.i("using_tgt_field") > 0;
+    info->charge_mC = D.d("EXPER%charge");
+    for (int i = 0; i < 3; ++i) {
+      info->Eloss_ave[i] = X.Eloss_ave[i]; info->Eloss_min[i] = X.Eloss_min[i]; info->Eloss_max[i] = X.Eloss_max[i];
+      info->teff_ave[i] = X.teff_ave[i]; info->teff_min[i] = X.teff_min[i]; info->teff_max[i] = X.teff_max[i];
+      info->musc_max[i] = X.musc_max[i];
+    }
+    info->musc_nsig_max = 3.5;                           // target.f:569-577 (extreme_target_musc's nsig_max)
+    info->slop_total_Em_used = slop_total_Em_used;
+    const int nA_ = (int)std::lround(c.targ.A);
+    if (c.doing_deuterium || c.doing_heavy) std::snprintf(info->theory_file, sizeof info->theory_file, "%s", theory_file_for(nA_));
   }
 }
 

@@ -2,13 +2,15 @@
 // for machines without the Fortran driver.  Reads a CTP deck, loads the optics and physics tables from a copy of
 // the reference's working directory (hms/forward_cosy.dat, benharsf_12.dat, deut.dat, ...), runs the loop on one
 // GPU, normalises (simc.f:366-432) and writes
-//   <out>.hist  run summary: counters, normalisation, resolutions, STOP counters, the 24 acceptance histograms
+//   <out>.hist  subroutine report of the reference (simc.f:644-1139), same formats
+//   <out>.gen   the acceptance histograms (simc.f:539-612)
+//   <out>.geni  the STOP counters of the spectrometers (simc.f:446-537)
 //   <out>.bin   ntuple in the reference's unformatted layout (with --ntuple 1; the deck's Nntu is not read)
-// The .hist text is this program's own format (key = value), not the reference's 600-line report.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "../../include/simc_b200.h"
@@ -101,6 +103,7 @@ int main(int argc, char** argv) {
     }
   }
 
+  const std::time_t t_begin = std::time(nullptr);
   simc_accum acc;
   if ((rc = simc_b200_accum_clear(h, &acc))) return die(h, "simc_b200_accum_clear", rc);
   simc_ntuple_file* nt = nullptr;
@@ -149,34 +152,22 @@ int main(int argc, char** argv) {
   simc_results res;
   simc_b200_normalise(&cfg, &acc, ngen, charge, &res);
 
-  FILE* f = std::fopen((out + ".hist").c_str(), "w");
-  if (!f) { std::fprintf(stderr, "simc_b200: cannot write %s.hist\n", out.c_str()); return 1; }
-  std::fprintf(f, "deck = %s\nseed = %lld\n", deck.c_str(), seed);
-  std::fprintf(f, "Ngen (request) = %d\nNtried = %lld\nNcontribute = %lld\nNpasscuts = %lld\nNcontribute_no_rad_proton = %lld\nN_unsupported = %lld\n",
-               ngen, (long long)acc.ntried, (long long)acc.ncontribute, (long long)acc.npasscuts,
-               (long long)acc.ncontribute_no_rad_proton, (long long)acc.unsupported);
-  std::fprintf(f, "charge_mC = %.10g\nluminosity_per_ub = %.10g\ngenvol = %.10g\nnormfac = %.10g\n", charge, res.luminosity, res.genvol, res.normfac);
-  std::fprintf(f, "wtcontribute = %.10g\nnormalised_yield = %.10g\nsigcc_ave = %.10g\n", fx(acc.wtcontribute), res.yield, res.central_sigcc_ave);
-  static const char* en[8] = {"e.delta", "e.xptar", "e.yptar", "e.ytar", "p.delta", "p.xptar", "p.yptar", "p.ytar"};
-  for (int k = 0; k < 8; ++k) std::fprintf(f, "aveerr.%s = %.8g\nresol.%s = %.8g\n", en[k], res.aveerr[k], en[k], res.resol[k]);
-  for (int w = 0; w < 2; ++w) {
-    const int arm = w == 0 ? cfg.electron_arm : cfg.hadron_arm;
-    std::fprintf(f, "%s arm (spectrometer %d): trials = %lld, successes = %lld, reached hut = %lld\n", w == 0 ? "electron" : "hadron", arm,
-                 (long long)acc.stop[w][0], (long long)acc.stop[w][1], (long long)acc.stop[w][2]);
-    for (int c = 1; 2 + c < SIMC_NSTOP; ++c)
-      if (acc.stop[w][2 + c]) std::fprintf(f, "  STOP_%s = %lld\n", simc_b200_stop_name(arm, c), (long long)acc.stop[w][2 + c]);
+  // the reference's three text files (simc.f:446-1139)
+  simc_report_info info;
+  if ((rc = simc_b200_report_info_from_deck(deck.c_str(), deck_dir.c_str(), data.c_str(), &info, err, sizeof err))) {
+    std::fprintf(stderr, "simc_b200: %s\n", err); return 1;
   }
-  static const char* hn[SIMC_H_PER_SET] = {"e.delta", "e.yptar", "e.xptar", "p.delta", "p.yptar", "p.xptar", "Em", "Pm"};
-  std::fprintf(f, "# histograms: name, then 50 rows: bin centre, geni counts, gen counts, RECON (weighted, normalised; Em/Pm: counts)\n");
-  for (int k = 0; k < SIMC_H_PER_SET; ++k) {
-    std::fprintf(f, "hist %s\n", hn[k]);
-    for (int b = 0; b < SIMC_NHIST; ++b) {
-      const simc_axis& ax = cfg.hist_axis[0][k];
-      const double recon = k < 6 ? fx(acc.hist_w[k][b]) * res.normfac : (double)acc.hist_n[0][k][b];
-      std::fprintf(f, " %.6g %lld %lld %.8g\n", ax.min + (b + 0.5) * ax.bin, (long long)acc.hist_n[2][k][b], (long long)acc.hist_n[1][k][b], recon);
-    }
+  info.random_seed = (int32_t)seed;
+  simc_central central;
+  if ((rc = simc_b200_central_event(h, &cfg, &info, &central))) return die(h, "simc_b200_central_event", rc);
+  const std::time_t t_end = std::time(nullptr);
+  char ts1[64], ts2[64];
+  std::snprintf(ts1, sizeof ts1, "%s", std::ctime(&t_begin));
+  std::snprintf(ts2, sizeof ts2, "%s", std::ctime(&t_end));
+  if ((rc = simc_b200_write_geni((out + ".geni").c_str(), &cfg, &acc)) || (rc = simc_b200_write_gen((out + ".gen").c_str(), &cfg, &acc)) ||
+      (rc = simc_b200_write_hist((out + ".hist").c_str(), &cfg, &info, &central, &acc, &res, ts1, ts2))) {
+    std::fprintf(stderr, "simc_b200: cannot write %s.{geni,gen,hist}\n", out.c_str()); return 1;
   }
-  std::fclose(f);
   std::printf("simc_b200: %lld tries, %lld successes, normalised yield %.6g for %.4g mC -> %s.hist%s\n", (long long)acc.ntried,
               (long long)acc.nsuccess, res.yield, charge, out.c_str(), want_ntuple ? " + .bin" : "");
   simc_b200_destroy(h);

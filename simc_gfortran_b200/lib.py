@@ -154,6 +154,30 @@ class Results(C.Structure):
                 ("central_sigcc_ave", C.c_double), ("nevent", C.c_int64), ("aveerr", C.c_double * 8), ("resol", C.c_double * 8)]
 
 
+class ReportInfo(C.Structure):
+    """simc_report_info (include/simc_b200.h): init-only values subroutine report prints."""
+    _fields_ = [("ngen", C.c_int32), ("random_seed", C.c_int32), ("one_tail", C.c_int32),
+                ("doing_pizero", C.c_int32), ("pizero_ngamma", C.c_int32), ("use_first_cer", C.c_int32), ("using_tgt_field", C.c_int32),
+                ("doing_hyddelta", C.c_int32), ("doing_deutdelta", C.c_int32), ("doing_hedelta", C.c_int32),
+                ("doing_hydrho", C.c_int32), ("doing_deutrho", C.c_int32), ("doing_herho", C.c_int32), ("pad", C.c_int32),
+                ("charge_mC", C.c_double),
+                ("Eloss_ave", C.c_double * 3), ("Eloss_min", C.c_double * 3), ("Eloss_max", C.c_double * 3),
+                ("teff_ave", C.c_double * 3), ("teff_min", C.c_double * 3), ("teff_max", C.c_double * 3),
+                ("musc_max", C.c_double * 3), ("musc_nsig_max", C.c_double), ("slop_total_Em_used", C.c_double),
+                ("theory_file", C.c_char * 128)]
+
+
+class Central(C.Structure):
+    """simc_central: event_central as calculate_central fills it (simc.f:1143-1306)."""
+    _fields_ = [("e_delta", C.c_double), ("e_xptar", C.c_double), ("e_yptar", C.c_double), ("p_delta", C.c_double),
+                ("p_xptar", C.c_double), ("p_yptar", C.c_double),
+                ("Q2", C.c_double), ("q", C.c_double), ("nu", C.c_double), ("Em", C.c_double), ("Pm", C.c_double),
+                ("W", C.c_double), ("MM", C.c_double), ("sigcc", C.c_double),
+                ("hardcorfac", C.c_double), ("etatzai", C.c_double), ("frac", C.c_double * 3), ("lambda_", C.c_double * 3),
+                ("bt", C.c_double * 2), ("c_int", C.c_double * 4), ("c_ext", C.c_double * 4), ("c", C.c_double * 4),
+                ("g_int", C.c_double), ("g_ext", C.c_double), ("g", C.c_double * 4)]
+
+
 def load_library():
     """Loads libsimc_b200.so from the package directory; raises if it has not been built."""
     global _lib
@@ -214,6 +238,12 @@ def load_library():
     L.simc_b200_load_fdss_file.argtypes = [C.c_void_p, C.c_char_p]
     L.simc_b200_set_sf_em_widths.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.simc_b200_normalise.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+    L.simc_b200_report_info_from_deck.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
+    L.simc_b200_central_event.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_write_geni.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_format_real.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    L.simc_b200_write_gen.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_write_hist.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p]
     L.simc_b200_ntuple_tags.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.simc_b200_ntuple_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.simc_b200_ntuple_append.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -292,6 +322,39 @@ def normalise(cfg: RunConfig, acc, ngen: int, charge_mC: float) -> Results:
     if rc:
         raise SimcError(rc, "simc_b200_normalise")
     return r
+
+
+def report_info_from_deck(deck_path: str, extra_deck_dir: str | None = None, data_dir: str | None = None) -> ReportInfo:
+    L = load_library()
+    info = ReportInfo()
+    err = C.create_string_buffer(512)
+    extra = (extra_deck_dir or os.path.dirname(os.path.abspath(deck_path))).encode()
+    rc = L.simc_b200_report_info_from_deck(deck_path.encode(), extra, data_dir.encode() if data_dir else None, C.byref(info), err, 512)
+    if rc:
+        raise SimcError(rc, err.value.decode())
+    return info
+
+
+def central_event(cfg: RunConfig, info: ReportInfo, sim=None) -> Central:
+    """calculate_central (simc.f:1143-1306).  sim: a Simc handle with the run's tables for central%sigcc (GPU); without
+    it the kinematics and the radiative constants only (host)."""
+    L = load_library()
+    c = Central()
+    rc = L.simc_b200_central_event(sim.h if sim is not None else None, C.byref(cfg), C.byref(info), C.byref(c))
+    if rc:
+        raise SimcError(rc, "simc_b200_central_event")
+    return c
+
+
+def write_reports(base: str, cfg: RunConfig, info: ReportInfo, central: Central, acc, res: Results, t1: str, t2: str):
+    """<base>.geni, <base>.gen, <base>.hist in the reference's layout (simc.f:446-1139)."""
+    L = load_library()
+    for rc, what in ((L.simc_b200_write_geni((base + ".geni").encode(), C.byref(cfg), C.byref(acc)), "geni"),
+                     (L.simc_b200_write_gen((base + ".gen").encode(), C.byref(cfg), C.byref(acc)), "gen"),
+                     (L.simc_b200_write_hist((base + ".hist").encode(), C.byref(cfg), C.byref(info), C.byref(central), C.byref(acc),
+                                             C.byref(res), t1.encode(), t2.encode()), "hist")):
+        if rc:
+            raise SimcError(rc, "simc_b200_write_" + what)
 
 
 def ntuple_tags(cfg: RunConfig):

@@ -1,6 +1,6 @@
 """End-to-end test of the stand-alone driver `simc_b200` (what program simc does around its loop): deck ->
-optics and tables from a working directory laid out like the reference's -> run -> normalised .hist summary and
-.bin ntuple.  Compared with the same run made through the Python host API on the same files."""
+optics and tables from a working directory laid out like the reference's -> run -> the reference's .hist / .gen / .geni
+text files and the .bin ntuple.  Compared with the same run made through the Python host API on the same files."""
 import os
 import re
 import subprocess
@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from simc_gfortran_b200 import Simc, config_from_deck, load_optics_fixture
+from simc_gfortran_b200 import Simc, central_event, config_from_deck, load_optics_fixture, report_info_from_deck, write_reports
 from simc_gfortran_b200.lib import normalise, ntuple_tags, read_ntuple_file
 from simc_gfortran_b200.optics import write_cosy_files
 
@@ -39,12 +39,23 @@ def run_driver(workdir, ngen, out, extra=()):
     r = subprocess.run([DRIVER, deck, "--data", str(workdir), "--out", str(workdir / out), "--seed", "5", *extra],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr + r.stdout
+    return deck, parse_hist(str(workdir / out) + ".hist")
+
+
+def parse_hist(path):
+    """The numbers of subroutine report (simc.f:913-967) the tests look at."""
     hist = {}
-    for line in open(str(workdir / out) + ".hist"):
-        m = re.match(r"^([A-Za-z_.() ]+?) = ([-+0-9.eE]+)$", line.strip())
+    for line in open(path):
+        m = re.match(r"^\s+(Ntried|Ncontribute|Ngen \(request\))\s*=\s*(-?\d+)$", line.rstrip())
+        if m:
+            hist[m.group(1)] = int(m.group(2))
+        m = re.match(r"^\s+(CENTRAL.sigcc|AVERAGE.sigcc|normfac|genvol|charge)\s=\s+([-0-9.E+]+)", line.rstrip())
         if m:
             hist[m.group(1)] = float(m.group(2))
-    return deck, hist
+        m = re.match(r"^\s+MeV: wtcontr=\s+([-0-9.E+]+)$", line.rstrip())
+        if m:
+            hist["wtcontr"] = float(m.group(1))
+    return hist
 
 
 def test_fixed_number_of_tries(workdir):
@@ -57,17 +68,28 @@ def test_fixed_number_of_tries(workdir):
         acc = sim.accum_clear()
         sim.run(0, 60000, 5, acc)
         rows, _ = sim.ntuple_batch(0, 60000, 5)
+        res = normalise(cfg, acc, ngen, charge)
+        info = report_info_from_deck(deck)
+        info.random_seed = 5
+        central = central_event(cfg, info, sim)
+        write_reports(str(workdir / "py"), cfg, info, central, acc, res, "t1", "t2")
     finally:
         sim.close()
-    res = normalise(cfg, acc, ngen, charge)
-    assert hist["Ntried"] == 60000 and hist["Ncontribute"] == acc.ncontribute and hist["Npasscuts"] == acc.npasscuts
-    assert abs(hist["normalised_yield"] / res.yield_ - 1) < 1e-8 and abs(hist["normfac"] / res.normfac - 1) < 1e-8
-    assert abs(hist["resol.e.delta"] - res.resol[0]) < 1e-6 * abs(res.resol[0])
+    assert hist["Ntried"] == 60000 and hist["Ncontribute"] == acc.ncontribute and hist["Ngen (request)"] == -60000
+    assert abs(hist["wtcontr"] * 60000 / res.yield_ - 1) < 1e-7 and abs(hist["normfac"] / res.normfac - 1) < 1e-5
+    # central%sigcc: sigep at the spectrometer settings (calculate_central), through the weight kernel
+    assert hist["CENTRAL.sigcc"] > 0 and abs(hist["CENTRAL.sigcc"] / central.sigcc - 1) < 1e-5
+    assert 0.1 < hist["CENTRAL.sigcc"] / hist["AVERAGE.sigcc"] < 100.0
+    # the driver's three text files are byte for byte what the host API writes for the same run (but for the times)
+    for ext in (".geni", ".gen"):
+        assert open(str(workdir / "tries") + ext).read() == open(str(workdir / "py") + ext).read(), ext
+    a, b = open(str(workdir / "tries.hist")).read().split("\n"), open(str(workdir / "py.hist")).read().split("\n")
+    assert len(a) == len(b) and a[:1] == b[:1] and a[3:] == b[3:]
     tags, vals = read_ntuple_file(str(workdir / "tries.bin"))
     assert tags == ntuple_tags(cfg) and vals.shape == rows.shape == (acc.ncontribute, 46)
     assert np.array_equal(vals, rows)                   # same kernels, same tries: identical rows
     # the weights in the file, normalised, give the yield of the summary (events inside the cuts)
-    assert hist["normalised_yield"] <= vals[:, 43].sum() * res.normfac * (1 + 1e-9)
+    assert res.yield_ <= vals[:, 43].sum() * res.normfac * (1 + 1e-9)
 
 
 def test_until_n_successes(workdir):
