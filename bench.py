@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("SIMC_B200_MODE", "strict"), choices=["strict", "fast"])
     ap.add_argument("--cpu-tries", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true",
+                    help="long sweeps (BASELINE configs[4]: 1e11 tries): the device-timed steps only, `e2e` is null")
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: the headline C1)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -262,7 +264,7 @@ def main():
     acc_e2e = sim.accum_clear()
     ar0, ar1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     allreduce_ms = 0.0
-    for k in range(args.steps):
+    for k in range(0 if args.skip_e2e else args.steps):
         if world == 1:
             sim.run(first_try(100 + k), n, seed, acc_e2e)
         else:
@@ -283,7 +285,7 @@ def main():
         # the accumulators of the device-timed steps were fetched per rank above: fold them on the host
         from simc_gfortran_b200.multi import allreduce_accum
         acc = allreduce_accum(acc)
-        assert acc_e2e.ntried == n * args.steps * world, (acc_e2e.ntried, n, args.steps, world)
+        assert args.skip_e2e or acc_e2e.ntried == n * args.steps * world, (acc_e2e.ntried, n, args.steps, world)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
@@ -327,7 +329,8 @@ def main():
                        "rng": "Philox4x32-10 keyed (seed, try index)",
                        "l2": "inputs are generated on chip; the per-stage state buffers (%.0f MB per batch) exceed the 126 MB L2"
                              % (110 * 8 * args.batch / 1e6)},
-            "e2e": {"value": tries_total / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": 32,
+            "e2e": None if args.skip_e2e else
+                   {"value": tries_total / (e2e_ms * 1e-3), "unit": "events/s", "h2d_bytes_per_step": 32,
                     "d2h_bytes_per_step": C.sizeof(Accum),
                     "note": "simc_b200_run() through the C ABI with host accumulators; a Monte Carlo step's only input "
                             "is (first_try, n_tries, seed)"},
