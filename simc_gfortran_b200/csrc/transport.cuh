@@ -295,45 +295,54 @@ __device__ __forceinline__ void ldg128(const double* p, double& a, double& b) {
 struct GaussQueue {
   unsigned base;          // shared address of row 0 of this thread's column
   int pos, avail;         // warp-uniform: next entry, entries left
+  int ts_pos;             // warp-uniform: next multiple-scattering width of the chunk (rows kGaussQ + m)
   uint32_t draw_before;   // draw counter before entry 0
 };
 constexpr unsigned kRowBytes = kBlock * 8u;
 __device__ __forceinline__ void gq_init(GaussQueue& q, const double* pw) {
-  q.base = (unsigned)__cvta_generic_to_shared(pw); q.pos = 0; q.avail = 0; q.draw_before = 0u;
+  q.base = (unsigned)__cvta_generic_to_shared(pw); q.pos = 0; q.avail = 0; q.ts_pos = 0; q.draw_before = 0u;
 }
 __device__ __forceinline__ unsigned gq_draw_addr(const GaussQueue& q, int k) {
   // 32-bit words behind the 2*Q double rows, two per 8-byte slot of the thread's OWN column (other threads'
   // columns may hold a power table at the same time: warps do not walk the program in step)
   return q.base + (unsigned)(2 * kGaussQ + (k >> 1)) * kRowBytes + (unsigned)(k & 1) * 4u;
 }
-// All 32 lanes call; `live` lanes draw n_new Gaussians behind the `q.avail` entries still queued (moved to the front).
+// Gaussians an op takes from the queue (warp-uniform: flags and op constants only)
+__device__ __forceinline__ int gauss_need(const ArmOp* o, bool ms_flag, bool wcs_flag) {
+  const int op = o->op;
+  if (op == OP_DC_PLANE) return wcs_flag ? 2 : 0;
+  if (op == OP_MUSC) return (ms_flag && o->a != 0.) ? 2 : 0;
+  if (op == OP_MUSC_EXT) return (ms_flag && o->a != 0.) ? 4 : 0;
+  return 0;
+}
+// musc.f:52 / musc_ext.f:45: theta_sigma = Es/p/beta * sqrt(radw) * (1 + 0.088*log10(radw/beta**2)), with
+// mc1 = 13.6/p/beta and mbeta2 = beta**2 of the track (musc_refresh) and b = sqrt(radw) from the host
+__device__ __forceinline__ double musc_width(double mc1, double mbeta2, double a, double b) {
+  return mc1 * b * (1 + 0.088 * fastlog::log10(a / mbeta2));
+}
+// One chunk of the queue.  All 32 lanes call, with an EMPTY queue (chunks end on op boundaries, so the queue runs dry
+// exactly where the next gauss op starts).  The chunk = the ops from `pc` on whose Gaussians fit kGaussQ entries, up to
+// the end of the stretch (`rem` Gaussians away, optics_host.cpp).  `live` lanes
+//   1. draw the chunk's Gaussians at their own pace (polar rejection, gauss1.f),
+//   2. transform them two at a time -- log, divide and square root inlined, two independent chains per warp,
+//   3. evaluate the multiple-scattering width of every musc / musc_ext op of the chunk, two at a time as well (they
+//      depend on the op's constants and on the track's p and beta only, which nothing in a hut changes): the walk
+//      through the ops afterwards calls no library routine.
 // Queue and generator go in and out by value, so that the caller's copies stay in registers.
-struct GqOut { uint32_t draw, h2, h3, draw_before; };
-__device__ __noinline__ GqOut gq_fill_v(GaussQueue q, DevRng rng, int n_new, bool live) {
+struct GqOut { uint32_t draw, h2, h3, draw_before; int n_new; };
+__device__ __noinline__ GqOut gq_fill_v(const ArmDev* arm, GaussQueue q, DevRng rng, int pc, int op_end, int rem, bool ms_flag,
+                                        bool wcs_flag, double mc1, double mbeta2, bool live) {
   const unsigned mask = 0xffffffffu;
-  // entries left over from the last fill go to the front
-  if (q.pos > 0) {
-    if (q.avail > 0) {
-      uint32_t db;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(db) : "r"(gq_draw_addr(q, q.pos - 1)));
-      q.draw_before = db;
-      for (int j = 0; j < q.avail; ++j) {
-        const double g = lds_f64(q.base + (unsigned)(q.pos + j) * kRowBytes);
-        uint32_t d;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(gq_draw_addr(q, q.pos + j)));
-        sts_f64(q.base + (unsigned)j * kRowBytes, g);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(gq_draw_addr(q, j)), "r"(d) : "memory");
-      }
-    } else {
-      q.draw_before = rng.draw;
-    }
-    q.pos = 0;
-  } else if (q.avail == 0) {
-    q.draw_before = rng.draw;
+  // ---- the chunk: whole ops only
+  int n_new = 0, pc_end = pc;
+  for (; pc_end < op_end && n_new < rem; ++pc_end) {
+    const int nd = gauss_need(&arm->ops[pc_end], ms_flag, wcs_flag);
+    if (n_new + nd > kGaussQ) break;
+    n_new += nd;
   }
-  const int first = q.avail;
-  const int target = live ? first + n_new : 0;
-  int k = live ? first : 0;
+  q.draw_before = rng.draw;
+  const int target = live ? n_new : 0;
+  int k = 0;
   uint32_t draw = rng.draw, h2 = rng.h2, h3 = rng.h3;
   const uint32_t t0 = rng.t0, t1 = rng.t1, stream = rng.stream;
   while (__any_sync(mask, k < target)) {
@@ -364,24 +373,50 @@ __device__ __noinline__ GqOut gq_fill_v(GaussQueue q, DevRng rng, int n_new, boo
   // gauss1.f: g = v1*sqrt(-2.*log(s)/s); |g| <= 12 for the smallest s the 52-bit uniforms can give, so the
   // nsigmax = 99 test of these calls can never fire
   if (live) {
-#pragma unroll 2
-    for (int j = first; j < first + n_new; ++j) {
-      const double v1 = lds_f64(q.base + (unsigned)j * kRowBytes);
-      const double sq = lds_f64(q.base + (unsigned)(kGaussQ + j) * kRowBytes);
-      sts_f64(q.base + (unsigned)j * kRowBytes, v1 * sqrt(-2. * m::log(sq) / sq));
+    int j = 0;
+    for (; j + 1 < n_new; j += 2) {
+      const double va = lds_f64(q.base + (unsigned)j * kRowBytes), vb = lds_f64(q.base + (unsigned)(j + 1) * kRowBytes);
+      const double sa = lds_f64(q.base + (unsigned)(kGaussQ + j) * kRowBytes), sb = lds_f64(q.base + (unsigned)(kGaussQ + j + 1) * kRowBytes);
+      const double ga = va * sqrt(-2. * fastlog::log(sa) / sa);
+      const double gb = vb * sqrt(-2. * fastlog::log(sb) / sb);
+      sts_f64(q.base + (unsigned)j * kRowBytes, ga);
+      sts_f64(q.base + (unsigned)(j + 1) * kRowBytes, gb);
+    }
+    if (j < n_new) {
+      const double va = lds_f64(q.base + (unsigned)j * kRowBytes), sa = lds_f64(q.base + (unsigned)(kGaussQ + j) * kRowBytes);
+      sts_f64(q.base + (unsigned)j * kRowBytes, va * sqrt(-2. * fastlog::log(sa) / sa));
+    }
+    // the widths of the chunk's multiple-scattering ops go where the s values were
+    if (ms_flag) {
+      int m = 0;
+      bool have = false;
+      double a0 = 0., b0 = 0.;
+      for (int p = pc; p < pc_end; ++p) {
+        const ArmOp* o = &arm->ops[p];
+        if (!((o->op == OP_MUSC || o->op == OP_MUSC_EXT) && o->a != 0.)) continue;
+        if (!have) { a0 = o->a; b0 = o->b; have = true; continue; }
+        const double w0 = musc_width(mc1, mbeta2, a0, b0);
+        const double w1 = musc_width(mc1, mbeta2, o->a, o->b);
+        sts_f64(q.base + (unsigned)(kGaussQ + m) * kRowBytes, w0);
+        sts_f64(q.base + (unsigned)(kGaussQ + m + 1) * kRowBytes, w1);
+        m += 2; have = false;
+      }
+      if (have) sts_f64(q.base + (unsigned)(kGaussQ + m) * kRowBytes, musc_width(mc1, mbeta2, a0, b0));
     }
   }
   __syncwarp();
   GqOut o;
-  o.draw = draw; o.h2 = h2; o.h3 = h3; o.draw_before = q.draw_before;
+  o.draw = draw; o.h2 = h2; o.h3 = h3; o.draw_before = q.draw_before; o.n_new = n_new;
   return o;
 }
-__device__ __forceinline__ void gq_fill(GaussQueue& q, DevRng& rng, int n_new, bool live) {
-  const GqOut o = gq_fill_v(q, rng, n_new, live);
+__device__ __forceinline__ void gq_fill(const ArmDev* arm, GaussQueue& q, DevRng& rng, int pc, int op_end, int rem, bool ms_flag,
+                                        bool wcs_flag, double mc1, double mbeta2, bool live) {
+  const GqOut o = gq_fill_v(arm, q, rng, pc, op_end, rem, ms_flag, wcs_flag, mc1, mbeta2, live);
   rng.draw = o.draw; rng.h2 = o.h2; rng.h3 = o.h3;
-  q.draw_before = o.draw_before; q.avail += n_new; q.pos = 0;
+  q.draw_before = o.draw_before; q.avail = o.n_new; q.pos = 0; q.ts_pos = 0;
 }
 __device__ __forceinline__ double gq_at(const GaussQueue& q, int k) { return lds_f64(q.base + (unsigned)k * kRowBytes); }
+__device__ __forceinline__ double gq_ts(const GaussQueue& q, int m) { return lds_f64(q.base + (unsigned)(kGaussQ + m) * kRowBytes); }
 // The draw counter of a track that stops now, with q.avail Gaussians drawn ahead but not consumed
 __device__ __forceinline__ uint32_t gq_draw_consumed(const GaussQueue& q) {
   if (q.pos == 0) return q.draw_before;
@@ -720,19 +755,19 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       }
       continue;
     }
-    // this op's Gaussians: entries [qoff, qoff + need) of the queue; pos/avail stay warp-uniform
-    int qoff = 0;
+    // this op's Gaussians: entries [qoff, qoff + need) of the queue, and its width if it is a multiple-scattering op;
+    // pos / avail / ts_pos stay warp-uniform
+    int qoff = 0, tsoff = 0;
     if (use_q && (op == OP_MUSC || op == OP_MUSC_EXT || op == OP_DC_PLANE)) {
-      const int need = op == OP_DC_PLANE ? (f.wcs_flag ? 2 : 0) : ((f.ms_flag && a != 0.) ? (op == OP_MUSC ? 2 : 4) : 0);
-      if (need > gq.avail) {
+      const int need = gauss_need(o, f.ms_flag, f.wcs_flag);
+      if (need > gq.avail) {          // (avail == 0: chunks end on op boundaries)
         const unsigned code = (unsigned)o->code;      // Gaussians from this op to the end of the stretch (optics_host.cpp)
         const int rem = (f.ms_flag ? (int)(code & 0xffffu) : 0) + (f.wcs_flag ? (int)(code >> 16) : 0);
-        int n_new = rem - gq.avail;
-        if (n_new > kGaussQ - gq.avail) n_new = kGaussQ - gq.avail;
-        gq_fill(gq, rng, n_new, alive);
+        gq_fill(arm, gq, rng, pc, op_end, rem, f.ms_flag, f.wcs_flag, t.mc1, t.mbeta2, alive);
       }
       qoff = gq.pos;
       gq.pos += need; gq.avail -= need;
+      if (op != OP_DC_PLANE && need > 0) tsoff = gq.ts_pos++;
     }
     if (!alive || pc < skip_until) continue;
     bool stop = false;
@@ -772,7 +807,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
       case OP_RESMULT_ONE: res.resmult = 1.0; break;
       case OP_MUSC:        // musc.f:46-55, called as musc(m2,p,radw,dydzs,dxdzs)
         if (f.ms_flag && a != 0.) {
-          const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
+          const double ts = use_q ? gq_ts(gq, tsoff) : t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           double g1, g2;
           if (use_q) { g1 = gq_at(gq, qoff); g2 = gq_at(gq, qoff + 1); }
           else gauss2(rng, g1, g2);
@@ -782,7 +817,7 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
         break;
       case OP_MUSC_EXT:    // musc_ext.f:37-51, called as musc_ext(m2,p,radw,drift,dydzs,dxdzs,ys,xs)
         if (f.ms_flag && a != 0.) {
-          const double ts = t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
+          const double ts = use_q ? gq_ts(gq, tsoff) : t.mc1 * b * (1 + 0.088 * m::log10(a / t.mbeta2));
           double g1, g2;
           if (use_q) { g1 = gq_at(gq, qoff); g2 = gq_at(gq, qoff + 1); }
           else gauss2(rng, g1, g2);
