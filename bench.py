@@ -40,9 +40,9 @@ def deck_of(args):
 
 
 def sf_table():
-    """Spectral function of C2 (tests/golden/benharsf_12.npz = the reference's benharsf_12.dat)."""
+    """Spectral function of C2 (simc_gfortran_b200/data/benharsf_12.npz = the reference's benharsf_12.dat)."""
     import numpy as np
-    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
     return z["pm"], z["em"], z["sf_proton"]
 
 
@@ -212,9 +212,9 @@ def main():
         sim.set_sf_table(*sf_table())
     if cfg.doing_semi:          # tables of C4: the reference's cteq5/cteq5m.tbl and deut.dat as fixtures
         import numpy as np
-        z = np.load(os.path.join(ROOT, "tests", "golden", "cteq5m.npz"))
+        z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "cteq5m.npz"))
         sim.set_cteq5_table({k: (z[k] if z[k].ndim else z[k].item()) for k in z.files})
-        z = np.load(os.path.join(ROOT, "tests", "golden", "pfermi_deut.npz"))
+        z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "pfermi_deut.npz"))
         sim.set_pfermi_table(z["pval"], z["mprob"])
     optics = {"e": load_optics_fixture(cfg.electron_arm), "p": load_optics_fixture(cfg.hadron_arm)}
     sim.set_optics(optics["e"])

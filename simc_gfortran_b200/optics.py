@@ -1,8 +1,9 @@
 """COSY optics tables as arrays (the layout simc_b200_set_optics takes).
 
 The reference reads them from ``hms/forward_cosy.dat`` etc. (shared/transp.f:294-474,
-hms/mc_hms_recon.f:70-102).  ``tests/golden/optics_*.npz`` holds the parsed tables of the
-shipped files so that GPU tests do not need the reference tree; ``write_cosy_files`` turns
+hms/mc_hms_recon.f:70-102).  ``simc_gfortran_b200/data/optics_*.npz`` holds the parsed tables of the
+reference's five file pairs (data the package ships, made by tools/make_fixtures.py) so that the bench and the GPU
+tests do not need the reference tree; ``write_cosy_files`` turns
 tables back into the reference's fixed-column text format so the file reader of the library
 can be exercised anywhere.
 """
@@ -13,7 +14,7 @@ import os
 
 import numpy as np
 
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 @dataclasses.dataclass
@@ -45,7 +46,7 @@ _ARM_NAME = {1: "hms", 2: "sos", 3: "hrsr", 4: "hrsl", 5: "shms"}
 
 
 def load_optics_fixture(arm: int) -> OpticsTables:
-    return OpticsTables.load(os.path.join(GOLDEN_DIR, f"optics_{_ARM_NAME[arm]}.npz"))
+    return OpticsTables.load(os.path.join(DATA_DIR, f"optics_{_ARM_NAME[arm]}.npz"))
 
 
 def _g(v: float, width: int, digits: int) -> str:

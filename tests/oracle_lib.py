@@ -178,14 +178,14 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def load_cteq5_fixture():
-    """tests/golden/cteq5m.npz (tools/make_fixtures.py: the reference's cteq5/cteq5m.tbl)."""
-    z = np.load(os.path.join(GOLDEN, "cteq5m.npz"))
+    """simc_gfortran_b200/data/cteq5m.npz (tools/make_fixtures.py: the reference's cteq5/cteq5m.tbl)."""
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "cteq5m.npz"))
     return {k: (z[k] if z[k].ndim else z[k].item()) for k in z.files}
 
 
 def load_pfermi_fixture():
-    """tests/golden/pfermi_deut.npz (the reference's deut.dat)."""
-    z = np.load(os.path.join(GOLDEN, "pfermi_deut.npz"))
+    """simc_gfortran_b200/data/pfermi_deut.npz (the reference's deut.dat)."""
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "pfermi_deut.npz"))
     return z["pval"], z["mprob"]
 
 

@@ -20,7 +20,7 @@ SC[6] = SC[9] = 1.0  # deForest cross sections ~1e2
 
 @pytest.fixture(scope="module")
 def sf():
-    return np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    return np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
 
 
 @pytest.fixture(scope="module")

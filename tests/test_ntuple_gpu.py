@@ -28,7 +28,7 @@ def test_ntuple_rows(oracle_with_optics, name):
         for arm in arms:
             sim.set_optics(load_optics_fixture(arm))
         if cfg.doing_heavy:
-            z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+            z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
             sim.set_sf_table(z["pm"], z["em"], z["sf_proton"])
             oracle_with_optics.set_sf_table(z["pm"], z["em"], z["sf_proton"])
         n = 30000

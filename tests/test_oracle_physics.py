@@ -16,7 +16,7 @@ def deck(name):
 
 
 def test_spectral_function_is_normalised(oracle):
-    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
     oracle.set_sf_table(z["pm"], z["em"], z["sf_proton"])
     pm, em = np.meshgrid(z["pm"], z["em"], indexing="ij")
     d = oracle.sf_batch(em.ravel(), pm.ravel())
@@ -34,7 +34,7 @@ def test_spectral_function_is_normalised(oracle):
 
 
 def test_carbon_eep_events(oracle_with_optics):
-    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
     oracle_with_optics.set_sf_table(z["pm"], z["em"], z["sf_proton"])
     cfg = deck("c2_eep_carbon_hms_sos.inp")
     assert cfg.doing_heavy and not cfg.doing_hyd_elast and cfg.VERTEXedge.Pm.max == 790.0

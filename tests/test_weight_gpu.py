@@ -20,7 +20,7 @@ NAMES = ["success", "pass_cuts", "weight", "sigcc", "sigcc_recon", "recon.Em", "
 
 
 def sf_table():
-    z = np.load(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"))
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"))
     return z["pm"], z["em"], z["sf_proton"]
 
 

@@ -51,7 +51,7 @@ def main():
 
 
 def make_sf():
-    """benharsf_12.dat (the reference's data file for A = 12, dbase.f:600) -> tests/golden/benharsf_12.npz"""
+    """benharsf_12.dat (the reference's data file for A = 12, dbase.f:600) -> simc_gfortran_b200/data/benharsf_12.npz"""
     rows = []
     with open(os.path.join(REF, "benharsf_12.dat")) as f:
         n_pm, n_em = (int(x) for x in f.readline().split())
@@ -59,7 +59,7 @@ def make_sf():
             if line.strip():
                 rows.append([float(x) for x in line.split()])
     a = np.array(rows).reshape(n_pm, n_em, 6)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "benharsf_12.npz"), pm=a[:, 0, 0], em=a[0, :, 1],
+    np.savez_compressed(os.path.join(ROOT, "simc_gfortran_b200", "data", "benharsf_12.npz"), pm=a[:, 0, 0], em=a[0, :, 1],
                         sf_proton=a[:, :, 2], sf_neutron=a[:, :, 3], dpm=a[:, 0, 4], dem=a[0, :, 5])
     print("benharsf_12", n_pm, n_em, "sum", a[:, :, 2].sum())
 
@@ -96,9 +96,9 @@ def read_cteq5_tbl(path):
 
 def make_semi():
     """cteq5/cteq5m.tbl (SetCtq5 with Iset = 1, semi_physics.f:226-229) and deut.dat (dbase.f:564) ->
-    tests/golden/cteq5m.npz, tests/golden/pfermi_deut.npz"""
+    simc_gfortran_b200/data/cteq5m.npz, simc_gfortran_b200/data/pfermi_deut.npz"""
     t = read_cteq5_tbl(os.path.join(REF, "cteq5", "cteq5m.tbl"))
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cteq5m.npz"), **t)
+    np.savez_compressed(os.path.join(ROOT, "simc_gfortran_b200", "data", "cteq5m.npz"), **t)
     print("cteq5m", t["nx"], t["nt"], t["nfmx"], t["lam"], len(t["upd"]))
     rows = []
     with open(os.path.join(REF, "deut.dat")) as f:
@@ -106,7 +106,7 @@ def make_semi():
             if line.strip():
                 rows.append([float(x.replace("d", "e").replace("D", "e")) for x in line.split()])
     a = np.array(rows)[:2000]
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pfermi_deut.npz"), pval=a[:, 0], mprob=a[:, 1])
+    np.savez_compressed(os.path.join(ROOT, "simc_gfortran_b200", "data", "pfermi_deut.npz"), pval=a[:, 0], mprob=a[:, 1])
     print("deut.dat", a.shape, a[-1])
 
 
