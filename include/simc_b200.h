@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define SIMC_B200_ABI_VERSION 2
+#define SIMC_B200_ABI_VERSION 3
 
 /* ---- spectrometer ids: electron_arm / hadron_arm numbering of dbase.f:247-263 */
 enum {
@@ -50,7 +50,9 @@ enum {
   SIMC_ARM_SOS  = 2,
   SIMC_ARM_HRSR = 3,
   SIMC_ARM_HRSL = 4,
-  SIMC_ARM_SHMS = 5
+  SIMC_ARM_SHMS = 5,
+  SIMC_ARM_CALO_RIGHT = 7,   /* calorimeter on the HMS side (calo/mc_calo.f; dbase.f:247-259) */
+  SIMC_ARM_CALO_LEFT  = 8    /* calorimeter on the SOS / SHMS side */
 };
 
 /* ---- status codes */
@@ -133,10 +135,12 @@ typedef struct {
   int32_t doing_tail[3];
   int32_t hardwired_rad;
   int32_t deForest_flag;                     /* 0 = sigcc1, 1 = sigcc2, -1 = sigcc1 on shell (physics_proton.f:39-45) */
+  int32_t doing_pizero, pizero_ngamma;       /* dbase.f:1006-1007: pi0 -> gamma gamma into a calorimeter arm (SIMC_ARM_CALO_*) */
 
   /* /gnrl/ scalars */
   double Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave;
   double dE_edge_test, Egamma_gen_max, ctau, transparency;
+  double drift_to_cal;                       /* cm from the target to the calorimeter front (dbase.f:1104, calo/mc_calo.f:139) */
   /* /radccom/ run-level */
   double etatzai, Egamma_tot_max, Egamma1_max, Egamma2_max, Egamma3_max, Egamma_res_limit;
 
@@ -403,10 +407,10 @@ int simc_b200_transport_batch_device(simc_handle* h, int arm_id, int64_t n,
 
 /* whole-event parity entry point: per-try records instead of accumulators.
  * rec[k*n+i], k = 0..SIMC_EVENT_NREC-1 (see simc_b200_event_field_name). */
-#define SIMC_EVENT_NREC 56
+#define SIMC_EVENT_NREC 60
 /* Columns of one ntuple row, results_ntu_write (results_write.f:1-269): 46 for (e,e'p), 53 for pion, 55
  * for kaon and 56 for semi-inclusive production (no target field). */
-#define SIMC_NTUPLE_MAXCOL 56
+#define SIMC_NTUPLE_MAXCOL 68      /* widest rows: rho production 59, pi0 -> gamma gamma 65 / 68 columns (NtupleInit.f:101-343) */
 int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t seed,
                           double* rec_soa, int32_t* status);
 const char* simc_b200_event_field_name(int k);

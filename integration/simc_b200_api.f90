@@ -8,9 +8,9 @@ module simc_b200_api
   use iso_c_binding
   implicit none
 
-  integer(c_int32_t), parameter :: SIMC_B200_ABI_VERSION = 2
+  integer(c_int32_t), parameter :: SIMC_B200_ABI_VERSION = 3
   integer(c_int), parameter :: SIMC_NHIST = 50, SIMC_H_PER_SET = 8, SIMC_NSTOP = 64
-  integer(c_int), parameter :: SIMC_NTUPLE_MAXCOL = 56
+  integer(c_int), parameter :: SIMC_NTUPLE_MAXCOL = 68
 
   ! ---- basic records (modules.f:5-12, 35-38, 170-184, 202-215, 150-165, 195)
   type, bind(C) :: simc_cut
@@ -75,8 +75,10 @@ module simc_b200_api
     integer(c_int32_t) :: doing_tail(3)
     integer(c_int32_t) :: hardwired_rad
     integer(c_int32_t) :: deForest_flag
+    integer(c_int32_t) :: doing_pizero, pizero_ngamma
     real(c_double) :: Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave
     real(c_double) :: dE_edge_test, Egamma_gen_max, ctau, transparency
+    real(c_double) :: drift_to_cal
     real(c_double) :: etatzai, Egamma_tot_max, Egamma1_max, Egamma2_max, Egamma3_max, Egamma_res_limit
     type(simc_gen_limits) :: gen
     type(simc_spectrometer) :: spec_e, spec_p

@@ -81,6 +81,8 @@
 	enddo
 	cfg%hardwired_rad   = merge(1,0,hardwired_rad)
 	cfg%deForest_flag   = deForest_flag
+	cfg%doing_pizero    = merge(1,0,doing_pizero)
+	cfg%pizero_ngamma   = pizero_ngamma
 ! ... /gnrl/ scalars, ctau of /decd/
 	cfg%Mh = Mh
 	cfg%Mh2 = Mh2
@@ -91,6 +93,7 @@
 	cfg%Egamma_gen_max = Egamma_gen_max
 	cfg%ctau = ctau
 	cfg%transparency = transparency
+	cfg%drift_to_cal = drift_to_cal
 ! ... /radccom/ run-level
 	cfg%etatzai = etatzai
 	cfg%Egamma_tot_max = Egamma_tot_max

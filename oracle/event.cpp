@@ -9,6 +9,7 @@
 namespace simc_oracle {
 
 using std::acos;
+using std::asin;
 using std::atan;
 using std::atan2;
 using std::cos;
@@ -70,11 +71,138 @@ double sigep(const Event& vertex) {
   return sigMott(vertex.e.E, vertex.e.theta, vertex.Q2) * vertex.e.E / vertex.Ein * Wp;
 }
 
+// generate_rho.f:1-131: the rho is thrown flat in cos(theta), phi in the virtual photon - nucleon centre of mass with a
+// Breit-Wigner mass, then boosted to the lab.  Three random numbers; replaces COMMON Mh, Mh2.
+bool generate_rho(Sim& s, Event& vertex) {
+  const simc_run_config& cfg = *s.cfg;
+  Rng& rng = *s.rng;
+  const double nu = vertex.nu, Q2 = vertex.Q2, q = vertex.q;
+  const double qux = vertex.uq.x, quy = vertex.uq.y, quz = vertex.uq.z;
+  const double bx = -(q * qux + s.pferx * s.pfer) / (nu + s.efer);
+  const double by = -(q * quy + s.pfery * s.pfer) / (nu + s.efer);
+  const double bz = -(q * quz + s.pferz * s.pfer) / (nu + s.efer);
+  const double betacm = sqrt(bx * bx + by * by + bz * bz);
+  if (betacm > 1.0) return false;
+  const double gammacm = 1. / sqrt(1.0 - betacm * betacm);
+  const double ss = -Q2 + s.efer * s.efer + 2. * nu * s.efer;
+  s.Mh = K::Mrho;
+  s.Mh = s.Mh + 0.5 * 150.2 * tan((2. * rng.grnd() - 1.) * atan(2. * 500. / 150.2));
+  s.Mh2 = s.Mh * s.Mh;
+  s.ntup.rhomass = s.Mh;
+  s.trk.Mh2_final = s.Mh;                       // as written (generate_rho.f:82); rho_decay overwrites it
+  const double Erhocm = (ss + s.Mh2 - cfg.targ.Mrec_struck * cfg.targ.Mrec_struck) / 2. / sqrt(ss);
+  if (Erhocm < s.Mh) return false;
+  const double Prhocm = sqrt(Erhocm * Erhocm - s.Mh2);
+  const double rph = rng.grnd() * 2. * K::pi;
+  const double rth1 = rng.grnd() * 2. - 1.;
+  const double rth = acos(rth1);
+  const double pxr = Prhocm * sin(rth) * cos(rph);
+  const double pyr = Prhocm * sin(rth) * sin(rph);
+  const double pzr = Prhocm * cos(rth);
+  const double er = Erhocm;
+  double ef, pxf, pyf, pzf, pf;
+  loren(gammacm, bx, by, bz, er, pxr, pyr, pzr, ef, pxf, pyf, pzf, pf);
+  vertex.p.delta = 100. * (pf / cfg.spec_p.P - 1.);
+  vertex.p.P = pf;
+  vertex.p.E = ef;
+  vertex.up.x = pxf / pf;
+  vertex.up.y = pyf / pf;
+  vertex.up.z = pzf / pf;
+  vertex.p.xptar = acos(pzf / pf);              // "not really used for anything" (generate_rho.f:123-126)
+  vertex.p.yptar = atan2(pyf, pxf);
+  return true;
+}
+
+// rho_decay.f:1-163: rho0 -> pi+ pi-, the detected pion flat in phi and ~ sin^2 + 2 eps R cos^2 in the rho rest frame
+// (rejection loop), boosted to the lab; `orig` becomes the pion that enters the hadron arm and COMMON Mh = Mpi.
+bool rho_decay(Sim& s, Event& orig, double p_spec, double epsilon) {
+  const simc_run_config& cfg = *s.cfg;
+  Rng& rng = *s.rng;
+  const double R_rho = 0.33 * std::pow(orig.Q2 / K::Mrho2, 0.61);
+  const double ph = orig.p.P;
+  const double beta = ph / sqrt(ph * ph + s.Mh2);
+  const double gamma = 1. / sqrt(1. - beta * beta);
+  const double rph = rng.grnd() * 2. * K::pi;
+  double rth;
+  for (;;) {
+    const double rth1 = rng.grnd() * 2. - 1.;
+    rth = acos(rth1);
+    const double norm = (1.0 + 2.0 * epsilon * R_rho) * rng.grnd();
+    const double dist = powi(sin(rth), 2) + 2.0 * epsilon * R_rho * powi(cos(rth), 2);
+    if (!(dist < norm)) break;
+  }
+  s.ntup.rhotheta = rth;
+  const double er = s.ntup.rhomass / 2.0;
+  if (er < K::Mpi) return false;
+  const double pr = sqrt(er * er - K::Mpi2);
+  const double pxr = pr * sin(rth) * cos(rph);
+  const double pyr = pr * sin(rth) * sin(rph);
+  const double pzr = pr * cos(rth);
+  const double bx = -beta * orig.up.x, by = -beta * orig.up.y, bz = -beta * orig.up.z;
+  double ef, pxf, pyf, pzf, pf;
+  loren(gamma, bx, by, bz, er, pxr, pyr, pzr, ef, pxf, pyf, pzf, pf);
+  const int arm = cfg.hadron_arm;
+  const double th0 = cfg.spec_p.theta;
+  double pzprime;
+  if (arm == 1 || arm == 3) pzprime = pzf * cos(th0) - pyf * sin(th0);
+  else if (arm == 2 || arm == 4 || arm == 5) pzprime = pzf * cos(th0) + pyf * sin(th0);
+  else throw std::runtime_error("Unknown spectrometer setup dude!");
+  if (pzprime < 0.0) return false;
+  const double th_oop = asin(pxf / pf);
+  const double cos_th_inp = pzf / pf / cos(th_oop);
+  double th_inp = acos(cos_th_inp);
+  if (arm == 1 || arm == 3) {
+    if (pyf < 0.0) th_inp = th0 - th_inp;
+    else th_inp = th0 + th_inp;
+  } else {
+    if (pyf > 0.0) th_inp = th_inp - th0;
+    else th_inp = th_inp + th0;
+  }
+  if ((th_inp > K::pi / 2.) || (th_oop > K::pi / 2.)) return false;
+  orig.up.x = pxf / pf;
+  orig.up.y = pyf / pf;
+  orig.up.z = pzf / pf;
+  orig.p.xptar = tan(th_oop);
+  orig.p.yptar = tan(th_inp);
+  orig.p.delta = 100. * (pf / p_spec - 1.);
+  orig.p.P = pf;
+  s.Mh = K::Mpi;
+  s.Mh2 = K::Mpi2;
+  s.trk.Mh2_final = s.Mh2;
+  orig.p.E = sqrt(orig.p.P * orig.p.P + s.Mh2);
+  physics_angles(cfg.spec_p.theta, cfg.spec_p.phi, orig.p.xptar, orig.p.yptar, orig.p.theta, orig.p.phi);
+  return true;
+}
+
+// pizero_decay.f:1-97: pi0 -> gamma gamma, flat in cos(theta) and phi in the pi0 rest frame, boosted to the lab.  Two
+// random numbers.  (The routine's own energy / momentum sums only print a warning.)
+void pizero_decay(Sim& s, const Event& vertex) {
+  Rng& rng = *s.rng;
+  const double Mgamma = 0.0;
+  const double ph = vertex.p.P;
+  const double eh = sqrt(ph * ph + s.Mh * s.Mh);
+  const double beta = ph / eh;
+  const double gamma = 1. / sqrt(1. - beta * beta);
+  const double rph = rng.grnd() * 2. * K::pi;
+  const double rth1 = rng.grnd() * 2. - 1.;
+  const double rth = acos(rth1);
+  const double er = s.Mh / 2.0;
+  const double pr = sqrt(er * er - Mgamma * Mgamma);
+  const double pxr1 = pr * sin(rth) * cos(rph), pyr1 = pr * sin(rth) * sin(rph), pzr1 = pr * cos(rth);
+  const double pxr2 = -pxr1, pyr2 = -pyr1, pzr2 = -pzr1;
+  const double bx = -beta * vertex.up.x, by = -beta * vertex.up.y, bz = -beta * vertex.up.z;
+  double pf1, pf2;
+  double* g1 = s.ntup.gamma1;
+  double* g2 = s.ntup.gamma2;
+  loren(gamma, bx, by, bz, er, pxr1, pyr1, pzr1, g1[0], g1[1], g1[2], g1[3], pf1);
+  loren(gamma, bx, by, bz, er, pxr2, pyr2, pzr2, g2[0], g2[1], g2[2], g2[3], pf2);
+}
+
 // event.f:432-1052
 bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
-  const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
+  double Mh = s.Mh, Mh2 = s.Mh2;          // COMMON: generate_rho replaces them (rho production only)
   main.jacobian = 1.0;
   vertex.ue.x = sin(vertex.e.theta) * cos(vertex.e.phi);
   vertex.ue.y = sin(vertex.e.theta) * sin(vertex.e.phi);
@@ -163,6 +291,9 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     if (vertex.p.E <= Mh) return false;
     vertex.p.P = sqrt(vertex.p.E * vertex.p.E - Mh2);
     vertex.p.delta = (vertex.p.P - cfg.spec_p.P) * 100. / cfg.spec_p.P;
+  } else if (cfg.doing_rho) {                    // :701-708: the rho is thrown in 4 pi in the photon-nucleon c.m.
+    if (!generate_rho(s, vertex)) return false;
+    Mh = s.Mh; Mh2 = s.Mh2;
   } else if (cfg.doing_phsp) {
     vertex.p.P = cfg.spec_p.P;
     vertex.p.E = sqrt(Mh2 + vertex.p.P * vertex.p.P);
@@ -191,6 +322,7 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
     main.phi_pq = atan2(p_new_y, p_new_x);
     if (main.phi_pq < 0.e0) main.phi_pq = main.phi_pq + 2. * K::pi;
+    if (cfg.doing_pizero) pizero_decay(s, vertex);        // :899-901
   }
 
   // :880-955 missing momentum
@@ -213,8 +345,8 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     vertex.Mrec = sqrt(vertex.Emiss * vertex.Emiss - vertex.Pmiss * vertex.Pmiss);
     vertex.Em = targ.Mtar_struck + vertex.Mrec - targ.M;
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
-  } else if (cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_delta) {   // doing_hyddelta: hydrogen only here
-    vertex.Trec = 0.0;
+  } else if (cfg.doing_hydpi || cfg.doing_hydkaon || cfg.doing_delta || (cfg.doing_rho && std::lround(targ.A) == 1)) {
+    vertex.Trec = 0.0;                         // doing_hyddelta, doing_hydrho: hydrogen only here
   } else if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {
     vertex.Trec = sqrt(vertex.Mrec * vertex.Mrec + vertex.Pm * vertex.Pm) - vertex.Mrec;
   } else if (cfg.doing_semi) {
@@ -305,7 +437,7 @@ bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
     if (Emin > Emax) return false;
     main.gen_weight = main.gen_weight * (Emax - Emin) / (gen.p.E.max - gen.p.E.min);
     vertex.p.E = Emin + rng.grnd() * (Emax - Emin);
-    vertex.p.P = sqrt(vertex.p.E * vertex.p.E - cfg.Mh2);
+    vertex.p.P = sqrt(vertex.p.E * vertex.p.E - s.Mh2);
     vertex.p.delta = 100. * (vertex.p.P - cfg.spec_p.P) / cfg.spec_p.P;
   }
   if (cfg.doing_deuterium || cfg.doing_heavy || cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || cfg.doing_rho ||
@@ -372,6 +504,9 @@ bool generate(Sim& s, EventMain& main, Event& vertex, Event& orig) {
                  vertex.Pm >= cfg.VERTEXedge.Pm.min && vertex.Pm <= cfg.VERTEXedge.Pm.max);
     if (success) orig = vertex;
   }
+  // :420-422.  The reference calls rho_decay whatever generate_rad returned; for a try that already failed it would
+  // only burn random numbers of a stream nobody reads again (and `orig` is then the previous event's): skipped.
+  if (cfg.doing_rho && success) success = rho_decay(s, orig, cfg.spec_p.P, main.epsilon);
   return success;
 }
 
@@ -382,13 +517,29 @@ static void run_arm(Sim& s, int arm_id, const ArmOptics* o, ArmCall& a) {
   else if (arm_id == 5) mc_shms(s.trk, *o, a);
   else if (arm_id == 2) mc_sos(s.trk, *o, a);
   else if (arm_id == 3 || arm_id == 4) mc_hrs(s.trk, *o, a, arm_id == 3);
-  else throw std::runtime_error("oracle: spectrometer not restated (calorimeter arms are out of scope)");
+  else throw std::runtime_error("oracle: spectrometer not restated");
+}
+
+// calo/mc_calo.f:1-191: the calorimeter arm.  A field-free drift to the front face and the two half-size cuts (the
+// NPS: 30 x 36 blocks of 2.05 cm); dpp, y and the slopes are returned as they came in.
+namespace calo_stop { enum { OK = 0, SLIT_HOR, SLIT_VERT }; }
+static void mc_calo(Track& t, ArmCall& a, double drift_to_cal) {
+  const double h_entr = 30.75, v_entr = 36.9;
+  a.ok_spec = false;
+  bool dflag = false;
+  t.xs = a.x; t.ys = a.y; t.zs = a.z; t.dxdzs = a.dxdz; t.dydzs = a.dydz; t.dpps = a.dpp;
+  double p = a.p_spec * (1. + t.dpps / 100.);
+  project(t, drift_to_cal, a.decay_flag, dflag, a.m2, p, a.pathlen);
+  if (fabs(t.ys) > h_entr) { a.stop_code = calo_stop::SLIT_HOR; return; }
+  if (fabs(t.xs) > v_entr) { a.stop_code = calo_stop::SLIT_VERT; return; }
+  a.x_fp = t.xs; a.y_fp = t.ys; a.dx_fp = t.dxdzs; a.dy_fp = t.dydzs;
+  a.ok_spec = true;
 }
 
 // simc.f:1310-1852 (using_tgt_field = .false., no calorimeter arms)
 bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
   const simc_run_config& cfg = *s.cfg;
-  const double Mh2 = cfg.Mh2, Mh = cfg.Mh;
+  const double Mh2 = s.Mh2, Mh = s.Mh;      // rho production: the decay pion's (rho_decay.f:150-153)
   s.ntup.resfac = 0.0;
   double fry;
   if (cfg.correct_raster) fry = -main.target.rastery;
@@ -431,7 +582,42 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     a.fry = (arm == 1 || arm == 5 || arm == 6) ? xtar_init_P : fry;
     a.using_coll = (arm == 1) ? cfg.using_HMScoll : (arm == 5 ? cfg.using_SHMScoll : 0);
     s.trk.calls = s.calls[1];
-    run_arm(s, arm, s.optics_p, a);
+    if (arm == 7 || arm == 8) {                      // simc.f:1489-1564
+      if (cfg.doing_pizero) {                        // one call per photon
+        const double* g1 = s.ntup.gamma1;
+        const double* g2 = s.ntup.gamma2;
+        const double cth = cos(cfg.spec_p.theta), sth = sin(cfg.spec_p.theta);
+        double exrot1, eyrot1, ezrot1, exrot2, eyrot2, ezrot2;
+        if (arm == 8) {
+          exrot1 = g1[1]; eyrot1 = g1[2] * cth - g1[3] * sth; ezrot1 = g1[2] * sth + g1[3] * cth;
+          exrot2 = g2[1]; eyrot2 = g2[2] * cth - g2[3] * sth; ezrot2 = g2[2] * sth + g2[3] * cth;
+        } else {
+          exrot1 = g1[1]; eyrot1 = g1[2] * cth + g1[3] * sth; ezrot1 = -g1[2] * sth + g1[3] * cth;
+          exrot2 = g2[1]; eyrot2 = g2[2] * cth + g2[3] * sth; ezrot2 = -g2[2] * sth + g2[3] * cth;
+        }
+        a.dxdz = exrot1 / ezrot1; a.dydz = eyrot1 / ezrot1;
+        mc_calo(s.trk, a, cfg.drift_to_cal);
+        const bool ok_gamma1 = a.ok_spec;
+        const int stop1 = a.stop_code;
+        s.ntup.xcal_gamma1 = -1.0e10; s.ntup.ycal_gamma1 = -1.0e10;
+        if (ok_gamma1) { s.ntup.xcal_gamma1 = a.x_fp; s.ntup.ycal_gamma1 = a.y_fp; }
+        a.dxdz = exrot2 / ezrot2; a.dydz = eyrot2 / ezrot2;
+        a.stop_code = 0;
+        mc_calo(s.trk, a, cfg.drift_to_cal);
+        const bool ok_gamma2 = a.ok_spec;
+        s.ntup.xcal_gamma2 = -1.0e10; s.ntup.ycal_gamma2 = -1.0e10;
+        if (ok_gamma2) { s.ntup.xcal_gamma2 = a.x_fp; s.ntup.ycal_gamma2 = a.y_fp; }
+        a.ok_spec = false;
+        if (cfg.pizero_ngamma == 2) a.ok_spec = ok_gamma1 && ok_gamma2;
+        else if (cfg.pizero_ngamma == 1) a.ok_spec = ok_gamma1 || ok_gamma2;
+        else throw std::runtime_error("pizero_ngamma not set correctly (should be 1 or 2), stopping");
+        if (!a.ok_spec && a.stop_code == 0) a.stop_code = stop1;     // our bookkeeping: where the first lost photon stopped
+      } else {
+        mc_calo(s.trk, a, cfg.drift_to_cal);
+      }
+    } else {
+      run_arm(s, arm, s.optics_p, a);
+    }
     s.ntup.resfac = a.resmult;
     for (int k = 0; k < 3; ++k) s.coll_steps[1][k] = a.coll_steps[k];
     s.stop_p = a.ok_spec ? 0 : a.stop_code;
@@ -443,6 +629,11 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     main.RECON_p.z = a.y;
     main.FP_p.x = a.x_fp; main.FP_p.dx = a.dx_fp; main.FP_p.y = a.y_fp; main.FP_p.dy = a.dy_fp;
     main.FP_p.path = a.pathlen;
+    if (cfg.doing_pizero) {                          // :1605-1609: "no pi0 reconstruction yet"
+      main.RECON_p.delta = main.SP_p.delta;
+      main.RECON_p.yptar = main.SP_p.yptar;
+      main.RECON_p.xptar = main.SP_p.xptar;
+    }
   } else {
     main.RECON_p.delta = main.SP_p.delta;
     main.RECON_p.yptar = main.SP_p.yptar;
@@ -533,7 +724,7 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
 bool complete_recon_ev(Sim& s, Event& recon) {
   const simc_run_config& cfg = *s.cfg;
   const simc_target& targ = cfg.targ;
-  const double Mh2 = cfg.Mh2;
+  const double Mh2 = s.Mh2;
   recon.Ein = cfg.Ebeam_vertex_ave - targ.Coulomb_ave;
   recon.ue.x = sin(recon.e.theta) * cos(recon.e.phi);
   recon.ue.y = sin(recon.e.theta) * sin(recon.e.phi);
@@ -653,12 +844,12 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
     main.sigcc_recon = deForest(cfg, recon);
   } else if (cfg.doing_pion) {
     main.sigcc = peepi(s, vertex, main);
-    if (cfg.which_pion == 2) {                    // :1464-1476 (doing_pizero is out of scope)
-      if (cfg.doing_hydpi) main.sigcc = 0.4 * main.sigcc;
-      else if (cfg.doing_deutpi) main.sigcc = 0.4 * main.sigcc + 0.8 * main.sigcc;
+    if (cfg.which_pion == 2) {                    // :1464-1476
+      if (cfg.doing_hydpi) main.sigcc = cfg.doing_pizero ? 0.55 * main.sigcc : 0.4 * main.sigcc;
+      else if (cfg.doing_deutpi) main.sigcc = cfg.doing_pizero ? 0.55 * main.sigcc : 0.4 * main.sigcc + 0.8 * main.sigcc;
     } else if (cfg.which_pion == 3) {             // :1477-1491
-      if (cfg.doing_hydpi) main.sigcc = 0.55 * main.sigcc;
-      else if (cfg.doing_deutpi) main.sigcc = 0.55 * main.sigcc + 0.99 * main.sigcc;
+      if (cfg.doing_hydpi) main.sigcc = cfg.doing_pizero ? 0 : 0.55 * main.sigcc;
+      else if (cfg.doing_deutpi) main.sigcc = cfg.doing_pizero ? 0.99 * main.sigcc : 0.55 * main.sigcc + 0.99 * main.sigcc;
     }
     main.sigcc_recon = 1.0;
     if (cfg.which_pion == 1 || cfg.which_pion == 11) tgtweight = cfg.targ.N;
@@ -666,6 +857,10 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
   } else if (cfg.doing_delta) {                 // :1511-1513
     main.sigcc = peedelta(s, vertex, main);
     main.sigcc_recon = 1.0;
+  } else if (cfg.doing_rho) {                   // :1515-1518
+    main.sigcc = peerho(s, vertex, main);
+    main.sigcc_recon = 1.0;
+    tgtweight = cfg.targ.Z + cfg.targ.N;
   } else if (cfg.doing_kaon) {
     main.sigcc = peeK(s, vertex, main, survivalprob);
     main.sigcc_recon = 1.0;
@@ -693,6 +888,7 @@ bool try_until_recon(Sim& s, EventMain& main, Event& vertex, Event& orig, Event&
   s.trk.rng = s.rng;
   s.trk.ctau = cfg.ctau;
   s.trk.Mh2_final = cfg.Mh2;
+  s.Mh = cfg.Mh; s.Mh2 = cfg.Mh2;
   s.trk.decdist = 0.0;
   s.ntup = NtupVars();
   s.stop_e = -1; s.stop_p = -1; s.hut_e = s.hut_p = false;

@@ -52,6 +52,11 @@ struct RadEv {
 struct NtupVars {
   double radphot = 0, radarm = 0, resfac = 0, sigcm = 0, sigcm1 = 0, sigcm2 = 0, krel = 0, mm = 0, mmA = 0, t = 0;
   double xfermi = 0;
+  double rhomass = 0, rhotheta = 0;        // generate_rho.f:81, rho_decay.f:62
+  // pi0 -> gamma gamma into a calorimeter arm: (E, px, py, pz) of the photons in the lab (pizero_decay.f:66-70) and
+  // where they hit the calorimeter front (simc.f:1524-1546)
+  double gamma1[4] = {0, 0, 0, 0}, gamma2[4] = {0, 0, 0, 0};
+  double xcal_gamma1 = 0, ycal_gamma1 = 0, xcal_gamma2 = 0, ycal_gamma2 = 0;
   double survivalprob = 1.0;       // local of complete_main (event.f:1373), kept for the parity records
 };
 
@@ -139,6 +144,9 @@ struct Sim {
   const FdssTable* fdss = nullptr;
   Rng* rng = nullptr;
   double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
+  // COMMON Mh, Mh2 (simulate.inc:91-92): run constants for every reaction but rho production, where generate_rho draws
+  // the rho mass of the event and rho_decay leaves the pion mass behind; set from cfg by try_until_recon
+  double Mh = 0, Mh2 = 0;
   RadEv rad;
   NtupVars ntup;
   Track trk;                     // COMMON /track/ + decdist, Mh2_final
@@ -185,6 +193,10 @@ bool complete_main(Sim& s, bool force_sigcc, EventMain& main, Event& vertex, Eve
 double sigep(const Event& vertex);
 double peepi(Sim& s, const Event& vertex, EventMain& main);                                             // physics_pion.f:1
 double peedelta(Sim& s, const Event& vertex, EventMain& main);                                          // physics_delta.f:1
+double peerho(Sim& s, const Event& vertex, EventMain& main);                                            // rho_physics.f:1
+void pizero_decay(Sim& s, const Event& vertex);                                                         // pizero_decay.f:1
+bool generate_rho(Sim& s, Event& vertex);                                                                // generate_rho.f:1
+bool rho_decay(Sim& s, Event& orig, double p_spec, double epsilon);                                      // rho_decay.f:1
 double peeK(Sim& s, const Event& vertex, EventMain& main, double& survivalprob);                        // physics_kaon.f:1
 double peepiX(Sim& s, const Event& vertex, EventMain& main, double& survivalprob, SemiDebug* dbg = nullptr); // semi_physics.f:1
 double peaked_rad_weight_public(Sim& s, const Event& vertex, double Egamma, double emin, double emax);  // radc.f:523                                                                       // physics_proton.f:1

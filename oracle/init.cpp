@@ -189,6 +189,7 @@ void init_from_kv(const char* text, simc_run_config& c) {
   c.doing_delta = D.flag("doing_delta"); c.doing_semi = D.flag("doing_semi"); c.doing_rho = D.flag("doing_rho");
   c.doing_hplus = D.flag("doing_hplus", 1); c.doing_decay = D.flag("doing_decay"); c.do_fermi = D.flag("do_fermi");
   c.which_pion = (int)D.i("which_pion"); c.which_kaon = (int)D.i("which_kaon");
+  c.doing_pizero = D.flag("doing_pizero"); c.pizero_ngamma = (int)D.i("pizero_ngamma"); c.drift_to_cal = D.d("drift_to_cal");
   c.ctau = D.d("ctau"); c.transparency = D.d("transparency"); c.use_benhar_sf = D.flag("use_benhar_sf");
   c.hard_cuts = D.flag("hard_cuts"); c.using_rad = D.flag("using_rad"); c.use_expon = (int)D.i("use_expon");
   c.intcor_mode = (int)D.i("intcor_mode"); c.mc_smear = D.flag("mc_smear");
@@ -209,6 +210,7 @@ void init_from_kv(const char* text, simc_run_config& c) {
   const long nA = std::lround(targ.A);
   if (c.doing_pion) {
     c.Mh = Mpi;
+    if (c.doing_pizero) c.Mh = 134.9766;          // dbase.f:140
     c.doing_hydpi = nA == 1; c.doing_deutpi = nA == 2; c.doing_hepi = nA >= 3;
     if (c.which_pion >= 10) { c.doing_hydpi = 1; c.doing_deutpi = 0; c.doing_hepi = 0; }
   } else if (c.doing_kaon) {
@@ -259,7 +261,15 @@ void init_from_kv(const char* text, simc_run_config& c) {
   else if (c.doing_delta) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mpi; }
   else if (c.doing_semi) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }
   else if (c.doing_rho) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }
-  else if (c.doing_pion) {
+  else if (c.doing_pion && c.doing_pizero) {       // dbase.f:330-347
+    switch (c.which_pion) {
+      case 0: targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; break;
+      case 1: targ.Mtar_struck = Mn; targ.Mrec_struck = Mn; break;
+      case 2: targ.Mtar_struck = Mp; targ.Mrec_struck = MDelta; break;
+      case 3: targ.Mtar_struck = Mn; targ.Mrec_struck = MDelta; break;
+      default: throw std::runtime_error("Bad value for which_pion");
+    }
+  } else if (c.doing_pion) {
     switch (c.which_pion) {
       case 0: targ.Mtar_struck = Mp; targ.Mrec_struck = Mn; break;
       case 1: targ.Mtar_struck = Mn; targ.Mrec_struck = Mp; break;

@@ -172,7 +172,8 @@ void fill_record(const Sim& s, const TryResult& r, const EventMain& main, const 
       main.SP_e.delta, main.SP_e.yptar, main.SP_e.xptar, main.SP_p.delta, main.SP_p.yptar, main.SP_p.xptar,
       recon.e.delta, recon.e.yptar, recon.e.xptar, recon.p.delta, recon.p.yptar, recon.p.xptar,
       recon.Em, recon.Pm, recon.W, s.rad.hardcorfac,
-      main.thetacm, main.phicm, s.ntup.sigcm, main.davejac, s.ntup.survivalprob, s.ntup.mm, main.wcm, main.t};
+      main.thetacm, main.phicm, s.ntup.sigcm, main.davejac, s.ntup.survivalprob, s.ntup.mm, main.wcm, main.t,
+      s.cfg->doing_rho ? orig.p.yptar : 0.0, s.cfg->doing_rho ? orig.p.xptar : 0.0, s.ntup.rhomass, s.ntup.rhotheta};
   for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[k * n + i] = v[k];
 }
 
@@ -223,6 +224,13 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[51] = main.W / 1.e3; ntu[52] = main.t / 1.e6; ntu[53] = main.phi_pq;
     ncol = 53;
     if (cfg.doing_kaon) { ntu[54] = s.ntup.sigcm1; ntu[55] = s.ntup.sigcm2; ncol = 55; }
+    if (cfg.doing_pizero) {                                    // results_write.f:167-180 (no target field)
+      ntu[54] = s.ntup.xcal_gamma1; ntu[55] = s.ntup.ycal_gamma1;
+      for (int k = 0; k < 4; ++k) ntu[56 + k] = s.ntup.gamma1[k];
+      ntu[60] = s.ntup.xcal_gamma2; ntu[61] = s.ntup.ycal_gamma2;
+      for (int k = 0; k < 4; ++k) ntu[62 + k] = s.ntup.gamma2[k];
+      ncol = 65;
+    }
   } else if (cfg.doing_semi || cfg.doing_rho) {      // results_write.f:187-213
     ntu[34] = s.ntup.mm / 1000.; ntu[35] = recon.p.P / 1000.; ntu[36] = s.ntup.t / 1.e6;
     ntu[37] = -main.target.rastery; ntu[38] = s.ntup.radphot / 1000.; ntu[39] = main.sigcc; ntu[40] = main.sigcent;
@@ -234,6 +242,10 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[54] = s.pfer / 1000. * std::fabs(dummy) / dummy;      // NaN for hydrogen (0/0), as in the reference
     ntu[55] = s.ntup.xfermi; ntu[56] = main.phi_pq;
     ncol = 56;
+    if (cfg.doing_rho) {                                       // results_write.f:226-230 (no target field)
+      ntu[57] = s.ntup.rhomass; ntu[58] = s.ntup.rhotheta; ntu[59] = s.ntup.mmA / 1000.;
+      ncol = 59;
+    }
   } else if (eep) {
     ntu[34] = corrsing / 1000.; ntu[35] = Pm_Heepx / 1000.; ntu[36] = Pm_Heepy / 1000.; ntu[37] = Pm_Heepz / 1000.;
     ntu[38] = recon.PmPar / 1000.; ntu[39] = recon.PmPer / 1000.; ntu[40] = recon.PmOop / 1000.;

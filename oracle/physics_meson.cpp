@@ -510,4 +510,152 @@ double peedelta(Sim& s, const Event& vertex, EventMain& main) {
   return 1.0 * C.jacobian * (gtpr * fac);
 }
 
+// rho_physics.f:1-402: p(e,e'rho)p after PYTHIA / the HERMES Monte Carlo.  sigma_T from a fit to photoproduction,
+// R = sigma_L/sigma_T and the Q2 dependence from HERMES, exponential t' slope b(c*delta_tau), virtual-photon flux.
+// Overwrites main%W (GeV) and main%t (GeV^2), as the reference does.
+double peerho(Sim& s, const Event& vertex, EventMain& main) {
+  const simc_run_config& cfg = *s.cfg;
+  const simc_target& targ = cfg.targ;
+  const double pi = K::pi;
+  const double Q2_g = vertex.Q2 / 1000000.;
+  const double phipq = main.phi_pq;
+  const double cospq = cos(phipq), sinpq = sin(phipq);
+  const double pfer = s.pfer, pferx = s.pferx, pfery = s.pfery, pferz = s.pferz;
+  s.efer = sqrt(pfer * pfer + targ.Mtar_struck * targ.Mtar_struck);
+  if (cfg.doing_deutpi || cfg.doing_hepi) {
+    s.efer = targ.M - sqrt(K::Mn * K::Mn + pfer * pfer);
+    if (cfg.doing_hepi) s.efer = s.efer - K::Mp;
+  }
+  const double efer = s.efer;
+  double tcos = vertex.up.x * vertex.uq.x + vertex.up.y * vertex.uq.y + vertex.up.z * vertex.uq.z;
+  if (tcos - 1. > 0. && tcos - 1. < 1.e-8) tcos = 1.0;
+  const double tsin = sqrt(1. - tcos * tcos);
+  double tfcos = pferx * vertex.uq.x + pfery * vertex.uq.y + pferz * vertex.uq.z;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double epsi = 1. / (1. + 2 * (1. + vertex.nu * vertex.nu / vertex.Q2) * powi(tan(vertex.e.theta / 2.), 2));
+  double ss = powi(vertex.nu + efer, 2) - powi(vertex.q + pfer * tfcos, 2) - powi(pfer * tfsin, 2);
+  ss = ss / 1.e6;
+  main.W = sqrt(ss);
+  double t = vertex.Q2 - K::Mrho2 + 2. * vertex.nu * vertex.p.E - 2. * vertex.p.P * vertex.q * tcos;
+  t = t / 1.e6;
+  main.t = t;
+
+  const double qx = -vertex.uq.y, qy = vertex.uq.x, qz = vertex.uq.z;
+  const double px = -pfery, py = pferx, pz = pferz;
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+  const double p_new_x = pfer * (px * new_x_x + py * new_x_y + pz * new_x_z);
+  const double p_new_y = pfer * (px * new_y_x + py * new_y_y + pz * new_y_z);
+  double phiqn;
+  if (p_new_x == 0.) phiqn = 0.;
+  else phiqn = atan2(p_new_y, p_new_x);
+  if (phiqn < 0.) phiqn = phiqn + 2. * pi;
+
+  const double pbeam = sqrt(vertex.Ein * vertex.Ein - K::Me * K::Me);
+  const double beam_newx = pbeam * new_x_z, beam_newy = pbeam * new_y_z, beam_newz = pbeam * vertex.uq.z;
+  const double bstar = sqrt(powi(vertex.q + pfer * tfcos, 2) + powi(pfer * tfsin, 2)) / (efer + vertex.nu);
+  const double gstar = 1. / sqrt(1. - bstar * bstar);
+  const double bstarz = (vertex.q + pfer * tfcos) / (efer + vertex.nu);
+  const double bstarx = p_new_x / (efer + vertex.nu);
+  const double bstary = p_new_y / (efer + vertex.nu);
+  const double zero = 0.e0;
+  double nustar, qstarx, qstary, qstarz, qstar;
+  loren(gstar, bstarx, bstary, bstarz, vertex.nu, zero, zero, vertex.q, nustar, qstarx, qstary, qstarz, qstar);
+  const double ppiz = vertex.p.P * tcos, ppix = vertex.p.P * tsin * cospq, ppiy = vertex.p.P * tsin * sinpq;
+  double epicm, ppicmx, ppicmy, ppicmz, ppicm;
+  loren(gstar, bstarx, bstary, bstarz, vertex.p.E, ppix, ppiy, ppiz, epicm, ppicmx, ppicmy, ppicmz, ppicm);
+  const double thetacm = acos((ppicmx * qstarx + ppicmy * qstary + ppicmz * qstarz) / ppicm / qstar);
+  main.pcm = ppicm;
+  double ebeamcm, pbeamcmx, pbeamcmy, pbeamcmz, pbeamcm;
+  loren(gstar, bstarx, bstary, bstarz, vertex.Ein, beam_newx, beam_newy, beam_newz, ebeamcm, pbeamcmx, pbeamcmy, pbeamcmz,
+        pbeamcm);
+  dummy = sqrt(powi(qstary * pbeamcmz - qstarz * pbeamcmy, 2) + powi(qstarz * pbeamcmx - qstarx * pbeamcmz, 2) +
+               powi(qstarx * pbeamcmy - qstary * pbeamcmx, 2));
+  new_y_x = (qstary * pbeamcmz - qstarz * pbeamcmy) / dummy;
+  new_y_y = (qstarz * pbeamcmx - qstarx * pbeamcmz) / dummy;
+  new_y_z = (qstarx * pbeamcmy - qstary * pbeamcmx) / dummy;
+  dummy = sqrt(powi(new_y_y * qstarz - new_y_z * qstary, 2) + powi(new_y_z * qstarx - new_y_x * qstarz, 2) +
+               powi(new_y_x * qstary - new_y_y * qstarx, 2));
+  new_x_x = (new_y_y * qstarz - new_y_z * qstary) / dummy;
+  new_x_y = (new_y_z * qstarx - new_y_x * qstarz) / dummy;
+  new_x_z = (new_y_x * qstary - new_y_y * qstarx) / dummy;
+  const double new_z_x = qstarx / qstar, new_z_y = qstary / qstar, new_z_z = qstarz / qstar;
+  const double ppicm_newx = ppicmx * new_x_x + ppicmy * new_x_y + ppicmz * new_x_z;
+  const double ppicm_newy = ppicmx * new_y_x + ppicmy * new_y_y + ppicmz * new_y_z;
+  double phicm = atan2(ppicm_newy, ppicm_newx);
+  if (phicm < 0.) phicm = 2. * 3.141592654 + phicm;
+  main.thetacm = thetacm;
+  main.phicm = phicm;
+
+  const double mt = targ.Mtar_struck / 1000.;
+  const double tmin = -(powi((-Q2_g - K::Mrho2 / 1.e6 - mt * mt + mt * mt) / (2. * sqrt(ss)), 2) - powi((qstar - ppicm) / 1000., 2));
+  const double tprime = fabs(t - tmin);
+  const double sig0 = 41.263 / std::pow(vertex.nu / 1000.0, 0.4765);
+  double R = 0.33 * std::pow(vertex.Q2 / K::Mrho2, 0.61);
+  if (R < 0.) R = 0.;
+  double sigt = sig0 * (1.0 + epsi * R) * std::pow(K::Mrho2 / (vertex.Q2 + K::Mrho2), 2.575);
+  if (sigt < 0.) sigt = 0.;
+  const double cdeltatau = K::hbarc / (sqrt(vertex.nu * vertex.nu + vertex.Q2 + K::Mrho2) - vertex.nu);
+  double brho;
+  if (cdeltatau < 2.0) {
+    brho = 4.4679 + 8.6106 * log10(cdeltatau);
+    if (brho < 1.0) brho = 1.0;
+  } else {
+    brho = 7.0;
+  }
+  const double sig219 = sigt * brho * exp(-brho * tprime) / 2.0 / pi;
+  double sig = sig219 / 1.e+06;
+  sig = sig * 2. * qstar * ppicm;
+  double gtpr = K::alpha / 2. / (pi * pi) * vertex.e.E / vertex.Ein * (ss - mt * mt) / 2. / ((efer - pfer * tfcos) / 1000.) / Q2_g /
+                (1. - epsi);
+  if (gtpr <= 0.) gtpr = 0.;
+
+  // the "full blown Jacobian" of rho_physics.f:281-351: main%davejac only (the weight does not use it)
+  const double psign = cos(phiqn) * cospq + sin(phiqn) * sinpq;
+  const double P = vertex.p.P, E = vertex.p.E;
+  const double square_root = vertex.q + pfer * tfcos - P * tcos;
+  const double dp_dcos_num = P + (P * P * tcos - psign * pfer * P * tfsin * tcos / tsin) / square_root;
+  const double dp_dcos_den = ((vertex.nu + efer - E) * P / E + P * tsin * tsin - psign * pfer * tfsin * tsin) / square_root - tcos;
+  const double dp_dcos = dp_dcos_num / dp_dcos_den;
+  const double dp_dphi_num = pfer * P * tsin * tfsin * (cos(phiqn) * sinpq - sin(phiqn) * cospq) / square_root;
+  const double dp_dphi_den = tcos + (pfer * tsin * tfsin * psign - P * tsin * tsin - (vertex.nu + efer - E) * P / E) / square_root;
+  const double dp_dphi = dp_dphi_num / dp_dphi_den;
+  const double dt_dcos_lab = 2. * (vertex.q * P + (vertex.q * tcos - vertex.nu * P / E) * dp_dcos);
+  const double dt_dphi_lab = 2. * (vertex.q * tcos - vertex.nu * P / E) * dp_dphi;
+  const double g1b2 = (gstar - 1.) / (bstar * bstar);
+  const double dpxdphi = P * tsin * (-sinpq + (gstar - 1.) * bstarx / (bstar * bstar) * (bstary * cospq - bstarx * sinpq)) +
+                         ((ppicmx + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dphi;
+  const double dpydphi = P * tsin * (cospq + (gstar - 1.) * bstary / (bstar * bstar) * (bstary * cospq - bstarx * sinpq)) +
+                         ((ppicmy + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dphi;
+  const double dpzdphi = P * (gstar - 1.) / (bstar * bstar) * bstarz * tsin * (bstary * cospq - bstarx * sinpq) +
+                         ((ppicmz + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dphi;
+  const double dpxdcos = -P * tcos / tsin * (cospq + (gstar - 1.) * bstarx / (bstar * bstar) *
+                                                         (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+                         ((ppicmx + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dcos;
+  const double dpydcos = -P * tcos / tsin * (sinpq + (gstar - 1.) * bstary / (bstar * bstar) *
+                                                         (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+                         ((ppicmy + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dcos;
+  const double dpzdcos = P * (1. - g1b2 * bstarz * tcos / tsin * (bstarx * cospq + bstary * sinpq - tsin / tcos * bstarz)) +
+                         ((ppicmz + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dcos;
+  const double dpxnewdphi = dpxdphi * new_x_x + dpydphi * new_x_y + dpzdphi * new_x_z;
+  const double dpynewdphi = dpxdphi * new_y_x + dpydphi * new_y_y + dpzdphi * new_y_z;
+  const double dphicmdphi = (dpynewdphi * ppicm_newx - ppicm_newy * dpxnewdphi) / (ppicm_newx * ppicm_newx + ppicm_newy * ppicm_newy);
+  const double dpxnewdcos = dpxdcos * new_x_x + dpydcos * new_x_y + dpzdcos * new_x_z;
+  const double dpynewdcos = dpxdcos * new_y_x + dpydcos * new_y_y + dpzdcos * new_y_z;
+  const double dphicmdcos = (dpynewdcos * ppicm_newx - ppicm_newy * dpxnewdcos) / (ppicm_newx * ppicm_newx + ppicm_newy * ppicm_newy);
+  main.davejac = fabs(dt_dcos_lab * dphicmdphi - dt_dphi_lab * dphicmdcos);
+  main.johnjac = 2 * (efer - 2 * pferz * pfer * E / P * tcos) * (vertex.q + pferz * pfer) * P /
+                     (efer + vertex.nu - (vertex.q + pferz * pfer) * E / P * tcos) -
+                 2 * P * pfer;
+  (void)new_z_x; (void)new_z_y; (void)new_z_z; (void)ebeamcm; (void)epicm; (void)nustar;
+  const double davesig = gtpr * sig;
+  double sigma_eerho = davesig / 1.e3;
+  if (sigma_eerho > 1.E10 || sigma_eerho < 0.) sigma_eerho = 0.;
+  s.ntup.sigcm = sig;
+  return sigma_eerho;
+}
+
 }  // namespace simc_oracle

@@ -618,8 +618,8 @@ bool generate_rad(Sim& s, EventMain& main, Event& vertex, Event& orig) {
   orig.e.P = orig.e.E;
   orig.e.delta = (orig.e.P - cfg.spec_e.P) / cfg.spec_e.P * 100.;
   orig.p.E = vertex.p.E - Egamma_used[3];
-  if (orig.p.E <= cfg.Mh) return false;
-  orig.p.P = sqrt(orig.p.E * orig.p.E - cfg.Mh2);
+  if (orig.p.E <= s.Mh) return false;
+  orig.p.P = sqrt(orig.p.E * orig.p.E - s.Mh2);
   orig.p.delta = (orig.p.P - cfg.spec_p.P) / cfg.spec_p.P * 100.;
   s.ntup.radphot = Egamma_used[1] + Egamma_used[2] + Egamma_used[3];
   s.ntup.radarm = ntail;

@@ -62,6 +62,11 @@ static bool arm_windows(int arm, double& s_Al, double& s_air, double& s_kevlar, 
   else if (arm == 2) { s_Al = 0.008 * inch_cm; s_air = 15; s_kevlar = 0.005 * inch_cm; s_mylar = 0.003 * inch_cm; }
   else if (arm == 3 || arm == 4) { s_Al = 0.013 * inch_cm; s_air = 15; s_kevlar = 0. * inch_cm; s_mylar = 0.010 * inch_cm; }
   else if (arm == 5 || arm == 6) { s_Al = (0.02 + 0.01) * inch_cm; s_air = 57.27; s_kevlar = 0.0; s_mylar = 0.0; }
+  // Calorimeter arms: the reference has no branch for them (target.f:73-101, 188-222), so its SAVEd locals keep what
+  // the previous call left (the other arm's windows, with the wall term added once more per call).  Restated as
+  // what the source defines for them: no window material at all, the target and its can only; arm 7 sits on the HMS
+  // side (theta + angle), arm 8 on the other.
+  else if (arm == 7 || arm == 8) { s_Al = 0.0; s_air = 0.0; s_kevlar = 0.0; s_mylar = 0.0; plus_angle = arm == 7; }
   else return false;
   return true;
 }

@@ -25,6 +25,7 @@ constexpr double Mpi = 139.57018, Mpi2 = Mpi * Mpi;
 constexpr double Mmu = 105.6583755;
 constexpr double Mpi0 = 134.9766;
 constexpr double Mk = 493.677, Mk2 = Mk * Mk;
+constexpr double Mrho = 769.3, Mrho2 = Mrho * Mrho;
 constexpr double amu = 931.49432;
 constexpr double hbarc = 197.327053;
 constexpr double pi = 3.141592653589793;

@@ -903,12 +903,28 @@ int validate_loop_config(simc_handle* h, bool need_optics = true) {
                     !c.doing_pion && !c.doing_kaon;
   const bool delta = c.doing_delta && !c.doing_pion && !c.doing_kaon && !c.doing_semi && !c.doing_eep &&
                      std::lround(c.targ.A) == 1;
-  if (!(c.doing_hyd_elast || meson || heavy || deut || semi || delta) || (c.doing_delta && !delta) || c.doing_rho ||
-      (c.doing_semi && !semi) || c.doing_phsp)
+  // H(e,e'rho0): the reference reads no momentum distribution for D(e,e'rho) (dbase.f:563 leaves doing_deutrho out, so
+  // pfer is always 0 there) and stops on A >= 3 (dbase.f:861-866): hydrogen only
+  const bool rho = c.doing_rho && !c.doing_pion && !c.doing_kaon && !c.doing_semi && !c.doing_eep && !c.doing_delta &&
+                   std::lround(c.targ.A) == 1;
+  if (!(c.doing_hyd_elast || meson || heavy || deut || semi || delta || rho) || (c.doing_delta && !delta) ||
+      (c.doing_rho && !rho) || (c.doing_semi && !semi) || c.doing_phsp)
     return fail(h, SIMC_ERR_ARG,
                 "this build of the event loop implements H(e,e'p), D(e,e'p), A(e,e'p) with a Benhar or an "
-                "independent-particle spectral function, H/D/A(e,e'pi+-), H/D/A(e,e'K+), H(e,e'p)pi0 and semi-inclusive "
-                "H/D(e,e'pi+-/K+-)X");
+                "independent-particle spectral function, H/D/A(e,e'pi+-), H/D/A(e,e'K+), H(e,e'p)pi0, H(e,e'rho0) and "
+                "semi-inclusive H/D(e,e'pi+-/K+-)X");
+  // calorimeter arms (calo/mc_calo.f): as the hadron arm only; with doing_pizero both decay photons are tracked
+  const bool calo_p = c.hadron_arm == SIMC_ARM_CALO_RIGHT || c.hadron_arm == SIMC_ARM_CALO_LEFT;
+  if (c.electron_arm == SIMC_ARM_CALO_RIGHT || c.electron_arm == SIMC_ARM_CALO_LEFT)
+    return fail(h, SIMC_ERR_ARG, "a calorimeter as the electron arm is not built (hadron arm only)");
+  if (c.doing_pizero && !(c.doing_pion && calo_p && (c.doing_hydpi || c.doing_deutpi) && c.which_pion <= 3))
+    return fail(h, SIMC_ERR_ARG, "doing_pizero: built for exclusive H/D(e,e'pi0) with a calorimeter as the hadron arm (hadron_arm = 7, 8)");
+  if (c.doing_pizero && c.pizero_ngamma != 1 && c.pizero_ngamma != 2)
+    return fail(h, SIMC_ERR_ARG, "pizero_ngamma not set correctly (should be 1 or 2)");
+  if (calo_p && (c.using_HMScoll || c.using_SHMScoll || c.doing_rho))
+    return fail(h, SIMC_ERR_ARG, "calorimeter hadron arm: no collimator stepping, no rho decay (rho_decay.f:96-104)");
+  if (rho && (c.hadron_arm < 1 || c.hadron_arm > 5))
+    return fail(h, SIMC_ERR_ARG, "doing_rho: rho_decay knows the hadron arms 1..5 only (rho_decay.f:96-104)");
   if (delta && c.using_rad)
     return fail(h, SIMC_ERR_ARG,
                 "doing_delta with using_rad: the reference sets no photon-energy limits for this reaction "
@@ -933,6 +949,7 @@ int validate_loop_config(simc_handle* h, bool need_optics = true) {
   if (need_optics) for (int arm : {c.electron_arm, c.hadron_arm}) {
     const bool used = (arm == c.electron_arm) ? c.using_E_arm_montecarlo : c.using_P_arm_montecarlo;
     if (!used) continue;
+    if (arm == c.hadron_arm && (arm == SIMC_ARM_CALO_RIGHT || arm == SIMC_ARM_CALO_LEFT)) continue;     // a calorimeter has no maps
     auto it = h->arms.find(arm);
     if (it == h->arms.end() || !it->second.loaded)
       return fail(h, SIMC_ERR_STATE, "simc_b200_run: load the optics of both spectrometers first");
@@ -1023,6 +1040,10 @@ int build_schedule(simc_handle* h, int arm_id, bool use_mc, bool decay, bool col
   const int mblock = map_block_threads(), mgrid = sms * map_min_blocks();
   auto push = [&](int kind, int b, int e, void* fn) { sc.st[sc.n++] = ArmStage{kind, b, e, fn, mblock, mgrid}; };
   auto it = h->arms.find(arm_id);
+  if (use_mc && (arm_id == SIMC_ARM_CALO_RIGHT || arm_id == SIMC_ARM_CALO_LEFT)) {     // no optics: one kernel does the arm
+    push(ARM_STAGE_CALO, 0, 0, nullptr);
+    return SIMC_OK;
+  }
   if (!use_mc || it == h->arms.end() || !it->second.loaded) {
     push(ARM_STAGE_ENTRY, 0, 0, nullptr);
     push(ARM_STAGE_LAST, 0, 0, nullptr);
@@ -1095,6 +1116,8 @@ int prepare_launch(simc_handle* h, LoopLaunch& a, uint64_t seed, int record, boo
   return SIMC_OK;
 }
 
+// rows of the device buffer simc_b200_event_batch and simc_b200_ntuple_batch share
+constexpr int kRecRows = SIMC_EVENT_NREC > SIMC_NTUPLE_MAXCOL ? SIMC_EVENT_NREC : SIMC_NTUPLE_MAXCOL;
 int run_batches(simc_handle* h, int64_t first_try, int64_t n_tries, uint64_t seed, int record, double* d_rec,
                 int* d_status) {
   int rc = validate_loop_config(h);
@@ -1292,7 +1315,7 @@ int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t
     if (h->d_rec) cudaFree(h->d_rec);
     if (h->d_status) cudaFree(h->d_status);
     h->d_rec = nullptr; h->d_status = nullptr; h->rec_n = 0;
-    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n));
+    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * kRecRows * (size_t)n));
     CU(h, cudaMalloc(&h->d_status, sizeof(int) * (size_t)n));
     h->rec_n = n;
   }
@@ -1302,7 +1325,7 @@ int simc_b200_event_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_t
   if (rc) return rc;
   // records of stages that were not reached read as zero
   CU(h, cudaMemsetAsync(h->d_state, 0, sizeof(double) * (size_t)strict::n_state_fields() * (size_t)h->loop_cap, h->stream));
-  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
+  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * kRecRows * (size_t)n, h->stream));
   rc = run_batches(h, first_try, n, seed, 1, h->d_rec, h->d_status);
   if (rc) return rc;
   CU(h, cudaMemcpyAsync(rec_soa, h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
@@ -1320,16 +1343,15 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   int rc = validate_loop_config(h);
   if (rc) return rc;
   const simc_run_config& c = h->cfg;
-  *n_cols = c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon || c.doing_delta) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
+  *n_cols = c.doing_pizero ? 65 : c.doing_rho ? 59 : c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon || c.doing_delta) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
   *n_rows = 0;
   if (n == 0) return SIMC_OK;
-  static_assert(SIMC_NTUPLE_MAXCOL <= SIMC_EVENT_NREC, "the record buffer is shared with simc_b200_event_batch");
   CU(h, cudaSetDevice(h->device));
   if (n > h->rec_n) {
     if (h->d_rec) cudaFree(h->d_rec);
     if (h->d_status) cudaFree(h->d_status);
     h->d_rec = nullptr; h->d_status = nullptr; h->rec_n = 0;
-    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * SIMC_EVENT_NREC * (size_t)n));
+    CU(h, cudaMalloc(&h->d_rec, sizeof(double) * kRecRows * (size_t)n));
     CU(h, cudaMalloc(&h->d_status, sizeof(int) * (size_t)n));
     h->rec_n = n;
   }
@@ -1338,7 +1360,7 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   // the accumulators of a run in progress must survive: park them
   std::vector<unsigned char> saved(h->acc_host.size());
   CU(h, cudaMemcpyAsync(saved.data(), h->d_acc, saved.size(), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * SIMC_EVENT_NREC * (size_t)n, h->stream));
+  CU(h, cudaMemsetAsync(h->d_rec, 0, sizeof(double) * kRecRows * (size_t)n, h->stream));
   rc = run_batches(h, first_try, n, seed, 2, h->d_rec, h->d_status);
   if (rc) {      // put the parked accumulators back before reporting the failure
     cudaMemcpyAsync(h->d_acc, saved.data(), saved.size(), cudaMemcpyHostToDevice, h->stream);
@@ -1457,7 +1479,7 @@ static const char* kEventFields[SIMC_EVENT_NREC] = {
     "SP.e.yptar", "SP.e.xptar", "SP.p.delta", "SP.p.yptar", "SP.p.xptar", "recon.e.delta", "recon.e.yptar",
     "recon.e.xptar", "recon.p.delta", "recon.p.yptar", "recon.p.xptar", "recon.Em", "recon.Pm", "recon.W",
     "hardcorfac", "main.thetacm", "main.phicm", "ntup.sigcm", "main.davejac", "survivalprob", "ntup.mm", "main.wcm",
-    "main.t"};
+    "main.t", "orig.p.yptar", "orig.p.xptar", "ntup.rhomass", "ntup.rhotheta"};       // the last four: rho production only
 const char* simc_b200_event_field_name(int k) { return (k >= 0 && k < SIMC_EVENT_NREC) ? kEventFields[k] : ""; }
 
 }  // extern "C"

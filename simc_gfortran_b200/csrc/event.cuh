@@ -15,6 +15,8 @@ namespace simc {
 #define SIMC_PI_D 3.141592653589793
 #define SIMC_ME 0.51099906
 #define SIMC_MP 938.27231
+#define SIMC_MPI 139.57018
+#define SIMC_MRHO 769.3
 #define SIMC_HBARC 197.327053
 #define SIMC_ALPHA (1. / 137.0359895)
 
@@ -82,8 +84,17 @@ struct EventState {
   double v_zhad, v_pt2, pfer, pferx, pfery, pferz, efer;
   // orig (fields that differ from vertex)
   double o_Ein, o_eE, o_edelta, o_pE, o_pP, o_pdelta;
+  // rho production only: the decay pion's angles in `orig` (rho_decay.f:142-146) and ntup%rhomass, ntup%rhotheta.
+  // With doing_pizero the last two hold rph and rth of pizero_decay (pizero_decay.f:43-45) instead: k_calo rebuilds
+  // the two photons from them.
+  double o_pyptar, o_pxptar, rho_mass, rho_theta;
   RadEvDev rad;
 };
+
+// Mass of the particle that enters the hadron arm and is reconstructed: COMMON Mh after generate.  A run constant for
+// every reaction but rho production, where rho_decay leaves the pion mass behind (rho_decay.f:150-153).
+SIMC_HD double detected_Mh(const simc_run_config& cfg) { return cfg.doing_rho ? SIMC_MPI : cfg.Mh; }
+SIMC_HD double detected_Mh2(const simc_run_config& cfg) { return cfg.doing_rho ? SIMC_MPI * SIMC_MPI : cfg.Mh2; }
 
 // trip_thru_target with typeflag = 1 (sampled energy loss): one |gauss1(10)| per material with
 // thick > 0, in the reference's order target, Al, air, kevlar, mylar (target.f:46-52,170-180).
@@ -202,6 +213,8 @@ SIMC_HD bool generate_finalize(const simc_run_config& cfg, EventState& s, bool o
     return ok;
   }
   const RadEvDev& R = s.rad;
+  const double Mh = cfg.doing_rho ? s.rho_mass : cfg.Mh;               // COMMON Mh: generate_rho's for rho production
+  const double Mh2 = cfg.doing_rho ? s.rho_mass * s.rho_mass : cfg.Mh2;
   if (ok) {
     s.o_Ein = s.v_Ein + R.Egamma_used[0];
     s.o_eE = s.v_eE - R.Egamma_used[1];
@@ -210,10 +223,10 @@ SIMC_HD bool generate_finalize(const simc_run_config& cfg, EventState& s, bool o
   if (ok) {
     s.o_edelta = (s.o_eE - cfg.spec_e.P) / cfg.spec_e.P * 100.;
     s.o_pE = s.v_pE - R.Egamma_used[2];
-    if (s.o_pE <= cfg.Mh) ok = false;
+    if (s.o_pE <= Mh) ok = false;
   }
   if (ok) {
-    s.o_pP = sqrt(s.o_pE * s.o_pE - cfg.Mh2);
+    s.o_pP = sqrt(s.o_pE * s.o_pE - Mh2);
     s.o_pdelta = (s.o_pP - cfg.spec_p.P) / cfg.spec_p.P * 100.;
   }
   return ok;
@@ -445,22 +458,111 @@ SIMC_HD bool generate_hyd_elast_second(const simc_run_config& cfg, const MatTabl
   return complete_ev_hyd_elast(cfg, mt, rng, gauss, s, run);
 }
 
+// ---- H(e,e'rho0): generate_rho.f:1-131.  The rho is thrown flat in cos(theta), phi in the virtual photon - nucleon
+// centre of mass with a Breit-Wigner mass and boosted to the lab: three random numbers, the rho's lab momentum,
+// energy and direction, and COMMON Mh for the rest of complete_ev (s.rho_mass).  Hydrogen: the nucleon is at rest
+// (pfer = 0, efer = Mtar_struck); the Fermi terms of the boost vanish identically.
+template <class RNG>
+SIMC_HD_CALL bool generate_rho(const simc_run_config& cfg, RNG& rng, EventState& s) {
+  using namespace mesondetail;
+  const double nu = s.v_nu, Q2 = s.v_Q2, q = s.v_q;
+  const double bx = -(q * s.uqx + s.pferx * s.pfer) / (nu + s.efer);
+  const double by = -(q * s.uqy + s.pfery * s.pfer) / (nu + s.efer);
+  const double bz = -(q * s.uqz + s.pferz * s.pfer) / (nu + s.efer);
+  const double betacm = sqrt(bx * bx + by * by + bz * bz);
+  if (betacm > 1.0) return false;
+  const double gammacm = 1. / sqrt(1.0 - betacm * betacm);
+  const double ss = -Q2 + s.efer * s.efer + 2. * nu * s.efer;
+  double Mh = SIMC_MRHO;
+  Mh = Mh + 0.5 * 150.2 * m::tan((2. * rng.uniform() - 1.) * m::atan(2. * 500. / 150.2));
+  const double Mh2 = Mh * Mh;
+  s.rho_mass = Mh;
+  const double Erhocm = (ss + Mh2 - cfg.targ.Mrec_struck * cfg.targ.Mrec_struck) / 2. / sqrt(ss);
+  if (Erhocm < Mh) return false;
+  const double Prhocm = sqrt(Erhocm * Erhocm - Mh2);
+  const double rph = rng.uniform() * 2. * SIMC_PI_D;
+  const double rth1 = rng.uniform() * 2. - 1.;
+  const double rth = m::acos(rth1);
+  const double srth = m::sin(rth);
+  const double pxr = Prhocm * srth * m::cos(rph);
+  const double pyr = Prhocm * srth * m::sin(rph);
+  const double pzr = Prhocm * m::cos(rth);
+  const MV4 f = loren(gammacm, bx, by, bz, Erhocm, pxr, pyr, pzr);
+  s.v_pdelta = 100. * (f.p / cfg.spec_p.P - 1.);
+  s.v_pP = f.p;
+  s.v_pE = f.e;
+  s.upx = f.x / f.p; s.upy = f.y / f.p; s.upz = f.z / f.p;
+  s.v_pxptar = m::acos(f.z / f.p);              // lab theta and phi of the rho, "not really used for anything"
+  s.v_pyptar = m::atan2(f.y, f.x);              // (generate_rho.f:123-126): they do reach the gen histograms
+  return true;
+}
+
+// rho_decay.f:1-163: rho0 -> pi+ pi- before the spectrometer.  The detected pion is thrown flat in phi and like
+// sin^2 + 2 eps R cos^2 (rejection loop, R = sigma_L/sigma_T of HERMES) in the rho rest frame and boosted to the lab;
+// `orig` becomes that pion and COMMON Mh the pion mass.  False: the pion cannot reach the hadron arm.
+template <class RNG>
+SIMC_HD_CALL bool rho_decay(const simc_run_config& cfg, RNG& rng, EventState& s) {
+  using namespace mesondetail;
+  const double epsilon = s.m_eps;
+  const double R_rho = 0.33 * m::pow(s.v_Q2 / (SIMC_MRHO * SIMC_MRHO), 0.61);
+  const double ph = s.o_pP;
+  const double beta = ph / sqrt(ph * ph + s.rho_mass * s.rho_mass);
+  const double gamma = 1. / sqrt(1. - beta * beta);
+  const double rph = rng.uniform() * 2. * SIMC_PI_D;
+  double rth, srth, crth;
+  for (;;) {
+    const double rth1 = rng.uniform() * 2. - 1.;
+    rth = m::acos(rth1);
+    const double norm = (1.0 + 2.0 * epsilon * R_rho) * rng.uniform();
+    srth = m::sin(rth); crth = m::cos(rth);
+    const double dist = srth * srth + 2.0 * epsilon * R_rho * (crth * crth);
+    if (!(dist < norm)) break;
+  }
+  s.rho_theta = rth;
+  const double er = s.rho_mass / 2.0;
+  if (er < SIMC_MPI) return false;
+  const double pr = sqrt(er * er - SIMC_MPI * SIMC_MPI);
+  const double pxr = pr * srth * m::cos(rph);
+  const double pyr = pr * srth * m::sin(rph);
+  const double pzr = pr * crth;
+  const MV4 f = loren(gamma, -beta * s.upx, -beta * s.upy, -beta * s.upz, er, pxr, pyr, pzr);
+  const int arm = cfg.hadron_arm;
+  const bool right = arm == 1 || arm == 3;      // HMS, HRS-R; the others (SOS, HRS-L, SHMS) sit on the left
+  const double th0 = cfg.spec_p.theta;
+  const double pzprime = right ? f.z * m::cos(th0) - f.y * m::sin(th0) : f.z * m::cos(th0) + f.y * m::sin(th0);
+  if (pzprime < 0.0) return false;
+  const double th_oop = m::asin(f.x / f.p);
+  const double cos_th_inp = f.z / f.p / m::cos(th_oop);
+  double th_inp = m::acos(cos_th_inp);
+  if (right) th_inp = f.y < 0.0 ? th0 - th_inp : th0 + th_inp;
+  else th_inp = f.y > 0.0 ? th_inp - th0 : th_inp + th0;
+  if ((th_inp > SIMC_PI_D / 2.) || (th_oop > SIMC_PI_D / 2.)) return false;
+  s.o_pxptar = m::tan(th_oop);
+  s.o_pyptar = m::tan(th_inp);
+  s.o_pdelta = 100. * (f.p / cfg.spec_p.P - 1.);
+  s.o_pP = f.p;
+  s.o_pE = sqrt(s.o_pP * s.o_pP + SIMC_MPI * SIMC_MPI);
+  return true;
+}
+
 // ---- H(e,e'pi) / H(e,e'K): complete_ev, event.f:432-1052 with doing_hydpi / doing_hydkaon ----------
 // Needs v_Ein, v_eE, the electron and hadron angles and tz; fills the hadron energy from the
 // two-body quadratic (event.f:634-698), W, epsilon, theta_pq, phi_pq, t (event.f:707-771), the
 // jacobian, Eloss/teff(2:3) and the radiative constants.
 template <class RNG, class GAUSS>
 SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, RNG& rng, GAUSS gauss, EventState& s, bool run) {
-  const double Mh = cfg.Mh, Mh2 = cfg.Mh2;
+  double Mh = cfg.Mh, Mh2 = cfg.Mh2;              // rho production: replaced by the mass generate_rho draws
   const simc_target& targ = cfg.targ;
   if (run) {
     s.jacobian = 1.0;
     s.uex = m::sin(s.v_etheta) * m::cos(s.v_ephi);
     s.uey = m::sin(s.v_etheta) * m::sin(s.v_ephi);
     s.uez = m::cos(s.v_etheta);
-    s.upx = m::sin(s.v_ptheta) * m::cos(s.v_pphi);
-    s.upy = m::sin(s.v_ptheta) * m::sin(s.v_pphi);
-    s.upz = m::cos(s.v_ptheta);
+    if (!cfg.doing_rho) {                           // event.f:507-511
+      s.upx = m::sin(s.v_ptheta) * m::cos(s.v_pphi);
+      s.upy = m::sin(s.v_ptheta) * m::sin(s.v_pphi);
+      s.upz = m::cos(s.v_ptheta);
+    }
     const double eP = s.v_eE;
     s.v_nu = s.v_Ein - s.v_eE;
     s.v_Q2 = 2 * s.v_Ein * s.v_eE * (1. - s.uez);
@@ -468,7 +570,10 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.uqx = -eP * s.uex / s.v_q;
     s.uqy = -eP * s.uey / s.v_q;
     s.uqz = (s.v_Ein - eP * s.uez) / s.v_q;
-    if (cfg.doing_deuterium) {                      // event.f:565-607: E_p from the two-body quadratic, |dEp'/dEm|
+    if (cfg.doing_rho) {                            // event.f:701-708: momentum, energy and direction of the rho
+      run = generate_rho(cfg, rng, s);
+      Mh = s.rho_mass; Mh2 = Mh * Mh;
+    } else if (cfg.doing_deuterium) {                      // event.f:565-607: E_p from the two-body quadratic, |dEp'/dEm|
       s.v_Em = targ.Mtar_struck + targ.Mrec - targ.M;
       const double Mrec = targ.M - targ.Mtar_struck + s.v_Em;
       const double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
@@ -495,7 +600,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
         s.v_Pm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
         s.v_Trec = sqrt(Mrec * Mrec + s.v_Pm * s.v_Pm) - Mrec;
       }
-    } else if (!cfg.doing_semi) {                   // semi-inclusive: the hadron energy was thrown (event.f:289-297)
+    } else if (!cfg.doing_semi && !cfg.doing_rho) { // semi-inclusive: the hadron energy was thrown (event.f:289-297)
       s.v_Pm = s.pfer;                              // event.f:633 (zero for hydrogen)
       double a = -1. * s.v_q * (s.uqx * s.upx + s.uqy * s.upy + s.uqz * s.upz);
       double b = s.v_q * s.v_q;
@@ -531,7 +636,7 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     s.jacobian = s.jacobian / (r * (r * r));
   }
   if (run && !cfg.doing_deuterium) {
-    if (!cfg.doing_semi) {
+    if (!cfg.doing_semi && !cfg.doing_rho) {
       s.v_pP = sqrt(s.v_pE * s.v_pE - Mh2);
       s.v_pdelta = (s.v_pP - cfg.spec_p.P) * 100. / cfg.spec_p.P;
     }
@@ -553,6 +658,11 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
     s.m_phipq = m::atan2(p_new_y, p_new_x);
     if (s.m_phipq < 0.e0) s.m_phipq = s.m_phipq + 2. * SIMC_PI_D;
+    if (cfg.doing_pizero) {                         // event.f:899-901: pizero_decay's two random numbers
+      s.rho_mass = rng.uniform() * 2. * SIMC_PI_D;
+      const double rth1 = rng.uniform() * 2. - 1.;
+      s.rho_theta = m::acos(rth1);
+    }
     s.v_Trec = 0.0;
     if (cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon) {   // event.f:945-947: recoil of the spectator system
       const double Mrec = targ.M - targ.Mtar_struck + s.v_Em;
@@ -580,8 +690,10 @@ SIMC_HD bool complete_ev_meson(const simc_run_config& cfg, const MatTable& mt, R
     // event.f:1013-1023: both arms' angles were generated
     double r = sqrt(1. + s.v_eyptar * s.v_eyptar + s.v_exptar * s.v_exptar);
     s.jacobian = s.jacobian / (r * (r * r));
-    r = sqrt(1. + s.v_pyptar * s.v_pyptar + s.v_pxptar * s.v_pxptar);
-    s.jacobian = s.jacobian / (r * (r * r));
+    if (!cfg.doing_rho) {                           // "we generate rho's in 4pi ... no stinkin' Jacobian" (event.f:1017-1023)
+      r = sqrt(1. + s.v_pyptar * s.v_pyptar + s.v_pxptar * s.v_pxptar);
+      s.jacobian = s.jacobian / (r * (r * r));
+    }
   }
   const double zpos = s.tz - targ.zoffset;
   SIMC_PHASE();
@@ -643,8 +755,11 @@ SIMC_HD bool generate_meson_first(const simc_run_config& cfg, const MatTable& mt
     s.gen_weight = 1.0;
     s.v_eyptar = gen.e.yptar.min + rng.uniform() * (gen.e.yptar.max - gen.e.yptar.min);
     s.v_exptar = gen.e.xptar.min + rng.uniform() * (gen.e.xptar.max - gen.e.xptar.min);
-    s.v_pyptar = gen.p.yptar.min + rng.uniform() * (gen.p.yptar.max - gen.p.yptar.min);
-    s.v_pxptar = gen.p.xptar.min + rng.uniform() * (gen.p.xptar.max - gen.p.xptar.min);
+    if (!cfg.doing_rho) {   // event.f:277-283.  Rho production throws no hadron angles: the reference converts whatever
+      // the previous event left in vertex%p%xptar/yptar; a try starts from zero here (DESIGN, known deviations)
+      s.v_pyptar = gen.p.yptar.min + rng.uniform() * (gen.p.yptar.max - gen.p.yptar.min);
+      s.v_pxptar = gen.p.xptar.min + rng.uniform() * (gen.p.xptar.max - gen.p.xptar.min);
+    }
     if (cfg.doing_semi) {   // hadron energy, event.f:289-297
       const double Emin = fmax(gen.p.E.min, gen.sumEgen.min - gen.e.E.max);
       const double Emax = fmin(gen.p.E.max, gen.sumEgen.max - gen.e.E.min);

@@ -469,7 +469,9 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       const ArmStage& st = sc.st[k];
       if (k == sc.n - 1) out = base + kArmLists;
       A.op_begin = st.begin; A.op_end = st.end; A.in_idx = in; A.out_idx = out;
-      if (st.kind == ARM_STAGE_ENTRY) {
+      if (st.kind == ARM_STAGE_CALO) {
+        k_calo<<<grid, kBlock, 0, s>>>(A);
+      } else if (st.kind == ARM_STAGE_ENTRY) {
         if (hadron) { if (coll) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
         else { if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
       } else if (st.kind == ARM_STAGE_COMPILED) {

@@ -45,6 +45,7 @@ enum StateField : int {
   F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
   F_ZHAD, F_PT2, F_PFER, F_EFER,
   F_PFERX, F_PFERY, F_PFERZ, F_GEN_PAD,
+  F_OPYP, F_OPXP, F_RHOMASS, F_RHOTHETA,        // rho production only: orig%p%yptar/xptar of the decay pion, ntup%rhomass/rhotheta
   F_GEN_END,
   // ---- written by the later stages
   F_STAGE = F_GEN_END, F_STOP_P, F_STOP_E, F_RESFAC,
@@ -217,13 +218,15 @@ struct GaussFn {
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
 constexpr int kRegenList = kRegenListIdx;
 
-struct GenFlags { bool semi, fermi, meson, heavy; };
+struct GenFlags { bool semi, fermi, meson, heavy, rho, xtra; };
 __device__ __forceinline__ GenFlags gen_flags(const simc_run_config& cfg) {
   GenFlags g;
   g.semi = cfg.doing_semi != 0;
   g.fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;   // nucleon momentum thrown
-  g.meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || g.semi || cfg.doing_deuterium;   // hadron energy from two-body kinematics (or thrown: semi)
+  g.rho = cfg.doing_rho != 0;                   // the rho is thrown in the photon-nucleon c.m. inside complete_ev
+  g.meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || g.semi || cfg.doing_deuterium || g.rho;   // hadron energy from two-body kinematics (or thrown: semi)
   g.heavy = cfg.doing_heavy != 0;
+  g.xtra = g.rho || cfg.doing_pizero;           // the record's last group is in use (rho: mass, decay angle; pi0: decay angles)
   return g;
 }
 
@@ -267,8 +270,10 @@ __device__ __forceinline__ void store_event(const LoopArgs& A, const GenFlags& g
   r[F_ZHAD] = (g.meson && g.semi) ? s.v_zhad : 0.0; r[F_PT2] = (g.meson && g.semi) ? s.v_pt2 : 0.0;
   r[F_PFER] = fm ? s.pfer : 0.0; r[F_EFER] = fm ? s.efer : 0.0;
   r[F_PFERX] = fm ? s.pferx : 0.0; r[F_PFERY] = fm ? s.pfery : 0.0; r[F_PFERZ] = fm ? s.pferz : 0.0; r[F_GEN_PAD] = 0.0;
+  r[F_OPYP] = g.rho ? s.o_pyptar : 0.0; r[F_OPXP] = g.rho ? s.o_pxptar : 0.0;
+  r[F_RHOMASS] = g.xtra ? s.rho_mass : 0.0; r[F_RHOTHETA] = g.xtra ? s.rho_theta : 0.0;
   // the groups past F_VPPHI only matter to the reactions that fill them
-  const int n_groups = hm ? F_GEN_END / 4 : (F_VQ + 1) / 4;
+  const int n_groups = g.xtra ? F_GEN_END / 4 : hm ? F_OPYP / 4 : (F_VQ + 1) / 4;
 #if SIMC_STATE_AOS
   double* rec = S.base + (long long)slot * kStateStride;
 #pragma unroll
@@ -291,7 +296,7 @@ __device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g,
   const StateBuf& S = A.st;
   double r[F_GEN_END];
   const bool hm = g.heavy || g.meson;
-  const int n_groups = hm ? F_GEN_END / 4 : (F_VQ + 1) / 4;
+  const int n_groups = g.xtra ? F_GEN_END / 4 : hm ? F_OPYP / 4 : (F_VQ + 1) / 4;
 #if SIMC_STATE_AOS
   const double* rec = S.base + (long long)slot * kStateStride;
 #pragma unroll
@@ -331,6 +336,7 @@ __device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g,
   s.v_zhad = r[F_ZHAD]; s.v_pt2 = r[F_PT2];
   s.pfer = r[F_PFER]; s.pferx = r[F_PFERX]; s.pfery = r[F_PFERY]; s.pferz = r[F_PFERZ];
   s.efer = (g.meson && (g.semi || g.fermi)) ? r[F_EFER] : A.cfg->targ.Mtar_struck;
+  s.o_pyptar = r[F_OPYP]; s.o_pxptar = r[F_OPXP]; s.rho_mass = r[F_RHOMASS]; s.rho_theta = r[F_RHOTHETA];
 }
 
 __device__ __forceinline__ void gen_shared_init(const LoopArgs& A, unsigned (*h_geni)[SIMC_NHIST], MatTable& mt_s) {
@@ -372,6 +378,7 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
+    s.o_pyptar = 0; s.o_pxptar = 0; s.rho_mass = 0; s.rho_theta = 0;
     // (tables by value: a reference into the kernel parameters handed to an out-of-line function would make the
     //  compiler copy all of LoopArgs to every thread's stack -- +600 bytes of frame, +10 % kernel time)
     if (g.meson) ok = generate_meson_first(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active, gr);
@@ -379,6 +386,9 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     else ok = generate_hyd_elast_first(cfg, mt_s, rng, GaussFn(), s, active, gr);
     const bool carry = active && ok && gr.which == 1;       // radc.f:324: complete_ev once more
     if (!carry) ok = generate_finalize(cfg, s, ok);
+    // event.f:420-422.  (The reference calls rho_decay whatever generate_rad returned; for a failed try that only
+    // burns random numbers of a stream nobody reads again.)
+    if (g.rho && !carry && ok) ok = rho_decay(cfg, rng, s);
     if (active && !carry) geni_hist(cfg, h_geni, s);
     const bool want_slot = active && (ok || carry || A.record_mode);
     const unsigned slot = warp_append(&A.counts[0], want_slot);
@@ -421,6 +431,7 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopAr
     // rad_flag = 2, 3: the tails behind tail 1 (radc.f:354-455)
     if (cfg.rad_flag >= 2) ok = (active && ok) ? generate_rad_basis_rest(cfg, rng, s, gr, true) : false;
     ok = generate_finalize(cfg, s, ok);
+    if (g.rho && ok) ok = rho_decay(cfg, rng, s);
     if (active) {
       geni_hist(cfg, h_geni, s);
       store_event(A, g, slot, itry, rng.draw, s, gr, ok, false);
@@ -495,7 +506,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
   const ArmDev* arm = &arm_c;        // program + map directory live in the kernel's constant bank
   const int arm_id = WHICH == 1 ? cfg.hadron_arm : cfg.electron_arm;
   const bool use_mc = WHICH == 1 ? cfg.using_P_arm_montecarlo != 0 : cfg.using_E_arm_montecarlo != 0;
-  const double Mh2 = cfg.Mh2;
+  const double Mh2 = detected_Mh2(cfg);
   ArmFlags f;
   f.ms_flag = cfg.mc_smear != 0; f.wcs_flag = cfg.mc_smear != 0;
   f.decay_flag = WHICH == 1 ? cfg.doing_decay != 0 : false;
@@ -534,6 +545,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         if (WHICH == 1) {
           S.ld4(F_OPP, slot, opP, opd, vpy, vpx);
           o_yptar = vpy; o_xptar = vpx;
+          if (cfg.doing_rho) { o_yptar = S.ld(F_OPYP, slot); o_xptar = S.ld(F_OPXP, slot); }      // the decay pion's
           // beam multiple scattering (simc.f:1365), then the hadron's (simc.f:1379-1399)
           if (cfg.mc_smear) {
             const double teff = tf0, p = oEin;
@@ -671,7 +683,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         physics_angles(sp.theta, sp.phi, rc_xptar + sp.off_xptar, rc_yptar + sp.off_yptar, rth, rph);
         if (cfg.correct_Eloss) {
           double el, rl;
-          trip_thru_target_fixed(cfg.targ, mt_s, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? cfg.Mh : SIMC_ME, 4,
+          trip_thru_target_fixed(cfg.targ, mt_s, WHICH == 1 ? 3 : 2, arm_id, 0.0, rE, rth, WHICH == 1 ? detected_Mh(cfg) : SIMC_ME, 4,
                                  el, rl);
           rE = rE + el;
           if (WHICH == 1) {
@@ -697,6 +709,160 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
     if (s_stop[i]) atomicAdd(&A.acc->stop[WHICH][i], (unsigned long long)s_stop[i]);
   for (int i = threadIdx.x; i < 48; i += kBlock)
     if (s_calls[i]) atomicAdd(&A.acc->transp_calls[WHICH][i], (unsigned long long)s_calls[i]);
+}
+
+// ---- calorimeter as the hadron arm (SIMC_ARM_CALO_*): simc.f:1374-1443, 1489-1564, 1595-1645 with calo/mc_calo.f ----
+// One kernel does what the three segments of k_arm do for a magnetic spectrometer: target multiple scattering, SP
+// quantities, TRANSPORT coordinates at z = 0, then mc_calo -- a field-free drift to the front face and the two
+// half-size cuts of the NPS -- once for the hadron or, with doing_pizero, once per decay photon (pizero_decay.f: the
+// photons are rebuilt from the two numbers complete_ev drew), and the arm's recon quantities.  mc_calo returns dpp,
+// y and the slopes as they came in.  Stop codes: 1 = slit_hor, 2 = slit_vert (caloSTOP_*, calo/struct_calo.inc).
+__global__ void __launch_bounds__(kBlock, 4) k_calo(LoopArgs A) {
+  using namespace mesondetail;
+  __shared__ unsigned s_stop[SIMC_NSTOP];
+  __shared__ MatTable mt_s;
+  for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kBlock) ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
+  for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
+  __syncthreads();
+  const simc_run_config& cfg = *A.cfg;
+  const StateBuf& S = A.st;
+  const unsigned n_in = A.counts[1 + A.in_idx];
+  const unsigned* in_list = A.lists + (long long)A.in_idx * A.st.cap;
+  unsigned* out_list = A.lists + (long long)A.out_idx * A.st.cap;
+  unsigned* out_count = &A.counts[1 + A.out_idx];
+  const simc_spectrometer& sp = cfg.spec_p;
+  const int arm_id = cfg.hadron_arm;
+  const double Mh2 = detected_Mh2(cfg);
+  const double h_entr = 30.75, v_entr = 36.9;         // half width / height of the NPS: 30 x 36 blocks of 2.05 cm
+  const long long stride = (long long)gridDim.x * kBlock;
+  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
+    const long long i = i0 + threadIdx.x;
+    const bool active = i < n_in;
+    bool ok = false;
+    unsigned slot = 0u;
+    if (active) {
+      slot = in_list[i];
+      DevRng rng;
+      rng.init((unsigned long long)(A.first_try + (long long)S.ld(F_TRY, slot)), 0u, (unsigned)S.ld(F_DRAW, slot));
+      double tx, ty, tz, rastery, el0, el1, el2, coul, tf0, tf1, tf2, genw, oEin, oeE, oed, opE, opP, opd, vpy, vpx;
+      S.ld4(F_TX, slot, tx, ty, tz, rastery);
+      S.ld4(F_ELOSS0, slot, el0, el1, el2, coul);
+      S.ld4(F_TEFF0, slot, tf0, tf1, tf2, genw);
+      S.ld4(F_OEIN, slot, oEin, oeE, oed, opE);
+      S.ld4(F_OPP, slot, opP, opd, vpy, vpx);
+      double dang0 = 0.0, dang1 = 0.0, ang0 = 0.0, ang1 = 0.0, sp_delta;
+      if (cfg.mc_smear) {                               // simc.f:1365
+        const double teff = tf0, p = oEin;
+        const double ts = 13.6 / p / 1. * sqrt(teff) * (1 + 0.088 * m::log10(teff / (1. * 1.)));
+        dang0 = ts * gauss1(rng, 3.5);
+        dang1 = ts * gauss1(rng, 3.5);
+      }
+      S.st(F_DANG0, slot, dang0); S.st(F_DANG1, slot, dang1);
+      if (cfg.using_Eloss) {
+        const double d = opE - el2;
+        sp_delta = (sqrt(fabs(d * d - Mh2)) - sp.P) / sp.P * 100.;
+      } else sp_delta = opd;
+      if (cfg.mc_smear) {
+        const double beta = opP / opE, teff = tf2;
+        const double ts = 13.6 / opP / beta * sqrt(teff) * (1 + 0.088 * m::log10(teff / (beta * beta)));
+        ang0 = ts * gauss1(rng, 3.5);
+        ang1 = ts * gauss1(rng, 3.5);
+      }
+      ArmEntry en;
+      arm_entry(sp, tx, ty, tz, sp_delta, vpy + ang0 + dang0, vpx + ang1 + dang1 * sp.cos_th, en);
+      S.st4(F_SPP_D, slot, en.sp_delta, en.sp_yptar, en.sp_xptar, en.sp_z);
+      warp_hist_add(s_stop, 0);                         // caloSTOP_trials, once per try as for the other arms
+      TrackDev t;
+      t.dpps = en.sp_delta; t.m2 = Mh2; t.p = sp.P * (1. + t.dpps / 100.); t.p_spec = sp.P;
+      t.pathlen = 0.0; t.decdist = 0.0; t.mh2_final = Mh2; t.ctau = cfg.ctau; t.dflag = false;
+      double x_fp = 0.0, y_fp = 0.0, dx_fp = 0.0, dy_fp = 0.0;
+      int stop_code = 0;
+      // one call of mc_calo (calo/mc_calo.f:120-152) for the slopes (dx, dy); false = it stopped on a slit
+      auto mc_calo = [&](double dx, double dy, int& code) {
+        t.xs = en.x; t.ys = en.y; t.dxdzs = dx; t.dydzs = dy;
+        project(t, rng, cfg.drift_to_cal, cfg.doing_decay != 0);
+        if (fabs(t.ys) > h_entr) { code = 1; return false; }
+        if (fabs(t.xs) > v_entr) { code = 2; return false; }
+        x_fp = t.xs; y_fp = t.ys; dx_fp = t.dxdzs; dy_fp = t.dydzs;
+        return true;
+      };
+      double rc_yptar = en.dy, rc_xptar = en.dx;        // what mc_calo hands back: its inputs
+      if (cfg.doing_pizero) {
+        // pizero_decay.f:37-70 from the two numbers complete_ev drew (rph, rth), then simc.f:1494-1556
+        const double Mh = cfg.Mh;
+        const double ph = S.ld(F_VPP, slot);
+        const double eh = sqrt(ph * ph + Mh * Mh);
+        const double beta = ph / eh;
+        const double gamma = 1. / sqrt(1. - beta * beta);
+        const double rph = S.ld(F_RHOMASS, slot), rth = S.ld(F_RHOTHETA, slot);
+        const double er = Mh / 2.0;
+        const double pr = sqrt(er * er - 0.0 * 0.0);
+        const double pxr1 = pr * m::sin(rth) * m::cos(rph), pyr1 = pr * m::sin(rth) * m::sin(rph), pzr1 = pr * m::cos(rth);
+        const double upx = S.ld(F_UPX, slot), upy = S.ld(F_UPY, slot), upz = S.ld(F_UPZ, slot);
+        const double bx = -beta * upx, by = -beta * upy, bz = -beta * upz;
+        const MV4 g1 = mesondetail::loren(gamma, bx, by, bz, er, pxr1, pyr1, pzr1);
+        const MV4 g2 = mesondetail::loren(gamma, bx, by, bz, er, -pxr1, -pyr1, -pzr1);
+        const double cth = m::cos(sp.theta), sth = m::sin(sp.theta);
+        double ey1, ez1, ey2, ez2;
+        if (arm_id == 8) {
+          ey1 = g1.y * cth - g1.z * sth; ez1 = g1.y * sth + g1.z * cth;
+          ey2 = g2.y * cth - g2.z * sth; ez2 = g2.y * sth + g2.z * cth;
+        } else {
+          ey1 = g1.y * cth + g1.z * sth; ez1 = -g1.y * sth + g1.z * cth;
+          ey2 = g2.y * cth + g2.z * sth; ez2 = -g2.y * sth + g2.z * cth;
+        }
+        int c1 = 0, c2 = 0;
+        const bool ok1 = mc_calo(g1.x / ez1, ey1 / ez1, c1);
+        const double xc1 = ok1 ? x_fp : -1.0e10, yc1 = ok1 ? y_fp : -1.0e10;
+        const bool ok2 = mc_calo(g2.x / ez2, ey2 / ez2, c2);
+        const double xc2 = ok2 ? x_fp : -1.0e10, yc2 = ok2 ? y_fp : -1.0e10;
+        ok = cfg.pizero_ngamma == 2 ? (ok1 && ok2) : (ok1 || ok2);
+        stop_code = c2 ? c2 : c1;                       // our bookkeeping of a lost pair: the second photon's slit, else the first's
+        rc_yptar = ey2 / ez2; rc_xptar = g2.x / ez2;    // dy_P_arm, dx_P_arm of the last call (replaced just below)
+        if (A.record_mode) {                            // ntuple columns 54-65 (results_write.f:167-180)
+          const double v[12] = {xc1, yc1, g1.e, g1.x, g1.y, g1.z, xc2, yc2, g2.e, g2.x, g2.y, g2.z};
+#pragma unroll
+          for (int k = 0; k < 12; ++k) S.st(F_NTU0 + 53 + k, slot, v[k]);
+        }
+      } else {
+        ok = mc_calo(en.dx, en.dy, stop_code);
+      }
+      S.st(F_DRAW, slot, (double)rng.draw);
+      if (A.record_mode) S.st(F_STOP_P, slot, (double)(ok ? 0 : stop_code));
+      warp_hist_add(s_stop, ok ? 1 : 2 + stop_code);
+      if (ok) {
+        double rc_delta = en.sp_delta, rc_z = en.y;
+        if (cfg.doing_pizero) { rc_yptar = en.sp_yptar; rc_xptar = en.sp_xptar; }       // simc.f:1605-1609
+        S.st4(F_RCP_D, slot, rc_delta, rc_yptar, rc_xptar, rc_z);
+        S.st(F_FPP_PATH, slot, t.pathlen);
+        S.st(F_FPP_DX, slot, dx_fp); S.st(F_FPP_DY, slot, dy_fp);
+        if (A.record_mode) {
+          S.st(F_FPP_X, slot, x_fp); S.st(F_FPP_Y, slot, y_fp);
+          S.st(F_DECDIST, slot, t.decdist); S.st(F_MH2FINAL, slot, t.mh2_final);
+          S.st(F_RESFAC, slot, 0.0);
+        }
+        double rP = sp.P * (1. + rc_delta / 100.);
+        double rE = sqrt(rP * rP + Mh2);
+        double rth, rph;
+        physics_angles(sp.theta, sp.phi, rc_xptar + sp.off_xptar, rc_yptar + sp.off_yptar, rth, rph);
+        if (cfg.correct_Eloss) {
+          double el, rl;
+          trip_thru_target_fixed(cfg.targ, mt_s, 3, arm_id, 0.0, rE, rth, detected_Mh(cfg), 4, el, rl);
+          rE = rE + el;
+          rE = fmax(rE, sqrt(Mh2 + 0.000001));
+          rP = sqrt(rE * rE - Mh2);
+        }
+        S.st4(F_RP_P, slot, rP, rE, rth, rph);
+        if (A.record_mode) S.st(F_STAGE, slot, 2.0);
+      }
+    }
+    __syncwarp();
+    const unsigned pos = warp_append(out_count, active && ok);
+    if (active && ok) out_list[pos] = slot;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock)
+    if (s_stop[i]) atomicAdd(&A.acc->stop[1][i], (unsigned long long)s_stop[i]);
 }
 
 // ---- stage 4: recon kinematics, weight, accumulation --------------------------------------------
@@ -767,7 +933,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
     const long long i = i0 + threadIdx.x;
     const bool active = i < n_in;
     bool success = false, pass_cuts = false, no_rad_p = false, low_w = false;
-    double weight = 0, sigcc = 0, rEm = 0, rPm = 0, sigcm1 = 0;
+    double weight = 0, sigcc = 0, rEm = 0, rPm = 0, sigcm1 = 0, johnjac = 0;
     double rec_vals[6] = {0, 0, 0, 0, 0, 0}, gen_vals[7] = {0, 0, 0, 0, 0, 0, 0}, err[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double cv[30], sv[8];
 #pragma unroll
@@ -793,8 +959,10 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       rPm = sqrt(Pmx * Pmx + Pmy * Pmy + Pmz * Pmz);
       const bool semi = cfg.doing_semi != 0;
       const bool fermi = cfg.doing_deutsemi || cfg.doing_deutpi || cfg.doing_deutkaon || cfg.doing_hepi || cfg.doing_hekaon;
-      const bool meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || semi;
+      const bool rho = cfg.doing_rho != 0;
+      const bool meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || semi || rho;
       const bool deut = cfg.doing_deuterium != 0;
+      const double Mh2_det = detected_Mh2(cfg);       // COMMON Mh2 when complete_recon_ev runs
       const bool heavy = cfg.doing_heavy != 0 || deut;          // (e,e'p) from a nucleus: deForest, A-1 recoil
       const double rTrec = heavy ? sqrt(rPm * rPm + cfg.targ.Mrec * cfg.targ.Mrec) - cfg.targ.Mrec : 0.0;   // event.f:1349
       // complete_main, event.f:1363-1569
@@ -863,15 +1031,20 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           mw = peepi(cfg, A.maid, mv);
           // event.f:1464-1490: Delta final states scale the pi-N cross section (empirical coefficients of 2021/2023)
           if (cfg.which_pion == 2) {
-            if (cfg.doing_hydpi) mw.sigcc = 0.4 * mw.sigcc;
-            else if (cfg.doing_deutpi) mw.sigcc = 0.4 * mw.sigcc + 0.8 * mw.sigcc;
+            if (cfg.doing_hydpi) mw.sigcc = cfg.doing_pizero ? 0.55 * mw.sigcc : 0.4 * mw.sigcc;
+            else if (cfg.doing_deutpi) mw.sigcc = cfg.doing_pizero ? 0.55 * mw.sigcc : 0.4 * mw.sigcc + 0.8 * mw.sigcc;
           } else if (cfg.which_pion == 3) {
-            if (cfg.doing_hydpi) mw.sigcc = 0.55 * mw.sigcc;
-            else if (cfg.doing_deutpi) mw.sigcc = 0.55 * mw.sigcc + 0.99 * mw.sigcc;
+            if (cfg.doing_hydpi) mw.sigcc = cfg.doing_pizero ? 0 : 0.55 * mw.sigcc;
+            else if (cfg.doing_deutpi) mw.sigcc = cfg.doing_pizero ? 0.99 * mw.sigcc : 0.55 * mw.sigcc + 0.99 * mw.sigcc;
           }
           tgtweight = (cfg.which_pion == 1 || cfg.which_pion == 11) ? cfg.targ.N : cfg.targ.Z;
         } else if (cfg.doing_delta) {
           mw = peedelta(cfg, mv);                      // event.f:1511-1513; tgtweight stays 1
+        } else if (rho) {                              // event.f:1515-1518
+          mw = peerho(cfg, mv, v_eth);
+          johnjac = mw.johnjac;
+          tgtweight = cfg.targ.Z + cfg.targ.N;
+          if (A.record_mode) S.st(F_MT, slot, mw.t_gev);      // peerho leaves its own t (GeV^2) in main%t
         } else {
           // the Saghai model only feeds ntuple column 54: evaluated where rows / records are produced
           mw = peeK(cfg, mv, A.record_mode ? A.saghai : SaghaiDev{nullptr, 0, 0, 0}, S.ld(F_MTHPQ, slot));
@@ -946,7 +1119,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         const double eb[12] = {red, rey, rex, rez, S.ld(F_FPE_X, slot), S.ld(F_FPE_DX, slot), S.ld(F_FPE_Y, slot),
                                S.ld(F_FPE_DY, slot), S.ld(F_OEDELTA, slot), S.ld(F_VEYP, slot), S.ld(F_VEXP, slot), cfg.spec_e.sin_th};
         const double pb[12] = {rpd, rpy, rpx, rpz, S.ld(F_FPP_X, slot), S.ld(F_FPP_DX, slot), S.ld(F_FPP_Y, slot),
-                               S.ld(F_FPP_DY, slot), S.ld(F_OPDELTA, slot), S.ld(F_VPYP, slot), S.ld(F_VPXP, slot), cfg.spec_p.sin_th};
+                               S.ld(F_FPP_DY, slot), S.ld(F_OPDELTA, slot), S.ld(rho ? F_OPYP : F_VPYP, slot), S.ld(rho ? F_OPXP : F_VPXP, slot), cfg.spec_p.sin_th};
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
           ntu[1 + k] = e_right ? eb[k] : pb[k];
@@ -958,23 +1131,29 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         ntu[30] = rEm / 1000.; ntu[31] = rPm / 1000.; ntu[32] = r_thpq; ntu[33] = r_phipq;
         const double radphot = S.ld(F_EG0, slot) + S.ld(F_EG1, slot) + S.ld(F_EG2, slot);
         const double wfinal = weight;                  // survival probability already applied above
-        if (semi) {          // results_write.f:187-213
+        if (semi || rho) {   // results_write.f:187-230
           const double mm2 = rEm * rEm - rPm * rPm;
           ntu[34] = (sqrt(fabs(mm2)) * fabs(mm2) / mm2) / 1000.;
           ntu[35] = rpP / 1000.;
-          ntu[36] = (Q2 - cfg.Mh2 + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
+          ntu[36] = (Q2 - Mh2_det + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
           ntu[37] = -S.ld(F_RASTERY, slot); ntu[38] = radphot / 1000.; ntu[39] = sigcc; ntu[40] = 0.0; ntu[41] = wfinal;
-          ntu[42] = !cfg.doing_decay ? survivalprob : S.ld(F_DECDIST, slot);
+          ntu[42] = (semi && !cfg.doing_decay) ? survivalprob : S.ld(F_DECDIST, slot);
           ntu[43] = sqrt(S.ld(F_MH2FINAL, slot));
           const double cth = m::cos(r_thpq);
           ntu[44] = rpE / nu; ntu[45] = S.ld(F_ZHAD, slot);
           ntu[46] = (rpP * rpP * (1.0 - cth * cth)) / 1.e06; ntu[47] = S.ld(F_PT2, slot) / 1.e06;
           ntu[48] = Q2 / 2. / SIMC_MP / nu; ntu[49] = v_Q2 / 2. / SIMC_MP / S.ld(F_VNU, slot);
-          ntu[50] = m::acos(S.ld(F_UQZ, slot)); ntu[51] = S.ld(F_SIGCM, slot); ntu[52] = S.ld(F_DAVEJAC, slot); ntu[53] = 0.0;
+          ntu[50] = m::acos(S.ld(F_UQZ, slot)); ntu[51] = S.ld(F_SIGCM, slot); ntu[52] = S.ld(F_DAVEJAC, slot); ntu[53] = johnjac;
           const double dummy = S.ld(F_PFERX, slot) * S.ld(F_UQX, slot) + S.ld(F_PFERY, slot) * S.ld(F_UQY, slot) +
                                S.ld(F_PFERZ, slot) * S.ld(F_UQZ, slot);
           ntu[54] = S.ld(F_PFER, slot) / 1000. * fabs(dummy) / dummy;     // NaN for hydrogen (0/0), as in the reference
-          ntu[55] = S.ld(F_XFERMI, slot); ntu[56] = S.ld(F_MPHIPQ, slot);
+          ntu[55] = semi ? S.ld(F_XFERMI, slot) : 0.0; ntu[56] = S.ld(F_MPHIPQ, slot);
+          if (rho) {         // results_write.f:226-230 (no target field)
+            const double e_A = nu + cfg.targ.M - rpE;
+            const double mmA2 = e_A * e_A - rPm * rPm;
+            ntu[57] = S.ld(F_RHOMASS, slot); ntu[58] = S.ld(F_RHOTHETA, slot);
+            ntu[59] = (sqrt(fabs(mmA2)) * fabs(mmA2) / mmA2) / 1000.;
+          }
         } else if (meson) {
           const double mm2 = rEm * rEm - rPm * rPm;
           const double e_A = nu + cfg.targ.M - rpE;
@@ -982,7 +1161,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           ntu[34] = (sqrt(fabs(mm2)) * fabs(mm2) / mm2) / 1000.;
           ntu[35] = (sqrt(fabs(mmA2)) * fabs(mmA2) / mmA2) / 1000.;
           ntu[36] = rpP / 1000.;
-          ntu[37] = (Q2 - cfg.Mh2 + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
+          ntu[37] = (Q2 - Mh2_det + 2 * (nu * rpE - rpP * q * m::cos(r_thpq))) / 1.e6;
           ntu[38] = PmPar / 1000.; ntu[39] = PmPer / 1000.; ntu[40] = PmOop / 1000.;
           ntu[41] = -S.ld(F_RASTERY, slot); ntu[42] = radphot / 1000.;
           double pdot = mv_pfer[1] * S.ld(F_UQX, slot) + mv_pfer[2] * S.ld(F_UQY, slot) + mv_pfer[3] * S.ld(F_UQZ, slot);
@@ -1007,7 +1186,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           ntu[45] = reth; ntu[46] = rpth;
         }
 #pragma unroll
-        for (int k = 0; k < SIMC_NTUPLE_MAXCOL; ++k) S.st(F_NTU0 + k, slot, ntu[k + 1]);
+        for (int k = 0; k < SIMC_NTUPLE_MAXCOL; ++k)
+          if (!(cfg.doing_pizero && k >= 53)) S.st(F_NTU0 + k, slot, ntu[k + 1]);      // columns 54-65 of a pi0 row: k_calo wrote them
       }
       if (success) {
         no_rad_p = S.ld(F_RADP, slot) == 0.0;
@@ -1025,11 +1205,12 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
         const double Ein_shift = S.ld(F_EINSHIFT, slot), Ee_shift = S.ld(F_EESHIFT, slot);
         const double v_pE = S.ld(F_VPE, slot);
         const double o_eE = S.ld(F_OEE, slot), o_pE = S.ld(F_OPE, slot);
+        const double o_py = rho ? S.ld(F_OPYP, slot) : v_py, o_px = rho ? S.ld(F_OPXP, slot) : v_px;      // the decay pion's
         const double o_Em = v_Em, o_Pm = v_Pm, o_Trec = v_Trec;     // orig = vertex for these (radc.f:476)
         const double eg0 = S.ld(F_EG0, slot), eg1 = S.ld(F_EG1, slot), eg2 = S.ld(F_EG2, slot);
         const double sumEgen = ((meson && !semi) || deut) ? v_eE - Ein_shift : v_eE + v_pE - Ein_shift;     // event.f:28-32
         const double c_[30] = {v_ed, v_ey, v_ex, v_pd, v_py, v_px, S.ld(F_MTREC, slot), sumEgen,
-                               o_eE - Ee_shift, v_ex, v_ey, o_pE, v_py, v_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
+                               o_eE - Ee_shift, v_ex, v_ey, o_pE, o_py, o_px, o_Em - Ein_shift + Ee_shift, o_Pm, o_Trec,
                                spe_d, spe_y, spe_x, spp_d, spp_y, spp_x, v_Trec, v_Em, v_Pm, eg0, eg1, eg2, eg0 + eg1 + eg2};
 #pragma unroll
         for (int k = 0; k < 30; ++k) cv[k] = c_[k];
@@ -1153,11 +1334,13 @@ __global__ void k_records(LoopArgs A, double* __restrict__ rec, int* __restrict_
         F_VEIN, F_VEE, F_VEDELTA, F_VEYP, F_VEXP, F_VPE, F_VPDELTA, F_VPYP, F_VPXP, F_VQ2,
         F_OEE, F_OPE, F_EG0, F_EG1, F_EG2, F_NTAIL, F_TX, F_TY, F_TZ, F_ELOSS0, F_ELOSS1, F_ELOSS2,
         F_SPE_D, F_SPE_Y, F_SPE_X, F_SPP_D, F_SPP_Y, F_SPP_X, F_RCE_D, F_RCE_Y, F_RCE_X, F_RCP_D, F_RCP_Y, F_RCP_X,
-        F_REM, F_RPM, F_RW, F_HARDCOR, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM, F_MT};
+        F_REM, F_RPM, F_RW, F_HARDCOR, F_THCM, F_PHICM, F_SIGCM, F_DAVEJAC, F_SURV, F_MM, F_WCM, F_MT,
+        F_OPYP, F_OPXP, F_RHOMASS, F_RHOTHETA};
     if (A.record_mode == 2) {        // ntuple columns instead of the parity record
       for (int k = 0; k < SIMC_NTUPLE_MAXCOL; ++k) rec[(long long)k * n + i] = S.ld(F_NTU0 + k, slot);
     } else {
-      for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = S.ld(fields[k], slot);
+      const int n_fields = A.cfg->doing_rho ? SIMC_EVENT_NREC : SIMC_EVENT_NREC - 4;     // the last four: rho production only
+      for (int k = 0; k < SIMC_EVENT_NREC; ++k) rec[(long long)k * n + i] = k < n_fields ? S.ld(fields[k], slot) : 0.0;
       rec[0 * n + i] = (double)stage;
     }
     status[i] = stage;

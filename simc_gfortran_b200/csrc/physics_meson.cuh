@@ -240,6 +240,7 @@ SIMC_HD_CALL double sigmaid_sig0(const MaidDev M, double q2, double w, double e0
 struct MesonWeight {
   double sigcc, sigcm, thetacm, phicm, pcm, wcm, davejac, johnjac;
   double sigcm1;              // peeK only: the Saghai model (ntup%sigcm1), 0 unless asked for
+  double t_gev;               // peerho only: the t it leaves in main%t (GeV^2)
   bool low_w;                 // W < 2 GeV: the reference would blend in the MAID table here
 };
 
@@ -313,6 +314,141 @@ SIMC_HD_CALL MesonWeight peedelta(const simc_run_config& cfg, const MesonVertex&
   const double fac = 1. / (1. - pferz * pfer / efer) * Mtar / efer;
   const double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * k_eq / v.Q2 / (1. - v.epsilon);
   w.sigcc = 1.0 * C.jacobian * (gtpr * fac);
+  return w;
+}
+
+// rho_physics.f:1-402: p(e,e'rho)p in the form PYTHIA uses with the HERMES modifications.  sigma_T from a fit to
+// photoproduction data, R = sigma_L/sigma_T = 0.33 (Q2/Mrho2)^0.61 and the (Mrho2/(Q2+Mrho2))^2.575 dependence from
+// HERMES, an exponential t' slope b(c delta tau), times the virtual-photon flux.  `v` holds the RHO's momentum,
+// energy and direction (vertex%p, vertex%up); theta_e is vertex%e%theta.  main%davejac ("full blown Jacobian",
+// :281-351) and main%johnjac only reach the ntuple.
+SIMC_HD_CALL MesonWeight peerho(const simc_run_config& cfg, const MesonVertex& v, double theta_e) {
+  using namespace mesondetail;
+  const double pi = 3.141592653589793, alpha = 1. / 137.0359895, hbarc = 197.327053, Me = 0.51099906;
+  const double Mrho2 = 769.3 * 769.3;
+  const double Mtar = cfg.targ.Mtar_struck;
+  const double Q2_g = v.Q2 / 1000000.;
+  const double cospq = m::cos(v.phi_pq), sinpq = m::sin(v.phi_pq);
+  const double pfer = v.pfer, pferx = v.pferx, pfery = v.pfery, pferz = v.pferz;
+  // rho_physics.f:93-98: on-shell struck nucleon (the off-shell forms belong to doing_deutpi / doing_hepi, never set here)
+  const double efer = sqrt(pfer * pfer + Mtar * Mtar);
+  double tcos = v.upx * v.uqx + v.upy * v.uqy + v.upz * v.uqz;
+  if (tcos - 1. > 0. && tcos - 1. < 1.e-8) tcos = 1.0;
+  const double tsin = sqrt(1. - tcos * tcos);
+  double tfcos = pferx * v.uqx + pfery * v.uqy + pferz * v.uqz;
+  if (tfcos - 1. > 0. && tfcos - 1. < 1.e-8) tfcos = 1.0;
+  const double tfsin = sqrt(1. - tfcos * tfcos);
+  const double th2 = m::tan(theta_e / 2.);
+  const double epsi = 1. / (1. + 2 * (1. + v.nu * v.nu / v.Q2) * (th2 * th2));
+  double ss = msq(v.nu + efer) - msq(v.q + pfer * tfcos) - msq(pfer * tfsin);
+  ss = ss / 1.e6;
+  double t = v.Q2 - Mrho2 + 2. * v.nu * v.pE - 2. * v.pP * v.q * tcos;
+  t = t / 1.e6;
+
+  const double qx = -v.uqy, qy = v.uqx, qz = v.uqz;
+  const double px = -pfery, py = pferx, pz = pferz;
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+  const double p_new_x = pfer * (px * new_x_x + py * new_x_y + pz * new_x_z);
+  const double p_new_y = pfer * (px * new_y_x + py * new_y_y + pz * new_y_z);
+  double phiqn;
+  if (p_new_x == 0.) phiqn = 0.;
+  else phiqn = m::atan2(p_new_y, p_new_x);
+  if (phiqn < 0.) phiqn = phiqn + 2. * pi;
+  const double cosqn = m::cos(phiqn), sinqn = m::sin(phiqn);
+
+  const double pbeam = sqrt(v.Ein * v.Ein - Me * Me);
+  const double beam_newx = pbeam * new_x_z, beam_newy = pbeam * new_y_z, beam_newz = pbeam * v.uqz;
+  const double bstar = sqrt(msq(v.q + pfer * tfcos) + msq(pfer * tfsin)) / (efer + v.nu);
+  const double gstar = 1. / sqrt(1. - bstar * bstar);
+  const double bstarz = (v.q + pfer * tfcos) / (efer + v.nu);
+  const double bstarx = p_new_x / (efer + v.nu);
+  const double bstary = p_new_y / (efer + v.nu);
+  const MV4 qs = loren(gstar, bstarx, bstary, bstarz, v.nu, 0.e0, 0.e0, v.q);
+  const double ppiz = v.pP * tcos, ppix = v.pP * tsin * cospq, ppiy = v.pP * tsin * sinpq;
+  const MV4 had = loren(gstar, bstarx, bstary, bstarz, v.pE, ppix, ppiy, ppiz);
+  const double thetacm = m::acos((had.x * qs.x + had.y * qs.y + had.z * qs.z) / had.p / qs.p);
+  const MV4 beam = loren(gstar, bstarx, bstary, bstarz, v.Ein, beam_newx, beam_newy, beam_newz);
+  dummy = sqrt(msq(qs.y * beam.z - qs.z * beam.y) + msq(qs.z * beam.x - qs.x * beam.z) + msq(qs.x * beam.y - qs.y * beam.x));
+  new_y_x = (qs.y * beam.z - qs.z * beam.y) / dummy;
+  new_y_y = (qs.z * beam.x - qs.x * beam.z) / dummy;
+  new_y_z = (qs.x * beam.y - qs.y * beam.x) / dummy;
+  dummy = sqrt(msq(new_y_y * qs.z - new_y_z * qs.y) + msq(new_y_z * qs.x - new_y_x * qs.z) + msq(new_y_x * qs.y - new_y_y * qs.x));
+  new_x_x = (new_y_y * qs.z - new_y_z * qs.y) / dummy;
+  new_x_y = (new_y_z * qs.x - new_y_x * qs.z) / dummy;
+  new_x_z = (new_y_x * qs.y - new_y_y * qs.x) / dummy;
+  const double ppicm_newx = had.x * new_x_x + had.y * new_x_y + had.z * new_x_z;
+  const double ppicm_newy = had.x * new_y_x + had.y * new_y_y + had.z * new_y_z;
+  double phicm = m::atan2(ppicm_newy, ppicm_newx);
+  if (phicm < 0.) phicm = 2. * 3.141592654 + phicm;
+
+  const double mt = Mtar / 1000.;
+  const double tmin = -(msq((-Q2_g - Mrho2 / 1.e6 - mt * mt + mt * mt) / (2. * sqrt(ss))) - msq((qs.p - had.p) / 1000.));
+  const double tprime = fabs(t - tmin);
+  const double sig0 = 41.263 / m::pow(v.nu / 1000.0, 0.4765);
+  double R = 0.33 * m::pow(v.Q2 / Mrho2, 0.61);
+  if (R < 0.) R = 0.;
+  double sigt = sig0 * (1.0 + epsi * R) * m::pow(Mrho2 / (v.Q2 + Mrho2), 2.575);
+  if (sigt < 0.) sigt = 0.;
+  const double cdeltatau = hbarc / (sqrt(v.nu * v.nu + v.Q2 + Mrho2) - v.nu);
+  double brho;
+  if (cdeltatau < 2.0) {
+    brho = 4.4679 + 8.6106 * m::log10(cdeltatau);
+    if (brho < 1.0) brho = 1.0;
+  } else {
+    brho = 7.0;
+  }
+  const double sig219 = sigt * brho * m::exp(-brho * tprime) / 2.0 / pi;
+  double sig = sig219 / 1.e+06;
+  sig = sig * 2. * qs.p * had.p;
+  double gtpr = alpha / 2. / (pi * pi) * v.eE / v.Ein * (ss - mt * mt) / 2. / ((efer - pfer * tfcos) / 1000.) / Q2_g / (1. - epsi);
+  if (gtpr <= 0.) gtpr = 0.;
+
+  const double psign = cosqn * cospq + sinqn * sinpq;
+  const double P = v.pP, E = v.pE;
+  const double square_root = v.q + pfer * tfcos - P * tcos;
+  const double dp_dcos_num = P + (P * P * tcos - psign * pfer * P * tfsin * tcos / tsin) / square_root;
+  const double dp_dcos_den = ((v.nu + efer - E) * P / E + P * tsin * tsin - psign * pfer * tfsin * tsin) / square_root - tcos;
+  const double dp_dcos = dp_dcos_num / dp_dcos_den;
+  const double dp_dphi_num = pfer * P * tsin * tfsin * (cosqn * sinpq - sinqn * cospq) / square_root;
+  const double dp_dphi_den = tcos + (pfer * tsin * tfsin * psign - P * tsin * tsin - (v.nu + efer - E) * P / E) / square_root;
+  const double dp_dphi = dp_dphi_num / dp_dphi_den;
+  const double dt_dcos_lab = 2. * (v.q * P + (v.q * tcos - v.nu * P / E) * dp_dcos);
+  const double dt_dphi_lab = 2. * (v.q * tcos - v.nu * P / E) * dp_dphi;
+  const double b2 = bstar * bstar;
+  const double dpxdphi = P * tsin * (-sinpq + (gstar - 1.) * bstarx / b2 * (bstary * cospq - bstarx * sinpq)) +
+                         ((had.x + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dphi;
+  const double dpydphi = P * tsin * (cospq + (gstar - 1.) * bstary / b2 * (bstary * cospq - bstarx * sinpq)) +
+                         ((had.y + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dphi;
+  const double dpzdphi = P * (gstar - 1.) / b2 * bstarz * tsin * (bstary * cospq - bstarx * sinpq) +
+                         ((had.z + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dphi;
+  const double dpxdcos = -P * tcos / tsin * (cospq + (gstar - 1.) * bstarx / b2 * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+                         ((had.x + gstar * bstarx * E) / P - gstar * bstarx * P / E) * dp_dcos;
+  const double dpydcos = -P * tcos / tsin * (sinpq + (gstar - 1.) * bstary / b2 * (bstarx * cospq + bstary * sinpq - bstarz * tsin / tcos)) +
+                         ((had.y + gstar * bstary * E) / P - gstar * bstary * P / E) * dp_dcos;
+  const double dpzdcos = P * (1. - (gstar - 1.) / b2 * bstarz * tcos / tsin * (bstarx * cospq + bstary * sinpq - tsin / tcos * bstarz)) +
+                         ((had.z + gstar * bstarz * E) / P - gstar * bstarz * P / E) * dp_dcos;
+  const double dpxnewdphi = dpxdphi * new_x_x + dpydphi * new_x_y + dpzdphi * new_x_z;
+  const double dpynewdphi = dpxdphi * new_y_x + dpydphi * new_y_y + dpzdphi * new_y_z;
+  const double den = ppicm_newx * ppicm_newx + ppicm_newy * ppicm_newy;
+  const double dphicmdphi = (dpynewdphi * ppicm_newx - ppicm_newy * dpxnewdphi) / den;
+  const double dpxnewdcos = dpxdcos * new_x_x + dpydcos * new_x_y + dpzdcos * new_x_z;
+  const double dpynewdcos = dpxdcos * new_y_x + dpydcos * new_y_y + dpzdcos * new_y_z;
+  const double dphicmdcos = (dpynewdcos * ppicm_newx - ppicm_newy * dpxnewdcos) / den;
+
+  MesonWeight w;
+  w.thetacm = thetacm; w.phicm = phicm; w.pcm = had.p; w.wcm = 0.0; w.sigcm1 = 0.0; w.low_w = false;
+  w.davejac = fabs(dt_dcos_lab * dphicmdphi - dt_dphi_lab * dphicmdcos);
+  w.johnjac = 2 * (efer - 2 * pferz * pfer * E / P * tcos) * (v.q + pferz * pfer) * P /
+                  (efer + v.nu - (v.q + pferz * pfer) * E / P * tcos) -
+              2 * P * pfer;
+  w.t_gev = t;
+  double sigma_eerho = gtpr * sig / 1.e3;
+  if (sigma_eerho > 1.E10 || sigma_eerho < 0.) sigma_eerho = 0.;
+  w.sigcc = sigma_eerho;
+  w.sigcm = sig;
   return w;
 }
 

@@ -21,9 +21,9 @@ const char* const kCommon[33] = {"hsdelta", "hsyptar", "hsxptar", "hsytar", "hsx
 const char* const kMeson[22] = {"missmass", "mmnuc", "phad", "t", "pmpar", "pmper", "pmoop", "fry", "radphot", "pfermi",
                                 "siglab", "sigcm", "Weight", "decdist", "Mhadron", "pdotqhat", "Q2i", "Wi", "ti", "phipqi",
                                 "saghai", "factor"};
-const char* const kSemi[23] = {"missmass", "ppi", "t", "fry", "radphot", "siglab", "sigcent", "Weight", "decdist", "Mhadron",
+const char* const kSemi[26] = {"missmass", "ppi", "t", "fry", "radphot", "siglab", "sigcent", "Weight", "decdist", "Mhadron",
                                "z", "zi", "pt2", "pt2i", "xbj", "xbji", "thqi", "sighad", "jacobian", "centjac", "pfermi",
-                               "xfermi", "phipqi"};
+                               "xfermi", "phipqi", "Mrho", "Thrho", "mmnuc"};     // the last three: doing_rho (NtupleInit.f:257-264)
 const char* const kEep[13] = {"corrsing", "Pmx", "Pmy", "Pmz", "PmPar", "PmPer", "PmOop", "fry", "radphot", "sigcc", "Weight",
                               "theta_e", "theta_p"};
 
@@ -115,7 +115,7 @@ int simc_b200_ntuple_tags(const simc_run_config* cfg, char (*tags)[17], int max_
   const char* const* tail;
   int n_tail;
   if (cfg->doing_pion || cfg->doing_kaon || cfg->doing_delta) { tail = kMeson; n_tail = cfg->doing_kaon ? 22 : 20; }
-  else if (cfg->doing_semi || cfg->doing_rho) { tail = kSemi; n_tail = 23; }
+  else if (cfg->doing_semi || cfg->doing_rho) { tail = kSemi; n_tail = cfg->doing_rho ? 26 : 23; }
   else if (cfg->doing_hyd_elast || cfg->doing_deuterium || cfg->doing_heavy) { tail = kEep; n_tail = 13; }
   else return SIMC_ERR_ARG;
   const int n = 33 + n_tail;

@@ -216,6 +216,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   c.doing_hplus = D.i("doing_hplus", 1) > 0;
   c.doing_rho = D.i("doing_rho") > 0;
   c.doing_decay = D.i("doing_decay") > 0;
+  c.doing_pizero = D.i("doing_pizero") > 0; c.pizero_ngamma = D.i("pizero_ngamma"); c.drift_to_cal = D.d("drift_to_cal");
   c.doing_phsp = D.i("doing_phsp") > 0;
   c.ctau = D.d("ctau");
   simc_target& targ = c.targ;
@@ -254,7 +255,6 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   c.use_offshell_rad = D.i("use_offshell_rad") > 0;
   c.Egamma_gen_max = D.d("Egamma_gen_max");
   if (D.i("using_tgt_field") > 0) throw std::runtime_error("using_tgt_field=1 (polarised-target field tracking) is out of scope");
-  if (D.i("doing_pizero") > 0) throw std::runtime_error("doing_pizero is out of scope");
   auto spedge = [&](simc_arm_cuts& a, const char* arm) {
     auto key = [&](const char* q, const char* mm) { return std::string("SPedge%") + arm + "%" + q + "%" + mm; };
     a.delta.min = D.d(key("delta", "min").c_str()); a.delta.max = D.d(key("delta", "max").c_str());
@@ -272,7 +272,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   const int nA = (int)std::lround(targ.A);
   if (c.doing_pion) {
     c.Mh = Mpi;
-    if (nA == 1 && c.which_pion == 1) throw std::runtime_error("Pi- production from Hydrogen not allowed!");
+    if (c.doing_pizero) c.Mh = 134.9766;          // dbase.f:140
+    if (nA == 1 && c.which_pion == 1 && !c.doing_pizero) throw std::runtime_error("Pi- production from Hydrogen not allowed!");
     if (nA <= 2 && c.which_pion >= 10) throw std::runtime_error("Coherent production from Hydrogen/Deuterium not allowed!");
     if (nA == 3 && c.which_pion == 11) throw std::runtime_error("Coherent Pi- production from 3He not allowed!");
     if (nA == 4 && c.which_pion >= 10) throw std::runtime_error("Coherent production from 4He not allowed!");
@@ -294,8 +295,11 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     c.do_fermi = D.i("do_fermi") > 0;
     if (c.doing_hydsemi && c.do_fermi) c.do_fermi = 0;      // 'Cannot do Fermi motion for Hydrogen!' (dbase.f:202-206)
     if (nA >= 3) throw std::runtime_error("semi-inclusive production from A >= 3 (doing_hesemi) is not implemented in this build");
-  } else if (c.doing_rho) {
+  } else if (c.doing_rho) {                      // dbase.f:209-214, 861-873
     c.Mh = 769.3;
+    if (nA >= 3) throw std::runtime_error("A(e,e'rho): not yet implemented (dbase.f:864)");
+    if (nA != 1) throw std::runtime_error("rho production (doing_rho) is only set up for a proton target: the reference "
+                                          "reads no momentum distribution for D(e,e'rho) (dbase.f:563)");
   } else {
     c.Mh = Mp;
     c.doing_eep = 1;
@@ -328,7 +332,13 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   if (c.doing_eep) { targ.Mtar_struck = Mp; targ.Mrec_struck = 0.0; }
   else if (c.doing_delta) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mpi; }
   else if (c.doing_semi || c.doing_rho) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }
-  else if (c.doing_pion) {
+  else if (c.doing_pion && c.doing_pizero) {       // dbase.f:330-347: the nucleon keeps its charge
+    if (c.which_pion == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }
+    else if (c.which_pion == 1) { targ.Mtar_struck = Mn; targ.Mrec_struck = Mn; }
+    else if (c.which_pion == 2) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1232.0; }
+    else if (c.which_pion == 3) { targ.Mtar_struck = Mn; targ.Mrec_struck = 1232.0; }
+    else throw std::runtime_error("Bad value for which_pion");
+  } else if (c.doing_pion) {
     if (c.which_pion == 0) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mn; }
     else if (c.which_pion == 1) { targ.Mtar_struck = Mn; targ.Mrec_struck = Mp; }
     else if (c.which_pion == 2 || c.which_pion == 3) { targ.Mtar_struck = Mp; targ.Mrec_struck = 1232.0; }
@@ -457,7 +467,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   // ---- limits_init, init.f:91-572
   auto slop_for = [](int arm, double* used) {
     if (arm == 2) { used[0] = 1.0; used[1] = 0.008; used[2] = 0.008; }
-    else { used[0] = 0.5; used[1] = 0.005; used[2] = 0.005; }          // simulate.inc:20-44
+    else if (arm >= 1 && arm <= 6) { used[0] = 0.5; used[1] = 0.005; used[2] = 0.005; }          // simulate.inc:20-44
+    // calorimeter arms (7, 8): init.f:157-204 has no branch for them, the slop stays zero
   };
   if (c.using_E_arm_montecarlo) slop_for(c.electron_arm, c.slop_MC_e_used);
   if (c.using_P_arm_montecarlo) slop_for(c.hadron_arm, c.slop_MC_p_used);
@@ -521,7 +532,7 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     edge.Em.max = c.cuts_Em.max + slop_total_Em;
     edge.Em.min = std::max(0.e0, edge.Em.min);
   }
-  if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_delta || c.doing_semi) {   // doing_delta: hydrogen only here
+  if (c.doing_hyd_elast || c.doing_hydpi || c.doing_hydkaon || c.doing_delta || c.doing_rho || c.doing_semi) {   // doing_delta, doing_rho: hydrogen only here
     VE.Em.min = 0.0; VE.Em.max = 0.0; VE.Pm.min = 0.0; VE.Pm.max = 0.0;
     VE.Mrec.min = 0.0; VE.Mrec.max = 0.0; VE.Trec.min = 0.0; VE.Trec.max = 0.0;
   } else if (c.doing_hepi || c.doing_hekaon) {        // init.f:353-357,379-386
@@ -657,6 +668,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     // semi-inclusive cross sections are a few nb/GeV/sr^2 = 1e-9 ub/MeV/sr^2; the weight needs the parton
     // tables, which a deck does not carry, so the scale is nominal
     c.w_ref = 1.0e-9;
+  } else if (c.doing_rho) {
+    c.w_ref = 1.0e-7;          // peerho at JLab kinematics: ~1e-7 ub/MeV/sr^2 (4 pi generation, steep t' slope): nominal
   } else if (c.doing_deuterium) {
     c.w_ref = 1.0e-5;          // sigma_cc1 (~1e2 ub/sr) x rho(Pm ~ 100 MeV/c) (~1e-7 MeV^-3): nominal
   } else if (c.doing_hyd_elast) {

@@ -142,6 +142,9 @@ SIMC_HD ArmWindows arm_windows(int arm) {
   if (arm == 1) { w.s_Al = 0.016 * inch_cm; w.s_air = 15; w.s_kevlar = 0.015 * inch_cm; w.s_mylar = 0.005 * inch_cm; w.plus_angle = true; }
   else if (arm == 2) { w.s_Al = 0.008 * inch_cm; w.s_air = 15; w.s_kevlar = 0.005 * inch_cm; w.s_mylar = 0.003 * inch_cm; }
   else if (arm == 3 || arm == 4) { w.s_Al = 0.013 * inch_cm; w.s_air = 15; w.s_kevlar = 0. * inch_cm; w.s_mylar = 0.010 * inch_cm; }
+  // calorimeter arms (7 on the HMS side, 8 on the other): the reference defines no windows for them (target.f:73-101,
+  // 188-222; its SAVEd locals keep what the previous call left): no window material, the target and its can only
+  else if (arm == 7 || arm == 8) { w.s_Al = 0.0; w.s_air = 0.0; w.s_kevlar = 0.0; w.s_mylar = 0.0; w.plus_angle = arm == 7; }
   else { w.s_Al = (0.02 + 0.01) * inch_cm; w.s_air = 57.27; w.s_kevlar = 0.0; w.s_mylar = 0.0; }
   return w;
 }

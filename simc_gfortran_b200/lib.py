@@ -14,11 +14,11 @@ import numpy as np
 ARM_HMS, ARM_SOS, ARM_HRSR, ARM_HRSL, ARM_SHMS = 1, 2, 3, 4, 5
 WEIGHT_NIN, WEIGHT_NOUT = 44, 15
 TRANSPORT_NIN, TRANSPORT_NOUT = 9, 12
-EVENT_NREC = 56
+EVENT_NREC = 60
 RADC_NOUT = 26
-NTUPLE_MAXCOL = 56
+NTUPLE_MAXCOL = 68
 NHIST, H_PER_SET, NSTOP = 50, 8, 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -101,14 +101,15 @@ _INT_FLAGS = (
 )
 _DBL_SCALARS = (
     "Mh", "Mh2", "Ebeam", "dEbeam", "Ebeam_vertex_ave",
-    "dE_edge_test", "Egamma_gen_max", "ctau", "transparency",
+    "dE_edge_test", "Egamma_gen_max", "ctau", "transparency", "drift_to_cal",
     "etatzai", "Egamma_tot_max", "Egamma1_max", "Egamma2_max", "Egamma3_max", "Egamma_res_limit",
 )
 
 
 class RunConfig(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FLAGS] +
-                [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("deForest_flag", C.c_int32)] +
+                [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("deForest_flag", C.c_int32),
+                 ("doing_pizero", C.c_int32), ("pizero_ngamma", C.c_int32)] +
                 [(n, C.c_double) for n in _DBL_SCALARS] +
                 [("gen", GenLimits), ("spec_e", Spectrometer), ("spec_p", Spectrometer),
                  ("cuts_Em", Cut), ("cuts_Pm", Cut), ("edge", Edge), ("VERTEXedge", Edge),

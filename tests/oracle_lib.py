@@ -9,6 +9,9 @@ import subprocess
 
 import numpy as np
 
+EVENT_NREC = 60          # SIMC_EVENT_NREC, SIMC_NTUPLE_MAXCOL of include/simc_b200.h
+NTUPLE_MAXCOL = 68
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
@@ -142,7 +145,7 @@ def _oracle_run(self, cfg, first, n, seed, threads=1, ranlux=False):
 
 
 def _oracle_event_batch(self, cfg, first, n, seed):
-    rec = np.zeros((56, n))
+    rec = np.zeros((EVENT_NREC, n))
     status = np.zeros(n, np.int32)
     self._check(self.L.oracle_event_batch(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(rec),
                                           _p(status)))
@@ -150,7 +153,7 @@ def _oracle_event_batch(self, cfg, first, n, seed):
 
 
 def _oracle_ntuple_batch(self, cfg, first, n, seed):
-    rows = np.zeros((max(n, 1), 56))
+    rows = np.zeros((max(n, 1), NTUPLE_MAXCOL))
     tries = np.zeros(max(n, 1), np.int64)
     nc, nr = C.c_int32(0), C.c_int64(0)
     self._check(self.L.oracle_ntuple_batch(C.byref(cfg), C.c_int64(first), C.c_int64(n), C.c_uint64(seed), _p(rows),

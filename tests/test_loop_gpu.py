@@ -32,7 +32,7 @@ F_EARM_ENTERED = [32, 33, 34]
 F_EARM = [38, 39, 40]
 F_DONE = [1, 5, 6, 9, 44, 45, 46]
 # natural scales for columns that pass through zero
-SCALE = np.ones(56)
+SCALE = np.ones(60)
 for k in (13, 14, 17, 18, 33, 34, 36, 37, 39, 40, 42, 43):
     SCALE[k] = 1e-2           # angles
 for k in (5, 6, 9):

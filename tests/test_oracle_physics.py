@@ -131,3 +131,65 @@ def test_generate_em_follows_the_spectral_function(oracle):
     first = (np.abs(em - sf["em"][0]) <= sf["dem"][0] / 2).mean()
     assert abs(first - frac[0]) < 4 * np.sqrt(frac[0] * (1 - frac[0]) / len(em)) + 1e-3
     assert em.min() >= sf["em"][0] - sf["dem"][0] / 2 and em.max() <= sf["em"][-1] + sf["dem"][-1] / 2
+
+
+def test_rho_production(oracle_with_optics):
+    """H(e,e'rho0): generate_rho.f, rho_decay.f, rho_physics.f restated.  The Breit-Wigner mass (a tangent transform of one
+    uniform number, cut at +-500 MeV), the decay-angle bookkeeping and the kinematics of the detected pion."""
+    cfg = deck("r1_eerho_hydrogen_sos_hms.inp")
+    assert cfg.doing_rho and abs(cfg.Mh - 769.3) < 1e-12
+    n = 200000
+    rec, stage = oracle_with_optics.event_batch(cfg, 0, n, 11)
+    m = rec[58]
+    thrown = m != 0.0                     # every try that reached generate_rho's first draw
+    assert thrown.mean() > 0.95
+    m = m[thrown]
+    assert np.all(np.abs(m - 769.3) <= 500.0)
+    # non-relativistic Breit-Wigner of width 150.2 MeV: P(|m - M| < Gamma/2) = atan(1) / atan(2*500/150.2)
+    inside = (np.abs(m - 769.3) < 75.1).mean()
+    expect = np.arctan(1.0) / np.arctan(2 * 500.0 / 150.2)
+    assert abs(inside - expect) < 4 * np.sqrt(expect * (1 - expect) / len(m))
+    assert abs(np.median(m) - 769.3) < 1.0
+    gen = stage >= 1
+    assert gen.sum() > 2000 and (stage == 4).sum() > 30
+    # after rho_decay: the pion points into the hadron arm's hemisphere, its energy is below the rho's
+    assert np.all(rec[21][gen] < rec[15][gen])                       # orig.p.E (pion) < vertex.p.E (rho)
+    assert np.all((rec[59][gen] >= 0) & (rec[59][gen] <= np.pi))
+    # hydrogen: no jacobian for the hadron angles, the electron's only (event.f:1013-1023)
+    r = np.sqrt(1 + rec[13][gen] ** 2 + rec[14][gen] ** 2)
+    assert np.allclose(rec[8][gen], 1 / r ** 3, rtol=1e-13)
+    # the weight: peerho is positive, falls with -t (steep exponential slope)
+    done = stage == 4
+    assert np.all(rec[6][done] > 0) and np.all(rec[6][done] < 1e-4)
+    rows, tries = oracle_with_optics.ntuple_batch(cfg, 0, n, 11)
+    assert rows.shape[1] == 59 and len(rows) == done.sum()
+    # p(e,e'pi)X with X = p + pi: the missing mass starts at Mp + Mpi; nucleus = nucleon for hydrogen
+    assert np.all(rows[:, 33] > 0.93827 + 0.13957 - 0.02)
+    assert np.allclose(rows[:, 58], rows[:, 33], rtol=1e-12)
+
+
+def test_pizero_into_calorimeter(oracle_with_optics):
+    """H(e,e'pi0)p with the NPS as the hadron arm: pizero_decay.f and calo/mc_calo.f restated.  The photons carry the pi0
+    four-momentum, a kept event has pizero_ngamma photons inside the calorimeter face, and the hit is the straight line
+    from the vertex over drift_to_cal."""
+    cfg = deck("z1_eepi0_hydrogen_hms_nps.inp")
+    assert cfg.doing_pizero and cfg.hadron_arm == 8 and abs(cfg.Mh - 134.9766) < 1e-12
+    n = 40000
+    rows, tries = oracle_with_optics.ntuple_batch(cfg, 0, n, 3)
+    assert rows.shape[1] == 65 and len(rows) > 80
+    g1, g2 = rows[:, 55:59], rows[:, 61:65]
+    tot = g1 + g2
+    assert np.allclose(np.sqrt(tot[:, 0] ** 2 - (tot[:, 1:] ** 2).sum(axis=1)), 134.9766, rtol=1e-9)
+    assert np.all(np.abs(rows[:, [53, 59]]) <= 36.9) and np.all(np.abs(rows[:, [54, 60]]) <= 30.75)
+    # photon 1 in the calorimeter frame (arm 8: rotation by +theta about x, simc.f:1496-1503), drifted 300 cm from the
+    # vertex position in that frame: ycal - y0 = 300 * ey/ez with |y0| of a few cm (10 cm target seen at 7.5 degrees)
+    th = cfg.spec_p.theta
+    ey = g1[:, 2] * np.cos(th) - g1[:, 3] * np.sin(th)
+    ez = g1[:, 2] * np.sin(th) + g1[:, 3] * np.cos(th)
+    assert np.all(np.abs(rows[:, 54] - 300.0 * ey / ez) < 2.0)
+    assert np.all(np.abs(rows[:, 53] - 300.0 * g1[:, 1] / ez) < 1.0)
+    one = type(cfg).from_buffer_copy(bytes(cfg))
+    one.pizero_ngamma = 1
+    rows1, _ = oracle_with_optics.ntuple_batch(one, 0, n, 3)
+    assert len(rows1) > len(rows)                     # one photon is enough: more events, some with a missed photon
+    assert ((rows1[:, 53] == -1.0e10) | (rows1[:, 59] == -1.0e10)).any()

@@ -1,0 +1,131 @@
+"""GPU parity tests of H(e,e'rho0)p -> pi+ pi- ("doing_rho": generate_rho.f, rho_decay.f, rho_physics.f; event.f:420-422,
+701-708, 1515-1518).  The rho is thrown in 4 pi in the photon-nucleon centre of mass with a Breit-Wigner mass inside
+complete_ev (three random numbers per pass), decays before the spectrometer (a rejection loop: a variable number of
+random numbers) and is weighted by peerho.  Kinematics of the reference's infiles/rhotest.inp (SOS electron, HMS pi-),
+radiation off as in that deck, and the same deck with the radiative tails on."""
+import os
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import Simc, SimcError, config_from_deck, load_optics_fixture
+from tests.test_loop_gpu import LOOSE, RECON_LOOSE, SCALE, accum_equal_exact, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECK = os.path.join(ROOT, "decks", "r1_eerho_hydrogen_sos_hms.inp")
+SC = SCALE.copy()
+for k in (5, 6):
+    SC[k] = 1e-9              # weights ~1e-7 ub/MeV/sr^2
+SC[50] = 1e-6                 # ntup%sigcm
+SC[51] = 1e3                  # davejac ~ 5e7
+SC[55] = 1e-2                 # main%t as peerho leaves it (GeV^2)
+SC[56] = SC[57] = 1e-2        # the decay pion's angles
+SC[58] = 1.0
+SC[59] = 1e-2
+
+
+def variant(cfg, **kw):
+    c = type(cfg).from_buffer_copy(bytes(cfg))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.fixture(scope="module", params=["norad", "rad"])
+def case(request, oracle_with_optics):
+    cfg = config_from_deck(DECK)[0]
+    if request.param == "rad":
+        # the deck's one_tail = -3 (no hadron tail); radc_init's constants need the flag at deck level
+        import tempfile
+        text = open(DECK).read().replace("using_rad = 0", "using_rad = 1")
+        with tempfile.NamedTemporaryFile("w", suffix=".inp", delete=False) as f:
+            f.write(text)
+        cfg = config_from_deck(f.name)[0]
+        os.unlink(f.name)
+        assert cfg.using_rad == 1 and cfg.doing_tail[0] == 1 and cfg.doing_tail[2] == 0
+    s = Simc(cfg, mode="strict")
+    for arm in (1, 2):
+        s.set_optics(load_optics_fixture(arm))
+    yield cfg, s, oracle_with_optics
+    s.close()
+
+
+def test_config(case):
+    cfg = case[0]
+    assert cfg.doing_rho == 1 and cfg.doing_pion == 0 and cfg.doing_eep == 0 and cfg.doing_decay == 1
+    assert abs(cfg.Mh - 769.3) < 1e-12                                                     # dbase.f:210
+    assert abs(cfg.targ.Mtar_struck - 938.27231) < 1e-9 and abs(cfg.targ.Mrec_struck - 938.27231) < 1e-9   # dbase.f:315-317
+
+
+def test_event_records(case):
+    cfg, sim, orc = case
+    n = 400000               # 4 pi generation: ~3e-4 of the tries reach both focal planes
+    ref, ref_stage = orc.event_batch(cfg, 0, n, 7)
+    rec, stage = sim.event_batch(0, n, 7)
+    assert np.array_equal(stage, ref_stage), f"{(stage != ref_stage).sum()} tries end at a different stage"
+    for k in (0, 2, 3, 4):
+        # try index, draws consumed (generate_rho's three per pass, rho_decay's rejection loop), stop codes
+        assert np.array_equal(rec[k], ref[k]), sim.event_field_names()[k]
+    names = sim.event_field_names()
+    gen = stage >= 1
+    done = stage == 4
+    assert gen.sum() > 5000 and done.sum() > 60
+    # vertex (the rho), orig (the decay pion), rho mass and decay angle, for every try that left generate
+    for k in (7, 8, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 26, 27, 28, 29, 30, 31, 35, 36, 37, 56, 57, 58, 59):
+        e = rel_err(rec[k][gen], ref[k][gen], SC[k])
+        assert e.max() <= LOOSE, (names[k], float(e.max()))
+    # the Breit-Wigner mass and the decay angle are what generate_rho / rho_decay drew
+    assert np.all(np.abs(rec[58][gen] - 769.3) <= 500.0 + 1e-9) and np.all((rec[59][gen] >= 0) & (rec[59][gen] <= np.pi))
+    for k in (1, 9, 41, 42, 43, 38, 39, 40, 44, 45, 46, 53):
+        e = rel_err(rec[k][done], ref[k][done], SC[k])
+        assert e.max() <= RECON_LOOSE, (names[k], float(e.max()))
+    for k in (5, 6, 48, 49, 50, 51, 55):
+        e = rel_err(rec[k][done], ref[k][done], SC[k])
+        assert e.max() <= (LOOSE if cfg.using_rad == 0 else RECON_LOOSE), (names[k], float(e.max()))
+
+
+def test_accumulators(case):
+    cfg, sim, orc = case
+    n = 300000
+    ref = orc.run(cfg, 0, n, 4, threads=8)
+    acc = sim.accum_clear()
+    sim.run(0, n, 4, acc)
+    accum_equal_exact(acc, ref)
+    assert acc.unsupported == ref.unsupported == 0 and acc.nsuccess > 40
+    a, b = acc.wtcontribute.value(), ref.wtcontribute.value()
+    assert abs(a - b) <= RECON_LOOSE * abs(b)
+
+
+def test_ntuple_rows(case):
+    cfg, sim, orc = case
+    n = 300000
+    ref, ref_tries = orc.ntuple_batch(cfg, 0, n, 5)
+    rows, tries = sim.ntuple_batch(0, n, 5)
+    assert rows.shape[1] == ref.shape[1] == 59               # NtupleInit.f:192-262: the semi-inclusive layout + Mrho, Thrho, mmnuc
+    assert np.array_equal(tries, ref_tries) and len(rows) > 40
+    assert np.all(np.isnan(rows[:, 53])) and np.all(np.isnan(ref[:, 53]))       # p_fermi column of a hydrogen run: 0/0
+    keep = [k for k in range(59) if k != 53]
+    scale = np.maximum(np.abs(ref).max(axis=0), 1e-30)
+    err = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-3 * scale[None, :])
+    assert err[:, keep].max() <= RECON_LOOSE, (int(np.argmax(err[:, keep].max(axis=0))), float(err[:, keep].max()))
+    # the detected particle is a pion: Mhadron column is Mpi or, after a decay in flight, Mmu; the missing mass of
+    # p(e,e'pi)X with X = p + pi starts at Mp + Mpi (within resolution)
+    assert set(np.round(rows[:, 42], 4)) <= {139.5702, 105.6584}
+    assert np.all(rows[:, 33] > 0.93 + 0.13)
+    assert np.all(np.abs(rows[:, 56] - 769.3) <= 500.0)
+
+
+def test_refusals(case):
+    cfg = case[0]
+    deut = variant(cfg)
+    deut.targ.A = 2.0
+    s = Simc(deut, mode="strict")
+    try:
+        for arm in (1, 2):
+            s.set_optics(load_optics_fixture(arm))
+        with pytest.raises(SimcError) as e:
+            s.run(0, 1000, 1, s.accum_clear())
+        assert "rho" in str(e.value)
+    finally:
+        s.close()
