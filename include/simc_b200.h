@@ -338,6 +338,21 @@ int simc_b200_read_saghai_file(const char* path, int which, float* tbl, char* ms
 int simc_b200_set_fdss_table(simc_handle* h, const double* parton);
 int simc_b200_load_fdss_file(simc_handle* h, const char* path);
 
+/* Field of the polarised target (using_tgt_field): replaces trgInit (trg_track.f:243-347, called from simc.f:154) and
+ * COMMON /trgFieldStrength/.  bz, br: B_field_z(iz, ir) and B_field_r(iz, ir) in T on 51 x 51 nodes 2 cm apart, in the
+ * file's reading order (ir outer, iz inner); both NULL: the uniform 5 T test field trgInit builds for a blank file
+ * name.  load_field_file reads trg_field_map.dat itself ("0": no field, blank: the test field). */
+int simc_b200_set_field_map(simc_handle* h, const double* bz, const double* br);
+int simc_b200_load_field_file(simc_handle* h, const char* path);
+/* stage-level parity entry point: track_from_tgt (trg_track.f:591-672; Runge-Kutta tracking from the vertex to the
+ * field-free plane z = 100 cm) on dumped vectors.  spect = -1 (electron arm) or +1; theta_deg: angle between the field
+ * axis and that spectrometer as handed to trgInit.  in[k*n+i], k = 0..6: { x, y, z, dx, dy (TRANSPORT coordinates,
+ * cm and slopes), mom (MeV/c, negative for a negative particle), mass (MeV) }; out[k*n+i], k = 0..5: { x, y, z, dx,
+ * dy of the image track, ok }. */
+#define SIMC_FIELD_NIN  7
+#define SIMC_FIELD_NOUT 6
+int simc_b200_field_batch(simc_handle* h, int spect, double theta_deg, int64_t n, const double* in_soa, double* out_soa);
+
 /* stage-level parity entry point for the semi-inclusive weight: peepiX (semi_physics.f:1-617) with
  * Ctq5Pdf, the Bosted fragmentation fit and F1F2IN21 on dumped vertex vectors.  in[k*n+i], k = 0..15:
  * { Ein, e.E, nu, Q2, q, uq.x, uq.y, uq.z, pt2, zhad, theta_pq, pfer, pferx, pfery, pferz, efer };

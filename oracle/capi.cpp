@@ -7,6 +7,7 @@
 #include <thread>
 #include <vector>
 #include "event.hpp"
+#include "field.hpp"
 
 using namespace simc_oracle;
 
@@ -478,6 +479,51 @@ int oracle_philox_block(const uint32_t* ctr, const uint32_t* key, uint32_t* out)
 int oracle_philox_uniforms(uint64_t seed, uint64_t try_index, int64_t n, double* out) {
   Rng r; r.seed_philox(seed, try_index);
   for (int64_t i = 0; i < n; ++i) out[i] = r.grnd();
+  return 0;
+}
+
+// ---- trg_track.f: field of the polarised target -------------------------------------------------------------
+static simc_oracle::TrgField g_field;
+// bz, br: 51 x 51 nodes in the file's reading order, or both null for the uniform test field; the angles as trgInit takes them
+int oracle_set_field_map(const double* bz, const double* br, double theta_e_deg, double theta_p_deg) {
+  g_field.init(bz, br, theta_e_deg, theta_p_deg);
+  return 0;
+}
+// track_from_tgt on rows (x, y, z, dx, dy, mom, mass) -> (x, y, z, dx, dy, ok)
+int oracle_field_batch(int spect, int64_t n, const double* in, double* out) {
+  if (!g_field.set) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    double x = in[0 * n + i], y = in[1 * n + i], z = in[2 * n + i], dx = in[3 * n + i], dy = in[4 * n + i];
+    const bool ok = simc_oracle::track_from_tgt(g_field, x, y, z, dx, dy, in[5 * n + i], in[6 * n + i], spect);
+    out[0 * n + i] = x; out[1 * n + i] = y; out[2 * n + i] = z; out[3 * n + i] = dx; out[4 * n + i] = dy;
+    out[5 * n + i] = ok ? 1.0 : 0.0;
+  }
+  return 0;
+}
+// trgField on points (x, y, z) -> (Bx, By, Bz)
+int oracle_field_at(int spect, int64_t n, const double* xyz, double* b) {
+  if (!g_field.set) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const double x[3] = {xyz[0 * n + i], xyz[1 * n + i], xyz[2 * n + i]};
+    double B[3];
+    simc_oracle::trgField(g_field, x, B, spect);
+    b[0 * n + i] = B[0]; b[1 * n + i] = B[1]; b[2 * n + i] = B[2];
+  }
+  return 0;
+}
+// n_steps Runge-Kutta steps of length dl (cm) from each state (x, y, z, vx, vy, vz): the state after every step,
+// traj[(step * 6 + k) * n + i].  E = signed energy (MeV).
+int oracle_field_steps(int spect, int64_t n, const double* u0, double E, double dl, int n_steps, double* traj) {
+  if (!g_field.set) return -1;
+  for (int64_t i = 0; i < n; ++i) {
+    double u[9] = {0}, u1[9] = {0};
+    for (int k = 0; k < 6; ++k) u[k] = u0[k * n + i];
+    const double ts = -dl / std::sqrt(u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);      // as trgTrackToPlane starts out
+    for (int s = 0; s < n_steps; ++s) {
+      simc_oracle::trgRK4(g_field, 90. / E, u, u1, -ts, spect);
+      for (int k = 0; k < 6; ++k) { u[k] = u1[k]; traj[((int64_t)s * 6 + k) * n + i] = u[k]; }
+    }
+  }
   return 0;
 }
 

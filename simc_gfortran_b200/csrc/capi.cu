@@ -73,6 +73,7 @@ struct simc_handle {
   double* d_pfm = nullptr; int pfm_n = 0;                  // momentum distribution: [pval | mprob]
   double* d_fdss = nullptr;                                // fDSS tables (physics_semi.cuh: FdssDev)
   float* d_saghai[2] = {nullptr, nullptr};                 // Saghai amplitude tables: [0] K+ Lambda, [1] K+ Sigma0
+  double* d_field = nullptr;                               // target field map (field.cuh: FieldDev), [Bz | Br] of 51 x 51 nodes
   double* d_maid[2] = {nullptr, nullptr};                  // MAID-2007 slices: [0] pi+ n (ipi 3), [1] pi- p (ipi 4)
   double* d_theory = nullptr; int theory_nrho = 0; double theory_efermi = 0;   // physics_heavy.cuh: TheoryDev
   // optional per-stage timing
@@ -243,6 +244,7 @@ void simc_b200_destroy(simc_handle* h) {
   if (h->d_pfm) cudaFree(h->d_pfm);
   if (h->d_theory) cudaFree(h->d_theory);
   for (double* p : h->d_maid) if (p) cudaFree(p);
+  if (h->d_field) cudaFree(h->d_field);
   for (float* p : h->d_saghai) if (p) cudaFree(p);
   if (h->d_fdss) cudaFree(h->d_fdss);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -477,6 +479,53 @@ int simc_b200_load_saghai_files(simc_handle* h, const char* dir) {
     if (rc) return rc;
   }
   return SIMC_OK;
+}
+
+// trgInit (trg_track.f:243-347): the field map of the polarised target.  bz, br: B_field_z(iz, ir), B_field_r(iz, ir)
+// in the file's reading order (ir outer, iz inner), 51 x 51 nodes 2 cm apart; both null: the uniform 5 T test field
+// (26 cm in z, 16 cm in r) trgInit builds for a blank file name.
+int simc_b200_set_field_map(simc_handle* h, const double* bz, const double* br) {
+  if (!h || ((bz == nullptr) != (br == nullptr))) return SIMC_ERR_ARG;
+  const int N = 51;
+  std::vector<double> img(2 * (size_t)N * N);
+  for (int ir = 0; ir < N; ++ir)
+    for (int iz = 0; iz < N; ++iz) {
+      const size_t k = (size_t)ir * N + iz;
+      if (bz) { img[k] = bz[k]; img[(size_t)N * N + k] = br[k]; }
+      else {
+        const double rr = 2. * (double)ir, zz = 2. * (double)iz;
+        img[k] = (rr <= 16. && zz <= 26.) ? 5.0 : 0.0;
+        img[(size_t)N * N + k] = 0.;
+      }
+    }
+  CU(h, cudaSetDevice(h->device));
+  if (!h->d_field) CU(h, cudaMalloc(&h->d_field, img.size() * sizeof(double)));
+  CU(h, cudaMemcpy(h->d_field, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+  return SIMC_OK;
+}
+
+// tgt_field_file (simc.f:154, trg_track.f:291-320): "0" = no field, blank = the uniform test field, else the map:
+// 2601 list-directed rows "z r Bz Br ..." with z running fastest.
+int simc_b200_load_field_file(simc_handle* h, const char* path) {
+  if (!h || !path) return SIMC_ERR_ARG;
+  std::string name(path);
+  while (!name.empty() && name.back() == ' ') name.pop_back();
+  if (name.empty()) return simc_b200_set_field_map(h, nullptr, nullptr);
+  const int N = 51;
+  std::vector<double> bz((size_t)N * N, 0.0), br((size_t)N * N, 0.0);
+  if (name != "0") {
+    FILE* f = std::fopen(name.c_str(), "r");
+    if (!f) return fail(h, SIMC_ERR_IO, "cannot open target field map " + name);
+    bool ok = true;
+    for (size_t k = 0; k < bz.size() && ok; ++k) {
+      double v[7];
+      ok = std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]) == 7;
+      bz[k] = v[2]; br[k] = v[3];
+    }
+    std::fclose(f);
+    if (!ok) return fail(h, SIMC_ERR_IO, "target field map " + name + ": fewer than 51 x 51 rows of seven numbers");
+  }
+  return simc_b200_set_field_map(h, bz.data(), br.data());
 }
 
 // maidtbl of sigmaid (physics_pion.f:596-625): the slice sig0 reads
@@ -1406,6 +1455,28 @@ int simc_b200_radc_batch(simc_handle* h, int64_t n, const double* in_soa, double
   cudaFree(d_in); cudaFree(d_out);
   h->launches += 1;
   if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_radc_batch");
+  return SIMC_OK;
+}
+
+int simc_b200_field_batch(simc_handle* h, int spect, double theta_deg, int64_t n, const double* in_soa, double* out_soa) {
+  if (!h) return SIMC_ERR_ARG;
+  if (n < 0 || (n > 0 && (!in_soa || !out_soa)) || (spect != 1 && spect != -1))
+    return fail(h, SIMC_ERR_ARG, "simc_b200_field_batch: bad argument");
+  if (!h->d_field) return fail(h, SIMC_ERR_STATE, "simc_b200_field_batch: set the field map first (simc_b200_set_field_map / load_field_file)");
+  if (n == 0) return SIMC_OK;
+  CU(h, cudaSetDevice(h->device));
+  double *d_in = nullptr, *d_out = nullptr;
+  CU(h, cudaMalloc(&d_in, sizeof(double) * SIMC_FIELD_NIN * (size_t)n));
+  CU(h, cudaMalloc(&d_out, sizeof(double) * SIMC_FIELD_NOUT * (size_t)n));
+  cudaError_t e = cudaMemcpyAsync(d_in, in_soa, sizeof(double) * SIMC_FIELD_NIN * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess)
+    e = h->strict ? strict::launch_field_batch(h->d_field, theta_deg, spect, n, d_in, d_out, h->stream)
+                  : fast::launch_field_batch(h->d_field, theta_deg, spect, n, d_in, d_out, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_soa, d_out, sizeof(double) * SIMC_FIELD_NOUT * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out);
+  h->launches += 1;
+  if (e != cudaSuccess) return cuda_fail(h, e, "simc_b200_field_batch");
   return SIMC_OK;
 }
 

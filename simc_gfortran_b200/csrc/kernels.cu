@@ -243,6 +243,29 @@ __global__ void k_radc_batch(const simc_run_config* __restrict__ cfg, long long 
   brem_onshell<kBremAll>(v.Ein, v.eE, 450., R.rad_proton_this_ev, bs, bh, dbs);
   out[23 * n + i] = bs; out[24 * n + i] = bh; out[25 * n + i] = dbs;
 }
+// Stage-level parity entry point: track_from_tgt (trg_track.f:591-672) on dumped vectors (simc_b200_field_batch).
+// in [7][n]: x, y, z, dx, dy (TRANSPORT coordinates of the arm), mom (MeV/c, signed by the charge), mass;
+// out [6][n]: x, y, z, dx, dy of the image track at z = 100 cm, ok.
+__global__ void k_field_batch(FieldDev F, int k, long long n, const double* __restrict__ in, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x = in[0 * n + i], y = in[1 * n + i], z = in[2 * n + i], dx = in[3 * n + i], dy = in[4 * n + i];
+  const bool ok = track_from_tgt(F, k, x, y, z, dx, dy, in[5 * n + i], in[6 * n + i]);
+  out[0 * n + i] = x; out[1 * n + i] = y; out[2 * n + i] = z; out[3 * n + i] = dx; out[4 * n + i] = dy;
+  out[5 * n + i] = ok ? 1.0 : 0.0;
+}
+cudaError_t launch_field_batch(const double* map, double theta_deg, int spect, long long n, const double* in, double* out,
+                               cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  FieldDev F;
+  F.map = map;
+  const double pi180 = 3.141592653 / 180.;            // trgInit's constant, trg_track.f:275
+  const int k = spect == -1 ? 0 : 1;
+  for (int j = 0; j < 2; ++j) { F.stht[j] = std::sin(theta_deg * pi180); F.ctht[j] = std::cos(theta_deg * pi180); }
+  k_field_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(F, k, n, in, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_radc_batch(const void* cfg, long long n, const double* in, double* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
   k_radc_batch<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const simc_run_config*)cfg, n, in, out);

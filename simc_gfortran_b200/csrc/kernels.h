@@ -91,6 +91,8 @@ cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long lo
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s);   // 0 gen, 1 P arm, 2 E arm, 3 finish, 4 records
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s);
 cudaError_t launch_log_batch(long long n, const double* x, double* out, cudaStream_t s);
+cudaError_t launch_field_batch(const double* map, double theta_deg, int spect, long long n, const double* in, double* out,
+                               cudaStream_t s);
 size_t dev_accum_bytes();
 int n_state_fields();
 void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);
@@ -102,6 +104,8 @@ cudaError_t launch_semi_batch(const void* cfg, const LoopLaunch& tables, long lo
 cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s);   // 0 gen, 1 P arm, 2 E arm, 3 finish, 4 records
 cudaError_t launch_fp64_peak(double* scratch, int blocks, int threads, int iters, int fma, cudaStream_t s);
 cudaError_t launch_log_batch(long long n, const double* x, double* out, cudaStream_t s);
+cudaError_t launch_field_batch(const double* map, double theta_deg, int spect, long long n, const double* in, double* out,
+                               cudaStream_t s);
 size_t dev_accum_bytes();
 int n_state_fields();
 void accum_to_host(const void* dev_accum_host_copy, void* simc_accum_out, int qexp_w);

@@ -15,6 +15,7 @@
 #pragma once
 #include "event.cuh"
 #include "transport.cuh"
+#include "field.cuh"
 #include "kernels.h"
 
 namespace simc {

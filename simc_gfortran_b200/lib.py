@@ -216,6 +216,9 @@ def load_library():
     L.simc_b200_transport_batch.argtypes = tb
     L.simc_b200_transport_batch_device.argtypes = tb
     L.simc_b200_sync.argtypes = [C.c_void_p]
+    L.simc_b200_set_field_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.simc_b200_load_field_file.argtypes = [C.c_void_p, C.c_char_p]
+    L.simc_b200_field_batch.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p]
     for name, args in (("simc_b200_accum_clear", [C.c_void_p, C.c_void_p]),
                        ("simc_b200_run", [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]),
                        ("simc_b200_run_async", [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]),
@@ -583,6 +586,28 @@ class Simc:
 
     def load_cteq5_file(self, path: str):
         self._check(self.L.simc_b200_load_cteq5_file(self.h, path.encode()))
+
+    # ---- field of the polarised target (trg_track.f)
+    def set_field_map(self, bz=None, br=None):
+        """bz, br: 51 x 51 nodes in the file's reading order (simc_b200_set_field_map); None: the uniform 5 T test field."""
+        if bz is None:
+            self._check(self.L.simc_b200_set_field_map(self.h, None, None))
+            return
+        bz = np.ascontiguousarray(bz, dtype=np.float64).ravel()
+        br = np.ascontiguousarray(br, dtype=np.float64).ravel()
+        assert bz.size == br.size == 51 * 51
+        self._check(self.L.simc_b200_set_field_map(self.h, _ptr(bz), _ptr(br)))
+
+    def load_field_file(self, path: str):
+        self._check(self.L.simc_b200_load_field_file(self.h, path.encode()))
+
+    def field_batch(self, spect: int, theta_deg: float, inp: np.ndarray) -> np.ndarray:
+        """track_from_tgt on rows (x, y, z, dx, dy, mom, mass) -> (x, y, z, dx, dy, ok)."""
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        assert inp.ndim == 2 and inp.shape[0] == 7
+        out = np.zeros((6, inp.shape[1]))
+        self._check(self.L.simc_b200_field_batch(self.h, int(spect), float(theta_deg), inp.shape[1], _ptr(inp), _ptr(out)))
+        return out
 
     def semi_batch(self, inp: np.ndarray) -> np.ndarray:
         inp = np.ascontiguousarray(inp, dtype=np.float64)

@@ -436,3 +436,56 @@ def _oracle_weight_batch(self, cfg, inp):
 
 Oracle.weight_inputs = _oracle_weight_inputs
 Oracle.weight_batch = _oracle_weight_batch
+
+
+def load_field_fixture():
+    """simc_gfortran_b200/data/trg_field_map.npz (tools/make_fixtures.py: the reference's trg_field_map.dat): bz, br."""
+    z = np.load(os.path.join(ROOT, "simc_gfortran_b200", "data", "trg_field_map.npz"))
+    return z["bz"], z["br"]
+
+
+def write_field_file(bz, br, path):
+    """Rows 'z r Bz Br |B| ratio diff' like trg_field_map.dat (trgInit reads them list-directed)."""
+    with open(path, "w") as f:
+        for ir in range(51):
+            for iz in range(51):
+                k = ir * 51 + iz
+                f.write("%8.3f%8.3f %.17g %.17g %.17g %.9f %12.1E\n" % (2.0 * iz, 2.0 * ir, bz[k], br[k], np.hypot(bz[k], br[k]), 1.0, 0.0))
+
+
+def _oracle_set_field_map(self, bz, br, theta_e_deg, theta_p_deg):
+    """trgInit; bz = br = None: the uniform 5 T test field."""
+    if bz is None:
+        self._check(self.L.oracle_set_field_map(None, None, C.c_double(theta_e_deg), C.c_double(theta_p_deg)))
+        return
+    bz = np.ascontiguousarray(bz, np.float64).ravel()
+    br = np.ascontiguousarray(br, np.float64).ravel()
+    self._check(self.L.oracle_set_field_map(_p(bz), _p(br), C.c_double(theta_e_deg), C.c_double(theta_p_deg)))
+
+
+def _oracle_field_batch(self, spect, inp):
+    inp = np.ascontiguousarray(inp, np.float64)
+    out = np.zeros((6, inp.shape[1]))
+    self._check(self.L.oracle_field_batch(int(spect), C.c_int64(inp.shape[1]), _p(inp), _p(out)))
+    return out
+
+
+def _oracle_field_at(self, spect, xyz):
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    out = np.zeros((3, xyz.shape[1]))
+    self._check(self.L.oracle_field_at(int(spect), C.c_int64(xyz.shape[1]), _p(xyz), _p(out)))
+    return out
+
+
+def _oracle_field_steps(self, spect, u0, E, dl, n_steps):
+    u0 = np.ascontiguousarray(u0, np.float64)
+    traj = np.zeros((n_steps, 6, u0.shape[1]))
+    self._check(self.L.oracle_field_steps(int(spect), C.c_int64(u0.shape[1]), _p(u0), C.c_double(E), C.c_double(dl),
+                                          int(n_steps), _p(traj)))
+    return traj
+
+
+Oracle.set_field_map = _oracle_set_field_map
+Oracle.field_batch = _oracle_field_batch
+Oracle.field_at = _oracle_field_at
+Oracle.field_steps = _oracle_field_steps

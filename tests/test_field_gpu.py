@@ -1,0 +1,85 @@
+"""GPU parity of the target-field tracking (csrc/field.cuh against oracle/field.cpp; trg_track.f): track_from_tgt on
+identical dumped vectors through simc_b200_field_batch, for the measured map (set from arrays and read from a file by
+the library's own reader), the uniform test field and no field; 1e-12 on the image track, `ok` flags identical."""
+import os
+
+import numpy as np
+import pytest
+
+from simc_gfortran_b200 import Simc, SimcError, config_from_deck
+from tests.oracle_lib import load_field_fixture, write_field_file
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DECK = os.path.join(ROOT, "decks", "c1_eep_hydrogen_hms_shms.inp")
+
+
+def vectors(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.array([rng.uniform(-1, 1, n), rng.uniform(-1.5, 1.5, n), rng.uniform(-3, 3, n), rng.uniform(-0.08, 0.08, n),
+                     rng.uniform(-0.05, 0.05, n), rng.choice([-1.0, 1.0], n) * rng.uniform(300, 6000, n),
+                     rng.choice([0.51099906, 139.57018, 493.677, 938.27231], n)])
+
+
+@pytest.fixture(scope="module")
+def sim():
+    s = Simc(config_from_deck(DECK)[0], mode="strict")
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("theta", [80.0, -100.0, 12.5, 0.0])
+def test_measured_map(sim, oracle, theta, tmp_path):
+    bz, br = load_field_fixture()
+    inp = vectors(20000, 3)
+    for how in ("arrays", "file"):
+        if how == "arrays":
+            sim.set_field_map(bz, br)
+        else:
+            path = str(tmp_path / "trg_field_map.dat")
+            write_field_file(bz, br, path)
+            sim.load_field_file(path)
+        for spect in (-1, 1):
+            oracle.set_field_map(bz, br, theta, theta)
+            ref = oracle.field_batch(spect, inp)
+            out = sim.field_batch(spect, theta, inp)
+            assert np.array_equal(out[5], ref[5]) and ref[5].mean() > 0.99
+            ok = ref[5] == 1
+            err = np.abs(out[:5, ok] - ref[:5, ok]) / np.maximum(np.abs(ref[:5, ok]), [[1.0], [1.0], [1.0], [1e-2], [1e-2]])
+            assert err.max() <= 1e-12, float(err.max())
+    # low momenta curl up in the field: tracks that never reach z = 100 cm come back with ok = 0 from both
+    slow = vectors(4000, 9)
+    slow[5] = np.sign(slow[5]) * np.abs(slow[5]) / 40.0
+    oracle.set_field_map(bz, br, theta, theta)
+    ref = oracle.field_batch(1, slow)
+    out = sim.field_batch(1, theta, slow)
+    assert np.array_equal(out[5], ref[5])
+    if abs(theta) > 45:
+        assert (ref[5] == 0).any()
+
+
+def test_uniform_and_zero_field(sim, oracle, tmp_path):
+    inp = vectors(5000, 4)
+    sim.set_field_map(None, None)
+    oracle.set_field_map(None, None, 30.0, 30.0)
+    ref, out = oracle.field_batch(1, inp), sim.field_batch(1, 30.0, inp)
+    assert np.array_equal(out[5], ref[5])
+    ok = ref[5] == 1
+    assert np.abs(out[:5, ok] - ref[:5, ok]).max() <= 1e-11
+    sim.load_field_file("0")                              # trgInit's "no field" option
+    out = sim.field_batch(-1, 30.0, inp)
+    assert np.all(out[5] == 1) and np.allclose(out[2], 100.0, atol=1e-9)
+    assert np.allclose(out[0], inp[0] + inp[3] * (100.0 - inp[2]), atol=1e-9) and np.allclose(out[3], inp[3], atol=1e-13)
+    sim.load_field_file(" ")                              # blank name: the uniform test field again
+    out2 = sim.field_batch(1, 30.0, inp)
+    assert np.array_equal(out2, sim.field_batch(1, 30.0, inp)) and np.abs(out2[:5, ok] - ref[:5, ok]).max() <= 1e-11
+
+
+def test_needs_a_map():
+    s = Simc(config_from_deck(DECK)[0], mode="strict")
+    try:
+        with pytest.raises(SimcError) as e:
+            s.field_batch(1, 0.0, vectors(4, 1))
+        assert "field map" in str(e.value)
+    finally:
+        s.close()

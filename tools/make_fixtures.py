@@ -212,7 +212,20 @@ def make_he3():
     print("he3", a.shape, n_pm, n_em)
 
 
+def make_field():
+    """trg_field_map.dat (trgInit, trg_track.f:305-313: 51 x 51 rows 'z r Bz Br ...', z fastest) ->
+    simc_gfortran_b200/data/trg_field_map.npz: bz, br in the file's reading order"""
+    a = np.loadtxt(os.path.join(REF, "trg_field_map.dat"))
+    assert a.shape == (51 * 51, 7)
+    np.savez_compressed(os.path.join(ROOT, "simc_gfortran_b200", "data", "trg_field_map.npz"), bz=a[:, 2], br=a[:, 3])
+    print("field map", a.shape, a[:, 2].max())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "field":
+        make_field()
+        sys.exit(0)
+    make_field()
     make_he3()
     make_fdss()
     make_maid()
