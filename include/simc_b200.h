@@ -136,11 +136,15 @@ typedef struct {
   int32_t hardwired_rad;
   int32_t deForest_flag;                     /* 0 = sigcc1, 1 = sigcc2, -1 = sigcc1 on shell (physics_proton.f:39-45) */
   int32_t doing_pizero, pizero_ngamma;       /* dbase.f:1006-1007: pi0 -> gamma gamma into a calorimeter arm (SIMC_ARM_CALO_*) */
+  int32_t using_tgt_field, pad_flags;        /* dbase.f:1102: track both arms through the polarised target's field (trg_track.f) */
 
   /* /gnrl/ scalars */
   double Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave;
   double dE_edge_test, Egamma_gen_max, ctau, transparency;
   double drift_to_cal;                       /* cm from the target to the calorimeter front (dbase.f:1104, calo/mc_calo.f:139) */
+  /* polarised target (simulate.inc:47): direction of the field axis (rad, after dbase.f:454-455), polarisation, and the
+   * charge sign of the detected hadron (dbase.f:296-423) */
+  double targ_Bangle, targ_Bphi, targ_pol, sign_hadron;
   /* /radccom/ run-level */
   double etatzai, Egamma_tot_max, Egamma1_max, Egamma2_max, Egamma3_max, Egamma_res_limit;
 

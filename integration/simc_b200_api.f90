@@ -76,9 +76,11 @@ module simc_b200_api
     integer(c_int32_t) :: hardwired_rad
     integer(c_int32_t) :: deForest_flag
     integer(c_int32_t) :: doing_pizero, pizero_ngamma
+    integer(c_int32_t) :: using_tgt_field, pad_flags
     real(c_double) :: Mh, Mh2, Ebeam, dEbeam, Ebeam_vertex_ave
     real(c_double) :: dE_edge_test, Egamma_gen_max, ctau, transparency
     real(c_double) :: drift_to_cal
+    real(c_double) :: targ_Bangle, targ_Bphi, targ_pol, sign_hadron
     real(c_double) :: etatzai, Egamma_tot_max, Egamma1_max, Egamma2_max, Egamma3_max, Egamma_res_limit
     type(simc_gen_limits) :: gen
     type(simc_spectrometer) :: spec_e, spec_p

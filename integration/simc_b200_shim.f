@@ -83,6 +83,8 @@
 	cfg%deForest_flag   = deForest_flag
 	cfg%doing_pizero    = merge(1,0,doing_pizero)
 	cfg%pizero_ngamma   = pizero_ngamma
+	cfg%using_tgt_field = merge(1,0,using_tgt_field)
+	cfg%pad_flags       = 0
 ! ... /gnrl/ scalars, ctau of /decd/
 	cfg%Mh = Mh
 	cfg%Mh2 = Mh2
@@ -94,6 +96,10 @@
 	cfg%ctau = ctau
 	cfg%transparency = transparency
 	cfg%drift_to_cal = drift_to_cal
+	cfg%targ_Bangle = targ_Bangle
+	cfg%targ_Bphi = targ_Bphi
+	cfg%targ_pol = targ_pol
+	cfg%sign_hadron = sign_hadron
 ! ... /radccom/ run-level
 	cfg%etatzai = etatzai
 	cfg%Egamma_tot_max = Egamma_tot_max

@@ -22,6 +22,9 @@ static SaghaiTable g_saghai;
 namespace simc_oracle { const SaghaiTable* saghai_tables() { return &g_saghai; } }
 static std::string g_err;
 
+static simc_oracle::TrgField g_field;          // COMMON /trgFieldStrength/ as oracle_set_field_map left it
+namespace simc_oracle { const TrgField* field_map() { return &g_field; } }
+
 extern "C" {
 
 const char* oracle_last_error() { return g_err.c_str(); }
@@ -483,7 +486,6 @@ int oracle_philox_uniforms(uint64_t seed, uint64_t try_index, int64_t n, double*
 }
 
 // ---- trg_track.f: field of the polarised target -------------------------------------------------------------
-static simc_oracle::TrgField g_field;
 // bz, br: 51 x 51 nodes in the file's reading order, or both null for the uniform test field; the angles as trgInit takes them
 int oracle_set_field_map(const double* bz, const double* br, double theta_e_deg, double theta_p_deg) {
   g_field.init(bz, br, theta_e_deg, theta_p_deg);

@@ -5,6 +5,7 @@
 // generate/complete_ev are restated where they share code, their cross sections are not (yet).
 #include <cmath>
 #include "event.hpp"
+#include "field.hpp"
 
 namespace simc_oracle {
 
@@ -566,8 +567,11 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     x_P_arm = x_P_arm - cfg.spec_p.off_x;
     y_P_arm = y_P_arm - cfg.spec_p.off_y;
     z_P_arm = z_P_arm - cfg.spec_p.off_z;
-    const double dx_P_arm = main.SP_p.xptar - cfg.spec_p.off_xptar;
-    const double dy_P_arm = main.SP_p.yptar - cfg.spec_p.off_yptar;
+    double dx_P_arm = main.SP_p.xptar - cfg.spec_p.off_xptar;
+    double dy_P_arm = main.SP_p.yptar - cfg.spec_p.off_yptar;
+    if (cfg.using_tgt_field)                          // simc.f:1425-1432 (its ok is overwritten by the arm's own)
+      track_from_tgt(*s.field, x_P_arm, y_P_arm, z_P_arm, dx_P_arm, dy_P_arm,
+                     cfg.sign_hadron * cfg.spec_p.P * (1 + main.SP_p.delta / 100.), Mh, 1);
     x_P_arm = x_P_arm - z_P_arm * dx_P_arm;
     y_P_arm = y_P_arm - z_P_arm * dy_P_arm;
     z_P_arm = 0.0;
@@ -622,6 +626,21 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     for (int k = 0; k < 3; ++k) s.coll_steps[1][k] = a.coll_steps[k];
     s.stop_p = a.ok_spec ? 0 : a.stop_code;
     s.hut_p = a.reached_hut;
+    if (cfg.using_tgt_field && a.ok_spec) {           // simc.f:1573-1587 (for a rejected track it changes nothing)
+      const double frx = cfg.correct_raster ? -main.target.rasterx : 0.0;
+      const double phad = cfg.spec_p.P * (1. + a.dpp / 100.0);
+      const double ctheta = cos(cfg.spec_p.theta), stheta = sin(cfg.spec_p.theta);
+      const bool right = arm == 1 || arm == 3;
+      if (!right && !(arm == 2 || arm == 4 || arm == 5))
+        throw std::runtime_error("Target field reconstruction not set up for your spectrometer");
+      const ArmOptics& o = *s.optics_p;
+      auto recon = [&](double& delta, double& dy, double& dx, double& y, double xxd) {
+        o.rec.eval(s.trk, xxd, delta, dy, dx, y, /*clamp_all=*/arm == 2);
+      };
+      a.ok_spec = track_to_tgt(*s.field, a.dpp, a.y, a.dxdz, a.dydz, frx, -fry, cfg.sign_hadron * phad, sqrt(a.m2), ctheta,
+                               right ? stheta : -stheta, 1, a.ok_spec, recon);
+      s.field_fail_p = !a.ok_spec;
+    }
     if (!a.ok_spec) return false;
     main.RECON_p.delta = a.dpp;
     main.RECON_p.yptar = a.dydz;
@@ -669,8 +688,11 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     x_E_arm = x_E_arm - cfg.spec_e.off_x;
     y_E_arm = y_E_arm - cfg.spec_e.off_y;
     z_E_arm = z_E_arm - cfg.spec_e.off_z;
-    const double dx_E_arm = main.SP_e.xptar - cfg.spec_e.off_xptar;
-    const double dy_E_arm = main.SP_e.yptar - cfg.spec_e.off_yptar;
+    double dx_E_arm = main.SP_e.xptar - cfg.spec_e.off_xptar;
+    double dy_E_arm = main.SP_e.yptar - cfg.spec_e.off_yptar;
+    if (cfg.using_tgt_field)                          // simc.f:1693-1700
+      track_from_tgt(*s.field, x_E_arm, y_E_arm, z_E_arm, dx_E_arm, dy_E_arm, -cfg.spec_e.P * (1 + main.SP_e.delta / 100.),
+                     K::Me, -1);
     x_E_arm = x_E_arm - z_E_arm * dx_E_arm;
     y_E_arm = y_E_arm - z_E_arm * dy_E_arm;
     z_E_arm = 0.0;
@@ -690,6 +712,20 @@ bool montecarlo(Sim& s, Event& orig, EventMain& main, Event& recon) {
     for (int k = 0; k < 3; ++k) s.coll_steps[0][k] = a.coll_steps[k];
     s.stop_e = a.ok_spec ? 0 : a.stop_code;
     s.hut_e = a.reached_hut;
+    if (cfg.using_tgt_field && a.ok_spec) {           // simc.f:1777-1790
+      const double frx = cfg.correct_raster ? -main.target.rasterx : 0.0;
+      const double pelec = cfg.spec_e.P * (1. + a.dpp / 100.0);
+      const double ctheta = cos(cfg.spec_e.theta), stheta = sin(cfg.spec_e.theta);
+      const bool right = arm == 1 || arm == 3;
+      if (!right && !(arm == 2 || arm == 4 || arm == 5))
+        throw std::runtime_error("Target field reconstruction not set up for your spectrometer");
+      const ArmOptics& o = *s.optics_e;
+      auto recon = [&](double& delta, double& dy, double& dx, double& y, double xxd) {
+        o.rec.eval(s.trk, xxd, delta, dy, dx, y, /*clamp_all=*/arm == 2);
+      };
+      a.ok_spec = track_to_tgt(*s.field, a.dpp, a.y, a.dxdz, a.dydz, frx, -fry, -1.0 * pelec, sqrt(K::Me2), ctheta,
+                               right ? stheta : -stheta, -1, a.ok_spec, recon);
+    }
     if (!a.ok_spec) return false;
     main.RECON_e.delta = a.dpp;
     main.RECON_e.yptar = a.dydz;
@@ -895,7 +931,8 @@ bool try_until_recon(Sim& s, EventMain& main, Event& vertex, Event& orig, Event&
   bool success = generate(s, main, vertex, orig);
   r.gen_success = success;
   r.stage = 0;
-  if (success) { success = montecarlo(s, orig, main, recon); r.stage = success ? 3 : (s.stop_p > 0 ? 1 : 2); }
+  s.field_fail_p = false;
+  if (success) { success = montecarlo(s, orig, main, recon); r.stage = success ? 3 : ((s.stop_p > 0 || s.field_fail_p) ? 1 : 2); }
   return success;
 }
 

@@ -142,6 +142,8 @@ struct Sim {
   const TheoryTable* theory = nullptr;
   const MaidTable* maid = nullptr;
   const FdssTable* fdss = nullptr;
+  const struct TrgField* field = nullptr;       // using_tgt_field: map + this run's angles (field.hpp)
+  bool field_fail_p = false;                    // track_to_tgt rejected the hadron arm's track (no STOP counter has it)
   Rng* rng = nullptr;
   double pfer = 0, pferx = 0, pfery = 0, pferz = 0, efer = 0;   // COMMON /pfermi_stuff/ (simulate.inc:212-217)
   // COMMON Mh, Mh2 (simulate.inc:91-92): run constants for every reaction but rho production, where generate_rho draws

@@ -29,6 +29,27 @@ void TrgField::init(const double* bz, const double* br, double theta_e_deg, doub
   set = true;
 }
 
+// simc.f:120-156 (angles in radians in, degrees out; the two arms differ in their second branch, as written)
+void field_arm_angles(double targ_Bangle, double targ_Bphi, double theta_e, double phi_e, double theta_p, double phi_p,
+                      double& ang_e_deg, double& ang_p_deg) {
+  const double pi = 3.141592653589793, degrad = 180. / pi;
+  double ang_targ_earm = 0.0, ang_targ_parm = 0.0;
+  if (degrad * std::fabs(targ_Bphi - phi_e) < .01) {
+    if (targ_Bangle >= theta_e) ang_targ_earm = -1 * std::sin(phi_e) * (targ_Bangle - theta_e);
+    else ang_targ_earm = +1 * std::sin(phi_e) * (theta_e - targ_Bangle);
+  } else if (degrad * std::fabs(targ_Bphi - phi_e) - 180.0 < .01) {
+    ang_targ_earm = +1 * std::sin(phi_e) * (targ_Bangle + theta_e);
+  }
+  if (degrad * std::fabs(targ_Bphi - phi_p) < .01) {
+    if (targ_Bangle >= theta_p) ang_targ_parm = -1 * std::sin(phi_p) * (targ_Bangle - theta_p);
+    else ang_targ_parm = +1 * std::sin(phi_p) * (targ_Bangle - theta_p);
+  } else if (degrad * std::fabs(targ_Bphi - phi_p) - 180.0 < .01) {
+    ang_targ_parm = +1 * std::sin(phi_p) * (targ_Bangle + theta_p);
+  }
+  ang_e_deg = ang_targ_earm * degrad;
+  ang_p_deg = ang_targ_parm * degrad;
+}
+
 // trg_track.f:350-447
 void trgField(const TrgField& F, const double x_[3], double B_[3], int spect) {
   const int k = spect == -1 ? 0 : 1;

@@ -21,6 +21,11 @@ struct TrgField {
   void init(const double* bz, const double* br, double theta_e_deg, double theta_p_deg);
 };
 
+const TrgField* field_map();               // what oracle_set_field_map stored (capi.cpp); never null, `set` says if filled
+// simc.f:120-156: the angles (degrees) between the field axis and the electron / hadron arm that trgInit is given
+void field_arm_angles(double targ_Bangle, double targ_Bphi, double theta_e, double phi_e, double theta_p, double phi_p,
+                      double& ang_e_deg, double& ang_p_deg);
+
 void trgField(const TrgField& F, const double x_[3], double B_[3], int spect);                 // trg_track.f:350-447
 void trgRK4(const TrgField& F, double factor, const double u0[9], double u1[9], double h, int spect);      // :492-533
 bool trgTrackToPlane(const TrgField& F, double u[9], double E, double dl, double a, double b, double c, double d, bool ok,

@@ -190,6 +190,8 @@ void init_from_kv(const char* text, simc_run_config& c) {
   c.doing_hplus = D.flag("doing_hplus", 1); c.doing_decay = D.flag("doing_decay"); c.do_fermi = D.flag("do_fermi");
   c.which_pion = (int)D.i("which_pion"); c.which_kaon = (int)D.i("which_kaon");
   c.doing_pizero = D.flag("doing_pizero"); c.pizero_ngamma = (int)D.i("pizero_ngamma"); c.drift_to_cal = D.d("drift_to_cal");
+  c.using_tgt_field = D.flag("using_tgt_field"); c.targ_pol = D.d("targ_pol");
+  c.targ_Bangle = D.d("targ_bangle") / degrad; c.targ_Bphi = D.d("targ_bphi") / degrad;          // dbase.f:454-455
   c.ctau = D.d("ctau"); c.transparency = D.d("transparency"); c.use_benhar_sf = D.flag("use_benhar_sf");
   c.hard_cuts = D.flag("hard_cuts"); c.using_rad = D.flag("using_rad"); c.use_expon = (int)D.i("use_expon");
   c.intcor_mode = (int)D.i("intcor_mode"); c.mc_smear = D.flag("mc_smear");
@@ -257,6 +259,10 @@ void init_from_kv(const char* text, simc_run_config& c) {
     Mrec_guess = targ.M - Mp;
     if (std::fabs(targ.Mrec - Mrec_guess) > 100.) targ.Mrec = Mrec_guess;
   }
+  // sign_hadron, dbase.f:296-423: the charge of the detected hadron (target-field tracking only)
+  c.sign_hadron = 1.0;
+  if (c.doing_semi || c.doing_rho) c.sign_hadron = c.doing_hplus ? 1.0 : -1.0;
+  else if (c.doing_pion) c.sign_hadron = (c.which_pion == 1 || c.which_pion == 3 || c.which_pion == 11) ? -1.0 : 1.0;
   if (c.doing_eep) { targ.Mtar_struck = Mp; targ.Mrec_struck = 0.0; }
   else if (c.doing_delta) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mpi; }
   else if (c.doing_semi) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }

@@ -7,6 +7,7 @@
 #include <thread>
 #include <vector>
 #include "event.hpp"
+#include "field.hpp"
 
 namespace simc_oracle {
 
@@ -264,12 +265,26 @@ void run_range(const simc_run_config& cfg, const ArmOptics* oe, const ArmOptics*
                uint64_t seed, simc_accum* acc, double* rec, int32_t* status, int64_t rec_stride, int64_t rec_off,
                RanluxState* ranlux, const SfTable* sf, double* ntu_rows, int64_t* n_rows, int* n_cols,
                int64_t* try_of_row, const PfermiTable* pfermi, const Cteq5Table* pdf, const TheoryTable* theory, const MaidTable* maid, const FdssTable* fdss) {
+  TrgField field_run;
+  const TrgField* field = nullptr;
+  if (cfg.using_tgt_field) {                    // simc.f:120-156: trgInit with the angles of this run's spectrometers
+    const TrgField* map = field_map();
+    if (!map->set) throw std::runtime_error("oracle: field map not set");
+    field_run = *map;
+    double ae, ap;
+    field_arm_angles(cfg.targ_Bangle, cfg.targ_Bphi, cfg.spec_e.theta, cfg.spec_e.phi, cfg.spec_p.theta, cfg.spec_p.phi, ae, ap);
+    const double pi180 = 3.141592653 / 180.;
+    field_run.B_stheta[0] = std::sin(ae * pi180); field_run.B_ctheta[0] = std::cos(ae * pi180);
+    field_run.B_stheta[1] = std::sin(ap * pi180); field_run.B_ctheta[1] = std::cos(ap * pi180);
+    field = &field_run;
+  }
   for (int64_t i = 0; i < n; ++i) {
     Rng rng;
     if (ranlux) { rng.mode = Rng::RANLUX; rng.rl = ranlux; rng.draw = 0; }   // the reference's sequential stream
     else rng.seed_philox(seed, (uint64_t)(first + i));
     Sim s;
     s.cfg = &cfg; s.optics_e = oe; s.optics_p = op; s.rng = &rng; s.sf = sf; s.pfermi = pfermi; s.pdf = pdf; s.theory = theory; s.maid = maid; s.fdss = fdss;
+    s.field = field;
     EventMain main;
     Event vertex, orig, recon;
     const TryResult r = one_try(s, main, vertex, orig, recon);

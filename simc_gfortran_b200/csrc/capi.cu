@@ -962,6 +962,17 @@ int validate_loop_config(simc_handle* h, bool need_optics = true) {
                 "this build of the event loop implements H(e,e'p), D(e,e'p), A(e,e'p) with a Benhar or an "
                 "independent-particle spectral function, H/D/A(e,e'pi+-), H/D/A(e,e'K+), H(e,e'p)pi0, H(e,e'rho0) and "
                 "semi-inclusive H/D(e,e'pi+-/K+-)X");
+  // using_tgt_field (trg_track.f): both arms tracked through the target's field, magnetic spectrometers only
+  if (c.using_tgt_field) {
+    if (!h->d_field)
+      return fail(h, SIMC_ERR_STATE, "using_tgt_field: set the field map first (simc_b200_set_field_map / load_field_file)");
+    if (c.electron_arm < 1 || c.electron_arm > 5 || c.hadron_arm < 1 || c.hadron_arm > 5)
+      return fail(h, SIMC_ERR_ARG, "Target field reconstruction not set up for your spectrometer (simc.f:1583-1586)");
+    if (c.using_HMScoll || c.using_SHMScoll)
+      return fail(h, SIMC_ERR_ARG, "using_tgt_field with collimator stepping (using_HMScoll / using_SHMScoll) is not built");
+    if (!c.using_E_arm_montecarlo || !c.using_P_arm_montecarlo)
+      return fail(h, SIMC_ERR_ARG, "using_tgt_field needs both spectrometer Monte Carlos (spect_mode = 0)");
+  }
   // calorimeter arms (calo/mc_calo.f): as the hadron arm only; with doing_pizero both decay photons are tracked
   const bool calo_p = c.hadron_arm == SIMC_ARM_CALO_RIGHT || c.hadron_arm == SIMC_ARM_CALO_LEFT;
   if (c.electron_arm == SIMC_ARM_CALO_RIGHT || c.electron_arm == SIMC_ARM_CALO_LEFT)
@@ -1138,6 +1149,24 @@ int prepare_launch(simc_handle* h, LoopLaunch& a, uint64_t seed, int record, boo
   auto coll = [&](int arm) { return arm == SIMC_ARM_HMS ? h->cfg.using_HMScoll : arm == SIMC_ARM_SHMS ? h->cfg.using_SHMScoll : 0; };
   a.coll_e = coll(h->cfg.electron_arm); a.coll_p = coll(h->cfg.hadron_arm);
   a.using_rad = h->cfg.using_rad;
+  a.field_map = nullptr; a.field_theta_e_deg = 0.0; a.field_theta_p_deg = 0.0;
+  if (h->cfg.using_tgt_field) {          // simc.f:120-156: the angle between the field axis and each arm, then trgInit
+    const simc_run_config& c = h->cfg;
+    const double degrad = 180. / 3.141592653589793;
+    double ang[2] = {0.0, 0.0};
+    for (int w = 0; w < 2; ++w) {
+      const simc_spectrometer& sp = w == 0 ? c.spec_e : c.spec_p;
+      if (degrad * std::fabs(c.targ_Bphi - sp.phi) < .01) {
+        if (c.targ_Bangle >= sp.theta) ang[w] = -1 * std::sin(sp.phi) * (c.targ_Bangle - sp.theta);
+        else ang[w] = w == 0 ? +1 * std::sin(sp.phi) * (sp.theta - c.targ_Bangle)      // as written: the two arms differ here
+                             : +1 * std::sin(sp.phi) * (c.targ_Bangle - sp.theta);    // (simc.f:125 against :139)
+      } else if (degrad * std::fabs(c.targ_Bphi - sp.phi) - 180.0 < .01) {
+        ang[w] = +1 * std::sin(sp.phi) * (c.targ_Bangle + sp.theta);
+      }     // else: the reference prints an error and goes on with the angle it had (zero)
+    }
+    a.field_map = h->d_field;
+    a.field_theta_e_deg = ang[0] * degrad; a.field_theta_p_deg = ang[1] * degrad;
+  }
   if (with_arms) {
     rc = build_schedule(h, h->cfg.hadron_arm, h->cfg.using_P_arm_montecarlo != 0, h->cfg.doing_decay != 0, a.coll_p != 0, a.sched_p);
     if (rc) return rc;
@@ -1392,6 +1421,9 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   int rc = validate_loop_config(h);
   if (rc) return rc;
   const simc_run_config& c = h->cfg;
+  if (c.using_tgt_field)
+    return fail(h, SIMC_ERR_ARG, "simc_b200_ntuple_batch: the eight polarised-target columns of the ntuple (results_write.f:154-162, "
+                                 "212-220) are not built; the loop itself (simc_b200_run, simc_b200_event_batch) runs with the field");
   *n_cols = c.doing_pizero ? 65 : c.doing_rho ? 59 : c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon || c.doing_delta) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
   *n_rows = 0;
   if (n == 0) return SIMC_OK;

@@ -70,7 +70,7 @@ SIMC_HD_CALL double sigep(double Ein, double eE, double etheta, double Q2v) {
 // and /radccom/ that later stages read.
 struct EventState {
   // main%target
-  double tx, ty, tz, rastery, Eloss[3], teff[3], Coulomb;
+  double tx, ty, tz, rastery, rasterx, Eloss[3], teff[3], Coulomb;
   // main
   double gen_weight, jacobian, Ein_shift, Ee_shift, Trec;
   // vertex
@@ -380,6 +380,7 @@ SIMC_HD bool generate_hyd_elast_first(const simc_run_config& cfg, const MatTable
     s.ty = s.ty + t6;
     s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
     s.rastery = t6;
+    s.rasterx = t5;
     trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
     if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
     s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
@@ -746,6 +747,7 @@ SIMC_HD bool generate_meson_first(const simc_run_config& cfg, const MatTable& mt
     s.ty = s.ty + t6;
     s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
     s.rastery = t6;
+    s.rasterx = t5;
     trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
     if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
     s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;
@@ -973,6 +975,7 @@ SIMC_HD bool generate_heavy_first(const simc_run_config& cfg, const MatTable& mt
     s.ty = s.ty + t6;
     s.tz = (0.5 - rng.uniform()) * targ.length + targ.zoffset;
     s.rastery = t6;
+    s.rasterx = t5;
     trip_thru_target_sampled(cfg, mt, rng, gauss, 1, s.tz - targ.zoffset, cfg.Ebeam, 0.0, SIMC_ME, s.Eloss[0], s.teff[0]);
     if (!cfg.using_Eloss) s.Eloss[0] = 0.0;
     s.Coulomb = cfg.using_Coulomb ? targ.Coulomb_constant : 0.0;

@@ -157,6 +157,10 @@ static cudaError_t ensure_smem_opt_in_locked() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   done[dev] = true;
   return cudaSuccess;
@@ -464,6 +468,13 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
   A.saghai = SaghaiDev{a.saghai_buf, a.saghai_n[0], a.saghai_n[1], a.saghai_n[2]};
   A.fdss.buf = a.fdss_buf;
   A.theory.buf = a.theory_buf; A.theory.nrho = a.theory_nrho; A.theory.e_fermi = a.theory_efermi;
+  A.field.map = a.field_map;
+  {
+    const double pi180 = 3.141592653 / 180.;          // trgInit's constant (trg_track.f:275)
+    A.field.stht[0] = std::sin(a.field_theta_e_deg * pi180); A.field.ctht[0] = std::cos(a.field_theta_e_deg * pi180);
+    A.field.stht[1] = std::sin(a.field_theta_p_deg * pi180); A.field.ctht[1] = std::cos(a.field_theta_p_deg * pi180);
+  }
+  const bool field = a.field_map != nullptr;
   A.pfm.pval = a.pfm_buf; A.pfm.mprob = a.pfm_buf ? a.pfm_buf + a.pfm_n : nullptr; A.pfm.nump = a.pfm_n;
   const long long need = (a.n_tries + kBlock - 1) / kBlock;
   const unsigned grid = (unsigned)(need < a.grid_blocks ? need : a.grid_blocks);
@@ -495,8 +506,15 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       if (st.kind == ARM_STAGE_CALO) {
         k_calo<<<grid, kBlock, 0, s>>>(A);
       } else if (st.kind == ARM_STAGE_ENTRY) {
-        if (hadron) { if (coll) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
-        else { if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
+        if (hadron) {
+          if (field) k_arm<1, 4><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else if (coll) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        } else {
+          if (field) k_arm<0, 4><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        }
       } else if (st.kind == ARM_STAGE_COMPILED) {
         // generated straight-line kernel (mapgen.h); ABI in mapgen.h
         long long fs = state_field_stride(a.cap), ss = state_slot_stride();
@@ -516,8 +534,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         if (hadron) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         else k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
       } else {
-        if (hadron) k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
-        else k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        if (hadron) { if (field) k_arm<1, 5><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<1, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
+        else { if (field) k_arm<0, 5><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); else k_arm<0, 1><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm); }
       }
       in = out; out = out + 1;
     }

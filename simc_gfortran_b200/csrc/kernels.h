@@ -64,6 +64,10 @@ struct LoopLaunch {
   int grid_blocks;            // persistent grid for the stage kernels
   int coll_e, coll_p;         // the arm steps pions through its collimator (using_HMScoll / using_SHMScoll)
   int using_rad;              // radiative corrections on: second generation pass (k_regen) and k_radw are launched
+  // using_tgt_field: the map (device, field.cuh: FieldDev) and trgInit's angles (degrees) between the field axis and
+  // the electron / hadron spectrometer (simc.f:120-156); field_map null = no field tracking
+  const double* field_map;
+  double field_theta_e_deg, field_theta_p_deg;
   ArmSchedule sched_e, sched_p;
   double mats[45];            // MatTable (target.cuh): 5 materials x 9 energy-loss constants, made on the host
   const double* sf_pm;        // Benhar spectral function (device): Pm axis, Em axis, values [n_pm][n_em]

@@ -45,7 +45,7 @@ enum StateField : int {
   F_UQX, F_UQY, F_UQZ, F_MEPS,
   F_MTHPQ, F_MPHIPQ, F_MT, F_MW,
   F_ZHAD, F_PT2, F_PFER, F_EFER,
-  F_PFERX, F_PFERY, F_PFERZ, F_GEN_PAD,
+  F_PFERX, F_PFERY, F_PFERZ, F_RASTERX,         // F_RASTERX: main%target%rasterx, read by the target-field tracking only
   F_OPYP, F_OPXP, F_RHOMASS, F_RHOTHETA,        // rho production only: orig%p%yptar/xptar of the decay pion, ntup%rhomass/rhotheta
   F_GEN_END,
   // ---- written by the later stages
@@ -138,6 +138,7 @@ struct LoopArgs {
   MaidDev maid;                    // MAID-2007 slice of peepi's low-W branch (null unless set)
   SaghaiDev saghai;                // Saghai amplitude tables of peeK's ntuple column sigcm1 (null unless set)
   TheoryDev theory;                // independent-particle spectral function (D(e,e'p), A(e,e'p) without use_benhar_sf)
+  FieldDev field;                  // field of the polarised target (using_tgt_field only; map null otherwise)
   StateBuf st;
   unsigned* lists;                 // [kLoopLists][cap] (kernels.h)
   unsigned* counts;                // [0] slots handed out, [1 + l] length of list l
@@ -219,7 +220,7 @@ struct GaussFn {
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
 constexpr int kRegenList = kRegenListIdx;
 
-struct GenFlags { bool semi, fermi, meson, heavy, rho, xtra; };
+struct GenFlags { bool semi, fermi, meson, heavy, rho, xtra, field; };
 __device__ __forceinline__ GenFlags gen_flags(const simc_run_config& cfg) {
   GenFlags g;
   g.semi = cfg.doing_semi != 0;
@@ -227,6 +228,7 @@ __device__ __forceinline__ GenFlags gen_flags(const simc_run_config& cfg) {
   g.rho = cfg.doing_rho != 0;                   // the rho is thrown in the photon-nucleon c.m. inside complete_ev
   g.meson = cfg.doing_pion || cfg.doing_kaon || cfg.doing_delta || g.semi || cfg.doing_deuterium || g.rho;   // hadron energy from two-body kinematics (or thrown: semi)
   g.heavy = cfg.doing_heavy != 0;
+  g.field = cfg.using_tgt_field != 0;           // the raster's x position travels with the record (track_to_tgt)
   g.xtra = g.rho || cfg.doing_pizero;           // the record's last group is in use (rho: mass, decay angle; pi0: decay angles)
   return g;
 }
@@ -270,11 +272,11 @@ __device__ __forceinline__ void store_event(const LoopArgs& A, const GenFlags& g
   const bool fm = g.meson && (g.semi || g.fermi);
   r[F_ZHAD] = (g.meson && g.semi) ? s.v_zhad : 0.0; r[F_PT2] = (g.meson && g.semi) ? s.v_pt2 : 0.0;
   r[F_PFER] = fm ? s.pfer : 0.0; r[F_EFER] = fm ? s.efer : 0.0;
-  r[F_PFERX] = fm ? s.pferx : 0.0; r[F_PFERY] = fm ? s.pfery : 0.0; r[F_PFERZ] = fm ? s.pferz : 0.0; r[F_GEN_PAD] = 0.0;
+  r[F_PFERX] = fm ? s.pferx : 0.0; r[F_PFERY] = fm ? s.pfery : 0.0; r[F_PFERZ] = fm ? s.pferz : 0.0; r[F_RASTERX] = s.rasterx;
   r[F_OPYP] = g.rho ? s.o_pyptar : 0.0; r[F_OPXP] = g.rho ? s.o_pxptar : 0.0;
   r[F_RHOMASS] = g.xtra ? s.rho_mass : 0.0; r[F_RHOTHETA] = g.xtra ? s.rho_theta : 0.0;
   // the groups past F_VPPHI only matter to the reactions that fill them
-  const int n_groups = g.xtra ? F_GEN_END / 4 : hm ? F_OPYP / 4 : (F_VQ + 1) / 4;
+  const int n_groups = g.xtra ? F_GEN_END / 4 : (hm || g.field) ? F_OPYP / 4 : (F_VQ + 1) / 4;
 #if SIMC_STATE_AOS
   double* rec = S.base + (long long)slot * kStateStride;
 #pragma unroll
@@ -297,7 +299,7 @@ __device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g,
   const StateBuf& S = A.st;
   double r[F_GEN_END];
   const bool hm = g.heavy || g.meson;
-  const int n_groups = g.xtra ? F_GEN_END / 4 : hm ? F_OPYP / 4 : (F_VQ + 1) / 4;
+  const int n_groups = g.xtra ? F_GEN_END / 4 : (hm || g.field) ? F_OPYP / 4 : (F_VQ + 1) / 4;
 #if SIMC_STATE_AOS
   const double* rec = S.base + (long long)slot * kStateStride;
 #pragma unroll
@@ -337,6 +339,7 @@ __device__ __forceinline__ void load_event(const LoopArgs& A, const GenFlags& g,
   s.v_zhad = r[F_ZHAD]; s.v_pt2 = r[F_PT2];
   s.pfer = r[F_PFER]; s.pferx = r[F_PFERX]; s.pfery = r[F_PFERY]; s.pferz = r[F_PFERZ];
   s.efer = (g.meson && (g.semi || g.fermi)) ? r[F_EFER] : A.cfg->targ.Mtar_struck;
+  s.rasterx = r[F_RASTERX];
   s.o_pyptar = r[F_OPYP]; s.o_pxptar = r[F_OPXP]; s.rho_mass = r[F_RHOMASS]; s.rho_theta = r[F_RHOTHETA];
 }
 
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
     s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
     s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
-    s.o_pyptar = 0; s.o_pxptar = 0; s.rho_mass = 0; s.rho_theta = 0;
+    s.o_pyptar = 0; s.o_pxptar = 0; s.rho_mass = 0; s.rho_theta = 0; s.rasterx = 0;
     // (tables by value: a reference into the kernel parameters handed to an out-of-line function would make the
     //  compiler copy all of LoopArgs to every thread's stack -- +600 bytes of frame, +10 % kernel time)
     if (g.meson) ok = generate_meson_first(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active, gr);
@@ -484,10 +487,84 @@ __global__ void __launch_bounds__(kBlock, 4) k_radw(LoopArgs A, int list_idx) {
 // program (always the whole hut), reconstruction, and the arm's recon quantities.  Compiled stretches (mapgen.h)
 // run between them on the same track fields (F_TK_*).
 // SEG_ = 3: SEG 0 built with the collimator stepping (using_HMScoll / using_SHMScoll).
+// track_to_tgt (trg_track.f:738-877; field.cuh has the single-track form) for the lanes of a warp at once: the arm's
+// reconstruction map is evaluated by the whole warp (eval_poly), so every lane walks the iteration as long as one
+// lane needs it.  ALL 32 LANES MUST CALL; `on`: the lane has a reconstructed track.  `orec` is the arm's OP_RECON op.
+__device__ __forceinline__ bool track_to_tgt_warp(const FieldDev& F, int k, const ArmDev* arm, const ArmOp* orec, const ArmResult& res,
+                                                  double* pw, unsigned ring, bool on, double& delta, double& y, double& dx, double& dy,
+                                                  double frx, double fry, double mom, double mass, double ctheta, double stheta) {
+  using namespace fielddetail;
+  const double cc = 29.9792458;
+  bool ok = on;
+  double xx = -fry;
+  double vel = fabs(mom) / sqrt(mom * mom + mass * mass) * cc;
+  double eng = sign1(mom) * sqrt(mom * mom + mass * mass);
+  const double mom_0 = mom / (1.e0 + delta / 100.e0);
+  FieldState vT, vTx;
+  vT.x = vT.y = vT.z = vT.vx = vT.vy = 0.0; vT.vz = 1.0;
+  auto start = [&](double x0) {
+    vT.x = x0 + 100. * dx;
+    vT.y = y + 100. * dy;
+    vT.z = 100.;
+    vT.vz = vel / sqrt(1 + dy * dy + dx * dx);
+    vT.vx = dx * vT.vz;
+    vT.vy = dy * vT.vz;
+  };
+  if (on) {
+    start(-fry);
+    ok = track_to_plane(F, k, vT, eng, 1., 0., -ctheta, stheta, frx, ok);
+  }
+  int n = 0;
+  double delx = 1.;
+  // the focal-plane track the reconstruction sees (mc_hms.f:421-424); the HRS shift of y_fp is applied afterwards
+  const double yfp = res.y_fp + orec->a;
+  for (;;) {
+    const bool go = on && (delx > .0001) && (n < 10) && ok;
+    if (!__any_sync(0xffffffffu, go)) break;
+    if (go) {
+      delx = fabs(-fry - vT.x);
+      vTx = vT;
+      vTx.x = -fry;
+      ok = track_to_plane(F, k, vT, eng, 1., 0., 0., 1., 0., ok);
+      ok = track_to_plane(F, k, vTx, eng, 1., 0., 0., 1., 0., ok);
+      xx = xx + fmin(1., fmax(-1., (vTx.x - vT.x)));
+    }
+    double hut[5];
+    hut[0] = res.x_fp / 100.; hut[1] = res.dx_fp; hut[2] = yfp / 100.; hut[3] = res.dy_fp; hut[4] = xx / 100.;
+    if (fabs(hut[4]) <= 1.e-30) hut[4] = 1.e-30;
+    if (orec->i0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (fabs(hut[i]) <= 1.e-30) hut[i] = 1.e-30;
+    }
+    double sum[4];
+    eval_poly<4>(arm->tab.rec, arm->tab.recs, hut, pw, ring, sum);
+    if (go) {
+      dx = sum[0]; y = sum[1] * 100.; dy = sum[2]; delta = sum[3] * 100.;
+      mom = mom_0 * (1.e0 + delta / 100.e0);
+      vel = fabs(mom) / sqrt(mom * mom + mass * mass) * cc;
+      eng = sign1(mom) * sqrt(mom * mom + mass * mass);
+      start(xx);
+      ok = track_to_plane(F, k, vT, eng, 1., 0., -ctheta, stheta, frx, ok);
+      n = n + 1;
+    }
+  }
+  if (on) {
+    if (delx > .2) ok = false;
+    dy = vT.vy / vT.vz;
+    dx = vT.vx / vT.vz;
+    y = vT.y;
+  }
+  return ok;
+}
+
+// SEG_ = 4, 5: SEG 0 / SEG 1 built with the tracking through the polarised target's field (using_tgt_field):
+// track_from_tgt in front of the arm (simc.f:1425-1432, 1693-1700), track_to_tgt behind its reconstruction (:1573-1587).
 template <int WHICH, int SEG_>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
-  constexpr int SEG = SEG_ == 3 ? 0 : SEG_;
+  constexpr int SEG = (SEG_ == 3 || SEG_ == 4) ? 0 : SEG_ == 5 ? 1 : SEG_;
   constexpr bool kColl = SEG_ == 3;
+  constexpr bool kField = SEG_ == 4 || SEG_ == 5;
   extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
@@ -578,6 +655,17 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
           }
         }
         arm_entry(sp, tx, ty, tz, sp_delta, o_yptar + ang0 + dang0, o_xptar + ang1 + dang1 * sp.cos_th, en);
+        if (kField) {
+          // the position before the drift to z = 0 (simc.f:1405-1421), through the field to the field-free image track
+          // (track_from_tgt), then the drift back (:1437-1442); its `ok` is overwritten by the arm's own (:1463)
+          double x = -ty, y = -tx * sp.cos_th - tz * sp.sin_th * m::sin(sp.phi), z = tz * sp.cos_th + tx * sp.sin_th * m::sin(sp.phi);
+          x = x - sp.off_x; y = y - sp.off_y; z = z - sp.off_z;
+          double dx = en.dx, dy = en.dy;
+          const double mom = (WHICH == 1 ? cfg.sign_hadron : -1.0) * sp.P * (1 + sp_delta / 100.);
+          track_from_tgt(A.field, WHICH == 1 ? 1 : 0, x, y, z, dx, dy, mom, WHICH == 1 ? detected_Mh(cfg) : SIMC_ME);
+          x = x - z * dx; y = y - z * dy;
+          en.x = x; en.y = y; en.dx = dx; en.dy = dy; en.sp_z = y;
+        }
         S.st4(WHICH == 1 ? F_SPP_D : F_SPE_D, slot, en.sp_delta, en.sp_yptar, en.sp_xptar, en.sp_z);
         const double fry_raster = cfg.correct_raster ? -rastery : 0.0;
         fry = (arm_id == 1 || arm_id == 5) ? en.x : fry_raster;    // xtar_init, simc.f:1441,1463
@@ -650,10 +738,24 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
+        if (kField) {          // simc.f:1573-1587 / :1777-1790
+          const ArmOp* orec = arm->ops;
+          while (orec->op != OP_RECON && orec->op != OP_END) ++orec;
+          double frx = 0.0, fry_r = 0.0;
+          if (ok && cfg.correct_raster) { fry_r = -S.ld(F_RASTERY, slot); frx = -S.ld(F_RASTERX, slot); }
+          const double pmag = sp.P * (1. + rc_delta / 100.0);
+          const double mom = (WHICH == 1 ? cfg.sign_hadron : -1.0) * pmag;
+          const double mass = WHICH == 1 ? sqrt(t.m2) : sqrt(SIMC_ME * SIMC_ME);
+          const bool right = arm_id == 1 || arm_id == 3;          // HMS, HRS-R; the left arms take -stheta
+          const double ctheta = m::cos(sp.theta), stheta = right ? m::sin(sp.theta) : -m::sin(sp.theta);
+          ok = track_to_tgt_warp(A.field, WHICH == 1 ? 1 : 0, arm, orec, res, pw_s + threadIdx.x, ring, ok, rc_delta, rc_z, rc_xptar,
+                                 rc_yptar, frx, -fry_r, mom, mass, ctheta, stheta);
+        }
         path = t.pathlen; resmult = res.resmult;
         if (active) {
           if (res.reached_hut) warp_count(&s_stop[2]);
-          warp_hist_add(s_stop, ok ? 1 : (2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1));
+          // (a try the arm accepted counts as one of its successes even when track_to_tgt then fails: simc.f:1573-1592)
+          warp_hist_add(s_stop, res.ok ? 1 : (2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1));
         }
       } else {
         ok = active;

@@ -254,7 +254,8 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
   c.dE_edge_test = D.d("dE_edge_test");
   c.use_offshell_rad = D.i("use_offshell_rad") > 0;
   c.Egamma_gen_max = D.d("Egamma_gen_max");
-  if (D.i("using_tgt_field") > 0) throw std::runtime_error("using_tgt_field=1 (polarised-target field tracking) is out of scope");
+  c.using_tgt_field = D.i("using_tgt_field") > 0; c.targ_pol = D.d("targ_pol");
+  c.targ_Bangle = D.d("targ_Bangle") / degrad; c.targ_Bphi = D.d("targ_Bphi") / degrad;        // dbase.f:454-455
   auto spedge = [&](simc_arm_cuts& a, const char* arm) {
     auto key = [&](const char* q, const char* mm) { return std::string("SPedge%") + arm + "%" + q + "%" + mm; };
     a.delta.min = D.d(key("delta", "min").c_str()); a.delta.max = D.d(key("delta", "max").c_str());
@@ -329,6 +330,10 @@ void config_from_deck(const std::string& path, const std::string& extra_dir, con
     const double Mrec_guess = targ.M - Mp;
     if (std::fabs(targ.Mrec - Mrec_guess) > 100.) targ.Mrec = Mrec_guess;
   }
+  // sign_hadron, dbase.f:296-423: the charge of the detected hadron (target-field tracking only)
+  c.sign_hadron = 1.0;
+  if (c.doing_semi || c.doing_rho) c.sign_hadron = c.doing_hplus ? 1.0 : -1.0;
+  else if (c.doing_pion) c.sign_hadron = (c.which_pion == 1 || c.which_pion == 3 || c.which_pion == 11) ? -1.0 : 1.0;
   if (c.doing_eep) { targ.Mtar_struck = Mp; targ.Mrec_struck = 0.0; }
   else if (c.doing_delta) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mpi; }
   else if (c.doing_semi || c.doing_rho) { targ.Mtar_struck = Mp; targ.Mrec_struck = Mp; }

@@ -102,6 +102,7 @@ _INT_FLAGS = (
 _DBL_SCALARS = (
     "Mh", "Mh2", "Ebeam", "dEbeam", "Ebeam_vertex_ave",
     "dE_edge_test", "Egamma_gen_max", "ctau", "transparency", "drift_to_cal",
+    "targ_Bangle", "targ_Bphi", "targ_pol", "sign_hadron",
     "etatzai", "Egamma_tot_max", "Egamma1_max", "Egamma2_max", "Egamma3_max", "Egamma_res_limit",
 )
 
@@ -109,7 +110,8 @@ _DBL_SCALARS = (
 class RunConfig(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in _INT_FLAGS] +
                 [("doing_tail", C.c_int32 * 3), ("hardwired_rad", C.c_int32), ("deForest_flag", C.c_int32),
-                 ("doing_pizero", C.c_int32), ("pizero_ngamma", C.c_int32)] +
+                 ("doing_pizero", C.c_int32), ("pizero_ngamma", C.c_int32),
+                 ("using_tgt_field", C.c_int32), ("pad_flags", C.c_int32)] +
                 [(n, C.c_double) for n in _DBL_SCALARS] +
                 [("gen", GenLimits), ("spec_e", Spectrometer), ("spec_p", Spectrometer),
                  ("cuts_Em", Cut), ("cuts_Pm", Cut), ("edge", Edge), ("VERTEXedge", Edge),

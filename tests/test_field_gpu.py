@@ -83,3 +83,90 @@ def test_needs_a_map():
         assert "field map" in str(e.value)
     finally:
         s.close()
+
+
+# ---- the whole loop with using_tgt_field: both arms tracked through the target's field -------------------------------
+POLDECK = os.path.join(ROOT, "decks", "w1_poltar_eepi_hydrogen_hms_shms.inp")
+
+
+@pytest.fixture(scope="module")
+def polcase(oracle_with_optics):
+    from simc_gfortran_b200 import load_optics_fixture
+    cfg = config_from_deck(POLDECK)[0]
+    bz, br = load_field_fixture()
+    oracle_with_optics.set_field_map(bz, br, 0.0, 0.0)        # the run takes its angles from the deck (simc.f:120-156)
+    s = Simc(cfg, mode="strict")
+    for arm in (1, 5):
+        s.set_optics(load_optics_fixture(arm))
+    s.set_field_map(bz, br)
+    yield cfg, s, oracle_with_optics
+    s.close()
+
+
+def test_loop_with_field_records(polcase):
+    from tests.test_loop_gpu import LOOSE, RECON_LOOSE, SCALE, rel_err
+    cfg, sim, orc = polcase
+    assert cfg.using_tgt_field == 1 and abs(cfg.targ_Bangle - np.radians(80.0)) < 1e-15 and cfg.sign_hadron == 1.0
+    n = 40000
+    ref, ref_stage = orc.event_batch(cfg, 0, n, 7)
+    rec, stage = sim.event_batch(0, n, 7)
+    assert np.array_equal(stage, ref_stage), f"{(stage != ref_stage).sum()} tries end at a different stage"
+    for k in (0, 2, 3, 4):
+        assert np.array_equal(rec[k], ref[k]), sim.event_field_names()[k]
+    names = sim.event_field_names()
+    done = stage == 4
+    assert done.sum() > 100
+    sc = SCALE.copy()
+    for k in (5, 6):
+        sc[k] = 1e-9
+    # SP quantities: the generated ones (the field does not touch them); recon: iterated against the field
+    for fields, mask, tol in (((32, 33, 34), stage >= 2, LOOSE), ((35, 36, 37), stage >= 1, LOOSE),
+                              ((41, 42, 43), stage >= 2, RECON_LOOSE), ((38, 39, 40, 1, 5, 6, 44, 45, 46), done, RECON_LOOSE)):
+        for k in fields:
+            e = rel_err(rec[k][mask], ref[k][mask], sc[k])
+            assert e.max() <= tol, (names[k], float(e.max()))
+    # the field matters: the same tries without it end differently and reconstruct differently
+    off = type(cfg).from_buffer_copy(bytes(cfg))
+    off.using_tgt_field = 0
+    from simc_gfortran_b200 import load_optics_fixture
+    s0 = Simc(off, mode="strict")
+    try:
+        for arm in (1, 5):
+            s0.set_optics(load_optics_fixture(arm))
+        rec0, stage0 = s0.event_batch(0, n, 7)
+    finally:
+        s0.close()
+    assert (stage0 != stage).mean() > 0.01
+    # reconstruction against the field recovers the vertex angles: resolution of the electron's yptar stays at the
+    # mrad level (without track_to_tgt it would be off by the field's bend, tens of mrad)
+    assert np.std(rec[39][done] - rec[33][done]) < 3e-3
+
+
+def test_loop_with_field_accumulators(polcase):
+    from tests.test_loop_gpu import RECON_LOOSE, accum_equal_exact
+    cfg, sim, orc = polcase
+    n = 40000
+    ref = orc.run(cfg, 0, n, 4, threads=8)
+    acc = sim.accum_clear()
+    sim.run(0, n, 4, acc)
+    accum_equal_exact(acc, ref)
+    assert acc.nsuccess > 100
+    a, b = acc.wtcontribute.value(), ref.wtcontribute.value()
+    assert abs(a - b) <= RECON_LOOSE * abs(b)
+
+
+def test_field_refusals(polcase):
+    cfg, sim, orc = polcase
+    with pytest.raises(SimcError) as e:
+        sim.ntuple_batch(0, 100, 1)
+    assert "polarised-target columns" in str(e.value)
+    s = Simc(cfg, mode="strict")              # no map set
+    try:
+        from simc_gfortran_b200 import load_optics_fixture
+        for arm in (1, 5):
+            s.set_optics(load_optics_fixture(arm))
+        with pytest.raises(SimcError) as e:
+            s.run(0, 100, 1, s.accum_clear())
+        assert "field map" in str(e.value)
+    finally:
+        s.close()
