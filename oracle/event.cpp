@@ -175,6 +175,49 @@ bool rho_decay(Sim& s, Event& orig, double p_spec, double epsilon) {
   return true;
 }
 
+// The polarised-target block both complete_ev (event.f:796-895) and complete_recon_ev (:1187-1263) carry: angle of the
+// target polarisation about q relative to the scattering plane (phi_targ) and to the reaction plane (beta), the
+// "Sivers" and "Collins" combinations with phi_pq, and the polar angle between q and the polarisation.
+static void poltarg_block(const simc_run_config& cfg, const Vec3& uq, const Vec3& up, double phi_pq, double& phi_targ,
+                          double& beta, double& phi_s, double& phi_c, double& theta_tarq) {
+  double qx = -uq.y, qy = uq.x, qz = uq.z;
+  double targx = -cfg.targ_pol * sin(fabs(cfg.targ_Bangle));
+  double targy = 0.0;
+  double targz = cfg.targ_pol * cos(fabs(cfg.targ_Bangle));
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  double new_x_x = -qx * qz / dummy;
+  double new_x_y = -qy * qz / dummy;
+  double new_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  double new_y_x = qy / dummy;
+  double new_y_y = -qx / dummy;
+  double new_y_z = 0.0;
+  const double p_new_x = targx * new_x_x + targy * new_x_y + targz * new_x_z;
+  const double p_new_y = targx * new_y_x + targy * new_y_y + targz * new_y_z;
+  phi_targ = atan2(p_new_y, p_new_x);
+  if (phi_targ < 0.) phi_targ = 2. * K::pi + phi_targ;
+  const double px = -up.y, py = up.x, pz = up.z;
+  dummy = sqrt(powi(qy * pz - qz * py, 2) + powi(qz * px - qx * pz, 2) + powi(qx * py - qy * px, 2));
+  new_y_x = (qy * pz - qz * py) / dummy;
+  new_y_y = (qz * px - qx * pz) / dummy;
+  new_y_z = (qx * py - qy * px) / dummy;
+  dummy = sqrt(powi(new_y_y * qz - new_y_z * qy, 2) + powi(new_y_z * qx - new_y_x * qz, 2) + powi(new_y_x * qy - new_y_y * qx, 2));
+  new_x_x = (new_y_y * qz - new_y_z * qy) / dummy;
+  new_x_y = (new_y_z * qx - new_y_x * qz) / dummy;
+  new_x_z = (new_y_x * qy - new_y_y * qx) / dummy;
+  const double targ_new_x = targx * new_x_x + targy * new_x_y + targz * new_x_z;
+  const double targ_new_y = targx * new_y_x + targy * new_y_y + targz * new_y_z;
+  beta = atan2(targ_new_y, targ_new_x);
+  if (beta < 0.) beta = 2 * K::pi + beta;
+  phi_s = phi_pq - phi_targ;
+  if (phi_s < 0.) phi_s = 2 * K::pi + phi_s;
+  phi_c = phi_pq + phi_targ;
+  if (phi_c > 2. * K::pi) phi_c = phi_c - 2 * K::pi;
+  if (phi_c < 0.0) phi_c = 2 * K::pi + phi_c;
+  dummy = sqrt((qx * qx + qy * qy + qz * qz)) * sqrt((targx * targx + targy * targy + targz * targz));
+  theta_tarq = acos((qx * targx + qy * targy + qz * targz) / dummy);
+}
+
 // pizero_decay.f:1-97: pi0 -> gamma gamma, flat in cos(theta) and phi in the pi0 rest frame, boosted to the lab.  Two
 // random numbers.  (The routine's own energy / momentum sums only print a warning.)
 void pizero_decay(Sim& s, const Event& vertex) {
@@ -323,6 +366,8 @@ bool complete_ev(Sim& s, EventMain& main, Event& vertex) {
     const double p_new_y = px * new_y_x + py * new_y_y + pz * new_y_z;
     main.phi_pq = atan2(p_new_y, p_new_x);
     if (main.phi_pq < 0.e0) main.phi_pq = main.phi_pq + 2. * K::pi;
+    if (cfg.using_tgt_field)                              // :796-895
+      poltarg_block(cfg, vertex.uq, vertex.up, main.phi_pq, main.phi_targ, main.beta, vertex.phi_s, vertex.phi_c, main.theta_tarq);
     if (cfg.doing_pizero) pizero_decay(s, vertex);        // :899-901
   }
 
@@ -794,6 +839,8 @@ bool complete_recon_ev(Sim& s, Event& recon) {
   if ((p_new_x * p_new_x + p_new_y * p_new_y) == 0.) recon.phi_pq = 0.0;
   else recon.phi_pq = acos(p_new_x / sqrt(p_new_x * p_new_x + p_new_y * p_new_y));
   if (p_new_y < 0.) recon.phi_pq = 2 * K::pi - recon.phi_pq;
+  if (cfg.using_tgt_field)                                // :1187-1263
+    poltarg_block(cfg, recon.uq, recon.up, recon.phi_pq, recon.phi_targ, recon.beta, recon.phi_s, recon.phi_c, recon.theta_tarq);
   recon.Pmx = recon.p.P * recon.up.x - recon.q * recon.uq.x;
   recon.Pmy = recon.p.P * recon.up.y - recon.q * recon.uq.y;
   recon.Pmz = recon.p.P * recon.up.z - recon.q * recon.uq.z;

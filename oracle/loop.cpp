@@ -224,7 +224,12 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[48] = std::sqrt(s.trk.Mh2_final); ntu[49] = pfer / 1000. * dummy; ntu[50] = vertex.Q2 / 1.e6;
     ntu[51] = main.W / 1.e3; ntu[52] = main.t / 1.e6; ntu[53] = main.phi_pq;
     ncol = 53;
-    if (cfg.doing_kaon) { ntu[54] = s.ntup.sigcm1; ntu[55] = s.ntup.sigcm2; ncol = 55; }
+    if (cfg.using_tgt_field) {                                 // results_write.f:154-166
+      ntu[54] = recon.theta_tarq; ntu[55] = recon.phi_targ; ntu[56] = recon.beta; ntu[57] = recon.phi_s; ntu[58] = recon.phi_c;
+      ntu[59] = main.beta; ntu[60] = vertex.phi_s; ntu[61] = vertex.phi_c;
+      ncol = 61;
+      if (cfg.doing_kaon) { ntu[62] = s.ntup.sigcm1; ntu[63] = s.ntup.sigcm2; ncol = 63; }
+    } else if (cfg.doing_kaon) { ntu[54] = s.ntup.sigcm1; ntu[55] = s.ntup.sigcm2; ncol = 55; }
     if (cfg.doing_pizero) {                                    // results_write.f:167-180 (no target field)
       ntu[54] = s.ntup.xcal_gamma1; ntu[55] = s.ntup.ycal_gamma1;
       for (int k = 0; k < 4; ++k) ntu[56 + k] = s.ntup.gamma1[k];
@@ -243,7 +248,12 @@ int fill_ntuple(const Sim& s, const EventMain& main, const Event& vertex, const 
     ntu[54] = s.pfer / 1000. * std::fabs(dummy) / dummy;      // NaN for hydrogen (0/0), as in the reference
     ntu[55] = s.ntup.xfermi; ntu[56] = main.phi_pq;
     ncol = 56;
-    if (cfg.doing_rho) {                                       // results_write.f:226-230 (no target field)
+    if (cfg.using_tgt_field) {                                 // results_write.f:212-225
+      ntu[57] = recon.theta_tarq; ntu[58] = recon.phi_targ; ntu[59] = recon.beta; ntu[60] = recon.phi_s; ntu[61] = recon.phi_c;
+      ntu[62] = main.beta; ntu[63] = vertex.phi_s; ntu[64] = vertex.phi_c;
+      ncol = 64;
+      if (cfg.doing_rho) { ntu[65] = s.ntup.rhomass; ntu[66] = s.ntup.rhotheta; ncol = 67; }      // 67 tags, the last never filled
+    } else if (cfg.doing_rho) {                                // results_write.f:226-230
       ntu[57] = s.ntup.rhomass; ntu[58] = s.ntup.rhotheta; ntu[59] = s.ntup.mmA / 1000.;
       ncol = 59;
     }

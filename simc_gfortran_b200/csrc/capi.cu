@@ -1421,10 +1421,10 @@ int simc_b200_ntuple_batch(simc_handle* h, int64_t first_try, int64_t n, uint64_
   int rc = validate_loop_config(h);
   if (rc) return rc;
   const simc_run_config& c = h->cfg;
-  if (c.using_tgt_field)
-    return fail(h, SIMC_ERR_ARG, "simc_b200_ntuple_batch: the eight polarised-target columns of the ntuple (results_write.f:154-162, "
-                                 "212-220) are not built; the loop itself (simc_b200_run, simc_b200_event_batch) runs with the field");
   *n_cols = c.doing_pizero ? 65 : c.doing_rho ? 59 : c.doing_semi ? 56 : (c.doing_pion || c.doing_kaon || c.doing_delta) ? (c.doing_kaon ? 55 : 53) : 46;      // NtupleInit.f:33-343
+  // eight more columns for a polarised target in the meson layouts (NtupleInit.f:142-160, 239-256); rho's third tag
+  // (mmnuc) stays behind them
+  if (c.using_tgt_field && *n_cols != 46) *n_cols += 8;
   *n_rows = 0;
   if (n == 0) return SIMC_OK;
   CU(h, cudaSetDevice(h->device));

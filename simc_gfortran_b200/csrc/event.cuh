@@ -66,6 +66,48 @@ SIMC_HD_CALL double sigep(double Ein, double eE, double etheta, double Q2v) {
   return sigMott * eE / Ein * Wp;
 }
 
+// Azimuthal angles of a polarised target (using_tgt_field): event.f:796-895 for the vertex, :1187-1263 for the
+// reconstructed event -- the same construction from the unit vectors of q and of the hadron and phi_pq.  The target
+// polarisation lies in the horizontal plane at |targ_Bangle| to the beam ("replay" coordinates: x right, y down).
+struct PolTargAngles { double phi_targ, beta, phi_s, phi_c, theta_tarq; };
+SIMC_HD_CALL PolTargAngles poltarg_angles(double targ_pol, double targ_Bangle, double uqx, double uqy, double uqz, double upx,
+                                          double upy, double upz, double phi_pq) {
+  PolTargAngles A;
+  const double qx = -uqy, qy = uqx, qz = uqz;
+  const double targx = -targ_pol * m::sin(fabs(targ_Bangle)), targy = 0.0, targz = targ_pol * m::cos(fabs(targ_Bangle));
+  double dummy = sqrt((qx * qx + qy * qy) * (qx * qx + qy * qy + qz * qz));
+  double new_x_x = -qx * qz / dummy, new_x_y = -qy * qz / dummy, new_x_z = (qx * qx + qy * qy) / dummy;
+  dummy = sqrt(qx * qx + qy * qy);
+  double new_y_x = qy / dummy, new_y_y = -qx / dummy, new_y_z = 0.0;
+  const double p_new_x = targx * new_x_x + targy * new_x_y + targz * new_x_z;
+  const double p_new_y = targx * new_y_x + targy * new_y_y + targz * new_y_z;
+  A.phi_targ = m::atan2(p_new_y, p_new_x);
+  if (A.phi_targ < 0.) A.phi_targ = 2. * SIMC_PI_D + A.phi_targ;
+  const double px = -upy, py = upx, pz = upz;
+  dummy = sqrt((qy * pz - qz * py) * (qy * pz - qz * py) + (qz * px - qx * pz) * (qz * px - qx * pz) +
+               (qx * py - qy * px) * (qx * py - qy * px));
+  new_y_x = (qy * pz - qz * py) / dummy;
+  new_y_y = (qz * px - qx * pz) / dummy;
+  new_y_z = (qx * py - qy * px) / dummy;
+  dummy = sqrt((new_y_y * qz - new_y_z * qy) * (new_y_y * qz - new_y_z * qy) + (new_y_z * qx - new_y_x * qz) * (new_y_z * qx - new_y_x * qz) +
+               (new_y_x * qy - new_y_y * qx) * (new_y_x * qy - new_y_y * qx));
+  new_x_x = (new_y_y * qz - new_y_z * qy) / dummy;
+  new_x_y = (new_y_z * qx - new_y_x * qz) / dummy;
+  new_x_z = (new_y_x * qy - new_y_y * qx) / dummy;
+  const double targ_new_x = targx * new_x_x + targy * new_x_y + targz * new_x_z;
+  const double targ_new_y = targx * new_y_x + targy * new_y_y + targz * new_y_z;
+  A.beta = m::atan2(targ_new_y, targ_new_x);
+  if (A.beta < 0.) A.beta = 2 * SIMC_PI_D + A.beta;
+  A.phi_s = phi_pq - A.phi_targ;
+  if (A.phi_s < 0.) A.phi_s = 2 * SIMC_PI_D + A.phi_s;
+  A.phi_c = phi_pq + A.phi_targ;
+  if (A.phi_c > 2. * SIMC_PI_D) A.phi_c = A.phi_c - 2 * SIMC_PI_D;
+  if (A.phi_c < 0.0) A.phi_c = 2 * SIMC_PI_D + A.phi_c;
+  dummy = sqrt((qx * qx + qy * qy + qz * qz)) * sqrt((targx * targx + targy * targy + targz * targz));
+  A.theta_tarq = m::acos((qx * targx + qy * targy + qz * targz) / dummy);
+  return A;
+}
+
 // State of one try between the stages of the loop: the parts of `main`, `vertex`, `orig`
 // and /radccom/ that later stages read.
 struct EventState {

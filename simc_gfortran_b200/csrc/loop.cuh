@@ -1251,7 +1251,14 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
                                S.ld(F_PFERZ, slot) * S.ld(F_UQZ, slot);
           ntu[54] = S.ld(F_PFER, slot) / 1000. * fabs(dummy) / dummy;     // NaN for hydrogen (0/0), as in the reference
           ntu[55] = semi ? S.ld(F_XFERMI, slot) : 0.0; ntu[56] = S.ld(F_MPHIPQ, slot);
-          if (rho) {         // results_write.f:226-230 (no target field)
+          if (cfg.using_tgt_field) {       // results_write.f:212-225
+            const PolTargAngles ra = poltarg_angles(cfg.targ_pol, cfg.targ_Bangle, uqx, uqy, uqz, upx, upy, upz, r_phipq);
+            const PolTargAngles va = poltarg_angles(cfg.targ_pol, cfg.targ_Bangle, S.ld(F_UQX, slot), S.ld(F_UQY, slot), S.ld(F_UQZ, slot),
+                                                    S.ld(F_UPX, slot), S.ld(F_UPY, slot), S.ld(F_UPZ, slot), S.ld(F_MPHIPQ, slot));
+            ntu[57] = ra.theta_tarq; ntu[58] = ra.phi_targ; ntu[59] = ra.beta; ntu[60] = ra.phi_s; ntu[61] = ra.phi_c;
+            ntu[62] = va.beta; ntu[63] = va.phi_s; ntu[64] = va.phi_c;
+            if (rho) { ntu[65] = S.ld(F_RHOMASS, slot); ntu[66] = S.ld(F_RHOTHETA, slot); }       // (the 67th tag, mmnuc, is never filled)
+          } else if (rho) {  // results_write.f:226-230
             const double e_A = nu + cfg.targ.M - rpE;
             const double mmA2 = e_A * e_A - rPm * rPm;
             ntu[57] = S.ld(F_RHOMASS, slot); ntu[58] = S.ld(F_RHOTHETA, slot);
@@ -1275,7 +1282,14 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
           ntu[48] = sqrt(S.ld(F_MH2FINAL, slot));
           ntu[49] = mv_pfer[0] / 1000. * pdot;
           ntu[50] = v_Q2 / 1.e6; ntu[51] = S.ld(F_MW, slot) / 1.e3; ntu[52] = S.ld(F_MT, slot) / 1.e6; ntu[53] = S.ld(F_MPHIPQ, slot);
-          if (cfg.doing_kaon) { ntu[54] = sigcm1; ntu[55] = S.ld(F_SIGCM, slot); }
+          if (cfg.using_tgt_field) {       // results_write.f:154-166
+            const PolTargAngles ra = poltarg_angles(cfg.targ_pol, cfg.targ_Bangle, uqx, uqy, uqz, upx, upy, upz, r_phipq);
+            const PolTargAngles va = poltarg_angles(cfg.targ_pol, cfg.targ_Bangle, S.ld(F_UQX, slot), S.ld(F_UQY, slot), S.ld(F_UQZ, slot),
+                                                    S.ld(F_UPX, slot), S.ld(F_UPY, slot), S.ld(F_UPZ, slot), S.ld(F_MPHIPQ, slot));
+            ntu[54] = ra.theta_tarq; ntu[55] = ra.phi_targ; ntu[56] = ra.beta; ntu[57] = ra.phi_s; ntu[58] = ra.phi_c;
+            ntu[59] = va.beta; ntu[60] = va.phi_s; ntu[61] = va.phi_c;
+            if (cfg.doing_kaon) { ntu[62] = sigcm1; ntu[63] = S.ld(F_SIGCM, slot); }
+          } else if (cfg.doing_kaon) { ntu[54] = sigcm1; ntu[55] = S.ld(F_SIGCM, slot); }
         } else {
           const double sh = m::sin(reth / 2.);
           const double poftheta = SIMC_MP * cfg.Ebeam / (2 * cfg.Ebeam * (sh * sh) + SIMC_MP);

@@ -118,11 +118,28 @@ int simc_b200_ntuple_tags(const simc_run_config* cfg, char (*tags)[17], int max_
   else if (cfg->doing_semi || cfg->doing_rho) { tail = kSemi; n_tail = cfg->doing_rho ? 26 : 23; }
   else if (cfg->doing_hyd_elast || cfg->doing_deuterium || cfg->doing_heavy) { tail = kEep; n_tail = 13; }
   else return SIMC_ERR_ARG;
-  const int n = 33 + n_tail;
+  // polarised target: eight tags behind "phipqi" (the 20th meson / 23rd semi-inclusive tag), NtupleInit.f:142-160, 239-256
+  static const char* const kPol[8] = {"th_tarq", "phitarq", "beta", "phis", "phic", "betai", "phisi", "phici"};
+  const bool pol = cfg->using_tgt_field && tail != kEep;
+  const int pol_at = tail == kMeson ? 20 : 23;
+  // pi0 -> gamma gamma: twelve tags behind the meson ones (NtupleInit.f:163-187)
+  static const char* const kPi0[12] = {"xcal_gamma1", "ycal_gamma1", "Egamma1", "Pgamma1x", "Pgamma1y", "Pgamma1z",
+                                       "xcal_gamma2", "ycal_gamma2", "Egamma2", "Pgamma2x", "Pgamma2y", "Pgamma2z"};
+  const bool pi0 = cfg->doing_pizero && tail == kMeson;
+  const int n = 33 + n_tail + (pol ? 8 : 0) + (pi0 ? 12 : 0);
   if (n > max_tags) return SIMC_ERR_ARG;
   for (int i = 0; i < n; ++i) {
     std::memset(tags[i], 0, 17);
-    std::strncpy(tags[i], i < 33 ? kCommon[i] : tail[i - 33], 16);
+    const char* t;
+    if (i < 33) t = kCommon[i];
+    else {
+      const int j = i - 33;
+      if (pi0 && j >= n_tail + (pol ? 8 : 0)) t = kPi0[j - n_tail - (pol ? 8 : 0)];
+      else if (!pol || j < pol_at) t = tail[j];
+      else if (j < pol_at + 8) t = kPol[j - pol_at];
+      else t = tail[j - 8];
+    }
+    std::strncpy(tags[i], t, 16);
   }
   return n;
 }

@@ -155,11 +155,32 @@ def test_loop_with_field_accumulators(polcase):
     assert abs(a - b) <= RECON_LOOSE * abs(b)
 
 
+def test_loop_with_field_ntuple(polcase):
+    """The pion layout with the eight polarised-target columns (results_write.f:154-162): theta_tarq, phi_targ, beta,
+    phi_s, phi_c of the reconstructed event, beta, phi_s, phi_c of the vertex."""
+    from tests.test_loop_gpu import RECON_LOOSE
+    cfg, sim, orc = polcase
+    n = 40000
+    ref, ref_tries = orc.ntuple_batch(cfg, 0, n, 5)
+    rows, tries = sim.ntuple_batch(0, n, 5)
+    assert rows.shape[1] == ref.shape[1] == 61 and np.array_equal(tries, ref_tries) and len(rows) > 100
+    scale = np.maximum(np.abs(ref).max(axis=0), 1e-30)
+    err = np.abs(rows - ref) / np.maximum(np.abs(ref), 1e-3 * scale[None, :])
+    assert err.max() <= RECON_LOOSE, (int(np.argmax(err.max(axis=0))), float(err.max()))
+    pol = rows[:, 53:61]
+    assert np.all((pol[:, 1:] >= 0) & (pol[:, 1:] <= 2 * np.pi)) and np.all((pol[:, 0] >= 0) & (pol[:, 0] <= np.pi))
+    # Sivers angle = phi_pq - phi_targ (mod 2 pi) for the reconstructed event (columns 33, 55, 57)
+    d = np.mod(rows[:, 32] - pol[:, 1], 2 * np.pi)
+    assert np.allclose(np.mod(d - pol[:, 3] + np.pi, 2 * np.pi) - np.pi, 0.0, atol=1e-9)
+    # q is nearly along the beam and the polarisation at 80 degrees to it
+    assert np.all(np.abs(pol[:, 0] - np.radians(80.0)) < np.radians(25.0))
+    from simc_gfortran_b200.lib import ntuple_tags
+    tags = ntuple_tags(cfg)
+    assert len(tags) == 61 and tags[52] == "phipqi" and tags[53:61] == ["th_tarq", "phitarq", "beta", "phis", "phic", "betai", "phisi", "phici"]
+
+
 def test_field_refusals(polcase):
     cfg, sim, orc = polcase
-    with pytest.raises(SimcError) as e:
-        sim.ntuple_batch(0, 100, 1)
-    assert "polarised-target columns" in str(e.value)
     s = Simc(cfg, mode="strict")              # no map set
     try:
         from simc_gfortran_b200 import load_optics_fixture

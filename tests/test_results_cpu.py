@@ -90,3 +90,31 @@ def test_ntuple_file_is_fortran_unformatted_sequential(tmp_path):
     assert raw[12:16] == (16).to_bytes(4, "little") and raw[16:32] == b"hsdelta" + b" " * 9
     tags, vals = read_ntuple_file(path)
     assert tags == ntuple_tags(cfg) and np.array_equal(vals, rows)
+
+
+def test_ntuple_tags_of_the_new_layouts():
+    """Tags of NtupleInit.f:101-343 for the layouts added in round 2: rho (59), pi0 -> gamma gamma (65: the reference's
+    tags for the photon columns are named in NtupleInit.f:163-184; here the row layout is checked, the file header takes
+    the meson tags), and the eight polarised-target tags behind phipqi."""
+    import os
+    from simc_gfortran_b200 import config_from_deck
+    from simc_gfortran_b200.lib import ntuple_tags
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rho = config_from_deck(os.path.join(root, "decks", "r1_eerho_hydrogen_sos_hms.inp"))[0]
+    t = ntuple_tags(rho)
+    assert len(t) == 59 and t[33] == "missmass" and t[55] == "phipqi" and t[56:] == ["Mrho", "Thrho", "mmnuc"]
+    pol = config_from_deck(os.path.join(root, "decks", "w1_poltar_eepi_hydrogen_hms_shms.inp"))[0]
+    t = ntuple_tags(pol)
+    assert len(t) == 61 and t[52] == "phipqi" and t[53:] == ["th_tarq", "phitarq", "beta", "phis", "phic", "betai", "phisi", "phici"]
+    rho.using_tgt_field = 1
+    t = ntuple_tags(rho)
+    assert len(t) == 67 and t[56:64] == ["th_tarq", "phitarq", "beta", "phis", "phic", "betai", "phisi", "phici"] and t[64:] == ["Mrho", "Thrho", "mmnuc"]
+
+
+def test_ntuple_tags_pizero():
+    import os
+    from simc_gfortran_b200 import config_from_deck
+    from simc_gfortran_b200.lib import ntuple_tags
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = ntuple_tags(config_from_deck(os.path.join(root, "decks", "z1_eepi0_hydrogen_hms_nps.inp"))[0])
+    assert len(t) == 65 and t[52] == "phipqi" and t[53:56] == ["xcal_gamma1", "ycal_gamma1", "Egamma1"] and t[64] == "Pgamma2z"
