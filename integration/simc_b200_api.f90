@@ -226,6 +226,26 @@ module simc_b200_api
       integer(c_int), value :: ipi
       character(kind=c_char), intent(in) :: path(*)
     end function
+    ! field of the polarised target: replaces trgInit (trg_track.f:243-347, simc.f:154)
+    integer(c_int) function simc_b200_load_field_file(h, path) bind(C, name='simc_b200_load_field_file')
+      import
+      type(c_ptr), value :: h
+      character(kind=c_char), intent(in) :: path(*)
+    end function
+    integer(c_int) function simc_b200_set_field_map(h, bz, br) bind(C, name='simc_b200_set_field_map')
+      import
+      type(c_ptr), value :: h
+      real(c_double), intent(in) :: bz(*), br(*)
+    end function
+    integer(c_int) function simc_b200_field_batch(h, spect, theta_deg, n, in_soa, out_soa) bind(C, name='simc_b200_field_batch')
+      import
+      type(c_ptr), value :: h
+      integer(c_int), value :: spect
+      real(c_double), value :: theta_deg
+      integer(c_int64_t), value :: n
+      real(c_double), intent(in) :: in_soa(*)
+      real(c_double), intent(out) :: out_soa(*)
+    end function
     integer(c_int) function simc_b200_load_saghai_files(h, dir) bind(C, name='simc_b200_load_saghai_files')
       import
       type(c_ptr), value :: h

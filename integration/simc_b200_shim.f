@@ -643,6 +643,9 @@
 	if (doing_pion .and. (which_pion.eq.1 .or. which_pion.eq.11 .or. which_pion.eq.3))
      >		ierr = simc_b200_load_maid_file(hnd, 4_c_int, c_path('maidpimp.dat'))
 	if (doing_kaon) ierr = simc_b200_load_saghai_files(hnd, c_path('.'))
+! ... the field map trgInit reads (simc.f:154); the angles between the field axis and the two arms (simc.f:120-152) are
+! ... rebuilt by the library from targ_Bangle, targ_Bphi and the spectrometer angles it was given
+	if (using_tgt_field) ierr = simc_b200_load_field_file(hnd, c_path(trim(tgt_field_file)))
 	if (Nntu.gt.0) allocate(rows(chunk*SIMC_NTUPLE_MAXCOL))
 
 	first = 0

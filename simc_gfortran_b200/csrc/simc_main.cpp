@@ -65,6 +65,7 @@ int main(int argc, char** argv) {
   rc = simc_b200_create(&cfg, device, &h);
   if (rc) return die(nullptr, "simc_b200_create", rc);
   for (int arm : {cfg.electron_arm, cfg.hadron_arm}) {
+    if (arm == cfg.hadron_arm && (arm == SIMC_ARM_CALO_RIGHT || arm == SIMC_ARM_CALO_LEFT)) continue;     // a calorimeter has no maps
     const ArmFiles f = arm_files(arm);
     if (!f.fwd) { std::fprintf(stderr, "simc_b200: spectrometer %d has no single-arm Monte Carlo here\n", arm); return 1; }
     rc = simc_b200_load_optics(h, arm, (data + "/" + f.fwd).c_str(), (data + "/" + f.rec).c_str());
@@ -96,6 +97,9 @@ int main(int argc, char** argv) {
     if (FILE* t = std::fopen(f.c_str(), "r")) { std::fclose(t); if ((rc = simc_b200_load_maid_file(h, piminus ? 4 : 3, f.c_str()))) return die(h, "simc_b200_load_maid_file", rc); }
   }
 
+  if (cfg.using_tgt_field) {  // trgInit (simc.f:154): tgt_field_file of the deck is trg_field_map.dat in every shipped deck
+    if ((rc = simc_b200_load_field_file(h, (data + "/trg_field_map.dat").c_str()))) return die(h, "simc_b200_load_field_file", rc);
+  }
   if (cfg.doing_kaon) {       // optional: the Saghai model only fills ntuple column 54 (zero without its tables)
     if (FILE* t = std::fopen((data + "/saghai_proton.dat").c_str(), "r")) {
       std::fclose(t);
