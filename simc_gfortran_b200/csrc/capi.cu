@@ -35,6 +35,7 @@ struct ArmSlot {
   // compiled stretches of the program (mapgen.h): one generated kernel per RNG-free stretch
   std::vector<StretchSpec> stretches;
   int hut_begin = 0;                     // first op that is not static
+  int recon_pc = -1;                     // the program's OP_RECON (-1: none); compiled as one more kernel, jit.fns[stretches.size()]
   JitModule jit;
   bool jit_ready = false;
   int jit_strict = -1;                   // arithmetic variant the module was generated for
@@ -49,6 +50,7 @@ struct simc_handle {
   int device = 0;
   int strict = 1;
   int compiled_maps = 1;               // run RNG-free stretches of the arm programs as generated kernels (mapgen.h)
+  int compiled_recon = 1;              // ... and the reconstruction map behind the hut (SIMC_B200_COMPILED_RECON=0: interpreter)
   cudaStream_t stream = nullptr;
   std::map<int, ArmSlot> arms;
   std::string err;
@@ -122,6 +124,15 @@ void plan_stretches(ArmSlot& s) {
   cuts.push_back(hut);
   for (size_t k = 0; k + 1 < cuts.size(); ++k)
     if (cuts[k + 1] > cuts[k]) s.stretches.push_back(StretchSpec{cuts[k], cuts[k + 1]});
+  s.recon_pc = -1;
+  for (int pc = hut; pc < (int)ops.size(); ++pc)
+    if (ops[pc].op == OP_RECON) { s.recon_pc = pc; break; }
+}
+// What goes into one generated translation unit: the stretches, then the reconstruction map as a kernel of its own
+std::vector<StretchSpec> source_specs(const ArmSlot& s) {
+  std::vector<StretchSpec> v = s.stretches;
+  if (s.recon_pc >= 0) v.push_back(StretchSpec{s.recon_pc, s.recon_pc + 1});
+  return v;
 }
 
 // Launch shape of the generated kernels: two CTAs of 256 threads per SM (128 registers per thread).  The warps of a
@@ -211,6 +222,8 @@ int simc_b200_create(const simc_run_config* cfg, int device, simc_handle** out) 
   h->strict = !(mode && std::strcmp(mode, "fast") == 0);
   const char* cm = std::getenv("SIMC_B200_COMPILED_MAPS");
   h->compiled_maps = !(cm && std::strcmp(cm, "0") == 0);
+  const char* cr = std::getenv("SIMC_B200_COMPILED_RECON");
+  h->compiled_recon = !(cr && std::strcmp(cr, "0") == 0);
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
     std::string m = std::string("simc_b200_create: ") + cudaGetErrorString(e);
     delete h;
@@ -780,7 +793,7 @@ int simc_b200_precompile_optics(int arm_id, int n_classes, const int32_t* fwd_cl
     ArmSlot s;
     s.host = compile_arm(arm_id, f, r);
     plan_stretches(s);
-    const std::string src = generate_stretch_source(s.host, s.stretches, strict_mode != 0, map_block_threads(), map_min_blocks());
+    const std::string src = generate_stretch_source(s.host, source_specs(s), strict_mode != 0, map_block_threads(), map_min_blocks());
     if (dump_source_path && *dump_source_path) {
       FILE* fp = std::fopen(dump_source_path, "w");
       if (fp) { std::fwrite(src.data(), 1, src.size(), fp); std::fclose(fp); }
@@ -1076,14 +1089,14 @@ int ensure_compiled(simc_handle* h, ArmSlot& s) {
   if (s.stretches.empty()) { s.jit_ready = true; return SIMC_OK; }
   std::string src, cubin, err;
   try {
-    src = generate_stretch_source(s.host, s.stretches, h->strict != 0, map_block_threads(), map_min_blocks());
+    src = generate_stretch_source(s.host, source_specs(s), h->strict != 0, map_block_threads(), map_min_blocks());
   } catch (const std::exception& e) {
     return fail(h, SIMC_ERR_STATE, std::string("map compiler: ") + e.what());
   }
   bool cached = false;
   if (!jit_compile_cubin(src, jit_default_cache_dir(), cubin, &cached, err)) return fail(h, SIMC_ERR_STATE, err);
   std::vector<std::string> names;
-  for (size_t k = 0; k < s.stretches.size(); ++k) names.push_back("seg_" + std::to_string(k));
+  for (size_t k = 0; k < source_specs(s).size(); ++k) names.push_back("seg_" + std::to_string(k));
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaFree(0));                                    // the primary context is current for the driver API
   if (!jit_load(cubin, names, s.jit, err)) return fail(h, SIMC_ERR_CUDA, err);
@@ -1131,6 +1144,15 @@ int build_schedule(simc_handle* h, int arm_id, bool use_mc, bool decay, bool col
     if (sc.n >= kArmLists - 1) break;
     push(ARM_STAGE_MIDDLE, pos, tab.mid_op[k], nullptr);
     pos = tab.mid_op[k];
+  }
+  // the reconstruction map as a compiled kernel of its own: hut (interpreter, up to OP_RECON), map, recon quantities
+  const bool split_recon = compiled && !s.stretches.empty() && s.recon_pc > pos && !h->cfg.using_tgt_field &&
+                           sc.n + 3 <= kArmLists && (int)s.jit.fns.size() > (int)s.stretches.size() && h->compiled_recon;
+  if (split_recon) {
+    push(ARM_STAGE_HUT, pos, s.recon_pc, nullptr);
+    push(ARM_STAGE_COMPILED, s.recon_pc, s.recon_pc + 1, s.jit.fns[s.stretches.size()]);
+    push(ARM_STAGE_TAIL, 0, 0, nullptr);
+    return SIMC_OK;
   }
   push(ARM_STAGE_LAST, pos, n_ops, nullptr);
   return SIMC_OK;

@@ -161,6 +161,10 @@ static cudaError_t ensure_smem_opt_in_locked() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_arm<0, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   done[dev] = true;
   return cudaSuccess;
@@ -530,6 +534,12 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         void* args[] = {&tk, &fs, &ss, &in_list, &in_count, &out_list, &out_count, &stop_acc, &calls_acc, &stop_field};
         const int rc = jit_launch(st.fn, (unsigned)st.grid, (unsigned)st.block, (void*)s, args);
         if (rc != 0) return cudaErrorLaunchFailure;
+      } else if (st.kind == ARM_STAGE_HUT) {
+        if (hadron) k_arm<1, 6><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        else k_arm<0, 6><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+      } else if (st.kind == ARM_STAGE_TAIL) {
+        if (hadron) k_arm<1, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        else k_arm<0, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
       } else if (st.kind == ARM_STAGE_MIDDLE) {
         if (hadron) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         else k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);

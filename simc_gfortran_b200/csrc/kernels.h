@@ -19,7 +19,10 @@ constexpr int kLoopCounts = 32;                 // [0] slots handed out, [1 + l]
 // stretch; MIDDLE: k_arm<W,2>, the interpreter on a stretch; LAST: k_arm<W,1>, the interpreter up to the end of the
 // program, reconstruction and the arm's recon quantities.  Survivors are compacted between stages.
 enum ArmStageKind : int { ARM_STAGE_ENTRY = 0, ARM_STAGE_COMPILED = 1, ARM_STAGE_MIDDLE = 2, ARM_STAGE_LAST = 3,
-                          ARM_STAGE_CALO = 4 };     // the whole arm in one kernel: a calorimeter as the hadron arm (k_calo)
+                          ARM_STAGE_CALO = 4,       // the whole arm in one kernel: a calorimeter as the hadron arm (k_calo)
+                          // the last stage in three: HUT = interpreter up to (not including) OP_RECON, the map as a
+                          // compiled kernel (ARM_STAGE_COMPILED), TAIL = the arm's recon quantities
+                          ARM_STAGE_HUT = 5, ARM_STAGE_TAIL = 6 };
 struct ArmStage { int kind; int begin, end; void* fn; int block, grid; };   // block / grid: launch shape of a compiled stage
 struct ArmSchedule { int n; ArmStage st[kArmLists]; };
 

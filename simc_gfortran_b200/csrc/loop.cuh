@@ -562,9 +562,14 @@ __device__ __forceinline__ bool track_to_tgt_warp(const FieldDev& F, int k, cons
 // track_from_tgt in front of the arm (simc.f:1425-1432, 1693-1700), track_to_tgt behind its reconstruction (:1573-1587).
 template <int WHICH, int SEG_>
 __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
-  constexpr int SEG = (SEG_ == 3 || SEG_ == 4) ? 0 : SEG_ == 5 ? 1 : SEG_;
+  constexpr int SEG = (SEG_ == 3 || SEG_ == 4) ? 0 : (SEG_ == 5 || SEG_ == 6 || SEG_ == 7) ? 1 : SEG_;
   constexpr bool kColl = SEG_ == 3;
   constexpr bool kField = SEG_ == 4 || SEG_ == 5;
+  // SEG_ = 6, 7: SEG 1 in two kernels around the compiled reconstruction map (kernels.h: ARM_STAGE_HUT / _TAIL).
+  // 6 runs the hut up to OP_RECON and leaves the fitted focal-plane track in the track rows; the generated kernel
+  // turns them into the reconstructed target quantities (mapgen.cpp: OP_RECON); 7 makes the arm's recon quantities.
+  constexpr bool kHutOnly = SEG_ == 6;
+  constexpr bool kTail = SEG_ == 7;
   extern __shared__ double pw_s[];
   __shared__ unsigned s_stop[SIMC_NSTOP];
   __shared__ unsigned s_calls[48];
@@ -734,7 +739,38 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
       // a hadron that decayed before the collimator carries its daughter's mass (Mh2_final, simulate.inc:92)
       t.mh2_final = (WHICH == 1) ? t.m2 : Mh2; t.ctau = cfg.ctau;
       musc_refresh(t);
-      if (use_mc) {
+      if (kTail) {
+        // the generated reconstruction kernel left: xs = y_tgt, dxdzs = dph, dydzs = dth, dpps = delta (mapgen.cpp)
+        ok = active;
+        rc_delta = t.dpps; rc_yptar = t.dydzs; rc_xptar = t.dxdzs; rc_z = t.xs; path = t.pathlen;
+        if (active) warp_hist_add(s_stop, 1);
+      } else if (kHutOnly) {
+        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
+        ok = active && alive;          // reached OP_RECON
+        if (active) {
+          if (res.reached_hut) warp_count(&s_stop[2]);
+          if (!ok) warp_hist_add(s_stop, 2 + res.stop_code < SIMC_NSTOP ? 2 + res.stop_code : -1);
+          if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)(ok ? 0 : res.stop_code));
+          S.st(F_DRAW, slot, (double)rng.draw);
+        }
+        if (ok) {
+          // the fitted track for the reconstruction map, path length and decay bookkeeping for the rows behind it
+          S.st4(F_TK_XS, slot, res.x_fp, res.y_fp, res.dx_fp, res.dy_fp);
+          S.st4(F_TK_DPP, slot, t.dpps, t.p, t.m2, t.pathlen);
+          const ArmOp* orec = &arm->ops[op_end];
+          const double yfp_out = orec->a != 0. ? res.y_fp - orec->a : res.y_fp;      // hrsl/mc_hrsl.f:525: shifted afterwards
+          if (WHICH == 1) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
+          if (A.record_mode) {
+            if (WHICH == 1) {
+              S.st(F_FPP_X, slot, res.x_fp); S.st(F_FPP_Y, slot, yfp_out);
+              S.st(F_DECDIST, slot, t.decdist); S.st(F_MH2FINAL, slot, t.mh2_final);
+            } else {
+              S.st(F_FPE_X, slot, res.x_fp); S.st(F_FPE_DX, slot, res.dx_fp); S.st(F_FPE_Y, slot, yfp_out);
+              S.st(F_FPE_DY, slot, res.dy_fp);
+            }
+          }
+        }
+      } else if (use_mc) {
         run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
         ok = active && res.ok;
         rc_delta = res.dpp_rec; rc_yptar = res.dth_rec; rc_xptar = res.dph_rec; rc_z = res.y_rec;
@@ -762,15 +798,15 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         rc_delta = S.ld(WHICH == 1 ? F_SPP_D : F_SPE_D, slot); rc_yptar = S.ld(WHICH == 1 ? F_SPP_Y : F_SPE_Y, slot);
         rc_xptar = S.ld(WHICH == 1 ? F_SPP_X : F_SPE_X, slot);
       }
-      if (active) {
+      if (active && !kHutOnly && !kTail) {
         if (A.record_mode) S.st(WHICH == 1 ? F_STOP_P : F_STOP_E, slot, (double)(ok ? 0 : res.stop_code));
         S.st(F_DRAW, slot, (double)rng.draw);
       }
-      if (ok) {
+      if (ok && !kHutOnly) {
         S.st4(WHICH == 1 ? F_RCP_D : F_RCE_D, slot, rc_delta, rc_yptar, rc_xptar, rc_z);
         S.st(WHICH == 1 ? F_FPP_PATH : F_FPE_PATH, slot, path);
-        if (WHICH == 1) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
-        if (A.record_mode) {
+        if (WHICH == 1 && !kTail) { S.st(F_FPP_DX, slot, res.dx_fp); S.st(F_FPP_DY, slot, res.dy_fp); }
+        if (A.record_mode && !kTail) {
           if (WHICH == 1) {
             S.st(F_FPP_X, slot, res.x_fp); S.st(F_FPP_Y, slot, res.y_fp);
             S.st(F_DECDIST, slot, t.decdist); S.st(F_MH2FINAL, slot, t.mh2_final);

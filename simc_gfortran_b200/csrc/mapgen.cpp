@@ -160,6 +160,30 @@ void emit_op(Out& o, const CompiledArm& arm, const ArmOp& op, bool strict) {
       break;
     case OP_COLL: case OP_COLL_DATA:       // using_HMScoll / using_SHMScoll off: the plain aperture checks follow
       break;
+    case OP_RECON: {       // mc_hms.f:419-437 + mc_hms_recon.f:104-137 on the fitted focal-plane track, which the hut
+                           // kernel left in the track rows (xs, dx, ys, dy = x_fp, dx_fp, y_fp, dy_fp); out: the
+                           // reconstructed target quantities in the same rows (xs = y_tgt, dx = dph, dy = dth, dpp = delta)
+      const CosyTerms& m = arm.rec;
+      o.line("      {   // reconstruction map: " + std::to_string(m.n()) + " terms");
+      o.line("      count_call(s_calls, 47);");
+      o.line("      double h0 = xs / 100., h1 = dx, h2 = ys / 100., h3 = dy, h4 = fry / 100.;");
+      o.line("      if (fabs(h4) <= 1.e-30) h4 = 1.e-30;");
+      if (op.i0) {         // sos/mc_sos_recon.f:79-81: every variable is kept off zero
+        o.line("      if (fabs(h0) <= 1.e-30) h0 = 1.e-30;");
+        o.line("      if (fabs(h1) <= 1.e-30) h1 = 1.e-30;");
+        o.line("      if (fabs(h2) <= 1.e-30) h2 = 1.e-30;");
+        o.line("      if (fabs(h3) <= 1.e-30) h3 = 1.e-30;");
+      }
+      o.line("      const double x = h0, t = h1, y = h2, p = h3, d = h4;");
+      o.line("      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;");
+      emit_map(o, m, strict);
+      o.line("      dx = s0;");
+      o.line("      xs = s1 * 100.;");
+      o.line("      dy = s2;");
+      o.line("      dpp = s3 * 100.;");
+      o.line("      }");
+      break;
+    }
     default:
       throw std::runtime_error("map compiler: op " + std::to_string(op.op) + " is not static");
   }
@@ -220,25 +244,26 @@ std::string generate_stretch_source(const CompiledArm& arm, const std::vector<St
     o.line("    const bool active = i < n_in;");
     o.line("    bool alive = active;");
     o.line("    unsigned slot = 0u;");
-    o.line("    double xs = 0., ys = 0., dx = 0., dy = 0., dpp = 0., path = 0., xt = 0., yt = 0.;");
+    o.line("    double xs = 0., ys = 0., dx = 0., dy = 0., dpp = 0., path = 0., xt = 0., yt = 0., fry = 0.;");
     o.line("    int stop_code = -1;");
     o.line("    if (active) {");
     o.line("      slot = in_list[i];");
     o.line("      double* const t = tk + (long long)slot * ss;");
     o.line("      xs = t[0 * fs]; ys = t[1 * fs]; dx = t[2 * fs]; dy = t[3 * fs];");
     o.line("      dpp = t[4 * fs]; path = t[7 * fs];");
+    if (segs[k].end - segs[k].begin == 1 && arm.ops.at(segs[k].begin).op == OP_RECON) o.line("      fry = t[10 * fs];");
     o.line("    }");
     for (int pc = segs[k].begin; pc < segs[k].end; ++pc) {
       const ArmOp& op = arm.ops.at(pc);
       if (op.op == OP_COLL || op.op == OP_COLL_DATA) continue;
       // the warps of the CTA enter every map together: its code is tens of KB of straight line, and warps that
       // drift apart in it stall on instruction fetch (each streams the code through the cache on its own)
-      if (op.op == OP_TRANSP) o.line("    __syncthreads();");
+      if (op.op == OP_TRANSP || op.op == OP_RECON) o.line("    __syncthreads();");
       o.line("    if (alive) {");
       emit_op(o, arm, op, strict);
       o.line("    }");
     }
-    o.line("    (void)xt; (void)yt;");
+    o.line("    (void)xt; (void)yt; (void)fry;");
     o.line("    const bool ok = alive;");
     o.line("    if (active) {");
     o.line("      double* const t = tk + (long long)slot * ss;");
