@@ -105,3 +105,48 @@ def test_missing_file_is_an_error(workdir, tmp_path):
     open(deck, "w").write(txt)
     r = subprocess.run([DRIVER, deck, "--data", str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "load_optics" in r.stderr
+
+
+def run_deck(workdir, deck_name, ngen, out, extra=()):
+    txt = open(os.path.join(ROOT, "decks", deck_name)).read()
+    txt, n = re.subn(r"ngen = -?\d+", f"ngen = {ngen}", txt, count=1)
+    assert n == 1
+    deck = str(workdir / f"deck_{out}.inp")
+    open(deck, "w").write(txt)
+    r = subprocess.run([DRIVER, deck, "--data", str(workdir), "--out", str(workdir / out), "--seed", "9", "--ntuple", "1", *extra],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout
+    return deck, parse_hist(str(workdir / out) + ".hist")
+
+
+def test_polarised_target_and_calorimeter_decks(workdir):
+    """The driver on the two decks that need more than maps: using_tgt_field (it reads trg_field_map.dat from the data
+    directory, like trgInit) and the pi0 deck with the NPS calorimeter as the hadron arm (no maps for that arm).  The
+    .bin files carry the wider rows (61 and 65 columns) under the reference's tags."""
+    from tests.oracle_lib import load_field_fixture, write_field_file
+    bz, br = load_field_fixture()
+    write_field_file(bz, br, str(workdir / "trg_field_map.dat"))
+    n = 60000
+    deck, hist = run_deck(workdir, "w1_poltar_eepi_hydrogen_hms_shms.inp", -n, "pol")
+    cfg = config_from_deck(deck)[0]
+    sim = Simc(cfg, mode="strict")
+    try:
+        for arm, (fwd, rec) in FILES.items():
+            sim.load_optics(arm, str(workdir / fwd), str(workdir / rec))
+        sim.load_field_file(str(workdir / "trg_field_map.dat"))
+        acc = sim.accum_clear()
+        sim.run(0, n, 9, acc)
+        rows, _ = sim.ntuple_batch(0, n, 9)
+    finally:
+        sim.close()
+    assert hist["Ntried"] == n and hist["Ncontribute"] == acc.ncontribute > 100
+    tags, vals = read_ntuple_file(str(workdir / "pol.bin"))
+    assert tags == ntuple_tags(cfg) and len(tags) == 61 and tags[53] == "th_tarq"
+    assert vals.shape == rows.shape and np.array_equal(vals, rows)
+    deck, hist = run_deck(workdir, "z1_eepi0_hydrogen_hms_nps.inp", -n, "pi0")
+    cfg = config_from_deck(deck)[0]
+    tags, vals = read_ntuple_file(str(workdir / "pi0.bin"))
+    assert hist["Ntried"] == n and hist["Ncontribute"] == len(vals) > 100
+    assert tags == ntuple_tags(cfg) and len(tags) == 65 and tags[55] == "Egamma1"
+    g = vals[:, 55:59] + vals[:, 61:65]
+    assert np.allclose(np.sqrt(g[:, 0] ** 2 - (g[:, 1:] ** 2).sum(axis=1)), 134.9766, rtol=1e-9)
