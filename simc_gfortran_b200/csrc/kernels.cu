@@ -535,8 +535,10 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         const int rc = jit_launch(st.fn, (unsigned)st.grid, (unsigned)st.block, (void*)s, args);
         if (rc != 0) return cudaErrorLaunchFailure;
       } else if (st.kind == ARM_STAGE_HUT) {
-        if (hadron) k_arm<1, 6><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
-        else k_arm<0, 6><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        // five CTAs per SM (96 registers, 40 KB of queue each): a grid of 5 x SMs x ... keeps the persistent loop balanced
+        const unsigned hgrid = (unsigned)std::min<long long>(need, (long long)a.grid_blocks / 4 * SIMC_HUT_MIN_BLOCKS);
+        if (hadron) k_arm<1, 6><<<hgrid, kBlock, kQueueBytes, s>>>(A, arm);
+        else k_arm<0, 6><<<hgrid, kBlock, kQueueBytes, s>>>(A, arm);
       } else if (st.kind == ARM_STAGE_TAIL) {
         if (hadron) k_arm<1, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         else k_arm<0, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);

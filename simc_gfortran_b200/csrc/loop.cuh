@@ -560,8 +560,11 @@ __device__ __forceinline__ bool track_to_tgt_warp(const FieldDev& F, int k, cons
 
 // SEG_ = 4, 5: SEG 0 / SEG 1 built with the tracking through the polarised target's field (using_tgt_field):
 // track_from_tgt in front of the arm (simc.f:1425-1432, 1693-1700), track_to_tgt behind its reconstruction (:1573-1587).
+#ifndef SIMC_HUT_MIN_BLOCKS
+#define SIMC_HUT_MIN_BLOCKS 5
+#endif
 template <int WHICH, int SEG_>
-__global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
+__global__ void __launch_bounds__(kBlock, SEG_ == 6 ? SIMC_HUT_MIN_BLOCKS : SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
   constexpr int SEG = (SEG_ == 3 || SEG_ == 4) ? 0 : (SEG_ == 5 || SEG_ == 6 || SEG_ == 7) ? 1 : SEG_;
   constexpr bool kColl = SEG_ == 3;
   constexpr bool kField = SEG_ == 4 || SEG_ == 5;
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A,
         rc_delta = t.dpps; rc_yptar = t.dydzs; rc_xptar = t.dxdzs; rc_z = t.xs; path = t.pathlen;
         if (active) warp_hist_add(s_stop, 1);
       } else if (kHutOnly) {
-        run_arm(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
+        run_arm<false, true>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls);
         ok = active && alive;          // reached OP_RECON
         if (active) {
           if (res.reached_hut) warp_count(&s_stop[2]);

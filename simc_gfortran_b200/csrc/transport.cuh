@@ -30,11 +30,16 @@ static_assert(kBlock == kArmBlockThreads, "the record offsets are compiled for t
 // shared power table of a COSY map: [kPolyEntries][kBlock] doubles, dynamic shared memory (49 KB).  The hut has
 // no map before its reconstruction, so the same columns hold each thread's queue of Gaussians there
 // (GaussQueue below), which needs one row more: kPowRows rows of kBlock doubles.
-constexpr int kGaussQ = 20;                      // Gaussians a thread draws ahead
+#ifndef SIMC_GAUSS_Q
+#define SIMC_GAUSS_Q 16
+#endif
+constexpr int kGaussQ = SIMC_GAUSS_Q;            // Gaussians a thread draws ahead (16: the queue of a CTA is 40 KB, five CTAs per SM)
 constexpr int kPowRows = kPolyEntries + 1;
 static_assert(2 * kGaussQ + (kGaussQ + 1) / 2 <= kPowRows, "the Gaussian queue must fit the thread's column");
 constexpr int kPowDoubles = kPowRows * kBlock;
 constexpr size_t kPowBytes = sizeof(double) * kPowDoubles;
+// dynamic shared memory of a kernel that only needs the queue (the hut in front of a compiled reconstruction map)
+constexpr size_t kQueueBytes = sizeof(double) * (size_t)(2 * kGaussQ + (kGaussQ + 1) / 2) * kBlock;
 
 struct ArmDev {                           // lives in global memory, read through warp-uniform loads
   ArmTablesDev tab;
@@ -703,7 +708,9 @@ __device__ __forceinline__ bool collimator_steps_body(const ArmOp* o, TrackDev& 
 // `pw` = this thread's column of the CTA's shared power table.
 // WITH_COLL: the kernel was built with the collimator stepping of OP_COLL (only launched for decks that ask for
 // it, so that the other kernels do not carry its call).
-template <bool WITH_COLL = false>
+// NO_MAPS: the op range holds no COSY map (the hut in front of a compiled reconstruction map): their code, and the
+// registers it needs, stay out of the kernel.
+template <bool WITH_COLL = false, bool NO_MAPS = false>
 __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& rng, const ArmFlags f,
                                         double fry, double* pw, unsigned ring, ArmResult& res, HutState& hs,
                                         bool& alive, int op_begin, int op_end, unsigned* call_counts = nullptr,
@@ -722,13 +729,13 @@ __device__ __forceinline__ void run_arm(const ArmDev* arm, TrackDev& t, DevRng& 
     if (op == OP_END) break;
     const double a = o->a, b = o->b, c = o->c, d = o->d;
     // the two map evaluations are warp-cooperative: every lane goes in, dead ones compute on stale values
-    if (op == OP_TRANSP) {
+    if (!NO_MAPS && op == OP_TRANSP) {
       const int klass = o->i0;
       if (call_counts) warp_count_if_alive(&call_counts[klass - 1], alive);
       transp(arm, t, rng, klass, a, f.decay_flag, pw, ring, alive);
       continue;
     }
-    if (op == OP_RECON) {     // mc_hms.f:419-437 + mc_hms_recon.f:104-137
+    if (!NO_MAPS && op == OP_RECON) {     // mc_hms.f:419-437 + mc_hms_recon.f:104-137
       double hut[5];
       hut[0] = res.x_fp / 100.;
       hut[1] = res.dx_fp;
