@@ -491,7 +491,7 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     {
       const long long gneed = (a.n_tries + kGenBlock - 1) / kGenBlock;
-      const long long gmax = (long long)a.grid_blocks * kBlock / kGenBlock;        // same number of resident threads
+      const long long gmax = (long long)a.grid_blocks / 4 * SIMC_GEN_MIN_BLOCKS;     // one wave of resident CTAs (grid_blocks = 4 per SM)
       k_generate<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
       if (a.using_rad) k_regen<<<(unsigned)(gneed < gmax ? gneed : gmax), kGenBlock, 0, s>>>(A);
     }
@@ -552,14 +552,18 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       in = out; out = out + 1;
     }
   } else if (stage == 3) {
-    if (a.using_rad) k_radw<<<grid, kBlock, 0, s>>>(A, a.record_mode ? 0 : 2 * kArmLists);
-    k_finish<<<grid, kBlock, 0, s>>>(A);
+    const long long fneed = (a.n_tries + kFinBlock - 1) / kFinBlock;
+    const unsigned fgrid = (unsigned)std::min<long long>(fneed, (long long)a.grid_blocks / 4 * SIMC_FIN_MIN_BLOCKS);
+    if (a.using_rad) k_radw<<<fgrid, kFinBlock, 0, s>>>(A, a.record_mode ? 0 : 2 * kArmLists);
+    k_finish<<<fgrid, kFinBlock, 0, s>>>(A);
   }
   else if (stage == 4 && a.record_mode && a.rec) k_records<<<grid, kBlock, 0, s>>>(A, a.rec, a.status, a.n_tries);
   else if (stage == 5) {      // simc_b200_weight_batch: a.rec = input rows, a.wb_out = output rows, a.n_tries rows
     const unsigned nb = (unsigned)((a.n_tries + 255) / 256);
     k_wb_load<<<nb, 256, 0, s>>>(A, a.n_tries, a.rec);
-    k_finish<<<grid, kBlock, 0, s>>>(A);
+    const long long fneed = (a.n_tries + kFinBlock - 1) / kFinBlock;
+    const unsigned fgrid = (unsigned)std::min<long long>(fneed, (long long)a.grid_blocks / 4 * SIMC_FIN_MIN_BLOCKS);
+    k_finish<<<fgrid, kFinBlock, 0, s>>>(A);
     k_wb_store<<<nb, 256, 0, s>>>(A, a.n_tries, a.wb_out);
   }
   return cudaGetLastError();

@@ -212,12 +212,20 @@ struct GaussFn {
 // SM streams it through the instruction cache at its own position; fewer, larger CTAs (whose warps the
 // phase barriers keep together) mean fewer streams.  Registers are capped at 65536 / (block * min blocks).
 #ifndef SIMC_GEN_BLOCK
-#define SIMC_GEN_BLOCK 256
+#define SIMC_GEN_BLOCK 512
 #endif
 #ifndef SIMC_GEN_MIN_BLOCKS
 #define SIMC_GEN_MIN_BLOCKS 2
 #endif
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
+// launch shape of the end-of-loop kernels (k_radw, k_finish): straight-line code on compacted survivors as well
+#ifndef SIMC_FIN_BLOCK
+#define SIMC_FIN_BLOCK 256
+#endif
+#ifndef SIMC_FIN_MIN_BLOCKS
+#define SIMC_FIN_MIN_BLOCKS 4
+#endif
+constexpr int kFinBlock = SIMC_FIN_BLOCK;
 constexpr int kRegenList = kRegenListIdx;
 
 struct GenFlags { bool semi, fermi, meson, heavy, rho, xtra, field; };
@@ -448,12 +456,12 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopAr
 
 // peaked_rad_weight (radc.f:523-646) and main%gen_weight = gen_weight * rad_weight / hardcorfac (radc.f:518) for
 // the tries of list `list_idx`: the survivors of both arms in a run, every generated try in record mode.
-__global__ void __launch_bounds__(kBlock, 4) k_radw(LoopArgs A, int list_idx) {
+__global__ void __launch_bounds__(kFinBlock, SIMC_FIN_MIN_BLOCKS) k_radw(LoopArgs A, int list_idx) {
   const simc_run_config& cfg = *A.cfg;
   const StateBuf& S = A.st;
   const unsigned n_in = A.counts[1 + list_idx];
   const unsigned* in_list = A.lists + (long long)list_idx * A.st.cap;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n_in; i += (long long)gridDim.x * kBlock) {
+  for (long long i = (long long)blockIdx.x * kFinBlock + threadIdx.x; i < n_in; i += (long long)gridDim.x * kFinBlock) {
     const unsigned slot = in_list[i];
     const int which = (int)S.ld(F_RD_WHICH, slot);
     double rad_weight = 1;
@@ -1053,16 +1061,13 @@ __device__ __forceinline__ void warp_count_if(unsigned* dst, bool flag) {
   if ((threadIdx.x & 31u) == 0 && m) atomicAdd(dst, (unsigned)__popc(m));
 }
 
-#ifndef SIMC_FIN_MIN_BLOCKS
-#define SIMC_FIN_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs A) {
+__global__ void __launch_bounds__(kFinBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs A) {
   __shared__ BlockAcc B;
   {
     unsigned long long* w = (unsigned long long*)&B;
-    for (int i = threadIdx.x; i < (int)(sizeof(BlockAcc) / 8); i += kBlock) w[i] = 0ULL;
+    for (int i = threadIdx.x; i < (int)(sizeof(BlockAcc) / 8); i += kFinBlock) w[i] = 0ULL;
     __syncthreads();
-    for (int i = threadIdx.x; i < 40; i += kBlock) { B.mins[i] = 0x7fffffffffffffffLL; B.maxs[i] = (long long)0x8000000000000000ULL; }
+    for (int i = threadIdx.x; i < 40; i += kFinBlock) { B.mins[i] = 0x7fffffffffffffffLL; B.maxs[i] = (long long)0x8000000000000000ULL; }
     __syncthreads();
   }
   const simc_run_config& cfg = *A.cfg;
@@ -1070,8 +1075,8 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
   DevAccum* acc = A.acc;
   const unsigned n_in = A.counts[1 + 2 * kArmLists];
   const unsigned* in_list = A.lists + (long long)(2 * kArmLists) * A.st.cap;
-  const long long stride = (long long)gridDim.x * kBlock;
-  for (long long i0 = (long long)blockIdx.x * kBlock; i0 < n_in; i0 += stride) {
+  const long long stride = (long long)gridDim.x * kFinBlock;
+  for (long long i0 = (long long)blockIdx.x * kFinBlock; i0 < n_in; i0 += stride) {
     const long long i = i0 + threadIdx.x;
     const bool active = i < n_in;
     bool success = false, pass_cuts = false, no_rad_p = false, low_w = false;
@@ -1416,7 +1421,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
   }
   __syncthreads();
   // ---- flush the CTA's accumulators
-  for (int k = threadIdx.x; k < 18; k += kBlock) {
+  for (int k = threadIdx.x; k < 18; k += kFinBlock) {
     unsigned long long* dst = k == 0 ? acc->wt : k == 1 ? acc->sigcc : k < 10 ? acc->sumerr[k - 2] : acc->sumerr2[k - 10];
     const unsigned long long lo = B.sums[k][0], hi = B.sums[k][1];
     if (lo | hi) {
@@ -1425,7 +1430,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       if (hi + carry) atomicAdd(&dst[1], hi + carry);
     }
   }
-  for (int k = threadIdx.x; k < 6 * SIMC_NHIST; k += kBlock) {
+  for (int k = threadIdx.x; k < 6 * SIMC_NHIST; k += kFinBlock) {
     const unsigned long long lo = (&B.hist_w[0][0][0])[2 * k], hi = (&B.hist_w[0][0][0])[2 * k + 1];
     if (lo | hi) {
       unsigned long long* dst = &acc->hist_w[0][0][0] + 2 * k;
@@ -1434,7 +1439,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
       if (hi + carry) atomicAdd(&dst[1], hi + carry);
     }
   }
-  for (int k = threadIdx.x; k < 9 * SIMC_NHIST; k += kBlock) {
+  for (int k = threadIdx.x; k < 9 * SIMC_NHIST; k += kFinBlock) {
     const unsigned v = (&B.hist_n[0][0])[k];
     if (!v) continue;
     const int h = k / SIMC_NHIST, b = k % SIMC_NHIST;
@@ -1442,7 +1447,7 @@ __global__ void __launch_bounds__(kBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopArgs
     atomicAdd(dst, (unsigned long long)v);
   }
   if (threadIdx.x < 6 && B.counters[threadIdx.x]) atomicAdd(&acc->counters[1 + threadIdx.x], (unsigned long long)B.counters[threadIdx.x]);
-  for (int k = threadIdx.x; k < 40; k += kBlock) {
+  for (int k = threadIdx.x; k < 40; k += kFinBlock) {
     if (B.mins[k] == 0x7fffffffffffffffLL) continue;
     if (k < 32) { atomicMin(&acc->contrib_lo[k], B.mins[k]); atomicMax(&acc->contrib_hi[k], B.maxs[k]); }
     else { atomicMin(&acc->slop_lo[k - 32], B.mins[k]); atomicMax(&acc->slop_hi[k - 32], B.maxs[k]); }
