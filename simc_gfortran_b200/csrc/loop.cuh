@@ -82,12 +82,30 @@ static_assert(F_TK_YS == F_TK_XS + 1 && F_TK_DX == F_TK_XS + 2 && F_TK_DY == F_T
 #define SIMC_STATE_AOS 1
 #endif
 constexpr int kStateStride = (F_NFIELDS + 15) / 16 * 16;      // records start on 128-byte lines
+#ifndef SIMC_STATE_ST_HINT
+#define SIMC_STATE_ST_HINT 0
+#endif
+#ifndef SIMC_STATE_LD_HINT
+#define SIMC_STATE_LD_HINT 0
+#endif
 // 32-byte accesses (sm_100: ld/st.global.v4.f64), for groups of four fields that start at a multiple of four
 __device__ __forceinline__ void st_v4(double* p, double a, double b, double c, double d) {
+#if SIMC_STATE_ST_HINT == 1
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#elif SIMC_STATE_ST_HINT == 2
+  asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#endif
 }
 __device__ __forceinline__ void ld_v4(const double* p, double& a, double& b, double& c, double& d) {
+#if SIMC_STATE_LD_HINT == 1
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#elif SIMC_STATE_LD_HINT == 2
+  asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
   asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#endif
 }
 struct StateBuf {
   double* base;
@@ -388,9 +406,14 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
     s.v_pdelta = 0; s.v_pyptar = 0; s.v_pxptar = 0; s.v_edelta = 0; s.v_Pm = 0; s.v_Em = 0;
     s.v_eyptar = 0; s.v_exptar = 0; s.tz = 0;
     // every thread of the CTA walks through the generation code (SIMC_PHASE); the reaction is a run constant
-    s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
-    s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
-    s.o_pyptar = 0; s.o_pxptar = 0; s.rho_mass = 0; s.rho_theta = 0; s.rasterx = 0;
+    // (fields only meson / nuclear reactions use: H(e,e'p) neither reads them nor stores them, store_event, and
+    //  leaving them untouched keeps a quarter of the local frame's lines clean)
+    if (g.meson || g.heavy) {
+      s.pfer = 0; s.pferx = 0; s.pfery = 0; s.pferz = 0; s.efer = cfg.targ.Mtar_struck; s.v_zhad = 0; s.v_pt2 = 0;
+      s.m_eps = 0; s.m_thpq = 0; s.m_phipq = 0; s.m_t = 0; s.m_W = 0; s.m_tmin = 0;
+      s.o_pyptar = 0; s.o_pxptar = 0; s.rho_mass = 0; s.rho_theta = 0;
+    }
+    s.rasterx = 0;
     // (tables by value: a reference into the kernel parameters handed to an out-of-line function would make the
     //  compiler copy all of LoopArgs to every thread's stack -- +600 bytes of frame, +10 % kernel time)
     if (g.meson) ok = generate_meson_first(cfg, mt_s, A.pfm, A.sf, rng, GaussFn(), s, active, gr);
