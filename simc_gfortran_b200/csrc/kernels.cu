@@ -507,16 +507,20 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
       const ArmStage& st = sc.st[k];
       if (k == sc.n - 1) out = base + kArmLists;
       A.op_begin = st.begin; A.op_end = st.end; A.in_idx = in; A.out_idx = out;
+      // kernels that run no op of the program (loop.cuh: SEG_ 7, 8): no dynamic shared memory, more CTAs per SM
+      const unsigned lgrid = (unsigned)std::min<long long>(need, (long long)a.grid_blocks / 4 * SIMC_LIGHT_MIN_BLOCKS);
       if (st.kind == ARM_STAGE_CALO) {
         k_calo<<<grid, kBlock, 0, s>>>(A);
       } else if (st.kind == ARM_STAGE_ENTRY) {
         if (hadron) {
           if (field) k_arm<1, 4><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
           else if (coll) k_arm<1, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else if (st.begin == st.end) k_arm<1, 8><<<lgrid, kBlock, 0, s>>>(A, arm);
           else k_arm<1, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         } else {
           if (field) k_arm<0, 4><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
           else if (coll) k_arm<0, 3><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+          else if (st.begin == st.end) k_arm<0, 8><<<lgrid, kBlock, 0, s>>>(A, arm);
           else k_arm<0, 0><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         }
       } else if (st.kind == ARM_STAGE_COMPILED) {
@@ -540,8 +544,8 @@ cudaError_t launch_loop_stage(const LoopLaunch& a, int stage, cudaStream_t s) {
         if (hadron) k_arm<1, 6><<<hgrid, kBlock, kQueueBytes, s>>>(A, arm);
         else k_arm<0, 6><<<hgrid, kBlock, kQueueBytes, s>>>(A, arm);
       } else if (st.kind == ARM_STAGE_TAIL) {
-        if (hadron) k_arm<1, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
-        else k_arm<0, 7><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
+        if (hadron) k_arm<1, 7><<<lgrid, kBlock, 0, s>>>(A, arm);
+        else k_arm<0, 7><<<lgrid, kBlock, 0, s>>>(A, arm);
       } else if (st.kind == ARM_STAGE_MIDDLE) {
         if (hadron) k_arm<1, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);
         else k_arm<0, 2><<<grid, kBlock, kArmSmemBytes, s>>>(A, arm);

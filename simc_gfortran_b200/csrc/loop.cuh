@@ -236,6 +236,18 @@ struct GaussFn {
 #define SIMC_GEN_MIN_BLOCKS 2
 #endif
 constexpr int kGenBlock = SIMC_GEN_BLOCK;
+// Run constants in shared memory (bit 0: generation kernels, bit 1: k_radw / k_finish, bit 2: k_arm): the routines read
+// simc_run_config through a reference all along their straight-line code; in global memory those warp-uniform loads
+// share the L1 with the local frames of up to 1024 threads and miss it a third of the time.
+#ifndef SIMC_CFG_SMEM
+#define SIMC_CFG_SMEM 0
+#endif
+static_assert(sizeof(simc_run_config) % 8 == 0, "copied as 8-byte words");
+// (the caller's next __syncthreads() publishes the copy)
+__device__ __forceinline__ void cfg_to_shared(simc_run_config& dst, const simc_run_config* src, int nthreads) {
+  for (int i = threadIdx.x; i < (int)(sizeof(simc_run_config) / 8); i += nthreads)
+    ((unsigned long long*)&dst)[i] = ((const unsigned long long*)src)[i];
+}
 // launch shape of the end-of-loop kernels (k_radw, k_finish): straight-line code on compacted survivors as well
 #ifndef SIMC_FIN_BLOCK
 #define SIMC_FIN_BLOCK 256
@@ -391,8 +403,14 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
   // the out-of-line energy-loss routines take the material table by reference: give them shared memory,
   // not a generic pointer into the kernel-parameter bank
   __shared__ MatTable mt_s;
-  gen_shared_init(A, h_geni, mt_s);
+#if SIMC_CFG_SMEM & 1
+  __shared__ simc_run_config cfg_s;
+  cfg_to_shared(cfg_s, A.cfg, kGenBlock);
+  const simc_run_config& cfg = cfg_s;
+#else
   const simc_run_config& cfg = *A.cfg;
+#endif
+  gen_shared_init(A, h_geni, mt_s);
   const GenFlags g = gen_flags(cfg);
   const long long stride = (long long)gridDim.x * kGenBlock;
   for (long long i0 = (long long)blockIdx.x * kGenBlock; i0 < A.n_tries; i0 += stride) {
@@ -442,8 +460,14 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_generate(Loo
 __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopArgs A) {
   __shared__ unsigned h_geni[SIMC_H_PER_SET][SIMC_NHIST];
   __shared__ MatTable mt_s;
-  gen_shared_init(A, h_geni, mt_s);
+#if SIMC_CFG_SMEM & 1
+  __shared__ simc_run_config cfg_s;
+  cfg_to_shared(cfg_s, A.cfg, kGenBlock);
+  const simc_run_config& cfg = cfg_s;
+#else
   const simc_run_config& cfg = *A.cfg;
+#endif
+  gen_shared_init(A, h_geni, mt_s);
   const GenFlags g = gen_flags(cfg);
   const StateBuf& S = A.st;
   const unsigned n_in = A.counts[1 + kRegenList];
@@ -480,7 +504,14 @@ __global__ void __launch_bounds__(kGenBlock, SIMC_GEN_MIN_BLOCKS) k_regen(LoopAr
 // peaked_rad_weight (radc.f:523-646) and main%gen_weight = gen_weight * rad_weight / hardcorfac (radc.f:518) for
 // the tries of list `list_idx`: the survivors of both arms in a run, every generated try in record mode.
 __global__ void __launch_bounds__(kFinBlock, SIMC_FIN_MIN_BLOCKS) k_radw(LoopArgs A, int list_idx) {
+#if SIMC_CFG_SMEM & 2
+  __shared__ simc_run_config cfg_s;
+  cfg_to_shared(cfg_s, A.cfg, kFinBlock);
+  __syncthreads();
+  const simc_run_config& cfg = cfg_s;
+#else
   const simc_run_config& cfg = *A.cfg;
+#endif
   const StateBuf& S = A.st;
   const unsigned n_in = A.counts[1 + list_idx];
   const unsigned* in_list = A.lists + (long long)list_idx * A.st.cap;
@@ -594,9 +625,18 @@ __device__ __forceinline__ bool track_to_tgt_warp(const FieldDev& F, int k, cons
 #ifndef SIMC_HUT_MIN_BLOCKS
 #define SIMC_HUT_MIN_BLOCKS 5
 #endif
+// SEG_ = 8: SEG 0 of a schedule whose first stretch is compiled (no op of the program runs here: target multiple
+// scattering, SP quantities, TRANSPORT coordinates only).  It and the tail (7) need neither the power table nor the
+// record ring, are bound by the latency of their gathers, and are launched without dynamic shared memory at
+// SIMC_LIGHT_MIN_BLOCKS CTAs per SM.
+#ifndef SIMC_LIGHT_MIN_BLOCKS
+#define SIMC_LIGHT_MIN_BLOCKS 6
+#endif
 template <int WHICH, int SEG_>
-__global__ void __launch_bounds__(kBlock, SEG_ == 6 ? SIMC_HUT_MIN_BLOCKS : SIMC_ARM_MIN_BLOCKS) k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
-  constexpr int SEG = (SEG_ == 3 || SEG_ == 4) ? 0 : (SEG_ == 5 || SEG_ == 6 || SEG_ == 7) ? 1 : SEG_;
+__global__ void __launch_bounds__(kBlock, SEG_ == 6 ? SIMC_HUT_MIN_BLOCKS : (SEG_ == 7 || SEG_ == 8) ? SIMC_LIGHT_MIN_BLOCKS : SIMC_ARM_MIN_BLOCKS)
+k_arm(LoopArgs A, const __grid_constant__ ArmDev arm_c) {
+  constexpr int SEG = (SEG_ == 3 || SEG_ == 4 || SEG_ == 8) ? 0 : (SEG_ == 5 || SEG_ == 6 || SEG_ == 7) ? 1 : SEG_;
+  constexpr bool kNoOps = SEG_ == 8;
   constexpr bool kColl = SEG_ == 3;
   constexpr bool kField = SEG_ == 4 || SEG_ == 5;
   // SEG_ = 6, 7: SEG 1 in two kernels around the compiled reconstruction map (kernels.h: ARM_STAGE_HUT / _TAIL).
@@ -611,9 +651,16 @@ __global__ void __launch_bounds__(kBlock, SEG_ == 6 ? SIMC_HUT_MIN_BLOCKS : SIMC
   for (int i = threadIdx.x; i < (int)(sizeof(MatTable) / sizeof(double)); i += kBlock) ((double*)&mt_s)[i] = ((const double*)&A.mt)[i];
   for (int i = threadIdx.x; i < SIMC_NSTOP; i += kBlock) s_stop[i] = 0u;
   for (int i = threadIdx.x; i < 48; i += kBlock) s_calls[i] = 0u;
+#if SIMC_CFG_SMEM & 4
+  __shared__ simc_run_config cfg_s;
+  cfg_to_shared(cfg_s, A.cfg, kBlock);
   __syncthreads();
-  const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
+  const simc_run_config& cfg = cfg_s;
+#else
+  __syncthreads();
   const simc_run_config& cfg = *A.cfg;
+#endif
+  const unsigned ring = (unsigned)__cvta_generic_to_shared(pw_s) + (unsigned)kPowBytes + (threadIdx.x >> 5) * kRingBytesPerWarp;
   const StateBuf& S = A.st;
   const unsigned n_in = A.counts[1 + A.in_idx];
   const unsigned* in_list = A.lists + (long long)A.in_idx * A.st.cap;
@@ -718,7 +765,7 @@ __global__ void __launch_bounds__(kBlock, SEG_ == 6 ? SIMC_HUT_MIN_BLOCKS : SIMC
       musc_refresh(t);
       if (use_mc) {
         if (active) warp_count(&s_stop[0]);
-        run_arm<kColl>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls, s_stop);
+        if (!kNoOps) run_arm<kColl>(arm, t, rng, f, fry, pw_s + threadIdx.x, ring, res, hs, alive, op_begin, op_end, s_calls, s_stop);
         ok = alive;
       } else {
         ok = active;
@@ -1091,9 +1138,15 @@ __global__ void __launch_bounds__(kFinBlock, SIMC_FIN_MIN_BLOCKS) k_finish(LoopA
     for (int i = threadIdx.x; i < (int)(sizeof(BlockAcc) / 8); i += kFinBlock) w[i] = 0ULL;
     __syncthreads();
     for (int i = threadIdx.x; i < 40; i += kFinBlock) { B.mins[i] = 0x7fffffffffffffffLL; B.maxs[i] = (long long)0x8000000000000000ULL; }
-    __syncthreads();
   }
+#if SIMC_CFG_SMEM & 2
+  __shared__ simc_run_config cfg_s;
+  cfg_to_shared(cfg_s, A.cfg, kFinBlock);
+  const simc_run_config& cfg = cfg_s;
+#else
   const simc_run_config& cfg = *A.cfg;
+#endif
+  __syncthreads();
   const StateBuf& S = A.st;
   DevAccum* acc = A.acc;
   const unsigned n_in = A.counts[1 + 2 * kArmLists];
